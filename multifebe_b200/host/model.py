@@ -1,0 +1,155 @@
+"""Flat (C-ABI ready) description of one elastic BE region, built the way the reference's host does.
+
+Mirrors, for the `be` / ordinary-boundary case used by the harmonic 3D hot path:
+  * default BEM formulation   src/assign_default_bem_formulation.f90:74-93 (part-rim nodes -> SBIE-MCA, delta 0.05)
+  * collocation points        src/build_data_at_collocation_points.f90:124-160,285-310
+  * DOF numbering             src/build_auxiliary_variables_mechanics_harmonic.f90:151-198
+  * material                  src/read_regions.f90:717-722  (mu_c = mu(1+2i xi), lambda_c = 2 mu_c nu/(1-2nu))
+Everything here is O(N) host bookkeeping; the arrays it produces are exactly what crosses the C ABI
+(include/mfb.h) and what the oracle consumes.
+"""
+import numpy as np
+from . import shape as sh
+
+MCA_BOUNDARY_DELTA = 0.05          # assign_default_bem_formulation.f90:40
+NODAL_XI_MARK = -9.0               # colloc_xi marker for nodal SBIE collocation
+
+
+class Material:
+    def __init__(self, rho=1.0, mu=1.0, nu=0.25, xi=0.02):
+        self.rho, self.mu_r, self.nu_r, self.xi = float(rho), float(mu), float(nu), float(xi)
+        self.mu = self.mu_r * (1.0 + 1j * 2.0 * self.xi)
+        self.nu = complex(self.nu_r)
+        self.lam = 2.0 * self.mu * self.nu_r / (1.0 - 2.0 * self.nu_r)
+        self.c1 = np.sqrt((self.lam + 2.0 * self.mu) / self.rho)
+        self.c2 = np.sqrt(self.mu / self.rho)
+
+
+class Model:
+    """bcs: {part_id: ([ctype_x, ctype_y, ctype_z], [value_x, value_y, value_z])}, ctype 0 = u known, 1 = t known."""
+
+    def __init__(self, mesh, bcs, reversed_parts=(), qsi_relative_error=1e-6, qsi_ns_max=16,
+                 precalset_gln=(2, 3, 4, 5, 6, 7, 8, 9), geometric_tolerance=1e-6):
+        self.mesh = mesh
+        nn = len(mesh.nodes)
+        ne = mesh.n_elem
+        self.n_node, self.n_elem = nn, ne
+        self.node_x = mesh.nodes
+        self.etype = mesh.etype.astype(np.int32)
+        self.elem_ptr = np.zeros(ne + 1, dtype=np.int32)
+        self.elem_ptr[1:] = np.cumsum([len(c) for c in mesh.conn])
+        self.elem_node = np.concatenate(mesh.conn).astype(np.int32)
+        self.elem_reversed = np.array([1 if int(p) in reversed_parts else 0 for p in mesh.part], dtype=np.uint8)
+        self.qsi_relative_error, self.qsi_ns_max = float(qsi_relative_error), int(qsi_ns_max)
+        self.precalset_gln = np.array(precalset_gln, dtype=np.int32)
+        self.geometric_tolerance = float(geometric_tolerance)
+
+        # --- part rims: nodes of edges that belong to a single element of the part (data_structures.f90:1617-1636)
+        node_part = -np.ones(nn, dtype=np.int64)
+        edge_count = {}
+        for e in range(ne):
+            c, p = mesh.conn[e], int(mesh.part[e])
+            for v in c:
+                if node_part[v] not in (-1, p):
+                    raise ValueError("node %d is shared by two boundaries; each boundary must own its nodes" % v)
+                node_part[v] = p
+            for ed in sh.edges_of(int(mesh.etype[e])):
+                key = (p,) + tuple(sorted((int(c[ed[0]]), int(c[ed[1]]))))
+                edge_count.setdefault(key, []).append([int(c[k]) for k in ed])
+        in_boundary = np.zeros(nn, dtype=bool)
+        for key, lst in edge_count.items():
+            if len(lst) == 1:
+                in_boundary[lst[0]] = True
+        self.in_boundary = in_boundary
+        self.node_part = node_part
+
+        # --- boundary conditions per node
+        self.ctype = np.zeros((nn, 3), dtype=np.int32)
+        self.cvalue = np.zeros((nn, 3), dtype=np.complex128)
+        for v in range(nn):
+            ct, cv = bcs[int(node_part[v])]
+            self.ctype[v] = ct
+            self.cvalue[v] = cv
+
+        # --- DOF numbering: region -> boundary (part id order) -> element -> node, first visit
+        parts = sorted(set(int(p) for p in mesh.part))
+        order = [e for p in parts for e in range(ne) if int(mesh.part[e]) == p]
+        self.elem_order = np.array(order, dtype=np.int32)
+        self.row = -np.ones((nn, 3), dtype=np.int32)
+        self.col_u = -np.ones((nn, 3), dtype=np.int32)
+        self.col_t = -np.ones((nn, 3), dtype=np.int32)
+        row = col = 0
+        seen = np.zeros(nn, dtype=bool)
+        for e in order:
+            for v in mesh.conn[e]:
+                if seen[v]:
+                    continue
+                seen[v] = True
+                for k in range(3):
+                    self.row[v, k] = row; row += 1
+                    if self.ctype[v, k] == 0:
+                        self.col_t[v, k] = col
+                    elif self.ctype[v, k] == 1:
+                        self.col_u[v, k] = col
+                    else:
+                        raise ValueError("only ctype 0/1 are supported on this path")
+                    col += 1
+        assert row == col
+        self.n_dof = row
+
+        # --- collocation points (loop order of build_lse_mechanics_bem_harela.f90:1118-1136)
+        cx, cnode, celem, ckn, cxi = [], [], [], [], []
+        collocated = np.zeros(nn, dtype=bool)
+        for e in order:
+            et = int(mesh.etype[e]); c = mesh.conn[e]
+            xn = self.node_x[c]
+            for kn, v in enumerate(c):
+                if in_boundary[v]:
+                    xi = sh.move_xi_from_edge(et, sh.XI_NODES[et][kn], MCA_BOUNDARY_DELTA)
+                    cx.append(sh.position(et, xn, xi)); cxi.append(xi)
+                elif not collocated[v]:
+                    collocated[v] = True
+                    cx.append(sh.position(et, xn, sh.XI_NODES[et][kn])); cxi.append([NODAL_XI_MARK, NODAL_XI_MARK])
+                else:
+                    continue
+                cnode.append(v); celem.append(e); ckn.append(kn)
+        self.colloc_x = np.ascontiguousarray(cx, dtype=np.float64)
+        self.colloc_node = np.array(cnode, dtype=np.int32)
+        self.colloc_elem = np.array(celem, dtype=np.int32)
+        self.colloc_kn = np.array(ckn, dtype=np.int32)
+        self.colloc_xi = np.ascontiguousarray(cxi, dtype=np.float64)
+        self.n_colloc = len(cnode)
+
+    # --- reference's assign_solution_mechanics_harmonic.f90:192-205: nodal u,t from the solution vector
+    def nodal_solution(self, x):
+        u = np.zeros((self.n_node, 3), dtype=np.complex128)
+        t = np.zeros((self.n_node, 3), dtype=np.complex128)
+        for k in range(3):
+            known_u = self.ctype[:, k] == 0
+            u[known_u, k] = self.cvalue[known_u, k]
+            t[known_u, k] = x[self.col_t[known_u, k]]
+            t[~known_u, k] = self.cvalue[~known_u, k]
+            u[~known_u, k] = x[self.col_u[~known_u, k]]
+        return u, t
+
+
+# the reference's harmonic cube tutorial (docs/examples/ME-TH-EL-001/case_files/t3.dat:38-55), by physical name
+# of t3.msh: 1 front(z=1) 2 right(x=1) 3 back(z=0) 4 left(x=0) 5 top(y=1) 6 bottom(y=0)
+ME_TH_EL_001_BCS = {
+    1: ([1, 1, 0], [0, 0, 0]), 2: ([1, 1, 1], [1, 0, 0]), 3: ([1, 1, 0], [0, 0, 0]),
+    4: ([0, 0, 0], [0, 0, 0]), 5: ([1, 0, 1], [0, 0, 0]), 6: ([1, 0, 1], [0, 0, 0]),
+}
+
+
+def cube_bcs():
+    """Same physical problem on cube_mesh() part ids (1 x=0, 2 x=L, 3 y=0, 4 y=L, 5 z=0, 6 z=L):
+    x=0 clamped, x=L unit normal traction, lateral faces: zero normal displacement, zero shear (1D P-wave column)."""
+    return {1: ([0, 0, 0], [0, 0, 0]), 2: ([1, 1, 1], [1, 0, 0]),
+            3: ([1, 0, 1], [0, 0, 0]), 4: ([1, 0, 1], [0, 0, 0]),
+            5: ([1, 1, 0], [0, 0, 0]), 6: ([1, 1, 0], [0, 0, 0])}
+
+
+def column_analytic_u(x1, omega, mat, L=1.0, P=1.0):
+    """u1(x1) of the clamped-free P-wave column (docs/examples/ME-TH-EL-001/doc_src/ME-TH-EL-001.tex:32-56)."""
+    k = omega / mat.c1
+    return -P * (np.exp(-1j * k * x1) - np.exp(1j * k * x1)) / ((mat.lam + 2 * mat.mu) * 1j * k * (np.exp(-1j * k * L) + np.exp(1j * k * L)))

@@ -1,0 +1,164 @@
+"""ctypes loader for the CPU oracle (TEST INFRASTRUCTURE ONLY -- see harela3d_oracle.cpp header).
+
+May be imported only by tests/, bench.py's cpu_baseline / --impl reference legs and
+__graft_entry__.smoke().  Never by multifebe_b200/.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        L.orc_setup.restype = C.c_void_p
+        L.orc_telles_barr.restype = C.c_double
+        L.orc_telles_barr.argtypes = [C.c_double]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _ri(z):
+    z = complex(z)
+    return np.array([z.real, z.imag], dtype=np.float64)
+
+
+class Oracle:
+    """Oracle handle for one Model (multifebe_b200.host.Model)."""
+
+    def __init__(self, model):
+        L = lib()
+        m = self.m = model
+        self._keep = [np.ascontiguousarray(a) for a in (
+            m.node_x, m.etype, m.elem_ptr, m.elem_node, m.elem_reversed, m.colloc_x, m.colloc_node, m.colloc_elem,
+            m.colloc_kn, m.colloc_xi, m.row, m.col_u, m.col_t, m.ctype, m.precalset_gln)]
+        k = self._keep
+        self.h = C.c_void_p(L.orc_setup(
+            C.c_int(m.n_node), _p(k[0]), C.c_int(m.n_elem), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]),
+            C.c_int(m.n_colloc), _p(k[5]), _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9]),
+            _p(k[10]), _p(k[11]), _p(k[12]), _p(k[13]), C.c_int(m.n_dof),
+            C.c_double(m.qsi_relative_error), C.c_int(m.qsi_ns_max), C.c_int(len(m.precalset_gln)), _p(k[14]),
+            C.c_double(m.geometric_tolerance)))
+
+    def __del__(self):
+        try:
+            lib().orc_free(self.h)
+        except Exception:
+            pass
+
+    def assemble(self, omega, mat, nthreads=0):
+        """-> A (n_dof x n_dof, Fortran order), b (n_dof), stats dict.  One frequency, A and b start at zero."""
+        n = self.m.n_dof
+        A = np.zeros((n, n), dtype=np.complex128, order="F")
+        b = np.zeros(n, dtype=np.complex128)
+        st = np.zeros(44, dtype=np.int64)
+        cv = np.ascontiguousarray(self.m.cvalue)
+        err = lib().orc_assemble(self.h, C.c_double(omega), _p(_ri(mat.lam)), _p(_ri(mat.mu)), C.c_double(mat.rho),
+                                 _p(_ri(mat.nu)), _p(cv), _p(A), _p(b), C.c_int(nthreads), _p(st))
+        if err:
+            raise RuntimeError("oracle: invalid normals/tangents configuration in free-term")
+        stats = {"pairs_regular": {g: int(st[g]) for g in range(33) if st[g]}, "pts_regular": int(st[33]),
+                 "pairs_adaptive": int(st[34]), "leaves": int(st[35]), "pts_adaptive": int(st[36]),
+                 "pairs_singular": int(st[37]), "pts_singular": int(st[38]), "li_points": int(st[39])}
+        return A, b, stats
+
+    def pair(self, e, x_i, omega, mat):
+        """h, g (n,3,3) complex of one (collocation point, element) pair and the integration mode."""
+        nn = int(self.m.elem_ptr[e + 1] - self.m.elem_ptr[e])
+        h = np.zeros((nn, 3, 3), dtype=np.complex128)
+        g = np.zeros((nn, 3, 3), dtype=np.complex128)
+        st = np.zeros(8, dtype=np.int64)
+        x_i = np.ascontiguousarray(x_i, dtype=np.float64)
+        mode = lib().orc_pair(self.h, C.c_int(e), _p(x_i), C.c_double(omega), _p(_ri(mat.lam)), _p(_ri(mat.mu)),
+                              C.c_double(mat.rho), _p(h), _p(g), _p(st))
+        return h, g, mode, st
+
+    def pair_mode(self, e, x_i):
+        x_i = np.ascontiguousarray(x_i, dtype=np.float64)
+        d = C.c_double(0.0)
+        bx = np.zeros(2)
+        mode = lib().orc_pair_mode(self.h, C.c_int(e), _p(x_i), C.byref(d), _p(bx))
+        return mode, d.value, bx
+
+    def element_data(self, e):
+        cl, br, g = C.c_double(), C.c_double(), C.c_int()
+        bc = np.zeros(3)
+        lib().orc_element_data(self.h, C.c_int(e), C.byref(cl), C.byref(g), _p(bc), C.byref(br))
+        return cl.value, g.value, bc, br.value
+
+
+def zexp_decomposed(z):
+    E = np.zeros(7, dtype=np.complex128)
+    lib().orc_zexp_decomposed(_p(_ri(z)), _p(E))
+    return E
+
+
+def fundamental_solutions(x, n, x_i, omega, mat):
+    u = np.zeros((3, 3), dtype=np.complex128)
+    t = np.zeros((3, 3), dtype=np.complex128)
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (x, n, x_i)]
+    lib().orc_fundamental_solutions(_p(a[0]), _p(a[1]), _p(a[2]), C.c_double(omega), _p(_ri(mat.lam)), _p(_ri(mat.mu)),
+                                    C.c_double(mat.rho), _p(u), _p(t))
+    return u, t
+
+
+def qs_n(telles, etype, f, re, d, barxi):
+    bx = np.ascontiguousarray(barxi, dtype=np.float64)
+    return lib().orc_qs_n(C.c_int(int(telles)), C.c_int(etype), C.c_int(f), C.c_double(re), C.c_double(d), _p(bx))
+
+
+def nearest(etype, x_nodes, x_i):
+    x = np.ascontiguousarray(x_nodes, dtype=np.float64)
+    xi = np.ascontiguousarray(x_i, dtype=np.float64)
+    bx = np.zeros(2)
+    rmin, d, method = C.c_double(), C.c_double(), C.c_int()
+    lib().orc_nearest(C.c_int(etype), _p(x), _p(xi), _p(bx), C.byref(rmin), C.byref(d), C.byref(method))
+    return bx, rmin.value, d.value, method.value
+
+
+def tables(family, n):
+    L = lib()
+    if family == 3:
+        npt = L.orc_wantri_n(C.c_int(n))
+        x = np.zeros(2 * npt); w = np.zeros(npt)
+    else:
+        x = np.zeros(n); w = np.zeros(n)
+    L.orc_tables(C.c_int(family), C.c_int(n), _p(x), _p(w))
+    return x, w
+
+
+def freeterm(normals, tangents, nu, tol=1e-6):
+    n = np.ascontiguousarray(normals, dtype=np.float64)
+    t = np.ascontiguousarray(tangents, dtype=np.float64)
+    c = np.zeros((3, 3), dtype=np.complex128)
+    err = lib().orc_freeterm(C.c_int(len(n)), _p(n), _p(t), C.c_double(tol), _p(_ri(nu)), _p(c))
+    return c, err
+
+
+def lu_solve(A, b):
+    """The reference's solve_lse_c default path (src/solve_lse_c.f90:124,176): zgetrf + zgetrs from the
+    OpenBLAS the interpreter ships (scipy-bundled OpenBLAS; MultiFEBE links an unpinned OpenBLAS)."""
+    from scipy.linalg import lapack
+    lu, piv, info = lapack.zgetrf(A, overwrite_a=False)
+    if info != 0:
+        raise RuntimeError("zgetrf info=%d" % info)
+    x, info = lapack.zgetrs(lu, piv, b)
+    if info != 0:
+        raise RuntimeError("zgetrs info=%d" % info)
+    return x, lu, piv
