@@ -1,0 +1,122 @@
+/* mfb.h -- C ABI of the B200-native hot path of MultiFEBE's time-harmonic 3D elastodynamic BEM.
+ *
+ * The reference (MultiFEBE v2.0.1, Fortran 2003) has no FFI/plugin interface; the two seams this
+ * library replaces are Fortran call sites operating on `module problem_variables` globals:
+ *
+ *   seam 1  subroutine build_lse_mechanics_bem_harela(kf,kr)      src/build_lse_mechanics_bem_harela.f90:22-968
+ *           called from build_lse_mechanics_harmonic              src/build_lse_mechanics_harmonic.f90:88
+ *           after `A_c=0; b_c=0` (:73-74).  Replaced by mfb_harela3d_setup (once per run: everything that does
+ *           not depend on omega) + mfb_harela3d_assemble (once per frequency).
+ *   seam 2  subroutine solve_lse_c(n_dof,A,ipiv,...,n_rhs,b,factorize,scaling,condition,refine)
+ *                                                                 src/solve_lse_c.f90:25-219 (zgetrf :124, zgetrs :176)
+ *           called from src/multifebe.f90:111-112.  Replaced by mfb_zsolve.
+ *   loop    do kf=1,n_frequencies (src/multifebe.f90:107-124)     -> mfb_harela3d_solve_frequency (device-resident
+ *           assemble + LU + solve of one frequency; the frequency shard of a multi-GPU sweep calls it per owned kf).
+ *
+ * Conventions: plain C, host pointers, no derived types.  All arrays are flat, 0-based indices, column-major
+ * matrices, complex numbers interleaved (re,im) == complex(real64) == `mfb_z`.  Every function returns 0 on success,
+ * <0 for an invalid argument / missing device, >0 for a numerical failure (e.g. singular pivot = LAPACK info);
+ * mfb_last_error() returns the message (the Fortran shim maps nonzero to fbem_error_message + stop, as the reference
+ * does at src/solve_lse_c.f90:129-133).  One caller thread per context; one context per GPU (one process per GPU).
+ * There is no CPU fallback: every compute entry point fails with MFB_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef MFB_H
+#define MFB_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { double re, im; } mfb_z;
+typedef struct mfb_ctx mfb_ctx;
+typedef struct mfb_problem mfb_problem;
+
+#define MFB_OK 0
+#define MFB_ERR_ARG (-1)
+#define MFB_ERR_NO_DEVICE (-2)
+#define MFB_ERR_CUDA (-3)
+#define MFB_ERR_UNSUPPORTED (-4)
+
+/* element type ids == lib/fbem/src/shape_functions.f90:198-206 */
+#define MFB_TRI3 5
+#define MFB_TRI6 6
+#define MFB_QUAD4 7
+#define MFB_QUAD8 8
+#define MFB_QUAD9 9
+
+const char* mfb_last_error(void);
+int mfb_version(void);
+
+/* Bind a context to CUDA device `device` (LOCAL_RANK under torchrun).  Fails (MFB_ERR_NO_DEVICE) without a GPU. */
+int mfb_init(int device, mfb_ctx** ctx);
+void mfb_finalize(mfb_ctx* ctx);
+
+/* Once per run.  Replaces the omega-independent part of build_lse_mechanics_bem_harela + the per-element data the
+ * reference recomputes every frequency (fbem_bem_element / init_precalculated_datasets, lib/fbem/src/bem_general.f90:163-759;
+ * csize, n_phi, bounding ball, src/build_data_of_be_elements.f90:62-110) and builds the quadrature plan
+ * (fbem_bem_harela3d_sbie_auto decisions, lib/fbem/src/bem_harela3d.f90:1474-1538, incl. the adaptive-subdivision leaf list
+ * of _sbie_ext_adp :1050-1172 and the polar/line-integral data of _sbie_int :1174-1472) and the Mantic free terms' geometry.
+ *   node_x[3*n_node]; etype[n_elem] in MFB_TRI3..MFB_QUAD9; elem_ptr[n_elem+1], elem_node[] = element(:)%node (0-based,
+ *   isoparametric: geometric == functional nodes, continuous); elem_reversed[n_elem] = region%boundary_reversion;
+ *   collocation points in the order of the reference's kb_col/ke_col/kn_col loop (build_lse_mechanics_bem_harela.f90:1118-1136):
+ *   colloc_x[3*n_colloc] = x_i_sbie / x_i_sbie_mca, colloc_node = sn_col (its 3 rows receive the equation), colloc_elem /
+ *   colloc_kn = owning element and local node (free-term pass :273-747), colloc_xi[2*n_colloc] = xi_i_sbie_mca, or (-9,-9)
+ *   for a nodal SBIE point; row/col_u/col_t/ctype[3*n_node] = node%row(k,1), node%col(k,1), node%col(3+k,1), node%ctype(k,1)
+ *   (0-based, -1 = none; ctype 0: u known, 1: t known) from build_auxiliary_variables_mechanics_harmonic.f90:151-198;
+ *   settings = [settings] section defaults of src/read_settings.f90:74-216. */
+int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
+                       const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
+                       const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
+                       const int* row, const int* col_u, const int* col_t, const int* ctype, int n_dof,
+                       double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
+                       double geometric_tolerance, mfb_problem** problem);
+void mfb_problem_free(mfb_problem* problem);
+
+/* Once per frequency.  == `A_c=0; b_c=0` + build_lse_mechanics_bem_harela(kf,kr) for one elastic BE region with
+ * ordinary `be` boundaries: integrates every (collocation point, element) pair, adds the free terms and scatters per
+ * assemble_bem_harela_equation.f90:78-113 into the device-resident system.  lambda/mu/nu = region%property_c(6,2,3),
+ * rho = property_r(1); cvalue[3*n_node] = node%cvalue_c(k,1,1).  If A (n_dof x n_dof col-major, ld = n_dof) / b are non-NULL
+ * the assembled system is also copied to the host (the reference's A_c, b_c). */
+int mfb_harela3d_assemble(mfb_problem* problem, double omega, const mfb_z* lambda, const mfb_z* mu, double rho,
+                          const mfb_z* nu, const mfb_z* cvalue, mfb_z* A, mfb_z* b);
+
+/* == solve_lse_c(n_dof,A,ipiv,..,n_rhs,b,factorize,scaling=F,condition=F,refine=F): in-place LU with partial pivoting
+ * (zgetrf) + triangular solves (zgetrs).  A == NULL: use the device-resident system of the last mfb_harela3d_assemble (and
+ * keep the factors on the device); otherwise A (lda x n, host) is uploaded, overwritten by the LU factors on return.
+ * ipiv (1-based, LAPACK convention) may be NULL.  b (ldb = n, nrhs columns; NULL with A == NULL: device-resident rhs) is
+ * overwritten by the solution.  factorize = 0 re-uses the factors of the previous call (multifebe.f90:119-120).
+ * Returns >0 (= LAPACK info) on an exactly singular pivot. */
+int mfb_zsolve(mfb_problem* problem, int n, mfb_z* A, int lda, int* ipiv, mfb_z* b, int nrhs, int factorize);
+
+/* One iteration of the frequency loop (src/multifebe.f90:107-124) kept on the device: assemble, factorise, solve;
+ * x[n_dof] receives the solution (what assign_solution_mechanics_harmonic.f90:192-205 reads from b_c). */
+int mfb_harela3d_solve_frequency(mfb_problem* problem, double omega, const mfb_z* lambda, const mfb_z* mu, double rho,
+                                 const mfb_z* nu, const mfb_z* cvalue, mfb_z* x);
+
+/* Plan statistics and per-phase device timings (CUDA events) of the last call; see mfb_stat_id. */
+enum mfb_stat_id {
+  MFB_STAT_PAIRS_REGULAR = 0, MFB_STAT_POINTS_REGULAR = 1, MFB_STAT_PAIRS_ADAPTIVE = 2, MFB_STAT_LEAVES = 3,
+  MFB_STAT_POINTS_ADAPTIVE = 4, MFB_STAT_PAIRS_SINGULAR = 5, MFB_STAT_POINTS_SINGULAR = 6, MFB_STAT_NEAR_PAIRS = 7,
+  MFB_STAT_MS_ZERO = 8, MFB_STAT_MS_REGULAR = 9, MFB_STAT_MS_ADAPTIVE = 10, MFB_STAT_MS_SINGULAR = 11,
+  MFB_STAT_MS_FREETERM = 12, MFB_STAT_MS_LU = 13, MFB_STAT_MS_SOLVE = 14, MFB_STAT_MS_GEMM = 15, MFB_STAT_MS_PANEL = 16,
+  MFB_STAT_LAUNCHES = 17, MFB_STAT_MS_SETUP_HOST = 18, MFB_STAT_MS_ASSEMBLE = 19, MFB_STAT_FLOPS_REGULAR = 20,
+  MFB_STAT_MS_TRSM = 21, MFB_STAT_MS_SWAP = 22, MFB_STAT_COUNT = 32
+};
+int mfb_get_stats(mfb_problem* problem, double* stats /* MFB_STAT_COUNT doubles */);
+
+/* Per-pair integration mode chosen by the plan (for parity tests of the discrete decisions):
+ * 2..30 = regular rule gln of the precalculated set, 100 = adaptive (Telles + subdivision), 200 = singular. */
+int mfb_plan_modes(mfb_problem* problem, int n_pairs, const int* colloc, const int* elem, int* mode);
+
+/* Micro-benchmarks used to measure the roofline denominators on the box (FP64 FMA pipe, FP64 tensor (DMMA) pipe,
+ * device copy bandwidth): returns TFLOP/s or GB/s. */
+int mfb_measure_peaks(mfb_ctx* ctx, double* dfma_tflops, double* dmma_tflops, double* copy_gbs);
+
+/* Standalone complex GEMM used by the LU trailing update (C -= A*B on planar re/im storage); exposed for tests/bench.
+ * C (m x n), A (m x k), B (k x n), all host col-major interleaved complex. */
+int mfb_zgemm_minus(mfb_ctx* ctx, int m, int n, int k, const mfb_z* A, int lda, const mfb_z* B, int ldb, mfb_z* C, int ldc,
+                    double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,56 @@
+"""Build libmfb.so (the C-ABI shared library) in-tree with nvcc for sm_100a.
+
+    python -m multifebe_b200.build [--force]
+
+nvcc cross-compiles without a GPU.  The host planner (plan_host.cpp) is compiled by the system g++ with
+-ffp-contract=off (its arithmetic feeds discrete quadrature decisions, see csrc/plan_host.h).
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libmfb.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+GXX = "/usr/bin/g++"   # the image's $CXX wrapper lacks libgomp.spec
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+SOURCES_CU = ["api.cu", "assembly.cu", "lu.cu"]
+DEPS = SOURCES_CU + ["plan_host.cpp", "plan_host.h", "assembly.cuh", "lu.cuh", "bem_math.cuh",
+                     os.path.join("..", "..", "include", "mfb.h"), os.path.join("..", "..", "data", "quad_tables.h")]
+
+
+def _stale():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and not _stale():
+        return OUT
+    bdir = os.path.join(HERE, "build")
+    os.makedirs(bdir, exist_ok=True)
+    objs = []
+    o = os.path.join(bdir, "plan_host.o")
+    cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-c",
+           os.path.join(CSRC, "plan_host.cpp"), "-o", o]
+    subprocess.check_call(cmd)
+    objs.append(o)
+    for src in SOURCES_CU:
+        o = os.path.join(bdir, src.replace(".cu", ".o"))
+        cmd = [NVCC, "-ccbin", GXX, "-O3", "-std=c++17", "-lineinfo"] + ARCH + [
+            "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off,-fcx-fortran-rules",
+            "-Xptxas", "-v" if verbose else "-O3", "-c", os.path.join(CSRC, src), "-o", o]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+        objs.append(o)
+    cmd = [NVCC, "-ccbin", GXX, "-shared", "-o", OUT] + objs + ["-Xcompiler", "-fopenmp", "-lquadmath", "-lcudart", "-lgomp"] + ARCH
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

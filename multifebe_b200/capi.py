@@ -1,0 +1,154 @@
+"""ctypes binding of libmfb.so (include/mfb.h) + the host-side mirror of the reference's call sites.
+
+The reference is a Fortran program without an FFI; its two seams on this path are the subroutines
+`build_lse_mechanics_bem_harela(kf,kr)` (src/build_lse_mechanics_bem_harela.f90:22) and `solve_lse_c(...)`
+(src/solve_lse_c.f90:25).  `Problem` exposes methods with those names and argument meaning so the parity tests read like
+the reference's own call sequence (src/multifebe.f90:107-124):
+
+    prob = Problem(ctx, model)                       # build_data + build_auxiliary_variables (once)
+    A, b = prob.build_lse_mechanics_bem_harela(omega, material)   # A_c, b_c of this frequency
+    x = prob.solve_lse_c()                           # zgetrf + zgetrs on the device-resident system
+
+There is no CPU fallback: loading fails loudly if libmfb.so is missing and mfb_init fails without a CUDA device.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+STAT = dict(PAIRS_REGULAR=0, POINTS_REGULAR=1, PAIRS_ADAPTIVE=2, LEAVES=3, POINTS_ADAPTIVE=4, PAIRS_SINGULAR=5,
+            POINTS_SINGULAR=6, NEAR_PAIRS=7, MS_ZERO=8, MS_REGULAR=9, MS_ADAPTIVE=10, MS_SINGULAR=11, MS_FREETERM=12,
+            MS_LU=13, MS_SOLVE=14, MS_GEMM=15, MS_PANEL=16, LAUNCHES=17, MS_SETUP_HOST=18, MS_ASSEMBLE=19,
+            FLOPS_REGULAR=20, MS_TRSM=21, MS_SWAP=22)
+STAT_COUNT = 32
+
+
+class MfbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("mfb error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    """Load libmfb.so (built in-tree by multifebe_b200.build).  Raises if absent -- never falls back to another path."""
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libmfb.so")
+        if not os.path.exists(so):
+            raise ImportError("multifebe_b200/libmfb.so is not built; run `python -m multifebe_b200.build` "
+                              "(there is no CPU fallback for this path)")
+        L = C.CDLL(so)
+        L.mfb_last_error.restype = C.c_char_p
+        _LIB = L
+    return _LIB
+
+
+def _check(code):
+    if code != 0:
+        raise MfbError(code, lib().mfb_last_error().decode())
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _z(v):
+    v = complex(v)
+    return np.array([v.real, v.imag], dtype=np.float64)
+
+
+class Context:
+    """One context per GPU (one process per GPU)."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _check(lib().mfb_init(C.c_int(device), C.byref(self.h)))
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib().mfb_finalize(self.h)
+            self.h = C.c_void_p()
+
+    def measure_peaks(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _check(lib().mfb_measure_peaks(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"dfma_tflops": a.value, "dmma_tflops": b.value, "copy_gbs": c.value}
+
+    def zgemm_minus(self, Cm, A, B):
+        """C -= A @ B on the device (FP64 tensor pipe); returns (C, ms)."""
+        A = np.asfortranarray(A, dtype=np.complex128); B = np.asfortranarray(B, dtype=np.complex128)
+        Cm = np.asfortranarray(Cm, dtype=np.complex128).copy(order="F")
+        m, k = A.shape; n = B.shape[1]
+        ms = C.c_double()
+        _check(lib().mfb_zgemm_minus(self.h, C.c_int(m), C.c_int(n), C.c_int(k), _p(A), C.c_int(m), _p(B), C.c_int(k), _p(Cm),
+                                     C.c_int(m), C.byref(ms)))
+        return Cm, ms.value
+
+
+class Problem:
+    def __init__(self, ctx, model):
+        self.ctx, self.m = ctx, model
+        m = model
+        k = self._keep = [np.ascontiguousarray(a) for a in (
+            m.node_x, m.etype, m.elem_ptr, m.elem_node, m.elem_reversed, m.colloc_x, m.colloc_node, m.colloc_elem,
+            m.colloc_kn, m.colloc_xi, m.row, m.col_u, m.col_t, m.ctype, m.precalset_gln)]
+        self.h = C.c_void_p()
+        _check(lib().mfb_harela3d_setup(
+            ctx.h, C.c_int(m.n_node), _p(k[0]), C.c_int(m.n_elem), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]),
+            C.c_int(m.n_colloc), _p(k[5]), _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9]), _p(k[10]), _p(k[11]), _p(k[12]), _p(k[13]),
+            C.c_int(m.n_dof), C.c_double(m.qsi_relative_error), C.c_int(m.qsi_ns_max), C.c_int(len(m.precalset_gln)), _p(k[14]),
+            C.c_double(m.geometric_tolerance), C.byref(self.h)))
+        self._cv = np.ascontiguousarray(m.cvalue, dtype=np.complex128)
+
+    def close(self):
+        if self.h:
+            lib().mfb_problem_free(self.h)
+            self.h = C.c_void_p()
+
+    # ---- seam 1: build_lse_mechanics_bem_harela(kf,kr) after A_c=0; b_c=0 ----
+    def build_lse_mechanics_bem_harela(self, omega, mat, want_host=True):
+        n = self.m.n_dof
+        A = b = None
+        if want_host:
+            A = np.zeros((n, n), dtype=np.complex128, order="F")
+            b = np.zeros(n, dtype=np.complex128)
+        _check(lib().mfb_harela3d_assemble(self.h, C.c_double(omega), _p(_z(mat.lam)), _p(_z(mat.mu)), C.c_double(mat.rho),
+                                           _p(_z(mat.nu)), _p(self._cv), _p(A) if want_host else None, _p(b) if want_host else None))
+        return A, b
+
+    # ---- seam 2: solve_lse_c(n_dof,A,ipiv,...,n_rhs,b,factorize,scaling=F,condition=F,refine=F) ----
+    def solve_lse_c(self, A=None, b=None, factorize=True, want_ipiv=False):
+        """A=None, b=None: factorise/solve the device-resident system of the last assembly; returns x (and ipiv).
+        With host A (n x n) and b (n or n x nrhs): LAPACK zgesv semantics, A is overwritten by the LU factors."""
+        n = self.m.n_dof
+        ipiv = np.zeros(n, dtype=np.int32)
+        if A is not None and not (A.flags.f_contiguous and A.dtype == np.complex128):
+            raise ValueError("A must be a Fortran-ordered complex128 array (it is overwritten by the LU factors)")
+        if b is None:
+            raise ValueError("pass the right-hand side b (use solve_frequency for the fully device-resident path)")
+        bb = np.asfortranarray(b, dtype=np.complex128).reshape(n, -1, order="F").copy(order="F")
+        _check(lib().mfb_zsolve(self.h, C.c_int(n), _p(A) if A is not None else None, C.c_int(n), _p(ipiv), _p(bb),
+                                C.c_int(bb.shape[1]), C.c_int(int(factorize))))
+        x = bb[:, 0] if np.ndim(b) == 1 else bb
+        return (x, ipiv) if want_ipiv else x
+
+    # ---- one iteration of the frequency loop, device resident ----
+    def solve_frequency(self, omega, mat):
+        x = np.zeros(self.m.n_dof, dtype=np.complex128)
+        _check(lib().mfb_harela3d_solve_frequency(self.h, C.c_double(omega), _p(_z(mat.lam)), _p(_z(mat.mu)), C.c_double(mat.rho),
+                                                  _p(_z(mat.nu)), _p(self._cv), _p(x)))
+        return x
+
+    def stats(self):
+        s = np.zeros(STAT_COUNT)
+        _check(lib().mfb_get_stats(self.h, _p(s)))
+        return {k: float(s[i]) for k, i in STAT.items()}
+
+    def plan_modes(self, colloc, elem):
+        c = np.ascontiguousarray(colloc, dtype=np.int32); e = np.ascontiguousarray(elem, dtype=np.int32)
+        out = np.zeros(len(c), dtype=np.int32)
+        _check(lib().mfb_plan_modes(self.h, C.c_int(len(c)), _p(c), _p(e), _p(out)))
+        return out

@@ -1,0 +1,643 @@
+// api.cu -- C ABI (include/mfb.h) of the B200-native harmonic 3D BEM hot path: contexts, problem set-up
+// (host planning + device residency), per-frequency assembly, LU solve.  No CPU fallback: without a CUDA device
+// every entry point fails with MFB_ERR_NO_DEVICE.
+#include "../../include/mfb.h"
+#include "assembly.cuh"
+#include "lu.cuh"
+#include "plan_host.h"
+#include "../../data/quad_tables.h"
+#include <algorithm>
+#include <chrono>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include <omp.h>
+
+using namespace mfbd;
+typedef std::complex<double> cd;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                                        \
+  do {                                                                                                                  \
+    cudaError_t e__ = (call);                                                                                           \
+    if (e__ != cudaSuccess) return fail(MFB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));             \
+  } while (0)
+
+struct mfb_ctx {
+  int device; cudaStream_t stream; DevTables tables; double* tables_buf;
+};
+
+struct GroupHost {
+  int et, nn, n_elem, slot0;
+  std::vector<int> elem_ids;
+  DevGroup dev;
+  std::vector<void*> owned;
+  // work lists
+  DevAdaptive adp; DevSingular sing;
+};
+
+struct mfb_problem {
+  mfb_ctx* ctx;
+  int n_node, n_elem, n_colloc, n_dof, ldp;
+  long long lda;
+  mfbh::Settings settings;
+  std::vector<mfbh::Elem> elems;       // by original element id
+  std::vector<int> slot_of_elem, elem_of_slot, cpos_of_colloc;
+  std::vector<GroupHost> groups;
+  std::vector<void*> owned;
+  DevColloc colloc; DevSystem sys; DevClassify cls; DevFreeTerm ft;
+  unsigned char* plan;
+  double* d_cvalue;
+  int* d_ipiv; int* d_perm; std::vector<int> h_ipiv;
+  LuWork lu; bool lu_ready; bool factored;
+  double stats[MFB_STAT_COUNT];
+  cudaEvent_t ev[8];
+  std::vector<int> set_gln;
+};
+
+extern "C" const char* mfb_last_error(void) { return g_err.c_str(); }
+extern "C" int mfb_version(void) { return 100; }
+
+template <class T>
+static int upload(std::vector<void*>& owned, const std::vector<T>& h, T** d, cudaStream_t st) {
+  size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  CK(cudaMalloc((void**)d, bytes));
+  owned.push_back(*d);
+  if (!h.empty()) CK(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  return 0;
+}
+#define UP(owned, h, d)                                        \
+  do {                                                         \
+    int r__ = upload(owned, h, d, st);                         \
+    if (r__) return r__;                                       \
+  } while (0)
+
+extern "C" int mfb_init(int device, mfb_ctx** out) {
+  if (!out) return fail(MFB_ERR_ARG, "mfb_init: null output");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return fail(MFB_ERR_NO_DEVICE, "mfb_init: no CUDA device (this library has no CPU path)");
+  if (device < 0 || device >= n) return fail(MFB_ERR_ARG, "mfb_init: device index out of range");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(MFB_ERR_NO_DEVICE, "mfb_init: kernels are built for sm_100a only");
+  mfb_ctx* c = new mfb_ctx();
+  c->device = device;
+  CK(cudaStreamCreate(&c->stream));
+  // Gauss-Legendre tables on the device (packed: rule n starts at n(n-1)/2)
+  CK(cudaMalloc((void**)&c->tables_buf, 4 * 528 * sizeof(double)));
+  CK(cudaMemcpy(c->tables_buf, QT_GL11_X, 528 * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->tables_buf + 528, QT_GL11_W, 528 * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->tables_buf + 2 * 528, QT_GL01_X, 528 * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->tables_buf + 3 * 528, QT_GL01_W, 528 * 8, cudaMemcpyHostToDevice));
+  c->tables.gl11_x = c->tables_buf; c->tables.gl11_w = c->tables_buf + 528; c->tables.gl01_x = c->tables_buf + 2 * 528; c->tables.gl01_w = c->tables_buf + 3 * 528;
+  *out = c;
+  return MFB_OK;
+}
+extern "C" void mfb_finalize(mfb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->tables_buf);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" void mfb_problem_free(mfb_problem* p) {
+  if (!p) return;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  for (void* q : p->owned) cudaFree(q);
+  for (auto& g : p->groups) for (void* q : g.owned) cudaFree(q);
+  if (p->lu_ready) lu_work_free(p->lu);
+  for (int i = 0; i < 8; i++) cudaEventDestroy(p->ev[i]);
+  delete p;
+}
+
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
+                                  const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
+                                  const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
+                                  const int* row, const int* col_u, const int* col_t, const int* ctype, int n_dof,
+                                  double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
+                                  double geometric_tolerance, mfb_problem** out) {
+  if (!ctx || !out || !node_x || !etype || !elem_ptr || !elem_node || !colloc_x || !colloc_node || !colloc_elem || !colloc_kn || !colloc_xi ||
+      !row || !col_u || !col_t || !ctype || !precalset_gln)
+    return fail(MFB_ERR_ARG, "mfb_harela3d_setup: null argument");
+  if (n_node <= 0 || n_elem <= 0 || n_colloc <= 0 || n_dof <= 0 || n_precalsets <= 0 || n_precalsets > MAX_SETS)
+    return fail(MFB_ERR_ARG, "mfb_harela3d_setup: invalid size");
+  for (int e = 0; e < n_elem; e++) {
+    if (etype[e] < MFB_TRI3 || etype[e] > MFB_QUAD9) return fail(MFB_ERR_UNSUPPORTED, "mfb_harela3d_setup: element type must be tri3/tri6/quad4/quad8/quad9");
+    if (elem_ptr[e + 1] - elem_ptr[e] != mfbh::nodes_of(etype[e])) return fail(MFB_ERR_ARG, "mfb_harela3d_setup: elem_ptr inconsistent with etype");
+  }
+  for (int i = 0; i < 3 * n_node; i++)
+    if (ctype[i] != 0 && ctype[i] != 1) return fail(MFB_ERR_UNSUPPORTED, "mfb_harela3d_setup: only ctype 0 (u known) / 1 (t known) are supported");
+  double t_host0 = now_ms();
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  mfb_problem* p = new mfb_problem();
+  *out = nullptr;
+  p->ctx = ctx; p->n_node = n_node; p->n_elem = n_elem; p->n_colloc = n_colloc; p->n_dof = n_dof;
+  p->lu_ready = false; p->factored = false; p->plan = nullptr;
+  memset(p->stats, 0, sizeof(p->stats));
+  for (int i = 0; i < 8; i++) cudaEventCreate(&p->ev[i]);
+  mfbh::Settings& S = p->settings;
+  S.qsi_relative_error = qsi_relative_error; S.qsi_ns_max = qsi_ns_max; S.geometric_tolerance = geometric_tolerance;
+  S.ps_gln.assign(precalset_gln, precalset_gln + n_precalsets);
+  p->set_gln = S.ps_gln;
+  mfbh::init_settings(S);
+
+  // ---- per-element data (csize, n_phi, bounding ball) ----
+  p->elems.resize(n_elem);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int e = 0; e < n_elem; e++) {
+    mfbh::Elem& el = p->elems[e];
+    el.et = etype[e]; el.nn = mfbh::nodes_of(el.et); el.reversed = elem_reversed && elem_reversed[e];
+    for (int k = 0; k < el.nn; k++) for (int c = 0; c < 3; c++) el.x[3 * k + c] = node_x[3 * (size_t)elem_node[elem_ptr[e] + k] + c];
+    mfbh::element_data(el, S);
+  }
+  // ---- element slots: sorted by type ----
+  p->slot_of_elem.assign(n_elem, -1); p->elem_of_slot.clear();
+  const int types[5] = {MFB_TRI3, MFB_TRI6, MFB_QUAD4, MFB_QUAD8, MFB_QUAD9};
+  for (int t = 0; t < 5; t++) {
+    GroupHost g; g.et = types[t]; g.nn = mfbh::nodes_of(g.et); g.slot0 = (int)p->elem_of_slot.size();
+    for (int e = 0; e < n_elem; e++) if (etype[e] == g.et) { p->slot_of_elem[e] = (int)p->elem_of_slot.size(); p->elem_of_slot.push_back(e); g.elem_ids.push_back(e); }
+    g.n_elem = (int)g.elem_ids.size();
+    memset(&g.dev, 0, sizeof(g.dev)); memset(&g.adp, 0, sizeof(g.adp)); memset(&g.sing, 0, sizeof(g.sing));
+    if (g.n_elem > 0) p->groups.push_back(g);
+  }
+  // ---- collocation points sorted by matrix row ----
+  std::vector<int> order(n_colloc);
+  for (int c = 0; c < n_colloc; c++) order[c] = c;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return row[3 * colloc_node[a]] < row[3 * colloc_node[b]]; });
+  p->cpos_of_colloc.assign(n_colloc, 0);
+  const int ldp = (n_colloc + 31) / 32 * 32; p->ldp = ldp;
+  std::vector<double> h_cx(3 * (size_t)ldp, 0.0); std::vector<int> h_crow(3 * (size_t)ldp, 0);
+  for (int q = 0; q < n_colloc; q++) {
+    int c = order[q]; p->cpos_of_colloc[c] = q;
+    for (int k = 0; k < 3; k++) {
+      h_cx[(size_t)k * ldp + q] = colloc_x[3 * (size_t)c + k];
+      int r = row[3 * colloc_node[c] + k];
+      if (r < 0 || r >= n_dof) { mfb_problem_free(p); return fail(MFB_ERR_ARG, "mfb_harela3d_setup: collocation node without a valid row"); }
+      h_crow[(size_t)k * ldp + q] = r;
+    }
+  }
+  double* d_cx; int* d_crow;
+  UP(p->owned, h_cx, &d_cx); UP(p->owned, h_crow, &d_crow);
+  p->colloc.n_colloc = n_colloc; p->colloc.ldp = ldp; p->colloc.cx = d_cx; p->colloc.crow = d_crow;
+
+  // ---- flat scatter descriptors over all slots ----
+  std::vector<int> slot_off(n_elem + 1, 0);
+  for (int s = 0; s < n_elem; s++) slot_off[s + 1] = slot_off[s] + 3 * p->elems[p->elem_of_slot[s]].nn;
+  std::vector<int> h_ecol(slot_off[n_elem]); std::vector<unsigned char> h_ekind(slot_off[n_elem]);
+  for (int s = 0; s < n_elem; s++) {
+    int e = p->elem_of_slot[s], nn = p->elems[e].nn;
+    for (int j = 0; j < nn; j++) for (int k = 0; k < 3; k++) {
+      int node = elem_node[elem_ptr[e] + j];
+      int ct = ctype[3 * node + k];
+      int col = (ct == 0) ? col_t[3 * node + k] : col_u[3 * node + k];
+      if (col < 0 || col >= n_dof) { mfb_problem_free(p); return fail(MFB_ERR_ARG, "mfb_harela3d_setup: missing column for an unknown"); }
+      h_ecol[slot_off[s] + j * 3 + k] = col; h_ekind[slot_off[s] + j * 3 + k] = (unsigned char)ct;
+    }
+  }
+  int *d_ecol, *d_slot_off; unsigned char* d_ekind; double* d_ecv;
+  UP(p->owned, h_ecol, &d_ecol); UP(p->owned, h_ekind, &d_ekind); UP(p->owned, slot_off, &d_slot_off);
+  CK(cudaMalloc((void**)&d_ecv, (size_t)slot_off[n_elem] * 2 * sizeof(double))); p->owned.push_back(d_ecv);
+
+  // ---- groups: geometry, point sets ----
+  for (auto& g : p->groups) {
+    DevGroup& D = g.dev;
+    D.et = g.et; D.nn = g.nn; D.n_elem = g.n_elem; D.slot0 = g.slot0;
+    std::vector<double> h_xn((size_t)g.n_elem * 3 * g.nn), h_ball((size_t)g.n_elem * 5);
+    std::vector<int> h_enode((size_t)g.n_elem * g.nn), h_glnfar(g.n_elem);
+    std::vector<unsigned char> h_rev(g.n_elem);
+    for (int i = 0; i < g.n_elem; i++) {
+      int e = g.elem_ids[i]; const mfbh::Elem& el = p->elems[e];
+      for (int q = 0; q < 3 * g.nn; q++) h_xn[(size_t)i * 3 * g.nn + q] = el.x[q];
+      for (int j = 0; j < g.nn; j++) h_enode[(size_t)i * g.nn + j] = elem_node[elem_ptr[e] + j];
+      h_ball[5 * (size_t)i] = el.bc[0]; h_ball[5 * (size_t)i + 1] = el.bc[1]; h_ball[5 * (size_t)i + 2] = el.bc[2]; h_ball[5 * (size_t)i + 3] = el.br; h_ball[5 * (size_t)i + 4] = el.cl;
+      h_glnfar[i] = el.gln_far; h_rev[i] = el.reversed ? 1 : 0;
+    }
+    double *d_xn, *d_ball; int *d_enode, *d_glnfar; unsigned char* d_rev;
+    UP(g.owned, h_xn, &d_xn); UP(g.owned, h_ball, &d_ball); UP(g.owned, h_enode, &d_enode); UP(g.owned, h_glnfar, &d_glnfar); UP(g.owned, h_rev, &d_rev);
+    D.xn = d_xn; D.ball = d_ball; D.enode = d_enode; D.gln_far = d_glnfar; D.erev = d_rev;
+    D.ecol = d_ecol + slot_off[g.slot0]; D.ekind = d_ekind + slot_off[g.slot0]; D.ecv = d_ecv + 2 * (size_t)slot_off[g.slot0];
+    D.n_sets = n_precalsets;
+    for (int s = 0; s < n_precalsets; s++) {
+      int gln = precalset_gln[s];
+      if (gln < 1 || gln > 30) { mfb_problem_free(p); return fail(MFB_ERR_ARG, "mfb_harela3d_setup: precalset gln out of range"); }
+      int ngp = mfbh::pointset_size(g.et, gln), rec = 6 + g.nn;
+      D.set_gln[s] = gln; D.ngp[s] = ngp;
+      std::vector<double> h_pts((size_t)g.n_elem * ngp * rec);
+#pragma omp parallel for schedule(static)
+      for (int i = 0; i < g.n_elem; i++) mfbh::build_pointset(p->elems[g.elem_ids[i]], gln, &h_pts[(size_t)i * ngp * rec]);
+      double* d_pts; UP(g.owned, h_pts, &d_pts); D.pts[s] = d_pts;
+      CK(cudaStreamSynchronize(st));  // h_pts goes out of scope
+    }
+    CK(cudaStreamSynchronize(st));
+  }
+
+  // ---- K0: classify all pairs on the device, fetch the near list ----
+  for (int n = 0; n < 32; n++) p->cls.far_thr[n] = S.far_thr[n];
+  p->cls.far_dmax = S.far_dmax;
+  p->cls.ps_gln_max = *std::max_element(S.ps_gln.begin(), S.ps_gln.end());
+  CK(cudaMalloc((void**)&p->plan, (size_t)n_elem * ldp)); p->owned.push_back(p->plan);
+  for (auto& g : p->groups) launch_classify(g.dev, p->colloc, p->cls, p->plan, st);
+  unsigned long long* d_counter; CK(cudaMalloc((void**)&d_counter, 8)); p->owned.push_back(d_counter);
+  CK(cudaMemsetAsync(d_counter, 0, 8, st));
+  launch_count_near(p->plan, n_elem, p->colloc, d_counter, nullptr, 0, st);
+  unsigned long long n_near = 0;
+  CK(cudaMemcpyAsync(&n_near, d_counter, 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+  std::vector<int2> near(n_near);
+  if (n_near > 0) {
+    int2* d_list; CK(cudaMalloc((void**)&d_list, n_near * sizeof(int2)));
+    CK(cudaMemsetAsync(d_counter, 0, 8, st));
+    launch_count_near(p->plan, n_elem, p->colloc, d_counter, d_list, n_near, st);
+    CK(cudaMemcpyAsync(near.data(), d_list, n_near * sizeof(int2), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+    cudaFree(d_list);
+  }
+  std::sort(near.begin(), near.end(), [](const int2& a, const int2& b) { return a.y != b.y ? a.y < b.y : a.x < b.x; });
+
+  // ---- host planning of the near pairs ----
+  std::vector<mfbh::NearPlan> plans(n_near);
+#pragma omp parallel for schedule(dynamic, 16)
+  for (long long i = 0; i < (long long)n_near; i++) {
+    int cpos = near[i].x, slot = near[i].y;
+    double xi[3] = {h_cx[cpos], h_cx[(size_t)ldp + cpos], h_cx[2 * (size_t)ldp + cpos]};
+    mfbh::plan_near_pair(p->elems[p->elem_of_slot[slot]], xi, S, plans[i]);
+  }
+  std::vector<int> pc_cpos, pc_slot; std::vector<unsigned char> pc_val;
+  long long pts_regular_near = 0, n_adp = 0, n_leaves = 0, pts_adp = 0, n_sing = 0, pts_sing = 0;
+  for (auto& g : p->groups) {
+    std::vector<int> a_cpos, a_elem, a_leaf0(1, 0), a_gln; std::vector<double> a_leafd;
+    std::vector<int> s_cpos, s_elem, s_ray0(1, 0); std::vector<double> s_d, s_rays;
+    for (unsigned long long i = 0; i < n_near; i++) {
+      int cpos = near[i].x, slot = near[i].y;
+      if (slot < g.slot0 || slot >= g.slot0 + g.n_elem) continue;
+      const mfbh::NearPlan& np = plans[i];
+      pc_cpos.push_back(cpos); pc_slot.push_back(slot);
+      if (np.mode == 0) { pc_val.push_back((unsigned char)np.set); pts_regular_near += np.points; }
+      else if (np.mode == 1) {
+        pc_val.push_back(PLAN_ADAPTIVE);
+        a_cpos.push_back(cpos); a_elem.push_back(slot - g.slot0);
+        for (const auto& lf : np.leaves) {
+          for (int q = 0; q < 8; q++) a_leafd.push_back(lf.xi_s[q]);
+          for (int q = 0; q < 4; q++) a_leafd.push_back(lf.tp1[q]);
+          for (int q = 0; q < 4; q++) a_leafd.push_back(lf.tp2[q]);
+          a_gln.push_back(lf.gln);
+        }
+        a_leaf0.push_back((int)a_gln.size());
+        n_adp++; n_leaves += (long long)np.leaves.size(); pts_adp += np.points;
+      } else {
+        pc_val.push_back(PLAN_SINGULAR);
+        s_cpos.push_back(cpos); s_elem.push_back(slot - g.slot0);
+        s_d.push_back(np.xi_i[0]); s_d.push_back(np.xi_i[1]);
+        for (int q = 0; q < 3; q++) s_d.push_back(np.x_i[q]);
+        for (int q = 0; q < 9; q++) s_d.push_back(np.hli[q]);
+        for (const auto& r : np.rays) { s_rays.push_back(r.ct); s_rays.push_back(r.st); s_rays.push_back(r.rhoij); s_rays.push_back(r.w); }
+        s_ray0.push_back((int)(s_rays.size() / 4));
+        n_sing++; pts_sing += np.points;
+      }
+    }
+    int *d1, *d2, *d3, *d4; double* d5;
+    UP(g.owned, a_cpos, &d1); UP(g.owned, a_elem, &d2); UP(g.owned, a_leaf0, &d3); UP(g.owned, a_gln, &d4); UP(g.owned, a_leafd, &d5);
+    g.adp.n_pairs = (int)a_cpos.size(); g.adp.pair_cpos = d1; g.adp.pair_elem = d2; g.adp.pair_leaf0 = d3; g.adp.leaf_gln = d4; g.adp.leaf_d = d5;
+    int *e1, *e2, *e3; double *e4, *e5;
+    UP(g.owned, s_cpos, &e1); UP(g.owned, s_elem, &e2); UP(g.owned, s_ray0, &e3); UP(g.owned, s_d, &e4); UP(g.owned, s_rays, &e5);
+    g.sing.n_pairs = (int)s_cpos.size(); g.sing.pair_cpos = e1; g.sing.pair_elem = e2; g.sing.pair_ray0 = e3; g.sing.pair_d = e4; g.sing.rays = e5;
+    CK(cudaStreamSynchronize(st));
+  }
+  {
+    int *d1, *d2; unsigned char* d3;
+    std::vector<void*> tmp;
+    UP(tmp, pc_cpos, &d1); UP(tmp, pc_slot, &d2); UP(tmp, pc_val, &d3);
+    launch_patch_plan(p->plan, p->colloc, (int)pc_cpos.size(), d1, d2, d3, st);
+    CK(cudaStreamSynchronize(st));
+    for (void* q : tmp) cudaFree(q);
+  }
+
+  // ---- free-term entries (geometry only): src/build_lse_mechanics_bem_harela.f90:273-747 ----
+  {
+    // node -> (element, local node) incidences
+    std::vector<int> cnt(n_node + 1, 0);
+    for (int e = 0; e < n_elem; e++) for (int k = elem_ptr[e]; k < elem_ptr[e + 1]; k++) cnt[elem_node[k] + 1]++;
+    for (int i = 0; i < n_node; i++) cnt[i + 1] += cnt[i];
+    std::vector<int> n2e(cnt[n_node]), n2k(cnt[n_node]), pos(cnt.begin(), cnt.end() - 1);
+    for (int e = 0; e < n_elem; e++) for (int k = elem_ptr[e]; k < elem_ptr[e + 1]; k++) { int nd = elem_node[k]; n2e[pos[nd]] = e; n2k[pos[nd]] = k - elem_ptr[e]; pos[nd]++; }
+    std::vector<int> f_cpos, f_slot, f_jk, f_l; std::vector<double> f_val;
+    for (int c = 0; c < n_colloc; c++) {
+      int e = colloc_elem[c], kn = colloc_kn[c], sn = colloc_node[c];
+      if (e < 0 || e >= n_elem || kn < 0 || kn >= p->elems[e].nn) { mfb_problem_free(p); return fail(MFB_ERR_ARG, "mfb_harela3d_setup: invalid colloc_elem/colloc_kn"); }
+      const mfbh::Elem& el = p->elems[e];
+      int cpos = p->cpos_of_colloc[c], slot = p->slot_of_elem[e];
+      bool mca = !(colloc_xi[2 * c] == -9.0 && colloc_xi[2 * c + 1] == -9.0);
+      if (!mca) {
+        double xi_i[2]; mfbh::node_xi(el.et, kn, xi_i);
+        double cp = 0.5, sum_b[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (mfbh::xi_on_element_boundary(el.et, xi_i)) {
+          int b0 = cnt[sn], ne = cnt[sn + 1] - b0;
+          std::vector<double> ns(3 * ne), ts(3 * ne);
+          for (int k = 0; k < ne; k++) { const mfbh::Elem& ee = p->elems[n2e[b0 + k]]; mfbh::node_normal_tangent(ee.et, ee.x, n2k[b0 + k], el.reversed, &ns[3 * k], &ts[3 * k]); }
+          if (mfbh::mantic_terms(ne, ns.data(), ts.data(), geometric_tolerance, &cp, sum_b)) { mfb_problem_free(p); return fail(2, "mfb_harela3d_setup: the normals/tangents configuration is not valid (free term)"); }
+        }
+        for (int l = 0; l < 3; l++) for (int k = 0; k < 3; k++) {
+          f_cpos.push_back(cpos); f_slot.push_back(slot); f_jk.push_back(kn * 3 + k); f_l.push_back(l);
+          f_val.push_back(l == k ? cp : 0.0); f_val.push_back(sum_b[3 * l + k]);
+        }
+      } else {
+        double phi[9]; mfbh::shape_values(el.et, &colloc_xi[2 * c], phi);
+        for (int l = 0; l < 3; l++) for (int j = 0; j < el.nn; j++) {
+          f_cpos.push_back(cpos); f_slot.push_back(slot); f_jk.push_back(j * 3 + l); f_l.push_back(l);
+          f_val.push_back(0.5 * phi[j]); f_val.push_back(0.0);
+        }
+      }
+    }
+    int *d1, *d2, *d3, *d4; double* d5;
+    UP(p->owned, f_cpos, &d1); UP(p->owned, f_slot, &d2); UP(p->owned, f_jk, &d3); UP(p->owned, f_l, &d4); UP(p->owned, f_val, &d5);
+    p->ft.n = (int)f_cpos.size(); p->ft.cpos = d1; p->ft.slot = d2; p->ft.jk = d3; p->ft.l = d4; p->ft.val = d5;
+    p->ft.slot_off = d_slot_off; p->ft.ecol = d_ecol; p->ft.ekind = d_ekind; p->ft.ecv = d_ecv;
+    CK(cudaStreamSynchronize(st));
+  }
+
+  // ---- device-resident system ----
+  p->lda = ((long long)n_dof + 31) / 32 * 32;
+  double* dA; CK(cudaMalloc((void**)&dA, (size_t)2 * p->lda * n_dof * sizeof(double))); p->owned.push_back(dA);
+  double* db; CK(cudaMalloc((void**)&db, (size_t)2 * p->lda * sizeof(double))); p->owned.push_back(db);
+  p->sys.Are = dA; p->sys.Aim = dA + (size_t)p->lda * n_dof; p->sys.lda = p->lda; p->sys.n_dof = n_dof; p->sys.bre = db; p->sys.bim = db + p->lda;
+  CK(cudaMalloc((void**)&p->d_cvalue, (size_t)6 * n_node * sizeof(double))); p->owned.push_back(p->d_cvalue);
+  CK(cudaMalloc((void**)&p->d_ipiv, (size_t)n_dof * sizeof(int))); p->owned.push_back(p->d_ipiv);
+  CK(cudaMalloc((void**)&p->d_perm, (size_t)n_dof * sizeof(int))); p->owned.push_back(p->d_perm);
+  p->h_ipiv.assign(n_dof, 0);
+
+  // statistics of the plan
+  {
+    std::vector<unsigned char> h_plan((size_t)n_elem * ldp);
+    CK(cudaMemcpy(h_plan.data(), p->plan, h_plan.size(), cudaMemcpyDeviceToHost));
+    long long pairs = 0, pts = 0; double flops = 0.0;
+    for (auto& g : p->groups)
+      for (int i = 0; i < g.n_elem; i++)
+        for (int q = 0; q < n_colloc; q++) {
+          unsigned char m = h_plan[(size_t)(g.slot0 + i) * ldp + q];
+          if (m < MAX_SETS) { pairs++; pts += g.dev.ngp[m]; flops += (double)g.dev.ngp[m] * (585.0 + 72.0 * g.nn) + 144.0 * g.nn; }
+        }
+    p->stats[MFB_STAT_PAIRS_REGULAR] = (double)pairs; p->stats[MFB_STAT_POINTS_REGULAR] = (double)pts; p->stats[MFB_STAT_FLOPS_REGULAR] = flops;
+    p->stats[MFB_STAT_PAIRS_ADAPTIVE] = (double)n_adp; p->stats[MFB_STAT_LEAVES] = (double)n_leaves; p->stats[MFB_STAT_POINTS_ADAPTIVE] = (double)pts_adp;
+    p->stats[MFB_STAT_PAIRS_SINGULAR] = (double)n_sing; p->stats[MFB_STAT_POINTS_SINGULAR] = (double)pts_sing; p->stats[MFB_STAT_NEAR_PAIRS] = (double)n_near;
+  }
+  p->stats[MFB_STAT_MS_SETUP_HOST] = now_ms() - t_host0;
+  *out = p;
+  return MFB_OK;
+}
+
+// fbem_bem_harela3d_calculate_parameters (SBIE subset): lib/fbem/src/bem_harela3d.f90:143-287
+static void host_kparams(cd lambda, cd mu, double rho, double omega, KParams& K) {
+  const cd im(0.0, 1.0);
+  cd c1 = std::sqrt((lambda + 2.0 * mu) / rho), c2 = std::sqrt(mu / rho);
+  cd k1 = omega / c1, k2 = omega / c2;
+  cd c1_2 = c1 * c1, c2_2 = c2 * c2, c1_3 = c1_2 * c1, c1_4 = c1_2 * c1_2, k2_2 = k2 * k2;
+  cd ik1 = im * k1, ik2 = im * k2, ik1_2 = ik1 * ik1, ik2_2 = ik2 * ik2, r = c2_2 / c1_2;
+  double om2 = omega * omega;
+  cd psi[7], chi[7], T1[11], T2[10], T3[10];
+  psi[1] = 0.5 * (1.0 + r); psi[2] = -1.0 / 3.0 * (2.0 / c2 + c2_2 / c1_3) * im * omega; psi[3] = im * k1 / k2_2;
+  psi[4] = 1.0 / ik2; psi[5] = 1.0 / k2_2; psi[6] = -1.0 / k2_2;
+  chi[1] = -0.5 * (1.0 - r); chi[2] = -r; chi[3] = -3.0 * r / ik1; chi[4] = 3.0 / ik2; chi[5] = -3.0 * r / ik1_2; chi[6] = 3.0 / ik2_2;
+  T1[1] = 3.0 * (r - 1.0); T1[2] = -0.25 * (1.0 / c2_2 - c2_2 / c1_4) * om2; T1[3] = -2.0 * im * k1 * r; T1[4] = 2.0 * im * k2;
+  T1[5] = -12.0 * r; T1[6] = 12.0; T1[7] = -r * 30.0 / ik1; T1[8] = 30.0 / ik2; T1[9] = -r * 30.0 / ik1_2; T1[10] = 30.0 / ik2_2;
+  T2[1] = -r; T2[2] = -0.25 * (1.0 / c2_2 + c2_2 / c1_4) * om2; T2[3] = -im * k2; T2[4] = 2.0 * r; T2[5] = -3.0;
+  T2[6] = r * 6.0 / ik1; T2[7] = -6.0 / ik2; T2[8] = r * 6.0 / ik1_2; T2[9] = -6.0 / ik2_2;
+  T3[1] = r; T3[2] = 0.25 * (3.0 * c2_2 / c1_4 - 2.0 / c1_2 + 1.0 / c2_2) * om2; T3[3] = (2.0 * r - 1.0) * im * k1; T3[4] = 4.0 * r - 1.0;
+  T3[5] = -2.0; T3[6] = r * 6.0 / ik1; T3[7] = -6.0 / ik2; T3[8] = r * 6.0 / ik1_2; T3[9] = -6.0 / ik2_2;
+  auto cv = [](cd z) { return mk(z.real(), z.imag()); };
+  memset(&K, 0, sizeof(K));
+  K.k1 = cv(k1); K.k2 = cv(k2);
+  for (int i = 1; i <= 6; i++) { K.psi[i] = cv(psi[i]); K.chi[i] = cv(chi[i]); }
+  for (int i = 1; i <= 10; i++) K.T1[i] = cv(T1[i]);
+  for (int i = 1; i <= 9; i++) { K.T2[i] = cv(T2[i]); K.T3[i] = cv(T3[i]); }
+  const double c_1_4pi = 0.07957747154594767280411105048;
+  K.cte_u = cv(c_1_4pi / mu); K.cte_t = c_1_4pi;
+}
+
+static int assemble_device(mfb_problem* p, double omega, cd lambda, cd mu, double rho, cd nu, const mfb_z* cvalue) {
+  cudaStream_t st = p->ctx->stream;
+  KParams K; host_kparams(lambda, mu, rho, omega, K);
+  set_kparams(K, st);
+  CK(cudaMemcpyAsync(p->d_cvalue, cvalue, (size_t)6 * p->n_node * sizeof(double), cudaMemcpyHostToDevice, st));
+  for (auto& g : p->groups) launch_gather_cv(g.dev, p->d_cvalue, st);
+  CK(cudaEventRecord(p->ev[0], st));
+  CK(cudaMemsetAsync(p->sys.Are, 0, (size_t)2 * p->lda * p->n_dof * sizeof(double), st));
+  CK(cudaMemsetAsync(p->sys.bre, 0, (size_t)2 * p->lda * sizeof(double), st));
+  CK(cudaEventRecord(p->ev[1], st));
+  for (auto& g : p->groups) launch_regular(g.dev, p->colloc, p->sys, p->plan, st);
+  CK(cudaEventRecord(p->ev[2], st));
+  for (auto& g : p->groups) launch_adaptive(g.dev, p->colloc, p->sys, g.adp, p->ctx->tables, st);
+  CK(cudaEventRecord(p->ev[3], st));
+  for (auto& g : p->groups) launch_singular(g.dev, p->colloc, p->sys, g.sing, p->ctx->tables, st);
+  CK(cudaEventRecord(p->ev[4], st));
+  const double c_pi = 3.14159265358979323846264338328;
+  cd F = -1.0 / (8.0 * c_pi * (1.0 - nu));
+  launch_freeterm(p->colloc, p->sys, p->ft, mk(F.real(), F.imag()), st);
+  CK(cudaEventRecord(p->ev[5], st));
+  CK(cudaGetLastError());
+  p->factored = false;
+  return MFB_OK;
+}
+static int collect_assembly_times(mfb_problem* p) {
+  CK(cudaEventSynchronize(p->ev[5]));
+  float t;
+  cudaEventElapsedTime(&t, p->ev[0], p->ev[1]); p->stats[MFB_STAT_MS_ZERO] = t;
+  cudaEventElapsedTime(&t, p->ev[1], p->ev[2]); p->stats[MFB_STAT_MS_REGULAR] = t;
+  cudaEventElapsedTime(&t, p->ev[2], p->ev[3]); p->stats[MFB_STAT_MS_ADAPTIVE] = t;
+  cudaEventElapsedTime(&t, p->ev[3], p->ev[4]); p->stats[MFB_STAT_MS_SINGULAR] = t;
+  cudaEventElapsedTime(&t, p->ev[4], p->ev[5]); p->stats[MFB_STAT_MS_FREETERM] = t;
+  cudaEventElapsedTime(&t, p->ev[0], p->ev[5]); p->stats[MFB_STAT_MS_ASSEMBLE] = t;
+  int launches = 1;  // our kernels only (memsets/copies are not counted): freeterm + per group gather_cv, regular, adaptive, singular
+  for (auto& g : p->groups) launches += 2 + (g.adp.n_pairs > 0) + (g.sing.n_pairs > 0);
+  p->stats[MFB_STAT_LAUNCHES] = launches;
+  return MFB_OK;
+}
+
+// copy a planar device matrix to an interleaved host matrix in column chunks (bounded staging buffer)
+static int download_matrix(mfb_problem* p, const double* re, const double* im, long long ld, int rows, int cols, mfb_z* host, long long ldh) {
+  cudaStream_t st = p->ctx->stream;
+  int chunk = (int)std::max<long long>(1, std::min<long long>(cols, (256ll << 20) / (16ll * rows)));
+  double* stage; CK(cudaMalloc((void**)&stage, (size_t)chunk * rows * 16));
+  for (int c0 = 0; c0 < cols; c0 += chunk) {
+    int nc = std::min(chunk, cols - c0);
+    launch_interleave(re + (long long)c0 * ld, im + (long long)c0 * ld, ld, rows, nc, stage, rows, st);
+    CK(cudaMemcpy2DAsync(host + (long long)c0 * ldh, (size_t)ldh * 16, stage, (size_t)rows * 16, (size_t)rows * 16, nc, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  cudaFree(stage);
+  return MFB_OK;
+}
+static int upload_matrix(mfb_problem* p, const mfb_z* host, long long ldh, int rows, int cols, double* re, double* im, long long ld) {
+  cudaStream_t st = p->ctx->stream;
+  int chunk = (int)std::max<long long>(1, std::min<long long>(cols, (256ll << 20) / (16ll * rows)));
+  double* stage; CK(cudaMalloc((void**)&stage, (size_t)chunk * rows * 16));
+  for (int c0 = 0; c0 < cols; c0 += chunk) {
+    int nc = std::min(chunk, cols - c0);
+    CK(cudaMemcpy2DAsync(stage, (size_t)rows * 16, host + (long long)c0 * ldh, (size_t)ldh * 16, (size_t)rows * 16, nc, cudaMemcpyHostToDevice, st));
+    launch_deinterleave(stage, rows, rows, nc, re + (long long)c0 * ld, im + (long long)c0 * ld, ld, st);
+    CK(cudaStreamSynchronize(st));
+  }
+  cudaFree(stage);
+  return MFB_OK;
+}
+
+extern "C" int mfb_harela3d_assemble(mfb_problem* p, double omega, const mfb_z* lambda, const mfb_z* mu, double rho, const mfb_z* nu,
+                                     const mfb_z* cvalue, mfb_z* A, mfb_z* b) {
+  if (!p || !lambda || !mu || !nu || !cvalue) return fail(MFB_ERR_ARG, "mfb_harela3d_assemble: null argument");
+  CK(cudaSetDevice(p->ctx->device));
+  int r = assemble_device(p, omega, cd(lambda->re, lambda->im), cd(mu->re, mu->im), rho, cd(nu->re, nu->im), cvalue);
+  if (r) return r;
+  r = collect_assembly_times(p);
+  if (r) return r;
+  if (A) { r = download_matrix(p, p->sys.Are, p->sys.Aim, p->lda, p->n_dof, p->n_dof, A, p->n_dof); if (r) return r; }
+  if (b) { r = download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, b, p->n_dof); if (r) return r; }
+  return MFB_OK;
+}
+
+static bool lu_timing() { const char* e = getenv("MFB_LU_TIMING"); return e && e[0] == '1'; }
+static int ensure_lu(mfb_problem* p) {
+  if (!p->lu_ready) {
+    if (lu_work_alloc(p->lu, p->n_dof, 128) != 0) return fail(MFB_ERR_CUDA, "LU workspace allocation failed");
+    p->lu_ready = true;
+  }
+  return MFB_OK;
+}
+// factorise the device-resident system and bring the pivots back (permutation vector for the solves)
+static int factor_device(mfb_problem* p, int n, bool timing) {
+  cudaStream_t st = p->ctx->stream;
+  int r = ensure_lu(p); if (r) return r;
+  CK(cudaEventRecord(p->ev[6], st));
+  int e = zgetrf_planar(p->sys.Are, p->sys.Aim, p->lda, n, p->d_ipiv, p->lu, st, timing);
+  if (e) return fail(MFB_ERR_CUDA, std::string("zgetrf_planar: ") + cudaGetErrorString((cudaError_t)e));
+  CK(cudaEventRecord(p->ev[7], st));
+  int info = 0;
+  CK(cudaMemcpyAsync(p->h_ipiv.data(), p->d_ipiv, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&info, p->lu.info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_LU] = t;
+  p->stats[MFB_STAT_LAUNCHES] += (double)p->lu.launches;
+  p->stats[MFB_STAT_MS_PANEL] = p->lu.ms_panel; p->stats[MFB_STAT_MS_SWAP] = p->lu.ms_swap; p->stats[MFB_STAT_MS_TRSM] = p->lu.ms_trsm; p->stats[MFB_STAT_MS_GEMM] = p->lu.ms_gemm;
+  std::vector<int> perm(n);
+  for (int i = 0; i < n; i++) perm[i] = i;
+  for (int i = 0; i < n; i++) { int q = p->h_ipiv[i] - 1; if (q != i) std::swap(perm[i], perm[q]); }
+  CK(cudaMemcpyAsync(p->d_perm, perm.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  p->factored = true;
+  if (info > 0) { char buf[128]; snprintf(buf, sizeof(buf), "zgetrf: U(%d,%d) is exactly zero, the matrix is singular", info, info); return fail(info, buf); }
+  return MFB_OK;
+}
+
+extern "C" int mfb_zsolve(mfb_problem* p, int n, mfb_z* A, int lda, int* ipiv, mfb_z* b, int nrhs, int factorize) {
+  if (!p) return fail(MFB_ERR_ARG, "mfb_zsolve: null problem");
+  if (n != p->n_dof) return fail(MFB_ERR_ARG, "mfb_zsolve: n must equal the problem's n_dof");
+  if (nrhs < 0 || (A && lda < n)) return fail(MFB_ERR_ARG, "mfb_zsolve: invalid nrhs/lda");
+  CK(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  int r;
+  if (factorize) {
+    if (A) { r = upload_matrix(p, A, lda, n, n, p->sys.Are, p->sys.Aim, p->lda); if (r) return r; }
+    r = factor_device(p, n, lu_timing());
+    if (ipiv) memcpy(ipiv, p->h_ipiv.data(), (size_t)n * sizeof(int));
+    if (A) { int r2 = download_matrix(p, p->sys.Are, p->sys.Aim, p->lda, n, n, A, lda); if (r2) return r2; }
+    if (r) return r;
+  } else if (!p->factored) return fail(MFB_ERR_ARG, "mfb_zsolve: factorize=0 but no factors are resident");
+  if (nrhs == 0) return MFB_OK;
+  double *bre = p->sys.bre, *bim = p->sys.bim; long long ldb = p->lda;
+  double* tmp = nullptr;
+  if (b) {
+    if (nrhs > 1) { CK(cudaMalloc((void**)&tmp, (size_t)2 * p->lda * nrhs * sizeof(double))); bre = tmp; bim = tmp + (size_t)p->lda * nrhs; }
+    r = upload_matrix(p, b, n, n, nrhs, bre, bim, ldb); if (r) return r;
+  } else if (nrhs != 1) return fail(MFB_ERR_ARG, "mfb_zsolve: device-resident rhs has a single column");
+  CK(cudaEventRecord(p->ev[6], st));
+  int e = zgetrs_planar(p->sys.Are, p->sys.Aim, p->lda, n, p->d_perm, bre, bim, ldb, nrhs, st);
+  if (e) return fail(MFB_ERR_CUDA, std::string("zgetrs_planar: ") + cudaGetErrorString((cudaError_t)e));
+  CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
+  float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
+  if (b) { r = download_matrix(p, bre, bim, ldb, n, nrhs, b, n); if (r) return r; }
+  if (tmp) cudaFree(tmp);
+  return MFB_OK;
+}
+
+extern "C" int mfb_harela3d_solve_frequency(mfb_problem* p, double omega, const mfb_z* lambda, const mfb_z* mu, double rho, const mfb_z* nu,
+                                            const mfb_z* cvalue, mfb_z* x) {
+  if (!p || !lambda || !mu || !nu || !cvalue || !x) return fail(MFB_ERR_ARG, "mfb_harela3d_solve_frequency: null argument");
+  CK(cudaSetDevice(p->ctx->device));
+  int r = assemble_device(p, omega, cd(lambda->re, lambda->im), cd(mu->re, mu->im), rho, cd(nu->re, nu->im), cvalue);
+  if (r) return r;
+  r = factor_device(p, p->n_dof, lu_timing());
+  int r2 = collect_assembly_times(p); if (r2) return r2;
+  if (r) return r;
+  cudaStream_t st = p->ctx->stream;
+  CK(cudaEventRecord(p->ev[6], st));
+  int e = zgetrs_planar(p->sys.Are, p->sys.Aim, p->lda, p->n_dof, p->d_perm, p->sys.bre, p->sys.bim, p->lda, 1, st);
+  if (e) return fail(MFB_ERR_CUDA, std::string("zgetrs_planar: ") + cudaGetErrorString((cudaError_t)e));
+  CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
+  float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
+  return download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, x, p->n_dof);
+}
+
+extern "C" int mfb_get_stats(mfb_problem* p, double* stats) {
+  if (!p || !stats) return fail(MFB_ERR_ARG, "mfb_get_stats: null argument");
+  memcpy(stats, p->stats, sizeof(p->stats));
+  return MFB_OK;
+}
+
+extern "C" int mfb_plan_modes(mfb_problem* p, int n_pairs, const int* colloc, const int* elem, int* mode) {
+  if (!p || !colloc || !elem || !mode) return fail(MFB_ERR_ARG, "mfb_plan_modes: null argument");
+  CK(cudaSetDevice(p->ctx->device));
+  std::vector<unsigned char> h((size_t)p->n_elem * p->ldp);
+  CK(cudaMemcpy(h.data(), p->plan, h.size(), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n_pairs; i++) {
+    if (colloc[i] < 0 || colloc[i] >= p->n_colloc || elem[i] < 0 || elem[i] >= p->n_elem) return fail(MFB_ERR_ARG, "mfb_plan_modes: index out of range");
+    unsigned char m = h[(size_t)p->slot_of_elem[elem[i]] * p->ldp + p->cpos_of_colloc[colloc[i]]];
+    mode[i] = (m < MAX_SETS) ? p->set_gln[m] : (m == PLAN_ADAPTIVE ? 100 : (m == PLAN_SINGULAR ? 200 : -1));
+  }
+  return MFB_OK;
+}
+
+extern "C" int mfb_measure_peaks(mfb_ctx* ctx, double* dfma_tflops, double* dmma_tflops, double* copy_gbs) {
+  if (!ctx) return fail(MFB_ERR_ARG, "mfb_measure_peaks: null context");
+  CK(cudaSetDevice(ctx->device));
+  if (dfma_tflops) *dfma_tflops = bench_dfma(ctx->stream);
+  if (dmma_tflops) *dmma_tflops = bench_dmma(ctx->stream);
+  if (copy_gbs) *copy_gbs = bench_copy(ctx->stream);
+  CK(cudaGetLastError());
+  return MFB_OK;
+}
+
+extern "C" int mfb_zgemm_minus(mfb_ctx* ctx, int m, int n, int k, const mfb_z* A, int lda, const mfb_z* B, int ldb, mfb_z* C, int ldc, double* ms) {
+  if (!ctx || !A || !B || !C) return fail(MFB_ERR_ARG, "mfb_zgemm_minus: null argument");
+  if (m <= 0 || n <= 0 || k <= 0 || (k & 1)) return fail(MFB_ERR_ARG, "mfb_zgemm_minus: k must be even and sizes positive");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  long long la = (m + 31) / 32 * 32, lb = (k + 31) / 32 * 32, lc = la;
+  double *dA, *dB, *dC, *stage;
+  size_t smax = std::max(std::max((size_t)m * k, (size_t)k * n), (size_t)m * n);
+  CK(cudaMalloc((void**)&dA, 2 * la * k * 8)); CK(cudaMalloc((void**)&dB, 2 * lb * n * 8)); CK(cudaMalloc((void**)&dC, 2 * lc * n * 8));
+  CK(cudaMalloc((void**)&stage, smax * 16));
+  CK(cudaMemsetAsync(dA, 0, 2 * la * k * 8, st)); CK(cudaMemsetAsync(dB, 0, 2 * lb * n * 8, st));
+  CK(cudaMemcpy2DAsync(stage, (size_t)m * 16, A, (size_t)lda * 16, (size_t)m * 16, k, cudaMemcpyHostToDevice, st));
+  launch_deinterleave(stage, m, m, k, dA, dA + la * k, la, st);
+  CK(cudaMemcpy2DAsync(stage, (size_t)k * 16, B, (size_t)ldb * 16, (size_t)k * 16, n, cudaMemcpyHostToDevice, st));
+  launch_deinterleave(stage, k, k, n, dB, dB + lb * n, lb, st);
+  CK(cudaMemcpy2DAsync(stage, (size_t)m * 16, C, (size_t)ldc * 16, (size_t)m * 16, n, cudaMemcpyHostToDevice, st));
+  launch_deinterleave(stage, m, m, n, dC, dC + lc * n, lc, st);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  CK(cudaEventRecord(e0, st));
+  zgemm_minus_planar(m, n, k, dA, dA + la * k, la, dB, dB + lb * n, lb, dC, dC + lc * n, lc, st);
+  CK(cudaEventRecord(e1, st)); CK(cudaEventSynchronize(e1));
+  float t; cudaEventElapsedTime(&t, e0, e1); if (ms) *ms = t;
+  launch_interleave(dC, dC + lc * n, lc, m, n, stage, m, st);
+  CK(cudaMemcpy2DAsync(C, (size_t)ldc * 16, stage, (size_t)m * 16, (size_t)m * 16, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(stage); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CK(cudaGetLastError());
+  return MFB_OK;
+}

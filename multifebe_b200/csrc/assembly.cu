@@ -1,0 +1,406 @@
+// assembly.cu -- sm_100a kernels of the harmonic 3D SBIE influence-matrix assembly.
+//
+//   K0 k_classify   ball test + rule thresholds per (collocation point, element) pair -> 1 plan byte
+//                   (far branch of fbem_bem_harela3d_sbie_auto, lib/fbem/src/bem_harela3d.f90:1501-1506,1522-1531)
+//   K1 k_regular    regular quadrature with precalculated point sets (fbem_bem_harela3d_sbie_ext_pre, :628-700)
+//                   fused with the BC-aware scatter (src/assemble_bem_harela_equation.f90:78-113)
+//   K2 k_adaptive   Telles + subdivision leaves (fbem_bem_harela3d_sbie_ext_st, :702-1048), one warp per pair
+//   K3 k_singular   polar-transformation interior integration (fbem_bem_harela3d_sbie_int, :1174-1472), one warp per pair
+//   K5 k_freeterm   free-term entries (src/build_lse_mechanics_bem_harela.f90:273-747)
+//
+// Mapping of K1: a warp owns 32 consecutive collocation points (sorted by matrix row, so that for a fixed matrix
+// column the 32 lanes x 3 load directions address 96 consecutive rows of the column-major planar matrix) and walks
+// a chunk of elements; the element's point set is read through warp-uniform loads, the 9*n complex accumulators of
+// the pair live in registers, and the result goes to the matrix with coalesced RED.ADD.F64 (several elements share a
+// node/column and MCA points share rows, so plain stores are not possible).  The right-hand side contribution of each
+// lane is reduced in registers over the whole element chunk and flushed once.
+#include "assembly.cuh"
+#include <cstdio>
+
+namespace mfbd {
+
+__constant__ KParams c_kp;
+
+void set_kparams(const KParams& kp, cudaStream_t st) { cudaMemcpyToSymbolAsync(c_kp, &kp, sizeof(KParams), 0, cudaMemcpyHostToDevice, st); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// K0: classification.  d must be bit-identical to the host/reference value (it feeds a discrete decision), hence the
+// explicit round-to-nearest intrinsics (no FMA contraction): r = c - x_i; rmin = sqrt(r.r) - R; far iff rmin > 4R;
+// d = rmin/cl; gln_near = first n with d >= far_thr[n].
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void k_classify(DevGroup g, DevColloc c, DevClassify k, unsigned char* __restrict__ plan) {
+  int cpos = blockIdx.x * blockDim.x + threadIdx.x;
+  int e = blockIdx.y;
+  if (cpos >= c.ldp) return;
+  unsigned char out = PLAN_NONE;
+  if (cpos < c.n_colloc) {
+    const double* b = g.ball + 5 * (size_t)e;
+    double r0 = __dsub_rn(b[0], c.cx[cpos]), r1 = __dsub_rn(b[1], c.cx[c.ldp + cpos]), r2 = __dsub_rn(b[2], c.cx[2 * c.ldp + cpos]);
+    double rr = __dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2));
+    double rmin = __dsub_rn(__dsqrt_rn(rr), b[3]);
+    if (rmin > __dmul_rn(4.0, b[3])) {
+      double d = __ddiv_rn(rmin, b[4]);
+      int gn = 31;
+      if (d >= k.far_dmax) gn = 2;
+      else {
+#pragma unroll 1
+        for (int n = 2; n <= 30; n++) if (d >= k.far_thr[n]) { gn = n; break; }
+      }
+      if (!(d > 2.0)) gn = 31;  // cannot happen for a ball that contains the element (R >= cl/2); be safe -> host
+      int gln = max(g.gln_far[e], gn);
+      out = PLAN_NEAR;
+      if (gn <= 30 && gln <= k.ps_gln_max) {
+        for (int s = 0; s < g.n_sets; s++) if (g.set_gln[s] >= gln) { out = (unsigned char)s; break; }
+      }
+    } else out = PLAN_NEAR;
+  }
+  plan[(size_t)(g.slot0 + e) * c.ldp + cpos] = out;
+}
+void launch_classify(const DevGroup& g, const DevColloc& c, const DevClassify& k, unsigned char* plan, cudaStream_t st) {
+  if (g.n_elem == 0) return;
+  dim3 grid((c.ldp + 255) / 256, g.n_elem);
+  k_classify<<<grid, 256, 0, st>>>(g, c, k, plan);
+}
+
+__global__ void k_collect_near(const unsigned char* __restrict__ plan, long long n_slots, DevColloc c, unsigned long long* counter,
+                               int2* list, unsigned long long capacity) {
+  long long total = n_slots * c.ldp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (plan[i] == PLAN_NEAR) {
+      unsigned long long p = atomicAdd(counter, 1ull);
+      if (list && p < capacity) list[p] = make_int2((int)(i % c.ldp), (int)(i / c.ldp));
+    }
+  }
+}
+void launch_count_near(const unsigned char* plan, long long n_slots, const DevColloc& c, unsigned long long* counter, int2* list,
+                       unsigned long long capacity, cudaStream_t st) {
+  k_collect_near<<<1184, 256, 0, st>>>(plan, n_slots, c, counter, list, capacity);
+}
+__global__ void k_patch_plan(unsigned char* plan, DevColloc c, int n, const int* cpos, const int* slot, const unsigned char* val) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) plan[(size_t)slot[i] * c.ldp + cpos[i]] = val[i];
+}
+void launch_patch_plan(unsigned char* plan, const DevColloc& c, int n, const int* cpos, const int* slot, const unsigned char* val, cudaStream_t st) {
+  if (n > 0) k_patch_plan<<<(n + 255) / 256, 256, 0, st>>>(plan, c, n, cpos, slot, val);
+}
+
+// prescribed values per (element, j, k), refreshed once per frequency
+__global__ void k_gather_cv(DevGroup g, const double* __restrict__ cvalue) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int per = 3 * g.nn;
+  if (i >= g.n_elem * per) return;
+  int e = i / per, jk = i % per, j = jk / 3, k = jk % 3;
+  int node = g.enode[e * g.nn + j];
+  g.ecv[2 * (size_t)i] = cvalue[2 * (3 * (size_t)node + k)];
+  g.ecv[2 * (size_t)i + 1] = cvalue[2 * (3 * (size_t)node + k) + 1];
+}
+void launch_gather_cv(const DevGroup& g, const double* cvalue, cudaStream_t st) {
+  int n = g.n_elem * 3 * g.nn;
+  if (n > 0) k_gather_cv<<<(n + 255) / 256, 256, 0, st>>>(g, cvalue);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Scatter of one pair's accumulators (assemble_bem_harela_equation.f90:78-113).  `mine(j*3+k)` selects which entries
+// this lane writes (all for K1; a lane-strided subset after the warp reduction of K2/K3).
+// ------------------------------------------------------------------------------------------------------------------
+template <int NN, int NL, class Pred>
+__device__ __forceinline__ void scatter_pair(const Acc<NN, NL>& a, const int* __restrict__ ecol, const unsigned char* __restrict__ ekind,
+                                             const double* __restrict__ ecv, bool rev, const DevSystem& s, int il,
+                                             int r0, int r1, int r2, double* bre, double* bim, Pred mine) {
+  const double ct = rev ? -c_kp.cte_t : c_kp.cte_t;
+  const cplx cu = c_kp.cte_u;
+#pragma unroll
+  for (int j = 0; j < NN; j++) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const int jk = j * 3 + k;
+      if (!mine(jk)) continue;
+      const int col = ecol[jk];
+      const int kind = ekind[jk];
+      const double cvr = ecv[2 * jk], cvi = ecv[2 * jk + 1];
+      double* Ar = s.Are + (size_t)col * s.lda;
+      double* Ai = s.Aim + (size_t)col * s.lda;
+#pragma unroll
+      for (int ll = 0; ll < NL; ll++) {
+        const int l = (NL == 3) ? ll : il;
+        const int row = (l == 0) ? r0 : (l == 1 ? r1 : r2);
+        const int q = (ll * 3 + k) * NN + j;
+        double hr = ct * a.hr[q], hi = ct * a.hi[q];
+        double gr = cu.re * a.gr[q] - cu.im * a.gi[q], gi = cu.re * a.gi[q] + cu.im * a.gr[q];
+        double ar, ai, br, bi;
+        if (kind == 0) { ar = -gr; ai = -gi; br = -(hr * cvr - hi * cvi); bi = -(hr * cvi + hi * cvr); }
+        else { ar = hr; ai = hi; br = gr * cvr - gi * cvi; bi = gr * cvi + gi * cvr; }
+        atomicAdd(Ar + row, ar);
+        atomicAdd(Ai + row, ai);
+        bre[l] += br; bim[l] += bi;
+      }
+    }
+  }
+}
+struct AllEntries { __device__ __forceinline__ bool operator()(int) const { return true; } };
+struct LaneEntries { int lane; __device__ __forceinline__ bool operator()(int jk) const { return (jk & 31) == lane; } };
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1: regular pairs.  NL = 3: all load directions at once (9*NN complex accumulators, elements with <= 4 nodes);
+// NL = 1: one load direction per pass (3*NN accumulators) for 6/8/9-node elements.
+// ------------------------------------------------------------------------------------------------------------------
+const int K1_WARPS = 4;
+const int K1_ECHUNK = 32;
+
+template <int ET, int NL>
+__global__ void __launch_bounds__(K1_WARPS * 32) k_regular(DevGroup g, DevColloc c, DevSystem s, const unsigned char* __restrict__ plan) {
+  const int NN = ElemTraits<ET>::NN;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cpos = (blockIdx.x * K1_WARPS + warp) * 32 + lane;
+  const bool valid = cpos < c.n_colloc;
+  const int cp = valid ? cpos : c.n_colloc - 1;
+  const double xc[3] = {c.cx[cp], c.cx[c.ldp + cp], c.cx[2 * c.ldp + cp]};
+  const int r0 = c.crow[cp], r1 = c.crow[c.ldp + cp], r2 = c.crow[2 * c.ldp + cp];
+  double bre[3] = {0.0, 0.0, 0.0}, bim[3] = {0.0, 0.0, 0.0};
+  const int e0 = blockIdx.y * K1_ECHUNK, e1 = min(e0 + K1_ECHUNK, g.n_elem);
+  for (int e = e0; e < e1; e++) {
+    unsigned char m = valid ? plan[(size_t)(g.slot0 + e) * c.ldp + cpos] : PLAN_NONE;
+    unsigned todo = __ballot_sync(0xffffffffu, m < MAX_SETS);
+    while (todo) {
+      const int leader = __ffs(todo) - 1;
+      const int sset = __shfl_sync(0xffffffffu, (int)m, leader);
+      const unsigned grp = __ballot_sync(0xffffffffu, (int)m == sset);
+      todo &= ~grp;
+      if ((int)m == sset) {
+        const int ngp = g.ngp[sset];
+        const double* P = g.pts[sset] + (size_t)e * ngp * (6 + NN);
+        const int* ecol = g.ecol + (size_t)e * 3 * NN;
+        const unsigned char* ekind = g.ekind + (size_t)e * 3 * NN;
+        const double* ecv = g.ecv + (size_t)e * 6 * NN;
+        const bool rev = g.erev[e] != 0;
+#pragma unroll 1
+        for (int il = 0; il < (NL == 3 ? 1 : 3); il++) {
+          Acc<NN, NL> acc; acc.zero();
+#pragma unroll 1
+          for (int kp = 0; kp < ngp; kp++) {
+            const double* q = P + (size_t)kp * (6 + NN);
+            double x[3] = {__ldg(q), __ldg(q + 1), __ldg(q + 2)}, n[3] = {__ldg(q + 3), __ldg(q + 4), __ldg(q + 5)}, w[NN];
+#pragma unroll
+            for (int j = 0; j < NN; j++) w[j] = __ldg(q + 6 + j);
+            accumulate_exterior<NN, NL>(acc, c_kp, x, n, xc, w, il);
+          }
+          scatter_pair<NN, NL>(acc, ecol, ekind, ecv, rev, s, il, r0, r1, r2, bre, bim, AllEntries());
+        }
+      }
+    }
+  }
+  if (valid) {
+    if (bre[0] != 0.0 || bim[0] != 0.0) { atomicAdd(s.bre + r0, bre[0]); atomicAdd(s.bim + r0, bim[0]); }
+    if (bre[1] != 0.0 || bim[1] != 0.0) { atomicAdd(s.bre + r1, bre[1]); atomicAdd(s.bim + r1, bim[1]); }
+    if (bre[2] != 0.0 || bim[2] != 0.0) { atomicAdd(s.bre + r2, bre[2]); atomicAdd(s.bim + r2, bim[2]); }
+  }
+}
+
+void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, cudaStream_t st) {
+  if (g.n_elem == 0) return;
+  dim3 grid((c.n_colloc + 32 * K1_WARPS - 1) / (32 * K1_WARPS), (g.n_elem + K1_ECHUNK - 1) / K1_ECHUNK);
+  dim3 block(K1_WARPS * 32);
+  switch (g.et) {
+    case 5: k_regular<5, 3><<<grid, block, 0, st>>>(g, c, s, plan); break;
+    case 7: k_regular<7, 3><<<grid, block, 0, st>>>(g, c, s, plan); break;
+    case 6: k_regular<6, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
+    case 8: k_regular<8, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
+    case 9: k_regular<9, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
+  }
+}
+
+// warp all-reduce of every accumulator
+template <int NN, int NL>
+__device__ __forceinline__ void warp_reduce(Acc<NN, NL>& a) {
+#pragma unroll
+  for (int i = 0; i < NL * 3 * NN; i++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a.hr[i] += __shfl_xor_sync(0xffffffffu, a.hr[i], o); a.hi[i] += __shfl_xor_sync(0xffffffffu, a.hi[i], o);
+      a.gr[i] += __shfl_xor_sync(0xffffffffu, a.gr[i], o); a.gi[i] += __shfl_xor_sync(0xffffffffu, a.gi[i], o);
+    }
+  }
+}
+__device__ __forceinline__ void flush_b(const DevSystem& s, int r0, int r1, int r2, const double* bre, const double* bim) {
+  if (bre[0] != 0.0 || bim[0] != 0.0) { atomicAdd(s.bre + r0, bre[0]); atomicAdd(s.bim + r0, bim[0]); }
+  if (bre[1] != 0.0 || bim[1] != 0.0) { atomicAdd(s.bre + r1, bre[1]); atomicAdd(s.bim + r1, bim[1]); }
+  if (bre[2] != 0.0 || bim[2] != 0.0) { atomicAdd(s.bre + r2, bre[2]); atomicAdd(s.bim + r2, bim[2]); }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2: adaptive pairs -- one warp per pair, lanes stride over the gln x gln points of every leaf.
+// ------------------------------------------------------------------------------------------------------------------
+template <int ET, int NL>
+__global__ void __launch_bounds__(128) k_adaptive(DevGroup g, DevColloc c, DevSystem s, DevAdaptive a, DevTables t) {
+  const int NN = ElemTraits<ET>::NN;
+  const bool tri = (ElemTraits<ET>::NV == 3);
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= a.n_pairs) return;
+  const int cpos = a.pair_cpos[p], e = a.pair_elem[p];
+  const double xc[3] = {c.cx[cpos], c.cx[c.ldp + cpos], c.cx[2 * c.ldp + cpos]};
+  const int r0 = c.crow[cpos], r1 = c.crow[c.ldp + cpos], r2 = c.crow[2 * c.ldp + cpos];
+  double xn[3 * NN];
+#pragma unroll
+  for (int i = 0; i < 3 * NN; i++) xn[i] = g.xn[(size_t)e * 3 * NN + i];
+  const double* gx = tri ? t.gl01_x : t.gl11_x;
+  const double* gw = tri ? t.gl01_w : t.gl11_w;
+  double bre[3] = {0.0, 0.0, 0.0}, bim[3] = {0.0, 0.0, 0.0};
+#pragma unroll 1
+  for (int il = 0; il < (NL == 3 ? 1 : 3); il++) {
+    Acc<NN, NL> acc; acc.zero();
+#pragma unroll 1
+    for (int lf = a.pair_leaf0[p]; lf < a.pair_leaf0[p + 1]; lf++) {
+      const double* L = a.leaf_d + 16 * (size_t)lf;
+      double xi_s[8], tp1[4], tp2[4];
+#pragma unroll
+      for (int i = 0; i < 8; i++) xi_s[i] = __ldg(L + i);
+#pragma unroll
+      for (int i = 0; i < 4; i++) { tp1[i] = __ldg(L + 8 + i); tp2[i] = __ldg(L + 12 + i); }
+      const int gln = a.leaf_gln[lf], off = gln * (gln - 1) / 2;
+#pragma unroll 1
+      for (int idx = lane; idx < gln * gln; idx += 32) {
+        const int k1 = idx / gln, k2 = idx - k1 * gln;
+        double x[3], n[3], w[NN];
+        leaf_point<ET>(xn, xi_s, tp1, tp2, __ldg(gx + off + k1), __ldg(gw + off + k1), __ldg(gx + off + k2), __ldg(gw + off + k2), x, n, w);
+        accumulate_exterior<NN, NL>(acc, c_kp, x, n, xc, w, il);
+      }
+    }
+    warp_reduce<NN, NL>(acc);
+    LaneEntries le; le.lane = lane;
+    scatter_pair<NN, NL>(acc, g.ecol + (size_t)e * 3 * NN, g.ekind + (size_t)e * 3 * NN, g.ecv + (size_t)e * 6 * NN, g.erev[e] != 0, s, il,
+                         r0, r1, r2, bre, bim, le);
+  }
+  flush_b(s, r0, r1, r2, bre, bim);
+}
+void launch_adaptive(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevAdaptive& a, const DevTables& t, cudaStream_t st) {
+  if (a.n_pairs == 0) return;
+  dim3 grid((a.n_pairs + 3) / 4), block(128);
+  switch (g.et) {
+    case 5: k_adaptive<5, 3><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 7: k_adaptive<7, 3><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 6: k_adaptive<6, 1><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 8: k_adaptive<8, 1><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 9: k_adaptive<9, 1><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K3: singular pairs -- one warp per pair, lanes stride over (ray, radial point); 15 radial Gauss-Legendre points on
+// [0,1] per ray (ngp_rho = 15, bem_harela3d.f90:1298); the line-integral term phi_i*T2(1)*hli (:1462-1466) is added
+// after the reduction.
+// ------------------------------------------------------------------------------------------------------------------
+template <int ET, int NL>
+__global__ void __launch_bounds__(128) k_singular(DevGroup g, DevColloc c, DevSystem s, DevSingular a, DevTables t) {
+  const int NN = ElemTraits<ET>::NN;
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= a.n_pairs) return;
+  const int cpos = a.pair_cpos[p], e = a.pair_elem[p];
+  const int r0 = c.crow[cpos], r1 = c.crow[c.ldp + cpos], r2 = c.crow[2 * c.ldp + cpos];
+  const double* D = a.pair_d + 14 * (size_t)p;
+  const double xi_i0 = D[0], xi_i1 = D[1];
+  const double xc[3] = {D[2], D[3], D[4]};
+  double xn[3 * NN];
+#pragma unroll
+  for (int i = 0; i < 3 * NN; i++) xn[i] = g.xn[(size_t)e * 3 * NN + i];
+  double phi_i[NN];
+  { double d1[NN], d2[NN]; shape<ET>(xi_i0, xi_i1, phi_i, d1, d2); }
+  const int ray0 = a.pair_ray0[p], nray = a.pair_ray0[p + 1] - ray0;
+  const double* gx = t.gl01_x + 15 * 14 / 2;
+  const double* gw = t.gl01_w + 15 * 14 / 2;
+  double bre[3] = {0.0, 0.0, 0.0}, bim[3] = {0.0, 0.0, 0.0};
+#pragma unroll 1
+  for (int il = 0; il < (NL == 3 ? 1 : 3); il++) {
+    Acc<NN, NL> acc; acc.zero();
+#pragma unroll 1
+    for (int idx = lane; idx < nray * 15; idx += 32) {
+      const int kr_ = idx / 15, kk = idx - kr_ * 15;
+      const double* R = a.rays + 4 * (size_t)(ray0 + kr_);
+      const double ct = __ldg(R), sn = __ldg(R + 1), rhoij = __ldg(R + 2), wray = __ldg(R + 3);
+      const double rho = rhoij * __ldg(gx + kk), wrad = __ldg(gw + kk);
+      double phi[NN], x[3], n[3], jg;
+      geometry_at<ET>(xn, xi_i0 + rho * ct, xi_i1 + rho * sn, phi, x, n, jg);
+      const double jw = jg * rho * wray * wrad;
+      accumulate_interior<NN, NL>(acc, c_kp, x, n, xc, phi, phi_i, jw, il);
+    }
+    warp_reduce<NN, NL>(acc);
+    // + phi_i(j) * T2(1) * hli(l,k)
+    const cplx t21 = c_kp.T2[1];
+#pragma unroll
+    for (int ll = 0; ll < NL; ll++) {
+      const int l = (NL == 3) ? ll : il;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const double hl = D[5 + 3 * l + k];
+#pragma unroll
+        for (int j = 0; j < NN; j++) { acc.hr[(ll * 3 + k) * NN + j] += phi_i[j] * t21.re * hl; acc.hi[(ll * 3 + k) * NN + j] += phi_i[j] * t21.im * hl; }
+      }
+    }
+    LaneEntries le; le.lane = lane;
+    scatter_pair<NN, NL>(acc, g.ecol + (size_t)e * 3 * NN, g.ekind + (size_t)e * 3 * NN, g.ecv + (size_t)e * 6 * NN, g.erev[e] != 0, s, il,
+                         r0, r1, r2, bre, bim, le);
+  }
+  flush_b(s, r0, r1, r2, bre, bim);
+}
+void launch_singular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevSingular& a, const DevTables& t, cudaStream_t st) {
+  if (a.n_pairs == 0) return;
+  dim3 grid((a.n_pairs + 3) / 4), block(128);
+  switch (g.et) {
+    case 5: k_singular<5, 3><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 7: k_singular<7, 3><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 6: k_singular<6, 1><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 8: k_singular<8, 1><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 9: k_singular<9, 1><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K5: free-term entries (h-type): ctype 1 -> A(row,col_u) += c ; ctype 0 -> b(row) -= c*u_prescribed
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void k_freeterm(DevColloc c, DevSystem s, DevFreeTerm f, cplx F) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= f.n) return;
+  const int cpos = f.cpos[i], l = f.l[i];
+  const int row = c.crow[l * c.ldp + cpos];
+  const int o = f.slot_off[f.slot[i]] + f.jk[i];
+  // value = alpha + beta*F, F = -1/(8 pi (1-nu)) (Mantic; bem_harela3d.f90:538) -- alpha,beta are geometry-only
+  const double vr = f.val[2 * i] + f.val[2 * i + 1] * F.re, vi = f.val[2 * i + 1] * F.im;
+  if (f.ekind[o] == 1) {
+    atomicAdd(s.Are + (size_t)f.ecol[o] * s.lda + row, vr);
+    atomicAdd(s.Aim + (size_t)f.ecol[o] * s.lda + row, vi);
+  } else {
+    const double cvr = f.ecv[2 * (size_t)o], cvi = f.ecv[2 * (size_t)o + 1];
+    atomicAdd(s.bre + row, -(vr * cvr - vi * cvi));
+    atomicAdd(s.bim + row, -(vr * cvi + vi * cvr));
+  }
+}
+void launch_freeterm(const DevColloc& c, const DevSystem& s, const DevFreeTerm& f, cplx F, cudaStream_t st) {
+  if (f.n > 0) k_freeterm<<<(f.n + 255) / 256, 256, 0, st>>>(c, s, f, F);
+}
+
+// planar <-> interleaved complex (host interface format), column-major
+__global__ void k_interleave(const double* __restrict__ re, const double* __restrict__ im, long long ld, int rows, int cols, double* __restrict__ out, long long ldo) {
+  long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long cidx = i / rows, r = i - cidx * rows;
+    out[2 * (cidx * ldo + r)] = re[cidx * ld + r];
+    out[2 * (cidx * ldo + r) + 1] = im[cidx * ld + r];
+  }
+}
+__global__ void k_deinterleave(const double* __restrict__ in, long long ldi, int rows, int cols, double* __restrict__ re, double* __restrict__ im, long long ld) {
+  long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long cidx = i / rows, r = i - cidx * rows;
+    re[cidx * ld + r] = in[2 * (cidx * ldi + r)];
+    im[cidx * ld + r] = in[2 * (cidx * ldi + r) + 1];
+  }
+}
+void launch_interleave(const double* re, const double* im, long long ld, int rows, int cols, double* out, long long ldo, cudaStream_t st) {
+  k_interleave<<<2368, 256, 0, st>>>(re, im, ld, rows, cols, out, ldo);
+}
+void launch_deinterleave(const double* in, long long ldi, int rows, int cols, double* re, double* im, long long ld, cudaStream_t st) {
+  k_deinterleave<<<2368, 256, 0, st>>>(in, ldi, rows, cols, re, im, ld);
+}
+
+}  // namespace mfbd

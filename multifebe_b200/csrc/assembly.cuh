@@ -1,0 +1,77 @@
+// assembly.cuh -- device-side data layout and launchers of the B200 assembly kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include "bem_math.cuh"
+
+namespace mfbd {
+
+const int MAX_SETS = 16;
+const unsigned char PLAN_NEAR = 250;      // classifier could not settle the pair with the ball test -> host planner
+const unsigned char PLAN_ADAPTIVE = 254;  // Telles + subdivision leaf list (kernel K2)
+const unsigned char PLAN_SINGULAR = 253;  // polar transformation (kernel K3)
+const unsigned char PLAN_NONE = 255;
+
+// One element-type group (elements sorted by type; "slot" = position in that order).
+struct DevGroup {
+  int et, nn, n_elem, slot0;     // slot0: first element slot of the group
+  const double* xn;              // [n_elem][3*nn] node coordinates
+  const int* ecol;               // [n_elem][3*nn] column of A for (node j, dof k); index j*3+k
+  const unsigned char* ekind;    // [n_elem][3*nn] 0: u known (A -= g, b -= h*u), 1: t known (A += h, b += g*t)
+  const int* enode;              // [n_elem][nn]   global node ids
+  const unsigned char* erev;     // [n_elem] reversed orientation (h -> -h)
+  double* ecv;                   // [n_elem][3*nn][2] prescribed value of (j,k), refreshed per frequency
+  const double* ball;            // [n_elem][5]: centre(3), radius, characteristic length
+  const int* gln_far;            // [n_elem]
+  int n_sets; int set_gln[MAX_SETS]; int ngp[MAX_SETS];
+  const double* pts[MAX_SETS];   // [n_elem][ngp][6+nn]: x(3), n(3), phi_j*J*w
+};
+
+struct DevSystem {
+  double *Are, *Aim; long long lda; int n_dof;   // planar (split re/im) column-major system matrix
+  double *bre, *bim;
+};
+
+struct DevColloc {
+  int n_colloc, ldp;             // ldp = n_colloc rounded up to 32
+  const double* cx;              // [3][ldp] collocation points (SoA), sorted by row
+  const int* crow;               // [3][ldp] A rows of the three equations of each collocation point
+};
+
+struct DevClassify {
+  double far_thr[32]; double far_dmax; int ps_gln_max;
+};
+
+// adaptive (quasi-singular) work lists of one group
+struct DevAdaptive {
+  int n_pairs; const int* pair_cpos; const int* pair_elem; const int* pair_leaf0;  // [n_pairs+1]
+  const double* leaf_d;          // [n_leaves][16]: xi_s(8), tp1(4), tp2(4)
+  const int* leaf_gln;           // [n_leaves]
+};
+// singular work lists of one group
+struct DevSingular {
+  int n_pairs; const int* pair_cpos; const int* pair_elem; const int* pair_ray0;   // [n_pairs+1]
+  const double* pair_d;          // [n_pairs][14]: xi_i(2), x_i(3), hli(9)
+  const double* rays;            // [n_rays][4]: cos, sin, rhoij, w
+};
+// free-term entries: value added to h(j,l,k) of the collocation point before the BC-aware scatter
+struct DevFreeTerm {
+  int n; const int* cpos; const int* slot; const int* jk; const int* l; const double* val;  // val[n][2] = (alpha, beta): value = alpha + beta*F
+  const int* slot_off;           // [n_slots+1] offset of each element slot in the flat (j,k) arrays below
+  const int* ecol; const unsigned char* ekind; const double* ecv;   // flat over all groups
+};
+struct DevTables { const double *gl11_x, *gl11_w, *gl01_x, *gl01_w; };  // packed, rule n at offset n(n-1)/2
+
+void set_kparams(const KParams& kp, cudaStream_t st);
+void launch_classify(const DevGroup& g, const DevColloc& c, const DevClassify& k, unsigned char* plan, cudaStream_t st);
+void launch_count_near(const unsigned char* plan, long long n_slots, const DevColloc& c, unsigned long long* counter, int2* list,
+                       unsigned long long capacity, cudaStream_t st);
+void launch_patch_plan(unsigned char* plan, const DevColloc& c, int n, const int* cpos, const int* slot, const unsigned char* val, cudaStream_t st);
+void launch_gather_cv(const DevGroup& g, const double* cvalue, cudaStream_t st);
+void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, cudaStream_t st);
+void launch_adaptive(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevAdaptive& a, const DevTables& t, cudaStream_t st);
+void launch_singular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevSingular& a, const DevTables& t, cudaStream_t st);
+void launch_freeterm(const DevColloc& c, const DevSystem& s, const DevFreeTerm& f, cplx F, cudaStream_t st);
+void launch_interleave(const double* re, const double* im, long long ld, int rows, int cols, double* out, long long ldo, cudaStream_t st);
+void launch_deinterleave(const double* in, long long ldi, int rows, int cols, double* re, double* im, long long ld, cudaStream_t st);
+
+}  // namespace mfbd

@@ -1,0 +1,38 @@
+// lu.cuh -- blocked right-looking complex LU (partial pivoting) + triangular solves on planar (split re/im) storage.
+// Replaces OpenBLAS zgetrf/zgetrs behind solve_lse_c (src/solve_lse_c.f90:124,176).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace mfbd {
+
+struct LuWork {
+  int nb;                 // block size
+  int n_sm;
+  double *cand_val;       // [2][grid]         pivot candidates (|re|+|im|)
+  int *cand_row;          // [2][grid]
+  double *cand_data;      // [2][grid][2*nb]   candidate rows (re, im)
+  double *diag_data;      // [2][2*nb]         current diagonal row
+  double *ninv_re, *ninv_im;   // nb x nb: -inv(L11)
+  double *t_re, *t_im; long long ldt;  // nb x n scratch for the U12 block row
+  int *info;              // device flag: first zero pivot (1-based), 0 = ok
+  float ms_panel, ms_swap, ms_trsm, ms_gemm; long long launches;
+  cudaEvent_t ev[8];
+};
+
+int lu_work_alloc(LuWork& w, int n, int nb);
+void lu_work_free(LuWork& w);
+
+// In-place LU of the n x n planar matrix; ipiv (device, 1-based, LAPACK convention).  Returns cudaError as int (0 ok).
+int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuWork& w, cudaStream_t st, bool timing);
+// Solve with the factors: b (planar, n x nrhs, ldb) overwritten by the solution.
+int zgetrs_planar(const double* Are, const double* Aim, long long lda, int n, const int* ipiv, double* bre, double* bim, long long ldb,
+                  int nrhs, cudaStream_t st);
+// C -= A*B on planar storage (the trailing-matrix update; FP64 tensor pipe, mma.sync m8n8k4).  k must be a multiple of 4.
+void zgemm_minus_planar(int m, int n, int k, const double* Are, const double* Aim, long long lda, const double* Bre, const double* Bim,
+                        long long ldb, double* Cre, double* Cim, long long ldc, cudaStream_t st);
+// micro-benchmarks (TFLOP/s, GB/s)
+double bench_dfma(cudaStream_t st);
+double bench_dmma(cudaStream_t st);
+double bench_copy(cudaStream_t st);
+
+}  // namespace mfbd
