@@ -88,9 +88,20 @@ int mfb_harela3d_assemble(mfb_problem* problem, double omega, const mfb_z* lambd
 int mfb_zsolve(mfb_problem* problem, int n, mfb_z* A, int lda, int* ipiv, mfb_z* b, int nrhs, int factorize);
 
 /* One iteration of the frequency loop (src/multifebe.f90:107-124) kept on the device: assemble, factorise, solve;
- * x[n_dof] receives the solution (what assign_solution_mechanics_harmonic.f90:192-205 reads from b_c). */
+ * x[n_dof] receives the solution (what assign_solution_mechanics_harmonic.f90:192-205 reads from b_c); x == NULL keeps it on
+ * the device (mfb_get_solution).  cvalue == NULL (here and in mfb_harela3d_assemble) re-uses the prescribed values of the
+ * previous call (boundary conditions do not change along a frequency sweep). */
 int mfb_harela3d_solve_frequency(mfb_problem* problem, double omega, const mfb_z* lambda, const mfb_z* mu, double rho,
                                  const mfb_z* nu, const mfb_z* cvalue, mfb_z* x);
+
+/* Solution of the last mfb_harela3d_solve_frequency / device-resident mfb_zsolve (x[n_dof]). */
+int mfb_get_solution(mfb_problem* problem, mfb_z* x);
+
+/* Diagnostics on the assembled, not yet factorised, device-resident system (the analogue of the reference's optional
+ * zgerfs report, src/solve_lse_c.f90:191-206): componentwise backward error berr = max_i |Ax-b|_i / (|A||x|+|b|)_i and
+ * max|Ax-b| / max(|A||x|+|b|) for a candidate solution x; selected entries A(rows[i], cols[i]) (0-based). */
+int mfb_residual(mfb_problem* problem, const mfb_z* x, double* berr, double* rel_resid);
+int mfb_get_entries(mfb_problem* problem, int n, const int* rows, const int* cols, mfb_z* out);
 
 /* Plan statistics and per-phase device timings (CUDA events) of the last call; see mfb_stat_id. */
 enum mfb_stat_id {
@@ -99,13 +110,19 @@ enum mfb_stat_id {
   MFB_STAT_MS_ZERO = 8, MFB_STAT_MS_REGULAR = 9, MFB_STAT_MS_ADAPTIVE = 10, MFB_STAT_MS_SINGULAR = 11,
   MFB_STAT_MS_FREETERM = 12, MFB_STAT_MS_LU = 13, MFB_STAT_MS_SOLVE = 14, MFB_STAT_MS_GEMM = 15, MFB_STAT_MS_PANEL = 16,
   MFB_STAT_LAUNCHES = 17, MFB_STAT_MS_SETUP_HOST = 18, MFB_STAT_MS_ASSEMBLE = 19, MFB_STAT_FLOPS_REGULAR = 20,
-  MFB_STAT_MS_TRSM = 21, MFB_STAT_MS_SWAP = 22, MFB_STAT_COUNT = 32
+  MFB_STAT_MS_TRSM = 21, MFB_STAT_MS_SWAP = 22, MFB_STAT_LU_LAUNCHES = 23, MFB_STAT_GEMM_LAUNCHES = 24,
+  MFB_STAT_GEMM_FLOPS = 25, MFB_STAT_COUNT = 32
 };
 int mfb_get_stats(mfb_problem* problem, double* stats /* MFB_STAT_COUNT doubles */);
 
 /* Per-pair integration mode chosen by the plan (for parity tests of the discrete decisions):
  * 2..30 = regular rule gln of the precalculated set, 100 = adaptive (Telles + subdivision), 200 = singular. */
 int mfb_plan_modes(mfb_problem* problem, int n_pairs, const int* colloc, const int* elem, int* mode);
+
+/* CUDA-event marks on the context's own stream (the stream every kernel of this library is launched on), so that a caller
+ * can time a region on the device: mark(slot) records, elapsed(slot0, slot1) synchronises on slot1 and returns milliseconds. */
+int mfb_stream_mark(mfb_ctx* ctx, int slot /* 0..7 */);
+int mfb_stream_elapsed(mfb_ctx* ctx, int slot0, int slot1, double* ms);
 
 /* Micro-benchmarks used to measure the roofline denominators on the box (FP64 FMA pipe, FP64 tensor (DMMA) pipe,
  * device copy bandwidth): returns TFLOP/s or GB/s. */

@@ -21,7 +21,7 @@ _LIB = None
 STAT = dict(PAIRS_REGULAR=0, POINTS_REGULAR=1, PAIRS_ADAPTIVE=2, LEAVES=3, POINTS_ADAPTIVE=4, PAIRS_SINGULAR=5,
             POINTS_SINGULAR=6, NEAR_PAIRS=7, MS_ZERO=8, MS_REGULAR=9, MS_ADAPTIVE=10, MS_SINGULAR=11, MS_FREETERM=12,
             MS_LU=13, MS_SOLVE=14, MS_GEMM=15, MS_PANEL=16, LAUNCHES=17, MS_SETUP_HOST=18, MS_ASSEMBLE=19,
-            FLOPS_REGULAR=20, MS_TRSM=21, MS_SWAP=22)
+            FLOPS_REGULAR=20, MS_TRSM=21, MS_SWAP=22, LU_LAUNCHES=23, GEMM_LAUNCHES=24, GEMM_FLOPS=25)
 STAT_COUNT = 32
 
 
@@ -71,6 +71,14 @@ class Context:
         if self.h:
             lib().mfb_finalize(self.h)
             self.h = C.c_void_p()
+
+    def mark(self, slot):
+        _check(lib().mfb_stream_mark(self.h, C.c_int(slot)))
+
+    def elapsed_ms(self, slot0, slot1):
+        ms = C.c_double()
+        _check(lib().mfb_stream_elapsed(self.h, C.c_int(slot0), C.c_int(slot1), C.byref(ms)))
+        return ms.value
 
     def measure_peaks(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()
@@ -136,11 +144,31 @@ class Problem:
         return (x, ipiv) if want_ipiv else x
 
     # ---- one iteration of the frequency loop, device resident ----
-    def solve_frequency(self, omega, mat):
-        x = np.zeros(self.m.n_dof, dtype=np.complex128)
+    def solve_frequency(self, omega, mat, host=True):
+        """host=True: prescribed values go up from host memory and the solution comes back to host memory (the call the
+        Fortran loop body would make).  host=False: everything stays on the device (get_solution() fetches x)."""
+        x = np.zeros(self.m.n_dof, dtype=np.complex128) if host else None
         _check(lib().mfb_harela3d_solve_frequency(self.h, C.c_double(omega), _p(_z(mat.lam)), _p(_z(mat.mu)), C.c_double(mat.rho),
-                                                  _p(_z(mat.nu)), _p(self._cv), _p(x)))
+                                                  _p(_z(mat.nu)), _p(self._cv) if host else None, _p(x) if host else None))
         return x
+
+    def get_solution(self):
+        x = np.zeros(self.m.n_dof, dtype=np.complex128)
+        _check(lib().mfb_get_solution(self.h, _p(x)))
+        return x
+
+    def residual(self, x):
+        """(berr, rel_resid) of x against the assembled, unfactorised device-resident system."""
+        xx = np.ascontiguousarray(x, dtype=np.complex128)
+        a, b = C.c_double(), C.c_double()
+        _check(lib().mfb_residual(self.h, _p(xx), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def get_entries(self, rows, cols):
+        r = np.ascontiguousarray(rows, dtype=np.int32); c = np.ascontiguousarray(cols, dtype=np.int32)
+        out = np.zeros(len(r), dtype=np.complex128)
+        _check(lib().mfb_get_entries(self.h, C.c_int(len(r)), _p(r), _p(c), _p(out)))
+        return out
 
     def stats(self):
         s = np.zeros(STAT_COUNT)

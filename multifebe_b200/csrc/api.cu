@@ -29,7 +29,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
   } while (0)
 
 struct mfb_ctx {
-  int device; cudaStream_t stream; DevTables tables; double* tables_buf;
+  int device; cudaStream_t stream; DevTables tables; double* tables_buf; cudaEvent_t marks[8];
 };
 
 struct GroupHost {
@@ -54,7 +54,7 @@ struct mfb_problem {
   unsigned char* plan;
   double* d_cvalue;
   int* d_ipiv; int* d_perm; std::vector<int> h_ipiv;
-  LuWork lu; bool lu_ready; bool factored;
+  LuWork lu; bool lu_ready; bool factored; bool have_cvalue; bool assembled; int asm_launches;
   double stats[MFB_STAT_COUNT];
   cudaEvent_t ev[8];
   std::vector<int> set_gln;
@@ -88,6 +88,7 @@ extern "C" int mfb_init(int device, mfb_ctx** out) {
   mfb_ctx* c = new mfb_ctx();
   c->device = device;
   CK(cudaStreamCreate(&c->stream));
+  for (int i = 0; i < 8; i++) CK(cudaEventCreate(&c->marks[i]));
   // Gauss-Legendre tables on the device (packed: rule n starts at n(n-1)/2)
   CK(cudaMalloc((void**)&c->tables_buf, 4 * 528 * sizeof(double)));
   CK(cudaMemcpy(c->tables_buf, QT_GL11_X, 528 * 8, cudaMemcpyHostToDevice));
@@ -102,6 +103,7 @@ extern "C" void mfb_finalize(mfb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaFree(c->tables_buf);
+  for (int i = 0; i < 8; i++) cudaEventDestroy(c->marks[i]);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -142,7 +144,7 @@ extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x
   mfb_problem* p = new mfb_problem();
   *out = nullptr;
   p->ctx = ctx; p->n_node = n_node; p->n_elem = n_elem; p->n_colloc = n_colloc; p->n_dof = n_dof;
-  p->lu_ready = false; p->factored = false; p->plan = nullptr;
+  p->lu_ready = false; p->factored = false; p->plan = nullptr; p->have_cvalue = false; p->assembled = false;
   memset(p->stats, 0, sizeof(p->stats));
   for (int i = 0; i < 8; i++) cudaEventCreate(&p->ev[i]);
   mfbh::Settings& S = p->settings;
@@ -425,8 +427,11 @@ static int assemble_device(mfb_problem* p, double omega, cd lambda, cd mu, doubl
   cudaStream_t st = p->ctx->stream;
   KParams K; host_kparams(lambda, mu, rho, omega, K);
   set_kparams(K, st);
-  CK(cudaMemcpyAsync(p->d_cvalue, cvalue, (size_t)6 * p->n_node * sizeof(double), cudaMemcpyHostToDevice, st));
-  for (auto& g : p->groups) launch_gather_cv(g.dev, p->d_cvalue, st);
+  if (cvalue) {
+    CK(cudaMemcpyAsync(p->d_cvalue, cvalue, (size_t)6 * p->n_node * sizeof(double), cudaMemcpyHostToDevice, st));
+    for (auto& g : p->groups) launch_gather_cv(g.dev, p->d_cvalue, st);
+    p->have_cvalue = true;
+  } else if (!p->have_cvalue) return fail(MFB_ERR_ARG, "cvalue == NULL but no prescribed values are resident yet");
   CK(cudaEventRecord(p->ev[0], st));
   CK(cudaMemsetAsync(p->sys.Are, 0, (size_t)2 * p->lda * p->n_dof * sizeof(double), st));
   CK(cudaMemsetAsync(p->sys.bre, 0, (size_t)2 * p->lda * sizeof(double), st));
@@ -442,7 +447,10 @@ static int assemble_device(mfb_problem* p, double omega, cd lambda, cd mu, doubl
   launch_freeterm(p->colloc, p->sys, p->ft, mk(F.real(), F.imag()), st);
   CK(cudaEventRecord(p->ev[5], st));
   CK(cudaGetLastError());
-  p->factored = false;
+  p->factored = false; p->assembled = true;
+  // our kernels only (memsets/copies are not counted): free term + per group regular, adaptive, singular (+ gather_cv)
+  p->asm_launches = 1;
+  for (auto& g : p->groups) p->asm_launches += 1 + (cvalue ? 1 : 0) + (g.adp.n_pairs > 0) + (g.sing.n_pairs > 0);
   return MFB_OK;
 }
 static int collect_assembly_times(mfb_problem* p) {
@@ -454,9 +462,7 @@ static int collect_assembly_times(mfb_problem* p) {
   cudaEventElapsedTime(&t, p->ev[3], p->ev[4]); p->stats[MFB_STAT_MS_SINGULAR] = t;
   cudaEventElapsedTime(&t, p->ev[4], p->ev[5]); p->stats[MFB_STAT_MS_FREETERM] = t;
   cudaEventElapsedTime(&t, p->ev[0], p->ev[5]); p->stats[MFB_STAT_MS_ASSEMBLE] = t;
-  int launches = 1;  // our kernels only (memsets/copies are not counted): freeterm + per group gather_cv, regular, adaptive, singular
-  for (auto& g : p->groups) launches += 2 + (g.adp.n_pairs > 0) + (g.sing.n_pairs > 0);
-  p->stats[MFB_STAT_LAUNCHES] = launches;
+  p->stats[MFB_STAT_LAUNCHES] = p->asm_launches;
   return MFB_OK;
 }
 
@@ -490,7 +496,7 @@ static int upload_matrix(mfb_problem* p, const mfb_z* host, long long ldh, int r
 
 extern "C" int mfb_harela3d_assemble(mfb_problem* p, double omega, const mfb_z* lambda, const mfb_z* mu, double rho, const mfb_z* nu,
                                      const mfb_z* cvalue, mfb_z* A, mfb_z* b) {
-  if (!p || !lambda || !mu || !nu || !cvalue) return fail(MFB_ERR_ARG, "mfb_harela3d_assemble: null argument");
+  if (!p || !lambda || !mu || !nu) return fail(MFB_ERR_ARG, "mfb_harela3d_assemble: null argument");
   CK(cudaSetDevice(p->ctx->device));
   int r = assemble_device(p, omega, cd(lambda->re, lambda->im), cd(mu->re, mu->im), rho, cd(nu->re, nu->im), cvalue);
   if (r) return r;
@@ -501,7 +507,8 @@ extern "C" int mfb_harela3d_assemble(mfb_problem* p, double omega, const mfb_z* 
   return MFB_OK;
 }
 
-static bool lu_timing() { const char* e = getenv("MFB_LU_TIMING"); return e && e[0] == '1'; }
+// per-phase LU timings use pre-created events recorded on the stream without synchronising; MFB_LU_TIMING=0 disables them
+static bool lu_timing() { const char* e = getenv("MFB_LU_TIMING"); return !(e && e[0] == '0'); }
 static int ensure_lu(mfb_problem* p) {
   if (!p->lu_ready) {
     if (lu_work_alloc(p->lu, p->n_dof, 128) != 0) return fail(MFB_ERR_CUDA, "LU workspace allocation failed");
@@ -522,7 +529,9 @@ static int factor_device(mfb_problem* p, int n, bool timing) {
   CK(cudaMemcpyAsync(&info, p->lu.info, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_LU] = t;
-  p->stats[MFB_STAT_LAUNCHES] += (double)p->lu.launches;
+  if (timing) lu_collect_times(p->lu);
+  p->stats[MFB_STAT_LU_LAUNCHES] = (double)p->lu.launches;
+  p->stats[MFB_STAT_GEMM_LAUNCHES] = (double)p->lu.gemm_launches; p->stats[MFB_STAT_GEMM_FLOPS] = p->lu.gemm_flops;
   p->stats[MFB_STAT_MS_PANEL] = p->lu.ms_panel; p->stats[MFB_STAT_MS_SWAP] = p->lu.ms_swap; p->stats[MFB_STAT_MS_TRSM] = p->lu.ms_trsm; p->stats[MFB_STAT_MS_GEMM] = p->lu.ms_gemm;
   std::vector<int> perm(n);
   for (int i = 0; i < n; i++) perm[i] = i;
@@ -543,6 +552,7 @@ extern "C" int mfb_zsolve(mfb_problem* p, int n, mfb_z* A, int lda, int* ipiv, m
   int r;
   if (factorize) {
     if (A) { r = upload_matrix(p, A, lda, n, n, p->sys.Are, p->sys.Aim, p->lda); if (r) return r; }
+    p->assembled = false;
     r = factor_device(p, n, lu_timing());
     if (ipiv) memcpy(ipiv, p->h_ipiv.data(), (size_t)n * sizeof(int));
     if (A) { int r2 = download_matrix(p, p->sys.Are, p->sys.Aim, p->lda, n, n, A, lda); if (r2) return r2; }
@@ -567,7 +577,7 @@ extern "C" int mfb_zsolve(mfb_problem* p, int n, mfb_z* A, int lda, int* ipiv, m
 
 extern "C" int mfb_harela3d_solve_frequency(mfb_problem* p, double omega, const mfb_z* lambda, const mfb_z* mu, double rho, const mfb_z* nu,
                                             const mfb_z* cvalue, mfb_z* x) {
-  if (!p || !lambda || !mu || !nu || !cvalue || !x) return fail(MFB_ERR_ARG, "mfb_harela3d_solve_frequency: null argument");
+  if (!p || !lambda || !mu || !nu) return fail(MFB_ERR_ARG, "mfb_harela3d_solve_frequency: null argument");
   CK(cudaSetDevice(p->ctx->device));
   int r = assemble_device(p, omega, cd(lambda->re, lambda->im), cd(mu->re, mu->im), rho, cd(nu->re, nu->im), cvalue);
   if (r) return r;
@@ -580,7 +590,56 @@ extern "C" int mfb_harela3d_solve_frequency(mfb_problem* p, double omega, const 
   if (e) return fail(MFB_ERR_CUDA, std::string("zgetrs_planar: ") + cudaGetErrorString((cudaError_t)e));
   CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
   float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
+  p->assembled = false;
+  if (!x) return MFB_OK;   // solution stays on the device (mfb_get_solution)
   return download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, x, p->n_dof);
+}
+
+extern "C" int mfb_get_solution(mfb_problem* p, mfb_z* x) {
+  if (!p || !x) return fail(MFB_ERR_ARG, "mfb_get_solution: null argument");
+  CK(cudaSetDevice(p->ctx->device));
+  return download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, x, p->n_dof);
+}
+
+extern "C" int mfb_get_entries(mfb_problem* p, int n, const int* rows, const int* cols, mfb_z* out) {
+  if (!p || !rows || !cols || !out || n < 0) return fail(MFB_ERR_ARG, "mfb_get_entries: invalid argument");
+  if (!p->assembled) return fail(MFB_ERR_ARG, "mfb_get_entries: no assembled (unfactorised) system is resident");
+  for (int i = 0; i < n; i++) if (rows[i] < 0 || rows[i] >= p->n_dof || cols[i] < 0 || cols[i] >= p->n_dof) return fail(MFB_ERR_ARG, "mfb_get_entries: index out of range");
+  CK(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  int *dr, *dc; double* dout;
+  CK(cudaMalloc((void**)&dr, (size_t)std::max(n, 1) * 4)); CK(cudaMalloc((void**)&dc, (size_t)std::max(n, 1) * 4)); CK(cudaMalloc((void**)&dout, (size_t)std::max(n, 1) * 16));
+  CK(cudaMemcpyAsync(dr, rows, (size_t)n * 4, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(dc, cols, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  launch_get_entries(p->sys, n, dr, dc, dout, st);
+  CK(cudaMemcpyAsync(out, dout, (size_t)n * 16, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+  cudaFree(dr); cudaFree(dc); cudaFree(dout);
+  return MFB_OK;
+}
+
+extern "C" int mfb_residual(mfb_problem* p, const mfb_z* x, double* berr, double* rel_resid) {
+  if (!p || !x) return fail(MFB_ERR_ARG, "mfb_residual: null argument");
+  if (!p->assembled) return fail(MFB_ERR_ARG, "mfb_residual: no assembled (unfactorised) system is resident");
+  CK(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  const int n = p->n_dof;
+  double* d; CK(cudaMalloc((void**)&d, (size_t)5 * n * sizeof(double)));
+  std::vector<double> hx(2 * (size_t)n);
+  for (int i = 0; i < n; i++) { hx[i] = x[i].re; hx[n + i] = x[i].im; }
+  CK(cudaMemcpyAsync(d, hx.data(), (size_t)2 * n * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(d + 2 * (size_t)n, 0, (size_t)3 * n * 8, st));
+  launch_residual(p->sys, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, d + 4 * (size_t)n, st);
+  std::vector<double> h(3 * (size_t)n);
+  CK(cudaMemcpyAsync(h.data(), d + 2 * (size_t)n, (size_t)3 * n * 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+  cudaFree(d);
+  double be = 0.0, rmax = 0.0, smax = 0.0;
+  for (int i = 0; i < n; i++) {
+    double r = fabs(h[i]) + fabs(h[n + i]), sc = h[2 * (size_t)n + i];
+    if (sc > 0.0 && r / sc > be) be = r / sc;
+    rmax = std::max(rmax, r); smax = std::max(smax, sc);
+  }
+  if (berr) *berr = be;
+  if (rel_resid) *rel_resid = smax > 0.0 ? rmax / smax : 0.0;
+  return MFB_OK;
 }
 
 extern "C" int mfb_get_stats(mfb_problem* p, double* stats) {
@@ -599,6 +658,20 @@ extern "C" int mfb_plan_modes(mfb_problem* p, int n_pairs, const int* colloc, co
     unsigned char m = h[(size_t)p->slot_of_elem[elem[i]] * p->ldp + p->cpos_of_colloc[colloc[i]]];
     mode[i] = (m < MAX_SETS) ? p->set_gln[m] : (m == PLAN_ADAPTIVE ? 100 : (m == PLAN_SINGULAR ? 200 : -1));
   }
+  return MFB_OK;
+}
+
+extern "C" int mfb_stream_mark(mfb_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot >= 8) return fail(MFB_ERR_ARG, "mfb_stream_mark: invalid argument");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->marks[slot], ctx->stream));
+  return MFB_OK;
+}
+extern "C" int mfb_stream_elapsed(mfb_ctx* ctx, int slot0, int slot1, double* ms) {
+  if (!ctx || !ms || slot0 < 0 || slot0 >= 8 || slot1 < 0 || slot1 >= 8) return fail(MFB_ERR_ARG, "mfb_stream_elapsed: invalid argument");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventSynchronize(ctx->marks[slot1]));
+  float t; CK(cudaEventElapsedTime(&t, ctx->marks[slot0], ctx->marks[slot1])); *ms = t;
   return MFB_OK;
 }
 

@@ -396,6 +396,35 @@ __global__ void k_deinterleave(const double* __restrict__ in, long long ldi, int
     im[cidx * ld + r] = in[2 * (cidx * ldi + r) + 1];
   }
 }
+// r = A x - b and the componentwise scale s_i = sum_j |A_ij||x_j| + |b_i| (zgerfs-style backward error), planar storage.
+// grid = (row blocks of 256, column chunks); partial sums are combined with atomics (rr, ri, ss are zeroed by the caller).
+__global__ void k_residual(DevSystem s, const double* __restrict__ xre, const double* __restrict__ xim, int cchunk, double* rr, double* ri, double* ss) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = blockIdx.y * cchunk, c1 = min(c0 + cchunk, s.n_dof);
+  if (i >= s.n_dof) return;
+  double ar = 0.0, ai = 0.0, as = 0.0;
+  for (int j = c0; j < c1; j++) {
+    const double a = s.Are[(size_t)j * s.lda + i], b = s.Aim[(size_t)j * s.lda + i], xr = xre[j], xi = xim[j];
+    ar += a * xr - b * xi; ai += a * xi + b * xr;
+    as += (fabs(a) + fabs(b)) * (fabs(xr) + fabs(xi));
+  }
+  if (blockIdx.y == 0) { ar -= s.bre[i]; ai -= s.bim[i]; as += fabs(s.bre[i]) + fabs(s.bim[i]); }
+  atomicAdd(rr + i, ar); atomicAdd(ri + i, ai); atomicAdd(ss + i, as);
+}
+void launch_residual(const DevSystem& s, const double* xre, const double* xim, double* rr, double* ri, double* ss, cudaStream_t st) {
+  const int cchunk = 512;
+  dim3 grid((s.n_dof + 255) / 256, (s.n_dof + cchunk - 1) / cchunk);
+  k_residual<<<grid, 256, 0, st>>>(s, xre, xim, cchunk, rr, ri, ss);
+}
+// selected entries A(rows[i], cols[i]) -> out[i] (interleaved complex)
+__global__ void k_get_entries(DevSystem s, int n, const int* __restrict__ rows, const int* __restrict__ cols, double* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { out[2 * i] = s.Are[(size_t)cols[i] * s.lda + rows[i]]; out[2 * i + 1] = s.Aim[(size_t)cols[i] * s.lda + rows[i]]; }
+}
+void launch_get_entries(const DevSystem& s, int n, const int* rows, const int* cols, double* out, cudaStream_t st) {
+  if (n > 0) k_get_entries<<<(n + 255) / 256, 256, 0, st>>>(s, n, rows, cols, out);
+}
+
 void launch_interleave(const double* re, const double* im, long long ld, int rows, int cols, double* out, long long ldo, cudaStream_t st) {
   k_interleave<<<2368, 256, 0, st>>>(re, im, ld, rows, cols, out, ldo);
 }

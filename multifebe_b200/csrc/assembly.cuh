@@ -71,6 +71,8 @@ void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, c
 void launch_adaptive(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevAdaptive& a, const DevTables& t, cudaStream_t st);
 void launch_singular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevSingular& a, const DevTables& t, cudaStream_t st);
 void launch_freeterm(const DevColloc& c, const DevSystem& s, const DevFreeTerm& f, cplx F, cudaStream_t st);
+void launch_residual(const DevSystem& s, const double* xre, const double* xim, double* rr, double* ri, double* ss, cudaStream_t st);
+void launch_get_entries(const DevSystem& s, int n, const int* rows, const int* cols, double* out, cudaStream_t st);
 void launch_interleave(const double* re, const double* im, long long ld, int rows, int cols, double* out, long long ldo, cudaStream_t st);
 void launch_deinterleave(const double* in, long long ldi, int rows, int cols, double* re, double* im, long long ld, cudaStream_t st);
 

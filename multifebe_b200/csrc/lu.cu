@@ -306,23 +306,37 @@ int lu_work_alloc(LuWork& w, int n, int nb) {
   A((void**)&w.t_re, (size_t)2 * nb * (size_t)n * sizeof(double));
   w.t_im = w.t_re + (size_t)nb * n;
   A((void**)&w.info, sizeof(int));
-  for (int i = 0; i < 8; i++) cudaEventCreate(&w.ev[i]);
-  w.ms_panel = w.ms_swap = w.ms_trsm = w.ms_gemm = 0.f;
+  w.n_evs = 5 * ((n + nb - 1) / nb);
+  w.evs = new cudaEvent_t[w.n_evs];
+  for (int i = 0; i < w.n_evs; i++) cudaEventCreate(&w.evs[i]);
+  w.ms_panel = w.ms_swap = w.ms_trsm = w.ms_gemm = 0.f; w.n_steps_timed = 0; w.gemm_launches = 0; w.gemm_flops = 0.0;
   return (int)e;
 }
 void lu_work_free(LuWork& w) {
   cudaFree(w.cand_val); cudaFree(w.cand_row); cudaFree(w.cand_data); cudaFree(w.diag_data); cudaFree(w.ninv_re); cudaFree(w.t_re); cudaFree(w.info);
-  for (int i = 0; i < 8; i++) cudaEventDestroy(w.ev[i]);
+  for (int i = 0; i < w.n_evs; i++) cudaEventDestroy(w.evs[i]);
+  delete[] w.evs;
+}
+void lu_collect_times(LuWork& w) {
+  w.ms_panel = w.ms_swap = w.ms_trsm = w.ms_gemm = 0.f;
+  for (int s = 0; s < w.n_steps_timed; s++) {
+    cudaEvent_t* ev = w.evs + 5 * s; float t;
+    cudaEventElapsedTime(&t, ev[0], ev[1]); w.ms_panel += t;
+    cudaEventElapsedTime(&t, ev[1], ev[2]); w.ms_swap += t;
+    cudaEventElapsedTime(&t, ev[2], ev[3]); w.ms_trsm += t;
+    cudaEventElapsedTime(&t, ev[3], ev[4]); w.ms_gemm += t;
+  }
 }
 
 int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuWork& w, cudaStream_t st, bool timing) {
   const int nb = w.nb;
   cudaMemsetAsync(w.info, 0, sizeof(int), st);
-  w.ms_panel = w.ms_swap = w.ms_trsm = w.ms_gemm = 0.f; w.launches = 0;
+  w.launches = 0; w.gemm_launches = 0; w.gemm_flops = 0.0; w.n_steps_timed = 0;
   for (int k0 = 0; k0 < n; k0 += nb) {
+    cudaEvent_t* ev = w.evs + 5 * (k0 / nb);
     const int nbw = (n - k0 < nb) ? (n - k0) : nb;
     const int m = n - k0;
-    if (timing) cudaEventRecord(w.ev[0], st);
+    if (timing) cudaEventRecord(ev[0], st);
     // ---- panel ----
     int G = w.n_sm;
     int rpc = (m + G - 1) / G; if (rpc < 32) rpc = 32;
@@ -333,12 +347,12 @@ int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuW
     cudaError_t e = cudaLaunchCooperativeKernel((void*)k_panel, dim3(G), dim3(256), args, 0, st);
     if (e != cudaSuccess) return (int)e;
     w.launches += 1 + (k0 > 0) + (n - k0 - nbw > 0) * 4;
-    if (timing) cudaEventRecord(w.ev[1], st);
+    if (timing) cudaEventRecord(ev[1], st);
     // ---- interchanges outside the panel ----
     if (k0 > 0) k_laswp<<<(k0 + 127) / 128, 128, 0, st>>>(Are, Aim, lda, 0, k0, k0, nbw, ipiv);
     const int nrest = n - k0 - nbw;
     if (nrest > 0) k_laswp<<<(nrest + 127) / 128, 128, 0, st>>>(Are, Aim, lda, k0 + nbw, n, k0, nbw, ipiv);
-    if (timing) cudaEventRecord(w.ev[2], st);
+    if (timing) cudaEventRecord(ev[2], st);
     if (nrest > 0) {
       // ---- U12 = inv(L11) * A12 as T = 0 - N*A12 with N = -inv(L11) ----
       double* sc_re = w.ninv_re + (size_t)2 * nb * nb; double* sc_im = sc_re + (size_t)nb * nb;
@@ -349,19 +363,13 @@ int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuW
       zgemm_minus_planar(nbw, nrest, nbw, w.ninv_re, w.ninv_im, nb, B_re, B_im, lda, w.t_re, w.t_im, w.ldt, st);
       cudaMemcpy2DAsync((void*)B_re, lda * 8, w.t_re, w.ldt * 8, (size_t)nbw * 8, nrest, cudaMemcpyDeviceToDevice, st);
       cudaMemcpy2DAsync((void*)B_im, lda * 8, w.t_im, w.ldt * 8, (size_t)nbw * 8, nrest, cudaMemcpyDeviceToDevice, st);
-      if (timing) cudaEventRecord(w.ev[3], st);
+      if (timing) cudaEventRecord(ev[3], st);
       // ---- trailing update A22 -= A21 * U12 ----
       zgemm_minus_planar(nrest, nrest, nbw, Are + (long long)k0 * lda + k0 + nbw, Aim + (long long)k0 * lda + k0 + nbw, lda, B_re, B_im, lda,
                          Are + (long long)(k0 + nbw) * lda + k0 + nbw, Aim + (long long)(k0 + nbw) * lda + k0 + nbw, lda, st);
-      if (timing) cudaEventRecord(w.ev[4], st);
-    }
-    if (timing) {
-      cudaEventSynchronize(nrest > 0 ? w.ev[4] : w.ev[2]);
-      float t;
-      cudaEventElapsedTime(&t, w.ev[0], w.ev[1]); w.ms_panel += t;
-      cudaEventElapsedTime(&t, w.ev[1], w.ev[2]); w.ms_swap += t;
-      if (nrest > 0) { cudaEventElapsedTime(&t, w.ev[2], w.ev[3]); w.ms_trsm += t; cudaEventElapsedTime(&t, w.ev[3], w.ev[4]); w.ms_gemm += t; }
-    }
+      w.gemm_launches += 1; w.gemm_flops += 8.0 * (double)nrest * (double)nrest * (double)nbw;
+    } else if (timing) cudaEventRecord(ev[3], st);
+    if (timing) { cudaEventRecord(ev[4], st); w.n_steps_timed++; }
   }
   return (int)cudaGetLastError();
 }

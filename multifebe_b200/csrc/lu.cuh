@@ -15,9 +15,11 @@ struct LuWork {
   double *ninv_re, *ninv_im;   // nb x nb: -inv(L11)
   double *t_re, *t_im; long long ldt;  // nb x n scratch for the U12 block row
   int *info;              // device flag: first zero pivot (1-based), 0 = ok
-  float ms_panel, ms_swap, ms_trsm, ms_gemm; long long launches;
-  cudaEvent_t ev[8];
+  float ms_panel, ms_swap, ms_trsm, ms_gemm; long long launches; long long gemm_launches; double gemm_flops;
+  cudaEvent_t* evs; int n_evs, n_steps_timed;   // 5 events per block step, recorded without synchronising
 };
+// sums the per-phase event times of the last timed factorisation (call after the stream has been synchronised)
+void lu_collect_times(LuWork& w);
 
 int lu_work_alloc(LuWork& w, int n, int nb);
 void lu_work_free(LuWork& w);

@@ -1255,6 +1255,47 @@ int orc_assemble(void* h, double omega, const double* lambda_ri, const double* m
   return err;
 }
 
+// Bounded sample of one frequency's assembly for the CPU baseline: every element against the collocation points
+// c = c_offset, c_offset + c_stride, ... with the reference's parallel structure (OpenMP dynamic over integration elements,
+// critical scatter).  Each sampled collocation point gets its own three rows in the compact matrix
+// A_s (3*n_sample x n_dof, column-major).  Returns the number of sampled collocation points.
+int orc_assemble_colloc_sample(void* h, double omega, const double* lambda_ri, const double* mu_ri, double rho, const double* cvalue_ri,
+                               int c_offset, int c_stride, double* A_ri, double* b_ri, int nthreads, long long* points_out) {
+  Model* m = (Model*)h; cd* A = (cd*)A_ri; cd* b = (cd*)b_ri; const cd* cvalue = (const cd*)cvalue_ri;
+  Params p; calculate_parameters(cd(lambda_ri[0], lambda_ri[1]), cd(mu_ri[0], mu_ri[1]), rho, omega, p);
+  std::vector<int> cs; for (int c = c_offset; c < m->n_colloc; c += c_stride) cs.push_back(c);
+  const long long ns = (long long)cs.size(), ld = 3 * ns;
+  Stats total; memset(&total, 0, sizeof(total));
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel
+  {
+    Stats st; memset(&st, 0, sizeof(st));
+#pragma omp for schedule(dynamic)
+    for (int e = 0; e < m->n_elem; e++) {
+      const Element& el = m->elem[e];
+      cd hh[81], gg[81];
+      for (long long q = 0; q < ns; q++) {
+        sbie_auto(el, &m->cx[3 * cs[q]], p, m->qsp, m->ns_max, hh, gg, st);
+#pragma omp critical
+        for (int il = 0; il < 3; il++) {
+          long long row = 3 * q + il;
+          for (int ik = 0; ik < 3; ik++)
+            for (int kn = 0; kn < el.nn; kn++) {
+              int sn = m->enode[m->eptr[e] + kn];
+              cd hv = hh[(kn * 3 + il) * 3 + ik], gv = gg[(kn * 3 + il) * 3 + ik];
+              if (m->ctype[3 * sn + ik] == 0) { long long col = m->col_t[3 * sn + ik]; A[row + ld * col] = A[row + ld * col] - gv; b[row] = b[row] - hv * cvalue[3 * sn + ik]; }
+              else { long long col = m->col_u[3 * sn + ik]; A[row + ld * col] = A[row + ld * col] + hv; b[row] = b[row] + gv * cvalue[3 * sn + ik]; }
+            }
+        }
+      }
+    }
+#pragma omp critical
+    stats_add(total, st);
+  }
+  if (points_out) *points_out = total.pts_regular + total.pts_adaptive + total.pts_singular;
+  return (int)ns;
+}
+
 // h,g (n x 3 x 3, [j][l][k] interleaved complex) of one (collocation point, element) pair; returns the integration mode.
 int orc_pair(void* h, int e, const double* x_i, double omega, const double* lambda_ri, const double* mu_ri, double rho, double* h_ri, double* g_ri, long long* stats_out) {
   Model* m = (Model*)h; Params p; calculate_parameters(cd(lambda_ri[0], lambda_ri[1]), cd(mu_ri[0], mu_ri[1]), rho, omega, p);

@@ -78,6 +78,19 @@ class Oracle:
                  "pairs_singular": int(st[37]), "pts_singular": int(st[38]), "li_points": int(st[39])}
         return A, b, stats
 
+    def assemble_colloc_sample(self, omega, mat, c_offset, c_stride, nthreads=0):
+        """Bounded sample for the CPU baseline: all elements x every c_stride-th collocation point.
+        -> (compact A_s (3*n_sample x n_dof), b_s, n_sample, quadrature points evaluated)."""
+        ns = len(range(c_offset, self.m.n_colloc, c_stride))
+        A = np.zeros((3 * ns, self.m.n_dof), dtype=np.complex128, order="F")
+        b = np.zeros(3 * ns, dtype=np.complex128)
+        pts = C.c_longlong(0)
+        cv = np.ascontiguousarray(self.m.cvalue)
+        n = lib().orc_assemble_colloc_sample(self.h, C.c_double(omega), _p(_ri(mat.lam)), _p(_ri(mat.mu)), C.c_double(mat.rho), _p(cv),
+                                             C.c_int(c_offset), C.c_int(c_stride), _p(A), _p(b), C.c_int(nthreads), C.byref(pts))
+        assert n == ns
+        return A, b, ns, pts.value
+
     def pair(self, e, x_i, omega, mat):
         """h, g (n,3,3) complex of one (collocation point, element) pair and the integration mode."""
         nn = int(self.m.elem_ptr[e + 1] - self.m.elem_ptr[e])
