@@ -14,21 +14,16 @@
 #include "lu.cuh"
 #include <cooperative_groups.h>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 namespace cg = cooperative_groups;
 
 namespace mfbd {
 
 // ------------------------------------------------------------------------------------------------------------------
-// ZGEMM (C -= A*B), planar complex, column-major
+// ZGEMM (C -= A*B), planar complex, column-major.  CTA tile (32*WM) x (32*WN), one 32x32 warp tile per warp
+// (4 x 4 DMMA.8x8x4 tiles, re and im accumulators in registers), BK-deep k-tiles through a cp.async ring.
 // ------------------------------------------------------------------------------------------------------------------
-const int BM = 128, BN = 64, BK = 16, STAGES = 3;
-const int SA_LD = BM + 4;   // doubles; (4k + m) mod 16 distinct for the 16 lanes of a half warp
-const int SB_LD = BK + 4;
-const int SA_STAGE = 2 * BK * SA_LD;  // doubles (re plane, im plane)
-const int SB_STAGE = 2 * BN * SB_LD;
-const int GEMM_SMEM = STAGES * (SA_STAGE + SB_STAGE) * 8;
-
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
@@ -40,14 +35,27 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256, 1) k_zgemm_minus(int M, int N, int K, const double* __restrict__ Are, const double* __restrict__ Aim,
-                                                        long long lda, const double* __restrict__ Bre, const double* __restrict__ Bim, long long ldb,
-                                                        double* __restrict__ Cre, double* __restrict__ Cim, long long ldc) {
+template <int WM, int WN, int BK, int STAGES>
+struct GemmCfg {
+  static const int BM = 32 * WM, BN = 32 * WN, T = 32 * WM * WN;
+  static const int SA_LD = BM + 4;   // doubles; (4k + m) mod 16 distinct for the 16 lanes of a half warp
+  static const int SB_LD = BK + 4;
+  static const int SA_STAGE = 2 * BK * SA_LD;  // doubles (re plane, im plane)
+  static const int SB_STAGE = 2 * BN * SB_LD;
+  static const int SMEM = STAGES * (SA_STAGE + SB_STAGE) * 8;
+};
+
+template <int WM, int WN, int BK, int STAGES, int MINB>
+__global__ void __launch_bounds__(32 * WM * WN, MINB)
+k_zgemm_minus(int M, int N, int K, const double* __restrict__ Are, const double* __restrict__ Aim, long long lda, const double* __restrict__ Bre,
+              const double* __restrict__ Bim, long long ldb, double* __restrict__ Cre, double* __restrict__ Cim, long long ldc) {
+  typedef GemmCfg<WM, WN, BK, STAGES> C;
+  constexpr int BM = C::BM, BN = C::BN, T = C::T, SA_LD = C::SA_LD, SB_LD = C::SB_LD, SA_STAGE = C::SA_STAGE, SB_STAGE = C::SB_STAGE;
   extern __shared__ __align__(16) double smem[];
   double* sA = smem;
   double* sB = smem + STAGES * SA_STAGE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp & 3, wn = warp >> 2;          // 4 warps along M (32 rows each), 2 along N (32 cols each)
+  const int wm = warp % WM, wn = warp / WM;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int gid = lane >> 2, tig = lane & 3;
   const int KT = (K + BK - 1) / BK;
@@ -57,8 +65,8 @@ __global__ void __launch_bounds__(256, 1) k_zgemm_minus(int M, int N, int K, con
     double* a = sA + stage * SA_STAGE;
     double* b = sB + stage * SB_STAGE;
 #pragma unroll
-    for (int i = 0; i < (2 * BK * (BM / 2)) / 256; i++) {
-      int idx = tid + 256 * i;
+    for (int i = 0; i < (2 * BK * (BM / 2)) / T; i++) {
+      int idx = tid + T * i;
       int p = idx / (BK * (BM / 2)), rem = idx % (BK * (BM / 2)), k = rem / (BM / 2), c2 = rem % (BM / 2);
       int m = m0 + 2 * c2, kk = k0 + k;
       const double* src = (p ? Aim : Are) + (long long)kk * lda + m;
@@ -67,8 +75,8 @@ __global__ void __launch_bounds__(256, 1) k_zgemm_minus(int M, int N, int K, con
       cp_async16(a + (p * BK + k) * SA_LD + 2 * c2, src, bytes);
     }
 #pragma unroll
-    for (int i = 0; i < (2 * BN * (BK / 2)) / 256; i++) {
-      int idx = tid + 256 * i;
+    for (int i = 0; i < (2 * BN * (BK / 2)) / T; i++) {
+      int idx = tid + T * i;
       int p = idx / (BN * (BK / 2)), rem = idx % (BN * (BK / 2)), nn = rem / (BK / 2), c2 = rem % (BK / 2);
       int n = n0 + nn, kk = k0 + 2 * c2;
       const double* src = (p ? Bim : Bre) + (long long)n * ldb + kk;
@@ -78,7 +86,9 @@ __global__ void __launch_bounds__(256, 1) k_zgemm_minus(int M, int N, int K, con
     }
   };
 
-  // accumulators start from C (C -= A*B is computed as C += A*(-B))
+  for (int s = 0; s < STAGES - 1; s++) { if (s < KT) load_stage(s, s); cp_async_commit(); }
+
+  // accumulators start from C (C -= A*B is computed as C += A*(-B)); these loads overlap the first k-tiles in flight
   double cr[4][4][2], ci[4][4][2];
 #pragma unroll
   for (int mi = 0; mi < 4; mi++)
@@ -92,7 +102,6 @@ __global__ void __launch_bounds__(256, 1) k_zgemm_minus(int M, int N, int K, con
         ci[mi][ni][h] = ok ? Cim[(long long)n * ldc + m] : 0.0;
       }
 
-  for (int s = 0; s < STAGES - 1; s++) { if (s < KT) load_stage(s, s); cp_async_commit(); }
   for (int kt = 0; kt < KT; kt++) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
@@ -135,68 +144,98 @@ __global__ void __launch_bounds__(256, 1) k_zgemm_minus(int M, int N, int K, con
       }
 }
 
+template <int WM, int WN, int BK, int STAGES, int MINB>
+static void launch_gemm_cfg(int m, int n, int k, const double* Are, const double* Aim, long long lda, const double* Bre, const double* Bim,
+                            long long ldb, double* Cre, double* Cim, long long ldc, cudaStream_t st) {
+  typedef GemmCfg<WM, WN, BK, STAGES> C;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_zgemm_minus<WM, WN, BK, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM); attr = true; }
+  dim3 grid((m + C::BM - 1) / C::BM, (n + C::BN - 1) / C::BN);
+  k_zgemm_minus<WM, WN, BK, STAGES, MINB><<<grid, C::T, C::SMEM, st>>>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc);
+}
+
+static int gemm_cfg() {
+  static int cfg = -1;
+  if (cfg < 0) { const char* e = getenv("MFB_GEMM_CFG"); cfg = e ? atoi(e) : 2; }
+  return cfg;
+}
+
 void zgemm_minus_planar(int m, int n, int k, const double* Are, const double* Aim, long long lda, const double* Bre, const double* Bim,
                         long long ldb, double* Cre, double* Cim, long long ldc, cudaStream_t st) {
   if (m <= 0 || n <= 0 || k <= 0) return;
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_zgemm_minus, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM); attr = true; }
-  dim3 grid((m + BM - 1) / BM, (n + BN - 1) / BN);
-  k_zgemm_minus<<<grid, 256, GEMM_SMEM, st>>>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc);
+  switch (gemm_cfg()) {
+    case 0: launch_gemm_cfg<4, 2, 16, 3, 1>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 128 x 64, 8 warps, 1 CTA/SM
+    case 2: launch_gemm_cfg<2, 2, 16, 2, 2>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 64 x 64, 2-stage
+    case 3: launch_gemm_cfg<4, 1, 16, 3, 2>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 128 x 32, 4 warps
+    case 4: launch_gemm_cfg<2, 2, 8, 4, 2>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;    // 64 x 64, BK 8, 4-stage
+    default: launch_gemm_cfg<2, 2, 16, 3, 2>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;  // 64 x 64, 4 warps, 2 CTA/SM
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Panel factorisation (cooperative, one grid barrier per column)
+// Sub-panel factorisation (cooperative): LU with partial pivoting of the (n - c0) x ib block column starting at (c0, c0).
+// Every CTA keeps its slab of rows in shared memory for the whole kernel; per column there is ONE grid barrier: pivot
+// candidates travel together with a copy of their row, and the rank-1 update of column j is fused with the pivot search
+// of column j+1.  Pivot = max |re|+|im|, first occurrence (izamax).  Row interchanges are applied inside the ib columns
+// only; the caller applies them to the other columns with k_laswp.
 // ------------------------------------------------------------------------------------------------------------------
-struct PanelArgs {
-  double *Are, *Aim; long long lda; int n, k0, nbw, rpc;
-  int* ipiv; double* cand_val; int* cand_row; double* cand_data; double* diag_data; int* info; int nb;
+struct SubPanelArgs {
+  double *Are, *Aim; long long lda; int n, c0, ib, rpc, rpcp;
+  int* ipiv; double* cand_val; int* cand_row; double* cand_data; double* diag_data; int* info; int ldc;   // ldc = stride of a candidate row record (>= 2*ib)
 };
 
 __device__ __forceinline__ void block_argmax(double v, int row, double* s_val, int* s_row, double& best, int& brow) {
   const int tid = threadIdx.x;
-  s_val[tid] = v; s_row[tid] = row;
-  __syncthreads();
-  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
-    if (tid < o) {
-      double v2 = s_val[tid + o]; int r2 = s_row[tid + o];
-      if (v2 > s_val[tid] || (v2 == s_val[tid] && r2 < s_row[tid])) { s_val[tid] = v2; s_row[tid] = r2; }
-    }
-    __syncthreads();
+  // warp-level reduction first
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double v2 = __shfl_xor_sync(0xffffffffu, v, o); int r2 = __shfl_xor_sync(0xffffffffu, row, o);
+    if (v2 > v || (v2 == v && r2 < row)) { v = v2; row = r2; }
   }
-  best = s_val[0]; brow = s_row[0];
+  if ((tid & 31) == 0) { s_val[tid >> 5] = v; s_row[tid >> 5] = row; }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  v = s_val[0]; row = s_row[0];
+  for (int w = 1; w < nw; w++) { double v2 = s_val[w]; int r2 = s_row[w]; if (v2 > v || (v2 == v && r2 < row)) { v = v2; row = r2; } }
+  best = v; brow = row;
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_panel(PanelArgs a) {
+const int SP_MAXIB = 32;
+
+__global__ void __launch_bounds__(256) k_subpanel(SubPanelArgs a) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double s_val[256]; __shared__ int s_row[256];
-  __shared__ double s_ure[256], s_uim[256];
+  extern __shared__ __align__(16) double slab[];      // [2][ib][rpcp]
+  __shared__ double s_val[8]; __shared__ int s_row[8];
+  __shared__ double s_ure[SP_MAXIB], s_uim[SP_MAXIB];
   const int tid = threadIdx.x, c = blockIdx.x, G = gridDim.x;
-  const int rs = a.k0 + c * a.rpc, re = min(rs + a.rpc, a.n);
-  double* Are = a.Are; double* Aim = a.Aim; const long long lda = a.lda;
-  const int nbw = a.nbw, k0 = a.k0;
+  const int ib = a.ib, c0 = a.c0, rpcp = a.rpcp;
+  const int rs = c0 + c * a.rpc, re = min(rs + a.rpc, a.n), nloc = max(re - rs, 0);
+  double* sre = slab; double* sim = slab + (size_t)ib * rpcp;
+  const long long lda = a.lda;
   const int BIG = 0x7fffffff;
 
+  for (int idx = tid; idx < ib * nloc; idx += blockDim.x) {
+    int jj = idx / nloc, i = idx - jj * nloc;
+    sre[jj * rpcp + i] = a.Are[(long long)(c0 + jj) * lda + rs + i];
+    sim[jj * rpcp + i] = a.Aim[(long long)(c0 + jj) * lda + rs + i];
+  }
+  __syncthreads();
   // candidate for column 0
   {
     double v = -1.0; int r = BIG;
-    for (int i = rs + tid; i < re; i += blockDim.x) {
-      double t = fabs(Are[(long long)k0 * lda + i]) + fabs(Aim[(long long)k0 * lda + i]);
-      if (t > v) { v = t; r = i; }
-    }
+    for (int i = tid; i < nloc; i += blockDim.x) { double t = fabs(sre[i]) + fabs(sim[i]); if (t > v) { v = t; r = rs + i; } }
     double best; int brow; block_argmax(v, r, s_val, s_row, best, brow);
     if (tid == 0) { a.cand_val[c] = best; a.cand_row[c] = brow; }
-    if (brow != BIG) for (int jj = tid; jj < nbw; jj += blockDim.x) {
-      a.cand_data[((size_t)c) * 2 * a.nb + jj] = Are[(long long)(k0 + jj) * lda + brow];
-      a.cand_data[((size_t)c) * 2 * a.nb + a.nb + jj] = Aim[(long long)(k0 + jj) * lda + brow];
+    if (brow != BIG && tid < ib) {
+      a.cand_data[(size_t)c * a.ldc + tid] = sre[tid * rpcp + brow - rs];
+      a.cand_data[(size_t)c * a.ldc + ib + tid] = sim[tid * rpcp + brow - rs];
     }
-    if (k0 >= rs && k0 < re) for (int jj = tid; jj < nbw; jj += blockDim.x) {
-      a.diag_data[jj] = Are[(long long)(k0 + jj) * lda + k0]; a.diag_data[a.nb + jj] = Aim[(long long)(k0 + jj) * lda + k0];
-    }
+    if (c == 0 && tid < ib) { a.diag_data[tid] = sre[tid * rpcp]; a.diag_data[ib + tid] = sim[tid * rpcp]; }
   }
-  for (int j = 0; j < nbw; j++) {
+  for (int j = 0; j < ib; j++) {
     const int buf = j & 1, nbuf = buf ^ 1;
-    const int dj = k0 + j;   // diagonal row / global column
+    const int dj = c0 + j;
     __threadfence();
     grid.sync();
     // ---- reduce the G candidates (every CTA does it redundantly) ----
@@ -206,61 +245,66 @@ __global__ void __launch_bounds__(256) k_panel(PanelArgs a) {
       if (t > v || (t == v && rr < r)) { v = t; r = rr; }
     }
     double best; int p; block_argmax(v, r, s_val, s_row, best, p);
-    const int cstar = (p - k0) / a.rpc;
-    const double* cd = a.cand_data + ((size_t)buf * G + cstar) * 2 * a.nb;
-    for (int jj = tid; jj < nbw; jj += blockDim.x) { s_ure[jj] = cd[jj]; s_uim[jj] = cd[a.nb + jj]; }
+    const int cstar = (p - c0) / a.rpc;
+    if (tid < ib) {
+      const double* cd = a.cand_data + ((size_t)buf * G + cstar) * a.ldc;
+      s_ure[tid] = cd[tid]; s_uim[tid] = cd[ib + tid];
+    }
     __syncthreads();
     const double pr = s_ure[j], pi = s_uim[j];
     const bool zero_pivot = (pr == 0.0 && pi == 0.0);
     if (c == 0 && tid == 0) { a.ipiv[dj] = p + 1; if (zero_pivot) atomicCAS(a.info, 0, dj + 1); }
-    // ---- row interchange inside the panel ----
-    if (p != dj) {
+    // ---- row interchange inside the slab ----
+    if (p != dj && tid < ib) {
       if (p >= rs && p < re) {   // row p receives the old diagonal row
-        const double* dd = a.diag_data + (size_t)buf * 2 * a.nb;
-        for (int jj = tid; jj < nbw; jj += blockDim.x) { Are[(long long)(k0 + jj) * lda + p] = dd[jj]; Aim[(long long)(k0 + jj) * lda + p] = dd[a.nb + jj]; }
-      }
-      if (dj >= rs && dj < re) { // diagonal row receives the pivot row
-        for (int jj = tid; jj < nbw; jj += blockDim.x) { Are[(long long)(k0 + jj) * lda + dj] = s_ure[jj]; Aim[(long long)(k0 + jj) * lda + dj] = s_uim[jj]; }
+        const double* dd = a.diag_data + (size_t)buf * a.ldc;
+        sre[tid * rpcp + p - rs] = dd[tid]; sim[tid * rpcp + p - rs] = dd[ib + tid];
       }
     }
     __syncthreads();
-    // ---- scale column j and rank-1 update of the rest of the panel; fused pivot search for column j+1 ----
+    if (p != dj && tid < ib && c == 0) { sre[tid * rpcp + j] = s_ure[tid]; sim[tid * rpcp + j] = s_uim[tid]; }   // diagonal row receives the pivot row
+    __syncthreads();
+    // ---- scale column j, rank-1 update of the columns to its right, fused pivot search for column j+1 ----
     double ir = 0.0, ii = 0.0;
-    if (!zero_pivot) {  // reciprocal 1/pivot (zgetf2 scales by the reciprocal), Smith's algorithm
+    if (!zero_pivot) {  // reciprocal of the pivot (zgetf2 scales by the reciprocal), Smith's algorithm
       if (fabs(pr) >= fabs(pi)) { double t = pi / pr, d = pr + pi * t; ir = 1.0 / d; ii = -t / d; }
       else { double t = pr / pi, d = pr * t + pi; ir = t / d; ii = -1.0 / d; }
     }
     double nv = -1.0; int nr = BIG;
-    for (int i = rs + tid; i < re; i += blockDim.x) {
-      if (i <= dj) continue;
-      double lr = Are[(long long)dj * lda + i], li = Aim[(long long)dj * lda + i];
-      if (!zero_pivot) { double t = lr * ir - li * ii; li = lr * ii + li * ir; lr = t; Are[(long long)dj * lda + i] = lr; Aim[(long long)dj * lda + i] = li; }
-      for (int jj = j + 1; jj < nbw; jj++) {
-        long long o = (long long)(k0 + jj) * lda + i;
-        double xr = Are[o], xi = Aim[o];
+    for (int i = tid; i < nloc; i += blockDim.x) {
+      if (rs + i <= dj) continue;
+      double lr = sre[j * rpcp + i], li = sim[j * rpcp + i];
+      if (!zero_pivot) { double t = lr * ir - li * ii; li = lr * ii + li * ir; lr = t; sre[j * rpcp + i] = lr; sim[j * rpcp + i] = li; }
+      for (int jj = j + 1; jj < ib; jj++) {
+        double xr = sre[jj * rpcp + i], xi = sim[jj * rpcp + i];
         xr -= lr * s_ure[jj] - li * s_uim[jj];
         xi -= lr * s_uim[jj] + li * s_ure[jj];
-        Are[o] = xr; Aim[o] = xi;
-        if (jj == j + 1) { double t = fabs(xr) + fabs(xi); if (t > nv) { nv = t; nr = i; } }
+        sre[jj * rpcp + i] = xr; sim[jj * rpcp + i] = xi;
+        if (jj == j + 1) { double t = fabs(xr) + fabs(xi); if (t > nv) { nv = t; nr = rs + i; } }
       }
     }
-    if (j + 1 < nbw) {
-      double nbest; int nbrow; block_argmax(nv, nr, s_val, s_row, nbest, nbrow);   // includes the __syncthreads that orders the updates
+    if (j + 1 < ib) {
+      double nbest; int nbrow; block_argmax(nv, nr, s_val, s_row, nbest, nbrow);   // its barrier also orders the slab updates
       if (tid == 0) { a.cand_val[nbuf * G + c] = nbest; a.cand_row[nbuf * G + c] = nbrow; }
-      if (nbrow != BIG) for (int jj = tid; jj < nbw; jj += blockDim.x) {
-        a.cand_data[((size_t)nbuf * G + c) * 2 * a.nb + jj] = Are[(long long)(k0 + jj) * lda + nbrow];
-        a.cand_data[((size_t)nbuf * G + c) * 2 * a.nb + a.nb + jj] = Aim[(long long)(k0 + jj) * lda + nbrow];
+      if (nbrow != BIG && tid < ib) {
+        a.cand_data[((size_t)nbuf * G + c) * a.ldc + tid] = sre[tid * rpcp + nbrow - rs];
+        a.cand_data[((size_t)nbuf * G + c) * a.ldc + ib + tid] = sim[tid * rpcp + nbrow - rs];
       }
-      const int nd = dj + 1;
-      if (nd >= rs && nd < re) for (int jj = tid; jj < nbw; jj += blockDim.x) {
-        a.diag_data[(size_t)nbuf * 2 * a.nb + jj] = Are[(long long)(k0 + jj) * lda + nd];
-        a.diag_data[(size_t)nbuf * 2 * a.nb + a.nb + jj] = Aim[(long long)(k0 + jj) * lda + nd];
+      if (c == 0 && tid < ib) {
+        a.diag_data[(size_t)nbuf * a.ldc + tid] = sre[tid * rpcp + j + 1];
+        a.diag_data[(size_t)nbuf * a.ldc + ib + tid] = sim[tid * rpcp + j + 1];
       }
     }
   }
+  __syncthreads();
+  for (int idx = tid; idx < ib * nloc; idx += blockDim.x) {
+    int jj = idx / nloc, i = idx - jj * nloc;
+    a.Are[(long long)(c0 + jj) * lda + rs + i] = sre[jj * rpcp + i];
+    a.Aim[(long long)(c0 + jj) * lda + rs + i] = sim[jj * rpcp + i];
+  }
 }
 
-// row interchanges of one block step applied to columns [c0,c1) (outside the panel)
+// row interchanges ipiv[k0 .. k0+nbw) applied to columns [c0,c1)
 __global__ void k_laswp(double* Are, double* Aim, long long lda, int c0, int c1, int k0, int nbw, const int* __restrict__ ipiv) {
   int col = c0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= c1) return;
@@ -271,41 +315,62 @@ __global__ void k_laswp(double* Are, double* Aim, long long lda, int c0, int c1,
   }
 }
 
-// N = -inv(L11), L11 = unit lower nbw x nbw block at (k0,k0).  Thread c owns column c of the inverse.
-__global__ void k_trtri_neg(const double* __restrict__ Are, const double* __restrict__ Aim, long long lda, int k0, int nbw,
-                            double* xt_re, double* xt_im, double* nre, double* nim, int ldn) {
-  int c = threadIdx.x;
-  if (c < nbw) {
-    // xt[k*ldn + c] = X(k,c) (coalesced scratch)
-    for (int i = 0; i < nbw; i++) { xt_re[i * ldn + c] = (i == c) ? 1.0 : 0.0; xt_im[i * ldn + c] = 0.0; }
-    for (int i = c + 1; i < nbw; i++) {
-      double sr = 0.0, si = 0.0;
-      for (int k = c; k < i; k++) {
-        double lr = Are[(long long)(k0 + k) * lda + k0 + i], li = Aim[(long long)(k0 + k) * lda + k0 + i];
-        double xr = xt_re[k * ldn + c], xi = xt_im[k * ldn + c];
-        sr += lr * xr - li * xi; si += lr * xi + li * xr;
-      }
-      xt_re[i * ldn + c] = -sr; xt_im[i * ldn + c] = -si;
-    }
-    for (int i = 0; i < nbw; i++) { nre[(long long)c * ldn + i] = -xt_re[i * ldn + c]; nim[(long long)c * ldn + i] = -xt_im[i * ldn + c]; }
+// X = inv(L) * B in place: L = unit lower nbw x nbw block at (r0,r0), B = rows r0..r0+nbw of columns [c0,c1).
+// One CTA per TRSM_TC columns; B tile in shared memory; warps own rows (warp-uniform L loads), lanes own columns.
+const int TRSM_TC = 32;
+__global__ void __launch_bounds__(256) k_trsm_lu(double* Are, double* Aim, long long lda, int r0, int nbw, int c0, int c1) {
+  extern __shared__ __align__(16) double sb[];     // [2][nbw][TRSM_TC+1]
+  const int LD = TRSM_TC + 1;
+  double* br = sb; double* bi = sb + (size_t)nbw * LD;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int cb = c0 + blockIdx.x * TRSM_TC, ncol = min(TRSM_TC, c1 - cb);
+  // load: thread (i = tid % nbw-chunk, col) coalesced along rows
+  for (int idx = tid; idx < nbw * TRSM_TC; idx += blockDim.x) {
+    int cc = idx / nbw, i = idx - cc * nbw;
+    bool ok = cc < ncol;
+    br[i * LD + cc] = ok ? Are[(long long)(cb + cc) * lda + r0 + i] : 0.0;
+    bi[i * LD + cc] = ok ? Aim[(long long)(cb + cc) * lda + r0 + i] : 0.0;
   }
+  __syncthreads();
+  for (int j = 0; j < nbw - 1; j++) {
+    const double xr = br[j * LD + lane], xi = bi[j * LD + lane];
+    const double* lre = Are + (long long)(r0 + j) * lda + r0;
+    const double* lim = Aim + (long long)(r0 + j) * lda + r0;
+#pragma unroll 4
+    for (int i = j + 1 + warp; i < nbw; i += nw) {
+      const double lr = __ldg(lre + i), li = __ldg(lim + i);
+      br[i * LD + lane] -= lr * xr - li * xi;
+      bi[i * LD + lane] -= lr * xi + li * xr;
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < nbw * TRSM_TC; idx += blockDim.x) {
+    int cc = idx / nbw, i = idx - cc * nbw;
+    if (cc < ncol) { Are[(long long)(cb + cc) * lda + r0 + i] = br[i * LD + cc]; Aim[(long long)(cb + cc) * lda + r0 + i] = bi[i * LD + cc]; }
+  }
+}
+static void launch_trsm(double* Are, double* Aim, long long lda, int r0, int nbw, int c0, int c1, cudaStream_t st) {
+  if (c1 <= c0 || nbw <= 1) return;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_trsm_lu, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * (TRSM_TC + 1) * 8); attr = true; }
+  size_t smem = (size_t)2 * nbw * (TRSM_TC + 1) * 8;
+  k_trsm_lu<<<(c1 - c0 + TRSM_TC - 1) / TRSM_TC, 256, smem, st>>>(Are, Aim, lda, r0, nbw, c0, c1);
 }
 
 int lu_work_alloc(LuWork& w, int n, int nb) {
   w.nb = nb;
+  const char* e_ib = getenv("MFB_LU_IB");
+  w.ib = e_ib ? atoi(e_ib) : 16;
+  if (w.ib < 4 || w.ib > SP_MAXIB || (w.ib & 3) || nb % w.ib) w.ib = 16;
   cudaDeviceProp prop; int dev; cudaGetDevice(&dev); cudaGetDeviceProperties(&prop, dev);
   w.n_sm = prop.multiProcessorCount;
   size_t G = (size_t)w.n_sm;
   cudaError_t e = cudaSuccess;
   auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
   A((void**)&w.cand_val, 2 * G * sizeof(double)); A((void**)&w.cand_row, 2 * G * sizeof(int));
-  A((void**)&w.cand_data, 2 * G * 2 * nb * sizeof(double)); A((void**)&w.diag_data, 2 * 2 * nb * sizeof(double));
-  A((void**)&w.ninv_re, (size_t)4 * nb * nb * sizeof(double));   // N re, N im, scratch re, scratch im
-  w.ninv_im = w.ninv_re + (size_t)nb * nb;
-  w.ldt = nb;
-  A((void**)&w.t_re, (size_t)2 * nb * (size_t)n * sizeof(double));
-  w.t_im = w.t_re + (size_t)nb * n;
+  A((void**)&w.cand_data, 2 * G * 2 * SP_MAXIB * sizeof(double)); A((void**)&w.diag_data, 2 * 2 * SP_MAXIB * sizeof(double));
   A((void**)&w.info, sizeof(int));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_subpanel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   w.n_evs = 5 * ((n + nb - 1) / nb);
   w.evs = new cudaEvent_t[w.n_evs];
   for (int i = 0; i < w.n_evs; i++) cudaEventCreate(&w.evs[i]);
@@ -313,7 +378,7 @@ int lu_work_alloc(LuWork& w, int n, int nb) {
   return (int)e;
 }
 void lu_work_free(LuWork& w) {
-  cudaFree(w.cand_val); cudaFree(w.cand_row); cudaFree(w.cand_data); cudaFree(w.diag_data); cudaFree(w.ninv_re); cudaFree(w.t_re); cudaFree(w.info);
+  cudaFree(w.cand_val); cudaFree(w.cand_row); cudaFree(w.cand_data); cudaFree(w.diag_data); cudaFree(w.info);
   for (int i = 0; i < w.n_evs; i++) cudaEventDestroy(w.evs[i]);
   delete[] w.evs;
 }
@@ -328,6 +393,40 @@ void lu_collect_times(LuWork& w) {
   }
 }
 
+// Panel = block column [k0, k0+nbw): sub-panels of ib columns (cooperative kernel above); after each sub-panel its row
+// interchanges are applied to the rest of the panel, then U12' = inv(L11') A12' and A22' -= L21' U12' inside the panel.
+static int factor_panel(double* Are, double* Aim, long long lda, int n, int k0, int nbw, int* ipiv, LuWork& w, cudaStream_t st) {
+  for (int j0 = 0; j0 < nbw; j0 += w.ib) {
+    const int ib = (nbw - j0 < w.ib) ? (nbw - j0) : w.ib;
+    const int c0 = k0 + j0, m = n - c0;
+    int G = w.n_sm;
+    int rpc = (m + G - 1) / G; if (rpc < 64) rpc = 64;
+    G = (m + rpc - 1) / rpc;
+    SubPanelArgs pa; pa.Are = Are; pa.Aim = Aim; pa.lda = lda; pa.n = n; pa.c0 = c0; pa.ib = ib; pa.rpc = rpc; pa.rpcp = rpc | 1;
+    pa.ipiv = ipiv; pa.cand_val = w.cand_val; pa.cand_row = w.cand_row; pa.cand_data = w.cand_data; pa.diag_data = w.diag_data; pa.info = w.info;
+    pa.ldc = 2 * SP_MAXIB;
+    void* args[] = {&pa};
+    size_t smem = (size_t)2 * ib * pa.rpcp * sizeof(double);
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_subpanel, dim3(G), dim3(256), args, smem, st);
+    if (e != cudaSuccess) return (int)e;
+    w.launches += 1;
+    // interchanges of this sub-panel on the other columns of the panel
+    if (j0 > 0) { k_laswp<<<(j0 + 127) / 128, 128, 0, st>>>(Are, Aim, lda, k0, c0, c0, ib, ipiv); w.launches++; }
+    const int nright = nbw - j0 - ib;
+    if (nright > 0) {
+      k_laswp<<<(nright + 127) / 128, 128, 0, st>>>(Are, Aim, lda, c0 + ib, k0 + nbw, c0, ib, ipiv);
+      launch_trsm(Are, Aim, lda, c0, ib, c0 + ib, k0 + nbw, st);
+      const int mrest = n - c0 - ib;
+      if (mrest > 0)
+        zgemm_minus_planar(mrest, nright, ib, Are + (long long)c0 * lda + c0 + ib, Aim + (long long)c0 * lda + c0 + ib, lda,
+                           Are + (long long)(c0 + ib) * lda + c0, Aim + (long long)(c0 + ib) * lda + c0, lda,
+                           Are + (long long)(c0 + ib) * lda + c0 + ib, Aim + (long long)(c0 + ib) * lda + c0 + ib, lda, st);
+      w.launches += 3;
+    }
+  }
+  return 0;
+}
+
 int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuWork& w, cudaStream_t st, bool timing) {
   const int nb = w.nb;
   cudaMemsetAsync(w.info, 0, sizeof(int), st);
@@ -335,39 +434,24 @@ int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuW
   for (int k0 = 0; k0 < n; k0 += nb) {
     cudaEvent_t* ev = w.evs + 5 * (k0 / nb);
     const int nbw = (n - k0 < nb) ? (n - k0) : nb;
-    const int m = n - k0;
     if (timing) cudaEventRecord(ev[0], st);
-    // ---- panel ----
-    int G = w.n_sm;
-    int rpc = (m + G - 1) / G; if (rpc < 32) rpc = 32;
-    G = (m + rpc - 1) / rpc;
-    PanelArgs pa; pa.Are = Are; pa.Aim = Aim; pa.lda = lda; pa.n = n; pa.k0 = k0; pa.nbw = nbw; pa.rpc = rpc; pa.ipiv = ipiv;
-    pa.cand_val = w.cand_val; pa.cand_row = w.cand_row; pa.cand_data = w.cand_data; pa.diag_data = w.diag_data; pa.info = w.info; pa.nb = nb;
-    void* args[] = {&pa};
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_panel, dim3(G), dim3(256), args, 0, st);
-    if (e != cudaSuccess) return (int)e;
-    w.launches += 1 + (k0 > 0) + (n - k0 - nbw > 0) * 4;
+    int e = factor_panel(Are, Aim, lda, n, k0, nbw, ipiv, w, st);
+    if (e) return e;
     if (timing) cudaEventRecord(ev[1], st);
     // ---- interchanges outside the panel ----
-    if (k0 > 0) k_laswp<<<(k0 + 127) / 128, 128, 0, st>>>(Are, Aim, lda, 0, k0, k0, nbw, ipiv);
+    if (k0 > 0) { k_laswp<<<(k0 + 127) / 128, 128, 0, st>>>(Are, Aim, lda, 0, k0, k0, nbw, ipiv); w.launches++; }
     const int nrest = n - k0 - nbw;
-    if (nrest > 0) k_laswp<<<(nrest + 127) / 128, 128, 0, st>>>(Are, Aim, lda, k0 + nbw, n, k0, nbw, ipiv);
+    if (nrest > 0) { k_laswp<<<(nrest + 127) / 128, 128, 0, st>>>(Are, Aim, lda, k0 + nbw, n, k0, nbw, ipiv); w.launches++; }
     if (timing) cudaEventRecord(ev[2], st);
     if (nrest > 0) {
-      // ---- U12 = inv(L11) * A12 as T = 0 - N*A12 with N = -inv(L11) ----
-      double* sc_re = w.ninv_re + (size_t)2 * nb * nb; double* sc_im = sc_re + (size_t)nb * nb;
-      k_trtri_neg<<<1, nb, 0, st>>>(Are, Aim, lda, k0, nbw, sc_re, sc_im, w.ninv_re, w.ninv_im, nb);
-      cudaMemsetAsync(w.t_re, 0, (size_t)nb * (size_t)nrest * sizeof(double), st);
-      cudaMemsetAsync(w.t_im, 0, (size_t)nb * (size_t)nrest * sizeof(double), st);
-      const double* B_re = Are + (long long)(k0 + nbw) * lda + k0; const double* B_im = Aim + (long long)(k0 + nbw) * lda + k0;
-      zgemm_minus_planar(nbw, nrest, nbw, w.ninv_re, w.ninv_im, nb, B_re, B_im, lda, w.t_re, w.t_im, w.ldt, st);
-      cudaMemcpy2DAsync((void*)B_re, lda * 8, w.t_re, w.ldt * 8, (size_t)nbw * 8, nrest, cudaMemcpyDeviceToDevice, st);
-      cudaMemcpy2DAsync((void*)B_im, lda * 8, w.t_im, w.ldt * 8, (size_t)nbw * 8, nrest, cudaMemcpyDeviceToDevice, st);
+      // ---- U12 = inv(L11) * A12 (forward substitution, ztrsm) ----
+      launch_trsm(Are, Aim, lda, k0, nbw, k0 + nbw, n, st);
       if (timing) cudaEventRecord(ev[3], st);
       // ---- trailing update A22 -= A21 * U12 ----
-      zgemm_minus_planar(nrest, nrest, nbw, Are + (long long)k0 * lda + k0 + nbw, Aim + (long long)k0 * lda + k0 + nbw, lda, B_re, B_im, lda,
+      zgemm_minus_planar(nrest, nrest, nbw, Are + (long long)k0 * lda + k0 + nbw, Aim + (long long)k0 * lda + k0 + nbw, lda,
+                         Are + (long long)(k0 + nbw) * lda + k0, Aim + (long long)(k0 + nbw) * lda + k0, lda,
                          Are + (long long)(k0 + nbw) * lda + k0 + nbw, Aim + (long long)(k0 + nbw) * lda + k0 + nbw, lda, st);
-      w.gemm_launches += 1; w.gemm_flops += 8.0 * (double)nrest * (double)nrest * (double)nbw;
+      w.launches += 2; w.gemm_launches += 1; w.gemm_flops += 8.0 * (double)nrest * (double)nrest * (double)nbw;
     } else if (timing) cudaEventRecord(ev[3], st);
     if (timing) { cudaEventRecord(ev[4], st); w.n_steps_timed++; }
   }
@@ -375,32 +459,36 @@ int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuW
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Triangular solves (zgetrs, 'N'): b := P b ; L y = b (unit lower) ; U x = y.  Blocked by TS rows.
+// Triangular solves (zgetrs, 'N'): b := P b ; L y = b (unit lower) ; U x = y.  Blocked by TS rows: the diagonal block is
+// staged in shared memory, the off-diagonal update is a bandwidth-bound GEMV (64 rows x 4 column groups per CTA).
 // ------------------------------------------------------------------------------------------------------------------
-const int TS = 128;
+const int TS = 64;
 __global__ void k_permute(const double* __restrict__ sre, const double* __restrict__ sim, double* dre, double* dim_, const int* __restrict__ perm, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { dre[i] = sre[perm[i]]; dim_[i] = sim[perm[i]]; }
 }
-// diagonal block solve, one CTA of TS threads, one right-hand side
-__global__ void k_trsv_diag(const double* __restrict__ Are, const double* __restrict__ Aim, long long lda, int kb, int nbw, double* bre, double* bim, int lower) {
+__global__ void __launch_bounds__(TS) k_trsv_diag(const double* __restrict__ Are, const double* __restrict__ Aim, long long lda, int kb, int nbw, double* bre, double* bim, int lower) {
+  extern __shared__ __align__(16) double sdiag[];   // [2][TS][TS+1]
+  double* sr = sdiag; double* si = sdiag + TS * (TS + 1);
   __shared__ double yr[TS], yi[TS];
-  int i = threadIdx.x;
+  const int i = threadIdx.x;
+  for (int j = 0; j < nbw; j++) if (i < nbw) { sr[j * (TS + 1) + i] = Are[(long long)(kb + j) * lda + kb + i]; si[j * (TS + 1) + i] = Aim[(long long)(kb + j) * lda + kb + i]; }
   double vr = 0.0, vi = 0.0;
   if (i < nbw) { vr = bre[kb + i]; vi = bim[kb + i]; }
+  __syncthreads();
   if (lower) {
     for (int j = 0; j < nbw; j++) {
       if (i == j) { yr[j] = vr; yi[j] = vi; }
       __syncthreads();
       if (i > j && i < nbw) {
-        double lr = Are[(long long)(kb + j) * lda + kb + i], li = Aim[(long long)(kb + j) * lda + kb + i];
+        double lr = sr[j * (TS + 1) + i], li = si[j * (TS + 1) + i];
         vr -= lr * yr[j] - li * yi[j]; vi -= lr * yi[j] + li * yr[j];
       }
     }
   } else {
     for (int j = nbw - 1; j >= 0; j--) {
       if (i == j) {
-        double ur = Are[(long long)(kb + j) * lda + kb + j], ui = Aim[(long long)(kb + j) * lda + kb + j];
+        double ur = sr[j * (TS + 1) + j], ui = si[j * (TS + 1) + j];
         double qr, qi;   // (vr + i vi)/(ur + i ui), Smith
         if (fabs(ur) >= fabs(ui)) { double t = ui / ur, d = ur + ui * t; qr = (vr + vi * t) / d; qi = (vi - vr * t) / d; }
         else { double t = ur / ui, d = ur * t + ui; qr = (vr * t + vi) / d; qi = (vi * t - vr) / d; }
@@ -408,27 +496,36 @@ __global__ void k_trsv_diag(const double* __restrict__ Are, const double* __rest
       }
       __syncthreads();
       if (i < j) {
-        double ur = Are[(long long)(kb + j) * lda + kb + i], ui = Aim[(long long)(kb + j) * lda + kb + i];
+        double ur = sr[j * (TS + 1) + i], ui = si[j * (TS + 1) + i];
         vr -= ur * yr[j] - ui * yi[j]; vi -= ur * yi[j] + ui * yr[j];
       }
     }
   }
   if (i < nbw) { bre[kb + i] = vr; bim[kb + i] = vi; }
 }
-// b[r0:r1) -= A[r0:r1, kb:kb+nbw) * x[kb:kb+nbw)
-__global__ void k_gemv_update(const double* __restrict__ Are, const double* __restrict__ Aim, long long lda, int r0, int r1, int kb, int nbw, double* bre, double* bim) {
+// b[r0:r1) -= A[r0:r1, kb:kb+nbw) * x[kb:kb+nbw); CTA = 64 rows x 4 column groups
+__global__ void __launch_bounds__(256) k_gemv_update(const double* __restrict__ Are, const double* __restrict__ Aim, long long lda, int r0, int r1, int kb, int nbw, double* bre, double* bim) {
   __shared__ double xr[TS], xi[TS];
-  if (threadIdx.x < nbw) { xr[threadIdx.x] = bre[kb + threadIdx.x]; xi[threadIdx.x] = bim[kb + threadIdx.x]; }
+  __shared__ double pr[4][64], pi[4][64];
+  const int tid = threadIdx.x, li = tid & 63, cg_ = tid >> 6;
+  if (tid < nbw) { xr[tid] = bre[kb + tid]; xi[tid] = bim[kb + tid]; }
   __syncthreads();
-  int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= r1) return;
+  const int i = r0 + blockIdx.x * 64 + li;
   double sr = 0.0, si = 0.0;
-#pragma unroll 4
-  for (int j = 0; j < nbw; j++) {
-    double ar = Are[(long long)(kb + j) * lda + i], ai = Aim[(long long)(kb + j) * lda + i];
-    sr += ar * xr[j] - ai * xi[j]; si += ar * xi[j] + ai * xr[j];
+  if (i < r1) {
+    const int per = (nbw + 3) / 4, j0 = cg_ * per, j1 = min(j0 + per, nbw);
+#pragma unroll 8
+    for (int j = j0; j < j1; j++) {
+      double ar = Are[(long long)(kb + j) * lda + i], ai = Aim[(long long)(kb + j) * lda + i];
+      sr += ar * xr[j] - ai * xi[j]; si += ar * xi[j] + ai * xr[j];
+    }
   }
-  bre[i] -= sr; bim[i] -= si;
+  pr[cg_][li] = sr; pi[cg_][li] = si;
+  __syncthreads();
+  if (cg_ == 0 && i < r1) {
+    bre[i] -= pr[0][li] + pr[1][li] + pr[2][li] + pr[3][li];
+    bim[i] -= pi[0][li] + pi[1][li] + pi[2][li] + pi[3][li];
+  }
 }
 
 int zgetrs_planar(const double* Are, const double* Aim, long long lda, int n, const int* ipiv_host_perm_dev, double* bre, double* bim, long long ldb,
@@ -436,6 +533,9 @@ int zgetrs_planar(const double* Are, const double* Aim, long long lda, int n, co
   // ipiv_host_perm_dev: device array perm[i] = source row of row i after all interchanges (built on the host from ipiv)
   double* tmp = nullptr;
   if (cudaMalloc((void**)&tmp, (size_t)2 * n * sizeof(double)) != cudaSuccess) return (int)cudaGetLastError();
+  const size_t dsm = (size_t)2 * TS * (TS + 1) * sizeof(double);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_trsv_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm); attr = true; }
   for (int c = 0; c < nrhs; c++) {
     double* br = bre + (long long)c * ldb; double* bi = bim + (long long)c * ldb;
     k_permute<<<(n + 255) / 256, 256, 0, st>>>(br, bi, tmp, tmp + n, ipiv_host_perm_dev, n);
@@ -443,15 +543,15 @@ int zgetrs_planar(const double* Are, const double* Aim, long long lda, int n, co
     cudaMemcpyAsync(bi, tmp + n, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
     for (int kb = 0; kb < n; kb += TS) {
       int nbw = (n - kb < TS) ? n - kb : TS;
-      k_trsv_diag<<<1, TS, 0, st>>>(Are, Aim, lda, kb, nbw, br, bi, 1);
+      k_trsv_diag<<<1, TS, dsm, st>>>(Are, Aim, lda, kb, nbw, br, bi, 1);
       int r0 = kb + nbw;
-      if (r0 < n) k_gemv_update<<<(n - r0 + TS - 1) / TS, TS, 0, st>>>(Are, Aim, lda, r0, n, kb, nbw, br, bi);
+      if (r0 < n) k_gemv_update<<<(n - r0 + 63) / 64, 256, 0, st>>>(Are, Aim, lda, r0, n, kb, nbw, br, bi);
     }
     int nblk = (n + TS - 1) / TS;
     for (int b = nblk - 1; b >= 0; b--) {
       int kb = b * TS, nbw = (n - kb < TS) ? n - kb : TS;
-      k_trsv_diag<<<1, TS, 0, st>>>(Are, Aim, lda, kb, nbw, br, bi, 0);
-      if (kb > 0) k_gemv_update<<<(kb + TS - 1) / TS, TS, 0, st>>>(Are, Aim, lda, 0, kb, kb, nbw, br, bi);
+      k_trsv_diag<<<1, TS, dsm, st>>>(Are, Aim, lda, kb, nbw, br, bi, 0);
+      if (kb > 0) k_gemv_update<<<(kb + 63) / 64, 256, 0, st>>>(Are, Aim, lda, 0, kb, kb, nbw, br, bi);
     }
   }
   cudaStreamSynchronize(st);

@@ -6,14 +6,13 @@
 namespace mfbd {
 
 struct LuWork {
-  int nb;                 // block size
+  int nb;                 // outer block size
+  int ib;                 // sub-panel width (columns kept in shared memory by the cooperative panel kernel)
   int n_sm;
   double *cand_val;       // [2][grid]         pivot candidates (|re|+|im|)
   int *cand_row;          // [2][grid]
-  double *cand_data;      // [2][grid][2*nb]   candidate rows (re, im)
-  double *diag_data;      // [2][2*nb]         current diagonal row
-  double *ninv_re, *ninv_im;   // nb x nb: -inv(L11)
-  double *t_re, *t_im; long long ldt;  // nb x n scratch for the U12 block row
+  double *cand_data;      // [2][grid][2*32]   candidate rows (re, im)
+  double *diag_data;      // [2][2*32]         current diagonal row
   int *info;              // device flag: first zero pivot (1-based), 0 = ok
   float ms_panel, ms_swap, ms_trsm, ms_gemm; long long launches; long long gemm_launches; double gemm_flops;
   cudaEvent_t* evs; int n_evs, n_steps_timed;   // 5 events per block step, recorded without synchronising
