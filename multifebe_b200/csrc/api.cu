@@ -58,6 +58,8 @@ struct mfb_problem {
   double stats[MFB_STAT_COUNT];
   cudaEvent_t ev[8];
   std::vector<int> set_gln;
+  std::vector<int> rowperm, colperm;   // host row / column -> internal row / column of the device-resident assembled system
+  int *d_rowperm, *d_colperm; bool rows_permuted;   // rows_permuted: the resident matrix/factors are in the internal order
 };
 
 extern "C" const char* mfb_last_error(void) { return g_err.c_str(); }
@@ -119,6 +121,15 @@ extern "C" void mfb_problem_free(mfb_problem* p) {
   delete p;
 }
 
+// 30-bit Morton key of a point inside the box [lo, lo+ext]^3 (spatial clustering of tiles and element chunks)
+static unsigned morton3(const double* x, const double* lo, double inv_ext) {
+  unsigned key = 0;
+  unsigned q[3];
+  for (int c = 0; c < 3; c++) { double t = (x[c] - lo[c]) * inv_ext; t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t); q[c] = (unsigned)(t * 1023.0 + 0.5); }
+  for (int b = 9; b >= 0; b--) for (int c = 0; c < 3; c++) key = (key << 1) | ((q[c] >> b) & 1u);
+  return key;
+}
+
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
@@ -162,35 +173,119 @@ extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x
     for (int k = 0; k < el.nn; k++) for (int c = 0; c < 3; c++) el.x[3 * k + c] = node_x[3 * (size_t)elem_node[elem_ptr[e] + k] + c];
     mfbh::element_data(el, S);
   }
-  // ---- element slots: sorted by type ----
+  // ---- bounding box of the mesh (Morton keys) ----
+  double bb_lo[3] = {1e300, 1e300, 1e300}, bb_hi[3] = {-1e300, -1e300, -1e300};
+  for (int i = 0; i < n_node; i++) for (int c = 0; c < 3; c++) { bb_lo[c] = std::min(bb_lo[c], node_x[3 * (size_t)i + c]); bb_hi[c] = std::max(bb_hi[c], node_x[3 * (size_t)i + c]); }
+  const double bb_ext = std::max(std::max(bb_hi[0] - bb_lo[0], bb_hi[1] - bb_lo[1]), std::max(bb_hi[2] - bb_lo[2], 1e-300));
+  const double bb_inv = 1.0 / bb_ext;
+  // ---- element slots: sorted by type, spatially clustered inside a type (a chunk of consecutive slots is a compact patch:
+  //      its columns stay in L2 between the elements that share them, and a tile sees one quadrature rule for most chunks) ----
   p->slot_of_elem.assign(n_elem, -1); p->elem_of_slot.clear();
   const int types[5] = {MFB_TRI3, MFB_TRI6, MFB_QUAD4, MFB_QUAD8, MFB_QUAD9};
   for (int t = 0; t < 5; t++) {
     GroupHost g; g.et = types[t]; g.nn = mfbh::nodes_of(g.et); g.slot0 = (int)p->elem_of_slot.size();
-    for (int e = 0; e < n_elem; e++) if (etype[e] == g.et) { p->slot_of_elem[e] = (int)p->elem_of_slot.size(); p->elem_of_slot.push_back(e); g.elem_ids.push_back(e); }
+    std::vector<std::pair<unsigned, int>> keyed;
+    for (int e = 0; e < n_elem; e++) if (etype[e] == g.et) {
+      double ctr[3] = {0, 0, 0};
+      for (int k = 0; k < g.nn; k++) for (int c = 0; c < 3; c++) ctr[c] += p->elems[e].x[3 * k + c] / g.nn;
+      keyed.push_back(std::make_pair(morton3(ctr, bb_lo, bb_inv), e));
+    }
+    std::stable_sort(keyed.begin(), keyed.end());
+    for (auto& ke : keyed) { p->slot_of_elem[ke.second] = (int)p->elem_of_slot.size(); p->elem_of_slot.push_back(ke.second); g.elem_ids.push_back(ke.second); }
     g.n_elem = (int)g.elem_ids.size();
     memset(&g.dev, 0, sizeof(g.dev)); memset(&g.adp, 0, sizeof(g.adp)); memset(&g.sing, 0, sizeof(g.sing));
     if (g.n_elem > 0) p->groups.push_back(g);
   }
-  // ---- collocation points sorted by matrix row ----
-  std::vector<int> order(n_colloc);
-  for (int c = 0; c < n_colloc; c++) order[c] = c;
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return row[3 * colloc_node[a]] < row[3 * colloc_node[b]]; });
-  p->cpos_of_colloc.assign(n_colloc, 0);
-  const int ldp = (n_colloc + 31) / 32 * 32; p->ldp = ldp;
-  std::vector<double> h_cx(3 * (size_t)ldp, 0.0); std::vector<int> h_crow(3 * (size_t)ldp, 0);
-  for (int q = 0; q < n_colloc; q++) {
-    int c = order[q]; p->cpos_of_colloc[c] = q;
-    for (int k = 0; k < 3; k++) {
-      h_cx[(size_t)k * ldp + q] = colloc_x[3 * (size_t)c + k];
-      int r = row[3 * colloc_node[c] + k];
-      if (r < 0 || r >= n_dof) { mfb_problem_free(p); return fail(MFB_ERR_ARG, "mfb_harela3d_setup: collocation node without a valid row"); }
-      h_crow[(size_t)k * ldp + q] = r;
+  // ---- collocation tiles and the internal row order (DevColloc) ----
+  // Row nodes = nodes that own collocation points.  They are ordered by (number of collocation points, Morton key); the
+  // internal matrix rows follow that order (3 consecutive rows per node), so that every block of <= 32 consecutive row
+  // nodes of one multiplicity class is a 16-byte aligned run of rows, spatially compact, with all its layers full.
+  // A class with an odd number of nodes gives its last node to the loose tiles (keeps every later run aligned).
+  std::vector<std::vector<int>> node_collocs(n_node);
+  for (int c = 0; c < n_colloc; c++) {
+    int nd = colloc_node[c];
+    if (nd < 0 || nd >= n_node) { mfb_problem_free(p); return fail(MFB_ERR_ARG, "mfb_harela3d_setup: colloc_node out of range"); }
+    for (int k = 0; k < 3; k++) { int r = row[3 * nd + k]; if (r < 0 || r >= n_dof) { mfb_problem_free(p); return fail(MFB_ERR_ARG, "mfb_harela3d_setup: collocation node without a valid row"); } }
+    node_collocs[nd].push_back(c);
+  }
+  struct RowNode { int mult; unsigned key; int node; };
+  std::vector<RowNode> rn;
+  for (int nd = 0; nd < n_node; nd++) if (!node_collocs[nd].empty()) rn.push_back({(int)node_collocs[nd].size(), morton3(&node_x[3 * (size_t)nd], bb_lo, bb_inv), nd});
+  std::stable_sort(rn.begin(), rn.end(), [](const RowNode& a, const RowNode& b) { return a.mult != b.mult ? a.mult < b.mult : a.key < b.key; });
+  std::vector<int> bulk_nodes, loose_nodes;
+  {
+    std::vector<char> row_used(n_dof, 0);
+    size_t i = 0;
+    while (i < rn.size()) {
+      size_t j = i; while (j < rn.size() && rn[j].mult == rn[i].mult) j++;
+      size_t cnt = j - i;
+      for (size_t q = i; q < j; q++) {
+        const int nd = rn[q].node;
+        bool dup = false;
+        for (int k = 0; k < 3; k++) { if (row_used[row[3 * nd + k]]) dup = true; row_used[row[3 * nd + k]] = 1; }
+        if (dup) { mfb_problem_free(p); return fail(MFB_ERR_ARG, "mfb_harela3d_setup: two collocation nodes share a matrix row"); }
+        if ((cnt & 1) && q == j - 1) loose_nodes.push_back(nd); else bulk_nodes.push_back(nd);
+      }
+      i = j;
     }
   }
-  double* d_cx; int* d_crow;
-  UP(p->owned, h_cx, &d_cx); UP(p->owned, h_crow, &d_crow);
-  p->colloc.n_colloc = n_colloc; p->colloc.ldp = ldp; p->colloc.cx = d_cx; p->colloc.crow = d_crow;
+  p->rowperm.assign(n_dof, -1);
+  {
+    int next = 0;
+    for (int nd : bulk_nodes) for (int k = 0; k < 3; k++) p->rowperm[row[3 * nd + k]] = next++;
+    for (int nd : loose_nodes) for (int k = 0; k < 3; k++) p->rowperm[row[3 * nd + k]] = next++;
+    for (int r = 0; r < n_dof; r++) if (p->rowperm[r] < 0) p->rowperm[r] = next++;   // rows that no collocation point feeds
+  }
+  std::vector<int> t_row0, t_nbytes, lane_colloc;   // lane_colloc[32*tile + lane] = host collocation index or -1
+  for (size_t i = 0; i < bulk_nodes.size();) {
+    const int mult = (int)node_collocs[bulk_nodes[i]].size();
+    size_t j = i; while (j < bulk_nodes.size() && j - i < 32 && (int)node_collocs[bulk_nodes[j]].size() == mult) j++;
+    for (int layer = 0; layer < mult; layer++) {
+      t_row0.push_back(3 * (int)i); t_nbytes.push_back(24 * (int)(j - i));
+      for (size_t q = i; q < i + 32; q++) lane_colloc.push_back(q < j ? node_collocs[bulk_nodes[q]][layer] : -1);
+    }
+    i = j;
+  }
+  {
+    std::vector<int> loose;
+    for (int nd : loose_nodes) for (int c : node_collocs[nd]) loose.push_back(c);
+    for (size_t i = 0; i < loose.size(); i += 32) {
+      t_row0.push_back(0); t_nbytes.push_back(0);
+      for (size_t q = i; q < i + 32; q++) lane_colloc.push_back(q < loose.size() ? loose[q] : -1);
+    }
+  }
+  const int n_tiles = (int)t_row0.size();
+  const int ldp = 32 * n_tiles; p->ldp = ldp;
+  p->cpos_of_colloc.assign(n_colloc, 0);
+  std::vector<double> h_cx(3 * (size_t)ldp, 0.0); std::vector<int> h_crow(3 * (size_t)ldp, -1);
+  for (int q = 0; q < ldp; q++) {
+    const int c = lane_colloc[q];
+    if (c < 0) continue;
+    p->cpos_of_colloc[c] = q;
+    for (int k = 0; k < 3; k++) {
+      h_cx[(size_t)k * ldp + q] = colloc_x[3 * (size_t)c + k];
+      h_crow[(size_t)k * ldp + q] = p->rowperm[row[3 * colloc_node[c] + k]];
+    }
+  }
+  double* d_cx; int *d_crow, *d_trow0, *d_tnbytes;
+  UP(p->owned, h_cx, &d_cx); UP(p->owned, h_crow, &d_crow); UP(p->owned, t_row0, &d_trow0); UP(p->owned, t_nbytes, &d_tnbytes);
+  // Columns: when every collocation node pairs row k with the column of its unknown k (the reference's numbering,
+  // build_auxiliary_variables_mechanics_harmonic.f90:151-198) the columns follow the same permutation, so that the strong
+  // diagonal stays on the diagonal and partial pivoting keeps finding its pivot in place; otherwise columns keep their order.
+  {
+    bool paired = true;
+    for (const RowNode& q : rn) for (int k = 0; k < 3; k++) {
+      const int nd = q.node, ct = ctype[3 * nd + k];
+      const int col = (ct == 0) ? col_t[3 * nd + k] : col_u[3 * nd + k];
+      if (col != row[3 * nd + k]) paired = false;
+    }
+    p->colperm.resize(n_dof);
+    for (int i = 0; i < n_dof; i++) p->colperm[i] = paired ? p->rowperm[i] : i;
+  }
+  UP(p->owned, p->rowperm, &p->d_rowperm); UP(p->owned, p->colperm, &p->d_colperm);
+  p->colloc.n_colloc = ldp; p->colloc.ldp = ldp; p->colloc.cx = d_cx; p->colloc.crow = d_crow;
+  p->colloc.n_tiles = n_tiles; p->colloc.tile_row0 = d_trow0; p->colloc.tile_nbytes = d_tnbytes;
+  p->rows_permuted = false;
 
   // ---- flat scatter descriptors over all slots ----
   std::vector<int> slot_off(n_elem + 1, 0);
@@ -203,7 +298,7 @@ extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x
       int ct = ctype[3 * node + k];
       int col = (ct == 0) ? col_t[3 * node + k] : col_u[3 * node + k];
       if (col < 0 || col >= n_dof) { mfb_problem_free(p); return fail(MFB_ERR_ARG, "mfb_harela3d_setup: missing column for an unknown"); }
-      h_ecol[slot_off[s] + j * 3 + k] = col; h_ekind[slot_off[s] + j * 3 + k] = (unsigned char)ct;
+      h_ecol[slot_off[s] + j * 3 + k] = p->colperm[col]; h_ekind[slot_off[s] + j * 3 + k] = (unsigned char)ct;
     }
   }
   int *d_ecol, *d_slot_off; unsigned char* d_ekind; double* d_ecv;
@@ -216,17 +311,28 @@ extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x
     D.et = g.et; D.nn = g.nn; D.n_elem = g.n_elem; D.slot0 = g.slot0;
     std::vector<double> h_xn((size_t)g.n_elem * 3 * g.nn), h_ball((size_t)g.n_elem * 5);
     std::vector<int> h_enode((size_t)g.n_elem * g.nn), h_glnfar(g.n_elem);
-    std::vector<unsigned char> h_rev(g.n_elem);
+    std::vector<unsigned char> h_rev(g.n_elem), h_info(g.n_elem);
     for (int i = 0; i < g.n_elem; i++) {
       int e = g.elem_ids[i]; const mfbh::Elem& el = p->elems[e];
+      {
+        unsigned info = 8u | (el.reversed ? 16u : 0u);
+        for (int k = 0; k < 3; k++) {
+          const int ct0 = ctype[3 * elem_node[elem_ptr[e]] + k];
+          for (int j = 1; j < g.nn; j++) if (ctype[3 * elem_node[elem_ptr[e] + j] + k] != ct0) info &= ~8u;
+          if (ct0 == 1) info |= (1u << k);
+        }
+        h_info[i] = (unsigned char)info;
+      }
       for (int q = 0; q < 3 * g.nn; q++) h_xn[(size_t)i * 3 * g.nn + q] = el.x[q];
       for (int j = 0; j < g.nn; j++) h_enode[(size_t)i * g.nn + j] = elem_node[elem_ptr[e] + j];
       h_ball[5 * (size_t)i] = el.bc[0]; h_ball[5 * (size_t)i + 1] = el.bc[1]; h_ball[5 * (size_t)i + 2] = el.bc[2]; h_ball[5 * (size_t)i + 3] = el.br; h_ball[5 * (size_t)i + 4] = el.cl;
       h_glnfar[i] = el.gln_far; h_rev[i] = el.reversed ? 1 : 0;
     }
-    double *d_xn, *d_ball; int *d_enode, *d_glnfar; unsigned char* d_rev;
+    double *d_xn, *d_ball; int *d_enode, *d_glnfar; unsigned char *d_rev, *d_info, *d_cvnz;
     UP(g.owned, h_xn, &d_xn); UP(g.owned, h_ball, &d_ball); UP(g.owned, h_enode, &d_enode); UP(g.owned, h_glnfar, &d_glnfar); UP(g.owned, h_rev, &d_rev);
-    D.xn = d_xn; D.ball = d_ball; D.enode = d_enode; D.gln_far = d_glnfar; D.erev = d_rev;
+    UP(g.owned, h_info, &d_info);
+    CK(cudaMalloc((void**)&d_cvnz, (size_t)g.n_elem)); g.owned.push_back(d_cvnz);
+    D.xn = d_xn; D.ball = d_ball; D.enode = d_enode; D.gln_far = d_glnfar; D.erev = d_rev; D.einfo = d_info; D.ecvnz = d_cvnz;
     D.ecol = d_ecol + slot_off[g.slot0]; D.ekind = d_ekind + slot_off[g.slot0]; D.ecv = d_ecv + 2 * (size_t)slot_off[g.slot0];
     D.n_sets = n_precalsets;
     for (int s = 0; s < n_precalsets; s++) {
@@ -382,7 +488,7 @@ extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x
     long long pairs = 0, pts = 0; double flops = 0.0;
     for (auto& g : p->groups)
       for (int i = 0; i < g.n_elem; i++)
-        for (int q = 0; q < n_colloc; q++) {
+        for (int q = 0; q < ldp; q++) {
           unsigned char m = h_plan[(size_t)(g.slot0 + i) * ldp + q];
           if (m < MAX_SETS) { pairs++; pts += g.dev.ngp[m]; flops += (double)g.dev.ngp[m] * (585.0 + 72.0 * g.nn) + 144.0 * g.nn; }
         }
@@ -422,11 +528,20 @@ static void host_kparams(cd lambda, cd mu, double rho, double omega, KParams& K)
   const double c_1_4pi = 0.07957747154594767280411105048;
   K.cte_u = cv(c_1_4pi / mu); K.cte_t = c_1_4pi;
 }
+// pre-scaled copy for the regular kernel: psi, chi times -cte_u (slot 0 = coefficient of the bare E2(z2)/r term), T times cte_t
+static void scale_kparams(const KParams& K, KParams& Q) {
+  Q = K;
+  const cplx mu_ = mk(-K.cte_u.re, -K.cte_u.im);
+  Q.psi[0] = mu_; Q.chi[0] = mu_;
+  for (int i = 1; i <= 6; i++) { Q.psi[i] = K.psi[i] * mu_; Q.chi[i] = K.chi[i] * mu_; }
+  for (int i = 1; i <= 10; i++) Q.T1[i] = K.T1[i] * K.cte_t;
+  for (int i = 1; i <= 9; i++) { Q.T2[i] = K.T2[i] * K.cte_t; Q.T3[i] = K.T3[i] * K.cte_t; }
+}
 
 static int assemble_device(mfb_problem* p, double omega, cd lambda, cd mu, double rho, cd nu, const mfb_z* cvalue) {
   cudaStream_t st = p->ctx->stream;
-  KParams K; host_kparams(lambda, mu, rho, omega, K);
-  set_kparams(K, st);
+  KParams K, Q; host_kparams(lambda, mu, rho, omega, K); scale_kparams(K, Q);
+  set_kparams(K, Q, st);
   if (cvalue) {
     CK(cudaMemcpyAsync(p->d_cvalue, cvalue, (size_t)6 * p->n_node * sizeof(double), cudaMemcpyHostToDevice, st));
     for (auto& g : p->groups) launch_gather_cv(g.dev, p->d_cvalue, st);
@@ -447,7 +562,7 @@ static int assemble_device(mfb_problem* p, double omega, cd lambda, cd mu, doubl
   launch_freeterm(p->colloc, p->sys, p->ft, mk(F.real(), F.imag()), st);
   CK(cudaEventRecord(p->ev[5], st));
   CK(cudaGetLastError());
-  p->factored = false; p->assembled = true;
+  p->factored = false; p->assembled = true; p->rows_permuted = true;
   // our kernels only (memsets/copies are not counted): free term + per group regular, adaptive, singular (+ gather_cv)
   p->asm_launches = 1;
   for (auto& g : p->groups) p->asm_launches += 1 + (cvalue ? 1 : 0) + (g.adp.n_pairs > 0) + (g.sing.n_pairs > 0);
@@ -467,27 +582,28 @@ static int collect_assembly_times(mfb_problem* p) {
 }
 
 // copy a planar device matrix to an interleaved host matrix in column chunks (bounded staging buffer)
-static int download_matrix(mfb_problem* p, const double* re, const double* im, long long ld, int rows, int cols, mfb_z* host, long long ldh) {
+static int download_matrix(mfb_problem* p, const double* re, const double* im, long long ld, int rows, int cols, mfb_z* host, long long ldh, const int* rowperm = nullptr,
+                           const int* colperm = nullptr) {
   cudaStream_t st = p->ctx->stream;
   int chunk = (int)std::max<long long>(1, std::min<long long>(cols, (256ll << 20) / (16ll * rows)));
   double* stage; CK(cudaMalloc((void**)&stage, (size_t)chunk * rows * 16));
   for (int c0 = 0; c0 < cols; c0 += chunk) {
     int nc = std::min(chunk, cols - c0);
-    launch_interleave(re + (long long)c0 * ld, im + (long long)c0 * ld, ld, rows, nc, stage, rows, st);
+    launch_interleave(re, im, ld, rows, nc, stage, rows, rowperm, colperm, c0, st);
     CK(cudaMemcpy2DAsync(host + (long long)c0 * ldh, (size_t)ldh * 16, stage, (size_t)rows * 16, (size_t)rows * 16, nc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
   cudaFree(stage);
   return MFB_OK;
 }
-static int upload_matrix(mfb_problem* p, const mfb_z* host, long long ldh, int rows, int cols, double* re, double* im, long long ld) {
+static int upload_matrix(mfb_problem* p, const mfb_z* host, long long ldh, int rows, int cols, double* re, double* im, long long ld, const int* rowperm = nullptr) {
   cudaStream_t st = p->ctx->stream;
   int chunk = (int)std::max<long long>(1, std::min<long long>(cols, (256ll << 20) / (16ll * rows)));
   double* stage; CK(cudaMalloc((void**)&stage, (size_t)chunk * rows * 16));
   for (int c0 = 0; c0 < cols; c0 += chunk) {
     int nc = std::min(chunk, cols - c0);
     CK(cudaMemcpy2DAsync(stage, (size_t)rows * 16, host + (long long)c0 * ldh, (size_t)ldh * 16, (size_t)rows * 16, nc, cudaMemcpyHostToDevice, st));
-    launch_deinterleave(stage, rows, rows, nc, re + (long long)c0 * ld, im + (long long)c0 * ld, ld, st);
+    launch_deinterleave(stage, rows, rows, nc, re + (long long)c0 * ld, im + (long long)c0 * ld, ld, rowperm, st);
     CK(cudaStreamSynchronize(st));
   }
   cudaFree(stage);
@@ -502,8 +618,9 @@ extern "C" int mfb_harela3d_assemble(mfb_problem* p, double omega, const mfb_z* 
   if (r) return r;
   r = collect_assembly_times(p);
   if (r) return r;
-  if (A) { r = download_matrix(p, p->sys.Are, p->sys.Aim, p->lda, p->n_dof, p->n_dof, A, p->n_dof); if (r) return r; }
-  if (b) { r = download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, b, p->n_dof); if (r) return r; }
+  // the device-resident system is in internal row order; the host sees the reference's row order
+  if (A) { r = download_matrix(p, p->sys.Are, p->sys.Aim, p->lda, p->n_dof, p->n_dof, A, p->n_dof, p->d_rowperm, p->d_colperm); if (r) return r; }
+  if (b) { r = download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, b, p->n_dof, p->d_rowperm); if (r) return r; }
   return MFB_OK;
 }
 
@@ -551,7 +668,7 @@ extern "C" int mfb_zsolve(mfb_problem* p, int n, mfb_z* A, int lda, int* ipiv, m
   cudaStream_t st = p->ctx->stream;
   int r;
   if (factorize) {
-    if (A) { r = upload_matrix(p, A, lda, n, n, p->sys.Are, p->sys.Aim, p->lda); if (r) return r; }
+    if (A) { r = upload_matrix(p, A, lda, n, n, p->sys.Are, p->sys.Aim, p->lda); if (r) return r; p->rows_permuted = false; }
     p->assembled = false;
     r = factor_device(p, n, lu_timing());
     if (ipiv) memcpy(ipiv, p->h_ipiv.data(), (size_t)n * sizeof(int));
@@ -563,14 +680,14 @@ extern "C" int mfb_zsolve(mfb_problem* p, int n, mfb_z* A, int lda, int* ipiv, m
   double* tmp = nullptr;
   if (b) {
     if (nrhs > 1) { CK(cudaMalloc((void**)&tmp, (size_t)2 * p->lda * nrhs * sizeof(double))); bre = tmp; bim = tmp + (size_t)p->lda * nrhs; }
-    r = upload_matrix(p, b, n, n, nrhs, bre, bim, ldb); if (r) return r;
+    r = upload_matrix(p, b, n, n, nrhs, bre, bim, ldb, p->rows_permuted ? p->d_rowperm : nullptr); if (r) return r;
   } else if (nrhs != 1) return fail(MFB_ERR_ARG, "mfb_zsolve: device-resident rhs has a single column");
   CK(cudaEventRecord(p->ev[6], st));
   int e = zgetrs_planar(p->sys.Are, p->sys.Aim, p->lda, n, p->d_perm, bre, bim, ldb, nrhs, st);
   if (e) return fail(MFB_ERR_CUDA, std::string("zgetrs_planar: ") + cudaGetErrorString((cudaError_t)e));
   CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
   float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
-  if (b) { r = download_matrix(p, bre, bim, ldb, n, nrhs, b, n); if (r) return r; }
+  if (b) { r = download_matrix(p, bre, bim, ldb, n, nrhs, b, n, p->rows_permuted ? p->d_colperm : nullptr); if (r) return r; }
   if (tmp) cudaFree(tmp);
   return MFB_OK;
 }
@@ -592,13 +709,13 @@ extern "C" int mfb_harela3d_solve_frequency(mfb_problem* p, double omega, const 
   float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
   p->assembled = false;
   if (!x) return MFB_OK;   // solution stays on the device (mfb_get_solution)
-  return download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, x, p->n_dof);
+  return download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, x, p->n_dof, p->d_colperm);
 }
 
 extern "C" int mfb_get_solution(mfb_problem* p, mfb_z* x) {
   if (!p || !x) return fail(MFB_ERR_ARG, "mfb_get_solution: null argument");
   CK(cudaSetDevice(p->ctx->device));
-  return download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, x, p->n_dof);
+  return download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, x, p->n_dof, p->rows_permuted ? p->d_colperm : nullptr);
 }
 
 extern "C" int mfb_get_entries(mfb_problem* p, int n, const int* rows, const int* cols, mfb_z* out) {
@@ -609,7 +726,9 @@ extern "C" int mfb_get_entries(mfb_problem* p, int n, const int* rows, const int
   cudaStream_t st = p->ctx->stream;
   int *dr, *dc; double* dout;
   CK(cudaMalloc((void**)&dr, (size_t)std::max(n, 1) * 4)); CK(cudaMalloc((void**)&dc, (size_t)std::max(n, 1) * 4)); CK(cudaMalloc((void**)&dout, (size_t)std::max(n, 1) * 16));
-  CK(cudaMemcpyAsync(dr, rows, (size_t)n * 4, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(dc, cols, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  std::vector<int> irows(rows, rows + n), icols(cols, cols + n);
+  if (p->rows_permuted) for (int i = 0; i < n; i++) { irows[i] = p->rowperm[rows[i]]; icols[i] = p->colperm[cols[i]]; }
+  CK(cudaMemcpyAsync(dr, irows.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(dc, icols.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
   launch_get_entries(p->sys, n, dr, dc, dout, st);
   CK(cudaMemcpyAsync(out, dout, (size_t)n * 16, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
   cudaFree(dr); cudaFree(dc); cudaFree(dout);
@@ -624,7 +743,7 @@ extern "C" int mfb_residual(mfb_problem* p, const mfb_z* x, double* berr, double
   const int n = p->n_dof;
   double* d; CK(cudaMalloc((void**)&d, (size_t)5 * n * sizeof(double)));
   std::vector<double> hx(2 * (size_t)n);
-  for (int i = 0; i < n; i++) { hx[i] = x[i].re; hx[n + i] = x[i].im; }
+  for (int i = 0; i < n; i++) { const int q = p->rows_permuted ? p->colperm[i] : i; hx[q] = x[i].re; hx[n + q] = x[i].im; }
   CK(cudaMemcpyAsync(d, hx.data(), (size_t)2 * n * 8, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(d + 2 * (size_t)n, 0, (size_t)3 * n * 8, st));
   launch_residual(p->sys, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, d + 4 * (size_t)n, st);
@@ -697,17 +816,17 @@ extern "C" int mfb_zgemm_minus(mfb_ctx* ctx, int m, int n, int k, const mfb_z* A
   CK(cudaMalloc((void**)&stage, smax * 16));
   CK(cudaMemsetAsync(dA, 0, 2 * la * k * 8, st)); CK(cudaMemsetAsync(dB, 0, 2 * lb * n * 8, st));
   CK(cudaMemcpy2DAsync(stage, (size_t)m * 16, A, (size_t)lda * 16, (size_t)m * 16, k, cudaMemcpyHostToDevice, st));
-  launch_deinterleave(stage, m, m, k, dA, dA + la * k, la, st);
+  launch_deinterleave(stage, m, m, k, dA, dA + la * k, la, nullptr, st);
   CK(cudaMemcpy2DAsync(stage, (size_t)k * 16, B, (size_t)ldb * 16, (size_t)k * 16, n, cudaMemcpyHostToDevice, st));
-  launch_deinterleave(stage, k, k, n, dB, dB + lb * n, lb, st);
+  launch_deinterleave(stage, k, k, n, dB, dB + lb * n, lb, nullptr, st);
   CK(cudaMemcpy2DAsync(stage, (size_t)m * 16, C, (size_t)ldc * 16, (size_t)m * 16, n, cudaMemcpyHostToDevice, st));
-  launch_deinterleave(stage, m, m, n, dC, dC + lc * n, lc, st);
+  launch_deinterleave(stage, m, m, n, dC, dC + lc * n, lc, nullptr, st);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   CK(cudaEventRecord(e0, st));
   zgemm_minus_planar(m, n, k, dA, dA + la * k, la, dB, dB + lb * n, lb, dC, dC + lc * n, lc, st);
   CK(cudaEventRecord(e1, st)); CK(cudaEventSynchronize(e1));
   float t; cudaEventElapsedTime(&t, e0, e1); if (ms) *ms = t;
-  launch_interleave(dC, dC + lc * n, lc, m, n, stage, m, st);
+  launch_interleave(dC, dC + lc * n, lc, m, n, stage, m, nullptr, nullptr, 0, st);
   CK(cudaMemcpy2DAsync(C, (size_t)ldc * 16, stage, (size_t)m * 16, (size_t)m * 16, n, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(stage); cudaEventDestroy(e0); cudaEventDestroy(e1);

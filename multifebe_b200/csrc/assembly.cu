@@ -19,9 +19,13 @@
 
 namespace mfbd {
 
-__constant__ KParams c_kp;
+__constant__ KParams c_kp;   // parameters as the reference defines them (K2, K3)
+__constant__ KParams c_kq;   // pre-scaled copy for K1 (see kernel_scalars_scaled)
 
-void set_kparams(const KParams& kp, cudaStream_t st) { cudaMemcpyToSymbolAsync(c_kp, &kp, sizeof(KParams), 0, cudaMemcpyHostToDevice, st); }
+void set_kparams(const KParams& kp, const KParams& kp_scaled, cudaStream_t st) {
+  cudaMemcpyToSymbolAsync(c_kp, &kp, sizeof(KParams), 0, cudaMemcpyHostToDevice, st);
+  cudaMemcpyToSymbolAsync(c_kq, &kp_scaled, sizeof(KParams), 0, cudaMemcpyHostToDevice, st);
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // K0: classification.  d must be bit-identical to the host/reference value (it feeds a discrete decision), hence the
@@ -33,7 +37,7 @@ __global__ void k_classify(DevGroup g, DevColloc c, DevClassify k, unsigned char
   int e = blockIdx.y;
   if (cpos >= c.ldp) return;
   unsigned char out = PLAN_NONE;
-  if (cpos < c.n_colloc) {
+  if (c.crow[cpos] >= 0) {
     const double* b = g.ball + 5 * (size_t)e;
     double r0 = __dsub_rn(b[0], c.cx[cpos]), r1 = __dsub_rn(b[1], c.cx[c.ldp + cpos]), r2 = __dsub_rn(b[2], c.cx[2 * c.ldp + cpos]);
     double rr = __dadd_rn(__dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1)), __dmul_rn(r2, r2));
@@ -84,19 +88,24 @@ void launch_patch_plan(unsigned char* plan, const DevColloc& c, int n, const int
   if (n > 0) k_patch_plan<<<(n + 255) / 256, 256, 0, st>>>(plan, c, n, cpos, slot, val);
 }
 
-// prescribed values per (element, j, k), refreshed once per frequency
+// prescribed values per (element, j, k) and the "some value is nonzero" flag, refreshed once per frequency
 __global__ void k_gather_cv(DevGroup g, const double* __restrict__ cvalue) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int per = 3 * g.nn;
-  if (i >= g.n_elem * per) return;
-  int e = i / per, jk = i % per, j = jk / 3, k = jk % 3;
-  int node = g.enode[e * g.nn + j];
-  g.ecv[2 * (size_t)i] = cvalue[2 * (3 * (size_t)node + k)];
-  g.ecv[2 * (size_t)i + 1] = cvalue[2 * (3 * (size_t)node + k) + 1];
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.n_elem) return;
+  bool nz = false;
+  for (int j = 0; j < g.nn; j++) {
+    const int node = g.enode[e * g.nn + j];
+    for (int k = 0; k < 3; k++) {
+      const double vr = cvalue[2 * (3 * (size_t)node + k)], vi = cvalue[2 * (3 * (size_t)node + k) + 1];
+      const size_t i = (size_t)e * 3 * g.nn + j * 3 + k;
+      g.ecv[2 * i] = vr; g.ecv[2 * i + 1] = vi;
+      nz = nz || vr != 0.0 || vi != 0.0;
+    }
+  }
+  g.ecvnz[e] = nz ? 1 : 0;
 }
 void launch_gather_cv(const DevGroup& g, const double* cvalue, cudaStream_t st) {
-  int n = g.n_elem * 3 * g.nn;
-  if (n > 0) k_gather_cv<<<(n + 255) / 256, 256, 0, st>>>(g, cvalue);
+  if (g.n_elem > 0) k_gather_cv<<<(g.n_elem + 127) / 128, 128, 0, st>>>(g, cvalue);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -152,10 +161,10 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_regular(DevGroup g, DevColloc
   const int NN = ElemTraits<ET>::NN;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cpos = (blockIdx.x * K1_WARPS + warp) * 32 + lane;
-  const bool valid = cpos < c.n_colloc;
-  const int cp = valid ? cpos : c.n_colloc - 1;
-  const double xc[3] = {c.cx[cp], c.cx[c.ldp + cp], c.cx[2 * c.ldp + cp]};
-  const int r0 = c.crow[cp], r1 = c.crow[c.ldp + cp], r2 = c.crow[2 * c.ldp + cp];
+  if (cpos - lane >= c.ldp) return;
+  const int r0 = c.crow[cpos], r1 = c.crow[c.ldp + cpos], r2 = c.crow[2 * c.ldp + cpos];
+  const bool valid = r0 >= 0;
+  const double xc[3] = {c.cx[cpos], c.cx[c.ldp + cpos], c.cx[2 * c.ldp + cpos]};
   double bre[3] = {0.0, 0.0, 0.0}, bim[3] = {0.0, 0.0, 0.0};
   const int e0 = blockIdx.y * K1_ECHUNK, e1 = min(e0 + K1_ECHUNK, g.n_elem);
   for (int e = e0; e < e1; e++) {
@@ -196,13 +205,193 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_regular(DevGroup g, DevColloc
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// K1 (bulk): regular pairs of 3- and 4-node elements, the kernel that carries the assembly.
+//   * a warp owns one collocation TILE (32 lanes = 32 points whose 96 matrix rows are consecutive, see DevColloc) and
+//     walks a chunk of elements; the element's point set is read with warp-uniform loads;
+//   * per Gauss point only what the boundary conditions of the element need is formed: the traction-kernel combination
+//     for a t-known dof (its h goes to A), the displacement-kernel combination for a u-known dof (its g goes to A);
+//     the other one only if the element carries a nonzero prescribed value (it then goes to b).  Kernel parameters are
+//     pre-scaled on the host so that the accumulators are matrix entries;
+//   * the pair's 9*NN complex entries are staged in shared memory as [column][plane][96 rows] and added to the planar
+//     matrix by the TMA: one cp.reduce.async.bulk (.add.f64, SASS UBLKRED) per column and plane, 768 bytes each, issued
+//     by 2*3*NN lanes.  The LSU never sees the matrix update (RED.F64 from registers costs 2.3 SM-cycles per lane and
+//     entry, 5x the arithmetic of a far pair; profiles/r01_microbench_red.md).
+// ------------------------------------------------------------------------------------------------------------------
+const int KB_WARPS = 4;
+const int KB_ECHUNK = 32;
+
+template <int NN>
+struct AccA { double re[9 * NN], im[9 * NN]; };   // [(l*3+k)*NN + j]: entry of load direction l (row) and dof k of node j (column)
+
+template <int NN>
+__device__ __forceinline__ void k1_point(AccA<NN>& a, double* bacc, const double* __restrict__ q, const double* xc, double sgn, unsigned info,
+                                         bool cvnz, const unsigned char* __restrict__ ekind, const double* __restrict__ ecv) {
+  const double x0 = __ldg(q), x1 = __ldg(q + 1), x2 = __ldg(q + 2);
+  const double n[3] = {sgn * __ldg(q + 3), sgn * __ldg(q + 4), sgn * __ldg(q + 5)};
+  double w[NN];
+#pragma unroll
+  for (int j = 0; j < NN; j++) w[j] = __ldg(q + 6 + j);
+  const double rv0 = x0 - xc[0], rv1 = x1 - xc[1], rv2 = x2 - xc[2];
+  const double r2 = fma(rv0, rv0, fma(rv1, rv1, rv2 * rv2));
+  const double d1r1 = rsqrt(r2), r = r2 * d1r1;
+  KScal k; kernel_scalars_scaled(c_kq, r, d1r1, k);
+  const double dx[3] = {rv0 * d1r1, rv1 * d1r1, rv2 * d1r1};
+  const double drdn = fma(dx[0], n[0], fma(dx[1], n[1], dx[2] * n[2]));
+  const cplx t1d = k.T1 * drdn;
+  if ((info & 8u) && !cvnz) {
+#pragma unroll
+    for (int kk = 0; kk < 3; kk++) {
+      if ((info >> kk) & 1u) {
+#pragma unroll
+        for (int l = 0; l < 3; l++) {
+          const double dd = dx[l] * dx[kk], c2 = (l == kk) ? fma(dx[kk], n[l], drdn) : dx[kk] * n[l], c3 = dx[l] * n[kk];
+          const double fr = fma(t1d.re, dd, fma(k.T2.re, c2, k.T3.re * c3)), fi = fma(t1d.im, dd, fma(k.T2.im, c2, k.T3.im * c3));
+#pragma unroll
+          for (int j = 0; j < NN; j++) { a.re[(l * 3 + kk) * NN + j] = fma(fr, w[j], a.re[(l * 3 + kk) * NN + j]); a.im[(l * 3 + kk) * NN + j] = fma(fi, w[j], a.im[(l * 3 + kk) * NN + j]); }
+        }
+      } else {
+#pragma unroll
+        for (int l = 0; l < 3; l++) {
+          const double dd = dx[l] * dx[kk];
+          const double fr = (l == kk) ? fma(-k.chi.re, dd, k.psi.re) : -k.chi.re * dd, fi = (l == kk) ? fma(-k.chi.im, dd, k.psi.im) : -k.chi.im * dd;
+#pragma unroll
+          for (int j = 0; j < NN; j++) { a.re[(l * 3 + kk) * NN + j] = fma(fr, w[j], a.re[(l * 3 + kk) * NN + j]); a.im[(l * 3 + kk) * NN + j] = fma(fi, w[j], a.im[(l * 3 + kk) * NN + j]); }
+        }
+      }
+    }
+  } else {
+    // general element: both combinations; per (node, dof) one goes to A, the other (times the prescribed value) to b
+    double ftr[9], fti[9], fur[9], fui[9];
+#pragma unroll
+    for (int l = 0; l < 3; l++)
+#pragma unroll
+      for (int kk = 0; kk < 3; kk++) {
+        const double dd = dx[l] * dx[kk], c2 = (l == kk) ? fma(dx[kk], n[l], drdn) : dx[kk] * n[l], c3 = dx[l] * n[kk];
+        ftr[l * 3 + kk] = fma(t1d.re, dd, fma(k.T2.re, c2, k.T3.re * c3)); fti[l * 3 + kk] = fma(t1d.im, dd, fma(k.T2.im, c2, k.T3.im * c3));
+        fur[l * 3 + kk] = (l == kk) ? fma(-k.chi.re, dd, k.psi.re) : -k.chi.re * dd; fui[l * 3 + kk] = (l == kk) ? fma(-k.chi.im, dd, k.psi.im) : -k.chi.im * dd;
+      }
+#pragma unroll
+    for (int j = 0; j < NN; j++)
+#pragma unroll
+      for (int kk = 0; kk < 3; kk++) {
+        const bool tk = ekind[j * 3 + kk] != 0;   // warp-uniform
+        const double cvr = w[j] * __ldg(ecv + 2 * (j * 3 + kk)), cvi = w[j] * __ldg(ecv + 2 * (j * 3 + kk) + 1);
+#pragma unroll
+        for (int l = 0; l < 3; l++) {
+          const double ar = tk ? ftr[l * 3 + kk] : fur[l * 3 + kk], ai = tk ? fti[l * 3 + kk] : fui[l * 3 + kk];
+          const double orr = tk ? fur[l * 3 + kk] : ftr[l * 3 + kk], oi = tk ? fui[l * 3 + kk] : fti[l * 3 + kk];
+          a.re[(l * 3 + kk) * NN + j] = fma(ar, w[j], a.re[(l * 3 + kk) * NN + j]); a.im[(l * 3 + kk) * NN + j] = fma(ai, w[j], a.im[(l * 3 + kk) * NN + j]);
+          bacc[l] -= orr * cvr - oi * cvi; bacc[3 + l] -= orr * cvi + oi * cvr;
+        }
+      }
+  }
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int ET>
+__global__ void __launch_bounds__(KB_WARPS * 32, 2) k_regular_bulk(DevGroup g, DevColloc c, DevSystem s, const unsigned char* __restrict__ plan) {
+  constexpr int NN = ElemTraits<ET>::NN, NC = 3 * NN;
+  static_assert(2 * NC <= 32, "one bulk operation per lane");
+  extern __shared__ __align__(128) double k1_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tile = blockIdx.x * KB_WARPS + warp;
+  if (tile >= c.n_tiles) return;
+  double* buf = k1_smem + (size_t)warp * (2 * NC * 96);
+  const int cpos = tile * 32 + lane;
+  const int r0 = c.crow[cpos], r1 = c.crow[c.ldp + cpos], r2 = c.crow[2 * c.ldp + cpos];
+  const bool valid = r0 >= 0;
+  const double xc[3] = {c.cx[cpos], c.cx[c.ldp + cpos], c.cx[2 * c.ldp + cpos]};
+  const int row0 = c.tile_row0[tile], nbytes = c.tile_nbytes[tile];
+  double bacc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  bool pending = false;
+  const int e0 = blockIdx.y * KB_ECHUNK, e1 = min(e0 + KB_ECHUNK, g.n_elem);
+#pragma unroll 1
+  for (int e = e0; e < e1; e++) {
+    const unsigned char m = valid ? plan[(size_t)(g.slot0 + e) * c.ldp + cpos] : PLAN_NONE;
+    unsigned todo = __ballot_sync(0xffffffffu, m < MAX_SETS);
+    if (todo == 0u) continue;
+    const unsigned info = g.einfo[e];
+    const bool cvnz = g.ecvnz[e] != 0;
+    const double sgn = (info & 16u) ? -1.0 : 1.0;
+    const int* ecol = g.ecol + (size_t)e * NC;
+    const unsigned char* ekind = g.ekind + (size_t)e * NC;
+    const double* ecv = g.ecv + (size_t)e * 2 * NC;
+    AccA<NN> acc;
+#pragma unroll
+    for (int i = 0; i < 9 * NN; i++) { acc.re[i] = 0.0; acc.im[i] = 0.0; }
+    while (todo) {
+      const int leader = __ffs(todo) - 1;
+      const int sset = __shfl_sync(0xffffffffu, (int)m, leader);
+      const unsigned grp = __ballot_sync(0xffffffffu, (int)m == sset);
+      todo &= ~grp;
+      if ((int)m == sset) {
+        const int ngp = g.ngp[sset];
+        const double* P = g.pts[sset] + (size_t)e * ngp * (6 + NN);
+#pragma unroll 1
+        for (int kp = 0; kp < ngp; kp++) k1_point<NN>(acc, bacc, P + (size_t)kp * (6 + NN), xc, sgn, info, cvnz, ekind, ecv);
+      }
+    }
+    if (nbytes > 0) {
+      if (pending && lane < 2 * NC) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous flush has left the buffer
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < NN; j++)
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+          for (int l = 0; l < 3; l++) {
+            buf[(2 * (j * 3 + k)) * 96 + 3 * lane + l] = acc.re[(l * 3 + k) * NN + j];
+            buf[(2 * (j * 3 + k) + 1) * 96 + 3 * lane + l] = acc.im[(l * 3 + k) * NN + j];
+          }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane < 2 * NC) {
+        const int col = __ldg(ecol + (lane >> 1));
+        double* dst = ((lane & 1) ? s.Aim : s.Are) + (size_t)col * s.lda + row0;
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(buf + lane * 96)), "r"(nbytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      pending = true;
+    } else if (m < MAX_SETS) {
+#pragma unroll
+      for (int j = 0; j < NN; j++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const int col = __ldg(ecol + j * 3 + k);
+          double* Ar = s.Are + (size_t)col * s.lda; double* Ai = s.Aim + (size_t)col * s.lda;
+          atomicAdd(Ar + r0, acc.re[(0 * 3 + k) * NN + j]); atomicAdd(Ai + r0, acc.im[(0 * 3 + k) * NN + j]);
+          atomicAdd(Ar + r1, acc.re[(1 * 3 + k) * NN + j]); atomicAdd(Ai + r1, acc.im[(1 * 3 + k) * NN + j]);
+          atomicAdd(Ar + r2, acc.re[(2 * 3 + k) * NN + j]); atomicAdd(Ai + r2, acc.im[(2 * 3 + k) * NN + j]);
+        }
+    }
+  }
+  if (pending && lane < 2 * NC) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (valid) {
+    if (bacc[0] != 0.0 || bacc[3] != 0.0) { atomicAdd(s.bre + r0, bacc[0]); atomicAdd(s.bim + r0, bacc[3]); }
+    if (bacc[1] != 0.0 || bacc[4] != 0.0) { atomicAdd(s.bre + r1, bacc[1]); atomicAdd(s.bim + r1, bacc[4]); }
+    if (bacc[2] != 0.0 || bacc[5] != 0.0) { atomicAdd(s.bre + r2, bacc[2]); atomicAdd(s.bim + r2, bacc[5]); }
+  }
+}
+
+template <int ET>
+static void launch_regular_bulk(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, cudaStream_t st) {
+  constexpr int NC = 3 * ElemTraits<ET>::NN;
+  const int smem = KB_WARPS * 2 * NC * 96 * (int)sizeof(double);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_regular_bulk<ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  dim3 grid((c.n_tiles + KB_WARPS - 1) / KB_WARPS, (g.n_elem + KB_ECHUNK - 1) / KB_ECHUNK);
+  k_regular_bulk<ET><<<grid, KB_WARPS * 32, smem, st>>>(g, c, s, plan);
+}
+
 void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, cudaStream_t st) {
   if (g.n_elem == 0) return;
-  dim3 grid((c.n_colloc + 32 * K1_WARPS - 1) / (32 * K1_WARPS), (g.n_elem + K1_ECHUNK - 1) / K1_ECHUNK);
+  dim3 grid((c.ldp + 32 * K1_WARPS - 1) / (32 * K1_WARPS), (g.n_elem + K1_ECHUNK - 1) / K1_ECHUNK);
   dim3 block(K1_WARPS * 32);
   switch (g.et) {
-    case 5: k_regular<5, 3><<<grid, block, 0, st>>>(g, c, s, plan); break;
-    case 7: k_regular<7, 3><<<grid, block, 0, st>>>(g, c, s, plan); break;
+    case 5: launch_regular_bulk<5>(g, c, s, plan, st); break;
+    case 7: launch_regular_bulk<7>(g, c, s, plan, st); break;
     case 6: k_regular<6, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
     case 8: k_regular<8, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
     case 9: k_regular<9, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
@@ -379,21 +568,27 @@ void launch_freeterm(const DevColloc& c, const DevSystem& s, const DevFreeTerm& 
   if (f.n > 0) k_freeterm<<<(f.n + 255) / 256, 256, 0, st>>>(c, s, f, F);
 }
 
-// planar <-> interleaved complex (host interface format), column-major
-__global__ void k_interleave(const double* __restrict__ re, const double* __restrict__ im, long long ld, int rows, int cols, double* __restrict__ out, long long ldo) {
+// planar <-> interleaved complex (host interface format), column-major; rowperm (or NULL) maps a host row to the
+// library's internal row
+__global__ void k_interleave(const double* __restrict__ re, const double* __restrict__ im, long long ld, int rows, int cols, double* __restrict__ out, long long ldo,
+                             const int* __restrict__ rowperm, const int* __restrict__ colperm, int col0) {
   long long total = (long long)rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long cidx = i / rows, r = i - cidx * rows;
-    out[2 * (cidx * ldo + r)] = re[cidx * ld + r];
-    out[2 * (cidx * ldo + r) + 1] = im[cidx * ld + r];
+    long long ri = rowperm ? rowperm[r] : r;
+    long long ci = colperm ? colperm[col0 + cidx] : col0 + cidx;
+    out[2 * (cidx * ldo + r)] = re[ci * ld + ri];
+    out[2 * (cidx * ldo + r) + 1] = im[ci * ld + ri];
   }
 }
-__global__ void k_deinterleave(const double* __restrict__ in, long long ldi, int rows, int cols, double* __restrict__ re, double* __restrict__ im, long long ld) {
+__global__ void k_deinterleave(const double* __restrict__ in, long long ldi, int rows, int cols, double* __restrict__ re, double* __restrict__ im, long long ld,
+                               const int* __restrict__ rowperm) {
   long long total = (long long)rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long cidx = i / rows, r = i - cidx * rows;
-    re[cidx * ld + r] = in[2 * (cidx * ldi + r)];
-    im[cidx * ld + r] = in[2 * (cidx * ldi + r) + 1];
+    long long ri = rowperm ? rowperm[r] : r;
+    re[cidx * ld + ri] = in[2 * (cidx * ldi + r)];
+    im[cidx * ld + ri] = in[2 * (cidx * ldi + r) + 1];
   }
 }
 // r = A x - b and the componentwise scale s_i = sum_j |A_ij||x_j| + |b_i| (zgerfs-style backward error), planar storage.
@@ -425,11 +620,13 @@ void launch_get_entries(const DevSystem& s, int n, const int* rows, const int* c
   if (n > 0) k_get_entries<<<(n + 255) / 256, 256, 0, st>>>(s, n, rows, cols, out);
 }
 
-void launch_interleave(const double* re, const double* im, long long ld, int rows, int cols, double* out, long long ldo, cudaStream_t st) {
-  k_interleave<<<2368, 256, 0, st>>>(re, im, ld, rows, cols, out, ldo);
+// out[:, 0:cols) = host columns [col0, col0+cols) of the planar matrix (re, im): internal column colperm[c] (or c), internal row rowperm[r] (or r)
+void launch_interleave(const double* re, const double* im, long long ld, int rows, int cols, double* out, long long ldo, const int* rowperm,
+                       const int* colperm, int col0, cudaStream_t st) {
+  k_interleave<<<2368, 256, 0, st>>>(re, im, ld, rows, cols, out, ldo, rowperm, colperm, col0);
 }
-void launch_deinterleave(const double* in, long long ldi, int rows, int cols, double* re, double* im, long long ld, cudaStream_t st) {
-  k_deinterleave<<<2368, 256, 0, st>>>(in, ldi, rows, cols, re, im, ld);
+void launch_deinterleave(const double* in, long long ldi, int rows, int cols, double* re, double* im, long long ld, const int* rowperm, cudaStream_t st) {
+  k_deinterleave<<<2368, 256, 0, st>>>(in, ldi, rows, cols, re, im, ld, rowperm);
 }
 
 }  // namespace mfbd

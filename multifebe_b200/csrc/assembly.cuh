@@ -20,6 +20,8 @@ struct DevGroup {
   const int* enode;              // [n_elem][nn]   global node ids
   const unsigned char* erev;     // [n_elem] reversed orientation (h -> -h)
   double* ecv;                   // [n_elem][3*nn][2] prescribed value of (j,k), refreshed per frequency
+  const unsigned char* einfo;    // [n_elem] bits 0-2: kind of dof k (when the same for every node j), bit 3: kinds uniform over j, bit 4: reversed
+  unsigned char* ecvnz;          // [n_elem] 1 when some prescribed value of the element is nonzero (refreshed per frequency)
   const double* ball;            // [n_elem][5]: centre(3), radius, characteristic length
   const int* gln_far;            // [n_elem]
   int n_sets; int set_gln[MAX_SETS]; int ngp[MAX_SETS];
@@ -31,10 +33,18 @@ struct DevSystem {
   double *bre, *bim;
 };
 
+// Collocation points live in TILES of 32 lanes (position cpos = 32*tile + lane, padding lanes have crow = -1).  A tile
+// is one layer of a block of <= 32 row nodes whose 3 x cnt matrix rows are consecutive in the library's INTERNAL row order
+// (row0 even, cnt even => the block's rows of one matrix column are one 16-byte aligned run of nbytes = 24*cnt bytes that
+// a single bulk reduce can update); layer l holds the l-th collocation point of every node of the block (MCA nodes have
+// several).  Loose tiles (nbytes = 0) hold arbitrary points and are flushed with per-lane RED.
 struct DevColloc {
-  int n_colloc, ldp;             // ldp = n_colloc rounded up to 32
-  const double* cx;              // [3][ldp] collocation points (SoA), sorted by row
-  const int* crow;               // [3][ldp] A rows of the three equations of each collocation point
+  int n_colloc, ldp;             // ldp = 32 * n_tiles = number of lane positions (n_colloc == ldp on the device)
+  const double* cx;              // [3][ldp] collocation points (SoA)
+  const int* crow;               // [3][ldp] internal A rows of the three equations of each collocation point, -1 = padding lane
+  int n_tiles;
+  const int* tile_row0;          // [n_tiles] first internal row of the tile's run
+  const int* tile_nbytes;        // [n_tiles] 24*cnt, or 0 for a loose tile
 };
 
 struct DevClassify {
@@ -61,7 +71,7 @@ struct DevFreeTerm {
 };
 struct DevTables { const double *gl11_x, *gl11_w, *gl01_x, *gl01_w; };  // packed, rule n at offset n(n-1)/2
 
-void set_kparams(const KParams& kp, cudaStream_t st);
+void set_kparams(const KParams& kp, const KParams& kp_scaled, cudaStream_t st);
 void launch_classify(const DevGroup& g, const DevColloc& c, const DevClassify& k, unsigned char* plan, cudaStream_t st);
 void launch_count_near(const unsigned char* plan, long long n_slots, const DevColloc& c, unsigned long long* counter, int2* list,
                        unsigned long long capacity, cudaStream_t st);
@@ -73,7 +83,8 @@ void launch_singular(const DevGroup& g, const DevColloc& c, const DevSystem& s, 
 void launch_freeterm(const DevColloc& c, const DevSystem& s, const DevFreeTerm& f, cplx F, cudaStream_t st);
 void launch_residual(const DevSystem& s, const double* xre, const double* xim, double* rr, double* ri, double* ss, cudaStream_t st);
 void launch_get_entries(const DevSystem& s, int n, const int* rows, const int* cols, double* out, cudaStream_t st);
-void launch_interleave(const double* re, const double* im, long long ld, int rows, int cols, double* out, long long ldo, cudaStream_t st);
-void launch_deinterleave(const double* in, long long ldi, int rows, int cols, double* re, double* im, long long ld, cudaStream_t st);
+void launch_interleave(const double* re, const double* im, long long ld, int rows, int cols, double* out, long long ldo, const int* rowperm,
+                       const int* colperm, int col0, cudaStream_t st);
+void launch_deinterleave(const double* in, long long ldi, int rows, int cols, double* re, double* im, long long ld, const int* rowperm, cudaStream_t st);
 
 }  // namespace mfbd

@@ -37,15 +37,26 @@ struct KParams {
 // E_2..E_5 of z (returned already divided: e2 = E2/r, e3 = E3/r^2, e4 = E4/r^3, e5 = E5/r^4)
 struct EnR { cplx e2, e3, e4, e5; };
 
+// 1/(m+5)!, m = 0..16: E5(z) = z^5 * sum_m z^m/(m+5)!  (|z| <= 1: the first neglected term is 1/22! = 9e-22)
+#define MFB_E5_COEFFS {1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0, 1.0 / 40320.0, 1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0, \
+    1.0 / 479001600.0, 1.0 / 6227020800.0, 1.0 / 87178291200.0, 1.0 / 1307674368000.0, 1.0 / 20922789888000.0, \
+    1.0 / 355687428096000.0, 1.0 / 6402373705728000.0, 1.0 / 121645100408832000.0, 1.0 / 2432902008176640000.0, \
+    1.0 / 51090942171709440000.0}
+
 MFB_HD void zexp_E2_5(cplx z, cplx& E2, cplx& E3, cplx& E4, cplx& E5) {
-  double a2 = z.re * z.re + z.im * z.im;
-  cplx z2 = z * z, z3 = z2 * z, z4 = z2 * z2;
+  const double a2 = z.re * z.re + z.im * z.im;
+  const cplx z2 = z * z, z3 = z2 * z, z4 = z2 * z2;
   if (a2 <= 1.0) {
-    // E5 = z^5/5! * (1 + z/6 (1 + z/7 (1 + ... z/21)))  -- 16 terms: 5!/21! < 3e-18
-    cplx s = mk(1.0, 0.0);
+    const double c[17] = MFB_E5_COEFFS;
+    // Horner in z with real coefficients: 4 FMA-class operations per term
+    double sr = c[16], si = 0.0;
 #pragma unroll
-    for (int k = 21; k >= 6; k--) { cplx t = z * (1.0 / (double)k); s = cfma(t, s, mk(1.0, 0.0)); }
-    E5 = (z4 * z) * s * (1.0 / 120.0);
+    for (int m = 15; m >= 0; m--) {
+      const double tr = fma(sr, z.re, fma(-si, z.im, c[m]));
+      si = fma(sr, z.im, si * z.re);
+      sr = tr;
+    }
+    E5 = (z4 * z) * mk(sr, si);
     E4 = cfmar(z4, 1.0 / 24.0, E5);
     E3 = cfmar(z3, 1.0 / 6.0, E4);
     E2 = cfmar(z2, 0.5, E3);
@@ -89,6 +100,40 @@ MFB_HD void kernel_scalars(const KParams& p, double r, KScal& k) {
   t = cfma(p.T2[7], E42, t); t = cfma(p.T2[8], E51, t); t = cfma(p.T2[9], E52, t);
   k.T2 = t;
   t = REGULAR_ONLY ? p.T3[2] : (p.T3[1] * d1r2 + p.T3[2]);
+  t = cfma(p.T3[3], E21, t); t = cfma(p.T3[4], E31, t); t = cfma(p.T3[5], E32, t); t = cfma(p.T3[6], E41, t);
+  t = cfma(p.T3[7], E42, t); t = cfma(p.T3[8], E51, t); t = cfma(p.T3[9], E52, t);
+  k.T3 = t;
+  k.d1r1 = d1r1; k.d1r2 = d1r2;
+}
+
+// Kernel scalars for the regular (K1) kernel with PRE-SCALED parameters: q.psi/q.chi carry the factor -cte_u (their slot 0 is
+// the coefficient of the bare E2(z2)/r term), q.T1..T3 carry cte_t, so that psi*delta - chi*r,l*r,k is directly the
+// matrix contribution -g/(4 pi mu) of a u-known column and the T combination directly +h/(4 pi) of a t-known column.
+// Takes r and 1/r (from rsqrt) instead of dividing.
+MFB_HD void kernel_scalars_scaled(const KParams& p, double r, double d1r1, KScal& k) {
+  const double d1r2 = d1r1 * d1r1, d1r3 = d1r2 * d1r1, d1r4 = d1r2 * d1r2;
+  const cplx z1 = mk(p.k1.im * r, -p.k1.re * r), z2 = mk(p.k2.im * r, -p.k2.re * r);
+  cplx A2, A3, A4, A5, B2, B3, B4, B5;
+  zexp_E2_5(z1, A2, A3, A4, A5);
+  zexp_E2_5(z2, B2, B3, B4, B5);
+  const cplx E21 = A2 * d1r1, E22 = B2 * d1r1, E31 = A3 * d1r2, E32 = B3 * d1r2;
+  const cplx E41 = A4 * d1r3, E42 = B4 * d1r3, E51 = A5 * d1r4, E52 = B5 * d1r4;
+  cplx t;
+  t = cfmar(p.psi[1], d1r1, p.psi[2]);
+  t = cfma(p.psi[0], E22, t); t = cfma(p.psi[3], E31, t); t = cfma(p.psi[4], E32, t); t = cfma(p.psi[5], E41, t); t = cfma(p.psi[6], E42, t);
+  k.psi = t;
+  t = p.chi[1] * d1r1;
+  t = cfma(p.chi[0], E22, t); t = cfma(p.chi[2], E21, t); t = cfma(p.chi[3], E31, t); t = cfma(p.chi[4], E32, t); t = cfma(p.chi[5], E41, t); t = cfma(p.chi[6], E42, t);
+  k.chi = t;
+  t = cfmar(p.T1[1], d1r2, p.T1[2]);
+  t = cfma(p.T1[3], E21, t); t = cfma(p.T1[4], E22, t); t = cfma(p.T1[5], E31, t); t = cfma(p.T1[6], E32, t);
+  t = cfma(p.T1[7], E41, t); t = cfma(p.T1[8], E42, t); t = cfma(p.T1[9], E51, t); t = cfma(p.T1[10], E52, t);
+  k.T1 = t;
+  t = cfmar(p.T2[1], d1r2, p.T2[2]);
+  t = cfma(p.T2[3], E22, t); t = cfma(p.T2[4], E31, t); t = cfma(p.T2[5], E32, t); t = cfma(p.T2[6], E41, t);
+  t = cfma(p.T2[7], E42, t); t = cfma(p.T2[8], E51, t); t = cfma(p.T2[9], E52, t);
+  k.T2 = t;
+  t = cfmar(p.T3[1], d1r2, p.T3[2]);
   t = cfma(p.T3[3], E21, t); t = cfma(p.T3[4], E31, t); t = cfma(p.T3[5], E32, t); t = cfma(p.T3[6], E41, t);
   t = cfma(p.T3[7], E42, t); t = cfma(p.T3[8], E51, t); t = cfma(p.T3[9], E52, t);
   k.T3 = t;
