@@ -224,9 +224,12 @@ const int KB_ECHUNK = 32;
 template <int NN>
 struct AccA { double re[9 * NN], im[9 * NN]; };   // [(l*3+k)*NN + j]: entry of load direction l (row) and dof k of node j (column)
 
-template <int NN>
+// One Gauss point of one pair.  GEN = false: element whose boundary-condition kinds are the same for all its nodes and
+// whose prescribed values are all zero (the common case): only the combination that goes to the matrix is formed.
+// GEN = true: any element: both combinations, per (node, dof) one goes to A and the other, times the prescribed value, to b.
+template <int NN, bool GEN>
 __device__ __forceinline__ void k1_point(AccA<NN>& a, double* bacc, const double* __restrict__ q, const double* xc, double sgn, unsigned info,
-                                         bool cvnz, const unsigned char* __restrict__ ekind, const double* __restrict__ ecv) {
+                                         const unsigned char* __restrict__ ekind, const double* __restrict__ ecv) {
   const double x0 = __ldg(q), x1 = __ldg(q + 1), x2 = __ldg(q + 2);
   const double n[3] = {sgn * __ldg(q + 3), sgn * __ldg(q + 4), sgn * __ldg(q + 5)};
   double w[NN];
@@ -239,7 +242,7 @@ __device__ __forceinline__ void k1_point(AccA<NN>& a, double* bacc, const double
   const double dx[3] = {rv0 * d1r1, rv1 * d1r1, rv2 * d1r1};
   const double drdn = fma(dx[0], n[0], fma(dx[1], n[1], dx[2] * n[2]));
   const cplx t1d = k.T1 * drdn;
-  if ((info & 8u) && !cvnz) {
+  if (!GEN) {
 #pragma unroll
     for (int kk = 0; kk < 3; kk++) {
       if ((info >> kk) & 1u) {
@@ -261,128 +264,230 @@ __device__ __forceinline__ void k1_point(AccA<NN>& a, double* bacc, const double
       }
     }
   } else {
-    // general element: both combinations; per (node, dof) one goes to A, the other (times the prescribed value) to b
-    double ftr[9], fti[9], fur[9], fui[9];
 #pragma unroll
-    for (int l = 0; l < 3; l++)
+    for (int kk = 0; kk < 3; kk++) {
+      double ftr[3], fti[3], fur[3], fui[3];
 #pragma unroll
-      for (int kk = 0; kk < 3; kk++) {
+      for (int l = 0; l < 3; l++) {
         const double dd = dx[l] * dx[kk], c2 = (l == kk) ? fma(dx[kk], n[l], drdn) : dx[kk] * n[l], c3 = dx[l] * n[kk];
-        ftr[l * 3 + kk] = fma(t1d.re, dd, fma(k.T2.re, c2, k.T3.re * c3)); fti[l * 3 + kk] = fma(t1d.im, dd, fma(k.T2.im, c2, k.T3.im * c3));
-        fur[l * 3 + kk] = (l == kk) ? fma(-k.chi.re, dd, k.psi.re) : -k.chi.re * dd; fui[l * 3 + kk] = (l == kk) ? fma(-k.chi.im, dd, k.psi.im) : -k.chi.im * dd;
+        ftr[l] = fma(t1d.re, dd, fma(k.T2.re, c2, k.T3.re * c3)); fti[l] = fma(t1d.im, dd, fma(k.T2.im, c2, k.T3.im * c3));
+        fur[l] = (l == kk) ? fma(-k.chi.re, dd, k.psi.re) : -k.chi.re * dd; fui[l] = (l == kk) ? fma(-k.chi.im, dd, k.psi.im) : -k.chi.im * dd;
       }
 #pragma unroll
-    for (int j = 0; j < NN; j++)
-#pragma unroll
-      for (int kk = 0; kk < 3; kk++) {
-        const bool tk = ekind[j * 3 + kk] != 0;   // warp-uniform
+      for (int j = 0; j < NN; j++) {
+        const bool tk = ekind[j * 3 + kk] != 0;
         const double cvr = w[j] * __ldg(ecv + 2 * (j * 3 + kk)), cvi = w[j] * __ldg(ecv + 2 * (j * 3 + kk) + 1);
 #pragma unroll
         for (int l = 0; l < 3; l++) {
-          const double ar = tk ? ftr[l * 3 + kk] : fur[l * 3 + kk], ai = tk ? fti[l * 3 + kk] : fui[l * 3 + kk];
-          const double orr = tk ? fur[l * 3 + kk] : ftr[l * 3 + kk], oi = tk ? fui[l * 3 + kk] : fti[l * 3 + kk];
+          const double ar = tk ? ftr[l] : fur[l], ai = tk ? fti[l] : fui[l], orr = tk ? fur[l] : ftr[l], oi = tk ? fui[l] : fti[l];
           a.re[(l * 3 + kk) * NN + j] = fma(ar, w[j], a.re[(l * 3 + kk) * NN + j]); a.im[(l * 3 + kk) * NN + j] = fma(ai, w[j], a.im[(l * 3 + kk) * NN + j]);
           bacc[l] -= orr * cvr - oi * cvi; bacc[3 + l] -= orr * cvi + oi * cvr;
         }
       }
+    }
   }
 }
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-template <int ET>
-__global__ void __launch_bounds__(KB_WARPS * 32, 2) k_regular_bulk(DevGroup g, DevColloc c, DevSystem s, const unsigned char* __restrict__ plan) {
+const int KB_QCAP = 64;        // entries per deferred queue (at most 31 waiting + 32 new)
+const int KB_INPLACE_MIN = 10; // fewer lanes than this with the in-place set: defer them too
+const int KB_SMEM_QUEUE = MAX_SETS * KB_QCAP * 2;   // bytes per warp
+
+// Work of one warp: a stream of tasks (one collocation tile x one range of elements) fetched from a global counter.
+// Pairs whose plan asks for the lowest rule (set 0, ~90 % of all pairs) are integrated IN PLACE, lane = collocation point
+// of the tile, all lanes on the same element, and flushed by bulk reduce.  Pairs with any other rule are DEFERRED: pushed
+// to a per-set queue in shared memory and integrated 32 at a time, one (point, element) pair per lane, flushed with
+// per-lane RED, as soon as a queue holds a full warp: the lane occupancy of the high-order rules goes from ~25 % to
+// ~100 % (a tile sees several rules for the elements around the switch distances of the rule estimator).  Both kinds of
+// batch run through the same code (one copy of the point arithmetic: the instruction cache matters here).
+// GEN = false handles the elements with uniform kinds and zero prescribed values, GEN = true the others.
+template <int ET, bool GEN>
+__global__ void __launch_bounds__(KB_WARPS * 32, 2) k_regular_bulk(DevGroup g, DevColloc c, DevSystem s, const unsigned char* __restrict__ plan,
+                                                                  int erange, int n_ranges, int* __restrict__ task_counter) {
   constexpr int NN = ElemTraits<ET>::NN, NC = 3 * NN;
-  static_assert(2 * NC <= 32, "one bulk operation per lane");
   extern __shared__ __align__(128) double k1_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tile = blockIdx.x * KB_WARPS + warp;
-  if (tile >= c.n_tiles) return;
   double* buf = k1_smem + (size_t)warp * (2 * NC * 96);
-  const int cpos = tile * 32 + lane;
-  const int r0 = c.crow[cpos], r1 = c.crow[c.ldp + cpos], r2 = c.crow[2 * c.ldp + cpos];
-  const bool valid = r0 >= 0;
-  const double xc[3] = {c.cx[cpos], c.cx[c.ldp + cpos], c.cx[2 * c.ldp + cpos]};
-  const int row0 = c.tile_row0[tile], nbytes = c.tile_nbytes[tile];
-  double bacc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  unsigned short* queue = reinterpret_cast<unsigned short*>(k1_smem + (size_t)KB_WARPS * (2 * NC * 96)) + (size_t)warp * (MAX_SETS * KB_QCAP);
+  int* qcnt = reinterpret_cast<int*>(reinterpret_cast<unsigned short*>(k1_smem + (size_t)KB_WARPS * (2 * NC * 96)) + (size_t)KB_WARPS * (MAX_SETS * KB_QCAP)) + warp * MAX_SETS;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int n_tasks = c.n_tiles * n_ranges;
   bool pending = false;
-  const int e0 = blockIdx.y * KB_ECHUNK, e1 = min(e0 + KB_ECHUNK, g.n_elem);
-#pragma unroll 1
-  for (int e = e0; e < e1; e++) {
-    const unsigned char m = valid ? plan[(size_t)(g.slot0 + e) * c.ldp + cpos] : PLAN_NONE;
-    unsigned todo = __ballot_sync(0xffffffffu, m < MAX_SETS);
-    if (todo == 0u) continue;
-    const unsigned info = g.einfo[e];
-    const bool cvnz = g.ecvnz[e] != 0;
-    const double sgn = (info & 16u) ? -1.0 : 1.0;
-    const int* ecol = g.ecol + (size_t)e * NC;
-    const unsigned char* ekind = g.ekind + (size_t)e * NC;
-    const double* ecv = g.ecv + (size_t)e * 2 * NC;
-    AccA<NN> acc;
-#pragma unroll
-    for (int i = 0; i < 9 * NN; i++) { acc.re[i] = 0.0; acc.im[i] = 0.0; }
-    while (todo) {
-      const int leader = __ffs(todo) - 1;
-      const int sset = __shfl_sync(0xffffffffu, (int)m, leader);
-      const unsigned grp = __ballot_sync(0xffffffffu, (int)m == sset);
-      todo &= ~grp;
-      if ((int)m == sset) {
-        const int ngp = g.ngp[sset];
-        const double* P = g.pts[sset] + (size_t)e * ngp * (6 + NN);
-#pragma unroll 1
-        for (int kp = 0; kp < ngp; kp++) k1_point<NN>(acc, bacc, P + (size_t)kp * (6 + NN), xc, sgn, info, cvnz, ekind, ecv);
-      }
-    }
-    if (nbytes > 0) {
-      if (pending && lane < 2 * NC) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous flush has left the buffer
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < NN; j++)
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-#pragma unroll
-          for (int l = 0; l < 3; l++) {
-            buf[(2 * (j * 3 + k)) * 96 + 3 * lane + l] = acc.re[(l * 3 + k) * NN + j];
-            buf[(2 * (j * 3 + k) + 1) * 96 + 3 * lane + l] = acc.im[(l * 3 + k) * NN + j];
-          }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane < 2 * NC) {
-        const int col = __ldg(ecol + (lane >> 1));
-        double* dst = ((lane & 1) ? s.Aim : s.Are) + (size_t)col * s.lda + row0;
-        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(buf + lane * 96)), "r"(nbytes) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-      pending = true;
-    } else if (m < MAX_SETS) {
-#pragma unroll
-      for (int j = 0; j < NN; j++)
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          const int col = __ldg(ecol + j * 3 + k);
-          double* Ar = s.Are + (size_t)col * s.lda; double* Ai = s.Aim + (size_t)col * s.lda;
-          atomicAdd(Ar + r0, acc.re[(0 * 3 + k) * NN + j]); atomicAdd(Ai + r0, acc.im[(0 * 3 + k) * NN + j]);
-          atomicAdd(Ar + r1, acc.re[(1 * 3 + k) * NN + j]); atomicAdd(Ai + r1, acc.im[(1 * 3 + k) * NN + j]);
-          atomicAdd(Ar + r2, acc.re[(2 * 3 + k) * NN + j]); atomicAdd(Ai + r2, acc.im[(2 * 3 + k) * NN + j]);
+  for (;;) {
+    int task = 0;
+    if (lane == 0) task = atomicAdd(task_counter, 1);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= n_tasks) break;
+    const int range = task / c.n_tiles, tile = task - range * c.n_tiles;   // consecutive tasks: same elements, consecutive tiles
+    if (lane < MAX_SETS) qcnt[lane] = 0;
+    __syncwarp();
+    const int cpos = tile * 32 + lane;
+    const int r0 = c.crow[cpos];
+    const bool valid = r0 >= 0;
+    const double xc[3] = {c.cx[cpos], c.cx[c.ldp + cpos], c.cx[2 * c.ldp + cpos]};
+    const int row0 = c.tile_row0[tile], nbytes = c.tile_nbytes[tile];
+    double bacc_t[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const int e0 = range * erange, e1 = min(e0 + erange, g.n_elem);
+    const unsigned char* pl = plan + (size_t)g.slot0 * c.ldp + cpos;
+    int e = e0, ecur = 0, drain = 0;
+    unsigned char m = PLAN_NONE, m_next = (valid && e0 < e1) ? pl[(size_t)e0 * c.ldp] : PLAN_NONE;
+    unsigned fullsets = 0u;      // sets whose queue holds >= 32 entries
+    bool inplace_todo = false;
+    for (;;) {
+      // ---- select the next batch (all control flow here is warp-uniform) ----
+      int sset, el, src; bool act, inplace;
+      if (fullsets) {
+        sset = __ffs(fullsets) - 1;
+        int cnt = qcnt[sset];
+        const unsigned short ent = queue[sset * KB_QCAP + cnt - 32 + lane];
+        __syncwarp();
+        cnt -= 32;
+        if (lane == 0) qcnt[sset] = cnt;
+        __syncwarp();
+        if (cnt < 32) fullsets &= ~(1u << sset);
+        src = ent & 31; el = e0 + (ent >> 5); act = true; inplace = false;
+      } else if (inplace_todo) {
+        inplace_todo = false;
+        sset = 0; el = ecur; src = lane; act = (m == 0); inplace = true;
+      } else if (e < e1) {
+        m = m_next; ecur = e; e++;
+        m_next = (valid && e < e1) ? pl[(size_t)e * c.ldp] : PLAN_NONE;
+        const unsigned gen_e = GEN ? 1u : 0u;
+        const unsigned info_e = g.einfo[ecur];
+        const bool is_gen = !(info_e & 8u) || (g.ecvnz[ecur] != 0);
+        if (is_gen != (gen_e != 0u)) continue;
+        const unsigned reg = __ballot_sync(0xffffffffu, m < MAX_SETS);
+        if (reg == 0u) continue;
+        const unsigned in0 = __ballot_sync(0xffffffffu, m == 0);
+        inplace_todo = __popc(in0) >= KB_INPLACE_MIN;
+        if (inplace_todo && lane < 3) {   // pull the next element's first point set towards L1 while this one is integrated
+          const double* Pn = g.pts[0] + (size_t)(ecur + 1) * g.ngp[0] * (6 + NN);
+          if (ecur + 1 < e1) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(Pn) + 128 * lane));
         }
+        unsigned todo = inplace_todo ? (reg & ~in0) : reg;
+        while (todo) {
+          const int leader = __ffs(todo) - 1;
+          const int qs = __shfl_sync(0xffffffffu, (int)m, leader);
+          const unsigned grp = __ballot_sync(0xffffffffu, (int)m == qs) & todo;
+          todo &= ~grp;
+          const int base = qcnt[qs];
+          if ((grp >> lane) & 1u) queue[qs * KB_QCAP + base + __popc(grp & lt_mask)] = (unsigned short)(((ecur - e0) << 5) | lane);
+          __syncwarp();
+          const int cnt = base + __popc(grp);
+          if (lane == 0) qcnt[qs] = cnt;
+          if (cnt >= 32) fullsets |= 1u << qs;
+          __syncwarp();
+        }
+        continue;
+      } else if (drain < g.n_sets) {
+        sset = drain++;
+        const int cnt = qcnt[sset];
+        if (cnt == 0) continue;
+        act = lane < cnt;
+        const unsigned short ent = act ? queue[sset * KB_QCAP + lane] : (unsigned short)0;
+        src = ent & 31; el = e0 + (ent >> 5); inplace = false;
+      } else break;
+
+      // ---- integrate the batch: one pair per lane ----
+      const double xs[3] = {__shfl_sync(0xffffffffu, xc[0], src), __shfl_sync(0xffffffffu, xc[1], src), __shfl_sync(0xffffffffu, xc[2], src)};
+      const int rs = __shfl_sync(0xffffffffu, r0, src);
+      const int* ecol = g.ecol + (size_t)el * NC;
+      int mycol = 0;
+      if (inplace && lane < NC) mycol = __ldg(ecol + lane);   // columns of the element, needed by the flush only
+      AccA<NN> acc;
+#pragma unroll
+      for (int i = 0; i < 9 * NN; i++) { acc.re[i] = 0.0; acc.im[i] = 0.0; }
+      double bacc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      if (act) {
+        const unsigned info = g.einfo[el];
+        const double sgn = (info & 16u) ? -1.0 : 1.0;
+        const int ngp = g.ngp[sset];
+        const double* P = g.pts[sset] + (size_t)el * ngp * (6 + NN);
+        const unsigned char* ekind = g.ekind + (size_t)el * NC;
+        const double* ecv = g.ecv + (size_t)el * 2 * NC;
+#pragma unroll 1
+        for (int kp = 0; kp < ngp; kp++) k1_point<NN, GEN>(acc, bacc, P + (size_t)kp * (6 + NN), xs, sgn, info, ekind, ecv);
+      }
+      // ---- flush ----
+      if (inplace && nbytes > 0) {
+        if (pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous flush has left the buffer
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < NN; j++)
+#pragma unroll
+          for (int k = 0; k < 3; k++)
+#pragma unroll
+            for (int l = 0; l < 3; l++) {
+              buf[(2 * (j * 3 + k)) * 96 + 3 * lane + l] = acc.re[(l * 3 + k) * NN + j];
+              buf[(2 * (j * 3 + k) + 1) * 96 + 3 * lane + l] = acc.im[(l * 3 + k) * NN + j];
+            }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < NC; q++) {
+          const int col = __shfl_sync(0xffffffffu, mycol, q);
+          if (lane == 0) {
+            double* dre = s.Are + (size_t)col * s.lda + row0;
+            double* dim_ = s.Aim + (size_t)col * s.lda + row0;
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dre), "r"(smem_u32(buf + (2 * q) * 96)), "r"(nbytes) : "memory");
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dim_), "r"(smem_u32(buf + (2 * q + 1) * 96)), "r"(nbytes) : "memory");
+          }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        pending = true;
+        if (GEN) {
+#pragma unroll
+          for (int i = 0; i < 6; i++) bacc_t[i] += bacc[i];
+        }
+      } else if (act) {
+#pragma unroll
+        for (int j = 0; j < NN; j++)
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            const int col = __ldg(ecol + j * 3 + k);
+            double* Ar = s.Are + (size_t)col * s.lda + rs; double* Ai = s.Aim + (size_t)col * s.lda + rs;
+#pragma unroll
+            for (int l = 0; l < 3; l++) { atomicAdd(Ar + l, acc.re[(l * 3 + k) * NN + j]); atomicAdd(Ai + l, acc.im[(l * 3 + k) * NN + j]); }
+          }
+        if (GEN) {
+#pragma unroll
+          for (int l = 0; l < 3; l++)
+            if (bacc[l] != 0.0 || bacc[3 + l] != 0.0) { atomicAdd(s.bre + rs + l, bacc[l]); atomicAdd(s.bim + rs + l, bacc[3 + l]); }
+        }
+      }
+    }
+    if (GEN && valid) {
+#pragma unroll
+      for (int l = 0; l < 3; l++)
+        if (bacc_t[l] != 0.0 || bacc_t[3 + l] != 0.0) { atomicAdd(s.bre + r0 + l, bacc_t[l]); atomicAdd(s.bim + r0 + l, bacc_t[3 + l]); }
     }
   }
-  if (pending && lane < 2 * NC) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  if (valid) {
-    if (bacc[0] != 0.0 || bacc[3] != 0.0) { atomicAdd(s.bre + r0, bacc[0]); atomicAdd(s.bim + r0, bacc[3]); }
-    if (bacc[1] != 0.0 || bacc[4] != 0.0) { atomicAdd(s.bre + r1, bacc[1]); atomicAdd(s.bim + r1, bacc[4]); }
-    if (bacc[2] != 0.0 || bacc[5] != 0.0) { atomicAdd(s.bre + r2, bacc[2]); atomicAdd(s.bim + r2, bacc[5]); }
-  }
+  if (pending && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+static int* g_task_counters = nullptr;   // two counters per launch slot, zeroed before each launch
 template <int ET>
 static void launch_regular_bulk(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, cudaStream_t st) {
   constexpr int NC = 3 * ElemTraits<ET>::NN;
-  const int smem = KB_WARPS * 2 * NC * 96 * (int)sizeof(double);
+  const int smem = KB_WARPS * (2 * NC * 96 * (int)sizeof(double) + KB_SMEM_QUEUE + MAX_SETS * (int)sizeof(int));
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_regular_bulk<ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-  dim3 grid((c.n_tiles + KB_WARPS - 1) / KB_WARPS, (g.n_elem + KB_ECHUNK - 1) / KB_ECHUNK);
-  k_regular_bulk<ET><<<grid, KB_WARPS * 32, smem, st>>>(g, c, s, plan);
+  if (!attr) {
+    cudaFuncSetAttribute(k_regular_bulk<ET, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_regular_bulk<ET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  if (!g_task_counters) cudaMalloc((void**)&g_task_counters, 2 * sizeof(int));
+  cudaMemsetAsync(g_task_counters, 0, 2 * sizeof(int), st);
+  // element ranges: long enough for the deferred queues to fill, short enough for the dynamic schedule to balance
+  // (<= 2048 elements: queue entries carry an 11-bit element offset)
+  int erange = 512;
+  const int n_ranges = (g.n_elem + erange - 1) / erange;
+  int dev = 0, n_sm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const int n_tasks = c.n_tiles * n_ranges;
+  int ctas = 2 * n_sm; if (ctas * KB_WARPS > n_tasks) ctas = (n_tasks + KB_WARPS - 1) / KB_WARPS;
+  k_regular_bulk<ET, false><<<ctas, KB_WARPS * 32, smem, st>>>(g, c, s, plan, erange, n_ranges, g_task_counters);
+  k_regular_bulk<ET, true><<<ctas, KB_WARPS * 32, smem, st>>>(g, c, s, plan, erange, n_ranges, g_task_counters + 1);
 }
 
 void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, cudaStream_t st) {

@@ -8,6 +8,7 @@
 // taken on the host (plan_host.cpp) or by threshold comparison (classify kernel).
 #pragma once
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define MFB_HD __host__ __device__ __forceinline__
@@ -37,38 +38,121 @@ struct KParams {
 // E_2..E_5 of z (returned already divided: e2 = E2/r, e3 = E3/r^2, e4 = E4/r^3, e5 = E5/r^4)
 struct EnR { cplx e2, e3, e4, e5; };
 
+// ---- branch-free exp / sincos for the kernel arguments ---------------------------------------------------------------
+// z = -i k r has Re z = Im(k) r <= 0 (damped medium) and |Im z| = Re(k) r bounded by (wavenumber x model size), far inside
+// the range where a three-constant Cody-Waite reduction is exact.  No slow path, no special cases: straight-line code
+// that the scheduler can interleave for z1 and z2 (the library routines cost a call and several branches each).
+MFB_HD double mfb_round_magic(double x, int& q) {   // nearest integer of |x| < 2^31 and its int value
+  const double MAGIC = 6755399441055744.0;         // 1.5 * 2^52
+  double t = x + MAGIC;
+#if defined(__CUDA_ARCH__)
+  q = __double2loint(t);
+#else
+  long long bits; memcpy(&bits, &t, 8); q = (int)(bits & 0xffffffffll);
+#endif
+  return t - MAGIC;
+}
+MFB_HD double mfb_exp(double a) {   // e^a, a in [-700, 700]; Taylor degree 13 on |f| <= ln2/2 (remainder 4e-18)
+  a = fmax(a, -700.0);
+  int n; const double nd = mfb_round_magic(a * 1.4426950408889634074, n);
+  double f = fma(nd, -6.93147180369123816490e-01, a);
+  f = fma(nd, -1.90821492927058770002e-10, f);
+  double p = 1.0 / 6227020800.0;
+  p = fma(p, f, 1.0 / 479001600.0); p = fma(p, f, 1.0 / 39916800.0); p = fma(p, f, 1.0 / 3628800.0); p = fma(p, f, 1.0 / 362880.0);
+  p = fma(p, f, 1.0 / 40320.0); p = fma(p, f, 1.0 / 5040.0); p = fma(p, f, 1.0 / 720.0); p = fma(p, f, 1.0 / 120.0);
+  p = fma(p, f, 1.0 / 24.0); p = fma(p, f, 1.0 / 6.0); p = fma(p, f, 0.5); p = fma(p, f, 1.0); p = fma(p, f, 1.0);
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+#else
+  return ldexp(p, n);
+#endif
+}
+MFB_HD void mfb_sincos(double b, double& sn, double& cs) {   // |b| < 1e5; kernels of fdlibm's __kernel_sin/__kernel_cos on |t| <= pi/4
+  int q; const double nd = mfb_round_magic(b * 6.36619772367581382433e-01, q);
+  double t = fma(nd, -1.57079632673412561417e+00, b);
+  t = fma(nd, -6.07710050650619224932e-11, t);
+  t = fma(nd, -2.02226624879595063154e-21, t);
+  const double z = t * t;
+  double ps = 1.58969099521155010221e-10;
+  ps = fma(ps, z, -2.50507602534068634195e-08); ps = fma(ps, z, 2.75573137070700676789e-06); ps = fma(ps, z, -1.98412698298579493134e-04);
+  ps = fma(ps, z, 8.33333333332248946124e-03); ps = fma(ps, z, -1.66666666666666324348e-01);
+  const double s = fma(t * z, ps, t);
+  double pc = -1.13596475577881948265e-11;
+  pc = fma(pc, z, 2.08757232129817482790e-09); pc = fma(pc, z, -2.75573143513906633035e-07); pc = fma(pc, z, 2.48015872894767294178e-05);
+  pc = fma(pc, z, -1.38888888888741095749e-03); pc = fma(pc, z, 4.16666666666666019037e-02);
+  const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
+  const double a0 = (q & 1) ? c : s, a1 = (q & 1) ? s : c;
+  sn = (q & 2) ? -a0 : a0;
+  cs = ((q + 1) & 2) ? -a1 : a1;
+}
+
 // 1/(m+5)!, m = 0..16: E5(z) = z^5 * sum_m z^m/(m+5)!  (|z| <= 1: the first neglected term is 1/22! = 9e-22)
 #define MFB_E5_COEFFS {1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0, 1.0 / 40320.0, 1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0, \
     1.0 / 479001600.0, 1.0 / 6227020800.0, 1.0 / 87178291200.0, 1.0 / 1307674368000.0, 1.0 / 20922789888000.0, \
     1.0 / 355687428096000.0, 1.0 / 6402373705728000.0, 1.0 / 121645100408832000.0, 1.0 / 2432902008176640000.0, \
     1.0 / 51090942171709440000.0}
 
-MFB_HD void zexp_E2_5(cplx z, cplx& E2, cplx& E3, cplx& E4, cplx& E5) {
-  const double a2 = z.re * z.re + z.im * z.im;
+#if defined(__CUDACC__)
+static __device__ __constant__ double c_e5_coeffs[17] = MFB_E5_COEFFS;
+#endif
+MFB_HD double mfb_e5_coeff(int m) {
+#if defined(__CUDA_ARCH__)
+  return c_e5_coeffs[m];
+#else
+  const double c[17] = MFB_E5_COEFFS; return c[m];
+#endif
+}
+MFB_HD void zexp_series(cplx z, cplx& E2, cplx& E3, cplx& E4, cplx& E5) {   // |z| <= 1
   const cplx z2 = z * z, z3 = z2 * z, z4 = z2 * z2;
-  if (a2 <= 1.0) {
-    const double c[17] = MFB_E5_COEFFS;
-    // Horner in z with real coefficients: 4 FMA-class operations per term
-    double sr = c[16], si = 0.0;
-#pragma unroll
-    for (int m = 15; m >= 0; m--) {
-      const double tr = fma(sr, z.re, fma(-si, z.im, c[m]));
-      si = fma(sr, z.im, si * z.re);
-      sr = tr;
-    }
-    E5 = (z4 * z) * mk(sr, si);
-    E4 = cfmar(z4, 1.0 / 24.0, E5);
-    E3 = cfmar(z3, 1.0 / 6.0, E4);
-    E2 = cfmar(z2, 0.5, E3);
-  } else {
-    double ex = exp(z.re), sn, cs;
-    sincos(z.im, &sn, &cs);
-    cplx E1 = mk(ex * cs - 1.0, ex * sn);
-    E2 = E1 - z;
-    E3 = cfmar(z2, -0.5, E2);
-    E4 = cfmar(z3, -1.0 / 6.0, E3);
-    E5 = cfmar(z4, -1.0 / 24.0, E4);
+  // Horner in z with real coefficients: 4 FMA-class operations per term (rolled: the series branch is the rare one)
+  double sr = mfb_e5_coeff(16), si = 0.0;
+#pragma unroll 1
+  for (int m = 15; m >= 0; m--) {
+    const double tr = fma(sr, z.re, fma(-si, z.im, mfb_e5_coeff(m)));
+    si = fma(sr, z.im, si * z.re);
+    sr = tr;
   }
+  E5 = (z4 * z) * mk(sr, si);
+  E4 = cfmar(z4, 1.0 / 24.0, E5);
+  E3 = cfmar(z3, 1.0 / 6.0, E4);
+  E2 = cfmar(z2, 0.5, E3);
+}
+// two arguments in one rolled loop (two independent chains)
+MFB_HD void zexp_series2(cplx za, cplx zb, cplx& A2, cplx& A3, cplx& A4, cplx& A5, cplx& B2, cplx& B3, cplx& B4, cplx& B5) {
+  double ar = mfb_e5_coeff(16), ai = 0.0, br = ar, bi = 0.0;
+#pragma unroll 1
+  for (int m = 15; m >= 0; m--) {
+    const double cm = mfb_e5_coeff(m);
+    const double tr = fma(ar, za.re, fma(-ai, za.im, cm)), ur = fma(br, zb.re, fma(-bi, zb.im, cm));
+    ai = fma(ar, za.im, ai * za.re); bi = fma(br, zb.im, bi * zb.re);
+    ar = tr; br = ur;
+  }
+  { const cplx z2 = za * za, z3 = z2 * za, z4 = z2 * z2;
+    A5 = (z4 * za) * mk(ar, ai); A4 = cfmar(z4, 1.0 / 24.0, A5); A3 = cfmar(z3, 1.0 / 6.0, A4); A2 = cfmar(z2, 0.5, A3); }
+  { const cplx z2 = zb * zb, z3 = z2 * zb, z4 = z2 * z2;
+    B5 = (z4 * zb) * mk(br, bi); B4 = cfmar(z4, 1.0 / 24.0, B5); B3 = cfmar(z3, 1.0 / 6.0, B4); B2 = cfmar(z2, 0.5, B3); }
+}
+MFB_HD void zexp_direct(cplx z, cplx& E2, cplx& E3, cplx& E4, cplx& E5) {   // |z| > 1
+  const cplx z2 = z * z, z3 = z2 * z, z4 = z2 * z2;
+  double ex = mfb_exp(z.re), sn, cs;
+  mfb_sincos(z.im, sn, cs);
+  cplx E1 = mk(fma(ex, cs, -1.0), ex * sn);
+  E2 = E1 - z;
+  E3 = cfmar(z2, -0.5, E2);
+  E4 = cfmar(z3, -1.0 / 6.0, E3);
+  E5 = cfmar(z4, -1.0 / 24.0, E4);
+}
+MFB_HD void zexp_E2_5(cplx z, cplx& E2, cplx& E3, cplx& E4, cplx& E5) {
+  if (z.re * z.re + z.im * z.im <= 1.0) zexp_series(z, E2, E3, E4, E5); else zexp_direct(z, E2, E3, E4, E5);
+}
+// both arguments at once: the common cases (both direct / both series) are straight-line code for the two arguments
+// together, which the scheduler interleaves (the polynomial chains of one hide the latency of the other)
+MFB_HD void zexp_pair(cplx z1, cplx z2, cplx& A2, cplx& A3, cplx& A4, cplx& A5, cplx& B2, cplx& B3, cplx& B4, cplx& B5) {
+  const bool s1 = z1.re * z1.re + z1.im * z1.im <= 1.0, s2 = z2.re * z2.re + z2.im * z2.im <= 1.0;
+  // |z1| <= |z2| on this path (k1 is the P wavenumber), but nothing here relies on it
+  if (!s1 && !s2) { zexp_direct(z1, A2, A3, A4, A5); zexp_direct(z2, B2, B3, B4, B5); }
+  else if (s1 && s2) zexp_series2(z1, z2, A2, A3, A4, A5, B2, B3, B4, B5);
+  else { zexp_E2_5(z1, A2, A3, A4, A5); zexp_E2_5(z2, B2, B3, B4, B5); }
 }
 
 struct KScal { cplx psi, chi, T1, T2, T3; double d1r1, d1r2; };
@@ -114,8 +198,7 @@ MFB_HD void kernel_scalars_scaled(const KParams& p, double r, double d1r1, KScal
   const double d1r2 = d1r1 * d1r1, d1r3 = d1r2 * d1r1, d1r4 = d1r2 * d1r2;
   const cplx z1 = mk(p.k1.im * r, -p.k1.re * r), z2 = mk(p.k2.im * r, -p.k2.re * r);
   cplx A2, A3, A4, A5, B2, B3, B4, B5;
-  zexp_E2_5(z1, A2, A3, A4, A5);
-  zexp_E2_5(z2, B2, B3, B4, B5);
+  zexp_pair(z1, z2, A2, A3, A4, A5, B2, B3, B4, B5);
   const cplx E21 = A2 * d1r1, E22 = B2 * d1r1, E31 = A3 * d1r2, E32 = B3 * d1r2;
   const cplx E41 = A4 * d1r3, E42 = B4 * d1r3, E51 = A5 * d1r4, E52 = B5 * d1r4;
   cplx t;
