@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
     objs.append(o)
     for src in SOURCES_CU:
         o = os.path.join(bdir, src.replace(".cu", ".o"))
-        cmd = [NVCC, "-ccbin", GXX, "-O3", "-std=c++17", "-lineinfo"] + ARCH + [
+        cmd = [NVCC, "-ccbin", GXX, "-O3", "-std=c++17", "-lineinfo"] + os.environ.get("MFB_NVCC_FLAGS", "").split() + ARCH + [
             "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off,-fcx-fortran-rules",
             "-Xptxas", "-v" if verbose else "-O3", "-c", os.path.join(CSRC, src), "-o", o]
         if verbose:

@@ -35,7 +35,7 @@ def lib():
     """Load libmfb.so (built in-tree by multifebe_b200.build).  Raises if absent -- never falls back to another path."""
     global _LIB
     if _LIB is None:
-        so = os.path.join(_HERE, "libmfb.so")
+        so = os.environ.get("MFB_LIB") or os.path.join(_HERE, "libmfb.so")   # MFB_LIB: development builds (kernel variants)
         if not os.path.exists(so):
             raise ImportError("multifebe_b200/libmfb.so is not built; run `python -m multifebe_b200.build` "
                               "(there is no CPU fallback for this path)")

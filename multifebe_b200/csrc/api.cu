@@ -59,7 +59,8 @@ struct mfb_problem {
   cudaEvent_t ev[8];
   std::vector<int> set_gln;
   std::vector<int> rowperm, colperm;   // host row / column -> internal row / column of the device-resident assembled system
-  int *d_rowperm, *d_colperm; bool rows_permuted;   // rows_permuted: the resident matrix/factors are in the internal order
+  int *d_rowperm, *d_colperm; bool rows_permuted;
+  alignas(64) unsigned char tmapA[128]; bool have_tmap;   // CUtensorMap of the planar system matrix (K1 flush)   // rows_permuted: the resident matrix/factors are in the internal order
 };
 
 extern "C" const char* mfb_last_error(void) { return g_err.c_str(); }
@@ -184,11 +185,19 @@ extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x
   const int types[5] = {MFB_TRI3, MFB_TRI6, MFB_QUAD4, MFB_QUAD8, MFB_QUAD9};
   for (int t = 0; t < 5; t++) {
     GroupHost g; g.et = types[t]; g.nn = mfbh::nodes_of(g.et); g.slot0 = (int)p->elem_of_slot.size();
-    std::vector<std::pair<unsigned, int>> keyed;
+    std::vector<std::pair<unsigned long long, int>> keyed;
     for (int e = 0; e < n_elem; e++) if (etype[e] == g.et) {
       double ctr[3] = {0, 0, 0};
       for (int k = 0; k < g.nn; k++) for (int c = 0; c < 3; c++) ctr[c] += p->elems[e].x[3 * k + c] / g.nn;
-      keyed.push_back(std::make_pair(morton3(ctr, bb_lo, bb_inv), e));
+      // boundary-condition signature first (elements of one K1 class end up in the same ranges), then space
+      unsigned sig = 0;
+      for (int k = 0; k < 3; k++) {
+        const int ct0 = ctype[3 * elem_node[elem_ptr[e]] + k];
+        bool uni = true;
+        for (int j = 1; j < g.nn; j++) if (ctype[3 * elem_node[elem_ptr[e] + j] + k] != ct0) uni = false;
+        sig = sig * 3 + (uni ? (unsigned)ct0 : 2u);
+      }
+      keyed.push_back(std::make_pair((unsigned long long)sig << 32 | morton3(ctr, bb_lo, bb_inv), e));
     }
     std::stable_sort(keyed.begin(), keyed.end());
     for (auto& ke : keyed) { p->slot_of_elem[ke.second] = (int)p->elem_of_slot.size(); p->elem_of_slot.push_back(ke.second); g.elem_ids.push_back(ke.second); }
@@ -332,8 +341,32 @@ extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x
     UP(g.owned, h_xn, &d_xn); UP(g.owned, h_ball, &d_ball); UP(g.owned, h_enode, &d_enode); UP(g.owned, h_glnfar, &d_glnfar); UP(g.owned, h_rev, &d_rev);
     UP(g.owned, h_info, &d_info);
     CK(cudaMalloc((void**)&d_cvnz, (size_t)g.n_elem)); g.owned.push_back(d_cvnz);
+    {
+      // K1 element ranges: K1_ERANGE elements for the first 4/5 of the group, a quarter of that for the rest (the dynamic
+      // schedule hands out the short tasks last, which trims the tail of the kernel)
+      std::vector<int> rs(1, 0), rof(g.n_elem);
+      const int tail_from = g.n_elem - g.n_elem / 5;
+      for (int e = 0; e < g.n_elem;) {
+        int len = (e < tail_from) ? K1_ERANGE : K1_ERANGE / 4;
+        if (e < tail_from && e + len > tail_from) len = tail_from - e;
+        const int e1 = std::min(g.n_elem, e + len);
+        for (int q = e; q < e1; q++) rof[q] = (int)rs.size() - 1;
+        rs.push_back(e1); e = e1;
+      }
+      int *d_rs, *d_rof, *d_rm;
+      UP(g.owned, rs, &d_rs); UP(g.owned, rof, &d_rof);
+      D.n_ranges = (int)rs.size() - 1; D.range_start = d_rs; D.range_of = d_rof;
+      CK(cudaMalloc((void**)&d_rm, sizeof(int) * D.n_ranges)); g.owned.push_back(d_rm); D.range_modes = d_rm;
+    }
     D.xn = d_xn; D.ball = d_ball; D.enode = d_enode; D.gln_far = d_glnfar; D.erev = d_rev; D.einfo = d_info; D.ecvnz = d_cvnz;
     D.ecol = d_ecol + slot_off[g.slot0]; D.ekind = d_ekind + slot_off[g.slot0]; D.ecv = d_ecv + 2 * (size_t)slot_off[g.slot0];
+    D.has_mixed = 0;
+    for (int i = 0; i < g.n_elem; i++) if (!(h_info[i] & 8u)) D.has_mixed = 1;
+    D.cols3 = 1;
+    for (int i = 0; i < g.n_elem && D.cols3; i++) {
+      const int so = slot_off[g.slot0 + i];
+      for (int j = 0; j < g.nn; j++) for (int k = 1; k < 3; k++) if (h_ecol[so + j * 3 + k] != h_ecol[so + j * 3] + k) D.cols3 = 0;
+    }
     D.n_sets = n_precalsets;
     for (int s = 0; s < n_precalsets; s++) {
       int gln = precalset_gln[s];
@@ -476,6 +509,8 @@ extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x
   double* dA; CK(cudaMalloc((void**)&dA, (size_t)2 * p->lda * n_dof * sizeof(double))); p->owned.push_back(dA);
   double* db; CK(cudaMalloc((void**)&db, (size_t)2 * p->lda * sizeof(double))); p->owned.push_back(db);
   p->sys.Are = dA; p->sys.Aim = dA + (size_t)p->lda * n_dof; p->sys.lda = p->lda; p->sys.n_dof = n_dof; p->sys.bre = db; p->sys.bim = db + p->lda;
+  p->have_tmap = make_matrix_tensor_map(p->tmapA, p->sys.Are, p->lda, n_dof) == 0;
+  if (!p->have_tmap) { mfb_problem_free(p); return fail(MFB_ERR_CUDA, "mfb_harela3d_setup: cuTensorMapEncodeTiled failed (driver too old for sm_100a TMA?)"); }
   CK(cudaMalloc((void**)&p->d_cvalue, (size_t)6 * n_node * sizeof(double))); p->owned.push_back(p->d_cvalue);
   CK(cudaMalloc((void**)&p->d_ipiv, (size_t)n_dof * sizeof(int))); p->owned.push_back(p->d_ipiv);
   CK(cudaMalloc((void**)&p->d_perm, (size_t)n_dof * sizeof(int))); p->owned.push_back(p->d_perm);
@@ -551,7 +586,7 @@ static int assemble_device(mfb_problem* p, double omega, cd lambda, cd mu, doubl
   CK(cudaMemsetAsync(p->sys.Are, 0, (size_t)2 * p->lda * p->n_dof * sizeof(double), st));
   CK(cudaMemsetAsync(p->sys.bre, 0, (size_t)2 * p->lda * sizeof(double), st));
   CK(cudaEventRecord(p->ev[1], st));
-  for (auto& g : p->groups) launch_regular(g.dev, p->colloc, p->sys, p->plan, st);
+  for (auto& g : p->groups) launch_regular(g.dev, p->colloc, p->sys, p->plan, p->have_tmap ? p->tmapA : nullptr, st);
   CK(cudaEventRecord(p->ev[2], st));
   for (auto& g : p->groups) launch_adaptive(g.dev, p->colloc, p->sys, g.adp, p->ctx->tables, st);
   CK(cudaEventRecord(p->ev[3], st));

@@ -15,6 +15,7 @@
 // node/column and MCA points share rows, so plain stores are not possible).  The right-hand side contribution of each
 // lane is reduced in registers over the whole element chunk and flushed once.
 #include "assembly.cuh"
+#include <cuda.h>
 #include <cstdio>
 
 namespace mfbd {
@@ -103,9 +104,14 @@ __global__ void k_gather_cv(DevGroup g, const double* __restrict__ cvalue) {
     }
   }
   g.ecvnz[e] = nz ? 1 : 0;
+  const int mode = !(g.einfo[e] & 8u) ? 2 : (nz ? 1 : 0);
+  atomicOr(g.range_modes + g.range_of[e], 1 << mode);
 }
 void launch_gather_cv(const DevGroup& g, const double* cvalue, cudaStream_t st) {
-  if (g.n_elem > 0) k_gather_cv<<<(g.n_elem + 127) / 128, 128, 0, st>>>(g, cvalue);
+  if (g.n_elem > 0) {
+    cudaMemsetAsync(g.range_modes, 0, sizeof(int) * g.n_ranges, st);
+    k_gather_cv<<<(g.n_elem + 127) / 128, 128, 0, st>>>(g, cvalue);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -219,39 +225,55 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_regular(DevGroup g, DevColloc
 //     entry, 5x the arithmetic of a far pair; profiles/r01_microbench_red.md).
 // ------------------------------------------------------------------------------------------------------------------
 const int KB_WARPS = 4;
-const int KB_ECHUNK = 32;
+#ifndef MFB_KB_WARPS_FAST
+#define MFB_KB_WARPS_FAST 4
+#endif
+const int KB_WARPS_FAST = MFB_KB_WARPS_FAST;   // warps per CTA of the MODE 0 kernel (2 CTAs per SM)
 
 template <int NN>
 struct AccA { double re[9 * NN], im[9 * NN]; };   // [(l*3+k)*NN + j]: entry of load direction l (row) and dof k of node j (column)
 
-// One Gauss point of one pair.  GEN = false: element whose boundary-condition kinds are the same for all its nodes and
-// whose prescribed values are all zero (the common case): only the combination that goes to the matrix is formed.
-// GEN = true: any element: both combinations, per (node, dof) one goes to A and the other, times the prescribed value, to b.
-template <int NN, bool GEN>
-__device__ __forceinline__ void k1_point(AccA<NN>& a, double* bacc, const double* __restrict__ q, const double* xc, double sgn, unsigned info,
+// One Gauss point of one pair; rec = (x[3], n[3], w[NN]) of the point.
+// MODE 0: element whose boundary-condition kinds are the same for all its nodes and whose prescribed values are all zero
+//         (the common case): only the combination that goes to the matrix is formed.
+// MODE 1: uniform kinds, some prescribed value nonzero: the other combination times S_k = sum_j w_j cv_jk goes to b.
+// MODE 2: any element: both combinations, per (node, dof) one goes to A and the other, times the prescribed value, to b.
+template <int NN, int MODE>
+__device__ __forceinline__ void k1_point(AccA<NN>& a, double* bacc, const double* rec, const double* xc, double sgn, unsigned info,
                                          const unsigned char* __restrict__ ekind, const double* __restrict__ ecv) {
-  const double x0 = __ldg(q), x1 = __ldg(q + 1), x2 = __ldg(q + 2);
-  const double n[3] = {sgn * __ldg(q + 3), sgn * __ldg(q + 4), sgn * __ldg(q + 5)};
-  double w[NN];
-#pragma unroll
-  for (int j = 0; j < NN; j++) w[j] = __ldg(q + 6 + j);
-  const double rv0 = x0 - xc[0], rv1 = x1 - xc[1], rv2 = x2 - xc[2];
+  const double n[3] = {sgn * rec[3], sgn * rec[4], sgn * rec[5]};
+  const double* w = rec + 6;
+  const double rv0 = rec[0] - xc[0], rv1 = rec[1] - xc[1], rv2 = rec[2] - xc[2];
   const double r2 = fma(rv0, rv0, fma(rv1, rv1, rv2 * rv2));
   const double d1r1 = rsqrt(r2), r = r2 * d1r1;
-  KScal k; kernel_scalars_scaled(c_kq, r, d1r1, k);
+  // S_k = sum_j w_j * prescribed value of (node j, dof k): requested first, used last
+  double sk[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (MODE == 1) {
+#pragma unroll
+    for (int kk = 0; kk < 3; kk++)
+#pragma unroll
+      for (int j = 0; j < NN; j++) { sk[kk] = fma(w[j], __ldg(ecv + 2 * (j * 3 + kk)), sk[kk]); sk[3 + kk] = fma(w[j], __ldg(ecv + 2 * (j * 3 + kk) + 1), sk[3 + kk]); }
+  }
+  KScal k; kernel_scalars_scaled(c_kq, r, d1r1, k, MODE != 0 || (info & 7u) != 7u, MODE != 0 || (info & 7u) != 0u);
   const double dx[3] = {rv0 * d1r1, rv1 * d1r1, rv2 * d1r1};
   const double drdn = fma(dx[0], n[0], fma(dx[1], n[1], dx[2] * n[2]));
   const cplx t1d = k.T1 * drdn;
-  if (!GEN) {
+  if (MODE < 2) {
 #pragma unroll
     for (int kk = 0; kk < 3; kk++) {
-      if ((info >> kk) & 1u) {
+      const bool tk = (info >> kk) & 1u;
+      const double skr = sk[kk], ski = sk[3 + kk];
+      if (tk) {
 #pragma unroll
         for (int l = 0; l < 3; l++) {
           const double dd = dx[l] * dx[kk], c2 = (l == kk) ? fma(dx[kk], n[l], drdn) : dx[kk] * n[l], c3 = dx[l] * n[kk];
           const double fr = fma(t1d.re, dd, fma(k.T2.re, c2, k.T3.re * c3)), fi = fma(t1d.im, dd, fma(k.T2.im, c2, k.T3.im * c3));
 #pragma unroll
           for (int j = 0; j < NN; j++) { a.re[(l * 3 + kk) * NN + j] = fma(fr, w[j], a.re[(l * 3 + kk) * NN + j]); a.im[(l * 3 + kk) * NN + j] = fma(fi, w[j], a.im[(l * 3 + kk) * NN + j]); }
+          if (MODE == 1) {
+            const double orr = (l == kk) ? fma(-k.chi.re, dd, k.psi.re) : -k.chi.re * dd, oi = (l == kk) ? fma(-k.chi.im, dd, k.psi.im) : -k.chi.im * dd;
+            bacc[l] -= orr * skr - oi * ski; bacc[3 + l] -= orr * ski + oi * skr;
+          }
         }
       } else {
 #pragma unroll
@@ -260,6 +282,11 @@ __device__ __forceinline__ void k1_point(AccA<NN>& a, double* bacc, const double
           const double fr = (l == kk) ? fma(-k.chi.re, dd, k.psi.re) : -k.chi.re * dd, fi = (l == kk) ? fma(-k.chi.im, dd, k.psi.im) : -k.chi.im * dd;
 #pragma unroll
           for (int j = 0; j < NN; j++) { a.re[(l * 3 + kk) * NN + j] = fma(fr, w[j], a.re[(l * 3 + kk) * NN + j]); a.im[(l * 3 + kk) * NN + j] = fma(fi, w[j], a.im[(l * 3 + kk) * NN + j]); }
+          if (MODE == 1) {
+            const double c2 = (l == kk) ? fma(dx[kk], n[l], drdn) : dx[kk] * n[l], c3 = dx[l] * n[kk];
+            const double orr = fma(t1d.re, dd, fma(k.T2.re, c2, k.T3.re * c3)), oi = fma(t1d.im, dd, fma(k.T2.im, c2, k.T3.im * c3));
+            bacc[l] -= orr * skr - oi * ski; bacc[3 + l] -= orr * ski + oi * skr;
+          }
         }
       }
     }
@@ -289,6 +316,8 @@ __device__ __forceinline__ void k1_point(AccA<NN>& a, double* bacc, const double
 }
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// volatile so that the request for point kp+1 stays ahead of the arithmetic of point kp (the compiler otherwise sinks it)
+__device__ __forceinline__ double ldg_ahead(const double* p) { double v; asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
 
 const int KB_QCAP = 64;        // entries per deferred queue (at most 31 waiting + 32 new)
 const int KB_INPLACE_MIN = 10; // fewer lanes than this with the in-place set: defer them too
@@ -301,18 +330,20 @@ const int KB_SMEM_QUEUE = MAX_SETS * KB_QCAP * 2;   // bytes per warp
 // per-lane RED, as soon as a queue holds a full warp: the lane occupancy of the high-order rules goes from ~25 % to
 // ~100 % (a tile sees several rules for the elements around the switch distances of the rule estimator).  Both kinds of
 // batch run through the same code (one copy of the point arithmetic: the instruction cache matters here).
-// GEN = false handles the elements with uniform kinds and zero prescribed values, GEN = true the others.
-template <int ET, bool GEN>
-__global__ void __launch_bounds__(KB_WARPS * 32, 2) k_regular_bulk(DevGroup g, DevColloc c, DevSystem s, const unsigned char* __restrict__ plan,
-                                                                  int erange, int n_ranges, int* __restrict__ task_counter) {
+// One instantiation per element class (MODE 0/1/2 of k1_point); an element is visited by the kernel of its class only.
+template <int ET, int MODE, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_constant__ CUtensorMap tmap, DevGroup g, DevColloc c, DevSystem s,
+                                                                  const unsigned char* __restrict__ plan,
+                                                                  int* __restrict__ task_counter) {
   constexpr int NN = ElemTraits<ET>::NN, NC = 3 * NN;
   extern __shared__ __align__(128) double k1_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr bool GEN = MODE != 0;
   double* buf = k1_smem + (size_t)warp * (2 * NC * 96);
-  unsigned short* queue = reinterpret_cast<unsigned short*>(k1_smem + (size_t)KB_WARPS * (2 * NC * 96)) + (size_t)warp * (MAX_SETS * KB_QCAP);
-  int* qcnt = reinterpret_cast<int*>(reinterpret_cast<unsigned short*>(k1_smem + (size_t)KB_WARPS * (2 * NC * 96)) + (size_t)KB_WARPS * (MAX_SETS * KB_QCAP)) + warp * MAX_SETS;
+  unsigned short* queue = reinterpret_cast<unsigned short*>(k1_smem + (size_t)WARPS * (2 * NC * 96)) + (size_t)warp * (MAX_SETS * KB_QCAP);
+  int* qcnt = reinterpret_cast<int*>(reinterpret_cast<unsigned short*>(k1_smem + (size_t)WARPS * (2 * NC * 96)) + (size_t)WARPS * (MAX_SETS * KB_QCAP)) + warp * MAX_SETS;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int n_tasks = c.n_tiles * n_ranges;
+  const int n_tasks = c.n_tiles * g.n_ranges;
   bool pending = false;
   for (;;) {
     int task = 0;
@@ -320,6 +351,7 @@ __global__ void __launch_bounds__(KB_WARPS * 32, 2) k_regular_bulk(DevGroup g, D
     task = __shfl_sync(0xffffffffu, task, 0);
     if (task >= n_tasks) break;
     const int range = task / c.n_tiles, tile = task - range * c.n_tiles;   // consecutive tasks: same elements, consecutive tiles
+    if (!((g.range_modes[range] >> MODE) & 1)) continue;                   // no element of this kernel's class in the range
     if (lane < MAX_SETS) qcnt[lane] = 0;
     __syncwarp();
     const int cpos = tile * 32 + lane;
@@ -328,10 +360,11 @@ __global__ void __launch_bounds__(KB_WARPS * 32, 2) k_regular_bulk(DevGroup g, D
     const double xc[3] = {c.cx[cpos], c.cx[c.ldp + cpos], c.cx[2 * c.ldp + cpos]};
     const int row0 = c.tile_row0[tile], nbytes = c.tile_nbytes[tile];
     double bacc_t[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    const int e0 = range * erange, e1 = min(e0 + erange, g.n_elem);
+    const int e0 = g.range_start[range], e1 = g.range_start[range + 1];
     const unsigned char* pl = plan + (size_t)g.slot0 * c.ldp + cpos;
     int e = e0, ecur = 0, drain = 0;
     unsigned char m = PLAN_NONE, m_next = (valid && e0 < e1) ? pl[(size_t)e0 * c.ldp] : PLAN_NONE;
+    unsigned info_next = g.einfo[e0], cvnz_next = g.ecvnz[e0];   // element class of the next element, requested one element ahead like its plan byte
     unsigned fullsets = 0u;      // sets whose queue holds >= 32 entries
     bool inplace_todo = false;
     for (;;) {
@@ -353,10 +386,10 @@ __global__ void __launch_bounds__(KB_WARPS * 32, 2) k_regular_bulk(DevGroup g, D
       } else if (e < e1) {
         m = m_next; ecur = e; e++;
         m_next = (valid && e < e1) ? pl[(size_t)e * c.ldp] : PLAN_NONE;
-        const unsigned gen_e = GEN ? 1u : 0u;
-        const unsigned info_e = g.einfo[ecur];
-        const bool is_gen = !(info_e & 8u) || (g.ecvnz[ecur] != 0);
-        if (is_gen != (gen_e != 0u)) continue;
+        const unsigned info_e = info_next, cvnz_e = cvnz_next;
+        if (e < e1) { info_next = g.einfo[e]; cvnz_next = g.ecvnz[e]; }
+        const int mode_e = !(info_e & 8u) ? 2 : (cvnz_e != 0 ? 1 : 0);
+        if (mode_e != MODE) continue;
         const unsigned reg = __ballot_sync(0xffffffffu, m < MAX_SETS);
         if (reg == 0u) continue;
         const unsigned in0 = __ballot_sync(0xffffffffu, m == 0);
@@ -394,7 +427,7 @@ __global__ void __launch_bounds__(KB_WARPS * 32, 2) k_regular_bulk(DevGroup g, D
       const int rs = __shfl_sync(0xffffffffu, r0, src);
       const int* ecol = g.ecol + (size_t)el * NC;
       int mycol = 0;
-      if (inplace && lane < NC) mycol = __ldg(ecol + lane);   // columns of the element, needed by the flush only
+      if (inplace && lane < NN) mycol = __ldg(ecol + 3 * lane);   // first column of every node of the element, needed by the flush only
       AccA<NN> acc;
 #pragma unroll
       for (int i = 0; i < 9 * NN; i++) { acc.re[i] = 0.0; acc.im[i] = 0.0; }
@@ -406,33 +439,45 @@ __global__ void __launch_bounds__(KB_WARPS * 32, 2) k_regular_bulk(DevGroup g, D
         const double* P = g.pts[sset] + (size_t)el * ngp * (6 + NN);
         const unsigned char* ekind = g.ekind + (size_t)el * NC;
         const double* ecv = g.ecv + (size_t)el * 2 * NC;
+        // the record of point kp+1 is requested before point kp is integrated
+        double rec[6 + NN];
+#pragma unroll
+        for (int i = 0; i < 6 + NN; i++) rec[i] = ldg_ahead(P + i);
 #pragma unroll 1
-        for (int kp = 0; kp < ngp; kp++) k1_point<NN, GEN>(acc, bacc, P + (size_t)kp * (6 + NN), xs, sgn, info, ekind, ecv);
+        for (int kp = 0; kp < ngp; kp++) {
+          double cur[6 + NN];
+#pragma unroll
+          for (int i = 0; i < 6 + NN; i++) cur[i] = rec[i];
+          if (kp + 1 < ngp) {
+#pragma unroll
+            for (int i = 0; i < 6 + NN; i++) rec[i] = ldg_ahead(P + (size_t)(kp + 1) * (6 + NN) + i);
+          }
+          k1_point<NN, MODE>(acc, bacc, cur, xs, sgn, info, ekind, ecv);
+        }
       }
       // ---- flush ----
       if (inplace && nbytes > 0) {
         if (pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous flush has left the buffer
         __syncwarp();
+        // staging layout = the TMA box of one node: [node j][plane][dof k][96 rows]
 #pragma unroll
         for (int j = 0; j < NN; j++)
 #pragma unroll
           for (int k = 0; k < 3; k++)
 #pragma unroll
             for (int l = 0; l < 3; l++) {
-              buf[(2 * (j * 3 + k)) * 96 + 3 * lane + l] = acc.re[(l * 3 + k) * NN + j];
-              buf[(2 * (j * 3 + k) + 1) * 96 + 3 * lane + l] = acc.im[(l * 3 + k) * NN + j];
+              buf[((j * 2 + 0) * 3 + k) * 96 + 3 * lane + l] = acc.re[(l * 3 + k) * NN + j];
+              buf[((j * 2 + 1) * 3 + k) * 96 + 3 * lane + l] = acc.im[(l * 3 + k) * NN + j];
             }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
 #pragma unroll
-        for (int q = 0; q < NC; q++) {
-          const int col = __shfl_sync(0xffffffffu, mycol, q);
-          if (lane == 0) {
-            double* dre = s.Are + (size_t)col * s.lda + row0;
-            double* dim_ = s.Aim + (size_t)col * s.lda + row0;
-            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dre), "r"(smem_u32(buf + (2 * q) * 96)), "r"(nbytes) : "memory");
-            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dim_), "r"(smem_u32(buf + (2 * q + 1) * 96)), "r"(nbytes) : "memory");
-          }
+        for (int j = 0; j < NN; j++) {
+          const int col = __shfl_sync(0xffffffffu, mycol, j);
+          if (lane == 0)
+            asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&tmap), "r"(row0), "r"(col), "r"(0),
+                         "r"(smem_u32(buf + j * 576))
+                         : "memory");
         }
         if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         pending = true;
@@ -466,37 +511,72 @@ __global__ void __launch_bounds__(KB_WARPS * 32, 2) k_regular_bulk(DevGroup g, D
   if (pending && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-static int* g_task_counters = nullptr;   // two counters per launch slot, zeroed before each launch
-template <int ET>
-static void launch_regular_bulk(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, cudaStream_t st) {
+static int* g_task_counters = nullptr;   // one counter per kernel of a launch, zeroed before each launch
+template <int ET, int MODE, int WARPS>
+static void launch_bulk_mode(const CUtensorMap& tmap, const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, int n_sm,
+                             cudaStream_t st) {
   constexpr int NC = 3 * ElemTraits<ET>::NN;
-  const int smem = KB_WARPS * (2 * NC * 96 * (int)sizeof(double) + KB_SMEM_QUEUE + MAX_SETS * (int)sizeof(int));
+  const int smem = WARPS * (2 * NC * 96 * (int)sizeof(double) + KB_SMEM_QUEUE + MAX_SETS * (int)sizeof(int));
   static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_regular_bulk<ET, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(k_regular_bulk<ET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
-  if (!g_task_counters) cudaMalloc((void**)&g_task_counters, 2 * sizeof(int));
-  cudaMemsetAsync(g_task_counters, 0, 2 * sizeof(int), st);
-  // element ranges: long enough for the deferred queues to fill, short enough for the dynamic schedule to balance
-  // (<= 2048 elements: queue entries carry an 11-bit element offset)
-  int erange = 512;
-  const int n_ranges = (g.n_elem + erange - 1) / erange;
+  if (!attr) { cudaFuncSetAttribute(k_regular_bulk<ET, MODE, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  const int n_tasks = c.n_tiles * g.n_ranges;
+  int ctas = 2 * n_sm; if (ctas * WARPS > n_tasks) ctas = (n_tasks + WARPS - 1) / WARPS;
+  k_regular_bulk<ET, MODE, WARPS><<<ctas, WARPS * 32, smem, st>>>(tmap, g, c, s, plan, g_task_counters + MODE);
+}
+template <int ET>
+static void launch_regular_bulk(const CUtensorMap& tmap, const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, cudaStream_t st) {
+  if (!g_task_counters) cudaMalloc((void**)&g_task_counters, 4 * sizeof(int));
+  cudaMemsetAsync(g_task_counters, 0, 4 * sizeof(int), st);
   int dev = 0, n_sm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  const int n_tasks = c.n_tiles * n_ranges;
-  int ctas = 2 * n_sm; if (ctas * KB_WARPS > n_tasks) ctas = (n_tasks + KB_WARPS - 1) / KB_WARPS;
-  k_regular_bulk<ET, false><<<ctas, KB_WARPS * 32, smem, st>>>(g, c, s, plan, erange, n_ranges, g_task_counters);
-  k_regular_bulk<ET, true><<<ctas, KB_WARPS * 32, smem, st>>>(g, c, s, plan, erange, n_ranges, g_task_counters + 1);
+  // the three element classes run concurrently (their tails overlap); everything joins the caller's stream again
+  static cudaStream_t aux[2] = {nullptr, nullptr}; static cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  if (!aux[0]) {
+    for (int i = 0; i < 2; i++) { cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking); cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming); }
+    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+  }
+  cudaEventRecord(ev_fork, st);
+  cudaStreamWaitEvent(aux[0], ev_fork, 0);
+  launch_bulk_mode<ET, 1, KB_WARPS>(tmap, g, c, s, plan, n_sm, aux[0]);
+  cudaEventRecord(ev_join[0], aux[0]);
+  if (g.has_mixed) {
+    cudaStreamWaitEvent(aux[1], ev_fork, 0);
+    launch_bulk_mode<ET, 2, KB_WARPS>(tmap, g, c, s, plan, n_sm, aux[1]);
+    cudaEventRecord(ev_join[1], aux[1]);
+  }
+  launch_bulk_mode<ET, 0, KB_WARPS_FAST>(tmap, g, c, s, plan, n_sm, st);
+  cudaStreamWaitEvent(st, ev_join[0], 0);
+  if (g.has_mixed) cudaStreamWaitEvent(st, ev_join[1], 0);
 }
 
-void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, cudaStream_t st) {
+// 3-D tensor map of the planar system matrix for the K1 flush: (row, column, plane), box = 96 rows x 3 columns x 2 planes
+// (the three dofs of one node, both planes, for the 32 collocation points of a tile), FLOAT64, no swizzle.
+int make_matrix_tensor_map(void* out_128B, double* Are, long long lda, int n_dof) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                               CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return 1;
+    encode = (EncodeFn)fn;
+  }
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+  cuuint64_t dims[3] = {(cuuint64_t)n_dof, (cuuint64_t)n_dof, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)lda * 8, (cuuint64_t)lda * (cuuint64_t)n_dof * 8};
+  cuuint32_t box[3] = {96, 3, 2}, estr[3] = {1, 1, 1};
+  CUresult r = encode(reinterpret_cast<CUtensorMap*>(out_128B), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, Are, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2;
+}
+
+void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, const void* tmap, cudaStream_t st) {
   if (g.n_elem == 0) return;
   dim3 grid((c.ldp + 32 * K1_WARPS - 1) / (32 * K1_WARPS), (g.n_elem + K1_ECHUNK - 1) / K1_ECHUNK);
   dim3 block(K1_WARPS * 32);
   switch (g.et) {
-    case 5: launch_regular_bulk<5>(g, c, s, plan, st); break;
-    case 7: launch_regular_bulk<7>(g, c, s, plan, st); break;
+    case 5: if (g.cols3 && tmap) { launch_regular_bulk<5>(*reinterpret_cast<const CUtensorMap*>(tmap), g, c, s, plan, st); break; }
+            k_regular<5, 3><<<grid, block, 0, st>>>(g, c, s, plan); break;
+    case 7: if (g.cols3 && tmap) { launch_regular_bulk<7>(*reinterpret_cast<const CUtensorMap*>(tmap), g, c, s, plan, st); break; }
+            k_regular<7, 3><<<grid, block, 0, st>>>(g, c, s, plan); break;
     case 6: k_regular<6, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
     case 8: k_regular<8, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
     case 9: k_regular<9, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;

@@ -6,6 +6,7 @@
 namespace mfbd {
 
 const int MAX_SETS = 16;
+const int K1_ERANGE = 512;                // elements per K1 task at most (<= 2048: queue entries carry an 11-bit element offset)
 const unsigned char PLAN_NEAR = 250;      // classifier could not settle the pair with the ball test -> host planner
 const unsigned char PLAN_ADAPTIVE = 254;  // Telles + subdivision leaf list (kernel K2)
 const unsigned char PLAN_SINGULAR = 253;  // polar transformation (kernel K3)
@@ -24,6 +25,12 @@ struct DevGroup {
   unsigned char* ecvnz;          // [n_elem] 1 when some prescribed value of the element is nonzero (refreshed per frequency)
   const double* ball;            // [n_elem][5]: centre(3), radius, characteristic length
   const int* gln_far;            // [n_elem]
+  int n_ranges;                  // K1 tasks = (collocation tile) x (element range); long ranges first, short ones last (load balance)
+  const int* range_start;        // [n_ranges+1]
+  const int* range_of;           // [n_elem] range of an element
+  int* range_modes;              // [n_ranges] bit m set: the range holds elements of K1 mode m (refreshed per frequency)
+  int has_mixed;                 // 1: some element has boundary-condition kinds that differ between its nodes (K1 mode 2)
+  int cols3;                     // 1: the three dof columns of every element node are consecutive (col(j,k) = col(j,0) + k)
   int n_sets; int set_gln[MAX_SETS]; int ngp[MAX_SETS];
   const double* pts[MAX_SETS];   // [n_elem][ngp][6+nn]: x(3), n(3), phi_j*J*w
 };
@@ -77,7 +84,8 @@ void launch_count_near(const unsigned char* plan, long long n_slots, const DevCo
                        unsigned long long capacity, cudaStream_t st);
 void launch_patch_plan(unsigned char* plan, const DevColloc& c, int n, const int* cpos, const int* slot, const unsigned char* val, cudaStream_t st);
 void launch_gather_cv(const DevGroup& g, const double* cvalue, cudaStream_t st);
-void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, cudaStream_t st);
+void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, const void* tmap, cudaStream_t st);
+int make_matrix_tensor_map(void* out_128B, double* Are, long long lda, int n_dof);
 void launch_adaptive(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevAdaptive& a, const DevTables& t, cudaStream_t st);
 void launch_singular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevSingular& a, const DevTables& t, cudaStream_t st);
 void launch_freeterm(const DevColloc& c, const DevSystem& s, const DevFreeTerm& f, cplx F, cudaStream_t st);

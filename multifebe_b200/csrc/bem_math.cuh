@@ -194,7 +194,8 @@ MFB_HD void kernel_scalars(const KParams& p, double r, KScal& k) {
 // the coefficient of the bare E2(z2)/r term), q.T1..T3 carry cte_t, so that psi*delta - chi*r,l*r,k is directly the
 // matrix contribution -g/(4 pi mu) of a u-known column and the T combination directly +h/(4 pi) of a t-known column.
 // Takes r and 1/r (from rsqrt) instead of dividing.
-MFB_HD void kernel_scalars_scaled(const KParams& p, double r, double d1r1, KScal& k) {
+// need_g / need_h: form psi, chi (displacement kernel) / T1..T3 (traction kernel) only when a column of the element uses them.
+MFB_HD void kernel_scalars_scaled(const KParams& p, double r, double d1r1, KScal& k, bool need_g = true, bool need_h = true) {
   const double d1r2 = d1r1 * d1r1, d1r3 = d1r2 * d1r1, d1r4 = d1r2 * d1r2;
   const cplx z1 = mk(p.k1.im * r, -p.k1.re * r), z2 = mk(p.k2.im * r, -p.k2.re * r);
   cplx A2, A3, A4, A5, B2, B3, B4, B5;
@@ -202,24 +203,29 @@ MFB_HD void kernel_scalars_scaled(const KParams& p, double r, double d1r1, KScal
   const cplx E21 = A2 * d1r1, E22 = B2 * d1r1, E31 = A3 * d1r2, E32 = B3 * d1r2;
   const cplx E41 = A4 * d1r3, E42 = B4 * d1r3, E51 = A5 * d1r4, E52 = B5 * d1r4;
   cplx t;
-  t = cfmar(p.psi[1], d1r1, p.psi[2]);
-  t = cfma(p.psi[0], E22, t); t = cfma(p.psi[3], E31, t); t = cfma(p.psi[4], E32, t); t = cfma(p.psi[5], E41, t); t = cfma(p.psi[6], E42, t);
-  k.psi = t;
-  t = p.chi[1] * d1r1;
-  t = cfma(p.chi[0], E22, t); t = cfma(p.chi[2], E21, t); t = cfma(p.chi[3], E31, t); t = cfma(p.chi[4], E32, t); t = cfma(p.chi[5], E41, t); t = cfma(p.chi[6], E42, t);
-  k.chi = t;
-  t = cfmar(p.T1[1], d1r2, p.T1[2]);
-  t = cfma(p.T1[3], E21, t); t = cfma(p.T1[4], E22, t); t = cfma(p.T1[5], E31, t); t = cfma(p.T1[6], E32, t);
-  t = cfma(p.T1[7], E41, t); t = cfma(p.T1[8], E42, t); t = cfma(p.T1[9], E51, t); t = cfma(p.T1[10], E52, t);
-  k.T1 = t;
-  t = cfmar(p.T2[1], d1r2, p.T2[2]);
-  t = cfma(p.T2[3], E22, t); t = cfma(p.T2[4], E31, t); t = cfma(p.T2[5], E32, t); t = cfma(p.T2[6], E41, t);
-  t = cfma(p.T2[7], E42, t); t = cfma(p.T2[8], E51, t); t = cfma(p.T2[9], E52, t);
-  k.T2 = t;
-  t = cfmar(p.T3[1], d1r2, p.T3[2]);
-  t = cfma(p.T3[3], E21, t); t = cfma(p.T3[4], E31, t); t = cfma(p.T3[5], E32, t); t = cfma(p.T3[6], E41, t);
-  t = cfma(p.T3[7], E42, t); t = cfma(p.T3[8], E51, t); t = cfma(p.T3[9], E52, t);
-  k.T3 = t;
+  k.psi = mk(0.0, 0.0); k.chi = k.psi; k.T1 = k.psi; k.T2 = k.psi; k.T3 = k.psi;
+  if (need_g) {
+    t = cfmar(p.psi[1], d1r1, p.psi[2]);
+    t = cfma(p.psi[0], E22, t); t = cfma(p.psi[3], E31, t); t = cfma(p.psi[4], E32, t); t = cfma(p.psi[5], E41, t); t = cfma(p.psi[6], E42, t);
+    k.psi = t;
+    t = p.chi[1] * d1r1;
+    t = cfma(p.chi[0], E22, t); t = cfma(p.chi[2], E21, t); t = cfma(p.chi[3], E31, t); t = cfma(p.chi[4], E32, t); t = cfma(p.chi[5], E41, t); t = cfma(p.chi[6], E42, t);
+    k.chi = t;
+  }
+  if (need_h) {
+    t = cfmar(p.T1[1], d1r2, p.T1[2]);
+    t = cfma(p.T1[3], E21, t); t = cfma(p.T1[4], E22, t); t = cfma(p.T1[5], E31, t); t = cfma(p.T1[6], E32, t);
+    t = cfma(p.T1[7], E41, t); t = cfma(p.T1[8], E42, t); t = cfma(p.T1[9], E51, t); t = cfma(p.T1[10], E52, t);
+    k.T1 = t;
+    t = cfmar(p.T2[1], d1r2, p.T2[2]);
+    t = cfma(p.T2[3], E22, t); t = cfma(p.T2[4], E31, t); t = cfma(p.T2[5], E32, t); t = cfma(p.T2[6], E41, t);
+    t = cfma(p.T2[7], E42, t); t = cfma(p.T2[8], E51, t); t = cfma(p.T2[9], E52, t);
+    k.T2 = t;
+    t = cfmar(p.T3[1], d1r2, p.T3[2]);
+    t = cfma(p.T3[3], E21, t); t = cfma(p.T3[4], E31, t); t = cfma(p.T3[5], E32, t); t = cfma(p.T3[6], E41, t);
+    t = cfma(p.T3[7], E42, t); t = cfma(p.T3[8], E51, t); t = cfma(p.T3[9], E52, t);
+    k.T3 = t;
+  }
   k.d1r1 = d1r1; k.d1r2 = d1r2;
 }
 
