@@ -663,7 +663,9 @@ extern "C" int mfb_harela3d_assemble(mfb_problem* p, double omega, const mfb_z* 
 static bool lu_timing() { const char* e = getenv("MFB_LU_TIMING"); return !(e && e[0] == '0'); }
 static int ensure_lu(mfb_problem* p) {
   if (!p->lu_ready) {
-    if (lu_work_alloc(p->lu, p->n_dof, 128) != 0) return fail(MFB_ERR_CUDA, "LU workspace allocation failed");
+    int nb = 256;
+    if (const char* e = getenv("MFB_LU_NB")) { int v = atoi(e); if (v >= 32 && v <= 1024 && v % 32 == 0) nb = v; }
+    if (lu_work_alloc(p->lu, p->n_dof, nb) != 0) return fail(MFB_ERR_CUDA, "LU workspace allocation failed");
     p->lu_ready = true;
   }
   return MFB_OK;

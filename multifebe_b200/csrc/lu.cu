@@ -144,6 +144,130 @@ k_zgemm_minus(int M, int N, int K, const double* __restrict__ Are, const double*
       }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// ZGEMM, 3M form (C -= A*B with three real products instead of four, the ZGEMM3M of the BLAS):
+//   X = Ar*Br, Y = Ai*Bi, Z = (Ar+Ai)*(Br+Bi);  Cr -= X - Y;  Ci -= Z - X - Y.
+// 25 % fewer DMMA per complex product; the sums Ar+Ai, Br+Bi are formed on the fragments (one DADD per fragment element).
+// Normwise as accurate as the 4-product form (the BLAS offers it for exactly this use); the imaginary part loses the
+// componentwise bound, which an LU with partial pivoting does not rely on.  Warp tile 32 x (8*NI), accumulators X, Y, Z in
+// registers, C read in the epilogue only.  Same shared-memory staging as k_zgemm_minus.
+// ------------------------------------------------------------------------------------------------------------------
+template <int WM, int WN, int NI>
+struct Gemm3Cfg {
+  static const int BK = 16, STAGES = 2;
+  static const int BM = 32 * WM, BN = 8 * NI * WN, T = 32 * WM * WN;
+  static const int SA_LD = BM + 4, SB_LD = BK + 4;
+  static const int SA_STAGE = 2 * BK * SA_LD, SB_STAGE = 2 * BN * SB_LD;
+  static const int SMEM = STAGES * (SA_STAGE + SB_STAGE) * 8;
+};
+template <int WM, int WN, int NI, int MINB>
+__global__ void __launch_bounds__(32 * WM * WN, MINB)
+k_zgemm3m_minus(int M, int N, int K, const double* __restrict__ Are, const double* __restrict__ Aim, long long lda, const double* __restrict__ Bre,
+                const double* __restrict__ Bim, long long ldb, double* __restrict__ Cre, double* __restrict__ Cim, long long ldc) {
+  typedef Gemm3Cfg<WM, WN, NI> C;
+  constexpr int BM = C::BM, BN = C::BN, BK = C::BK, STAGES = C::STAGES, T = C::T, SA_LD = C::SA_LD, SB_LD = C::SB_LD, SA_STAGE = C::SA_STAGE, SB_STAGE = C::SB_STAGE;
+  extern __shared__ __align__(16) double smem[];
+  double* sA = smem;
+  double* sB = smem + STAGES * SA_STAGE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp % WM, wn = warp / WM;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int KT = (K + BK - 1) / BK;
+  auto load_stage = [&](int stage, int kt) {
+    const int k0 = kt * BK;
+    double* a = sA + stage * SA_STAGE;
+    double* b = sB + stage * SB_STAGE;
+#pragma unroll
+    for (int i = 0; i < (2 * BK * (BM / 2) + T - 1) / T; i++) {
+      int idx = tid + T * i;
+      if ((2 * BK * (BM / 2)) % T != 0 && idx >= 2 * BK * (BM / 2)) break;
+      int p = idx / (BK * (BM / 2)), rem = idx % (BK * (BM / 2)), k = rem / (BM / 2), c2 = rem % (BM / 2);
+      int m = m0 + 2 * c2, kk = k0 + k;
+      const double* src = (p ? Aim : Are) + (long long)kk * lda + m;
+      int bytes = (kk < K) ? max(0, min(16, (M - m) * 8)) : 0;
+      if (bytes == 0) src = (p ? Aim : Are);
+      cp_async16(a + (p * BK + k) * SA_LD + 2 * c2, src, bytes);
+    }
+#pragma unroll
+    for (int i = 0; i < (2 * BN * (BK / 2) + T - 1) / T; i++) {
+      int idx = tid + T * i;
+      if ((2 * BN * (BK / 2)) % T != 0 && idx >= 2 * BN * (BK / 2)) break;
+      int p = idx / (BN * (BK / 2)), rem = idx % (BN * (BK / 2)), nn = rem / (BK / 2), c2 = rem % (BK / 2);
+      int n = n0 + nn, kk = k0 + 2 * c2;
+      const double* src = (p ? Bim : Bre) + (long long)n * ldb + kk;
+      int bytes = (n < N) ? max(0, min(16, (K - kk) * 8)) : 0;
+      if (bytes == 0) src = (p ? Bim : Bre);
+      cp_async16(b + (p * BN + nn) * SB_LD + 2 * c2, src, bytes);
+    }
+  };
+  for (int s = 0; s < STAGES - 1; s++) { if (s < KT) load_stage(s, s); cp_async_commit(); }
+  // C enters through the accumulators (its loads overlap the first k-tiles in flight, the epilogue only stores):
+  // x = -Cr + X, y = Y, z = -(Ci + Cr) + Z  =>  Cr' = y - x,  Ci' = x + y - z
+  double x[4][NI][2], y[4][NI][2], z[4][NI][2];
+#pragma unroll
+  for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+    for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        int m = m0 + wm * 32 + mi * 8 + gid, n = n0 + wn * 8 * NI + ni * 8 + 2 * tig + h;
+        const bool ok = (m < M) && (n < N);
+        const double cr = ok ? Cre[(long long)n * ldc + m] : 0.0, ci = ok ? Cim[(long long)n * ldc + m] : 0.0;
+        x[mi][ni][h] = -cr; y[mi][ni][h] = 0.0; z[mi][ni][h] = -(ci + cr);
+      }
+  for (int kt = 0; kt < KT; kt++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    { int nk = kt + STAGES - 1; if (nk < KT) load_stage(nk % STAGES, nk); cp_async_commit(); }
+    const double* a = sA + (kt % STAGES) * SA_STAGE;
+    const double* b = sB + (kt % STAGES) * SB_STAGE;
+#pragma unroll
+    for (int k4 = 0; k4 < BK / 4; k4++) {
+      double ar[4], ai[4], sa[4];
+#pragma unroll
+      for (int mi = 0; mi < 4; mi++) {
+        int off = (k4 * 4 + tig) * SA_LD + wm * 32 + mi * 8 + gid;
+        ar[mi] = a[off]; ai[mi] = a[BK * SA_LD + off]; sa[mi] = ar[mi] + ai[mi];
+      }
+#pragma unroll
+      for (int ni = 0; ni < NI; ni++) {
+        int off = (wn * 8 * NI + ni * 8 + gid) * SB_LD + k4 * 4 + tig;
+        const double br = b[off], bi = b[BN * SB_LD + off], sb = br + bi;
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) {
+          dmma(x[mi][ni][0], x[mi][ni][1], ar[mi], br);
+          dmma(y[mi][ni][0], y[mi][ni][1], ai[mi], bi);
+          dmma(z[mi][ni][0], z[mi][ni][1], sa[mi], sb);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+    for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        int m = m0 + wm * 32 + mi * 8 + gid, n = n0 + wn * 8 * NI + ni * 8 + 2 * tig + h;
+        if (m < M && n < N) {
+          const long long o = (long long)n * ldc + m;
+          Cre[o] = y[mi][ni][h] - x[mi][ni][h];
+          Cim[o] = (x[mi][ni][h] + y[mi][ni][h]) - z[mi][ni][h];
+        }
+      }
+}
+template <int WM, int WN, int NI, int MINB>
+static void launch_gemm3m(int m, int n, int k, const double* Are, const double* Aim, long long lda, const double* Bre, const double* Bim,
+                          long long ldb, double* Cre, double* Cim, long long ldc, cudaStream_t st) {
+  typedef Gemm3Cfg<WM, WN, NI> C;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_zgemm3m_minus<WM, WN, NI, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM); attr = true; }
+  dim3 grid((m + C::BM - 1) / C::BM, (n + C::BN - 1) / C::BN);
+  k_zgemm3m_minus<WM, WN, NI, MINB><<<grid, C::T, C::SMEM, st>>>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc);
+}
+
 template <int WM, int WN, int BK, int STAGES, int MINB>
 static void launch_gemm_cfg(int m, int n, int k, const double* Are, const double* Aim, long long lda, const double* Bre, const double* Bim,
                             long long ldb, double* Cre, double* Cim, long long ldc, cudaStream_t st) {
@@ -156,7 +280,7 @@ static void launch_gemm_cfg(int m, int n, int k, const double* Are, const double
 
 static int gemm_cfg() {
   static int cfg = -1;
-  if (cfg < 0) { const char* e = getenv("MFB_GEMM_CFG"); cfg = e ? atoi(e) : 2; }
+  if (cfg < 0) { const char* e = getenv("MFB_GEMM_CFG"); cfg = e ? atoi(e) : 15; }
   return cfg;
 }
 
@@ -164,6 +288,13 @@ void zgemm_minus_planar(int m, int n, int k, const double* Are, const double* Ai
                         long long ldb, double* Cre, double* Cim, long long ldc, cudaStream_t st) {
   if (m <= 0 || n <= 0 || k <= 0) return;
   switch (gemm_cfg()) {
+    case 10: launch_gemm3m<2, 2, 4, 2>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 3M, 64 x 64, warp 32 x 32, 2 CTA/SM
+    case 11: launch_gemm3m<2, 4, 2, 1>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 3M, 64 x 64, 8 warps of 32 x 16, 1 CTA/SM
+    case 12: launch_gemm3m<2, 2, 2, 2>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 3M, 64 x 32, warp 32 x 16, 2 CTA/SM
+    case 13: launch_gemm3m<4, 2, 2, 1>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 3M, 128 x 32, 8 warps of 32 x 16, 1 CTA/SM
+    case 14: launch_gemm3m<2, 2, 3, 2>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 3M, 64 x 48, warp 32 x 24, 2 CTA/SM
+    case 15: launch_gemm3m<2, 2, 2, 3>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 3M, 64 x 32, warp 32 x 16, 3 CTA/SM
+    case 16: launch_gemm3m<2, 4, 2, 2>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 3M, 64 x 64, 8 warps of 32 x 16, 2 CTA/SM
     case 0: launch_gemm_cfg<4, 2, 16, 3, 1>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 128 x 64, 8 warps, 1 CTA/SM
     case 2: launch_gemm_cfg<2, 2, 16, 2, 2>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 64 x 64, 2-stage
     case 3: launch_gemm_cfg<4, 1, 16, 3, 2>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 128 x 32, 4 warps
@@ -349,12 +480,30 @@ __global__ void __launch_bounds__(256) k_trsm_lu(double* Are, double* Aim, long 
     if (cc < ncol) { Are[(long long)(cb + cc) * lda + r0 + i] = br[i * LD + cc]; Aim[(long long)(cb + cc) * lda + r0 + i] = bi[i * LD + cc]; }
   }
 }
-static void launch_trsm(double* Are, double* Aim, long long lda, int r0, int nbw, int c0, int c1, cudaStream_t st) {
-  if (c1 <= c0 || nbw <= 1) return;
+// U12 = inv(L11) A12 for the nbw x nbw unit lower block at (r0,r0) and columns [c0,c1): blocked forward substitution,
+// TRSM_TB rows at a time by substitution in shared memory, the rows below updated on the tensor pipe (returns launches).
+const int TRSM_TB = 32;
+static int launch_trsm(double* Are, double* Aim, long long lda, int r0, int nbw, int c0, int c1, cudaStream_t st) {
+  if (c1 <= c0 || nbw <= 1) return 0;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(k_trsm_lu, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * (TRSM_TC + 1) * 8); attr = true; }
-  size_t smem = (size_t)2 * nbw * (TRSM_TC + 1) * 8;
-  k_trsm_lu<<<(c1 - c0 + TRSM_TC - 1) / TRSM_TC, 256, smem, st>>>(Are, Aim, lda, r0, nbw, c0, c1);
+  int launches = 0;
+  for (int jb = 0; jb < nbw; jb += TRSM_TB) {
+    const int tb = (nbw - jb < TRSM_TB) ? (nbw - jb) : TRSM_TB;
+    if (tb > 1) {
+      size_t smem = (size_t)2 * tb * (TRSM_TC + 1) * 8;
+      k_trsm_lu<<<(c1 - c0 + TRSM_TC - 1) / TRSM_TC, 256, smem, st>>>(Are, Aim, lda, r0 + jb, tb, c0, c1);
+      launches++;
+    }
+    const int mrest = nbw - jb - tb;
+    if (mrest > 0) {
+      zgemm_minus_planar(mrest, c1 - c0, tb, Are + (long long)(r0 + jb) * lda + r0 + jb + tb, Aim + (long long)(r0 + jb) * lda + r0 + jb + tb, lda,
+                         Are + (long long)c0 * lda + r0 + jb, Aim + (long long)c0 * lda + r0 + jb, lda,
+                         Are + (long long)c0 * lda + r0 + jb + tb, Aim + (long long)c0 * lda + r0 + jb + tb, lda, st);
+      launches++;
+    }
+  }
+  return launches;
 }
 
 int lu_work_alloc(LuWork& w, int n, int nb) {
@@ -364,6 +513,11 @@ int lu_work_alloc(LuWork& w, int n, int nb) {
   if (w.ib < 4 || w.ib > SP_MAXIB || (w.ib & 3) || nb % w.ib) w.ib = 16;
   cudaDeviceProp prop; int dev; cudaGetDevice(&dev); cudaGetDeviceProperties(&prop, dev);
   w.n_sm = prop.multiProcessorCount;
+  const char* e_la = getenv("MFB_LU_LOOKAHEAD");
+  w.lookahead = e_la ? atoi(e_la) : 1;
+  const char* e_pc = getenv("MFB_LU_PANEL_CTAS");
+  w.panel_ctas = e_pc ? atoi(e_pc) : w.n_sm;
+  if (w.panel_ctas < 1 || w.panel_ctas > w.n_sm) w.panel_ctas = w.n_sm;
   size_t G = (size_t)w.n_sm;
   cudaError_t e = cudaSuccess;
   auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
@@ -374,19 +528,27 @@ int lu_work_alloc(LuWork& w, int n, int nb) {
   w.n_evs = 5 * ((n + nb - 1) / nb);
   w.evs = new cudaEvent_t[w.n_evs];
   for (int i = 0; i < w.n_evs; i++) cudaEventCreate(&w.evs[i]);
+  const int n_steps = (n + nb - 1) / nb;
+  w.pevs = new cudaEvent_t[2 * n_steps];
+  for (int i = 0; i < 2 * n_steps; i++) cudaEventCreate(&w.pevs[i]);
+  int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&w.panel_stream, cudaStreamNonBlocking, hi);
+  cudaEventCreateWithFlags(&w.ev_next_cols, cudaEventDisableTiming); cudaEventCreateWithFlags(&w.ev_panel_done, cudaEventDisableTiming);
   w.ms_panel = w.ms_swap = w.ms_trsm = w.ms_gemm = 0.f; w.n_steps_timed = 0; w.gemm_launches = 0; w.gemm_flops = 0.0;
   return (int)e;
 }
 void lu_work_free(LuWork& w) {
   cudaFree(w.cand_val); cudaFree(w.cand_row); cudaFree(w.cand_data); cudaFree(w.diag_data); cudaFree(w.info);
   for (int i = 0; i < w.n_evs; i++) cudaEventDestroy(w.evs[i]);
-  delete[] w.evs;
+  for (int i = 0; i < 2 * (w.n_evs / 5); i++) cudaEventDestroy(w.pevs[i]);
+  cudaEventDestroy(w.ev_next_cols); cudaEventDestroy(w.ev_panel_done); cudaStreamDestroy(w.panel_stream);
+  delete[] w.evs; delete[] w.pevs;
 }
 void lu_collect_times(LuWork& w) {
   w.ms_panel = w.ms_swap = w.ms_trsm = w.ms_gemm = 0.f;
   for (int s = 0; s < w.n_steps_timed; s++) {
     cudaEvent_t* ev = w.evs + 5 * s; float t;
-    cudaEventElapsedTime(&t, ev[0], ev[1]); w.ms_panel += t;
+    cudaEventElapsedTime(&t, w.pevs[2 * s], w.pevs[2 * s + 1]); w.ms_panel += t;   // on its own stream: overlaps the trailing update under look-ahead
     cudaEventElapsedTime(&t, ev[1], ev[2]); w.ms_swap += t;
     cudaEventElapsedTime(&t, ev[2], ev[3]); w.ms_trsm += t;
     cudaEventElapsedTime(&t, ev[3], ev[4]); w.ms_gemm += t;
@@ -399,7 +561,7 @@ static int factor_panel(double* Are, double* Aim, long long lda, int n, int k0, 
   for (int j0 = 0; j0 < nbw; j0 += w.ib) {
     const int ib = (nbw - j0 < w.ib) ? (nbw - j0) : w.ib;
     const int c0 = k0 + j0, m = n - c0;
-    int G = w.n_sm;
+    int G = w.panel_ctas;
     int rpc = (m + G - 1) / G; if (rpc < 64) rpc = 64;
     G = (m + rpc - 1) / rpc;
     SubPanelArgs pa; pa.Are = Are; pa.Aim = Aim; pa.lda = lda; pa.n = n; pa.c0 = c0; pa.ib = ib; pa.rpc = rpc; pa.rpcp = rpc | 1;
@@ -415,43 +577,65 @@ static int factor_panel(double* Are, double* Aim, long long lda, int n, int k0, 
     const int nright = nbw - j0 - ib;
     if (nright > 0) {
       k_laswp<<<(nright + 127) / 128, 128, 0, st>>>(Are, Aim, lda, c0 + ib, k0 + nbw, c0, ib, ipiv);
-      launch_trsm(Are, Aim, lda, c0, ib, c0 + ib, k0 + nbw, st);
+      w.launches += 1 + launch_trsm(Are, Aim, lda, c0, ib, c0 + ib, k0 + nbw, st);
       const int mrest = n - c0 - ib;
-      if (mrest > 0)
+      if (mrest > 0) {
         zgemm_minus_planar(mrest, nright, ib, Are + (long long)c0 * lda + c0 + ib, Aim + (long long)c0 * lda + c0 + ib, lda,
                            Are + (long long)(c0 + ib) * lda + c0, Aim + (long long)(c0 + ib) * lda + c0, lda,
                            Are + (long long)(c0 + ib) * lda + c0 + ib, Aim + (long long)(c0 + ib) * lda + c0 + ib, lda, st);
-      w.launches += 3;
+        w.launches++;
+      }
     }
   }
   return 0;
 }
 
+// Right-looking blocked LU with one panel of look-ahead: as soon as the trailing update of step k has finished the columns of
+// panel k+1, that panel is factorised on a high-priority stream while the main stream updates the remaining columns.
 int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuWork& w, cudaStream_t st, bool timing) {
   const int nb = w.nb;
   cudaMemsetAsync(w.info, 0, sizeof(int), st);
   w.launches = 0; w.gemm_launches = 0; w.gemm_flops = 0.0; w.n_steps_timed = 0;
-  for (int k0 = 0; k0 < n; k0 += nb) {
-    cudaEvent_t* ev = w.evs + 5 * (k0 / nb);
-    const int nbw = (n - k0 < nb) ? (n - k0) : nb;
-    if (timing) cudaEventRecord(ev[0], st);
-    int e = factor_panel(Are, Aim, lda, n, k0, nbw, ipiv, w, st);
+  cudaStream_t ps = w.lookahead ? w.panel_stream : st;
+  auto gemm = [&](int r0, int k0, int kw, int c0, int c1) {   // A[r0:n, c0:c1] -= A[r0:n, k0:k0+kw] * A[k0:k0+kw, c0:c1]
+    if (c1 <= c0 || r0 >= n) return;
+    zgemm_minus_planar(n - r0, c1 - c0, kw, Are + (long long)k0 * lda + r0, Aim + (long long)k0 * lda + r0, lda,
+                       Are + (long long)c0 * lda + k0, Aim + (long long)c0 * lda + k0, lda, Are + (long long)c0 * lda + r0, Aim + (long long)c0 * lda + r0, lda, st);
+    w.launches++; w.gemm_launches++; w.gemm_flops += 8.0 * (double)(n - r0) * (double)(c1 - c0) * (double)kw;
+  };
+  // first panel
+  {
+    if (w.lookahead) { cudaEventRecord(w.ev_next_cols, st); cudaStreamWaitEvent(ps, w.ev_next_cols, 0); }
+    if (timing) cudaEventRecord(w.pevs[0], ps);
+    int e = factor_panel(Are, Aim, lda, n, 0, (n < nb) ? n : nb, ipiv, w, ps);
     if (e) return e;
+    if (timing) cudaEventRecord(w.pevs[1], ps);
+    if (w.lookahead) { cudaEventRecord(w.ev_panel_done, ps); cudaStreamWaitEvent(st, w.ev_panel_done, 0); }
+  }
+  for (int k0 = 0, step = 0; k0 < n; k0 += nb, step++) {
+    cudaEvent_t* ev = w.evs + 5 * step;
+    const int nbw = (n - k0 < nb) ? (n - k0) : nb;
+    const int c_next = k0 + nbw;                                  // first column of the next panel
+    const int nbw_next = (n - c_next < nb) ? (n - c_next) : nb;   // its width (0 at the end)
     if (timing) cudaEventRecord(ev[1], st);
-    // ---- interchanges outside the panel ----
+    // ---- interchanges of panel k outside the panel ----
     if (k0 > 0) { k_laswp<<<(k0 + 127) / 128, 128, 0, st>>>(Are, Aim, lda, 0, k0, k0, nbw, ipiv); w.launches++; }
-    const int nrest = n - k0 - nbw;
-    if (nrest > 0) { k_laswp<<<(nrest + 127) / 128, 128, 0, st>>>(Are, Aim, lda, k0 + nbw, n, k0, nbw, ipiv); w.launches++; }
+    if (c_next < n) { k_laswp<<<(n - c_next + 127) / 128, 128, 0, st>>>(Are, Aim, lda, c_next, n, k0, nbw, ipiv); w.launches++; }
     if (timing) cudaEventRecord(ev[2], st);
-    if (nrest > 0) {
-      // ---- U12 = inv(L11) * A12 (forward substitution, ztrsm) ----
-      launch_trsm(Are, Aim, lda, k0, nbw, k0 + nbw, n, st);
+    if (c_next < n) {
+      // ---- U12 = inv(L11) * A12 ----
+      w.launches += launch_trsm(Are, Aim, lda, k0, nbw, c_next, n, st);
       if (timing) cudaEventRecord(ev[3], st);
-      // ---- trailing update A22 -= A21 * U12 ----
-      zgemm_minus_planar(nrest, nrest, nbw, Are + (long long)k0 * lda + k0 + nbw, Aim + (long long)k0 * lda + k0 + nbw, lda,
-                         Are + (long long)(k0 + nbw) * lda + k0, Aim + (long long)(k0 + nbw) * lda + k0, lda,
-                         Are + (long long)(k0 + nbw) * lda + k0 + nbw, Aim + (long long)(k0 + nbw) * lda + k0 + nbw, lda, st);
-      w.launches += 2; w.gemm_launches += 1; w.gemm_flops += 8.0 * (double)nrest * (double)nrest * (double)nbw;
+      // ---- trailing update, the columns of the next panel first ----
+      gemm(c_next, k0, nbw, c_next, c_next + nbw_next);
+      if (w.lookahead) { cudaEventRecord(w.ev_next_cols, st); cudaStreamWaitEvent(ps, w.ev_next_cols, 0); }
+      if (timing) cudaEventRecord(w.pevs[2 * (step + 1)], ps);
+      int e = factor_panel(Are, Aim, lda, n, c_next, nbw_next, ipiv, w, ps);
+      if (e) return e;
+      if (timing) cudaEventRecord(w.pevs[2 * (step + 1) + 1], ps);
+      if (w.lookahead) cudaEventRecord(w.ev_panel_done, ps);
+      gemm(c_next, k0, nbw, c_next + nbw_next, n);
+      if (w.lookahead) cudaStreamWaitEvent(st, w.ev_panel_done, 0);
     } else if (timing) cudaEventRecord(ev[3], st);
     if (timing) { cudaEventRecord(ev[4], st); w.n_steps_timed++; }
   }

@@ -16,6 +16,10 @@ struct LuWork {
   int *info;              // device flag: first zero pivot (1-based), 0 = ok
   float ms_panel, ms_swap, ms_trsm, ms_gemm; long long launches; long long gemm_launches; double gemm_flops;
   cudaEvent_t* evs; int n_evs, n_steps_timed;   // 5 events per block step, recorded without synchronising
+  cudaStream_t panel_stream;                    // high-priority stream of the look-ahead panel factorisation
+  cudaEvent_t ev_next_cols, ev_panel_done;      // next panel's columns updated / next panel factorised
+  cudaEvent_t* pevs;                            // 2 events per block step on the panel stream (panel timing under look-ahead)
+  int lookahead, panel_ctas;
 };
 // sums the per-phase event times of the last timed factorisation (call after the stream has been synchronised)
 void lu_collect_times(LuWork& w);
