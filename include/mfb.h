@@ -111,7 +111,7 @@ enum mfb_stat_id {
   MFB_STAT_MS_FREETERM = 12, MFB_STAT_MS_LU = 13, MFB_STAT_MS_SOLVE = 14, MFB_STAT_MS_GEMM = 15, MFB_STAT_MS_PANEL = 16,
   MFB_STAT_LAUNCHES = 17, MFB_STAT_MS_SETUP_HOST = 18, MFB_STAT_MS_ASSEMBLE = 19, MFB_STAT_FLOPS_REGULAR = 20,
   MFB_STAT_MS_TRSM = 21, MFB_STAT_MS_SWAP = 22, MFB_STAT_LU_LAUNCHES = 23, MFB_STAT_GEMM_LAUNCHES = 24,
-  MFB_STAT_GEMM_FLOPS = 25, MFB_STAT_COUNT = 32
+  MFB_STAT_GEMM_FLOPS = 25, MFB_STAT_GEMM_EXEC_FLOPS = 26, MFB_STAT_COUNT = 32
 };
 int mfb_get_stats(mfb_problem* problem, double* stats /* MFB_STAT_COUNT doubles */);
 

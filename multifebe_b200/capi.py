@@ -21,7 +21,7 @@ _LIB = None
 STAT = dict(PAIRS_REGULAR=0, POINTS_REGULAR=1, PAIRS_ADAPTIVE=2, LEAVES=3, POINTS_ADAPTIVE=4, PAIRS_SINGULAR=5,
             POINTS_SINGULAR=6, NEAR_PAIRS=7, MS_ZERO=8, MS_REGULAR=9, MS_ADAPTIVE=10, MS_SINGULAR=11, MS_FREETERM=12,
             MS_LU=13, MS_SOLVE=14, MS_GEMM=15, MS_PANEL=16, LAUNCHES=17, MS_SETUP_HOST=18, MS_ASSEMBLE=19,
-            FLOPS_REGULAR=20, MS_TRSM=21, MS_SWAP=22, LU_LAUNCHES=23, GEMM_LAUNCHES=24, GEMM_FLOPS=25)
+            FLOPS_REGULAR=20, MS_TRSM=21, MS_SWAP=22, LU_LAUNCHES=23, GEMM_LAUNCHES=24, GEMM_FLOPS=25, GEMM_EXEC_FLOPS=26)
 STAT_COUNT = 32
 
 

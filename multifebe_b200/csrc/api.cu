@@ -600,7 +600,8 @@ static int assemble_device(mfb_problem* p, double omega, cd lambda, cd mu, doubl
   p->factored = false; p->assembled = true; p->rows_permuted = true;
   // our kernels only (memsets/copies are not counted): free term + per group regular, adaptive, singular (+ gather_cv)
   p->asm_launches = 1;
-  for (auto& g : p->groups) p->asm_launches += 1 + (cvalue ? 1 : 0) + (g.adp.n_pairs > 0) + (g.sing.n_pairs > 0);
+  for (auto& g : p->groups)   // K1: one kernel per element class on 3/4-node elements (classes 0, 1 and, if present, 2)
+    p->asm_launches += (((g.et == 5 || g.et == 7) && g.dev.cols3) ? 2 + g.dev.has_mixed : 1) + (cvalue ? 1 : 0) + (g.adp.n_pairs > 0) + (g.sing.n_pairs > 0);
   return MFB_OK;
 }
 static int collect_assembly_times(mfb_problem* p) {
@@ -685,7 +686,7 @@ static int factor_device(mfb_problem* p, int n, bool timing) {
   float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_LU] = t;
   if (timing) lu_collect_times(p->lu);
   p->stats[MFB_STAT_LU_LAUNCHES] = (double)p->lu.launches;
-  p->stats[MFB_STAT_GEMM_LAUNCHES] = (double)p->lu.gemm_launches; p->stats[MFB_STAT_GEMM_FLOPS] = p->lu.gemm_flops;
+  p->stats[MFB_STAT_GEMM_LAUNCHES] = (double)p->lu.gemm_launches; p->stats[MFB_STAT_GEMM_FLOPS] = p->lu.gemm_flops; p->stats[MFB_STAT_GEMM_EXEC_FLOPS] = p->lu.gemm_exec_flops;
   p->stats[MFB_STAT_MS_PANEL] = p->lu.ms_panel; p->stats[MFB_STAT_MS_SWAP] = p->lu.ms_swap; p->stats[MFB_STAT_MS_TRSM] = p->lu.ms_trsm; p->stats[MFB_STAT_MS_GEMM] = p->lu.ms_gemm;
   std::vector<int> perm(n);
   for (int i = 0; i < n; i++) perm[i] = i;

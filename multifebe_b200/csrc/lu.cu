@@ -152,6 +152,9 @@ k_zgemm_minus(int M, int N, int K, const double* __restrict__ Are, const double*
 // componentwise bound, which an LU with partial pivoting does not rely on.  Warp tile 32 x (8*NI), accumulators X, Y, Z in
 // registers, C read in the epilogue only.  Same shared-memory staging as k_zgemm_minus.
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef MFB_GEMM3M_PRELOAD
+#define MFB_GEMM3M_PRELOAD 1
+#endif
 template <int WM, int WN, int NI>
 struct Gemm3Cfg {
   static const int BK = 16, STAGES = 2;
@@ -213,8 +216,16 @@ k_zgemm3m_minus(int M, int N, int K, const double* __restrict__ Are, const doubl
       for (int h = 0; h < 2; h++) {
         int m = m0 + wm * 32 + mi * 8 + gid, n = n0 + wn * 8 * NI + ni * 8 + 2 * tig + h;
         const bool ok = (m < M) && (n < N);
+#if MFB_GEMM3M_PRELOAD
         const double cr = ok ? Cre[(long long)n * ldc + m] : 0.0, ci = ok ? Cim[(long long)n * ldc + m] : 0.0;
         x[mi][ni][h] = -cr; y[mi][ni][h] = 0.0; z[mi][ni][h] = -(ci + cr);
+#else
+        if (ok) {   // pull the C tile into L2 now; it is read in the epilogue
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(Cre + (long long)n * ldc + m));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(Cim + (long long)n * ldc + m));
+        }
+        x[mi][ni][h] = 0.0; y[mi][ni][h] = 0.0; z[mi][ni][h] = 0.0;
+#endif
       }
   for (int kt = 0; kt < KT; kt++) {
     cp_async_wait<STAGES - 2>();
@@ -253,8 +264,13 @@ k_zgemm3m_minus(int M, int N, int K, const double* __restrict__ Are, const doubl
         int m = m0 + wm * 32 + mi * 8 + gid, n = n0 + wn * 8 * NI + ni * 8 + 2 * tig + h;
         if (m < M && n < N) {
           const long long o = (long long)n * ldc + m;
+#if MFB_GEMM3M_PRELOAD
           Cre[o] = y[mi][ni][h] - x[mi][ni][h];
           Cim[o] = (x[mi][ni][h] + y[mi][ni][h]) - z[mi][ni][h];
+#else
+          Cre[o] -= x[mi][ni][h] - y[mi][ni][h];
+          Cim[o] -= z[mi][ni][h] - x[mi][ni][h] - y[mi][ni][h];
+#endif
         }
       }
 }
@@ -595,13 +611,14 @@ static int factor_panel(double* Are, double* Aim, long long lda, int n, int k0, 
 int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuWork& w, cudaStream_t st, bool timing) {
   const int nb = w.nb;
   cudaMemsetAsync(w.info, 0, sizeof(int), st);
-  w.launches = 0; w.gemm_launches = 0; w.gemm_flops = 0.0; w.n_steps_timed = 0;
+  w.launches = 0; w.gemm_launches = 0; w.gemm_flops = 0.0; w.gemm_exec_flops = 0.0; w.n_steps_timed = 0;
   cudaStream_t ps = w.lookahead ? w.panel_stream : st;
   auto gemm = [&](int r0, int k0, int kw, int c0, int c1) {   // A[r0:n, c0:c1] -= A[r0:n, k0:k0+kw] * A[k0:k0+kw, c0:c1]
     if (c1 <= c0 || r0 >= n) return;
     zgemm_minus_planar(n - r0, c1 - c0, kw, Are + (long long)k0 * lda + r0, Aim + (long long)k0 * lda + r0, lda,
                        Are + (long long)c0 * lda + k0, Aim + (long long)c0 * lda + k0, lda, Are + (long long)c0 * lda + r0, Aim + (long long)c0 * lda + r0, lda, st);
     w.launches++; w.gemm_launches++; w.gemm_flops += 8.0 * (double)(n - r0) * (double)(c1 - c0) * (double)kw;
+    w.gemm_exec_flops += (gemm_cfg() >= 10 ? 6.0 : 8.0) * (double)(n - r0) * (double)(c1 - c0) * (double)kw;
   };
   // first panel
   {

@@ -14,7 +14,7 @@ struct LuWork {
   double *cand_data;      // [2][grid][2*32]   candidate rows (re, im)
   double *diag_data;      // [2][2*32]         current diagonal row
   int *info;              // device flag: first zero pivot (1-based), 0 = ok
-  float ms_panel, ms_swap, ms_trsm, ms_gemm; long long launches; long long gemm_launches; double gemm_flops;
+  float ms_panel, ms_swap, ms_trsm, ms_gemm; long long launches; long long gemm_launches; double gemm_flops, gemm_exec_flops;   // algorithmic (8mnk) and executed (6mnk with the 3M kernel) flops of the trailing updates
   cudaEvent_t* evs; int n_evs, n_steps_timed;   // 5 events per block step, recorded without synchronising
   cudaStream_t panel_stream;                    // high-priority stream of the look-ahead panel factorisation
   cudaEvent_t ev_next_cols, ev_panel_done;      // next panel's columns updated / next panel factorised
