@@ -230,31 +230,37 @@ const int KB_WARPS = 4;
 #endif
 const int KB_WARPS_FAST = MFB_KB_WARPS_FAST;   // warps per CTA of the MODE 0 kernel (2 CTAs per SM)
 
+const int KB_CACHE_GP = 4;   // in-place batches of up to this many points keep their kernel scalars in shared memory between node chunks
+// 3/4-node elements are accumulated whole; 6/8/9-node elements in NCH chunks of NW = 3 nodes (27 complex accumulators)
+template <int NN_>
+struct K1Shape {
+  static const int NN = NN_, NW = (NN_ <= 4) ? NN_ : 3, NCH = (NN_ + NW - 1) / NW;
+  static const int STAGE = 2 * 3 * NW * 96;                            // doubles per warp: staging of NW node boxes
+  static const int CACHE = (NCH > 1) ? KB_CACHE_GP * 10 * 32 : 0;      // doubles per warp
+  static const int SMEM_PER_WARP = (STAGE + CACHE) * 8 + MAX_SETS * 64 * 2 + MAX_SETS * 4;
+};
+
 template <int NN>
 struct AccA { double re[9 * NN], im[9 * NN]; };   // [(l*3+k)*NN + j]: entry of load direction l (row) and dof k of node j (column)
 
-// One Gauss point of one pair; rec = (x[3], n[3], w[NN]) of the point.
+// One Gauss point of one pair, accumulated for NW nodes of the element (all of them for 3/4-node elements, a chunk of
+// three for 6/8/9-node elements).  rec = (x[3], n[3]) of the point, w[NW] = phi_j*J*weight of the chunk's nodes.
 // MODE 0: element whose boundary-condition kinds are the same for all its nodes and whose prescribed values are all zero
 //         (the common case): only the combination that goes to the matrix is formed.
-// MODE 1: uniform kinds, some prescribed value nonzero: the other combination times S_k = sum_j w_j cv_jk goes to b.
-// MODE 2: any element: both combinations, per (node, dof) one goes to A and the other, times the prescribed value, to b.
-template <int NN, int MODE>
-__device__ __forceinline__ void k1_point(AccA<NN>& a, double* bacc, const double* rec, const double* xc, double sgn, unsigned info,
-                                         const unsigned char* __restrict__ ekind, const double* __restrict__ ecv) {
+// MODE 1: uniform kinds, some prescribed value nonzero: the other combination times S_k = sum_j w_j cv_jk (sk, over ALL nodes
+//         of the element, formed by the caller) goes to b when do_b.
+// MODE 2: any element: both combinations, per (node, dof) one goes to A and the other, times the prescribed value, to b;
+//         ekind / ecv point at the chunk's first node.
+// have_ks: the kernel scalars of this point are already in ks (cached by the pass over the first chunk of nodes).
+template <int NW, int MODE>
+__device__ __forceinline__ void k1_point(AccA<NW>& a, double* bacc, const double* rec, const double* w, const double* sk, bool do_b, const double* xc,
+                                         double sgn, unsigned info, const unsigned char* __restrict__ ekind, const double* __restrict__ ecv, bool have_ks,
+                                         KScal& k) {
   const double n[3] = {sgn * rec[3], sgn * rec[4], sgn * rec[5]};
-  const double* w = rec + 6;
   const double rv0 = rec[0] - xc[0], rv1 = rec[1] - xc[1], rv2 = rec[2] - xc[2];
   const double r2 = fma(rv0, rv0, fma(rv1, rv1, rv2 * rv2));
   const double d1r1 = rsqrt(r2), r = r2 * d1r1;
-  // S_k = sum_j w_j * prescribed value of (node j, dof k): requested first, used last
-  double sk[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  if (MODE == 1) {
-#pragma unroll
-    for (int kk = 0; kk < 3; kk++)
-#pragma unroll
-      for (int j = 0; j < NN; j++) { sk[kk] = fma(w[j], __ldg(ecv + 2 * (j * 3 + kk)), sk[kk]); sk[3 + kk] = fma(w[j], __ldg(ecv + 2 * (j * 3 + kk) + 1), sk[3 + kk]); }
-  }
-  KScal k; kernel_scalars_scaled(c_kq, r, d1r1, k, MODE != 0 || (info & 7u) != 7u, MODE != 0 || (info & 7u) != 0u);
+  if (!have_ks) kernel_scalars_scaled(c_kq, r, d1r1, k, MODE != 0 || (info & 7u) != 7u, MODE != 0 || (info & 7u) != 0u);
   const double dx[3] = {rv0 * d1r1, rv1 * d1r1, rv2 * d1r1};
   const double drdn = fma(dx[0], n[0], fma(dx[1], n[1], dx[2] * n[2]));
   const cplx t1d = k.T1 * drdn;
@@ -262,15 +268,15 @@ __device__ __forceinline__ void k1_point(AccA<NN>& a, double* bacc, const double
 #pragma unroll
     for (int kk = 0; kk < 3; kk++) {
       const bool tk = (info >> kk) & 1u;
-      const double skr = sk[kk], ski = sk[3 + kk];
+      const double skr = (MODE == 1) ? sk[kk] : 0.0, ski = (MODE == 1) ? sk[3 + kk] : 0.0;
       if (tk) {
 #pragma unroll
         for (int l = 0; l < 3; l++) {
           const double dd = dx[l] * dx[kk], c2 = (l == kk) ? fma(dx[kk], n[l], drdn) : dx[kk] * n[l], c3 = dx[l] * n[kk];
           const double fr = fma(t1d.re, dd, fma(k.T2.re, c2, k.T3.re * c3)), fi = fma(t1d.im, dd, fma(k.T2.im, c2, k.T3.im * c3));
 #pragma unroll
-          for (int j = 0; j < NN; j++) { a.re[(l * 3 + kk) * NN + j] = fma(fr, w[j], a.re[(l * 3 + kk) * NN + j]); a.im[(l * 3 + kk) * NN + j] = fma(fi, w[j], a.im[(l * 3 + kk) * NN + j]); }
-          if (MODE == 1) {
+          for (int j = 0; j < NW; j++) { a.re[(l * 3 + kk) * NW + j] = fma(fr, w[j], a.re[(l * 3 + kk) * NW + j]); a.im[(l * 3 + kk) * NW + j] = fma(fi, w[j], a.im[(l * 3 + kk) * NW + j]); }
+          if (MODE == 1 && do_b) {
             const double orr = (l == kk) ? fma(-k.chi.re, dd, k.psi.re) : -k.chi.re * dd, oi = (l == kk) ? fma(-k.chi.im, dd, k.psi.im) : -k.chi.im * dd;
             bacc[l] -= orr * skr - oi * ski; bacc[3 + l] -= orr * ski + oi * skr;
           }
@@ -281,8 +287,8 @@ __device__ __forceinline__ void k1_point(AccA<NN>& a, double* bacc, const double
           const double dd = dx[l] * dx[kk];
           const double fr = (l == kk) ? fma(-k.chi.re, dd, k.psi.re) : -k.chi.re * dd, fi = (l == kk) ? fma(-k.chi.im, dd, k.psi.im) : -k.chi.im * dd;
 #pragma unroll
-          for (int j = 0; j < NN; j++) { a.re[(l * 3 + kk) * NN + j] = fma(fr, w[j], a.re[(l * 3 + kk) * NN + j]); a.im[(l * 3 + kk) * NN + j] = fma(fi, w[j], a.im[(l * 3 + kk) * NN + j]); }
-          if (MODE == 1) {
+          for (int j = 0; j < NW; j++) { a.re[(l * 3 + kk) * NW + j] = fma(fr, w[j], a.re[(l * 3 + kk) * NW + j]); a.im[(l * 3 + kk) * NW + j] = fma(fi, w[j], a.im[(l * 3 + kk) * NW + j]); }
+          if (MODE == 1 && do_b) {
             const double c2 = (l == kk) ? fma(dx[kk], n[l], drdn) : dx[kk] * n[l], c3 = dx[l] * n[kk];
             const double orr = fma(t1d.re, dd, fma(k.T2.re, c2, k.T3.re * c3)), oi = fma(t1d.im, dd, fma(k.T2.im, c2, k.T3.im * c3));
             bacc[l] -= orr * skr - oi * ski; bacc[3 + l] -= orr * ski + oi * skr;
@@ -301,13 +307,14 @@ __device__ __forceinline__ void k1_point(AccA<NN>& a, double* bacc, const double
         fur[l] = (l == kk) ? fma(-k.chi.re, dd, k.psi.re) : -k.chi.re * dd; fui[l] = (l == kk) ? fma(-k.chi.im, dd, k.psi.im) : -k.chi.im * dd;
       }
 #pragma unroll
-      for (int j = 0; j < NN; j++) {
+      for (int j = 0; j < NW; j++) {
+        if (w[j] == 0.0) continue;   // padding node of a short last chunk (its ekind/ecv are out of range)
         const bool tk = ekind[j * 3 + kk] != 0;
         const double cvr = w[j] * __ldg(ecv + 2 * (j * 3 + kk)), cvi = w[j] * __ldg(ecv + 2 * (j * 3 + kk) + 1);
 #pragma unroll
         for (int l = 0; l < 3; l++) {
           const double ar = tk ? ftr[l] : fur[l], ai = tk ? fti[l] : fui[l], orr = tk ? fur[l] : ftr[l], oi = tk ? fui[l] : fti[l];
-          a.re[(l * 3 + kk) * NN + j] = fma(ar, w[j], a.re[(l * 3 + kk) * NN + j]); a.im[(l * 3 + kk) * NN + j] = fma(ai, w[j], a.im[(l * 3 + kk) * NN + j]);
+          a.re[(l * 3 + kk) * NW + j] = fma(ar, w[j], a.re[(l * 3 + kk) * NW + j]); a.im[(l * 3 + kk) * NW + j] = fma(ai, w[j], a.im[(l * 3 + kk) * NW + j]);
           bacc[l] -= orr * cvr - oi * cvi; bacc[3 + l] -= orr * cvi + oi * cvr;
         }
       }
@@ -335,13 +342,15 @@ template <int ET, int MODE, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_constant__ CUtensorMap tmap, DevGroup g, DevColloc c, DevSystem s,
                                                                   const unsigned char* __restrict__ plan,
                                                                   int* __restrict__ task_counter) {
-  constexpr int NN = ElemTraits<ET>::NN, NC = 3 * NN;
+  typedef K1Shape<ElemTraits<ET>::NN> SH;
+  constexpr int NN = SH::NN, NC = 3 * NN, NW = SH::NW, NCH = SH::NCH, RECN = 6 + NN;
   extern __shared__ __align__(128) double k1_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr bool GEN = MODE != 0;
-  double* buf = k1_smem + (size_t)warp * (2 * NC * 96);
-  unsigned short* queue = reinterpret_cast<unsigned short*>(k1_smem + (size_t)WARPS * (2 * NC * 96)) + (size_t)warp * (MAX_SETS * KB_QCAP);
-  int* qcnt = reinterpret_cast<int*>(reinterpret_cast<unsigned short*>(k1_smem + (size_t)WARPS * (2 * NC * 96)) + (size_t)WARPS * (MAX_SETS * KB_QCAP)) + warp * MAX_SETS;
+  double* buf = k1_smem + (size_t)warp * SH::STAGE;
+  double* kcache = k1_smem + (size_t)WARPS * SH::STAGE + (size_t)warp * SH::CACHE;   // [point][10 scalars][32 lanes], chunked elements only
+  unsigned short* queue = reinterpret_cast<unsigned short*>(k1_smem + (size_t)WARPS * (SH::STAGE + SH::CACHE)) + (size_t)warp * (MAX_SETS * KB_QCAP);
+  int* qcnt = reinterpret_cast<int*>(reinterpret_cast<unsigned short*>(k1_smem + (size_t)WARPS * (SH::STAGE + SH::CACHE)) + (size_t)WARPS * (MAX_SETS * KB_QCAP)) + warp * MAX_SETS;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int n_tasks = c.n_tiles * g.n_ranges;
   bool pending = false;
@@ -395,7 +404,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
         const unsigned in0 = __ballot_sync(0xffffffffu, m == 0);
         inplace_todo = __popc(in0) >= KB_INPLACE_MIN;
         if (inplace_todo && lane < 3) {   // pull the next element's first point set towards L1 while this one is integrated
-          const double* Pn = g.pts[0] + (size_t)(ecur + 1) * g.ngp[0] * (6 + NN);
+          const double* Pn = g.pts[0] + (size_t)(ecur + 1) * g.ngp[0] * RECN;
           if (ecur + 1 < e1) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(Pn) + 128 * lane));
         }
         unsigned todo = inplace_todo ? (reg & ~in0) : reg;
@@ -422,83 +431,119 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
         src = ent & 31; el = e0 + (ent >> 5); inplace = false;
       } else break;
 
-      // ---- integrate the batch: one pair per lane ----
+      // ---- integrate the batch: one pair per lane; 6/8/9-node elements in chunks of three nodes ----
       const double xs[3] = {__shfl_sync(0xffffffffu, xc[0], src), __shfl_sync(0xffffffffu, xc[1], src), __shfl_sync(0xffffffffu, xc[2], src)};
       const int rs = __shfl_sync(0xffffffffu, r0, src);
       const int* ecol = g.ecol + (size_t)el * NC;
-      int mycol = 0;
-      if (inplace && lane < NN) mycol = __ldg(ecol + 3 * lane);   // first column of every node of the element, needed by the flush only
-      AccA<NN> acc;
-#pragma unroll
-      for (int i = 0; i < 9 * NN; i++) { acc.re[i] = 0.0; acc.im[i] = 0.0; }
-      double bacc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      if (act) {
-        const unsigned info = g.einfo[el];
-        const double sgn = (info & 16u) ? -1.0 : 1.0;
-        const int ngp = g.ngp[sset];
-        const double* P = g.pts[sset] + (size_t)el * ngp * (6 + NN);
-        const unsigned char* ekind = g.ekind + (size_t)el * NC;
-        const double* ecv = g.ecv + (size_t)el * 2 * NC;
-        // the record of point kp+1 is requested before point kp is integrated
-        double rec[6 + NN];
-#pragma unroll
-        for (int i = 0; i < 6 + NN; i++) rec[i] = ldg_ahead(P + i);
+      const int ngp = g.ngp[sset];
+      // the kernel scalars of the first chunk's pass are kept in shared memory for the other chunks (in-place batches of few points)
+      const bool use_cache = (NCH > 1) && inplace && ngp <= KB_CACHE_GP;
 #pragma unroll 1
-        for (int kp = 0; kp < ngp; kp++) {
-          double cur[6 + NN];
+      for (int ch = 0; ch < NCH; ch++) {
+        const int j0 = ch * NW;
+        int mycol = 0;
+        if (inplace && lane < NW && j0 + lane < NN) mycol = __ldg(ecol + 3 * (j0 + lane));   // first column of the chunk's nodes, needed by the flush only
+        AccA<NW> acc;
 #pragma unroll
-          for (int i = 0; i < 6 + NN; i++) cur[i] = rec[i];
-          if (kp + 1 < ngp) {
+        for (int i = 0; i < 9 * NW; i++) { acc.re[i] = 0.0; acc.im[i] = 0.0; }
+        double bacc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (act) {
+          const unsigned info = g.einfo[el];
+          const double sgn = (info & 16u) ? -1.0 : 1.0;
+          const double* P = g.pts[sset] + (size_t)el * ngp * RECN;
+          const unsigned char* ekind = g.ekind + (size_t)el * NC + 3 * j0;
+          const double* ecv = g.ecv + (size_t)el * 2 * NC + 6 * j0;
+          // the record of point kp+1 is requested before point kp is integrated
+          double rec[6 + NW];
 #pragma unroll
-            for (int i = 0; i < 6 + NN; i++) rec[i] = ldg_ahead(P + (size_t)(kp + 1) * (6 + NN) + i);
-          }
-          k1_point<NN, MODE>(acc, bacc, cur, xs, sgn, info, ekind, ecv);
-        }
-      }
-      // ---- flush ----
-      if (inplace && nbytes > 0) {
-        if (pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous flush has left the buffer
-        __syncwarp();
-        // staging layout = the TMA box of one node: [node j][plane][dof k][96 rows]
+          for (int i = 0; i < 6; i++) rec[i] = ldg_ahead(P + i);
 #pragma unroll
-        for (int j = 0; j < NN; j++)
+          for (int i = 0; i < NW; i++) rec[6 + i] = (j0 + i < NN) ? ldg_ahead(P + 6 + j0 + i) : 0.0;
+#pragma unroll 1
+          for (int kp = 0; kp < ngp; kp++) {
+            double cur[6 + NW];
 #pragma unroll
-          for (int k = 0; k < 3; k++)
+            for (int i = 0; i < 6 + NW; i++) cur[i] = rec[i];
+            if (kp + 1 < ngp) {
+              const double* Pn = P + (size_t)(kp + 1) * RECN;
 #pragma unroll
-            for (int l = 0; l < 3; l++) {
-              buf[((j * 2 + 0) * 3 + k) * 96 + 3 * lane + l] = acc.re[(l * 3 + k) * NN + j];
-              buf[((j * 2 + 1) * 3 + k) * 96 + 3 * lane + l] = acc.im[(l * 3 + k) * NN + j];
+              for (int i = 0; i < 6; i++) rec[i] = ldg_ahead(Pn + i);
+#pragma unroll
+              for (int i = 0; i < NW; i++) rec[6 + i] = (j0 + i < NN) ? ldg_ahead(Pn + 6 + j0 + i) : 0.0;
             }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
+            double sk[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            if (MODE == 1 && ch == 0) {   // S_k over all the nodes of the element
+              const double* wall = P + (size_t)kp * RECN + 6;
+              const double* ecv0 = g.ecv + (size_t)el * 2 * NC;
 #pragma unroll
-        for (int j = 0; j < NN; j++) {
-          const int col = __shfl_sync(0xffffffffu, mycol, j);
-          if (lane == 0)
-            asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&tmap), "r"(row0), "r"(col), "r"(0),
-                         "r"(smem_u32(buf + j * 576))
-                         : "memory");
-        }
-        if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        pending = true;
-        if (GEN) {
+              for (int kk = 0; kk < 3; kk++)
 #pragma unroll
-          for (int i = 0; i < 6; i++) bacc_t[i] += bacc[i];
-        }
-      } else if (act) {
-#pragma unroll
-        for (int j = 0; j < NN; j++)
-#pragma unroll
-          for (int k = 0; k < 3; k++) {
-            const int col = __ldg(ecol + j * 3 + k);
-            double* Ar = s.Are + (size_t)col * s.lda + rs; double* Ai = s.Aim + (size_t)col * s.lda + rs;
-#pragma unroll
-            for (int l = 0; l < 3; l++) { atomicAdd(Ar + l, acc.re[(l * 3 + k) * NN + j]); atomicAdd(Ai + l, acc.im[(l * 3 + k) * NN + j]); }
+                for (int j = 0; j < NN; j++) {
+                  const double wj = (NCH == 1) ? cur[6 + j < 6 + NW ? 6 + j : 6] : __ldg(wall + j);
+                  sk[kk] = fma(wj, __ldg(ecv0 + 2 * (j * 3 + kk)), sk[kk]); sk[3 + kk] = fma(wj, __ldg(ecv0 + 2 * (j * 3 + kk) + 1), sk[3 + kk]);
+                }
+            }
+            KScal ks;
+            const bool have_ks = use_cache && ch > 0;
+            if (have_ks) {
+              const double* kc = kcache + (size_t)kp * 320 + lane;
+              ks.psi = mk(kc[0], kc[32]); ks.chi = mk(kc[64], kc[96]); ks.T1 = mk(kc[128], kc[160]); ks.T2 = mk(kc[192], kc[224]); ks.T3 = mk(kc[256], kc[288]);
+            }
+            k1_point<NW, MODE>(acc, bacc, cur, cur + 6, sk, ch == 0, xs, sgn, info, ekind, ecv, have_ks, ks);
+            if (use_cache && ch == 0) {
+              double* kc = kcache + (size_t)kp * 320 + lane;
+              kc[0] = ks.psi.re; kc[32] = ks.psi.im; kc[64] = ks.chi.re; kc[96] = ks.chi.im; kc[128] = ks.T1.re; kc[160] = ks.T1.im;
+              kc[192] = ks.T2.re; kc[224] = ks.T2.im; kc[256] = ks.T3.re; kc[288] = ks.T3.im;
+            }
           }
-        if (GEN) {
+        }
+        // ---- flush of the chunk ----
+        if (inplace && nbytes > 0) {
+          if (pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous flush has left the buffer
+          __syncwarp();
+          // staging layout = the TMA box of one node: [node j][plane][dof k][96 rows]
 #pragma unroll
-          for (int l = 0; l < 3; l++)
-            if (bacc[l] != 0.0 || bacc[3 + l] != 0.0) { atomicAdd(s.bre + rs + l, bacc[l]); atomicAdd(s.bim + rs + l, bacc[3 + l]); }
+          for (int j = 0; j < NW; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+              for (int l = 0; l < 3; l++) {
+                buf[((j * 2 + 0) * 3 + k) * 96 + 3 * lane + l] = acc.re[(l * 3 + k) * NW + j];
+                buf[((j * 2 + 1) * 3 + k) * 96 + 3 * lane + l] = acc.im[(l * 3 + k) * NW + j];
+              }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < NW; j++) {
+            const int col = __shfl_sync(0xffffffffu, mycol, j);
+            if (lane == 0 && j0 + j < NN)
+              asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&tmap), "r"(row0), "r"(col), "r"(0),
+                           "r"(smem_u32(buf + j * 576))
+                           : "memory");
+          }
+          if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          pending = true;
+          if (GEN) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) bacc_t[i] += bacc[i];
+          }
+        } else if (act) {
+#pragma unroll
+          for (int j = 0; j < NW; j++) {
+            if (j0 + j >= NN) continue;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              const int col = __ldg(ecol + (j0 + j) * 3 + k);
+              double* Ar = s.Are + (size_t)col * s.lda + rs; double* Ai = s.Aim + (size_t)col * s.lda + rs;
+#pragma unroll
+              for (int l = 0; l < 3; l++) { atomicAdd(Ar + l, acc.re[(l * 3 + k) * NW + j]); atomicAdd(Ai + l, acc.im[(l * 3 + k) * NW + j]); }
+            }
+          }
+          if (GEN) {
+#pragma unroll
+            for (int l = 0; l < 3; l++)
+              if (bacc[l] != 0.0 || bacc[3 + l] != 0.0) { atomicAdd(s.bre + rs + l, bacc[l]); atomicAdd(s.bim + rs + l, bacc[3 + l]); }
+          }
         }
       }
     }
@@ -515,8 +560,7 @@ static int* g_task_counters = nullptr;   // one counter per kernel of a launch, 
 template <int ET, int MODE, int WARPS>
 static void launch_bulk_mode(const CUtensorMap& tmap, const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, int n_sm,
                              cudaStream_t st) {
-  constexpr int NC = 3 * ElemTraits<ET>::NN;
-  const int smem = WARPS * (2 * NC * 96 * (int)sizeof(double) + KB_SMEM_QUEUE + MAX_SETS * (int)sizeof(int));
+  const int smem = WARPS * K1Shape<ElemTraits<ET>::NN>::SMEM_PER_WARP;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(k_regular_bulk<ET, MODE, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
   const int n_tasks = c.n_tiles * g.n_ranges;
@@ -577,9 +621,12 @@ void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, c
             k_regular<5, 3><<<grid, block, 0, st>>>(g, c, s, plan); break;
     case 7: if (g.cols3 && tmap) { launch_regular_bulk<7>(*reinterpret_cast<const CUtensorMap*>(tmap), g, c, s, plan, st); break; }
             k_regular<7, 3><<<grid, block, 0, st>>>(g, c, s, plan); break;
-    case 6: k_regular<6, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
-    case 8: k_regular<8, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
-    case 9: k_regular<9, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
+    case 6: if (g.cols3 && tmap) { launch_regular_bulk<6>(*reinterpret_cast<const CUtensorMap*>(tmap), g, c, s, plan, st); break; }
+            k_regular<6, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
+    case 8: if (g.cols3 && tmap) { launch_regular_bulk<8>(*reinterpret_cast<const CUtensorMap*>(tmap), g, c, s, plan, st); break; }
+            k_regular<8, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
+    case 9: if (g.cols3 && tmap) { launch_regular_bulk<9>(*reinterpret_cast<const CUtensorMap*>(tmap), g, c, s, plan, st); break; }
+            k_regular<9, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
   }
 }
 

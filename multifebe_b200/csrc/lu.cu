@@ -309,6 +309,9 @@ void zgemm_minus_planar(int m, int n, int k, const double* Are, const double* Ai
     case 12: launch_gemm3m<2, 2, 2, 2>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 3M, 64 x 32, warp 32 x 16, 2 CTA/SM
     case 13: launch_gemm3m<4, 2, 2, 1>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 3M, 128 x 32, 8 warps of 32 x 16, 1 CTA/SM
     case 14: launch_gemm3m<2, 2, 3, 2>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 3M, 64 x 48, warp 32 x 24, 2 CTA/SM
+    case 17: launch_gemm3m<4, 4, 2, 1>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 3M, 128 x 64, 16 warps of 32 x 16
+    case 18: launch_gemm3m<4, 2, 2, 2>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 3M, 128 x 32, 8 warps of 32 x 16, 2 CTA/SM
+    case 19: launch_gemm3m<2, 4, 2, 3>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 3M, 64 x 64, 8 warps of 32 x 16, 3 CTA/SM
     case 15: launch_gemm3m<2, 2, 2, 3>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 3M, 64 x 32, warp 32 x 16, 3 CTA/SM
     case 16: launch_gemm3m<2, 4, 2, 2>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 3M, 64 x 64, 8 warps of 32 x 16, 2 CTA/SM
     case 0: launch_gemm_cfg<4, 2, 16, 3, 1>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 128 x 64, 8 warps, 1 CTA/SM
