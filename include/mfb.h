@@ -111,7 +111,9 @@ enum mfb_stat_id {
   MFB_STAT_MS_FREETERM = 12, MFB_STAT_MS_LU = 13, MFB_STAT_MS_SOLVE = 14, MFB_STAT_MS_GEMM = 15, MFB_STAT_MS_PANEL = 16,
   MFB_STAT_LAUNCHES = 17, MFB_STAT_MS_SETUP_HOST = 18, MFB_STAT_MS_ASSEMBLE = 19, MFB_STAT_FLOPS_REGULAR = 20,
   MFB_STAT_MS_TRSM = 21, MFB_STAT_MS_SWAP = 22, MFB_STAT_LU_LAUNCHES = 23, MFB_STAT_GEMM_LAUNCHES = 24,
-  MFB_STAT_GEMM_FLOPS = 25, MFB_STAT_GEMM_EXEC_FLOPS = 26, MFB_STAT_COUNT = 32
+  MFB_STAT_GEMM_FLOPS = 25, MFB_STAT_GEMM_EXEC_FLOPS = 26,
+  /* single-frequency multi-GPU mode (mfb_dist_*): redistribution row slabs -> column owners, distributed LU, back substitution, whole call */
+  MFB_STAT_MS_REDIST = 27, MFB_STAT_MS_DIST_LU = 28, MFB_STAT_MS_DIST_SOLVE = 29, MFB_STAT_MS_DIST_TOTAL = 30, MFB_STAT_COUNT = 32
 };
 int mfb_get_stats(mfb_problem* problem, double* stats /* MFB_STAT_COUNT doubles */);
 
@@ -132,6 +134,32 @@ int mfb_measure_peaks(mfb_ctx* ctx, double* dfma_tflops, double* dmma_tflops, do
  * C (m x n), A (m x k), B (k x n), all host col-major interleaved complex. */
 int mfb_zgemm_minus(mfb_ctx* ctx, int m, int n, int k, const mfb_z* A, int lda, const mfb_z* B, int ldb, mfb_z* C, int ldc,
                     double* ms);
+
+/* ---- One frequency over several GPUs (shard 2) --------------------------------------------------
+ * One process per GPU, every process holds the same mfb_problem (mesh + plan replicated).  Rank r assembles a contiguous
+ * run of collocation-row blocks (the rows of build_lse_mechanics_bem_harela's kn_col loop it owns, all columns), the row
+ * slabs move once to the owners of the matrix columns (block-cyclic, block = nb columns, NCCL send/recv), and the LU
+ * (solve_lse_c -> zgetrf/zgetrs) runs distributed: per block column the owner factorises the panel, NCCL broadcasts it,
+ * every rank interchanges / solves / updates its own columns on the FP64 tensor pipe; the right-hand side rides along as
+ * a replicated extra column and the back substitution reduces one block of partial sums per step.  The solution is
+ * returned on every rank.  All mfb_dist_* calls are collective over the ranks of the communicator.
+ *   mfb_dist_unique_id   rank 0 creates the 128-byte NCCL id; the host distributes it (MPI_Bcast / torch.distributed)
+ *   mfb_dist_init        joins the communicator (nb <= 0: default 256) and allocates the local column storage
+ *   mfb_dist_init_loopback  test mode: `nranks` virtual ranks on ONE GPU, collectives are device copies (no NCCL)
+ *   mfb_dist_solve_frequency  == mfb_harela3d_solve_frequency, distributed
+ *   mfb_dist_zsolve      == zgesv on a host matrix every rank passes in full (tests of the distributed LU)
+ * Host-only helpers (no GPU needed): mfb_dist_layout (local -> global column map of a rank) and
+ * mfb_dist_partition_tiles (collocation tiles -> ranks, row_bounds[nranks+1]). */
+int mfb_dist_unique_id(char* id128);
+int mfb_dist_init(mfb_problem* problem, int rank, int nranks, const char* id128, int nb);
+int mfb_dist_init_loopback(mfb_problem* problem, int nranks, int nb);
+int mfb_dist_info(mfb_problem* problem, int* rank, int* nranks, int* row_bounds, int* n_local_cols);
+int mfb_dist_solve_frequency(mfb_problem* problem, double omega, const mfb_z* lambda, const mfb_z* mu, double rho,
+                             const mfb_z* nu, const mfb_z* cvalue, mfb_z* x);
+int mfb_dist_zsolve(mfb_problem* problem, int n, const mfb_z* A, int lda, const mfb_z* b, mfb_z* x, int* ipiv);
+int mfb_dist_layout(int n, int nb, int nranks, int rank, int* n_local_cols, int* local_to_global);
+int mfb_dist_partition_tiles(int n_tiles, const int* tile_row0, const int* tile_nbytes, int n_dof, int nranks, int* tile_rank,
+                             int* row_bounds);
 
 #ifdef __cplusplus
 }

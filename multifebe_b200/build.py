@@ -15,8 +15,8 @@ OUT = os.path.join(HERE, "libmfb.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 GXX = "/usr/bin/g++"   # the image's $CXX wrapper lacks libgomp.spec
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-SOURCES_CU = ["api.cu", "assembly.cu", "lu.cu"]
-DEPS = SOURCES_CU + ["plan_host.cpp", "plan_host.h", "assembly.cuh", "lu.cuh", "bem_math.cuh",
+SOURCES_CU = ["api.cu", "assembly.cu", "lu.cu", "dist.cu"]
+DEPS = SOURCES_CU + ["plan_host.cpp", "plan_host.h", "assembly.cuh", "lu.cuh", "dist.cuh", "bem_math.cuh",
                      os.path.join("..", "..", "include", "mfb.h"), os.path.join("..", "..", "data", "quad_tables.h")]
 
 
@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
             print(" ".join(cmd))
         subprocess.check_call(cmd)
         objs.append(o)
-    cmd = [NVCC, "-ccbin", GXX, "-shared", "-o", OUT] + objs + ["-Xcompiler", "-fopenmp", "-lquadmath", "-lcudart", "-lgomp"] + ARCH
+    cmd = [NVCC, "-ccbin", GXX, "-shared", "-o", OUT] + objs + ["-Xcompiler", "-fopenmp", "-lquadmath", "-lcudart", "-lgomp", "-ldl"] + ARCH
     subprocess.check_call(cmd)
     return OUT
 

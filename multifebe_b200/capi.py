@@ -21,7 +21,8 @@ _LIB = None
 STAT = dict(PAIRS_REGULAR=0, POINTS_REGULAR=1, PAIRS_ADAPTIVE=2, LEAVES=3, POINTS_ADAPTIVE=4, PAIRS_SINGULAR=5,
             POINTS_SINGULAR=6, NEAR_PAIRS=7, MS_ZERO=8, MS_REGULAR=9, MS_ADAPTIVE=10, MS_SINGULAR=11, MS_FREETERM=12,
             MS_LU=13, MS_SOLVE=14, MS_GEMM=15, MS_PANEL=16, LAUNCHES=17, MS_SETUP_HOST=18, MS_ASSEMBLE=19,
-            FLOPS_REGULAR=20, MS_TRSM=21, MS_SWAP=22, LU_LAUNCHES=23, GEMM_LAUNCHES=24, GEMM_FLOPS=25, GEMM_EXEC_FLOPS=26)
+            FLOPS_REGULAR=20, MS_TRSM=21, MS_SWAP=22, LU_LAUNCHES=23, GEMM_LAUNCHES=24, GEMM_FLOPS=25, GEMM_EXEC_FLOPS=26,
+            MS_REDIST=27, MS_DIST_LU=28, MS_DIST_SOLVE=29, MS_DIST_TOTAL=30)
 STAT_COUNT = 32
 
 
@@ -57,6 +58,30 @@ def _p(a):
 def _z(v):
     v = complex(v)
     return np.array([v.real, v.imag], dtype=np.float64)
+
+
+def dist_unique_id():
+    """128-byte NCCL id created by rank 0 (the host broadcasts it to the other ranks, e.g. with torch.distributed)."""
+    buf = C.create_string_buffer(128)
+    _check(lib().mfb_dist_unique_id(buf))
+    return buf.raw
+
+
+def dist_layout(n, nb, nranks, rank):
+    """Global column of every local column of `rank` in the block-cyclic layout of the distributed LU (host only)."""
+    ncl = C.c_int()
+    _check(lib().mfb_dist_layout(C.c_int(n), C.c_int(nb), C.c_int(nranks), C.c_int(rank), C.byref(ncl), None))
+    out = np.zeros(ncl.value, dtype=np.int32)
+    _check(lib().mfb_dist_layout(C.c_int(n), C.c_int(nb), C.c_int(nranks), C.c_int(rank), C.byref(ncl), _p(out)))
+    return out
+
+
+def dist_partition_tiles(tile_row0, tile_nbytes, n_dof, nranks):
+    """(tile_rank, row_bounds): owner rank of every collocation tile and the internal-row range of every rank (host only)."""
+    r0 = np.ascontiguousarray(tile_row0, dtype=np.int32); nby = np.ascontiguousarray(tile_nbytes, dtype=np.int32)
+    tr = np.zeros(len(r0), dtype=np.int32); rb = np.zeros(nranks + 1, dtype=np.int32)
+    _check(lib().mfb_dist_partition_tiles(C.c_int(len(r0)), _p(r0), _p(nby), C.c_int(n_dof), C.c_int(nranks), _p(tr), _p(rb)))
+    return tr, rb
 
 
 class Context:
@@ -169,6 +194,34 @@ class Problem:
         out = np.zeros(len(r), dtype=np.complex128)
         _check(lib().mfb_get_entries(self.h, C.c_int(len(r)), _p(r), _p(c), _p(out)))
         return out
+
+    # ---- one frequency over several GPUs (mfb_dist_*; collective over the ranks) ----
+    def dist_init(self, rank, nranks, unique_id, nb=0):
+        _check(lib().mfb_dist_init(self.h, C.c_int(rank), C.c_int(nranks), C.c_char_p(unique_id), C.c_int(nb)))
+
+    def dist_init_loopback(self, nranks, nb=0):
+        """Test mode: `nranks` virtual ranks on this GPU (the collectives become device copies)."""
+        _check(lib().mfb_dist_init_loopback(self.h, C.c_int(nranks), C.c_int(nb)))
+
+    def dist_info(self):
+        r, n, ncl = C.c_int(), C.c_int(), C.c_int()
+        _check(lib().mfb_dist_info(self.h, C.byref(r), C.byref(n), None, C.byref(ncl)))
+        rb = np.zeros(n.value + 1, dtype=np.int32)
+        _check(lib().mfb_dist_info(self.h, None, None, _p(rb), None))
+        return {"rank": r.value, "nranks": n.value, "row_bounds": rb, "n_local_cols": ncl.value}
+
+    def dist_solve_frequency(self, omega, mat, host=True):
+        x = np.zeros(self.m.n_dof, dtype=np.complex128)
+        _check(lib().mfb_dist_solve_frequency(self.h, C.c_double(omega), _p(_z(mat.lam)), _p(_z(mat.mu)), C.c_double(mat.rho),
+                                              _p(_z(mat.nu)), _p(self._cv) if host else None, _p(x)))
+        return x
+
+    def dist_zsolve(self, A, b, want_ipiv=False):
+        n = self.m.n_dof
+        A = np.asfortranarray(A, dtype=np.complex128); b = np.ascontiguousarray(b, dtype=np.complex128)
+        x = np.zeros(n, dtype=np.complex128); ipiv = np.zeros(n, dtype=np.int32)
+        _check(lib().mfb_dist_zsolve(self.h, C.c_int(n), _p(A), C.c_int(n), _p(b), _p(x), _p(ipiv)))
+        return (x, ipiv) if want_ipiv else x
 
     def stats(self):
         s = np.zeros(STAT_COUNT)

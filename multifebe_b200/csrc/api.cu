@@ -4,6 +4,7 @@
 #include "../../include/mfb.h"
 #include "assembly.cuh"
 #include "lu.cuh"
+#include "dist.cuh"
 #include "plan_host.h"
 #include "../../data/quad_tables.h"
 #include <algorithm>
@@ -41,6 +42,19 @@ struct GroupHost {
   DevAdaptive adp; DevSingular sing;
 };
 
+// single-frequency multi-GPU mode (mfb_dist_*): row-block assembly + block-cyclic column LU (lu.cuh, dist.cuh)
+struct DistState {
+  bool on = false, loopback = false;
+  int rank = 0, P = 1, nb = 256;
+  DistComm* comm = nullptr;
+  DistLU lu;
+  std::vector<int> rb, tile_rank;          // internal-row boundaries [P+1]; owner rank of every collocation tile
+  unsigned char* d_mask = nullptr;         // [n_tiles] tile_active of the rank being assembled
+  double *sendbuf = nullptr, *recvbuf = nullptr, *bsum = nullptr;
+  std::vector<size_t> soff, roff, ns, nr;
+  cudaEvent_t ev[6];
+};
+
 struct mfb_problem {
   mfb_ctx* ctx;
   int n_node, n_elem, n_colloc, n_dof, ldp;
@@ -60,6 +74,8 @@ struct mfb_problem {
   std::vector<int> set_gln;
   std::vector<int> rowperm, colperm;   // host row / column -> internal row / column of the device-resident assembled system
   int *d_rowperm, *d_colperm; bool rows_permuted;
+  std::vector<int> h_tile_row0, h_tile_nbytes;   // host copies of DevColloc::tile_row0 / tile_nbytes (row partition of the multi-GPU mode)
+  DistState dist;
   alignas(64) unsigned char tmapA[128]; bool have_tmap;   // CUtensorMap of the planar system matrix (K1 flush)   // rows_permuted: the resident matrix/factors are in the internal order
 };
 
@@ -111,6 +127,17 @@ extern "C" void mfb_finalize(mfb_ctx* c) {
   delete c;
 }
 
+static void dist_release(mfb_problem* p) {
+  DistState& d = p->dist;
+  if (!d.on) return;
+  for (auto& R : d.lu.r) dist_rank_free(R);
+  d.lu.r.clear();
+  cudaFree(d.d_mask); cudaFree(d.sendbuf); cudaFree(d.recvbuf); cudaFree(d.bsum);
+  for (int i = 0; i < 6; i++) cudaEventDestroy(d.ev[i]);
+  delete d.comm; d.comm = nullptr; d.on = false;
+  p->colloc.tile_active = nullptr;
+}
+
 extern "C" void mfb_problem_free(mfb_problem* p) {
   if (!p) return;
   cudaSetDevice(p->ctx->device);
@@ -119,6 +146,7 @@ extern "C" void mfb_problem_free(mfb_problem* p) {
   for (auto& g : p->groups) for (void* q : g.owned) cudaFree(q);
   if (p->lu_ready) lu_work_free(p->lu);
   for (int i = 0; i < 8; i++) cudaEventDestroy(p->ev[i]);
+  dist_release(p);
   delete p;
 }
 
@@ -293,7 +321,8 @@ extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x
   }
   UP(p->owned, p->rowperm, &p->d_rowperm); UP(p->owned, p->colperm, &p->d_colperm);
   p->colloc.n_colloc = ldp; p->colloc.ldp = ldp; p->colloc.cx = d_cx; p->colloc.crow = d_crow;
-  p->colloc.n_tiles = n_tiles; p->colloc.tile_row0 = d_trow0; p->colloc.tile_nbytes = d_tnbytes;
+  p->colloc.n_tiles = n_tiles; p->colloc.tile_row0 = d_trow0; p->colloc.tile_nbytes = d_tnbytes; p->colloc.tile_active = nullptr;
+  p->h_tile_row0 = t_row0; p->h_tile_nbytes = t_nbytes;
   p->rows_permuted = false;
 
   // ---- flat scatter descriptors over all slots ----
@@ -870,4 +899,218 @@ extern "C" int mfb_zgemm_minus(mfb_ctx* ctx, int m, int n, int k, const mfb_z* A
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(stage); cudaEventDestroy(e0); cudaEventDestroy(e1);
   CK(cudaGetLastError());
   return MFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Single-frequency multi-GPU mode: collocation-row blocks for the assembly, block-cyclic columns for the
+// LU, NCCL to move row slabs to their column owners once and to broadcast each factorised panel.
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int mfb_dist_layout(int n, int nb, int nranks, int rank, int* n_local_cols, int* local_to_global) {
+  if (n <= 0 || nb <= 0 || nranks <= 0 || rank < 0 || rank >= nranks) return fail(MFB_ERR_ARG, "mfb_dist_layout: invalid argument");
+  const int ncl = dist_ncols_local(n, nb, nranks, rank);
+  if (n_local_cols) *n_local_cols = ncl;
+  if (local_to_global) for (int lc = 0; lc < ncl; lc++) local_to_global[lc] = (lc / nb * nranks + rank) * nb + lc % nb;
+  return MFB_OK;
+}
+
+// Tiles -> ranks.  Bulk tiles come in row order and the layers of one row block share row0, so a rank gets a contiguous
+// run of row blocks (about n_tiles / nranks tiles, layers counted); loose tiles (arbitrary rows of the last internal
+// rows) go to the last rank, whose row range extends to n_dof.  row_bounds[nranks + 1].
+extern "C" int mfb_dist_partition_tiles(int n_tiles, const int* tile_row0, const int* tile_nbytes, int n_dof, int nranks, int* tile_rank, int* row_bounds) {
+  if (n_tiles <= 0 || !tile_row0 || !tile_nbytes || nranks <= 0 || !tile_rank || !row_bounds) return fail(MFB_ERR_ARG, "mfb_dist_partition_tiles: invalid argument");
+  int r = 0, acc = 0, bulk_end = 0;
+  row_bounds[0] = 0;
+  for (int t = 0; t < n_tiles;) {
+    if (tile_nbytes[t] == 0) { tile_rank[t] = nranks - 1; t++; continue; }
+    int t1 = t; while (t1 < n_tiles && tile_nbytes[t1] > 0 && tile_row0[t1] == tile_row0[t]) t1++;
+    if (r < nranks - 1 && acc > 0 && (long long)acc * nranks >= (long long)n_tiles * (r + 1)) { r++; row_bounds[r] = tile_row0[t]; }
+    for (int q = t; q < t1; q++) tile_rank[q] = r;
+    acc += t1 - t;
+    bulk_end = std::max(bulk_end, tile_row0[t] + tile_nbytes[t] / 8);
+    t = t1;
+  }
+  for (int q = r + 1; q < nranks; q++) row_bounds[q] = bulk_end;
+  row_bounds[nranks] = n_dof;
+  return MFB_OK;
+}
+
+extern "C" int mfb_dist_unique_id(char* id128) {
+  if (!id128) return fail(MFB_ERR_ARG, "mfb_dist_unique_id: null argument");
+  std::string err;
+  if (nccl_unique_id(id128, err)) return fail(MFB_ERR_CUDA, "mfb_dist_unique_id: " + err);
+  return MFB_OK;
+}
+
+static int dist_setup(mfb_problem* p, int rank, int nranks, bool loopback, const char* id128, int nb) {
+  if (!p) return fail(MFB_ERR_ARG, "mfb_dist_init: null problem");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(MFB_ERR_ARG, "mfb_dist_init: invalid rank / nranks");
+  if (nb <= 0) nb = 256;
+  if (nb % 32 || nb > 1024) return fail(MFB_ERR_ARG, "mfb_dist_init: block size must be a multiple of 32, at most 1024");
+  CK(cudaSetDevice(p->ctx->device));
+  dist_release(p);
+  DistState& d = p->dist;
+  d.loopback = loopback; d.rank = rank; d.P = nranks; d.nb = nb;
+  if (loopback) d.comm = make_loopback_comm(nranks);
+  else { std::string err; d.comm = make_nccl_comm(rank, nranks, id128, err); if (!d.comm) return fail(MFB_ERR_CUDA, "mfb_dist_init: " + err); }
+  const int n = p->n_dof, n_tiles = p->colloc.n_tiles;
+  d.rb.assign(nranks + 1, 0); d.tile_rank.assign(n_tiles, 0);
+  int r = mfb_dist_partition_tiles(n_tiles, p->h_tile_row0.data(), p->h_tile_nbytes.data(), n, nranks, d.tile_rank.data(), d.rb.data());
+  if (r) return r;
+  d.on = true;
+  for (int i = 0; i < 6; i++) cudaEventCreate(&d.ev[i]);
+  CK(cudaMalloc((void**)&d.d_mask, (size_t)n_tiles));
+  CK(cudaMalloc((void**)&d.bsum, (size_t)2 * p->lda * sizeof(double)));
+  d.lu.n = n; d.lu.nb = nb; d.lu.nblk = (n + nb - 1) / nb; d.lu.P = nranks; d.lu.lda = p->lda; d.lu.comm = d.comm; d.lu.ms_lu = d.lu.ms_solve = 0.f;
+  const int n_local = loopback ? nranks : 1;
+  d.lu.r.resize(n_local);
+  for (int i = 0; i < n_local; i++) {
+    int e = dist_rank_alloc(d.lu.r[i], loopback ? i : rank, n, p->lda, nb, nranks, p->ctx->stream, !loopback);
+    if (e) return fail(MFB_ERR_CUDA, "mfb_dist_init: allocation of the distributed LU workspace failed");
+  }
+  if (!loopback) {
+    std::vector<unsigned char> mask(n_tiles);
+    for (int t = 0; t < n_tiles; t++) mask[t] = d.tile_rank[t] == rank;
+    CK(cudaMemcpy(d.d_mask, mask.data(), n_tiles, cudaMemcpyHostToDevice));
+    const size_t my_rows = (size_t)(d.rb[rank + 1] - d.rb[rank]), my_cols = (size_t)d.lu.r[0].ncl;
+    d.soff.assign(nranks, 0); d.roff.assign(nranks, 0); d.ns.assign(nranks, 0); d.nr.assign(nranks, 0);
+    size_t so = 0, ro = 0;
+    for (int q = 0; q < nranks; q++) {
+      if (q == rank) continue;
+      d.ns[q] = 2 * (size_t)dist_ncols_local(n, nb, nranks, q) * my_rows; d.soff[q] = so; so += d.ns[q];
+      d.nr[q] = 2 * my_cols * (size_t)(d.rb[q + 1] - d.rb[q]); d.roff[q] = ro; ro += d.nr[q];
+    }
+    CK(cudaMalloc((void**)&d.sendbuf, std::max<size_t>(so, 1) * sizeof(double)));
+    CK(cudaMalloc((void**)&d.recvbuf, std::max<size_t>(ro, 1) * sizeof(double)));
+  }
+  return MFB_OK;
+}
+extern "C" int mfb_dist_init(mfb_problem* p, int rank, int nranks, const char* id128, int nb) {
+  if (!id128) return fail(MFB_ERR_ARG, "mfb_dist_init: null unique id");
+  return dist_setup(p, rank, nranks, false, id128, nb);
+}
+extern "C" int mfb_dist_init_loopback(mfb_problem* p, int nranks, int nb) { return dist_setup(p, 0, nranks, true, nullptr, nb); }
+
+extern "C" int mfb_dist_info(mfb_problem* p, int* rank, int* nranks, int* row_bounds /* nranks + 1 */, int* n_local_cols) {
+  if (!p || !p->dist.on) return fail(MFB_ERR_ARG, "mfb_dist_info: the problem is not in multi-GPU mode");
+  const DistState& d = p->dist;
+  if (rank) *rank = d.rank;
+  if (nranks) *nranks = d.P;
+  if (row_bounds) for (int q = 0; q <= d.P; q++) row_bounds[q] = d.rb[q];
+  if (n_local_cols) *n_local_cols = d.lu.r[0].ncl;
+  return MFB_OK;
+}
+
+// factorise + solve the distributed system whose local columns (and right-hand side column) are in place; x (host) or NULL
+static int dist_factor_solve(mfb_problem* p, mfb_z* x) {
+  DistState& d = p->dist;
+  cudaStream_t st = p->ctx->stream;
+  CK(cudaEventRecord(d.ev[2], st));
+  int e = zgetrf_dist(d.lu);
+  if (e) return fail(MFB_ERR_CUDA, std::string("zgetrf_dist: ") + (e > 0 ? cudaGetErrorString((cudaError_t)e) : d.comm->last_error()));
+  CK(cudaEventRecord(d.ev[3], st));
+  e = zgetrs_dist(d.lu);
+  if (e) return fail(MFB_ERR_CUDA, std::string("zgetrs_dist: ") + (e > 0 ? cudaGetErrorString((cudaError_t)e) : d.comm->last_error()));
+  CK(cudaEventRecord(d.ev[4], st));
+  CK(cudaStreamSynchronize(st));
+  float t;
+  cudaEventElapsedTime(&t, d.ev[2], d.ev[3]); p->stats[MFB_STAT_MS_DIST_LU] = t;
+  cudaEventElapsedTime(&t, d.ev[3], d.ev[4]); p->stats[MFB_STAT_MS_DIST_SOLVE] = t;
+  double fl = 0.0; long long launches = 0; int info = 0;
+  for (auto& R : d.lu.r) {
+    fl += R.gemm_flops; launches += R.w.launches;
+    int i1 = 0; CK(cudaMemcpy(&i1, R.w.info, sizeof(int), cudaMemcpyDeviceToHost));
+    if (i1 > 0 && (info == 0 || i1 < info)) info = i1;
+  }
+  p->stats[MFB_STAT_GEMM_FLOPS] = fl; p->stats[MFB_STAT_LU_LAUNCHES] = (double)launches;
+  p->factored = false; p->assembled = false;
+  if (info > 0) { char buf[128]; snprintf(buf, sizeof(buf), "zgetrf (distributed): U(%d,%d) is exactly zero, the matrix is singular", info, info); return fail(info, buf); }
+  if (!x) return MFB_OK;
+  DistRank& R0 = d.lu.r[0];
+  return download_matrix(p, R0.xfin, R0.xfin + p->lda, p->lda, p->n_dof, 1, x, p->n_dof, p->rows_permuted ? p->d_colperm : nullptr);
+}
+
+extern "C" int mfb_dist_solve_frequency(mfb_problem* p, double omega, const mfb_z* lambda, const mfb_z* mu, double rho, const mfb_z* nu,
+                                        const mfb_z* cvalue, mfb_z* x) {
+  if (!p || !lambda || !mu || !nu) return fail(MFB_ERR_ARG, "mfb_dist_solve_frequency: null argument");
+  DistState& d = p->dist;
+  if (!d.on) return fail(MFB_ERR_ARG, "mfb_dist_solve_frequency: call mfb_dist_init first");
+  CK(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  const int n = p->n_dof, P = d.P, nb = d.nb; const long long lda = p->lda;
+  const cd la(lambda->re, lambda->im), m_(mu->re, mu->im), nu_(nu->re, nu->im);
+  CK(cudaEventRecord(d.ev[0], st));
+  if (!d.loopback) {
+    DistRank& R = d.lu.r[0];
+    p->colloc.tile_active = d.d_mask;
+    int r = assemble_device(p, omega, la, m_, rho, nu_, cvalue);
+    p->colloc.tile_active = nullptr;
+    if (r) return r;
+    CK(cudaEventRecord(d.ev[1], st));
+    // the right-hand side: every rank holds the rows it assembled; sum -> replicated
+    int rk = d.rank; double* bb = p->sys.bre;
+    if (P > 1 && d.comm->allreduce_sum(&rk, &bb, (size_t)2 * lda, &st, 1)) return fail(MFB_ERR_CUDA, std::string("allreduce of the right-hand side: ") + d.comm->last_error());
+    // row slab -> column owners
+    std::vector<double*> sp(P, nullptr), rp(P, nullptr);
+    for (int q = 0; q < P; q++) {
+      if (q == d.rank) continue;
+      sp[q] = d.sendbuf + d.soff[q]; rp[q] = d.recvbuf + d.roff[q];
+      launch_pack_slab(p->sys.Are, p->sys.Aim, lda, n, nb, P, q, d.rb[d.rank], d.rb[d.rank + 1], sp[q], st);
+    }
+    if (P > 1 && d.comm->exchange(sp.data(), d.ns.data(), rp.data(), d.nr.data(), st)) return fail(MFB_ERR_CUDA, std::string("redistribution: ") + d.comm->last_error());
+    launch_copy_own(p->sys.Are, p->sys.Aim, lda, n, nb, P, d.rank, d.rb[d.rank], d.rb[d.rank + 1], R.Lre, R.Lim, st);
+    for (int q = 0; q < P; q++) if (q != d.rank) launch_unpack_slab(rp[q], R.ncl, d.rb[q], d.rb[q + 1], R.Lre, R.Lim, lda, st);
+    CK(cudaMemcpyAsync(R.Lre + (size_t)R.ncl * lda, p->sys.bre, (size_t)lda * 8, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(R.Lim + (size_t)R.ncl * lda, p->sys.bim, (size_t)lda * 8, cudaMemcpyDeviceToDevice, st));
+  } else {
+    // virtual ranks, one after the other on this GPU: assemble the rank's row blocks, hand the slab to every column owner
+    CK(cudaMemsetAsync(d.bsum, 0, (size_t)2 * lda * 8, st));
+    std::vector<unsigned char> mask(p->colloc.n_tiles);
+    for (int r = 0; r < P; r++) {
+      for (int t = 0; t < p->colloc.n_tiles; t++) mask[t] = d.tile_rank[t] == r;
+      CK(cudaMemcpyAsync(d.d_mask, mask.data(), mask.size(), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st));
+      p->colloc.tile_active = d.d_mask;
+      int rr = assemble_device(p, omega, la, m_, rho, nu_, r == 0 ? cvalue : nullptr);
+      p->colloc.tile_active = nullptr;
+      if (rr) return rr;
+      for (int q = 0; q < P; q++) launch_copy_own(p->sys.Are, p->sys.Aim, lda, n, nb, P, q, d.rb[r], d.rb[r + 1], d.lu.r[q].Lre, d.lu.r[q].Lim, st);
+      launch_add_into(d.bsum, p->sys.bre, (size_t)2 * lda, st);
+    }
+    CK(cudaEventRecord(d.ev[1], st));
+    for (int q = 0; q < P; q++) {
+      DistRank& R = d.lu.r[q];
+      CK(cudaMemcpyAsync(R.Lre + (size_t)R.ncl * lda, d.bsum, (size_t)lda * 8, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(R.Lim + (size_t)R.ncl * lda, d.bsum + lda, (size_t)lda * 8, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  p->rows_permuted = true;
+  int r = dist_factor_solve(p, x);
+  float t;
+  cudaEventElapsedTime(&t, d.ev[0], d.ev[1]); p->stats[MFB_STAT_MS_ASSEMBLE] = t;
+  cudaEventElapsedTime(&t, d.ev[1], d.ev[2]); p->stats[MFB_STAT_MS_REDIST] = t;
+  cudaEventElapsedTime(&t, d.ev[0], d.ev[4]); p->stats[MFB_STAT_MS_DIST_TOTAL] = t;
+  return r;
+}
+
+// Test / seam-2 entry of the multi-GPU mode: factorise and solve a host matrix that EVERY rank passes in full (each rank
+// keeps only its block-cyclic columns).  A (lda x n, host, not overwritten), b (n) -> x (n), host row / column order.
+extern "C" int mfb_dist_zsolve(mfb_problem* p, int n, const mfb_z* A, int lda_h, const mfb_z* b, mfb_z* x, int* ipiv) {
+  if (!p || !A || !b || !x) return fail(MFB_ERR_ARG, "mfb_dist_zsolve: null argument");
+  DistState& d = p->dist;
+  if (!d.on) return fail(MFB_ERR_ARG, "mfb_dist_zsolve: call mfb_dist_init first");
+  if (n != p->n_dof || lda_h < n) return fail(MFB_ERR_ARG, "mfb_dist_zsolve: n must equal the problem's n_dof");
+  CK(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  const long long lda = p->lda;
+  int r = upload_matrix(p, A, lda_h, n, n, p->sys.Are, p->sys.Aim, lda); if (r) return r;
+  r = upload_matrix(p, b, n, n, 1, p->sys.bre, p->sys.bim, lda); if (r) return r;
+  p->rows_permuted = false; p->assembled = false; p->factored = false;
+  CK(cudaEventRecord(d.ev[0], st)); CK(cudaEventRecord(d.ev[1], st));
+  for (auto& R : d.lu.r) {
+    launch_copy_own(p->sys.Are, p->sys.Aim, lda, n, d.nb, d.P, R.rank, 0, n, R.Lre, R.Lim, st);
+    CK(cudaMemcpyAsync(R.Lre + (size_t)R.ncl * lda, p->sys.bre, (size_t)lda * 8, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(R.Lim + (size_t)R.ncl * lda, p->sys.bim, (size_t)lda * 8, cudaMemcpyDeviceToDevice, st));
+  }
+  r = dist_factor_solve(p, x);
+  if (ipiv) CK(cudaMemcpy(ipiv, d.lu.r[0].ipiv, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  return r;
 }

@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_regular(DevGroup g, DevColloc
   const int cpos = (blockIdx.x * K1_WARPS + warp) * 32 + lane;
   if (cpos - lane >= c.ldp) return;
   const int r0 = c.crow[cpos], r1 = c.crow[c.ldp + cpos], r2 = c.crow[2 * c.ldp + cpos];
-  const bool valid = r0 >= 0;
+  const bool valid = r0 >= 0 && (!c.tile_active || c.tile_active[cpos >> 5]);
   const double xc[3] = {c.cx[cpos], c.cx[c.ldp + cpos], c.cx[2 * c.ldp + cpos]};
   double bre[3] = {0.0, 0.0, 0.0}, bim[3] = {0.0, 0.0, 0.0};
   const int e0 = blockIdx.y * K1_ECHUNK, e1 = min(e0 + K1_ECHUNK, g.n_elem);
@@ -361,6 +361,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
     if (task >= n_tasks) break;
     const int range = task / c.n_tiles, tile = task - range * c.n_tiles;   // consecutive tasks: same elements, consecutive tiles
     if (!((g.range_modes[range] >> MODE) & 1)) continue;                   // no element of this kernel's class in the range
+    if (c.tile_active && !c.tile_active[tile]) continue;                   // row block of another rank
     if (lane < MAX_SETS) qcnt[lane] = 0;
     __syncwarp();
     const int cpos = tile * 32 + lane;
@@ -659,6 +660,7 @@ __global__ void __launch_bounds__(128) k_adaptive(DevGroup g, DevColloc c, DevSy
   const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (p >= a.n_pairs) return;
   const int cpos = a.pair_cpos[p], e = a.pair_elem[p];
+  if (c.tile_active && !c.tile_active[cpos >> 5]) return;
   const double xc[3] = {c.cx[cpos], c.cx[c.ldp + cpos], c.cx[2 * c.ldp + cpos]};
   const int r0 = c.crow[cpos], r1 = c.crow[c.ldp + cpos], r2 = c.crow[2 * c.ldp + cpos];
   double xn[3 * NN];
@@ -718,6 +720,7 @@ __global__ void __launch_bounds__(128) k_singular(DevGroup g, DevColloc c, DevSy
   const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (p >= a.n_pairs) return;
   const int cpos = a.pair_cpos[p], e = a.pair_elem[p];
+  if (c.tile_active && !c.tile_active[cpos >> 5]) return;
   const int r0 = c.crow[cpos], r1 = c.crow[c.ldp + cpos], r2 = c.crow[2 * c.ldp + cpos];
   const double* D = a.pair_d + 14 * (size_t)p;
   const double xi_i0 = D[0], xi_i1 = D[1];
@@ -783,6 +786,7 @@ __global__ void k_freeterm(DevColloc c, DevSystem s, DevFreeTerm f, cplx F) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= f.n) return;
   const int cpos = f.cpos[i], l = f.l[i];
+  if (c.tile_active && !c.tile_active[cpos >> 5]) return;
   const int row = c.crow[l * c.ldp + cpos];
   const int o = f.slot_off[f.slot[i]] + f.jk[i];
   // value = alpha + beta*F, F = -1/(8 pi (1-nu)) (Mantic; bem_harela3d.f90:538) -- alpha,beta are geometry-only

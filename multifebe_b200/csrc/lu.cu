@@ -468,24 +468,27 @@ __global__ void k_laswp(double* Are, double* Aim, long long lda, int c0, int c1,
 // X = inv(L) * B in place: L = unit lower nbw x nbw block at (r0,r0), B = rows r0..r0+nbw of columns [c0,c1).
 // One CTA per TRSM_TC columns; B tile in shared memory; warps own rows (warp-uniform L loads), lanes own columns.
 const int TRSM_TC = 32;
-__global__ void __launch_bounds__(256) k_trsm_lu(double* Are, double* Aim, long long lda, int r0, int nbw, int c0, int c1) {
+// L (Lre/Lim, ldl) points at the top-left of the unit lower block, B (Bre/Bim, ldb) at the first of its nbw rows in column 0 of
+// the ncols columns to solve (the two may live in different arrays: the distributed LU keeps L in the broadcast panel).
+__global__ void __launch_bounds__(256) k_trsm_lu(const double* __restrict__ Lre, const double* __restrict__ Lim, long long ldl, double* Bre, double* Bim,
+                                                 long long ldb, int nbw, int ncols) {
   extern __shared__ __align__(16) double sb[];     // [2][nbw][TRSM_TC+1]
   const int LD = TRSM_TC + 1;
   double* br = sb; double* bi = sb + (size_t)nbw * LD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  const int cb = c0 + blockIdx.x * TRSM_TC, ncol = min(TRSM_TC, c1 - cb);
+  const int cb = blockIdx.x * TRSM_TC, ncol = min(TRSM_TC, ncols - cb);
   // load: thread (i = tid % nbw-chunk, col) coalesced along rows
   for (int idx = tid; idx < nbw * TRSM_TC; idx += blockDim.x) {
     int cc = idx / nbw, i = idx - cc * nbw;
     bool ok = cc < ncol;
-    br[i * LD + cc] = ok ? Are[(long long)(cb + cc) * lda + r0 + i] : 0.0;
-    bi[i * LD + cc] = ok ? Aim[(long long)(cb + cc) * lda + r0 + i] : 0.0;
+    br[i * LD + cc] = ok ? Bre[(long long)(cb + cc) * ldb + i] : 0.0;
+    bi[i * LD + cc] = ok ? Bim[(long long)(cb + cc) * ldb + i] : 0.0;
   }
   __syncthreads();
   for (int j = 0; j < nbw - 1; j++) {
     const double xr = br[j * LD + lane], xi = bi[j * LD + lane];
-    const double* lre = Are + (long long)(r0 + j) * lda + r0;
-    const double* lim = Aim + (long long)(r0 + j) * lda + r0;
+    const double* lre = Lre + (long long)j * ldl;
+    const double* lim = Lim + (long long)j * ldl;
 #pragma unroll 4
     for (int i = j + 1 + warp; i < nbw; i += nw) {
       const double lr = __ldg(lre + i), li = __ldg(lim + i);
@@ -496,14 +499,14 @@ __global__ void __launch_bounds__(256) k_trsm_lu(double* Are, double* Aim, long 
   }
   for (int idx = tid; idx < nbw * TRSM_TC; idx += blockDim.x) {
     int cc = idx / nbw, i = idx - cc * nbw;
-    if (cc < ncol) { Are[(long long)(cb + cc) * lda + r0 + i] = br[i * LD + cc]; Aim[(long long)(cb + cc) * lda + r0 + i] = bi[i * LD + cc]; }
+    if (cc < ncol) { Bre[(long long)(cb + cc) * ldb + i] = br[i * LD + cc]; Bim[(long long)(cb + cc) * ldb + i] = bi[i * LD + cc]; }
   }
 }
 // U12 = inv(L11) A12 for the nbw x nbw unit lower block at (r0,r0) and columns [c0,c1): blocked forward substitution,
 // TRSM_TB rows at a time by substitution in shared memory, the rows below updated on the tensor pipe (returns launches).
 const int TRSM_TB = 32;
-static int launch_trsm(double* Are, double* Aim, long long lda, int r0, int nbw, int c0, int c1, cudaStream_t st) {
-  if (c1 <= c0 || nbw <= 1) return 0;
+static int launch_trsm_ext(const double* Lre, const double* Lim, long long ldl, double* Bre, double* Bim, long long ldb, int nbw, int ncols, cudaStream_t st) {
+  if (ncols <= 0 || nbw <= 1) return 0;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(k_trsm_lu, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * (TRSM_TC + 1) * 8); attr = true; }
   int launches = 0;
@@ -511,18 +514,22 @@ static int launch_trsm(double* Are, double* Aim, long long lda, int r0, int nbw,
     const int tb = (nbw - jb < TRSM_TB) ? (nbw - jb) : TRSM_TB;
     if (tb > 1) {
       size_t smem = (size_t)2 * tb * (TRSM_TC + 1) * 8;
-      k_trsm_lu<<<(c1 - c0 + TRSM_TC - 1) / TRSM_TC, 256, smem, st>>>(Are, Aim, lda, r0 + jb, tb, c0, c1);
+      k_trsm_lu<<<(ncols + TRSM_TC - 1) / TRSM_TC, 256, smem, st>>>(Lre + (long long)jb * ldl + jb, Lim + (long long)jb * ldl + jb, ldl, Bre + jb, Bim + jb, ldb, tb, ncols);
       launches++;
     }
     const int mrest = nbw - jb - tb;
     if (mrest > 0) {
-      zgemm_minus_planar(mrest, c1 - c0, tb, Are + (long long)(r0 + jb) * lda + r0 + jb + tb, Aim + (long long)(r0 + jb) * lda + r0 + jb + tb, lda,
-                         Are + (long long)c0 * lda + r0 + jb, Aim + (long long)c0 * lda + r0 + jb, lda,
-                         Are + (long long)c0 * lda + r0 + jb + tb, Aim + (long long)c0 * lda + r0 + jb + tb, lda, st);
+      zgemm_minus_planar(mrest, ncols, tb, Lre + (long long)jb * ldl + jb + tb, Lim + (long long)jb * ldl + jb + tb, ldl, Bre + jb, Bim + jb, ldb,
+                         Bre + jb + tb, Bim + jb + tb, ldb, st);
       launches++;
     }
   }
   return launches;
+}
+static int launch_trsm(double* Are, double* Aim, long long lda, int r0, int nbw, int c0, int c1, cudaStream_t st) {
+  if (c1 <= c0) return 0;
+  return launch_trsm_ext(Are + (long long)r0 * lda + r0, Aim + (long long)r0 * lda + r0, lda, Are + (long long)c0 * lda + r0, Aim + (long long)c0 * lda + r0, lda, nbw,
+                         c1 - c0, st);
 }
 
 int lu_work_alloc(LuWork& w, int n, int nb) {
@@ -760,6 +767,174 @@ int zgetrs_planar(const double* Are, const double* Aim, long long lda, int n, co
   }
   cudaStreamSynchronize(st);
   cudaFree(tmp);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Distributed LU over P ranks, 1-D block-cyclic columns (see lu.cuh).  The kernels are the single-GPU ones: a panel is
+// factorised in place in the owner's local columns (a column-shifted base pointer lets the global-index code address the
+// local storage), packed (rows k0..n only) and broadcast together with its pivots; the other ranks read L11 / L21 from
+// the packed copy.
+// ------------------------------------------------------------------------------------------------------------------
+int dist_rank_alloc(DistRank& R, int rank, int n, long long lda, int nb, int P, cudaStream_t main_stream, bool separate_comm) {
+  R.rank = rank; R.ncl = dist_ncols_local(n, nb, P, rank); R.gemm_flops = 0.0;
+  R.Lre = R.Lim = nullptr; R.pbuf[0] = R.pbuf[1] = nullptr; R.xfin = nullptr; R.ipiv = nullptr;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+  double* L = nullptr;
+  A((void**)&L, (size_t)2 * lda * (R.ncl + 1) * sizeof(double));
+  R.Lre = L; R.Lim = L + (size_t)lda * (R.ncl + 1);
+  for (int i = 0; i < 2; i++) A((void**)&R.pbuf[i], (size_t)2 * nb * lda * sizeof(double) + (size_t)nb * sizeof(int) + 16);
+  A((void**)&R.xfin, (size_t)2 * lda * sizeof(double));
+  A((void**)&R.ipiv, (size_t)n * sizeof(int));
+  if (e != cudaSuccess) return (int)e;
+  int le = lu_work_alloc(R.w, n, nb);
+  if (le) return le;
+  cudaEventCreateWithFlags(&R.ev_panel, cudaEventDisableTiming); cudaEventCreateWithFlags(&R.ev_cols, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&R.ev_free, cudaEventDisableTiming);
+  R.main = main_stream; R.comm = separate_comm ? R.w.panel_stream : main_stream;
+  return 0;
+}
+void dist_rank_free(DistRank& R) {
+  cudaFree(R.Lre); cudaFree(R.pbuf[0]); cudaFree(R.pbuf[1]); cudaFree(R.xfin); cudaFree(R.ipiv);
+  lu_work_free(R.w);
+  cudaEventDestroy(R.ev_panel); cudaEventDestroy(R.ev_cols); cudaEventDestroy(R.ev_free);
+}
+
+int zgetrf_dist(DistLU& D) {
+  const int n = D.n, nb = D.nb, P = D.P, nblk = D.nblk, NL = (int)D.r.size();
+  const long long lda = D.lda;
+  std::vector<int> ranks(NL); std::vector<void*> bufs(NL); std::vector<cudaStream_t> sts(NL);
+  for (int i = 0; i < NL; i++) { ranks[i] = D.r[i].rank; sts[i] = D.r[i].comm; D.r[i].gemm_flops = 0.0; D.r[i].w.launches = 0; cudaMemsetAsync(D.r[i].w.info, 0, sizeof(int), D.r[i].main); }
+  auto width = [&](int k) { return (n - k * nb < nb) ? (n - k * nb) : nb; };
+  // first local column that belongs to a global block > k
+  auto nright = [&](const DistRank& R, int k) { int c = (k >= R.rank) ? ((k - R.rank) / P + 1) * nb : 0; return c < R.ncl ? c : R.ncl; };
+  auto panel_bytes = [&](int k) { const long long m = n - (long long)k * nb, mp = (m + 1) & ~1ll; return (size_t)2 * width(k) * mp * sizeof(double) + (size_t)width(k) * sizeof(int); };
+  // owner: factorise panel k in place (stream R.comm), pack rows k0..n + pivots into pbuf[k & 1]
+  auto factor_and_pack = [&](DistRank& R, int k) -> int {
+    const int k0 = k * nb, nbw = width(k), lc = dist_local_col(k, P, nb);
+    const long long m = n - k0, mp = (m + 1) & ~1ll;
+    double* Are = R.Lre + ((long long)lc - k0) * lda; double* Aim = R.Lim + ((long long)lc - k0) * lda;   // global column k0 -> local column lc
+    int e = factor_panel(Are, Aim, lda, n, k0, nbw, R.ipiv, R.w, R.comm);
+    if (e) return e;
+    double* pb = R.pbuf[k & 1];
+    cudaMemcpy2DAsync(pb, (size_t)mp * 8, R.Lre + (long long)lc * lda + k0, (size_t)lda * 8, (size_t)m * 8, nbw, cudaMemcpyDeviceToDevice, R.comm);
+    cudaMemcpy2DAsync(pb + (size_t)nbw * mp, (size_t)mp * 8, R.Lim + (long long)lc * lda + k0, (size_t)lda * 8, (size_t)m * 8, nbw, cudaMemcpyDeviceToDevice, R.comm);
+    cudaMemcpyAsync(pb + (size_t)2 * nbw * mp, R.ipiv + k0, (size_t)nbw * sizeof(int), cudaMemcpyDeviceToDevice, R.comm);
+    return 0;
+  };
+  auto bcast_panel = [&](int k) -> int {
+    for (int i = 0; i < NL; i++) bufs[i] = D.r[i].pbuf[k & 1];
+    int e = D.comm->bcast_bytes(dist_owner(k, P), ranks.data(), bufs.data(), panel_bytes(k), sts.data(), NL);
+    if (e) return e;
+    const int k0 = k * nb, nbw = width(k);
+    const long long m = n - k0, mp = (m + 1) & ~1ll;
+    for (int i = 0; i < NL; i++) {
+      DistRank& R = D.r[i];
+      if (R.rank != dist_owner(k, P)) cudaMemcpyAsync(R.ipiv + k0, R.pbuf[k & 1] + (size_t)2 * nbw * mp, (size_t)nbw * sizeof(int), cudaMemcpyDeviceToDevice, R.comm);
+      cudaEventRecord(R.ev_panel, R.comm);
+    }
+    return 0;
+  };
+  // A[k0:n, c0:c1) of the local columns: U12 = inv(L11) A12, A22 -= L21 U12, with L from the packed panel k
+  auto update_cols = [&](DistRank& R, int k, int c0, int c1) {
+    if (c1 <= c0) return;
+    const int k0 = k * nb, nbw = width(k);
+    const long long m = n - k0, mp = (m + 1) & ~1ll;
+    const double* Pre = R.pbuf[k & 1]; const double* Pim = Pre + (size_t)nbw * mp;
+    double* Bre = R.Lre + (long long)c0 * lda + k0; double* Bim = R.Lim + (long long)c0 * lda + k0;
+    R.w.launches += launch_trsm_ext(Pre, Pim, mp, Bre, Bim, lda, nbw, c1 - c0, R.main);
+    const int mrest = (int)m - nbw;
+    if (mrest > 0) {
+      zgemm_minus_planar(mrest, c1 - c0, nbw, Pre + nbw, Pim + nbw, mp, Bre, Bim, lda, Bre + nbw, Bim + nbw, lda, R.main);
+      R.w.launches++; R.gemm_flops += 8.0 * (double)mrest * (double)(c1 - c0) * (double)nbw;
+    }
+  };
+  // ---- panel 0 ----
+  for (int i = 0; i < NL; i++) {
+    DistRank& R = D.r[i];
+    if (R.comm != R.main) { cudaEventRecord(R.ev_free, R.main); cudaStreamWaitEvent(R.comm, R.ev_free, 0); }   // the local columns are complete
+    if (R.rank == dist_owner(0, P)) { int e = factor_and_pack(R, 0); if (e) return e; }
+  }
+  { int e = bcast_panel(0); if (e) return e; }
+  for (int k = 0; k < nblk; k++) {
+    const int k0 = k * nb, nbw = width(k);
+    const bool has_next = k + 1 < nblk;
+    for (int i = 0; i < NL; i++) {
+      DistRank& R = D.r[i];
+      if (R.comm != R.main) cudaEventRecord(R.ev_free, R.main);      // everything of step k-1 (last reader of pbuf[(k+1) & 1]) is behind this point
+      cudaStreamWaitEvent(R.main, R.ev_panel, 0);
+      // ---- interchanges of panel k on every local column outside the panel (the right-hand side column included) ----
+      const bool mine = R.rank == dist_owner(k, P);
+      const int lc = dist_local_col(k, P, nb), ctot = R.ncl + 1;
+      const int a1 = mine ? lc : ctot;                // [0, a1) and [a0, ctot)
+      const int a0 = mine ? lc + nbw : ctot;
+      if (a1 > 0) { k_laswp<<<(a1 + 127) / 128, 128, 0, R.main>>>(R.Lre, R.Lim, lda, 0, a1, k0, nbw, R.ipiv); R.w.launches++; }
+      if (a0 < ctot) { k_laswp<<<(ctot - a0 + 127) / 128, 128, 0, R.main>>>(R.Lre, R.Lim, lda, a0, ctot, k0, nbw, R.ipiv); R.w.launches++; }
+      // ---- look-ahead: the owner of panel k+1 updates that panel's columns first and factorises it on the other stream ----
+      if (has_next && R.rank == dist_owner(k + 1, P)) {
+        const int cr = nright(R, k), nbw_next = width(k + 1);
+        update_cols(R, k, cr, cr + nbw_next);
+        if (R.comm != R.main) { cudaEventRecord(R.ev_cols, R.main); cudaStreamWaitEvent(R.comm, R.ev_cols, 0); }
+        int e = factor_and_pack(R, k + 1); if (e) return e;
+      } else if (has_next && R.comm != R.main) cudaStreamWaitEvent(R.comm, R.ev_free, 0);
+    }
+    if (has_next) { int e = bcast_panel(k + 1); if (e) return e; }
+    for (int i = 0; i < NL; i++) {
+      DistRank& R = D.r[i];
+      int cr = nright(R, k);
+      if (has_next && R.rank == dist_owner(k + 1, P)) cr += width(k + 1);
+      update_cols(R, k, cr, R.ncl + 1);
+    }
+  }
+  return (int)cudaGetLastError();
+}
+
+__global__ void k_vec_copy2(double* dre, double* dim_, const double* __restrict__ sre, const double* __restrict__ sim, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { dre[i] = sre[i]; dim_[i] = sim[i]; }
+}
+
+// U x = y by column blocks from the last to the first: the partial sums  -U(:, j) x_j  of the blocks already solved live
+// with the rank that owns column block j; the block's right-hand side is their sum over the ranks (one small reduce per
+// block), the owner solves its diagonal block and updates its own partial sums above it.
+int zgetrs_dist(DistLU& D) {
+  const int n = D.n, nb = D.nb, P = D.P, nblk = D.nblk, NL = (int)D.r.size();
+  const long long lda = D.lda;
+  std::vector<int> ranks(NL); std::vector<double*> a(NL), b(NL); std::vector<cudaStream_t> sts(NL);
+  const size_t dsm = (size_t)2 * TS * (TS + 1) * sizeof(double);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_trsv_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm); attr = true; }
+  for (int i = 0; i < NL; i++) {
+    DistRank& R = D.r[i];
+    ranks[i] = R.rank; sts[i] = R.main;
+    double* vre = R.Lre + (long long)R.ncl * lda; double* vim = R.Lim + (long long)R.ncl * lda;
+    if (R.rank != 0) { cudaMemsetAsync(vre, 0, (size_t)lda * 8, R.main); cudaMemsetAsync(vim, 0, (size_t)lda * 8, R.main); }   // y is counted once
+    cudaMemsetAsync(R.xfin, 0, (size_t)2 * lda * 8, R.main);
+  }
+  for (int k = nblk - 1; k >= 0; k--) {
+    const int k0 = k * nb, nbw = (n - k0 < nb) ? (n - k0) : nb, own = dist_owner(k, P);
+    for (int i = 0; i < NL; i++) { a[i] = D.r[i].Lre + (long long)D.r[i].ncl * lda + k0; b[i] = D.r[i].Lim + (long long)D.r[i].ncl * lda + k0; }
+    if (P > 1) { int e = D.comm->reduce_sum2(own, ranks.data(), a.data(), b.data(), (size_t)nbw, sts.data(), NL); if (e) return e; }
+    for (int i = 0; i < NL; i++) {
+      DistRank& R = D.r[i];
+      if (R.rank != own) continue;
+      const int lc = dist_local_col(k, P, nb);
+      const double* Are = R.Lre + ((long long)lc - k0) * lda; const double* Aim = R.Lim + ((long long)lc - k0) * lda;
+      double* vre = R.Lre + (long long)R.ncl * lda; double* vim = R.Lim + (long long)R.ncl * lda;
+      const int nsub = (nbw + TS - 1) / TS;
+      for (int sb = nsub - 1; sb >= 0; sb--) {
+        const int kb = k0 + sb * TS, w = (k0 + nbw - kb < TS) ? (k0 + nbw - kb) : TS;
+        k_trsv_diag<<<1, TS, dsm, R.main>>>(Are, Aim, lda, kb, w, vre, vim, 0);
+        if (kb > 0) k_gemv_update<<<(kb + 63) / 64, 256, 0, R.main>>>(Are, Aim, lda, 0, kb, kb, w, vre, vim);
+      }
+      k_vec_copy2<<<(nbw + 255) / 256, 256, 0, R.main>>>(R.xfin + k0, R.xfin + lda + k0, vre + k0, vim + k0, nbw);
+    }
+  }
+  if (P > 1) {
+    for (int i = 0; i < NL; i++) a[i] = D.r[i].xfin;
+    int e = D.comm->allreduce_sum(ranks.data(), a.data(), (size_t)2 * lda, sts.data(), NL); if (e) return e;
+  }
   return (int)cudaGetLastError();
 }
 

@@ -2,6 +2,7 @@
 // Replaces OpenBLAS zgetrf/zgetrs behind solve_lse_c (src/solve_lse_c.f90:124,176).
 #pragma once
 #include <cuda_runtime.h>
+#include <vector>
 
 namespace mfbd {
 
@@ -35,6 +36,60 @@ int zgetrs_planar(const double* Are, const double* Aim, long long lda, int n, co
 // C -= A*B on planar storage (the trailing-matrix update; FP64 tensor pipe, mma.sync m8n8k4).  k must be a multiple of 4.
 void zgemm_minus_planar(int m, int n, int k, const double* Are, const double* Aim, long long lda, const double* Bre, const double* Bim,
                         long long ldb, double* Cre, double* Cim, long long ldc, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------------------------
+// Distributed LU of ONE system over P ranks (one GPU each): 1-D block-cyclic COLUMN layout, block = nb columns, block j
+// lives on rank j % P as its local block j / P.  Every rank holds all n rows of its columns plus a replicated copy of the
+// right-hand side as one extra local column, so that the forward substitution happens inside the factorisation.
+// Per step the owner factorises the panel and the panel (L11, L21, pivots) is BROADCAST; everybody then interchanges,
+// solves (TRSM) and updates (GEMM on the FP64 tensor pipe) its own columns.  One panel of look-ahead hides the broadcast.
+// The collectives are behind DistComm: NCCL between processes, or plain device copies between the virtual ranks of one
+// process (single-GPU self test of the index logic).
+// ------------------------------------------------------------------------------------------------------------------
+struct DistRank {
+  int rank, ncl;                 // global rank; local columns (without the right-hand-side column)
+  double *Lre, *Lim;             // planar lda x (ncl + 1), column ncl = right-hand side / solution workspace
+  double* pbuf[2];               // packed panel: [2 planes][nbw][mp] doubles + nbw pivots (int) behind them
+  double* xfin;                  // [2][lda] solution blocks of the columns this rank owns (zero elsewhere)
+  int* ipiv;                     // [n] device, 1-based global rows
+  LuWork w;                      // panel workspace of the cooperative kernel
+  cudaStream_t main, comm;       // trailing updates / panel factorisation + broadcast (the same stream in loopback mode)
+  cudaEvent_t ev_panel, ev_cols, ev_free;
+  double gemm_flops;
+};
+struct DistComm {
+  int P;                                             // world size
+  virtual ~DistComm() {}
+  // every call is made once per phase with the buffers / streams of ALL ranks local to this process (global ranks in `ranks`)
+  virtual int bcast_bytes(int root, const int* ranks, void* const* bufs, size_t bytes, cudaStream_t const* st, int n_local) = 0;
+  virtual int reduce_sum2(int root, const int* ranks, double* const* a, double* const* b, size_t count, cudaStream_t const* st, int n_local) = 0;   // two vectors, in place at the root
+  virtual int allreduce_sum(const int* ranks, double* const* bufs, size_t count, cudaStream_t const* st, int n_local) = 0;
+  // point-to-point exchange of the redistribution (processes only): send[q] (ns[q] doubles) to rank q, recv[q] (nr[q]) from rank q, q != own rank
+  virtual int exchange(double* const* send, const size_t* ns, double* const* recv, const size_t* nr, cudaStream_t st) { (void)send; (void)ns; (void)recv; (void)nr; (void)st; return -1; }
+  virtual const char* last_error() { return ""; }
+};
+struct DistLU {
+  int n, nb, nblk, P; long long lda;
+  std::vector<DistRank> r;       // the ranks local to this process
+  DistComm* comm;
+  float ms_lu, ms_solve;
+};
+inline int dist_owner(int blk, int P) { return blk % P; }
+inline int dist_local_col(int blk, int P, int nb) { return (blk / P) * nb; }
+// number of local columns of rank r (blocks j = r, r+P, ... < nblk; only the globally last block may be narrower)
+inline int dist_ncols_local(int n, int nb, int P, int r) {
+  const int nblk = (n + nb - 1) / nb; int c = 0;
+  for (int j = r; j < nblk; j += P) c += (n - j * nb < nb) ? (n - j * nb) : nb;
+  return c;
+}
+// main_stream: the stream the caller assembles on; separate_comm: panel factorisation + broadcasts on their own high-priority stream
+int dist_rank_alloc(DistRank& R, int rank, int n, long long lda, int nb, int P, cudaStream_t main_stream, bool separate_comm);
+void dist_rank_free(DistRank& R);
+// factorise (the right-hand side column rides along: it ends as y = inv(L) P b on every rank)
+int zgetrf_dist(DistLU& D);
+// back substitution U x = y; the solution (planar, internal column order) ends in xfin of every rank
+int zgetrs_dist(DistLU& D);
+
 // micro-benchmarks (TFLOP/s, GB/s)
 double bench_dfma(cudaStream_t st);
 double bench_dmma(cudaStream_t st);

@@ -104,3 +104,40 @@ def test_material_follows_read_regions():
     mat = Material(2.0, 3.0, 0.3, 0.05)
     assert mat.mu == 3.0 * (1 + 0.1j) and abs(mat.lam - 2 * mat.mu * 0.3 / 0.4) < 1e-15
     assert abs(mat.c2 ** 2 * 2.0 - mat.mu) < 1e-14 and abs(mat.c1 ** 2 * 2.0 - (mat.lam + 2 * mat.mu)) < 1e-14
+
+
+# ---- host logic of the single-frequency multi-GPU mode (no device needed) ----
+@pytest.mark.parametrize("n,nb,nranks", [(30258, 256, 8), (1386, 256, 2), (1000, 32, 3), (64, 32, 4), (31, 32, 2)])
+def test_block_cyclic_layout_covers_every_column_once(n, nb, nranks):
+    from multifebe_b200 import capi
+    seen = np.zeros(n, dtype=int)
+    for r in range(nranks):
+        cols = capi.dist_layout(n, nb, nranks, r)
+        assert np.all(np.diff(cols) > 0)                       # local order = global order
+        assert np.all((cols // nb) % nranks == r)              # block j lives on rank j % P
+        seen[cols] += 1
+    assert np.all(seen == 1)
+
+
+def test_tile_partition_keeps_row_blocks_whole_and_balanced():
+    from multifebe_b200 import capi
+    # 40 row blocks of 32 nodes (96 rows), the last 6 with two layers (MCA rim nodes), then 2 loose tiles
+    row0, nbytes = [], []
+    for i in range(40):
+        for _ in range(2 if i >= 34 else 1):
+            row0.append(96 * i); nbytes.append(24 * 32)
+    row0 += [0, 0]; nbytes += [0, 0]
+    n_dof = 96 * 40 + 30
+    for nranks in (1, 2, 3, 8):
+        tr, rb = capi.dist_partition_tiles(row0, nbytes, n_dof, nranks)
+        assert rb[0] == 0 and rb[-1] == n_dof and np.all(np.diff(rb) >= 0)
+        assert np.all(tr[-2:] == nranks - 1)                   # loose tiles -> last rank, whose rows run to n_dof
+        for t in range(len(row0) - 2):
+            assert rb[tr[t]] <= row0[t] and row0[t] + 96 <= rb[tr[t] + 1]          # a tile's rows belong to its rank
+        for t in range(1, len(row0) - 2):
+            if row0[t] == row0[t - 1]:
+                assert tr[t] == tr[t - 1]                      # layers of one row block stay together
+        counts = np.bincount(tr, minlength=nranks)
+        assert counts.max() - counts.min() <= 4
+    tr, rb = capi.dist_partition_tiles([0, 0], [24 * 4, 0], 20, 4)      # fewer row blocks than ranks
+    assert list(tr) == [0, 3] and list(rb) == [0, 12, 12, 12, 20]
