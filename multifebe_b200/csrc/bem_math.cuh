@@ -102,35 +102,41 @@ MFB_HD double mfb_e5_coeff(int m) {
   const double c[17] = MFB_E5_COEFFS; return c[m];
 #endif
 }
+// The series sum S(z) = sum_m z^m/(m+5)! is split into its even and odd parts, S = Se(w) + z So(w) with w = z^2: two
+// independent Horner chains of 8 steps instead of one of 16 (the kernels run at low occupancy, so the length of the
+// dependent chain is what this branch costs).  Real coefficients: 4 FMA-class operations per step.
 MFB_HD void zexp_series(cplx z, cplx& E2, cplx& E3, cplx& E4, cplx& E5) {   // |z| <= 1
   const cplx z2 = z * z, z3 = z2 * z, z4 = z2 * z2;
-  // Horner in z with real coefficients: 4 FMA-class operations per term (rolled: the series branch is the rare one)
-  double sr = mfb_e5_coeff(16), si = 0.0;
+  double er = mfb_e5_coeff(16), ei = 0.0, orr = 0.0, oi = 0.0;
 #pragma unroll 1
-  for (int m = 15; m >= 0; m--) {
-    const double tr = fma(sr, z.re, fma(-si, z.im, mfb_e5_coeff(m)));
-    si = fma(sr, z.im, si * z.re);
-    sr = tr;
+  for (int m = 14; m >= 0; m -= 2) {
+    const double tr = fma(er, z2.re, fma(-ei, z2.im, mfb_e5_coeff(m))), ur = fma(orr, z2.re, fma(-oi, z2.im, mfb_e5_coeff(m + 1)));
+    ei = fma(er, z2.im, ei * z2.re); oi = fma(orr, z2.im, oi * z2.re);
+    er = tr; orr = ur;
   }
-  E5 = (z4 * z) * mk(sr, si);
+  const cplx S = cfma(z, mk(orr, oi), mk(er, ei));
+  E5 = (z4 * z) * S;
   E4 = cfmar(z4, 1.0 / 24.0, E5);
   E3 = cfmar(z3, 1.0 / 6.0, E4);
   E2 = cfmar(z2, 0.5, E3);
 }
-// two arguments in one rolled loop (two independent chains)
+// two arguments in one rolled loop (four independent chains)
 MFB_HD void zexp_series2(cplx za, cplx zb, cplx& A2, cplx& A3, cplx& A4, cplx& A5, cplx& B2, cplx& B3, cplx& B4, cplx& B5) {
-  double ar = mfb_e5_coeff(16), ai = 0.0, br = ar, bi = 0.0;
+  const cplx wa = za * za, wb = zb * zb;
+  double aer = mfb_e5_coeff(16), aei = 0.0, aor = 0.0, aoi = 0.0, ber = aer, bei = 0.0, bor = 0.0, boi = 0.0;
 #pragma unroll 1
-  for (int m = 15; m >= 0; m--) {
-    const double cm = mfb_e5_coeff(m);
-    const double tr = fma(ar, za.re, fma(-ai, za.im, cm)), ur = fma(br, zb.re, fma(-bi, zb.im, cm));
-    ai = fma(ar, za.im, ai * za.re); bi = fma(br, zb.im, bi * zb.re);
-    ar = tr; br = ur;
+  for (int m = 14; m >= 0; m -= 2) {
+    const double ce = mfb_e5_coeff(m), co = mfb_e5_coeff(m + 1);
+    const double t1 = fma(aer, wa.re, fma(-aei, wa.im, ce)), t2 = fma(aor, wa.re, fma(-aoi, wa.im, co));
+    const double t3 = fma(ber, wb.re, fma(-bei, wb.im, ce)), t4 = fma(bor, wb.re, fma(-boi, wb.im, co));
+    aei = fma(aer, wa.im, aei * wa.re); aoi = fma(aor, wa.im, aoi * wa.re);
+    bei = fma(ber, wb.im, bei * wb.re); boi = fma(bor, wb.im, boi * wb.re);
+    aer = t1; aor = t2; ber = t3; bor = t4;
   }
-  { const cplx z2 = za * za, z3 = z2 * za, z4 = z2 * z2;
-    A5 = (z4 * za) * mk(ar, ai); A4 = cfmar(z4, 1.0 / 24.0, A5); A3 = cfmar(z3, 1.0 / 6.0, A4); A2 = cfmar(z2, 0.5, A3); }
-  { const cplx z2 = zb * zb, z3 = z2 * zb, z4 = z2 * z2;
-    B5 = (z4 * zb) * mk(br, bi); B4 = cfmar(z4, 1.0 / 24.0, B5); B3 = cfmar(z3, 1.0 / 6.0, B4); B2 = cfmar(z2, 0.5, B3); }
+  { const cplx z3 = wa * za, z4 = wa * wa, S = cfma(za, mk(aor, aoi), mk(aer, aei));
+    A5 = (z4 * za) * S; A4 = cfmar(z4, 1.0 / 24.0, A5); A3 = cfmar(z3, 1.0 / 6.0, A4); A2 = cfmar(wa, 0.5, A3); }
+  { const cplx z3 = wb * zb, z4 = wb * wb, S = cfma(zb, mk(bor, boi), mk(ber, bei));
+    B5 = (z4 * zb) * S; B4 = cfmar(z4, 1.0 / 24.0, B5); B3 = cfmar(z3, 1.0 / 6.0, B4); B2 = cfmar(wb, 0.5, B3); }
 }
 MFB_HD void zexp_direct(cplx z, cplx& E2, cplx& E3, cplx& E4, cplx& E5) {   // |z| > 1
   const cplx z2 = z * z, z3 = z2 * z, z4 = z2 * z2;
