@@ -202,7 +202,15 @@ static void zexp_decomposed(cd z, cd* E /*0..6*/) {
 struct Params {
   cd lambda, mu; double rho, omega; cd c1, c2, k1, k2;
   cd psi[7], chi[7], T1[11], T2[10], T3[10]; cd cte_u, cte_t;
+  // static elasticity (lib/fbem/src/bem_staela3d.f90): Kelvin solution, cte_u = cteu1, cte_t = ctet1 of :617-622
+  bool statics = false; double cteu2 = 0.0, ctet2 = 0.0;
 };
+// constants of fbem_bem_staela3d_sbie_ext_pre / _ext_st / _int: bem_staela3d.f90:617-622
+static void calculate_parameters_static(double mu, double nu, Params& p) {
+  p.statics = true; p.mu = mu; p.lambda = 2.0 * mu * nu / (1.0 - 2.0 * nu); p.rho = 0.0; p.omega = 0.0;
+  p.cte_u = 1.0 / (16.0 * c_pi * mu * (1.0 - nu)); p.cteu2 = 3.0 - 4.0 * nu;
+  p.cte_t = -1.0 / (8.0 * c_pi * (1.0 - nu)); p.ctet2 = 1.0 - 2.0 * nu;
+}
 static void calculate_parameters(cd lambda, cd mu, double rho, double omega, Params& p) {
   const cd im(0.0, 1.0);
   cd c1 = std::sqrt((lambda + 2.0 * mu) / rho), c2 = std::sqrt(mu / rho);
@@ -259,6 +267,18 @@ static inline void add_exterior_point(const Params& p, const double* x, const do
                                       const double* pphijw, const double* sphijw, cd* h, cd* g) {
   double rv[3] = {x[0] - x_i[0], x[1] - x_i[1], x[2] - x_i[2]};
   double r = sqrt(dot3(rv, rv));
+  if (p.statics) {   // fbem_bem_staela3d_sbie_ext_pre: bem_staela3d.f90:629-645 (the same point formula in _ext_st :930-950)
+    double d1r = 1.0 / r, d1r2 = d1r * d1r;
+    double drdx[3] = {rv[0] * d1r, rv[1] * d1r, rv[2] * d1r};
+    double drdn = dot3(drdx, n);
+    for (int il = 0; il < 3; il++)
+      for (int ik = 0; ik < 3; ik++) {
+        double fs_u = d1r * (p.cteu2 * dkr[il][ik] + drdx[il] * drdx[ik]);
+        double fs_t = d1r2 * ((p.ctet2 * dkr[il][ik] + 3.0 * drdx[il] * drdx[ik]) * drdn + p.ctet2 * (n[il] * drdx[ik] - n[ik] * drdx[il]));
+        for (int j = 0; j < nn; j++) { h[(j * 3 + il) * 3 + ik] += fs_t * pphijw[j]; g[(j * 3 + il) * 3 + ik] += fs_u * sphijw[j]; }
+      }
+    return;
+  }
   KernelScalars ks; kernel_scalars(p, r, false, ks);
   double drdx[3] = {rv[0] * ks.d1r1, rv[1] * ks.d1r1, rv[2] * ks.d1r1};
   double drdn = dot3(drdx, n);
@@ -982,6 +1002,24 @@ static void sbie_int(const Element& e, const double* xi_i, const Params& p, cd* 
         double n[3] = {N[0] / jg, N[1] / jg, N[2] / jg};
         double rv[3] = {x[0] - x_i[0], x[1] - x_i[1], x[2] - x_i[2]};
         double r = sqrt(dot3(rv, rv));
+        if (p.statics) {   // fbem_bem_staela3d_sbie_int: bem_staela3d.f90:1284-1320
+          double d1r = 1.0 / r, d1r2 = d1r * d1r;
+          double drdx[3] = {rv[0] * d1r, rv[1] * d1r, rv[2] * d1r}, drdn = dot3(drdx, n);
+          double jw = jg * rho * jthetap * w_ang * w_rad;
+          double fjw[9]; for (int j = 0; j < nn; j++) fjw[j] = phi[j] * jw;
+          for (int il = 0; il < 3; il++) for (int ik = 0; ik < 3; ik++) {
+            double fs_u = d1r * (p.cteu2 * dkr[il][ik] + drdx[il] * drdx[ik]);
+            double fs_t = d1r2 * drdn * (p.ctet2 * dkr[il][ik] + 3.0 * drdx[il] * drdx[ik]);
+            double fs_c = d1r2 * p.ctet2 * (n[il] * drdx[ik] - n[ik] * drdx[il]);
+            for (int j = 0; j < nn; j++) {
+              h[(j * 3 + il) * 3 + ik] += fs_t * fjw[j];
+              g[(j * 3 + il) * 3 + ik] += fs_u * fjw[j];
+              h[(j * 3 + il) * 3 + ik] += fs_c * (phi[j] - phi_i[j]) * jw;
+            }
+          }
+          st.pts_singular++;
+          continue;
+        }
         KernelScalars k; kernel_scalars(p, r, true, k);
         double dr1 = k.d1r1, dr2 = k.d1r2;
         double drdx[3] = {rv[0] * dr1, rv[1] * dr1, rv[2] * dr1}, drdn = dot3(drdx, n);
@@ -1012,7 +1050,8 @@ static void sbie_int(const Element& e, const double* xi_i, const Params& p, cd* 
       double xi_s[2]; staela3d_sbie_int_li(ety, xe, xi_s, x_i, 5, qsl, 1, 16, hli, st);
     }
   }
-  for (int il = 0; il < 3; il++) for (int ik = 0; ik < 3; ik++) for (int j = 0; j < nn; j++) h[(j * 3 + il) * 3 + ik] += phi_i[j] * p.T2[1] * hli[il][ik];
+  const cd c_li = p.statics ? cd(p.ctet2) : p.T2[1];   // bem_staela3d.f90:1373 / bem_harela3d.f90:1462-1466
+  for (int il = 0; il < 3; il++) for (int ik = 0; ik < 3; ik++) for (int j = 0; j < nn; j++) h[(j * 3 + il) * 3 + ik] += phi_i[j] * c_li * hli[il][ik];
   for (int i = 0; i < 9 * nn; i++) { h[i] = p.cte_t * h[i]; g[i] = p.cte_u * g[i]; }
   if (e.reverse) for (int i = 0; i < 9 * nn; i++) h[i] = -h[i];
 }
@@ -1193,11 +1232,42 @@ static void scatter(const Model* m, int e, int sn_col, const cd* hp, const cd* g
 }
 
 // One frequency: accumulates (+=) this region's BIE rows into A (col-major n_dof x n_dof) and b.
+static int assemble_impl(Model* m, const Params& p, cd nu, const cd* cvalue, cd* A, cd* b, int nthreads, long long* stats_out);
 int orc_assemble(void* h, double omega, const double* lambda_ri, const double* mu_ri, double rho, const double* nu_ri,
                  const double* cvalue_ri, double* A_ri, double* b_ri, int nthreads, long long* stats_out /*44*/) {
-  Model* m = (Model*)h; cd* A = (cd*)A_ri; cd* b = (cd*)b_ri; const cd* cvalue = (const cd*)cvalue_ri;
   Params p; calculate_parameters(cd(lambda_ri[0], lambda_ri[1]), cd(mu_ri[0], mu_ri[1]), rho, omega, p);
-  cd nu(nu_ri[0], nu_ri[1]);
+  return assemble_impl((Model*)h, p, cd(nu_ri[0], nu_ri[1]), (const cd*)cvalue_ri, (cd*)A_ri, (cd*)b_ri, nthreads, stats_out);
+}
+// Static elasticity: build_lse_mechanics_bem_staela (src/build_lse_mechanics_bem_staela.f90; same element / collocation loops,
+// free-term pass :273-520 with fbem_bem_staela3d_sbie_freeterm, scatter assemble_bem_staela_equation.f90) with the Kelvin
+// kernels of lib/fbem/src/bem_staela3d.f90:524-1381.  Real in, real out (A col-major n_dof x n_dof, b); the traversal is the
+// harmonic one (the reference's static and harmonic integrators differ only in the point formulas), evaluated in real
+// arithmetic and carried in complex containers whose imaginary parts stay exactly zero.
+int orc_assemble_static(void* h, double mu, double nu, const double* cvalue_r, double* A_r, double* b_r, int nthreads, long long* stats_out) {
+  Model* m = (Model*)h; const long long n = m->n_dof;
+  Params p; calculate_parameters_static(mu, nu, p);
+  std::vector<cd> A((size_t)n * n, cd(0.0, 0.0)), b((size_t)n, cd(0.0, 0.0)), cv((size_t)3 * m->n_node);
+  for (size_t i = 0; i < cv.size(); i++) cv[i] = cvalue_r[i];
+  int err = assemble_impl(m, p, cd(nu, 0.0), cv.data(), A.data(), b.data(), nthreads, stats_out);
+  for (size_t i = 0; i < A.size(); i++) { if (A[i].imag() != 0.0) err = 7; A_r[i] += A[i].real(); }
+  for (size_t i = 0; i < b.size(); i++) { if (b[i].imag() != 0.0) err = 7; b_r[i] += b[i].real(); }
+  return err;
+}
+// u*, t* of Kelvin (fbem_bem_staela3d_sbie_u / _t, bem_staela3d.f90:408-461), [l][k]
+void orc_fundamental_solutions_static(const double* x, const double* n, const double* x_i, double mu, double nu, double* u, double* t) {
+  Params p; calculate_parameters_static(mu, nu, p);
+  double one = 1.0; cd h[9], g[9]; for (int i = 0; i < 9; i++) { h[i] = 0; g[i] = 0; }
+  add_exterior_point(p, x, n, x_i, 1, &one, &one, h, g);
+  for (int i = 0; i < 9; i++) { u[i] = (p.cte_u * g[i]).real(); t[i] = (p.cte_t * h[i]).real(); }
+}
+int orc_pair_static(void* h, int e, const double* x_i, double mu, double nu, double* h_r, double* g_r) {
+  Model* m = (Model*)h; Params p; calculate_parameters_static(mu, nu, p);
+  Stats st; memset(&st, 0, sizeof(st)); cd hh[81], gg[81];
+  int mode = sbie_auto(m->elem[e], x_i, p, m->qsp, m->ns_max, hh, gg, st);
+  for (int i = 0; i < 9 * m->elem[e].nn; i++) { h_r[i] = hh[i].real(); g_r[i] = gg[i].real(); }
+  return mode;
+}
+static int assemble_impl(Model* m, const Params& p, cd nu, const cd* cvalue, cd* A, cd* b, int nthreads, long long* stats_out) {
   Stats total; memset(&total, 0, sizeof(total));
   if (nthreads > 0) omp_set_num_threads(nthreads);
 #pragma omp parallel

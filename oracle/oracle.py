@@ -78,6 +78,30 @@ class Oracle:
                  "pairs_singular": int(st[37]), "pts_singular": int(st[38]), "li_points": int(st[39])}
         return A, b, stats
 
+    def assemble_static(self, mat, nthreads=0):
+        """Static elasticity (build_lse_mechanics_bem_staela + assemble_bem_staela_equation): real A, b and the plan stats."""
+        n = self.m.n_dof
+        A = np.zeros((n, n), dtype=np.float64, order="F")
+        b = np.zeros(n, dtype=np.float64)
+        st = np.zeros(44, dtype=np.int64)
+        cv = np.ascontiguousarray(self.m.cvalue.real, dtype=np.float64)
+        err = lib().orc_assemble_static(self.h, C.c_double(mat.mu_r), C.c_double(mat.nu_r), _p(cv), _p(A), _p(b), C.c_int(nthreads), _p(st))
+        if err == 7:
+            raise RuntimeError("oracle: the static assembly produced a nonzero imaginary part")
+        if err:
+            raise RuntimeError("oracle: invalid normals/tangents configuration in free-term")
+        stats = {"pairs_regular": {g: int(st[g]) for g in range(33) if st[g]}, "pts_regular": int(st[33]),
+                 "pairs_adaptive": int(st[34]), "leaves": int(st[35]), "pts_adaptive": int(st[36]),
+                 "pairs_singular": int(st[37]), "pts_singular": int(st[38]), "li_points": int(st[39])}
+        return A, b, stats
+
+    def pair_static(self, e, x_i, mat):
+        nn = int(self.m.elem_ptr[e + 1] - self.m.elem_ptr[e])
+        h = np.zeros((nn, 3, 3)); g = np.zeros((nn, 3, 3))
+        x_i = np.ascontiguousarray(x_i, dtype=np.float64)
+        mode = lib().orc_pair_static(self.h, C.c_int(e), _p(x_i), C.c_double(mat.mu_r), C.c_double(mat.nu_r), _p(h), _p(g))
+        return h, g, mode
+
     def assemble_colloc_sample(self, omega, mat, c_offset, c_stride, nthreads=0):
         """Bounded sample for the CPU baseline: all elements x every c_stride-th collocation point.
         -> (compact A_s (3*n_sample x n_dof), b_s, n_sample, quadrature points evaluated)."""
@@ -162,6 +186,26 @@ def freeterm(normals, tangents, nu, tol=1e-6):
     c = np.zeros((3, 3), dtype=np.complex128)
     err = lib().orc_freeterm(C.c_int(len(n)), _p(n), _p(t), C.c_double(tol), _p(_ri(nu)), _p(c))
     return c, err
+
+
+def fundamental_solutions_static(x, n, x_i, mat):
+    """Kelvin u*, t* (3,3) [l][k] (fbem_bem_staela3d_sbie_u / _t, lib/fbem/src/bem_staela3d.f90:408-461)."""
+    u = np.zeros((3, 3)); t = np.zeros((3, 3))
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (x, n, x_i)]
+    lib().orc_fundamental_solutions_static(_p(a[0]), _p(a[1]), _p(a[2]), C.c_double(mat.mu_r), C.c_double(mat.nu_r), _p(u), _p(t))
+    return u, t
+
+
+def lu_solve_real(A, b):
+    """The reference's solve_lse_r default path (src/solve_lse_r.f90:137,189): dgetrf + dgetrs (scipy-bundled OpenBLAS)."""
+    from scipy.linalg import lapack
+    lu, piv, info = lapack.dgetrf(A, overwrite_a=False)
+    if info != 0:
+        raise RuntimeError("dgetrf info=%d" % info)
+    x, info = lapack.dgetrs(lu, piv, b)
+    if info != 0:
+        raise RuntimeError("dgetrs info=%d" % info)
+    return x, lu, piv
 
 
 def lu_solve(A, b):
