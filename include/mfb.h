@@ -135,6 +135,20 @@ int mfb_measure_peaks(mfb_ctx* ctx, double* dfma_tflops, double* dmma_tflops, do
 int mfb_zgemm_minus(mfb_ctx* ctx, int m, int n, int k, const mfb_z* A, int lda, const mfb_z* B, int ldb, mfb_z* C, int ldc,
                     double* ms);
 
+/* ---- Static 3D elasticity (BASELINE config 2) ------------------------------------------------
+ * The same mfb_problem serves the static analysis: mesh, collocation points, DOF maps and the quadrature plan do not depend on
+ * the kernel (fbem_bem_staela3d_sbie_auto takes the decisions of its harmonic twin, lib/fbem/src/bem_staela3d.f90:524-589).
+ *   mfb_staela3d_assemble  == `A_r=0; b_r=0` + build_lse_mechanics_bem_staela(kr) (src/build_lse_mechanics_static.f90:60-66,
+ *                          src/build_lse_mechanics_bem_staela.f90) with the Kelvin kernels of fbem_bem_staela3d_sbie_ext_pre /
+ *                          _ext_adp / _int (bem_staela3d.f90:592-1381) and the scatter of assemble_bem_staela_equation.f90.
+ *                          mu, nu = region%property_r(2,3); cvalue[3*n_node] = node%cvalue_r(k,1,1); A (n_dof x n_dof col-major) /
+ *                          b real, or NULL to keep the system on the device only.  Real arithmetic, real plane only.
+ *   mfb_dsolve             == solve_lse_r (src/solve_lse_r.f90:25-232, dgetrf :137 + dgetrs :189), conventions of mfb_zsolve.
+ *   mfb_staela3d_solve     assemble + factorise + solve on the device, x[n_dof] = solution (host column order). */
+int mfb_staela3d_assemble(mfb_problem* problem, double mu, double nu, const double* cvalue, double* A, double* b);
+int mfb_dsolve(mfb_problem* problem, int n, double* A, int lda, int* ipiv, double* b, int nrhs, int factorize);
+int mfb_staela3d_solve(mfb_problem* problem, double mu, double nu, const double* cvalue, double* x);
+
 /* ---- One frequency over several GPUs (shard 2) --------------------------------------------------
  * One process per GPU, every process holds the same mfb_problem (mesh + plan replicated).  Rank r assembles a contiguous
  * run of collocation-row blocks (the rows of build_lse_mechanics_bem_harela's kn_col loop it owns, all columns), the row

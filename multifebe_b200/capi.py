@@ -195,6 +195,37 @@ class Problem:
         _check(lib().mfb_get_entries(self.h, C.c_int(len(r)), _p(r), _p(c), _p(out)))
         return out
 
+    # ---- static elasticity: build_lse_mechanics_bem_staela(kr) / solve_lse_r(...) ----
+    def build_lse_mechanics_bem_staela(self, mat, want_host=True):
+        """A_r, b_r of the static analysis (real); mat.mu_r, mat.nu_r = region%property_r(2,3)."""
+        n = self.m.n_dof
+        A = np.zeros((n, n), dtype=np.float64, order="F") if want_host else None
+        b = np.zeros(n, dtype=np.float64) if want_host else None
+        cv = np.ascontiguousarray(self._cv.real, dtype=np.float64)
+        _check(lib().mfb_staela3d_assemble(self.h, C.c_double(mat.mu_r), C.c_double(mat.nu_r), _p(cv),
+                                           _p(A) if want_host else None, _p(b) if want_host else None))
+        return A, b
+
+    def solve_lse_r(self, A=None, b=None, factorize=True, want_ipiv=False):
+        """LAPACK dgesv semantics with host A (overwritten by the LU factors) and b; A=None uses the resident static system."""
+        n = self.m.n_dof
+        ipiv = np.zeros(n, dtype=np.int32)
+        if A is not None and not (A.flags.f_contiguous and A.dtype == np.float64):
+            raise ValueError("A must be a Fortran-ordered float64 array (it is overwritten by the LU factors)")
+        if b is None:
+            raise ValueError("pass the right-hand side b (use solve_static for the fully device-resident path)")
+        bb = np.asfortranarray(b, dtype=np.float64).reshape(n, -1, order="F").copy(order="F")
+        _check(lib().mfb_dsolve(self.h, C.c_int(n), _p(A) if A is not None else None, C.c_int(n), _p(ipiv), _p(bb),
+                                C.c_int(bb.shape[1]), C.c_int(int(factorize))))
+        x = bb[:, 0] if np.ndim(b) == 1 else bb
+        return (x, ipiv) if want_ipiv else x
+
+    def solve_static(self, mat):
+        x = np.zeros(self.m.n_dof, dtype=np.float64)
+        cv = np.ascontiguousarray(self._cv.real, dtype=np.float64)
+        _check(lib().mfb_staela3d_solve(self.h, C.c_double(mat.mu_r), C.c_double(mat.nu_r), _p(cv), _p(x)))
+        return x
+
     # ---- one frequency over several GPUs (mfb_dist_*; collective over the ranks) ----
     def dist_init(self, rank, nranks, unique_id, nb=0):
         _check(lib().mfb_dist_init(self.h, C.c_int(rank), C.c_int(nranks), C.c_char_p(unique_id), C.c_int(nb)))

@@ -76,6 +76,8 @@ struct mfb_problem {
   int *d_rowperm, *d_colperm; bool rows_permuted;
   std::vector<int> h_tile_row0, h_tile_nbytes;   // host copies of DevColloc::tile_row0 / tile_nbytes (row partition of the multi-GPU mode)
   DistState dist;
+  alignas(64) unsigned char tmapS[128]; bool have_tmapS;   // one-plane box: K1 flush of the static (real) assembly
+  bool real_resident;                                      // the resident system / factors are real (static path): Are only
   alignas(64) unsigned char tmapA[128]; bool have_tmap;   // CUtensorMap of the planar system matrix (K1 flush)   // rows_permuted: the resident matrix/factors are in the internal order
 };
 
@@ -538,7 +540,9 @@ extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x
   double* dA; CK(cudaMalloc((void**)&dA, (size_t)2 * p->lda * n_dof * sizeof(double))); p->owned.push_back(dA);
   double* db; CK(cudaMalloc((void**)&db, (size_t)2 * p->lda * sizeof(double))); p->owned.push_back(db);
   p->sys.Are = dA; p->sys.Aim = dA + (size_t)p->lda * n_dof; p->sys.lda = p->lda; p->sys.n_dof = n_dof; p->sys.bre = db; p->sys.bim = db + p->lda;
-  p->have_tmap = make_matrix_tensor_map(p->tmapA, p->sys.Are, p->lda, n_dof) == 0;
+  p->have_tmap = make_matrix_tensor_map(p->tmapA, p->sys.Are, p->lda, n_dof, 2) == 0;
+  p->have_tmapS = make_matrix_tensor_map(p->tmapS, p->sys.Are, p->lda, n_dof, 1) == 0;
+  p->real_resident = false;
   if (!p->have_tmap) { mfb_problem_free(p); return fail(MFB_ERR_CUDA, "mfb_harela3d_setup: cuTensorMapEncodeTiled failed (driver too old for sm_100a TMA?)"); }
   CK(cudaMalloc((void**)&p->d_cvalue, (size_t)6 * n_node * sizeof(double))); p->owned.push_back(p->d_cvalue);
   CK(cudaMalloc((void**)&p->d_ipiv, (size_t)n_dof * sizeof(int))); p->owned.push_back(p->d_ipiv);
@@ -602,9 +606,25 @@ static void scale_kparams(const KParams& K, KParams& Q) {
   for (int i = 1; i <= 9; i++) { Q.T2[i] = K.T2[i] * K.cte_t; Q.T3[i] = K.T3[i] * K.cte_t; }
 }
 
+// Static elasticity as the parameter set of the harmonic kernels: only the 1/r (psi, chi) and 1/r^2 (T1..T3) coefficients
+// survive, k1 = k2 = 0 (every E_m term vanishes), all real.  With r_c = c2^2/c1^2 = (1-2nu)/(2(1-nu)) these are Kelvin's
+// u*, t* exactly as fbem_bem_staela3d_sbie_u/_t write them (lib/fbem/src/bem_staela3d.f90:408-461):
+// cte_u psi(1) = (3-4nu)/(16 pi mu (1-nu)), -cte_u chi(1) = 1/(16 pi mu (1-nu)), cte_t T1(1) = -3/(8 pi (1-nu)), cte_t T2(1) = -(1-2nu)/(8 pi (1-nu)) = -cte_t T3(1).
+static void host_kparams_static(double mu, double nu, KParams& K) {
+  memset(&K, 0, sizeof(K));
+  const double rc = (1.0 - 2.0 * nu) / (2.0 * (1.0 - nu));
+  K.psi[1] = mk(0.5 * (1.0 + rc), 0.0); K.chi[1] = mk(-0.5 * (1.0 - rc), 0.0);
+  K.T1[1] = mk(3.0 * (rc - 1.0), 0.0); K.T2[1] = mk(-rc, 0.0); K.T3[1] = mk(rc, 0.0);
+  const double c_1_4pi = 0.07957747154594767280411105048;
+  K.cte_u = mk(c_1_4pi / mu, 0.0); K.cte_t = c_1_4pi;
+}
+static int assemble_device_k(mfb_problem* p, const KParams& K, const KParams& Q, cd nu, const mfb_z* cvalue, bool statics);
 static int assemble_device(mfb_problem* p, double omega, cd lambda, cd mu, double rho, cd nu, const mfb_z* cvalue) {
-  cudaStream_t st = p->ctx->stream;
   KParams K, Q; host_kparams(lambda, mu, rho, omega, K); scale_kparams(K, Q);
+  return assemble_device_k(p, K, Q, nu, cvalue, false);
+}
+static int assemble_device_k(mfb_problem* p, const KParams& K, const KParams& Q, cd nu, const mfb_z* cvalue, bool statics) {
+  cudaStream_t st = p->ctx->stream;
   set_kparams(K, Q, st);
   if (cvalue) {
     CK(cudaMemcpyAsync(p->d_cvalue, cvalue, (size_t)6 * p->n_node * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -615,7 +635,10 @@ static int assemble_device(mfb_problem* p, double omega, cd lambda, cd mu, doubl
   CK(cudaMemsetAsync(p->sys.Are, 0, (size_t)2 * p->lda * p->n_dof * sizeof(double), st));
   CK(cudaMemsetAsync(p->sys.bre, 0, (size_t)2 * p->lda * sizeof(double), st));
   CK(cudaEventRecord(p->ev[1], st));
-  for (auto& g : p->groups) launch_regular(g.dev, p->colloc, p->sys, p->plan, p->have_tmap ? p->tmapA : nullptr, st);
+  {
+    const void* tm = statics ? (p->have_tmapS ? p->tmapS : nullptr) : (p->have_tmap ? p->tmapA : nullptr);
+    for (auto& g : p->groups) launch_regular(g.dev, p->colloc, p->sys, p->plan, tm, statics, st);
+  }
   CK(cudaEventRecord(p->ev[2], st));
   for (auto& g : p->groups) launch_adaptive(g.dev, p->colloc, p->sys, g.adp, p->ctx->tables, st);
   CK(cudaEventRecord(p->ev[3], st));
@@ -626,7 +649,7 @@ static int assemble_device(mfb_problem* p, double omega, cd lambda, cd mu, doubl
   launch_freeterm(p->colloc, p->sys, p->ft, mk(F.real(), F.imag()), st);
   CK(cudaEventRecord(p->ev[5], st));
   CK(cudaGetLastError());
-  p->factored = false; p->assembled = true; p->rows_permuted = true;
+  p->factored = false; p->assembled = true; p->rows_permuted = true; p->real_resident = statics;
   // our kernels only (memsets/copies are not counted): free term + per group regular, adaptive, singular (+ gather_cv)
   p->asm_launches = 1;
   for (auto& g : p->groups)   // K1: one kernel per element class on 3/4-node elements (classes 0, 1 and, if present, 2)
@@ -705,7 +728,7 @@ static int factor_device(mfb_problem* p, int n, bool timing) {
   cudaStream_t st = p->ctx->stream;
   int r = ensure_lu(p); if (r) return r;
   CK(cudaEventRecord(p->ev[6], st));
-  int e = zgetrf_planar(p->sys.Are, p->sys.Aim, p->lda, n, p->d_ipiv, p->lu, st, timing);
+  int e = zgetrf_planar(p->sys.Are, p->real_resident ? nullptr : p->sys.Aim, p->lda, n, p->d_ipiv, p->lu, st, timing);
   if (e) return fail(MFB_ERR_CUDA, std::string("zgetrf_planar: ") + cudaGetErrorString((cudaError_t)e));
   CK(cudaEventRecord(p->ev[7], st));
   int info = 0;
@@ -735,7 +758,8 @@ extern "C" int mfb_zsolve(mfb_problem* p, int n, mfb_z* A, int lda, int* ipiv, m
   cudaStream_t st = p->ctx->stream;
   int r;
   if (factorize) {
-    if (A) { r = upload_matrix(p, A, lda, n, n, p->sys.Are, p->sys.Aim, p->lda); if (r) return r; p->rows_permuted = false; }
+    if (A) { r = upload_matrix(p, A, lda, n, n, p->sys.Are, p->sys.Aim, p->lda); if (r) return r; p->rows_permuted = false; p->real_resident = false; }
+    else if (p->real_resident) return fail(MFB_ERR_ARG, "mfb_zsolve: the resident system is real (static assembly); use mfb_dsolve");
     p->assembled = false;
     r = factor_device(p, n, lu_timing());
     if (ipiv) memcpy(ipiv, p->h_ipiv.data(), (size_t)n * sizeof(int));
@@ -1113,4 +1137,108 @@ extern "C" int mfb_dist_zsolve(mfb_problem* p, int n, const mfb_z* A, int lda_h,
   r = dist_factor_solve(p, x);
   if (ipiv) CK(cudaMemcpy(ipiv, d.lu.r[0].ipiv, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
   return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Static 3D elasticity: build_lse_mechanics_bem_staela + assemble_bem_staela_equation +
+// solve_lse_r (dgetrf / dgetrs) on the same problem object (mesh, collocation tiles and quadrature plan do not depend on
+// the kernel: fbem_bem_staela3d_sbie_auto takes the decisions of fbem_bem_harela3d_sbie_auto, bem_staela3d.f90:524-589).
+// ---------------------------------------------------------------------------------------------------------------------
+static int download_real(mfb_problem* p, const double* re, long long ld, int rows, int cols, double* host, long long ldh, const int* rowperm, const int* colperm) {
+  cudaStream_t st = p->ctx->stream;
+  int chunk = (int)std::max<long long>(1, std::min<long long>(cols, (256ll << 20) / (8ll * rows)));
+  double* stage; CK(cudaMalloc((void**)&stage, (size_t)chunk * rows * 8));
+  for (int c0 = 0; c0 < cols; c0 += chunk) {
+    int nc = std::min(chunk, cols - c0);
+    launch_gather_real(re, ld, rows, nc, stage, rows, rowperm, colperm, c0, st);
+    CK(cudaMemcpy2DAsync(host + (long long)c0 * ldh, (size_t)ldh * 8, stage, (size_t)rows * 8, (size_t)rows * 8, nc, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  cudaFree(stage);
+  return MFB_OK;
+}
+static int upload_real(mfb_problem* p, const double* host, long long ldh, int rows, int cols, double* re, long long ld, const int* rowperm) {
+  cudaStream_t st = p->ctx->stream;
+  int chunk = (int)std::max<long long>(1, std::min<long long>(cols, (256ll << 20) / (8ll * rows)));
+  double* stage; CK(cudaMalloc((void**)&stage, (size_t)chunk * rows * 8));
+  for (int c0 = 0; c0 < cols; c0 += chunk) {
+    int nc = std::min(chunk, cols - c0);
+    CK(cudaMemcpy2DAsync(stage, (size_t)rows * 8, host + (long long)c0 * ldh, (size_t)ldh * 8, (size_t)rows * 8, nc, cudaMemcpyHostToDevice, st));
+    launch_scatter_real(stage, rows, rows, nc, re + (long long)c0 * ld, ld, rowperm, st);
+    CK(cudaStreamSynchronize(st));
+  }
+  cudaFree(stage);
+  return MFB_OK;
+}
+static int assemble_static_device(mfb_problem* p, double mu, double nu, const double* cvalue) {
+  if (!(mu > 0.0) || !(nu > -1.0 && nu < 0.5)) return fail(MFB_ERR_ARG, "static assembly: mu must be positive and nu in (-1, 0.5)");
+  KParams K, Q; host_kparams_static(mu, nu, K); scale_kparams(K, Q);
+  std::vector<mfb_z> cv;
+  if (cvalue) { cv.resize((size_t)3 * p->n_node); for (size_t i = 0; i < cv.size(); i++) { cv[i].re = cvalue[i]; cv[i].im = 0.0; } }
+  int r = assemble_device_k(p, K, Q, cd(nu, 0.0), cvalue ? cv.data() : nullptr, true);
+  if (r) return r;
+  if (cvalue) CK(cudaStreamSynchronize(p->ctx->stream));   // cv is a local staging buffer
+  return MFB_OK;
+}
+extern "C" int mfb_staela3d_assemble(mfb_problem* p, double mu, double nu, const double* cvalue, double* A, double* b) {
+  if (!p) return fail(MFB_ERR_ARG, "mfb_staela3d_assemble: null problem");
+  CK(cudaSetDevice(p->ctx->device));
+  int r = assemble_static_device(p, mu, nu, cvalue); if (r) return r;
+  r = collect_assembly_times(p); if (r) return r;
+  if (A) { r = download_real(p, p->sys.Are, p->lda, p->n_dof, p->n_dof, A, p->n_dof, p->d_rowperm, p->d_colperm); if (r) return r; }
+  if (b) { r = download_real(p, p->sys.bre, p->lda, p->n_dof, 1, b, p->n_dof, p->d_rowperm, nullptr); if (r) return r; }
+  return MFB_OK;
+}
+// solve_lse_r(n_dof,A,ipiv,...,n_rhs,b,factorize,...) (src/solve_lse_r.f90:25-232: dgetrf :137, dgetrs :189): same conventions as
+// mfb_zsolve with real arrays.  A == NULL: the device-resident system of the last mfb_staela3d_assemble.
+extern "C" int mfb_dsolve(mfb_problem* p, int n, double* A, int lda, int* ipiv, double* b, int nrhs, int factorize) {
+  if (!p) return fail(MFB_ERR_ARG, "mfb_dsolve: null problem");
+  if (n != p->n_dof) return fail(MFB_ERR_ARG, "mfb_dsolve: n must equal the problem's n_dof");
+  if (nrhs < 0 || (A && lda < n)) return fail(MFB_ERR_ARG, "mfb_dsolve: invalid nrhs/lda");
+  CK(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  int r;
+  if (factorize) {
+    if (A) { r = upload_real(p, A, lda, n, n, p->sys.Are, p->lda, nullptr); if (r) return r; p->rows_permuted = false; p->real_resident = true; }
+    else if (!p->real_resident) return fail(MFB_ERR_ARG, "mfb_dsolve: the resident system is complex (harmonic assembly); use mfb_zsolve");
+    p->assembled = false;
+    r = factor_device(p, n, lu_timing());
+    if (ipiv) memcpy(ipiv, p->h_ipiv.data(), (size_t)n * sizeof(int));
+    if (A) { int r2 = download_real(p, p->sys.Are, p->lda, n, n, A, lda, nullptr, nullptr); if (r2) return r2; }
+    if (r) return r;
+  } else if (!p->factored || !p->real_resident) return fail(MFB_ERR_ARG, "mfb_dsolve: factorize=0 but no real factors are resident");
+  if (nrhs == 0) return MFB_OK;
+  double* bre = p->sys.bre; long long ldb = p->lda;
+  double* tmp = nullptr;
+  if (b) {
+    if (nrhs > 1) { CK(cudaMalloc((void**)&tmp, (size_t)p->lda * nrhs * sizeof(double))); bre = tmp; }
+    r = upload_real(p, b, n, n, nrhs, bre, ldb, p->rows_permuted ? p->d_rowperm : nullptr); if (r) return r;
+  } else if (nrhs != 1) return fail(MFB_ERR_ARG, "mfb_dsolve: device-resident rhs has a single column");
+  CK(cudaEventRecord(p->ev[6], st));
+  int e = zgetrs_planar(p->sys.Are, nullptr, p->lda, n, p->d_perm, bre, nullptr, ldb, nrhs, st);
+  if (e) return fail(MFB_ERR_CUDA, std::string("dgetrs (planar): ") + cudaGetErrorString((cudaError_t)e));
+  CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
+  float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
+  if (b) { r = download_real(p, bre, ldb, n, nrhs, b, n, p->rows_permuted ? p->d_colperm : nullptr, nullptr); if (r) return r; }
+  if (tmp) cudaFree(tmp);
+  return MFB_OK;
+}
+// assemble + dgetrf + dgetrs without leaving the device (the body of the static driver, src/multifebe.f90: build_lse_mechanics_static,
+// solve_lse_r, assign_solution): x[n_dof] = solution in the host's column order
+extern "C" int mfb_staela3d_solve(mfb_problem* p, double mu, double nu, const double* cvalue, double* x) {
+  if (!p) return fail(MFB_ERR_ARG, "mfb_staela3d_solve: null problem");
+  CK(cudaSetDevice(p->ctx->device));
+  int r = assemble_static_device(p, mu, nu, cvalue); if (r) return r;
+  r = factor_device(p, p->n_dof, lu_timing());
+  int r2 = collect_assembly_times(p); if (r2) return r2;
+  if (r) return r;
+  cudaStream_t st = p->ctx->stream;
+  CK(cudaEventRecord(p->ev[6], st));
+  int e = zgetrs_planar(p->sys.Are, nullptr, p->lda, p->n_dof, p->d_perm, p->sys.bre, nullptr, p->lda, 1, st);
+  if (e) return fail(MFB_ERR_CUDA, std::string("dgetrs (planar): ") + cudaGetErrorString((cudaError_t)e));
+  CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
+  float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
+  p->assembled = false;
+  if (!x) return MFB_OK;
+  return download_real(p, p->sys.bre, p->lda, p->n_dof, 1, x, p->n_dof, p->d_colperm, nullptr);
 }

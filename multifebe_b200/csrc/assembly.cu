@@ -252,7 +252,9 @@ struct AccA { double re[9 * NN], im[9 * NN]; };   // [(l*3+k)*NN + j]: entry of 
 // MODE 2: any element: both combinations, per (node, dof) one goes to A and the other, times the prescribed value, to b;
 //         ekind / ecv point at the chunk's first node.
 // have_ks: the kernel scalars of this point are already in ks (cached by the pass over the first chunk of nodes).
-template <int NW, int MODE>
+// ST: static elasticity (Kelvin kernels, lib/fbem/src/bem_staela3d.f90:629-645): the kernel scalars are the 1/r and 1/r^2 terms
+//     alone and everything is real -- no imaginary accumulators, no exponentials.
+template <int NW, int MODE, bool ST>
 __device__ __forceinline__ void k1_point(AccA<NW>& a, double* bacc, const double* rec, const double* w, const double* sk, bool do_b, const double* xc,
                                          double sgn, unsigned info, const unsigned char* __restrict__ ekind, const double* __restrict__ ecv, bool have_ks,
                                          KScal& k) {
@@ -260,7 +262,11 @@ __device__ __forceinline__ void k1_point(AccA<NW>& a, double* bacc, const double
   const double rv0 = rec[0] - xc[0], rv1 = rec[1] - xc[1], rv2 = rec[2] - xc[2];
   const double r2 = fma(rv0, rv0, fma(rv1, rv1, rv2 * rv2));
   const double d1r1 = rsqrt(r2), r = r2 * d1r1;
-  if (!have_ks) kernel_scalars_scaled(c_kq, r, d1r1, k, MODE != 0 || (info & 7u) != 7u, MODE != 0 || (info & 7u) != 0u);
+  if (ST) {
+    const double d1r2 = d1r1 * d1r1;
+    k.psi = mk(c_kq.psi[1].re * d1r1, 0.0); k.chi = mk(c_kq.chi[1].re * d1r1, 0.0);
+    k.T1 = mk(c_kq.T1[1].re * d1r2, 0.0); k.T2 = mk(c_kq.T2[1].re * d1r2, 0.0); k.T3 = mk(c_kq.T3[1].re * d1r2, 0.0);
+  } else if (!have_ks) kernel_scalars_scaled(c_kq, r, d1r1, k, MODE != 0 || (info & 7u) != 7u, MODE != 0 || (info & 7u) != 0u);
   const double dx[3] = {rv0 * d1r1, rv1 * d1r1, rv2 * d1r1};
   const double drdn = fma(dx[0], n[0], fma(dx[1], n[1], dx[2] * n[2]));
   const cplx t1d = k.T1 * drdn;
@@ -273,25 +279,33 @@ __device__ __forceinline__ void k1_point(AccA<NW>& a, double* bacc, const double
 #pragma unroll
         for (int l = 0; l < 3; l++) {
           const double dd = dx[l] * dx[kk], c2 = (l == kk) ? fma(dx[kk], n[l], drdn) : dx[kk] * n[l], c3 = dx[l] * n[kk];
-          const double fr = fma(t1d.re, dd, fma(k.T2.re, c2, k.T3.re * c3)), fi = fma(t1d.im, dd, fma(k.T2.im, c2, k.T3.im * c3));
+          const double fr = fma(t1d.re, dd, fma(k.T2.re, c2, k.T3.re * c3)), fi = ST ? 0.0 : fma(t1d.im, dd, fma(k.T2.im, c2, k.T3.im * c3));
 #pragma unroll
-          for (int j = 0; j < NW; j++) { a.re[(l * 3 + kk) * NW + j] = fma(fr, w[j], a.re[(l * 3 + kk) * NW + j]); a.im[(l * 3 + kk) * NW + j] = fma(fi, w[j], a.im[(l * 3 + kk) * NW + j]); }
+          for (int j = 0; j < NW; j++) { a.re[(l * 3 + kk) * NW + j] = fma(fr, w[j], a.re[(l * 3 + kk) * NW + j]); if (!ST) a.im[(l * 3 + kk) * NW + j] = fma(fi, w[j], a.im[(l * 3 + kk) * NW + j]); }
           if (MODE == 1 && do_b) {
-            const double orr = (l == kk) ? fma(-k.chi.re, dd, k.psi.re) : -k.chi.re * dd, oi = (l == kk) ? fma(-k.chi.im, dd, k.psi.im) : -k.chi.im * dd;
-            bacc[l] -= orr * skr - oi * ski; bacc[3 + l] -= orr * ski + oi * skr;
+            const double orr = (l == kk) ? fma(-k.chi.re, dd, k.psi.re) : -k.chi.re * dd;
+            if (ST) bacc[l] -= orr * skr;
+            else {
+              const double oi = (l == kk) ? fma(-k.chi.im, dd, k.psi.im) : -k.chi.im * dd;
+              bacc[l] -= orr * skr - oi * ski; bacc[3 + l] -= orr * ski + oi * skr;
+            }
           }
         }
       } else {
 #pragma unroll
         for (int l = 0; l < 3; l++) {
           const double dd = dx[l] * dx[kk];
-          const double fr = (l == kk) ? fma(-k.chi.re, dd, k.psi.re) : -k.chi.re * dd, fi = (l == kk) ? fma(-k.chi.im, dd, k.psi.im) : -k.chi.im * dd;
+          const double fr = (l == kk) ? fma(-k.chi.re, dd, k.psi.re) : -k.chi.re * dd, fi = ST ? 0.0 : ((l == kk) ? fma(-k.chi.im, dd, k.psi.im) : -k.chi.im * dd);
 #pragma unroll
-          for (int j = 0; j < NW; j++) { a.re[(l * 3 + kk) * NW + j] = fma(fr, w[j], a.re[(l * 3 + kk) * NW + j]); a.im[(l * 3 + kk) * NW + j] = fma(fi, w[j], a.im[(l * 3 + kk) * NW + j]); }
+          for (int j = 0; j < NW; j++) { a.re[(l * 3 + kk) * NW + j] = fma(fr, w[j], a.re[(l * 3 + kk) * NW + j]); if (!ST) a.im[(l * 3 + kk) * NW + j] = fma(fi, w[j], a.im[(l * 3 + kk) * NW + j]); }
           if (MODE == 1 && do_b) {
             const double c2 = (l == kk) ? fma(dx[kk], n[l], drdn) : dx[kk] * n[l], c3 = dx[l] * n[kk];
-            const double orr = fma(t1d.re, dd, fma(k.T2.re, c2, k.T3.re * c3)), oi = fma(t1d.im, dd, fma(k.T2.im, c2, k.T3.im * c3));
-            bacc[l] -= orr * skr - oi * ski; bacc[3 + l] -= orr * ski + oi * skr;
+            const double orr = fma(t1d.re, dd, fma(k.T2.re, c2, k.T3.re * c3));
+            if (ST) bacc[l] -= orr * skr;
+            else {
+              const double oi = fma(t1d.im, dd, fma(k.T2.im, c2, k.T3.im * c3));
+              bacc[l] -= orr * skr - oi * ski; bacc[3 + l] -= orr * ski + oi * skr;
+            }
           }
         }
       }
@@ -303,8 +317,8 @@ __device__ __forceinline__ void k1_point(AccA<NW>& a, double* bacc, const double
 #pragma unroll
       for (int l = 0; l < 3; l++) {
         const double dd = dx[l] * dx[kk], c2 = (l == kk) ? fma(dx[kk], n[l], drdn) : dx[kk] * n[l], c3 = dx[l] * n[kk];
-        ftr[l] = fma(t1d.re, dd, fma(k.T2.re, c2, k.T3.re * c3)); fti[l] = fma(t1d.im, dd, fma(k.T2.im, c2, k.T3.im * c3));
-        fur[l] = (l == kk) ? fma(-k.chi.re, dd, k.psi.re) : -k.chi.re * dd; fui[l] = (l == kk) ? fma(-k.chi.im, dd, k.psi.im) : -k.chi.im * dd;
+        ftr[l] = fma(t1d.re, dd, fma(k.T2.re, c2, k.T3.re * c3)); fti[l] = ST ? 0.0 : fma(t1d.im, dd, fma(k.T2.im, c2, k.T3.im * c3));
+        fur[l] = (l == kk) ? fma(-k.chi.re, dd, k.psi.re) : -k.chi.re * dd; fui[l] = ST ? 0.0 : ((l == kk) ? fma(-k.chi.im, dd, k.psi.im) : -k.chi.im * dd);
       }
 #pragma unroll
       for (int j = 0; j < NW; j++) {
@@ -313,9 +327,14 @@ __device__ __forceinline__ void k1_point(AccA<NW>& a, double* bacc, const double
         const double cvr = w[j] * __ldg(ecv + 2 * (j * 3 + kk)), cvi = w[j] * __ldg(ecv + 2 * (j * 3 + kk) + 1);
 #pragma unroll
         for (int l = 0; l < 3; l++) {
-          const double ar = tk ? ftr[l] : fur[l], ai = tk ? fti[l] : fui[l], orr = tk ? fur[l] : ftr[l], oi = tk ? fui[l] : fti[l];
-          a.re[(l * 3 + kk) * NW + j] = fma(ar, w[j], a.re[(l * 3 + kk) * NW + j]); a.im[(l * 3 + kk) * NW + j] = fma(ai, w[j], a.im[(l * 3 + kk) * NW + j]);
-          bacc[l] -= orr * cvr - oi * cvi; bacc[3 + l] -= orr * cvi + oi * cvr;
+          const double ar = tk ? ftr[l] : fur[l], orr = tk ? fur[l] : ftr[l];
+          a.re[(l * 3 + kk) * NW + j] = fma(ar, w[j], a.re[(l * 3 + kk) * NW + j]);
+          if (ST) bacc[l] -= orr * cvr;
+          else {
+            const double ai = tk ? fti[l] : fui[l], oi = tk ? fui[l] : fti[l];
+            a.im[(l * 3 + kk) * NW + j] = fma(ai, w[j], a.im[(l * 3 + kk) * NW + j]);
+            bacc[l] -= orr * cvr - oi * cvi; bacc[3 + l] -= orr * cvi + oi * cvr;
+          }
         }
       }
     }
@@ -338,7 +357,8 @@ const int KB_SMEM_QUEUE = MAX_SETS * KB_QCAP * 2;   // bytes per warp
 // ~100 % (a tile sees several rules for the elements around the switch distances of the rule estimator).  Both kinds of
 // batch run through the same code (one copy of the point arithmetic: the instruction cache matters here).
 // One instantiation per element class (MODE 0/1/2 of k1_point); an element is visited by the kernel of its class only.
-template <int ET, int MODE, int WARPS>
+// ST = static elasticity: real arithmetic, only the real plane of the matrix is updated (tensor map with a one-plane box).
+template <int ET, int MODE, int WARPS, bool ST>
 __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_constant__ CUtensorMap tmap, DevGroup g, DevColloc c, DevSystem s,
                                                                   const unsigned char* __restrict__ plan,
                                                                   int* __restrict__ task_counter) {
@@ -438,7 +458,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
       const int* ecol = g.ecol + (size_t)el * NC;
       const int ngp = g.ngp[sset];
       // the kernel scalars of the first chunk's pass are kept in shared memory for the other chunks (in-place batches of few points)
-      const bool use_cache = (NCH > 1) && inplace && ngp <= KB_CACHE_GP;
+      const bool use_cache = !ST && (NCH > 1) && inplace && ngp <= KB_CACHE_GP;
 #pragma unroll 1
       for (int ch = 0; ch < NCH; ch++) {
         const int j0 = ch * NW;
@@ -481,7 +501,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
 #pragma unroll
                 for (int j = 0; j < NN; j++) {
                   const double wj = (NCH == 1) ? cur[6 + j < 6 + NW ? 6 + j : 6] : __ldg(wall + j);
-                  sk[kk] = fma(wj, __ldg(ecv0 + 2 * (j * 3 + kk)), sk[kk]); sk[3 + kk] = fma(wj, __ldg(ecv0 + 2 * (j * 3 + kk) + 1), sk[3 + kk]);
+                  sk[kk] = fma(wj, __ldg(ecv0 + 2 * (j * 3 + kk)), sk[kk]);
+                  if (!ST) sk[3 + kk] = fma(wj, __ldg(ecv0 + 2 * (j * 3 + kk) + 1), sk[3 + kk]);
                 }
             }
             KScal ks;
@@ -490,7 +511,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
               const double* kc = kcache + (size_t)kp * 320 + lane;
               ks.psi = mk(kc[0], kc[32]); ks.chi = mk(kc[64], kc[96]); ks.T1 = mk(kc[128], kc[160]); ks.T2 = mk(kc[192], kc[224]); ks.T3 = mk(kc[256], kc[288]);
             }
-            k1_point<NW, MODE>(acc, bacc, cur, cur + 6, sk, ch == 0, xs, sgn, info, ekind, ecv, have_ks, ks);
+            k1_point<NW, MODE, ST>(acc, bacc, cur, cur + 6, sk, ch == 0, xs, sgn, info, ekind, ecv, have_ks, ks);
             if (use_cache && ch == 0) {
               double* kc = kcache + (size_t)kp * 320 + lane;
               kc[0] = ks.psi.re; kc[32] = ks.psi.im; kc[64] = ks.chi.re; kc[96] = ks.chi.im; kc[128] = ks.T1.re; kc[160] = ks.T1.im;
@@ -502,15 +523,18 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
         if (inplace && nbytes > 0) {
           if (pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous flush has left the buffer
           __syncwarp();
-          // staging layout = the TMA box of one node: [node j][plane][dof k][96 rows]
+          // staging layout = the TMA box of one node: [node j][plane][dof k][96 rows] (static: one plane)
 #pragma unroll
           for (int j = 0; j < NW; j++)
 #pragma unroll
             for (int k = 0; k < 3; k++)
 #pragma unroll
               for (int l = 0; l < 3; l++) {
-                buf[((j * 2 + 0) * 3 + k) * 96 + 3 * lane + l] = acc.re[(l * 3 + k) * NW + j];
-                buf[((j * 2 + 1) * 3 + k) * 96 + 3 * lane + l] = acc.im[(l * 3 + k) * NW + j];
+                if (ST) buf[(j * 3 + k) * 96 + 3 * lane + l] = acc.re[(l * 3 + k) * NW + j];
+                else {
+                  buf[((j * 2 + 0) * 3 + k) * 96 + 3 * lane + l] = acc.re[(l * 3 + k) * NW + j];
+                  buf[((j * 2 + 1) * 3 + k) * 96 + 3 * lane + l] = acc.im[(l * 3 + k) * NW + j];
+                }
               }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
@@ -519,7 +543,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
             const int col = __shfl_sync(0xffffffffu, mycol, j);
             if (lane == 0 && j0 + j < NN)
               asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&tmap), "r"(row0), "r"(col), "r"(0),
-                           "r"(smem_u32(buf + j * 576))
+                           "r"(smem_u32(buf + j * (ST ? 288 : 576)))
                            : "memory");
           }
           if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -537,13 +561,13 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
               const int col = __ldg(ecol + (j0 + j) * 3 + k);
               double* Ar = s.Are + (size_t)col * s.lda + rs; double* Ai = s.Aim + (size_t)col * s.lda + rs;
 #pragma unroll
-              for (int l = 0; l < 3; l++) { atomicAdd(Ar + l, acc.re[(l * 3 + k) * NW + j]); atomicAdd(Ai + l, acc.im[(l * 3 + k) * NW + j]); }
+              for (int l = 0; l < 3; l++) { atomicAdd(Ar + l, acc.re[(l * 3 + k) * NW + j]); if (!ST) atomicAdd(Ai + l, acc.im[(l * 3 + k) * NW + j]); }
             }
           }
           if (GEN) {
 #pragma unroll
             for (int l = 0; l < 3; l++)
-              if (bacc[l] != 0.0 || bacc[3 + l] != 0.0) { atomicAdd(s.bre + rs + l, bacc[l]); atomicAdd(s.bim + rs + l, bacc[3 + l]); }
+              if (bacc[l] != 0.0 || bacc[3 + l] != 0.0) { atomicAdd(s.bre + rs + l, bacc[l]); if (!ST) atomicAdd(s.bim + rs + l, bacc[3 + l]); }
           }
         }
       }
@@ -551,24 +575,24 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
     if (GEN && valid) {
 #pragma unroll
       for (int l = 0; l < 3; l++)
-        if (bacc_t[l] != 0.0 || bacc_t[3 + l] != 0.0) { atomicAdd(s.bre + r0 + l, bacc_t[l]); atomicAdd(s.bim + r0 + l, bacc_t[3 + l]); }
+        if (bacc_t[l] != 0.0 || bacc_t[3 + l] != 0.0) { atomicAdd(s.bre + r0 + l, bacc_t[l]); if (!ST) atomicAdd(s.bim + r0 + l, bacc_t[3 + l]); }
     }
   }
   if (pending && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 static int* g_task_counters = nullptr;   // one counter per kernel of a launch, zeroed before each launch
-template <int ET, int MODE, int WARPS>
+template <int ET, int MODE, int WARPS, bool ST>
 static void launch_bulk_mode(const CUtensorMap& tmap, const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, int n_sm,
                              cudaStream_t st) {
   const int smem = WARPS * K1Shape<ElemTraits<ET>::NN>::SMEM_PER_WARP;
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_regular_bulk<ET, MODE, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  if (!attr) { cudaFuncSetAttribute(k_regular_bulk<ET, MODE, WARPS, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
   const int n_tasks = c.n_tiles * g.n_ranges;
   int ctas = 2 * n_sm; if (ctas * WARPS > n_tasks) ctas = (n_tasks + WARPS - 1) / WARPS;
-  k_regular_bulk<ET, MODE, WARPS><<<ctas, WARPS * 32, smem, st>>>(tmap, g, c, s, plan, g_task_counters + MODE);
+  k_regular_bulk<ET, MODE, WARPS, ST><<<ctas, WARPS * 32, smem, st>>>(tmap, g, c, s, plan, g_task_counters + MODE);
 }
-template <int ET>
+template <int ET, bool ST>
 static void launch_regular_bulk(const CUtensorMap& tmap, const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, cudaStream_t st) {
   if (!g_task_counters) cudaMalloc((void**)&g_task_counters, 4 * sizeof(int));
   cudaMemsetAsync(g_task_counters, 0, 4 * sizeof(int), st);
@@ -581,21 +605,21 @@ static void launch_regular_bulk(const CUtensorMap& tmap, const DevGroup& g, cons
   }
   cudaEventRecord(ev_fork, st);
   cudaStreamWaitEvent(aux[0], ev_fork, 0);
-  launch_bulk_mode<ET, 1, KB_WARPS>(tmap, g, c, s, plan, n_sm, aux[0]);
+  launch_bulk_mode<ET, 1, KB_WARPS, ST>(tmap, g, c, s, plan, n_sm, aux[0]);
   cudaEventRecord(ev_join[0], aux[0]);
   if (g.has_mixed) {
     cudaStreamWaitEvent(aux[1], ev_fork, 0);
-    launch_bulk_mode<ET, 2, KB_WARPS>(tmap, g, c, s, plan, n_sm, aux[1]);
+    launch_bulk_mode<ET, 2, KB_WARPS, ST>(tmap, g, c, s, plan, n_sm, aux[1]);
     cudaEventRecord(ev_join[1], aux[1]);
   }
-  launch_bulk_mode<ET, 0, KB_WARPS_FAST>(tmap, g, c, s, plan, n_sm, st);
+  launch_bulk_mode<ET, 0, KB_WARPS_FAST, ST>(tmap, g, c, s, plan, n_sm, st);
   cudaStreamWaitEvent(st, ev_join[0], 0);
   if (g.has_mixed) cudaStreamWaitEvent(st, ev_join[1], 0);
 }
 
 // 3-D tensor map of the planar system matrix for the K1 flush: (row, column, plane), box = 96 rows x 3 columns x 2 planes
 // (the three dofs of one node, both planes, for the 32 collocation points of a tile), FLOAT64, no swizzle.
-int make_matrix_tensor_map(void* out_128B, double* Are, long long lda, int n_dof) {
+int make_matrix_tensor_map(void* out_128B, double* Are, long long lda, int n_dof, int box_planes) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   static EncodeFn encode = nullptr;
@@ -607,26 +631,34 @@ int make_matrix_tensor_map(void* out_128B, double* Are, long long lda, int n_dof
   static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
   cuuint64_t dims[3] = {(cuuint64_t)n_dof, (cuuint64_t)n_dof, 2};
   cuuint64_t strides[2] = {(cuuint64_t)lda * 8, (cuuint64_t)lda * (cuuint64_t)n_dof * 8};
-  cuuint32_t box[3] = {96, 3, 2}, estr[3] = {1, 1, 1};
+  cuuint32_t box[3] = {96, 3, (cuuint32_t)box_planes}, estr[3] = {1, 1, 1};
   CUresult r = encode(reinterpret_cast<CUtensorMap*>(out_128B), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, Are, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 2;
 }
 
-void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, const void* tmap, cudaStream_t st) {
+template <int ET>
+static void launch_regular_et(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, const void* tmap, bool statics, cudaStream_t st) {
+  if (statics) launch_regular_bulk<ET, true>(*reinterpret_cast<const CUtensorMap*>(tmap), g, c, s, plan, st);
+  else launch_regular_bulk<ET, false>(*reinterpret_cast<const CUtensorMap*>(tmap), g, c, s, plan, st);
+}
+// tmap: tensor map of the planar matrix whose box has two planes (harmonic) or one (statics = true); without it, or for
+// elements whose dof columns are not consecutive, the general kernel runs (in a static run it works with the harmonic
+// parameter set whose frequency-dependent coefficients are zero, see set_kparams).
+void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, const void* tmap, bool statics, cudaStream_t st) {
   if (g.n_elem == 0) return;
   dim3 grid((c.ldp + 32 * K1_WARPS - 1) / (32 * K1_WARPS), (g.n_elem + K1_ECHUNK - 1) / K1_ECHUNK);
   dim3 block(K1_WARPS * 32);
   switch (g.et) {
-    case 5: if (g.cols3 && tmap) { launch_regular_bulk<5>(*reinterpret_cast<const CUtensorMap*>(tmap), g, c, s, plan, st); break; }
+    case 5: if (g.cols3 && tmap) { launch_regular_et<5>(g, c, s, plan, tmap, statics, st); break; }
             k_regular<5, 3><<<grid, block, 0, st>>>(g, c, s, plan); break;
-    case 7: if (g.cols3 && tmap) { launch_regular_bulk<7>(*reinterpret_cast<const CUtensorMap*>(tmap), g, c, s, plan, st); break; }
+    case 7: if (g.cols3 && tmap) { launch_regular_et<7>(g, c, s, plan, tmap, statics, st); break; }
             k_regular<7, 3><<<grid, block, 0, st>>>(g, c, s, plan); break;
-    case 6: if (g.cols3 && tmap) { launch_regular_bulk<6>(*reinterpret_cast<const CUtensorMap*>(tmap), g, c, s, plan, st); break; }
+    case 6: if (g.cols3 && tmap) { launch_regular_et<6>(g, c, s, plan, tmap, statics, st); break; }
             k_regular<6, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
-    case 8: if (g.cols3 && tmap) { launch_regular_bulk<8>(*reinterpret_cast<const CUtensorMap*>(tmap), g, c, s, plan, st); break; }
+    case 8: if (g.cols3 && tmap) { launch_regular_et<8>(g, c, s, plan, tmap, statics, st); break; }
             k_regular<8, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
-    case 9: if (g.cols3 && tmap) { launch_regular_bulk<9>(*reinterpret_cast<const CUtensorMap*>(tmap), g, c, s, plan, st); break; }
+    case 9: if (g.cols3 && tmap) { launch_regular_et<9>(g, c, s, plan, tmap, statics, st); break; }
             k_regular<9, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
   }
 }
@@ -863,6 +895,31 @@ void launch_interleave(const double* re, const double* im, long long ld, int row
 }
 void launch_deinterleave(const double* in, long long ldi, int rows, int cols, double* re, double* im, long long ld, const int* rowperm, cudaStream_t st) {
   k_deinterleave<<<2368, 256, 0, st>>>(in, ldi, rows, cols, re, im, ld, rowperm);
+}
+
+// real matrices of the static path (host interface: plain column-major doubles)
+__global__ void k_gather_real(const double* __restrict__ re, long long ld, int rows, int cols, double* __restrict__ out, long long ldo, const int* __restrict__ rowperm,
+                              const int* __restrict__ colperm, int col0) {
+  long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long cidx = i / rows, r = i - cidx * rows;
+    long long ri = rowperm ? rowperm[r] : r, ci = colperm ? colperm[col0 + cidx] : col0 + cidx;
+    out[cidx * ldo + r] = re[ci * ld + ri];
+  }
+}
+__global__ void k_scatter_real(const double* __restrict__ in, long long ldi, int rows, int cols, double* __restrict__ re, long long ld, const int* __restrict__ rowperm) {
+  long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long cidx = i / rows, r = i - cidx * rows;
+    long long ri = rowperm ? rowperm[r] : r;
+    re[cidx * ld + ri] = in[cidx * ldi + r];
+  }
+}
+void launch_gather_real(const double* re, long long ld, int rows, int cols, double* out, long long ldo, const int* rowperm, const int* colperm, int col0, cudaStream_t st) {
+  k_gather_real<<<2368, 256, 0, st>>>(re, ld, rows, cols, out, ldo, rowperm, colperm, col0);
+}
+void launch_scatter_real(const double* in, long long ldi, int rows, int cols, double* re, long long ld, const int* rowperm, cudaStream_t st) {
+  k_scatter_real<<<2368, 256, 0, st>>>(in, ldi, rows, cols, re, ld, rowperm);
 }
 
 }  // namespace mfbd

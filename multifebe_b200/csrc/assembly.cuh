@@ -85,8 +85,11 @@ void launch_count_near(const unsigned char* plan, long long n_slots, const DevCo
                        unsigned long long capacity, cudaStream_t st);
 void launch_patch_plan(unsigned char* plan, const DevColloc& c, int n, const int* cpos, const int* slot, const unsigned char* val, cudaStream_t st);
 void launch_gather_cv(const DevGroup& g, const double* cvalue, cudaStream_t st);
-void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, const void* tmap, cudaStream_t st);
-int make_matrix_tensor_map(void* out_128B, double* Are, long long lda, int n_dof);
+void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, const void* tmap, bool statics, cudaStream_t st);
+int make_matrix_tensor_map(void* out_128B, double* Are, long long lda, int n_dof, int box_planes);
+// real plane only, host row/column order: out[:, 0:cols) = host columns [col0, col0 + cols)
+void launch_gather_real(const double* re, long long ld, int rows, int cols, double* out, long long ldo, const int* rowperm, const int* colperm, int col0, cudaStream_t st);
+void launch_scatter_real(const double* in, long long ldi, int rows, int cols, double* re, long long ld, const int* rowperm, cudaStream_t st);
 void launch_adaptive(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevAdaptive& a, const DevTables& t, cudaStream_t st);
 void launch_singular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevSingular& a, const DevTables& t, cudaStream_t st);
 void launch_freeterm(const DevColloc& c, const DevSystem& s, const DevFreeTerm& f, cplx F, cudaStream_t st);

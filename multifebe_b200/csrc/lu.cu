@@ -20,6 +20,10 @@ namespace cg = cooperative_groups;
 
 namespace mfbd {
 
+// A NULL imaginary plane means a REAL matrix (static path, solve_lse_r): offsets must keep it NULL.
+__host__ __device__ inline double* poff(double* p, long long o) { return p ? p + o : nullptr; }
+__host__ __device__ inline const double* poff(const double* p, long long o) { return p ? p + o : nullptr; }
+
 // ------------------------------------------------------------------------------------------------------------------
 // ZGEMM (C -= A*B), planar complex, column-major.  CTA tile (32*WM) x (32*WN), one 32x32 warp tile per warp
 // (4 x 4 DMMA.8x8x4 tiles, re and im accumulators in registers), BK-deep k-tiles through a cp.async ring.
@@ -274,6 +278,98 @@ k_zgemm3m_minus(int M, int N, int K, const double* __restrict__ Are, const doubl
         }
       }
 }
+// Real GEMM (C -= A*B) for the real LU of the static path (solve_lse_r -> dgetrf): the same tiling and staging as the 3M
+// kernel with one plane and one accumulator set; C enters through the accumulators (x = -C + A*B, C' = -x).
+template <int WM, int WN, int NI, int MINB>
+__global__ void __launch_bounds__(32 * WM * WN, MINB)
+k_dgemm_minus(int M, int N, int K, const double* __restrict__ A, long long lda, const double* __restrict__ B, long long ldb, double* __restrict__ Cm, long long ldc) {
+  typedef Gemm3Cfg<WM, WN, NI> C;
+  constexpr int BM = C::BM, BN = C::BN, BK = C::BK, STAGES = C::STAGES, T = C::T, SA_LD = C::SA_LD, SB_LD = C::SB_LD;
+  constexpr int SA_STAGE = BK * SA_LD, SB_STAGE = BN * SB_LD;
+  extern __shared__ __align__(16) double smem[];
+  double* sA = smem;
+  double* sB = smem + STAGES * SA_STAGE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp % WM, wn = warp / WM;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int KT = (K + BK - 1) / BK;
+  auto load_stage = [&](int stage, int kt) {
+    const int k0 = kt * BK;
+    double* a = sA + stage * SA_STAGE;
+    double* b = sB + stage * SB_STAGE;
+#pragma unroll
+    for (int i = 0; i < (BK * (BM / 2) + T - 1) / T; i++) {
+      int idx = tid + T * i;
+      if ((BK * (BM / 2)) % T != 0 && idx >= BK * (BM / 2)) break;
+      int k = idx / (BM / 2), c2 = idx % (BM / 2);
+      int m = m0 + 2 * c2, kk = k0 + k;
+      const double* src = A + (long long)kk * lda + m;
+      int bytes = (kk < K) ? max(0, min(16, (M - m) * 8)) : 0;
+      if (bytes == 0) src = A;
+      cp_async16(a + k * SA_LD + 2 * c2, src, bytes);
+    }
+#pragma unroll
+    for (int i = 0; i < (BN * (BK / 2) + T - 1) / T; i++) {
+      int idx = tid + T * i;
+      if ((BN * (BK / 2)) % T != 0 && idx >= BN * (BK / 2)) break;
+      int nn = idx / (BK / 2), c2 = idx % (BK / 2);
+      int n = n0 + nn, kk = k0 + 2 * c2;
+      const double* src = B + (long long)n * ldb + kk;
+      int bytes = (n < N) ? max(0, min(16, (K - kk) * 8)) : 0;
+      if (bytes == 0) src = B;
+      cp_async16(b + nn * SB_LD + 2 * c2, src, bytes);
+    }
+  };
+  for (int s = 0; s < STAGES - 1; s++) { if (s < KT) load_stage(s, s); cp_async_commit(); }
+  double x[4][NI][2];
+#pragma unroll
+  for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+    for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        int m = m0 + wm * 32 + mi * 8 + gid, n = n0 + wn * 8 * NI + ni * 8 + 2 * tig + h;
+        x[mi][ni][h] = ((m < M) && (n < N)) ? -Cm[(long long)n * ldc + m] : 0.0;
+      }
+  for (int kt = 0; kt < KT; kt++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    { int nk = kt + STAGES - 1; if (nk < KT) load_stage(nk % STAGES, nk); cp_async_commit(); }
+    const double* a = sA + (kt % STAGES) * SA_STAGE;
+    const double* b = sB + (kt % STAGES) * SB_STAGE;
+#pragma unroll
+    for (int k4 = 0; k4 < BK / 4; k4++) {
+      double ar[4];
+#pragma unroll
+      for (int mi = 0; mi < 4; mi++) ar[mi] = a[(k4 * 4 + tig) * SA_LD + wm * 32 + mi * 8 + gid];
+#pragma unroll
+      for (int ni = 0; ni < NI; ni++) {
+        const double br = b[(wn * 8 * NI + ni * 8 + gid) * SB_LD + k4 * 4 + tig];
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) dmma(x[mi][ni][0], x[mi][ni][1], ar[mi], br);
+      }
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+    for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        int m = m0 + wm * 32 + mi * 8 + gid, n = n0 + wn * 8 * NI + ni * 8 + 2 * tig + h;
+        if (m < M && n < N) Cm[(long long)n * ldc + m] = -x[mi][ni][h];
+      }
+}
+void dgemm_minus(int m, int n, int k, const double* A, long long lda, const double* B, long long ldb, double* Cm, long long ldc, cudaStream_t st) {
+  if (m <= 0 || n <= 0 || k <= 0) return;
+  typedef Gemm3Cfg<2, 2, 4> C;   // 64 x 64 CTA tile, warp 32 x 32, 2 CTAs per SM
+  const int smem = C::STAGES * (C::BK * C::SA_LD + C::BN * C::SB_LD) * 8;
+  dim3 grid((m + C::BM - 1) / C::BM, (n + C::BN - 1) / C::BN);
+  k_dgemm_minus<2, 2, 4, 2><<<grid, C::T, smem, st>>>(m, n, k, A, lda, B, ldb, Cm, ldc);
+}
+
 template <int WM, int WN, int NI, int MINB>
 static void launch_gemm3m(int m, int n, int k, const double* Are, const double* Aim, long long lda, const double* Bre, const double* Bim,
                           long long ldb, double* Cre, double* Cim, long long ldc, cudaStream_t st) {
@@ -303,6 +399,7 @@ static int gemm_cfg() {
 void zgemm_minus_planar(int m, int n, int k, const double* Are, const double* Aim, long long lda, const double* Bre, const double* Bim,
                         long long ldb, double* Cre, double* Cim, long long ldc, cudaStream_t st) {
   if (m <= 0 || n <= 0 || k <= 0) return;
+  if (!Aim) { dgemm_minus(m, n, k, Are, lda, Bre, ldb, Cre, ldc, st); return; }   // real system (imaginary planes absent)
   switch (gemm_cfg()) {
     case 10: launch_gemm3m<2, 2, 4, 2>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 3M, 64 x 64, warp 32 x 32, 2 CTA/SM
     case 11: launch_gemm3m<2, 4, 2, 1>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc, st); break;   // 3M, 64 x 64, 8 warps of 32 x 16, 1 CTA/SM
@@ -353,6 +450,8 @@ __device__ __forceinline__ void block_argmax(double v, int row, double* s_val, i
 
 const int SP_MAXIB = 32;
 
+// CX = false: real matrix (a.Aim == NULL): the imaginary plane is neither read nor written, the pivot is max |re| (idamax).
+template <bool CX>
 __global__ void __launch_bounds__(256) k_subpanel(SubPanelArgs a) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) double slab[];      // [2][ib][rpcp]
@@ -368,7 +467,7 @@ __global__ void __launch_bounds__(256) k_subpanel(SubPanelArgs a) {
   for (int idx = tid; idx < ib * nloc; idx += blockDim.x) {
     int jj = idx / nloc, i = idx - jj * nloc;
     sre[jj * rpcp + i] = a.Are[(long long)(c0 + jj) * lda + rs + i];
-    sim[jj * rpcp + i] = a.Aim[(long long)(c0 + jj) * lda + rs + i];
+    sim[jj * rpcp + i] = CX ? a.Aim[(long long)(c0 + jj) * lda + rs + i] : 0.0;
   }
   __syncthreads();
   // candidate for column 0
@@ -450,7 +549,7 @@ __global__ void __launch_bounds__(256) k_subpanel(SubPanelArgs a) {
   for (int idx = tid; idx < ib * nloc; idx += blockDim.x) {
     int jj = idx / nloc, i = idx - jj * nloc;
     a.Are[(long long)(c0 + jj) * lda + rs + i] = sre[jj * rpcp + i];
-    a.Aim[(long long)(c0 + jj) * lda + rs + i] = sim[jj * rpcp + i];
+    if (CX) a.Aim[(long long)(c0 + jj) * lda + rs + i] = sim[jj * rpcp + i];
   }
 }
 
@@ -461,7 +560,7 @@ __global__ void k_laswp(double* Are, double* Aim, long long lda, int c0, int c1,
   double* ar = Are + (long long)col * lda; double* ai = Aim + (long long)col * lda;
   for (int j = 0; j < nbw; j++) {
     int p = ipiv[k0 + j] - 1, d = k0 + j;
-    if (p != d) { double t = ar[d]; ar[d] = ar[p]; ar[p] = t; t = ai[d]; ai[d] = ai[p]; ai[p] = t; }
+    if (p != d) { double t = ar[d]; ar[d] = ar[p]; ar[p] = t; if (Aim) { t = ai[d]; ai[d] = ai[p]; ai[p] = t; } }
   }
 }
 
@@ -482,7 +581,7 @@ __global__ void __launch_bounds__(256) k_trsm_lu(const double* __restrict__ Lre,
     int cc = idx / nbw, i = idx - cc * nbw;
     bool ok = cc < ncol;
     br[i * LD + cc] = ok ? Bre[(long long)(cb + cc) * ldb + i] : 0.0;
-    bi[i * LD + cc] = ok ? Bim[(long long)(cb + cc) * ldb + i] : 0.0;
+    bi[i * LD + cc] = (ok && Bim) ? Bim[(long long)(cb + cc) * ldb + i] : 0.0;
   }
   __syncthreads();
   for (int j = 0; j < nbw - 1; j++) {
@@ -491,7 +590,7 @@ __global__ void __launch_bounds__(256) k_trsm_lu(const double* __restrict__ Lre,
     const double* lim = Lim + (long long)j * ldl;
 #pragma unroll 4
     for (int i = j + 1 + warp; i < nbw; i += nw) {
-      const double lr = __ldg(lre + i), li = __ldg(lim + i);
+      const double lr = __ldg(lre + i), li = Lim ? __ldg(lim + i) : 0.0;
       br[i * LD + lane] -= lr * xr - li * xi;
       bi[i * LD + lane] -= lr * xi + li * xr;
     }
@@ -499,7 +598,7 @@ __global__ void __launch_bounds__(256) k_trsm_lu(const double* __restrict__ Lre,
   }
   for (int idx = tid; idx < nbw * TRSM_TC; idx += blockDim.x) {
     int cc = idx / nbw, i = idx - cc * nbw;
-    if (cc < ncol) { Bre[(long long)(cb + cc) * ldb + i] = br[i * LD + cc]; Bim[(long long)(cb + cc) * ldb + i] = bi[i * LD + cc]; }
+    if (cc < ncol) { Bre[(long long)(cb + cc) * ldb + i] = br[i * LD + cc]; if (Bim) Bim[(long long)(cb + cc) * ldb + i] = bi[i * LD + cc]; }
   }
 }
 // U12 = inv(L11) A12 for the nbw x nbw unit lower block at (r0,r0) and columns [c0,c1): blocked forward substitution,
@@ -514,13 +613,13 @@ static int launch_trsm_ext(const double* Lre, const double* Lim, long long ldl, 
     const int tb = (nbw - jb < TRSM_TB) ? (nbw - jb) : TRSM_TB;
     if (tb > 1) {
       size_t smem = (size_t)2 * tb * (TRSM_TC + 1) * 8;
-      k_trsm_lu<<<(ncols + TRSM_TC - 1) / TRSM_TC, 256, smem, st>>>(Lre + (long long)jb * ldl + jb, Lim + (long long)jb * ldl + jb, ldl, Bre + jb, Bim + jb, ldb, tb, ncols);
+      k_trsm_lu<<<(ncols + TRSM_TC - 1) / TRSM_TC, 256, smem, st>>>(Lre + (long long)jb * ldl + jb, poff(Lim, (long long)jb * ldl + jb), ldl, Bre + jb, poff(Bim, jb), ldb, tb, ncols);
       launches++;
     }
     const int mrest = nbw - jb - tb;
     if (mrest > 0) {
-      zgemm_minus_planar(mrest, ncols, tb, Lre + (long long)jb * ldl + jb + tb, Lim + (long long)jb * ldl + jb + tb, ldl, Bre + jb, Bim + jb, ldb,
-                         Bre + jb + tb, Bim + jb + tb, ldb, st);
+      zgemm_minus_planar(mrest, ncols, tb, Lre + (long long)jb * ldl + jb + tb, poff(Lim, (long long)jb * ldl + jb + tb), ldl, Bre + jb, poff(Bim, jb), ldb,
+                         Bre + jb + tb, poff(Bim, jb + tb), ldb, st);
       launches++;
     }
   }
@@ -528,7 +627,7 @@ static int launch_trsm_ext(const double* Lre, const double* Lim, long long ldl, 
 }
 static int launch_trsm(double* Are, double* Aim, long long lda, int r0, int nbw, int c0, int c1, cudaStream_t st) {
   if (c1 <= c0) return 0;
-  return launch_trsm_ext(Are + (long long)r0 * lda + r0, Aim + (long long)r0 * lda + r0, lda, Are + (long long)c0 * lda + r0, Aim + (long long)c0 * lda + r0, lda, nbw,
+  return launch_trsm_ext(Are + (long long)r0 * lda + r0, poff(Aim, (long long)r0 * lda + r0), lda, Are + (long long)c0 * lda + r0, poff(Aim, (long long)c0 * lda + r0), lda, nbw,
                          c1 - c0, st);
 }
 
@@ -550,7 +649,8 @@ int lu_work_alloc(LuWork& w, int n, int nb) {
   A((void**)&w.cand_val, 2 * G * sizeof(double)); A((void**)&w.cand_row, 2 * G * sizeof(int));
   A((void**)&w.cand_data, 2 * G * 2 * SP_MAXIB * sizeof(double)); A((void**)&w.diag_data, 2 * 2 * SP_MAXIB * sizeof(double));
   A((void**)&w.info, sizeof(int));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_subpanel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_subpanel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_subpanel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   w.n_evs = 5 * ((n + nb - 1) / nb);
   w.evs = new cudaEvent_t[w.n_evs];
   for (int i = 0; i < w.n_evs; i++) cudaEventCreate(&w.evs[i]);
@@ -595,7 +695,8 @@ static int factor_panel(double* Are, double* Aim, long long lda, int n, int k0, 
     pa.ldc = 2 * SP_MAXIB;
     void* args[] = {&pa};
     size_t smem = (size_t)2 * ib * pa.rpcp * sizeof(double);
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_subpanel, dim3(G), dim3(256), args, smem, st);
+    cudaError_t e = Aim ? cudaLaunchCooperativeKernel((void*)k_subpanel<true>, dim3(G), dim3(256), args, smem, st)
+                        : cudaLaunchCooperativeKernel((void*)k_subpanel<false>, dim3(G), dim3(256), args, smem, st);
     if (e != cudaSuccess) return (int)e;
     w.launches += 1;
     // interchanges of this sub-panel on the other columns of the panel
@@ -606,9 +707,9 @@ static int factor_panel(double* Are, double* Aim, long long lda, int n, int k0, 
       w.launches += 1 + launch_trsm(Are, Aim, lda, c0, ib, c0 + ib, k0 + nbw, st);
       const int mrest = n - c0 - ib;
       if (mrest > 0) {
-        zgemm_minus_planar(mrest, nright, ib, Are + (long long)c0 * lda + c0 + ib, Aim + (long long)c0 * lda + c0 + ib, lda,
-                           Are + (long long)(c0 + ib) * lda + c0, Aim + (long long)(c0 + ib) * lda + c0, lda,
-                           Are + (long long)(c0 + ib) * lda + c0 + ib, Aim + (long long)(c0 + ib) * lda + c0 + ib, lda, st);
+        zgemm_minus_planar(mrest, nright, ib, Are + (long long)c0 * lda + c0 + ib, poff(Aim, (long long)c0 * lda + c0 + ib), lda,
+                           Are + (long long)(c0 + ib) * lda + c0, poff(Aim, (long long)(c0 + ib) * lda + c0), lda,
+                           Are + (long long)(c0 + ib) * lda + c0 + ib, poff(Aim, (long long)(c0 + ib) * lda + c0 + ib), lda, st);
         w.launches++;
       }
     }
@@ -625,10 +726,11 @@ int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuW
   cudaStream_t ps = w.lookahead ? w.panel_stream : st;
   auto gemm = [&](int r0, int k0, int kw, int c0, int c1) {   // A[r0:n, c0:c1] -= A[r0:n, k0:k0+kw] * A[k0:k0+kw, c0:c1]
     if (c1 <= c0 || r0 >= n) return;
-    zgemm_minus_planar(n - r0, c1 - c0, kw, Are + (long long)k0 * lda + r0, Aim + (long long)k0 * lda + r0, lda,
-                       Are + (long long)c0 * lda + k0, Aim + (long long)c0 * lda + k0, lda, Are + (long long)c0 * lda + r0, Aim + (long long)c0 * lda + r0, lda, st);
-    w.launches++; w.gemm_launches++; w.gemm_flops += 8.0 * (double)(n - r0) * (double)(c1 - c0) * (double)kw;
-    w.gemm_exec_flops += (gemm_cfg() >= 10 ? 6.0 : 8.0) * (double)(n - r0) * (double)(c1 - c0) * (double)kw;
+    zgemm_minus_planar(n - r0, c1 - c0, kw, Are + (long long)k0 * lda + r0, poff(Aim, (long long)k0 * lda + r0), lda,
+                       Are + (long long)c0 * lda + k0, poff(Aim, (long long)c0 * lda + k0), lda, Are + (long long)c0 * lda + r0, poff(Aim, (long long)c0 * lda + r0), lda, st);
+    const double mnk = (double)(n - r0) * (double)(c1 - c0) * (double)kw;
+    w.launches++; w.gemm_launches++; w.gemm_flops += (Aim ? 8.0 : 2.0) * mnk;
+    w.gemm_exec_flops += (Aim ? (gemm_cfg() >= 10 ? 6.0 : 8.0) : 2.0) * mnk;
   };
   // first panel
   {
@@ -676,16 +778,16 @@ int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuW
 const int TS = 64;
 __global__ void k_permute(const double* __restrict__ sre, const double* __restrict__ sim, double* dre, double* dim_, const int* __restrict__ perm, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { dre[i] = sre[perm[i]]; dim_[i] = sim[perm[i]]; }
+  if (i < n) { dre[i] = sre[perm[i]]; if (sim) dim_[i] = sim[perm[i]]; }
 }
 __global__ void __launch_bounds__(TS) k_trsv_diag(const double* __restrict__ Are, const double* __restrict__ Aim, long long lda, int kb, int nbw, double* bre, double* bim, int lower) {
   extern __shared__ __align__(16) double sdiag[];   // [2][TS][TS+1]
   double* sr = sdiag; double* si = sdiag + TS * (TS + 1);
   __shared__ double yr[TS], yi[TS];
   const int i = threadIdx.x;
-  for (int j = 0; j < nbw; j++) if (i < nbw) { sr[j * (TS + 1) + i] = Are[(long long)(kb + j) * lda + kb + i]; si[j * (TS + 1) + i] = Aim[(long long)(kb + j) * lda + kb + i]; }
+  for (int j = 0; j < nbw; j++) if (i < nbw) { sr[j * (TS + 1) + i] = Are[(long long)(kb + j) * lda + kb + i]; si[j * (TS + 1) + i] = Aim ? Aim[(long long)(kb + j) * lda + kb + i] : 0.0; }
   double vr = 0.0, vi = 0.0;
-  if (i < nbw) { vr = bre[kb + i]; vi = bim[kb + i]; }
+  if (i < nbw) { vr = bre[kb + i]; vi = bim ? bim[kb + i] : 0.0; }
   __syncthreads();
   if (lower) {
     for (int j = 0; j < nbw; j++) {
@@ -712,14 +814,14 @@ __global__ void __launch_bounds__(TS) k_trsv_diag(const double* __restrict__ Are
       }
     }
   }
-  if (i < nbw) { bre[kb + i] = vr; bim[kb + i] = vi; }
+  if (i < nbw) { bre[kb + i] = vr; if (bim) bim[kb + i] = vi; }
 }
 // b[r0:r1) -= A[r0:r1, kb:kb+nbw) * x[kb:kb+nbw); CTA = 64 rows x 4 column groups
 __global__ void __launch_bounds__(256) k_gemv_update(const double* __restrict__ Are, const double* __restrict__ Aim, long long lda, int r0, int r1, int kb, int nbw, double* bre, double* bim) {
   __shared__ double xr[TS], xi[TS];
   __shared__ double pr[4][64], pi[4][64];
   const int tid = threadIdx.x, li = tid & 63, cg_ = tid >> 6;
-  if (tid < nbw) { xr[tid] = bre[kb + tid]; xi[tid] = bim[kb + tid]; }
+  if (tid < nbw) { xr[tid] = bre[kb + tid]; xi[tid] = bim ? bim[kb + tid] : 0.0; }
   __syncthreads();
   const int i = r0 + blockIdx.x * 64 + li;
   double sr = 0.0, si = 0.0;
@@ -727,7 +829,7 @@ __global__ void __launch_bounds__(256) k_gemv_update(const double* __restrict__ 
     const int per = (nbw + 3) / 4, j0 = cg_ * per, j1 = min(j0 + per, nbw);
 #pragma unroll 8
     for (int j = j0; j < j1; j++) {
-      double ar = Are[(long long)(kb + j) * lda + i], ai = Aim[(long long)(kb + j) * lda + i];
+      double ar = Are[(long long)(kb + j) * lda + i], ai = Aim ? Aim[(long long)(kb + j) * lda + i] : 0.0;
       sr += ar * xr[j] - ai * xi[j]; si += ar * xi[j] + ai * xr[j];
     }
   }
@@ -735,7 +837,7 @@ __global__ void __launch_bounds__(256) k_gemv_update(const double* __restrict__ 
   __syncthreads();
   if (cg_ == 0 && i < r1) {
     bre[i] -= pr[0][li] + pr[1][li] + pr[2][li] + pr[3][li];
-    bim[i] -= pi[0][li] + pi[1][li] + pi[2][li] + pi[3][li];
+    if (bim) bim[i] -= pi[0][li] + pi[1][li] + pi[2][li] + pi[3][li];
   }
 }
 
@@ -748,10 +850,10 @@ int zgetrs_planar(const double* Are, const double* Aim, long long lda, int n, co
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(k_trsv_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm); attr = true; }
   for (int c = 0; c < nrhs; c++) {
-    double* br = bre + (long long)c * ldb; double* bi = bim + (long long)c * ldb;
+    double* br = bre + (long long)c * ldb; double* bi = poff(bim, (long long)c * ldb);
     k_permute<<<(n + 255) / 256, 256, 0, st>>>(br, bi, tmp, tmp + n, ipiv_host_perm_dev, n);
     cudaMemcpyAsync(br, tmp, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
-    cudaMemcpyAsync(bi, tmp + n, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
+    if (bi) cudaMemcpyAsync(bi, tmp + n, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
     for (int kb = 0; kb < n; kb += TS) {
       int nbw = (n - kb < TS) ? n - kb : TS;
       k_trsv_diag<<<1, TS, dsm, st>>>(Are, Aim, lda, kb, nbw, br, bi, 1);

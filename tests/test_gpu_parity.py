@@ -265,3 +265,82 @@ def test_distributed_frequency_on_virtual_ranks_matches_single_gpu(gpu_ctx, orac
     x3 = pr.solve_frequency(omega, MAT)       # the single-GPU path still works on the same problem afterwards
     assert relerr(x3, x1) < 1e-13
     pr.close()
+
+
+# ---- static 3D elasticity: Kelvin kernels in real arithmetic + real LU, against the static oracle ----
+SMAT = Material(1.0, 1.3, 0.25, 0.0)
+
+
+@pytest.mark.parametrize("et,m", [(shape.TRI3, 3), (shape.TRI6, 2), (shape.QUAD4, 3), (shape.QUAD8, 2), (shape.QUAD9, 2)])
+def test_static_assembly_and_solution_parity(gpu_ctx, oracle_lib, et, m):
+    from multifebe_b200 import capi
+    md = Model(cube_mesh(m, et), cube_bcs())
+    pr = capi.Problem(gpu_ctx, md)
+    A, b = pr.build_lse_mechanics_bem_staela(SMAT)
+    Ao, bo, st = oracle_lib.Oracle(md).assemble_static(SMAT)
+    assert A.dtype == np.float64 and relerr(A, Ao) < TOL_A and relerr(b, bo) < TOL_A
+    xo, _, _ = oracle_lib.lu_solve_real(Ao, bo)
+    x1 = pr.solve_lse_r(A.copy(order="F"), b)              # seam 2 with host arrays (dgesv semantics)
+    x2 = pr.solve_static(SMAT)                             # fused, device resident
+    assert relerr(x1, xo) < TOL_X and relerr(x2, xo) < TOL_X
+    # the exact solution of the reference's tutorial ME-ST-EL-002: u1 = P x1 / (lambda + 2 mu) (linear elements: to quadrature error)
+    u, t = md.nodal_solution(x2)
+    lam2mu = 2.0 * SMAT.mu_r * SMAT.nu_r / (1.0 - 2.0 * SMAT.nu_r) + 2.0 * SMAT.mu_r
+    assert np.abs(u[:, 0].real - md.node_x[:, 0] / lam2mu).max() < 2e-5 / lam2mu
+    # a harmonic frequency on the same problem afterwards (the two paths share the resident matrix)
+    xh = pr.solve_frequency(3.0, MAT)
+    Ah, bh, _ = oracle_lib.Oracle(md).assemble(3.0, MAT)
+    assert relerr(xh, oracle_lib.lu_solve(Ah, bh)[0]) < TOL_X
+    pr.close()
+
+
+def test_static_nondefault_settings_reversed_boundary_and_open_patch(gpu_ctx, oracle_lib):
+    from multifebe_b200 import capi
+    cases = [
+        Model(cube_mesh(2, shape.QUAD8), cube_bcs(), qsi_relative_error=1e-4, qsi_ns_max=3, precalset_gln=(2, 4, 6)),
+        Model(cube_mesh(2, shape.TRI3), cube_bcs(), reversed_parts=(1, 2, 3, 4, 5, 6), qsi_relative_error=1e-8),
+        Model(halfspace_patch(4, shape.QUAD9), {1: ([1, 1, 1], [0, 0, 0]), 2: ([0, 0, 0], [0, 0, 1.0])}),
+        Model(halfspace_patch(5, shape.TRI6), {1: ([1, 1, 1], [0.1, 0, 0.3]), 2: ([0, 1, 0], [1.0, 0.5, 0.2])}),
+    ]
+    for md in cases:
+        pr = capi.Problem(gpu_ctx, md)
+        A, b = pr.build_lse_mechanics_bem_staela(SMAT)
+        Ao, bo, _ = oracle_lib.Oracle(md).assemble_static(SMAT)
+        assert relerr(A, Ao) < TOL_A and relerr(b, bo) < TOL_A
+        xo, _, _ = oracle_lib.lu_solve_real(Ao, bo)
+        assert relerr(pr.solve_static(SMAT), xo) < TOL_X
+        pr.close()
+
+
+@pytest.mark.parametrize("n_target", [18 * 4, 18 * 36, 18 * 100])
+def test_real_lu_against_lapack(gpu_ctx, n_target):
+    from scipy.linalg import lapack
+    pr, n = _problem_of_size(gpu_ctx, n_target)
+    rng = np.random.default_rng(n + 1)
+    A = np.asfortranarray(rng.standard_normal((n, n)))
+    A[:, 3] *= 1e-3; A[5, :] *= 40.0
+    B = np.asfortranarray(rng.standard_normal((n, 3)))
+    lu_ref, piv_ref, info = lapack.dgetrf(A)
+    x_ref, info = lapack.dgetrs(lu_ref, piv_ref, B)
+    Af = A.copy(order="F")
+    x, ipiv = pr.solve_lse_r(Af, B, want_ipiv=True)
+    assert np.array_equal(ipiv - 1, piv_ref)                      # the pivot sequence of dgetrf (idamax semantics)
+    assert relerr(Af, lu_ref) < 1e-10 and relerr(x, x_ref) < 1e-9
+    b2 = rng.standard_normal(n)
+    assert relerr(pr.solve_lse_r(None, b2, factorize=False), np.linalg.solve(A, b2)) < 1e-9
+    with pytest.raises(capi_error()):
+        pr_zsolve_on_real(pr, n)
+    pr.close()
+
+
+def capi_error():
+    from multifebe_b200 import capi
+    return capi.MfbError
+
+
+def pr_zsolve_on_real(pr, n):
+    """mfb_zsolve must refuse to factorise a resident REAL system (A = NULL) instead of reading a stale imaginary plane."""
+    import ctypes as C
+    from multifebe_b200 import capi
+    b = np.zeros(n, dtype=np.complex128)
+    capi._check(capi.lib().mfb_zsolve(pr.h, C.c_int(n), None, C.c_int(n), None, capi._p(b), C.c_int(1), C.c_int(1)))
