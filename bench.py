@@ -111,6 +111,137 @@ def cpu_arm(md, mat, omega, budget_points=6e7, lu_n=6144, repeat=1):
             "assembly_s_per_step": t_asm, "lu_s_per_step": t_lu, "assembly_gentries_per_s": n * n / t_asm / 1e9}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# --workload static: BASELINE config 2 (ME-ST-EL-002 refined: static elastic cube, quad9, ~10k DOF; staela assembly + real LU)
+# ---------------------------------------------------------------------------------------------------------------------
+STATIC_METRIC = "static 3D BEM end-to-end solves/s (assemble + dgetrf + dgetrs) on the ME-ST-EL-002 cube refined to quad9, 9522 DOF"
+
+
+def static_workload(args):
+    from multifebe_b200.host import Model, Material, cube_mesh, cube_bcs, shape
+    et = {"tri3": shape.TRI3, "tri6": shape.TRI6, "quad4": shape.QUAD4, "quad8": shape.QUAD8, "quad9": shape.QUAD9}[args.static_etype]
+    md = Model(cube_mesh(args.static_m, et), cube_bcs())
+    mat = Material(1.0, 1.0, 0.25, 0.0)
+    name = "static S-cube %s m=%d (ME-ST-EL-002 BCs): %d elements, %d nodes, %d DOF" % (args.static_etype, args.static_m, md.n_elem, md.n_node, md.n_dof)
+    return md, mat, name
+
+
+def cpu_arm_static(md, mat, budget_points=6e7, lu_n=6144):
+    """Reference algorithm of the static path on the host cores: oracle (Kelvin kernels, OpenMP over integration elements +
+    critical scatter) on a bounded sample of the collocation points + OpenBLAS dgetrf/dgetrs, scaled to one full solve."""
+    from oracle import oracle as orc
+    from scipy.linalg import lapack
+    ncores = os.cpu_count()
+    o = orc.Oracle(md)
+    n = md.n_dof
+    stride = max(1, int(round(md.n_elem * md.n_colloc * 30.0 / budget_points)))
+    t0 = time.time(); _, _, ns, pts = o.assemble_colloc_sample_static(mat, stride // 2, stride, nthreads=ncores); t1 = time.time()
+    t_asm = (t1 - t0) * md.n_colloc / ns
+    lu_n = min(lu_n, n)
+    rng = np.random.default_rng(0)
+    A = np.asfortranarray(rng.standard_normal((lu_n, lu_n))); b = rng.standard_normal(lu_n)
+    t0 = time.time(); lu, piv, info = lapack.dgetrf(A, overwrite_a=True); x, info = lapack.dgetrs(lu, piv, b); t2 = time.time()
+    t_lu = (t2 - t0) * (n / lu_n) ** 3
+    sample = ("assembly: static oracle on all %d elements x every %d-th collocation point (%d of %d points, %.1f s) scaled by %d/%d; "
+              "LU: OpenBLAS dgetrf+dgetrs at n=%d (%.2f s) scaled by (%d/%d)^3" % (md.n_elem, stride, ns, md.n_colloc, t_asm * ns / md.n_colloc,
+                                                                                   md.n_colloc, ns, lu_n, t2 - t0, n, lu_n))
+    return {"value": 1.0 / (t_asm + t_lu), "unit": "solves/s", "cores": ncores, "kind": "port", "sample": sample,
+            "assembly_s_per_step": t_asm, "lu_s_per_step": t_lu}
+
+
+def run_static(args):
+    """N ranks = N independent replicas of the same static solve (the static analysis has a single system: nothing to shard)."""
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    md, mat, name = static_workload(args)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cpu_arm_static(md, mat, budget_points=2e6, lu_n=1024)
+        res = [cpu_arm_static(md, mat) for _ in range(args.steps)]
+        v = float(np.mean([r["value"] for r in res])); cb = dict(res[-1]); cb["value"] = v
+        print(json.dumps({"impl": "reference", "metric": STATIC_METRIC, "value": v, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": name, "note": "reference algorithm on host cores (oracle port; no Fortran compiler here), bounded sample scaled to a full solve"},
+                          "cpu_baseline": cb, "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    from multifebe_b200 import capi
+    ctx = capi.Context(local)
+    t0 = time.time(); pr = capi.Problem(ctx, md); t_setup = time.time() - t0
+    n = md.n_dof
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        ctx.mark(7); ctx.elapsed_ms(7, 7)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def reduce_max(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        x = pr.solve_static(mat)
+    # device-resident arm: the library's own events around assemble + LU + solve (prescribed values resident, solution stays on the device
+    # until the single download the call ends with; its 76 KB are inside the e2e arm below)
+    acc = {}
+    barrier(); w0 = time.time()
+    for s in range(args.steps):
+        x = pr.solve_static(mat)
+        st = pr.stats()
+        for k in ("MS_ASSEMBLE", "MS_REGULAR", "MS_ADAPTIVE", "MS_SINGULAR", "MS_ZERO", "MS_LU", "MS_SOLVE", "MS_GEMM", "MS_PANEL", "LAUNCHES", "LU_LAUNCHES", "GEMM_LAUNCHES", "GEMM_FLOPS"):
+            acc[k] = acc.get(k, 0.0) + st[k]
+    barrier(); windows = [(w0, time.time())]
+    K = args.steps
+    ms_dev = reduce_max((acc["MS_ASSEMBLE"] + acc["MS_LU"] + acc["MS_SOLVE"]) / K)
+    # e2e arm: wall clock of the C-ABI call with host buffers (cvalue up, x down), max over ranks
+    barrier(); t0 = time.time(); w0 = t0
+    for s in range(args.steps):
+        x = pr.solve_static(mat)
+    barrier(); ms_e2e = reduce_max((time.time() - t0) * 1e3 / K); windows.append((w0, time.time()))
+    peaks = ctx.measure_peaks() if rank == 0 else None
+    if rank == 0:
+        u, t = md.nodal_solution(x)
+        lam2mu = 2.0 * mat.mu_r * mat.nu_r / (1.0 - 2.0 * mat.nu_r) + 2.0 * mat.mu_r
+        err = float(np.abs(u[:, 0].real - md.node_x[:, 0] / lam2mu).max() * lam2mu)
+        gemm_tf = acc["GEMM_FLOPS"] / max(acc["MS_GEMM"], 1e-9) / 1e9
+        out = {"metric": STATIC_METRIC, "value": world * 1e3 / ms_dev, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": name, "sharding": "replicas only: the static analysis is one system, every rank solves the same problem",
+                          "l2": "L2 flushed between steps by the assembly itself (it rewrites the %.2f GB matrix, larger than the 126 MB L2)" % (8.0 * n * n / 1e9),
+                          "setup_s_once_per_mesh": t_setup},
+               "clocks": clocks.summary(windows),
+               "e2e": {"value": world * 1e3 / ms_e2e, "unit": "solves/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(md.cvalue.size * 8 + 1024), "d2h_bytes_per_step": int(8 * n + 4 * n),
+                       "api": "mfb_staela3d_solve (host cvalue in, host x out)"},
+               "gpu_launches": int(acc["LAUNCHES"] + acc["LU_LAUNCHES"]),
+               "roofline": {"kernel": "k_dgemm_minus (real LU trailing update, DMMA.8x8x4)", "bound": "tensor", "achieved": gemm_tf, "peak": peaks["dmma_tflops"], "unit": "TFLOP/s",
+                            "frac": gemm_tf / peaks["dmma_tflops"], "traffic": None, "avg_launch_ms": acc["MS_GEMM"] / max(acc["GEMM_LAUNCHES"], 1),
+                            "launches_per_step": acc["GEMM_LAUNCHES"] / K, "share_of_step": (acc["MS_GEMM"] / K) / ms_dev,
+                            "note": "2mnk flops per launch / CUDA-event time of the trailing updates; at this size the factorisation is bound by the panel "
+                                    "(one grid barrier per column), not by the GEMM: see lu.ms_panel_on_lookahead_stream",
+                            "peak_source": "FP64 tensor (DMMA) micro-benchmark measured live (mfb_measure_peaks)"},
+               "assembly": {"ms": acc["MS_ASSEMBLE"] / K, "ms_regular": acc["MS_REGULAR"] / K, "ms_adaptive": acc["MS_ADAPTIVE"] / K, "ms_singular": acc["MS_SINGULAR"] / K,
+                            "gentries_per_s": n * n / (acc["MS_ASSEMBLE"] / K * 1e-3) / 1e9, "matrix_write_gbs": 8.0 * n * n / (acc["MS_ASSEMBLE"] / K * 1e-3) / 1e9},
+               "lu": {"ms": acc["MS_LU"] / K, "tflops": 2.0 / 3.0 * n ** 3 / (acc["MS_LU"] / K) / 1e9, "ms_gemm": acc["MS_GEMM"] / K, "ms_panel_on_lookahead_stream": acc["MS_PANEL"] / K,
+                      "ms_dgetrs": acc["MS_SOLVE"] / K},
+               "exact_solution_max_error": err, "peaks_measured_live": peaks}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_arm_static(md, mat)
+        print(json.dumps(out), flush=True)
+    pr.close(); ctx.close()
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -307,8 +438,13 @@ def main():
     ap.add_argument("--etype", default="tri3")
     ap.add_argument("--m", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="harmonic", choices=["harmonic", "static"], help="harmonic: the headline 30k-DOF sweep (default); static: BASELINE config 2")
+    ap.add_argument("--static-etype", default="quad9")
+    ap.add_argument("--static-m", type=int, default=11)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "static":
+        run_static(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

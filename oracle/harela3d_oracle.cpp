@@ -1329,10 +1329,19 @@ static int assemble_impl(Model* m, const Params& p, cd nu, const cd* cvalue, cd*
 // c = c_offset, c_offset + c_stride, ... with the reference's parallel structure (OpenMP dynamic over integration elements,
 // critical scatter).  Each sampled collocation point gets its own three rows in the compact matrix
 // A_s (3*n_sample x n_dof, column-major).  Returns the number of sampled collocation points.
+static int sample_impl(Model* m, const Params& p, const cd* cvalue, int c_offset, int c_stride, cd* A, cd* b, int nthreads, long long* points_out);
 int orc_assemble_colloc_sample(void* h, double omega, const double* lambda_ri, const double* mu_ri, double rho, const double* cvalue_ri,
                                int c_offset, int c_stride, double* A_ri, double* b_ri, int nthreads, long long* points_out) {
-  Model* m = (Model*)h; cd* A = (cd*)A_ri; cd* b = (cd*)b_ri; const cd* cvalue = (const cd*)cvalue_ri;
   Params p; calculate_parameters(cd(lambda_ri[0], lambda_ri[1]), cd(mu_ri[0], mu_ri[1]), rho, omega, p);
+  return sample_impl((Model*)h, p, (const cd*)cvalue_ri, c_offset, c_stride, (cd*)A_ri, (cd*)b_ri, nthreads, points_out);
+}
+// the same bounded sample with the static (Kelvin) kernels; complex containers, imaginary parts stay zero
+int orc_assemble_colloc_sample_static(void* h, double mu, double nu, const double* cvalue_ri, int c_offset, int c_stride, double* A_ri, double* b_ri,
+                                      int nthreads, long long* points_out) {
+  Params p; calculate_parameters_static(mu, nu, p);
+  return sample_impl((Model*)h, p, (const cd*)cvalue_ri, c_offset, c_stride, (cd*)A_ri, (cd*)b_ri, nthreads, points_out);
+}
+static int sample_impl(Model* m, const Params& p, const cd* cvalue, int c_offset, int c_stride, cd* A, cd* b, int nthreads, long long* points_out) {
   std::vector<int> cs; for (int c = c_offset; c < m->n_colloc; c += c_stride) cs.push_back(c);
   const long long ns = (long long)cs.size(), ld = 3 * ns;
   Stats total; memset(&total, 0, sizeof(total));

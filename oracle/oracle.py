@@ -115,6 +115,18 @@ class Oracle:
         assert n == ns
         return A, b, ns, pts.value
 
+    def assemble_colloc_sample_static(self, mat, c_offset, c_stride, nthreads=0):
+        """The bounded CPU-baseline sample with the static kernels (complex containers with zero imaginary parts)."""
+        ns = len(range(c_offset, self.m.n_colloc, c_stride))
+        A = np.zeros((3 * ns, self.m.n_dof), dtype=np.complex128, order="F")
+        b = np.zeros(3 * ns, dtype=np.complex128)
+        pts = C.c_longlong(0)
+        cv = np.ascontiguousarray(self.m.cvalue)
+        n = lib().orc_assemble_colloc_sample_static(self.h, C.c_double(mat.mu_r), C.c_double(mat.nu_r), _p(cv), C.c_int(c_offset), C.c_int(c_stride),
+                                                    _p(A), _p(b), C.c_int(nthreads), C.byref(pts))
+        assert n == ns
+        return A, b, ns, pts.value
+
     def pair(self, e, x_i, omega, mat):
         """h, g (n,3,3) complex of one (collocation point, element) pair and the integration mode."""
         nn = int(self.m.elem_ptr[e + 1] - self.m.elem_ptr[e])
