@@ -344,3 +344,51 @@ def pr_zsolve_on_real(pr, n):
     from multifebe_b200 import capi
     b = np.zeros(n, dtype=np.complex128)
     capi._check(capi.lib().mfb_zsolve(pr.h, C.c_int(n), None, C.c_int(n), None, capi._p(b), C.c_int(1), C.c_int(1)))
+
+
+def test_static_full_size_properties_config2(gpu_ctx, oracle_lib):
+    """BASELINE config 2 size (static cube, quad9 m=11: 9522 DOF, 726 elements): spot parity of assembled entries against
+    static oracle pair integrals, residual of the real LU solution on the re-assembled system, exact column solution."""
+    from multifebe_b200 import capi
+    md = Model(cube_mesh(11, shape.QUAD9), cube_bcs())
+    assert md.n_dof == 9522
+    pr = capi.Problem(gpu_ctx, md)
+    pr.build_lse_mechanics_bem_staela(SMAT, want_host=False)
+    o = oracle_lib.Oracle(md)
+    rng = np.random.default_rng(12)
+    node_elems, colloc_of_node = {}, {}
+    for e, c in enumerate(md.mesh.conn):
+        for kn, v in enumerate(c):
+            node_elems.setdefault(int(v), []).append((e, kn))
+    for c in range(md.n_colloc):
+        colloc_of_node.setdefault(int(md.colloc_node[c]), []).append(c)
+    rows, cols, expect = [], [], []
+    for sn in rng.integers(0, md.n_node, 16):
+        sn = int(sn)
+        own = set(int(md.colloc_elem[c]) for c in colloc_of_node[sn]) | set(e for e, _ in node_elems[sn])
+        d = np.linalg.norm(md.node_x - md.node_x[sn], axis=1)
+        for j in (int(rng.integers(0, md.n_node)), int(np.argsort(d)[30]), int(np.argsort(d)[90])):
+            if any(e in own for e, _ in node_elems[j]):
+                continue
+            blk = np.zeros((3, 3))
+            for c in colloc_of_node[sn]:
+                for e, kn in node_elems[j]:
+                    h, g, mode = o.pair_static(e, md.colloc_x[c], SMAT)
+                    for k in range(3):
+                        blk[:, k] += (-g[kn, :, k]) if md.ctype[j, k] == 0 else h[kn, :, k]
+            for l in range(3):
+                for k in range(3):
+                    rows.append(md.row[sn, l]); cols.append(md.col_t[j, k] if md.ctype[j, k] == 0 else md.col_u[j, k]); expect.append(blk[l, k])
+    got = pr.get_entries(rows, cols)
+    expect = np.array(expect)
+    assert len(expect) > 200 and np.abs(got.imag).max() == 0.0
+    scale = np.abs(expect).reshape(-1, 9).max(axis=1).repeat(9)
+    assert (np.abs(got.real - expect) / scale).max() < TOL_A
+    x = pr.solve_static(SMAT)
+    pr.build_lse_mechanics_bem_staela(SMAT, want_host=False)
+    berr, rel = pr.residual(x.astype(np.complex128))
+    assert berr < 1e-11 and rel < 1e-13
+    u, t = md.nodal_solution(x)
+    lam2mu = 2.0 * SMAT.mu_r * SMAT.nu_r / (1.0 - 2.0 * SMAT.nu_r) + 2.0 * SMAT.mu_r
+    assert np.abs(u[:, 0].real - md.node_x[:, 0] / lam2mu).max() * lam2mu < 2e-5
+    pr.close()
