@@ -14,7 +14,9 @@
 #include "lu.cuh"
 #include <cooperative_groups.h>
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 namespace cg = cooperative_groups;
 
@@ -449,6 +451,7 @@ __device__ __forceinline__ void block_argmax(double v, int row, double* s_val, i
 }
 
 const int SP_MAXIB = 32;
+const int SP_CLUSTER_SMEM = 200 * 1024;   // dynamic shared memory a CTA of the cluster panel kernel may use for its slab
 
 // CX = false: real matrix (a.Aim == NULL): the imaginary plane is neither read nor written, the pivot is max |re| (idamax).
 template <bool CX>
@@ -553,6 +556,130 @@ __global__ void __launch_bounds__(256) k_subpanel(SubPanelArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Sub-panel factorisation inside ONE thread-block cluster (sm_90+ clusters; 16 CTAs = non-portable size on sm_100a).
+// Same algorithm and pivot rule as k_subpanel, but the per-column exchange never leaves the cluster: every CTA publishes
+// its pivot candidate (value, row, a copy of the row) in its OWN shared memory, a hardware cluster barrier replaces the
+// grid barrier, and the winner's row and the diagonal row are read through distributed shared memory.  The grid-wide
+// version pays a grid barrier plus two dependent L2 round trips per column (~5 us); this one ~1.5 us, and it occupies
+// 16 SMs instead of all of them, so the trailing update of the look-ahead keeps the rest of the GPU.  The slab of a CTA
+// (rows x ib columns, one plane for a real matrix) must fit its shared memory: the caller picks ib or falls back.
+// ------------------------------------------------------------------------------------------------------------------
+template <bool CX>
+__global__ void __launch_bounds__(256) k_subpanel_cluster(SubPanelArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) double slab[];      // [planes][ib][rpcp]
+  __shared__ double s_val[8]; __shared__ int s_row[8];
+  __shared__ double s_ure[SP_MAXIB], s_uim[SP_MAXIB];
+  __shared__ double c_val[2]; __shared__ int c_row[2];
+  __shared__ double c_data[2][2 * SP_MAXIB];          // candidate row of this CTA (re | im), double buffered over the columns
+  __shared__ double d_data[2][2 * SP_MAXIB];          // current diagonal row (CTA 0)
+  __shared__ int s_p;
+  const int tid = threadIdx.x, c = (int)cluster.block_rank(), G = (int)cluster.num_blocks();
+  const int ib = a.ib, c0 = a.c0, rpcp = a.rpcp;
+  const int rs = c0 + c * a.rpc, re = min(rs + a.rpc, a.n), nloc = max(re - rs, 0);
+  double* sre = slab; double* sim = slab + (size_t)ib * rpcp;   // sim is used only when CX
+  const long long lda = a.lda;
+  const int BIG = 0x7fffffff;
+  for (int idx = tid; idx < ib * nloc; idx += blockDim.x) {
+    int jj = idx / nloc, i = idx - jj * nloc;
+    sre[jj * rpcp + i] = a.Are[(long long)(c0 + jj) * lda + rs + i];
+    if (CX) sim[jj * rpcp + i] = a.Aim[(long long)(c0 + jj) * lda + rs + i];
+  }
+  __syncthreads();
+  {
+    double v = -1.0; int r = BIG;
+    for (int i = tid; i < nloc; i += blockDim.x) { double t = fabs(sre[i]) + (CX ? fabs(sim[i]) : 0.0); if (t > v) { v = t; r = rs + i; } }
+    double best; int brow; block_argmax(v, r, s_val, s_row, best, brow);
+    if (tid == 0) { c_val[0] = best; c_row[0] = brow; }
+    if (brow != BIG && tid < ib) { c_data[0][tid] = sre[tid * rpcp + brow - rs]; c_data[0][ib + tid] = CX ? sim[tid * rpcp + brow - rs] : 0.0; }
+    if (c == 0 && tid < ib) { d_data[0][tid] = sre[tid * rpcp]; d_data[0][ib + tid] = CX ? sim[tid * rpcp] : 0.0; }
+  }
+  for (int j = 0; j < ib; j++) {
+    const int buf = j & 1, nbuf = buf ^ 1;
+    const int dj = c0 + j;
+    cluster.sync();                                   // candidates of column j are visible cluster-wide
+    if (tid < 32) {                                   // G <= 16 candidates: one warp
+      double v = -1.0; int r = BIG;
+      if (tid < G) { v = *cluster.map_shared_rank(&c_val[buf], tid); r = *cluster.map_shared_rank(&c_row[buf], tid); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        double v2 = __shfl_xor_sync(0xffffffffu, v, o); int r2 = __shfl_xor_sync(0xffffffffu, r, o);
+        if (v2 > v || (v2 == v && r2 < r)) { v = v2; r = r2; }
+      }
+      if (tid == 0) s_p = r;
+    }
+    __syncthreads();
+    const int p = s_p;
+    const int cstar = (p - c0) / a.rpc;
+    if (tid < ib) {
+      const double* cd = cluster.map_shared_rank(&c_data[buf][0], cstar);
+      s_ure[tid] = cd[tid]; s_uim[tid] = cd[ib + tid];
+    }
+    if (p != dj && tid < ib && p >= rs && p < re) {   // row p receives the old diagonal row
+      const double* dd = cluster.map_shared_rank(&d_data[buf][0], 0);
+      sre[tid * rpcp + p - rs] = dd[tid]; if (CX) sim[tid * rpcp + p - rs] = dd[ib + tid];
+    }
+    __syncthreads();
+    const double pr = s_ure[j], pi = s_uim[j];
+    const bool zero_pivot = (pr == 0.0 && pi == 0.0);
+    if (c == 0 && tid == 0) { a.ipiv[dj] = p + 1; if (zero_pivot) atomicCAS(a.info, 0, dj + 1); }
+    if (p != dj && tid < ib && c == 0) { sre[tid * rpcp + j] = s_ure[tid]; if (CX) sim[tid * rpcp + j] = s_uim[tid]; }   // diagonal row receives the pivot row
+    __syncthreads();
+    double ir = 0.0, ii = 0.0;
+    if (!zero_pivot) {
+      if (!CX) ir = 1.0 / pr;
+      else if (fabs(pr) >= fabs(pi)) { double t = pi / pr, d = pr + pi * t; ir = 1.0 / d; ii = -t / d; }
+      else { double t = pr / pi, d = pr * t + pi; ir = t / d; ii = -1.0 / d; }
+    }
+    double nv = -1.0; int nr = BIG;
+    for (int i = tid; i < nloc; i += blockDim.x) {
+      if (rs + i <= dj) continue;
+      double lr = sre[j * rpcp + i], li = CX ? sim[j * rpcp + i] : 0.0;
+      if (!zero_pivot) {
+        if (CX) { double t = lr * ir - li * ii; li = lr * ii + li * ir; lr = t; sre[j * rpcp + i] = lr; sim[j * rpcp + i] = li; }
+        else { lr = lr * ir; sre[j * rpcp + i] = lr; }
+      }
+      for (int jj = j + 1; jj < ib; jj++) {
+        double xr = sre[jj * rpcp + i];
+        if (CX) {
+          double xi = sim[jj * rpcp + i];
+          xr -= lr * s_ure[jj] - li * s_uim[jj];
+          xi -= lr * s_uim[jj] + li * s_ure[jj];
+          sre[jj * rpcp + i] = xr; sim[jj * rpcp + i] = xi;
+          if (jj == j + 1) { double t = fabs(xr) + fabs(xi); if (t > nv) { nv = t; nr = rs + i; } }
+        } else {
+          xr -= lr * s_ure[jj];
+          sre[jj * rpcp + i] = xr;
+          if (jj == j + 1) { double t = fabs(xr); if (t > nv) { nv = t; nr = rs + i; } }
+        }
+      }
+    }
+    if (j + 1 < ib) {
+      double nbest; int nbrow; block_argmax(nv, nr, s_val, s_row, nbest, nbrow);   // its barrier also orders the slab updates
+      if (tid == 0) { c_val[nbuf] = nbest; c_row[nbuf] = nbrow; }
+      if (nbrow != BIG && tid < ib) { c_data[nbuf][tid] = sre[tid * rpcp + nbrow - rs]; c_data[nbuf][ib + tid] = CX ? sim[tid * rpcp + nbrow - rs] : 0.0; }
+      if (c == 0 && tid < ib) { d_data[nbuf][tid] = sre[tid * rpcp + j + 1]; d_data[nbuf][ib + tid] = CX ? sim[tid * rpcp + j + 1] : 0.0; }
+    }
+  }
+  cluster.sync();    // nobody leaves (and frees its shared memory) while a neighbour may still read it
+  for (int idx = tid; idx < ib * nloc; idx += blockDim.x) {
+    int jj = idx / nloc, i = idx - jj * nloc;
+    a.Are[(long long)(c0 + jj) * lda + rs + i] = sre[jj * rpcp + i];
+    if (CX) a.Aim[(long long)(c0 + jj) * lda + rs + i] = sim[jj * rpcp + i];
+  }
+}
+// launch on a cluster of `cl` CTAs; returns cudaError
+template <bool CX>
+static cudaError_t launch_subpanel_cluster(const SubPanelArgs& pa, int cl, size_t smem, cudaStream_t st) {
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(cl); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_subpanel_cluster<CX>, pa);
+}
+
 // row interchanges ipiv[k0 .. k0+nbw) applied to columns [c0,c1)
 __global__ void k_laswp(double* Are, double* Aim, long long lda, int c0, int c1, int k0, int nbw, const int* __restrict__ ipiv) {
   int col = c0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -564,18 +691,117 @@ __global__ void k_laswp(double* Are, double* Aim, long long lda, int c0, int c1,
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// In-panel update after a sub-panel of ib columns at (c0, c0): for the panel columns [cA, cB) to its right,
+// U12 = inv(L11) A12 and A22 -= L21 U12 in ONE launch (these used to be a TRSM kernel plus a GEMM kernel per sub-panel;
+// inside a panel both are latency, not throughput).  CTA (x, y): column block y of PU_TC columns; every CTA redoes the
+// tiny forward substitution of its column block in shared memory; x = 0 stores U12, x >= 1 updates PU_RB rows: one row per
+// thread, its L21 row (ib values) in registers, U12 broadcast from shared memory, C read and written once, coalesced.
+// U12 overwrites A12, which every CTA of the column block reads first: the CTA that arrives LAST at the block's counter
+// (after its own read) stores it and re-arms the counter.
+// k_laswp2: the row interchanges of the sub-panel on the panel columns left and right of it, one launch.
+// ------------------------------------------------------------------------------------------------------------------
+const int PU_TC = 32, PU_RB = 128;
+template <bool CX, int IBM>
+__global__ void __launch_bounds__(256) k_panel_update(double* Are, double* Aim, long long lda, int n, int c0, int ib, int cA, int cB, int* __restrict__ arrive) {
+  __shared__ double ur[IBM][PU_TC + 1], ui[CX ? IBM : 1][PU_TC + 1];
+  __shared__ double lr[IBM][IBM + 1], li[CX ? IBM : 1][IBM + 1];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cb = cA + blockIdx.y * PU_TC, ncol = min(PU_TC, cB - cb);
+  for (int idx = tid; idx < IBM * PU_TC; idx += 256) {
+    const int cc = idx / IBM, i = idx - cc * IBM;
+    const bool ok = cc < ncol && i < ib;
+    ur[i][cc] = ok ? Are[(long long)(cb + cc) * lda + c0 + i] : 0.0;
+    if (CX) ui[i][cc] = ok ? Aim[(long long)(cb + cc) * lda + c0 + i] : 0.0;
+  }
+  for (int idx = tid; idx < IBM * IBM; idx += 256) {
+    const int j = idx / IBM, i = idx - j * IBM;
+    const bool ok = i < ib && j < ib && i > j;
+    lr[i][j] = ok ? Are[(long long)(c0 + j) * lda + c0 + i] : 0.0;
+    if (CX) li[i][j] = ok ? Aim[(long long)(c0 + j) * lda + c0 + i] : 0.0;
+  }
+  __syncthreads();
+  if (tid == 0) {                                          // A12 has been read: arrive
+    __threadfence();
+    const int prev = atomicAdd(arrive + blockIdx.y, 1);
+    s_last = (prev == (int)gridDim.x - 1);
+    if (s_last) arrive[blockIdx.y] = 0;
+  }
+  for (int j = 0; j < ib - 1; j++) {                       // forward substitution, unit lower L11; lanes = columns, warps = rows
+    const double xr = ur[j][lane], xi = CX ? ui[j][lane] : 0.0;
+    for (int i = j + 1 + warp; i < ib; i += 8) {
+      if (CX) { ur[i][lane] -= lr[i][j] * xr - li[i][j] * xi; ui[i][lane] -= lr[i][j] * xi + li[i][j] * xr; }
+      else ur[i][lane] -= lr[i][j] * xr;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (s_last) {
+    for (int idx = tid; idx < ib * PU_TC; idx += 256) {
+      const int cc = idx / ib, i = idx - cc * ib;
+      if (cc < ncol) { Are[(long long)(cb + cc) * lda + c0 + i] = ur[i][cc]; if (CX) Aim[(long long)(cb + cc) * lda + c0 + i] = ui[i][cc]; }
+    }
+  }
+  const int r = c0 + ib + blockIdx.x * PU_RB + (tid & (PU_RB - 1)), half = tid / PU_RB;
+  if (r >= n) return;
+  double Lr[IBM], Li[CX ? IBM : 1];
+#pragma unroll
+  for (int k = 0; k < IBM; k++) {
+    Lr[k] = (k < ib) ? Are[(long long)(c0 + k) * lda + r] : 0.0;
+    if (CX) Li[k] = (k < ib) ? Aim[(long long)(c0 + k) * lda + r] : 0.0;
+  }
+  const int cc0 = half * (PU_TC / 2), cc1 = min(cc0 + PU_TC / 2, ncol);
+#pragma unroll 4
+  for (int cc = cc0; cc < cc1; cc++) {
+    const long long o = (long long)(cb + cc) * lda + r;
+    double sr = Are[o], si = CX ? Aim[o] : 0.0;
+#pragma unroll
+    for (int k = 0; k < IBM; k++) {
+      if (CX) { sr = fma(-Lr[k], ur[k][cc], fma(Li[k], ui[k][cc], sr)); si = fma(-Lr[k], ui[k][cc], fma(-Li[k], ur[k][cc], si)); }
+      else sr = fma(-Lr[k], ur[k][cc], sr);
+    }
+    Are[o] = sr; if (CX) Aim[o] = si;
+  }
+}
+template <bool CX>
+static void launch_panel_update(double* Are, double* Aim, long long lda, int n, int c0, int ib, int cA, int cB, int* arrive, cudaStream_t st) {
+  const int mrest = n - c0 - ib;
+  dim3 grid(mrest > 0 ? (mrest + PU_RB - 1) / PU_RB : 1, (cB - cA + PU_TC - 1) / PU_TC);
+  if (ib <= 8) k_panel_update<CX, 8><<<grid, 256, 0, st>>>(Are, Aim, lda, n, c0, ib, cA, cB, arrive);
+  else if (ib <= 16) k_panel_update<CX, 16><<<grid, 256, 0, st>>>(Are, Aim, lda, n, c0, ib, cA, cB, arrive);
+  else k_panel_update<CX, 32><<<grid, 256, 0, st>>>(Are, Aim, lda, n, c0, ib, cA, cB, arrive);
+}
+// interchanges ipiv[k0 .. k0+nbw) on the columns [a0,a1) and [b0,b1)
+__global__ void k_laswp2(double* Are, double* Aim, long long lda, int a0, int a1, int b0, int b1, int k0, int nbw, const int* __restrict__ ipiv) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int col = (t < a1 - a0) ? a0 + t : b0 + (t - (a1 - a0));
+  if (t >= (a1 - a0) + (b1 - b0)) return;
+  double* ar = Are + (long long)col * lda; double* ai = Aim + (long long)col * lda;
+  for (int j = 0; j < nbw; j++) {
+    int p = ipiv[k0 + j] - 1, d = k0 + j;
+    if (p != d) { double t2 = ar[d]; ar[d] = ar[p]; ar[p] = t2; if (Aim) { t2 = ai[d]; ai[d] = ai[p]; ai[p] = t2; } }
+  }
+}
+
 // X = inv(L) * B in place: L = unit lower nbw x nbw block at (r0,r0), B = rows r0..r0+nbw of columns [c0,c1).
 // One CTA per TRSM_TC columns; B tile in shared memory; warps own rows (warp-uniform L loads), lanes own columns.
 const int TRSM_TC = 32;
+const int TRSM_TB = 32;    // rows solved per k_trsm_lu launch (the L block is staged in shared memory)
 // L (Lre/Lim, ldl) points at the top-left of the unit lower block, B (Bre/Bim, ldb) at the first of its nbw rows in column 0 of
 // the ncols columns to solve (the two may live in different arrays: the distributed LU keeps L in the broadcast panel).
 __global__ void __launch_bounds__(256) k_trsm_lu(const double* __restrict__ Lre, const double* __restrict__ Lim, long long ldl, double* Bre, double* Bim,
                                                  long long ldb, int nbw, int ncols) {
   extern __shared__ __align__(16) double sb[];     // [2][nbw][TRSM_TC+1]
+  __shared__ double slr[TRSM_TB][TRSM_TB + 1], sli[TRSM_TB][TRSM_TB + 1];   // the L block (nbw <= TRSM_TB): a global load per substitution step was the latency of this kernel
   const int LD = TRSM_TC + 1;
   double* br = sb; double* bi = sb + (size_t)nbw * LD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int cb = blockIdx.x * TRSM_TC, ncol = min(TRSM_TC, ncols - cb);
+  for (int idx = tid; idx < nbw * nbw; idx += blockDim.x) {
+    const int j = idx / nbw, i = idx - j * nbw;
+    slr[i][j] = Lre[(long long)j * ldl + i]; sli[i][j] = Lim ? Lim[(long long)j * ldl + i] : 0.0;
+  }
   // load: thread (i = tid % nbw-chunk, col) coalesced along rows
   for (int idx = tid; idx < nbw * TRSM_TC; idx += blockDim.x) {
     int cc = idx / nbw, i = idx - cc * nbw;
@@ -586,11 +812,9 @@ __global__ void __launch_bounds__(256) k_trsm_lu(const double* __restrict__ Lre,
   __syncthreads();
   for (int j = 0; j < nbw - 1; j++) {
     const double xr = br[j * LD + lane], xi = bi[j * LD + lane];
-    const double* lre = Lre + (long long)j * ldl;
-    const double* lim = Lim + (long long)j * ldl;
 #pragma unroll 4
     for (int i = j + 1 + warp; i < nbw; i += nw) {
-      const double lr = __ldg(lre + i), li = Lim ? __ldg(lim + i) : 0.0;
+      const double lr = slr[i][j], li = sli[i][j];
       br[i * LD + lane] -= lr * xr - li * xi;
       bi[i * LD + lane] -= lr * xi + li * xr;
     }
@@ -603,7 +827,6 @@ __global__ void __launch_bounds__(256) k_trsm_lu(const double* __restrict__ Lre,
 }
 // U12 = inv(L11) A12 for the nbw x nbw unit lower block at (r0,r0) and columns [c0,c1): blocked forward substitution,
 // TRSM_TB rows at a time by substitution in shared memory, the rows below updated on the tensor pipe (returns launches).
-const int TRSM_TB = 32;
 static int launch_trsm_ext(const double* Lre, const double* Lim, long long ldl, double* Bre, double* Bim, long long ldb, int nbw, int ncols, cudaStream_t st) {
   if (ncols <= 0 || nbw <= 1) return 0;
   static bool attr = false;
@@ -643,12 +866,35 @@ int lu_work_alloc(LuWork& w, int n, int nb) {
   const char* e_pc = getenv("MFB_LU_PANEL_CTAS");
   w.panel_ctas = e_pc ? atoi(e_pc) : w.n_sm;
   if (w.panel_ctas < 1 || w.panel_ctas > w.n_sm) w.panel_ctas = w.n_sm;
+  // cluster-resident panel: 16 CTAs (non-portable cluster size) if the device takes it, else 8; MFB_LU_CLUSTER=0 disables it
+  {
+    const char* e_cl = getenv("MFB_LU_CLUSTER");
+    int want = e_cl ? atoi(e_cl) : 16;
+    if (want != 0 && want != 8 && want != 16) want = 16;
+    w.cluster = 0;
+    const char* e_mr = getenv("MFB_LU_CLUSTER_MAX_ROWS");
+    w.cluster_max_rows = e_mr ? atoi(e_mr) : (1 << 30);
+    const char* e_ci = getenv("MFB_LU_CLUSTER_IB");
+    w.cluster_ib = e_ci ? atoi(e_ci) : 32;
+    if (want > 0) {
+      bool ok = cudaFuncSetAttribute(k_subpanel_cluster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_CLUSTER_SMEM) == cudaSuccess &&
+                cudaFuncSetAttribute(k_subpanel_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_CLUSTER_SMEM) == cudaSuccess;
+      if (ok && want == 16)
+        ok = cudaFuncSetAttribute(k_subpanel_cluster<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+             cudaFuncSetAttribute(k_subpanel_cluster<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+      if (ok) w.cluster = want;
+      cudaGetLastError();
+    }
+  }
+  { const char* e_fp = getenv("MFB_LU_FUSED_PANEL_UPDATE"); w.fused_panel_update = e_fp ? atoi(e_fp) : 2; }
   size_t G = (size_t)w.n_sm;
   cudaError_t e = cudaSuccess;
   auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
   A((void**)&w.cand_val, 2 * G * sizeof(double)); A((void**)&w.cand_row, 2 * G * sizeof(int));
   A((void**)&w.cand_data, 2 * G * 2 * SP_MAXIB * sizeof(double)); A((void**)&w.diag_data, 2 * 2 * SP_MAXIB * sizeof(double));
   A((void**)&w.info, sizeof(int));
+  A((void**)&w.pu_arrive, 64 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(w.pu_arrive, 0, 64 * sizeof(int));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_subpanel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_subpanel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   w.n_evs = 5 * ((n + nb - 1) / nb);
@@ -664,7 +910,7 @@ int lu_work_alloc(LuWork& w, int n, int nb) {
   return (int)e;
 }
 void lu_work_free(LuWork& w) {
-  cudaFree(w.cand_val); cudaFree(w.cand_row); cudaFree(w.cand_data); cudaFree(w.diag_data); cudaFree(w.info);
+  cudaFree(w.cand_val); cudaFree(w.cand_row); cudaFree(w.cand_data); cudaFree(w.diag_data); cudaFree(w.info); cudaFree(w.pu_arrive);
   for (int i = 0; i < w.n_evs; i++) cudaEventDestroy(w.evs[i]);
   for (int i = 0; i < 2 * (w.n_evs / 5); i++) cudaEventDestroy(w.pevs[i]);
   cudaEventDestroy(w.ev_next_cols); cudaEventDestroy(w.ev_panel_done); cudaStreamDestroy(w.panel_stream);
@@ -684,33 +930,68 @@ void lu_collect_times(LuWork& w) {
 // Panel = block column [k0, k0+nbw): sub-panels of ib columns (cooperative kernel above); after each sub-panel its row
 // interchanges are applied to the rest of the panel, then U12' = inv(L11') A12' and A22' -= L21' U12' inside the panel.
 static int factor_panel(double* Are, double* Aim, long long lda, int n, int k0, int nbw, int* ipiv, LuWork& w, cudaStream_t st) {
-  for (int j0 = 0; j0 < nbw; j0 += w.ib) {
-    const int ib = (nbw - j0 < w.ib) ? (nbw - j0) : w.ib;
+  // Sub-panel width of this panel: the cluster kernel needs the slab of a CTA (rows/cluster x ib, one or two planes) in
+  // shared memory; take the configured width if it fits, else 8 columns, else the grid-wide kernel.
+  const int planes = Aim ? 2 : 1;
+  int ib_panel = w.ib; bool use_cluster = false;
+  if (w.cluster > 1 && (n - k0) <= w.cluster_max_rows) {
+    const int cands[3] = {w.cluster_ib, w.ib, 8};           // widest first: every sub-panel launch has a fixed cost
+    for (int t = 0; t < 3 && !use_cluster; t++) {
+      const int rpc = (n - k0 + w.cluster - 1) / w.cluster;
+      if (cands[t] >= 8 && cands[t] <= SP_MAXIB && nbw % cands[t] == 0 &&
+          (size_t)planes * cands[t] * (rpc | 1) * sizeof(double) <= (size_t)SP_CLUSTER_SMEM) { ib_panel = cands[t]; use_cluster = true; }
+    }
+  }
+  for (int j0 = 0; j0 < nbw; j0 += ib_panel) {
+    const int ib = (nbw - j0 < ib_panel) ? (nbw - j0) : ib_panel;
     const int c0 = k0 + j0, m = n - c0;
-    int G = w.panel_ctas;
-    int rpc = (m + G - 1) / G; if (rpc < 64) rpc = 64;
-    G = (m + rpc - 1) / rpc;
-    SubPanelArgs pa; pa.Are = Are; pa.Aim = Aim; pa.lda = lda; pa.n = n; pa.c0 = c0; pa.ib = ib; pa.rpc = rpc; pa.rpcp = rpc | 1;
+    SubPanelArgs pa; pa.Are = Are; pa.Aim = Aim; pa.lda = lda; pa.n = n; pa.c0 = c0; pa.ib = ib;
     pa.ipiv = ipiv; pa.cand_val = w.cand_val; pa.cand_row = w.cand_row; pa.cand_data = w.cand_data; pa.diag_data = w.diag_data; pa.info = w.info;
     pa.ldc = 2 * SP_MAXIB;
-    void* args[] = {&pa};
-    size_t smem = (size_t)2 * ib * pa.rpcp * sizeof(double);
-    cudaError_t e = Aim ? cudaLaunchCooperativeKernel((void*)k_subpanel<true>, dim3(G), dim3(256), args, smem, st)
-                        : cudaLaunchCooperativeKernel((void*)k_subpanel<false>, dim3(G), dim3(256), args, smem, st);
-    if (e != cudaSuccess) return (int)e;
+    cudaError_t e = cudaSuccess;
+    bool done = false;
+    if (use_cluster) {
+      int G = w.cluster;                                    // a smaller (power of two) cluster for a short sub-panel: >= 64 rows per CTA
+      while (G > 1 && (m + G - 1) / G < 64) G >>= 1;
+      const int rpc = (m + G - 1) / G;
+      pa.rpc = rpc; pa.rpcp = rpc | 1;
+      const size_t smem = (size_t)planes * ib * pa.rpcp * sizeof(double);
+      e = Aim ? launch_subpanel_cluster<true>(pa, G, smem, st) : launch_subpanel_cluster<false>(pa, G, smem, st);
+      if (e == cudaSuccess) done = true;
+      else { cudaGetLastError(); w.cluster = 0; use_cluster = false; }   // cluster launch not available: grid-wide kernel from now on
+    }
+    if (!done) {
+      int G = w.panel_ctas;
+      int rpc = (m + G - 1) / G; if (rpc < 64) rpc = 64;
+      G = (m + rpc - 1) / rpc;
+      pa.rpc = rpc; pa.rpcp = rpc | 1;
+      void* args[] = {&pa};
+      size_t smem = (size_t)2 * ib * pa.rpcp * sizeof(double);
+      e = Aim ? cudaLaunchCooperativeKernel((void*)k_subpanel<true>, dim3(G), dim3(256), args, smem, st)
+              : cudaLaunchCooperativeKernel((void*)k_subpanel<false>, dim3(G), dim3(256), args, smem, st);
+      if (e != cudaSuccess) return (int)e;
+    }
     w.launches += 1;
-    // interchanges of this sub-panel on the other columns of the panel
-    if (j0 > 0) { k_laswp<<<(j0 + 127) / 128, 128, 0, st>>>(Are, Aim, lda, k0, c0, c0, ib, ipiv); w.launches++; }
+    // interchanges of this sub-panel on the other columns of the panel, then U12' = inv(L11') A12' and A22' -= L21' U12'
     const int nright = nbw - j0 - ib;
+    if (j0 > 0 || nright > 0) {
+      const int cnt = j0 + nright;
+      k_laswp2<<<(cnt + 127) / 128, 128, 0, st>>>(Are, Aim, lda, k0, c0, c0 + ib, k0 + nbw, c0, ib, ipiv); w.launches++;
+    }
     if (nright > 0) {
-      k_laswp<<<(nright + 127) / 128, 128, 0, st>>>(Are, Aim, lda, c0 + ib, k0 + nbw, c0, ib, ipiv);
-      w.launches += 1 + launch_trsm(Are, Aim, lda, c0, ib, c0 + ib, k0 + nbw, st);
-      const int mrest = n - c0 - ib;
-      if (mrest > 0) {
-        zgemm_minus_planar(mrest, nright, ib, Are + (long long)c0 * lda + c0 + ib, poff(Aim, (long long)c0 * lda + c0 + ib), lda,
-                           Are + (long long)(c0 + ib) * lda + c0, poff(Aim, (long long)(c0 + ib) * lda + c0), lda,
-                           Are + (long long)(c0 + ib) * lda + c0 + ib, poff(Aim, (long long)(c0 + ib) * lda + c0 + ib), lda, st);
+      if (w.fused_panel_update == 1 || (w.fused_panel_update == 2 && n - c0 <= 16384)) {   // 2 = auto: short panels are latency, tall ones belong on the tensor pipe
+        if (Aim) launch_panel_update<true>(Are, Aim, lda, n, c0, ib, c0 + ib, k0 + nbw, w.pu_arrive, st);
+        else launch_panel_update<false>(Are, Aim, lda, n, c0, ib, c0 + ib, k0 + nbw, w.pu_arrive, st);
         w.launches++;
+      } else {
+        w.launches += launch_trsm(Are, Aim, lda, c0, ib, c0 + ib, k0 + nbw, st);
+        const int mrest = n - c0 - ib;
+        if (mrest > 0) {
+          zgemm_minus_planar(mrest, nright, ib, Are + (long long)c0 * lda + c0 + ib, poff(Aim, (long long)c0 * lda + c0 + ib), lda,
+                             Are + (long long)(c0 + ib) * lda + c0, poff(Aim, (long long)(c0 + ib) * lda + c0), lda,
+                             Are + (long long)(c0 + ib) * lda + c0 + ib, poff(Aim, (long long)(c0 + ib) * lda + c0 + ib), lda, st);
+          w.launches++;
+        }
       }
     }
   }
@@ -780,12 +1061,15 @@ __global__ void k_permute(const double* __restrict__ sre, const double* __restri
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { dre[i] = sre[perm[i]]; if (sim) dim_[i] = sim[perm[i]]; }
 }
-__global__ void __launch_bounds__(TS) k_trsv_diag(const double* __restrict__ Are, const double* __restrict__ Aim, long long lda, int kb, int nbw, double* bre, double* bim, int lower) {
+__global__ void __launch_bounds__(256) k_trsv_diag(const double* __restrict__ Are, const double* __restrict__ Aim, long long lda, int kb, int nbw, double* bre, double* bim, int lower) {
   extern __shared__ __align__(16) double sdiag[];   // [2][TS][TS+1]
   double* sr = sdiag; double* si = sdiag + TS * (TS + 1);
   __shared__ double yr[TS], yi[TS];
   const int i = threadIdx.x;
-  for (int j = 0; j < nbw; j++) if (i < nbw) { sr[j * (TS + 1) + i] = Are[(long long)(kb + j) * lda + kb + i]; si[j * (TS + 1) + i] = Aim ? Aim[(long long)(kb + j) * lda + kb + i] : 0.0; }
+  for (int idx = threadIdx.x; idx < nbw * nbw; idx += blockDim.x) {      // 256 threads fetch the block; the first TS solve
+    const int j = idx / nbw, ii = idx - j * nbw;
+    sr[j * (TS + 1) + ii] = Are[(long long)(kb + j) * lda + kb + ii]; si[j * (TS + 1) + ii] = Aim ? Aim[(long long)(kb + j) * lda + kb + ii] : 0.0;
+  }
   double vr = 0.0, vi = 0.0;
   if (i < nbw) { vr = bre[kb + i]; vi = bim ? bim[kb + i] : 0.0; }
   __syncthreads();
@@ -856,14 +1140,14 @@ int zgetrs_planar(const double* Are, const double* Aim, long long lda, int n, co
     if (bi) cudaMemcpyAsync(bi, tmp + n, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
     for (int kb = 0; kb < n; kb += TS) {
       int nbw = (n - kb < TS) ? n - kb : TS;
-      k_trsv_diag<<<1, TS, dsm, st>>>(Are, Aim, lda, kb, nbw, br, bi, 1);
+      k_trsv_diag<<<1, 256, dsm, st>>>(Are, Aim, lda, kb, nbw, br, bi, 1);
       int r0 = kb + nbw;
       if (r0 < n) k_gemv_update<<<(n - r0 + 63) / 64, 256, 0, st>>>(Are, Aim, lda, r0, n, kb, nbw, br, bi);
     }
     int nblk = (n + TS - 1) / TS;
     for (int b = nblk - 1; b >= 0; b--) {
       int kb = b * TS, nbw = (n - kb < TS) ? n - kb : TS;
-      k_trsv_diag<<<1, TS, dsm, st>>>(Are, Aim, lda, kb, nbw, br, bi, 0);
+      k_trsv_diag<<<1, 256, dsm, st>>>(Are, Aim, lda, kb, nbw, br, bi, 0);
       if (kb > 0) k_gemv_update<<<(kb + 63) / 64, 256, 0, st>>>(Are, Aim, lda, 0, kb, kb, nbw, br, bi);
     }
   }
@@ -1027,7 +1311,7 @@ int zgetrs_dist(DistLU& D) {
       const int nsub = (nbw + TS - 1) / TS;
       for (int sb = nsub - 1; sb >= 0; sb--) {
         const int kb = k0 + sb * TS, w = (k0 + nbw - kb < TS) ? (k0 + nbw - kb) : TS;
-        k_trsv_diag<<<1, TS, dsm, R.main>>>(Are, Aim, lda, kb, w, vre, vim, 0);
+        k_trsv_diag<<<1, 256, dsm, R.main>>>(Are, Aim, lda, kb, w, vre, vim, 0);
         if (kb > 0) k_gemv_update<<<(kb + 63) / 64, 256, 0, R.main>>>(Are, Aim, lda, 0, kb, kb, w, vre, vim);
       }
       k_vec_copy2<<<(nbw + 255) / 256, 256, 0, R.main>>>(R.xfin + k0, R.xfin + lda + k0, vre + k0, vim + k0, nbw);

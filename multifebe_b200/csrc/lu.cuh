@@ -15,12 +15,16 @@ struct LuWork {
   double *cand_data;      // [2][grid][2*32]   candidate rows (re, im)
   double *diag_data;      // [2][2*32]         current diagonal row
   int *info;              // device flag: first zero pivot (1-based), 0 = ok
+  int *pu_arrive;         // [64] arrival counters of k_panel_update (one per column block; self re-arming)
   float ms_panel, ms_swap, ms_trsm, ms_gemm; long long launches; long long gemm_launches; double gemm_flops, gemm_exec_flops;   // algorithmic (8mnk) and executed (6mnk with the 3M kernel) flops of the trailing updates
   cudaEvent_t* evs; int n_evs, n_steps_timed;   // 5 events per block step, recorded without synchronising
   cudaStream_t panel_stream;                    // high-priority stream of the look-ahead panel factorisation
   cudaEvent_t ev_next_cols, ev_panel_done;      // next panel's columns updated / next panel factorised
   cudaEvent_t* pevs;                            // 2 events per block step on the panel stream (panel timing under look-ahead)
   int lookahead, panel_ctas;
+  int fused_panel_update;                      // 1: TRSM + update of the panel columns right of a sub-panel in one kernel (k_panel_update)
+  int cluster_ib;                              // preferred sub-panel width of the cluster kernel (if the slab fits)
+  int cluster, cluster_max_rows;               // CTAs of the cluster-resident panel kernel (0 = grid-wide kernel only); tallest panel it takes
 };
 // sums the per-phase event times of the last timed factorisation (call after the stream has been synchronised)
 void lu_collect_times(LuWork& w);
