@@ -931,12 +931,14 @@ void lu_collect_times(LuWork& w) {
 // interchanges are applied to the rest of the panel, then U12' = inv(L11') A12' and A22' -= L21' U12' inside the panel.
 static int factor_panel(double* Are, double* Aim, long long lda, int n, int k0, int nbw, int* ipiv, LuWork& w, cudaStream_t st) {
   // Sub-panel width of this panel: the cluster kernel needs the slab of a CTA (rows/cluster x ib, one or two planes) in
-  // shared memory; take the configured width if it fits, else 8 columns, else the grid-wide kernel.
+  // shared memory; 32 columns if they fit, else the configured width, else the grid-wide kernel.
   const int planes = Aim ? 2 : 1;
   int ib_panel = w.ib; bool use_cluster = false;
   if (w.cluster > 1 && (n - k0) <= w.cluster_max_rows) {
-    const int cands[3] = {w.cluster_ib, w.ib, 8};           // widest first: every sub-panel launch has a fixed cost
-    for (int t = 0; t < 3 && !use_cluster; t++) {
+    // widest first (every sub-panel launch has a fixed cost); narrower than the configured width never pays: measured, the
+    // cluster kernel beats the grid-wide one only while a CTA's slab holds >= 16 columns (profiles/r01_panel_vs_m.log)
+    const int cands[2] = {w.cluster_ib, w.ib};
+    for (int t = 0; t < 2 && !use_cluster; t++) {
       const int rpc = (n - k0 + w.cluster - 1) / w.cluster;
       if (cands[t] >= 8 && cands[t] <= SP_MAXIB && nbw % cands[t] == 0 &&
           (size_t)planes * cands[t] * (rpc | 1) * sizeof(double) <= (size_t)SP_CLUSTER_SMEM) { ib_panel = cands[t]; use_cluster = true; }
