@@ -28,6 +28,9 @@ if ROOT not in sys.path:
 
 import numpy as np
 
+# NCCL's own log lines (e.g. "NCCL version ..." under NCCL_DEBUG=VERSION) must not land on stdout, which carries the ONE JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 METRIC = "harmonic 3D BEM end-to-end solves/s (assemble + zgetrf + zgetrs per frequency) at N=30258 DOF; assembly Gentries/s beside it"
 N_FREQ = 64
 
