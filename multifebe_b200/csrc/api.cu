@@ -774,7 +774,7 @@ extern "C" int mfb_zsolve(mfb_problem* p, int n, mfb_z* A, int lda, int* ipiv, m
     r = upload_matrix(p, b, n, n, nrhs, bre, bim, ldb, p->rows_permuted ? p->d_rowperm : nullptr); if (r) return r;
   } else if (nrhs != 1) return fail(MFB_ERR_ARG, "mfb_zsolve: device-resident rhs has a single column");
   CK(cudaEventRecord(p->ev[6], st));
-  int e = zgetrs_planar(p->sys.Are, p->sys.Aim, p->lda, n, p->d_perm, bre, bim, ldb, nrhs, st);
+  int e = zgetrs_planar(p->sys.Are, p->sys.Aim, p->lda, n, p->d_perm, bre, bim, ldb, nrhs, st, p->lu.inv);
   if (e) return fail(MFB_ERR_CUDA, std::string("zgetrs_planar: ") + cudaGetErrorString((cudaError_t)e));
   CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
   float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
@@ -794,7 +794,7 @@ extern "C" int mfb_harela3d_solve_frequency(mfb_problem* p, double omega, const 
   if (r) return r;
   cudaStream_t st = p->ctx->stream;
   CK(cudaEventRecord(p->ev[6], st));
-  int e = zgetrs_planar(p->sys.Are, p->sys.Aim, p->lda, p->n_dof, p->d_perm, p->sys.bre, p->sys.bim, p->lda, 1, st);
+  int e = zgetrs_planar(p->sys.Are, p->sys.Aim, p->lda, p->n_dof, p->d_perm, p->sys.bre, p->sys.bim, p->lda, 1, st, p->lu.inv);
   if (e) return fail(MFB_ERR_CUDA, std::string("zgetrs_planar: ") + cudaGetErrorString((cudaError_t)e));
   CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
   float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
@@ -1215,7 +1215,7 @@ extern "C" int mfb_dsolve(mfb_problem* p, int n, double* A, int lda, int* ipiv, 
     r = upload_real(p, b, n, n, nrhs, bre, ldb, p->rows_permuted ? p->d_rowperm : nullptr); if (r) return r;
   } else if (nrhs != 1) return fail(MFB_ERR_ARG, "mfb_dsolve: device-resident rhs has a single column");
   CK(cudaEventRecord(p->ev[6], st));
-  int e = zgetrs_planar(p->sys.Are, nullptr, p->lda, n, p->d_perm, bre, nullptr, ldb, nrhs, st);
+  int e = zgetrs_planar(p->sys.Are, nullptr, p->lda, n, p->d_perm, bre, nullptr, ldb, nrhs, st, p->lu.inv);
   if (e) return fail(MFB_ERR_CUDA, std::string("dgetrs (planar): ") + cudaGetErrorString((cudaError_t)e));
   CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
   float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
@@ -1234,7 +1234,7 @@ extern "C" int mfb_staela3d_solve(mfb_problem* p, double mu, double nu, const do
   if (r) return r;
   cudaStream_t st = p->ctx->stream;
   CK(cudaEventRecord(p->ev[6], st));
-  int e = zgetrs_planar(p->sys.Are, nullptr, p->lda, p->n_dof, p->d_perm, p->sys.bre, nullptr, p->lda, 1, st);
+  int e = zgetrs_planar(p->sys.Are, nullptr, p->lda, p->n_dof, p->d_perm, p->sys.bre, nullptr, p->lda, 1, st, p->lu.inv);
   if (e) return fail(MFB_ERR_CUDA, std::string("dgetrs (planar): ") + cudaGetErrorString((cudaError_t)e));
   CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
   float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;

@@ -451,6 +451,8 @@ __device__ __forceinline__ void block_argmax(double v, int row, double* s_val, i
 }
 
 const int SP_MAXIB = 32;
+const int TS = 64;         // diagonal block of the triangular solves (zgetrs)
+void lu_invert_diagonal_blocks(const double* Are, const double* Aim, long long lda, int n, double* inv, cudaStream_t st);
 const int SP_CLUSTER_SMEM = 200 * 1024;   // dynamic shared memory a CTA of the cluster panel kernel may use for its slab
 
 // CX = false: real matrix (a.Aim == NULL): the imaginary plane is neither read nor written, the pivot is max |re| (idamax).
@@ -894,6 +896,7 @@ int lu_work_alloc(LuWork& w, int n, int nb) {
   A((void**)&w.cand_data, 2 * G * 2 * SP_MAXIB * sizeof(double)); A((void**)&w.diag_data, 2 * 2 * SP_MAXIB * sizeof(double));
   A((void**)&w.info, sizeof(int));
   A((void**)&w.pu_arrive, 64 * sizeof(int));
+  { const char* e_si = getenv("MFB_LU_SOLVE_INV"); w.inv = nullptr; if (e_si && atoi(e_si) != 0) A((void**)&w.inv, (size_t)((n + TS - 1) / TS) * 4 * TS * TS * sizeof(double)); }
   if (e == cudaSuccess) e = cudaMemset(w.pu_arrive, 0, 64 * sizeof(int));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_subpanel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_subpanel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -910,7 +913,7 @@ int lu_work_alloc(LuWork& w, int n, int nb) {
   return (int)e;
 }
 void lu_work_free(LuWork& w) {
-  cudaFree(w.cand_val); cudaFree(w.cand_row); cudaFree(w.cand_data); cudaFree(w.diag_data); cudaFree(w.info); cudaFree(w.pu_arrive);
+  cudaFree(w.cand_val); cudaFree(w.cand_row); cudaFree(w.cand_data); cudaFree(w.diag_data); cudaFree(w.info); cudaFree(w.pu_arrive); cudaFree(w.inv);
   for (int i = 0; i < w.n_evs; i++) cudaEventDestroy(w.evs[i]);
   for (int i = 0; i < 2 * (w.n_evs / 5); i++) cudaEventDestroy(w.pevs[i]);
   cudaEventDestroy(w.ev_next_cols); cudaEventDestroy(w.ev_panel_done); cudaStreamDestroy(w.panel_stream);
@@ -1051,6 +1054,7 @@ int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuW
     } else if (timing) cudaEventRecord(ev[3], st);
     if (timing) { cudaEventRecord(ev[4], st); w.n_steps_timed++; }
   }
+  if (w.inv) lu_invert_diagonal_blocks(Are, Aim, lda, n, w.inv, st);   // for the solves (zgetrs_planar)
   return (int)cudaGetLastError();
 }
 
@@ -1058,7 +1062,6 @@ int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuW
 // Triangular solves (zgetrs, 'N'): b := P b ; L y = b (unit lower) ; U x = y.  Blocked by TS rows: the diagonal block is
 // staged in shared memory, the off-diagonal update is a bandwidth-bound GEMV (64 rows x 4 column groups per CTA).
 // ------------------------------------------------------------------------------------------------------------------
-const int TS = 64;
 __global__ void k_permute(const double* __restrict__ sre, const double* __restrict__ sim, double* dre, double* dim_, const int* __restrict__ perm, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { dre[i] = sre[perm[i]]; if (sim) dim_[i] = sim[perm[i]]; }
@@ -1127,11 +1130,124 @@ __global__ void __launch_bounds__(256) k_gemv_update(const double* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Solves with precomputed inverses of the TS x TS diagonal blocks (computed once per factorisation): a substitution step is
+// then one small matrix-vector product instead of a TS-step serial chain, fused into the kernel that updates the rows
+// below / above.  inv layout: [block][0 = L, 1 = U][plane][TS*TS] column-major.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TS) k_trtri_blocks(const double* __restrict__ Are, const double* __restrict__ Aim, long long lda, int n, double* __restrict__ inv) {
+  extern __shared__ __align__(16) double sd[];      // D[2][TS][TS+1], X[2][TS][TS+1]
+  double* dr = sd; double* di = sd + TS * (TS + 1); double* xr = sd + 2 * TS * (TS + 1); double* xi = sd + 3 * TS * (TS + 1);
+  const int blk = blockIdx.x, upper = blockIdx.y, kb = blk * TS, nbw = min(TS, n - kb), j = threadIdx.x;
+  for (int c = 0; c < nbw; c++) if (j < nbw) { dr[j * (TS + 1) + c] = Are[(long long)(kb + c) * lda + kb + j]; di[j * (TS + 1) + c] = Aim ? Aim[(long long)(kb + c) * lda + kb + j] : 0.0; }
+  for (int i = 0; i < TS; i++) { xr[i * (TS + 1) + j] = 0.0; xi[i * (TS + 1) + j] = 0.0; }     // X[i][j], column j is private to thread j
+  __syncthreads();
+  if (j < nbw) {
+    if (!upper) {                                   // unit lower: x_j = 1, x_i = -sum_{k=j}^{i-1} L[i][k] x_k
+      xr[j * (TS + 1) + j] = 1.0;
+      for (int i = j + 1; i < nbw; i++) {
+        double sr = 0.0, si = 0.0;
+        for (int k = j; k < i; k++) {
+          const double lr = dr[i * (TS + 1) + k], li = di[i * (TS + 1) + k], vr = xr[k * (TS + 1) + j], vi = xi[k * (TS + 1) + j];
+          sr += lr * vr - li * vi; si += lr * vi + li * vr;
+        }
+        xr[i * (TS + 1) + j] = -sr; xi[i * (TS + 1) + j] = -si;
+      }
+    } else {                                        // upper: x_j = 1/U[j][j], x_i = -(sum_{k=i+1}^{j} U[i][k] x_k) / U[i][i]
+      auto cdiv = [](double ar, double ai, double br, double bi, double& qr, double& qi) {
+        if (fabs(br) >= fabs(bi)) { double t = bi / br, d = br + bi * t; qr = (ar + ai * t) / d; qi = (ai - ar * t) / d; }
+        else { double t = br / bi, d = br * t + bi; qr = (ar * t + ai) / d; qi = (ai * t - ar) / d; }
+      };
+      double qr, qi; cdiv(1.0, 0.0, dr[j * (TS + 1) + j], di[j * (TS + 1) + j], qr, qi);
+      xr[j * (TS + 1) + j] = qr; xi[j * (TS + 1) + j] = qi;
+      for (int i = j - 1; i >= 0; i--) {
+        double sr = 0.0, si = 0.0;
+        for (int k = i + 1; k <= j; k++) {
+          const double ur = dr[i * (TS + 1) + k], ui = di[i * (TS + 1) + k], vr = xr[k * (TS + 1) + j], vi = xi[k * (TS + 1) + j];
+          sr += ur * vr - ui * vi; si += ur * vi + ui * vr;
+        }
+        cdiv(-sr, -si, dr[i * (TS + 1) + i], di[i * (TS + 1) + i], qr, qi);
+        xr[i * (TS + 1) + j] = qr; xi[i * (TS + 1) + j] = qi;
+      }
+    }
+  }
+  __syncthreads();
+  double* o = inv + ((size_t)blk * 2 + upper) * 2 * TS * TS;
+  for (int c = 0; c < TS; c++) { o[c * TS + j] = xr[j * (TS + 1) + c]; o[TS * TS + c * TS + j] = xi[j * (TS + 1) + c]; }   // o[col c][row j]
+}
+// one block step: x_k = inv(D_k) w_k (redone by every CTA; CTA 0 stores it to xout), then w[rows of this CTA] -= A[rows, kb:kb+nbw) x_k
+__global__ void __launch_bounds__(256) k_solve_step(const double* __restrict__ Are, const double* __restrict__ Aim, long long lda, const double* __restrict__ invb, int kb, int nbw,
+                                                    int r0, int r1, double* wre, double* wim, double* xore, double* xoim) {
+  __shared__ double xr[TS], xi[TS], vr[TS], vi[TS];
+  __shared__ double pr[4][TS], pi[4][TS];
+  const int tid = threadIdx.x, li = tid & 63, part = tid >> 6;
+  if (tid < TS) { vr[tid] = (tid < nbw) ? wre[kb + tid] : 0.0; vi[tid] = (tid < nbw && wim) ? wim[kb + tid] : 0.0; }
+  __syncthreads();
+  {
+    double sr = 0.0, si = 0.0;
+    const double* ir = invb; const double* ii = invb + TS * TS;
+#pragma unroll 4
+    for (int c = part * 16; c < part * 16 + 16; c++) {
+      const double ar = ir[c * TS + li], ai = ii[c * TS + li];
+      sr += ar * vr[c] - ai * vi[c]; si += ar * vi[c] + ai * vr[c];
+    }
+    pr[part][li] = sr; pi[part][li] = si;
+  }
+  __syncthreads();
+  if (tid < TS) { xr[tid] = pr[0][tid] + pr[1][tid] + pr[2][tid] + pr[3][tid]; xi[tid] = pi[0][tid] + pi[1][tid] + pi[2][tid] + pi[3][tid]; }
+  __syncthreads();
+  if (blockIdx.x == 0 && tid < nbw) { xore[kb + tid] = xr[tid]; if (xoim) xoim[kb + tid] = xi[tid]; }
+  const int i = r0 + blockIdx.x * 64 + li;
+  double sr = 0.0, si = 0.0;
+  if (i < r1) {
+    const int per = (nbw + 3) / 4, j0 = part * per, j1 = min(j0 + per, nbw);
+#pragma unroll 8
+    for (int j = j0; j < j1; j++) {
+      const double ar = Are[(long long)(kb + j) * lda + i], ai = Aim ? Aim[(long long)(kb + j) * lda + i] : 0.0;
+      sr += ar * xr[j] - ai * xi[j]; si += ar * xi[j] + ai * xr[j];
+    }
+  }
+  __syncthreads();
+  pr[part][li] = sr; pi[part][li] = si;
+  __syncthreads();
+  if (part == 0 && i < r1) {
+    wre[i] -= pr[0][li] + pr[1][li] + pr[2][li] + pr[3][li];
+    if (wim) wim[i] -= pi[0][li] + pi[1][li] + pi[2][li] + pi[3][li];
+  }
+}
+void lu_invert_diagonal_blocks(const double* Are, const double* Aim, long long lda, int n, double* inv, cudaStream_t st) {
+  const size_t sm = (size_t)4 * TS * (TS + 1) * sizeof(double);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_trtri_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); attr = true; }
+  k_trtri_blocks<<<dim3((n + TS - 1) / TS, 2), TS, sm, st>>>(Are, Aim, lda, n, inv);
+}
+
 int zgetrs_planar(const double* Are, const double* Aim, long long lda, int n, const int* ipiv_host_perm_dev, double* bre, double* bim, long long ldb,
-                  int nrhs, cudaStream_t st) {
+                  int nrhs, cudaStream_t st, const double* inv) {
   // ipiv_host_perm_dev: device array perm[i] = source row of row i after all interchanges (built on the host from ipiv)
   double* tmp = nullptr;
   if (cudaMalloc((void**)&tmp, (size_t)2 * n * sizeof(double)) != cudaSuccess) return (int)cudaGetLastError();
+  if (inv) {   // diagonal-block inverses available: one fused launch per block step
+    const int nblk = (n + TS - 1) / TS;
+    for (int c = 0; c < nrhs; c++) {
+      double* br = bre + (long long)c * ldb; double* bi = poff(bim, (long long)c * ldb);
+      double* wr = tmp; double* wi = bim ? tmp + n : nullptr;
+      k_permute<<<(n + 255) / 256, 256, 0, st>>>(br, bi, wr, wi, ipiv_host_perm_dev, n);
+      for (int b = 0; b < nblk; b++) {          // L y = P b: w = tmp is the running right-hand side, y goes to b
+        const int kb = b * TS, nbw = (n - kb < TS) ? n - kb : TS, r0 = kb + nbw;
+        k_solve_step<<<r0 < n ? (n - r0 + 63) / 64 : 1, 256, 0, st>>>(Are, Aim, lda, inv + ((size_t)b * 2 + 0) * 2 * TS * TS, kb, nbw, r0, n, wr, wi, br, bi);
+      }
+      for (int b = nblk - 1; b >= 0; b--) {     // U x = y: b (holding y) is the running right-hand side, x goes to tmp
+        const int kb = b * TS, nbw = (n - kb < TS) ? n - kb : TS;
+        k_solve_step<<<kb > 0 ? (kb + 63) / 64 : 1, 256, 0, st>>>(Are, Aim, lda, inv + ((size_t)b * 2 + 1) * 2 * TS * TS, kb, nbw, 0, kb, br, bi, wr, wi);
+      }
+      cudaMemcpyAsync(br, wr, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
+      if (bi) cudaMemcpyAsync(bi, wi, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    return (int)cudaGetLastError();
+  }
   const size_t dsm = (size_t)2 * TS * (TS + 1) * sizeof(double);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(k_trsv_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm); attr = true; }

@@ -15,6 +15,7 @@ struct LuWork {
   double *cand_data;      // [2][grid][2*32]   candidate rows (re, im)
   double *diag_data;      // [2][2*32]         current diagonal row
   int *info;              // device flag: first zero pivot (1-based), 0 = ok
+  double *inv;            // inverses of the 64 x 64 diagonal blocks of L and U of the last factorisation (NULL: substitution kernels)
   int *pu_arrive;         // [64] arrival counters of k_panel_update (one per column block; self re-arming)
   float ms_panel, ms_swap, ms_trsm, ms_gemm; long long launches; long long gemm_launches; double gemm_flops, gemm_exec_flops;   // algorithmic (8mnk) and executed (6mnk with the 3M kernel) flops of the trailing updates
   cudaEvent_t* evs; int n_evs, n_steps_timed;   // 5 events per block step, recorded without synchronising
@@ -35,8 +36,9 @@ void lu_work_free(LuWork& w);
 // In-place LU of the n x n planar matrix; ipiv (device, 1-based, LAPACK convention).  Returns cudaError as int (0 ok).
 int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuWork& w, cudaStream_t st, bool timing);
 // Solve with the factors: b (planar, n x nrhs, ldb) overwritten by the solution.
+// inv = LuWork::inv of the factorisation (or NULL: serial substitution on the diagonal blocks).
 int zgetrs_planar(const double* Are, const double* Aim, long long lda, int n, const int* ipiv, double* bre, double* bim, long long ldb,
-                  int nrhs, cudaStream_t st);
+                  int nrhs, cudaStream_t st, const double* inv = nullptr);
 // C -= A*B on planar storage (the trailing-matrix update; FP64 tensor pipe, mma.sync m8n8k4).  k must be a multiple of 4.
 void zgemm_minus_planar(int m, int n, int k, const double* Are, const double* Aim, long long lda, const double* Bre, const double* Bim,
                         long long ldb, double* Cre, double* Cim, long long ldc, cudaStream_t st);

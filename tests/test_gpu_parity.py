@@ -392,3 +392,15 @@ def test_static_full_size_properties_config2(gpu_ctx, oracle_lib):
     lam2mu = 2.0 * SMAT.mu_r * SMAT.nu_r / (1.0 - 2.0 * SMAT.nu_r) + 2.0 * SMAT.mu_r
     assert np.abs(u[:, 0].real - md.node_x[:, 0] / lam2mu).max() * lam2mu < 2e-5
     pr.close()
+
+
+@pytest.mark.parametrize("et,m", [(shape.TRI3, 2), (shape.TRI6, 1), (shape.QUAD4, 2), (shape.QUAD8, 1), (shape.QUAD9, 1)])
+def test_static_against_committed_golden_vectors(gpu_ctx, et, m):
+    from multifebe_b200 import capi
+    gold = np.load(os.path.join(HERE, "golden", "oracle_static.npz"))
+    md = Model(cube_mesh(m, et), cube_bcs())
+    pr = capi.Problem(gpu_ctx, md)
+    A, b = pr.build_lse_mechanics_bem_staela(SMAT)
+    assert relerr(A, gold[f"A:{et}:{m}"]) < TOL_A and relerr(b, gold[f"b:{et}:{m}"]) < TOL_A
+    assert relerr(pr.solve_static(SMAT), gold[f"x:{et}:{m}"]) < TOL_X
+    pr.close()

@@ -58,3 +58,18 @@ def test_static_rigid_body_identity(oracle_lib):
     for k in range(3):
         v = np.zeros(md.n_dof); v[md.col_u[:, k]] = 1.0
         assert np.abs(A @ v).max() < 5e-6 * np.abs(A).max()
+
+
+def test_static_oracle_reproduces_the_committed_vectors(oracle_lib):
+    """tests/golden/oracle_static.npz (tools/gen_golden.py static): regression vectors of the static oracle."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_static.npz"))
+    for et, m in [(shape.TRI3, 2), (shape.QUAD9, 1)]:
+        md = Model(cube_mesh(m, et), cube_bcs())
+        o = oracle_lib.Oracle(md)
+        A, b, _ = o.assemble_static(MAT)
+        assert np.abs(A - gold[f"A:{et}:{m}"]).max() <= 1e-13 * np.abs(A).max() and np.abs(b - gold[f"b:{et}:{m}"]).max() <= 1e-13 * np.abs(b).max()
+        for key in ("reg", "adp", "sing"):
+            v = gold[f"pair:{et}:{key}"]; c, e, mode = int(v[0]), int(v[1]), int(v[2]); nn = md.elem_ptr[e + 1] - md.elem_ptr[e]
+            h, g, mode2 = o.pair_static(e, md.colloc_x[c], MAT)
+            assert mode2 == mode and np.allclose(h.ravel(), v[3:3 + 9 * nn], rtol=0, atol=1e-13 * np.abs(v[3:]).max())
