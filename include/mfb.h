@@ -59,8 +59,8 @@ void mfb_finalize(mfb_ctx* ctx);
  *   isoparametric: geometric == functional nodes, continuous); elem_reversed[n_elem] = region%boundary_reversion;
  *   collocation points in the order of the reference's kb_col/ke_col/kn_col loop (build_lse_mechanics_bem_harela.f90:1118-1136):
  *   colloc_x[3*n_colloc] = x_i_sbie / x_i_sbie_mca, colloc_node = sn_col (its 3 rows receive the equation), colloc_elem /
- *   colloc_kn = owning element and local node (free-term pass :273-747), colloc_xi[2*n_colloc] = xi_i_sbie_mca, or (-9,-9)
- *   for a nodal SBIE point; row/col_u/col_t/ctype[3*n_node] = node%row(k,1), node%col(k,1), node%col(3+k,1), node%ctype(k,1)
+ *   colloc_kn = owning element and local node (free-term pass :273-747; colloc_elem = -1: a point off the boundary, no
+ *   free term), colloc_xi[2*n_colloc] = xi_i_sbie_mca, or (-9,-9) for a nodal SBIE point; row/col_u/col_t/ctype[3*n_node] = node%row(k,1), node%col(k,1), node%col(3+k,1), node%ctype(k,1)
  *   (0-based, -1 = none; ctype 0: u known, 1: t known) from build_auxiliary_variables_mechanics_harmonic.f90:151-198;
  *   settings = [settings] section defaults of src/read_settings.f90:74-216. */
 int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
@@ -101,6 +101,11 @@ int mfb_get_solution(mfb_problem* problem, mfb_z* x);
  * zgerfs report, src/solve_lse_c.f90:191-206): componentwise backward error berr = max_i |Ax-b|_i / (|A||x|+|b|)_i and
  * max|Ax-b| / max(|A||x|+|b|) for a candidate solution x; selected entries A(rows[i], cols[i]) (0-based). */
 int mfb_residual(mfb_problem* problem, const mfb_z* x, double* berr, double* rel_resid);
+/* r[n_dof] = A x - b of the same system.  Interior points (displacement part): a problem whose collocation
+ * points lie inside the region (colloc_elem = -1 marks them: no free term; their rows belong to dummy nodes that no element
+ * uses) assembles Somigliana's identity, so u(x_ip) = -(A x - b) at those rows with x = the boundary solution -- the values
+ * the reference stores in internalpoint%value_c(k,0) (src/calculate_internal_points_mechanics_bem_harela.f90:160-178). */
+int mfb_residual_vector(mfb_problem* problem, const mfb_z* x, mfb_z* r);
 int mfb_get_entries(mfb_problem* problem, int n, const int* rows, const int* cols, mfb_z* out);
 
 /* Plan statistics and per-phase device timings (CUDA events) of the last call; see mfb_stat_id. */

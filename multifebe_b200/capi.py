@@ -189,6 +189,13 @@ class Problem:
         _check(lib().mfb_residual(self.h, _p(xx), C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def residual_vector(self, x):
+        """r = A x - b of the assembled, unfactorised device-resident system (host order)."""
+        xx = np.ascontiguousarray(x, dtype=np.complex128)
+        r = np.zeros(self.m.n_dof, dtype=np.complex128)
+        _check(lib().mfb_residual_vector(self.h, _p(xx), _p(r)))
+        return r
+
     def get_entries(self, rows, cols):
         r = np.ascontiguousarray(rows, dtype=np.int32); c = np.ascontiguousarray(cols, dtype=np.int32)
         out = np.zeros(len(r), dtype=np.complex128)
@@ -264,3 +271,32 @@ class Problem:
         out = np.zeros(len(c), dtype=np.int32)
         _check(lib().mfb_plan_modes(self.h, C.c_int(len(c)), _p(c), _p(e), _p(out)))
         return out
+
+
+class InternalPoints:
+    """Displacements at points inside the region from the boundary solution (the displacement part of the reference's
+    calculate_internal_points_mechanics_bem_harela, src/calculate_internal_points_mechanics_bem_harela.f90:160-178): a second
+    problem on the same mesh whose collocation points are the interior points (host.InternalPointsModel)."""
+
+    def __init__(self, ctx, model, points):
+        from .host import InternalPointsModel
+        self.base = model
+        self.ipm = InternalPointsModel(model, points)
+        self.pr = Problem(ctx, self.ipm)
+
+    def close(self):
+        self.pr.close()
+
+    def _u(self, x):
+        xa = np.zeros(self.ipm.n_dof, dtype=np.complex128); xa[:self.base.n_dof] = x
+        r = self.pr.residual_vector(xa)
+        return -r[self.base.n_dof:].reshape(-1, 3)
+
+    def displacements(self, omega, mat, x):
+        """u (n_points, 3) complex at frequency omega for the boundary solution vector x of that frequency."""
+        self.pr.build_lse_mechanics_bem_harela(omega, mat, want_host=False)
+        return self._u(x)
+
+    def displacements_static(self, mat, x):
+        self.pr.build_lse_mechanics_bem_staela(mat, want_host=False)
+        return self._u(np.asarray(x, dtype=np.complex128)).real

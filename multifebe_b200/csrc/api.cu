@@ -503,6 +503,7 @@ extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x
     std::vector<int> f_cpos, f_slot, f_jk, f_l; std::vector<double> f_val;
     for (int c = 0; c < n_colloc; c++) {
       int e = colloc_elem[c], kn = colloc_kn[c], sn = colloc_node[c];
+      if (e == -1) continue;   // a point off the boundary (interior point of the region): Somigliana's identity has no free term there
       if (e < 0 || e >= n_elem || kn < 0 || kn >= p->elems[e].nn) { mfb_problem_free(p); return fail(MFB_ERR_ARG, "mfb_harela3d_setup: invalid colloc_elem/colloc_kn"); }
       const mfbh::Elem& el = p->elems[e];
       int cpos = p->cpos_of_colloc[c], slot = p->slot_of_elem[e];
@@ -1241,4 +1242,27 @@ extern "C" int mfb_staela3d_solve(mfb_problem* p, double mu, double nu, const do
   p->assembled = false;
   if (!x) return MFB_OK;
   return download_real(p, p->sys.bre, p->lda, p->n_dof, 1, x, p->n_dof, p->d_colperm, nullptr);
+}
+
+// r = A x - b of the assembled, not yet factorised, device-resident system (host row and column order).  With collocation points
+// placed INSIDE the region (colloc_elem = -1 at set-up: no free term) the rows of those points are Somigliana's identity, i.e.
+// u(x_ip) = sum_e (g t - h u) = -(A x - b) at those rows: the displacement part of the reference's interior-point pass
+// (src/calculate_internal_points_mechanics_bem_harela.f90:160-178 with fbem_bem_harela3d_sbie_auto, :372-420).
+extern "C" int mfb_residual_vector(mfb_problem* p, const mfb_z* x, mfb_z* r) {
+  if (!p || !x || !r) return fail(MFB_ERR_ARG, "mfb_residual_vector: null argument");
+  if (!p->assembled) return fail(MFB_ERR_ARG, "mfb_residual_vector: no assembled (unfactorised) system is resident");
+  CK(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  const int n = p->n_dof;
+  double* d; CK(cudaMalloc((void**)&d, (size_t)5 * n * sizeof(double)));
+  std::vector<double> hx(2 * (size_t)n);
+  for (int i = 0; i < n; i++) { const int q = p->rows_permuted ? p->colperm[i] : i; hx[q] = x[i].re; hx[n + q] = x[i].im; }
+  CK(cudaMemcpyAsync(d, hx.data(), (size_t)2 * n * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(d + 2 * (size_t)n, 0, (size_t)3 * n * 8, st));
+  launch_residual(p->sys, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, d + 4 * (size_t)n, st);
+  std::vector<double> h(2 * (size_t)n);
+  CK(cudaMemcpyAsync(h.data(), d + 2 * (size_t)n, (size_t)2 * n * 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+  cudaFree(d);
+  for (int i = 0; i < n; i++) { const int q = p->rows_permuted ? p->rowperm[i] : i; r[i].re = h[q]; r[i].im = h[n + q]; }
+  return MFB_OK;
 }

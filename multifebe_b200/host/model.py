@@ -153,3 +153,36 @@ def column_analytic_u(x1, omega, mat, L=1.0, P=1.0):
     """u1(x1) of the clamped-free P-wave column (docs/examples/ME-TH-EL-001/doc_src/ME-TH-EL-001.tex:32-56)."""
     k = omega / mat.c1
     return -P * (np.exp(-1j * k * x1) - np.exp(1j * k * x1)) / ((mat.lam + 2 * mat.mu) * 1j * k * (np.exp(-1j * k * L) + np.exp(1j * k * L)))
+
+
+class InternalPointsModel:
+    """The flat arrays of a problem whose collocation points are points INSIDE the region of `model` (reference: [internal points]
+    section, src/calculate_internal_points_mechanics_bem_harela.f90): same elements, boundary conditions and columns as the
+    boundary problem; every interior point gets a dummy node (used by no element) that owns its three rows, placed after the
+    boundary rows; colloc_elem = -1 tells the library that there is no free term."""
+
+    def __init__(self, model, points):
+        m = model
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        nip = len(pts)
+        self.base, self.points, self.n_points = m, pts, nip
+        self.mesh = m.mesh
+        self.n_node, self.n_elem = m.n_node + nip, m.n_elem
+        self.node_x = np.ascontiguousarray(np.vstack([m.node_x, pts]))
+        self.etype, self.elem_ptr, self.elem_node, self.elem_reversed = m.etype, m.elem_ptr, m.elem_node, m.elem_reversed
+        self.qsi_relative_error, self.qsi_ns_max = m.qsi_relative_error, m.qsi_ns_max
+        self.precalset_gln, self.geometric_tolerance = m.precalset_gln, m.geometric_tolerance
+        self.n_dof = m.n_dof + 3 * nip
+        dummy_rows = (m.n_dof + np.arange(3 * nip, dtype=np.int32)).reshape(nip, 3)
+        none = -np.ones((nip, 3), dtype=np.int32)
+        self.row = np.ascontiguousarray(np.vstack([m.row, dummy_rows]), dtype=np.int32)
+        self.col_u = np.ascontiguousarray(np.vstack([m.col_u, none]), dtype=np.int32)
+        self.col_t = np.ascontiguousarray(np.vstack([m.col_t, none]), dtype=np.int32)
+        self.ctype = np.ascontiguousarray(np.vstack([m.ctype, np.ones((nip, 3), dtype=np.int32)]), dtype=np.int32)
+        self.cvalue = np.ascontiguousarray(np.vstack([m.cvalue, np.zeros((nip, 3), dtype=np.complex128)]))
+        self.colloc_x = pts
+        self.colloc_node = (m.n_node + np.arange(nip)).astype(np.int32)
+        self.colloc_elem = -np.ones(nip, dtype=np.int32)
+        self.colloc_kn = np.zeros(nip, dtype=np.int32)
+        self.colloc_xi = np.full((nip, 2), NODAL_XI_MARK, dtype=np.float64)
+        self.n_colloc = nip

@@ -1,0 +1,74 @@
+"""Displacements at interior points (displacement part): Somigliana's identity u(x) = sum_e (g t - h u)
+with the same integrators as the boundary equations (src/calculate_internal_points_mechanics_bem_harela.f90:160-178, :372-420).
+CPU: the composition from oracle pair integrals against exact solutions.  GPU: the library against that composition."""
+import numpy as np
+import pytest
+from multifebe_b200.host import Model, Material, InternalPointsModel, cube_mesh, cube_bcs, column_analytic_u, shape
+
+MAT = Material(1.0, 1.0, 0.25, 0.03)
+SMAT = Material(1.0, 1.3, 0.25, 0.0)
+PTS = np.array([[0.5, 0.5, 0.5], [0.2, 0.7, 0.4], [0.93, 0.5, 0.5], [0.31, 0.08, 0.77], [0.5, 0.5, 0.985]])   # two of them close to the boundary
+
+
+def oracle_interior_u(o, md, x, pts, pair):
+    u, t = md.nodal_solution(x)
+    out = np.zeros((len(pts), 3), dtype=np.complex128)
+    for ip, xp in enumerate(pts):
+        for e in range(md.n_elem):
+            h, g = pair(e, xp)
+            nodes = md.mesh.conn[e]
+            out[ip] += np.einsum("jlk,jk->l", g, t[nodes]) - np.einsum("jlk,jk->l", h, u[nodes])
+    return out
+
+
+def test_interior_points_model_layout():
+    md = Model(cube_mesh(2, shape.TRI3), cube_bcs())
+    ipm = InternalPointsModel(md, PTS)
+    assert ipm.n_dof == md.n_dof + 15 and ipm.n_node == md.n_node + 5 and ipm.n_colloc == 5
+    assert np.all(ipm.colloc_elem == -1) and np.all(ipm.colloc_node >= md.n_node)
+    assert np.array_equal(ipm.row[:md.n_node], md.row) and ipm.row[md.n_node:].min() == md.n_dof
+    assert len(set(ipm.row.ravel().tolist())) == ipm.n_dof            # every row owned once
+
+
+def test_static_interior_displacements_exact(oracle_lib):
+    md = Model(cube_mesh(3, shape.QUAD4), cube_bcs())
+    o = oracle_lib.Oracle(md)
+    A, b, _ = o.assemble_static(SMAT)
+    x, _, _ = oracle_lib.lu_solve_real(A, b)
+    ui = oracle_interior_u(o, md, x, PTS, lambda e, xp: o.pair_static(e, xp, SMAT)[:2])
+    lam2mu = 2.0 * SMAT.mu_r * SMAT.nu_r / (1.0 - 2.0 * SMAT.nu_r) + 2.0 * SMAT.mu_r
+    assert np.abs(ui[:, 0].real - PTS[:, 0] / lam2mu).max() * lam2mu < 5e-5 and np.abs(ui[:, 1:]).max() * lam2mu < 5e-5
+
+
+def test_harmonic_interior_displacements_follow_the_column_solution(oracle_lib):
+    md = Model(cube_mesh(5, shape.QUAD9), cube_bcs())
+    o = oracle_lib.Oracle(md)
+    omega = 2.0
+    A, b, _ = o.assemble(omega, MAT)
+    x, _, _ = oracle_lib.lu_solve(A, b)
+    ui = oracle_interior_u(o, md, x, PTS[:3], lambda e, xp: o.pair(e, xp, omega, MAT)[:2])
+    ua = column_analytic_u(PTS[:3, 0], omega, MAT)
+    assert np.abs(ui[:, 0] - ua).max() < 2e-3 * np.abs(ua).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("et,m", [(shape.TRI3, 4), (shape.QUAD9, 2), (shape.QUAD4, 3)])
+def test_gpu_interior_displacements_match_the_oracle_composition(gpu_ctx, oracle_lib, et, m):
+    from multifebe_b200 import capi
+    md = Model(cube_mesh(m, et), cube_bcs())
+    pr = capi.Problem(gpu_ctx, md)
+    ip = capi.InternalPoints(gpu_ctx, md, PTS)
+    o = oracle_lib.Oracle(md)
+    omega = 3.0
+    x = pr.solve_frequency(omega, MAT)
+    ug = ip.displacements(omega, MAT, x)
+    uo = oracle_interior_u(o, md, x, PTS, lambda e, xp: o.pair(e, xp, omega, MAT)[:2])
+    assert np.abs(ug - uo).max() < 1e-10 * np.abs(uo).max()
+    xs = pr.solve_static(SMAT)
+    us = ip.displacements_static(SMAT, xs)
+    uso = oracle_interior_u(o, md, xs.astype(np.complex128), PTS, lambda e, xp: o.pair_static(e, xp, SMAT)[:2])
+    assert np.abs(us - uso.real).max() < 1e-10 * np.abs(uso).max()
+    lam2mu = 2.0 * SMAT.mu_r * SMAT.nu_r / (1.0 - 2.0 * SMAT.nu_r) + 2.0 * SMAT.mu_r
+    if et != shape.TRI3 or m >= 4:
+        assert np.abs(us[:, 0] - PTS[:, 0] / lam2mu).max() * lam2mu < 1e-4
+    ip.close(); pr.close()
