@@ -896,7 +896,7 @@ int lu_work_alloc(LuWork& w, int n, int nb) {
   A((void**)&w.cand_data, 2 * G * 2 * SP_MAXIB * sizeof(double)); A((void**)&w.diag_data, 2 * 2 * SP_MAXIB * sizeof(double));
   A((void**)&w.info, sizeof(int));
   A((void**)&w.pu_arrive, 64 * sizeof(int));
-  { const char* e_si = getenv("MFB_LU_SOLVE_INV"); w.inv = nullptr; if (e_si && atoi(e_si) != 0) A((void**)&w.inv, (size_t)((n + TS - 1) / TS) * 4 * TS * TS * sizeof(double)); }
+  { const char* e_si = getenv("MFB_LU_SOLVE_INV"); w.inv = nullptr; if (!e_si || atoi(e_si) != 0) A((void**)&w.inv, (size_t)((n + TS - 1) / TS) * 4 * TS * TS * sizeof(double)); }
   if (e == cudaSuccess) e = cudaMemset(w.pu_arrive, 0, 64 * sizeof(int));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_subpanel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_subpanel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
