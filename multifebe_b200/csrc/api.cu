@@ -986,6 +986,7 @@ static int dist_setup(mfb_problem* p, int rank, int nranks, bool loopback, const
   CK(cudaMalloc((void**)&d.d_mask, (size_t)n_tiles));
   CK(cudaMalloc((void**)&d.bsum, (size_t)2 * p->lda * sizeof(double)));
   d.lu.n = n; d.lu.nb = nb; d.lu.nblk = (n + nb - 1) / nb; d.lu.P = nranks; d.lu.lda = p->lda; d.lu.comm = d.comm; d.lu.ms_lu = d.lu.ms_solve = 0.f;
+  { const char* e = getenv("MFB_DIST_OWNER_WAITS"); d.lu.owner_waits_for_panel = e ? atoi(e) : 1; }
   const int n_local = loopback ? nranks : 1;
   d.lu.r.resize(n_local);
   for (int i = 0; i < n_local; i++) {

@@ -1282,27 +1282,27 @@ int zgetrs_planar(const double* Are, const double* Aim, long long lda, int n, co
 // ------------------------------------------------------------------------------------------------------------------
 int dist_rank_alloc(DistRank& R, int rank, int n, long long lda, int nb, int P, cudaStream_t main_stream, bool separate_comm) {
   R.rank = rank; R.ncl = dist_ncols_local(n, nb, P, rank); R.gemm_flops = 0.0;
-  R.Lre = R.Lim = nullptr; R.pbuf[0] = R.pbuf[1] = nullptr; R.xfin = nullptr; R.ipiv = nullptr;
+  R.Lre = R.Lim = nullptr; R.pbuf[0] = R.pbuf[1] = R.pbuf[2] = nullptr; R.xfin = nullptr; R.ipiv = nullptr;
   cudaError_t e = cudaSuccess;
   auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
   double* L = nullptr;
   A((void**)&L, (size_t)2 * lda * (R.ncl + 1) * sizeof(double));
   R.Lre = L; R.Lim = L + (size_t)lda * (R.ncl + 1);
-  for (int i = 0; i < 2; i++) A((void**)&R.pbuf[i], (size_t)2 * nb * lda * sizeof(double) + (size_t)nb * sizeof(int) + 16);
+  for (int i = 0; i < 3; i++) A((void**)&R.pbuf[i], (size_t)2 * nb * lda * sizeof(double) + (size_t)nb * sizeof(int) + 16);
   A((void**)&R.xfin, (size_t)2 * lda * sizeof(double));
   A((void**)&R.ipiv, (size_t)n * sizeof(int));
   if (e != cudaSuccess) return (int)e;
   int le = lu_work_alloc(R.w, n, nb);
   if (le) return le;
   cudaEventCreateWithFlags(&R.ev_panel, cudaEventDisableTiming); cudaEventCreateWithFlags(&R.ev_cols, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&R.ev_free, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&R.ev_free[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&R.ev_free[1], cudaEventDisableTiming);
   R.main = main_stream; R.comm = separate_comm ? R.w.panel_stream : main_stream;
   return 0;
 }
 void dist_rank_free(DistRank& R) {
-  cudaFree(R.Lre); cudaFree(R.pbuf[0]); cudaFree(R.pbuf[1]); cudaFree(R.xfin); cudaFree(R.ipiv);
+  cudaFree(R.Lre); cudaFree(R.pbuf[0]); cudaFree(R.pbuf[1]); cudaFree(R.pbuf[2]); cudaFree(R.xfin); cudaFree(R.ipiv);
   lu_work_free(R.w);
-  cudaEventDestroy(R.ev_panel); cudaEventDestroy(R.ev_cols); cudaEventDestroy(R.ev_free);
+  cudaEventDestroy(R.ev_panel); cudaEventDestroy(R.ev_cols); cudaEventDestroy(R.ev_free[0]); cudaEventDestroy(R.ev_free[1]);
 }
 
 int zgetrf_dist(DistLU& D) {
@@ -1310,33 +1310,41 @@ int zgetrf_dist(DistLU& D) {
   const long long lda = D.lda;
   std::vector<int> ranks(NL); std::vector<void*> bufs(NL); std::vector<cudaStream_t> sts(NL);
   for (int i = 0; i < NL; i++) { ranks[i] = D.r[i].rank; sts[i] = D.r[i].comm; D.r[i].gemm_flops = 0.0; D.r[i].w.launches = 0; cudaMemsetAsync(D.r[i].w.info, 0, sizeof(int), D.r[i].main); }
+  // MFB_DIST_TRACE=<file prefix>: per-step CUDA events of this rank (main stream: panel received, next-panel columns updated,
+  // step finished; panel stream: panel factorised + packed, broadcast finished), written as CSV after the factorisation
+  const char* trace = (NL == 1) ? getenv("MFB_DIST_TRACE") : nullptr;
+  std::vector<cudaEvent_t> tev;
+  if (trace) { tev.resize((size_t)6 * (nblk + 1)); for (auto& e : tev) cudaEventCreate(&e); cudaEventRecord(tev[0], D.r[0].main); }
+  auto mark = [&](int k, int which, cudaStream_t st) { if (trace) cudaEventRecord(tev[(size_t)6 * (k + 1) + which], st); };
   auto width = [&](int k) { return (n - k * nb < nb) ? (n - k * nb) : nb; };
   // first local column that belongs to a global block > k
   auto nright = [&](const DistRank& R, int k) { int c = (k >= R.rank) ? ((k - R.rank) / P + 1) * nb : 0; return c < R.ncl ? c : R.ncl; };
   auto panel_bytes = [&](int k) { const long long m = n - (long long)k * nb, mp = (m + 1) & ~1ll; return (size_t)2 * width(k) * mp * sizeof(double) + (size_t)width(k) * sizeof(int); };
-  // owner: factorise panel k in place (stream R.comm), pack rows k0..n + pivots into pbuf[k & 1]
+  // owner: factorise panel k in place (stream R.comm), pack rows k0..n + pivots into pbuf[k % 3]
   auto factor_and_pack = [&](DistRank& R, int k) -> int {
     const int k0 = k * nb, nbw = width(k), lc = dist_local_col(k, P, nb);
     const long long m = n - k0, mp = (m + 1) & ~1ll;
     double* Are = R.Lre + ((long long)lc - k0) * lda; double* Aim = R.Lim + ((long long)lc - k0) * lda;   // global column k0 -> local column lc
     int e = factor_panel(Are, Aim, lda, n, k0, nbw, R.ipiv, R.w, R.comm);
     if (e) return e;
-    double* pb = R.pbuf[k & 1];
+    mark(k, 3, R.comm);
+    double* pb = R.pbuf[k % 3];
     cudaMemcpy2DAsync(pb, (size_t)mp * 8, R.Lre + (long long)lc * lda + k0, (size_t)lda * 8, (size_t)m * 8, nbw, cudaMemcpyDeviceToDevice, R.comm);
     cudaMemcpy2DAsync(pb + (size_t)nbw * mp, (size_t)mp * 8, R.Lim + (long long)lc * lda + k0, (size_t)lda * 8, (size_t)m * 8, nbw, cudaMemcpyDeviceToDevice, R.comm);
     cudaMemcpyAsync(pb + (size_t)2 * nbw * mp, R.ipiv + k0, (size_t)nbw * sizeof(int), cudaMemcpyDeviceToDevice, R.comm);
     return 0;
   };
   auto bcast_panel = [&](int k) -> int {
-    for (int i = 0; i < NL; i++) bufs[i] = D.r[i].pbuf[k & 1];
+    for (int i = 0; i < NL; i++) bufs[i] = D.r[i].pbuf[k % 3];
     int e = D.comm->bcast_bytes(dist_owner(k, P), ranks.data(), bufs.data(), panel_bytes(k), sts.data(), NL);
     if (e) return e;
     const int k0 = k * nb, nbw = width(k);
     const long long m = n - k0, mp = (m + 1) & ~1ll;
     for (int i = 0; i < NL; i++) {
       DistRank& R = D.r[i];
-      if (R.rank != dist_owner(k, P)) cudaMemcpyAsync(R.ipiv + k0, R.pbuf[k & 1] + (size_t)2 * nbw * mp, (size_t)nbw * sizeof(int), cudaMemcpyDeviceToDevice, R.comm);
+      if (R.rank != dist_owner(k, P)) cudaMemcpyAsync(R.ipiv + k0, R.pbuf[k % 3] + (size_t)2 * nbw * mp, (size_t)nbw * sizeof(int), cudaMemcpyDeviceToDevice, R.comm);
       cudaEventRecord(R.ev_panel, R.comm);
+      mark(k, 4, R.comm);
     }
     return 0;
   };
@@ -1345,7 +1353,7 @@ int zgetrf_dist(DistLU& D) {
     if (c1 <= c0) return;
     const int k0 = k * nb, nbw = width(k);
     const long long m = n - k0, mp = (m + 1) & ~1ll;
-    const double* Pre = R.pbuf[k & 1]; const double* Pim = Pre + (size_t)nbw * mp;
+    const double* Pre = R.pbuf[k % 3]; const double* Pim = Pre + (size_t)nbw * mp;
     double* Bre = R.Lre + (long long)c0 * lda + k0; double* Bim = R.Lim + (long long)c0 * lda + k0;
     R.w.launches += launch_trsm_ext(Pre, Pim, mp, Bre, Bim, lda, nbw, c1 - c0, R.main);
     const int mrest = (int)m - nbw;
@@ -1357,7 +1365,7 @@ int zgetrf_dist(DistLU& D) {
   // ---- panel 0 ----
   for (int i = 0; i < NL; i++) {
     DistRank& R = D.r[i];
-    if (R.comm != R.main) { cudaEventRecord(R.ev_free, R.main); cudaStreamWaitEvent(R.comm, R.ev_free, 0); }   // the local columns are complete
+    if (R.comm != R.main) { cudaEventRecord(R.ev_free[0], R.main); cudaStreamWaitEvent(R.comm, R.ev_free[0], 0); }   // the local columns are complete
     if (R.rank == dist_owner(0, P)) { int e = factor_and_pack(R, 0); if (e) return e; }
   }
   { int e = bcast_panel(0); if (e) return e; }
@@ -1366,8 +1374,11 @@ int zgetrf_dist(DistLU& D) {
     const bool has_next = k + 1 < nblk;
     for (int i = 0; i < NL; i++) {
       DistRank& R = D.r[i];
-      if (R.comm != R.main) cudaEventRecord(R.ev_free, R.main);      // everything of step k-1 (last reader of pbuf[(k+1) & 1]) is behind this point
+      // three panel buffers: the broadcast of panel k+1 overwrites the buffer last read by step k-2, i.e. it may start as soon as
+      // this rank's main stream has begun step k-1 (event recorded there) -- one more step of slack than with two buffers
+      if (R.comm != R.main) cudaEventRecord(R.ev_free[k & 1], R.main);
       cudaStreamWaitEvent(R.main, R.ev_panel, 0);
+      mark(k, 0, R.main);
       // ---- interchanges of panel k on every local column outside the panel (the right-hand side column included) ----
       const bool mine = R.rank == dist_owner(k, P);
       const int lc = dist_local_col(k, P, nb), ctot = R.ncl + 1;
@@ -1379,9 +1390,14 @@ int zgetrf_dist(DistLU& D) {
       if (has_next && R.rank == dist_owner(k + 1, P)) {
         const int cr = nright(R, k), nbw_next = width(k + 1);
         update_cols(R, k, cr, cr + nbw_next);
+        mark(k, 1, R.main);
         if (R.comm != R.main) { cudaEventRecord(R.ev_cols, R.main); cudaStreamWaitEvent(R.comm, R.ev_cols, 0); }
         int e = factor_and_pack(R, k + 1); if (e) return e;
-      } else if (has_next && R.comm != R.main) cudaStreamWaitEvent(R.comm, R.ev_free, 0);
+        // The panel is the critical path of the distributed factorisation (every rank waits for its broadcast), and run beside
+        // this rank's own trailing update it takes three times as long (traced: 3.5 instead of 1.2 ms at m = 20k): the owner
+        // holds its trailing update back until the panel is packed.  It pays for it one step in eight.
+        if (R.comm != R.main && D.owner_waits_for_panel) { cudaEventRecord(R.ev_cols, R.comm); cudaStreamWaitEvent(R.main, R.ev_cols, 0); }
+      } else if (has_next && R.comm != R.main && k >= 1) cudaStreamWaitEvent(R.comm, R.ev_free[(k - 1) & 1], 0);
     }
     if (has_next) { int e = bcast_panel(k + 1); if (e) return e; }
     for (int i = 0; i < NL; i++) {
@@ -1389,7 +1405,27 @@ int zgetrf_dist(DistLU& D) {
       int cr = nright(R, k);
       if (has_next && R.rank == dist_owner(k + 1, P)) cr += width(k + 1);
       update_cols(R, k, cr, R.ncl + 1);
+      mark(k, 2, R.main);
     }
+  }
+  if (trace) {
+    cudaStreamSynchronize(D.r[0].main); cudaStreamSynchronize(D.r[0].comm);
+    char fn[512]; snprintf(fn, sizeof(fn), "%s_rank%d.csv", trace, D.r[0].rank);
+    if (FILE* f = fopen(fn, "w")) {
+      fprintf(f, "step,owner,t_panel_received,t_next_cols_updated,t_step_done,t_panel_factorised,t_bcast_done\n");
+      for (int k = 0; k < nblk; k++) {
+        fprintf(f, "%d,%d", k, dist_owner(k, P));
+        for (int w = 0; w < 5; w++) {
+          float t = -1.f;
+          if (cudaEventQuery(tev[(size_t)6 * (k + 1) + w]) == cudaSuccess && cudaEventElapsedTime(&t, tev[0], tev[(size_t)6 * (k + 1) + w]) != cudaSuccess) t = -1.f;
+          fprintf(f, ",%.3f", t);
+        }
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+    cudaGetLastError();
+    for (auto& e : tev) cudaEventDestroy(e);
   }
   return (int)cudaGetLastError();
 }

@@ -55,12 +55,12 @@ void zgemm_minus_planar(int m, int n, int k, const double* Are, const double* Ai
 struct DistRank {
   int rank, ncl;                 // global rank; local columns (without the right-hand-side column)
   double *Lre, *Lim;             // planar lda x (ncl + 1), column ncl = right-hand side / solution workspace
-  double* pbuf[2];               // packed panel: [2 planes][nbw][mp] doubles + nbw pivots (int) behind them
+  double* pbuf[3];               // packed panel: [2 planes][nbw][mp] doubles + nbw pivots (int) behind them
   double* xfin;                  // [2][lda] solution blocks of the columns this rank owns (zero elsewhere)
   int* ipiv;                     // [n] device, 1-based global rows
   LuWork w;                      // panel workspace of the cooperative kernel
   cudaStream_t main, comm;       // trailing updates / panel factorisation + broadcast (the same stream in loopback mode)
-  cudaEvent_t ev_panel, ev_cols, ev_free;
+  cudaEvent_t ev_panel, ev_cols, ev_free[2];
   double gemm_flops;
 };
 struct DistComm {
@@ -79,6 +79,7 @@ struct DistLU {
   std::vector<DistRank> r;       // the ranks local to this process
   DistComm* comm;
   float ms_lu, ms_solve;
+  int owner_waits_for_panel;     // 1 (default): the owner of the next panel runs its trailing update after that panel, not beside it
 };
 inline int dist_owner(int blk, int P) { return blk % P; }
 inline int dist_local_col(int blk, int P, int nb) { return (blk / P) * nb; }
