@@ -169,12 +169,18 @@ struct Gemm3Cfg {
   static const int SA_STAGE = 2 * BK * SA_LD, SB_STAGE = 2 * BN * SB_LD;
   static const int SMEM = STAGES * (SA_STAGE + SB_STAGE) * 8;
 };
-template <int WM, int WN, int NI, int MINB>
+// PSA: the operand sum Ar + Ai comes PRE-SUMMED from a third plane Asum (same layout as A) instead of being formed on the
+// fragments: four of the six DADDs per k-step leave the FP64 pipe they share with the DMMAs (the stall samples of the ncu
+// source page sit on exactly these DADDs); costs a third shared-memory plane for A (72.7 KB per CTA).  MEASURED SLOWER
+// (LU 2160 instead of 1982 ms at 30258 DOF: the extra plane's staging and fragment loads cost more than the DADDs saved), so it
+// is an opt-in experiment (MFB_GEMM_PRESUM=1), not the default.
+template <int WM, int WN, int NI, int MINB, bool PSA>
 __global__ void __launch_bounds__(32 * WM * WN, MINB)
-k_zgemm3m_minus(int M, int N, int K, const double* __restrict__ Are, const double* __restrict__ Aim, long long lda, const double* __restrict__ Bre,
-                const double* __restrict__ Bim, long long ldb, double* __restrict__ Cre, double* __restrict__ Cim, long long ldc) {
+k_zgemm3m_minus(int M, int N, int K, const double* __restrict__ Are, const double* __restrict__ Aim, const double* __restrict__ Asum, long long lda,
+                const double* __restrict__ Bre, const double* __restrict__ Bim, long long ldb, double* __restrict__ Cre, double* __restrict__ Cim, long long ldc) {
   typedef Gemm3Cfg<WM, WN, NI> C;
-  constexpr int BM = C::BM, BN = C::BN, BK = C::BK, STAGES = C::STAGES, T = C::T, SA_LD = C::SA_LD, SB_LD = C::SB_LD, SA_STAGE = C::SA_STAGE, SB_STAGE = C::SB_STAGE;
+  constexpr int NPA = PSA ? 3 : 2;
+  constexpr int BM = C::BM, BN = C::BN, BK = C::BK, STAGES = C::STAGES, T = C::T, SA_LD = C::SA_LD, SB_LD = C::SB_LD, SA_STAGE = NPA * BK * C::SA_LD, SB_STAGE = C::SB_STAGE;
   extern __shared__ __align__(16) double smem[];
   double* sA = smem;
   double* sB = smem + STAGES * SA_STAGE;
@@ -188,14 +194,15 @@ k_zgemm3m_minus(int M, int N, int K, const double* __restrict__ Are, const doubl
     double* a = sA + stage * SA_STAGE;
     double* b = sB + stage * SB_STAGE;
 #pragma unroll
-    for (int i = 0; i < (2 * BK * (BM / 2) + T - 1) / T; i++) {
+    for (int i = 0; i < (NPA * BK * (BM / 2) + T - 1) / T; i++) {
       int idx = tid + T * i;
-      if ((2 * BK * (BM / 2)) % T != 0 && idx >= 2 * BK * (BM / 2)) break;
+      if ((NPA * BK * (BM / 2)) % T != 0 && idx >= NPA * BK * (BM / 2)) break;
       int p = idx / (BK * (BM / 2)), rem = idx % (BK * (BM / 2)), k = rem / (BM / 2), c2 = rem % (BM / 2);
       int m = m0 + 2 * c2, kk = k0 + k;
-      const double* src = (p ? Aim : Are) + (long long)kk * lda + m;
+      const double* base = (p == 0) ? Are : (p == 1 ? Aim : Asum);
+      const double* src = base + (long long)kk * lda + m;
       int bytes = (kk < K) ? max(0, min(16, (M - m) * 8)) : 0;
-      if (bytes == 0) src = (p ? Aim : Are);
+      if (bytes == 0) src = base;
       cp_async16(a + (p * BK + k) * SA_LD + 2 * c2, src, bytes);
     }
 #pragma unroll
@@ -245,7 +252,7 @@ k_zgemm3m_minus(int M, int N, int K, const double* __restrict__ Are, const doubl
 #pragma unroll
       for (int mi = 0; mi < 4; mi++) {
         int off = (k4 * 4 + tig) * SA_LD + wm * 32 + mi * 8 + gid;
-        ar[mi] = a[off]; ai[mi] = a[BK * SA_LD + off]; sa[mi] = ar[mi] + ai[mi];
+        ar[mi] = a[off]; ai[mi] = a[BK * SA_LD + off]; sa[mi] = PSA ? a[2 * BK * SA_LD + off] : ar[mi] + ai[mi];
       }
 #pragma unroll
       for (int ni = 0; ni < NI; ni++) {
@@ -377,9 +384,33 @@ static void launch_gemm3m(int m, int n, int k, const double* Are, const double* 
                           long long ldb, double* Cre, double* Cim, long long ldc, cudaStream_t st) {
   typedef Gemm3Cfg<WM, WN, NI> C;
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_zgemm3m_minus<WM, WN, NI, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM); attr = true; }
+  if (!attr) { cudaFuncSetAttribute(k_zgemm3m_minus<WM, WN, NI, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM); attr = true; }
   dim3 grid((m + C::BM - 1) / C::BM, (n + C::BN - 1) / C::BN);
-  k_zgemm3m_minus<WM, WN, NI, MINB><<<grid, C::T, C::SMEM, st>>>(m, n, k, Are, Aim, lda, Bre, Bim, ldb, Cre, Cim, ldc);
+  k_zgemm3m_minus<WM, WN, NI, MINB, false><<<grid, C::T, C::SMEM, st>>>(m, n, k, Are, Aim, nullptr, lda, Bre, Bim, ldb, Cre, Cim, ldc);
+}
+// trailing update with the pre-summed A plane (Asum = Are + Aim, same lda): the 64 x 32 / 3 CTAs-per-SM shape
+void zgemm_minus_planar_psa(int m, int n, int k, const double* Are, const double* Aim, const double* Asum, long long lda, const double* Bre, const double* Bim,
+                            long long ldb, double* Cre, double* Cim, long long ldc, cudaStream_t st) {
+  if (m <= 0 || n <= 0 || k <= 0) return;
+  typedef Gemm3Cfg<2, 2, 2> C;
+  constexpr int SMEM = C::STAGES * (3 * C::BK * C::SA_LD + C::SB_STAGE) * 8;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_zgemm3m_minus<2, 2, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); attr = true; }
+  dim3 grid((m + C::BM - 1) / C::BM, (n + C::BN - 1) / C::BN);
+  k_zgemm3m_minus<2, 2, 2, 3, true><<<grid, C::T, SMEM, st>>>(m, n, k, Are, Aim, Asum, lda, Bre, Bim, ldb, Cre, Cim, ldc);
+}
+// S = Re + Im of an (rows x cols) block (column-major, ld each)
+__global__ void k_sum_planes(const double* __restrict__ re, const double* __restrict__ im, long long ld, double* __restrict__ out, long long ldo, int rows, int cols) {
+  const long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long c = i / rows, r = i - c * rows;
+    out[c * ldo + r] = re[c * ld + r] + im[c * ld + r];
+  }
+}
+void launch_sum_planes(const double* re, const double* im, long long ld, double* out, long long ldo, int rows, int cols, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return;
+  long long total = (long long)rows * cols; int g = (int)std::min<long long>((total + 255) / 256, 1184);
+  k_sum_planes<<<g, 256, 0, st>>>(re, im, ld, out, ldo, rows, cols);
 }
 
 template <int WM, int WN, int BK, int STAGES, int MINB>
@@ -896,6 +927,8 @@ int lu_work_alloc(LuWork& w, int n, int nb) {
   A((void**)&w.cand_data, 2 * G * 2 * SP_MAXIB * sizeof(double)); A((void**)&w.diag_data, 2 * 2 * SP_MAXIB * sizeof(double));
   A((void**)&w.info, sizeof(int));
   A((void**)&w.pu_arrive, 64 * sizeof(int));
+  { const char* e_ps = getenv("MFB_GEMM_PRESUM"); w.asum[0] = w.asum[1] = nullptr;
+    if (e_ps && atoi(e_ps) != 0) { const size_t ldn = ((size_t)n + 31) / 32 * 32; A((void**)&w.asum[0], ldn * nb * sizeof(double)); A((void**)&w.asum[1], ldn * nb * sizeof(double)); } }
   { const char* e_si = getenv("MFB_LU_SOLVE_INV"); w.inv = nullptr; if (!e_si || atoi(e_si) != 0) A((void**)&w.inv, (size_t)((n + TS - 1) / TS) * 4 * TS * TS * sizeof(double)); }
   if (e == cudaSuccess) e = cudaMemset(w.pu_arrive, 0, 64 * sizeof(int));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_subpanel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -913,7 +946,7 @@ int lu_work_alloc(LuWork& w, int n, int nb) {
   return (int)e;
 }
 void lu_work_free(LuWork& w) {
-  cudaFree(w.cand_val); cudaFree(w.cand_row); cudaFree(w.cand_data); cudaFree(w.diag_data); cudaFree(w.info); cudaFree(w.pu_arrive); cudaFree(w.inv);
+  cudaFree(w.cand_val); cudaFree(w.cand_row); cudaFree(w.cand_data); cudaFree(w.diag_data); cudaFree(w.info); cudaFree(w.pu_arrive); cudaFree(w.inv); cudaFree(w.asum[0]); cudaFree(w.asum[1]);
   for (int i = 0; i < w.n_evs; i++) cudaEventDestroy(w.evs[i]);
   for (int i = 0; i < 2 * (w.n_evs / 5); i++) cudaEventDestroy(w.pevs[i]);
   cudaEventDestroy(w.ev_next_cols); cudaEventDestroy(w.ev_panel_done); cudaStreamDestroy(w.panel_stream);
@@ -1012,6 +1045,10 @@ int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuW
   cudaStream_t ps = w.lookahead ? w.panel_stream : st;
   auto gemm = [&](int r0, int k0, int kw, int c0, int c1) {   // A[r0:n, c0:c1] -= A[r0:n, k0:k0+kw] * A[k0:k0+kw, c0:c1]
     if (c1 <= c0 || r0 >= n) return;
+    if (Aim && w.asum[0] && gemm_cfg() == 15)
+      zgemm_minus_planar_psa(n - r0, c1 - c0, kw, Are + (long long)k0 * lda + r0, Aim + (long long)k0 * lda + r0, w.asum[(k0 / nb) & 1] + r0, lda,
+                             Are + (long long)c0 * lda + k0, Aim + (long long)c0 * lda + k0, lda, Are + (long long)c0 * lda + r0, Aim + (long long)c0 * lda + r0, lda, st);
+    else
     zgemm_minus_planar(n - r0, c1 - c0, kw, Are + (long long)k0 * lda + r0, poff(Aim, (long long)k0 * lda + r0), lda,
                        Are + (long long)c0 * lda + k0, poff(Aim, (long long)c0 * lda + k0), lda, Are + (long long)c0 * lda + r0, poff(Aim, (long long)c0 * lda + r0), lda, st);
     const double mnk = (double)(n - r0) * (double)(c1 - c0) * (double)kw;
@@ -1024,6 +1061,7 @@ int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuW
     if (timing) cudaEventRecord(w.pevs[0], ps);
     int e = factor_panel(Are, Aim, lda, n, 0, (n < nb) ? n : nb, ipiv, w, ps);
     if (e) return e;
+    if (Aim && w.asum[0] && n > nb) launch_sum_planes(Are + nb, Aim + nb, lda, w.asum[0] + nb, lda, n - nb, nb, ps);   // L21 of panel 0
     if (timing) cudaEventRecord(w.pevs[1], ps);
     if (w.lookahead) { cudaEventRecord(w.ev_panel_done, ps); cudaStreamWaitEvent(st, w.ev_panel_done, 0); }
   }
@@ -1047,6 +1085,9 @@ int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuW
       if (timing) cudaEventRecord(w.pevs[2 * (step + 1)], ps);
       int e = factor_panel(Are, Aim, lda, n, c_next, nbw_next, ipiv, w, ps);
       if (e) return e;
+      if (Aim && w.asum[0] && c_next + nbw_next < n)   // L21 of panel step+1: rows below it, for the trailing update of the next step
+        launch_sum_planes(Are + (long long)c_next * lda + c_next + nbw_next, Aim + (long long)c_next * lda + c_next + nbw_next, lda,
+                          w.asum[(step + 1) & 1] + c_next + nbw_next, lda, n - c_next - nbw_next, nbw_next, ps);
       if (timing) cudaEventRecord(w.pevs[2 * (step + 1) + 1], ps);
       if (w.lookahead) cudaEventRecord(w.ev_panel_done, ps);
       gemm(c_next, k0, nbw, c_next + nbw_next, n);

@@ -15,6 +15,7 @@ struct LuWork {
   double *cand_data;      // [2][grid][2*32]   candidate rows (re, im)
   double *diag_data;      // [2][2*32]         current diagonal row
   int *info;              // device flag: first zero pivot (1-based), 0 = ok
+  double *asum[2];        // Ar + Ai of the L21 panel of the current / next step (pre-summed operand of the 3M trailing update)
   double *inv;            // inverses of the 64 x 64 diagonal blocks of L and U of the last factorisation (NULL: substitution kernels)
   int *pu_arrive;         // [64] arrival counters of k_panel_update (one per column block; self re-arming)
   float ms_panel, ms_swap, ms_trsm, ms_gemm; long long launches; long long gemm_launches; double gemm_flops, gemm_exec_flops;   // algorithmic (8mnk) and executed (6mnk with the 3M kernel) flops of the trailing updates
