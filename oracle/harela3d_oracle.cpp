@@ -202,6 +202,7 @@ static void zexp_decomposed(cd z, cd* E /*0..6*/) {
 struct Params {
   cd lambda, mu; double rho, omega; cd c1, c2, k1, k2;
   cd psi[7], chi[7], T1[11], T2[10], T3[10]; cd cte_u, cte_t;
+  cd S1[12], S2[12], S3[13], S4[11], S5[12]; cd cte_d, cte_s;   // hypersingular equation (d*, s*): bem_harela3d.f90:219-287
   // static elasticity (lib/fbem/src/bem_staela3d.f90): Kelvin solution, cte_u = cteu1, cte_t = ctet1 of :617-622
   bool statics = false; double cteu2 = 0.0, ctet2 = 0.0;
 };
@@ -234,6 +235,25 @@ static void calculate_parameters(cd lambda, cd mu, double rho, double omega, Par
   p.T3[3] = (2.0 * c2_2 / c1_2 - 1.0) * im * k1; p.T3[4] = 4.0 * c2_2 / c1_2 - 1.0; p.T3[5] = -2.0;
   p.T3[6] = r * 6.0 / ik1; p.T3[7] = -6.0 / ik2; p.T3[8] = r * 6.0 / ik1_2; p.T3[9] = -6.0 / ik2_2;
   p.cte_u = c_1_4pi / mu; p.cte_t = c_1_4pi;
+  // S1..S5, cte_d, cte_s: bem_harela3d.f90:219-287
+  cd k1_2 = k1 * k1, c1_5 = c1_4 * c1, c2_3 = c2_2 * c2, om3 = om2 * omega;
+  p.S1[1] = 3.0 * (1.0 - 2.0 * c2_2 / c1_2); p.S1[2] = -0.5 * c2_2 / c1_4 * om2; p.S1[3] = k2_2; p.S1[4] = 4.0 * im * k1 * k1_2 / k2_2;
+  p.S1[5] = -7.0 * im * k2; p.S1[6] = 24.0 * k1_2 / k2_2; p.S1[7] = -27.0; p.S1[8] = 60.0 * k1_2 / k2_2 / ik1; p.S1[9] = -60.0 / ik2;
+  p.S1[10] = 60.0 * k1_2 / k2_2 / ik1_2; p.S1[11] = -60.0 / ik2_2;
+  p.S2[1] = 6.0 * c2_2 / c1_2; p.S2[2] = (0.5 / c2_2 + 1.5 * c2_2 / c1_4 - 1.0 / c1_2) * om2; p.S2[3] = 2.0 * c2_2 / c1_4 * (c1_2 / c2_2 - 2.0) * om2;
+  p.S2[4] = 2.0 * im * c2_2 / c1_3 * (8.0 - 3.0 * c1_2 / c2_2) * omega; p.S2[5] = -4.0 * im * k2; p.S2[6] = 6.0 * c2_2 / c1_2 * (6.0 - c1_2 / c2_2);
+  p.S2[7] = -24.0; p.S2[8] = c2_2 / c1_2 * 60.0 / ik1; p.S2[9] = -60.0 / ik2; p.S2[10] = 60.0 / ik2_2; p.S2[11] = -60.0 / ik2_2;
+  p.S3[1] = 30.0 * (1.0 - c2_2 / c1_2); p.S3[2] = 1.5 * (1.0 / c2_2 - c2_2 / c1_4) * om2; p.S3[3] = -4.0 * c2_2 / c1_2 * k1_2; p.S3[4] = 4.0 * k2_2;
+  p.S3[5] = 40.0 * c2_2 / c1_2 * im * k1; p.S3[6] = -40.0 * im * k2; p.S3[7] = 180.0 * c2_2 / c1_2; p.S3[8] = -180.0;
+  p.S3[9] = 420.0 * c2_2 / c1_2 / ik1; p.S3[10] = -420.0 / ik2; p.S3[11] = 420.0 / ik2_2; p.S3[12] = -420.0 / ik2_2;
+  p.S4[1] = 2.0 * c2_2 / c1_2; p.S4[2] = 0.5 * (c2_2 / c1_4 + 1.0 / c2_2) * om2; p.S4[3] = -2.0 / 5.0 * (1.0 / c2_3 + 2.0 / 3.0 * c2_2 / c1_5) * im * om3;
+  p.S4[4] = 2.0 * im * k2; p.S4[5] = -4.0 * c2_2 / c1_2; p.S4[6] = 6.0; p.S4[7] = -12.0 * c2_2 / c1_2 / ik1; p.S4[8] = 12.0 / ik2;
+  p.S4[9] = -12.0 / ik2_2; p.S4[10] = 12.0 / ik2_2;
+  p.S5[1] = 2.0 * (1.0 - 3.0 * c2_2 / c1_2); p.S5[2] = (-2.0 / c1_2 + 0.5 / c2_2 + 0.5 * c2_2 / c1_4) * om2;
+  p.S5[3] = (8.0 / 3.0 / c1_3 + 4.0 / 15.0 / c2_3 - 1.0 / c1 / c2_2 - 24.0 / 15.0 * c2_2 / c1_5) * im * om3;
+  p.S5[4] = (-4.0 / c1_2 + 1.0 / c2_2 + 4.0 * c2_2 / c1_4) * om2; p.S5[5] = 4.0 * im * (1.0 / c1 - 2.0 * c2_2 / c1_3) * omega;
+  p.S5[6] = 4.0 * (1.0 - 3.0 * c2_2 / c1_2); p.S5[7] = 4.0; p.S5[8] = 12.0 * im * k1 / k2_2; p.S5[9] = -12.0 * im / k2; p.S5[10] = 12.0 / k2_2; p.S5[11] = -12.0 / k2_2;
+  p.cte_d = c_1_4pi; p.cte_s = c_1_4pi * mu;
 }
 
 // Kernel scalars psi, chi, TT1..3 at distance r (bem_harela3d.f90:663-685).  `regular_only` drops the
@@ -287,6 +307,39 @@ static inline void add_exterior_point(const Params& p, const double* x, const do
       cd fs_u = ks.psi * dkr[il][ik] - ks.chi * drdx[il] * drdx[ik];
       cd fs_t = ks.TT1 * drdx[il] * drdx[ik] * drdn + ks.TT2 * (drdn * dkr[il][ik] + drdx[ik] * n[il]) + ks.TT3 * drdx[il] * n[ik];
       for (int j = 0; j < nn; j++) { h[(j * 3 + il) * 3 + ik] += fs_t * pphijw[j]; g[(j * 3 + il) * 3 + ik] += fs_u * sphijw[j]; }
+    }
+}
+
+// One exterior Gauss point of the hypersingular equation: m(:,l,k) += s*_lk pphijw, l(:,l,k) += d*_lk sphijw with the unit normal
+// n_i at the collocation point (fbem_bem_harela3d_hbie_ext_pre, bem_harela3d.f90:2606-2654; the same formulas in _ext_st)
+static inline void add_exterior_point_hbie(const Params& p, const double* x, const double* n, const double* x_i, const double* n_i, int nn,
+                                           const double* pphijw, const double* sphijw, cd* m, cd* l) {
+  double rv[3] = {x[0] - x_i[0], x[1] - x_i[1], x[2] - x_i[2]};
+  double r = sqrt(dot3(rv, rv));
+  double d1r1 = 1.0 / r, d1r2 = d1r1 * d1r1, d1r3 = d1r2 * d1r1, d1r4 = d1r3 * d1r1, d1r5 = d1r4 * d1r1;
+  double drdx[3] = {rv[0] * d1r1, rv[1] * d1r1, rv[2] * d1r1};
+  double drdn = dot3(drdx, n), drdni = -dot3(drdx, n_i), n_dot_ni = dot3(n, n_i);
+  const cd mim(-0.0, -1.0);
+  cd z[2] = {mim * p.k1 * r, mim * p.k2 * r};
+  cd E1[7], E2[7];
+  zexp_decomposed(z[0], E1); zexp_decomposed(z[1], E2);
+  cd E21 = E1[2] * d1r1, E22 = E2[2] * d1r1, E31 = E1[3] * d1r2, E32 = E2[3] * d1r2, E41 = E1[4] * d1r3, E42 = E2[4] * d1r3;
+  cd E51 = E1[5] * d1r4, E52 = E2[5] * d1r4, E61 = E1[6] * d1r5, E62 = E2[6] * d1r5;
+  cd TT1 = p.T1[1] * d1r2 + p.T1[2] + p.T1[3] * E21 + p.T1[4] * E22 + p.T1[5] * E31 + p.T1[6] * E32 + p.T1[7] * E41 + p.T1[8] * E42 + p.T1[9] * E51 + p.T1[10] * E52;
+  cd TT2 = p.T2[1] * d1r2 + p.T2[2] + p.T2[3] * E22 + p.T2[4] * E31 + p.T2[5] * E32 + p.T2[6] * E41 + p.T2[7] * E42 + p.T2[8] * E51 + p.T2[9] * E52;
+  cd TT3 = p.T3[1] * d1r2 + p.T3[2] + p.T3[3] * E21 + p.T3[4] * E31 + p.T3[5] * E32 + p.T3[6] * E41 + p.T3[7] * E42 + p.T3[8] * E51 + p.T3[9] * E52;
+  cd S1 = p.S1[1] * d1r3 + p.S1[2] * d1r1 + p.S1[3] * E22 + p.S1[4] * E31 + p.S1[5] * E32 + p.S1[6] * E41 + p.S1[7] * E42 + p.S1[8] * E51 + p.S1[9] * E52 + p.S1[10] * E61 + p.S1[11] * E62;
+  cd S2 = p.S2[1] * d1r3 + p.S2[2] * d1r1 + p.S2[3] * E21 + p.S2[4] * E31 + p.S2[5] * E32 + p.S2[6] * E41 + p.S2[7] * E42 + p.S2[8] * E51 + p.S2[9] * E52 + p.S2[10] * E61 + p.S2[11] * E62;
+  cd S3 = p.S3[1] * d1r3 + p.S3[2] * d1r1 + p.S3[3] * E21 + p.S3[4] * E22 + p.S3[5] * E31 + p.S3[6] * E32 + p.S3[7] * E41 + p.S3[8] * E42 + p.S3[9] * E51 + p.S3[10] * E52 + p.S3[11] * E61 + p.S3[12] * E62;
+  cd S4 = p.S4[1] * d1r3 + p.S4[2] * d1r1 + p.S4[3] + p.S4[4] * E32 + p.S4[5] * E41 + p.S4[6] * E42 + p.S4[7] * E51 + p.S4[8] * E52 + p.S4[9] * E61 + p.S4[10] * E62;
+  cd S5 = p.S5[1] * d1r3 + p.S5[2] * d1r1 + p.S5[3] + p.S5[4] * E21 + p.S5[5] * E31 + p.S5[6] * E41 + p.S5[7] * E42 + p.S5[8] * E51 + p.S5[9] * E52 + p.S5[10] * E61 + p.S5[11] * E62;
+  for (int il = 0; il < 3; il++)
+    for (int ik = 0; ik < 3; ik++) {
+      cd fs_d = TT1 * drdx[il] * drdx[ik] * drdni - TT2 * (-drdni * dkr[il][ik] + drdx[il] * n_i[ik]) - TT3 * drdx[ik] * n_i[il];
+      cd fs_s = S1 * (drdx[il] * n_i[ik] * drdn - drdx[ik] * n[il] * drdni - dkr[il][ik] * drdn * drdni + drdx[il] * drdx[ik] * n_dot_ni)
+              + S2 * (drdx[ik] * n_i[il] * drdn - drdx[il] * n[ik] * drdni) + S3 * drdx[il] * drdx[ik] * drdn * drdni
+              + S4 * (dkr[il][ik] * n_dot_ni + n_i[ik] * n[il]) + S5 * n[ik] * n_i[il];
+      for (int j = 0; j < nn; j++) { m[(j * 3 + il) * 3 + ik] += fs_s * pphijw[j]; l[(j * 3 + il) * 3 + ik] += fs_d * sphijw[j]; }
     }
 }
 
@@ -757,16 +810,22 @@ static void stats_add(Stats& a, const Stats& b) {
 }
 
 // fbem_bem_harela3d_sbie_ext_pre: bem_harela3d.f90:628-700
-static void sbie_ext_pre(const PSet& s, const Element& e, const double* x_i, const Params& p, cd* h, cd* g) {
+// n_i != NULL: the hypersingular equation with the unit normal n_i at the collocation point (fbem_bem_harela3d_hbie_ext_pre
+// :2573-2662, _ext_st :2664-3042, _ext_adp :3044-3167, _auto :3632-3697): the same traversal with the d*, s* point formulas,
+// the estimator called with f = 7 instead of 5, h <- m (scaled by cte_s), g <- l (scaled by cte_d).
+static void sbie_ext_pre(const PSet& s, const Element& e, const double* x_i, const Params& p, cd* h, cd* g, const double* n_i = nullptr) {
   int nn = e.nn;
   for (int i = 0; i < 9 * nn; i++) { h[i] = 0.0; g[i] = 0.0; }
-  for (int kip = 0; kip < s.ngp; kip++)
-    add_exterior_point(p, &s.x[3 * kip], &s.n[3 * kip], x_i, nn, &s.pphijw[nn * kip], &s.pphijw[nn * kip], h, g);
-  for (int i = 0; i < 9 * nn; i++) { h[i] = p.cte_t * h[i]; g[i] = p.cte_u * g[i]; }
+  for (int kip = 0; kip < s.ngp; kip++) {
+    if (n_i) add_exterior_point_hbie(p, &s.x[3 * kip], &s.n[3 * kip], x_i, n_i, nn, &s.pphijw[nn * kip], &s.pphijw[nn * kip], h, g);
+    else add_exterior_point(p, &s.x[3 * kip], &s.n[3 * kip], x_i, nn, &s.pphijw[nn * kip], &s.pphijw[nn * kip], h, g);
+  }
+  for (int i = 0; i < 9 * nn; i++) { h[i] = (n_i ? p.cte_s : p.cte_t) * h[i]; g[i] = (n_i ? p.cte_d : p.cte_u) * g[i]; }
   if (e.reverse) for (int i = 0; i < 9 * nn; i++) h[i] = -h[i];
 }
 // fbem_bem_harela3d_sbie_ext_st: bem_harela3d.f90:702-1048
-static void sbie_ext_st(const Element& e, const double* xi_s, const double* x_i, const double* barxip, double barr, const Params& p, int gln, cd* h, cd* g) {
+static void sbie_ext_st(const Element& e, const double* xi_s, const double* x_i, const double* barxip, double barr, const Params& p, int gln, cd* h, cd* g,
+                        const double* n_i = nullptr) {
   int nn = e.nn; bool tri = (e.et == TRI3 || e.et == TRI6);
   for (int i = 0; i < 9 * nn; i++) { h[i] = 0.0; g[i] = 0.0; }
   double tp1[4], tp2[4];
@@ -795,14 +854,16 @@ static void sbie_ext_st(const Element& e, const double* xi_s, const double* x_i,
       double n[3] = {N[0] / jg, N[1] / jg, N[2] / jg};
       double jw = tri ? jg * js * jqt * jt1 * jt2 * w1 * w2 : jg * js * jt1 * jt2 * w1 * w2;
       double pj[9]; for (int k = 0; k < nn; k++) pj[k] = phi[k] * jw;
-      add_exterior_point(p, x, n, x_i, nn, pj, pj, h, g);
+      if (n_i) add_exterior_point_hbie(p, x, n, x_i, n_i, nn, pj, pj, h, g);
+      else add_exterior_point(p, x, n, x_i, nn, pj, pj, h, g);
     }
   }
-  for (int i = 0; i < 9 * nn; i++) { h[i] = p.cte_t * h[i]; g[i] = p.cte_u * g[i]; }
+  for (int i = 0; i < 9 * nn; i++) { h[i] = (n_i ? p.cte_s : p.cte_t) * h[i]; g[i] = (n_i ? p.cte_d : p.cte_u) * g[i]; }
   if (e.reverse) for (int i = 0; i < 9 * nn; i++) h[i] = -h[i];
 }
 // fbem_bem_harela3d_sbie_ext_adp: bem_harela3d.f90:1050-1172
-static void sbie_ext_adp(const Element& e, double* xi_s, const double* x_i, const Params& p, const QsParams& qsp, int ks, int ns, cd* h, cd* g, Stats& st) {
+static void sbie_ext_adp(const Element& e, double* xi_s, const double* x_i, const Params& p, const QsParams& qsp, int ks, int ns, cd* h, cd* g, Stats& st,
+                         const double* n_i = nullptr) {
   int nn = e.nn, nv = n_vertices_of(e.et);
   double barxip[2], rmin, d; int method;
   if (ks == 1) {
@@ -815,7 +876,7 @@ static void sbie_ext_adp(const Element& e, double* xi_s, const double* x_i, cons
     double cl = characteristic_length(e.et, x_s, 1.e-12);
     nearest_element_point_bem(e.et, x_s, cl, x_i, barxip, rmin, d, method);
   }
-  int gln_near = qs_n_estimation(true, e.et, 5, qsp, d, barxip);
+  int gln_near = qs_n_estimation(true, e.et, n_i ? 7 : 5, qsp, d, barxip);
   bool subdivide = false;
   if (ks == ns) { if (gln_near == 0) gln_near = 30; } else if (gln_near == 0) subdivide = true;
   if (subdivide) {
@@ -823,22 +884,22 @@ static void sbie_ext_adp(const Element& e, double* xi_s, const double* x_i, cons
     auto mid = [&](int a, int b, double* o) { o[0] = 0.50 * (xi_s[2 * a] + xi_s[2 * b]); o[1] = 0.50 * (xi_s[2 * a + 1] + xi_s[2 * b + 1]); };
     auto cpy = [&](int a, double* o) { o[0] = xi_s[2 * a]; o[1] = xi_s[2 * a + 1]; };
     if (nv == 3) {
-      cpy(0, t); mid(0, 1, t + 2); mid(0, 2, t + 4); sbie_ext_adp(e, t, x_i, p, qsp, ks + 1, ns, h, g, st);
-      cpy(1, t); mid(1, 2, t + 2); mid(0, 1, t + 4); sbie_ext_adp(e, t, x_i, p, qsp, ks + 1, ns, h, g, st);
-      cpy(2, t); mid(0, 2, t + 2); mid(1, 2, t + 4); sbie_ext_adp(e, t, x_i, p, qsp, ks + 1, ns, h, g, st);
-      mid(0, 1, t); mid(1, 2, t + 2); mid(0, 2, t + 4); sbie_ext_adp(e, t, x_i, p, qsp, ks + 1, ns, h, g, st);
+      cpy(0, t); mid(0, 1, t + 2); mid(0, 2, t + 4); sbie_ext_adp(e, t, x_i, p, qsp, ks + 1, ns, h, g, st, n_i);
+      cpy(1, t); mid(1, 2, t + 2); mid(0, 1, t + 4); sbie_ext_adp(e, t, x_i, p, qsp, ks + 1, ns, h, g, st, n_i);
+      cpy(2, t); mid(0, 2, t + 2); mid(1, 2, t + 4); sbie_ext_adp(e, t, x_i, p, qsp, ks + 1, ns, h, g, st, n_i);
+      mid(0, 1, t); mid(1, 2, t + 2); mid(0, 2, t + 4); sbie_ext_adp(e, t, x_i, p, qsp, ks + 1, ns, h, g, st, n_i);
     } else {
       auto ctr = [&](double* o) { o[0] = 0.25 * (xi_s[0] + xi_s[2] + xi_s[4] + xi_s[6]); o[1] = 0.25 * (xi_s[1] + xi_s[3] + xi_s[5] + xi_s[7]); };
-      cpy(0, t); mid(0, 1, t + 2); ctr(t + 4); mid(0, 3, t + 6); sbie_ext_adp(e, t, x_i, p, qsp, ks + 1, ns, h, g, st);
-      mid(0, 1, t); cpy(1, t + 2); mid(1, 2, t + 4); ctr(t + 6); sbie_ext_adp(e, t, x_i, p, qsp, ks + 1, ns, h, g, st);
-      ctr(t); mid(1, 2, t + 2); cpy(2, t + 4); mid(2, 3, t + 6); sbie_ext_adp(e, t, x_i, p, qsp, ks + 1, ns, h, g, st);
-      mid(0, 3, t); ctr(t + 2); mid(2, 3, t + 4); cpy(3, t + 6); sbie_ext_adp(e, t, x_i, p, qsp, ks + 1, ns, h, g, st);
+      cpy(0, t); mid(0, 1, t + 2); ctr(t + 4); mid(0, 3, t + 6); sbie_ext_adp(e, t, x_i, p, qsp, ks + 1, ns, h, g, st, n_i);
+      mid(0, 1, t); cpy(1, t + 2); mid(1, 2, t + 4); ctr(t + 6); sbie_ext_adp(e, t, x_i, p, qsp, ks + 1, ns, h, g, st, n_i);
+      ctr(t); mid(1, 2, t + 2); cpy(2, t + 4); mid(2, 3, t + 6); sbie_ext_adp(e, t, x_i, p, qsp, ks + 1, ns, h, g, st, n_i);
+      mid(0, 3, t); ctr(t + 2); mid(2, 3, t + 4); cpy(3, t + 6); sbie_ext_adp(e, t, x_i, p, qsp, ks + 1, ns, h, g, st, n_i);
     }
   } else {
     double barr = telles_barr_any(d);
     int gln = std::max(gln_near, e.gln_far);
     cd ht[81], gt[81];
-    sbie_ext_st(e, xi_s, x_i, barxip, barr, p, gln, ht, gt);
+    sbie_ext_st(e, xi_s, x_i, barxip, barr, p, gln, ht, gt, n_i);
     for (int i = 0; i < 9 * nn; i++) { h[i] = h[i] + ht[i]; g[i] = g[i] + gt[i]; }
     st.leaves++; st.pts_adaptive += (long long)gln * gln;
   }
@@ -1056,22 +1117,23 @@ static void sbie_int(const Element& e, const double* xi_i, const Params& p, cd* 
   if (e.reverse) for (int i = 0; i < 9 * nn; i++) h[i] = -h[i];
 }
 // fbem_bem_harela3d_sbie_auto: bem_harela3d.f90:1474-1538.  Returns mode: 1..30 regular gln (ps), 100 adaptive, 200 singular.
-static int sbie_auto(const Element& e, const double* x_i, const Params& p, const QsParams& qsp, int ns, cd* h, cd* g, Stats& st) {
+static int sbie_auto(const Element& e, const double* x_i, const Params& p, const QsParams& qsp, int ns, cd* h, cd* g, Stats& st, const double* n_i = nullptr) {
   double r[3] = {e.bc[0] - x_i[0], e.bc[1] - x_i[1], e.bc[2] - x_i[2]};
   double rmin = sqrt(dot3(r, r)) - e.br, barxi[2], d; int delta, method;
   if (rmin > (4.0 * e.br)) { delta = 0; barxi[0] = 0.0; barxi[1] = 0.0; d = rmin / e.cl; }
   else { nearest_element_point_bem(e.et, e.x, e.cl, x_i, barxi, rmin, d, method); delta = (d <= 1.e-12) ? 1 : 0; }
+  if (delta == 1 && n_i) return -1;   // fbem_bem_harela3d_hbie_int (collocation point ON the element) is not restated: interior points never get here
   if (delta == 1) { st.pairs_singular++; sbie_int(e, barxi, p, h, g, st); return 200; }
-  int gln_near = qs_n_estimation(false, e.et, 5, qsp, d, barxi);
+  int gln_near = qs_n_estimation(false, e.et, n_i ? 7 : 5, qsp, d, barxi);
   int gln = std::max(e.gln_far, gln_near);
   if (gln <= e.ps_gln_max && gln_near > 0) {
     int ps = 0; for (size_t i = 0; i < e.ps.size(); i++) if (e.ps[i].gln >= gln) { ps = (int)i; break; }
-    sbie_ext_pre(e.ps[ps], e, x_i, p, h, g);
+    sbie_ext_pre(e.ps[ps], e, x_i, p, h, g, n_i);
     st.pairs_regular[e.ps[ps].gln]++; st.pts_regular += e.ps[ps].ngp;
     return e.ps[ps].gln;
   }
   double xi_s[8]; st.pairs_adaptive++;
-  sbie_ext_adp(e, xi_s, x_i, p, qsp, 1, ns, h, g, st);
+  sbie_ext_adp(e, xi_s, x_i, p, qsp, 1, ns, h, g, st, n_i);
   return 100;
 }
 
@@ -1382,6 +1444,21 @@ int orc_pair(void* h, int e, const double* x_i, double omega, const double* lamb
   int mode = sbie_auto(m->elem[e], x_i, p, m->qsp, m->ns_max, (cd*)h_ri, (cd*)g_ri, st);
   if (stats_out) { stats_out[0] = st.pts_regular; stats_out[1] = st.leaves; stats_out[2] = st.pts_adaptive; stats_out[3] = st.pts_singular; stats_out[4] = st.li_points; }
   return mode;
+}
+// m, l (n x 3 x 3) of the hypersingular equation for a point OFF the element with unit normal n_i (fbem_bem_harela3d_hbie_auto)
+int orc_pair_hbie(void* h, int e, const double* x_i, const double* n_i, double omega, const double* lambda_ri, const double* mu_ri, double rho, double* m_ri, double* l_ri) {
+  Model* md = (Model*)h; Params p; calculate_parameters(cd(lambda_ri[0], lambda_ri[1]), cd(mu_ri[0], mu_ri[1]), rho, omega, p);
+  Stats st; memset(&st, 0, sizeof(st));
+  return sbie_auto(md->elem[e], x_i, p, md->qsp, md->ns_max, (cd*)m_ri, (cd*)l_ri, st, n_i);
+}
+// d*, s* (fbem_bem_harela3d_hbie_d / _s, bem_harela3d.f90:2472-2568), [l][k] interleaved complex
+void orc_fundamental_solutions_hbie(const double* x, const double* n, const double* x_i, const double* n_i, double omega, const double* lambda_ri, const double* mu_ri, double rho,
+                                    double* d_ri, double* s_ri) {
+  Params p; calculate_parameters(cd(lambda_ri[0], lambda_ri[1]), cd(mu_ri[0], mu_ri[1]), rho, omega, p);
+  double one = 1.0; cd mm[9], ll[9]; for (int i = 0; i < 9; i++) { mm[i] = 0; ll[i] = 0; }
+  add_exterior_point_hbie(p, x, n, x_i, n_i, 1, &one, &one, mm, ll);
+  cd* d = (cd*)d_ri; cd* s = (cd*)s_ri;
+  for (int i = 0; i < 9; i++) { d[i] = p.cte_d * ll[i]; s[i] = p.cte_s * mm[i]; }
 }
 // plan only (mode per pair) -- for comparing discrete decisions with the product's planner
 int orc_pair_mode(void* h, int e, const double* x_i, double* d_out, double* barxi_out) {

@@ -138,6 +138,16 @@ class Oracle:
                               C.c_double(mat.rho), _p(h), _p(g), _p(st))
         return h, g, mode, st
 
+    def pair_hbie(self, e, x_i, n_i, omega, mat):
+        """m, l (n,3,3) complex of the hypersingular equation for a point off the element with unit normal n_i, and the mode."""
+        nn = int(self.m.elem_ptr[e + 1] - self.m.elem_ptr[e])
+        m = np.zeros((nn, 3, 3), dtype=np.complex128); l = np.zeros((nn, 3, 3), dtype=np.complex128)
+        x_i = np.ascontiguousarray(x_i, dtype=np.float64); n_i = np.ascontiguousarray(n_i, dtype=np.float64)
+        mode = lib().orc_pair_hbie(self.h, C.c_int(e), _p(x_i), _p(n_i), C.c_double(omega), _p(_ri(mat.lam)), _p(_ri(mat.mu)), C.c_double(mat.rho), _p(m), _p(l))
+        if mode < 0:
+            raise RuntimeError("oracle: hypersingular integration with the collocation point on the element is not restated")
+        return m, l, mode
+
     def pair_mode(self, e, x_i):
         x_i = np.ascontiguousarray(x_i, dtype=np.float64)
         d = C.c_double(0.0)
@@ -198,6 +208,14 @@ def freeterm(normals, tangents, nu, tol=1e-6):
     c = np.zeros((3, 3), dtype=np.complex128)
     err = lib().orc_freeterm(C.c_int(len(n)), _p(n), _p(t), C.c_double(tol), _p(_ri(nu)), _p(c))
     return c, err
+
+
+def fundamental_solutions_hbie(x, n, x_i, n_i, omega, mat):
+    """d*, s* (3,3) [l][k] (fbem_bem_harela3d_hbie_d / _s, lib/fbem/src/bem_harela3d.f90:2472-2568)."""
+    d = np.zeros((3, 3), dtype=np.complex128); s = np.zeros((3, 3), dtype=np.complex128)
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (x, n, x_i, n_i)]
+    lib().orc_fundamental_solutions_hbie(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), C.c_double(omega), _p(_ri(mat.lam)), _p(_ri(mat.mu)), C.c_double(mat.rho), _p(d), _p(s))
+    return d, s
 
 
 def fundamental_solutions_static(x, n, x_i, mat):

@@ -72,3 +72,60 @@ def test_gpu_interior_displacements_match_the_oracle_composition(gpu_ctx, oracle
     if et != shape.TRI3 or m >= 4:
         assert np.abs(us[:, 0] - PTS[:, 0] / lam2mu).max() * lam2mu < 1e-4
     ip.close(); pr.close()
+
+
+# ---- stresses at interior points: the hypersingular kernels d*, s* of the oracle (fbem_bem_harela3d_hbie_*, exterior branches) ----
+def test_hbie_kernels_are_the_traction_operator_applied_to_u_and_t(oracle_lib):
+    """d*_lk = sigma-operator (at the collocation point, normal n_i) of u*_.k, s*_lk the same of t*_.k: finite differences of the
+    (independently pinned) u*, t* with respect to x_i pin the d*, s* formulas and the S1..S5 coefficient tables."""
+    rng = np.random.default_rng(4)
+    lam, mu = MAT.lam, MAT.mu
+    for omega in (0.3, 2.0, 9.0):
+        for _ in range(4):
+            x_i = rng.uniform(-0.5, 0.5, 3); x = x_i + rng.uniform(0.3, 1.5) * rng.standard_normal(3)
+            n = rng.standard_normal(3); n /= np.linalg.norm(n); n_i = rng.standard_normal(3); n_i /= np.linalg.norm(n_i)
+            d, s = oracle_lib.fundamental_solutions_hbie(x, n, x_i, n_i, omega, MAT)
+            hstep = 1e-5
+            du = np.zeros((3, 3, 3), dtype=complex); dt = np.zeros((3, 3, 3), dtype=complex)     # [m][l][k] = d/dx_i,m of u*_lk
+            for m in range(3):
+                e = np.zeros(3); e[m] = hstep
+                up, tp = oracle_lib.fundamental_solutions(x, n, x_i + e, omega, MAT); um, tm = oracle_lib.fundamental_solutions(x, n, x_i - e, omega, MAT)
+                du[m] = (up - um) / (2 * hstep); dt[m] = (tp - tm) / (2 * hstep)
+
+            def sigma_op(df):
+                out = np.zeros((3, 3), dtype=complex)
+                for l in range(3):
+                    for k in range(3):
+                        out[l, k] = lam * n_i[l] * sum(df[p, p, k] for p in range(3)) + mu * sum(n_i[m] * (df[m, l, k] + df[l, m, k]) for m in range(3))
+                return out
+            assert np.abs(d - sigma_op(du)).max() < 2e-6 * np.abs(d).max()
+            assert np.abs(s - sigma_op(dt)).max() < 2e-6 * np.abs(s).max()
+
+
+def oracle_interior_stress(o, md, x, pts, omega, mat):
+    u, t = md.nodal_solution(x)
+    sig = np.zeros((len(pts), 3, 3), dtype=np.complex128)       # [point][l][kc]: traction component l on the plane with normal e_kc
+    for ip, xp in enumerate(pts):
+        for kc in range(3):
+            n_i = np.zeros(3); n_i[kc] = 1.0
+            for e in range(md.n_elem):
+                m, l, mode = o.pair_hbie(e, xp, n_i, omega, mat)
+                nodes = md.mesh.conn[e]
+                sig[ip, :, kc] += np.einsum("jlk,jk->l", l, t[nodes]) - np.einsum("jlk,jk->l", m, u[nodes])
+    return sig
+
+
+def test_harmonic_interior_stresses_follow_the_column_solution(oracle_lib):
+    md = Model(cube_mesh(5, shape.QUAD9), cube_bcs())
+    o = oracle_lib.Oracle(md)
+    omega = 2.0
+    A, b, _ = o.assemble(omega, MAT)
+    x, _, _ = oracle_lib.lu_solve(A, b)
+    pts = PTS[:2]
+    sig = oracle_interior_stress(o, md, x, pts, omega, MAT)
+    k = omega / MAT.c1
+    s11 = np.cos(k * pts[:, 0]) / np.cos(k * 1.0)                # P cos(k x)/cos(k L)
+    s22 = MAT.lam / (MAT.lam + 2 * MAT.mu) * s11
+    assert np.abs(sig[:, 0, 0] - s11).max() < 5e-3 and np.abs(sig[:, 1, 1] - s22).max() < 5e-3 and np.abs(sig[:, 2, 2] - s22).max() < 5e-3
+    off = sig.copy(); off[:, 0, 0] = 0; off[:, 1, 1] = 0; off[:, 2, 2] = 0
+    assert np.abs(off).max() < 5e-3
