@@ -69,6 +69,18 @@ int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x, int n_ele
                        const int* row, const int* col_u, const int* col_t, const int* ctype, int n_dof,
                        double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
                        double geometric_tolerance, mfb_problem** problem);
+/* The same set-up for the HYPERSINGULAR equation at points off the boundary (interior-point stresses):
+ * fbem_bem_harela3d_hbie_auto (lib/fbem/src/bem_harela3d.f90:3632-3697) with its exterior branches _ext_pre :2573-2662 and
+ * _ext_adp :3044-3167 (estimator order 7 instead of 5, kernels d*, s*).  colloc_n[3*n_colloc] = unit normal n_i of every
+ * collocation point; colloc_elem must be -1 (a point on an element would need fbem_bem_harela3d_hbie_int: unsupported).
+ * With three collocation points per interior point (n_i = e_1, e_2, e_3) the rows of -(A x - b) are the traction vectors on
+ * the three coordinate planes, i.e. the stress tensor (src/calculate_internal_points_mechanics_bem_harela.f90:404-470). */
+int mfb_harela3d_setup_hbie(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
+                            const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
+                            const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
+                            const double* colloc_n, const int* row, const int* col_u, const int* col_t, const int* ctype, int n_dof,
+                            double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
+                            double geometric_tolerance, mfb_problem** problem);
 void mfb_problem_free(mfb_problem* problem);
 
 /* Once per frequency.  == `A_c=0; b_c=0` + build_lse_mechanics_bem_harela(kf,kr) for one elastic BE region with

@@ -129,11 +129,20 @@ class Problem:
             m.node_x, m.etype, m.elem_ptr, m.elem_node, m.elem_reversed, m.colloc_x, m.colloc_node, m.colloc_elem,
             m.colloc_kn, m.colloc_xi, m.row, m.col_u, m.col_t, m.ctype, m.precalset_gln)]
         self.h = C.c_void_p()
-        _check(lib().mfb_harela3d_setup(
-            ctx.h, C.c_int(m.n_node), _p(k[0]), C.c_int(m.n_elem), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]),
-            C.c_int(m.n_colloc), _p(k[5]), _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9]), _p(k[10]), _p(k[11]), _p(k[12]), _p(k[13]),
-            C.c_int(m.n_dof), C.c_double(m.qsi_relative_error), C.c_int(m.qsi_ns_max), C.c_int(len(m.precalset_gln)), _p(k[14]),
-            C.c_double(m.geometric_tolerance), C.byref(self.h)))
+        cn = getattr(m, "colloc_n", None)
+        if cn is None:
+            _check(lib().mfb_harela3d_setup(
+                ctx.h, C.c_int(m.n_node), _p(k[0]), C.c_int(m.n_elem), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]),
+                C.c_int(m.n_colloc), _p(k[5]), _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9]), _p(k[10]), _p(k[11]), _p(k[12]), _p(k[13]),
+                C.c_int(m.n_dof), C.c_double(m.qsi_relative_error), C.c_int(m.qsi_ns_max), C.c_int(len(m.precalset_gln)), _p(k[14]),
+                C.c_double(m.geometric_tolerance), C.byref(self.h)))
+        else:   # hypersingular equation at points off the boundary (interior-point stresses)
+            cn = np.ascontiguousarray(cn, dtype=np.float64); k.append(cn)
+            _check(lib().mfb_harela3d_setup_hbie(
+                ctx.h, C.c_int(m.n_node), _p(k[0]), C.c_int(m.n_elem), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]),
+                C.c_int(m.n_colloc), _p(k[5]), _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9]), _p(cn), _p(k[10]), _p(k[11]), _p(k[12]), _p(k[13]),
+                C.c_int(m.n_dof), C.c_double(m.qsi_relative_error), C.c_int(m.qsi_ns_max), C.c_int(len(m.precalset_gln)), _p(k[14]),
+                C.c_double(m.geometric_tolerance), C.byref(self.h)))
         self._cv = np.ascontiguousarray(m.cvalue, dtype=np.complex128)
 
     def close(self):
@@ -280,12 +289,28 @@ class InternalPoints:
 
     def __init__(self, ctx, model, points):
         from .host import InternalPointsModel
-        self.base = model
+        self.ctx, self.base, self._points = ctx, model, points
         self.ipm = InternalPointsModel(model, points)
         self.pr = Problem(ctx, self.ipm)
+        self.ipm_s = self.pr_s = None      # the hypersingular problem of the stresses, built on first use
 
     def close(self):
         self.pr.close()
+        if self.pr_s is not None:
+            self.pr_s.close()
+
+    def stresses(self, omega, mat, x):
+        """sigma (n_points, 3, 3) complex: sigma[p, l, k] = component l of the traction on the plane with normal e_k at point p
+        (internalpoint%value_c(l,k), src/calculate_internal_points_mechanics_bem_harela.f90:404-470), harmonic analysis."""
+        from .host import InternalPointsModel
+        if self.pr_s is None:
+            self.ipm_s = InternalPointsModel(self.base, self._points, stress=True)
+            self.pr_s = Problem(self.ctx, self.ipm_s)
+        self.pr_s.build_lse_mechanics_bem_harela(omega, mat, want_host=False)
+        xa = np.zeros(self.ipm_s.n_dof, dtype=np.complex128); xa[:self.base.n_dof] = x
+        r = self.pr_s.residual_vector(xa)
+        t = -r[self.base.n_dof:].reshape(-1, 3, 3)      # [point][plane k][component l]
+        return np.transpose(t, (0, 2, 1))
 
     def _u(self, x):
         xa = np.zeros(self.ipm.n_dof, dtype=np.complex128); xa[:self.base.n_dof] = x

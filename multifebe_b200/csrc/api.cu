@@ -77,6 +77,7 @@ struct mfb_problem {
   std::vector<int> h_tile_row0, h_tile_nbytes;   // host copies of DevColloc::tile_row0 / tile_nbytes (row partition of the multi-GPU mode)
   DistState dist;
   alignas(64) unsigned char tmapS[128]; bool have_tmapS;   // one-plane box: K1 flush of the static (real) assembly
+  bool hbie;                                               // hypersingular equation at points off the boundary (interior-point stresses)
   bool real_resident;                                      // the resident system / factors are real (static path): Are only
   alignas(64) unsigned char tmapA[128]; bool have_tmap;   // CUtensorMap of the planar system matrix (K1 flush)   // rows_permuted: the resident matrix/factors are in the internal order
 };
@@ -163,12 +164,39 @@ static unsigned morton3(const double* x, const double* lo, double inv_ext) {
 
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
+                      const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
+                      const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
+                      const int* row, const int* col_u, const int* col_t, const int* ctype, int n_dof,
+                      double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
+                      double geometric_tolerance, const double* colloc_n /* NULL, or 3 per collocation point: hypersingular equation */, mfb_problem** out);
 extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
                                   const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
                                   const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
                                   const int* row, const int* col_u, const int* col_t, const int* ctype, int n_dof,
                                   double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
                                   double geometric_tolerance, mfb_problem** out) {
+  return setup_impl(ctx, n_node, node_x, n_elem, etype, elem_ptr, elem_node, elem_reversed, n_colloc, colloc_x, colloc_node, colloc_elem, colloc_kn, colloc_xi,
+                    row, col_u, col_t, ctype, n_dof, qsi_relative_error, qsi_ns_max, n_precalsets, precalset_gln, geometric_tolerance, nullptr, out);
+}
+// Hypersingular equation for points OFF the boundary (interior-point stresses): fbem_bem_harela3d_hbie_auto with its exterior
+// branches (_ext_pre :2573-2662, _ext_adp :3044-3167); colloc_n[3*n_colloc] = unit normal n_i of each collocation point.
+extern "C" int mfb_harela3d_setup_hbie(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
+                                       const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
+                                       const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi, const double* colloc_n,
+                                       const int* row, const int* col_u, const int* col_t, const int* ctype, int n_dof,
+                                       double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
+                                       double geometric_tolerance, mfb_problem** out) {
+  if (!colloc_n) return fail(MFB_ERR_ARG, "mfb_harela3d_setup_hbie: null colloc_n");
+  return setup_impl(ctx, n_node, node_x, n_elem, etype, elem_ptr, elem_node, elem_reversed, n_colloc, colloc_x, colloc_node, colloc_elem, colloc_kn, colloc_xi,
+                    row, col_u, col_t, ctype, n_dof, qsi_relative_error, qsi_ns_max, n_precalsets, precalset_gln, geometric_tolerance, colloc_n, out);
+}
+static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
+                      const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
+                      const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
+                      const int* row, const int* col_u, const int* col_t, const int* ctype, int n_dof,
+                      double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
+                      double geometric_tolerance, const double* colloc_n, mfb_problem** out) {
   if (!ctx || !out || !node_x || !etype || !elem_ptr || !elem_node || !colloc_x || !colloc_node || !colloc_elem || !colloc_kn || !colloc_xi ||
       !row || !col_u || !col_t || !ctype || !precalset_gln)
     return fail(MFB_ERR_ARG, "mfb_harela3d_setup: null argument");
@@ -193,6 +221,8 @@ extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x
   S.qsi_relative_error = qsi_relative_error; S.qsi_ns_max = qsi_ns_max; S.geometric_tolerance = geometric_tolerance;
   S.ps_gln.assign(precalset_gln, precalset_gln + n_precalsets);
   p->set_gln = S.ps_gln;
+  S.f = colloc_n ? 7 : 5;     // order of the estimator's model function: fbem_bem_harela3d_sbie_auto :1522 / _hbie_auto :3677
+  p->hbie = colloc_n != nullptr;
   mfbh::init_settings(S);
 
   // ---- per-element data (csize, n_phi, bounding ball) ----
@@ -306,6 +336,12 @@ extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x
       h_crow[(size_t)k * ldp + q] = p->rowperm[row[3 * colloc_node[c] + k]];
     }
   }
+  double* d_cn = nullptr;
+  if (colloc_n) {
+    std::vector<double> h_cn(3 * (size_t)ldp, 0.0);
+    for (int q = 0; q < ldp; q++) { const int c = lane_colloc[q]; if (c >= 0) for (int k = 0; k < 3; k++) h_cn[(size_t)k * ldp + q] = colloc_n[3 * (size_t)c + k]; }
+    UP(p->owned, h_cn, &d_cn);
+  }
   double* d_cx; int *d_crow, *d_trow0, *d_tnbytes;
   UP(p->owned, h_cx, &d_cx); UP(p->owned, h_crow, &d_crow); UP(p->owned, t_row0, &d_trow0); UP(p->owned, t_nbytes, &d_tnbytes);
   // Columns: when every collocation node pairs row k with the column of its unknown k (the reference's numbering,
@@ -323,7 +359,7 @@ extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x
   }
   UP(p->owned, p->rowperm, &p->d_rowperm); UP(p->owned, p->colperm, &p->d_colperm);
   p->colloc.n_colloc = ldp; p->colloc.ldp = ldp; p->colloc.cx = d_cx; p->colloc.crow = d_crow;
-  p->colloc.n_tiles = n_tiles; p->colloc.tile_row0 = d_trow0; p->colloc.tile_nbytes = d_tnbytes; p->colloc.tile_active = nullptr;
+  p->colloc.n_tiles = n_tiles; p->colloc.tile_row0 = d_trow0; p->colloc.tile_nbytes = d_tnbytes; p->colloc.tile_active = nullptr; p->colloc.cn = d_cn;
   p->h_tile_row0 = t_row0; p->h_tile_nbytes = t_nbytes;
   p->rows_permuted = false;
 
@@ -492,6 +528,7 @@ extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x
     for (void* q : tmp) cudaFree(q);
   }
 
+  if (p->hbie && n_sing > 0) { mfb_problem_free(p); return fail(MFB_ERR_UNSUPPORTED, "mfb_harela3d_setup_hbie: a collocation point lies on an element (hypersingular interior integration is not built)"); }
   // ---- free-term entries (geometry only): src/build_lse_mechanics_bem_harela.f90:273-747 ----
   {
     // node -> (element, local node) incidences
@@ -596,6 +633,31 @@ static void host_kparams(cd lambda, cd mu, double rho, double omega, KParams& K)
   for (int i = 1; i <= 9; i++) { K.T2[i] = cv(T2[i]); K.T3[i] = cv(T3[i]); }
   const double c_1_4pi = 0.07957747154594767280411105048;
   K.cte_u = cv(c_1_4pi / mu); K.cte_t = c_1_4pi;
+  // hypersingular kernels: S1..S5, cte_d, cte_s (bem_harela3d.f90:219-287)
+  {
+    const cd k1_2 = k1 * k1, c1_5 = c1_4 * c1, c2_3 = c2_2 * c2; const double om3 = om2 * omega;
+    cd S1[12], S2[12], S3[13], S4[11], S5[12];
+    S1[1] = 3.0 * (1.0 - 2.0 * c2_2 / c1_2); S1[2] = -0.5 * c2_2 / c1_4 * om2; S1[3] = k2_2; S1[4] = 4.0 * im * k1 * k1_2 / k2_2;
+    S1[5] = -7.0 * im * k2; S1[6] = 24.0 * k1_2 / k2_2; S1[7] = -27.0; S1[8] = 60.0 * k1_2 / k2_2 / ik1; S1[9] = -60.0 / ik2;
+    S1[10] = 60.0 * k1_2 / k2_2 / ik1_2; S1[11] = -60.0 / ik2_2;
+    S2[1] = 6.0 * c2_2 / c1_2; S2[2] = (0.5 / c2_2 + 1.5 * c2_2 / c1_4 - 1.0 / c1_2) * om2; S2[3] = 2.0 * c2_2 / c1_4 * (c1_2 / c2_2 - 2.0) * om2;
+    S2[4] = 2.0 * im * c2_2 / c1_3 * (8.0 - 3.0 * c1_2 / c2_2) * omega; S2[5] = -4.0 * im * k2; S2[6] = 6.0 * c2_2 / c1_2 * (6.0 - c1_2 / c2_2);
+    S2[7] = -24.0; S2[8] = c2_2 / c1_2 * 60.0 / ik1; S2[9] = -60.0 / ik2; S2[10] = 60.0 / ik2_2; S2[11] = -60.0 / ik2_2;
+    S3[1] = 30.0 * (1.0 - c2_2 / c1_2); S3[2] = 1.5 * (1.0 / c2_2 - c2_2 / c1_4) * om2; S3[3] = -4.0 * c2_2 / c1_2 * k1_2; S3[4] = 4.0 * k2_2;
+    S3[5] = 40.0 * c2_2 / c1_2 * im * k1; S3[6] = -40.0 * im * k2; S3[7] = 180.0 * c2_2 / c1_2; S3[8] = -180.0;
+    S3[9] = 420.0 * c2_2 / c1_2 / ik1; S3[10] = -420.0 / ik2; S3[11] = 420.0 / ik2_2; S3[12] = -420.0 / ik2_2;
+    S4[1] = 2.0 * c2_2 / c1_2; S4[2] = 0.5 * (c2_2 / c1_4 + 1.0 / c2_2) * om2; S4[3] = -2.0 / 5.0 * (1.0 / c2_3 + 2.0 / 3.0 * c2_2 / c1_5) * im * om3;
+    S4[4] = 2.0 * im * k2; S4[5] = -4.0 * c2_2 / c1_2; S4[6] = 6.0; S4[7] = -12.0 * c2_2 / c1_2 / ik1; S4[8] = 12.0 / ik2;
+    S4[9] = -12.0 / ik2_2; S4[10] = 12.0 / ik2_2;
+    S5[1] = 2.0 * (1.0 - 3.0 * c2_2 / c1_2); S5[2] = (-2.0 / c1_2 + 0.5 / c2_2 + 0.5 * c2_2 / c1_4) * om2;
+    S5[3] = (8.0 / 3.0 / c1_3 + 4.0 / 15.0 / c2_3 - 1.0 / c1 / c2_2 - 24.0 / 15.0 * c2_2 / c1_5) * im * om3;
+    S5[4] = (-4.0 / c1_2 + 1.0 / c2_2 + 4.0 * c2_2 / c1_4) * om2; S5[5] = 4.0 * im * (1.0 / c1 - 2.0 * c2_2 / c1_3) * omega;
+    S5[6] = 4.0 * (1.0 - 3.0 * c2_2 / c1_2); S5[7] = 4.0; S5[8] = 12.0 * im * k1 / k2_2; S5[9] = -12.0 * im / k2; S5[10] = 12.0 / k2_2; S5[11] = -12.0 / k2_2;
+    for (int i = 1; i <= 11; i++) { K.S1[i] = cv(S1[i]); K.S2[i] = cv(S2[i]); K.S5[i] = cv(S5[i]); }
+    for (int i = 1; i <= 12; i++) K.S3[i] = cv(S3[i]);
+    for (int i = 1; i <= 10; i++) K.S4[i] = cv(S4[i]);
+    K.cte_d = c_1_4pi; K.cte_s = cv(c_1_4pi * mu);
+  }
 }
 // pre-scaled copy for the regular kernel: psi, chi times -cte_u (slot 0 = coefficient of the bare E2(z2)/r term), T times cte_t
 static void scale_kparams(const KParams& K, KParams& Q) {
@@ -1173,6 +1235,7 @@ static int upload_real(mfb_problem* p, const double* host, long long ldh, int ro
   return MFB_OK;
 }
 static int assemble_static_device(mfb_problem* p, double mu, double nu, const double* cvalue) {
+  if (p->hbie) return fail(MFB_ERR_UNSUPPORTED, "static assembly: the hypersingular (interior stress) problem is built for the harmonic kernels only");
   if (!(mu > 0.0) || !(nu > -1.0 && nu < 0.5)) return fail(MFB_ERR_ARG, "static assembly: mu must be positive and nu in (-1, 0.5)");
   KParams K, Q; host_kparams_static(mu, nu, K); scale_kparams(K, Q);
   std::vector<mfb_z> cv;

@@ -121,9 +121,11 @@ void launch_gather_cv(const DevGroup& g, const double* cvalue, cudaStream_t st) 
 template <int NN, int NL, class Pred>
 __device__ __forceinline__ void scatter_pair(const Acc<NN, NL>& a, const int* __restrict__ ecol, const unsigned char* __restrict__ ekind,
                                              const double* __restrict__ ecv, bool rev, const DevSystem& s, int il,
-                                             int r0, int r1, int r2, double* bre, double* bim, Pred mine) {
-  const double ct = rev ? -c_kp.cte_t : c_kp.cte_t;
-  const cplx cu = c_kp.cte_u;
+                                             int r0, int r1, int r2, double* bre, double* bim, Pred mine, bool hbie = false) {
+  // h (or m of the hypersingular equation) is scaled by cte_t (cte_s) and changes sign on a reversed element; g (l) by cte_u (cte_d)
+  const cplx ch0 = hbie ? c_kp.cte_s : mk(c_kp.cte_t, 0.0);
+  const cplx ch = rev ? mk(-ch0.re, -ch0.im) : ch0;
+  const cplx cu = hbie ? mk(c_kp.cte_d, 0.0) : c_kp.cte_u;
 #pragma unroll
   for (int j = 0; j < NN; j++) {
 #pragma unroll
@@ -140,7 +142,7 @@ __device__ __forceinline__ void scatter_pair(const Acc<NN, NL>& a, const int* __
         const int l = (NL == 3) ? ll : il;
         const int row = (l == 0) ? r0 : (l == 1 ? r1 : r2);
         const int q = (ll * 3 + k) * NN + j;
-        double hr = ct * a.hr[q], hi = ct * a.hi[q];
+        double hr = ch.re * a.hr[q] - ch.im * a.hi[q], hi = ch.re * a.hi[q] + ch.im * a.hr[q];
         double gr = cu.re * a.gr[q] - cu.im * a.gi[q], gi = cu.re * a.gi[q] + cu.im * a.gr[q];
         double ar, ai, br, bi;
         if (kind == 0) { ar = -gr; ai = -gi; br = -(hr * cvr - hi * cvi); bi = -(hr * cvi + hi * cvr); }
@@ -162,7 +164,8 @@ struct LaneEntries { int lane; __device__ __forceinline__ bool operator()(int jk
 const int K1_WARPS = 4;
 const int K1_ECHUNK = 32;
 
-template <int ET, int NL>
+// HB: hypersingular equation (interior-point stresses): the collocation point carries a unit normal (DevColloc::cn)
+template <int ET, int NL, bool HB>
 __global__ void __launch_bounds__(K1_WARPS * 32) k_regular(DevGroup g, DevColloc c, DevSystem s, const unsigned char* __restrict__ plan) {
   const int NN = ElemTraits<ET>::NN;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -171,6 +174,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_regular(DevGroup g, DevColloc
   const int r0 = c.crow[cpos], r1 = c.crow[c.ldp + cpos], r2 = c.crow[2 * c.ldp + cpos];
   const bool valid = r0 >= 0 && (!c.tile_active || c.tile_active[cpos >> 5]);
   const double xc[3] = {c.cx[cpos], c.cx[c.ldp + cpos], c.cx[2 * c.ldp + cpos]};
+  double ni[3] = {0.0, 0.0, 0.0};
+  if (HB) { ni[0] = c.cn[cpos]; ni[1] = c.cn[c.ldp + cpos]; ni[2] = c.cn[2 * c.ldp + cpos]; }
   double bre[3] = {0.0, 0.0, 0.0}, bim[3] = {0.0, 0.0, 0.0};
   const int e0 = blockIdx.y * K1_ECHUNK, e1 = min(e0 + K1_ECHUNK, g.n_elem);
   for (int e = e0; e < e1; e++) {
@@ -197,9 +202,10 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_regular(DevGroup g, DevColloc
             double x[3] = {__ldg(q), __ldg(q + 1), __ldg(q + 2)}, n[3] = {__ldg(q + 3), __ldg(q + 4), __ldg(q + 5)}, w[NN];
 #pragma unroll
             for (int j = 0; j < NN; j++) w[j] = __ldg(q + 6 + j);
-            accumulate_exterior<NN, NL>(acc, c_kp, x, n, xc, w, il);
+            if (HB) accumulate_exterior_hbie<NN, NL>(acc, c_kp, x, n, xc, ni, w, il);
+            else accumulate_exterior<NN, NL>(acc, c_kp, x, n, xc, w, il);
           }
-          scatter_pair<NN, NL>(acc, ecol, ekind, ecv, rev, s, il, r0, r1, r2, bre, bim, AllEntries());
+          scatter_pair<NN, NL>(acc, ecol, ekind, ecv, rev, s, il, r0, r1, r2, bre, bim, AllEntries(), HB);
         }
       }
     }
@@ -649,17 +655,27 @@ void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, c
   if (g.n_elem == 0) return;
   dim3 grid((c.ldp + 32 * K1_WARPS - 1) / (32 * K1_WARPS), (g.n_elem + K1_ECHUNK - 1) / K1_ECHUNK);
   dim3 block(K1_WARPS * 32);
+  if (c.cn) {   // hypersingular equation: the general kernel (a handful of interior points, not a hot path)
+    switch (g.et) {
+      case 5: k_regular<5, 3, true><<<grid, block, 0, st>>>(g, c, s, plan); break;
+      case 7: k_regular<7, 3, true><<<grid, block, 0, st>>>(g, c, s, plan); break;
+      case 6: k_regular<6, 1, true><<<grid, block, 0, st>>>(g, c, s, plan); break;
+      case 8: k_regular<8, 1, true><<<grid, block, 0, st>>>(g, c, s, plan); break;
+      case 9: k_regular<9, 1, true><<<grid, block, 0, st>>>(g, c, s, plan); break;
+    }
+    return;
+  }
   switch (g.et) {
     case 5: if (g.cols3 && tmap) { launch_regular_et<5>(g, c, s, plan, tmap, statics, st); break; }
-            k_regular<5, 3><<<grid, block, 0, st>>>(g, c, s, plan); break;
+            k_regular<5, 3, false><<<grid, block, 0, st>>>(g, c, s, plan); break;
     case 7: if (g.cols3 && tmap) { launch_regular_et<7>(g, c, s, plan, tmap, statics, st); break; }
-            k_regular<7, 3><<<grid, block, 0, st>>>(g, c, s, plan); break;
+            k_regular<7, 3, false><<<grid, block, 0, st>>>(g, c, s, plan); break;
     case 6: if (g.cols3 && tmap) { launch_regular_et<6>(g, c, s, plan, tmap, statics, st); break; }
-            k_regular<6, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
+            k_regular<6, 1, false><<<grid, block, 0, st>>>(g, c, s, plan); break;
     case 8: if (g.cols3 && tmap) { launch_regular_et<8>(g, c, s, plan, tmap, statics, st); break; }
-            k_regular<8, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
+            k_regular<8, 1, false><<<grid, block, 0, st>>>(g, c, s, plan); break;
     case 9: if (g.cols3 && tmap) { launch_regular_et<9>(g, c, s, plan, tmap, statics, st); break; }
-            k_regular<9, 1><<<grid, block, 0, st>>>(g, c, s, plan); break;
+            k_regular<9, 1, false><<<grid, block, 0, st>>>(g, c, s, plan); break;
   }
 }
 
@@ -684,7 +700,7 @@ __device__ __forceinline__ void flush_b(const DevSystem& s, int r0, int r1, int 
 // ------------------------------------------------------------------------------------------------------------------
 // K2: adaptive pairs -- one warp per pair, lanes stride over the gln x gln points of every leaf.
 // ------------------------------------------------------------------------------------------------------------------
-template <int ET, int NL>
+template <int ET, int NL, bool HB>
 __global__ void __launch_bounds__(128) k_adaptive(DevGroup g, DevColloc c, DevSystem s, DevAdaptive a, DevTables t) {
   const int NN = ElemTraits<ET>::NN;
   const bool tri = (ElemTraits<ET>::NV == 3);
@@ -695,6 +711,8 @@ __global__ void __launch_bounds__(128) k_adaptive(DevGroup g, DevColloc c, DevSy
   if (c.tile_active && !c.tile_active[cpos >> 5]) return;
   const double xc[3] = {c.cx[cpos], c.cx[c.ldp + cpos], c.cx[2 * c.ldp + cpos]};
   const int r0 = c.crow[cpos], r1 = c.crow[c.ldp + cpos], r2 = c.crow[2 * c.ldp + cpos];
+  double ni[3] = {0.0, 0.0, 0.0};
+  if (HB) { ni[0] = c.cn[cpos]; ni[1] = c.cn[c.ldp + cpos]; ni[2] = c.cn[2 * c.ldp + cpos]; }
   double xn[3 * NN];
 #pragma unroll
   for (int i = 0; i < 3 * NN; i++) xn[i] = g.xn[(size_t)e * 3 * NN + i];
@@ -718,25 +736,36 @@ __global__ void __launch_bounds__(128) k_adaptive(DevGroup g, DevColloc c, DevSy
         const int k1 = idx / gln, k2 = idx - k1 * gln;
         double x[3], n[3], w[NN];
         leaf_point<ET>(xn, xi_s, tp1, tp2, __ldg(gx + off + k1), __ldg(gw + off + k1), __ldg(gx + off + k2), __ldg(gw + off + k2), x, n, w);
-        accumulate_exterior<NN, NL>(acc, c_kp, x, n, xc, w, il);
+        if (HB) accumulate_exterior_hbie<NN, NL>(acc, c_kp, x, n, xc, ni, w, il);
+        else accumulate_exterior<NN, NL>(acc, c_kp, x, n, xc, w, il);
       }
     }
     warp_reduce<NN, NL>(acc);
     LaneEntries le; le.lane = lane;
     scatter_pair<NN, NL>(acc, g.ecol + (size_t)e * 3 * NN, g.ekind + (size_t)e * 3 * NN, g.ecv + (size_t)e * 6 * NN, g.erev[e] != 0, s, il,
-                         r0, r1, r2, bre, bim, le);
+                         r0, r1, r2, bre, bim, le, HB);
   }
   flush_b(s, r0, r1, r2, bre, bim);
 }
 void launch_adaptive(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevAdaptive& a, const DevTables& t, cudaStream_t st) {
   if (a.n_pairs == 0) return;
   dim3 grid((a.n_pairs + 3) / 4), block(128);
+  if (c.cn) {
+    switch (g.et) {
+      case 5: k_adaptive<5, 3, true><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+      case 7: k_adaptive<7, 3, true><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+      case 6: k_adaptive<6, 1, true><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+      case 8: k_adaptive<8, 1, true><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+      case 9: k_adaptive<9, 1, true><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    }
+    return;
+  }
   switch (g.et) {
-    case 5: k_adaptive<5, 3><<<grid, block, 0, st>>>(g, c, s, a, t); break;
-    case 7: k_adaptive<7, 3><<<grid, block, 0, st>>>(g, c, s, a, t); break;
-    case 6: k_adaptive<6, 1><<<grid, block, 0, st>>>(g, c, s, a, t); break;
-    case 8: k_adaptive<8, 1><<<grid, block, 0, st>>>(g, c, s, a, t); break;
-    case 9: k_adaptive<9, 1><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 5: k_adaptive<5, 3, false><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 7: k_adaptive<7, 3, false><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 6: k_adaptive<6, 1, false><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 8: k_adaptive<8, 1, false><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 9: k_adaptive<9, 1, false><<<grid, block, 0, st>>>(g, c, s, a, t); break;
   }
 }
 

@@ -52,6 +52,7 @@ struct DevColloc {
   int n_tiles;
   const int* tile_row0;          // [n_tiles] first internal row of the tile's run
   const int* tile_nbytes;        // [n_tiles] 24*cnt, or 0 for a loose tile
+  const double* cn;              // [3][ldp] unit normal at the collocation point, or NULL: hypersingular equation (interior-point stresses)
   const unsigned char* tile_active;   // [n_tiles] or NULL = all: tiles (row blocks) this rank assembles (single-frequency multi-GPU mode)
 };
 

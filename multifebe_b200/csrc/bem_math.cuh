@@ -33,6 +33,8 @@ struct KParams {
   cplx k1, k2;
   cplx psi[7], chi[7], T1[11], T2[10], T3[10];
   cplx cte_u; double cte_t;
+  cplx S1[12], S2[12], S3[13], S4[11], S5[12];   // hypersingular kernels d*, s* (bem_harela3d.f90:219-280)
+  cplx cte_s; double cte_d;
 };
 
 // E_2..E_5 of z (returned already divided: e2 = E2/r, e3 = E3/r^2, e4 = E4/r^3, e5 = E5/r^4)
@@ -161,6 +163,22 @@ MFB_HD void zexp_pair(cplx z1, cplx z2, cplx& A2, cplx& A3, cplx& A4, cplx& A5, 
   else { zexp_E2_5(z1, A2, A3, A4, A5); zexp_E2_5(z2, B2, B3, B4, B5); }
 }
 
+// E_2..E_6 for the hypersingular kernels (not a hot path: general form, both branches of numerical.f90:1258-1330)
+MFB_HD void zexp_E2_6(cplx z, cplx& E2, cplx& E3, cplx& E4, cplx& E5, cplx& E6) {
+  const cplx z2 = z * z, z3 = z2 * z, z4 = z2 * z2, z5 = z4 * z;
+  if (z.re * z.re + z.im * z.im <= 1.0) {
+    double c[18]; c[0] = 1.0 / 720.0;
+    for (int m = 1; m < 18; m++) c[m] = c[m - 1] / (double)(m + 6);
+    double sr = c[17], si = 0.0;
+    for (int m = 16; m >= 0; m--) { const double tr = fma(sr, z.re, fma(-si, z.im, c[m])); si = fma(sr, z.im, si * z.re); sr = tr; }
+    E6 = (z5 * z) * mk(sr, si);
+    E5 = cfmar(z5, 1.0 / 120.0, E6); E4 = cfmar(z4, 1.0 / 24.0, E5); E3 = cfmar(z3, 1.0 / 6.0, E4); E2 = cfmar(z2, 0.5, E3);
+  } else {
+    zexp_direct(z, E2, E3, E4, E5);
+    E6 = cfmar(z5, -1.0 / 120.0, E5);
+  }
+}
+
 struct KScal { cplx psi, chi, T1, T2, T3; double d1r1, d1r2; };
 
 // regular_only: drop the static 1/r^2 parts of T1..T3 (interior integration, bem_harela3d.f90:1394-1401)
@@ -274,6 +292,80 @@ MFB_HD void accumulate_exterior(Acc<NN, NL>& a, const KParams& p, const double* 
         const int q = (ll * 3 + kk) * NN + j;
         a.hr[q] += ft.re * w[j]; a.hi[q] += ft.im * w[j];
         a.gr[q] += fu.re * w[j]; a.gi[q] += fu.im * w[j];
+      }
+    }
+  }
+}
+
+// Exterior point of the HYPERSINGULAR equation (fbem_bem_harela3d_hbie_ext_pre, bem_harela3d.f90:2606-2654): ni = unit normal at
+// the collocation point; the s* combination goes to a.h (the reference's m), the d* combination to a.g (its l).
+template <int NN, int NL>
+MFB_HD void accumulate_exterior_hbie(Acc<NN, NL>& a, const KParams& p, const double* x, const double* n, const double* xc, const double* ni,
+                                     const double* w, int il) {
+  const double rv0 = x[0] - xc[0], rv1 = x[1] - xc[1], rv2 = x[2] - xc[2];
+  const double r = sqrt(rv0 * rv0 + rv1 * rv1 + rv2 * rv2);
+  const double d1r1 = 1.0 / r, d1r2 = d1r1 * d1r1, d1r3 = d1r2 * d1r1, d1r4 = d1r2 * d1r2, d1r5 = d1r4 * d1r1;
+  const double dx[3] = {rv0 * d1r1, rv1 * d1r1, rv2 * d1r1};
+  const double drdn = dx[0] * n[0] + dx[1] * n[1] + dx[2] * n[2], drdni = -(dx[0] * ni[0] + dx[1] * ni[1] + dx[2] * ni[2]);
+  const double nni = n[0] * ni[0] + n[1] * ni[1] + n[2] * ni[2];
+  const cplx z1 = mk(p.k1.im * r, -p.k1.re * r), z2 = mk(p.k2.im * r, -p.k2.re * r);
+  cplx A2, A3, A4, A5, A6, B2, B3, B4, B5, B6;
+  zexp_E2_6(z1, A2, A3, A4, A5, A6); zexp_E2_6(z2, B2, B3, B4, B5, B6);
+  const cplx E21 = A2 * d1r1, E22 = B2 * d1r1, E31 = A3 * d1r2, E32 = B3 * d1r2, E41 = A4 * d1r3, E42 = B4 * d1r3;
+  const cplx E51 = A5 * d1r4, E52 = B5 * d1r4, E61 = A6 * d1r5, E62 = B6 * d1r5;
+  cplx t;
+  t = cfmar(p.T1[1], d1r2, p.T1[2]);
+  t = cfma(p.T1[3], E21, t); t = cfma(p.T1[4], E22, t); t = cfma(p.T1[5], E31, t); t = cfma(p.T1[6], E32, t);
+  t = cfma(p.T1[7], E41, t); t = cfma(p.T1[8], E42, t); t = cfma(p.T1[9], E51, t); t = cfma(p.T1[10], E52, t);
+  const cplx TT1 = t;
+  t = cfmar(p.T2[1], d1r2, p.T2[2]);
+  t = cfma(p.T2[3], E22, t); t = cfma(p.T2[4], E31, t); t = cfma(p.T2[5], E32, t); t = cfma(p.T2[6], E41, t);
+  t = cfma(p.T2[7], E42, t); t = cfma(p.T2[8], E51, t); t = cfma(p.T2[9], E52, t);
+  const cplx TT2 = t;
+  t = cfmar(p.T3[1], d1r2, p.T3[2]);
+  t = cfma(p.T3[3], E21, t); t = cfma(p.T3[4], E31, t); t = cfma(p.T3[5], E32, t); t = cfma(p.T3[6], E41, t);
+  t = cfma(p.T3[7], E42, t); t = cfma(p.T3[8], E51, t); t = cfma(p.T3[9], E52, t);
+  const cplx TT3 = t;
+  t = p.S1[1] * d1r3 + p.S1[2] * d1r1;
+  t = cfma(p.S1[3], E22, t); t = cfma(p.S1[4], E31, t); t = cfma(p.S1[5], E32, t); t = cfma(p.S1[6], E41, t); t = cfma(p.S1[7], E42, t);
+  t = cfma(p.S1[8], E51, t); t = cfma(p.S1[9], E52, t); t = cfma(p.S1[10], E61, t); t = cfma(p.S1[11], E62, t);
+  const cplx S1 = t;
+  t = p.S2[1] * d1r3 + p.S2[2] * d1r1;
+  t = cfma(p.S2[3], E21, t); t = cfma(p.S2[4], E31, t); t = cfma(p.S2[5], E32, t); t = cfma(p.S2[6], E41, t); t = cfma(p.S2[7], E42, t);
+  t = cfma(p.S2[8], E51, t); t = cfma(p.S2[9], E52, t); t = cfma(p.S2[10], E61, t); t = cfma(p.S2[11], E62, t);
+  const cplx S2 = t;
+  t = p.S3[1] * d1r3 + p.S3[2] * d1r1;
+  t = cfma(p.S3[3], E21, t); t = cfma(p.S3[4], E22, t); t = cfma(p.S3[5], E31, t); t = cfma(p.S3[6], E32, t); t = cfma(p.S3[7], E41, t);
+  t = cfma(p.S3[8], E42, t); t = cfma(p.S3[9], E51, t); t = cfma(p.S3[10], E52, t); t = cfma(p.S3[11], E61, t); t = cfma(p.S3[12], E62, t);
+  const cplx S3 = t;
+  t = p.S4[1] * d1r3 + p.S4[2] * d1r1 + p.S4[3];
+  t = cfma(p.S4[4], E32, t); t = cfma(p.S4[5], E41, t); t = cfma(p.S4[6], E42, t); t = cfma(p.S4[7], E51, t); t = cfma(p.S4[8], E52, t);
+  t = cfma(p.S4[9], E61, t); t = cfma(p.S4[10], E62, t);
+  const cplx S4 = t;
+  t = p.S5[1] * d1r3 + p.S5[2] * d1r1 + p.S5[3];
+  t = cfma(p.S5[4], E21, t); t = cfma(p.S5[5], E31, t); t = cfma(p.S5[6], E41, t); t = cfma(p.S5[7], E42, t); t = cfma(p.S5[8], E51, t);
+  t = cfma(p.S5[9], E52, t); t = cfma(p.S5[10], E61, t); t = cfma(p.S5[11], E62, t);
+  const cplx S5 = t;
+#pragma unroll
+  for (int ll = 0; ll < NL; ll++) {
+    const int l = (NL == 3) ? ll : il;
+    const double dxl = (NL == 3) ? dx[ll] : (il == 0 ? dx[0] : (il == 1 ? dx[1] : dx[2]));
+    const double nl = (NL == 3) ? n[ll] : (il == 0 ? n[0] : (il == 1 ? n[1] : n[2]));
+    const double nil = (NL == 3) ? ni[ll] : (il == 0 ? ni[0] : (il == 1 ? ni[1] : ni[2]));
+#pragma unroll
+    for (int kk = 0; kk < 3; kk++) {
+      const double dl = (l == kk) ? 1.0 : 0.0;
+      // fs_d = TT1 r,l r,k drdni - TT2 (-drdni delta + r,l ni_k) - TT3 r,k ni_l
+      const double d1 = dxl * dx[kk] * drdni, d2 = -(-drdni * dl + dxl * ni[kk]), d3 = -dx[kk] * nil;
+      const cplx fd = mk(TT1.re * d1 + TT2.re * d2 + TT3.re * d3, TT1.im * d1 + TT2.im * d2 + TT3.im * d3);
+      const double s1 = dxl * ni[kk] * drdn - dx[kk] * nl * drdni - dl * drdn * drdni + dxl * dx[kk] * nni;
+      const double s2 = dx[kk] * nil * drdn - dxl * n[kk] * drdni, s3 = dxl * dx[kk] * drdn * drdni, s4 = dl * nni + ni[kk] * nl, s5 = n[kk] * nil;
+      const cplx fs = mk(S1.re * s1 + S2.re * s2 + S3.re * s3 + S4.re * s4 + S5.re * s5, S1.im * s1 + S2.im * s2 + S3.im * s3 + S4.im * s4 + S5.im * s5);
+#pragma unroll
+      for (int j = 0; j < NN; j++) {
+        const int q = (ll * 3 + kk) * NN + j;
+        a.hr[q] += fs.re * w[j]; a.hi[q] += fs.im * w[j];
+        a.gr[q] += fd.re * w[j]; a.gi[q] += fd.im * w[j];
       }
     }
   }

@@ -762,9 +762,9 @@ bool xi_on_element_boundary(int et, const double* xi) { return check_xi1xi2_edge
 static inline int qs_n(bool telles, int et, int f, const QsTable& q, double d, const double* barxi) { return qs_n_estimation(telles, et, f, q, d, barxi); }
 
 // N_far(d), d>2: curve 3 with nint (quasisingular_integration.f90:543-549); 31 stands for ">30".
-static int n_far(const QsTable& q, double d) {
+static int n_far(const QsTable& q, double d, int f) {
   const double bx[2] = {0.0, 0.0};
-  int n = qs_n(false, TRI3, 5, q, d, bx);
+  int n = qs_n(false, TRI3, f, q, d, bx);
   return n == 0 ? 31 : n;
 }
 static inline double from_bits(uint64_t u) { double d; memcpy(&d, &u, 8); return d; }
@@ -773,14 +773,14 @@ static inline uint64_t to_bits(double d) { uint64_t u; memcpy(&u, &d, 8); return
 void init_settings(Settings& s) {
   qs_table(s.qsi_relative_error, s.qs);
   qs_table(1.e-15, s.qs_li);
-  s.far_dmax = s.qs.dmax[2][5];
+  s.far_dmax = s.qs.dmax[2][s.f];
   // far_thr[n] = smallest double d > 2 with N_far(d) <= n, found by bisection over the ordered bit patterns of
   // positive doubles with the exact host estimator, so that the GPU only compares d against thresholds.
   double dlo = nextafter(2.0, 3.0), dhi = std::max(s.far_dmax, dlo);
   for (int n = 2; n <= 30; n++) {
-    if (n_far(s.qs, dlo) <= n) { s.far_thr[n] = dlo; continue; }
+    if (n_far(s.qs, dlo, s.f) <= n) { s.far_thr[n] = dlo; continue; }
     uint64_t lo = to_bits(dlo), hi = to_bits(dhi);  // N(lo) > n, N(hi) = 2 <= n
-    while (hi - lo > 1) { uint64_t mid = lo + (hi - lo) / 2; if (n_far(s.qs, from_bits(mid)) <= n) hi = mid; else lo = mid; }
+    while (hi - lo > 1) { uint64_t mid = lo + (hi - lo) / 2; if (n_far(s.qs, from_bits(mid), s.f) <= n) hi = mid; else lo = mid; }
     s.far_thr[n] = from_bits(hi);
   }
   s.far_thr[0] = s.far_thr[1] = s.far_thr[31] = 0.0;
@@ -829,7 +829,7 @@ static void collect_leaves(const Elem& e, double* xi_s, const double* x_i, const
     double cl = characteristic_length(e.et, x_s, 1.e-12);
     nearest_element_point_bem(e.et, x_s, cl, x_i, barxip, rmin, d, method);
   }
-  int gln_near = qs_n(true, e.et, 5, s.qs, d, barxip);
+  int gln_near = qs_n(true, e.et, s.f, s.qs, d, barxip);
   bool subdivide = false;
   if (ks == s.qsi_ns_max) { if (gln_near == 0) gln_near = 30; } else if (gln_near == 0) subdivide = true;
   if (!subdivide) {
@@ -941,7 +941,7 @@ void plan_near_pair(const Elem& e, const double* x_i, const Settings& s, NearPla
     nearest_element_point_bem(e.et, e.x, e.cl, x_i, barxi, rmin, d, method);
     if (d <= 1.e-12) { out.mode = 2; plan_singular(e, barxi, s, out); return; }
   }
-  int gln_near = qs_n(false, e.et, 5, s.qs, d, barxi);
+  int gln_near = qs_n(false, e.et, s.f, s.qs, d, barxi);
   int gln = std::max(e.gln_far, gln_near);
   int ps_gln_max = 0; for (int g : s.ps_gln) ps_gln_max = std::max(ps_gln_max, g);
   if (gln <= ps_gln_max && gln_near > 0) {

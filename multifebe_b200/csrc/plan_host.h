@@ -27,6 +27,8 @@ struct Settings {
   QsTable qs_li;    // for the 1e-15 line integrals of the singular path
   double far_thr[32];  // far_thr[n], n=2..30: smallest d>2 with N_far(d) <= n   (GPU classifier compares d against it)
   double far_dmax;     // d >= far_dmax -> gln_near = 2
+  int f = 5;           // order of the estimator's model function: 5 for the SBIE kernels, 7 for the hypersingular ones
+                       // (fbem_bem_harela3d_sbie_auto :1522 / _hbie_auto :3677)
 };
 void init_settings(Settings& s);
 

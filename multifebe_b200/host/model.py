@@ -161,11 +161,20 @@ class InternalPointsModel:
     boundary problem; every interior point gets a dummy node (used by no element) that owns its three rows, placed after the
     boundary rows; colloc_elem = -1 tells the library that there is no free term."""
 
-    def __init__(self, model, points):
+    def __init__(self, model, points, stress=False):
+        """stress=True: the hypersingular problem -- every point appears three times with the unit normals e_1, e_2, e_3
+        (colloc_n), so that its nine rows are the traction vectors on the three coordinate planes = the stress tensor."""
         m = model
-        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        pts0 = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        self.n_points = len(pts0)
+        self.colloc_n = None
+        if stress:
+            pts = np.repeat(pts0, 3, axis=0)
+            self.colloc_n = np.ascontiguousarray(np.tile(np.eye(3), (len(pts0), 1)))
+        else:
+            pts = pts0
         nip = len(pts)
-        self.base, self.points, self.n_points = m, pts, nip
+        self.base, self.points = m, pts0
         self.mesh = m.mesh
         self.n_node, self.n_elem = m.n_node + nip, m.n_elem
         self.node_x = np.ascontiguousarray(np.vstack([m.node_x, pts]))

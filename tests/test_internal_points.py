@@ -129,3 +129,29 @@ def test_harmonic_interior_stresses_follow_the_column_solution(oracle_lib):
     assert np.abs(sig[:, 0, 0] - s11).max() < 5e-3 and np.abs(sig[:, 1, 1] - s22).max() < 5e-3 and np.abs(sig[:, 2, 2] - s22).max() < 5e-3
     off = sig.copy(); off[:, 0, 0] = 0; off[:, 1, 1] = 0; off[:, 2, 2] = 0
     assert np.abs(off).max() < 5e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("et,m", [(shape.TRI3, 4), (shape.QUAD9, 2), (shape.QUAD8, 2)])
+def test_gpu_interior_stresses_match_the_oracle_composition(gpu_ctx, oracle_lib, et, m):
+    from multifebe_b200 import capi
+    md = Model(cube_mesh(m, et), cube_bcs())
+    pr = capi.Problem(gpu_ctx, md)
+    ip = capi.InternalPoints(gpu_ctx, md, PTS)
+    o = oracle_lib.Oracle(md)
+    omega = 3.0
+    x = pr.solve_frequency(omega, MAT)
+    sg = ip.stresses(omega, MAT, x)
+    so = oracle_interior_stress(o, md, x, PTS, omega, MAT)
+    assert np.abs(sg - so).max() < 1e-10 * np.abs(so).max()
+    ug = ip.displacements(omega, MAT, x)            # both problems live side by side
+    uo = oracle_interior_u(o, md, x, PTS, lambda e, xp: o.pair(e, xp, omega, MAT)[:2])
+    assert np.abs(ug - uo).max() < 1e-10 * np.abs(uo).max()
+    ip.close(); pr.close()
+
+
+def test_stress_model_layout():
+    md = Model(cube_mesh(2, shape.TRI3), cube_bcs())
+    ipm = InternalPointsModel(md, PTS, stress=True)
+    assert ipm.n_colloc == 15 and ipm.n_dof == md.n_dof + 45 and ipm.colloc_n.shape == (15, 3)
+    assert np.allclose(ipm.colloc_x[0], ipm.colloc_x[2]) and np.allclose(ipm.colloc_n[:3], np.eye(3))
