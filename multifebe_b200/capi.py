@@ -307,10 +307,22 @@ class InternalPoints:
             self.ipm_s = InternalPointsModel(self.base, self._points, stress=True)
             self.pr_s = Problem(self.ctx, self.ipm_s)
         self.pr_s.build_lse_mechanics_bem_harela(omega, mat, want_host=False)
+        return self._sigma(x)
+
+    def _sigma(self, x):
         xa = np.zeros(self.ipm_s.n_dof, dtype=np.complex128); xa[:self.base.n_dof] = x
         r = self.pr_s.residual_vector(xa)
         t = -r[self.base.n_dof:].reshape(-1, 3, 3)      # [point][plane k][component l]
         return np.transpose(t, (0, 2, 1))
+
+    def stresses_static(self, mat, x):
+        """The same for the static analysis (fbem_bem_staela3d_hbie_*): real sigma (n_points, 3, 3)."""
+        from .host import InternalPointsModel
+        if self.pr_s is None:
+            self.ipm_s = InternalPointsModel(self.base, self._points, stress=True)
+            self.pr_s = Problem(self.ctx, self.ipm_s)
+        self.pr_s.build_lse_mechanics_bem_staela(mat, want_host=False)
+        return self._sigma(np.asarray(x, dtype=np.complex128)).real
 
     def _u(self, x):
         xa = np.zeros(self.ipm.n_dof, dtype=np.complex128); xa[:self.base.n_dof] = x

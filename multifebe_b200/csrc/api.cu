@@ -680,6 +680,11 @@ static void host_kparams_static(double mu, double nu, KParams& K) {
   K.T1[1] = mk(3.0 * (rc - 1.0), 0.0); K.T2[1] = mk(-rc, 0.0); K.T3[1] = mk(rc, 0.0);
   const double c_1_4pi = 0.07957747154594767280411105048;
   K.cte_u = mk(c_1_4pi / mu, 0.0); K.cte_t = c_1_4pi;
+  // hypersingular kernels: the 1/r^3 coefficients alone (bem_harela3d.f90:219-280 at omega = 0) are d*, s* of
+  // fbem_bem_staela3d_hbie_ext_pre (bem_staela3d.f90:4428-4443): S1 = 3 nu/(1-nu), S2 = 3(1-2nu)/(1-nu), S3 = 15/(1-nu), ...
+  K.S1[1] = mk(3.0 * (1.0 - 2.0 * rc), 0.0); K.S2[1] = mk(6.0 * rc, 0.0); K.S3[1] = mk(30.0 * (1.0 - rc), 0.0);
+  K.S4[1] = mk(2.0 * rc, 0.0); K.S5[1] = mk(2.0 * (1.0 - 3.0 * rc), 0.0);
+  K.cte_d = c_1_4pi; K.cte_s = mk(c_1_4pi * mu, 0.0);
 }
 static int assemble_device_k(mfb_problem* p, const KParams& K, const KParams& Q, cd nu, const mfb_z* cvalue, bool statics);
 static int assemble_device(mfb_problem* p, double omega, cd lambda, cd mu, double rho, cd nu, const mfb_z* cvalue) {
@@ -1235,7 +1240,7 @@ static int upload_real(mfb_problem* p, const double* host, long long ldh, int ro
   return MFB_OK;
 }
 static int assemble_static_device(mfb_problem* p, double mu, double nu, const double* cvalue) {
-  if (p->hbie) return fail(MFB_ERR_UNSUPPORTED, "static assembly: the hypersingular (interior stress) problem is built for the harmonic kernels only");
+
   if (!(mu > 0.0) || !(nu > -1.0 && nu < 0.5)) return fail(MFB_ERR_ARG, "static assembly: mu must be positive and nu in (-1, 0.5)");
   KParams K, Q; host_kparams_static(mu, nu, K); scale_kparams(K, Q);
   std::vector<mfb_z> cv;

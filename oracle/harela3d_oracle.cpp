@@ -204,13 +204,15 @@ struct Params {
   cd psi[7], chi[7], T1[11], T2[10], T3[10]; cd cte_u, cte_t;
   cd S1[12], S2[12], S3[13], S4[11], S5[12]; cd cte_d, cte_s;   // hypersingular equation (d*, s*): bem_harela3d.f90:219-287
   // static elasticity (lib/fbem/src/bem_staela3d.f90): Kelvin solution, cte_u = cteu1, cte_t = ctet1 of :617-622
-  bool statics = false; double cteu2 = 0.0, ctet2 = 0.0;
+  bool statics = false; double cteu2 = 0.0, ctet2 = 0.0, nu_s = 0.0, ctes3 = 0.0;
 };
 // constants of fbem_bem_staela3d_sbie_ext_pre / _ext_st / _int: bem_staela3d.f90:617-622
 static void calculate_parameters_static(double mu, double nu, Params& p) {
   p.statics = true; p.mu = mu; p.lambda = 2.0 * mu * nu / (1.0 - 2.0 * nu); p.rho = 0.0; p.omega = 0.0;
   p.cte_u = 1.0 / (16.0 * c_pi * mu * (1.0 - nu)); p.cteu2 = 3.0 - 4.0 * nu;
   p.cte_t = -1.0 / (8.0 * c_pi * (1.0 - nu)); p.ctet2 = 1.0 - 2.0 * nu;
+  // hypersingular equation, fbem_bem_staela3d_hbie_ext_pre (bem_staela3d.f90:4408-4412): cted1 = cte_t, cted2 = ctes2 = ctet2
+  p.cte_d = p.cte_t; p.cte_s = mu / (4.0 * c_pi * (1.0 - nu)); p.nu_s = nu; p.ctes3 = 1.0 - 4.0 * nu;
 }
 static void calculate_parameters(cd lambda, cd mu, double rho, double omega, Params& p) {
   const cd im(0.0, 1.0);
@@ -319,6 +321,20 @@ static inline void add_exterior_point_hbie(const Params& p, const double* x, con
   double d1r1 = 1.0 / r, d1r2 = d1r1 * d1r1, d1r3 = d1r2 * d1r1, d1r4 = d1r3 * d1r1, d1r5 = d1r4 * d1r1;
   double drdx[3] = {rv[0] * d1r1, rv[1] * d1r1, rv[2] * d1r1};
   double drdn = dot3(drdx, n), drdni = -dot3(drdx, n_i), n_dot_ni = dot3(n, n_i);
+  if (p.statics) {   // fbem_bem_staela3d_hbie_ext_pre: bem_staela3d.f90:4428-4439
+    const double cted2 = p.ctet2, ctes2 = p.ctet2, ctes3 = p.ctes3, nu = p.nu_s;
+    for (int il = 0; il < 3; il++)
+      for (int ik = 0; ik < 3; ik++) {
+        double fs_d = d1r2 * ((cted2 * dkr[il][ik] + 3.0 * drdx[il] * drdx[ik]) * drdni + cted2 * (n_i[il] * drdx[ik] - n_i[ik] * drdx[il]));
+        double fs_s = d1r3 * (3.0 * (5.0 * drdx[il] * drdx[ik] - nu * dkr[il][ik]) * drdn * drdni
+                            + 3.0 * ctes2 * (drdx[ik] * n_i[il] * drdn - drdx[il] * n[ik] * drdni)
+                            + 3.0 * nu * (drdx[il] * n_i[ik] * drdn - drdx[ik] * n[il] * drdni)
+                            + (3.0 * nu * drdx[il] * drdx[ik] + ctes2 * dkr[il][ik]) * n_dot_ni
+                            + ctes2 * n[il] * n_i[ik] - ctes3 * n[ik] * n_i[il]);
+        for (int j = 0; j < nn; j++) { m[(j * 3 + il) * 3 + ik] += fs_s * pphijw[j]; l[(j * 3 + il) * 3 + ik] += fs_d * sphijw[j]; }
+      }
+    return;
+  }
   const cd mim(-0.0, -1.0);
   cd z[2] = {mim * p.k1 * r, mim * p.k2 * r};
   cd E1[7], E2[7];
@@ -1459,6 +1475,13 @@ void orc_fundamental_solutions_hbie(const double* x, const double* n, const doub
   add_exterior_point_hbie(p, x, n, x_i, n_i, 1, &one, &one, mm, ll);
   cd* d = (cd*)d_ri; cd* s = (cd*)s_ri;
   for (int i = 0; i < 9; i++) { d[i] = p.cte_d * ll[i]; s[i] = p.cte_s * mm[i]; }
+}
+int orc_pair_hbie_static(void* h, int e, const double* x_i, const double* n_i, double mu, double nu, double* m_r, double* l_r) {
+  Model* md = (Model*)h; Params p; calculate_parameters_static(mu, nu, p);
+  Stats st; memset(&st, 0, sizeof(st)); cd mm[81], ll[81];
+  int mode = sbie_auto(md->elem[e], x_i, p, md->qsp, md->ns_max, mm, ll, st, n_i);
+  for (int i = 0; i < 9 * md->elem[e].nn; i++) { m_r[i] = mm[i].real(); l_r[i] = ll[i].real(); }
+  return mode;
 }
 // plan only (mode per pair) -- for comparing discrete decisions with the product's planner
 int orc_pair_mode(void* h, int e, const double* x_i, double* d_out, double* barxi_out) {

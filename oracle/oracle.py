@@ -148,6 +148,16 @@ class Oracle:
             raise RuntimeError("oracle: hypersingular integration with the collocation point on the element is not restated")
         return m, l, mode
 
+    def pair_hbie_static(self, e, x_i, n_i, mat):
+        """Static (Kelvin) m, l (n,3,3) of the hypersingular equation (fbem_bem_staela3d_hbie_ext_pre / _ext_adp)."""
+        nn = int(self.m.elem_ptr[e + 1] - self.m.elem_ptr[e])
+        m = np.zeros((nn, 3, 3)); l = np.zeros((nn, 3, 3))
+        x_i = np.ascontiguousarray(x_i, dtype=np.float64); n_i = np.ascontiguousarray(n_i, dtype=np.float64)
+        mode = lib().orc_pair_hbie_static(self.h, C.c_int(e), _p(x_i), _p(n_i), C.c_double(mat.mu_r), C.c_double(mat.nu_r), _p(m), _p(l))
+        if mode < 0:
+            raise RuntimeError("oracle: hypersingular integration with the collocation point on the element is not restated")
+        return m, l, mode
+
     def pair_mode(self, e, x_i):
         x_i = np.ascontiguousarray(x_i, dtype=np.float64)
         d = C.c_double(0.0)

@@ -155,3 +155,45 @@ def test_stress_model_layout():
     ipm = InternalPointsModel(md, PTS, stress=True)
     assert ipm.n_colloc == 15 and ipm.n_dof == md.n_dof + 45 and ipm.colloc_n.shape == (15, 3)
     assert np.allclose(ipm.colloc_x[0], ipm.colloc_x[2]) and np.allclose(ipm.colloc_n[:3], np.eye(3))
+
+
+def test_static_interior_stresses_exact(oracle_lib):
+    """ME-ST-EL-002's exact solution: sigma_11 = P = 1, sigma_22 = sigma_33 = nu/(1-nu) = 1/3 (docs/examples/ME-ST-EL-002/doc_src/
+    ME-ST-EL-002.tex:29-44), at interior points, from the static hypersingular identity."""
+    md = Model(cube_mesh(3, shape.QUAD4), cube_bcs())
+    o = oracle_lib.Oracle(md)
+    A, b, _ = o.assemble_static(SMAT)
+    x, _, _ = oracle_lib.lu_solve_real(A, b)
+    u, t = md.nodal_solution(x)
+    for xp in PTS[:3]:
+        sig = np.zeros((3, 3))
+        for kc in range(3):
+            n_i = np.zeros(3); n_i[kc] = 1.0
+            for e in range(md.n_elem):
+                m, l, mode = o.pair_hbie_static(e, xp, n_i, SMAT)
+                nodes = md.mesh.conn[e]
+                sig[:, kc] += np.einsum("jlk,jk->l", l, t[nodes].real) - np.einsum("jlk,jk->l", m, u[nodes].real)
+        assert np.abs(sig - np.diag([1.0, 1.0 / 3.0, 1.0 / 3.0])).max() < 2e-4
+
+
+@pytest.mark.gpu
+def test_gpu_static_interior_stresses(gpu_ctx, oracle_lib):
+    from multifebe_b200 import capi
+    md = Model(cube_mesh(3, shape.QUAD4), cube_bcs())
+    pr = capi.Problem(gpu_ctx, md)
+    ip = capi.InternalPoints(gpu_ctx, md, PTS)
+    o = oracle_lib.Oracle(md)
+    xs = pr.solve_static(SMAT)
+    sg = ip.stresses_static(SMAT, xs)
+    u, t = md.nodal_solution(xs)
+    so = np.zeros_like(sg)
+    for ipt, xp in enumerate(PTS):
+        for kc in range(3):
+            n_i = np.zeros(3); n_i[kc] = 1.0
+            for e in range(md.n_elem):
+                m, l, mode = o.pair_hbie_static(e, xp, n_i, SMAT)
+                nodes = md.mesh.conn[e]
+                so[ipt, :, kc] += np.einsum("jlk,jk->l", l, t[nodes].real) - np.einsum("jlk,jk->l", m, u[nodes].real)
+    assert np.abs(sg - so).max() < 1e-10 * np.abs(so).max()
+    assert np.abs(sg[:3] - np.diag([1.0, 1.0 / 3.0, 1.0 / 3.0])).max() < 2e-4
+    ip.close(); pr.close()
