@@ -1,3 +1,4 @@
 from .mesh import Mesh, read_gmsh22, write_gmsh22, cube_mesh, halfspace_patch
-from .model import Model, Material, InternalPointsModel, ME_TH_EL_001_BCS, cube_bcs, column_analytic_u
+from .model import (Model, Material, InternalPointsModel, ME_TH_EL_001_BCS, cube_bcs, column_analytic_u,
+                    Fluid, FluidModel, room_bcs, room_analytic)
 from . import shape

@@ -26,11 +26,13 @@ class Material:
 
 
 class Model:
-    """bcs: {part_id: ([ctype_x, ctype_y, ctype_z], [value_x, value_y, value_z])}, ctype 0 = u known, 1 = t known."""
+    """bcs: {part_id: ([ctype_x, ctype_y, ctype_z], [value_x, value_y, value_z])}, ctype 0 = u known, 1 = t known.
+    ndof = equations / unknowns per node: 3 for an elastic solid region, 1 for an inviscid fluid region (FluidModel)."""
 
     def __init__(self, mesh, bcs, reversed_parts=(), qsi_relative_error=1e-6, qsi_ns_max=16,
-                 precalset_gln=(2, 3, 4, 5, 6, 7, 8, 9), geometric_tolerance=1e-6):
+                 precalset_gln=(2, 3, 4, 5, 6, 7, 8, 9), geometric_tolerance=1e-6, ndof=3):
         self.mesh = mesh
+        self.ndof = nd = int(ndof)
         nn = len(mesh.nodes)
         ne = mesh.n_elem
         self.n_node, self.n_elem = nn, ne
@@ -64,8 +66,8 @@ class Model:
         self.node_part = node_part
 
         # --- boundary conditions per node
-        self.ctype = np.zeros((nn, 3), dtype=np.int32)
-        self.cvalue = np.zeros((nn, 3), dtype=np.complex128)
+        self.ctype = np.zeros((nn, nd), dtype=np.int32)
+        self.cvalue = np.zeros((nn, nd), dtype=np.complex128)
         for v in range(nn):
             ct, cv = bcs[int(node_part[v])]
             self.ctype[v] = ct
@@ -75,9 +77,9 @@ class Model:
         parts = sorted(set(int(p) for p in mesh.part))
         order = [e for p in parts for e in range(ne) if int(mesh.part[e]) == p]
         self.elem_order = np.array(order, dtype=np.int32)
-        self.row = -np.ones((nn, 3), dtype=np.int32)
-        self.col_u = -np.ones((nn, 3), dtype=np.int32)
-        self.col_t = -np.ones((nn, 3), dtype=np.int32)
+        self.row = -np.ones((nn, nd), dtype=np.int32)
+        self.col_u = -np.ones((nn, nd), dtype=np.int32)
+        self.col_t = -np.ones((nn, nd), dtype=np.int32)
         row = col = 0
         seen = np.zeros(nn, dtype=bool)
         for e in order:
@@ -85,7 +87,7 @@ class Model:
                 if seen[v]:
                     continue
                 seen[v] = True
-                for k in range(3):
+                for k in range(nd):
                     self.row[v, k] = row; row += 1
                     if self.ctype[v, k] == 0:
                         self.col_t[v, k] = col
@@ -122,15 +124,52 @@ class Model:
 
     # --- reference's assign_solution_mechanics_harmonic.f90:192-205: nodal u,t from the solution vector
     def nodal_solution(self, x):
-        u = np.zeros((self.n_node, 3), dtype=np.complex128)
-        t = np.zeros((self.n_node, 3), dtype=np.complex128)
-        for k in range(3):
+        u = np.zeros((self.n_node, self.ndof), dtype=np.complex128)
+        t = np.zeros((self.n_node, self.ndof), dtype=np.complex128)
+        for k in range(self.ndof):
             known_u = self.ctype[:, k] == 0
             u[known_u, k] = self.cvalue[known_u, k]
             t[known_u, k] = x[self.col_t[known_u, k]]
             t[~known_u, k] = self.cvalue[~known_u, k]
             u[~known_u, k] = x[self.col_u[~known_u, k]]
         return u, t
+
+
+class Fluid:
+    """Inviscid fluid: `fluid c <c> rho <rho>` of the [materials] section (src/read_regions.f90:544-546, :599-604): region%property_r(1) =
+    rho, region%property_c(4) = c.  xi > 0 gives the hysteretic variant c (1 + 2 i xi)^(1/2) (the stiffness K = rho c^2 is damped)."""
+
+    def __init__(self, rho=1.25, c=343.0, xi=0.0):
+        self.rho, self.c_r, self.xi = float(rho), float(c), float(xi)
+        self.c = complex(self.c_r) * np.sqrt(1.0 + 2j * self.xi)
+
+
+class FluidModel(Model):
+    """One inviscid-fluid BE region (scalar wave propagation): one equation and one unknown per node.
+    bcs: {part_id: (ctype, value)}: ctype 0 = p known (Un unknown), 1 = Un known (p unknown), `conditions over be boundaries` of an
+    inviscid fluid boundary (src/read_conditions_bem_boundaries_mechanics.f90; scatter assemble_bem_harpot_equation.f90:78-96).
+    DOF numbering: build_auxiliary_variables_mechanics_harmonic.f90 (fluid boundary: row(1,1); col(1,1) = p or col(2,1) = Un).
+    col_u holds the column of p, col_t the column of Un."""
+
+    def __init__(self, mesh, bcs, **kw):
+        bcs3 = {p: ([int(ct)], [complex(cv)]) for p, (ct, cv) in bcs.items()}
+        Model.__init__(self, mesh, bcs3, ndof=1, **kw)
+
+    def nodal_solution(self, x):
+        p, un = Model.nodal_solution(self, x)
+        return p[:, 0], un[:, 0]
+
+
+# the reference's acoustic room tutorial (docs/examples/ME-TH-AC-001/case_files/room.dat: walls 1-4 rigid (Un = 0), p = 1 on one x-face,
+# p = 0 on the other) on cube_mesh() part ids (1 x=0, 2 x=L, 3 y=0, 4 y=L, 5 z=0, 6 z=L)
+def room_bcs(P=1.0):
+    return {1: (0, 0.0), 2: (0, P), 3: (1, 0.0), 4: (1, 0.0), 5: (1, 0.0), 6: (1, 0.0)}
+
+
+def room_analytic(x1, omega, fluid, L=1.0, P=1.0):
+    """p(x) = P sin(kx)/sin(kL), U_x(x) = P k cos(kx)/(rho omega^2 sin(kL)) (docs/examples/ME-TH-AC-001/doc_src/ME-TH-AC-001.tex:47-50)."""
+    k = omega / fluid.c
+    return P * np.sin(k * x1) / np.sin(k * L), P * k * np.cos(k * x1) / (fluid.rho * omega ** 2 * np.sin(k * L))
 
 
 # the reference's harmonic cube tutorial (docs/examples/ME-TH-EL-001/case_files/t3.dat:38-55), by physical name

@@ -205,7 +205,41 @@ struct Params {
   cd S1[12], S2[12], S3[13], S4[11], S5[12]; cd cte_d, cte_s;   // hypersingular equation (d*, s*): bem_harela3d.f90:219-287
   // static elasticity (lib/fbem/src/bem_staela3d.f90): Kelvin solution, cte_u = cteu1, cte_t = ctet1 of :617-622
   bool statics = false; double cteu2 = 0.0, ctet2 = 0.0, nu_s = 0.0, ctes3 = 0.0;
+  // scalar wave propagation (inviscid fluid / acoustics), lib/fbem/src/bem_harpot3d.f90:102-115: wavenumber k, P(1), Q(1:2).
+  // h, g of a pair are vectors over the element nodes: stored in h[0..nn), g[0..nn) of the 9*nn containers (the rest stays zero);
+  // cte_t = -1/(4 pi), cte_u = 1/(4 pi) carry the reference's `h=-h*c_1_4pi; g=g*c_1_4pi`.
+  bool pot = false; cd kp, P1, Q1, Q2;
 };
+// fbem_bem_harpot3d_calculate_parameters: lib/fbem/src/bem_harpot3d.f90:123-165 (SBIE subset P, Q)
+static void calculate_parameters_pot(double rho, cd c, double omega, Params& p) {
+  const cd im(0.0, 1.0);
+  cd k = omega / c;
+  p.pot = true; p.omega = omega; p.rho = rho; p.c1 = c; p.kp = k;
+  p.P1 = -im * k; p.Q1 = 0.5 * (k * k); p.Q2 = im * k;
+  p.cte_u = c_1_4pi; p.cte_t = -c_1_4pi;
+}
+// order f of the estimator's model function 1/r^f: 5 for the elastic SBIE (bem_harela3d.f90:1522), 7 for the elastic HBIE (:3677),
+// 3 for the scalar SBIE (bem_harpot3d.f90:1009, :693)
+static inline int estimator_f(const Params& p, const double* n_i) { return n_i ? 7 : (p.pot ? 3 : 5); }
+// fbem_decomposed_zexp: lib/fbem/src/numerical.f90:1138-1191 (E0..E4; used by fbem_bem_harpot3d_sbie_int)
+static void decomposed_zexp(cd z, cd* E /*0..4*/) {
+  double absz = std::abs(z);
+  if (absz <= 1.0) {
+    int n;
+    if (absz <= 1.e-6) n = 1;
+    else n = (int)lround(pow(10.0, 1.176 + 0.175 * log10(absz)));
+    cd term[20];
+    term[0] = cd(1.0, 0.0); term[1] = z;
+    double factorial = 1.0; cd zpowk = z;
+    for (int k = 2; k <= n + 4; k++) { factorial = factorial * (double)k; zpowk = zpowk * z; term[k] = zpowk / factorial; }
+    E[4] = cd(0.0, 0.0);
+    for (int k = n + 4; k >= 4; k--) E[4] = E[4] + term[k];
+    E[3] = E[4] + term[3]; E[2] = E[3] + term[2]; E[1] = E[2] + term[1]; E[0] = E[1] + term[0];
+  } else {
+    cd expz = std::exp(z), z2 = z * z, z3 = z2 * z;
+    E[0] = expz; E[1] = expz - 1.0; E[2] = E[1] - z; E[3] = E[2] - 0.5 * z2; E[4] = E[3] - 0.166666666666666667 * z3;
+  }
+}
 // constants of fbem_bem_staela3d_sbie_ext_pre / _ext_st / _int: bem_staela3d.f90:617-622
 static void calculate_parameters_static(double mu, double nu, Params& p) {
   p.statics = true; p.mu = mu; p.lambda = 2.0 * mu * nu / (1.0 - 2.0 * nu); p.rho = 0.0; p.omega = 0.0;
@@ -289,6 +323,18 @@ static inline void add_exterior_point(const Params& p, const double* x, const do
                                       const double* pphijw, const double* sphijw, cd* h, cd* g) {
   double rv[3] = {x[0] - x_i[0], x[1] - x_i[1], x[2] - x_i[2]};
   double r = sqrt(dot3(rv, rv));
+  if (p.pot) {   // fbem_bem_harpot3d_sbie_ext_pre: bem_harpot3d.f90:305-320 (the same point formula in _ext_st :451-466, :605-622)
+    double d1r1 = 1.0 / r, d1r2 = d1r1 * d1r1;
+    double drdx[3] = {rv[0] * d1r1, rv[1] * d1r1, rv[2] * d1r1};
+    double drdn = dot3(drdx, n);
+    cd E[7]; zexp_decomposed(cd(-0.0, -1.0) * p.kp * r, E);
+    cd E2r = E[2] * d1r1, E3r = E[3] * d1r2;
+    cd fs_P = d1r1 + p.P1 + E2r;
+    cd fs_Q = d1r2 + p.Q1 + p.Q2 * E2r + E3r;
+    cd fq = fs_Q * drdn;
+    for (int j = 0; j < nn; j++) { h[j] += fq * pphijw[j]; g[j] += fs_P * sphijw[j]; }
+    return;
+  }
   if (p.statics) {   // fbem_bem_staela3d_sbie_ext_pre: bem_staela3d.f90:629-645 (the same point formula in _ext_st :930-950)
     double d1r = 1.0 / r, d1r2 = d1r * d1r;
     double drdx[3] = {rv[0] * d1r, rv[1] * d1r, rv[2] * d1r};
@@ -892,7 +938,7 @@ static void sbie_ext_adp(const Element& e, double* xi_s, const double* x_i, cons
     double cl = characteristic_length(e.et, x_s, 1.e-12);
     nearest_element_point_bem(e.et, x_s, cl, x_i, barxip, rmin, d, method);
   }
-  int gln_near = qs_n_estimation(true, e.et, n_i ? 7 : 5, qsp, d, barxip);
+  int gln_near = qs_n_estimation(true, e.et, estimator_f(p, n_i), qsp, d, barxip);
   bool subdivide = false;
   if (ks == ns) { if (gln_near == 0) gln_near = 30; } else if (gln_near == 0) subdivide = true;
   if (subdivide) {
@@ -1079,6 +1125,18 @@ static void sbie_int(const Element& e, const double* xi_i, const Params& p, cd* 
         double n[3] = {N[0] / jg, N[1] / jg, N[2] / jg};
         double rv[3] = {x[0] - x_i[0], x[1] - x_i[1], x[2] - x_i[2]};
         double r = sqrt(dot3(rv, rv));
+        if (p.pot) {   // fbem_bem_harpot3d_sbie_int: bem_harpot3d.f90:905-957 (weakly singular: no CPV part, no line integrals)
+          double d1r = 1.0 / r, d1r2 = d1r * d1r;
+          double drdn = dot3(rv, N) * d1r / jg;
+          double jw = jg * rho * jthetap * w_ang * w_rad;
+          cd E[5]; decomposed_zexp(cd(-0.0, -1.0) * p.kp * r, E);
+          cd fs_P = d1r + p.P1 + d1r * E[2];
+          cd fs_Q = d1r2 + p.Q1 + p.Q2 * d1r * E[2] + d1r2 * E[3];
+          cd fq = fs_Q * drdn;
+          for (int j = 0; j < nn; j++) { double fjw = phi[j] * jw; h[j] += fq * fjw; g[j] += fs_P * fjw; }
+          st.pts_singular++;
+          continue;
+        }
         if (p.statics) {   // fbem_bem_staela3d_sbie_int: bem_staela3d.f90:1284-1320
           double d1r = 1.0 / r, d1r2 = d1r * d1r;
           double drdx[3] = {rv[0] * d1r, rv[1] * d1r, rv[2] * d1r}, drdn = dot3(drdx, n);
@@ -1116,6 +1174,11 @@ static void sbie_int(const Element& e, const double* xi_i, const Params& p, cd* 
       }
     }
   }
+  if (p.pot) {
+    for (int i = 0; i < nn; i++) { h[i] = p.cte_t * h[i]; g[i] = p.cte_u * g[i]; }
+    if (e.reverse) for (int i = 0; i < nn; i++) h[i] = -h[i];
+    return;
+  }
   // line integrals
   double hli[3][3] = {{0}}; QsParams qsl; qs_calculate_parameters(1.e-15, qsl);
   int nedges = n_edges_of(et), ety = edge_type_of(et), nne = n_nodes_of(ety);
@@ -1140,7 +1203,7 @@ static int sbie_auto(const Element& e, const double* x_i, const Params& p, const
   else { nearest_element_point_bem(e.et, e.x, e.cl, x_i, barxi, rmin, d, method); delta = (d <= 1.e-12) ? 1 : 0; }
   if (delta == 1 && n_i) return -1;   // fbem_bem_harela3d_hbie_int (collocation point ON the element) is not restated: interior points never get here
   if (delta == 1) { st.pairs_singular++; sbie_int(e, barxi, p, h, g, st); return 200; }
-  int gln_near = qs_n_estimation(false, e.et, n_i ? 7 : 5, qsp, d, barxi);
+  int gln_near = qs_n_estimation(false, e.et, estimator_f(p, n_i), qsp, d, barxi);
   int gln = std::max(e.gln_far, gln_near);
   if (gln <= e.ps_gln_max && gln_near > 0) {
     int ps = 0; for (size_t i = 0; i < e.ps.size(); i++) if (e.ps[i].gln >= gln) { ps = (int)i; break; }
@@ -1154,7 +1217,9 @@ static int sbie_auto(const Element& e, const double* x_i, const Params& p, const
 }
 
 // fbem_bem_harela3d_sbie_freeterm (Mantic C-matrix): bem_harela3d.f90:365-542
-static int sbie_freeterm(int ne, const double* n_in, const double* t_in, double tol, cd nu, cd c[3][3]) {
+// cp_out: the scalar free term c = (2 pi + sum_a)/(4 pi) alone == fbem_bem_pot3d_sbie_freeterm (lib/fbem/src/bem_stapot3d.f90:155-296:
+// the same sorting of the tangents and the same sum of dihedral angles, without the tensor part)
+static int sbie_freeterm(int ne, const double* n_in, const double* t_in, double tol, cd nu, cd c[3][3], double* cp_out = nullptr) {
   double ltol = (tol < 1.0e-12 || tol > 1.0e-3) ? 1.0e-6 : tol;
   std::vector<double> ln(3 * (ne + 2)), lt(3 * (ne + 2)), lti(3 * (ne + 1)), theta(ne + 1);
   std::vector<int> tc(ne + 1);
@@ -1189,6 +1254,7 @@ static int sbie_freeterm(int ne, const double* n_in, const double* t_in, double 
     sum_a = sum_a + nxndr * acos(ndn);
   }
   double cp = 1.0 / (4.0 * c_pi) * (2.0 * c_pi + sum_a);
+  if (cp_out) *cp_out = cp;
   double sum_b[3][3] = {{0}};
   for (int ki = 1; ki <= ne; ki++) {
     double rmr[3]; for (int k = 0; k < 3; k++) rmr[k] = lt[3 * (ki + 1) + k] - lt[3 * ki + k];
@@ -1247,6 +1313,7 @@ struct Model {
   std::vector<Element> elem; std::vector<int> eptr, enode;
   std::vector<double> cx; std::vector<int> cnode, celem, ckn; std::vector<double> cxi;
   std::vector<int> row, col_u, col_t, ctype;
+  int nd = 3;   // equations / unknowns per node: 3 (elastic solid), 1 (inviscid fluid: row(1), col(1) = p, col(2) = Un)
   QsParams qsp; int ns_max; double geometric_tolerance;
   std::vector<int> n2e_ptr, n2e_elem, n2e_kn;  // node -> (element, local node) incidences
   Stats last;
@@ -1402,6 +1469,115 @@ static int assemble_impl(Model* m, const Params& p, cd nu, const cd* cvalue, cd*
   }
   return err;
 }
+
+// -------------------------------------------------------------------------------------------------------------------------
+// Inviscid fluid (acoustic) BE region: build_lse_mechanics_bem_harpot (src/build_lse_mechanics_bem_harpot.f90: element loop
+// :211-217, free-term pass :243-660 with fbem_bem_pot3d_sbie_freeterm :533, collocation loop :722-1133 with
+// fbem_bem_harpot3d_sbie_auto :923) and the scatter of assemble_bem_harpot_equation.f90:78-96 (be boundary, ordinary class,
+// ctype 0: p known / Un unknown, ctype 1: Un known / p unknown).  One equation and one unknown per node:
+// row[n_node], col_p[n_node] = node%col(1,1), col_q[n_node] = node%col(2,1), ctype[n_node] = node%ctype(1,1).
+// -------------------------------------------------------------------------------------------------------------------------
+void* orc_setup_pot(int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr, const int* elem_node,
+                    const unsigned char* elem_reversed, int n_colloc, const double* colloc_x, const int* colloc_node,
+                    const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
+                    const int* row, const int* col_p, const int* col_q, const int* ctype, int n_dof,
+                    double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln, double geometric_tolerance) {
+  std::vector<int> r3(3 * n_node, -1), cu3(3 * n_node, -1), ct3(3 * n_node, -1), ty3(3 * n_node, 0);
+  Model* m = (Model*)orc_setup(n_node, node_x, n_elem, etype, elem_ptr, elem_node, elem_reversed, n_colloc, colloc_x, colloc_node, colloc_elem, colloc_kn,
+                               colloc_xi, r3.data(), cu3.data(), ct3.data(), ty3.data(), n_dof, qsi_relative_error, qsi_ns_max, n_precalsets, precalset_gln,
+                               geometric_tolerance);
+  m->nd = 1;
+  m->row.assign(row, row + n_node); m->col_u.assign(col_p, col_p + n_node); m->col_t.assign(col_q, col_q + n_node); m->ctype.assign(ctype, ctype + n_node);
+  return m;
+}
+static void scatter_pot(const Model* m, int e, int sn_col, const cd* hp, const cd* gp, const cd* cvalue, cd* A, cd* b) {
+  int nn = m->elem[e].nn; long long nd = m->n_dof;
+  long long row = m->row[sn_col];
+  for (int kn = 0; kn < nn; kn++) {
+    int sn = m->enode[m->eptr[e] + kn];
+    switch (m->ctype[sn]) {
+      case 0: { long long col = m->col_t[sn]; A[row + nd * col] = A[row + nd * col] - gp[kn]; b[row] = b[row] - hp[kn] * cvalue[sn]; break; }
+      case 1: { long long col = m->col_u[sn]; A[row + nd * col] = A[row + nd * col] + hp[kn]; b[row] = b[row] + gp[kn] * cvalue[sn]; break; }
+    }
+  }
+}
+int orc_assemble_pot(void* hd, double omega, double rho, const double* c_ri, const double* cvalue_ri, double* A_ri, double* b_ri, int nthreads,
+                     long long* stats_out /*44*/) {
+  Model* m = (Model*)hd; if (m->nd != 1) return 9;
+  Params p; calculate_parameters_pot(rho, cd(c_ri[0], c_ri[1]), omega, p);
+  const cd* cvalue = (const cd*)cvalue_ri; cd* A = (cd*)A_ri; cd* b = (cd*)b_ri;
+  Stats total; memset(&total, 0, sizeof(total));
+  const double d1J = rho * (omega * omega);   // rho*omega**2
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel
+  {
+    Stats st; memset(&st, 0, sizeof(st));
+#pragma omp for schedule(dynamic)
+    for (int e = 0; e < m->n_elem; e++) {
+      const Element& el = m->elem[e];
+      cd hh[81], gg[81];
+      for (int c = 0; c < m->n_colloc; c++) {
+        sbie_auto(el, &m->cx[3 * c], p, m->qsp, m->ns_max, hh, gg, st);
+        // the flux variable is the normal displacement Un = 1/(rho omega^2) dp/dn: gp=gp*d1J (build_lse_mechanics_bem_harpot.f90:751,1104)
+        for (int j = 0; j < el.nn; j++) gg[j] = gg[j] * d1J;
+#pragma omp critical
+        scatter_pot(m, e, m->cnode[c], hh, gg, cvalue, A, b);
+      }
+    }
+#pragma omp critical
+    stats_add(total, st);
+  }
+  int err = 0;
+  for (int c = 0; c < m->n_colloc; c++) {
+    int e = m->celem[c], kn = m->ckn[c], sn = m->cnode[c]; const Element& el = m->elem[e];
+    cd hp[9], gp[9]; for (int i = 0; i < el.nn; i++) { hp[i] = 0.0; gp[i] = 0.0; }
+    bool mca = (m->cxi[2 * c] != -9.0);
+    if (!mca) {
+      double xi_i[2]; xi_at_node(el.et, kn, xi_i);
+      double c_plus = 0.5;
+      if (check_xi1xi2_edge(el.et, xi_i)) {
+        int b0 = m->n2e_ptr[sn], ne = m->n2e_ptr[sn + 1] - b0;
+        std::vector<double> ns(3 * ne), ts(3 * ne);
+        for (int k = 0; k < ne; k++) {
+          const Element& ee = m->elem[m->n2e_elem[b0 + k]]; double n[3], tbp[3], tbm[3];
+          node_normal_tangents(ee.et, ee.x, m->n2e_kn[b0 + k], n, tbp, tbm);
+          for (int cc = 0; cc < 3; cc++) { ns[3 * k + cc] = el.reverse ? -n[cc] : n[cc]; ts[3 * k + cc] = el.reverse ? tbm[cc] : tbp[cc]; }
+        }
+        cd dummy[3][3];
+        if (sbie_freeterm(ne, ns.data(), ts.data(), m->geometric_tolerance, cd(0.0, 0.0), dummy, &c_plus)) err = 1;
+      }
+      hp[kn] = hp[kn] + c_plus;
+    } else {
+      double phi[9]; phi2d<double>(el.et, &m->cxi[2 * c], phi);
+      for (int j = 0; j < el.nn; j++) hp[j] = hp[j] + 0.5 * phi[j];
+    }
+    scatter_pot(m, e, sn, hp, gp, cvalue, A, b);
+  }
+  m->last = total;
+  if (stats_out) {
+    for (int i = 0; i < 33; i++) stats_out[i] = total.pairs_regular[i];
+    stats_out[33] = total.pts_regular; stats_out[34] = total.pairs_adaptive; stats_out[35] = total.leaves; stats_out[36] = total.pts_adaptive;
+    stats_out[37] = total.pairs_singular; stats_out[38] = total.pts_singular; stats_out[39] = total.li_points;
+  }
+  return err;
+}
+// h, g (n nodes each) of one (collocation point, element) pair through fbem_bem_harpot3d_sbie_auto; returns the mode
+int orc_pair_pot(void* hd, int e, const double* x_i, double omega, double rho, const double* c_ri, double* h_ri, double* g_ri) {
+  Model* m = (Model*)hd; Params p; calculate_parameters_pot(rho, cd(c_ri[0], c_ri[1]), omega, p);
+  Stats st; memset(&st, 0, sizeof(st)); cd hh[81], gg[81];
+  int mode = sbie_auto(m->elem[e], x_i, p, m->qsp, m->ns_max, hh, gg, st);
+  memcpy(h_ri, hh, sizeof(cd) * m->elem[e].nn); memcpy(g_ri, gg, sizeof(cd) * m->elem[e].nn);
+  return mode;
+}
+// p*, q* (fbem_bem_harpot3d_sbie_p / _q, bem_harpot3d.f90:229-273)
+void orc_fundamental_solutions_pot(const double* x, const double* n, const double* x_i, double omega, double rho, const double* c_ri, double* p_ri, double* q_ri) {
+  Params p; calculate_parameters_pot(rho, cd(c_ri[0], c_ri[1]), omega, p);
+  double one = 1.0; cd h[9], g[9]; for (int i = 0; i < 9; i++) { h[i] = 0; g[i] = 0; }
+  add_exterior_point(p, x, n, x_i, 1, &one, &one, h, g);
+  cd po = p.cte_u * g[0], qo = p.cte_t * h[0];
+  p_ri[0] = po.real(); p_ri[1] = po.imag(); q_ri[0] = qo.real(); q_ri[1] = qo.imag();
+}
+void orc_decomposed_zexp(const double* z_ri, double* E_ri /*5 complex*/) { cd E[5]; decomposed_zexp(cd(z_ri[0], z_ri[1]), E); memcpy(E_ri, E, sizeof(E)); }
 
 // Bounded sample of one frequency's assembly for the CPU baseline: every element against the collocation points
 // c = c_offset, c_offset + c_stride, ... with the reference's parallel structure (OpenMP dynamic over integration elements,
