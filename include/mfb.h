@@ -166,6 +166,30 @@ int mfb_staela3d_assemble(mfb_problem* problem, double mu, double nu, const doub
 int mfb_dsolve(mfb_problem* problem, int n, double* A, int lda, int* ipiv, double* b, int nrhs, int factorize);
 int mfb_staela3d_solve(mfb_problem* problem, double mu, double nu, const double* cvalue, double* x);
 
+/* ---- Inviscid fluid (acoustic) BE region (first brick) ----------------------------------------
+ * One fluid region with ordinary `be` boundaries: scalar wave propagation, ONE equation and ONE unknown per node.
+ *   mfb_harpot3d_setup     the arguments of mfb_harela3d_setup with one entry per node: row[n_node] = node%row(1,1), col_p[n_node] =
+ *                          node%col(1,1) (column of p where Un is prescribed), col_un[n_node] = node%col(2,1) (column of Un where p is
+ *                          prescribed), ctype[n_node] = node%ctype(1,1): 0 = p known, 1 = Un known (ctype 2, 3 -- impedance / radiation
+ *                          conditions of assemble_bem_harpot_equation.f90:97-110 -- are not built: MFB_ERR_UNSUPPORTED).  The quadrature
+ *                          plan uses the estimator order f = 3 of fbem_bem_harpot3d_sbie_auto (lib/fbem/src/bem_harpot3d.f90:961-1025).
+ *   mfb_harpot3d_assemble  == `A_c=0; b_c=0` + build_lse_mechanics_bem_harpot(kf,kr) (src/build_lse_mechanics_bem_harpot.f90: element
+ *                          loop :211-217, collocation loop :722-1133, free terms :243-660 with fbem_bem_pot3d_sbie_freeterm) with the
+ *                          kernels of fbem_bem_harpot3d_sbie_ext_pre / _ext_adp / _int (:276-959) and the scatter of
+ *                          assemble_bem_harpot_equation.f90:78-96.  rho = region%property_r(1), c = region%property_c(4);
+ *                          cvalue[n_node] = node%cvalue_c(1,1,1) (prescribed p or Un).  The flux unknown is the normal displacement
+ *                          Un = (dp/dn)/(rho omega^2) (:751, :1104).  A, b as in mfb_harela3d_assemble.
+ *   mfb_harpot3d_solve_frequency  assemble + zgetrf + zgetrs on the device; mfb_zsolve / mfb_get_solution / mfb_residual* / mfb_get_entries
+ *                          / mfb_plan_modes / mfb_get_stats work on such a problem as they do on an elastic one. */
+int mfb_harpot3d_setup(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
+                       const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
+                       const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
+                       const int* row, const int* col_p, const int* col_un, const int* ctype, int n_dof,
+                       double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
+                       double geometric_tolerance, mfb_problem** problem);
+int mfb_harpot3d_assemble(mfb_problem* problem, double omega, double rho, const mfb_z* c, const mfb_z* cvalue, mfb_z* A, mfb_z* b);
+int mfb_harpot3d_solve_frequency(mfb_problem* problem, double omega, double rho, const mfb_z* c, const mfb_z* cvalue, mfb_z* x);
+
 /* ---- One frequency over several GPUs (shard 2) --------------------------------------------------
  * One process per GPU, every process holds the same mfb_problem (mesh + plan replicated).  Rank r assembles a contiguous
  * run of collocation-row blocks (the rows of build_lse_mechanics_bem_harela's kn_col loop it owns, all columns), the row

@@ -15,8 +15,8 @@ OUT = os.path.join(HERE, "libmfb.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 GXX = "/usr/bin/g++"   # the image's $CXX wrapper lacks libgomp.spec
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-SOURCES_CU = ["api.cu", "assembly.cu", "lu.cu", "dist.cu"]
-DEPS = SOURCES_CU + ["plan_host.cpp", "plan_host.h", "assembly.cuh", "lu.cuh", "dist.cuh", "bem_math.cuh",
+SOURCES_CU = ["api.cu", "assembly.cu", "potential.cu", "lu.cu", "dist.cu"]
+DEPS = SOURCES_CU + ["plan_host.cpp", "plan_host.h", "assembly.cuh", "potential.cuh", "pot_math.cuh", "lu.cuh", "dist.cuh", "bem_math.cuh",
                      os.path.join("..", "..", "include", "mfb.h"), os.path.join("..", "..", "data", "quad_tables.h")]
 
 
@@ -25,6 +25,17 @@ def _stale():
         return True
     t = os.path.getmtime(OUT)
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+
+
+HEADERS = [d for d in DEPS if not d.endswith((".cu", ".cpp"))]
+
+
+def _obj_stale(obj, src):
+    """An object is rebuilt when its source or any header is newer (headers are few: no per-file dependency scan)."""
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in [src] + HEADERS)
 
 
 def build(force=False, verbose=False):
@@ -36,7 +47,8 @@ def build(force=False, verbose=False):
     o = os.path.join(bdir, "plan_host.o")
     cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-c",
            os.path.join(CSRC, "plan_host.cpp"), "-o", o]
-    subprocess.check_call(cmd)
+    if force or _obj_stale(o, "plan_host.cpp"):
+        subprocess.check_call(cmd)
     objs.append(o)
     for src in SOURCES_CU:
         o = os.path.join(bdir, src.replace(".cu", ".o"))
@@ -45,7 +57,8 @@ def build(force=False, verbose=False):
             "-Xptxas", "-v" if verbose else "-O3", "-c", os.path.join(CSRC, src), "-o", o]
         if verbose:
             print(" ".join(cmd))
-        subprocess.check_call(cmd)
+        if force or verbose or _obj_stale(o, src):
+            subprocess.check_call(cmd)
         objs.append(o)
     cmd = [NVCC, "-ccbin", GXX, "-shared", "-o", OUT] + objs + ["-Xcompiler", "-fopenmp", "-lquadmath", "-lcudart", "-lgomp", "-ldl"] + ARCH
     subprocess.check_call(cmd)

@@ -3,6 +3,7 @@
 // every entry point fails with MFB_ERR_NO_DEVICE.
 #include "../../include/mfb.h"
 #include "assembly.cuh"
+#include "potential.cuh"
 #include "lu.cuh"
 #include "dist.cuh"
 #include "plan_host.h"
@@ -77,6 +78,7 @@ struct mfb_problem {
   std::vector<int> h_tile_row0, h_tile_nbytes;   // host copies of DevColloc::tile_row0 / tile_nbytes (row partition of the multi-GPU mode)
   DistState dist;
   alignas(64) unsigned char tmapS[128]; bool have_tmapS;   // one-plane box: K1 flush of the static (real) assembly
+  int ndof;                                                // equations / unknowns per node: 3 (elastic solid), 1 (inviscid fluid, mfb_harpot3d_*)
   bool hbie;                                               // hypersingular equation at points off the boundary (interior-point stresses)
   bool real_resident;                                      // the resident system / factors are real (static path): Are only
   alignas(64) unsigned char tmapA[128]; bool have_tmap;   // CUtensorMap of the planar system matrix (K1 flush)   // rows_permuted: the resident matrix/factors are in the internal order
@@ -169,7 +171,8 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
                       const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
                       const int* row, const int* col_u, const int* col_t, const int* ctype, int n_dof,
                       double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
-                      double geometric_tolerance, const double* colloc_n /* NULL, or 3 per collocation point: hypersingular equation */, mfb_problem** out);
+                      double geometric_tolerance, const double* colloc_n /* NULL, or 3 per collocation point: hypersingular equation */,
+                      int ndof /* 3: elastic solid, 1: inviscid fluid */, mfb_problem** out);
 extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
                                   const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
                                   const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
@@ -177,7 +180,7 @@ extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x
                                   double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
                                   double geometric_tolerance, mfb_problem** out) {
   return setup_impl(ctx, n_node, node_x, n_elem, etype, elem_ptr, elem_node, elem_reversed, n_colloc, colloc_x, colloc_node, colloc_elem, colloc_kn, colloc_xi,
-                    row, col_u, col_t, ctype, n_dof, qsi_relative_error, qsi_ns_max, n_precalsets, precalset_gln, geometric_tolerance, nullptr, out);
+                    row, col_u, col_t, ctype, n_dof, qsi_relative_error, qsi_ns_max, n_precalsets, precalset_gln, geometric_tolerance, nullptr, 3, out);
 }
 // Hypersingular equation for points OFF the boundary (interior-point stresses): fbem_bem_harela3d_hbie_auto with its exterior
 // branches (_ext_pre :2573-2662, _ext_adp :3044-3167); colloc_n[3*n_colloc] = unit normal n_i of each collocation point.
@@ -189,14 +192,14 @@ extern "C" int mfb_harela3d_setup_hbie(mfb_ctx* ctx, int n_node, const double* n
                                        double geometric_tolerance, mfb_problem** out) {
   if (!colloc_n) return fail(MFB_ERR_ARG, "mfb_harela3d_setup_hbie: null colloc_n");
   return setup_impl(ctx, n_node, node_x, n_elem, etype, elem_ptr, elem_node, elem_reversed, n_colloc, colloc_x, colloc_node, colloc_elem, colloc_kn, colloc_xi,
-                    row, col_u, col_t, ctype, n_dof, qsi_relative_error, qsi_ns_max, n_precalsets, precalset_gln, geometric_tolerance, colloc_n, out);
+                    row, col_u, col_t, ctype, n_dof, qsi_relative_error, qsi_ns_max, n_precalsets, precalset_gln, geometric_tolerance, colloc_n, 3, out);
 }
 static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
                       const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
                       const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
                       const int* row, const int* col_u, const int* col_t, const int* ctype, int n_dof,
                       double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
-                      double geometric_tolerance, const double* colloc_n, mfb_problem** out) {
+                      double geometric_tolerance, const double* colloc_n, int ndof, mfb_problem** out) {
   if (!ctx || !out || !node_x || !etype || !elem_ptr || !elem_node || !colloc_x || !colloc_node || !colloc_elem || !colloc_kn || !colloc_xi ||
       !row || !col_u || !col_t || !ctype || !precalset_gln)
     return fail(MFB_ERR_ARG, "mfb_harela3d_setup: null argument");
@@ -206,14 +209,15 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
     if (etype[e] < MFB_TRI3 || etype[e] > MFB_QUAD9) return fail(MFB_ERR_UNSUPPORTED, "mfb_harela3d_setup: element type must be tri3/tri6/quad4/quad8/quad9");
     if (elem_ptr[e + 1] - elem_ptr[e] != mfbh::nodes_of(etype[e])) return fail(MFB_ERR_ARG, "mfb_harela3d_setup: elem_ptr inconsistent with etype");
   }
-  for (int i = 0; i < 3 * n_node; i++)
-    if (ctype[i] != 0 && ctype[i] != 1) return fail(MFB_ERR_UNSUPPORTED, "mfb_harela3d_setup: only ctype 0 (u known) / 1 (t known) are supported");
+  if (ndof != 1 && ndof != 3) return fail(MFB_ERR_ARG, "setup: ndof must be 3 (elastic solid) or 1 (inviscid fluid)");
+  for (int i = 0; i < ndof * n_node; i++)
+    if (ctype[i] != 0 && ctype[i] != 1) return fail(MFB_ERR_UNSUPPORTED, "mfb_harela3d_setup: only ctype 0 (u / p known) and 1 (t / Un known) are supported");
   double t_host0 = now_ms();
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   mfb_problem* p = new mfb_problem();
   *out = nullptr;
-  p->ctx = ctx; p->n_node = n_node; p->n_elem = n_elem; p->n_colloc = n_colloc; p->n_dof = n_dof;
+  p->ctx = ctx; p->n_node = n_node; p->n_elem = n_elem; p->n_colloc = n_colloc; p->n_dof = n_dof; p->ndof = ndof;
   p->lu_ready = false; p->factored = false; p->plan = nullptr; p->have_cvalue = false; p->assembled = false;
   memset(p->stats, 0, sizeof(p->stats));
   for (int i = 0; i < 8; i++) cudaEventCreate(&p->ev[i]);
@@ -221,7 +225,8 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
   S.qsi_relative_error = qsi_relative_error; S.qsi_ns_max = qsi_ns_max; S.geometric_tolerance = geometric_tolerance;
   S.ps_gln.assign(precalset_gln, precalset_gln + n_precalsets);
   p->set_gln = S.ps_gln;
-  S.f = colloc_n ? 7 : 5;     // order of the estimator's model function: fbem_bem_harela3d_sbie_auto :1522 / _hbie_auto :3677
+  // order of the estimator's model function: fbem_bem_harela3d_sbie_auto :1522 / _hbie_auto :3677 / fbem_bem_harpot3d_sbie_auto (bem_harpot3d.f90:1009)
+  S.f = colloc_n ? 7 : (ndof == 1 ? 3 : 5);
   p->hbie = colloc_n != nullptr;
   mfbh::init_settings(S);
 
@@ -251,10 +256,10 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
       for (int k = 0; k < g.nn; k++) for (int c = 0; c < 3; c++) ctr[c] += p->elems[e].x[3 * k + c] / g.nn;
       // boundary-condition signature first (elements of one K1 class end up in the same ranges), then space
       unsigned sig = 0;
-      for (int k = 0; k < 3; k++) {
-        const int ct0 = ctype[3 * elem_node[elem_ptr[e]] + k];
+      for (int k = 0; k < ndof; k++) {
+        const int ct0 = ctype[ndof * elem_node[elem_ptr[e]] + k];
         bool uni = true;
-        for (int j = 1; j < g.nn; j++) if (ctype[3 * elem_node[elem_ptr[e] + j] + k] != ct0) uni = false;
+        for (int j = 1; j < g.nn; j++) if (ctype[ndof * elem_node[elem_ptr[e] + j] + k] != ct0) uni = false;
         sig = sig * 3 + (uni ? (unsigned)ct0 : 2u);
       }
       keyed.push_back(std::make_pair((unsigned long long)sig << 32 | morton3(ctr, bb_lo, bb_inv), e));
@@ -274,7 +279,7 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
   for (int c = 0; c < n_colloc; c++) {
     int nd = colloc_node[c];
     if (nd < 0 || nd >= n_node) { mfb_problem_free(p); return fail(MFB_ERR_ARG, "mfb_harela3d_setup: colloc_node out of range"); }
-    for (int k = 0; k < 3; k++) { int r = row[3 * nd + k]; if (r < 0 || r >= n_dof) { mfb_problem_free(p); return fail(MFB_ERR_ARG, "mfb_harela3d_setup: collocation node without a valid row"); } }
+    for (int k = 0; k < ndof; k++) { int r = row[ndof * nd + k]; if (r < 0 || r >= n_dof) { mfb_problem_free(p); return fail(MFB_ERR_ARG, "mfb_harela3d_setup: collocation node without a valid row"); } }
     node_collocs[nd].push_back(c);
   }
   struct RowNode { int mult; unsigned key; int node; };
@@ -291,7 +296,7 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
       for (size_t q = i; q < j; q++) {
         const int nd = rn[q].node;
         bool dup = false;
-        for (int k = 0; k < 3; k++) { if (row_used[row[3 * nd + k]]) dup = true; row_used[row[3 * nd + k]] = 1; }
+        for (int k = 0; k < ndof; k++) { if (row_used[row[ndof * nd + k]]) dup = true; row_used[row[ndof * nd + k]] = 1; }
         if (dup) { mfb_problem_free(p); return fail(MFB_ERR_ARG, "mfb_harela3d_setup: two collocation nodes share a matrix row"); }
         if ((cnt & 1) && q == j - 1) loose_nodes.push_back(nd); else bulk_nodes.push_back(nd);
       }
@@ -301,8 +306,8 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
   p->rowperm.assign(n_dof, -1);
   {
     int next = 0;
-    for (int nd : bulk_nodes) for (int k = 0; k < 3; k++) p->rowperm[row[3 * nd + k]] = next++;
-    for (int nd : loose_nodes) for (int k = 0; k < 3; k++) p->rowperm[row[3 * nd + k]] = next++;
+    for (int nd : bulk_nodes) for (int k = 0; k < ndof; k++) p->rowperm[row[ndof * nd + k]] = next++;
+    for (int nd : loose_nodes) for (int k = 0; k < ndof; k++) p->rowperm[row[ndof * nd + k]] = next++;
     for (int r = 0; r < n_dof; r++) if (p->rowperm[r] < 0) p->rowperm[r] = next++;   // rows that no collocation point feeds
   }
   std::vector<int> t_row0, t_nbytes, lane_colloc;   // lane_colloc[32*tile + lane] = host collocation index or -1
@@ -310,7 +315,7 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
     const int mult = (int)node_collocs[bulk_nodes[i]].size();
     size_t j = i; while (j < bulk_nodes.size() && j - i < 32 && (int)node_collocs[bulk_nodes[j]].size() == mult) j++;
     for (int layer = 0; layer < mult; layer++) {
-      t_row0.push_back(3 * (int)i); t_nbytes.push_back(24 * (int)(j - i));
+      t_row0.push_back(ndof * (int)i); t_nbytes.push_back(8 * ndof * (int)(j - i));
       for (size_t q = i; q < i + 32; q++) lane_colloc.push_back(q < j ? node_collocs[bulk_nodes[q]][layer] : -1);
     }
     i = j;
@@ -331,10 +336,8 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
     const int c = lane_colloc[q];
     if (c < 0) continue;
     p->cpos_of_colloc[c] = q;
-    for (int k = 0; k < 3; k++) {
-      h_cx[(size_t)k * ldp + q] = colloc_x[3 * (size_t)c + k];
-      h_crow[(size_t)k * ldp + q] = p->rowperm[row[3 * colloc_node[c] + k]];
-    }
+    for (int k = 0; k < 3; k++) h_cx[(size_t)k * ldp + q] = colloc_x[3 * (size_t)c + k];
+    for (int k = 0; k < ndof; k++) h_crow[(size_t)k * ldp + q] = p->rowperm[row[ndof * colloc_node[c] + k]];   // a fluid node has one row: planes 1, 2 stay -1
   }
   double* d_cn = nullptr;
   if (colloc_n) {
@@ -349,10 +352,10 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
   // diagonal stays on the diagonal and partial pivoting keeps finding its pivot in place; otherwise columns keep their order.
   {
     bool paired = true;
-    for (const RowNode& q : rn) for (int k = 0; k < 3; k++) {
-      const int nd = q.node, ct = ctype[3 * nd + k];
-      const int col = (ct == 0) ? col_t[3 * nd + k] : col_u[3 * nd + k];
-      if (col != row[3 * nd + k]) paired = false;
+    for (const RowNode& q : rn) for (int k = 0; k < ndof; k++) {
+      const int nd = q.node, ct = ctype[ndof * nd + k];
+      const int col = (ct == 0) ? col_t[ndof * nd + k] : col_u[ndof * nd + k];
+      if (col != row[ndof * nd + k]) paired = false;
     }
     p->colperm.resize(n_dof);
     for (int i = 0; i < n_dof; i++) p->colperm[i] = paired ? p->rowperm[i] : i;
@@ -365,16 +368,16 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
 
   // ---- flat scatter descriptors over all slots ----
   std::vector<int> slot_off(n_elem + 1, 0);
-  for (int s = 0; s < n_elem; s++) slot_off[s + 1] = slot_off[s] + 3 * p->elems[p->elem_of_slot[s]].nn;
+  for (int s = 0; s < n_elem; s++) slot_off[s + 1] = slot_off[s] + ndof * p->elems[p->elem_of_slot[s]].nn;
   std::vector<int> h_ecol(slot_off[n_elem]); std::vector<unsigned char> h_ekind(slot_off[n_elem]);
   for (int s = 0; s < n_elem; s++) {
     int e = p->elem_of_slot[s], nn = p->elems[e].nn;
-    for (int j = 0; j < nn; j++) for (int k = 0; k < 3; k++) {
+    for (int j = 0; j < nn; j++) for (int k = 0; k < ndof; k++) {
       int node = elem_node[elem_ptr[e] + j];
-      int ct = ctype[3 * node + k];
-      int col = (ct == 0) ? col_t[3 * node + k] : col_u[3 * node + k];
+      int ct = ctype[ndof * node + k];
+      int col = (ct == 0) ? col_t[ndof * node + k] : col_u[ndof * node + k];
       if (col < 0 || col >= n_dof) { mfb_problem_free(p); return fail(MFB_ERR_ARG, "mfb_harela3d_setup: missing column for an unknown"); }
-      h_ecol[slot_off[s] + j * 3 + k] = p->colperm[col]; h_ekind[slot_off[s] + j * 3 + k] = (unsigned char)ct;
+      h_ecol[slot_off[s] + j * ndof + k] = p->colperm[col]; h_ekind[slot_off[s] + j * ndof + k] = (unsigned char)ct;
     }
   }
   int *d_ecol, *d_slot_off; unsigned char* d_ekind; double* d_ecv;
@@ -384,7 +387,7 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
   // ---- groups: geometry, point sets ----
   for (auto& g : p->groups) {
     DevGroup& D = g.dev;
-    D.et = g.et; D.nn = g.nn; D.n_elem = g.n_elem; D.slot0 = g.slot0;
+    D.et = g.et; D.nn = g.nn; D.n_elem = g.n_elem; D.slot0 = g.slot0; D.ndof = ndof;
     std::vector<double> h_xn((size_t)g.n_elem * 3 * g.nn), h_ball((size_t)g.n_elem * 5);
     std::vector<int> h_enode((size_t)g.n_elem * g.nn), h_glnfar(g.n_elem);
     std::vector<unsigned char> h_rev(g.n_elem), h_info(g.n_elem);
@@ -392,9 +395,9 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
       int e = g.elem_ids[i]; const mfbh::Elem& el = p->elems[e];
       {
         unsigned info = 8u | (el.reversed ? 16u : 0u);
-        for (int k = 0; k < 3; k++) {
-          const int ct0 = ctype[3 * elem_node[elem_ptr[e]] + k];
-          for (int j = 1; j < g.nn; j++) if (ctype[3 * elem_node[elem_ptr[e] + j] + k] != ct0) info &= ~8u;
+        for (int k = 0; k < ndof; k++) {
+          const int ct0 = ctype[ndof * elem_node[elem_ptr[e]] + k];
+          for (int j = 1; j < g.nn; j++) if (ctype[ndof * elem_node[elem_ptr[e] + j] + k] != ct0) info &= ~8u;
           if (ct0 == 1) info |= (1u << k);
         }
         h_info[i] = (unsigned char)info;
@@ -429,7 +432,7 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
     D.ecol = d_ecol + slot_off[g.slot0]; D.ekind = d_ekind + slot_off[g.slot0]; D.ecv = d_ecv + 2 * (size_t)slot_off[g.slot0];
     D.has_mixed = 0;
     for (int i = 0; i < g.n_elem; i++) if (!(h_info[i] & 8u)) D.has_mixed = 1;
-    D.cols3 = 1;
+    D.cols3 = (ndof == 3) ? 1 : 0;
     for (int i = 0; i < g.n_elem && D.cols3; i++) {
       const int so = slot_off[g.slot0 + i];
       for (int j = 0; j < g.nn; j++) for (int k = 1; k < 3; k++) if (h_ecol[so + j * 3 + k] != h_ecol[so + j * 3] + k) D.cols3 = 0;
@@ -554,14 +557,18 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
           for (int k = 0; k < ne; k++) { const mfbh::Elem& ee = p->elems[n2e[b0 + k]]; mfbh::node_normal_tangent(ee.et, ee.x, n2k[b0 + k], el.reversed, &ns[3 * k], &ts[3 * k]); }
           if (mfbh::mantic_terms(ne, ns.data(), ts.data(), geometric_tolerance, &cp, sum_b)) { mfb_problem_free(p); return fail(2, "mfb_harela3d_setup: the normals/tangents configuration is not valid (free term)"); }
         }
+        if (ndof == 1) {   // scalar free term c = cp (fbem_bem_pot3d_sbie_freeterm == the isotropic part of Mantic's matrix; build_lse_mechanics_bem_harpot.f90:533,549)
+          f_cpos.push_back(cpos); f_slot.push_back(slot); f_jk.push_back(kn); f_l.push_back(0);
+          f_val.push_back(cp); f_val.push_back(0.0);
+        } else
         for (int l = 0; l < 3; l++) for (int k = 0; k < 3; k++) {
           f_cpos.push_back(cpos); f_slot.push_back(slot); f_jk.push_back(kn * 3 + k); f_l.push_back(l);
           f_val.push_back(l == k ? cp : 0.0); f_val.push_back(sum_b[3 * l + k]);
         }
       } else {
         double phi[9]; mfbh::shape_values(el.et, &colloc_xi[2 * c], phi);
-        for (int l = 0; l < 3; l++) for (int j = 0; j < el.nn; j++) {
-          f_cpos.push_back(cpos); f_slot.push_back(slot); f_jk.push_back(j * 3 + l); f_l.push_back(l);
+        for (int l = 0; l < ndof; l++) for (int j = 0; j < el.nn; j++) {   // hp(:)=hp(:)+0.5d0*pphi_i (build_lse_mechanics_bem_harpot.f90:573)
+          f_cpos.push_back(cpos); f_slot.push_back(slot); f_jk.push_back(j * ndof + l); f_l.push_back(l);
           f_val.push_back(0.5 * phi[j]); f_val.push_back(0.0);
         }
       }
@@ -581,8 +588,8 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
   p->have_tmap = make_matrix_tensor_map(p->tmapA, p->sys.Are, p->lda, n_dof, 2) == 0;
   p->have_tmapS = make_matrix_tensor_map(p->tmapS, p->sys.Are, p->lda, n_dof, 1) == 0;
   p->real_resident = false;
-  if (!p->have_tmap) { mfb_problem_free(p); return fail(MFB_ERR_CUDA, "mfb_harela3d_setup: cuTensorMapEncodeTiled failed (driver too old for sm_100a TMA?)"); }
-  CK(cudaMalloc((void**)&p->d_cvalue, (size_t)6 * n_node * sizeof(double))); p->owned.push_back(p->d_cvalue);
+  if (ndof == 3 && !p->have_tmap) { mfb_problem_free(p); return fail(MFB_ERR_CUDA, "mfb_harela3d_setup: cuTensorMapEncodeTiled failed (driver too old for sm_100a TMA?)"); }
+  CK(cudaMalloc((void**)&p->d_cvalue, (size_t)2 * ndof * n_node * sizeof(double))); p->owned.push_back(p->d_cvalue);
   CK(cudaMalloc((void**)&p->d_ipiv, (size_t)n_dof * sizeof(int))); p->owned.push_back(p->d_ipiv);
   CK(cudaMalloc((void**)&p->d_perm, (size_t)n_dof * sizeof(int))); p->owned.push_back(p->d_perm);
   p->h_ipiv.assign(n_dof, 0);
@@ -596,7 +603,8 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
       for (int i = 0; i < g.n_elem; i++)
         for (int q = 0; q < ldp; q++) {
           unsigned char m = h_plan[(size_t)(g.slot0 + i) * ldp + q];
-          if (m < MAX_SETS) { pairs++; pts += g.dev.ngp[m]; flops += (double)g.dev.ngp[m] * (585.0 + 72.0 * g.nn) + 144.0 * g.nn; }
+          // algorithmic flops per Gauss point / pair: elastic 585 + 72 n / 144 n; scalar 96 + 8 n / 12 n
+          if (m < MAX_SETS) { pairs++; pts += g.dev.ngp[m]; flops += (ndof == 1) ? (double)g.dev.ngp[m] * (96.0 + 8.0 * g.nn) + 12.0 * g.nn : (double)g.dev.ngp[m] * (585.0 + 72.0 * g.nn) + 144.0 * g.nn; }
         }
     p->stats[MFB_STAT_PAIRS_REGULAR] = (double)pairs; p->stats[MFB_STAT_POINTS_REGULAR] = (double)pts; p->stats[MFB_STAT_FLOPS_REGULAR] = flops;
     p->stats[MFB_STAT_PAIRS_ADAPTIVE] = (double)n_adp; p->stats[MFB_STAT_LEAVES] = (double)n_leaves; p->stats[MFB_STAT_POINTS_ADAPTIVE] = (double)pts_adp;
@@ -692,6 +700,7 @@ static int assemble_device(mfb_problem* p, double omega, cd lambda, cd mu, doubl
   return assemble_device_k(p, K, Q, nu, cvalue, false);
 }
 static int assemble_device_k(mfb_problem* p, const KParams& K, const KParams& Q, cd nu, const mfb_z* cvalue, bool statics) {
+  if (p->ndof != 3) return fail(MFB_ERR_ARG, "this problem was set up for an inviscid fluid region (mfb_harpot3d_setup): use mfb_harpot3d_assemble / _solve_frequency");
   cudaStream_t st = p->ctx->stream;
   set_kparams(K, Q, st);
   if (cvalue) {
@@ -737,6 +746,48 @@ static int collect_assembly_times(mfb_problem* p) {
   return MFB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Inviscid fluid (acoustic) BE region (first brick): fbem_bem_harpot3d_calculate_parameters
+// (lib/fbem/src/bem_harpot3d.f90:123-165) + build_lse_mechanics_bem_harpot (src/build_lse_mechanics_bem_harpot.f90) with the
+// scatter of assemble_bem_harpot_equation.f90:78-96, on a problem set up with ndof = 1.
+// ---------------------------------------------------------------------------------------------------------------------
+static int assemble_pot_device(mfb_problem* p, double omega, double rho, cd c, const mfb_z* cvalue) {
+  if (p->ndof != 1) return fail(MFB_ERR_ARG, "this problem was set up for an elastic region: use mfb_harela3d_* / mfb_staela3d_*");
+  if (!(omega > 0.0) || !(rho > 0.0) || c == cd(0.0, 0.0)) return fail(MFB_ERR_ARG, "mfb_harpot3d: omega, rho must be positive and c nonzero");
+  cudaStream_t st = p->ctx->stream;
+  const double c_pi = 3.14159265358979323846264338328;
+  const cd im(0.0, 1.0), k = omega / c;
+  PotParams pp;
+  pp.k = mk(k.real(), k.imag());
+  { cd v = -im * k; pp.P1 = mk(v.real(), v.imag()); }
+  { cd v = 0.5 * (k * k); pp.Q1 = mk(v.real(), v.imag()); }
+  { cd v = im * k; pp.Q2 = mk(v.real(), v.imag()); }
+  pp.c4pi = 1.0 / (4.0 * c_pi); pp.d1J = rho * (omega * omega);
+  set_pot_params(pp, st);
+  if (cvalue) {
+    CK(cudaMemcpyAsync(p->d_cvalue, cvalue, (size_t)2 * p->n_node * sizeof(double), cudaMemcpyHostToDevice, st));
+    for (auto& g : p->groups) launch_gather_cv(g.dev, p->d_cvalue, st);
+    p->have_cvalue = true;
+  } else if (!p->have_cvalue) return fail(MFB_ERR_ARG, "cvalue == NULL but no prescribed values are resident yet");
+  CK(cudaEventRecord(p->ev[0], st));
+  CK(cudaMemsetAsync(p->sys.Are, 0, (size_t)2 * p->lda * p->n_dof * sizeof(double), st));
+  CK(cudaMemsetAsync(p->sys.bre, 0, (size_t)2 * p->lda * sizeof(double), st));
+  CK(cudaEventRecord(p->ev[1], st));
+  for (auto& g : p->groups) launch_pot_regular(g.dev, p->colloc, p->sys, p->plan, st);
+  CK(cudaEventRecord(p->ev[2], st));
+  for (auto& g : p->groups) launch_pot_adaptive(g.dev, p->colloc, p->sys, g.adp, p->ctx->tables, st);
+  CK(cudaEventRecord(p->ev[3], st));
+  for (auto& g : p->groups) launch_pot_singular(g.dev, p->colloc, p->sys, g.sing, p->ctx->tables, st);
+  CK(cudaEventRecord(p->ev[4], st));
+  launch_freeterm(p->colloc, p->sys, p->ft, mk(0.0, 0.0), st);
+  CK(cudaEventRecord(p->ev[5], st));
+  CK(cudaGetLastError());
+  p->factored = false; p->assembled = true; p->rows_permuted = true; p->real_resident = false;
+  p->asm_launches = 1;
+  for (auto& g : p->groups) p->asm_launches += 1 + (cvalue ? 1 : 0) + (g.adp.n_pairs > 0) + (g.sing.n_pairs > 0);
+  return MFB_OK;
+}
+
 // copy a planar device matrix to an interleaved host matrix in column chunks (bounded staging buffer)
 static int download_matrix(mfb_problem* p, const double* re, const double* im, long long ld, int rows, int cols, mfb_z* host, long long ldh, const int* rowperm = nullptr,
                            const int* colperm = nullptr) {
@@ -775,6 +826,27 @@ extern "C" int mfb_harela3d_assemble(mfb_problem* p, double omega, const mfb_z* 
   r = collect_assembly_times(p);
   if (r) return r;
   // the device-resident system is in internal row order; the host sees the reference's row order
+  if (A) { r = download_matrix(p, p->sys.Are, p->sys.Aim, p->lda, p->n_dof, p->n_dof, A, p->n_dof, p->d_rowperm, p->d_colperm); if (r) return r; }
+  if (b) { r = download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, b, p->n_dof, p->d_rowperm); if (r) return r; }
+  return MFB_OK;
+}
+
+extern "C" int mfb_harpot3d_setup(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
+                                  const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
+                                  const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
+                                  const int* row, const int* col_p, const int* col_un, const int* ctype, int n_dof,
+                                  double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
+                                  double geometric_tolerance, mfb_problem** out) {
+  return setup_impl(ctx, n_node, node_x, n_elem, etype, elem_ptr, elem_node, elem_reversed, n_colloc, colloc_x, colloc_node, colloc_elem, colloc_kn, colloc_xi,
+                    row, col_p, col_un, ctype, n_dof, qsi_relative_error, qsi_ns_max, n_precalsets, precalset_gln, geometric_tolerance, nullptr, 1, out);
+}
+extern "C" int mfb_harpot3d_assemble(mfb_problem* p, double omega, double rho, const mfb_z* c, const mfb_z* cvalue, mfb_z* A, mfb_z* b) {
+  if (!p || !c) return fail(MFB_ERR_ARG, "mfb_harpot3d_assemble: null argument");
+  CK(cudaSetDevice(p->ctx->device));
+  int r = assemble_pot_device(p, omega, rho, cd(c->re, c->im), cvalue);
+  if (r) return r;
+  r = collect_assembly_times(p);
+  if (r) return r;
   if (A) { r = download_matrix(p, p->sys.Are, p->sys.Aim, p->lda, p->n_dof, p->n_dof, A, p->n_dof, p->d_rowperm, p->d_colperm); if (r) return r; }
   if (b) { r = download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, b, p->n_dof, p->d_rowperm); if (r) return r; }
   return MFB_OK;
@@ -868,6 +940,25 @@ extern "C" int mfb_harela3d_solve_frequency(mfb_problem* p, double omega, const 
   float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
   p->assembled = false;
   if (!x) return MFB_OK;   // solution stays on the device (mfb_get_solution)
+  return download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, x, p->n_dof, p->d_colperm);
+}
+
+extern "C" int mfb_harpot3d_solve_frequency(mfb_problem* p, double omega, double rho, const mfb_z* c, const mfb_z* cvalue, mfb_z* x) {
+  if (!p || !c) return fail(MFB_ERR_ARG, "mfb_harpot3d_solve_frequency: null argument");
+  CK(cudaSetDevice(p->ctx->device));
+  int r = assemble_pot_device(p, omega, rho, cd(c->re, c->im), cvalue);
+  if (r) return r;
+  r = factor_device(p, p->n_dof, lu_timing());
+  int r2 = collect_assembly_times(p); if (r2) return r2;
+  if (r) return r;
+  cudaStream_t st = p->ctx->stream;
+  CK(cudaEventRecord(p->ev[6], st));
+  int e = zgetrs_planar(p->sys.Are, p->sys.Aim, p->lda, p->n_dof, p->d_perm, p->sys.bre, p->sys.bim, p->lda, 1, st, p->lu.inv);
+  if (e) return fail(MFB_ERR_CUDA, std::string("zgetrs_planar: ") + cudaGetErrorString((cudaError_t)e));
+  CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
+  float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
+  p->assembled = false;
+  if (!x) return MFB_OK;
   return download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, x, p->n_dof, p->d_colperm);
 }
 

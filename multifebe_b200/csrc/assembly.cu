@@ -94,11 +94,12 @@ __global__ void k_gather_cv(DevGroup g, const double* __restrict__ cvalue) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= g.n_elem) return;
   bool nz = false;
+  const int nd = g.ndof;
   for (int j = 0; j < g.nn; j++) {
     const int node = g.enode[e * g.nn + j];
-    for (int k = 0; k < 3; k++) {
-      const double vr = cvalue[2 * (3 * (size_t)node + k)], vi = cvalue[2 * (3 * (size_t)node + k) + 1];
-      const size_t i = (size_t)e * 3 * g.nn + j * 3 + k;
+    for (int k = 0; k < nd; k++) {
+      const double vr = cvalue[2 * (nd * (size_t)node + k)], vi = cvalue[2 * (nd * (size_t)node + k) + 1];
+      const size_t i = (size_t)e * nd * g.nn + j * nd + k;
       g.ecv[2 * i] = vr; g.ecv[2 * i + 1] = vi;
       nz = nz || vr != 0.0 || vi != 0.0;
     }

@@ -15,6 +15,7 @@ const unsigned char PLAN_NONE = 255;
 // One element-type group (elements sorted by type; "slot" = position in that order).
 struct DevGroup {
   int et, nn, n_elem, slot0;     // slot0: first element slot of the group
+  int ndof;                      // dofs per node: 3 (elastic; the strides below are written for it), 1 (inviscid fluid, potential.cuh: stride nn)
   const double* xn;              // [n_elem][3*nn] node coordinates
   const int* ecol;               // [n_elem][3*nn] column of A for (node j, dof k); index j*3+k
   const unsigned char* ekind;    // [n_elem][3*nn] 0: u known (A -= g, b -= h*u), 1: t known (A += h, b += g*t)
