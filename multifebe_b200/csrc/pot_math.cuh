@@ -27,14 +27,18 @@ MFB_HD double mfb_rsqrt(double x) {
 #endif
 }
 
-// E_2(z), E_3(z) of z = -i k r (lib/fbem/src/numerical.f90:1258-1330 keeps the same two branches): |z| <= 1 the series
-// E_3 = z^3/3! (1 + z/4 (1 + z/5 (...))) to 18 terms (first neglected term 1/21!), otherwise direct subtraction.
+// E_2(z), E_3(z) of z = -i k r.  The reference switches to the power series for |z| <= 1 (lib/fbem/src/numerical.f90:1258-1330) to
+// keep E_m accurate RELATIVE TO ITSELF; what reaches the matrix is 1/r + E_2/r and 1/r^2 + E_3/r^2 (+ bounded terms), where the
+// static 1 dominates E_m = O(|z|^m/m!) for |z| <= 1, so the direct subtraction e^z - 1 - z (- z^2/2), whose absolute error is a
+// few ulp of 1, is as accurate for the kernel as the series is.  The series is kept only where it is also the cheaper branch:
+// |z| <= 0.1, E_3 = z^3/3! (1 + z/4 (1 + z/5 (...))) with 9 terms (first neglected term |z|^9 3!/12! < 2e-17); otherwise the
+// branch-free exp / sincos of bem_math.cuh (45 FP64 instructions against 7 per series term).
 MFB_HD void pot_E23(cplx z, cplx& E2, cplx& E3) {
   const cplx z2 = z * z;
-  if (z.re * z.re + z.im * z.im <= 1.0) {
+  if (z.re * z.re + z.im * z.im <= 0.01) {
     double tr = 1.0, ti = 0.0;
 #pragma unroll
-    for (int m = 20; m >= 4; m--) {
+    for (int m = 12; m >= 4; m--) {
       const double inv = 1.0 / (double)m;
       const double ur = (z.re * tr - z.im * ti) * inv, ui = (z.re * ti + z.im * tr) * inv;
       tr = 1.0 + ur; ti = ui;

@@ -24,14 +24,19 @@ def _p(a):
 
 
 def test_E2_E3_both_branches(pmh):
-    for z in [1e-9 - 1e-8j, -0.001 - 0.02j, -0.05 - 0.6j, -0.02 - 0.9998j, -0.03 - 1.0003j, -0.2 - 3.0j, -1.5 - 40.0j, -0.0 - 250.0j]:
+    """The product uses the series only for |z| <= 0.1 and the direct subtraction above it (cheaper on the FP64 pipe): E_m must then
+    be accurate to a few ulp of the static term 1 that it is added to in the kernel (1/r + E_2/r, 1/r^2 + E_3/r^2), and to a few ulp
+    of the largest subtracted term when |z| > 1, as in the reference."""
+    for z in [1e-9 - 1e-8j, -0.001 - 0.02j, -0.004 - 0.0999j, -0.004 - 0.1001j, -0.05 - 0.6j, -0.02 - 0.9998j, -0.03 - 1.0003j, -0.2 - 3.0j,
+              -1.5 - 40.0j, -0.0 - 250.0j]:
         z_ri = np.array([z.real, z.imag]); out = np.zeros(4)
         pmh.pmh_E23(_p(z_ri), _p(out))
         E = orc.zexp_decomposed(z)
         E2, E3 = complex(out[0], out[1]), complex(out[2], out[3])
-        # the direct branch subtracts: its error is relative to |e^z| + |z|^2/2, as in the reference
-        scale2 = abs(E[2]) if abs(z) <= 1 else max(abs(E[2]), 1.0 + abs(z))
-        scale3 = abs(E[3]) if abs(z) <= 1 else max(abs(E[3]), 1.0 + abs(z) ** 2 / 2)
+        if abs(z) <= 0.1:
+            scale2, scale3 = abs(E[2]), abs(E[3])                      # series: accurate relative to itself
+        else:
+            scale2, scale3 = 1.0 + abs(z), 1.0 + abs(z) + abs(z) ** 2 / 2
         assert abs(E2 - E[2]) <= 4e-16 * scale2 + 1e-300 and abs(E3 - E[3]) <= 4e-16 * scale3 + 1e-300, (z, E2, E[2], E3, E[3])
 
 
