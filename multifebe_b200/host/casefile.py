@@ -1,0 +1,309 @@
+"""Reader of the reference's input (case) file for the analyses this library covers.
+
+Mirrors src/read_input_file.f90 for the sections the hot path consumes:
+  [problem]      src/read_problem.f90        n = 3D, type = mechanics, analysis = harmonic | static
+  [frequencies]  src/read_frequencies.f90:20-120  Hz | rad/s; list | lin | log(10)
+  [settings]     src/read_settings.f90:74-216     mesh_file_mode = 2 "<gmsh 2.2 file>", qsi_relative_error, qsi_ns_max, precalsets,
+                                                  geometric_tolerance
+  [materials]    src/read_materials.f90      fluid (two of K, rho, c; xi) / elastic_solid (two of E, nu, lambda, mu, K; rho, xi)
+  [boundaries]   src/read_boundaries.f90     `<id> <part> ordinary`
+  [regions]      src/read_regions.f90        one `be` region, full space, `material <id>` or the legacy in-line forms
+                                             `fluid rho c`, `viscoelastic rho mu nu xi`, `elastic rho mu nu`
+  [conditions over be boundaries]            src/read_conditions_bem_boundaries_mechanics_{harmonic,static}.f90: global-axes
+                                             conditions 0 / 1 per component; defaults (not listed) = 1 with value 0
+  [export]       src/read_export.f90:61-240  export_nso, real_format, integer_format, complex_notation
+Anything else the reference accepts (several regions, be-be / be-fe coupling, crack-like boundaries, local-axes or spring conditions,
+half-spaces, body loads, incident fields, symmetry planes, internal points, FE regions ...) raises CaseFileError naming the feature:
+the Fortran host keeps those.
+"""
+import os
+import re
+import numpy as np
+
+from .mesh import read_gmsh22
+from .model import Model, FluidModel, Material, Fluid
+from .fortran_format import DEFAULT_REAL_FORMAT, REAL_FORMATS
+
+
+class CaseFileError(ValueError):
+    pass
+
+
+def _sections(text):
+    """{section name: [non-empty lines]} (fbem_search_section: a line `[name]` opens a section)."""
+    out, cur = {}, None
+    for raw in text.replace("﻿", "").splitlines():
+        s = raw.strip()
+        m = re.fullmatch(r"\[(.+?)\]", s)
+        if m:
+            cur = m.group(1).strip().lower()
+            out[cur] = []
+        elif cur is not None and s:
+            out[cur].append(s)
+    return out
+
+
+def _keyword(lines, key):
+    """Value string after `key =` (fbem_search_keyword), or None."""
+    for s in lines:
+        m = re.match(r"\s*%s\s*=\s*(.*)$" % re.escape(key), s)
+        if m:
+            return m.group(1).strip()
+    return None
+
+
+def _fortran_float(tok):
+    return float(tok.lower().replace("d", "e"))
+
+
+def _fortran_complex(s):
+    """`(re,im)` list-directed complex, or a bare real."""
+    m = re.match(r"\(\s*([^,\s]+)\s*,\s*([^)\s]+)\s*\)", s.strip())
+    if m:
+        return complex(_fortran_float(m.group(1)), _fortran_float(m.group(2)))
+    return complex(_fortran_float(s.split()[0]))
+
+
+def _logical(s):
+    t = s.strip().lower().strip(".")
+    if t in ("t", "true"):
+        return True
+    if t in ("f", "false"):
+        return False
+    raise CaseFileError("invalid logical value %r" % s)
+
+
+def elastic_constants(given):
+    """Two of E, nu, lambda, mu, K -> all five (fbem_ela_properties, lib/fbem/src/harela_incident_field.f90:889-966)."""
+    g = dict(given)
+    if len(g) != 2:
+        raise CaseFileError("only 2 elastic constants are needed")
+    E, nu, lam, mu, K = (g.get(k) for k in ("E", "nu", "lambda", "mu", "K"))
+    if K is not None and E is not None:
+        lam = 3.0 * K * (3.0 * K - E) / (9.0 * K - E); mu = 3.0 * K * E / (9.0 * K - E); nu = (3.0 * K - E) / (6.0 * K)
+    elif K is not None and lam is not None:
+        E = 9.0 * K * (K - lam) / (3.0 * K - lam); mu = 1.5 * (K - lam); nu = lam / (3.0 * K - lam)
+    elif K is not None and mu is not None:
+        E = 9.0 * K * mu / (3.0 * K + mu); lam = K - 2.0 / 3.0 * mu; nu = 0.5 * (3.0 * K - 2.0 * mu) / (3.0 * K + mu)
+    elif K is not None and nu is not None:
+        E = 3.0 * K * (1.0 - 2.0 * nu); lam = 3.0 * K * nu / (1.0 + nu); mu = 1.5 * K * (1.0 - 2.0 * nu) / (1.0 + nu)
+    elif E is not None and lam is not None:
+        r = np.sqrt(E ** 2 + 9.0 * lam ** 2 + 2.0 * E * lam)
+        K = (E + 3.0 * lam + r) / 6.0; mu = (E - 3.0 * lam + r) / 4.0; nu = 2.0 * lam / (E + lam + r)
+    elif E is not None and mu is not None:
+        K = E * mu / (3.0 * mu - E) / 3.0; lam = mu * (E - 2.0 * mu) / (3.0 * mu - E); nu = 0.5 * E / mu - 1.0
+    elif E is not None and nu is not None:
+        K = E / (1.0 - 2.0 * nu) / 3.0; lam = E * nu / (1.0 + nu) / (1.0 - 2.0 * nu); mu = 0.5 * E / (1.0 + nu)
+    elif lam is not None and mu is not None:
+        K = lam + 2.0 * mu / 3.0; E = mu * (3.0 * lam + 2.0 * mu) / (lam + mu); nu = 0.5 * lam / (lam + mu)
+    elif lam is not None and nu is not None:
+        K = lam * (1.0 + nu) / (3.0 * nu); E = lam / nu * (1.0 + nu) * (1.0 - 2.0 * nu); mu = 0.5 * lam * (1.0 - 2.0 * nu) / nu
+    else:
+        K = 2.0 * mu * (1.0 + nu) / (1.0 - 2.0 * nu) / 3.0; E = 2.0 * mu * (1.0 + nu); lam = 2.0 * mu * nu / (1.0 - 2.0 * nu)
+    return {"E": E, "nu": nu, "lambda": lam, "mu": mu, "K": K}
+
+
+def read_frequencies(lines):
+    """(omega[rad/s] array, units 'f' | 'w'): src/read_frequencies.f90.  The list is stored in rad/s (Hz values times 2 pi)."""
+    units = {"hz": "f", "rad/s": "w"}.get(lines[0].lower())
+    if units is None:
+        raise CaseFileError('the frequency units can be only "Hz" or "rad/s"')
+    mode = {"list": 1, "lin": 2, "log10": 3, "log": 3}.get(lines[1].lower(), 0)
+    if mode == 0:
+        raise CaseFileError('the frequency specification mode is "list", "lin" or "log"')
+    n = int(lines[2].split()[0])
+    if mode == 1:
+        if n <= 0:
+            raise CaseFileError("the number of frequencies must be >=1")
+        # list-directed reads: one value per record
+        f = np.array([_fortran_float(lines[3 + i].split()[0]) for i in range(n)])
+    else:
+        if n < 2:
+            raise CaseFileError("the number of frequencies must be >=2")
+        f = np.zeros(n)
+        f[0] = _fortran_float(lines[3].split()[0]); f[-1] = _fortran_float(lines[4].split()[0])
+        if f[0] >= f[-1]:
+            raise CaseFileError("the range of frequencies is invalid")
+        if mode == 2:
+            delta = (f[-1] - f[0]) / float(n - 1)
+            for i in range(1, n - 1):
+                f[i] = f[0] + delta * float(i)
+        else:
+            delta = (np.log10(f[-1]) - np.log10(f[0])) / float(n - 1)
+            for i in range(1, n - 1):
+                f[i] = 10.0 ** (np.log10(f[0]) + delta * float(i))
+    if units == "f":
+        f = 6.28318530717958623199592693709 * f      # c_2pi of lib/fbem/src/numerical.f90
+    return f, units
+
+
+class CaseFile:
+    """Parsed case: .analysis ('harmonic' | 'static'), .omega, .frequency_units, .mesh, .material (Material | Fluid), .region_type
+    (1 fluid, 2 elastic: the region type codes of the result files), .boundaries [(id, part)], .bcs, settings and export options."""
+
+    def __init__(self, path):
+        self.path = os.path.abspath(path)
+        self.dir = os.path.dirname(self.path)
+        self.filename = os.path.basename(path)
+        sec = _sections(open(path, encoding="utf-8", errors="replace").read())
+        self._sec = sec
+        for unsupported in ("fe subregions", "be body loads", "be bodyloads", "symmetry planes", "internal points", "internal elements",
+                            "incident waves", "groups", "cross sections", "sensitivity"):
+            if sec.get(unsupported):
+                raise CaseFileError("section [%s] is outside the path this library covers" % unsupported)
+        # ---- [problem]
+        pb = sec.get("problem")
+        if pb is None:
+            raise CaseFileError("[problem]: this section is required")
+        if (_keyword(pb, "n") or "").upper() != "3D":
+            raise CaseFileError("[problem] n: only 3D problems are covered")
+        if (_keyword(pb, "type") or "mechanics").lower() != "mechanics":
+            raise CaseFileError("[problem] type: only `mechanics` is covered")
+        self.analysis = (_keyword(pb, "analysis") or "").lower()
+        if self.analysis not in ("harmonic", "static"):
+            raise CaseFileError("[problem] analysis: `harmonic` or `static`")
+        self.description = _keyword(pb, "description") or ""
+        # ---- [settings]
+        st = sec.get("settings", [])
+        v = _keyword(st, "mesh_file_mode")
+        m = re.match(r'(\d+)\s+"?([^"]+)"?', v or "")
+        if not m or int(m.group(1)) != 2:
+            raise CaseFileError('[settings] mesh_file_mode = 2 "<gmsh 2.2 mesh>" is required (other mesh modes are not covered)')
+        self.mesh_file = os.path.join(self.dir, m.group(2).strip())
+        self.qsi_relative_error = _fortran_float(_keyword(st, "qsi_relative_error") or "1e-6")
+        self.qsi_ns_max = int(_keyword(st, "qsi_ns_max") or 16)
+        pc = _keyword(st, "precalsets")
+        self.precalset_gln = tuple(int(t) for t in pc.split()[1:1 + int(pc.split()[0])]) if pc else (2, 3, 4, 5, 6, 7, 8, 9)
+        self.geometric_tolerance = _fortran_float(_keyword(st, "geometric_tolerance") or "1e-6")
+        for k in ("lse_scaling", "lse_condition", "lse_refine"):
+            if _keyword(st, k) and _logical(_keyword(st, k)):
+                raise CaseFileError("[settings] %s = T is not covered (plain zgesv / dgesv)" % k)
+        # ---- [frequencies]
+        self.omega, self.frequency_units = (np.zeros(0), "w")
+        if self.analysis == "harmonic":
+            if _keyword(st, "frequencies_file"):
+                raise CaseFileError("[settings] frequencies_file is not covered: put the list in [frequencies]")
+            if "frequencies" not in sec:
+                raise CaseFileError("[frequencies]: this section is required")
+            self.omega, self.frequency_units = read_frequencies(sec["frequencies"])
+        # ---- [materials]
+        self.materials = {}
+        ml = sec.get("materials", [])
+        if ml:
+            for s in ml[1:1 + int(ml[0].split()[0])]:
+                w = s.split()
+                props = {w[2 + 2 * j]: _fortran_float(w[3 + 2 * j]) for j in range((len(w) - 2) // 2)}
+                if (len(w) - 2) % 2:
+                    raise CaseFileError("material %s: wrong number of arguments" % w[0])
+                self.materials[int(w[0])] = (w[1], props)
+        # ---- [boundaries]
+        bl = sec.get("boundaries")
+        if not bl:
+            raise CaseFileError("[boundaries]: this section is required")
+        self.boundaries = []
+        for s in bl[1:1 + int(bl[0].split()[0])]:
+            w = s.split()
+            if len(w) < 3 or w[2].lower() != "ordinary":
+                raise CaseFileError("boundary %s: only `ordinary` boundaries are covered (crack-like boundaries stay with the Fortran host)" % w[0])
+            self.boundaries.append((int(w[0]), int(w[1])))
+        # ---- [regions]
+        rl = sec.get("regions")
+        if not rl:
+            raise CaseFileError("[regions]: this section is required")
+        if int(rl[0].split()[0]) != 1:
+            raise CaseFileError("[regions]: one BE region is covered (multi-region coupling: SURVEY.md 8f rank 3, not built)")
+        w = rl[1].split()
+        self.region_id = int(w[0])
+        if w[1].lower() != "be":
+            raise CaseFileError("region %d: only `be` regions are covered" % self.region_id)
+        if len(w) > 2 and w[2].lower() != "full-space":
+            raise CaseFileError("region %d: only the full-space fundamental solution is covered" % self.region_id)
+        w = [int(t) for t in rl[2].split()]
+        self.region_boundaries = w[1:1 + w[0]]
+        if any(b < 0 for b in self.region_boundaries):
+            # a negative id = the boundary is seen reversed from this region (region 2 of a be-be boundary)
+            raise CaseFileError("region %d: reversed boundaries belong to multi-region models, which are not covered" % self.region_id)
+        w = rl[3].split()
+        kind = w[0].lower()
+        if kind == "material":
+            mtype, props = self.materials[int(w[1])]
+            mtype = mtype.lower()
+            if mtype in ("fluid", "inviscid_fluid"):
+                kk = {k: props[k] for k in ("K", "rho", "c") if k in props}
+                if len(kk) != 2:
+                    raise CaseFileError("material %s: only 2 properties are needed" % w[1])
+                rho = kk["rho"] if "rho" in kk else kk["K"] / kk["c"] ** 2
+                c = kk["c"] if "c" in kk else np.sqrt(kk["K"] / kk["rho"])
+                self.material, self.region_type = Fluid(rho=rho, c=c, xi=props.get("xi", 0.0)), 1
+            elif mtype == "elastic_solid":
+                ec = elastic_constants({k: props[k] for k in ("E", "nu", "lambda", "mu", "K") if k in props})
+                if self.analysis == "harmonic" and ("rho" not in props or "xi" not in props):
+                    raise CaseFileError("material %s: rho and xi are required for the material of this region" % w[1])
+                self.material, self.region_type = Material(rho=props.get("rho", 1.0), mu=ec["mu"], nu=ec["nu"], xi=props.get("xi", 0.0)), 2
+            else:
+                raise CaseFileError("material type %r is not covered (fluid, elastic_solid)" % mtype)
+        elif kind in ("fluid", "inviscid_fluid"):
+            self.material, self.region_type = Fluid(rho=_fortran_float(w[1]), c=_fortran_float(w[2])), 1
+        elif kind == "viscoelastic":
+            self.material, self.region_type = Material(rho=_fortran_float(w[1]), mu=_fortran_float(w[2]), nu=_fortran_float(w[3]), xi=_fortran_float(w[4])), 2
+        elif kind == "elastic":
+            self.material, self.region_type = Material(rho=_fortran_float(w[1]), mu=_fortran_float(w[2]), nu=_fortran_float(w[3]), xi=0.0), 2
+        else:
+            raise CaseFileError("region %d: material specification %r is not covered" % (self.region_id, kind))
+        for s in rl[4:]:
+            if any(int(t) != 0 for t in s.split() if re.fullmatch(r"-?\d+", t)):
+                raise CaseFileError("region %d: BE body loads / incident fields are not covered" % self.region_id)
+        if self.analysis == "static" and self.region_type != 2:
+            raise CaseFileError("static analysis: only elastic solids are covered")
+        # ---- [conditions over be boundaries]
+        ndof = 1 if self.region_type == 1 else 3
+        self.bcs = {bid: ([1] * ndof, [0j] * ndof) for bid, _ in self.boundaries}     # defaults: t / Un = 0
+        cl = sec.get("conditions over be boundaries", [])
+        i = 0
+        while i < len(cl):
+            m = re.match(r"boundary\s+(\d+)\s*:\s*(.*)$", cl[i], re.I)
+            if not m:
+                raise CaseFileError("[conditions over be boundaries]: cannot parse %r" % cl[i])
+            bid = int(m.group(1))
+            if bid not in self.bcs:
+                raise CaseFileError("[conditions over be boundaries]: unknown boundary %d" % bid)
+            recs = [m.group(2)] + cl[i + 1:i + ndof]
+            ct, cv = [], []
+            for k in range(ndof):
+                w = recs[k].split(None, 1)
+                t = int(w[0])
+                if t not in (0, 1):
+                    raise CaseFileError("boundary %d: condition type %d is not covered (0: primary variable known, 1: secondary variable known)" % (bid, t))
+                ct.append(t); cv.append(_fortran_complex(w[1]))
+            self.bcs[bid] = (ct, cv)
+            i += ndof
+        # ---- [export]
+        ex = sec.get("export", [])
+        self.export_nso = _logical(_keyword(ex, "export_nso") or "T")
+        self.real_format = (_keyword(ex, "real_format") or DEFAULT_REAL_FORMAT).strip("'\" ").lower()
+        self.real_format = REAL_FORMATS.get(self.real_format, self.real_format)
+        self.integer_format = (_keyword(ex, "integer_format") or "").strip("'\" ").lower() or None
+        cn = (_keyword(ex, "complex_notation") or "cartesian").strip("'\" ").lower()
+        if cn not in ("polar", "cartesian"):
+            raise CaseFileError("[export] complex_notation: polar or cartesian")
+        self.complex_notation = cn
+        # ---- mesh: parts are the physical groups of the Gmsh file; a boundary is one part
+        self.mesh = read_gmsh22(self.mesh_file)
+        part_of_boundary = dict(self.boundaries)
+        used_parts = [part_of_boundary[b] for b in self.region_boundaries]
+        keep = [e for e in range(self.mesh.n_elem) if int(self.mesh.part[e]) in used_parts]
+        if len(keep) != self.mesh.n_elem:
+            raise CaseFileError("the mesh holds surface elements of parts that no boundary of the region uses")
+
+    def build_model(self):
+        """The flat model of the region (multifebe_b200.host.Model / FluidModel) with the reference's numbering: boundaries in the order of
+        the region's list (build_auxiliary_variables_mechanics_harmonic.f90:151-198)."""
+        part_of_boundary = dict(self.boundaries)
+        order = [part_of_boundary[b] for b in self.region_boundaries]
+        kw = dict(qsi_relative_error=self.qsi_relative_error, qsi_ns_max=self.qsi_ns_max, precalset_gln=self.precalset_gln,
+                  geometric_tolerance=self.geometric_tolerance, part_order=order)
+        if self.region_type == 1:
+            bcs = {part_of_boundary[b]: (ct[0], cv[0]) for b, (ct, cv) in self.bcs.items()}
+            return FluidModel(self.mesh, bcs, **kw)
+        bcs = {part_of_boundary[b]: (ct, cv) for b, (ct, cv) in self.bcs.items()}
+        return Model(self.mesh, bcs, **kw)

@@ -1,0 +1,114 @@
+"""Nodal-solutions file (*.nso) of the reference for the regions this library covers.
+
+Layout of src/export_solution_mechanics_harmonic_nso.f90 (header :62-150, rows :228-300) and
+src/export_solution_mechanics_static_nso.f90 for one BE region with ordinary boundaries:
+  harmonic row: kf, frequency (Hz or rad/s as in the case file), region id / class (1 = BE) / type (1 fluid, 2 elastic),
+                boundary id / class (1 = ordinary) / face (1), node id, x1 x2 x3, then the total field value_c(k_start:k_end) as
+                (Re, Im) or (|.|, arg) pairs -- fluid: p, Un; elastic: u1 u2 u3 t1 t2 t3 -- then the incident field (zero here).
+  static row:   0, 0.0, the same identification columns, then u1 u2 u3 t1 t2 t3 (real).
+Rows follow the region's boundary list; inside a boundary the nodes appear in first-visit order of the part's elements.
+"""
+import datetime
+import numpy as np
+
+from .fortran_format import RealFormat, fmt_int, int_width
+
+MULTIFEBE_VERSION = "2.0.1"      # the reference release this layout follows
+N_COLUMNS_3D = 44                # ncmax of the harmonic writer for problem%n = 3
+
+
+class NsoWriter:
+    def __init__(self, fh, case, model):
+        self.f, self.case, self.m = fh, case, model
+        self.rf = RealFormat(case.real_format)
+        ids = [len(case.omega), case.region_id, max(b for b, _ in case.boundaries), int(model.mesh.elem_ids.max()), int(model.mesh.node_ids.max())]
+        if case.integer_format in (None, "auto"):
+            self.wi = int_width(*ids)
+        elif case.integer_format == "max":
+            self.wi = 11
+        else:
+            self.wi = int(case.integer_format.lstrip("i"))
+        # rows: (boundary id, node index) in the reference's order
+        part_of_boundary = dict(case.boundaries)
+        self.rows = []
+        for b in case.region_boundaries:
+            seen = set()
+            for e in range(model.n_elem):
+                if int(model.mesh.part[e]) != part_of_boundary[b]:
+                    continue
+                for v in model.mesh.conn[e]:
+                    if int(v) not in seen:
+                        seen.add(int(v)); self.rows.append((b, int(v)))
+
+    def _i(self, n):
+        return fmt_int(n, self.wi)
+
+    def header(self):
+        c, w = self.case, self.f.write
+        w("# Program      : multifebe\n")
+        w("# Version      : %-5s\n" % MULTIFEBE_VERSION[:5])
+        w("# File_format  : nso\n")
+        w("# Problem_dim  : 3\n")
+        w("# Input_file   : %s\n" % c.filename)
+        w("# Description  : %s\n" % c.description)
+        w("# Timestamp    : %s\n" % datetime.datetime.now().strftime("%Y-%m-%d %H:%M:%S.%f")[:23])
+        w("\n")
+        w("# Columns  Description\n")
+        if c.analysis == "harmonic":
+            w("# C1-C2    Frequency index and value %s.\n" % ("f (Hz)" if c.frequency_units == "f" else "w (rad/s)"))
+        else:
+            w("# C1-C2    Step index and value.\n")
+        w("# C3-C5    Region id, class and type.\n")
+        w("# C6-C8    (if C4 == 1) Boundary id, class and face.\n" if c.analysis == "harmonic" else "# C6-C8    (if col C4 == 1) Boundary id, class and face.\n")
+        w("# C6-C8    (if C4 == 2) Subregion id, number of DOF and 0.\n" if c.analysis == "harmonic" else "# C6-C8    (if col C4 == 2) Subregion id, number of DOF and 0.\n")
+        w("# C9-C12   Node id, x1, x2 and x3.\n")
+        w("# >=C13    Node variables. Depend on the region class and type (see documentation).\n")
+        w("#\n")
+        if c.analysis != "harmonic":
+            return
+        w("# Complex notation: %s\n" % c.complex_notation)
+        w("#\n")
+        line = "#" + "_" * (self.wi - 3) + "C1"
+        for kc in range(2, N_COLUMNS_3D + 1):
+            nc = self.wi if 3 <= kc <= 9 else self.rf.w
+            line += "_" * (nc - len(str(kc)) - 1) + "C%d" % kc
+        w(line + "\n")
+
+    def _ident(self, kf, value, b, v):
+        x = self.m.node_x[v]
+        return (self._i(kf) + self.rf(value) + self._i(self.case.region_id) + self._i(1) + self._i(self.case.region_type) + self._i(b) + self._i(1) +
+                self._i(1) + self._i(int(self.m.mesh.node_ids[v])) + "".join(self.rf(t) for t in x))
+
+    def _cpair(self, z):
+        if self.case.complex_notation == "polar":
+            return self.rf(abs(z)) + self.rf(float(np.angle(z)))
+        return self.rf(z.real) + self.rf(z.imag)
+
+    def frequency(self, kf, x):
+        """Rows of frequency index kf (1-based) from the solution vector x of that frequency."""
+        c = self.case
+        omega = c.omega[kf - 1]
+        value = omega * 0.159154943091895335768883763373 if c.frequency_units == "f" else omega   # c_1_2pi
+        prim, sec = self.m.nodal_solution(np.asarray(x))
+        prim = np.asarray(prim).reshape(self.m.n_node, -1); sec = np.asarray(sec).reshape(self.m.n_node, -1)
+        nv = 2 * prim.shape[1]
+        zero = self._cpair(0j) * nv
+        out = []
+        for b, v in self.rows:
+            vals = "".join(self._cpair(complex(z)) for z in list(prim[v]) + list(sec[v]))
+            out.append(self._ident(kf, value, b, v) + vals + zero + "\n")
+        self.f.write("".join(out))
+
+    def static(self, x):
+        u, t = self.m.nodal_solution(np.asarray(x, dtype=np.complex128))
+        out = []
+        for b, v in self.rows:
+            vals = "".join(self.rf(float(z.real)) for z in list(u[v]) + list(t[v]))
+            out.append(self._ident(0, 0.0, b, v) + vals + "\n")
+        self.f.write("".join(out))
+
+
+def read_nso(path):
+    """Numeric rows of an *.nso file as a float array (comment lines skipped): for tests and post-processing."""
+    rows = [[float(t) for t in s.split()] for s in open(path) if s.strip() and not s.startswith("#")]
+    return np.array(rows)

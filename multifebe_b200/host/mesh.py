@@ -9,11 +9,14 @@ from .shape import TRI3, TRI6, QUAD4, QUAD8, QUAD9, GMSH_TYPE, GMSH_CODE, N_NODE
 
 
 class Mesh:
-    def __init__(self, nodes, etype, part, conn):
+    def __init__(self, nodes, etype, part, conn, node_ids=None, elem_ids=None):
         self.nodes = np.ascontiguousarray(nodes, dtype=np.float64)
         self.etype = np.asarray(etype, dtype=np.int32)
         self.part = np.asarray(part, dtype=np.int32)
         self.conn = [np.asarray(c, dtype=np.int32) for c in conn]
+        # identifiers of the mesh file (node()%id, element()%id of the reference: what the result files print); default 1..n
+        self.node_ids = np.arange(1, len(self.nodes) + 1, dtype=np.int64) if node_ids is None else np.asarray(node_ids, dtype=np.int64)
+        self.elem_ids = np.arange(1, len(self.conn) + 1, dtype=np.int64) if elem_ids is None else np.asarray(elem_ids, dtype=np.int64)
 
     @property
     def n_elem(self):
@@ -21,10 +24,12 @@ class Mesh:
 
 
 def read_gmsh22(path):
-    """Gmsh MSH 2.2 ASCII ($Nodes / $Elements); the first tag (physical entity) is the part/boundary id."""
+    """Gmsh MSH 2.2 ASCII ($Nodes / $Elements); the first tag (physical entity) is the part/boundary id.  Only surface elements are
+    kept (the boundary-element mesh); nodes that no kept element uses (geometry points, nodes of line elements) are dropped, the
+    identifiers of the file are kept in Mesh.node_ids / Mesh.elem_ids."""
     lines = open(path).read().split("\n")
     i = 0
-    ids, xyz, et, part, conn = {}, [], [], [], []
+    ids, xyz, et, part, conn, nid, eid = {}, [], [], [], [], [], []
     while i < len(lines):
         s = lines[i].strip()
         if s == "$Nodes":
@@ -32,6 +37,7 @@ def read_gmsh22(path):
             for k in range(n):
                 t = lines[i + 2 + k].split()
                 ids[int(t[0])] = k
+                nid.append(int(t[0]))
                 xyz.append([float(t[1]), float(t[2]), float(t[3])])
             i += n + 2
         elif s == "$Elements":
@@ -42,11 +48,17 @@ def read_gmsh22(path):
                 if gt in GMSH_TYPE:
                     et.append(GMSH_TYPE[gt])
                     part.append(t[3])
+                    eid.append(t[0])
                     conn.append([ids[v] for v in t[3 + ntags:3 + ntags + N_NODES[GMSH_TYPE[gt]]]])
             i += n + 2
         else:
             i += 1
-    return Mesh(np.array(xyz), et, part, conn)
+    used = np.zeros(len(xyz), dtype=bool)
+    for c in conn:
+        used[c] = True
+    remap = np.cumsum(used) - 1
+    conn = [[int(remap[v]) for v in c] for c in conn]
+    return Mesh(np.array(xyz)[used], et, part, conn, node_ids=np.array(nid)[used], elem_ids=eid)
 
 
 def write_gmsh22(mesh, path, names=None):

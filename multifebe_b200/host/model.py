@@ -30,7 +30,7 @@ class Model:
     ndof = equations / unknowns per node: 3 for an elastic solid region, 1 for an inviscid fluid region (FluidModel)."""
 
     def __init__(self, mesh, bcs, reversed_parts=(), qsi_relative_error=1e-6, qsi_ns_max=16,
-                 precalset_gln=(2, 3, 4, 5, 6, 7, 8, 9), geometric_tolerance=1e-6, ndof=3):
+                 precalset_gln=(2, 3, 4, 5, 6, 7, 8, 9), geometric_tolerance=1e-6, ndof=3, part_order=None):
         self.mesh = mesh
         self.ndof = nd = int(ndof)
         nn = len(mesh.nodes)
@@ -74,7 +74,10 @@ class Model:
             self.cvalue[v] = cv
 
         # --- DOF numbering: region -> boundary (part id order) -> element -> node, first visit
-        parts = sorted(set(int(p) for p in mesh.part))
+        # part_order: the boundaries in the order of the region's list in the case file (default: ascending part id)
+        parts = list(part_order) if part_order is not None else sorted(set(int(p) for p in mesh.part))
+        if sorted(parts) != sorted(set(int(p) for p in mesh.part)):
+            raise ValueError("part_order must list every part of the mesh once")
         order = [e for p in parts for e in range(ne) if int(mesh.part[e]) == p]
         self.elem_order = np.array(order, dtype=np.int32)
         self.row = -np.ones((nn, nd), dtype=np.int32)

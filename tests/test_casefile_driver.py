@@ -1,0 +1,323 @@
+"""Host formats either side of the hot path: the reference's case file + Gmsh 2.2 mesh in, its *.nso file out,
+and the stand-alone driver (python -m multifebe_b200 -i case.dat) run here with the ORACLE as the solver (no GPU in the CPU suite;
+tests/test_gpu_driver.py runs the same cases through the CUDA path)."""
+import io
+import os
+import sys
+import numpy as np
+import pytest
+
+from multifebe_b200.host import cube_mesh, write_gmsh22, shape, Material, Fluid, room_analytic
+from multifebe_b200.host.casefile import CaseFile, CaseFileError, read_frequencies, elastic_constants
+from multifebe_b200.host.export import read_nso, NsoWriter
+from multifebe_b200.host.fortran_format import RealFormat, fmt_real, fmt_int, int_width
+from multifebe_b200 import driver
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/docs/examples"
+
+# numbers as the reference printed them with real_format = eng_double (en27.16e3):
+# docs/examples/ME-ST-EL-002/doc_src/ME-ST-EL-002.tex:461-476 (its *.tot listing) -- golden vectors of the export format
+GOLDEN_EN27 = ["416.6665124818034194E-003", "-21.7024668712401838E-009", "0.0000000000000000E+000", "-646.6494794654632685E-012",
+               "89.2479633341829967E-009", "302.9093621814738513E-003", "-308.8234562630653990E-003", "149.1666871671048083E-009",
+               "2.2524860476320668E-009", "833.3332552543941674E-003", "15.2971017006141144E-009", "-302.9094707058440639E-003"]
+
+
+def test_engineering_format_reproduces_the_reference_listing():
+    rf = RealFormat("eng_double")
+    for s in GOLDEN_EN27:
+        out = rf(float(s))
+        assert len(out) == 27 and out.strip() == s
+
+
+def test_other_edit_descriptors():
+    assert RealFormat()(0.1) == "  100.00000000E-03"                      # default en18.8e2 (src/read_export.f90:66)
+    assert RealFormat()(-1234.5678) == "   -1.23456780E+03"
+    assert RealFormat()(999.999999996) == "    1.00000000E+03"              # rounding carries into the next group of three
+    assert RealFormat("sci_double")(0.41666651248180342) == "  0.4166665124818034E+000"
+    assert RealFormat("sci_simple")(-15.0) == " -0.15000000E+02"
+    assert RealFormat("sci_less")(0.0) == "  0.000E+00"
+    assert fmt_real(1.5e-7, "es", 12, 3, 2) == "   1.500E-07"
+    assert fmt_int(42, 5) == "   42" and fmt_int(123456, 4) == "****"
+    assert int_width(300, 1, 6, 744, 462) == 4                              # i4: digits of the largest id + 1 (:61)
+
+
+def test_frequency_lists():
+    om, u = read_frequencies(["rad/s", "lin", "300", "0.01", "15."])           # t3.dat
+    assert u == "w" and len(om) == 300 and om[0] == 0.01 and om[-1] == 15.0
+    delta = (15.0 - 0.01) / 299.0
+    assert om[7] == 0.01 + delta * 7.0
+    om, u = read_frequencies(["Hz", "lin", "50", "1.", "300.000000"])          # room.dat
+    assert u == "f" and np.allclose(om / (2 * np.pi), np.linspace(1.0, 300.0, 50), rtol=1e-14)
+    om, _ = read_frequencies(["rad/s", "log", "4", "1.", "1000."])
+    assert np.allclose(om, [1.0, 10.0, 100.0, 1000.0], rtol=1e-14)
+    om, _ = read_frequencies(["Hz", "list", "3", "5.", "2.", "9."])
+    assert np.allclose(om, 2 * np.pi * np.array([5.0, 2.0, 9.0]))
+    with pytest.raises(CaseFileError):
+        read_frequencies(["rpm", "lin", "3", "1.", "2."])
+    with pytest.raises(CaseFileError):
+        read_frequencies(["Hz", "lin", "3", "2.", "1."])
+
+
+def test_elastic_constants_all_pairs_agree():
+    full = elastic_constants({"E": 2.5, "nu": 0.25})
+    names = ["E", "nu", "lambda", "mu", "K"]
+    for i in range(5):
+        for j in range(i + 1, 5):
+            got = elastic_constants({names[i]: full[names[i]], names[j]: full[names[j]]})
+            for k in names:
+                assert abs(got[k] - full[k]) < 1e-12, (names[i], names[j], k)
+    with pytest.raises(CaseFileError):
+        elastic_constants({"E": 1.0})
+
+
+SOLID_DAT = """[problem]
+n = 3D
+type = mechanics
+analysis = %(analysis)s
+%(freq)s
+[settings]
+mesh_file_mode = 2 "cube.msh"
+
+[materials]
+1
+1 elastic_solid rho 1. mu 1. nu 0.2 xi 0.02
+
+[boundaries]
+6
+1 1 ordinary
+2 2 ordinary
+3 3 ordinary
+4 4 ordinary
+5 5 ordinary
+6 6 ordinary
+
+[regions]
+1
+
+1 be
+6 1 2 3 4 5 6
+material 1
+0
+0
+
+[export]
+real_format = eng_double
+
+[conditions over be boundaries]
+boundary 1: 0 %(z)s
+            0 %(z)s
+            0 %(z)s
+boundary 2: 1 %(one)s
+            1 %(z)s
+            1 %(z)s
+boundary 3: 1 %(z)s
+            0 %(z)s
+            1 %(z)s
+boundary 4: 1 %(z)s
+            0 %(z)s
+            1 %(z)s
+boundary 5: 1 %(z)s
+            1 %(z)s
+            0 %(z)s
+boundary 6: 1 %(z)s
+            1 %(z)s
+            0 %(z)s
+"""
+FLUID_DAT = """[problem]
+type = mechanics
+analysis = harmonic
+n = 3D
+
+[frequencies]
+Hz
+list
+2
+20.
+45.
+
+[settings]
+mesh_file_mode = 2 "cube.msh"
+
+[boundaries]
+6
+1 1 ordinary
+2 2 ordinary
+3 3 ordinary
+4 4 ordinary
+5 5 ordinary
+6 6 ordinary
+
+[materials]
+1
+1 fluid c 343. rho 1.25
+
+[regions]
+1
+1 be
+6 1 2 3 4 5 6
+material 1
+0
+0
+
+[conditions over be boundaries]
+boundary 1: 0 (0.,0.)
+boundary 2: 0 (1.,0.)
+boundary 3: 1 (0.,0.)
+boundary 4: 1 (0.,0.)
+"""
+
+
+def _write_case(tmp_path, text, et=shape.QUAD9, m=2):
+    write_gmsh22(cube_mesh(m, et), str(tmp_path / "cube.msh"))
+    p = tmp_path / "case.dat"
+    p.write_text(text)
+    return str(p)
+
+
+class OracleSolver:
+    """The driver's solver interface backed by the CPU oracle (tests only)."""
+
+    def __init__(self, case, model):
+        from oracle import oracle as orc
+        self.orc, self.case, self.model = orc, case, model
+        self.o = orc.PotOracle(model) if case.region_type == 1 else orc.Oracle(model)
+
+    def harmonic(self, omega):
+        A, b, _ = self.o.assemble(omega, self.case.material)
+        return np.linalg.solve(A, b)
+
+    def static(self):
+        A, b, _ = self.o.assemble_static(self.case.material)
+        return np.linalg.solve(A, b).astype(np.complex128)
+
+    def close(self):
+        pass
+
+
+def _run_with_oracle(path, **kw):
+    case = CaseFile(path)
+    return driver.run(path, solver=OracleSolver(case, case.build_model()), log=io.StringIO(), **kw), case
+
+
+def test_static_case_to_nso(tmp_path):
+    path = _write_case(tmp_path, SOLID_DAT % dict(analysis="static", freq="", z="0.", one="1."))
+    nso, case = _run_with_oracle(path)
+    assert nso == path + ".nso" and case.analysis == "static"
+    rows = read_nso(nso)
+    md = case.build_model()
+    assert rows.shape == (md.n_node, 12 + 6)
+    assert (rows[:, 0] == 0).all() and (rows[:, 1] == 0).all() and (rows[:, 2:5] == [1, 1, 2]).all() and (rows[:, 6:8] == 1).all()
+    # exact solution of the column: u1 = P x1 / (lambda + 2 mu)
+    mat = case.material
+    lam2mu = 2.0 * mat.mu_r * mat.nu_r / (1.0 - 2.0 * mat.nu_r) + 2.0 * mat.mu_r      # xi only enters the harmonic analysis
+    assert np.abs(rows[:, 12] - rows[:, 9] / lam2mu).max() < 5e-6                      # qsi_relative_error = 1e-6 quadrature
+    # every node of the mesh appears once, with its Gmsh id and coordinates
+    assert sorted(rows[:, 8].astype(int)) == list(range(1, md.n_node + 1))
+    assert np.abs(rows[:, 9:12] - md.node_x[rows[:, 8].astype(int) - 1]).max() < 1e-15
+    head = [s for s in open(nso) if s.startswith("#")]
+    assert head[0] == "# Program      : multifebe\n" and head[2] == "# File_format  : nso\n" and "# C1-C2    Step index and value.\n" in head
+
+
+def test_harmonic_fluid_case_to_nso(tmp_path):
+    path = _write_case(tmp_path, FLUID_DAT)
+    nso, case = _run_with_oracle(path)
+    rows = read_nso(nso)
+    md = case.build_model()
+    assert case.region_type == 1 and rows.shape == (2 * md.n_node, 12 + 4 + 4)
+    assert (rows[:md.n_node, 0] == 1).all() and (rows[md.n_node:, 0] == 2).all()
+    assert np.allclose(rows[:md.n_node, 1], 20.0, rtol=1e-8) and np.allclose(rows[md.n_node:, 1], 45.0, rtol=1e-8)   # printed in Hz
+    assert (rows[:, 4] == 1).all()                                                                                # region type 1 = fluid
+    for kf, f in enumerate((20.0, 45.0)):
+        r = rows[kf * md.n_node:(kf + 1) * md.n_node]
+        p = r[:, 12] + 1j * r[:, 13]
+        p_ex, _ = room_analytic(r[:, 9], 2 * np.pi * f, Fluid(1.25, 343.0))
+        assert np.abs(p - p_ex).max() < 5e-4            # default en18.8e2 keeps 9 significant digits; discretisation error 2e-4 (2 x 2 quad9)
+    assert (rows[:, 16:] == 0).all()                    # no incident field
+    # defaults: boundaries 5 and 6 are not listed -> Un = 0 prescribed
+    assert case.bcs[5] == ([1], [0j]) and case.bcs[6] == ([1], [0j])
+    hdr = [s for s in open(nso) if s.startswith("#_")]
+    assert len(hdr) == 1 and hdr[0].rstrip("\n").endswith("C44") and "C1-C2    Frequency index and value f (Hz)." in open(nso).read()
+    w = len(rows) and len(open(nso).read().splitlines()[-1])
+    assert w == 9 * 0 + 8 * int_width(2, 1, 6, md.n_elem, md.n_node) + (4 + 8) * 18     # 8 integer columns, 4 + 2*(2+2) real columns
+
+
+def test_harmonic_solid_case_polar_notation(tmp_path):
+    freq = "\n[frequencies]\nrad/s\nlin\n2\n0.5\n3.0\n"
+    text = (SOLID_DAT % dict(analysis="harmonic", freq=freq, z="(0.,0.)", one="(1.,0.)")).replace("real_format = eng_double", "real_format = sci_double\ncomplex_notation = polar")
+    path = _write_case(tmp_path, text, et=shape.QUAD8, m=1)
+    nso, case = _run_with_oracle(path, output=str(tmp_path / "out"))
+    assert nso == str(tmp_path / "out.nso")
+    rows = read_nso(nso)
+    md = case.build_model()
+    assert rows.shape == (2 * md.n_node, 12 + 12 + 12)
+    from multifebe_b200.host import column_analytic_u
+    r = rows[md.n_node:]
+    u1 = r[:, 12] * np.exp(1j * r[:, 13])
+    assert np.abs(u1 - column_analytic_u(r[:, 9], 3.0, case.material)).max() < 2e-2 * np.abs(u1).max()   # one quad8 per face: 1.2 % discretisation error
+    assert (r[:, 12] >= 0).all() and (np.abs(r[:, 13]) <= np.pi).all()
+
+
+def test_unsupported_features_are_named(tmp_path):
+    base = SOLID_DAT % dict(analysis="static", freq="", z="0.", one="1.")
+    for old, new, word in [("1 1 ordinary", "1 1 crack-like", "ordinary"), ("[regions]\n1\n", "[regions]\n2\n", "one BE region"),
+                           ("boundary 2: 1 1.", "boundary 2: 2 1.", "condition type 2"), ("n = 3D", "n = 2D", "3D"),
+                           ("1 be\n", "1 fe\n", "`be`"), ('mesh_file_mode = 2 "cube.msh"', "mesh_file_mode = 0", "mesh_file_mode"),
+                           ("6 1 2 3 4 5 6", "6 1 2 3 4 5 -6", "reversed")]:
+        assert old in base
+        path = _write_case(tmp_path, base.replace(old, new, 1))
+        with pytest.raises(CaseFileError) as ei:
+            CaseFile(path)
+        assert word in str(ei.value), (word, str(ei.value))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_reference_tutorial_case_files_parse():
+    c = CaseFile(os.path.join(REF, "ME-TH-EL-001/case_files/t3.dat"))
+    md = c.build_model()
+    assert (c.analysis, len(c.omega), c.region_type, md.n_node, md.n_elem, md.n_dof) == ("harmonic", 300, 2, 462, 744, 1386)
+    assert c.omega[0] == 0.01 and c.omega[-1] == 15.0 and c.material.nu_r == 0.2 and c.material.xi == 0.02
+    assert c.bcs[4] == ([0, 0, 0], [0j, 0j, 0j]) and c.bcs[2] == ([1, 1, 1], [1 + 0j, 0j, 0j])
+    c = CaseFile(os.path.join(REF, "ME-ST-EL-002/case_files/t2.dat"))
+    md = c.build_model()
+    assert (c.analysis, c.region_type, md.n_dof) == ("static", 2, 3 * md.n_node) and abs(c.material.mu_r - 0.4) < 1e-15 and c.material.nu_r == 0.25
+
+
+def _gloo_worker(rank, world, port, path, out):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    case = CaseFile(path)
+    nso = driver.run(path, output=path + ".w2", solver=OracleSolver(case, case.build_model()), rank=rank, world=world, dist=dist, log=io.StringIO())
+    out[rank] = nso
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_driver_writes_the_same_file(tmp_path):
+    """Frequency shard over two ranks (gloo): rank 0 writes the frequencies in order; the rows equal the single-rank file's."""
+    import torch.multiprocessing as mp
+    text = FLUID_DAT.replace("list\n2\n20.\n45.\n", "list\n3\n20.\n45.\n70.\n")
+    path = _write_case(tmp_path, text, et=shape.QUAD4, m=2)
+    nso1, _ = _run_with_oracle(path)
+    port = 31500 + (os.getpid() % 2000)
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_gloo_worker, args=(2, port, path, out), nprocs=2, join=True)
+        assert out[0] == path + ".w2.nso" and out[1] is None
+    a = [s for s in open(nso1) if s.startswith("#") and not s.startswith("# Timestamp")]
+    b = [s for s in open(path + ".w2.nso") if s.startswith("#") and not s.startswith("# Timestamp")]
+    assert a == b
+    # the oracle scatters under OpenMP in a nondeterministic order (like the reference): the last printed digit may differ
+    ra, rb = read_nso(nso1), read_nso(path + ".w2.nso")
+    assert ra.shape == rb.shape and np.array_equal(ra[:, :12], rb[:, :12]) and np.allclose(ra, rb, rtol=1e-7, atol=1e-12)
+
+
+def test_default_solver_is_the_gpu_and_fails_loudly_without_one(tmp_path):
+    """No CPU fallback: without a CUDA device the driver stops in mfb_init (the CPU suite runs on a box without a GPU)."""
+    from multifebe_b200 import capi
+    path = _write_case(tmp_path, FLUID_DAT, et=shape.QUAD4, m=1)
+    with pytest.raises(capi.MfbError) as e:
+        driver.run(path, log=io.StringIO())
+    assert e.value.code == -2

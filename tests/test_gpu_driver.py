@@ -1,0 +1,62 @@
+"""The stand-alone driver on the GPU: the reference's case file in, its *.nso file out, every solve through the C ABI.
+The rows are compared with the ones the same driver writes when the CPU oracle is its solver."""
+import io
+import os
+import subprocess
+import sys
+import numpy as np
+import pytest
+
+from multifebe_b200.host import shape
+from multifebe_b200.host.casefile import CaseFile
+from multifebe_b200.host.export import read_nso
+from multifebe_b200 import driver
+from test_casefile_driver import SOLID_DAT, FLUID_DAT, _write_case, _run_with_oracle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _compare(nso_gpu, nso_cpu, first_value_col=12):
+    a, b = read_nso(nso_gpu), read_nso(nso_cpu)
+    assert a.shape == b.shape and np.array_equal(a[:, :first_value_col], b[:, :first_value_col])
+    va, vb = a[:, first_value_col:], b[:, first_value_col:]
+    # primary (u, p) and secondary (t, Un) variables live on different scales: compare column pairs against their own maximum
+    for c in range(va.shape[1]):
+        sc = np.abs(vb[:, c]).max()
+        if sc > 0:
+            assert np.abs(va[:, c] - vb[:, c]).max() <= 1e-8 * max(sc, np.abs(vb).max() * 1e-6), c
+
+
+def test_static_case(tmp_path):
+    text = (SOLID_DAT % dict(analysis="static", freq="", z="0.", one="1.")).replace("eng_double", "sci_double")
+    path = _write_case(tmp_path, text, et=shape.QUAD9, m=2)
+    nso_cpu, _ = _run_with_oracle(path, output=path + ".cpu")
+    nso = driver.run(path, log=io.StringIO())
+    _compare(nso, nso_cpu)
+
+
+def test_harmonic_fluid_and_solid_cases(tmp_path):
+    d1 = tmp_path / "fluid"; d1.mkdir()
+    path = _write_case(d1, FLUID_DAT + "\n[export]\nreal_format = sci_double\n", et=shape.TRI6, m=2)
+    nso_cpu, _ = _run_with_oracle(path, output=path + ".cpu")
+    _compare(driver.run(path, log=io.StringIO()), nso_cpu)
+    d2 = tmp_path / "solid"; d2.mkdir()
+    freq = "\n[frequencies]\nrad/s\nlin\n3\n0.5\n6.0\n"
+    text = (SOLID_DAT % dict(analysis="harmonic", freq=freq, z="(0.,0.)", one="(1.,0.)")).replace("eng_double", "sci_double")
+    path = _write_case(d2, text, et=shape.TRI3, m=3)
+    nso_cpu, _ = _run_with_oracle(path, output=path + ".cpu")
+    _compare(driver.run(path, log=io.StringIO()), nso_cpu)
+
+
+def test_command_line(tmp_path):
+    """python -m multifebe_b200 -i case.dat -o out (options of src/process_command_line_options.f90)."""
+    path = _write_case(tmp_path, FLUID_DAT, et=shape.QUAD4, m=3)
+    out = str(tmp_path / "result")
+    r = subprocess.run([sys.executable, "-m", "multifebe_b200", "-i", path, "-o", out, "-b", "2"], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = read_nso(out + ".nso")
+    md = CaseFile(path).build_model()
+    assert rows.shape == (2 * md.n_node, 20) and "frequency 2 / 2 done" in r.stdout
+    r = subprocess.run([sys.executable, "-m", "multifebe_b200", "-i", str(tmp_path / "missing.dat")], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 2 and "Input file does not exist" in r.stdout
