@@ -359,6 +359,13 @@ class InternalPoints:
         self.pr.build_lse_mechanics_bem_harela(omega, mat, want_host=False)
         return self._u(x)
 
+    def pressures(self, omega, fluid, x):
+        """p (n_points) complex inside an inviscid fluid region for the boundary solution x (internalpoint%value_c(1,0) of
+        src/calculate_internal_points_mechanics_bem_harpot.f90): p(x_ip) = sum_e (g rho omega^2 Un - h p) = -(A x - b) at the interior rows."""
+        self.pr.build_lse_mechanics_bem_harpot(omega, fluid, want_host=False)
+        xa = np.zeros(self.ipm.n_dof, dtype=np.complex128); xa[:self.base.n_dof] = x
+        return -self.pr.residual_vector(xa)[self.base.n_dof:]
+
     def displacements_static(self, mat, x):
         self.pr.build_lse_mechanics_bem_staela(mat, want_host=False)
         return self._u(np.asarray(x, dtype=np.complex128)).real

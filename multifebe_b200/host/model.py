@@ -207,6 +207,10 @@ class InternalPointsModel:
         """stress=True: the hypersingular problem -- every point appears three times with the unit normals e_1, e_2, e_3
         (colloc_n), so that its nine rows are the traction vectors on the three coordinate planes = the stress tensor."""
         m = model
+        nd = int(getattr(m, "ndof", 3))          # 1: inviscid fluid region -- the interior rows give the pressure (calculate_internal_points_mechanics_bem_harpot.f90)
+        if stress and nd != 3:
+            raise ValueError("the hypersingular interior-point problem is built for elastic regions only")
+        self.ndof = nd
         pts0 = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
         self.n_points = len(pts0)
         self.colloc_n = None
@@ -223,14 +227,14 @@ class InternalPointsModel:
         self.etype, self.elem_ptr, self.elem_node, self.elem_reversed = m.etype, m.elem_ptr, m.elem_node, m.elem_reversed
         self.qsi_relative_error, self.qsi_ns_max = m.qsi_relative_error, m.qsi_ns_max
         self.precalset_gln, self.geometric_tolerance = m.precalset_gln, m.geometric_tolerance
-        self.n_dof = m.n_dof + 3 * nip
-        dummy_rows = (m.n_dof + np.arange(3 * nip, dtype=np.int32)).reshape(nip, 3)
-        none = -np.ones((nip, 3), dtype=np.int32)
+        self.n_dof = m.n_dof + nd * nip
+        dummy_rows = (m.n_dof + np.arange(nd * nip, dtype=np.int32)).reshape(nip, nd)
+        none = -np.ones((nip, nd), dtype=np.int32)
         self.row = np.ascontiguousarray(np.vstack([m.row, dummy_rows]), dtype=np.int32)
         self.col_u = np.ascontiguousarray(np.vstack([m.col_u, none]), dtype=np.int32)
         self.col_t = np.ascontiguousarray(np.vstack([m.col_t, none]), dtype=np.int32)
-        self.ctype = np.ascontiguousarray(np.vstack([m.ctype, np.ones((nip, 3), dtype=np.int32)]), dtype=np.int32)
-        self.cvalue = np.ascontiguousarray(np.vstack([m.cvalue, np.zeros((nip, 3), dtype=np.complex128)]))
+        self.ctype = np.ascontiguousarray(np.vstack([m.ctype, np.ones((nip, nd), dtype=np.int32)]), dtype=np.int32)
+        self.cvalue = np.ascontiguousarray(np.vstack([m.cvalue, np.zeros((nip, nd), dtype=np.complex128)]))
         self.colloc_x = pts
         self.colloc_node = (m.n_node + np.arange(nip)).astype(np.int32)
         self.colloc_elem = -np.ones(nip, dtype=np.int32)

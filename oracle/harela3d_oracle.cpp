@@ -1434,6 +1434,7 @@ static int assemble_impl(Model* m, const Params& p, cd nu, const cd* cvalue, cd*
   // free terms (serial): build_lse_mechanics_bem_harela.f90:273-747
   int err = 0;
   for (int c = 0; c < m->n_colloc; c++) {
+    if (m->celem[c] < 0) continue;   // a point off the boundary (interior point of the region): no free term
     int e = m->celem[c], kn = m->ckn[c], sn = m->cnode[c]; const Element& el = m->elem[e];
     cd hp[81], gp[81]; for (int i = 0; i < 9 * el.nn; i++) { hp[i] = 0.0; gp[i] = 0.0; }
     if (kn >= 0 && m->cxi[2 * c] == -9.0) {  // marker: nodal SBIE (xi not used)
@@ -1529,6 +1530,7 @@ int orc_assemble_pot(void* hd, double omega, double rho, const double* c_ri, con
   }
   int err = 0;
   for (int c = 0; c < m->n_colloc; c++) {
+    if (m->celem[c] < 0) continue;   // a point off the boundary (interior point of the region): no free term
     int e = m->celem[c], kn = m->ckn[c], sn = m->cnode[c]; const Element& el = m->elem[e];
     cd hp[9], gp[9]; for (int i = 0; i < el.nn; i++) { hp[i] = 0.0; gp[i] = 0.0; }
     bool mca = (m->cxi[2 * c] != -9.0);

@@ -86,3 +86,30 @@ def test_wrong_family_is_refused(gpu_ctx):
     with pytest.raises(capi.MfbError):
         pe.build_lse_mechanics_bem_harpot(1.0, AIR)
     pe.close()
+
+
+# Written after the round's GPU budget was spent: never run on hardware.  It uses only entry points that the tests above validate
+# (mfb_harpot3d_setup / _assemble with colloc_elem = -1 rows, mfb_residual_vector); non-strict so that the first hardware run reports
+# it either way (XPASS expected).
+@pytest.mark.xfail(reason="first hardware run pending (written without GPU access at the end of round 1)", strict=False)
+def test_interior_pressures_match_the_oracle_composition(gpu_ctx, oracle_lib):
+    from multifebe_b200 import capi
+    md = FluidModel(cube_mesh(3, shape.QUAD9), room_bcs(1.0))
+    omega = 2 * np.pi * 30.0
+    pts = np.array([[0.5, 0.5, 0.5], [0.2, 0.7, 0.4], [0.93, 0.5, 0.5], [0.31, 0.08, 0.77], [0.5, 0.5, 0.985]])
+    pr = capi.Problem(gpu_ctx, md)
+    x = pr.solve_frequency_fluid(omega, AIR)
+    ip = capi.InternalPoints(gpu_ctx, md, pts)
+    pin = ip.pressures(omega, AIR, x)
+    o = oracle_lib.PotOracle(md)
+    p, un = md.nodal_solution(x)
+    ref = np.zeros(len(pts), dtype=np.complex128)
+    for k, xp in enumerate(pts):
+        for e in range(md.n_elem):
+            h, g, _ = o.pair(e, xp, omega, AIR)
+            nodes = md.mesh.conn[e]
+            ref[k] += (g * AIR.rho * omega ** 2) @ un[nodes] - h @ p[nodes]
+    assert relerr(pin, ref) < 1e-10
+    p_ex, _ = room_analytic(pts[:, 0], omega, AIR)
+    assert np.abs(pin - p_ex).max() < 2e-4 * np.abs(p_ex).max()
+    ip.close(); pr.close()

@@ -88,3 +88,32 @@ def test_plan_uses_the_scalar_estimator_order():
     modes_p = [orc.PotOracle(md).pair(e, x_i, 1.0, fl)[2] for e in range(md.n_elem)]
     modes_e = [orc.Oracle(me).pair(e, x_i, 1.0, mat)[2] for e in range(me.n_elem)]
     assert all(a <= b for a, b in zip(modes_p, modes_e)) and any(a < b for a, b in zip(modes_p, modes_e))
+
+
+def test_interior_pressure_follows_the_room_solution():
+    """Interior points of a fluid region (src/calculate_internal_points_mechanics_bem_harpot.f90): p(x) = sum_e (g rho omega^2 Un - h p) with the
+    integrators of the boundary equations; ME-TH-AC-001 computes the field inside the room this way."""
+    from multifebe_b200.host import InternalPointsModel
+    md = FluidModel(cube_mesh(3, shape.QUAD9), room_bcs(1.0))
+    fl = Fluid(rho=1.25, c=343.0)
+    omega = 2 * np.pi * 30.0
+    o = orc.PotOracle(md)
+    A, b, _ = o.assemble(omega, fl)
+    x = np.linalg.solve(A, b)
+    p, un = md.nodal_solution(x)
+    pts = np.array([[0.5, 0.5, 0.5], [0.2, 0.7, 0.4], [0.93, 0.5, 0.5], [0.31, 0.08, 0.77]])
+    d1J = fl.rho * omega ** 2
+    pin = np.zeros(len(pts), dtype=np.complex128)
+    for ip, xp in enumerate(pts):
+        for e in range(md.n_elem):
+            h, g, _ = o.pair(e, xp, omega, fl)
+            nodes = md.mesh.conn[e]
+            pin[ip] += (g * d1J) @ un[nodes] - h @ p[nodes]
+    p_ex, _ = room_analytic(pts[:, 0], omega, fl)
+    assert np.abs(pin - p_ex).max() < 1e-4 * np.abs(p_ex).max()
+    # the interior-point problem the library assembles: same elements and columns, one extra row per point, no free term
+    ipm = InternalPointsModel(md, pts)
+    assert ipm.ndof == 1 and ipm.n_dof == md.n_dof + 4 and ipm.row.shape == (md.n_node + 4, 1) and np.all(ipm.colloc_elem == -1)
+    Ai, bi, _ = orc.PotOracle(ipm).assemble(omega, fl)
+    xa = np.zeros(ipm.n_dof, dtype=np.complex128); xa[:md.n_dof] = x
+    assert np.abs(-(Ai @ xa - bi)[md.n_dof:] - pin).max() < 1e-12 * np.abs(pin).max()
