@@ -125,6 +125,29 @@ def cube_mesh(m, etype=TRI3, L=1.0):
     return Mesh(np.array(nodes), et, pt, conn)
 
 
+def two_box_mesh(m, etype=TRI3, xs=0.5, L=1.0):
+    """The cube [0,L]^3 cut by the plane x = xs*L into two boxes that share ONE interface part (for two coupled BE regions): every face
+    of every box is its own part with unshared rim nodes, m x m cells per face, normals outward from the box that owns the face; the
+    interface is meshed once, with the normal +x (outward from the box x < xs*L = its region 1).
+    Parts: 1 x=0; 3, 4, 5, 6 = y=0, y=L, z=0, z=L of the first box; 7 interface; 2 x=L; 13, 14, 15, 16 the lateral faces of the second box."""
+    nodes, et, pt, conn = [], [], [], []
+    a, b = xs * L, (1.0 - xs) * L
+    ex, ey, ez, o = np.array([1.0, 0, 0]), np.array([0, L, 0.]), np.array([0, 0, L]), np.zeros(3)
+    _face_grid(o, ez, ey, m, etype, 1, nodes, et, pt, conn)                   # x=0, normal -x
+    _face_grid(o, a * ex, ez, m, etype, 3, nodes, et, pt, conn)               # y=0, normal -y
+    _face_grid(o + ey, ez, a * ex, m, etype, 4, nodes, et, pt, conn)          # y=L, normal +y
+    _face_grid(o, ey, a * ex, m, etype, 5, nodes, et, pt, conn)               # z=0, normal -z
+    _face_grid(o + ez, a * ex, ey, m, etype, 6, nodes, et, pt, conn)          # z=L, normal +z
+    _face_grid(o + a * ex, ey, ez, m, etype, 7, nodes, et, pt, conn)          # interface x=xs L, normal +x
+    o2 = o + a * ex
+    _face_grid(o2 + b * ex, ey, ez, m, etype, 2, nodes, et, pt, conn)         # x=L, normal +x
+    _face_grid(o2, b * ex, ez, m, etype, 13, nodes, et, pt, conn)
+    _face_grid(o2 + ey, ez, b * ex, m, etype, 14, nodes, et, pt, conn)
+    _face_grid(o2, ey, b * ex, m, etype, 15, nodes, et, pt, conn)
+    _face_grid(o2 + ez, b * ex, ey, m, etype, 16, nodes, et, pt, conn)
+    return Mesh(np.array(nodes), et, pt, conn)
+
+
 def halfspace_patch(m, etype=TRI3, L=1.0, footing=0.25):
     """S-halfspace(m): flat free-surface patch z=0 of side L (soil below, outward normal +z); part 1 = free
     surface, part 2 = central square footing of half-width `footing`*L (cells whose centre lies inside)."""

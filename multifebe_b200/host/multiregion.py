@@ -1,0 +1,257 @@
+"""Several BE regions coupled through be-be interface boundaries: host-side numbering and the
+per-region views, built the way the reference's host does.
+
+  * regions           src/read_regions.f90: every region lists its boundaries; a NEGATIVE id means the boundary is seen with reversed
+                      orientation from this region (it is region 2 of that boundary), so a boundary listed by two regions is a be-be
+                      interface whose mesh normal points out of its region 1.
+  * DOF numbering     src/build_auxiliary_variables_mechanics_harmonic.f90:68-900: regions -> boundaries -> elements -> nodes in
+                      first-visit order.  Ordinary boundary: as in host/model.py.  Interface (perfect bonding / perfect contact):
+                        fluid(1)-fluid(2)   rows (1,1), (1,2); columns p1, Un1          (p2 = p1, Un2 = -Un1)                     :593-622
+                        fluid(1)-solid(2)   row (1,1), column p1; rows (k,2), columns u2_k  (Un1 = u2.n1, t2 = -p1 n2)            :626-661
+                        solid(1)-fluid(2)   rows (k,1), columns u1_k; row (1,2), column p2  (t1 = -p2 n1, Un2 = u1.n2)            :751-792
+                        solid(1)-solid(2)   per k: rows (k,1), (k,2); columns u1_k, t1_k    (u2 = u1, t2 = -t1; ctype 0)          :800-836
+  * collocation       every region collocates at the nodes of ITS boundaries (nodal SBIE, or MCA on part rims as in host/model.py) and
+                      writes the equation into rows (., eq) with eq = 1 when the region is region 1 of the collocation boundary, else 2
+                      (src/build_lse_mechanics_bem_harela.f90:1118-1136, src/build_lse_mechanics_bem_harpot.f90).
+Only the numbering, the views and the nodal-solution map live here; the integrals are the single-region ones.  The device path for
+coupled regions is not built yet: this model feeds the multi-region oracle and the round-2 C ABI.
+"""
+import numpy as np
+from . import shape as sh
+from .model import MCA_BOUNDARY_DELTA, NODAL_XI_MARK
+
+SOLID, FLUID = "solid", "fluid"
+
+
+class Region:
+    def __init__(self, kind, material, boundaries):
+        """kind SOLID | FLUID; material host.Material | host.Fluid; boundaries: signed boundary ids (negative = reversed)."""
+        if kind not in (SOLID, FLUID):
+            raise ValueError("region kind must be 'solid' or 'fluid'")
+        self.kind, self.material, self.boundaries = kind, material, [int(b) for b in boundaries]
+        self.ndof = 3 if kind == SOLID else 1
+
+
+class RegionView:
+    """What one region's integrator needs (the flat arrays of host.Model, on the GLOBAL node set): its elements with the orientation
+    seen from the region, and its collocation points."""
+    pass
+
+
+class MultiRegionModel:
+    def __init__(self, mesh, regions, boundary_part, bcs, qsi_relative_error=1e-6, qsi_ns_max=16, precalset_gln=(2, 3, 4, 5, 6, 7, 8, 9),
+                 geometric_tolerance=1e-6):
+        """boundary_part {boundary id: part id of the mesh}; bcs {boundary id: (ctypes, values)} for the ORDINARY boundaries (solid: three
+        components, fluid: scalars), 0 = primary variable known, 1 = secondary variable known."""
+        self.mesh, self.regions = mesh, list(regions)
+        nn, ne = len(mesh.nodes), mesh.n_elem
+        self.n_node, self.n_elem = nn, ne
+        self.node_x = mesh.nodes
+        self.qsi_relative_error, self.qsi_ns_max = float(qsi_relative_error), int(qsi_ns_max)
+        self.precalset_gln = np.array(precalset_gln, dtype=np.int32)
+        self.geometric_tolerance = float(geometric_tolerance)
+        # --- boundaries: which regions use them
+        self.boundary_part = dict(boundary_part)
+        self.boundary_regions = {b: [None, None] for b in boundary_part}          # [region 1 (positive), region 2 (reversed)]
+        for kr, r in enumerate(self.regions):
+            for b in r.boundaries:
+                slot = 0 if b > 0 else 1
+                if abs(b) not in self.boundary_regions or self.boundary_regions[abs(b)][slot] is not None:
+                    raise ValueError("boundary %d: unknown, or listed twice with the same orientation" % abs(b))
+                self.boundary_regions[abs(b)][slot] = kr
+        for b, (r1, r2) in self.boundary_regions.items():
+            if r1 is None:
+                raise ValueError("boundary %d has no region 1 (it must be listed with a positive id by one region)" % b)
+        part_boundary = {p: b for b, p in self.boundary_part.items()}
+        # --- part rims (nodes of edges owned by a single element of the part) and node -> boundary
+        node_b = -np.ones(nn, dtype=np.int64)
+        edge_count = {}
+        for e in range(ne):
+            c, p = mesh.conn[e], int(mesh.part[e])
+            b = part_boundary[p]
+            for v in c:
+                if node_b[v] not in (-1, b):
+                    raise ValueError("node %d is shared by two boundaries; each boundary must own its nodes" % v)
+                node_b[v] = b
+            for ed in sh.edges_of(int(mesh.etype[e])):
+                key = (p,) + tuple(sorted((int(c[ed[0]]), int(c[ed[1]]))))
+                edge_count.setdefault(key, []).append([int(c[k]) for k in ed])
+        in_boundary = np.zeros(nn, dtype=bool)
+        for lst in edge_count.values():
+            if len(lst) == 1:
+                in_boundary[lst[0]] = True
+        self.node_boundary, self.in_boundary = node_b, in_boundary
+        self.elems_of_boundary = {b: [e for e in range(ne) if int(mesh.part[e]) == p] for b, p in self.boundary_part.items()}
+        # --- boundary conditions of the ordinary boundaries
+        self.ctype = {}
+        self.cvalue = {}
+        for b, (r1, r2) in self.boundary_regions.items():
+            if r2 is None:
+                nd = self.regions[r1].ndof
+                ct, cv = bcs[b]
+                ct = np.atleast_1d(np.asarray(ct, dtype=np.int32)); cv = np.atleast_1d(np.asarray(cv, dtype=np.complex128))
+                if len(ct) != nd or len(cv) != nd or not set(ct.tolist()) <= {0, 1}:
+                    raise ValueError("boundary %d: %d condition(s) of type 0 / 1 expected" % (b, nd))
+                self.ctype[b], self.cvalue[b] = ct, cv
+        # --- numbering.  row[(node, eq)] -> list of rows (1 or 3); col[(node, name)] -> column, names 'p1','un1','p2','u1k','t1k','u2k'
+        self.row, self.col = {}, {}
+        row = col = 0
+        used = np.zeros(nn, dtype=bool)
+        for kr, r in enumerate(self.regions):
+            for sb in r.boundaries:
+                b = abs(sb)
+                r1, r2 = self.boundary_regions[b]
+                for e in self.elems_of_boundary[b]:
+                    for v in mesh.conn[e]:
+                        v = int(v)
+                        if used[v]:
+                            continue
+                        used[v] = True
+                        if r2 is None:                                   # ordinary boundary of region r1
+                            nd = self.regions[r1].ndof
+                            self.row[(v, 1)] = list(range(row, row + nd)); row += nd
+                            for k in range(nd):
+                                name = ("t%d" if nd == 3 else "un%d") if self.ctype[b][k] == 0 else ("u%d" if nd == 3 else "p%d")
+                                self.col[(v, (name % 1) + (str(k) if nd == 3 else ""))] = col; col += 1
+                            continue
+                        k1, k2 = self.regions[r1].kind, self.regions[r2].kind
+                        if k1 == FLUID and k2 == FLUID:
+                            self.row[(v, 1)] = [row]; self.row[(v, 2)] = [row + 1]; row += 2
+                            self.col[(v, "p1")] = col; self.col[(v, "un1")] = col + 1; col += 2
+                        elif k1 == FLUID and k2 == SOLID:
+                            self.row[(v, 1)] = [row]; row += 1
+                            self.col[(v, "p1")] = col; col += 1
+                            self.row[(v, 2)] = list(range(row, row + 3)); row += 3
+                            for k in range(3):
+                                self.col[(v, "u2%d" % k)] = col; col += 1
+                        elif k1 == SOLID and k2 == FLUID:
+                            self.row[(v, 1)] = list(range(row, row + 3)); row += 3
+                            for k in range(3):
+                                self.col[(v, "u1%d" % k)] = col; col += 1
+                            self.row[(v, 2)] = [row]; row += 1
+                            self.col[(v, "p2")] = col; col += 1
+                        else:                                            # solid - solid, perfect bonding
+                            r1rows, r2rows = [], []
+                            for k in range(3):
+                                r1rows.append(row); r2rows.append(row + 1); row += 2
+                                self.col[(v, "u1%d" % k)] = col; self.col[(v, "t1%d" % k)] = col + 1; col += 2
+                            self.row[(v, 1)] = r1rows; self.row[(v, 2)] = r2rows
+        if row != col:
+            raise ValueError("the system is not square: %d equations, %d unknowns" % (row, col))
+        self.n_dof = row
+        # --- per-region views
+        self.views = [self._view(kr) for kr in range(len(self.regions))]
+
+    def _view(self, kr):
+        mesh, r = self.mesh, self.regions[kr]
+        v = RegionView()
+        v.kind, v.material, v.ndof = r.kind, r.material, r.ndof
+        elems, rev, ebnd = [], [], []
+        for sb in r.boundaries:
+            for e in self.elems_of_boundary[abs(sb)]:
+                elems.append(e); rev.append(1 if sb < 0 else 0); ebnd.append(abs(sb))
+        v.elem_global = np.array(elems, dtype=np.int32)
+        v.elem_boundary = np.array(ebnd, dtype=np.int32)
+        v.n_node, v.n_elem = self.n_node, len(elems)
+        v.node_x = self.node_x
+        v.mesh = mesh
+        v.etype = mesh.etype[elems].astype(np.int32)
+        v.elem_ptr = np.zeros(len(elems) + 1, dtype=np.int32)
+        v.elem_ptr[1:] = np.cumsum([len(mesh.conn[e]) for e in elems])
+        v.elem_node = np.concatenate([mesh.conn[e] for e in elems]).astype(np.int32)
+        v.elem_reversed = np.array(rev, dtype=np.uint8)
+        v.qsi_relative_error, v.qsi_ns_max = self.qsi_relative_error, self.qsi_ns_max
+        v.precalset_gln, v.geometric_tolerance = self.precalset_gln, self.geometric_tolerance
+        # collocation points of the region (loop order of the reference: boundaries, elements, nodes)
+        cx, cnode, celem, ckn, cxi, ceq = [], [], [], [], [], []
+        collocated = np.zeros(self.n_node, dtype=bool)
+        for le, e in enumerate(elems):
+            et = int(mesh.etype[e]); c = mesh.conn[e]
+            xn = self.node_x[c]
+            eq = 1 if self.boundary_regions[ebnd[le]][0] == kr else 2
+            for kn, nd in enumerate(c):
+                nd = int(nd)
+                if self.in_boundary[nd]:
+                    xi = sh.move_xi_from_edge(et, sh.XI_NODES[et][kn], MCA_BOUNDARY_DELTA)
+                    cx.append(sh.position(et, xn, xi)); cxi.append(xi)
+                elif not collocated[nd]:
+                    collocated[nd] = True
+                    cx.append(sh.position(et, xn, sh.XI_NODES[et][kn])); cxi.append([NODAL_XI_MARK, NODAL_XI_MARK])
+                else:
+                    continue
+                cnode.append(nd); celem.append(le); ckn.append(kn); ceq.append(eq)
+        v.colloc_x = np.ascontiguousarray(cx, dtype=np.float64)
+        v.colloc_node = np.array(cnode, dtype=np.int32)
+        v.colloc_elem = np.array(celem, dtype=np.int32)          # LOCAL element index of the view
+        v.colloc_kn = np.array(ckn, dtype=np.int32)
+        v.colloc_xi = np.ascontiguousarray(cxi, dtype=np.float64)
+        v.colloc_eq = np.array(ceq, dtype=np.int32)
+        v.n_colloc = len(cnode)
+        # placeholders for the single-region set-up signatures (the multi-region scatter does not use them)
+        z = np.zeros((self.n_node, r.ndof), dtype=np.int32)
+        v.row, v.col_u, v.col_t, v.ctype = z, z, z, np.ones((self.n_node, r.ndof), dtype=np.int32)
+        v.cvalue = np.zeros((self.n_node, r.ndof), dtype=np.complex128)
+        v.n_dof = 1
+        return v
+
+    # ---- nodal variables from the solution vector (assign_solution_mechanics_harmonic.f90 with the interface substitutions)
+    def nodal_solution(self, x, kr):
+        """Primary and secondary variables of region kr at the nodes of its boundaries: solid (u (n,3), t (n,3)), fluid (p (n), Un (n));
+        nodes the region does not touch are NaN.  Interface values follow the coupling relations listed in the module docstring, with
+        n = the mesh normal of the element node averaged over the node's elements (only used for the fluid-solid relations)."""
+        r = self.regions[kr]
+        nan = np.nan + 0j
+        if r.kind == SOLID:
+            P = np.full((self.n_node, 3), nan); S = np.full((self.n_node, 3), nan)
+        else:
+            P = np.full(self.n_node, nan); S = np.full(self.n_node, nan)
+        nrm = self.node_normals()
+        for sb in r.boundaries:
+            b = abs(sb)
+            r1, r2 = self.boundary_regions[b]
+            first = r1 == kr
+            for e in self.elems_of_boundary[b]:
+                for v in self.mesh.conn[e]:
+                    v = int(v)
+                    if r2 is None:
+                        for k in range(r.ndof):
+                            known = self.cvalue[b][k]
+                            if r.kind == SOLID:
+                                if self.ctype[b][k] == 0:
+                                    P[v, k] = known; S[v, k] = x[self.col[(v, "t1%d" % k)]]
+                                else:
+                                    S[v, k] = known; P[v, k] = x[self.col[(v, "u1%d" % k)]]
+                            else:
+                                if self.ctype[b][k] == 0:
+                                    P[v] = known; S[v] = x[self.col[(v, "un1")]]
+                                else:
+                                    S[v] = known; P[v] = x[self.col[(v, "p1")]]
+                        continue
+                    k1, k2 = self.regions[r1].kind, self.regions[r2].kind
+                    n1 = nrm[v]                                        # outward from region 1
+                    if k1 == FLUID and k2 == FLUID:
+                        P[v] = x[self.col[(v, "p1")]]; S[v] = x[self.col[(v, "un1")]] * (1.0 if first else -1.0)
+                    elif k1 == SOLID and k2 == SOLID:
+                        for k in range(3):
+                            P[v, k] = x[self.col[(v, "u1%d" % k)]]; S[v, k] = x[self.col[(v, "t1%d" % k)]] * (1.0 if first else -1.0)
+                    else:
+                        fl_first = k1 == FLUID
+                        pcol = self.col[(v, "p1" if fl_first else "p2")]
+                        u = np.array([x[self.col[(v, ("u2%d" if fl_first else "u1%d") % k)]] for k in range(3)])
+                        n_out = n1 if first else -n1                   # outward from THIS region
+                        if r.kind == FLUID:
+                            P[v] = x[pcol]; S[v] = u @ n_out
+                        else:
+                            P[v] = u; S[v] = -x[pcol] * n_out
+        return P, S
+
+    def node_normals(self):
+        """Unit mesh normal at every node (average of element(se)%n_fn over the node's elements, build_data_at_functional_nodes.f90:360-389)."""
+        acc = np.zeros((self.n_node, 3))
+        for e in range(self.n_elem):
+            et = int(self.mesh.etype[e]); c = self.mesh.conn[e]
+            for kn, v in enumerate(c):
+                acc[int(v)] += sh.unit_normal(et, self.node_x[c], sh.XI_NODES[et][kn])
+        nrm = np.linalg.norm(acc, axis=1)
+        nrm[nrm == 0] = 1.0
+        return acc / nrm[:, None]

@@ -66,3 +66,41 @@ def move_xi_from_edge(etype, xi, delta):
     if etype in (TRI3, TRI6):
         return np.array([xi[0] * (1.0 - delta) + 0.333333333333333333 * delta, xi[1] * (1.0 - delta) + 0.333333333333333333 * delta])
     return np.array([xi[0] * (1.0 - delta), xi[1] * (1.0 - delta)])
+
+
+def dphi(etype, xi):
+    """(dphi/dxi1, dphi/dxi2): the derivatives of `phi` (resources_shape_functions/dphidxi{1,2}_*.rc of the reference)."""
+    a1, a2 = float(xi[0]), float(xi[1])
+    if etype == TRI3:
+        return np.array([1.0, 0.0, -1.0]), np.array([0.0, 1.0, -1.0])
+    if etype == TRI6:
+        return (np.array([4.0 * a1 - 1.0, 0.0, 4.0 * a1 + 4.0 * a2 - 3.0, 4.0 * a2, -4.0 * a2, -4.0 * (a2 + 2.0 * a1 - 1.0)]),
+                np.array([0.0, 4.0 * a2 - 1.0, 4.0 * a1 + 4.0 * a2 - 3.0, 4.0 * a1, -4.0 * (2.0 * a2 + a1 - 1.0), -4.0 * a1]))
+    if etype == QUAD4:
+        a3, a4, a5, a6 = 0.25 * (1.0 + a1), 0.25 * (1.0 - a1), 1.0 + a2, 1.0 - a2
+        return np.array([-0.25 * a6, 0.25 * a6, 0.25 * a5, -0.25 * a5]), np.array([-a4, -a3, a3, a4])
+    if etype == QUAD8:
+        b3, b4, b5, b6 = a2 + 1.0, a2 - 1.0, a2 + 2.0 * a1, a2 - 2.0 * a1
+        d1 = np.array([-0.25 * b4 * b5, 0.25 * b4 * b6, 0.25 * b3 * b5, -0.25 * b3 * b6, a1 * b4, -0.5 * b3 * b4, -a1 * b3, 0.5 * b3 * b4])
+        c3, c4, c5, c6 = a1 + 1.0, a1 - 1.0, 2.0 * a2 + a1, 2.0 * a2 - a1
+        d2 = np.array([-0.25 * c4 * c5, 0.25 * c3 * c6, 0.25 * c3 * c5, -0.25 * c4 * c6, 0.5 * c3 * c4, -a2 * c3, -0.5 * c3 * c4, a2 * c4])
+        return d1, d2
+    if etype == QUAD9:
+        b3, b4, b5, b6, b7 = 2.0 * a1 + 1.0, 2.0 * a1 - 1.0, a2 + 1.0, a2 - 1.0, 0.25 * a2
+        b8 = b5 * b6; b9 = -0.5 * b8; b10 = -a1 * a2
+        d1 = np.array([b7 * b4 * b6, b7 * b3 * b6, b7 * b3 * b5, b7 * b4 * b5, b10 * b6, b9 * b3, b10 * b5, b9 * b4, 2.0 * a1 * b8])
+        c3, c4, c5, c6, c7 = 2.0 * a2 + 1.0, 2.0 * a2 - 1.0, a1 + 1.0, a1 - 1.0, 0.25 * a1
+        c8 = c5 * c6; c9 = -0.5 * c8
+        d2 = np.array([c7 * c6 * c4, c7 * c5 * c4, c7 * c5 * c3, c7 * c6 * c3, c9 * c4, b10 * c5, c9 * c3, b10 * c6, 2.0 * a2 * c8])
+        return d1, d2
+    raise ValueError("unsupported element type %r" % etype)
+
+
+def unit_normal(etype, x_nodes, xi):
+    """Unit normal T1 x T2 / |T1 x T2| of the element at xi (fbem_unormal3d)."""
+    d1, d2 = dphi(etype, xi)
+    t1 = np.zeros(3); t2 = np.zeros(3)
+    for k in range(N_NODES[etype]):
+        t1 = t1 + d1[k] * x_nodes[k]; t2 = t2 + d2[k] * x_nodes[k]
+    n = np.cross(t1, t2)
+    return n / np.sqrt(n @ n)

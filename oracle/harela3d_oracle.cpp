@@ -1579,6 +1579,12 @@ void orc_fundamental_solutions_pot(const double* x, const double* n, const doubl
   cd po = p.cte_u * g[0], qo = p.cte_t * h[0];
   p_ri[0] = po.real(); p_ri[1] = po.imag(); q_ri[0] = qo.real(); q_ri[1] = qo.imag();
 }
+// pieces of the free-term pass for the multi-region driver (oracle/multiregion.py): unit normal and the two element-boundary tangents at an
+// element node, and the scalar free term of fbem_bem_pot3d_sbie_freeterm
+void orc_node_normal_tangents(int et, const double* xn, int node, double* n, double* tbp, double* tbm) { node_normal_tangents(et, xn, node, n, tbp, tbm); }
+int orc_freeterm_pot(int ne, const double* n, const double* t, double tol, double* cp) {
+  cd dummy[3][3]; return sbie_freeterm(ne, n, t, tol, cd(0.0, 0.0), dummy, cp);
+}
 void orc_decomposed_zexp(const double* z_ri, double* E_ri /*5 complex*/) { cd E[5]; decomposed_zexp(cd(z_ri[0], z_ri[1]), E); memcpy(E_ri, E, sizeof(E)); }
 
 // Bounded sample of one frequency's assembly for the CPU baseline: every element against the collocation points

@@ -1,0 +1,159 @@
+"""CPU oracle for several BE regions coupled through be-be interfaces (TEST INFRASTRUCTURE ONLY, like oracle.py).
+
+The (collocation point, element) integrals are the pinned single-region ones of harela3d_oracle.cpp (fbem_bem_harela3d_sbie_auto /
+fbem_bem_harpot3d_sbie_auto through orc_pair / orc_pair_pot, which also apply the orientation of the element as seen from the region).
+This module restates the DRIVER around them for coupled regions:
+  * region loop, element loop, collocation loop   src/build_lse_mechanics_harmonic.f90 (do kr), src/build_lse_mechanics_bem_harela.f90:227-238,
+                                                  :972-1324, src/build_lse_mechanics_bem_harpot.f90:211-217, :722-1133
+  * free terms                                    build_lse_mechanics_bem_harela.f90:273-747, build_lse_mechanics_bem_harpot.f90:243-660
+  * scatter of an ordinary boundary               assemble_bem_harela_equation.f90:78-113, assemble_bem_harpot_equation.f90:78-96
+  * scatter of a be-be boundary                   assemble_bem_harela_equation.f90:161-331 (region 1) / :332-460 (region 2, reversed);
+                                                  assemble_bem_harpot_equation.f90:152-183 (region 1) / :213-236 (region 2)
+Parity status: unpinned by reference output (no Fortran compiler here); pinned by analytic two-layer solutions and by the equivalence of
+a split homogeneous body with the one-region model (tests/test_oracle_multiregion.py).
+"""
+import ctypes as C
+import numpy as np
+
+from . import oracle as orc
+from multifebe_b200.host import shape as sh
+from multifebe_b200.host.multiregion import SOLID, FLUID
+
+
+def _node_normal_tangents(et, xn, node):
+    n = np.zeros(3); tp = np.zeros(3); tm = np.zeros(3)
+    xn = np.ascontiguousarray(xn, dtype=np.float64)
+    orc.lib().orc_node_normal_tangents(C.c_int(et), orc._p(xn), C.c_int(node), orc._p(n), orc._p(tp), orc._p(tm))
+    return n, tp, tm
+
+
+class MultiRegionOracle:
+    def __init__(self, mrm):
+        self.m = mrm
+        self.h = [orc.Oracle(v) if v.kind == SOLID else orc.PotOracle(v) for v in mrm.views]
+        # node -> (local element, local node) incidences per region view
+        self.inc = []
+        for v in mrm.views:
+            d = {}
+            for le in range(v.n_elem):
+                for kn in range(v.elem_ptr[le], v.elem_ptr[le + 1]):
+                    d.setdefault(int(v.elem_node[kn]), []).append((le, kn - int(v.elem_ptr[le])))
+            self.inc.append(d)
+
+    # ---- free term of one collocation point: added to h of its own element (h[kn] += c, or h[:] += phi/2 for an MCA point)
+    def _free_term(self, kr, c, omega):
+        v = self.m.views[kr]
+        le, kn, sn = int(v.colloc_elem[c]), int(v.colloc_kn[c]), int(v.colloc_node[c])
+        et = int(v.etype[le]); nodes = v.elem_node[v.elem_ptr[le]:v.elem_ptr[le + 1]]
+        nn = len(nodes)
+        solid = v.kind == SOLID
+        hp = np.zeros((nn, 3, 3), dtype=np.complex128) if solid else np.zeros(nn, dtype=np.complex128)
+        if v.colloc_xi[c, 0] != -9.0:                                    # MCA point: 1/2 phi_j(xi_i)
+            phi = sh.phi(et, v.colloc_xi[c])
+            for j in range(nn):
+                if solid:
+                    hp[j] += 0.5 * phi[j] * np.eye(3)
+                else:
+                    hp[j] += 0.5 * phi[j]
+            return le, hp
+        on_edge = not (et == sh.QUAD9 and kn == 8)                       # only the centre node of quad9 lies inside its element
+        if not on_edge:
+            cfree = 0.5 * np.eye(3) if solid else 0.5
+        else:
+            rev = bool(v.elem_reversed[le])
+            ns, ts = [], []
+            for (le2, kn2) in self.inc[kr][sn]:
+                nodes2 = v.elem_node[v.elem_ptr[le2]:v.elem_ptr[le2 + 1]]
+                n, tbp, tbm = _node_normal_tangents(int(v.etype[le2]), v.node_x[nodes2], kn2)
+                ns.append(-n if rev else n); ts.append(tbm if rev else tbp)
+            if solid:
+                cfree, err = orc.freeterm(np.array(ns), np.array(ts), v.material.nu, self.m.geometric_tolerance)
+            else:
+                cp = C.c_double(0.0)
+                n_ = np.ascontiguousarray(ns, dtype=np.float64); t_ = np.ascontiguousarray(ts, dtype=np.float64)
+                err = orc.lib().orc_freeterm_pot(C.c_int(len(ns)), orc._p(n_), orc._p(t_), C.c_double(self.m.geometric_tolerance), C.byref(cp))
+                cfree = cp.value
+            if err:
+                raise RuntimeError("oracle: invalid normals/tangents configuration in free-term")
+        hp[kn] += cfree
+        return le, hp
+
+    # ---- scatter of one (collocation node, element) block of region kr
+    def _scatter(self, kr, le, sn_col, eq, h, g, A, b):
+        m = self.m
+        v = m.views[kr]
+        bnd = int(v.elem_boundary[le])
+        r1, r2 = m.boundary_regions[bnd]
+        nodes = v.elem_node[v.elem_ptr[le]:v.elem_ptr[le + 1]]
+        et = int(v.etype[le])
+        rows = m.row[(sn_col, eq)]
+        first = r1 == kr
+        solid = v.kind == SOLID
+        for kn, sn in enumerate(nodes):
+            sn = int(sn)
+            if r2 is None:                                                # ordinary boundary
+                ct, cv = m.ctype[bnd], m.cvalue[bnd]
+                if solid:
+                    for il in range(3):
+                        for ik in range(3):
+                            if ct[ik] == 0:
+                                A[rows[il], m.col[(sn, "t1%d" % ik)]] -= g[kn, il, ik]; b[rows[il]] -= h[kn, il, ik] * cv[ik]
+                            else:
+                                A[rows[il], m.col[(sn, "u1%d" % ik)]] += h[kn, il, ik]; b[rows[il]] += g[kn, il, ik] * cv[ik]
+                else:
+                    if ct[0] == 0:
+                        A[rows[0], m.col[(sn, "un1")]] -= g[kn]; b[rows[0]] -= h[kn] * cv[0]
+                    else:
+                        A[rows[0], m.col[(sn, "p1")]] += h[kn]; b[rows[0]] += g[kn] * cv[0]
+                continue
+            k1, k2 = m.regions[r1].kind, m.regions[r2].kind
+            # element(se_int)%n_fn(:,kn): unit normal of the element at its node, mesh orientation = outward from region 1
+            n_fn = sh.unit_normal(et, v.node_x[nodes], sh.XI_NODES[et][kn])
+            if solid:
+                other = k2 if first else k1
+                for il in range(3):
+                    for ik in range(3):
+                        if other == SOLID:                                # u1, t1 active; region 2: t2 = -t1
+                            A[rows[il], m.col[(sn, "u1%d" % ik)]] += h[kn, il, ik]
+                            A[rows[il], m.col[(sn, "t1%d" % ik)]] += (-g[kn, il, ik] if first else g[kn, il, ik])
+                        elif first:                                       # solid(1)-fluid(2): t1 = -p2 n1
+                            A[rows[il], m.col[(sn, "u1%d" % ik)]] += h[kn, il, ik]
+                            A[rows[il], m.col[(sn, "p2")]] += g[kn, il, ik] * n_fn[ik]
+                        else:                                             # fluid(1)-solid(2): t2 = -p1 n2 = +p1 n1
+                            A[rows[il], m.col[(sn, "u2%d" % ik)]] += h[kn, il, ik]
+                            A[rows[il], m.col[(sn, "p1")]] -= g[kn, il, ik] * n_fn[ik]
+            else:
+                other = k2 if first else k1
+                if other == FLUID:                                        # p1, Un1 active; region 2: Un2 = -Un1
+                    A[rows[0], m.col[(sn, "p1")]] += h[kn]
+                    A[rows[0], m.col[(sn, "un1")]] += (-g[kn] if first else g[kn])
+                elif first:                                               # fluid(1)-solid(2): Un1 = u2 . n1
+                    A[rows[0], m.col[(sn, "p1")]] += h[kn]
+                    for ik in range(3):
+                        A[rows[0], m.col[(sn, "u2%d" % ik)]] -= g[kn] * n_fn[ik]
+                else:                                                     # solid(1)-fluid(2): Un2 = u1 . n2 = -u1 . n1
+                    A[rows[0], m.col[(sn, "p2")]] += h[kn]
+                    for ik in range(3):
+                        A[rows[0], m.col[(sn, "u1%d" % ik)]] += g[kn] * n_fn[ik]
+
+    def assemble(self, omega):
+        """-> A (n_dof x n_dof), b of one frequency for the coupled system."""
+        m = self.m
+        n = m.n_dof
+        A = np.zeros((n, n), dtype=np.complex128); b = np.zeros(n, dtype=np.complex128)
+        for kr, v in enumerate(m.views):
+            hd, mat = self.h[kr], v.material
+            d1J = mat.rho * omega ** 2 if v.kind == FLUID else None
+            for c in range(v.n_colloc):
+                x_i, sn_col, eq = v.colloc_x[c], int(v.colloc_node[c]), int(v.colloc_eq[c])
+                le_own, hfree = self._free_term(kr, c, omega)
+                for le in range(v.n_elem):
+                    if v.kind == SOLID:
+                        h, g, _, _ = hd.pair(le, x_i, omega, mat)
+                    else:
+                        h, g, _ = hd.pair(le, x_i, omega, mat)
+                        g = g * d1J                                       # the flux unknown is Un = (dp/dn)/(rho omega^2)
+                    if le == le_own:
+                        h = h + hfree
+                    self._scatter(kr, le, sn_col, eq, h, g, A, b)
+        return A, b
