@@ -194,6 +194,55 @@ class MultiRegionModel:
         v.n_dof = 1
         return v
 
+    # ---- flat scatter descriptors of one region: the form in which the coupling crosses the C ABI
+    def scatter_descriptors(self, kr):
+        """Every case of assemble_bem_harela_equation.f90 / assemble_bem_harpot_equation.f90 reduced to one rule.  For the element instance
+        le of the region, its node j and source component k (solid: k = 0..2 = column index of the 3 x 3 block; fluid: k = 0):
+            A[row_l, hcol] += hcoef * h(j, l, k)          (hcol == -1: b[row_l] += hcoef * h;  -2: nothing)
+            A[row_l, gcol_t] += gcoef_t * g(j, l, k)      t = 0..2 (same conventions)
+        with g of a fluid element already multiplied by rho omega^2.  Index = (elem_ptr[le] + j) * ndof + k (g targets: * 3 + t).
+        Returns dict(hcol, hcoef, gcol, gcoef)."""
+        v, r = self.views[kr], self.regions[kr]
+        nd = r.ndof
+        n = int(v.elem_ptr[-1]) * nd
+        hcol = np.full(n, -2, dtype=np.int32); hcoef = np.zeros(n, dtype=np.complex128)
+        gcol = np.full((n, 3), -2, dtype=np.int32); gcoef = np.zeros((n, 3), dtype=np.complex128)
+        for le in range(v.n_elem):
+            bnd = int(v.elem_boundary[le])
+            r1, r2 = self.boundary_regions[bnd]
+            first = r1 == kr
+            et = int(v.etype[le])
+            nodes = v.elem_node[v.elem_ptr[le]:v.elem_ptr[le + 1]]
+            for j, sn in enumerate(nodes):
+                sn = int(sn)
+                n_fn = sh.unit_normal(et, self.node_x[nodes], sh.XI_NODES[et][j]) if r2 is not None else None
+                for k in range(nd):
+                    q = (int(v.elem_ptr[le]) + j) * nd + k
+                    if r2 is None:
+                        ct, cv = self.ctype[bnd][k], self.cvalue[bnd][k]
+                        prim = ("u1%d" % k) if nd == 3 else "p1"; sec = ("t1%d" % k) if nd == 3 else "un1"
+                        if ct == 0:
+                            hcol[q], hcoef[q] = -1, -cv; gcol[q, 0], gcoef[q, 0] = self.col[(sn, sec)], -1.0
+                        else:
+                            hcol[q], hcoef[q] = self.col[(sn, prim)], 1.0; gcol[q, 0], gcoef[q, 0] = -1, cv
+                        continue
+                    k1, k2 = self.regions[r1].kind, self.regions[r2].kind
+                    other = k2 if first else k1
+                    if r.kind == SOLID and other == SOLID:
+                        hcol[q], hcoef[q] = self.col[(sn, "u1%d" % k)], 1.0
+                        gcol[q, 0], gcoef[q, 0] = self.col[(sn, "t1%d" % k)], (-1.0 if first else 1.0)
+                    elif r.kind == SOLID:
+                        hcol[q], hcoef[q] = self.col[(sn, ("u1%d" if first else "u2%d") % k)], 1.0
+                        gcol[q, 0], gcoef[q, 0] = self.col[(sn, "p2" if first else "p1")], (n_fn[k] if first else -n_fn[k])
+                    elif other == FLUID:
+                        hcol[q], hcoef[q] = self.col[(sn, "p1")], 1.0
+                        gcol[q, 0], gcoef[q, 0] = self.col[(sn, "un1")], (-1.0 if first else 1.0)
+                    else:
+                        hcol[q], hcoef[q] = self.col[(sn, "p1" if first else "p2")], 1.0
+                        for t in range(3):
+                            gcol[q, t], gcoef[q, t] = self.col[(sn, ("u2%d" if first else "u1%d") % t)], (-n_fn[t] if first else n_fn[t])
+        return dict(hcol=hcol, hcoef=hcoef, gcol=gcol, gcoef=gcoef)
+
     # ---- nodal variables from the solution vector (assign_solution_mechanics_harmonic.f90 with the interface substitutions)
     def nodal_solution(self, x, kr):
         """Primary and secondary variables of region kr at the nodes of its boundaries: solid (u (n,3), t (n,3)), fluid (p (n), Un (n));

@@ -136,9 +136,33 @@ class MultiRegionOracle:
                     for ik in range(3):
                         A[rows[0], m.col[(sn, "u1%d" % ik)]] += g[kn] * n_fn[ik]
 
-    def assemble(self, omega):
-        """-> A (n_dof x n_dof), b of one frequency for the coupled system."""
+    def _scatter_flat(self, kr, le, sn_col, eq, h, g, A, b, D):
+        """The same scatter driven by the flat descriptors of MultiRegionModel.scatter_descriptors (what a device kernel consumes)."""
+        v = self.m.views[kr]
+        nd = v.ndof
+        rows = self.m.row[(sn_col, eq)]
+        nn = int(v.elem_ptr[le + 1] - v.elem_ptr[le])
+        for j in range(nn):
+            for k in range(nd):
+                q = (int(v.elem_ptr[le]) + j) * nd + k
+                for il, row in enumerate(rows):
+                    hv = h[j, il, k] if nd == 3 else h[j]
+                    gv = g[j, il, k] if nd == 3 else g[j]
+                    if D["hcol"][q] >= 0:
+                        A[row, D["hcol"][q]] += D["hcoef"][q] * hv
+                    elif D["hcol"][q] == -1:
+                        b[row] += D["hcoef"][q] * hv
+                    for t in range(3):
+                        c = D["gcol"][q, t]
+                        if c >= 0:
+                            A[row, c] += D["gcoef"][q, t] * gv
+                        elif c == -1:
+                            b[row] += D["gcoef"][q, t] * gv
+
+    def assemble(self, omega, flat=False):
+        """-> A (n_dof x n_dof), b of one frequency for the coupled system.  flat = True: scatter through the flat descriptors."""
         m = self.m
+        desc = [m.scatter_descriptors(kr) for kr in range(len(m.views))] if flat else None
         n = m.n_dof
         A = np.zeros((n, n), dtype=np.complex128); b = np.zeros(n, dtype=np.complex128)
         for kr, v in enumerate(m.views):
@@ -155,5 +179,8 @@ class MultiRegionOracle:
                         g = g * d1J                                       # the flux unknown is Un = (dp/dn)/(rho omega^2)
                     if le == le_own:
                         h = h + hfree
-                    self._scatter(kr, le, sn_col, eq, h, g, A, b)
+                    if flat:
+                        self._scatter_flat(kr, le, sn_col, eq, h, g, A, b, desc[kr])
+                    else:
+                        self._scatter(kr, le, sn_col, eq, h, g, A, b)
         return A, b

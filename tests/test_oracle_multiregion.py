@@ -169,3 +169,24 @@ def test_fluid_solid_column(solid_first):
     lo, hi = (xs + 1e-12, 1.0) if solid_first else (0.0, xs)
     wa, sa = field(np.clip(mrm.node_x[ok, 0], lo, hi))
     assert np.abs(p[ok] + sa).max() < 5e-3 * np.abs(sa).max()                                # p = -sigma
+
+
+@pytest.mark.parametrize("kinds", [(SOLID, SOLID), (FLUID, FLUID), (SOLID, FLUID), (FLUID, SOLID)])
+def test_flat_scatter_descriptors_reproduce_every_case(kinds):
+    """The one-rule descriptors (col_h, coef_h, col_g[3], coef_g[3] per element node and component: the form that crosses the C ABI) give
+    the same system as the case-by-case restatement of assemble_bem_har{ela,pot}_equation."""
+    mats = {SOLID: Material(2.0, 1.5, 0.25, 0.03), FLUID: Fluid(1.0, 1.2, 0.01)}
+    sb, fb = solid_bcs(0.7 + 0.2j), fluid_bcs(0.4 - 0.1j)
+    bcs = {}
+    for k, lat, ends in ((kinds[0], LAT1, (1,)), (kinds[1], LAT2, (2,))):
+        src = sb if k == SOLID else fb
+        bcs.update({q: src[q] for q in lat + ends})
+    bcs[3 if kinds[0] == SOLID else 13] = ([0, 1, 0], [0.1, 0.2j, -0.3]) if SOLID in kinds else bcs[3]     # a nonzero prescribed displacement too
+    if kinds[0] != SOLID and SOLID in kinds:
+        bcs[3] = fb[3]
+    mrm = MultiRegionModel(two_box_mesh(1, shape.QUAD8), [Region(kinds[0], mats[kinds[0]], [1, 3, 4, 5, 6, 7]), Region(kinds[1], mats[kinds[1]], [-7, 2, 13, 14, 15, 16])], BPART, bcs)
+    o = MultiRegionOracle(mrm)
+    A1, b1 = o.assemble(1.7)
+    A2, b2 = o.assemble(1.7, flat=True)
+    assert np.abs(A1 - A2).max() <= 1e-15 * np.abs(A1).max() and np.abs(b1 - b2).max() <= 1e-15 * max(np.abs(b1).max(), 1e-300)
+    assert np.abs(b1).max() > 0
