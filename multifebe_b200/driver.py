@@ -24,6 +24,9 @@ class GpuSolver:
     """One mfb_problem on one GPU: harmonic(omega) / static() -> solution vector in the reference's column order."""
 
     def __init__(self, case, model, device=0):
+        if case.multi:
+            raise CaseFileError("coupled BE regions: the device path is not built yet (DESIGN.md section 7.4); the case parses and numbers, "
+                                "but only the Fortran program solves it")
         from . import capi
         self.capi, self.case = capi, case
         self.ctx = capi.Context(device)
@@ -52,8 +55,8 @@ def run(case_path, output=None, solver=None, verbose=1, rank=0, world=1, dist=No
     model = case.build_model()
     out_base = output or case_path
     if verbose >= 1 and rank == 0:
-        log.write("multifebe_b200: %s analysis, region type %d, %d nodes, %d elements, %d DOF, %d frequencies, %d rank(s)\n" % (
-            case.analysis, case.region_type, model.n_node, model.n_elem, model.n_dof, len(case.omega), world))
+        log.write("multifebe_b200: %s analysis, %d region(s) of type %s, %d nodes, %d elements, %d DOF, %d frequencies, %d rank(s)\n" % (
+            case.analysis, len(case.regions), "/".join(str(r[1]) for r in case.regions), model.n_node, model.n_elem, model.n_dof, len(case.omega), world))
     own = solver is None
     if own:
         solver = GpuSolver(case, model, device_index)

@@ -7,12 +7,12 @@ Mirrors src/read_input_file.f90 for the sections the hot path consumes:
                                                   geometric_tolerance
   [materials]    src/read_materials.f90      fluid (two of K, rho, c; xi) / elastic_solid (two of E, nu, lambda, mu, K; rho, xi)
   [boundaries]   src/read_boundaries.f90     `<id> <part> ordinary`
-  [regions]      src/read_regions.f90        one `be` region, full space, `material <id>` or the legacy in-line forms
+  [regions]      src/read_regions.f90        `be` regions, full space (several regions sharing be-be boundaries: negative id = reversed), `material <id>` or the legacy in-line forms
                                              `fluid rho c`, `viscoelastic rho mu nu xi`, `elastic rho mu nu`
   [conditions over be boundaries]            src/read_conditions_bem_boundaries_mechanics_{harmonic,static}.f90: global-axes
                                              conditions 0 / 1 per component; defaults (not listed) = 1 with value 0
   [export]       src/read_export.f90:61-240  export_nso, real_format, integer_format, complex_notation
-Anything else the reference accepts (several regions, be-be / be-fe coupling, crack-like boundaries, local-axes or spring conditions,
+Anything else the reference accepts (be-fe coupling, poroelastic regions, crack-like boundaries, local-axes or spring conditions,
 half-spaces, body loads, incident fields, symmetry planes, internal points, FE regions ...) raises CaseFileError naming the feature:
 the Fortran host keeps those.
 """
@@ -210,54 +210,51 @@ class CaseFile:
         rl = sec.get("regions")
         if not rl:
             raise CaseFileError("[regions]: this section is required")
-        if int(rl[0].split()[0]) != 1:
-            raise CaseFileError("[regions]: one BE region is covered (multi-region coupling: SURVEY.md 8f rank 3, not built)")
-        w = rl[1].split()
-        self.region_id = int(w[0])
-        if w[1].lower() != "be":
-            raise CaseFileError("region %d: only `be` regions are covered" % self.region_id)
-        if len(w) > 2 and w[2].lower() != "full-space":
-            raise CaseFileError("region %d: only the full-space fundamental solution is covered" % self.region_id)
-        w = [int(t) for t in rl[2].split()]
-        self.region_boundaries = w[1:1 + w[0]]
-        if any(b < 0 for b in self.region_boundaries):
+        n_regions = int(rl[0].split()[0])
+        self.regions = []                     # (id, type code 1 fluid / 2 elastic, material, signed boundary ids)
+        k = 1
+        for kr_ in range(n_regions):
+            if k + 2 >= len(rl):
+                raise CaseFileError("[regions]: %d regions announced, the records of region number %d are missing" % (n_regions, kr_ + 1))
+            w = rl[k].split()
+            rid = int(w[0])
+            if w[1].lower() != "be":
+                raise CaseFileError("region %d: only `be` regions are covered" % rid)
+            if len(w) > 2 and w[2].lower() != "full-space":
+                raise CaseFileError("region %d: only the full-space fundamental solution is covered" % rid)
+            w = [int(t) for t in rl[k + 1].split()]
+            rb = w[1:1 + w[0]]
+            material, rtype = self._material(rid, rl[k + 2].split())
+            k += 3
+            # remaining records of the region: number of BE body loads and (harmonic analysis) of incident fields -- both must be 0
+            n_tail = 2 if self.analysis == "harmonic" else 1
+            for s_ in rl[k:k + n_tail]:
+                if not re.fullmatch(r"[\s0]+", s_):
+                    raise CaseFileError("region %d: BE body loads / incident fields are not covered" % rid)
+            k += n_tail
+            self.regions.append((rid, rtype, material, rb))
+        self.multi = n_regions > 1
+        listed = [abs(b) for r in self.regions for b in r[3]]
+        if not self.multi and any(b < 0 for b in self.regions[0][3]):
             # a negative id = the boundary is seen reversed from this region (region 2 of a be-be boundary)
-            raise CaseFileError("region %d: reversed boundaries belong to multi-region models, which are not covered" % self.region_id)
-        w = rl[3].split()
-        kind = w[0].lower()
-        if kind == "material":
-            mtype, props = self.materials[int(w[1])]
-            mtype = mtype.lower()
-            if mtype in ("fluid", "inviscid_fluid"):
-                kk = {k: props[k] for k in ("K", "rho", "c") if k in props}
-                if len(kk) != 2:
-                    raise CaseFileError("material %s: only 2 properties are needed" % w[1])
-                rho = kk["rho"] if "rho" in kk else kk["K"] / kk["c"] ** 2
-                c = kk["c"] if "c" in kk else np.sqrt(kk["K"] / kk["rho"])
-                self.material, self.region_type = Fluid(rho=rho, c=c, xi=props.get("xi", 0.0)), 1
-            elif mtype == "elastic_solid":
-                ec = elastic_constants({k: props[k] for k in ("E", "nu", "lambda", "mu", "K") if k in props})
-                if self.analysis == "harmonic" and ("rho" not in props or "xi" not in props):
-                    raise CaseFileError("material %s: rho and xi are required for the material of this region" % w[1])
-                self.material, self.region_type = Material(rho=props.get("rho", 1.0), mu=ec["mu"], nu=ec["nu"], xi=props.get("xi", 0.0)), 2
-            else:
-                raise CaseFileError("material type %r is not covered (fluid, elastic_solid)" % mtype)
-        elif kind in ("fluid", "inviscid_fluid"):
-            self.material, self.region_type = Fluid(rho=_fortran_float(w[1]), c=_fortran_float(w[2])), 1
-        elif kind == "viscoelastic":
-            self.material, self.region_type = Material(rho=_fortran_float(w[1]), mu=_fortran_float(w[2]), nu=_fortran_float(w[3]), xi=_fortran_float(w[4])), 2
-        elif kind == "elastic":
-            self.material, self.region_type = Material(rho=_fortran_float(w[1]), mu=_fortran_float(w[2]), nu=_fortran_float(w[3]), xi=0.0), 2
-        else:
-            raise CaseFileError("region %d: material specification %r is not covered" % (self.region_id, kind))
-        for s in rl[4:]:
-            if any(int(t) != 0 for t in s.split() if re.fullmatch(r"-?\d+", t)):
-                raise CaseFileError("region %d: BE body loads / incident fields are not covered" % self.region_id)
+            raise CaseFileError("region %d: reversed boundaries belong to multi-region models" % self.regions[0][0])
+        if self.multi and self.analysis == "static":
+            raise CaseFileError("[regions]: one BE region is covered in the static analysis")
+        self.region_id, self.region_type, self.material, self.region_boundaries = self.regions[0]
+        self.interfaces = sorted(b for b in set(listed) if listed.count(b) == 2)
         if self.analysis == "static" and self.region_type != 2:
             raise CaseFileError("static analysis: only elastic solids are covered")
         # ---- [conditions over be boundaries]
-        ndof = 1 if self.region_type == 1 else 3
-        self.bcs = {bid: ([1] * ndof, [0j] * ndof) for bid, _ in self.boundaries}     # defaults: t / Un = 0
+        region_of_boundary = {}
+        for rid, rtype, _, rb in self.regions:
+            for b in rb:
+                if b > 0:
+                    region_of_boundary[b] = rtype
+        for b, _ in self.boundaries:
+            if b not in region_of_boundary:
+                raise CaseFileError("boundary %d is not used with a positive id by any region" % b)
+        ndof_of = {b: (1 if region_of_boundary[b] == 1 else 3) for b, _ in self.boundaries}
+        self.bcs = {bid: ([1] * ndof_of[bid], [0j] * ndof_of[bid]) for bid, _ in self.boundaries if bid not in self.interfaces}   # defaults: t / Un = 0
         cl = sec.get("conditions over be boundaries", [])
         i = 0
         while i < len(cl):
@@ -265,8 +262,11 @@ class CaseFile:
             if not m:
                 raise CaseFileError("[conditions over be boundaries]: cannot parse %r" % cl[i])
             bid = int(m.group(1))
+            if bid in self.interfaces:
+                raise CaseFileError("boundary %d: conditions over be-be boundaries other than perfect bonding / contact (the default) are not covered" % bid)
             if bid not in self.bcs:
                 raise CaseFileError("[conditions over be boundaries]: unknown boundary %d" % bid)
+            ndof = ndof_of[bid]
             recs = [m.group(2)] + cl[i + 1:i + ndof]
             ct, cv = [], []
             for k in range(ndof):
@@ -290,18 +290,52 @@ class CaseFile:
         # ---- mesh: parts are the physical groups of the Gmsh file; a boundary is one part
         self.mesh = read_gmsh22(self.mesh_file)
         part_of_boundary = dict(self.boundaries)
-        used_parts = [part_of_boundary[b] for b in self.region_boundaries]
+        used_parts = [part_of_boundary[abs(b)] for r in self.regions for b in r[3]]
         keep = [e for e in range(self.mesh.n_elem) if int(self.mesh.part[e]) in used_parts]
         if len(keep) != self.mesh.n_elem:
-            raise CaseFileError("the mesh holds surface elements of parts that no boundary of the region uses")
+            raise CaseFileError("the mesh holds surface elements of parts that no boundary of the regions uses")
+
+    def _material(self, rid, w):
+        """(material, region type code) of the material record of a region: `material <id>` or the legacy in-line forms."""
+        kind = w[0].lower()
+        if kind == "material":
+            if int(w[1]) not in self.materials:
+                raise CaseFileError("region %d: unknown material %s" % (rid, w[1]))
+            mtype, props = self.materials[int(w[1])]
+            mtype = mtype.lower()
+            if mtype in ("fluid", "inviscid_fluid"):
+                kk = {k: props[k] for k in ("K", "rho", "c") if k in props}
+                if len(kk) != 2:
+                    raise CaseFileError("material %s: only 2 properties are needed" % w[1])
+                rho = kk["rho"] if "rho" in kk else kk["K"] / kk["c"] ** 2
+                c = kk["c"] if "c" in kk else np.sqrt(kk["K"] / kk["rho"])
+                return Fluid(rho=rho, c=c, xi=props.get("xi", 0.0)), 1
+            if mtype == "elastic_solid":
+                ec = elastic_constants({k: props[k] for k in ("E", "nu", "lambda", "mu", "K") if k in props})
+                if self.analysis == "harmonic" and ("rho" not in props or "xi" not in props):
+                    raise CaseFileError("material %s: rho and xi are required for the material of this region" % w[1])
+                return Material(rho=props.get("rho", 1.0), mu=ec["mu"], nu=ec["nu"], xi=props.get("xi", 0.0)), 2
+            raise CaseFileError("material type %r is not covered (fluid, elastic_solid)" % mtype)
+        if kind in ("fluid", "inviscid_fluid"):
+            return Fluid(rho=_fortran_float(w[1]), c=_fortran_float(w[2])), 1
+        if kind == "viscoelastic":
+            return Material(rho=_fortran_float(w[1]), mu=_fortran_float(w[2]), nu=_fortran_float(w[3]), xi=_fortran_float(w[4])), 2
+        if kind == "elastic":
+            return Material(rho=_fortran_float(w[1]), mu=_fortran_float(w[2]), nu=_fortran_float(w[3]), xi=0.0), 2
+        raise CaseFileError("region %d: material specification %r is not covered" % (rid, kind))
 
     def build_model(self):
-        """The flat model of the region (multifebe_b200.host.Model / FluidModel) with the reference's numbering: boundaries in the order of
-        the region's list (build_auxiliary_variables_mechanics_harmonic.f90:151-198)."""
+        """The flat model (multifebe_b200.host.Model / FluidModel, or MultiRegionModel for coupled regions) with the reference's numbering:
+        boundaries in the order of the regions' lists (build_auxiliary_variables_mechanics_harmonic.f90:151-198)."""
         part_of_boundary = dict(self.boundaries)
-        order = [part_of_boundary[b] for b in self.region_boundaries]
         kw = dict(qsi_relative_error=self.qsi_relative_error, qsi_ns_max=self.qsi_ns_max, precalset_gln=self.precalset_gln,
-                  geometric_tolerance=self.geometric_tolerance, part_order=order)
+                  geometric_tolerance=self.geometric_tolerance)
+        if self.multi:
+            from .multiregion import MultiRegionModel, Region, SOLID, FLUID
+            regs = [Region(FLUID if rtype == 1 else SOLID, mat, rb) for _, rtype, mat, rb in self.regions]
+            bcs = {b: ((ct[0], cv[0]) if len(ct) == 1 else (ct, cv)) for b, (ct, cv) in self.bcs.items()}
+            return MultiRegionModel(self.mesh, regs, part_of_boundary, bcs, **kw)
+        kw["part_order"] = [part_of_boundary[b] for b in self.region_boundaries]
         if self.region_type == 1:
             bcs = {part_of_boundary[b]: (ct[0], cv[0]) for b, (ct, cv) in self.bcs.items()}
             return FluidModel(self.mesh, bcs, **kw)

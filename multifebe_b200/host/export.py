@@ -21,24 +21,28 @@ class NsoWriter:
     def __init__(self, fh, case, model):
         self.f, self.case, self.m = fh, case, model
         self.rf = RealFormat(case.real_format)
-        ids = [len(case.omega), case.region_id, max(b for b, _ in case.boundaries), int(model.mesh.elem_ids.max()), int(model.mesh.node_ids.max())]
+        ids = [len(case.omega), max(r[0] for r in case.regions), max(b for b, _ in case.boundaries), int(model.mesh.elem_ids.max()), int(model.mesh.node_ids.max())]
         if case.integer_format in (None, "auto"):
             self.wi = int_width(*ids)
         elif case.integer_format == "max":
             self.wi = 11
         else:
             self.wi = int(case.integer_format.lstrip("i"))
-        # rows: (boundary id, node index) in the reference's order
+        # rows: (region index, region id, region type, boundary id, face, node index) in the reference's order; face = 2 when the region is
+        # region 2 of a be-be boundary (export_solution_mechanics_harmonic_nso.f90:326-333)
         part_of_boundary = dict(case.boundaries)
         self.rows = []
-        for b in case.region_boundaries:
-            seen = set()
-            for e in range(model.n_elem):
-                if int(model.mesh.part[e]) != part_of_boundary[b]:
-                    continue
-                for v in model.mesh.conn[e]:
-                    if int(v) not in seen:
-                        seen.add(int(v)); self.rows.append((b, int(v)))
+        for kr, (rid, rtype, _, rb) in enumerate(case.regions):
+            for sb in rb:
+                b = abs(sb)
+                face = 2 if sb < 0 else 1
+                seen = set()
+                for e in range(model.n_elem):
+                    if int(model.mesh.part[e]) != part_of_boundary[b]:
+                        continue
+                    for v in model.mesh.conn[e]:
+                        if int(v) not in seen:
+                            seen.add(int(v)); self.rows.append((kr, rid, rtype, b, face, int(v)))
 
     def _i(self, n):
         return fmt_int(n, self.wi)
@@ -74,10 +78,19 @@ class NsoWriter:
             line += "_" * (nc - len(str(kc)) - 1) + "C%d" % kc
         w(line + "\n")
 
-    def _ident(self, kf, value, b, v):
+    def _ident(self, kf, value, row):
+        kr, rid, rtype, b, face, v = row
         x = self.m.node_x[v]
-        return (self._i(kf) + self.rf(value) + self._i(self.case.region_id) + self._i(1) + self._i(self.case.region_type) + self._i(b) + self._i(1) +
-                self._i(1) + self._i(int(self.m.mesh.node_ids[v])) + "".join(self.rf(t) for t in x))
+        return (self._i(kf) + self.rf(value) + self._i(rid) + self._i(1) + self._i(rtype) + self._i(b) + self._i(1) +
+                self._i(face) + self._i(int(self.m.mesh.node_ids[v])) + "".join(self.rf(t) for t in x))
+
+    def _nodal(self, x):
+        """Per region: (primary, secondary) variables as (n_node, nvar) arrays."""
+        out = []
+        for kr in range(len(self.case.regions)):
+            prim, sec = self.m.nodal_solution(np.asarray(x), kr) if self.case.multi else self.m.nodal_solution(np.asarray(x))
+            out.append((np.asarray(prim).reshape(self.m.n_node, -1), np.asarray(sec).reshape(self.m.n_node, -1)))
+        return out
 
     def _cpair(self, z):
         if self.case.complex_notation == "polar":
@@ -89,22 +102,22 @@ class NsoWriter:
         c = self.case
         omega = c.omega[kf - 1]
         value = omega * 0.159154943091895335768883763373 if c.frequency_units == "f" else omega   # c_1_2pi
-        prim, sec = self.m.nodal_solution(np.asarray(x))
-        prim = np.asarray(prim).reshape(self.m.n_node, -1); sec = np.asarray(sec).reshape(self.m.n_node, -1)
-        nv = 2 * prim.shape[1]
-        zero = self._cpair(0j) * nv
+        nodal = self._nodal(x)
         out = []
-        for b, v in self.rows:
+        for row in self.rows:
+            prim, sec = nodal[row[0]]
+            v = row[5]
             vals = "".join(self._cpair(complex(z)) for z in list(prim[v]) + list(sec[v]))
-            out.append(self._ident(kf, value, b, v) + vals + zero + "\n")
+            out.append(self._ident(kf, value, row) + vals + self._cpair(0j) * (2 * prim.shape[1]) + "\n")
         self.f.write("".join(out))
 
     def static(self, x):
         u, t = self.m.nodal_solution(np.asarray(x, dtype=np.complex128))
         out = []
-        for b, v in self.rows:
+        for row in self.rows:
+            v = row[5]
             vals = "".join(self.rf(float(z.real)) for z in list(u[v]) + list(t[v]))
-            out.append(self._ident(0, 0.0, b, v) + vals + "\n")
+            out.append(self._ident(0, 0.0, row) + vals + "\n")
         self.f.write("".join(out))
 
 

@@ -260,7 +260,7 @@ def test_harmonic_solid_case_polar_notation(tmp_path):
 
 def test_unsupported_features_are_named(tmp_path):
     base = SOLID_DAT % dict(analysis="static", freq="", z="0.", one="1.")
-    for old, new, word in [("1 1 ordinary", "1 1 crack-like", "ordinary"), ("[regions]\n1\n", "[regions]\n2\n", "one BE region"),
+    for old, new, word in [("1 1 ordinary", "1 1 crack-like", "ordinary"), ("[regions]\n1\n", "[regions]\n2\n", "regions announced"),
                            ("boundary 2: 1 1.", "boundary 2: 2 1.", "condition type 2"), ("n = 3D", "n = 2D", "3D"),
                            ("1 be\n", "1 fe\n", "`be`"), ('mesh_file_mode = 2 "cube.msh"', "mesh_file_mode = 0", "mesh_file_mode"),
                            ("6 1 2 3 4 5 6", "6 1 2 3 4 5 -6", "reversed")]:
@@ -321,3 +321,118 @@ def test_default_solver_is_the_gpu_and_fails_loudly_without_one(tmp_path):
     with pytest.raises(capi.MfbError) as e:
         driver.run(path, log=io.StringIO())
     assert e.value.code == -2
+
+
+TWO_REGION_DAT = """[problem]
+n = 3D
+type = mechanics
+analysis = harmonic
+
+[frequencies]
+rad/s
+list
+1
+2.5
+
+[settings]
+mesh_file_mode = 2 "boxes.msh"
+
+[materials]
+2
+1 elastic_solid rho 1. mu 1. nu 0.25 xi 0.02
+2 fluid rho 1. c 1.2 xi 0.01
+
+[boundaries]
+11
+1 1 ordinary
+2 2 ordinary
+3 3 ordinary
+4 4 ordinary
+5 5 ordinary
+6 6 ordinary
+7 7 ordinary
+13 13 ordinary
+14 14 ordinary
+15 15 ordinary
+16 16 ordinary
+
+[regions]
+2
+
+1 be
+6 1 3 4 5 6 7
+material 1
+0
+0
+
+2 be
+6 -7 2 13 14 15 16
+material 2
+0
+0
+
+[export]
+real_format = sci_double
+
+[conditions over be boundaries]
+boundary 1: 0 (0.,0.)
+            0 (0.,0.)
+            0 (0.,0.)
+boundary 3: 1 (0.,0.)
+            0 (0.,0.)
+            1 (0.,0.)
+boundary 4: 1 (0.,0.)
+            0 (0.,0.)
+            1 (0.,0.)
+boundary 5: 1 (0.,0.)
+            1 (0.,0.)
+            0 (0.,0.)
+boundary 6: 1 (0.,0.)
+            1 (0.,0.)
+            0 (0.,0.)
+boundary 2: 0 (1.,0.)
+"""
+
+
+def test_two_region_case_parses_numbers_and_exports(tmp_path):
+    """A solid and a fluid region sharing boundary 7 (listed as -7 by the second region): the case file gives the MultiRegionModel of
+    tests/test_oracle_multiregion.py; the *.nso file lists the interface nodes twice, face 1 (solid side: u, t = -p n) and face 2 (fluid
+    side: p, Un = u.n).  The GPU solver refuses coupled regions by name."""
+    from multifebe_b200.host import two_box_mesh, MultiRegionModel
+    from oracle.multiregion import MultiRegionOracle
+    write_gmsh22(two_box_mesh(1, shape.QUAD9), str(tmp_path / "boxes.msh"))
+    path = str(tmp_path / "two.dat")
+    open(path, "w").write(TWO_REGION_DAT)
+    case = CaseFile(path)
+    md = case.build_model()
+    assert case.multi and case.interfaces == [7] and isinstance(md, MultiRegionModel) and [r[1] for r in case.regions] == [2, 1]
+    assert 7 not in case.bcs and case.bcs[13] == ([1], [0j]) and case.bcs[2] == ([0], [1 + 0j])
+
+    class Solver:
+        def harmonic(self, omega):
+            A, b = MultiRegionOracle(md).assemble(omega)
+            return np.linalg.solve(A, b)
+
+        def close(self):
+            pass
+    nso = driver.run(path, solver=Solver(), log=io.StringIO())
+    n1 = sum(len(set(int(v) for e in md.elems_of_boundary[abs(b)] for v in md.mesh.conn[e])) for b in case.regions[0][3])
+    n2 = sum(len(set(int(v) for e in md.elems_of_boundary[abs(b)] for v in md.mesh.conn[e])) for b in case.regions[1][3])
+    lines = [s for s in open(nso) if s.strip() and not s.startswith("#")]
+    assert len(lines) == n1 + n2
+    solid, fluid = rows_of(lines, 2), rows_of(lines, 1)
+    assert len(solid) == n1 and solid.shape[1] == 12 + 24 and len(fluid) == n2 and fluid.shape[1] == 12 + 8
+    # interface rows: boundary 7, face 1 in the solid region and face 2 in the fluid region, same nodes; sigma_xx = -p, u_x = Un2 * (-1)
+    s7 = solid[solid[:, 5] == 7]; f7 = fluid[fluid[:, 5] == 7]
+    assert (s7[:, 7] == 1).all() and (f7[:, 7] == 2).all() and np.array_equal(s7[:, 8], f7[:, 8])
+    t1 = s7[:, 18] + 1j * s7[:, 19]; p = f7[:, 12] + 1j * f7[:, 13]
+    assert np.abs(t1 + p).max() < 1e-12 * np.abs(p).max()
+    u1 = s7[:, 12] + 1j * s7[:, 13]; un2 = f7[:, 14] + 1j * f7[:, 15]
+    assert np.abs(u1 + un2).max() < 1e-12 * np.abs(u1).max()
+    with pytest.raises(CaseFileError) as ei:
+        driver.GpuSolver(case, md)
+    assert "coupled BE regions" in str(ei.value)
+
+
+def rows_of(lines, rtype):
+    return np.array([[float(t) for t in s.split()] for s in lines if int(s.split()[4]) == rtype])
