@@ -40,10 +40,26 @@ class GpuSolver:
     def static(self):
         return self.pr.solve_static(self.case.material)
 
+    # internal points of an elastic region (calculate_internal_points_mechanics_bem_harela / _staela): u (n,3) and sigma (n,3,3) from the boundary solution
+    def _ip(self, points):
+        if getattr(self, "_ipo", None) is None:
+            self._ipo = self.capi.InternalPoints(self.ctx, self.pr.m, points)
+        return self._ipo
+
+    def interior_harmonic(self, omega, x, points):
+        ip = self._ip(points)
+        return ip.displacements(omega, self.case.material, x), ip.stresses(omega, self.case.material, x)
+
+    def interior_static(self, x, points):
+        ip = self._ip(points)
+        return ip.displacements_static(self.case.material, x), ip.stresses_static(self.case.material, x)
+
     def stats(self):
         return self.pr.stats()
 
     def close(self):
+        if getattr(self, "_ipo", None) is not None:
+            self._ipo.close()
         self.pr.close(); self.ctx.close()
 
 
@@ -60,6 +76,7 @@ def run(case_path, output=None, solver=None, verbose=1, rank=0, world=1, dist=No
     own = solver is None
     if own:
         solver = GpuSolver(case, model, device_index)
+    ip_x = np.array([xp for _, _, xp in case.internal_points]) if case.internal_points else None
     nso = None
     fh = None
     if rank == 0 and case.export_nso:
@@ -73,14 +90,20 @@ def run(case_path, output=None, solver=None, verbose=1, rank=0, world=1, dist=No
                 x = solver.static()
                 if fh:
                     wr.static(x)
+                    if case.internal_points:
+                        wr.static_internal(*solver.interior_static(x, ip_x))
         else:
             sweep = FrequencySweep(case.omega, model.n_dof, lambda kf, om: solver.harmonic(om), rank=rank, world=world, dist=dist, device=device)
             for r in range(sweep.n_rounds()):
                 sweep.round(r)
                 if rank == 0:
                     for kf in range(r * world, min((r + 1) * world, len(case.omega))):   # in-order export, one frequency at a time
+                        xk = sweep.results.pop(kf)
                         if fh:
-                            wr.frequency(kf + 1, sweep.results.pop(kf))
+                            wr.frequency(kf + 1, xk)
+                            if case.internal_points:
+                                # the writer rank evaluates the interior identities of every frequency with its own problem objects
+                                wr.frequency_internal(kf + 1, *solver.interior_harmonic(case.omega[kf], xk, ip_x))
                         if verbose >= 2:
                             log.write("  frequency %d / %d done\n" % (kf + 1, len(case.omega)))
     finally:

@@ -11,9 +11,10 @@ Mirrors src/read_input_file.f90 for the sections the hot path consumes:
                                              `fluid rho c`, `viscoelastic rho mu nu xi`, `elastic rho mu nu`
   [conditions over be boundaries]            src/read_conditions_bem_boundaries_mechanics_{harmonic,static}.f90: global-axes
                                              conditions 0 / 1 per component; defaults (not listed) = 1 with value 0
+  [internal points]  src/read_internal_points.f90    `<id> <region> x1 x2 x3` (one elastic region)
   [export]       src/read_export.f90:61-240  export_nso, real_format, integer_format, complex_notation
 Anything else the reference accepts (be-fe coupling, poroelastic regions, crack-like boundaries, local-axes or spring conditions,
-half-spaces, body loads, incident fields, symmetry planes, internal points, FE regions ...) raises CaseFileError naming the feature:
+half-spaces, body loads, incident fields, symmetry planes, internal points of fluid regions, FE regions ...) raises CaseFileError naming the feature:
 the Fortran host keeps those.
 """
 import os
@@ -147,7 +148,7 @@ class CaseFile:
         self.filename = os.path.basename(path)
         sec = _sections(open(path, encoding="utf-8", errors="replace").read())
         self._sec = sec
-        for unsupported in ("fe subregions", "be body loads", "be bodyloads", "symmetry planes", "internal points", "internal elements",
+        for unsupported in ("fe subregions", "be body loads", "be bodyloads", "symmetry planes", "internal elements",
                             "incident waves", "groups", "cross sections", "sensitivity"):
             if sec.get(unsupported):
                 raise CaseFileError("section [%s] is outside the path this library covers" % unsupported)
@@ -277,6 +278,19 @@ class CaseFile:
                 ct.append(t); cv.append(_fortran_complex(w[1]))
             self.bcs[bid] = (ct, cv)
             i += ndof
+        # ---- [internal points] (src/read_internal_points.f90: `<id> <region> x1 x2 x3`): displacements and stresses inside an elastic region
+        self.internal_points = []             # (id, region index, x)
+        il = sec.get("internal points", [])
+        if il:
+            if self.multi or self.region_type != 2:
+                raise CaseFileError("[internal points]: covered for one elastic region (a fluid region would need the hypersingular fluid kernels)")
+            for s_ in il[1:1 + int(il[0].split()[0])]:
+                w = s_.split()
+                if int(w[1]) != self.region_id:
+                    raise CaseFileError("internal point %s: the indicated region does not exist" % w[0])
+                self.internal_points.append((int(w[0]), 0, np.array([_fortran_float(t) for t in w[2:5]])))
+            if len(set(i_ for i_, _, _ in self.internal_points)) != len(self.internal_points) or min(i_ for i_, _, _ in self.internal_points) <= 0:
+                raise CaseFileError("[internal points]: identifiers must be positive and unique")
         # ---- [export]
         ex = sec.get("export", [])
         self.export_nso = _logical(_keyword(ex, "export_nso") or "T")

@@ -21,7 +21,7 @@ class NsoWriter:
     def __init__(self, fh, case, model):
         self.f, self.case, self.m = fh, case, model
         self.rf = RealFormat(case.real_format)
-        ids = [len(case.omega), max(r[0] for r in case.regions), max(b for b, _ in case.boundaries), int(model.mesh.elem_ids.max()), int(model.mesh.node_ids.max())]
+        ids = [len(case.omega), max(r[0] for r in case.regions), max(b for b, _ in case.boundaries), max([i_ for i_, _, _ in case.internal_points] or [0]), int(model.mesh.elem_ids.max()), int(model.mesh.node_ids.max())]
         if case.integer_format in (None, "auto"):
             self.wi = int_width(*ids)
         elif case.integer_format == "max":
@@ -109,6 +109,35 @@ class NsoWriter:
             v = row[5]
             vals = "".join(self._cpair(complex(z)) for z in list(prim[v]) + list(sec[v]))
             out.append(self._ident(kf, value, row) + vals + self._cpair(0j) * (2 * prim.shape[1]) + "\n")
+        self.f.write("".join(out))
+
+    def _ip_ident(self, kf, value, pid, x):
+        """Columns 1-12 of an internal-point row: no boundary (0 0 0), the point id and its position (export_solution_mechanics_harmonic_nso.f90:401-405)."""
+        rid, rtype = self.case.regions[0][0], self.case.regions[0][1]
+        return (self._i(kf) + self.rf(value) + self._i(rid) + self._i(1) + self._i(rtype) + self._i(0) + self._i(0) + self._i(0) + self._i(pid) +
+                "".join(self.rf(t) for t in x))
+
+    def frequency_internal(self, kf, u, sigma):
+        """Internal-point rows of frequency kf: u_k, then t_k on the planes with normals e_1, e_2, e_3 (sigma[p, k, kc]), then the incident field
+        (zero) in the same order (:407-447)."""
+        c = self.case
+        omega = c.omega[kf - 1]
+        value = omega * 0.159154943091895335768883763373 if c.frequency_units == "f" else omega
+        out = []
+        for p, (pid, _, xp) in enumerate(c.internal_points):
+            vals = "".join(self._cpair(complex(z)) for z in u[p])
+            for kc in range(3):
+                vals += "".join(self._cpair(complex(sigma[p, k, kc])) for k in range(3))
+            out.append(self._ip_ident(kf, value, pid, xp) + vals + self._cpair(0j) * 12 + "\n")
+        self.f.write("".join(out))
+
+    def static_internal(self, u, sigma):
+        out = []
+        for p, (pid, _, xp) in enumerate(self.case.internal_points):
+            vals = "".join(self.rf(float(np.real(z))) for z in u[p])
+            for kc in range(3):
+                vals += "".join(self.rf(float(np.real(sigma[p, k, kc]))) for k in range(3))
+            out.append(self._ip_ident(0, 0.0, pid, xp) + vals + "\n")
         self.f.write("".join(out))
 
     def static(self, x):

@@ -191,6 +191,21 @@ class OracleSolver:
         A, b, _ = self.o.assemble_static(self.case.material)
         return np.linalg.solve(A, b).astype(np.complex128)
 
+    def interior_static(self, x, points):
+        """u and sigma at interior points from oracle pair integrals (Somigliana's identity and its hypersingular counterpart)."""
+        u, t = self.model.nodal_solution(np.asarray(x))
+        uu = np.zeros((len(points), 3)); sg = np.zeros((len(points), 3, 3))
+        for ip, xp in enumerate(points):
+            for e in range(self.model.n_elem):
+                nodes = self.model.mesh.conn[e]
+                h, g, _ = self.o.pair_static(e, xp, self.case.material)
+                uu[ip] += np.einsum("jlk,jk->l", g, t[nodes].real) - np.einsum("jlk,jk->l", h, u[nodes].real)
+                for kc in range(3):
+                    n_i = np.zeros(3); n_i[kc] = 1.0
+                    m_, l_, _ = self.o.pair_hbie_static(e, xp, n_i, self.case.material)
+                    sg[ip, :, kc] += np.einsum("jlk,jk->l", l_, t[nodes].real) - np.einsum("jlk,jk->l", m_, u[nodes].real)
+        return uu, sg
+
     def close(self):
         pass
 
@@ -436,3 +451,29 @@ def test_two_region_case_parses_numbers_and_exports(tmp_path):
 
 def rows_of(lines, rtype):
     return np.array([[float(t) for t in s.split()] for s in lines if int(s.split()[4]) == rtype])
+
+
+def test_internal_points_of_an_elastic_region(tmp_path):
+    """[internal points] of the case file -> rows with boundary columns 0 0 0, the point id, u_k and the tractions on the three coordinate
+    planes; ME-ST-EL-002's exact field (u1 = x1/(lambda+2mu), sigma_11 = 1, sigma_22 = sigma_33 = nu/(1-nu)) at the points."""
+    text = (SOLID_DAT % dict(analysis="static", freq="", z="0.", one="1.")).replace("eng_double", "sci_double")
+    text += "\n[internal points]\n3\n1 1 0.5 0.5 0.5\n2 1 0.2 0.7 0.4\n7 1 0.8 0.3 0.6\n"
+    path = _write_case(tmp_path, text, et=shape.QUAD4, m=3)
+    case = CaseFile(path)
+    md = case.build_model()
+    assert [p[0] for p in case.internal_points] == [1, 2, 7]
+
+    nso = driver.run(path, solver=OracleSolver(case, md), log=io.StringIO())
+    lines = [s for s in open(nso) if s.strip() and not s.startswith("#")]
+    ip_rows = np.array([[float(t) for t in s.split()] for s in lines[md.n_node:]])
+    assert len(lines) == md.n_node + 3 and ip_rows.shape == (3, 12 + 3 + 9)
+    assert (ip_rows[:, 5:8] == 0).all() and list(ip_rows[:, 8]) == [1, 2, 7] and np.allclose(ip_rows[:, 9:12], [[0.5, 0.5, 0.5], [0.2, 0.7, 0.4], [0.8, 0.3, 0.6]])
+    mat = case.material
+    lam2mu = 2.0 * mat.mu_r * mat.nu_r / (1.0 - 2.0 * mat.nu_r) + 2.0 * mat.mu_r
+    assert np.abs(ip_rows[:, 12] - ip_rows[:, 9] / lam2mu).max() < 1e-4
+    sig = ip_rows[:, 15:24].reshape(3, 3, 3)                     # [point][plane kc][component k]
+    exact = np.diag([1.0, mat.nu_r / (1.0 - mat.nu_r), mat.nu_r / (1.0 - mat.nu_r)])
+    assert np.abs(sig - exact).max() < 5e-4
+    # a fluid region has no internal-point support
+    with pytest.raises(CaseFileError):
+        CaseFile(_write_case(tmp_path, FLUID_DAT + "\n[internal points]\n1\n1 1 0.5 0.5 0.5\n"))

@@ -63,3 +63,19 @@ def test_command_line(tmp_path):
     assert rows.shape == (2 * md.n_node, 20) and "frequency 2 / 2 done" in r.stdout
     r = subprocess.run([sys.executable, "-m", "multifebe_b200", "-i", str(tmp_path / "missing.dat")], cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert r.returncode == 2 and "Input file does not exist" in r.stdout
+
+
+# Written after the round's GPU budget was spent (uses only GPU-validated entry points: capi.InternalPoints); non-strict until its first hardware run.
+@pytest.mark.xfail(reason="first hardware run pending (written without GPU access at the end of round 1)", strict=False)
+def test_static_case_with_internal_points(tmp_path):
+    text = (SOLID_DAT % dict(analysis="static", freq="", z="0.", one="1.")).replace("eng_double", "sci_double")
+    text += "\n[internal points]\n2\n1 1 0.5 0.5 0.5\n2 1 0.2 0.7 0.4\n"
+    path = _write_case(tmp_path, text, et=shape.QUAD4, m=3)
+    nso_cpu, _ = _run_with_oracle(path, output=path + ".cpu")
+    nso = driver.run(path, log=io.StringIO())
+    la = [s for s in open(nso) if s.strip() and not s.startswith("#")]
+    lb = [s for s in open(nso_cpu) if s.strip() and not s.startswith("#")]
+    assert len(la) == len(lb)
+    a = np.array([[float(t) for t in s.split()] for s in la[-2:]]); b = np.array([[float(t) for t in s.split()] for s in lb[-2:]])
+    assert np.array_equal(a[:, :12], b[:, :12])
+    assert np.abs(a[:, 12:15] - b[:, 12:15]).max() <= 1e-8 * np.abs(b[:, 12:15]).max() and np.abs(a[:, 15:] - b[:, 15:]).max() <= 1e-8 * np.abs(b[:, 15:]).max()
