@@ -477,3 +477,14 @@ def test_internal_points_of_an_elastic_region(tmp_path):
     # a fluid region has no internal-point support
     with pytest.raises(CaseFileError):
         CaseFile(_write_case(tmp_path, FLUID_DAT + "\n[internal points]\n1\n1 1 0.5 0.5 0.5\n"))
+
+
+def test_shipped_examples_parse_and_the_static_one_solves():
+    ex = os.path.join(ROOT, "examples")
+    sizes = {}
+    for name in ("room", "column_harmonic", "column_static"):
+        c = CaseFile(os.path.join(ex, name, name + ".dat"))
+        sizes[name] = (c.analysis, c.region_type, c.build_model().n_dof, len(c.omega), len(c.internal_points))
+    assert sizes == {"room": ("harmonic", 1, 486, 12, 0), "column_harmonic": ("harmonic", 2, 1458, 8, 3), "column_static": ("static", 2, 1170, 0, 3)}
+    c = CaseFile(os.path.join(ex, "room", "room.dat"))
+    assert abs(c.omega[0] / (2 * np.pi) - 5.0) < 1e-12 and abs(c.omega[-1] / (2 * np.pi) - 115.0) < 1e-9 and c.description.startswith("pressure waves")
