@@ -1,6 +1,7 @@
 """GPU parity tests of the acoustic (inviscid fluid) BE region (first brick), through the C ABI
 (mfb_harpot3d_*) against the CPU oracle on the same inputs.  Tolerances as for the elastic path: assembled entries within 1e-11
 relative (max-norm), solutions within 1e-8."""
+import os
 import numpy as np
 import pytest
 from multifebe_b200.host import Fluid, FluidModel, Model, Material, cube_mesh, cube_bcs, room_bcs, room_analytic, shape
@@ -88,10 +89,10 @@ def test_wrong_family_is_refused(gpu_ctx):
     pe.close()
 
 
-# Written after the round's GPU budget was spent: never run on hardware.  It uses only entry points that the tests above validate
-# (mfb_harpot3d_setup / _assemble with colloc_elem = -1 rows, mfb_residual_vector); non-strict so that the first hardware run reports
-# it either way (XPASS expected).
-@pytest.mark.xfail(reason="first hardware run pending (written without GPU access at the end of round 1)", strict=False)
+# Written after the round's GPU budget was spent: never run on hardware.  It only uses entry points the tests above validate, but an unvalidated
+# test that faulted on the device would take the CUDA context of the whole pytest process with it, so it runs on request only
+# (MFB_RUN_UNVALIDATED=1 python -m pytest tests -m gpu -k "interior_pressures or with_internal_points"): first thing to do in round 2.
+@pytest.mark.skipif(not os.environ.get("MFB_RUN_UNVALIDATED"), reason="first hardware run pending; set MFB_RUN_UNVALIDATED=1")
 def test_interior_pressures_match_the_oracle_composition(gpu_ctx, oracle_lib):
     from multifebe_b200 import capi
     md = FluidModel(cube_mesh(3, shape.QUAD9), room_bcs(1.0))
