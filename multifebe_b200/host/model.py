@@ -147,6 +147,34 @@ class Fluid:
         self.c = complex(self.c_r) * np.sqrt(1.0 + 2j * self.xi)
 
 
+class Poro:
+    """Biot poroelastic medium (`biot_poroelastic_medium` material, src/read_regions.f90:737-860): fluid and solid densities rhof, rhos, drained
+    Lame constants lambda, mu of the skeleton, hysteretic damping xi (applied to lambda, mu, R, Q), porosity phi, added density rhoa, Biot's
+    coupling parameters R, Q and the dissipation constant b.  rho1 = (1 - phi) rhos, rho2 = phi rhof (property_r(13:14))."""
+
+    def __init__(self, rhof=1000.0, rhos=2600.0, lam=1.0e8, mu=1.0e8, xi=0.0, phi=0.3, rhoa=0.0, R=1.0e8, Q=1.0e8, b=0.0):
+        self.rhof, self.rhos, self.phi, self.rhoa, self.b, self.xi = float(rhof), float(rhos), float(phi), float(rhoa), float(b), float(xi)
+        d = 1.0 + 2j * self.xi
+        self.lam, self.mu, self.R, self.Q = lam * d, mu * d, R * d, Q * d
+        self.rho1, self.rho2 = (1.0 - self.phi) * self.rhos, self.phi * self.rhof
+        self.nu = 0.5 * self.lam / (self.lam + self.mu)
+
+    def props(self):
+        """The argument list of fbem_bem_harpor3d_calculate_parameters (lambda, mu, rho1, rho2, rhoa, R, Q, b), flat."""
+        return np.array([self.lam.real, self.lam.imag, self.mu.real, self.mu.imag, self.rho1, self.rho2, self.rhoa,
+                         self.R.real, self.R.imag, self.Q.real, self.Q.imag, self.b], dtype=np.float64)
+
+
+class PoroModel(Model):
+    """One Biot poroelastic BE region: four equations and four unknowns per node, component 0 = fluid phase (tau known: ctype 0, Un known:
+    ctype 1), components 1..3 = solid skeleton (u_k known: 0, t_k known: 1) -- the open-pore conditions of an ordinary boundary
+    (assemble_bem_harpor_equation.f90:78-110, :140-170).  bcs: {part_id: ([ct_tau, ct_1, ct_2, ct_3], [values])}.  col_u holds the columns
+    of (tau, u_k), col_t those of (Un, t_k).  CPU side only so far (oracle); the device path is not built."""
+
+    def __init__(self, mesh, bcs, **kw):
+        Model.__init__(self, mesh, bcs, ndof=4, **kw)
+
+
 class FluidModel(Model):
     """One inviscid-fluid BE region (scalar wave propagation): one equation and one unknown per node.
     bcs: {part_id: (ctype, value)}: ctype 0 = p known (Un unknown), 1 = Un known (p unknown), `conditions over be boundaries` of an

@@ -209,6 +209,8 @@ struct Params {
   // h, g of a pair are vectors over the element nodes: stored in h[0..nn), g[0..nn) of the 9*nn containers (the rest stays zero);
   // cte_t = -1/(4 pi), cte_u = 1/(4 pi) carry the reference's `h=-h*c_1_4pi; g=g*c_1_4pi`.
   bool pot = false; cd kp, P1, Q1, Q2;
+  // Biot poroelastic medium (PorParams below): h, g are (n, 4, 4)
+  const struct PorParams* por = nullptr;
 };
 // fbem_bem_harpot3d_calculate_parameters: lib/fbem/src/bem_harpot3d.f90:123-165 (SBIE subset P, Q)
 static void calculate_parameters_pot(double rho, cd c, double omega, Params& p) {
@@ -218,9 +220,118 @@ static void calculate_parameters_pot(double rho, cd c, double omega, Params& p) 
   p.P1 = -im * k; p.Q1 = 0.5 * (k * k); p.Q2 = im * k;
   p.cte_u = c_1_4pi; p.cte_t = -c_1_4pi;
 }
+// -------------------------------------------------------------------------------------
+// Biot poroelastic medium: fbem_bem_harpor3d_parameters / _calculate_parameters, lib/fbem/src/bem_harpor3d.f90:91-134, 204-568 (SBIE subset:
+// eta, vartheta, psi, chi, W0, T01, T02, W1, W2, T1..T3, cte_u, cte_t; 1-based like the reference).  Variables of a node: 0 = fluid
+// equivalent stress tau (primary) / fluid normal displacement Un (secondary), 1..3 = solid displacement u_k / solid traction t_k.
+// h, g of a pair are (n, 4, 4): stored as h[(j*4 + il)*4 + ik].
+// -------------------------------------------------------------------------------------
+struct PorParams {
+  cd lambda, mu, nu, R, Q; double rho1, rho2, rhoa, b, omega;
+  cd rhohat11, rhohat22, rhohat12, Z, J, k1, k2, k3;
+  cd eta[4], vartheta[6], psi[9], chi[10], W0[7], T01[8], T02[9], W1[11], W2[10], T1[15], T2[13], T3[14];
+  cd cte_u[4][4], cte_t[4][4];
+};
+static void calculate_parameters_por(cd lambda, cd mu, double rho1, double rho2, double rhoa, cd R, cd Q, double b, double omega, PorParams& P) {
+  const cd im(0.0, 1.0);
+  cd rhohat11 = rho1 + rhoa - im * b / omega, rhohat12 = -rhoa + im * b / omega, rhohat22 = rho2 + rhoa - im * b / omega;
+  cd J = 1.0 / (rhohat22 * (omega * omega)), Z = rhohat12 / rhohat22;
+  cd k3 = std::sqrt(1.0 / (mu * J) * (rhohat11 / rhohat22 - Z * Z));
+  if (k3.real() < 0.0) k3 = -k3;
+  cd ca = lambda + 2.0 * mu;
+  cd cb = (lambda + 2.0 * mu) / (J * R) + mu * (k3 * k3) + 1.0 / J * ((Q / R - Z) * (Q / R - Z));
+  cd cc = mu / (J * R) * (k3 * k3);
+  cd k1 = std::sqrt(0.5 * (cb - std::sqrt(cb * cb - 4.0 * ca * cc)) / ca), k2 = std::sqrt(0.5 * (cb + std::sqrt(cb * cb - 4.0 * ca * cc)) / ca);
+  if (k1.real() < 0.0) k1 = -k1;
+  if (k2.real() < 0.0) k2 = -k2;
+  if (k1.real() > k2.real()) std::swap(k1, k2);
+  P.omega = omega; P.lambda = lambda; P.mu = mu; P.nu = 0.5 * lambda / (lambda + mu); P.rho1 = rho1; P.rho2 = rho2; P.rhoa = rhoa; P.R = R; P.Q = Q; P.b = b;
+  P.rhohat11 = rhohat11; P.rhohat22 = rhohat22; P.rhohat12 = rhohat12; P.Z = Z; P.J = J; P.k1 = k1; P.k2 = k2; P.k3 = k3;
+  const cd l2m = lambda + 2.0 * mu, k1_2 = k1 * k1, k2_2 = k2 * k2, k3_2 = k3 * k3, k1_3 = k1_2 * k1, k2_3 = k2_2 * k2;
+  cd alpha1 = k1_2 - mu / l2m * k3_2, alpha2 = k2_2 - mu / l2m * k3_2;
+  cd beta1 = mu / l2m * k1_2 - k1_2 * k2_2 / k3_2, beta2 = mu / l2m * k2_2 - k1_2 * k2_2 / k3_2;
+  cd vc = (Q / R - Z) / l2m, d12 = k1_2 - k2_2;
+  const cd ik1 = im * k1, ik2 = im * k2, ik3 = im * k3, QR = Q / R;
+  P.eta[1] = -(ik1 * alpha1 - ik2 * alpha2) / d12; P.eta[2] = alpha1 / d12; P.eta[3] = -alpha2 / d12;
+  P.vartheta[1] = 0.5 * vc; P.vartheta[2] = vc * ik1 / d12; P.vartheta[3] = -vc * ik2 / d12; P.vartheta[4] = vc / d12; P.vartheta[5] = -vc / d12;
+  P.psi[1] = 0.5 * (lambda + 3.0 * mu) / l2m; P.psi[2] = -1.0 / 3.0 * ((ik1 * beta1 - ik2 * beta2) / d12 + 2.0 * ik3);
+  P.psi[3] = -beta1 / ik1 / d12; P.psi[4] = beta2 / ik2 / d12; P.psi[5] = 1.0 / ik3; P.psi[6] = beta1 / k1_2 / d12; P.psi[7] = -beta2 / k2_2 / d12; P.psi[8] = -1.0 / k3_2;
+  P.chi[1] = -0.5 * (lambda + mu) / l2m; P.chi[2] = -beta1 / d12; P.chi[3] = beta2 / d12; P.chi[4] = -3.0 * beta1 / ik1 / d12; P.chi[5] = 3.0 * beta2 / ik2 / d12;
+  P.chi[6] = 3.0 / ik3; P.chi[7] = 3.0 * beta1 / k1_2 / d12; P.chi[8] = -3.0 * beta2 / k2_2 / d12; P.chi[9] = -3.0 / k3_2;
+  P.W0[1] = J; P.W0[2] = 0.5 * (Z * vc + J * (k1_2 * alpha1 - k2_2 * alpha2) / d12); P.W0[3] = (Z * vc + J * alpha1) * ik1 / d12;
+  P.W0[4] = -(Z * vc + J * alpha2) * ik2 / d12; P.W0[5] = (Z * vc + J * alpha1) / d12; P.W0[6] = -(Z * vc + J * alpha2) / d12;
+  P.T01[1] = mu * vc; P.T01[2] = -2.0 * mu * vc * k1_2 / d12; P.T01[3] = 2.0 * mu * vc * k2_2 / d12; P.T01[4] = 6.0 * mu * vc * ik1 / d12;
+  P.T01[5] = -6.0 * mu * vc * ik2 / d12; P.T01[6] = 6.0 * mu * vc / d12; P.T01[7] = -6.0 * mu * vc / d12;
+  P.T02[1] = mu * vc + Z; P.T02[2] = (lambda + 2.0 / 3.0 * mu) * vc * im * (k1_3 - k2_3) / d12 - QR * (ik1 * alpha1 - ik2 * alpha2) / d12;
+  P.T02[3] = (QR * alpha1 - lambda * vc * k1_2) / d12; P.T02[4] = -(QR * alpha2 - lambda * vc * k2_2) / d12; P.T02[5] = -2.0 * mu * vc * ik1 / d12;
+  P.T02[6] = 2.0 * mu * vc * ik2 / d12; P.T02[7] = -2.0 * mu * vc / d12; P.T02[8] = 2.0 * mu * vc / d12;
+  P.W1[1] = 0.5 * (QR * mu / l2m - Z); P.W1[2] = -(mu * vc * k1_2 + Z * beta1) / d12; P.W1[3] = (mu * vc * k2_2 + Z * beta2) / d12; P.W1[4] = Z;
+  P.W1[5] = 3.0 * (mu * vc * ik1 - Z * beta1 / ik1) / d12; P.W1[6] = -3.0 * (mu * vc * ik2 - Z * beta2 / ik2) / d12; P.W1[7] = 3.0 * Z / ik3;
+  P.W1[8] = 3.0 * (mu * vc + Z * beta1 / k1_2) / d12; P.W1[9] = -3.0 * (mu * vc + Z * beta2 / k2_2) / d12; P.W1[10] = -3.0 * Z / k3_2;
+  P.W2[1] = -0.5 * (QR * mu / l2m + Z); P.W2[2] = 1.0 / 3.0 * (mu * vc * im * (k1_3 - k2_3) / d12 + Z * ((ik1 * beta1 - ik2 * beta2) / d12 + 2.0 * ik3));
+  P.W2[3] = -Z; P.W2[4] = -(mu * vc * ik1 - Z * beta1 / ik1) / d12; P.W2[5] = (mu * vc * ik2 - Z * beta2 / ik2) / d12; P.W2[6] = -Z / ik3;
+  P.W2[7] = -(mu * vc + Z * beta1 / k1_2) / d12; P.W2[8] = (mu * vc + Z * beta2 / k2_2) / d12; P.W2[9] = Z / k3_2;
+  const cd kb = (k1_2 * beta1 - k2_2 * beta2) / d12;
+  P.T1[1] = -3.0 * (lambda + mu) / l2m; P.T1[2] = 0.25 * (kb - k3_2); P.T1[3] = -2.0 * ik1 * beta1 / d12; P.T1[4] = 2.0 * ik2 * beta2 / d12; P.T1[5] = 2.0 * ik3;
+  P.T1[6] = -12.0 * beta1 / d12; P.T1[7] = 12.0 * beta2 / d12; P.T1[8] = 12.0; P.T1[9] = -30.0 * beta1 / ik1 / d12; P.T1[10] = 30.0 * beta2 / ik2 / d12;
+  P.T1[11] = 30.0 / ik3; P.T1[12] = 30.0 * beta1 / k1_2 / d12; P.T1[13] = -30.0 * beta2 / k2_2 / d12; P.T1[14] = -30.0 / k3_2;
+  P.T2[1] = -mu / l2m; P.T2[2] = -0.25 * (kb + k3_2); P.T2[3] = -ik3; P.T2[4] = 2.0 * beta1 / d12; P.T2[5] = -2.0 * beta2 / d12; P.T2[6] = -3.0;
+  P.T2[7] = 6.0 * beta1 / ik1 / d12; P.T2[8] = -6.0 * beta2 / ik2 / d12; P.T2[9] = -6.0 / ik3; P.T2[10] = -6.0 * beta1 / k1_2 / d12; P.T2[11] = 6.0 * beta2 / k2_2 / d12;
+  P.T2[12] = 6.0 / k3_2;
+  const cd qv = QR * vc / J, lm = lambda / mu;
+  P.T3[1] = mu / l2m; P.T3[2] = 0.25 * (2.0 * qv - (2.0 * lm + 1.0) * kb + k3_2); P.T3[3] = (qv - lm * beta1) * ik1 / d12; P.T3[4] = -(qv - lm * beta2) * ik2 / d12;
+  P.T3[5] = (qv - (lm - 2.0) * beta1) / d12; P.T3[6] = -(qv - (lm - 2.0) * beta2) / d12; P.T3[7] = -2.0; P.T3[8] = 6.0 * beta1 / ik1 / d12;
+  P.T3[9] = -6.0 * beta2 / ik2 / d12; P.T3[10] = -6.0 / ik3; P.T3[11] = -6.0 * beta1 / k1_2 / d12; P.T3[12] = 6.0 * beta2 / k2_2 / d12; P.T3[13] = 6.0 / k3_2;
+  for (int a = 0; a < 4; a++) for (int c = 0; c < 4; c++) {
+    P.cte_u[a][c] = (a == 0) ? cd(-c_1_4pi) : (c == 0 ? -c_1_4pi / J : c_1_4pi / mu);
+    P.cte_t[a][c] = (a == 0) ? (c == 0 ? cd(-c_1_4pi) : cd(c_1_4pi)) : (c == 0 ? -c_1_4pi / mu : cd(c_1_4pi));
+  }
+}
+// Kernel scalars of the poroelastic fundamental solution at distance r (bem_harpor3d.f90:944-975); regular_only drops the static 1/r^2 parts
+// of W0 and TT1..TT3 as the interior integration does (:1720-1750), which adds them back where it integrates them in full.
+struct PorScalars { cd eta, vartheta, psi, chi, W0, T01, T02, W1, W2, TT1, TT2, TT3; double d1r1, d1r2; };
+static inline void por_scalars(const PorParams& p, double r, bool regular_only, PorScalars& k) {
+  double d1r1 = 1.0 / r, d1r2 = d1r1 * d1r1, d1r3 = d1r2 * d1r1, d1r4 = d1r3 * d1r1;
+  const cd mim(-0.0, -1.0);
+  cd E[3][7];
+  zexp_decomposed(mim * p.k1 * r, E[0]); zexp_decomposed(mim * p.k2 * r, E[1]); zexp_decomposed(mim * p.k3 * r, E[2]);
+  cd E2[3], E3[3], E4[3], E5[3];
+  for (int j = 0; j < 3; j++) { E2[j] = E[j][2] * d1r1; E3[j] = E[j][3] * d1r2; E4[j] = E[j][4] * d1r3; E5[j] = E[j][5] * d1r4; }
+  k.eta = d1r1 + p.eta[1] + p.eta[2] * E2[0] + p.eta[3] * E2[1];
+  k.vartheta = p.vartheta[1] + p.vartheta[2] * E2[0] + p.vartheta[3] * E2[1] + p.vartheta[4] * E3[0] + p.vartheta[5] * E3[1];
+  k.psi = p.psi[1] * d1r1 + p.psi[2] + E2[2] + p.psi[3] * E3[0] + p.psi[4] * E3[1] + p.psi[5] * E3[2] + p.psi[6] * E4[0] + p.psi[7] * E4[1] + p.psi[8] * E4[2];
+  k.chi = p.chi[1] * d1r1 + p.chi[2] * E2[0] + p.chi[3] * E2[1] + E2[2] + p.chi[4] * E3[0] + p.chi[5] * E3[1] + p.chi[6] * E3[2] + p.chi[7] * E4[0] + p.chi[8] * E4[1]
+        + p.chi[9] * E4[2];
+  cd W0r = p.W0[2] + p.W0[3] * E2[0] + p.W0[4] * E2[1] + p.W0[5] * E3[0] + p.W0[6] * E3[1];
+  k.T01 = p.T01[1] * d1r1 + p.T01[2] * E2[0] + p.T01[3] * E2[1] + p.T01[4] * E3[0] + p.T01[5] * E3[1] + p.T01[6] * E4[0] + p.T01[7] * E4[1];
+  k.T02 = p.T02[1] * d1r1 + p.T02[2] + p.T02[3] * E2[0] + p.T02[4] * E2[1] + p.T02[5] * E3[0] + p.T02[6] * E3[1] + p.T02[7] * E4[0] + p.T02[8] * E4[1];
+  k.W1 = p.W1[1] * d1r1 + p.W1[2] * E2[0] + p.W1[3] * E2[1] + p.W1[4] * E2[2] + p.W1[5] * E3[0] + p.W1[6] * E3[1] + p.W1[7] * E3[2] + p.W1[8] * E4[0] + p.W1[9] * E4[1]
+       + p.W1[10] * E4[2];
+  k.W2 = p.W2[1] * d1r1 + p.W2[2] + p.W2[3] * E2[2] + p.W2[4] * E3[0] + p.W2[5] * E3[1] + p.W2[6] * E3[2] + p.W2[7] * E4[0] + p.W2[8] * E4[1] + p.W2[9] * E4[2];
+  cd T1r = p.T1[2] + p.T1[3] * E2[0] + p.T1[4] * E2[1] + p.T1[5] * E2[2] + p.T1[6] * E3[0] + p.T1[7] * E3[1] + p.T1[8] * E3[2] + p.T1[9] * E4[0] + p.T1[10] * E4[1]
+           + p.T1[11] * E4[2] + p.T1[12] * E5[0] + p.T1[13] * E5[1] + p.T1[14] * E5[2];
+  cd T2r = p.T2[2] + p.T2[3] * E2[2] + p.T2[4] * E3[0] + p.T2[5] * E3[1] + p.T2[6] * E3[2] + p.T2[7] * E4[0] + p.T2[8] * E4[1] + p.T2[9] * E4[2] + p.T2[10] * E5[0]
+           + p.T2[11] * E5[1] + p.T2[12] * E5[2];
+  cd T3r = p.T3[2] + p.T3[3] * E2[0] + p.T3[4] * E2[1] + p.T3[5] * E3[0] + p.T3[6] * E3[1] + p.T3[7] * E3[2] + p.T3[8] * E4[0] + p.T3[9] * E4[1] + p.T3[10] * E4[2]
+           + p.T3[11] * E5[0] + p.T3[12] * E5[1] + p.T3[13] * E5[2];
+  if (regular_only) { k.W0 = W0r; k.TT1 = T1r; k.TT2 = T2r; k.TT3 = T3r; }
+  else { k.W0 = p.W0[1] * d1r2 + W0r; k.TT1 = p.T1[1] * d1r2 + T1r; k.TT2 = p.T2[1] * d1r2 + T2r; k.TT3 = p.T3[1] * d1r2 + T3r; }
+  k.d1r1 = d1r1; k.d1r2 = d1r2;
+}
 // order f of the estimator's model function 1/r^f: 5 for the elastic SBIE (bem_harela3d.f90:1522), 7 for the elastic HBIE (:3677),
 // 3 for the scalar SBIE (bem_harpot3d.f90:1009, :693)
-static inline int estimator_f(const Params& p, const double* n_i) { return n_i ? 7 : (p.pot ? 3 : 5); }
+static inline int estimator_f(const Params& p, const double* n_i) { return n_i ? 7 : (p.pot ? 3 : 5); }   // poroelastic SBIE: 5 (bem_harpor3d.f90:1949)
+static inline int nblk(const Params& p) { return p.por ? 16 : 9; }   // entries of one node block of h, g
+// constants and orientation of a finished pair: `h = cte_t h, g = cte_u g; if (reverse) h = -h` of every integrator
+static inline void finish_pair(const Params& p, bool reverse, const double* n_i, int nn, cd* h, cd* g) {
+  if (p.por) {
+    for (int j = 0; j < nn; j++) for (int a = 0; a < 4; a++) for (int c = 0; c < 4; c++) {
+      h[(j * 4 + a) * 4 + c] = p.por->cte_t[a][c] * h[(j * 4 + a) * 4 + c]; g[(j * 4 + a) * 4 + c] = p.por->cte_u[a][c] * g[(j * 4 + a) * 4 + c]; }
+  } else {
+    for (int i = 0; i < 9 * nn; i++) { h[i] = (n_i ? p.cte_s : p.cte_t) * h[i]; g[i] = (n_i ? p.cte_d : p.cte_u) * g[i]; }
+  }
+  if (reverse) for (int i = 0; i < nblk(p) * nn; i++) h[i] = -h[i];
+}
 // fbem_decomposed_zexp: lib/fbem/src/numerical.f90:1138-1191 (E0..E4; used by fbem_bem_harpot3d_sbie_int)
 static void decomposed_zexp(cd z, cd* E /*0..4*/) {
   double absz = std::abs(z);
@@ -323,6 +434,24 @@ static inline void add_exterior_point(const Params& p, const double* x, const do
                                       const double* pphijw, const double* sphijw, cd* h, cd* g) {
   double rv[3] = {x[0] - x_i[0], x[1] - x_i[1], x[2] - x_i[2]};
   double r = sqrt(dot3(rv, rv));
+  if (p.por) {   // fbem_bem_harpor3d_sbie_ext_pre: bem_harpor3d.f90:931-996 (the same point formula in _ext_st)
+    PorScalars k; por_scalars(*p.por, r, false, k);
+    double drdx[3] = {rv[0] * k.d1r1, rv[1] * k.d1r1, rv[2] * k.d1r1};
+    double drdn = dot3(drdx, n);
+    cd fs_u[4][4], fs_t[4][4];
+    fs_u[0][0] = k.eta; fs_t[0][0] = k.W0 * drdn;
+    for (int c = 0; c < 3; c++) {
+      fs_u[0][c + 1] = k.vartheta * drdx[c]; fs_u[c + 1][0] = k.vartheta * drdx[c];
+      fs_t[0][c + 1] = k.T01 * drdx[c] * drdn + k.T02 * n[c]; fs_t[c + 1][0] = k.W1 * drdx[c] * drdn + k.W2 * n[c];
+    }
+    for (int ik = 0; ik < 3; ik++) for (int il = 0; il < 3; il++) {
+      fs_u[il + 1][ik + 1] = k.psi * dkr[il][ik] - k.chi * drdx[il] * drdx[ik];
+      fs_t[il + 1][ik + 1] = k.TT1 * drdx[il] * drdx[ik] * drdn + k.TT2 * (drdn * dkr[il][ik] + drdx[ik] * n[il]) + k.TT3 * drdx[il] * n[ik];
+    }
+    for (int a = 0; a < 4; a++) for (int c = 0; c < 4; c++) for (int j = 0; j < nn; j++) {
+      h[(j * 4 + a) * 4 + c] += fs_t[a][c] * pphijw[j]; g[(j * 4 + a) * 4 + c] += fs_u[a][c] * sphijw[j]; }
+    return;
+  }
   if (p.pot) {   // fbem_bem_harpot3d_sbie_ext_pre: bem_harpot3d.f90:305-320 (the same point formula in _ext_st :451-466, :605-622)
     double d1r1 = 1.0 / r, d1r2 = d1r1 * d1r1;
     double drdx[3] = {rv[0] * d1r1, rv[1] * d1r1, rv[2] * d1r1};
@@ -877,19 +1006,18 @@ static void stats_add(Stats& a, const Stats& b) {
 // the estimator called with f = 7 instead of 5, h <- m (scaled by cte_s), g <- l (scaled by cte_d).
 static void sbie_ext_pre(const PSet& s, const Element& e, const double* x_i, const Params& p, cd* h, cd* g, const double* n_i = nullptr) {
   int nn = e.nn;
-  for (int i = 0; i < 9 * nn; i++) { h[i] = 0.0; g[i] = 0.0; }
+  for (int i = 0; i < nblk(p) * nn; i++) { h[i] = 0.0; g[i] = 0.0; }
   for (int kip = 0; kip < s.ngp; kip++) {
     if (n_i) add_exterior_point_hbie(p, &s.x[3 * kip], &s.n[3 * kip], x_i, n_i, nn, &s.pphijw[nn * kip], &s.pphijw[nn * kip], h, g);
     else add_exterior_point(p, &s.x[3 * kip], &s.n[3 * kip], x_i, nn, &s.pphijw[nn * kip], &s.pphijw[nn * kip], h, g);
   }
-  for (int i = 0; i < 9 * nn; i++) { h[i] = (n_i ? p.cte_s : p.cte_t) * h[i]; g[i] = (n_i ? p.cte_d : p.cte_u) * g[i]; }
-  if (e.reverse) for (int i = 0; i < 9 * nn; i++) h[i] = -h[i];
+  finish_pair(p, e.reverse, n_i, nn, h, g);
 }
 // fbem_bem_harela3d_sbie_ext_st: bem_harela3d.f90:702-1048
 static void sbie_ext_st(const Element& e, const double* xi_s, const double* x_i, const double* barxip, double barr, const Params& p, int gln, cd* h, cd* g,
                         const double* n_i = nullptr) {
   int nn = e.nn; bool tri = (e.et == TRI3 || e.et == TRI6);
-  for (int i = 0; i < 9 * nn; i++) { h[i] = 0.0; g[i] = 0.0; }
+  for (int i = 0; i < nblk(p) * nn; i++) { h[i] = 0.0; g[i] = 0.0; }
   double tp1[4], tp2[4];
   if (!tri) { telles11_parameters(barxip[0], barr, tp1); telles11_parameters(barxip[1], barr, tp2); }
   else {
@@ -920,8 +1048,7 @@ static void sbie_ext_st(const Element& e, const double* xi_s, const double* x_i,
       else add_exterior_point(p, x, n, x_i, nn, pj, pj, h, g);
     }
   }
-  for (int i = 0; i < 9 * nn; i++) { h[i] = (n_i ? p.cte_s : p.cte_t) * h[i]; g[i] = (n_i ? p.cte_d : p.cte_u) * g[i]; }
-  if (e.reverse) for (int i = 0; i < 9 * nn; i++) h[i] = -h[i];
+  finish_pair(p, e.reverse, n_i, nn, h, g);
 }
 // fbem_bem_harela3d_sbie_ext_adp: bem_harela3d.f90:1050-1172
 static void sbie_ext_adp(const Element& e, double* xi_s, const double* x_i, const Params& p, const QsParams& qsp, int ks, int ns, cd* h, cd* g, Stats& st,
@@ -929,7 +1056,7 @@ static void sbie_ext_adp(const Element& e, double* xi_s, const double* x_i, cons
   int nn = e.nn, nv = n_vertices_of(e.et);
   double barxip[2], rmin, d; int method;
   if (ks == 1) {
-    for (int i = 0; i < 9 * nn; i++) { h[i] = 0.0; g[i] = 0.0; }
+    for (int i = 0; i < nblk(p) * nn; i++) { h[i] = 0.0; g[i] = 0.0; }
     if (nv == 3) { xi_s[0] = 1; xi_s[1] = 0; xi_s[2] = 0; xi_s[3] = 1; xi_s[4] = 0; xi_s[5] = 0; }
     else { xi_s[0] = -1; xi_s[1] = -1; xi_s[2] = 1; xi_s[3] = -1; xi_s[4] = 1; xi_s[5] = 1; xi_s[6] = -1; xi_s[7] = 1; }
     nearest_element_point_bem(e.et, e.x, e.cl, x_i, barxip, rmin, d, method);
@@ -960,9 +1087,9 @@ static void sbie_ext_adp(const Element& e, double* xi_s, const double* x_i, cons
   } else {
     double barr = telles_barr_any(d);
     int gln = std::max(gln_near, e.gln_far);
-    cd ht[81], gt[81];
+    cd ht[144], gt[144];
     sbie_ext_st(e, xi_s, x_i, barxip, barr, p, gln, ht, gt, n_i);
-    for (int i = 0; i < 9 * nn; i++) { h[i] = h[i] + ht[i]; g[i] = g[i] + gt[i]; }
+    for (int i = 0; i < nblk(p) * nn; i++) { h[i] = h[i] + ht[i]; g[i] = g[i] + gt[i]; }
     st.leaves++; st.pts_adaptive += (long long)gln * gln;
   }
 }
@@ -1103,7 +1230,7 @@ static void staela3d_sbie_int_li(int et, const double* xn, double* xi_s, const d
 // fbem_bem_harela3d_sbie_int: bem_harela3d.f90:1174-1472
 static void sbie_int(const Element& e, const double* xi_i, const Params& p, cd* h, cd* g, Stats& st) {
   int nn = e.nn, et = e.et;
-  for (int i = 0; i < 9 * nn; i++) { h[i] = 0.0; g[i] = 0.0; }
+  for (int i = 0; i < nblk(p) * nn; i++) { h[i] = 0.0; g[i] = 0.0; }
   double phi_g[9], x_i[3] = {0, 0, 0}, phi_i[9];
   phi2d<double>(et, xi_i, phi_g);
   for (int k = 0; k < nn; k++) for (int c = 0; c < 3; c++) x_i[c] = x_i[c] + phi_g[k] * e.x[3 * k + c];
@@ -1125,6 +1252,33 @@ static void sbie_int(const Element& e, const double* xi_i, const Params& p, cd* 
         double n[3] = {N[0] / jg, N[1] / jg, N[2] / jg};
         double rv[3] = {x[0] - x_i[0], x[1] - x_i[1], x[2] - x_i[2]};
         double r = sqrt(dot3(rv, rv));
+        if (p.por) {   // fbem_bem_harpor3d_sbie_int: bem_harpor3d.f90:1690-1790 -- the solid block as in the elastic integrator (static 1/r^2 parts of
+                       // T1 and of the dr/dn delta term integrated in full, the remaining T2(1)/r^2 part through the CPV term and the line integrals);
+                       // the fluid and coupling blocks are weakly singular and integrated as they are
+          PorScalars k; por_scalars(*p.por, r, true, k);
+          const PorParams& P = *p.por;
+          double drdx[3] = {rv[0] * k.d1r1, rv[1] * k.d1r1, rv[2] * k.d1r1}, drdn = dot3(drdx, n);
+          double jw = jg * rho * jthetap * w_ang * w_rad;
+          cd fs_u[4][4], fs_t[4][4];
+          fs_u[0][0] = k.eta; fs_t[0][0] = (P.W0[1] * k.d1r2 + k.W0) * drdn;
+          for (int c = 0; c < 3; c++) {
+            fs_u[0][c + 1] = k.vartheta * drdx[c]; fs_u[c + 1][0] = k.vartheta * drdx[c];
+            fs_t[0][c + 1] = k.T01 * drdx[c] * drdn + k.T02 * n[c]; fs_t[c + 1][0] = k.W1 * drdx[c] * drdn + k.W2 * n[c];
+          }
+          for (int ik = 0; ik < 3; ik++) for (int il = 0; il < 3; il++) {
+            fs_u[il + 1][ik + 1] = k.psi * dkr[il][ik] - k.chi * drdx[il] * drdx[ik];
+            fs_t[il + 1][ik + 1] = (P.T1[1] * k.d1r2 + k.TT1) * drdx[il] * drdx[ik] * drdn + (P.T2[1] * k.d1r2 + k.TT2) * drdn * dkr[il][ik] + k.TT2 * drdx[ik] * n[il]
+                                 + k.TT3 * drdx[il] * n[ik];
+          }
+          for (int j = 0; j < nn; j++) {
+            double fjw = phi[j] * jw;
+            for (int a = 0; a < 4; a++) for (int c = 0; c < 4; c++) { h[(j * 4 + a) * 4 + c] += fs_t[a][c] * fjw; g[(j * 4 + a) * 4 + c] += fs_u[a][c] * fjw; }
+            for (int ik = 0; ik < 3; ik++) for (int il = 0; il < 3; il++)
+              h[(j * 4 + il + 1) * 4 + ik + 1] += P.T2[1] * k.d1r2 * (n[il] * drdx[ik] - n[ik] * drdx[il]) * (phi[j] - phi_i[j]) * jw;
+          }
+          st.pts_singular++;
+          continue;
+        }
         if (p.pot) {   // fbem_bem_harpot3d_sbie_int: bem_harpot3d.f90:905-957 (weakly singular: no CPV part, no line integrals)
           double d1r = 1.0 / r, d1r2 = d1r * d1r;
           double drdn = dot3(rv, N) * d1r / jg;
@@ -1190,10 +1344,14 @@ static void sbie_int(const Element& e, const double* xi_i, const Params& p, cd* 
       double xi_s[2]; staela3d_sbie_int_li(ety, xe, xi_s, x_i, 5, qsl, 1, 16, hli, st);
     }
   }
+  if (p.por) {   // bem_harpor3d.f90:1876-1880: the line-integral term of the solid block
+    for (int il = 0; il < 3; il++) for (int ik = 0; ik < 3; ik++) for (int j = 0; j < nn; j++) h[(j * 4 + il + 1) * 4 + ik + 1] += phi_i[j] * p.por->T2[1] * hli[il][ik];
+    finish_pair(p, e.reverse, nullptr, nn, h, g);
+    return;
+  }
   const cd c_li = p.statics ? cd(p.ctet2) : p.T2[1];   // bem_staela3d.f90:1373 / bem_harela3d.f90:1462-1466
   for (int il = 0; il < 3; il++) for (int ik = 0; ik < 3; ik++) for (int j = 0; j < nn; j++) h[(j * 3 + il) * 3 + ik] += phi_i[j] * c_li * hli[il][ik];
-  for (int i = 0; i < 9 * nn; i++) { h[i] = p.cte_t * h[i]; g[i] = p.cte_u * g[i]; }
-  if (e.reverse) for (int i = 0; i < 9 * nn; i++) h[i] = -h[i];
+  finish_pair(p, e.reverse, nullptr, nn, h, g);
 }
 // fbem_bem_harela3d_sbie_auto: bem_harela3d.f90:1474-1538.  Returns mode: 1..30 regular gln (ps), 100 adaptive, 200 singular.
 static int sbie_auto(const Element& e, const double* x_i, const Params& p, const QsParams& qsp, int ns, cd* h, cd* g, Stats& st, const double* n_i = nullptr) {
@@ -1578,6 +1736,124 @@ void orc_fundamental_solutions_pot(const double* x, const double* n, const doubl
   add_exterior_point(p, x, n, x_i, 1, &one, &one, h, g);
   cd po = p.cte_u * g[0], qo = p.cte_t * h[0];
   p_ri[0] = po.real(); p_ri[1] = po.imag(); q_ri[0] = qo.real(); q_ri[1] = qo.imag();
+}
+// -------------------------------------------------------------------------------------------------------------------------
+// Biot poroelastic BE region: build_lse_mechanics_bem_harpor (src/build_lse_mechanics_bem_harpor.f90: element loop, free-term pass :295-700
+// with c(0,0) = J c_pot, c(1:3,1:3) = Mantic's matrix of the drained skeleton, MCA points J phi/2 and phi/2; collocation loop with
+// fbem_bem_harpor3d_sbie_auto) and the scatter of assemble_bem_harpor_equation.f90:78-110, :140-170 for an ordinary `be` boundary with open-pore
+// conditions: fluid phase ctype(0) 0: tau known / Un unknown, 1: Un known / tau unknown; skeleton ctype(k) 0: u_k known, 1: t_k known.
+// Four equations and four unknowns per node: row[4*n_node], col_p (tau, u1, u2, u3), col_s (Un, t1, t2, t3), ctype[4*n_node].
+// props = lambda(2), mu(2), rho1, rho2, rhoa, R(2), Q(2), b.
+// -------------------------------------------------------------------------------------------------------------------------
+static void por_params_from(const double* props, double omega, PorParams& P) {
+  calculate_parameters_por(cd(props[0], props[1]), cd(props[2], props[3]), props[4], props[5], props[6], cd(props[7], props[8]), cd(props[9], props[10]), props[11], omega, P);
+}
+void* orc_setup_por(int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr, const int* elem_node,
+                    const unsigned char* elem_reversed, int n_colloc, const double* colloc_x, const int* colloc_node,
+                    const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
+                    const int* row, const int* col_p, const int* col_s, const int* ctype, int n_dof,
+                    double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln, double geometric_tolerance) {
+  std::vector<int> r3(3 * n_node, -1), ty3(3 * n_node, 0);
+  Model* m = (Model*)orc_setup(n_node, node_x, n_elem, etype, elem_ptr, elem_node, elem_reversed, n_colloc, colloc_x, colloc_node, colloc_elem, colloc_kn,
+                               colloc_xi, r3.data(), r3.data(), r3.data(), ty3.data(), n_dof, qsi_relative_error, qsi_ns_max, n_precalsets, precalset_gln,
+                               geometric_tolerance);
+  m->nd = 4;
+  m->row.assign(row, row + 4 * n_node); m->col_u.assign(col_p, col_p + 4 * n_node); m->col_t.assign(col_s, col_s + 4 * n_node); m->ctype.assign(ctype, ctype + 4 * n_node);
+  return m;
+}
+static void scatter_por(const Model* m, int e, int sn_col, const cd* hp, const cd* gp, const cd* cvalue, cd* A, cd* b) {
+  int nn = m->elem[e].nn; long long nd = m->n_dof;
+  for (int il = 0; il < 4; il++) {
+    long long row = m->row[4 * sn_col + il];
+    for (int ik = 0; ik < 4; ik++)
+      for (int kn = 0; kn < nn; kn++) {
+        int sn = m->enode[m->eptr[e] + kn];
+        cd hh = hp[(kn * 4 + il) * 4 + ik], gg = gp[(kn * 4 + il) * 4 + ik];
+        switch (m->ctype[4 * sn + ik]) {
+          case 0: { long long col = m->col_t[4 * sn + ik]; A[row + nd * col] = A[row + nd * col] - gg; b[row] = b[row] - hh * cvalue[4 * sn + ik]; break; }
+          case 1: { long long col = m->col_u[4 * sn + ik]; A[row + nd * col] = A[row + nd * col] + hh; b[row] = b[row] + gg * cvalue[4 * sn + ik]; break; }
+        }
+      }
+  }
+}
+int orc_assemble_por(void* hd, double omega, const double* props, const double* cvalue_ri, double* A_ri, double* b_ri, int nthreads, long long* stats_out /*44*/) {
+  Model* m = (Model*)hd; if (m->nd != 4) return 9;
+  PorParams P; por_params_from(props, omega, P);
+  Params p; p.por = &P;
+  const cd* cvalue = (const cd*)cvalue_ri; cd* A = (cd*)A_ri; cd* b = (cd*)b_ri;
+  Stats total; memset(&total, 0, sizeof(total));
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel
+  {
+    Stats st; memset(&st, 0, sizeof(st));
+#pragma omp for schedule(dynamic)
+    for (int e = 0; e < m->n_elem; e++) {
+      const Element& el = m->elem[e];
+      cd hh[144], gg[144];
+      for (int c = 0; c < m->n_colloc; c++) {
+        sbie_auto(el, &m->cx[3 * c], p, m->qsp, m->ns_max, hh, gg, st);
+#pragma omp critical
+        scatter_por(m, e, m->cnode[c], hh, gg, cvalue, A, b);
+      }
+    }
+#pragma omp critical
+    stats_add(total, st);
+  }
+  int err = 0;
+  for (int c = 0; c < m->n_colloc; c++) {
+    if (m->celem[c] < 0) continue;
+    int e = m->celem[c], kn = m->ckn[c], sn = m->cnode[c]; const Element& el = m->elem[e];
+    cd hp[144], gp[144]; for (int i = 0; i < 16 * el.nn; i++) { hp[i] = 0.0; gp[i] = 0.0; }
+    bool mca = (m->cxi[2 * c] != -9.0);
+    if (!mca) {
+      double xi_i[2]; xi_at_node(el.et, kn, xi_i);
+      double cpot = 0.5; cd cela[3][3];
+      for (int a = 0; a < 3; a++) for (int bb = 0; bb < 3; bb++) cela[a][bb] = (a == bb) ? 0.5 : 0.0;
+      if (check_xi1xi2_edge(el.et, xi_i)) {
+        int b0 = m->n2e_ptr[sn], ne = m->n2e_ptr[sn + 1] - b0;
+        std::vector<double> ns(3 * ne), ts(3 * ne);
+        for (int k = 0; k < ne; k++) {
+          const Element& ee = m->elem[m->n2e_elem[b0 + k]]; double n[3], tbp[3], tbm[3];
+          node_normal_tangents(ee.et, ee.x, m->n2e_kn[b0 + k], n, tbp, tbm);
+          for (int cc = 0; cc < 3; cc++) { ns[3 * k + cc] = el.reverse ? -n[cc] : n[cc]; ts[3 * k + cc] = el.reverse ? tbm[cc] : tbp[cc]; }
+        }
+        if (sbie_freeterm(ne, ns.data(), ts.data(), m->geometric_tolerance, P.nu, cela, &cpot)) err = 1;
+      }
+      hp[(kn * 4 + 0) * 4 + 0] += P.J * cpot;
+      for (int il = 0; il < 3; il++) for (int ik = 0; ik < 3; ik++) hp[(kn * 4 + il + 1) * 4 + ik + 1] += cela[il][ik];
+    } else {
+      double phi[9]; phi2d<double>(el.et, &m->cxi[2 * c], phi);
+      for (int j = 0; j < el.nn; j++) {
+        hp[(j * 4 + 0) * 4 + 0] += P.J * 0.5 * phi[j];
+        for (int il = 1; il < 4; il++) hp[(j * 4 + il) * 4 + il] += 0.5 * phi[j];
+      }
+    }
+    scatter_por(m, e, sn, hp, gp, cvalue, A, b);
+  }
+  m->last = total;
+  if (stats_out) {
+    for (int i = 0; i < 33; i++) stats_out[i] = total.pairs_regular[i];
+    stats_out[33] = total.pts_regular; stats_out[34] = total.pairs_adaptive; stats_out[35] = total.leaves; stats_out[36] = total.pts_adaptive;
+    stats_out[37] = total.pairs_singular; stats_out[38] = total.pts_singular; stats_out[39] = total.li_points;
+  }
+  return err;
+}
+// h, g (n, 4, 4) of one (collocation point, element) pair through fbem_bem_harpor3d_sbie_auto; returns the mode
+int orc_pair_por(void* hd, int e, const double* x_i, double omega, const double* props, double* h_ri, double* g_ri) {
+  Model* m = (Model*)hd; PorParams P; por_params_from(props, omega, P); Params p; p.por = &P;
+  Stats st; memset(&st, 0, sizeof(st)); cd hh[144], gg[144];
+  int mode = sbie_auto(m->elem[e], x_i, p, m->qsp, m->ns_max, hh, gg, st);
+  memcpy(h_ri, hh, sizeof(cd) * 16 * m->elem[e].nn); memcpy(g_ri, gg, sizeof(cd) * 16 * m->elem[e].nn);
+  return mode;
+}
+// u*, t* (4 x 4, [l][k]) and the wavenumbers k1, k2, k3, Z, J of the poroelastic fundamental solution
+void orc_fundamental_solutions_por(const double* x, const double* n, const double* x_i, double omega, const double* props, double* u_ri, double* t_ri, double* k_ri /*5 complex*/) {
+  PorParams P; por_params_from(props, omega, P); Params p; p.por = &P;
+  double one = 1.0; cd h[16], g[16]; for (int i = 0; i < 16; i++) { h[i] = 0; g[i] = 0; }
+  add_exterior_point(p, x, n, x_i, 1, &one, &one, h, g);
+  finish_pair(p, false, nullptr, 1, h, g);
+  memcpy(u_ri, g, sizeof(g)); memcpy(t_ri, h, sizeof(h));
+  cd kk[5] = {P.k1, P.k2, P.k3, P.Z, P.J}; memcpy(k_ri, kk, sizeof(kk));
 }
 // pieces of the free-term pass for the multi-region driver (oracle/multiregion.py): unit normal and the two element-boundary tangents at an
 // element node, and the scalar free term of fbem_bem_pot3d_sbie_freeterm

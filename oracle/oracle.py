@@ -317,3 +317,61 @@ def fundamental_solutions_pot(x, n, x_i, omega, fluid):
     po = np.zeros(2); qo = np.zeros(2)
     lib().orc_fundamental_solutions_pot(_p(x), _p(n), _p(x_i), C.c_double(omega), C.c_double(fluid.rho), _p(_ri(fluid.c)), _p(po), _p(qo))
     return complex(po[0], po[1]), complex(qo[0], qo[1])
+
+
+class PorOracle:
+    """Oracle handle for one PoroModel (Biot poroelastic BE region: fbem_bem_harpor3d_* + build_lse_mechanics_bem_harpor + the ordinary-boundary
+    scatter of assemble_bem_harpor_equation, four equations / unknowns per node)."""
+
+    def __init__(self, model):
+        L = lib()
+        L.orc_setup_por.restype = C.c_void_p
+        m = self.m = model
+        assert m.ndof == 4
+        self._keep = [np.ascontiguousarray(a) for a in (
+            m.node_x, m.etype, m.elem_ptr, m.elem_node, m.elem_reversed, m.colloc_x, m.colloc_node, m.colloc_elem,
+            m.colloc_kn, m.colloc_xi, m.row, m.col_u, m.col_t, m.ctype, m.precalset_gln)]
+        k = self._keep
+        self.h = C.c_void_p(L.orc_setup_por(
+            C.c_int(m.n_node), _p(k[0]), C.c_int(m.n_elem), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]),
+            C.c_int(m.n_colloc), _p(k[5]), _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9]),
+            _p(k[10]), _p(k[11]), _p(k[12]), _p(k[13]), C.c_int(m.n_dof),
+            C.c_double(m.qsi_relative_error), C.c_int(m.qsi_ns_max), C.c_int(len(m.precalset_gln)), _p(k[14]),
+            C.c_double(m.geometric_tolerance)))
+
+    def __del__(self):
+        try:
+            lib().orc_free(self.h)
+        except Exception:
+            pass
+
+    def assemble(self, omega, poro, nthreads=0):
+        n = self.m.n_dof
+        A = np.zeros((n, n), dtype=np.complex128, order="F")
+        b = np.zeros(n, dtype=np.complex128)
+        st = np.zeros(44, dtype=np.int64)
+        cv = np.ascontiguousarray(self.m.cvalue)
+        pr = poro.props()
+        err = lib().orc_assemble_por(self.h, C.c_double(omega), _p(pr), _p(cv), _p(A), _p(b), C.c_int(nthreads), _p(st))
+        if err:
+            raise RuntimeError("oracle: poroelastic assembly failed (%d)" % err)
+        stats = {"pairs_regular": {g: int(st[g]) for g in range(33) if st[g]}, "pts_regular": int(st[33]), "pairs_adaptive": int(st[34]),
+                 "leaves": int(st[35]), "pts_adaptive": int(st[36]), "pairs_singular": int(st[37]), "pts_singular": int(st[38])}
+        return A, b, stats
+
+    def pair(self, e, x_i, omega, poro):
+        nn = int(self.m.elem_ptr[e + 1] - self.m.elem_ptr[e])
+        h = np.zeros((nn, 4, 4), dtype=np.complex128); g = np.zeros((nn, 4, 4), dtype=np.complex128)
+        x_i = np.ascontiguousarray(x_i, dtype=np.float64)
+        pr = poro.props()
+        mode = lib().orc_pair_por(self.h, C.c_int(e), _p(x_i), C.c_double(omega), _p(pr), _p(h), _p(g))
+        return h, g, mode
+
+
+def fundamental_solutions_por(x, n, x_i, omega, poro):
+    """u*, t* (4 x 4, [l][k]) of the poroelastic fundamental solution and (k1, k2, k3, Z, J)."""
+    x, n, x_i = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, n, x_i))
+    u = np.zeros((4, 4), dtype=np.complex128); t = np.zeros((4, 4), dtype=np.complex128); k = np.zeros(5, dtype=np.complex128)
+    pr = poro.props()
+    lib().orc_fundamental_solutions_por(_p(x), _p(n), _p(x_i), C.c_double(omega), _p(pr), _p(u), _p(t), _p(k))
+    return u, t, k
