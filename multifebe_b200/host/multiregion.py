@@ -20,16 +20,27 @@ import numpy as np
 from . import shape as sh
 from .model import MCA_BOUNDARY_DELTA, NODAL_XI_MARK
 
-SOLID, FLUID = "solid", "fluid"
+SOLID, FLUID, PORO = "solid", "fluid", "poro"
 
 
 class Region:
     def __init__(self, kind, material, boundaries):
         """kind SOLID | FLUID; material host.Material | host.Fluid; boundaries: signed boundary ids (negative = reversed)."""
-        if kind not in (SOLID, FLUID):
-            raise ValueError("region kind must be 'solid' or 'fluid'")
+        if kind not in (SOLID, FLUID, PORO):
+            raise ValueError("region kind must be 'solid', 'fluid' or 'poro'")
         self.kind, self.material, self.boundaries = kind, material, [int(b) for b in boundaries]
-        self.ndof = 3 if kind == SOLID else 1
+        self.ndof = {SOLID: 3, FLUID: 1, PORO: 4}[kind]
+
+
+def _var_name(kind, k, secondary, side):
+    """Key of the column of component k of a node variable: solid u/t, fluid p/un, poroelastic tau/w (k = 0) and u/t (k = 1..3)."""
+    if kind == FLUID:
+        return ("un%d" if secondary else "p%d") % side
+    if kind == SOLID:
+        return ("t%d%d" if secondary else "u%d%d") % (side, k)
+    if k == 0:
+        return ("w%d" if secondary else "tau%d") % side
+    return ("t%d%d" if secondary else "u%d%d") % (side, k - 1)
 
 
 class RegionView:
@@ -40,9 +51,12 @@ class RegionView:
 
 class MultiRegionModel:
     def __init__(self, mesh, regions, boundary_part, bcs, qsi_relative_error=1e-6, qsi_ns_max=16, precalset_gln=(2, 3, 4, 5, 6, 7, 8, 9),
-                 geometric_tolerance=1e-6):
+                 geometric_tolerance=1e-6, interface_ctype=None):
         """boundary_part {boundary id: part id of the mesh}; bcs {boundary id: (ctypes, values)} for the ORDINARY boundaries (solid: three
-        components, fluid: scalars), 0 = primary variable known, 1 = secondary variable known."""
+        components, fluid: scalars, poroelastic: tau / Un then the three skeleton components), 0 = primary variable known, 1 = secondary
+        variable known.  interface_ctype {boundary id: 0 | 1}: condition of a fluid-poroelastic interface, 0 perfectly permeable (default),
+        1 perfectly impermeable (node%ctype(1,1) of such a boundary)."""
+        self.interface_ctype = dict(interface_ctype or {})
         self.mesh, self.regions = mesh, list(regions)
         nn, ne = len(mesh.nodes), mesh.n_elem
         self.n_node, self.n_elem = nn, ne
@@ -111,11 +125,30 @@ class MultiRegionModel:
                             nd = self.regions[r1].ndof
                             self.row[(v, 1)] = list(range(row, row + nd)); row += nd
                             for k in range(nd):
-                                name = ("t%d" if nd == 3 else "un%d") if self.ctype[b][k] == 0 else ("u%d" if nd == 3 else "p%d")
-                                self.col[(v, (name % 1) + (str(k) if nd == 3 else ""))] = col; col += 1
+                                self.col[(v, _var_name(self.regions[r1].kind, k, self.ctype[b][k] == 0, 1))] = col; col += 1
                             continue
                         k1, k2 = self.regions[r1].kind, self.regions[r2].kind
-                        if k1 == FLUID and k2 == FLUID:
+                        if PORO in (k1, k2):
+                            if {k1, k2} != {FLUID, PORO}:
+                                raise ValueError("boundary %d: of the interfaces of a poroelastic region only fluid-poroelastic ones are built" % b)
+                            imp = self.interface_ctype.get(b, 0) == 1
+                            fe, pe = (1, 2) if k1 == FLUID else (2, 1)           # equation index / variable suffix of the fluid and of the poroelastic side
+                            def number_poro():
+                                nonlocal row, col
+                                self.row[(v, pe)] = list(range(row, row + 4)); row += 4
+                                self.col[(v, "tau%d" % pe)] = col; col += 1
+                                if not imp:
+                                    self.col[(v, "w%d" % pe)] = col; col += 1
+                                for k in range(3):
+                                    self.col[(v, "u%d%d" % (pe, k))] = col; col += 1
+                            def number_fluid():
+                                nonlocal row, col
+                                self.row[(v, fe)] = [row]; row += 1
+                                if imp:
+                                    self.col[(v, "p%d" % fe)] = col; col += 1
+                            # the fluid equation comes first in both orders (:626-700 fluid(1)-poro(2), :990-1037 poro(1)-fluid(2))
+                            number_fluid(); number_poro()
+                        elif k1 == FLUID and k2 == FLUID:
                             self.row[(v, 1)] = [row]; self.row[(v, 2)] = [row + 1]; row += 2
                             self.col[(v, "p1")] = col; self.col[(v, "un1")] = col + 1; col += 2
                         elif k1 == FLUID and k2 == SOLID:
@@ -196,21 +229,22 @@ class MultiRegionModel:
 
     # ---- flat scatter descriptors of one region: the form in which the coupling crosses the C ABI
     def scatter_descriptors(self, kr):
-        """Every case of assemble_bem_harela_equation.f90 / assemble_bem_harpot_equation.f90 reduced to one rule.  For the element instance
-        le of the region, its node j and source component k (solid: k = 0..2 = column index of the 3 x 3 block; fluid: k = 0):
+        """Every case of assemble_bem_har{ela,pot,por}_equation.f90 reduced to one rule.  For the element instance le of the region, its node j
+        and source component k (solid: k = 0..2; fluid: k = 0; poroelastic: k = 0 fluid phase, 1..3 skeleton) = column index of the node block:
             A[row_l, hcol] += hcoef * h(j, l, k)          (hcol == -1: b[row_l] += hcoef * h;  -2: nothing)
-            A[row_l, gcol_t] += gcoef_t * g(j, l, k)      t = 0..2 (same conventions)
-        with g of a fluid element already multiplied by rho omega^2.  Index = (elem_ptr[le] + j) * ndof + k (g targets: * 3 + t).
+            A[row_l, gcol_t] += gcoef_t * g(j, l, k)      t = 0..3 (same conventions)
+        with g of a fluid element already multiplied by rho omega^2.  Index = (elem_ptr[le] + j) * ndof + k (g targets: * 4 + t).
         Returns dict(hcol, hcoef, gcol, gcoef)."""
         v, r = self.views[kr], self.regions[kr]
         nd = r.ndof
         n = int(v.elem_ptr[-1]) * nd
         hcol = np.full(n, -2, dtype=np.int32); hcoef = np.zeros(n, dtype=np.complex128)
-        gcol = np.full((n, 3), -2, dtype=np.int32); gcoef = np.zeros((n, 3), dtype=np.complex128)
+        gcol = np.full((n, 4), -2, dtype=np.int32); gcoef = np.zeros((n, 4), dtype=np.complex128)
         for le in range(v.n_elem):
             bnd = int(v.elem_boundary[le])
             r1, r2 = self.boundary_regions[bnd]
             first = r1 == kr
+            side = 1 if first else 2
             et = int(v.etype[le])
             nodes = v.elem_node[v.elem_ptr[le]:v.elem_ptr[le + 1]]
             for j, sn in enumerate(nodes):
@@ -220,14 +254,45 @@ class MultiRegionModel:
                     q = (int(v.elem_ptr[le]) + j) * nd + k
                     if r2 is None:
                         ct, cv = self.ctype[bnd][k], self.cvalue[bnd][k]
-                        prim = ("u1%d" % k) if nd == 3 else "p1"; sec = ("t1%d" % k) if nd == 3 else "un1"
                         if ct == 0:
-                            hcol[q], hcoef[q] = -1, -cv; gcol[q, 0], gcoef[q, 0] = self.col[(sn, sec)], -1.0
+                            hcol[q], hcoef[q] = -1, -cv; gcol[q, 0], gcoef[q, 0] = self.col[(sn, _var_name(r.kind, k, True, 1))], -1.0
                         else:
-                            hcol[q], hcoef[q] = self.col[(sn, prim)], 1.0; gcol[q, 0], gcoef[q, 0] = -1, cv
+                            hcol[q], hcoef[q] = self.col[(sn, _var_name(r.kind, k, False, 1))], 1.0; gcol[q, 0], gcoef[q, 0] = -1, cv
                         continue
                     k1, k2 = self.regions[r1].kind, self.regions[r2].kind
                     other = k2 if first else k1
+                    sgn = 1.0 if first else -1.0                              # n_fn is outward from region 1: the normal of THIS region is sgn * n_fn
+                    if PORO in (k1, k2):
+                        imp = self.interface_ctype.get(bnd, 0) == 1
+                        po = self.regions[r1 if k1 == PORO else r2].material
+                        ps = 1 if k1 == PORO else 2                           # side index of the poroelastic variables
+                        fs_ = 3 - ps
+                        phi = po.phi
+                        if r.kind == FLUID:                                   # assemble_bem_harpot_equation.f90:183-210 (region 1) / :236-262 (region 2)
+                            if imp:                                           # p active; Un = u . n
+                                hcol[q], hcoef[q] = self.col[(sn, "p%d" % fs_)], 1.0
+                                for t in range(3):
+                                    gcol[q, t], gcoef[q, t] = self.col[(sn, "u%d%d" % (ps, t))], -sgn * n_fn[t]
+                            else:                                             # p = -tau/phi; Un = phi w + (1 - phi) u . n, w seen from the fluid = -w of the poro side
+                                hcol[q], hcoef[q] = self.col[(sn, "tau%d" % ps)], -1.0 / phi
+                                gcol[q, 0], gcoef[q, 0] = self.col[(sn, "w%d" % ps)], phi
+                                for t in range(3):
+                                    gcol[q, 1 + t], gcoef[q, 1 + t] = self.col[(sn, "u%d%d" % (ps, t))], -sgn * (1.0 - phi) * n_fn[t]
+                        elif k == 0:                                          # fluid phase of the poroelastic side (assemble_bem_harpor_equation.f90:583-601 / :755-773)
+                            hcol[q], hcoef[q] = self.col[(sn, "tau%d" % ps)], 1.0
+                            if imp:                                           # Un = u . n
+                                for t in range(3):
+                                    gcol[q, t], gcoef[q, t] = self.col[(sn, "u%d%d" % (ps, t))], -sgn * n_fn[t]
+                            else:
+                                gcol[q, 0], gcoef[q, 0] = self.col[(sn, "w%d" % ps)], -1.0
+                        else:                                                 # skeleton (:603-625 / :776-799)
+                            hcol[q], hcoef[q] = self.col[(sn, "u%d%d" % (ps, k - 1))], 1.0
+                            if imp:                                           # t_k = -(p + tau) n_k
+                                gcol[q, 0], gcoef[q, 0] = self.col[(sn, "p%d" % fs_)], sgn * n_fn[k - 1]
+                                gcol[q, 1], gcoef[q, 1] = self.col[(sn, "tau%d" % ps)], sgn * n_fn[k - 1]
+                            else:                                             # t_k = (1 - phi)/phi tau n_k
+                                gcol[q, 0], gcoef[q, 0] = self.col[(sn, "tau%d" % ps)], -sgn * (1.0 - phi) / phi * n_fn[k - 1]
+                        continue
                     if r.kind == SOLID and other == SOLID:
                         hcol[q], hcoef[q] = self.col[(sn, "u1%d" % k)], 1.0
                         gcol[q, 0], gcoef[q, 0] = self.col[(sn, "t1%d" % k)], (-1.0 if first else 1.0)

@@ -17,7 +17,7 @@ import numpy as np
 
 from . import oracle as orc
 from multifebe_b200.host import shape as sh
-from multifebe_b200.host.multiregion import SOLID, FLUID
+from multifebe_b200.host.multiregion import SOLID, FLUID, PORO, _var_name
 
 
 def _node_normal_tangents(et, xn, node):
@@ -30,7 +30,7 @@ def _node_normal_tangents(et, xn, node):
 class MultiRegionOracle:
     def __init__(self, mrm):
         self.m = mrm
-        self.h = [orc.Oracle(v) if v.kind == SOLID else orc.PotOracle(v) for v in mrm.views]
+        self.h = [orc.Oracle(v) if v.kind == SOLID else (orc.PotOracle(v) if v.kind == FLUID else orc.PorOracle(v)) for v in mrm.views]
         # node -> (local element, local node) incidences per region view
         self.inc = []
         for v in mrm.views:
@@ -47,18 +47,24 @@ class MultiRegionOracle:
         et = int(v.etype[le]); nodes = v.elem_node[v.elem_ptr[le]:v.elem_ptr[le + 1]]
         nn = len(nodes)
         solid = v.kind == SOLID
-        hp = np.zeros((nn, 3, 3), dtype=np.complex128) if solid else np.zeros(nn, dtype=np.complex128)
+        poro = v.kind == PORO
+        if poro:                                                         # c(0,0) = J c_pot, c(1:3,1:3) = Mantic's matrix (build_lse_mechanics_bem_harpor.f90:583-615)
+            mat = v.material
+            J = 1.0 / ((mat.rho2 + mat.rhoa - 1j * mat.b / omega) * omega ** 2)
+        hp = np.zeros((nn, 3, 3), dtype=np.complex128) if solid else (np.zeros((nn, 4, 4), dtype=np.complex128) if poro else np.zeros(nn, dtype=np.complex128))
         if v.colloc_xi[c, 0] != -9.0:                                    # MCA point: 1/2 phi_j(xi_i)
             phi = sh.phi(et, v.colloc_xi[c])
             for j in range(nn):
                 if solid:
                     hp[j] += 0.5 * phi[j] * np.eye(3)
+                elif poro:
+                    hp[j] += 0.5 * phi[j] * np.diag([J, 1.0, 1.0, 1.0])
                 else:
                     hp[j] += 0.5 * phi[j]
             return le, hp
         on_edge = not (et == sh.QUAD9 and kn == 8)                       # only the centre node of quad9 lies inside its element
         if not on_edge:
-            cfree = 0.5 * np.eye(3) if solid else 0.5
+            cfree = 0.5 * np.eye(3) if solid else (0.5 * np.diag([J, 1.0, 1.0, 1.0]) if poro else 0.5)
         else:
             rev = bool(v.elem_reversed[le])
             ns, ts = [], []
@@ -68,6 +74,12 @@ class MultiRegionOracle:
                 ns.append(-n if rev else n); ts.append(tbm if rev else tbp)
             if solid:
                 cfree, err = orc.freeterm(np.array(ns), np.array(ts), v.material.nu, self.m.geometric_tolerance)
+            elif poro:
+                cela, err = orc.freeterm(np.array(ns), np.array(ts), mat.nu, self.m.geometric_tolerance)
+                cp = C.c_double(0.0)
+                n_ = np.ascontiguousarray(ns, dtype=np.float64); t_ = np.ascontiguousarray(ts, dtype=np.float64)
+                err = err or orc.lib().orc_freeterm_pot(C.c_int(len(ns)), orc._p(n_), orc._p(t_), C.c_double(self.m.geometric_tolerance), C.byref(cp))
+                cfree = np.zeros((4, 4), dtype=np.complex128); cfree[0, 0] = J * cp.value; cfree[1:, 1:] = cela
             else:
                 cp = C.c_double(0.0)
                 n_ = np.ascontiguousarray(ns, dtype=np.float64); t_ = np.ascontiguousarray(ts, dtype=np.float64)
@@ -91,6 +103,18 @@ class MultiRegionOracle:
         solid = v.kind == SOLID
         for kn, sn in enumerate(nodes):
             sn = int(sn)
+            if v.kind == PORO and r2 is None:                            # assemble_bem_harpor_equation.f90:78-110, :140-170 (open-pore conditions 0 / 1)
+                ct, cv = m.ctype[bnd], m.cvalue[bnd]
+                for il in range(4):
+                    for ik in range(4):
+                        if ct[ik] == 0:
+                            A[rows[il], m.col[(sn, _var_name(PORO, ik, True, 1))]] -= g[kn, il, ik]; b[rows[il]] -= h[kn, il, ik] * cv[ik]
+                        else:
+                            A[rows[il], m.col[(sn, _var_name(PORO, ik, False, 1))]] += h[kn, il, ik]; b[rows[il]] += g[kn, il, ik] * cv[ik]
+                continue
+            if r2 is not None and PORO in (m.regions[r1].kind, m.regions[r2].kind):
+                self._scatter_fluid_poro(kr, kn, sn, bnd, rows, first, sh.unit_normal(et, v.node_x[nodes], sh.XI_NODES[et][kn]), h, g, A)
+                continue
             if r2 is None:                                                # ordinary boundary
                 ct, cv = m.ctype[bnd], m.cvalue[bnd]
                 if solid:
@@ -136,6 +160,71 @@ class MultiRegionOracle:
                     for ik in range(3):
                         A[rows[0], m.col[(sn, "u1%d" % ik)]] += g[kn] * n_fn[ik]
 
+    def _scatter_fluid_poro(self, kr, kn, sn, bnd, rows, first, n_fn, h, g, A):
+        """be-be boundary between an inviscid fluid and a poroelastic medium, perfectly permeable (ctype 0) or impermeable (1), written out as
+        the reference does for each side and each order: assemble_bem_harpot_equation.f90:183-210 (fluid = region 1), :236-262 (fluid = region 2);
+        assemble_bem_harpor_equation.f90:577-626 (poroelastic = region 1), :749-801 (poroelastic = region 2).  n_fn = normal of region 1."""
+        m = self.m
+        v = m.views[kr]
+        r1, r2 = m.boundary_regions[bnd]
+        imp = m.interface_ctype.get(bnd, 0) == 1
+        poro_first = m.regions[r1].kind == PORO
+        phi = m.regions[r1 if poro_first else r2].material.phi
+        col = m.col
+        if v.kind == FLUID:
+            row = rows[0]
+            if first:                                                     # INVISCID FLUID (1) - POROELASTIC MEDIA (2)
+                if not imp:
+                    A[row, col[(sn, "tau2")]] -= h[kn] / phi
+                    A[row, col[(sn, "w2")]] += g[kn] * phi
+                    for ik in range(3):
+                        A[row, col[(sn, "u2%d" % ik)]] -= g[kn] * (1.0 - phi) * n_fn[ik]
+                else:
+                    A[row, col[(sn, "p1")]] += h[kn]
+                    for ik in range(3):
+                        A[row, col[(sn, "u2%d" % ik)]] -= g[kn] * n_fn[ik]
+            else:                                                         # POROELASTIC MEDIA (1) - INVISCID FLUID (2), seen from the fluid
+                if not imp:
+                    A[row, col[(sn, "tau1")]] -= h[kn] / phi
+                    A[row, col[(sn, "w1")]] += g[kn] * phi
+                    for ik in range(3):
+                        A[row, col[(sn, "u1%d" % ik)]] += g[kn] * (1.0 - phi) * n_fn[ik]
+                else:
+                    A[row, col[(sn, "p2")]] += h[kn]
+                    for ik in range(3):
+                        A[row, col[(sn, "u1%d" % ik)]] += g[kn] * n_fn[ik]
+            return
+        for il in range(4):
+            row = rows[il]
+            if first:                                                     # POROELASTIC MEDIA (1) - INVISCID FLUID (2)
+                A[row, col[(sn, "tau1")]] += h[kn, il, 0]
+                if not imp:
+                    A[row, col[(sn, "w1")]] -= g[kn, il, 0]
+                else:
+                    for ik in range(3):
+                        A[row, col[(sn, "u1%d" % ik)]] -= g[kn, il, 0] * n_fn[ik]
+                for ik in range(3):
+                    A[row, col[(sn, "u1%d" % ik)]] += h[kn, il, ik + 1]
+                    if not imp:
+                        A[row, col[(sn, "tau1")]] -= g[kn, il, ik + 1] * (1.0 - phi) / phi * n_fn[ik]
+                    else:
+                        A[row, col[(sn, "p2")]] += g[kn, il, ik + 1] * n_fn[ik]
+                        A[row, col[(sn, "tau1")]] += g[kn, il, ik + 1] * n_fn[ik]
+            else:                                                         # INVISCID FLUID (1) - POROELASTIC MEDIA (2), seen from the poroelastic medium
+                A[row, col[(sn, "tau2")]] += h[kn, il, 0]
+                if not imp:
+                    A[row, col[(sn, "w2")]] -= g[kn, il, 0]
+                else:
+                    for ik in range(3):
+                        A[row, col[(sn, "u2%d" % ik)]] += g[kn, il, 0] * n_fn[ik]
+                for ik in range(3):
+                    A[row, col[(sn, "u2%d" % ik)]] += h[kn, il, ik + 1]
+                    if not imp:
+                        A[row, col[(sn, "tau2")]] += g[kn, il, ik + 1] * (1.0 - phi) / phi * n_fn[ik]
+                    else:
+                        A[row, col[(sn, "p1")]] -= g[kn, il, ik + 1] * n_fn[ik]
+                        A[row, col[(sn, "tau2")]] -= g[kn, il, ik + 1] * n_fn[ik]
+
     def _scatter_flat(self, kr, le, sn_col, eq, h, g, A, b, D):
         """The same scatter driven by the flat descriptors of MultiRegionModel.scatter_descriptors (what a device kernel consumes)."""
         v = self.m.views[kr]
@@ -146,13 +235,13 @@ class MultiRegionOracle:
             for k in range(nd):
                 q = (int(v.elem_ptr[le]) + j) * nd + k
                 for il, row in enumerate(rows):
-                    hv = h[j, il, k] if nd == 3 else h[j]
-                    gv = g[j, il, k] if nd == 3 else g[j]
+                    hv = h[j, il, k] if nd > 1 else h[j]
+                    gv = g[j, il, k] if nd > 1 else g[j]
                     if D["hcol"][q] >= 0:
                         A[row, D["hcol"][q]] += D["hcoef"][q] * hv
                     elif D["hcol"][q] == -1:
                         b[row] += D["hcoef"][q] * hv
-                    for t in range(3):
+                    for t in range(4):
                         c = D["gcol"][q, t]
                         if c >= 0:
                             A[row, c] += D["gcoef"][q, t] * gv
@@ -174,6 +263,8 @@ class MultiRegionOracle:
                 for le in range(v.n_elem):
                     if v.kind == SOLID:
                         h, g, _, _ = hd.pair(le, x_i, omega, mat)
+                    elif v.kind == PORO:
+                        h, g, _ = hd.pair(le, x_i, omega, mat)
                     else:
                         h, g, _ = hd.pair(le, x_i, omega, mat)
                         g = g * d1J                                       # the flux unknown is Un = (dp/dn)/(rho omega^2)

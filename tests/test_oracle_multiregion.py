@@ -190,3 +190,117 @@ def test_flat_scatter_descriptors_reproduce_every_case(kinds):
     A2, b2 = o.assemble(1.7, flat=True)
     assert np.abs(A1 - A2).max() <= 1e-15 * np.abs(A1).max() and np.abs(b1 - b2).max() <= 1e-15 * max(np.abs(b1).max(), 1e-300)
     assert np.abs(b1).max() > 0
+
+
+# ---- poroelastic regions and the fluid-poroelastic interface (BASELINE config 4: harpor + harpot coupling) -------------------------------
+from multifebe_b200.host import Poro, PoroModel
+from multifebe_b200.host.multiregion import PORO
+
+PO = Poro(rhof=1.0, rhos=2.2, lam=1.2, mu=1.0, xi=0.02, phi=0.35, rhoa=0.15, R=0.8, Q=0.5, b=0.4)
+FL = Fluid(1.1, 1.3, 0.01)
+
+
+def poro_bcs_side(parts):
+    """sliding impermeable lateral faces of a poroelastic box: Un = 0, normal skeleton displacement 0, shear tractions 0."""
+    out = {}
+    for p_ in parts:
+        free = 2 if p_ in (3, 4, 13, 14) else 3
+        ct = [1, 1, 1, 1]; ct[free] = 0
+        out[p_] = (ct, [0, 0, 0, 0])
+    return out
+
+
+def test_one_poroelastic_region_through_the_multiregion_driver_equals_the_single_region_oracle():
+    mesh = cube_mesh(1, shape.QUAD9)
+    bcs = {1: ([1, 0, 0, 0], [0, 0, 0, 0]), 2: ([0, 1, 1, 1], [0, 1.0, 0, 0])}
+    bcs.update(poro_bcs_side((3, 4, 5, 6)))
+    md = PoroModel(mesh, bcs)
+    A0, b0, _ = orc.PorOracle(md).assemble(1.9, PO)
+    mrm = MultiRegionModel(mesh, [Region(PORO, PO, [1, 2, 3, 4, 5, 6])], {b: b for b in range(1, 7)}, bcs)
+    assert mrm.n_dof == md.n_dof
+    A1, b1 = MultiRegionOracle(mrm).assemble(1.9)
+    assert np.abs(A1 - A0).max() < 1e-13 * np.abs(A0).max() and np.abs(b1 - b0).max() < 1e-13 * np.abs(b0).max()
+    A2, b2 = MultiRegionOracle(mrm).assemble(1.9, flat=True)
+    assert np.abs(A2 - A1).max() <= 1e-15 * np.abs(A1).max() and np.abs(b2 - b1).max() <= 1e-15 * np.abs(b1).max()
+
+
+def fluid_poro_1d(omega, fl, po, xs, fluid_first, imp, P=1.0):
+    """Exact 1D column: an inviscid fluid layer against a saturated poroelastic layer.  Fluid end: p = P; poroelastic end: fixed and impermeable
+    (u = U = 0).  Interface: normal total stress continuous (sigma_s + tau = -p); permeable: p = -tau/phi and U_f = phi U + (1 - phi) u;
+    impermeable: U = u = U_f.  Unknowns: fluid (a, b) of p = a e^{-ikx} + b e^{ikx}, poroelastic (a1, b1, a2, b2)."""
+    M = np.array([[po.lam + 2 * po.mu + po.Q ** 2 / po.R, po.Q], [po.Q, po.R]])
+    rh11 = po.rho1 + po.rhoa - 1j * po.b / omega; rh12 = -po.rhoa + 1j * po.b / omega; rh22 = po.rho2 + po.rhoa - 1j * po.b / omega
+    k2, Y = np.linalg.eig(np.linalg.solve(M, omega ** 2 * np.array([[rh11, rh12], [rh12, rh22]])))
+    ks = np.sqrt(k2); ks = np.where(ks.real < 0, -ks, ks)
+    kf = omega / fl.c
+
+    def poro_rows(x):       # u, U, sigma_s, tau as rows over (a1, b1, a2, b2)
+        e = [np.exp(-1j * ks[0] * x), np.exp(1j * ks[0] * x), np.exp(-1j * ks[1] * x), np.exp(1j * ks[1] * x)]
+        d = [-1j * ks[0] * e[0], 1j * ks[0] * e[1], -1j * ks[1] * e[2], 1j * ks[1] * e[3]]
+        yv = [Y[:, 0], Y[:, 0], Y[:, 1], Y[:, 1]]
+        u = np.array([e[q] * yv[q][0] for q in range(4)]); U = np.array([e[q] * yv[q][1] for q in range(4)])
+        du = np.array([d[q] * yv[q][0] for q in range(4)]); dU = np.array([d[q] * yv[q][1] for q in range(4)])
+        return u, U, M[0, 0] * du + M[0, 1] * dU, M[1, 0] * du + M[1, 1] * dU
+
+    def fluid_rows(x):      # p, U_f = p'/(rho w^2) over (a, b)
+        e = np.array([np.exp(-1j * kf * x), np.exp(1j * kf * x)])
+        return e, np.array([-1j * kf, 1j * kf]) * e / (fl.rho * omega ** 2)
+    x_f, x_p = (0.0, 1.0) if fluid_first else (1.0, 0.0)
+    S = np.zeros((6, 6), dtype=complex); r = np.zeros(6, dtype=complex)
+    S[0, :2] = fluid_rows(x_f)[0]; r[0] = P
+    u, U, sg, ta = poro_rows(x_p); S[1, 2:] = u; S[2, 2:] = U
+    u, U, sg, ta = poro_rows(xs); pf, Uf = fluid_rows(xs)
+    S[3, :2] = pf; S[3, 2:] = sg + ta                       # sigma_s + tau + p = 0
+    if imp:
+        S[4, 2:] = U - u; S[5, :2] = Uf; S[5, 2:] = -u
+    else:
+        S[4, :2] = pf; S[4, 2:] = ta / po.phi               # p + tau/phi = 0
+        S[5, :2] = Uf; S[5, 2:] = -(po.phi * U + (1 - po.phi) * u)
+    c = np.linalg.solve(S, r)
+    return (lambda x: [row @ c[:2] for row in fluid_rows(x)]), (lambda x: [row @ c[2:] for row in poro_rows(x)])
+
+
+@pytest.mark.parametrize("fluid_first", [True, False])
+@pytest.mark.parametrize("imp", [False, True])
+def test_fluid_against_poroelastic_column(fluid_first, imp):
+    omega, xs = 2.0, 0.45
+    fb = fluid_bcs(1.0)
+    pend = ([1, 0, 0, 0], [0, 0, 0, 0])                      # poroelastic end: Un = 0, u = 0
+    if fluid_first:
+        regs = [Region(FLUID, FL, [1, 3, 4, 5, 6, 7]), Region(PORO, PO, [-7, 2, 13, 14, 15, 16])]
+        bcs = {1: (0, 1.0), 2: pend}; bcs.update({q: fb[q] for q in LAT1}); bcs.update(poro_bcs_side(LAT2))
+    else:
+        regs = [Region(PORO, PO, [1, 3, 4, 5, 6, 7]), Region(FLUID, FL, [-7, 2, 13, 14, 15, 16])]
+        bcs = {2: (0, 1.0), 1: pend}; bcs.update({q: fb[q] for q in LAT2}); bcs.update(poro_bcs_side(LAT1))
+    mrm = MultiRegionModel(two_box_mesh(2, shape.QUAD9, xs=xs), regs, BPART, bcs, interface_ctype={7: 1 if imp else 0})
+    o = MultiRegionOracle(mrm)
+    A, b = o.assemble(omega)
+    A2, b2 = o.assemble(omega, flat=True)
+    assert np.abs(A - A2).max() <= 1e-15 * np.abs(A).max() and np.abs(b - b2).max() <= 1e-15 * np.abs(b).max()
+    x = np.linalg.solve(A, b)
+    fluid, poro = fluid_poro_1d(omega, FL, PO, xs, fluid_first, imp)
+    kf_, kp_ = (0, 1) if fluid_first else (1, 0)
+    # pressure on the rigid walls of the fluid box, skeleton displacement and tau on the sliding sides of the poroelastic box
+    fl_side = LAT1 if fluid_first else LAT2; po_side = LAT2 if fluid_first else LAT1
+    errs = []
+    for bnd in fl_side:
+        for v in sorted(set(int(n) for e in mrm.elems_of_boundary[bnd] for n in mrm.mesh.conn[e])):
+            errs.append(abs(x[mrm.col[(v, "p1")]] - fluid(mrm.node_x[v, 0])[0]))
+    assert max(errs) < 1e-2                                   # |p| = O(1)
+    eu, et_ = [], []
+    for bnd in po_side:
+        for v in sorted(set(int(n) for e in mrm.elems_of_boundary[bnd] for n in mrm.mesh.conn[e])):
+            u, U, sg, ta = poro(mrm.node_x[v, 0])
+            eu.append(abs(x[mrm.col[(v, "u10")]] - u)); et_.append(abs(x[mrm.col[(v, "tau1")]] - ta))
+    uref = max(abs(poro(t)[0]) for t in np.linspace(0, 1, 11)); tref = max(abs(poro(t)[3]) for t in np.linspace(0, 1, 11))
+    assert max(eu) < 1e-2 * uref and max(et_) < 1e-2 * tref
+    # interface unknowns: tau and u on the poroelastic side; p (impermeable) or the relative fluid displacement w (permeable)
+    side = 2 if fluid_first else 1
+    u, U, sg, ta = poro(xs)
+    for v in sorted(set(int(n) for e in mrm.elems_of_boundary[7] for n in mrm.mesh.conn[e])):
+        assert abs(x[mrm.col[(v, "tau%d" % side)]] - ta) < 2e-2 * tref and abs(x[mrm.col[(v, "u%d0" % side)]] - u) < 2e-2 * uref
+        if imp:
+            assert abs(x[mrm.col[(v, "p%d" % (3 - side))]] - fluid(xs)[0]) < 2e-2
+        else:
+            n_out = -1.0 if fluid_first else 1.0              # outward normal of the poroelastic region at the interface, x component
+            assert abs(x[mrm.col[(v, "w%d" % side)]] - n_out * U) < 3e-2 * max(abs(U), uref)
