@@ -190,6 +190,30 @@ int mfb_harpot3d_setup(mfb_ctx* ctx, int n_node, const double* node_x, int n_ele
 int mfb_harpot3d_assemble(mfb_problem* problem, double omega, double rho, const mfb_z* c, const mfb_z* cvalue, mfb_z* A, mfb_z* b);
 int mfb_harpot3d_solve_frequency(mfb_problem* problem, double omega, double rho, const mfb_z* c, const mfb_z* cvalue, mfb_z* x);
 
+/* ---- Biot poroelastic BE region ------------------------------------------------------------
+ * One poroelastic region with ordinary `be` boundaries: FOUR equations and unknowns per node, component 0 = fluid phase (fluid equivalent
+ * stress tau | fluid normal displacement Un), components 1..3 = solid skeleton (u_k | t_k).
+ *   mfb_harpor3d_setup     the arguments of mfb_harela3d_setup with four entries per node: row[4*n_node] = node%row(0:3,1), col_p = node%col(0:3,1)
+ *                          (tau, u_k), col_s = node%col(4:7,1) (Un, t_k), ctype[4*n_node] = node%ctype(0:3,1): the open-pore conditions 0 (tau / u_k
+ *                          known) and 1 (Un / t_k known) of assemble_bem_harpor_equation.f90:78-110, :140-170 (the close-pore types 2..7 are refused).
+ *   mfb_harpor3d_assemble  == `A_c=0; b_c=0` + build_lse_mechanics_bem_harpor(kf,kr) (src/build_lse_mechanics_bem_harpor.f90) with the kernels
+ *                          of fbem_bem_harpor3d_sbie_ext_pre / _ext_adp / _int (lib/fbem/src/bem_harpor3d.f90:906-1890).  lambda, mu (drained, with
+ *                          damping) = region%property_c(3:4), rho1, rho2 = property_r(13:14), rhoa = property_r(9), R, Q = property_c(10:11),
+ *                          b = property_r(12); cvalue[4*n_node] = node%cvalue_c(0:3,1,1).
+ *   mfb_harpor3d_solve_frequency  assemble + zgetrf + zgetrs on the device.
+ * STATUS: compiled for sm_100a, not yet executed on hardware (written after the round's GPU budget was spent; parity suite:
+ * tests/test_gpu_poroelastic.py, MFB_RUN_UNVALIDATED=1). */
+int mfb_harpor3d_setup(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
+                       const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
+                       const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
+                       const int* row, const int* col_p, const int* col_s, const int* ctype, int n_dof,
+                       double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
+                       double geometric_tolerance, mfb_problem** problem);
+int mfb_harpor3d_assemble(mfb_problem* problem, double omega, const mfb_z* lambda, const mfb_z* mu, double rho1, double rho2, double rhoa,
+                          const mfb_z* R, const mfb_z* Q, double b, const mfb_z* cvalue, mfb_z* A, mfb_z* bvec);
+int mfb_harpor3d_solve_frequency(mfb_problem* problem, double omega, const mfb_z* lambda, const mfb_z* mu, double rho1, double rho2, double rhoa,
+                                 const mfb_z* R, const mfb_z* Q, double b, const mfb_z* cvalue, mfb_z* x);
+
 /* ---- One frequency over several GPUs (shard 2) --------------------------------------------------
  * One process per GPU, every process holds the same mfb_problem (mesh + plan replicated).  Rank r assembles a contiguous
  * run of collocation-row blocks (the rows of build_lse_mechanics_bem_harela's kn_col loop it owns, all columns), the row

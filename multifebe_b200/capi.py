@@ -131,7 +131,13 @@ class Problem:
         self.h = C.c_void_p()
         cn = getattr(m, "colloc_n", None)
         self.ndof = int(getattr(m, "ndof", 3))
-        if self.ndof == 1:   # inviscid fluid region: one equation / unknown per node (col_u = column of p, col_t = column of Un)
+        if self.ndof == 4:   # poroelastic region: four equations / unknowns per node (col_u = columns of tau, u_k; col_t = columns of Un, t_k)
+            _check(lib().mfb_harpor3d_setup(
+                ctx.h, C.c_int(m.n_node), _p(k[0]), C.c_int(m.n_elem), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]),
+                C.c_int(m.n_colloc), _p(k[5]), _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9]), _p(k[10]), _p(k[11]), _p(k[12]), _p(k[13]),
+                C.c_int(m.n_dof), C.c_double(m.qsi_relative_error), C.c_int(m.qsi_ns_max), C.c_int(len(m.precalset_gln)), _p(k[14]),
+                C.c_double(m.geometric_tolerance), C.byref(self.h)))
+        elif self.ndof == 1:   # inviscid fluid region: one equation / unknown per node (col_u = column of p, col_t = column of Un)
             _check(lib().mfb_harpot3d_setup(
                 ctx.h, C.c_int(m.n_node), _p(k[0]), C.c_int(m.n_elem), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]),
                 C.c_int(m.n_colloc), _p(k[5]), _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9]), _p(k[10]), _p(k[11]), _p(k[12]), _p(k[13]),
@@ -184,6 +190,25 @@ class Problem:
         x = np.zeros(self.m.n_dof, dtype=np.complex128) if host else None
         _check(lib().mfb_harpot3d_solve_frequency(self.h, C.c_double(omega), C.c_double(fluid.rho), _p(_z(fluid.c)),
                                                   _p(self._cv) if host else None, _p(x) if host else None))
+        return x
+
+    # ---- seam 1 for a poroelastic region: build_lse_mechanics_bem_harpor(kf,kr) (src/build_lse_mechanics_bem_harpor.f90:23) ----
+    def _por_args(self, omega, po):
+        return (C.c_double(omega), _p(_z(po.lam)), _p(_z(po.mu)), C.c_double(po.rho1), C.c_double(po.rho2), C.c_double(po.rhoa), _p(_z(po.R)), _p(_z(po.Q)),
+                C.c_double(po.b))
+
+    def build_lse_mechanics_bem_harpor(self, omega, poro, want_host=True):
+        n = self.m.n_dof
+        A = b = None
+        if want_host:
+            A = np.zeros((n, n), dtype=np.complex128, order="F")
+            b = np.zeros(n, dtype=np.complex128)
+        _check(lib().mfb_harpor3d_assemble(self.h, *self._por_args(omega, poro), _p(self._cv), _p(A) if want_host else None, _p(b) if want_host else None))
+        return A, b
+
+    def solve_frequency_poro(self, omega, poro, host=True):
+        x = np.zeros(self.m.n_dof, dtype=np.complex128) if host else None
+        _check(lib().mfb_harpor3d_solve_frequency(self.h, *self._por_args(omega, poro), _p(self._cv) if host else None, _p(x) if host else None))
         return x
 
     # ---- seam 2: solve_lse_c(n_dof,A,ipiv,...,n_rhs,b,factorize,scaling=F,condition=F,refine=F) ----

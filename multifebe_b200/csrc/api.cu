@@ -4,6 +4,7 @@
 #include "../../include/mfb.h"
 #include "assembly.cuh"
 #include "potential.cuh"
+#include "poro.cuh"
 #include "lu.cuh"
 #include "dist.cuh"
 #include "plan_host.h"
@@ -66,6 +67,7 @@ struct mfb_problem {
   std::vector<GroupHost> groups;
   std::vector<void*> owned;
   DevColloc colloc; DevSystem sys; DevClassify cls; DevFreeTerm ft;
+  DevFreeTerm ft0;                     // poroelastic regions: the fluid-phase free terms, whose multiplier is J (ft: skeleton, multiplier F)
   unsigned char* plan;
   double* d_cvalue;
   int* d_ipiv; int* d_perm; std::vector<int> h_ipiv;
@@ -209,7 +211,7 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
     if (etype[e] < MFB_TRI3 || etype[e] > MFB_QUAD9) return fail(MFB_ERR_UNSUPPORTED, "mfb_harela3d_setup: element type must be tri3/tri6/quad4/quad8/quad9");
     if (elem_ptr[e + 1] - elem_ptr[e] != mfbh::nodes_of(etype[e])) return fail(MFB_ERR_ARG, "mfb_harela3d_setup: elem_ptr inconsistent with etype");
   }
-  if (ndof != 1 && ndof != 3) return fail(MFB_ERR_ARG, "setup: ndof must be 3 (elastic solid) or 1 (inviscid fluid)");
+  if (ndof != 1 && ndof != 3 && ndof != 4) return fail(MFB_ERR_ARG, "setup: ndof must be 3 (elastic solid), 1 (inviscid fluid) or 4 (poroelastic medium)");
   for (int i = 0; i < ndof * n_node; i++)
     if (ctype[i] != 0 && ctype[i] != 1) return fail(MFB_ERR_UNSUPPORTED, "mfb_harela3d_setup: only ctype 0 (u / p known) and 1 (t / Un known) are supported");
   double t_host0 = now_ms();
@@ -331,7 +333,7 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
   const int n_tiles = (int)t_row0.size();
   const int ldp = 32 * n_tiles; p->ldp = ldp;
   p->cpos_of_colloc.assign(n_colloc, 0);
-  std::vector<double> h_cx(3 * (size_t)ldp, 0.0); std::vector<int> h_crow(3 * (size_t)ldp, -1);
+  std::vector<double> h_cx(3 * (size_t)ldp, 0.0); std::vector<int> h_crow((size_t)std::max(3, ndof) * ldp, -1);   // a poroelastic node has four rows
   for (int q = 0; q < ldp; q++) {
     const int c = lane_colloc[q];
     if (c < 0) continue;
@@ -398,7 +400,7 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
         for (int k = 0; k < ndof; k++) {
           const int ct0 = ctype[ndof * elem_node[elem_ptr[e]] + k];
           for (int j = 1; j < g.nn; j++) if (ctype[ndof * elem_node[elem_ptr[e] + j] + k] != ct0) info &= ~8u;
-          if (ct0 == 1) info |= (1u << k);
+          if (ct0 == 1 && k < 3) info |= (1u << k);   // bits 0-2 only (bit 3 is the uniform-kinds flag; the class bits serve the elastic K1 kernel)
         }
         h_info[i] = (unsigned char)info;
       }
@@ -541,6 +543,7 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
     std::vector<int> n2e(cnt[n_node]), n2k(cnt[n_node]), pos(cnt.begin(), cnt.end() - 1);
     for (int e = 0; e < n_elem; e++) for (int k = elem_ptr[e]; k < elem_ptr[e + 1]; k++) { int nd = elem_node[k]; n2e[pos[nd]] = e; n2k[pos[nd]] = k - elem_ptr[e]; pos[nd]++; }
     std::vector<int> f_cpos, f_slot, f_jk, f_l; std::vector<double> f_val;
+    std::vector<int> f0_cpos, f0_slot, f0_jk, f0_l; std::vector<double> f0_val;      // poroelastic fluid phase: value = beta * J
     for (int c = 0; c < n_colloc; c++) {
       int e = colloc_elem[c], kn = colloc_kn[c], sn = colloc_node[c];
       if (e == -1) continue;   // a point off the boundary (interior point of the region): Somigliana's identity has no free term there
@@ -557,7 +560,13 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
           for (int k = 0; k < ne; k++) { const mfbh::Elem& ee = p->elems[n2e[b0 + k]]; mfbh::node_normal_tangent(ee.et, ee.x, n2k[b0 + k], el.reversed, &ns[3 * k], &ts[3 * k]); }
           if (mfbh::mantic_terms(ne, ns.data(), ts.data(), geometric_tolerance, &cp, sum_b)) { mfb_problem_free(p); return fail(2, "mfb_harela3d_setup: the normals/tangents configuration is not valid (free term)"); }
         }
-        if (ndof == 1) {   // scalar free term c = cp (fbem_bem_pot3d_sbie_freeterm == the isotropic part of Mantic's matrix; build_lse_mechanics_bem_harpot.f90:533,549)
+        if (ndof == 4) {   // c(0,0) = J c_pot, c(1:3,1:3) = Mantic's matrix of the drained skeleton (build_lse_mechanics_bem_harpor.f90:583-615)
+          f0_cpos.push_back(cpos); f0_slot.push_back(slot); f0_jk.push_back(kn * 4); f0_l.push_back(0); f0_val.push_back(0.0); f0_val.push_back(cp);
+          for (int l = 0; l < 3; l++) for (int k = 0; k < 3; k++) {
+            f_cpos.push_back(cpos); f_slot.push_back(slot); f_jk.push_back(kn * 4 + k + 1); f_l.push_back(l + 1);
+            f_val.push_back(l == k ? cp : 0.0); f_val.push_back(sum_b[3 * l + k]);
+          }
+        } else if (ndof == 1) {   // scalar free term c = cp (fbem_bem_pot3d_sbie_freeterm == the isotropic part of Mantic's matrix; build_lse_mechanics_bem_harpot.f90:533,549)
           f_cpos.push_back(cpos); f_slot.push_back(slot); f_jk.push_back(kn); f_l.push_back(0);
           f_val.push_back(cp); f_val.push_back(0.0);
         } else
@@ -567,6 +576,12 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
         }
       } else {
         double phi[9]; mfbh::shape_values(el.et, &colloc_xi[2 * c], phi);
+        if (ndof == 4) {   // hp(:,0,0) += J phi/2, hp(:,l,l) += phi/2 (build_lse_mechanics_bem_harpor.f90:366-370)
+          for (int j = 0; j < el.nn; j++) {
+            f0_cpos.push_back(cpos); f0_slot.push_back(slot); f0_jk.push_back(j * 4); f0_l.push_back(0); f0_val.push_back(0.0); f0_val.push_back(0.5 * phi[j]);
+            for (int l = 1; l < 4; l++) { f_cpos.push_back(cpos); f_slot.push_back(slot); f_jk.push_back(j * 4 + l); f_l.push_back(l); f_val.push_back(0.5 * phi[j]); f_val.push_back(0.0); }
+          }
+        } else
         for (int l = 0; l < ndof; l++) for (int j = 0; j < el.nn; j++) {   // hp(:)=hp(:)+0.5d0*pphi_i (build_lse_mechanics_bem_harpot.f90:573)
           f_cpos.push_back(cpos); f_slot.push_back(slot); f_jk.push_back(j * ndof + l); f_l.push_back(l);
           f_val.push_back(0.5 * phi[j]); f_val.push_back(0.0);
@@ -577,6 +592,11 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
     UP(p->owned, f_cpos, &d1); UP(p->owned, f_slot, &d2); UP(p->owned, f_jk, &d3); UP(p->owned, f_l, &d4); UP(p->owned, f_val, &d5);
     p->ft.n = (int)f_cpos.size(); p->ft.cpos = d1; p->ft.slot = d2; p->ft.jk = d3; p->ft.l = d4; p->ft.val = d5;
     p->ft.slot_off = d_slot_off; p->ft.ecol = d_ecol; p->ft.ekind = d_ekind; p->ft.ecv = d_ecv;
+    {
+      int *e1, *e2, *e3, *e4; double* e5;
+      UP(p->owned, f0_cpos, &e1); UP(p->owned, f0_slot, &e2); UP(p->owned, f0_jk, &e3); UP(p->owned, f0_l, &e4); UP(p->owned, f0_val, &e5);
+      p->ft0 = p->ft; p->ft0.n = (int)f0_cpos.size(); p->ft0.cpos = e1; p->ft0.slot = e2; p->ft0.jk = e3; p->ft0.l = e4; p->ft0.val = e5;
+    }
     CK(cudaStreamSynchronize(st));
   }
 
@@ -604,7 +624,7 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
         for (int q = 0; q < ldp; q++) {
           unsigned char m = h_plan[(size_t)(g.slot0 + i) * ldp + q];
           // algorithmic flops per Gauss point / pair: elastic 585 + 72 n / 144 n; scalar 96 + 8 n / 12 n
-          if (m < MAX_SETS) { pairs++; pts += g.dev.ngp[m]; flops += (ndof == 1) ? (double)g.dev.ngp[m] * (96.0 + 8.0 * g.nn) + 12.0 * g.nn : (double)g.dev.ngp[m] * (585.0 + 72.0 * g.nn) + 144.0 * g.nn; }
+          if (m < MAX_SETS) { pairs++; pts += g.dev.ngp[m]; flops += (ndof == 4) ? (double)g.dev.ngp[m] * (1500.0 + 128.0 * g.nn) + 256.0 * g.nn : (ndof == 1) ? (double)g.dev.ngp[m] * (96.0 + 8.0 * g.nn) + 12.0 * g.nn : (double)g.dev.ngp[m] * (585.0 + 72.0 * g.nn) + 144.0 * g.nn; }
         }
     p->stats[MFB_STAT_PAIRS_REGULAR] = (double)pairs; p->stats[MFB_STAT_POINTS_REGULAR] = (double)pts; p->stats[MFB_STAT_FLOPS_REGULAR] = flops;
     p->stats[MFB_STAT_PAIRS_ADAPTIVE] = (double)n_adp; p->stats[MFB_STAT_LEAVES] = (double)n_leaves; p->stats[MFB_STAT_POINTS_ADAPTIVE] = (double)pts_adp;
@@ -752,7 +772,7 @@ static int collect_assembly_times(mfb_problem* p) {
 // scatter of assemble_bem_harpot_equation.f90:78-96, on a problem set up with ndof = 1.
 // ---------------------------------------------------------------------------------------------------------------------
 static int assemble_pot_device(mfb_problem* p, double omega, double rho, cd c, const mfb_z* cvalue) {
-  if (p->ndof != 1) return fail(MFB_ERR_ARG, "this problem was set up for an elastic region: use mfb_harela3d_* / mfb_staela3d_*");
+  if (p->ndof != 1) return fail(MFB_ERR_ARG, "this problem was not set up for an inviscid fluid region (mfb_harpot3d_setup)");
   if (!(omega > 0.0) || !(rho > 0.0) || c == cd(0.0, 0.0)) return fail(MFB_ERR_ARG, "mfb_harpot3d: omega, rho must be positive and c nonzero");
   cudaStream_t st = p->ctx->stream;
   const double c_pi = 3.14159265358979323846264338328;
@@ -784,6 +804,45 @@ static int assemble_pot_device(mfb_problem* p, double omega, double rho, cd c, c
   CK(cudaGetLastError());
   p->factored = false; p->assembled = true; p->rows_permuted = true; p->real_resident = false;
   p->asm_launches = 1;
+  for (auto& g : p->groups) p->asm_launches += 1 + (cvalue ? 1 : 0) + (g.adp.n_pairs > 0) + (g.sing.n_pairs > 0);
+  return MFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Biot poroelastic BE region: fbem_bem_harpor3d_calculate_parameters (por_params_host) + build_lse_mechanics_bem_harpor
+// with the open-pore scatter of assemble_bem_harpor_equation.f90:78-110, :140-170, on a problem set up with ndof = 4.
+// STATUS: never executed on hardware (see poro.cu).
+// ---------------------------------------------------------------------------------------------------------------------
+static int assemble_por_device(mfb_problem* p, double omega, cd lambda, cd mu, double rho1, double rho2, double rhoa, cd R, cd Q, double b, const mfb_z* cvalue) {
+  if (p->ndof != 4) return fail(MFB_ERR_ARG, "this problem was not set up for a poroelastic region (mfb_harpor3d_setup)");
+  if (!(omega > 0.0) || !(rho1 > 0.0) || !(rho2 > 0.0) || R == cd(0.0, 0.0) || mu == cd(0.0, 0.0)) return fail(MFB_ERR_ARG, "mfb_harpor3d: omega, rho1, rho2 must be positive, mu and R nonzero");
+  cudaStream_t st = p->ctx->stream;
+  PorParams pp; por_params_host(lambda, mu, rho1, rho2, rhoa, R, Q, b, omega, pp);
+  set_por_params(pp, st);
+  if (cvalue) {
+    CK(cudaMemcpyAsync(p->d_cvalue, cvalue, (size_t)8 * p->n_node * sizeof(double), cudaMemcpyHostToDevice, st));
+    for (auto& g : p->groups) launch_gather_cv(g.dev, p->d_cvalue, st);
+    p->have_cvalue = true;
+  } else if (!p->have_cvalue) return fail(MFB_ERR_ARG, "cvalue == NULL but no prescribed values are resident yet");
+  CK(cudaEventRecord(p->ev[0], st));
+  CK(cudaMemsetAsync(p->sys.Are, 0, (size_t)2 * p->lda * p->n_dof * sizeof(double), st));
+  CK(cudaMemsetAsync(p->sys.bre, 0, (size_t)2 * p->lda * sizeof(double), st));
+  CK(cudaEventRecord(p->ev[1], st));
+  for (auto& g : p->groups) launch_por_regular(g.dev, p->colloc, p->sys, p->plan, st);
+  CK(cudaEventRecord(p->ev[2], st));
+  for (auto& g : p->groups) launch_por_adaptive(g.dev, p->colloc, p->sys, g.adp, p->ctx->tables, st);
+  CK(cudaEventRecord(p->ev[3], st));
+  for (auto& g : p->groups) launch_por_singular(g.dev, p->colloc, p->sys, g.sing, p->ctx->tables, st);
+  CK(cudaEventRecord(p->ev[4], st));
+  const double c_pi = 3.14159265358979323846264338328;
+  const cd nu = 0.5 * lambda / (lambda + mu);
+  const cd F = -1.0 / (8.0 * c_pi * (1.0 - nu));
+  launch_freeterm(p->colloc, p->sys, p->ft, mk(F.real(), F.imag()), st);       // skeleton: Mantic's matrix
+  launch_freeterm(p->colloc, p->sys, p->ft0, pp.J, st);                        // fluid phase: J c_pot
+  CK(cudaEventRecord(p->ev[5], st));
+  CK(cudaGetLastError());
+  p->factored = false; p->assembled = true; p->rows_permuted = true; p->real_resident = false;
+  p->asm_launches = 2;
   for (auto& g : p->groups) p->asm_launches += 1 + (cvalue ? 1 : 0) + (g.adp.n_pairs > 0) + (g.sing.n_pairs > 0);
   return MFB_OK;
 }
@@ -849,6 +908,28 @@ extern "C" int mfb_harpot3d_assemble(mfb_problem* p, double omega, double rho, c
   if (r) return r;
   if (A) { r = download_matrix(p, p->sys.Are, p->sys.Aim, p->lda, p->n_dof, p->n_dof, A, p->n_dof, p->d_rowperm, p->d_colperm); if (r) return r; }
   if (b) { r = download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, b, p->n_dof, p->d_rowperm); if (r) return r; }
+  return MFB_OK;
+}
+
+extern "C" int mfb_harpor3d_setup(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
+                                  const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
+                                  const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
+                                  const int* row, const int* col_p, const int* col_s, const int* ctype, int n_dof,
+                                  double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
+                                  double geometric_tolerance, mfb_problem** out) {
+  return setup_impl(ctx, n_node, node_x, n_elem, etype, elem_ptr, elem_node, elem_reversed, n_colloc, colloc_x, colloc_node, colloc_elem, colloc_kn, colloc_xi,
+                    row, col_p, col_s, ctype, n_dof, qsi_relative_error, qsi_ns_max, n_precalsets, precalset_gln, geometric_tolerance, nullptr, 4, out);
+}
+extern "C" int mfb_harpor3d_assemble(mfb_problem* p, double omega, const mfb_z* lambda, const mfb_z* mu, double rho1, double rho2, double rhoa,
+                                     const mfb_z* R, const mfb_z* Q, double b, const mfb_z* cvalue, mfb_z* A, mfb_z* bb) {
+  if (!p || !lambda || !mu || !R || !Q) return fail(MFB_ERR_ARG, "mfb_harpor3d_assemble: null argument");
+  CK(cudaSetDevice(p->ctx->device));
+  int r = assemble_por_device(p, omega, cd(lambda->re, lambda->im), cd(mu->re, mu->im), rho1, rho2, rhoa, cd(R->re, R->im), cd(Q->re, Q->im), b, cvalue);
+  if (r) return r;
+  r = collect_assembly_times(p);
+  if (r) return r;
+  if (A) { r = download_matrix(p, p->sys.Are, p->sys.Aim, p->lda, p->n_dof, p->n_dof, A, p->n_dof, p->d_rowperm, p->d_colperm); if (r) return r; }
+  if (bb) { r = download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, bb, p->n_dof, p->d_rowperm); if (r) return r; }
   return MFB_OK;
 }
 
@@ -947,6 +1028,26 @@ extern "C" int mfb_harpot3d_solve_frequency(mfb_problem* p, double omega, double
   if (!p || !c) return fail(MFB_ERR_ARG, "mfb_harpot3d_solve_frequency: null argument");
   CK(cudaSetDevice(p->ctx->device));
   int r = assemble_pot_device(p, omega, rho, cd(c->re, c->im), cvalue);
+  if (r) return r;
+  r = factor_device(p, p->n_dof, lu_timing());
+  int r2 = collect_assembly_times(p); if (r2) return r2;
+  if (r) return r;
+  cudaStream_t st = p->ctx->stream;
+  CK(cudaEventRecord(p->ev[6], st));
+  int e = zgetrs_planar(p->sys.Are, p->sys.Aim, p->lda, p->n_dof, p->d_perm, p->sys.bre, p->sys.bim, p->lda, 1, st, p->lu.inv);
+  if (e) return fail(MFB_ERR_CUDA, std::string("zgetrs_planar: ") + cudaGetErrorString((cudaError_t)e));
+  CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
+  float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
+  p->assembled = false;
+  if (!x) return MFB_OK;
+  return download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, x, p->n_dof, p->d_colperm);
+}
+
+extern "C" int mfb_harpor3d_solve_frequency(mfb_problem* p, double omega, const mfb_z* lambda, const mfb_z* mu, double rho1, double rho2, double rhoa,
+                                            const mfb_z* R, const mfb_z* Q, double b, const mfb_z* cvalue, mfb_z* x) {
+  if (!p || !lambda || !mu || !R || !Q) return fail(MFB_ERR_ARG, "mfb_harpor3d_solve_frequency: null argument");
+  CK(cudaSetDevice(p->ctx->device));
+  int r = assemble_por_device(p, omega, cd(lambda->re, lambda->im), cd(mu->re, mu->im), rho1, rho2, rhoa, cd(R->re, R->im), cd(Q->re, Q->im), b, cvalue);
   if (r) return r;
   r = factor_device(p, p->n_dof, lu_timing());
   int r2 = collect_assembly_times(p); if (r2) return r2;

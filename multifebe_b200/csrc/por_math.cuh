@@ -1,8 +1,7 @@
 // por_math.cuh -- per-Gauss-point arithmetic of the Biot poroelastic SBIE kernels (host+device inline, like bem_math.cuh / pot_math.cuh).
 //
-// NOT YET USED BY A KERNEL: this header is the arithmetic core of the poroelastic device path planned for the next round (DESIGN.md
-// section 7.4); it is compiled for the host by tests/test_por_math_host.py and held to the oracle there, so that the kernels written
-// around it start from checked point formulas.
+// Used by the kernels of poro.cu (compiled, not yet run on hardware).  The header is also compiled for the HOST by
+// tests/test_por_math_host.py and held to the oracle there, so the point formulas and parameter tables are checked without a GPU.
 //
 // Node variables: 0 = fluid phase (tau | Un), 1..3 = skeleton (u_k | t_k).  The fundamental solution is evaluated in the reference's
 // regularised form (lib/fbem/src/bem_harpor3d.f90:944-996): twelve radial scalars, each a static part (1/r or 1/r^2) + a constant + a sum
@@ -13,9 +12,7 @@
 // times the constants cte_u(l,k), cte_t(l,k) (:545-556).
 #pragma once
 #include "bem_math.cuh"
-#if !defined(__CUDACC__)
 #include <complex>
-#endif
 
 namespace mfbd {
 
@@ -27,8 +24,6 @@ struct PorParams {
 };
 
 struct PorScal { cplx eta, vartheta, psi, chi, W0, T01, T02, W1, W2, T1, T2, T3; };
-
-MFB_HD cplx por_sum2(const cplx* c, int i0, const cplx* E) { return cfma(c[i0 + 1], E[1], c[i0] * E[0]); }   // c[i0] E(k1) + c[i0+1] E(k2)
 
 // The twelve radial scalars at distance r (d1r1 = 1/r).  REGULAR_ONLY drops the static 1/r^2 parts of W0, T1, T2, T3 (interior
 // integration, bem_harpor3d.f90:1720-1750; the caller adds back the ones it integrates in full).
@@ -147,7 +142,6 @@ MFB_HD void por_interior_blocks(const PorParams& p, const double* x, const doubl
     }
 }
 
-#if !defined(__CUDACC__)
 // fbem_bem_harpor3d_calculate_parameters (bem_harpor3d.f90:204-568, SBIE subset) on the host.  With a = (lambda + 2 mu), m = mu / a,
 // v = (Q/R - Z) / a, D = k1^2 - k2^2, alpha_j = k_j^2 - m k3^2, beta_j = m k_j^2 - k1^2 k2^2 / k3^2, and the shorthands
 // A_j = alpha_j / D, B_j = beta_j / D, V = v / D every table entry is a short product.
@@ -211,6 +205,5 @@ inline void por_params_host(std::complex<double> lambda, std::complex<double> mu
       set(P.cte_t[l][k], l == 0 ? cd(k == 0 ? -c4 : c4) : (k == 0 ? -c4 / mu : cd(c4)));
     }
 }
-#endif
 
 }  // namespace mfbd

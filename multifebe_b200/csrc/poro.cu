@@ -1,0 +1,318 @@
+// poro.cu -- sm_100a kernels of the Biot poroelastic SBIE assembly: four equations and four unknowns per node (0 = fluid phase tau | Un,
+// 1..3 = skeleton u_k | t_k), ordinary `be` boundaries with the open-pore conditions 0 / 1 per component.
+//
+//   R1 k_por_regular   regular quadrature with the precalculated point sets (fbem_bem_harpor3d_sbie_ext_pre, lib/fbem/src/bem_harpor3d.f90:906-1011)
+//                      fused with the BC-aware scatter (assemble_bem_harpor_equation.f90:78-110, :140-170)
+//   R2 k_por_adaptive  Telles + subdivision leaves (fbem_bem_harpor3d_sbie_ext_st :1013-1416, leaf list of _ext_adp :1418-1540)
+//   R3 k_por_singular  polar-transformation interior integration (fbem_bem_harpor3d_sbie_int :1542-1890): skeleton block with the CPV term and
+//                      the line integrals of the static solution, fluid and coupling blocks weakly singular
+// Free terms (c_00 = J c_pot, c_lk = Mantic's matrix of the drained skeleton, or phi_j/2 at MCA points) go through k_freeterm with two
+// lists (multipliers F and J).  The point arithmetic is por_math.cuh (checked on the host against the oracle).
+//
+// STATUS: written at the end of round 1 without GPU access -- compiled for sm_100a, never executed.  tests/test_gpu_poroelastic.py is the
+// parity suite for its first hardware run (MFB_RUN_UNVALIDATED=1).
+//
+// Mapping: as k_regular<ET, 1> of assembly.cu -- a warp owns a collocation tile, lane = collocation point, ONE equation (row l of the node
+// block) per pass, so that the pair's accumulators are 2 * 4 * NN complex numbers; the 4 x 4 point blocks are recomputed in every pass
+// (4x the arithmetic of a one-pass kernel: the register file does not hold 32 * NN complex accumulators; a later version can stage them
+// in shared memory).
+#include "poro.cuh"
+#include <cstdio>
+
+namespace mfbd {
+
+__constant__ PorParams c_por;
+
+void set_por_params(const PorParams& pp, cudaStream_t st) { cudaMemcpyToSymbolAsync(c_por, &pp, sizeof(PorParams), 0, cudaMemcpyHostToDevice, st); }
+
+// accumulators of one equation l of one pair: h(j, l, k), g(j, l, k), k = 0..3
+template <int NN>
+struct RAcc {
+  double hr[4 * NN], hi[4 * NN], gr[4 * NN], gi[4 * NN];     // [k * NN + j]
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < 4 * NN; i++) { hr[i] = 0.0; hi[i] = 0.0; gr[i] = 0.0; gi[i] = 0.0; }
+  }
+};
+
+// row l of the 4 x 4 blocks, selected with compile-time indices only
+__device__ __forceinline__ void por_row(const cplx f[4][4], int l, cplx out[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[k] = (l == 0) ? f[0][k] : (l == 1 ? f[1][k] : (l == 2 ? f[2][k] : f[3][k]));
+}
+
+template <int NN>
+__device__ __forceinline__ void por_accumulate_row(RAcc<NN>& a, const cplx fu[4][4], const cplx ft[4][4], int l, const double* w) {
+  cplx ur[4], tr[4];
+  por_row(fu, l, ur); por_row(ft, l, tr);
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int j = 0; j < NN; j++) {
+      a.hr[k * NN + j] = fma(tr[k].re, w[j], a.hr[k * NN + j]); a.hi[k * NN + j] = fma(tr[k].im, w[j], a.hi[k * NN + j]);
+      a.gr[k * NN + j] = fma(ur[k].re, w[j], a.gr[k * NN + j]); a.gi[k * NN + j] = fma(ur[k].im, w[j], a.gi[k * NN + j]);
+    }
+}
+
+// BC-aware scatter of equation l of one pair (assemble_bem_harpor_equation.f90:78-110, :140-170; open-pore conditions): entries selected by
+// `mine(j * 4 + k)`; h is scaled by cte_t(l, k) and changes sign on a reversed element, g by cte_u(l, k).
+template <int NN, class Pred>
+__device__ __forceinline__ void por_scatter_row(const RAcc<NN>& a, int l, const int* __restrict__ ecol, const unsigned char* __restrict__ ekind,
+                                                const double* __restrict__ ecv, bool rev, const DevSystem& s, int row, double& bre, double& bim, Pred mine) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const cplx ct0 = (l == 0) ? c_por.cte_t[0][k] : c_por.cte_t[1][k];     // cte_t(l, k) depends on l only through l == 0
+    const cplx cu = (l == 0) ? c_por.cte_u[0][k] : c_por.cte_u[1][k];
+    const cplx ct = rev ? mk(-ct0.re, -ct0.im) : ct0;
+#pragma unroll
+    for (int j = 0; j < NN; j++) {
+      const int jk = j * 4 + k;
+      if (!mine(jk)) continue;
+      const int q = k * NN + j;
+      const double hr = ct.re * a.hr[q] - ct.im * a.hi[q], hi = ct.re * a.hi[q] + ct.im * a.hr[q];
+      const double gr = cu.re * a.gr[q] - cu.im * a.gi[q], gi = cu.re * a.gi[q] + cu.im * a.gr[q];
+      const int col = ecol[jk];
+      const double cvr = ecv[2 * jk], cvi = ecv[2 * jk + 1];
+      double ar, ai;
+      if (ekind[jk] == 0) { ar = -gr; ai = -gi; bre -= hr * cvr - hi * cvi; bim -= hr * cvi + hi * cvr; }
+      else { ar = hr; ai = hi; bre += gr * cvr - gi * cvi; bim += gr * cvi + gi * cvr; }
+      atomicAdd(s.Are + (size_t)col * s.lda + row, ar);
+      atomicAdd(s.Aim + (size_t)col * s.lda + row, ai);
+    }
+  }
+}
+struct PorAll { __device__ __forceinline__ bool operator()(int) const { return true; } };
+struct PorLane { int lane; __device__ __forceinline__ bool operator()(int jk) const { return (jk & 31) == lane; } };
+
+// ------------------------------------------------------------------------------------------------------------------
+// R1: regular pairs
+// ------------------------------------------------------------------------------------------------------------------
+const int R1_WARPS = 4;
+const int R1_ECHUNK = 32;
+
+template <int ET>
+__global__ void __launch_bounds__(R1_WARPS * 32) k_por_regular(DevGroup g, DevColloc c, DevSystem s, const unsigned char* __restrict__ plan) {
+  constexpr int NN = ElemTraits<ET>::NN, RECN = 6 + NN;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tile = blockIdx.x * R1_WARPS + warp;
+  if (tile >= c.n_tiles) return;
+  if (c.tile_active && !c.tile_active[tile]) return;
+  const int cpos = tile * 32 + lane;
+  const int rows[4] = {c.crow[cpos], c.crow[c.ldp + cpos], c.crow[2 * c.ldp + cpos], c.crow[3 * c.ldp + cpos]};
+  const bool valid = rows[0] >= 0;
+  const double xc[3] = {c.cx[cpos], c.cx[c.ldp + cpos], c.cx[2 * c.ldp + cpos]};
+  double bre[4] = {0.0, 0.0, 0.0, 0.0}, bim[4] = {0.0, 0.0, 0.0, 0.0};
+  const int e0 = blockIdx.y * R1_ECHUNK, e1 = min(e0 + R1_ECHUNK, g.n_elem);
+  for (int e = e0; e < e1; e++) {
+    const unsigned char m = valid ? plan[(size_t)(g.slot0 + e) * c.ldp + cpos] : PLAN_NONE;
+    unsigned todo = __ballot_sync(0xffffffffu, m < MAX_SETS);
+    while (todo) {
+      const int leader = __ffs(todo) - 1;
+      const int sset = __shfl_sync(0xffffffffu, (int)m, leader);
+      const unsigned grp = __ballot_sync(0xffffffffu, (int)m == sset);
+      todo &= ~grp;
+      if ((int)m == sset) {
+        const int ngp = g.ngp[sset];
+        const double* P = g.pts[sset] + (size_t)e * ngp * RECN;
+        const int* ecol = g.ecol + (size_t)e * 4 * NN;
+        const unsigned char* ekind = g.ekind + (size_t)e * 4 * NN;
+        const double* ecv = g.ecv + (size_t)e * 8 * NN;
+        const bool rev = g.erev[e] != 0;
+#pragma unroll 1
+        for (int l = 0; l < 4; l++) {
+          RAcc<NN> acc; acc.zero();
+#pragma unroll 1
+          for (int kp = 0; kp < ngp; kp++) {
+            const double* q = P + (size_t)kp * RECN;
+            const double x[3] = {__ldg(q), __ldg(q + 1), __ldg(q + 2)}, n[3] = {__ldg(q + 3), __ldg(q + 4), __ldg(q + 5)};
+            double w[NN];
+#pragma unroll
+            for (int j = 0; j < NN; j++) w[j] = __ldg(q + 6 + j);
+            cplx fu[4][4], ft[4][4];
+            por_exterior_blocks(c_por, x, n, xc, fu, ft);
+            por_accumulate_row<NN>(acc, fu, ft, l, w);
+          }
+          const int row = (l == 0) ? rows[0] : (l == 1 ? rows[1] : (l == 2 ? rows[2] : rows[3]));
+          double br = 0.0, bi = 0.0;
+          por_scatter_row<NN>(acc, l, ecol, ekind, ecv, rev, s, row, br, bi, PorAll());
+          if (l == 0) { bre[0] += br; bim[0] += bi; } else if (l == 1) { bre[1] += br; bim[1] += bi; } else if (l == 2) { bre[2] += br; bim[2] += bi; } else { bre[3] += br; bim[3] += bi; }
+        }
+      }
+    }
+  }
+  if (valid) {
+#pragma unroll
+    for (int l = 0; l < 4; l++)
+      if (bre[l] != 0.0 || bim[l] != 0.0) { atomicAdd(s.bre + rows[l], bre[l]); atomicAdd(s.bim + rows[l], bim[l]); }
+  }
+}
+void launch_por_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, cudaStream_t st) {
+  if (g.n_elem == 0) return;
+  dim3 grid((c.n_tiles + R1_WARPS - 1) / R1_WARPS, (g.n_elem + R1_ECHUNK - 1) / R1_ECHUNK), block(R1_WARPS * 32);
+  switch (g.et) {
+    case 5: k_por_regular<5><<<grid, block, 0, st>>>(g, c, s, plan); break;
+    case 6: k_por_regular<6><<<grid, block, 0, st>>>(g, c, s, plan); break;
+    case 7: k_por_regular<7><<<grid, block, 0, st>>>(g, c, s, plan); break;
+    case 8: k_por_regular<8><<<grid, block, 0, st>>>(g, c, s, plan); break;
+    case 9: k_por_regular<9><<<grid, block, 0, st>>>(g, c, s, plan); break;
+  }
+}
+
+template <int NN>
+__device__ __forceinline__ void por_warp_reduce(RAcc<NN>& a) {
+#pragma unroll
+  for (int i = 0; i < 4 * NN; i++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a.hr[i] += __shfl_xor_sync(0xffffffffu, a.hr[i], o); a.hi[i] += __shfl_xor_sync(0xffffffffu, a.hi[i], o);
+      a.gr[i] += __shfl_xor_sync(0xffffffffu, a.gr[i], o); a.gi[i] += __shfl_xor_sync(0xffffffffu, a.gi[i], o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// R2: adaptive pairs -- one warp per pair, lanes stride over the gln x gln points of every leaf, one equation per pass
+// ------------------------------------------------------------------------------------------------------------------
+template <int ET>
+__global__ void __launch_bounds__(128) k_por_adaptive(DevGroup g, DevColloc c, DevSystem s, DevAdaptive a, DevTables t) {
+  constexpr int NN = ElemTraits<ET>::NN;
+  constexpr bool tri = (ElemTraits<ET>::NV == 3);
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= a.n_pairs) return;
+  const int cpos = a.pair_cpos[p], e = a.pair_elem[p];
+  if (c.tile_active && !c.tile_active[cpos >> 5]) return;
+  const double xc[3] = {c.cx[cpos], c.cx[c.ldp + cpos], c.cx[2 * c.ldp + cpos]};
+  double xn[3 * NN];
+#pragma unroll
+  for (int i = 0; i < 3 * NN; i++) xn[i] = g.xn[(size_t)e * 3 * NN + i];
+  const double* gx = tri ? t.gl01_x : t.gl11_x;
+  const double* gw = tri ? t.gl01_w : t.gl11_w;
+  const bool rev = g.erev[e] != 0;
+#pragma unroll 1
+  for (int l = 0; l < 4; l++) {
+    RAcc<NN> acc; acc.zero();
+#pragma unroll 1
+    for (int lf = a.pair_leaf0[p]; lf < a.pair_leaf0[p + 1]; lf++) {
+      const double* L = a.leaf_d + 16 * (size_t)lf;
+      double xi_s[8], tp1[4], tp2[4];
+#pragma unroll
+      for (int i = 0; i < 8; i++) xi_s[i] = __ldg(L + i);
+#pragma unroll
+      for (int i = 0; i < 4; i++) { tp1[i] = __ldg(L + 8 + i); tp2[i] = __ldg(L + 12 + i); }
+      const int gln = a.leaf_gln[lf], off = gln * (gln - 1) / 2;
+#pragma unroll 1
+      for (int idx = lane; idx < gln * gln; idx += 32) {
+        const int k1 = idx / gln, k2 = idx - k1 * gln;
+        double x[3], n[3], w[NN];
+        leaf_point<ET>(xn, xi_s, tp1, tp2, __ldg(gx + off + k1), __ldg(gw + off + k1), __ldg(gx + off + k2), __ldg(gw + off + k2), x, n, w);
+        cplx fu[4][4], ft[4][4];
+        por_exterior_blocks(c_por, x, n, xc, fu, ft);
+        por_accumulate_row<NN>(acc, fu, ft, l, w);
+      }
+    }
+    por_warp_reduce<NN>(acc);
+    const int row = c.crow[l * c.ldp + cpos];
+    double br = 0.0, bi = 0.0;
+    PorLane pl; pl.lane = lane;
+    por_scatter_row<NN>(acc, l, g.ecol + (size_t)e * 4 * NN, g.ekind + (size_t)e * 4 * NN, g.ecv + (size_t)e * 8 * NN, rev, s, row, br, bi, pl);
+    if (br != 0.0 || bi != 0.0) { atomicAdd(s.bre + row, br); atomicAdd(s.bim + row, bi); }
+  }
+}
+void launch_por_adaptive(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevAdaptive& a, const DevTables& t, cudaStream_t st) {
+  if (a.n_pairs == 0) return;
+  dim3 grid((a.n_pairs + 3) / 4), block(128);
+  switch (g.et) {
+    case 5: k_por_adaptive<5><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 6: k_por_adaptive<6><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 7: k_por_adaptive<7><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 8: k_por_adaptive<8><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 9: k_por_adaptive<9><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// R3: singular pairs -- one warp per pair, lanes stride over (ray, radial point), one equation per pass; the CPV kernel of the skeleton
+// block is integrated against (phi_j - phi_j(xi_i)) and the line-integral term phi_j(xi_i) T2(1) hli(l,k) (bem_harpor3d.f90:1876-1880) is
+// added after the reduction.
+// ------------------------------------------------------------------------------------------------------------------
+template <int ET>
+__global__ void __launch_bounds__(128) k_por_singular(DevGroup g, DevColloc c, DevSystem s, DevSingular a, DevTables t) {
+  constexpr int NN = ElemTraits<ET>::NN;
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= a.n_pairs) return;
+  const int cpos = a.pair_cpos[p], e = a.pair_elem[p];
+  if (c.tile_active && !c.tile_active[cpos >> 5]) return;
+  const double* D = a.pair_d + 14 * (size_t)p;
+  const double xi_i0 = D[0], xi_i1 = D[1];
+  const double xc[3] = {D[2], D[3], D[4]};
+  double xn[3 * NN];
+#pragma unroll
+  for (int i = 0; i < 3 * NN; i++) xn[i] = g.xn[(size_t)e * 3 * NN + i];
+  double phi_i[NN];
+  { double d1[NN], d2[NN]; shape<ET>(xi_i0, xi_i1, phi_i, d1, d2); }
+  const int ray0 = a.pair_ray0[p], nray = a.pair_ray0[p + 1] - ray0;
+  const double* gx = t.gl01_x + 15 * 14 / 2;
+  const double* gw = t.gl01_w + 15 * 14 / 2;
+  const bool rev = g.erev[e] != 0;
+#pragma unroll 1
+  for (int l = 0; l < 4; l++) {
+    RAcc<NN> acc; acc.zero();
+#pragma unroll 1
+    for (int idx = lane; idx < nray * 15; idx += 32) {
+      const int kr_ = idx / 15, kk = idx - kr_ * 15;
+      const double* R = a.rays + 4 * (size_t)(ray0 + kr_);
+      const double ct = __ldg(R), sn = __ldg(R + 1), rhoij = __ldg(R + 2), wray = __ldg(R + 3);
+      const double rho = rhoij * __ldg(gx + kk), wrad = __ldg(gw + kk);
+      double phi[NN], x[3], n[3], jg;
+      geometry_at<ET>(xn, xi_i0 + rho * ct, xi_i1 + rho * sn, phi, x, n, jg);
+      const double jw = jg * rho * wray * wrad;
+      double w[NN];
+#pragma unroll
+      for (int j = 0; j < NN; j++) w[j] = phi[j] * jw;
+      cplx fu[4][4], ft[4][4], fc[3][3];
+      por_interior_blocks(c_por, x, n, xc, fu, ft, fc);
+      por_accumulate_row<NN>(acc, fu, ft, l, w);
+      if (l > 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const cplx f = (l == 1) ? fc[0][k] : (l == 2 ? fc[1][k] : fc[2][k]);
+#pragma unroll
+          for (int j = 0; j < NN; j++) {
+            const double wc = (phi[j] - phi_i[j]) * jw;
+            acc.hr[(k + 1) * NN + j] = fma(f.re, wc, acc.hr[(k + 1) * NN + j]); acc.hi[(k + 1) * NN + j] = fma(f.im, wc, acc.hi[(k + 1) * NN + j]);
+          }
+        }
+      }
+    }
+    por_warp_reduce<NN>(acc);
+    if (l > 0) {
+      const cplx t21 = c_por.T2[1];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const double hl = D[5 + 3 * (l - 1) + k];
+#pragma unroll
+        for (int j = 0; j < NN; j++) { acc.hr[(k + 1) * NN + j] += phi_i[j] * t21.re * hl; acc.hi[(k + 1) * NN + j] += phi_i[j] * t21.im * hl; }
+      }
+    }
+    const int row = c.crow[l * c.ldp + cpos];
+    double br = 0.0, bi = 0.0;
+    PorLane pl; pl.lane = lane;
+    por_scatter_row<NN>(acc, l, g.ecol + (size_t)e * 4 * NN, g.ekind + (size_t)e * 4 * NN, g.ecv + (size_t)e * 8 * NN, rev, s, row, br, bi, pl);
+    if (br != 0.0 || bi != 0.0) { atomicAdd(s.bre + row, br); atomicAdd(s.bim + row, bi); }
+  }
+}
+void launch_por_singular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevSingular& a, const DevTables& t, cudaStream_t st) {
+  if (a.n_pairs == 0) return;
+  dim3 grid((a.n_pairs + 3) / 4), block(128);
+  switch (g.et) {
+    case 5: k_por_singular<5><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 6: k_por_singular<6><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 7: k_por_singular<7><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 8: k_por_singular<8><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 9: k_por_singular<9><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+  }
+}
+
+}  // namespace mfbd
