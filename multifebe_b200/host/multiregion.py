@@ -128,9 +128,22 @@ class MultiRegionModel:
                                 self.col[(v, _var_name(self.regions[r1].kind, k, self.ctype[b][k] == 0, 1))] = col; col += 1
                             continue
                         k1, k2 = self.regions[r1].kind, self.regions[r2].kind
-                        if PORO in (k1, k2):
+                        if {k1, k2} == {SOLID, PORO}:
+                            # perfect bonding, impervious contact (ctype 0): tau, u_k, t_k of the poroelastic side are active; its fluid-phase row first,
+                            # then the rows of both regions interleaved per component (:895-930 solid(1)-poro(2), :1065-1098 poro(1)-solid(2))
+                            pe = 1 if k1 == PORO else 2
+                            se_ = 3 - pe
+                            prow = [row]; row += 1
+                            self.col[(v, "tau%d" % pe)] = col; col += 1
+                            r1rows, r2rows = [], []
+                            for k in range(3):
+                                r1rows.append(row); r2rows.append(row + 1); row += 2
+                                self.col[(v, "u%d%d" % (pe, k))] = col; self.col[(v, "t%d%d" % (pe, k))] = col + 1; col += 2
+                            self.row[(v, pe)] = prow + (r1rows if pe == 1 else r2rows)
+                            self.row[(v, se_)] = r2rows if pe == 1 else r1rows
+                        elif PORO in (k1, k2):
                             if {k1, k2} != {FLUID, PORO}:
-                                raise ValueError("boundary %d: of the interfaces of a poroelastic region only fluid-poroelastic ones are built" % b)
+                                raise ValueError("boundary %d: poroelastic-poroelastic interfaces are not built" % b)
                             imp = self.interface_ctype.get(b, 0) == 1
                             fe, pe = (1, 2) if k1 == FLUID else (2, 1)           # equation index / variable suffix of the fluid and of the poroelastic side
                             def number_poro():
@@ -262,6 +275,20 @@ class MultiRegionModel:
                     k1, k2 = self.regions[r1].kind, self.regions[r2].kind
                     other = k2 if first else k1
                     sgn = 1.0 if first else -1.0                              # n_fn is outward from region 1: the normal of THIS region is sgn * n_fn
+                    if {k1, k2} == {SOLID, PORO}:     # assemble_bem_harela_equation.f90:262-285 / :430-455; assemble_bem_harpor_equation.f90:627-660 / :807-830
+                        ps = 1 if k1 == PORO else 2
+                        if r.kind == SOLID:               # u = u_p; t = -t_p -/+ tau n
+                            hcol[q], hcoef[q] = self.col[(sn, "u%d%d" % (ps, k))], 1.0
+                            gcol[q, 0], gcoef[q, 0] = self.col[(sn, "t%d%d" % (ps, k))], 1.0
+                            gcol[q, 1], gcoef[q, 1] = self.col[(sn, "tau%d" % ps)], -sgn * n_fn[k]
+                        elif k == 0:                      # Un = u . n (impervious contact)
+                            hcol[q], hcoef[q] = self.col[(sn, "tau%d" % ps)], 1.0
+                            for t in range(3):
+                                gcol[q, t], gcoef[q, t] = self.col[(sn, "u%d%d" % (ps, t))], -sgn * n_fn[t]
+                        else:
+                            hcol[q], hcoef[q] = self.col[(sn, "u%d%d" % (ps, k - 1))], 1.0
+                            gcol[q, 0], gcoef[q, 0] = self.col[(sn, "t%d%d" % (ps, k - 1))], -1.0
+                        continue
                     if PORO in (k1, k2):
                         imp = self.interface_ctype.get(bnd, 0) == 1
                         po = self.regions[r1 if k1 == PORO else r2].material

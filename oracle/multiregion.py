@@ -112,6 +112,9 @@ class MultiRegionOracle:
                         else:
                             A[rows[il], m.col[(sn, _var_name(PORO, ik, False, 1))]] += h[kn, il, ik]; b[rows[il]] += g[kn, il, ik] * cv[ik]
                 continue
+            if r2 is not None and {m.regions[r1].kind, m.regions[r2].kind} == {SOLID, PORO}:
+                self._scatter_solid_poro(kr, kn, sn, bnd, rows, first, sh.unit_normal(et, v.node_x[nodes], sh.XI_NODES[et][kn]), h, g, A)
+                continue
             if r2 is not None and PORO in (m.regions[r1].kind, m.regions[r2].kind):
                 self._scatter_fluid_poro(kr, kn, sn, bnd, rows, first, sh.unit_normal(et, v.node_x[nodes], sh.XI_NODES[et][kn]), h, g, A)
                 continue
@@ -159,6 +162,42 @@ class MultiRegionOracle:
                     A[rows[0], m.col[(sn, "p2")]] += h[kn]
                     for ik in range(3):
                         A[rows[0], m.col[(sn, "u1%d" % ik)]] += g[kn] * n_fn[ik]
+
+    def _scatter_solid_poro(self, kr, kn, sn, bnd, rows, first, n_fn, h, g, A):
+        """be-be boundary between a viscoelastic solid and a poroelastic medium, perfect bonding with impervious contact (ctype 0), written out
+        for each side and order: assemble_bem_harela_equation.f90:262-285 (solid = region 1), :430-455 (solid = region 2);
+        assemble_bem_harpor_equation.f90:627-660 (poroelastic = region 1), :807-830 (poroelastic = region 2).  n_fn = normal of region 1."""
+        m = self.m
+        v = m.views[kr]
+        r1, r2 = m.boundary_regions[bnd]
+        col = m.col
+        poro_first = m.regions[r1].kind == PORO
+        if v.kind == SOLID:
+            for il in range(3):
+                for ik in range(3):
+                    if first:                                             # VISCOELASTIC SOLID (1) - POROELASTIC MEDIA (2): u1 = u2, t1 = -t2 + tau2 n1
+                        A[rows[il], col[(sn, "u2%d" % ik)]] += h[kn, il, ik]
+                        A[rows[il], col[(sn, "t2%d" % ik)]] += g[kn, il, ik]
+                        A[rows[il], col[(sn, "tau2")]] -= g[kn, il, ik] * n_fn[ik]
+                    else:                                                 # POROELASTIC MEDIA (1) - VISCOELASTIC SOLID (2), seen from the solid
+                        A[rows[il], col[(sn, "u1%d" % ik)]] += h[kn, il, ik]
+                        A[rows[il], col[(sn, "t1%d" % ik)]] += g[kn, il, ik]
+                        A[rows[il], col[(sn, "tau1")]] += g[kn, il, ik] * n_fn[ik]
+            return
+        for il in range(4):
+            row = rows[il]
+            if first:                                                     # POROELASTIC MEDIA (1) - VISCOELASTIC SOLID (2): Un1 = u1 . n1
+                A[row, col[(sn, "tau1")]] += h[kn, il, 0]
+                for ik in range(3):
+                    A[row, col[(sn, "u1%d" % ik)]] -= g[kn, il, 0] * n_fn[ik]
+                    A[row, col[(sn, "u1%d" % ik)]] += h[kn, il, ik + 1]
+                    A[row, col[(sn, "t1%d" % ik)]] -= g[kn, il, ik + 1]
+            else:                                                         # VISCOELASTIC SOLID (1) - POROELASTIC MEDIA (2), seen from the poroelastic medium
+                A[row, col[(sn, "tau2")]] += h[kn, il, 0]
+                for ik in range(3):
+                    A[row, col[(sn, "u2%d" % ik)]] += g[kn, il, 0] * n_fn[ik]
+                    A[row, col[(sn, "u2%d" % ik)]] += h[kn, il, ik + 1]
+                    A[row, col[(sn, "t2%d" % ik)]] -= g[kn, il, ik + 1]
 
     def _scatter_fluid_poro(self, kr, kn, sn, bnd, rows, first, n_fn, h, g, A):
         """be-be boundary between an inviscid fluid and a poroelastic medium, perfectly permeable (ctype 0) or impermeable (1), written out as

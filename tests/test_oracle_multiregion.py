@@ -304,3 +304,73 @@ def test_fluid_against_poroelastic_column(fluid_first, imp):
         else:
             n_out = -1.0 if fluid_first else 1.0              # outward normal of the poroelastic region at the interface, x component
             assert abs(x[mrm.col[(v, "w%d" % side)]] - n_out * U) < 3e-2 * max(abs(U), uref)
+
+
+def solid_poro_1d(omega, ms, po, xs, solid_first, P=1.0):
+    """Exact 1D column: an elastic layer bonded to a saturated poroelastic layer through an impervious contact (u continuous, U = u,
+    total normal stress continuous: sigma_solid = sigma_s + tau).  Solid end: normal traction P on the free end; poroelastic end: fixed, impermeable."""
+    M = np.array([[po.lam + 2 * po.mu + po.Q ** 2 / po.R, po.Q], [po.Q, po.R]])
+    rh11 = po.rho1 + po.rhoa - 1j * po.b / omega; rh12 = -po.rhoa + 1j * po.b / omega; rh22 = po.rho2 + po.rhoa - 1j * po.b / omega
+    k2, Y = np.linalg.eig(np.linalg.solve(M, omega ** 2 * np.array([[rh11, rh12], [rh12, rh22]])))
+    kp = np.sqrt(k2); kp = np.where(kp.real < 0, -kp, kp)
+    ks = omega / ms.c1; Zs = ms.lam + 2 * ms.mu
+
+    def poro_rows(x):
+        e = [np.exp(-1j * kp[0] * x), np.exp(1j * kp[0] * x), np.exp(-1j * kp[1] * x), np.exp(1j * kp[1] * x)]
+        d = [-1j * kp[0] * e[0], 1j * kp[0] * e[1], -1j * kp[1] * e[2], 1j * kp[1] * e[3]]
+        yv = [Y[:, 0], Y[:, 0], Y[:, 1], Y[:, 1]]
+        u = np.array([e[q] * yv[q][0] for q in range(4)]); U = np.array([e[q] * yv[q][1] for q in range(4)])
+        du = np.array([d[q] * yv[q][0] for q in range(4)]); dU = np.array([d[q] * yv[q][1] for q in range(4)])
+        return u, U, M[0, 0] * du + M[0, 1] * dU, M[1, 0] * du + M[1, 1] * dU
+
+    def solid_rows(x):
+        e = np.array([np.exp(-1j * ks * x), np.exp(1j * ks * x)])
+        return e, Zs * np.array([-1j * ks, 1j * ks]) * e
+    x_s, x_p = (0.0, 1.0) if solid_first else (1.0, 0.0)
+    S = np.zeros((6, 6), dtype=complex); r = np.zeros(6, dtype=complex)
+    # traction on the solid end: t = sigma n, n = -x at x = 0 and +x at x = 1; prescribed t_x = P
+    S[0, :2] = solid_rows(x_s)[1] * (-1.0 if solid_first else 1.0); r[0] = P
+    u, U, sg, ta = poro_rows(x_p); S[1, 2:] = u; S[2, 2:] = U
+    u, U, sg, ta = poro_rows(xs); us, ss = solid_rows(xs)
+    S[3, :2] = us; S[3, 2:] = -u
+    S[4, 2:] = U - u
+    S[5, :2] = ss; S[5, 2:] = -(sg + ta)
+    c = np.linalg.solve(S, r)
+    return (lambda x: [row @ c[:2] for row in solid_rows(x)]), (lambda x: [row @ c[2:] for row in poro_rows(x)])
+
+
+@pytest.mark.parametrize("solid_first", [True, False])
+def test_solid_bonded_to_a_poroelastic_layer(solid_first):
+    ms = Material(1.8, 1.4, 0.25, 0.03)
+    omega, xs = 2.0, 0.5
+    sb = solid_bcs(1.0)
+    pend = ([1, 0, 0, 0], [0, 0, 0, 0])
+    if solid_first:
+        regs = [Region(SOLID, ms, [1, 3, 4, 5, 6, 7]), Region(PORO, PO, [-7, 2, 13, 14, 15, 16])]
+        bcs = {1: ([1, 1, 1], [1.0, 0, 0]), 2: pend}; bcs.update({q: sb[q] for q in LAT1}); bcs.update(poro_bcs_side(LAT2))
+    else:
+        regs = [Region(PORO, PO, [1, 3, 4, 5, 6, 7]), Region(SOLID, ms, [-7, 2, 13, 14, 15, 16])]
+        bcs = {2: ([1, 1, 1], [1.0, 0, 0]), 1: pend}; bcs.update({q: sb[q] for q in LAT2}); bcs.update(poro_bcs_side(LAT1))
+    mrm = MultiRegionModel(two_box_mesh(2, shape.QUAD9, xs=xs), regs, BPART, bcs)
+    o = MultiRegionOracle(mrm)
+    A, b = o.assemble(omega)
+    A2, b2 = o.assemble(omega, flat=True)
+    assert np.abs(A - A2).max() <= 1e-15 * np.abs(A).max() and np.abs(b - b2).max() <= 1e-15 * np.abs(b).max()
+    x = np.linalg.solve(A, b)
+    solid, poro = solid_poro_1d(omega, ms, PO, xs, solid_first)
+    uref = max(max(abs(solid(t)[0]) for t in np.linspace(0, 1, 11)), max(abs(poro(t)[0]) for t in np.linspace(0, 1, 11)))
+    tref = max(abs(poro(t)[3]) for t in np.linspace(0, 1, 11))
+    so_side = LAT1 if solid_first else LAT2; po_side = LAT2 if solid_first else LAT1
+    for bnd in so_side:
+        for v in sorted(set(int(n) for e in mrm.elems_of_boundary[bnd] for n in mrm.mesh.conn[e])):
+            assert abs(x[mrm.col[(v, "u10")]] - solid(mrm.node_x[v, 0])[0]) < 1e-2 * uref
+    for bnd in po_side:
+        for v in sorted(set(int(n) for e in mrm.elems_of_boundary[bnd] for n in mrm.mesh.conn[e])):
+            u, U, sg, ta = poro(mrm.node_x[v, 0])
+            assert abs(x[mrm.col[(v, "u10")]] - u) < 1e-2 * uref and abs(x[mrm.col[(v, "tau1")]] - ta) < 1e-2 * tref
+    side = 2 if solid_first else 1
+    u, U, sg, ta = poro(xs)
+    n_p = -1.0 if solid_first else 1.0                        # outward normal of the poroelastic region at the interface (x component)
+    for v in sorted(set(int(n) for e in mrm.elems_of_boundary[7] for n in mrm.mesh.conn[e])):
+        assert abs(x[mrm.col[(v, "u%d0" % side)]] - u) < 2e-2 * uref and abs(x[mrm.col[(v, "tau%d" % side)]] - ta) < 2e-2 * tref
+        assert abs(x[mrm.col[(v, "t%d0" % side)]] - n_p * sg) < 3e-2 * max(abs(sg), tref)       # skeleton traction t = sigma_s n
