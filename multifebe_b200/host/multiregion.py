@@ -141,9 +141,17 @@ class MultiRegionModel:
                                 self.col[(v, "u%d%d" % (pe, k))] = col; self.col[(v, "t%d%d" % (pe, k))] = col + 1; col += 2
                             self.row[(v, pe)] = prow + (r1rows if pe == 1 else r2rows)
                             self.row[(v, se_)] = r2rows if pe == 1 else r1rows
+                        elif k1 == PORO and k2 == PORO:
+                            # perfectly permeable contact (ctype 0): tau, Un, u_k, t_k of region 1 are active; rows of both regions interleaved per
+                            # component (build_auxiliary_variables_mechanics_harmonic.f90:1130-1230)
+                            if self.interface_ctype.get(b, 0) != 0:
+                                raise ValueError("boundary %d: of the poroelastic-poroelastic contacts only the perfectly permeable one is built" % b)
+                            r1rows, r2rows = [], []
+                            for k in range(4):
+                                r1rows.append(row); r2rows.append(row + 1); row += 2
+                                self.col[(v, _var_name(PORO, k, False, 1))] = col; self.col[(v, _var_name(PORO, k, True, 1))] = col + 1; col += 2
+                            self.row[(v, 1)] = r1rows; self.row[(v, 2)] = r2rows
                         elif PORO in (k1, k2):
-                            if {k1, k2} != {FLUID, PORO}:
-                                raise ValueError("boundary %d: poroelastic-poroelastic interfaces are not built" % b)
                             imp = self.interface_ctype.get(b, 0) == 1
                             fe, pe = (1, 2) if k1 == FLUID else (2, 1)           # equation index / variable suffix of the fluid and of the poroelastic side
                             def number_poro():
@@ -275,6 +283,22 @@ class MultiRegionModel:
                     k1, k2 = self.regions[r1].kind, self.regions[r2].kind
                     other = k2 if first else k1
                     sgn = 1.0 if first else -1.0                              # n_fn is outward from region 1: the normal of THIS region is sgn * n_fn
+                    if k1 == PORO and k2 == PORO:        # assemble_bem_harpor_equation.f90:696-722 (region 1) / :860-975 (region 2), perfectly permeable
+                        f1, f2 = self.regions[r1].material.phi, self.regions[r2].material.phi
+                        hcol[q] = self.col[(sn, _var_name(PORO, k, False, 1))]
+                        if first:
+                            hcoef[q] = 1.0
+                            gcol[q, 0], gcoef[q, 0] = self.col[(sn, _var_name(PORO, k, True, 1))], -1.0
+                        elif k == 0:                      # tau2 = phi2/phi1 tau1; Un2 = -phi1/phi2 Un1 - (1 - phi1/phi2) u1 . n1
+                            hcoef[q] = f2 / f1
+                            gcol[q, 0], gcoef[q, 0] = self.col[(sn, "w1")], f1 / f2
+                            for t in range(3):
+                                gcol[q, 1 + t], gcoef[q, 1 + t] = self.col[(sn, "u1%d" % t)], (1.0 - f1 / f2) * n_fn[t]
+                        else:                             # u2 = u1; t2 = -t1 - (1 - phi2/phi1) tau1 n1
+                            hcoef[q] = 1.0
+                            gcol[q, 0], gcoef[q, 0] = self.col[(sn, "t1%d" % (k - 1))], 1.0
+                            gcol[q, 1], gcoef[q, 1] = self.col[(sn, "tau1")], (1.0 - f2 / f1) * n_fn[k - 1]
+                        continue
                     if {k1, k2} == {SOLID, PORO}:     # assemble_bem_harela_equation.f90:262-285 / :430-455; assemble_bem_harpor_equation.f90:627-660 / :807-830
                         ps = 1 if k1 == PORO else 2
                         if r.kind == SOLID:               # u = u_p; t = -t_p -/+ tau n

@@ -112,6 +112,27 @@ class MultiRegionOracle:
                         else:
                             A[rows[il], m.col[(sn, _var_name(PORO, ik, False, 1))]] += h[kn, il, ik]; b[rows[il]] += g[kn, il, ik] * cv[ik]
                 continue
+            if r2 is not None and m.regions[r1].kind == PORO and m.regions[r2].kind == PORO:
+                # POROELASTIC MEDIA (1) - POROELASTIC MEDIA (2), perfectly permeable: assemble_bem_harpor_equation.f90:696-722 (region 1: every
+                # variable of region 1 unknown) and :860-975 (region 2: tau2 = phi2/phi1 tau1, Un2 = -phi1/phi2 Un1 - (1 - phi1/phi2) u1.n1, u2 = u1,
+                # t2 = -t1 - (1 - phi2/phi1) tau1 n1)
+                n_fn = sh.unit_normal(et, v.node_x[nodes], sh.XI_NODES[et][kn])
+                f1, f2 = m.regions[r1].material.phi, m.regions[r2].material.phi
+                for il in range(4):
+                    row = rows[il]
+                    if first:
+                        A[row, m.col[(sn, "tau1")]] += h[kn, il, 0]; A[row, m.col[(sn, "w1")]] -= g[kn, il, 0]
+                        for ik in range(3):
+                            A[row, m.col[(sn, "u1%d" % ik)]] += h[kn, il, ik + 1]; A[row, m.col[(sn, "t1%d" % ik)]] -= g[kn, il, ik + 1]
+                    else:
+                        A[row, m.col[(sn, "tau1")]] += h[kn, il, 0] * (f2 / f1)
+                        A[row, m.col[(sn, "w1")]] += g[kn, il, 0] * (f1 / f2)
+                        for ik in range(3):
+                            A[row, m.col[(sn, "u1%d" % ik)]] += g[kn, il, 0] * (1.0 - f1 / f2) * n_fn[ik]
+                            A[row, m.col[(sn, "u1%d" % ik)]] += h[kn, il, ik + 1]
+                            A[row, m.col[(sn, "t1%d" % ik)]] += g[kn, il, ik + 1]
+                            A[row, m.col[(sn, "tau1")]] += g[kn, il, ik + 1] * (1.0 - f2 / f1) * n_fn[ik]
+                continue
             if r2 is not None and {m.regions[r1].kind, m.regions[r2].kind} == {SOLID, PORO}:
                 self._scatter_solid_poro(kr, kn, sn, bnd, rows, first, sh.unit_normal(et, v.node_x[nodes], sh.XI_NODES[et][kn]), h, g, A)
                 continue

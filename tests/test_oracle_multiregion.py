@@ -374,3 +374,58 @@ def test_solid_bonded_to_a_poroelastic_layer(solid_first):
     for v in sorted(set(int(n) for e in mrm.elems_of_boundary[7] for n in mrm.mesh.conn[e])):
         assert abs(x[mrm.col[(v, "u%d0" % side)]] - u) < 2e-2 * uref and abs(x[mrm.col[(v, "tau%d" % side)]] - ta) < 2e-2 * tref
         assert abs(x[mrm.col[(v, "t%d0" % side)]] - n_p * sg) < 3e-2 * max(abs(sg), tref)       # skeleton traction t = sigma_s n
+
+
+def test_two_poroelastic_layers_permeable_contact():
+    """Two saturated layers in perfectly permeable contact: u continuous, pore pressure continuous (tau1/phi1 = tau2/phi2), relative fluid flux
+    continuous (phi1 (U1 - u) = phi2 (U2 - u)), total normal stress continuous.  Fixed impermeable base at x = 0, loaded drained top at x = 1."""
+    po1 = PO
+    po2 = Poro(rhof=1.0, rhos=2.6, lam=2.0, mu=1.5, xi=0.03, phi=0.2, rhoa=0.1, R=0.5, Q=0.7, b=0.8)
+    omega, xs = 2.0, 0.5
+
+    def modes(po):
+        M = np.array([[po.lam + 2 * po.mu + po.Q ** 2 / po.R, po.Q], [po.Q, po.R]])
+        rh11 = po.rho1 + po.rhoa - 1j * po.b / omega; rh12 = -po.rhoa + 1j * po.b / omega; rh22 = po.rho2 + po.rhoa - 1j * po.b / omega
+        k2, Y = np.linalg.eig(np.linalg.solve(M, omega ** 2 * np.array([[rh11, rh12], [rh12, rh22]])))
+        kp = np.sqrt(k2); kp = np.where(kp.real < 0, -kp, kp)
+
+        def rows(x):
+            e = [np.exp(-1j * kp[0] * x), np.exp(1j * kp[0] * x), np.exp(-1j * kp[1] * x), np.exp(1j * kp[1] * x)]
+            d = [-1j * kp[0] * e[0], 1j * kp[0] * e[1], -1j * kp[1] * e[2], 1j * kp[1] * e[3]]
+            yv = [Y[:, 0], Y[:, 0], Y[:, 1], Y[:, 1]]
+            u = np.array([e[q] * yv[q][0] for q in range(4)]); U = np.array([e[q] * yv[q][1] for q in range(4)])
+            du = np.array([d[q] * yv[q][0] for q in range(4)]); dU = np.array([d[q] * yv[q][1] for q in range(4)])
+            return u, U, M[0, 0] * du + M[0, 1] * dU, M[1, 0] * du + M[1, 1] * dU
+        return rows
+    r1, r2 = modes(po1), modes(po2)
+    S = np.zeros((8, 8), dtype=complex); rhs = np.zeros(8, dtype=complex)
+    u, U, sg, ta = r1(0.0); S[0, :4] = u; S[1, :4] = U
+    u, U, sg, ta = r2(1.0); S[2, 4:] = sg; rhs[2] = 1.0; S[3, 4:] = ta
+    ua, Ua, sa, tta = r1(xs); ub, Ub, sb_, ttb = r2(xs)
+    S[4, :4] = ua; S[4, 4:] = -ub
+    S[5, :4] = tta / po1.phi; S[5, 4:] = -ttb / po2.phi
+    S[6, :4] = po1.phi * (Ua - ua); S[6, 4:] = -po2.phi * (Ub - ub)
+    S[7, :4] = sa + tta; S[7, 4:] = -(sb_ + ttb)
+    c = np.linalg.solve(S, rhs)
+    f1 = lambda x: [row @ c[:4] for row in r1(x)]
+    f2 = lambda x: [row @ c[4:] for row in r2(x)]
+    regs = [Region(PORO, po1, [1, 3, 4, 5, 6, 7]), Region(PORO, po2, [-7, 2, 13, 14, 15, 16])]
+    bcs = {1: ([1, 0, 0, 0], [0, 0, 0, 0]), 2: ([0, 1, 1, 1], [0, 1.0, 0, 0])}
+    bcs.update(poro_bcs_side(LAT1)); bcs.update(poro_bcs_side(LAT2))
+    mrm = MultiRegionModel(two_box_mesh(2, shape.QUAD9, xs=xs), regs, BPART, bcs)
+    o = MultiRegionOracle(mrm)
+    A, b = o.assemble(omega)
+    A2, b2 = o.assemble(omega, flat=True)
+    assert np.abs(A - A2).max() <= 1e-15 * np.abs(A).max() and np.abs(b - b2).max() <= 1e-15 * np.abs(b).max()
+    x = np.linalg.solve(A, b)
+    uref = max(max(abs(f1(t)[0]) for t in np.linspace(0, xs, 6)), max(abs(f2(t)[0]) for t in np.linspace(xs, 1, 6)))
+    tref = max(max(abs(f1(t)[3]) for t in np.linspace(0, xs, 6)), max(abs(f2(t)[3]) for t in np.linspace(xs, 1, 6)))
+    for side, f in ((LAT1, f1), (LAT2, f2)):
+        for bnd in side:
+            for v in sorted(set(int(n) for e in mrm.elems_of_boundary[bnd] for n in mrm.mesh.conn[e])):
+                u, U, sg, ta = f(mrm.node_x[v, 0])
+                assert abs(x[mrm.col[(v, "u10")]] - u) < 1e-2 * uref and abs(x[mrm.col[(v, "tau1")]] - ta) < 1e-2 * tref
+    u, U, sg, ta = f1(xs)
+    for v in sorted(set(int(n) for e in mrm.elems_of_boundary[7] for n in mrm.mesh.conn[e])):
+        assert abs(x[mrm.col[(v, "u10")]] - u) < 2e-2 * uref and abs(x[mrm.col[(v, "tau1")]] - ta) < 2e-2 * tref
+        assert abs(x[mrm.col[(v, "w1")]] - U) < 3e-2 * max(abs(U), uref) and abs(x[mrm.col[(v, "t10")]] - sg) < 3e-2 * max(abs(sg), tref)
