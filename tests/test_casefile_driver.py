@@ -7,9 +7,9 @@ import sys
 import numpy as np
 import pytest
 
-from multifebe_b200.host import cube_mesh, write_gmsh22, shape, Material, Fluid, room_analytic
+from multifebe_b200.host import cube_mesh, write_gmsh22, shape, Fluid, room_analytic
 from multifebe_b200.host.casefile import CaseFile, CaseFileError, read_frequencies, elastic_constants
-from multifebe_b200.host.export import read_nso, NsoWriter
+from multifebe_b200.host.export import read_nso
 from multifebe_b200.host.fortran_format import RealFormat, fmt_real, fmt_int, int_width
 from multifebe_b200 import driver
 

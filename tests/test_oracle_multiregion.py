@@ -5,8 +5,7 @@ two-layer solutions: solid-solid, fluid-fluid and fluid-solid columns."""
 import numpy as np
 import pytest
 
-from multifebe_b200.host import (Material, Fluid, Model, FluidModel, MultiRegionModel, Region, SOLID, FLUID, two_box_mesh, cube_mesh, cube_bcs,
-                                 room_bcs, column_analytic_u, shape)
+from multifebe_b200.host import Material, Fluid, MultiRegionModel, Region, SOLID, FLUID, two_box_mesh, cube_mesh, column_analytic_u, shape
 from oracle import oracle as orc
 from oracle.multiregion import MultiRegionOracle
 
