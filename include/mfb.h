@@ -240,6 +240,10 @@ int mfb_dist_layout(int n, int nb, int nranks, int rank, int* n_local_cols, int*
 int mfb_dist_partition_tiles(int n_tiles, const int* tile_row0, const int* tile_nbytes, int n_dof, int nranks, int* tile_rank,
                              int* row_bounds);
 
+/* Host-only helper: geometry-only pieces of the free term at a boundary node (see api.cu); c_lk = cp delta_lk - sum_b[3*l+k] / (8 pi (1 - nu))
+ * for a solid (Mantic), c = cp for a fluid, c_00 = J cp for the fluid phase of a poroelastic medium.  normals / tangents: 3 per element. */
+int mfb_freeterm_terms(int n_elements, const double* normals, const double* tangents, double tol, double* cp, double* sum_b /* 9 */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,75 @@ def dist_partition_tiles(tile_row0, tile_nbytes, n_dof, nranks):
     return tr, rb
 
 
+def freeterm(normals, tangents, nu, tol=1e-6):
+    """(Mantic's matrix c (3 x 3, complex), scalar free term cp) of a boundary node from the unit normals / boundary tangents of its elements
+    (mfb_freeterm_terms; host only)."""
+    n = np.ascontiguousarray(normals, dtype=np.float64); t = np.ascontiguousarray(tangents, dtype=np.float64)
+    cp = C.c_double(0.0); sb = np.zeros(9)
+    _check(lib().mfb_freeterm_terms(C.c_int(len(n)), _p(n), _p(t), C.c_double(tol), C.byref(cp), _p(sb)))
+    return cp.value * np.eye(3) - sb.reshape(3, 3) / (8.0 * np.pi * (1.0 - complex(nu))), cp.value
+
+
+class CoupledProblem:
+    """Several BE regions (elastic solids, inviscid fluids, poroelastic media) coupled through be-be interfaces, on the GPU through the
+    single-region kernels: two auxiliary single-region assemblies per region (host/coupled.py), the column combination on the host, the
+    coupled system factorised and solved on the device (mfb_zsolve with host arrays).  First functional version: the local matrices travel
+    through host memory; the resident combination kernel is the next step."""
+
+    def __init__(self, ctx, mrm):
+        from .host.coupled import local_models
+        self.ctx, self.m = ctx, mrm
+        self.locals = [local_models(mrm, kr) for kr in range(len(mrm.regions))]      # kept between frequencies, like the plans of their problems
+        self.problems = {}
+        for mH, mG, _ in self.locals:
+            self.problems[id(mH)] = Problem(ctx, mH); self.problems[id(mG)] = Problem(ctx, mG)
+        self._solver = None
+
+    def _assemble_local(self, model, region, omega):
+        pr = self.problems[id(model)]
+        if region.kind == "solid":
+            return pr.build_lse_mechanics_bem_harela(omega, region.material)[0]
+        if region.kind == "fluid":
+            return pr.build_lse_mechanics_bem_harpot(omega, region.material)[0]
+        return pr.build_lse_mechanics_bem_harpor(omega, region.material)[0]
+
+    def assemble(self, omega):
+        """-> A, b of the coupled system (host arrays)."""
+        from .host import coupled
+        return coupled.assemble_coupled(self.m, omega, self._assemble_local, freeterm, locals_=self.locals)
+
+    def solve_frequency(self, omega):
+        """x of the coupled system: assembled as above, zgetrf + zgetrs on the device (LAPACK zgesv semantics through mfb_zsolve)."""
+        A, b = self.assemble(omega)
+        n = self.m.n_dof
+        if self._solver is None or self._solver.m.n_dof != n:
+            self._solver = _lu_only_problem(self.ctx, n)
+        return self._solver.solve_lse_c(np.asfortranarray(A), b)
+
+    def close(self):
+        for pr in self.problems.values():
+            pr.close()
+        if self._solver is not None:
+            self._solver.close()
+
+
+def _lu_only_problem(ctx, n):
+    """A minimal problem object whose only use is mfb_zsolve on host matrices of size n (mfb_zsolve is tied to a problem's n_dof): one tri3 element,
+    three nodes, rows and columns spread over n."""
+    from .host.coupled import LocalModel
+    m = LocalModel()
+    m.ndof, m.n_node, m.n_elem, m.n_colloc, m.n_dof = 1, 3, 1, 3, n
+    m.node_x = np.array([[0.0, 0, 0], [1.0, 0, 0], [0.0, 1, 0]])
+    m.etype = np.array([5], dtype=np.int32); m.elem_ptr = np.array([0, 3], dtype=np.int32); m.elem_node = np.array([0, 1, 2], dtype=np.int32)
+    m.elem_reversed = np.zeros(1, dtype=np.uint8)
+    m.colloc_x = np.array([[0.2, 0.2, 0.5], [0.6, 0.2, 0.5], [0.2, 0.6, 0.5]]); m.colloc_node = np.array([0, 1, 2], dtype=np.int32)
+    m.colloc_elem = -np.ones(3, dtype=np.int32); m.colloc_kn = np.zeros(3, dtype=np.int32); m.colloc_xi = np.full((3, 2), -9.0)
+    m.row = np.array([[0], [1], [2]], dtype=np.int32); m.col_u = np.array([[0], [1], [2]], dtype=np.int32); m.col_t = -np.ones((3, 1), dtype=np.int32)
+    m.ctype = np.ones((3, 1), dtype=np.int32); m.cvalue = np.zeros((3, 1), dtype=np.complex128)
+    m.qsi_relative_error, m.qsi_ns_max, m.precalset_gln, m.geometric_tolerance = 1e-6, 16, np.arange(2, 10, dtype=np.int32), 1e-6
+    return Problem(ctx, m)
+
+
 class Context:
     """One context per GPU (one process per GPU)."""
 

@@ -1189,6 +1189,17 @@ extern "C" int mfb_zgemm_minus(mfb_ctx* ctx, int m, int n, int k, const mfb_z* A
 // Single-frequency multi-GPU mode: collocation-row blocks for the assembly, block-cyclic columns for the
 // LU, NCCL to move row slabs to their column owners once and to broadcast each factorised panel.
 // ---------------------------------------------------------------------------------------------------------------------
+// Host-only helper (no GPU needed): the geometry-only pieces of the free term of a boundary node from the unit normals and the unit boundary
+// tangents of the elements that meet there -- cp = (2 pi + sum of the signed dihedral angles) / 4 pi (fbem_bem_pot3d_sbie_freeterm,
+// lib/fbem/src/bem_stapot3d.f90:155-296) and the tensor sum_b[9] of Mantic's formula, so that c_lk = cp delta_lk - sum_b[l][k] / (8 pi (1 - nu))
+// (fbem_bem_harela3d_sbie_freeterm, lib/fbem/src/bem_harela3d.f90:365-542).  Used by the coupled-region assembly of multifebe_b200/host/coupled.py,
+// whose auxiliary single-region problems are set up without free terms.  Returns 2 when the normals / tangents configuration is not valid.
+extern "C" int mfb_freeterm_terms(int n_elements, const double* normals, const double* tangents, double tol, double* cp, double* sum_b) {
+  if (n_elements <= 0 || !normals || !tangents || !cp || !sum_b) return fail(MFB_ERR_ARG, "mfb_freeterm_terms: invalid argument");
+  if (mfbh::mantic_terms(n_elements, normals, tangents, tol, cp, sum_b)) return fail(2, "mfb_freeterm_terms: the normals/tangents configuration is not valid");
+  return MFB_OK;
+}
+
 extern "C" int mfb_dist_layout(int n, int nb, int nranks, int rank, int* n_local_cols, int* local_to_global) {
   if (n <= 0 || nb <= 0 || nranks <= 0 || rank < 0 || rank >= nranks) return fail(MFB_ERR_ARG, "mfb_dist_layout: invalid argument");
   const int ncl = dist_ncols_local(n, nb, nranks, rank);

@@ -104,3 +104,32 @@ def unit_normal(etype, x_nodes, xi):
         t1 = t1 + d1[k] * x_nodes[k]; t2 = t2 + d2[k] * x_nodes[k]
     n = np.cross(t1, t2)
     return n / np.sqrt(n @ n)
+
+
+def node_normal_tangents(etype, x_nodes, node):
+    """(n, t+, t-) at element node `node`: unit normal and the unit tangents of the two element edges that meet there (pointing away from
+    the node along the boundary in the positive / negative sense), or along / against the edge for a mid-side node
+    (src/build_data_at_geometrical_nodes.f90:198-222, fbem_utangents_at_boundary, lib/fbem/src/geometry.f90:657-914)."""
+    xi = XI_NODES[etype][node]
+    d1, d2 = dphi(etype, xi)
+    T1 = np.zeros(3); T2 = np.zeros(3)
+    for k in range(N_NODES[etype]):
+        T1 = T1 + d1[k] * x_nodes[k]; T2 = T2 + d2[k] * x_nodes[k]
+    N = np.cross(T1, T2)
+    n = N / np.sqrt(N @ N)
+    t1 = T1 / np.sqrt(T1 @ T1); t2 = T2 / np.sqrt(T2 @ T2)
+    if etype in (TRI3, TRI6):
+        if etype == TRI3:
+            d3 = np.array([1.0, -1.0, 0.0])
+        else:
+            d3 = np.array([4.0 * xi[0] - 1.0, 4.0 * xi[0] - 3.0, 0.0, 4.0 * (1.0 - 2.0 * xi[0]), 0.0, 0.0])
+        T3 = np.zeros(3)
+        for k in range(N_NODES[etype]):
+            T3 = T3 + d3[k] * x_nodes[k]
+        t3 = T3 / np.sqrt(T3 @ T3)
+        table = {0: (-t3, -t1), 1: (-t2, t3), 2: (t1, t2), 3: (-t3, t3), 4: (-t2, t2), 5: (t1, -t1)}
+    else:
+        z = np.zeros(3)
+        table = {0: (t1, t2), 1: (t2, -t1), 2: (-t1, -t2), 3: (-t2, t1), 4: (t1, -t1), 5: (t2, -t2), 6: (-t1, t1), 7: (-t2, t2), 8: (z, z)}
+    tp, tm = table[node]
+    return n, tp, tm

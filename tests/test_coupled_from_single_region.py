@@ -1,0 +1,87 @@
+"""Coupled regions from single-region assemblies (multifebe_b200/host/coupled.py): the H / G auxiliary problems, the private interface nodes
+and the column combination through the flat descriptors must reproduce the multi-region oracle.  Here the single-region assembler is the CPU
+oracle; on the GPU it is Problem.build_lse_mechanics_bem_* (tests/test_gpu_coupled.py, pending its first hardware run)."""
+import ctypes as C
+import numpy as np
+import pytest
+
+from multifebe_b200.host import Material, Fluid, Poro, MultiRegionModel, Region, SOLID, FLUID, two_box_mesh, shape
+from multifebe_b200.host.multiregion import PORO
+from multifebe_b200.host.coupled import assemble_coupled, local_models
+from oracle import oracle as orc
+from oracle.multiregion import MultiRegionOracle
+from test_oracle_multiregion import BPART, LAT1, LAT2, solid_bcs, fluid_bcs, poro_bcs_side, PO
+
+MS, FL = Material(2.0, 1.5, 0.25, 0.03), Fluid(1.0, 1.2, 0.01)
+
+
+def oracle_local_assemble(model, region, omega):
+    if region.kind == SOLID:
+        return orc.Oracle(model).assemble(omega, region.material)[0]
+    if region.kind == FLUID:
+        return orc.PotOracle(model).assemble(omega, region.material)[0]
+    return orc.PorOracle(model).assemble(omega, region.material)[0]
+
+
+def oracle_freeterm(normals, tangents, nu, tol):
+    cm, err = orc.freeterm(normals, tangents, nu, tol)
+    cp = C.c_double(0.0)
+    n_ = np.ascontiguousarray(normals, dtype=np.float64); t_ = np.ascontiguousarray(tangents, dtype=np.float64)
+    err = err or orc.lib().orc_freeterm_pot(C.c_int(len(n_)), orc._p(n_), orc._p(t_), C.c_double(tol), C.byref(cp))
+    assert not err
+    return cm, cp.value
+
+
+def bcs_for(kind, lat, end, end_value):
+    if kind == SOLID:
+        sb = solid_bcs(1.0); out = {q: sb[q] for q in lat}; out[end] = ([0, 1, 0], [0.1, 0.2 - 0.1j, 0.0]) if end_value else ([0, 0, 0], [0, 0, 0])
+    elif kind == FLUID:
+        fb = fluid_bcs(1.0); out = {q: fb[q] for q in lat}; out[end] = (0, 0.7 + 0.1j) if end_value else (1, 0.0)
+    else:
+        out = poro_bcs_side(lat); out[end] = ([0, 1, 1, 1], [0.3, 1.0, 0.0, 0.2j]) if end_value else ([1, 0, 0, 0], [0, 0, 0, 0])
+    return out
+
+
+@pytest.mark.parametrize("kinds,ict", [((SOLID, SOLID), 0), ((FLUID, FLUID), 0), ((SOLID, FLUID), 0), ((FLUID, SOLID), 0), ((FLUID, PORO), 0), ((PORO, FLUID), 1),
+                                       ((SOLID, PORO), 0), ((PORO, PORO), 0)])
+@pytest.mark.parametrize("et", [shape.QUAD8, shape.TRI3])
+def test_coupled_system_from_single_region_assemblies(kinds, ict, et):
+    mats = {SOLID: MS, FLUID: FL, PORO: PO}
+    bcs = bcs_for(kinds[0], LAT1, 1, True); bcs.update(bcs_for(kinds[1], LAT2, 2, False))
+    mrm = MultiRegionModel(two_box_mesh(1, et), [Region(kinds[0], mats[kinds[0]], [1, 3, 4, 5, 6, 7]), Region(kinds[1], mats[kinds[1]], [-7, 2, 13, 14, 15, 16])],
+                           BPART, bcs, interface_ctype={7: ict})
+    omega = 1.7
+    A0, b0 = MultiRegionOracle(mrm).assemble(omega)
+    A1, b1 = assemble_coupled(mrm, omega, oracle_local_assemble, oracle_freeterm)
+    # columns of different variables live on different scales
+    sc = np.abs(A0).max(axis=0)
+    assert (np.abs(A1 - A0).max(axis=0) <= 1e-12 * sc).all(), (np.abs(A1 - A0).max(axis=0) / sc).max()
+    assert np.abs(b1 - b0).max() <= 1e-12 * np.abs(b0).max() and np.abs(b0).max() > 0
+
+
+def test_local_models_are_valid_single_region_inputs():
+    mrm = MultiRegionModel(two_box_mesh(1, shape.QUAD9), [Region(SOLID, MS, [1, 3, 4, 5, 6, 7]), Region(FLUID, FL, [-7, 2, 13, 14, 15, 16])], BPART,
+                           {**bcs_for(SOLID, LAT1, 1, True), **bcs_for(FLUID, LAT2, 2, False)})
+    for kr in (0, 1):
+        mH, mG, mp = local_models(mrm, kr)
+        nd = mrm.regions[kr].ndof
+        for m in (mH, mG):
+            assert m.row.shape == (m.n_node, nd) and (m.colloc_elem == -1).all() and m.n_dof >= mp["n_rows"]
+            used = m.row[m.row >= 0]
+            assert len(set(used.tolist())) == len(used) == mp["n_rows"]                      # every local row owned once
+            cols = (m.col_t if m is mG else m.col_u)
+            assert (cols[np.unique(m.elem_node)] >= 0).all() and cols.max() < m.n_dof        # every element node has its column
+        # private copies: the G problem has one node per (interface element, local node) more than the mesh
+        n_if = sum(len(mrm.mesh.conn[e]) for e in mrm.elems_of_boundary[7])
+        assert mG.n_node == mrm.n_node + n_if and mH.n_node == mrm.n_node
+
+
+def test_product_free_term_helper_gives_the_same_system():
+    """The same combination with the PRODUCT's free-term helper (mfb_freeterm_terms through capi.freeterm; host only) instead of the oracle's."""
+    from multifebe_b200 import capi
+    bcs = bcs_for(SOLID, LAT1, 1, True); bcs.update(bcs_for(PORO, LAT2, 2, False))
+    mrm = MultiRegionModel(two_box_mesh(2, shape.TRI3), [Region(SOLID, MS, [1, 3, 4, 5, 6, 7]), Region(PORO, PO, [-7, 2, 13, 14, 15, 16])], BPART, bcs)
+    A0, b0 = MultiRegionOracle(mrm).assemble(1.3)
+    A1, b1 = assemble_coupled(mrm, 1.3, oracle_local_assemble, capi.freeterm)
+    sc = np.abs(A0).max(axis=0)
+    assert (np.abs(A1 - A0).max(axis=0) <= 1e-12 * sc).all() and np.abs(b1 - b0).max() <= 1e-12 * np.abs(b0).max()

@@ -1,0 +1,35 @@
+"""Coupled BE regions on the GPU (capi.CoupledProblem: single-region kernels + the column combination of host/coupled.py) against the
+multi-region oracle.  Written after the round's GPU budget was spent: never run on hardware, runs on request only (MFB_RUN_UNVALIDATED=1).
+The solid / fluid pairings use GPU-validated kernels only; the poroelastic ones also need the unvalidated poro.cu."""
+import os
+import numpy as np
+import pytest
+from multifebe_b200.host import MultiRegionModel, Region, SOLID, FLUID, two_box_mesh, shape
+from multifebe_b200.host.multiregion import PORO
+from test_oracle_multiregion import BPART, LAT1, LAT2, PO
+from test_coupled_from_single_region import MS, FL, bcs_for
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.environ.get("MFB_RUN_UNVALIDATED"), reason="first hardware run pending; set MFB_RUN_UNVALIDATED=1")]
+
+
+@pytest.mark.parametrize("kinds,ict", [((SOLID, SOLID), 0), ((FLUID, FLUID), 0), ((SOLID, FLUID), 0), ((FLUID, SOLID), 0), ((FLUID, PORO), 0), ((PORO, FLUID), 1),
+                                       ((SOLID, PORO), 0), ((PORO, PORO), 0)])
+def test_coupled_system_and_solution(gpu_ctx, kinds, ict):
+    from multifebe_b200 import capi
+    from oracle.multiregion import MultiRegionOracle
+    mats = {SOLID: MS, FLUID: FL, PORO: PO}
+    bcs = bcs_for(kinds[0], LAT1, 1, True); bcs.update(bcs_for(kinds[1], LAT2, 2, False))
+    mrm = MultiRegionModel(two_box_mesh(2, shape.QUAD9), [Region(kinds[0], mats[kinds[0]], [1, 3, 4, 5, 6, 7]), Region(kinds[1], mats[kinds[1]], [-7, 2, 13, 14, 15, 16])],
+                           BPART, bcs, interface_ctype={7: ict})
+    omega = 1.7
+    cp = capi.CoupledProblem(gpu_ctx, mrm)
+    A, b = cp.assemble(omega)
+    A0, b0 = MultiRegionOracle(mrm).assemble(omega)
+    sc = np.abs(A0).max(axis=0)
+    assert (np.abs(A - A0).max(axis=0) <= 1e-11 * sc).all(), (np.abs(A - A0).max(axis=0) / sc).max()
+    assert np.abs(b - b0).max() <= 1e-11 * np.abs(b0).max()
+    x = cp.solve_frequency(omega)
+    x0 = np.linalg.solve(A0, b0)
+    # variables of different families live on different scales: compare every unknown against the largest of its kind (by column scale)
+    assert np.abs((x - x0) * sc).max() <= 1e-8 * np.abs(x0 * sc).max()
+    cp.close()
