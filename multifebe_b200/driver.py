@@ -27,6 +27,9 @@ class GpuSolver:
         if case.multi:
             raise CaseFileError("coupled BE regions: the device path is not built yet (DESIGN.md section 7.4); the case parses and numbers, "
                                 "but only the Fortran program solves it")
+        if case.region_type == 3 and not os.environ.get("MFB_RUN_UNVALIDATED"):
+            raise CaseFileError("poroelastic region: the device kernels (csrc/poro.cu) have not had their first hardware run yet; "
+                                "set MFB_RUN_UNVALIDATED=1 to use them (DESIGN.md section 0)")
         from . import capi
         self.capi, self.case = capi, case
         self.ctx = capi.Context(device)
@@ -35,6 +38,8 @@ class GpuSolver:
     def harmonic(self, omega):
         if self.case.region_type == 1:
             return self.pr.solve_frequency_fluid(omega, self.case.material)
+        if self.case.region_type == 3:
+            return self.pr.solve_frequency_poro(omega, self.case.material)
         return self.pr.solve_frequency(omega, self.case.material)
 
     def static(self):

@@ -5,7 +5,8 @@ Mirrors src/read_input_file.f90 for the sections the hot path consumes:
   [frequencies]  src/read_frequencies.f90:20-120  Hz | rad/s; list | lin | log(10)
   [settings]     src/read_settings.f90:74-216     mesh_file_mode = 2 "<gmsh 2.2 file>", qsi_relative_error, qsi_ns_max, precalsets,
                                                   geometric_tolerance
-  [materials]    src/read_materials.f90      fluid (two of K, rho, c; xi) / elastic_solid (two of E, nu, lambda, mu, K; rho, xi)
+  [materials]    src/read_materials.f90      fluid (two of K, rho, c; xi) / elastic_solid (two of E, nu, lambda, mu, K; rho, xi) /
+                                             biot_poroelastic_medium (phi, two elastic constants, Q, R, rho_f, rho_s, rho_a, xi, b)
   [boundaries]   src/read_boundaries.f90     `<id> <part> ordinary`
   [regions]      src/read_regions.f90        `be` regions, full space (several regions sharing be-be boundaries: negative id = reversed), `material <id>` or the legacy in-line forms
                                              `fluid rho c`, `viscoelastic rho mu nu xi`, `elastic rho mu nu`
@@ -13,7 +14,7 @@ Mirrors src/read_input_file.f90 for the sections the hot path consumes:
                                              conditions 0 / 1 per component; defaults (not listed) = 1 with value 0
   [internal points]  src/read_internal_points.f90    `<id> <region> x1 x2 x3` (one elastic region)
   [export]       src/read_export.f90:61-240  export_nso, real_format, integer_format, complex_notation
-Anything else the reference accepts (be-fe coupling, poroelastic regions, crack-like boundaries, local-axes or spring conditions,
+Anything else the reference accepts (be-fe coupling, crack-like boundaries, close-pore conditions, local-axes or spring conditions,
 half-spaces, body loads, incident fields, symmetry planes, internal points of fluid regions, FE regions ...) raises CaseFileError naming the feature:
 the Fortran host keeps those.
 """
@@ -22,7 +23,7 @@ import re
 import numpy as np
 
 from .mesh import read_gmsh22
-from .model import Model, FluidModel, Material, Fluid
+from .model import Model, FluidModel, PoroModel, Material, Fluid, Poro
 from .fortran_format import DEFAULT_REAL_FORMAT, REAL_FORMATS
 
 
@@ -254,7 +255,7 @@ class CaseFile:
         for b, _ in self.boundaries:
             if b not in region_of_boundary:
                 raise CaseFileError("boundary %d is not used with a positive id by any region" % b)
-        ndof_of = {b: (1 if region_of_boundary[b] == 1 else 3) for b, _ in self.boundaries}
+        ndof_of = {b: {1: 1, 2: 3, 3: 4}[region_of_boundary[b]] for b, _ in self.boundaries}
         self.bcs = {bid: ([1] * ndof_of[bid], [0j] * ndof_of[bid]) for bid, _ in self.boundaries if bid not in self.interfaces}   # defaults: t / Un = 0
         cl = sec.get("conditions over be boundaries", [])
         i = 0
@@ -329,7 +330,14 @@ class CaseFile:
                 if self.analysis == "harmonic" and ("rho" not in props or "xi" not in props):
                     raise CaseFileError("material %s: rho and xi are required for the material of this region" % w[1])
                 return Material(rho=props.get("rho", 1.0), mu=ec["mu"], nu=ec["nu"], xi=props.get("xi", 0.0)), 2
-            raise CaseFileError("material type %r is not covered (fluid, elastic_solid)" % mtype)
+            if mtype == "biot_poroelastic_medium":      # src/read_materials.f90:351-520, src/read_regions.f90:737-860
+                need = [k for k in ("phi", "Q", "R", "rho_f", "rho_s") if k not in props]
+                if need:
+                    raise CaseFileError("material %s: %s required for the material of this region" % (w[1], ", ".join(need)))
+                ec = elastic_constants({k: props[k] for k in ("E", "nu", "lambda", "mu", "K") if k in props})
+                return Poro(rhof=props["rho_f"], rhos=props["rho_s"], lam=ec["lambda"], mu=ec["mu"], xi=props.get("xi", 0.0), phi=props["phi"],
+                            rhoa=props.get("rho_a", 0.0), R=props["R"], Q=props["Q"], b=props.get("b", 0.0)), 3
+            raise CaseFileError("material type %r is not covered (fluid, elastic_solid, biot_poroelastic_medium)" % mtype)
         if kind in ("fluid", "inviscid_fluid"):
             return Fluid(rho=_fortran_float(w[1]), c=_fortran_float(w[2])), 1
         if kind == "viscoelastic":
@@ -346,12 +354,15 @@ class CaseFile:
                   geometric_tolerance=self.geometric_tolerance)
         if self.multi:
             from .multiregion import MultiRegionModel, Region, SOLID, FLUID
-            regs = [Region(FLUID if rtype == 1 else SOLID, mat, rb) for _, rtype, mat, rb in self.regions]
+            from .multiregion import PORO
+            regs = [Region({1: FLUID, 2: SOLID, 3: PORO}[rtype], mat, rb) for _, rtype, mat, rb in self.regions]
             bcs = {b: ((ct[0], cv[0]) if len(ct) == 1 else (ct, cv)) for b, (ct, cv) in self.bcs.items()}
             return MultiRegionModel(self.mesh, regs, part_of_boundary, bcs, **kw)
         kw["part_order"] = [part_of_boundary[b] for b in self.region_boundaries]
         if self.region_type == 1:
             bcs = {part_of_boundary[b]: (ct[0], cv[0]) for b, (ct, cv) in self.bcs.items()}
             return FluidModel(self.mesh, bcs, **kw)
+        if self.region_type == 3:
+            return PoroModel(self.mesh, {part_of_boundary[b]: (ct, cv) for b, (ct, cv) in self.bcs.items()}, **kw)
         bcs = {part_of_boundary[b]: (ct, cv) for b, (ct, cv) in self.bcs.items()}
         return Model(self.mesh, bcs, **kw)

@@ -368,6 +368,8 @@ class MultiRegionModel:
         n = the mesh normal of the element node averaged over the node's elements (only used for the fluid-solid relations)."""
         r = self.regions[kr]
         nan = np.nan + 0j
+        if r.kind == PORO:
+            return self._nodal_solution_poro(x, kr)
         if r.kind == SOLID:
             P = np.full((self.n_node, 3), nan); S = np.full((self.n_node, 3), nan)
         else:
@@ -396,6 +398,21 @@ class MultiRegionModel:
                         continue
                     k1, k2 = self.regions[r1].kind, self.regions[r2].kind
                     n1 = nrm[v]                                        # outward from region 1
+                    if PORO in (k1, k2):                               # this region is the fluid or the solid side of a poroelastic interface
+                        ps = 1 if k1 == PORO else 2
+                        n_p = n1 if ps == 1 else -n1                   # outward from the poroelastic region
+                        tau = x[self.col[(v, "tau%d" % ps)]]
+                        u = np.array([x[self.col[(v, "u%d%d" % (ps, k))]] for k in range(3)])
+                        if r.kind == FLUID:
+                            phi = self.regions[r1 if ps == 1 else r2].material.phi
+                            if self.interface_ctype.get(b, 0) == 1:    # impermeable: p active, Un = u . n_f
+                                P[v] = x[self.col[(v, "p%d" % (3 - ps))]]; S[v] = -(u @ n_p)
+                            else:                                      # permeable: p = -tau/phi, U_f.n = phi U.n + (1 - phi) u.n
+                                P[v] = -tau / phi; S[v] = -(phi * x[self.col[(v, "w%d" % ps)]] + (1.0 - phi) * (u @ n_p))
+                        else:                                          # bonded solid: u = u_p, t_s = -t_p - tau n_p
+                            tp = np.array([x[self.col[(v, "t%d%d" % (ps, k))]] for k in range(3)])
+                            P[v] = u; S[v] = -tp - tau * n_p
+                        continue
                     if k1 == FLUID and k2 == FLUID:
                         P[v] = x[self.col[(v, "p1")]]; S[v] = x[self.col[(v, "un1")]] * (1.0 if first else -1.0)
                     elif k1 == SOLID and k2 == SOLID:
@@ -410,6 +427,56 @@ class MultiRegionModel:
                             P[v] = x[pcol]; S[v] = u @ n_out
                         else:
                             P[v] = u; S[v] = -x[pcol] * n_out
+        return P, S
+
+    def _nodal_solution_poro(self, x, kr):
+        """(tau, u1, u2, u3) and (Un, t1, t2, t3) of a poroelastic region at the nodes of its boundaries (NaN elsewhere), with the interface
+        relations of assemble_bem_harpor_equation.f90 (fluid: permeable t_k = (1 - phi)/phi tau n_k, impermeable Un = u.n, t_k = -(p + tau) n_k;
+        bonded solid: Un = u.n; second side of a permeable poroelastic contact: tau2 = phi2/phi1 tau1, u2 = u1,
+        Un2 = -phi1/phi2 Un1 - (1 - phi1/phi2) u1.n1, t2 = -t1 - (1 - phi2/phi1) tau1 n1)."""
+        r = self.regions[kr]
+        nan = np.nan + 0j
+        P = np.full((self.n_node, 4), nan); S = np.full((self.n_node, 4), nan)
+        nrm = self.node_normals()
+        for sb in r.boundaries:
+            b = abs(sb)
+            r1, r2 = self.boundary_regions[b]
+            first = r1 == kr
+            for e in self.elems_of_boundary[b]:
+                for v in self.mesh.conn[e]:
+                    v = int(v)
+                    if r2 is None:
+                        for k in range(4):
+                            if self.ctype[b][k] == 0:
+                                P[v, k] = self.cvalue[b][k]; S[v, k] = x[self.col[(v, _var_name(PORO, k, True, 1))]]
+                            else:
+                                S[v, k] = self.cvalue[b][k]; P[v, k] = x[self.col[(v, _var_name(PORO, k, False, 1))]]
+                        continue
+                    other = self.regions[r2 if first else r1]
+                    n_out = nrm[v] if first else -nrm[v]               # outward from this region
+                    side = 1 if first else 2
+                    if other.kind == PORO:
+                        f1, f2 = self.regions[r1].material.phi, self.regions[r2].material.phi
+                        tau1 = x[self.col[(v, "tau1")]]; w1 = x[self.col[(v, "w1")]]
+                        u1 = np.array([x[self.col[(v, "u1%d" % k)]] for k in range(3)]); t1 = np.array([x[self.col[(v, "t1%d" % k)]] for k in range(3)])
+                        if first:
+                            P[v] = [tau1, *u1]; S[v] = [w1, *t1]
+                        else:
+                            n1 = nrm[v]
+                            P[v] = [f2 / f1 * tau1, *u1]
+                            S[v] = [-f1 / f2 * w1 - (1.0 - f1 / f2) * (u1 @ n1), *(-t1 - (1.0 - f2 / f1) * tau1 * n1)]
+                        continue
+                    tau = x[self.col[(v, "tau%d" % side)]]
+                    u = np.array([x[self.col[(v, "u%d%d" % (side, k))]] for k in range(3)])
+                    P[v] = [tau, *u]
+                    if other.kind == SOLID:
+                        S[v] = [u @ n_out, *[x[self.col[(v, "t%d%d" % (side, k))]] for k in range(3)]]
+                    elif self.interface_ctype.get(b, 0) == 1:
+                        pf = x[self.col[(v, "p%d" % (3 - side))]]
+                        S[v] = [u @ n_out, *(-(pf + tau) * n_out)]
+                    else:
+                        phi = r.material.phi
+                        S[v] = [x[self.col[(v, "w%d" % side)]], *((1.0 - phi) / phi * tau * n_out)]
         return P, S
 
     def node_normals(self):

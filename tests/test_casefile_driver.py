@@ -488,3 +488,104 @@ def test_shipped_examples_parse_and_the_static_one_solves():
     assert sizes == {"room": ("harmonic", 1, 486, 12, 0), "column_harmonic": ("harmonic", 2, 1458, 8, 3), "column_static": ("static", 2, 1170, 0, 3)}
     c = CaseFile(os.path.join(ex, "room", "room.dat"))
     assert abs(c.omega[0] / (2 * np.pi) - 5.0) < 1e-12 and abs(c.omega[-1] / (2 * np.pi) - 115.0) < 1e-9 and c.description.startswith("pressure waves")
+
+
+PORO_DAT = """[problem]
+n = 3D
+type = mechanics
+analysis = harmonic
+
+[frequencies]
+rad/s
+list
+1
+2.0
+
+[settings]
+mesh_file_mode = 2 "cube.msh"
+
+[materials]
+1
+1 biot_poroelastic_medium phi 0.35 lambda 1.2 mu 1.0 Q 0.5 R 0.8 rho_f 1.0 rho_s 2.2 rho_a 0.15 xi 0.02 b 0.4
+
+[boundaries]
+6
+1 1 ordinary
+2 2 ordinary
+3 3 ordinary
+4 4 ordinary
+5 5 ordinary
+6 6 ordinary
+
+[regions]
+1
+1 be
+6 1 2 3 4 5 6
+material 1
+0
+0
+
+[export]
+real_format = sci_double
+
+[conditions over be boundaries]
+boundary 1: 1 (0.,0.)
+            0 (0.,0.)
+            0 (0.,0.)
+            0 (0.,0.)
+boundary 2: 0 (0.,0.)
+            1 (1.,0.)
+            1 (0.,0.)
+            1 (0.,0.)
+boundary 3: 1 (0.,0.)
+            1 (0.,0.)
+            0 (0.,0.)
+            1 (0.,0.)
+boundary 4: 1 (0.,0.)
+            1 (0.,0.)
+            0 (0.,0.)
+            1 (0.,0.)
+boundary 5: 1 (0.,0.)
+            1 (0.,0.)
+            1 (0.,0.)
+            0 (0.,0.)
+boundary 6: 1 (0.,0.)
+            1 (0.,0.)
+            1 (0.,0.)
+            0 (0.,0.)
+"""
+
+
+def test_poroelastic_case_to_nso(tmp_path):
+    """A saturated column from its case file (biot_poroelastic_medium, four conditions per boundary): region type 3, rows with tau, u_k, Un, t_k;
+    the oracle-solved field follows the exact Biot solution of tests/test_oracle_poroelastic.py."""
+    from test_oracle_poroelastic import biot_column
+    path = _write_case(tmp_path, PORO_DAT, et=shape.QUAD9, m=2)
+    case = CaseFile(path)
+    md = case.build_model()
+    assert case.region_type == 3 and md.ndof == 4 and md.n_dof == 4 * md.n_node
+    po = case.material
+    assert (po.phi, po.rho1, po.rho2, po.rhoa, po.b) == (0.35, (1 - 0.35) * 2.2, 0.35 * 1.0, 0.15, 0.4) and abs(po.lam - 1.2 * (1 + 0.04j)) < 1e-15
+
+    class Solver:
+        def harmonic(self, omega):
+            from oracle import oracle as orc
+            A, b, _ = orc.PorOracle(md).assemble(omega, po)
+            return np.linalg.solve(A, b)
+
+        def close(self):
+            pass
+    nso = driver.run(path, solver=Solver(), log=io.StringIO())
+    rows = read_nso(nso)
+    assert rows.shape == (md.n_node, 12 + 16 + 16) and (rows[:, 4] == 3).all()
+    field, _ = biot_column(2.0, po)
+    ua, Ua, sa, ta = field(rows[:, 9])
+    u1 = rows[:, 14] + 1j * rows[:, 15]
+    assert np.abs(u1 - ua).max() < 4e-3 * np.abs(ua).max()
+    side = rows[:, 5] >= 3
+    tau = rows[:, 12] + 1j * rows[:, 13]
+    assert np.abs(tau[side] - ta[side]).max() < 4e-3 * np.abs(ta).max()
+    with pytest.raises(CaseFileError) as ei:          # the GPU solver will not run unvalidated kernels silently
+        os.environ.pop("MFB_RUN_UNVALIDATED", None)
+        driver.GpuSolver(case, md)
+    assert "poroelastic" in str(ei.value)

@@ -428,3 +428,60 @@ def test_two_poroelastic_layers_permeable_contact():
     for v in sorted(set(int(n) for e in mrm.elems_of_boundary[7] for n in mrm.mesh.conn[e])):
         assert abs(x[mrm.col[(v, "u10")]] - u) < 2e-2 * uref and abs(x[mrm.col[(v, "tau1")]] - ta) < 2e-2 * tref
         assert abs(x[mrm.col[(v, "w1")]] - U) < 3e-2 * max(abs(U), uref) and abs(x[mrm.col[(v, "t10")]] - sg) < 3e-2 * max(abs(sg), tref)
+
+
+@pytest.mark.parametrize("case", ["fluid_poro_perm", "poro_fluid_imp", "solid_poro", "poro_poro"])
+def test_nodal_variables_on_both_sides_of_poroelastic_interfaces(case):
+    """MultiRegionModel.nodal_solution rebuilds every node variable of both sides from the active unknowns: on the interface they must satisfy
+    the physical contact conditions (total normal stress, pressure, normal flux) that the reference's substitutions encode."""
+    omega, xs = 2.0, 0.5
+    fb, sb = fluid_bcs(1.0), solid_bcs(1.0)
+    pend = ([1, 0, 0, 0], [0, 0, 0, 0])
+    po2 = Poro(rhof=1.0, rhos=2.6, lam=2.0, mu=1.5, xi=0.03, phi=0.2, rhoa=0.1, R=0.5, Q=0.7, b=0.8)
+    if case == "fluid_poro_perm":
+        regs = [Region(FLUID, FL, [1, 3, 4, 5, 6, 7]), Region(PORO, PO, [-7, 2, 13, 14, 15, 16])]; ict = 0
+        bcs = {1: (0, 1.0), 2: pend}; bcs.update({q: fb[q] for q in LAT1}); bcs.update(poro_bcs_side(LAT2))
+    elif case == "poro_fluid_imp":
+        regs = [Region(PORO, PO, [1, 3, 4, 5, 6, 7]), Region(FLUID, FL, [-7, 2, 13, 14, 15, 16])]; ict = 1
+        bcs = {2: (0, 1.0), 1: pend}; bcs.update({q: fb[q] for q in LAT2}); bcs.update(poro_bcs_side(LAT1))
+    elif case == "solid_poro":
+        regs = [Region(SOLID, Material(1.8, 1.4, 0.25, 0.03), [1, 3, 4, 5, 6, 7]), Region(PORO, PO, [-7, 2, 13, 14, 15, 16])]; ict = 0
+        bcs = {1: ([1, 1, 1], [1.0, 0, 0]), 2: pend}; bcs.update({q: sb[q] for q in LAT1}); bcs.update(poro_bcs_side(LAT2))
+    else:
+        regs = [Region(PORO, PO, [1, 3, 4, 5, 6, 7]), Region(PORO, po2, [-7, 2, 13, 14, 15, 16])]; ict = 0
+        bcs = {1: pend, 2: ([0, 1, 1, 1], [0, 1.0, 0, 0])}; bcs.update(poro_bcs_side(LAT1)); bcs.update(poro_bcs_side(LAT2))
+    mrm = MultiRegionModel(two_box_mesh(1, shape.QUAD9, xs=xs), regs, BPART, bcs, interface_ctype={7: ict})
+    A, b = MultiRegionOracle(mrm).assemble(omega)
+    x = np.linalg.solve(A, b)
+    (P1, S1), (P2, S2) = mrm.nodal_solution(x, 0), mrm.nodal_solution(x, 1)
+    ifn = sorted(set(int(n) for e in mrm.elems_of_boundary[7] for n in mrm.mesh.conn[e]))
+
+    def total_normal_stress(kind, P, S, v, nx):      # sigma_xx seen from the region whose outward normal at the interface is nx * e_x
+        if kind == FLUID:
+            return -P[v]
+        if kind == SOLID:
+            return S[v, 0] * nx
+        return S[v, 1] * nx + P[v, 0]                # skeleton traction t_x = sigma_s n_x, plus tau
+
+    def normal_flux(kind, reg, P, S, v, nx):         # fluid displacement relative to ... : absolute normal displacement of the pore fluid / fluid
+        if kind == FLUID:
+            return S[v] * nx
+        if kind == SOLID:
+            return P[v, 0]
+        return S[v, 0] * nx                           # U_x
+    k1, k2 = regs[0].kind, regs[1].kind
+    for v in ifn:
+        s1 = total_normal_stress(k1, P1, S1, v, 1.0); s2 = total_normal_stress(k2, P2, S2, v, -1.0)
+        assert abs(s1 - s2) < 1e-10 * max(abs(s1), 1e-3)
+        # skeleton displacement continuous where both sides have one
+        if k1 != FLUID and k2 != FLUID:
+            u1 = P1[v, 1:] if k1 == PORO else P1[v]; u2 = P2[v, 1:] if k2 == PORO else P2[v]
+            assert np.abs(u1 - u2).max() == 0
+        if case == "fluid_poro_perm":                # p = -tau/phi; fluid flux U_f = phi U + (1 - phi) u
+            assert abs(P1[v] + P2[v, 0] / PO.phi) < 1e-12 and abs(S1[v] - (PO.phi * (-S2[v, 0]) + (1 - PO.phi) * P2[v, 1])) < 1e-12 * max(abs(S1[v]), 1e-3)
+        if case == "poro_fluid_imp":                 # U = u = U_f
+            assert abs(S1[v, 0] - P1[v, 1]) < 1e-12 and abs(-S2[v] - P1[v, 1]) < 1e-12
+        if case == "poro_poro":                      # pore pressure and relative flux continuous
+            assert abs(P1[v, 0] / PO.phi - P2[v, 0] / po2.phi) < 1e-12
+            q1 = PO.phi * (S1[v, 0] - P1[v, 1]); q2 = po2.phi * (-S2[v, 0] - P2[v, 1])
+            assert abs(q1 - q2) < 1e-12 * max(abs(q1), 1e-3)
