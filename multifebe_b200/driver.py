@@ -24,9 +24,16 @@ class GpuSolver:
     """One mfb_problem on one GPU: harmonic(omega) / static() -> solution vector in the reference's column order."""
 
     def __init__(self, case, model, device=0):
+        self.cp = None
         if case.multi:
-            raise CaseFileError("coupled BE regions: the device path is not built yet (DESIGN.md section 7.4); the case parses and numbers, "
-                                "but only the Fortran program solves it")
+            if not os.environ.get("MFB_RUN_UNVALIDATED"):
+                raise CaseFileError("coupled BE regions: the device path (capi.CoupledProblem, DESIGN.md section 7.4) has not had its first hardware "
+                                    "run yet; set MFB_RUN_UNVALIDATED=1 to use it")
+            from . import capi
+            self.capi, self.case = capi, case
+            self.ctx = capi.Context(device)
+            self.cp = capi.CoupledProblem(self.ctx, model)
+            return
         if case.region_type == 3 and not os.environ.get("MFB_RUN_UNVALIDATED"):
             raise CaseFileError("poroelastic region: the device kernels (csrc/poro.cu) have not had their first hardware run yet; "
                                 "set MFB_RUN_UNVALIDATED=1 to use them (DESIGN.md section 0)")
@@ -36,6 +43,8 @@ class GpuSolver:
         self.pr = capi.Problem(self.ctx, model)
 
     def harmonic(self, omega):
+        if self.cp is not None:
+            return self.cp.solve_frequency(omega)
         if self.case.region_type == 1:
             return self.pr.solve_frequency_fluid(omega, self.case.material)
         if self.case.region_type == 3:
@@ -63,6 +72,9 @@ class GpuSolver:
         return self.pr.stats()
 
     def close(self):
+        if self.cp is not None:
+            self.cp.close(); self.ctx.close()
+            return
         if getattr(self, "_ipo", None) is not None:
             self._ipo.close()
         self.pr.close(); self.ctx.close()
