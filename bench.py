@@ -245,6 +245,141 @@ def run_static(args):
         dist.barrier(); dist.destroy_process_group()
 
 
+ACOUSTIC_METRIC = "acoustic 3D BEM end-to-end solves/s (assemble + zgetrf + zgetrs of one frequency) on the ME-TH-AC-001 room refined to ~10k DOF"
+
+
+def acoustic_workload(args):
+    from multifebe_b200.host import FluidModel, Fluid, cube_mesh, room_bcs, shape
+    et = {"tri3": shape.TRI3, "tri6": shape.TRI6, "quad4": shape.QUAD4, "quad8": shape.QUAD8, "quad9": shape.QUAD9}[args.acoustic_etype]
+    md = FluidModel(cube_mesh(args.acoustic_m, et, L=3.0), room_bcs(1.0))
+    fl = Fluid(rho=1.25, c=343.0)
+    omega = 2.0 * np.pi * 40.0
+    name = "acoustic room L=3 m (ME-TH-AC-001 BCs) %s m=%d at 40 Hz: %d elements, %d nodes, %d DOF" % (args.acoustic_etype, args.acoustic_m, md.n_elem, md.n_node, md.n_dof)
+    return md, fl, name, omega
+
+
+def cpu_arm_acoustic(args, md, fl, omega, lu_n=4096, budget_pairs=4e6):
+    """Reference algorithm of the acoustic path on the host cores: the oracle (OpenMP over integration elements + critical scatter) on every
+    stride-th collocation point of the same mesh (same mix of regular, quasi-singular and singular pairs), scaled to all of them, + OpenBLAS
+    zgetrf/zgetrs scaled by n^3."""
+    import copy
+    from oracle import oracle as orc
+    from scipy.linalg import lapack
+    ncores = os.cpu_count()
+    stride = max(1, int(round(md.n_elem * md.n_colloc / budget_pairs)))
+    sub = copy.copy(md)
+    sel = np.arange(stride // 2, md.n_colloc, stride)
+    for name in ("colloc_x", "colloc_node", "colloc_elem", "colloc_kn", "colloc_xi"):
+        setattr(sub, name, np.ascontiguousarray(getattr(md, name)[sel]))
+    sub.n_colloc = len(sel)
+    o = orc.PotOracle(sub)
+    t0 = time.time(); o.assemble(omega, fl, nthreads=ncores); t_sample = time.time() - t0
+    t_asm = t_sample * md.n_colloc / len(sel)
+    n = md.n_dof
+    lu_n = min(lu_n, n)
+    rng = np.random.default_rng(0)
+    A = np.asfortranarray(rng.standard_normal((lu_n, lu_n)) + 1j * rng.standard_normal((lu_n, lu_n))); b = rng.standard_normal(lu_n) + 0j
+    t0 = time.time(); lu, piv, info = lapack.zgetrf(A, overwrite_a=True); x, info = lapack.zgetrs(lu, piv, b); t2 = time.time()
+    t_lu = (t2 - t0) * (n / lu_n) ** 3
+    sample = ("assembly: acoustic oracle on all %d elements x every %d-th collocation point (%d of %d points, %.1f s) scaled by %d/%d; LU: OpenBLAS "
+              "zgetrf+zgetrs at n=%d (%.2f s) scaled by (%d/%d)^3" % (md.n_elem, stride, len(sel), md.n_colloc, t_sample, md.n_colloc, len(sel), lu_n, t2 - t0, n, lu_n))
+    return {"value": 1.0 / (t_asm + t_lu), "unit": "solves/s", "cores": ncores, "kind": "port", "sample": sample, "assembly_s_per_step": t_asm, "lu_s_per_step": t_lu}
+
+
+def run_acoustic(args):
+    """One frequency of the acoustic room (ME-TH-AC-001 refined) per step; N ranks = N replicas solving the same frequency (a sweep would shard its
+    frequencies exactly as the headline workload does; this line measures the per-frequency cost of the scalar path)."""
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    md, mat, name, omega = acoustic_workload(args)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        res = [cpu_arm_acoustic(args, md, mat, omega) for _ in range(args.steps)]
+        v = float(np.mean([r["value"] for r in res])); cb = dict(res[-1]); cb["value"] = v
+        print(json.dumps({"impl": "reference", "metric": ACOUSTIC_METRIC, "value": v, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+                          "config": {"workload": name, "note": "reference algorithm on host cores (oracle port; no Fortran compiler here), bounded sample scaled to a full solve"},
+                          "cpu_baseline": cb, "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    from multifebe_b200 import capi
+    ctx = capi.Context(local)
+    t0 = time.time(); pr = capi.Problem(ctx, md); t_setup = time.time() - t0
+    n = md.n_dof
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        ctx.mark(7); ctx.elapsed_ms(7, 7)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def reduce_max(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        x = pr.solve_frequency_fluid(omega, mat)
+    # device-resident arm: the library's own events around assemble + LU + solve (prescribed values resident, solution stays on the device
+    # until the single download the call ends with; its 76 KB are inside the e2e arm below)
+    acc = {}
+    barrier(); w0 = time.time()
+    for s in range(args.steps):
+        x = pr.solve_frequency_fluid(omega, mat)
+        st = pr.stats()
+        for k in ("MS_ASSEMBLE", "MS_REGULAR", "MS_ADAPTIVE", "MS_SINGULAR", "MS_ZERO", "MS_LU", "MS_SOLVE", "MS_GEMM", "MS_PANEL", "LAUNCHES", "LU_LAUNCHES", "GEMM_LAUNCHES", "GEMM_FLOPS"):
+            acc[k] = acc.get(k, 0.0) + st[k]
+    barrier(); windows = [(w0, time.time())]
+    K = args.steps
+    ms_dev = reduce_max((acc["MS_ASSEMBLE"] + acc["MS_LU"] + acc["MS_SOLVE"]) / K)
+    # e2e arm: wall clock of the C-ABI call with host buffers (cvalue up, x down), max over ranks
+    barrier(); t0 = time.time(); w0 = t0
+    for s in range(args.steps):
+        x = pr.solve_frequency_fluid(omega, mat)
+    barrier(); ms_e2e = reduce_max((time.time() - t0) * 1e3 / K); windows.append((w0, time.time()))
+    peaks = ctx.measure_peaks() if rank == 0 else None
+    if rank == 0:
+        from multifebe_b200.host import room_analytic
+        pn, un = md.nodal_solution(x)
+        p_ex, _ = room_analytic(md.node_x[:, 0], omega, mat, L=3.0, P=1.0)
+        err = float(np.abs(pn - p_ex).max() / np.abs(p_ex).max())
+        gemm_tf = acc["GEMM_FLOPS"] / max(acc["MS_GEMM"], 1e-9) / 1e9
+        out = {"metric": ACOUSTIC_METRIC, "value": world * 1e3 / ms_dev, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+               "config": {"workload": name, "sharding": "replicas: every rank solves the same frequency (a sweep shards its frequencies like the headline workload)",
+                          "l2": "L2 flushed between steps by the assembly itself (it rewrites the %.2f GB matrix, larger than the 126 MB L2)" % (16.0 * n * n / 1e9),
+                          "setup_s_once_per_mesh": t_setup},
+               "clocks": clocks.summary(windows),
+               "e2e": {"value": world * 1e3 / ms_e2e, "unit": "solves/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(md.cvalue.size * 16 + 1024), "d2h_bytes_per_step": int(16 * n + 4 * n),
+                       "api": "mfb_harpot3d_solve_frequency (host cvalue in, host x out)"},
+               "gpu_launches": int(acc["LAUNCHES"] + acc["LU_LAUNCHES"]),
+               "roofline": {"kernel": "k_zgemm3m_minus (LU trailing update, 3M complex product on DMMA.8x8x4)", "bound": "tensor", "achieved": gemm_tf, "peak": peaks["dmma_tflops"], "unit": "TFLOP/s",
+                            "frac": gemm_tf / peaks["dmma_tflops"], "traffic": None, "avg_launch_ms": acc["MS_GEMM"] / max(acc["GEMM_LAUNCHES"], 1),
+                            "launches_per_step": acc["GEMM_LAUNCHES"] / K, "share_of_step": (acc["MS_GEMM"] / K) / ms_dev,
+                            "note": "executed tensor-pipe flops (6mnk per complex product) / CUDA-event time of the trailing updates; at this size the factorisation is bound "
+                                    "by the panel, not by the GEMM: see lu.ms_panel_on_lookahead_stream",
+                            "peak_source": "FP64 tensor (DMMA) micro-benchmark measured live (mfb_measure_peaks)"},
+               "assembly": {"ms": acc["MS_ASSEMBLE"] / K, "ms_regular": acc["MS_REGULAR"] / K, "ms_adaptive": acc["MS_ADAPTIVE"] / K, "ms_singular": acc["MS_SINGULAR"] / K,
+                            "gentries_per_s": n * n / (acc["MS_ASSEMBLE"] / K * 1e-3) / 1e9, "matrix_write_gbs": 16.0 * n * n / (acc["MS_ASSEMBLE"] / K * 1e-3) / 1e9},
+               "lu": {"ms": acc["MS_LU"] / K, "tflops": 8.0 / 3.0 * n ** 3 / (acc["MS_LU"] / K) / 1e9, "ms_gemm": acc["MS_GEMM"] / K, "ms_panel_on_lookahead_stream": acc["MS_PANEL"] / K,
+                      "ms_zgetrs": acc["MS_SOLVE"] / K},
+               "analytic_solution_rel_error": err, "peaks_measured_live": peaks}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_arm_acoustic(args, md, mat, omega)
+        print(json.dumps(out), flush=True)
+    pr.close(); ctx.close()
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -447,11 +582,16 @@ def main():
     ap.add_argument("--etype", default="tri3")
     ap.add_argument("--m", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="harmonic", choices=["harmonic", "static"], help="harmonic: the headline 30k-DOF sweep (default); static: BASELINE config 2")
+    ap.add_argument("--workload", default="harmonic", choices=["harmonic", "static", "acoustic"],
+                    help="harmonic: the headline 30k-DOF sweep (default); static: BASELINE config 2; acoustic: one frequency of the ME-TH-AC-001 room at ~10k DOF")
+    ap.add_argument("--acoustic-etype", default="quad9")
+    ap.add_argument("--acoustic-m", type=int, default=20)
     ap.add_argument("--static-etype", default="quad9")
     ap.add_argument("--static-m", type=int, default=11)
     args = ap.parse_args()
-    if args.workload == "static":
+    if args.workload == "acoustic":
+        run_acoustic(args)
+    elif args.workload == "static":
         run_static(args)
     elif args.impl == "reference":
         run_reference(args)
