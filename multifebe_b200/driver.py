@@ -156,6 +156,9 @@ def main(argv=None):
     except CaseFileError as e:
         print("multifebe_b200: %s" % e)
         return 1
+    except RuntimeError as e:          # capi.MfbError: no CUDA device, CUDA failure, singular system ... (there is no CPU path to fall back to)
+        print("multifebe_b200: %s" % e)
+        return 3
     finally:
         if world > 1:
             dist.destroy_process_group()
