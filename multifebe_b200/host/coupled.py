@@ -158,7 +158,7 @@ def assemble_coupled(mrm, omega, local_assemble, freeterm, locals_=None):
         mH, mG, mp = locals_[kr] if locals_ is not None else local_models(mrm, kr)
         AH = local_assemble(mH, r, omega)
         AG = local_assemble(mG, r, omega)
-        D = mrm.scatter_descriptors(kr)
+        D = mrm.scatter_descriptors(kr, omega)
         # local row -> global row
         rg = np.zeros(mp["n_rows"], dtype=np.int64)
         for (nde, eq), r0 in mp["row_of_node"].items():

@@ -106,8 +106,9 @@ class MultiRegionModel:
                 nd = self.regions[r1].ndof
                 ct, cv = bcs[b]
                 ct = np.atleast_1d(np.asarray(ct, dtype=np.int32)); cv = np.atleast_1d(np.asarray(cv, dtype=np.complex128))
-                if len(ct) != nd or len(cv) != nd or not set(ct.tolist()) <= {0, 1}:
-                    raise ValueError("boundary %d: %d condition(s) of type 0 / 1 expected" % (b, nd))
+                allowed = {0, 1, 2, 3} if self.regions[r1].kind == FLUID else {0, 1}     # fluid: 2 = rho c impedance, 3 = spherical radiation with radius cvalue
+                if len(ct) != nd or len(cv) != nd or not set(ct.tolist()) <= allowed:
+                    raise ValueError("boundary %d: %d condition(s) of type %s expected" % (b, nd, sorted(allowed)))
                 self.ctype[b], self.cvalue[b] = ct, cv
         # --- numbering.  row[(node, eq)] -> list of rows (1 or 3); col[(node, name)] -> column, names 'p1','un1','p2','u1k','t1k','u2k'
         self.row, self.col = {}, {}
@@ -251,7 +252,16 @@ class MultiRegionModel:
         return v
 
     # ---- flat scatter descriptors of one region: the form in which the coupling crosses the C ABI
-    def scatter_descriptors(self, kr):
+    def impedance_coefficient(self, kr, b, omega):
+        """Un = -coef * p on a fluid boundary with condition 2 (Un = -i/(rho c omega) p) or 3 (Un = -(i/(rho c omega) + 1/(2 R rho omega^2)) p,
+        R = the prescribed value): assemble_bem_harpot_equation.f90:97-110."""
+        mat = self.regions[kr].material
+        coef = 1j / (mat.rho * mat.c * omega)
+        if self.ctype[b][0] == 3:
+            coef = coef + 1.0 / (2.0 * self.cvalue[b][0] * mat.rho * omega ** 2)
+        return coef
+
+    def scatter_descriptors(self, kr, omega=None):
         """Every case of assemble_bem_har{ela,pot,por}_equation.f90 reduced to one rule.  For the element instance le of the region, its node j
         and source component k (solid: k = 0..2; fluid: k = 0; poroelastic: k = 0 fluid phase, 1..3 skeleton) = column index of the node block:
             A[row_l, hcol] += hcoef * h(j, l, k)          (hcol == -1: b[row_l] += hcoef * h;  -2: nothing)
@@ -277,7 +287,12 @@ class MultiRegionModel:
                     q = (int(v.elem_ptr[le]) + j) * nd + k
                     if r2 is None:
                         ct, cv = self.ctype[bnd][k], self.cvalue[bnd][k]
-                        if ct == 0:
+                        if ct in (2, 3):                              # p unknown, Un = -coef p: A(row, col_p) += h + coef g
+                            if omega is None:
+                                raise ValueError("boundary %d: impedance conditions need the frequency" % bnd)
+                            hcol[q], hcoef[q] = self.col[(sn, "p1")], 1.0
+                            gcol[q, 0], gcoef[q, 0] = self.col[(sn, "p1")], self.impedance_coefficient(kr, bnd, omega)
+                        elif ct == 0:
                             hcol[q], hcoef[q] = -1, -cv; gcol[q, 0], gcoef[q, 0] = self.col[(sn, _var_name(r.kind, k, True, 1))], -1.0
                         else:
                             hcol[q], hcoef[q] = self.col[(sn, _var_name(r.kind, k, False, 1))], 1.0; gcol[q, 0], gcoef[q, 0] = -1, cv
@@ -362,7 +377,7 @@ class MultiRegionModel:
         return dict(hcol=hcol, hcoef=hcoef, gcol=gcol, gcoef=gcoef)
 
     # ---- nodal variables from the solution vector (assign_solution_mechanics_harmonic.f90 with the interface substitutions)
-    def nodal_solution(self, x, kr):
+    def nodal_solution(self, x, kr, omega=None):
         """Primary and secondary variables of region kr at the nodes of its boundaries: solid (u (n,3), t (n,3)), fluid (p (n), Un (n));
         nodes the region does not touch are NaN.  Interface values follow the coupling relations listed in the module docstring, with
         n = the mesh normal of the element node averaged over the node's elements (only used for the fluid-solid relations)."""
@@ -393,8 +408,10 @@ class MultiRegionModel:
                             else:
                                 if self.ctype[b][k] == 0:
                                     P[v] = known; S[v] = x[self.col[(v, "un1")]]
-                                else:
+                                elif self.ctype[b][k] == 1:
                                     S[v] = known; P[v] = x[self.col[(v, "p1")]]
+                                else:
+                                    P[v] = x[self.col[(v, "p1")]]; S[v] = -self.impedance_coefficient(kr, b, omega) * P[v]
                         continue
                     k1, k2 = self.regions[r1].kind, self.regions[r2].kind
                     n1 = nrm[v]                                        # outward from region 1

@@ -151,8 +151,13 @@ class MultiRegionOracle:
                 else:
                     if ct[0] == 0:
                         A[rows[0], m.col[(sn, "un1")]] -= g[kn]; b[rows[0]] -= h[kn] * cv[0]
-                    else:
+                    elif ct[0] == 1:
                         A[rows[0], m.col[(sn, "p1")]] += h[kn]; b[rows[0]] += g[kn] * cv[0]
+                    elif ct[0] == 2:                                      # p unknown, Un = -i/(rho c omega) p (assemble_bem_harpot_equation.f90:97-102)
+                        A[rows[0], m.col[(sn, "p1")]] += h[kn] + 1j / v.material.rho / v.material.c / self._omega * g[kn]
+                    else:                                                 # p unknown, Un = -(i/(rho c omega) + 1/(2 R rho omega^2)) p (:103-110)
+                        A[rows[0], m.col[(sn, "p1")]] += h[kn] + (1j / v.material.rho / v.material.c / self._omega
+                                                                + 1.0 / (2.0 * cv[0] * v.material.rho * self._omega ** 2)) * g[kn]
                 continue
             k1, k2 = m.regions[r1].kind, m.regions[r2].kind
             # element(se_int)%n_fn(:,kn): unit normal of the element at its node, mesh orientation = outward from region 1
@@ -311,7 +316,8 @@ class MultiRegionOracle:
     def assemble(self, omega, flat=False):
         """-> A (n_dof x n_dof), b of one frequency for the coupled system.  flat = True: scatter through the flat descriptors."""
         m = self.m
-        desc = [m.scatter_descriptors(kr) for kr in range(len(m.views))] if flat else None
+        self._omega = omega
+        desc = [m.scatter_descriptors(kr, omega) for kr in range(len(m.views))] if flat else None
         n = m.n_dof
         A = np.zeros((n, n), dtype=np.complex128); b = np.zeros(n, dtype=np.complex128)
         for kr, v in enumerate(m.views):

@@ -85,3 +85,14 @@ def test_product_free_term_helper_gives_the_same_system():
     A1, b1 = assemble_coupled(mrm, 1.3, oracle_local_assemble, capi.freeterm)
     sc = np.abs(A0).max(axis=0)
     assert (np.abs(A1 - A0).max(axis=0) <= 1e-12 * sc).all() and np.abs(b1 - b0).max() <= 1e-12 * np.abs(b0).max()
+
+
+def test_impedance_condition_through_the_single_region_route():
+    """A rho c-terminated duct (fluid condition 2, which the single-region device entry points refuse) assembled through the H / G route."""
+    from multifebe_b200.host import cube_mesh
+    bcs = {1: (0, 1.0), 2: (2, 0.0), 3: (1, 0.0), 4: (1, 0.0), 5: (1, 0.0), 6: (3, 2.5)}
+    mrm = MultiRegionModel(cube_mesh(2, shape.QUAD4), [Region(FLUID, FL, [1, 2, 3, 4, 5, 6])], {b: b for b in range(1, 7)}, bcs)
+    A0, b0 = MultiRegionOracle(mrm).assemble(3.0)
+    A1, b1 = assemble_coupled(mrm, 3.0, oracle_local_assemble, oracle_freeterm)
+    sc = np.abs(A0).max(axis=0)
+    assert (np.abs(A1 - A0).max(axis=0) <= 1e-12 * sc).all() and np.abs(b1 - b0).max() <= 1e-12 * np.abs(b0).max()

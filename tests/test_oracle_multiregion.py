@@ -485,3 +485,30 @@ def test_nodal_variables_on_both_sides_of_poroelastic_interfaces(case):
             assert abs(P1[v, 0] / PO.phi - P2[v, 0] / po2.phi) < 1e-12
             q1 = PO.phi * (S1[v, 0] - P1[v, 1]); q2 = po2.phi * (-S2[v, 0] - P2[v, 1])
             assert abs(q1 - q2) < 1e-12 * max(abs(q1), 1e-3)
+
+
+def test_impedance_and_radiation_conditions_of_a_fluid_boundary():
+    """Condition 2 (Un = -i/(rho c omega) p, the rho c impedance): a duct driven at x = 0 and terminated by it at x = L carries the travelling wave
+    p = P e^{-ikx} alone.  Condition 3 adds the spherical-spreading term 1/(2 R rho omega^2); here only its assembly is compared (flat descriptors
+    against the case-by-case branch).  assemble_bem_harpot_equation.f90:97-110."""
+    fl = Fluid(1.2, 1.5)
+    omega = 4.0
+    bcs = {1: (0, 1.0), 2: (2, 0.0), 3: (1, 0.0), 4: (1, 0.0), 5: (1, 0.0), 6: (1, 0.0)}
+    mrm = MultiRegionModel(cube_mesh(3, shape.QUAD9), [Region(FLUID, fl, [1, 2, 3, 4, 5, 6])], {b: b for b in range(1, 7)}, bcs)
+    o = MultiRegionOracle(mrm)
+    A, b = o.assemble(omega)
+    A2, b2 = o.assemble(omega, flat=True)
+    assert np.abs(A - A2).max() <= 1e-15 * np.abs(A).max() and np.abs(b - b2).max() <= 1e-15 * np.abs(b).max()
+    x = np.linalg.solve(A, b)
+    p, un = mrm.nodal_solution(x, 0, omega)
+    k = omega / fl.c
+    ex = np.exp(-1j * k * mrm.node_x[:, 0])
+    assert np.abs(p - ex).max() < 2e-3
+    end = mrm.node_boundary == 2
+    assert np.abs(un[end] + 1j / (fl.rho * fl.c * omega) * p[end]).max() == 0          # Un = -i/(rho c omega) p; the exact value is -i k/(rho omega^2) e^{-ikL}
+    assert np.abs(un[end] - (-1j * k) * ex[end] / (fl.rho * omega ** 2)).max() < 2e-3 * k / (fl.rho * omega ** 2)
+    bcs[2] = (3, 2.5)
+    mrm3 = MultiRegionModel(cube_mesh(1, shape.QUAD8), [Region(FLUID, fl, [1, 2, 3, 4, 5, 6])], {b: b for b in range(1, 7)}, bcs)
+    o3 = MultiRegionOracle(mrm3)
+    A, b = o3.assemble(omega); A2, b2 = o3.assemble(omega, flat=True)
+    assert np.abs(A - A2).max() <= 1e-15 * np.abs(A).max() and np.abs(b - b2).max() <= 1e-15 * np.abs(b).max()
