@@ -9,6 +9,9 @@
                      reference output: the reference (Fortran) cannot be compiled or run here.
   oracle_static.npz  the same for the static (Kelvin) path: small assembled real systems, their dgetrf/dgetrs solutions and one
                      pair per integration mode (run with the argument `static` to write only this file).
+  oracle_widening.npz  the same for the paths of SURVEY.md 8f rank 3 (argument `widening`): acoustic and poroelastic single regions
+                     (A, b, x) and coupled two-region systems of the multi-region oracle (solid-fluid, fluid-poroelastic, solid-poroelastic,
+                     poroelastic-poroelastic).
 """
 import json, math, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -89,9 +92,89 @@ def oracle_static_vectors():
     return out
 
 
+# the cases of oracle_widening.npz, shared with tests/test_golden_widening.py
+def widening_cases():
+    from multifebe_b200.host import (Fluid, FluidModel, Poro, PoroModel, Material, MultiRegionModel, Region, SOLID, FLUID, cube_mesh, two_box_mesh, shape)
+    from multifebe_b200.host.multiregion import PORO
+    fl = Fluid(1.25, 343.0, 0.01); po = Poro(rhof=1.0, rhos=2.2, lam=1.2, mu=1.0, xi=0.02, phi=0.35, rhoa=0.15, R=0.8, Q=0.5, b=0.4)
+    ms = Material(2.0, 1.5, 0.25, 0.03); fl2 = Fluid(1.0, 1.2, 0.01)
+    po2 = Poro(rhof=1.0, rhos=2.6, lam=2.0, mu=1.5, xi=0.03, phi=0.2, rhoa=0.1, R=0.5, Q=0.7, b=0.8)
+    cases = {}
+    fbc = {1: (0, 0.3 - 0.1j), 2: (0, 1.0), 3: (1, 0.0), 4: (1, 2e-6 + 1e-6j), 5: (1, 0.0), 6: (0, -0.5)}
+    for et, m in [(shape.TRI3, 2), (shape.TRI6, 1), (shape.QUAD4, 2), (shape.QUAD8, 1), (shape.QUAD9, 1)]:
+        cases["acoustic:%d:%d" % (et, m)] = ("fluid", FluidModel(cube_mesh(m, et), fbc), fl, 2 * np.pi * 60.0)
+    pbc = {1: ([1, 0, 0, 0], [0.05 + 0.02j, 0, 0, 0]), 2: ([0, 1, 1, 1], [0.2, 1.0, 0, 0])}
+    for p_, free in ((3, 2), (4, 2), (5, 3), (6, 3)):
+        ct = [1, 1, 1, 1]; ct[free] = 0; pbc[p_] = (ct, [0, 0, 0, 0])
+    for et, m in [(shape.TRI3, 1), (shape.QUAD4, 1), (shape.QUAD9, 1)]:
+        cases["poro:%d:%d" % (et, m)] = ("poro", PoroModel(cube_mesh(m, et), pbc), po, 1.9)
+    bpart = {b: b for b in (1, 2, 3, 4, 5, 6, 7, 13, 14, 15, 16)}
+    lat1, lat2 = (3, 4, 5, 6), (13, 14, 15, 16)
+
+    def side_bcs(kind, lat, end, driven):
+        out = {}
+        for q in lat:
+            if kind == SOLID:
+                out[q] = ([1, 0, 1] if q in (3, 4, 13, 14) else [1, 1, 0], [0, 0, 0])
+            elif kind == FLUID:
+                out[q] = (1, 0.0)
+            else:
+                ct = [1, 1, 1, 1]; ct[2 if q in (3, 4, 13, 14) else 3] = 0; out[q] = (ct, [0, 0, 0, 0])
+        if kind == SOLID:
+            out[end] = ([0, 1, 0], [0.1, 0.2 - 0.1j, 0.0]) if driven else ([0, 0, 0], [0, 0, 0])
+        elif kind == FLUID:
+            out[end] = (0, 0.7 + 0.1j) if driven else (1, 0.0)
+        else:
+            out[end] = ([0, 1, 1, 1], [0.3, 1.0, 0.0, 0.2j]) if driven else ([1, 0, 0, 0], [0, 0, 0, 0])
+        return out
+    mats = {SOLID: ms, FLUID: fl2, PORO: po}
+    for kinds, ict in (((SOLID, FLUID), 0), ((FLUID, PORO), 0), ((PORO, FLUID), 1), ((SOLID, PORO), 0), ((PORO, PORO), 0)):
+        bcs = side_bcs(kinds[0], lat1, 1, True); bcs.update(side_bcs(kinds[1], lat2, 2, False))
+        m2 = po2 if kinds == (PORO, PORO) else mats[kinds[1]]
+        mrm = MultiRegionModel(two_box_mesh(1, shape.QUAD8), [Region(kinds[0], mats[kinds[0]], [1, 3, 4, 5, 6, 7]), Region(kinds[1], m2, [-7, 2, 13, 14, 15, 16])],
+                               bpart, bcs, interface_ctype={7: ict})
+        cases["coupled:%s-%s:%d" % (kinds[0], kinds[1], ict)] = ("coupled", mrm, None, 1.7)
+    return cases
+
+
+def widening_system(kind, model, mat, omega):
+    from oracle import oracle as orc
+    from oracle.multiregion import MultiRegionOracle
+    if kind == "fluid":
+        A, b, _ = orc.PotOracle(model).assemble(omega, mat)
+    elif kind == "poro":
+        A, b, _ = orc.PorOracle(model).assemble(omega, mat)
+    else:
+        A, b = MultiRegionOracle(model).assemble(omega)
+    return np.asarray(A), np.asarray(b)
+
+
+def oracle_widening_vectors():
+    out = {}
+    for key, (kind, model, mat, omega) in widening_cases().items():
+        A, b = widening_system(kind, model, mat, omega)
+        out["b:" + key] = b; out["x:" + key] = np.linalg.solve(A, b)
+        out["Av:" + key] = A @ widening_probe(len(b))                 # every entry of A enters these two products
+        out["vA:" + key] = widening_probe(len(b))[::-1] @ A
+        if key in FULL_MATRICES:
+            out["A:" + key] = A
+    return out
+
+
+FULL_MATRICES = ("acoustic:5:2", "poro:7:1", "coupled:fluid-poro:0")
+
+
+def widening_probe(n):
+    k = np.arange(n)
+    return np.cos(0.37 * k + 0.1) + 1j * np.sin(0.91 * k - 0.3)
+
+
 if __name__ == "__main__":
     gd = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gd, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "widening":
+        np.savez_compressed(os.path.join(gd, "oracle_widening.npz"), **oracle_widening_vectors())
+        print("widening fixtures written to", gd); sys.exit(0)
     np.savez_compressed(os.path.join(gd, "oracle_static.npz"), **oracle_static_vectors())
     if len(sys.argv) > 1 and sys.argv[1] == "static":
         print("static fixtures written to", gd); sys.exit(0)
