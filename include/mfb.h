@@ -240,6 +240,16 @@ int mfb_dist_layout(int n, int nb, int nranks, int rank, int* n_local_cols, int*
 int mfb_dist_partition_tiles(int n_tiles, const int* tile_row0, const int* tile_nbytes, int n_dof, int nranks, int* tile_rank,
                              int* row_bounds);
 
+/* ---- Resident combination of assembled systems (coupled regions from single-region assemblies; see api.cu) -- not yet run on hardware ----
+ * mfb_system_zero(dst) zeroes the resident system of dst and marks it assembled in host order; mfb_combine_columns adds
+ * coef[i] * src(r, src_col[i]) to dst(row_map[r], dst_col[i]) for the first n_rows host rows of the assembled system of src (dst_col = -1: the
+ * right-hand side); mfb_add_entries adds single entries (the free terms).  mfb_zsolve(dst, n, NULL, n, ipiv, NULL, 1, 1) then factorises and
+ * solves the accumulated system and mfb_get_solution returns x. */
+int mfb_system_zero(mfb_problem* problem);
+int mfb_combine_columns(mfb_problem* dst, mfb_problem* src, int n_rows, const int* row_map, int n_terms, const int* src_col, const int* dst_col,
+                        const mfb_z* coef);
+int mfb_add_entries(mfb_problem* dst, int n, const int* rows, const int* cols, const mfb_z* values);
+
 /* Host-only helper: geometry-only pieces of the free term at a boundary node (see api.cu); c_lk = cp delta_lk - sum_b[3*l+k] / (8 pi (1 - nu))
  * for a solid (Mantic), c = cp for a fluid, c_00 = J cp for the fluid phase of a poroelastic medium.  normals / tangents: 3 per element. */
 int mfb_freeterm_terms(int n_elements, const double* normals, const double* tangents, double tol, double* cp, double* sum_b /* 9 */);

@@ -5,6 +5,7 @@
 #include "assembly.cuh"
 #include "potential.cuh"
 #include "poro.cuh"
+#include "combine.cuh"
 #include "lu.cuh"
 #include "dist.cuh"
 #include "plan_host.h"
@@ -1189,6 +1190,71 @@ extern "C" int mfb_zgemm_minus(mfb_ctx* ctx, int m, int n, int k, const mfb_z* A
 // Single-frequency multi-GPU mode: collocation-row blocks for the assembly, block-cyclic columns for the
 // LU, NCCL to move row slabs to their column owners once and to broadcast each factorised panel.
 // ---------------------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------------
+// Resident combination of assembled systems (coupled regions from single-region assemblies, multifebe_b200/host/coupled.py).  STATUS: never
+// executed on hardware.
+//   mfb_system_zero      dst: zero the resident matrix and right-hand side and mark it "assembled, host order" (no row permutation), so that
+//                        mfb_zsolve(dst, n, NULL, ..., NULL, 1, 1) factorises and solves what the calls below accumulate
+//   mfb_combine_columns  dst(row_map[r], dst_col[i]) += coef[i] * src(r, src_col[i]) for the first n_rows host rows of the ASSEMBLED system of src
+//                        (host row / column indices on both sides; dst_col = -1: the right-hand side of dst); both problems on the same context
+//   mfb_add_entries      dst(rows[i], cols[i]) += values[i] (cols = -1: right-hand side) -- the free terms
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int mfb_system_zero(mfb_problem* p) {
+  if (!p) return fail(MFB_ERR_ARG, "mfb_system_zero: null problem");
+  CK(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  CK(cudaMemsetAsync(p->sys.Are, 0, (size_t)2 * p->lda * p->n_dof * sizeof(double), st));
+  CK(cudaMemsetAsync(p->sys.bre, 0, (size_t)2 * p->lda * sizeof(double), st));
+  p->factored = false; p->assembled = true; p->rows_permuted = false; p->real_resident = false;
+  return MFB_OK;
+}
+extern "C" int mfb_combine_columns(mfb_problem* dst, mfb_problem* src, int n_rows, const int* row_map, int n_terms, const int* src_col, const int* dst_col,
+                                   const mfb_z* coef) {
+  if (!dst || !src || !row_map || !src_col || !dst_col || !coef || n_rows < 0 || n_terms < 0) return fail(MFB_ERR_ARG, "mfb_combine_columns: invalid argument");
+  if (dst->ctx != src->ctx) return fail(MFB_ERR_ARG, "mfb_combine_columns: both problems must live on the same context");
+  if (!src->assembled || src->real_resident) return fail(MFB_ERR_ARG, "mfb_combine_columns: src holds no assembled complex system");
+  if (!dst->assembled || dst->rows_permuted) return fail(MFB_ERR_ARG, "mfb_combine_columns: call mfb_system_zero(dst) first");
+  if (n_rows > src->n_dof) return fail(MFB_ERR_ARG, "mfb_combine_columns: n_rows exceeds the size of src");
+  std::vector<int> sr(n_rows), dr(n_rows), sc(n_terms), dc(n_terms);
+  for (int r = 0; r < n_rows; r++) {
+    if (row_map[r] < 0 || row_map[r] >= dst->n_dof) return fail(MFB_ERR_ARG, "mfb_combine_columns: row_map out of range");
+    sr[r] = src->rows_permuted ? src->rowperm[r] : r; dr[r] = row_map[r];
+  }
+  for (int i = 0; i < n_terms; i++) {
+    if (src_col[i] < 0 || src_col[i] >= src->n_dof || dst_col[i] < -1 || dst_col[i] >= dst->n_dof) return fail(MFB_ERR_ARG, "mfb_combine_columns: column out of range");
+    sc[i] = src->rows_permuted ? src->colperm[src_col[i]] : src_col[i]; dc[i] = dst_col[i];
+  }
+  CK(cudaSetDevice(dst->ctx->device));
+  cudaStream_t st = dst->ctx->stream;
+  std::vector<void*> tmp;
+  int *d_sr, *d_dr, *d_sc, *d_dc; double* d_cf;
+  std::vector<double> cf(2 * (size_t)std::max(n_terms, 1));
+  for (int i = 0; i < n_terms; i++) { cf[2 * i] = coef[i].re; cf[2 * i + 1] = coef[i].im; }
+  UP(tmp, sr, &d_sr); UP(tmp, dr, &d_dr); UP(tmp, sc, &d_sc); UP(tmp, dc, &d_dc); UP(tmp, cf, &d_cf);
+  launch_combine(src->sys, dst->sys, n_rows, d_sr, d_dr, n_terms, d_sc, d_dc, d_cf, st);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  for (void* q : tmp) cudaFree(q);
+  return MFB_OK;
+}
+extern "C" int mfb_add_entries(mfb_problem* dst, int n, const int* rows, const int* cols, const mfb_z* values) {
+  if (!dst || !rows || !cols || !values || n < 0) return fail(MFB_ERR_ARG, "mfb_add_entries: invalid argument");
+  if (!dst->assembled || dst->rows_permuted) return fail(MFB_ERR_ARG, "mfb_add_entries: call mfb_system_zero(dst) first");
+  for (int i = 0; i < n; i++) if (rows[i] < 0 || rows[i] >= dst->n_dof || cols[i] < -1 || cols[i] >= dst->n_dof) return fail(MFB_ERR_ARG, "mfb_add_entries: index out of range");
+  CK(cudaSetDevice(dst->ctx->device));
+  cudaStream_t st = dst->ctx->stream;
+  std::vector<void*> tmp;
+  std::vector<int> r(rows, rows + n), c(cols, cols + n); std::vector<double> v(2 * (size_t)std::max(n, 1));
+  for (int i = 0; i < n; i++) { v[2 * i] = values[i].re; v[2 * i + 1] = values[i].im; }
+  int *d_r, *d_c; double* d_v;
+  UP(tmp, r, &d_r); UP(tmp, c, &d_c); UP(tmp, v, &d_v);
+  launch_add_entries(dst->sys, n, d_r, d_c, d_v, st);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  for (void* q : tmp) cudaFree(q);
+  return MFB_OK;
+}
+
 // Host-only helper (no GPU needed): the geometry-only pieces of the free term of a boundary node from the unit normals and the unit boundary
 // tangents of the elements that meet there -- cp = (2 pi + sum of the signed dihedral angles) / 4 pi (fbem_bem_pot3d_sbie_freeterm,
 // lib/fbem/src/bem_stapot3d.f90:155-296) and the tensor sum_b[9] of Mantic's formula, so that c_lk = cp delta_lk - sum_b[l][k] / (8 pi (1 - nu))

@@ -141,48 +141,66 @@ def free_term_block(mrm, kr, c, omega, freeterm):
     return le, blk
 
 
+def combination_terms(mrm, kr, mp, omega, freeterm):
+    """The coupled system as a list of column operations on the two local matrices of region kr, shared by the host and the device
+    combination: (row_map, terms_H, terms_G, entries) with row_map[r] = global row of local row r; terms_* = lists of (local column,
+    global column or -1 for the right-hand side, coefficient) -- `A[row_map, gcol] += coef * A_loc[:n_rows, lcol]`; entries = list of
+    (global row, global column or -1, value) for the free terms."""
+    v, r = mrm.views[kr], mrm.regions[kr]
+    nd = r.ndof
+    D = mrm.scatter_descriptors(kr, omega)
+    row_map = np.zeros(mp["n_rows"], dtype=np.int32)
+    for (nde, eq), r0 in mp["row_of_node"].items():
+        row_map[r0:r0 + nd] = mrm.row[(nde, eq)]
+    terms_H, terms_G, entries = [], [], []
+    done_h = set()
+    for le in range(v.n_elem):
+        for j, kn in enumerate(range(v.elem_ptr[le], v.elem_ptr[le + 1])):
+            nde = int(v.elem_node[kn])
+            for k in range(nd):
+                q = kn * nd + k
+                if (nde, k) not in done_h:                             # the H column of a node is shared by its elements: combine it once
+                    done_h.add((nde, k))
+                    if int(D["hcol"][q]) >= -1:
+                        terms_H.append((mp["cH"][(nde, k)], int(D["hcol"][q]), complex(D["hcoef"][q])))
+                cg = mp["cG"][(le, j, k)]
+                if mp["g_owner"][cg] == (le, j, k):                    # a per-node G column (ordinary boundary) is combined once
+                    for t in range(4):
+                        if int(D["gcol"][q, t]) >= -1:
+                            terms_G.append((cg, int(D["gcol"][q, t]), -complex(D["gcoef"][q, t])))     # the G problem holds -g
+    for c in range(v.n_colloc):                                        # free terms through the h descriptors of the own element
+        le, blk = free_term_block(mrm, kr, c, omega, freeterm)
+        rows_g = mrm.row[(int(v.colloc_node[c]), int(v.colloc_eq[c]))]
+        for j in range(blk.shape[0]):
+            for k in range(nd):
+                q = (int(v.elem_ptr[le]) + j) * nd + k
+                if int(D["hcol"][q]) < -1:
+                    continue
+                for l in range(nd):
+                    if blk[j, l, k] != 0:
+                        entries.append((int(rows_g[l]), int(D["hcol"][q]), complex(D["hcoef"][q] * blk[j, l, k])))
+    return row_map, terms_H, terms_G, entries
+
+
 def assemble_coupled(mrm, omega, local_assemble, freeterm, locals_=None):
-    """-> A (n_dof x n_dof), b of the coupled system at frequency omega from two single-region assemblies per region.
+    """-> A (n_dof x n_dof), b of the coupled system at frequency omega from two single-region assemblies per region (host combination).
     locals_[kr] = local_models(mrm, kr) when the caller keeps the auxiliary models (and the problems set up from them) between frequencies."""
     n = mrm.n_dof
     A = np.zeros((n, n), dtype=np.complex128); b = np.zeros(n, dtype=np.complex128)
-
-    def add(rows_g, col, coef, vec):
-        if col >= 0:
-            A[rows_g, col] += coef * vec
-        elif col == -1:
-            b[rows_g] += coef * vec
-    for kr, v in enumerate(mrm.views):
+    for kr in range(len(mrm.views)):
         r = mrm.regions[kr]
-        nd = r.ndof
         mH, mG, mp = locals_[kr] if locals_ is not None else local_models(mrm, kr)
-        AH = local_assemble(mH, r, omega)
-        AG = local_assemble(mG, r, omega)
-        D = mrm.scatter_descriptors(kr, omega)
-        # local row -> global row
-        rg = np.zeros(mp["n_rows"], dtype=np.int64)
-        for (nde, eq), r0 in mp["row_of_node"].items():
-            rg[r0:r0 + nd] = mrm.row[(nde, eq)]
-        done_h = set()
-        for le in range(v.n_elem):
-            for j, kn in enumerate(range(v.elem_ptr[le], v.elem_ptr[le + 1])):
-                nde = int(v.elem_node[kn])
-                for k in range(nd):
-                    q = kn * nd + k
-                    if (nde, k) not in done_h:                         # the H column of a node is shared by its elements: combine it once
-                        done_h.add((nde, k))
-                        add(rg, int(D["hcol"][q]), D["hcoef"][q], AH[:mp["n_rows"], mp["cH"][(nde, k)]])
-                    cg = mp["cG"][(le, j, k)]
-                    if mp["g_owner"][cg] == (le, j, k):                # a per-node G column (ordinary boundary) is combined once
-                        for t in range(4):
-                            add(rg, int(D["gcol"][q, t]), -D["gcoef"][q, t], AG[:mp["n_rows"], cg])
-        # free terms through the h descriptors of the own element
-        for c in range(v.n_colloc):
-            le, blk = free_term_block(mrm, kr, c, omega, freeterm)
-            rows_g = np.asarray(mrm.row[(int(v.colloc_node[c]), int(v.colloc_eq[c]))])
-            for j in range(blk.shape[0]):
-                for k in range(nd):
-                    q = (int(v.elem_ptr[le]) + j) * nd + k
-                    if blk[j, :, k].any():
-                        add(rows_g, int(D["hcol"][q]), D["hcoef"][q], blk[j, :, k])
+        row_map, terms_H, terms_G, entries = combination_terms(mrm, kr, mp, omega, freeterm)
+        for model, terms in ((mH, terms_H), (mG, terms_G)):
+            Aloc = local_assemble(model, r, omega)
+            for lcol, gcol, coef in terms:
+                if gcol >= 0:
+                    A[row_map, gcol] += coef * Aloc[:mp["n_rows"], lcol]
+                else:
+                    b[row_map] += coef * Aloc[:mp["n_rows"], lcol]
+        for row, gcol, val in entries:
+            if gcol >= 0:
+                A[row, gcol] += val
+            else:
+                b[row] += val
     return A, b

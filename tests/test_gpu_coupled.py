@@ -29,7 +29,9 @@ def test_coupled_system_and_solution(gpu_ctx, kinds, ict):
     assert (np.abs(A - A0).max(axis=0) <= 1e-11 * sc).all(), (np.abs(A - A0).max(axis=0) / sc).max()
     assert np.abs(b - b0).max() <= 1e-11 * np.abs(b0).max()
     x = cp.solve_frequency(omega)
+    xr = cp.solve_frequency_resident(omega)            # the combination done on the device (mfb_combine_columns / mfb_add_entries)
     x0 = np.linalg.solve(A0, b0)
+    assert np.abs((xr - x0) * sc).max() <= 1e-8 * np.abs(x0 * sc).max()
     # variables of different families live on different scales: compare every unknown against the largest of its kind (by column scale)
     assert np.abs((x - x0) * sc).max() <= 1e-8 * np.abs(x0 * sc).max()
     cp.close()
