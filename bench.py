@@ -380,6 +380,151 @@ def run_acoustic(args):
         dist.barrier(); dist.destroy_process_group()
 
 
+COUPLED_METRIC = ("poroelastic (harpor) + acoustic (harpot) coupled 3D BEM end-to-end solves/s (both regions assembled, be-be interface combination, zgetrf + zgetrs "
+                  "of one frequency) at ~20k DOF")
+
+
+def coupled_workload(args):
+    """BASELINE config 4: a water column (inviscid fluid) over a water-saturated poroelastic layer, two boxes of a 10 m cube that share one
+    perfectly bonded, permeable be-be interface; pressure prescribed on the far fluid face, sliding impermeable lateral walls, rigid
+    impermeable bottom."""
+    from multifebe_b200.host import MultiRegionModel, Region, FLUID, two_box_mesh, shape, Fluid, Poro
+    from multifebe_b200.host.multiregion import PORO
+    et = {"tri3": shape.TRI3, "tri6": shape.TRI6, "quad4": shape.QUAD4, "quad8": shape.QUAD8, "quad9": shape.QUAD9}[args.coupled_etype]
+    fl = Fluid(1000.0, 1500.0, 0.0)
+    po = Poro(rhof=1000.0, rhos=2650.0, lam=1.0e8, mu=1.0e8, xi=0.03, phi=0.35, rhoa=150.0, R=4.0e8, Q=7.0e8, b=1.0e6)
+    bcs = {1: (0, 1.0), 2: ([1, 0, 0, 0], [0, 0, 0, 0])}
+    for q in (3, 4, 5, 6):
+        bcs[q] = (1, 0.0)
+    for q in (13, 14, 15, 16):
+        ct = [1, 1, 1, 1]; ct[2 if q in (13, 14) else 3] = 0
+        bcs[q] = (ct, [0, 0, 0, 0])
+    parts = (1, 2, 3, 4, 5, 6, 7, 13, 14, 15, 16)
+    mrm = MultiRegionModel(two_box_mesh(args.coupled_m, et, L=10.0), [Region(FLUID, fl, [1, 3, 4, 5, 6, 7]), Region(PORO, po, [-7, 2, 13, 14, 15, 16])],
+                           {b: b for b in parts}, bcs, interface_ctype={7: 0})
+    omega = 2.0 * np.pi * 50.0
+    name = "water box | saturated poroelastic box, 10 m cube, %s m=%d per face at 50 Hz: %d DOF" % (args.coupled_etype, args.coupled_m, mrm.n_dof)
+    return mrm, name, omega
+
+
+def cpu_arm_coupled(args, mrm, omega, lu_n=4096, budget_pairs=4e6):
+    """Reference algorithm on the host cores: each region's oracle (one integration pass yields both H and G, as in the reference) on every
+    stride-th collocation point of the region's mesh, scaled to all of them, + OpenBLAS zgetrf/zgetrs scaled by n^3."""
+    import copy
+    from oracle import oracle as orc
+    from scipy.linalg import lapack
+    from multifebe_b200.host.coupled import local_models
+    ncores = os.cpu_count()
+    t_asm = 0.0; notes = []
+    for kr, region in enumerate(mrm.regions):
+        mH, _, _ = local_models(mrm, kr)
+        stride = max(1, int(round(mH.n_elem * mH.n_colloc / budget_pairs)))
+        sub = copy.copy(mH)
+        sel = np.arange(stride // 2, mH.n_colloc, stride)
+        for name in ("colloc_x", "colloc_node", "colloc_elem", "colloc_kn", "colloc_xi"):
+            setattr(sub, name, np.ascontiguousarray(getattr(mH, name)[sel]))
+        sub.n_colloc = len(sel)
+        o = (orc.PotOracle if region.kind == "fluid" else orc.PorOracle if region.kind == "poro" else orc.Oracle)(sub)
+        t0 = time.time(); o.assemble(omega, region.material, nthreads=ncores); t_s = time.time() - t0
+        t_asm += t_s * mH.n_colloc / len(sel)
+        notes.append("%s region: %d elements x %d of %d collocation points in %.1f s" % (region.kind, mH.n_elem, len(sel), mH.n_colloc, t_s))
+    n = mrm.n_dof
+    lu_n = min(lu_n, n)
+    rng = np.random.default_rng(0)
+    A = np.asfortranarray(rng.standard_normal((lu_n, lu_n)) + 1j * rng.standard_normal((lu_n, lu_n))); b = rng.standard_normal(lu_n) + 0j
+    t0 = time.time(); lu, piv, info = lapack.zgetrf(A, overwrite_a=True); x, info = lapack.zgetrs(lu, piv, b); t2 = time.time()
+    t_lu = (t2 - t0) * (n / lu_n) ** 3
+    sample = "assembly: " + "; ".join(notes) + ", each scaled to all its points; LU: OpenBLAS zgetrf+zgetrs at n=%d (%.2f s) scaled by (%d/%d)^3" % (lu_n, t2 - t0, n, lu_n)
+    return {"value": 1.0 / (t_asm + t_lu), "unit": "solves/s", "cores": ncores, "kind": "port", "sample": sample, "assembly_s_per_step": t_asm, "lu_s_per_step": t_lu}
+
+
+def run_coupled(args):
+    """One frequency of the fluid | poroelastic model per step (capi.CoupledProblem.solve_frequency_resident: single-region assemblies, device
+    combination, LU); N ranks = N replicas.  The device path of this workload has not run on hardware yet: it is
+    opt-in like its tests."""
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    mrm, name, omega = coupled_workload(args)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        res = [cpu_arm_coupled(args, mrm, omega) for _ in range(args.steps)]
+        v = float(np.mean([r["value"] for r in res])); cb = dict(res[-1]); cb["value"] = v
+        print(json.dumps({"impl": "reference", "metric": COUPLED_METRIC, "value": v, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+                          "config": {"workload": name, "note": "reference algorithm on host cores (oracle port; no Fortran compiler here), bounded sample scaled to a full solve"},
+                          "cpu_baseline": cb, "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
+    if not os.environ.get("MFB_RUN_UNVALIDATED"):
+        raise SystemExit("bench.py --workload coupled: the poroelastic and combination kernels have not had their first hardware run; set MFB_RUN_UNVALIDATED=1 "
+                         "(after tools/gpu_first_contact.sh is green)")
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    from multifebe_b200 import capi
+    ctx = capi.Context(local)
+    dev = torch.device("cuda", local)
+    t0 = time.time(); cp = capi.CoupledProblem(ctx, mrm); t_setup = time.time() - t0
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def reduce_max(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        x = cp.solve_frequency_resident(omega)
+    acc = {}
+    barrier(); t0 = time.time(); w0 = t0
+    for s in range(args.steps):
+        x = cp.solve_frequency_resident(omega)
+        for pr in list(cp.problems.values()):
+            st = pr.stats()
+            for k in ("MS_ASSEMBLE", "MS_REGULAR", "MS_ADAPTIVE", "MS_SINGULAR", "LAUNCHES"):
+                acc[k] = acc.get(k, 0.0) + st[k]
+        st = cp._solver.stats()
+        for k in ("MS_LU", "MS_SOLVE", "MS_GEMM", "MS_PANEL", "LU_LAUNCHES", "GEMM_LAUNCHES", "GEMM_FLOPS"):
+            acc[k] = acc.get(k, 0.0) + st[k]
+    barrier(); ms_e2e = reduce_max((time.time() - t0) * 1e3 / args.steps); windows = [(w0, time.time())]
+    K = args.steps
+    ms_dev = reduce_max((acc["MS_ASSEMBLE"] + acc["MS_LU"] + acc["MS_SOLVE"]) / K)
+    peaks = ctx.measure_peaks() if rank == 0 else None
+    if rank == 0:
+        n = mrm.n_dof
+        gemm_tf = acc["GEMM_FLOPS"] / max(acc["MS_GEMM"], 1e-9) / 1e9
+        out = {"metric": COUPLED_METRIC, "value": world * 1e3 / ms_dev, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+               "config": {"workload": name, "sharding": "replicas: every rank solves the same frequency",
+                          "l2": "every step rewrites the local and the coupled matrices (%.2f GB for the coupled one alone, larger than the 126 MB L2)" % (16.0 * n * n / 1e9),
+                          "setup_s_once_per_mesh": t_setup,
+                          "note": "value = library events of the four local assemblies + LU + solve (the combination kernels and the host-side term lists are "
+                                  "outside those events and inside e2e)"},
+               "clocks": clocks.summary(windows),
+               "e2e": {"value": world * 1e3 / ms_e2e, "unit": "solves/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(sum(m.cvalue.size for m3 in cp.locals for m in m3[:2]) * 16),
+                       "d2h_bytes_per_step": int(16 * n + 4 * n), "api": "mfb_harpot3d_assemble / mfb_harpor3d_assemble x2, mfb_combine_columns, mfb_add_entries, mfb_zsolve, mfb_get_solution"},
+               "gpu_launches": int(acc["LAUNCHES"] + acc["LU_LAUNCHES"]),
+               "roofline": {"kernel": "k_zgemm3m_minus (LU trailing update)", "bound": "tensor", "achieved": gemm_tf, "peak": peaks["dmma_tflops"], "unit": "TFLOP/s",
+                            "frac": gemm_tf / peaks["dmma_tflops"], "traffic": None, "share_of_step": (acc["MS_GEMM"] / K) / ms_dev,
+                            "peak_source": "FP64 tensor (DMMA) micro-benchmark measured live (mfb_measure_peaks)"},
+               "assembly": {"ms": acc["MS_ASSEMBLE"] / K, "ms_regular": acc["MS_REGULAR"] / K, "ms_adaptive": acc["MS_ADAPTIVE"] / K, "ms_singular": acc["MS_SINGULAR"] / K},
+               "lu": {"ms": acc["MS_LU"] / K, "tflops": 8.0 / 3.0 * n ** 3 / (acc["MS_LU"] / K) / 1e9, "ms_gemm": acc["MS_GEMM"] / K, "ms_zgetrs": acc["MS_SOLVE"] / K},
+               "peaks_measured_live": peaks}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_arm_coupled(args, mrm, omega)
+        print(json.dumps(out), flush=True)
+    cp.close(); ctx.close()
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -582,8 +727,10 @@ def main():
     ap.add_argument("--etype", default="tri3")
     ap.add_argument("--m", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="harmonic", choices=["harmonic", "static", "acoustic"],
-                    help="harmonic: the headline 30k-DOF sweep (default); static: BASELINE config 2; acoustic: one frequency of the ME-TH-AC-001 room at ~10k DOF")
+    ap.add_argument("--workload", default="harmonic", choices=["harmonic", "static", "acoustic", "coupled"],
+                    help="harmonic: the headline 30k-DOF sweep (default); static: BASELINE config 2; acoustic: one frequency of the ME-TH-AC-001 room at ~10k DOF; coupled: BASELINE config 4 (fluid | poroelastic, ~20k DOF; device path opt-in)")
+    ap.add_argument("--coupled-etype", default="quad9")
+    ap.add_argument("--coupled-m", type=int, default=13, help="cells per face side of the two-box model (13 -> 21870 DOF)")
     ap.add_argument("--acoustic-etype", default="quad9")
     ap.add_argument("--acoustic-m", type=int, default=20)
     ap.add_argument("--static-etype", default="quad9")
@@ -591,6 +738,8 @@ def main():
     args = ap.parse_args()
     if args.workload == "acoustic":
         run_acoustic(args)
+    elif args.workload == "coupled":
+        run_coupled(args)
     elif args.workload == "static":
         run_static(args)
     elif args.impl == "reference":

@@ -107,6 +107,7 @@ class CoupledProblem:
         for mH, mG, _ in self.locals:
             self.problems[id(mH)] = Problem(ctx, mH); self.problems[id(mG)] = Problem(ctx, mG)
         self._solver = None
+        self._terms = {}                                 # host/coupled.py::TermArrays per region, kept between frequencies
 
     def _assemble_local(self, model, region, omega):
         pr = self.problems[id(model)]
@@ -124,7 +125,7 @@ class CoupledProblem:
     def solve_frequency_resident(self, omega):
         """The same without moving matrices through the host: the local systems stay on the device, mfb_combine_columns / mfb_add_entries build
         the coupled system in the resident matrix of a solver problem, mfb_zsolve factorises and solves it there (not yet run on hardware)."""
-        from .host.coupled import combination_terms
+        from .host.coupled import TermArrays
         n = self.m.n_dof
         if self._solver is None or self._solver.m.n_dof != n:
             self._solver = _lu_only_problem(self.ctx, n)
@@ -132,9 +133,10 @@ class CoupledProblem:
         _check(lib().mfb_system_zero(dst.h))
         for kr, (mH, mG, mp) in enumerate(self.locals):
             region = self.m.regions[kr]
-            row_map, terms_H, terms_G, entries = combination_terms(self.m, kr, mp, omega, freeterm)
-            rm = np.ascontiguousarray(row_map, dtype=np.int32)
-            for model, terms in ((mH, terms_H), (mG, terms_G)):
+            if kr not in self._terms:
+                self._terms[kr] = TermArrays(self.m, kr, mp, freeterm)
+            ta = self._terms[kr].at(omega)
+            for model, (sc, dc, cf) in ((mH, ta.H), (mG, ta.G)):
                 pr = self.problems[id(model)]
                 if region.kind == "solid":
                     pr.build_lse_mechanics_bem_harela(omega, region.material, want_host=False)
@@ -142,13 +144,9 @@ class CoupledProblem:
                     pr.build_lse_mechanics_bem_harpot(omega, region.material, want_host=False)
                 else:
                     pr.build_lse_mechanics_bem_harpor(omega, region.material, want_host=False)
-                sc = np.array([t[0] for t in terms], dtype=np.int32); dc = np.array([t[1] for t in terms], dtype=np.int32)
-                cf = np.array([t[2] for t in terms], dtype=np.complex128)
-                _check(lib().mfb_combine_columns(dst.h, pr.h, C.c_int(len(rm)), _p(rm), C.c_int(len(terms)), _p(sc), _p(dc), _p(cf)))
-            if entries:
-                er = np.array([e[0] for e in entries], dtype=np.int32); ec = np.array([e[1] for e in entries], dtype=np.int32)
-                ev = np.array([e[2] for e in entries], dtype=np.complex128)
-                _check(lib().mfb_add_entries(dst.h, C.c_int(len(entries)), _p(er), _p(ec), _p(ev)))
+                _check(lib().mfb_combine_columns(dst.h, pr.h, C.c_int(len(ta.row_map)), _p(ta.row_map), C.c_int(len(sc)), _p(sc), _p(dc), _p(cf)))
+            if len(ta.E[0]):
+                _check(lib().mfb_add_entries(dst.h, C.c_int(len(ta.E[0])), _p(ta.E[0]), _p(ta.E[1]), _p(ta.E[2])))
         ipiv = np.zeros(n, dtype=np.int32)
         _check(lib().mfb_zsolve(dst.h, C.c_int(n), None, C.c_int(n), _p(ipiv), None, C.c_int(1), C.c_int(1)))
         return dst.get_solution()

@@ -109,7 +109,7 @@ def free_term_block(mrm, kr, c, omega, freeterm):
     nn = len(nodes)
     mat = r.material
     if r.kind == PORO:
-        J = 1.0 / ((mat.rho2 + mat.rhoa - 1j * mat.b / omega) * omega ** 2)
+        J = poro_J(mat, omega)
         unit = np.diag([J, 1.0, 1.0, 1.0]).astype(np.complex128)
     else:
         unit = np.eye(nd, dtype=np.complex128)
@@ -122,16 +122,24 @@ def free_term_block(mrm, kr, c, omega, freeterm):
     if et == sh.QUAD9 and kn == 8:
         blk[kn] = 0.5 * unit
         return le, blk
-    rev = bool(v.elem_reversed[le])
-    ns, ts = [], []
-    for le2 in range(v.n_elem):
-        nodes2 = v.elem_node[v.elem_ptr[le2]:v.elem_ptr[le2 + 1]]
-        for kn2, nde in enumerate(nodes2):
-            if int(nde) == sn:
-                n, tbp, tbm = sh.node_normal_tangents(int(v.etype[le2]), mrm.node_x[nodes2], kn2)
-                ns.append(-n if rev else n); ts.append(tbm if rev else tbp)
-    nu = mat.nu if r.kind != FLUID else 0.0
-    cm, cp = freeterm(np.array(ns), np.array(ts), nu, mrm.geometric_tolerance)
+    cache = mrm.__dict__.setdefault("_free_term_cache", {})              # geometry + Poisson's ratio only: kept between frequencies
+    if (kr, c) not in cache:
+        fans = mrm.__dict__.setdefault("_node_fans", {})
+        if kr not in fans:                                               # node -> [(element, local node)] of the region's boundary
+            fan = {}
+            for le2 in range(v.n_elem):
+                for kn2, nde in enumerate(v.elem_node[v.elem_ptr[le2]:v.elem_ptr[le2 + 1]]):
+                    fan.setdefault(int(nde), []).append((le2, kn2))
+            fans[kr] = fan
+        rev = bool(v.elem_reversed[le])
+        ns, ts = [], []
+        for le2, kn2 in fans[kr][sn]:
+            nodes2 = v.elem_node[v.elem_ptr[le2]:v.elem_ptr[le2 + 1]]
+            n, tbp, tbm = sh.node_normal_tangents(int(v.etype[le2]), mrm.node_x[nodes2], kn2)
+            ns.append(-n if rev else n); ts.append(tbm if rev else tbp)
+        nu = mat.nu if r.kind != FLUID else 0.0
+        cache[(kr, c)] = freeterm(np.array(ns), np.array(ts), nu, mrm.geometric_tolerance)
+    cm, cp = cache[(kr, c)]
     if r.kind == SOLID:
         blk[kn] = cm
     elif r.kind == FLUID:
@@ -178,8 +186,40 @@ def combination_terms(mrm, kr, mp, omega, freeterm):
                     continue
                 for l in range(nd):
                     if blk[j, l, k] != 0:
-                        entries.append((int(rows_g[l]), int(D["hcol"][q]), complex(D["hcoef"][q] * blk[j, l, k])))
+                        entries.append((int(rows_g[l]), int(D["hcol"][q]), complex(D["hcoef"][q] * blk[j, l, k]), r.kind == PORO and l == 0 and k == 0))
     return row_map, terms_H, terms_G, entries
+
+
+def poro_J(mat, omega):
+    """J = 1 / ((rho2 + rhoa - i b / omega) omega^2): the only frequency dependence of the free-term entries of a poroelastic region."""
+    return 1.0 / ((mat.rho2 + mat.rhoa - 1j * mat.b / omega) * omega ** 2)
+
+
+class TermArrays:
+    """combination_terms as flat arrays, kept between frequencies: the structure (columns, rows) does not depend on the frequency, and the
+    coefficients depend on it only through impedance conditions (then the lists are rebuilt) and through J in the fluid-phase free term of a
+    poroelastic region (rescaled in place)."""
+
+    def __init__(self, mrm, kr, mp, freeterm):
+        self.mrm, self.kr, self.mp, self.freeterm = mrm, kr, mp, freeterm
+        self.omega = None
+        self.omega_dependent = None
+
+    def at(self, omega):
+        r = self.mrm.regions[self.kr]
+        if self.omega_dependent is None:
+            D1, D2 = self.mrm.scatter_descriptors(self.kr, omega), self.mrm.scatter_descriptors(self.kr, 2.0 * omega)
+            self.omega_dependent = not (np.array_equal(D1["hcoef"], D2["hcoef"]) and np.array_equal(D1["gcoef"], D2["gcoef"]))
+        if self.omega is None or (self.omega_dependent and omega != self.omega):
+            row_map, tH, tG, en = combination_terms(self.mrm, self.kr, self.mp, omega, self.freeterm)
+            self.row_map = np.ascontiguousarray(row_map, dtype=np.int32)
+            self.H = tuple(np.array([t[i] for t in tH], dtype=dt) for i, dt in ((0, np.int32), (1, np.int32), (2, np.complex128)))
+            self.G = tuple(np.array([t[i] for t in tG], dtype=dt) for i, dt in ((0, np.int32), (1, np.int32), (2, np.complex128)))
+            self.E = [np.array([e[i] for e in en], dtype=dt) for i, dt in ((0, np.int32), (1, np.int32), (2, np.complex128), (3, bool))]
+        elif omega != self.omega and r.kind == PORO and len(self.E[2]):
+            self.E[2][self.E[3]] *= poro_J(r.material, omega) / poro_J(r.material, self.omega)
+        self.omega = omega
+        return self
 
 
 def assemble_coupled(mrm, omega, local_assemble, freeterm, locals_=None):
@@ -198,7 +238,7 @@ def assemble_coupled(mrm, omega, local_assemble, freeterm, locals_=None):
                     A[row_map, gcol] += coef * Aloc[:mp["n_rows"], lcol]
                 else:
                     b[row_map] += coef * Aloc[:mp["n_rows"], lcol]
-        for row, gcol, val in entries:
+        for row, gcol, val, _ in entries:
             if gcol >= 0:
                 A[row, gcol] += val
             else:

@@ -1,0 +1,30 @@
+"""The CPU (`--impl reference`) arms of bench.py's secondary workloads on tiny meshes: one JSON line each, carrying the keys the driver reads.
+The GPU arms are exercised on the box (profiles/)."""
+import json
+import os
+import subprocess
+import sys
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("extra", [["--workload", "coupled", "--coupled-m", "2"], ["--workload", "acoustic", "--acoustic-m", "3"]])
+def test_reference_arm_prints_one_contract_line(extra):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"] + extra, cwd=ROOT,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "solves/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+    assert "workload" in d["config"]
+
+
+def test_coupled_gpu_arm_is_opt_in_until_its_first_hardware_run():
+    env = {k: v for k, v in os.environ.items() if k != "MFB_RUN_UNVALIDATED"}
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "coupled", "--coupled-m", "1", "--steps", "1"], cwd=ROOT, env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode != 0 and "MFB_RUN_UNVALIDATED" in out.stderr

@@ -96,3 +96,36 @@ def test_impedance_condition_through_the_single_region_route():
     A1, b1 = assemble_coupled(mrm, 3.0, oracle_local_assemble, oracle_freeterm)
     sc = np.abs(A0).max(axis=0)
     assert (np.abs(A1 - A0).max(axis=0) <= 1e-12 * sc).all() and np.abs(b1 - b0).max() <= 1e-12 * np.abs(b0).max()
+
+
+def _same_terms(ta, ref):
+    row_map, tH, tG, en = ref
+    assert np.array_equal(ta.row_map, row_map)
+    for arr, lst in ((ta.H, tH), (ta.G, tG)):
+        assert np.array_equal(arr[0], [t[0] for t in lst]) and np.array_equal(arr[1], [t[1] for t in lst])
+        assert np.allclose(arr[2], [t[2] for t in lst], rtol=1e-14, atol=0)
+    assert np.array_equal(ta.E[0], [e[0] for e in en]) and np.array_equal(ta.E[1], [e[1] for e in en])
+    assert np.allclose(ta.E[2], [e[2] for e in en], rtol=1e-13, atol=0)
+
+
+def test_term_arrays_kept_between_frequencies_equal_fresh_term_lists():
+    """TermArrays (what CoupledProblem.solve_frequency_resident hands to the device): the second frequency reuses the structure, rescales J of a
+    poroelastic region, and rebuilds the lists when an impedance condition makes the coefficients frequency dependent."""
+    from multifebe_b200.host.coupled import TermArrays, combination_terms, local_models
+    from multifebe_b200.host import cube_mesh
+    bcs = bcs_for(FLUID, LAT1, 1, True); bcs.update(bcs_for(PORO, LAT2, 2, False))
+    mrm = MultiRegionModel(two_box_mesh(1, shape.QUAD8), [Region(FLUID, FL, [1, 3, 4, 5, 6, 7]), Region(PORO, PO, [-7, 2, 13, 14, 15, 16])], BPART, bcs,
+                           interface_ctype={7: 0})
+    for kr in range(2):
+        mp = local_models(mrm, kr)[2]
+        ta = TermArrays(mrm, kr, mp, oracle_freeterm)
+        for omega in (1.7, 0.9, 0.9, 3.1):
+            _same_terms(ta.at(omega), combination_terms(mrm, kr, mp, omega, oracle_freeterm))
+        assert ta.omega_dependent is False
+    duct = MultiRegionModel(cube_mesh(1, shape.QUAD8), [Region(FLUID, FL, [1, 2, 3, 4, 5, 6])], {b: b for b in range(1, 7)},
+                            {1: (0, 1.0), 2: (2, 0.0), 3: (1, 0.0), 4: (1, 0.0), 5: (1, 0.0), 6: (1, 0.0)})
+    mp = local_models(duct, 0)[2]
+    ta = TermArrays(duct, 0, mp, oracle_freeterm)
+    for omega in (4.0, 2.5):
+        _same_terms(ta.at(omega), combination_terms(duct, 0, mp, omega, oracle_freeterm))
+    assert ta.omega_dependent is True
