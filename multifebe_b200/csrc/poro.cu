@@ -17,6 +17,7 @@
 // (4x the arithmetic of a one-pass kernel: the register file does not hold 32 * NN complex accumulators; a later version can stage them
 // in shared memory).
 #include "poro.cuh"
+#include "por_pair.cuh"
 #include <cstdio>
 
 namespace mfbd {
@@ -25,35 +26,6 @@ __constant__ PorParams c_por;
 
 void set_por_params(const PorParams& pp, cudaStream_t st) { cudaMemcpyToSymbolAsync(c_por, &pp, sizeof(PorParams), 0, cudaMemcpyHostToDevice, st); }
 
-// accumulators of one equation l of one pair: h(j, l, k), g(j, l, k), k = 0..3
-template <int NN>
-struct RAcc {
-  double hr[4 * NN], hi[4 * NN], gr[4 * NN], gi[4 * NN];     // [k * NN + j]
-  __device__ __forceinline__ void zero() {
-#pragma unroll
-    for (int i = 0; i < 4 * NN; i++) { hr[i] = 0.0; hi[i] = 0.0; gr[i] = 0.0; gi[i] = 0.0; }
-  }
-};
-
-// row l of the 4 x 4 blocks, selected with compile-time indices only
-__device__ __forceinline__ void por_row(const cplx f[4][4], int l, cplx out[4]) {
-#pragma unroll
-  for (int k = 0; k < 4; k++) out[k] = (l == 0) ? f[0][k] : (l == 1 ? f[1][k] : (l == 2 ? f[2][k] : f[3][k]));
-}
-
-template <int NN>
-__device__ __forceinline__ void por_accumulate_row(RAcc<NN>& a, const cplx fu[4][4], const cplx ft[4][4], int l, const double* w) {
-  cplx ur[4], tr[4];
-  por_row(fu, l, ur); por_row(ft, l, tr);
-#pragma unroll
-  for (int k = 0; k < 4; k++)
-#pragma unroll
-    for (int j = 0; j < NN; j++) {
-      a.hr[k * NN + j] = fma(tr[k].re, w[j], a.hr[k * NN + j]); a.hi[k * NN + j] = fma(tr[k].im, w[j], a.hi[k * NN + j]);
-      a.gr[k * NN + j] = fma(ur[k].re, w[j], a.gr[k * NN + j]); a.gi[k * NN + j] = fma(ur[k].im, w[j], a.gi[k * NN + j]);
-    }
-}
-
 // BC-aware scatter of equation l of one pair (assemble_bem_harpor_equation.f90:78-110, :140-170; open-pore conditions): entries selected by
 // `mine(j * 4 + k)`; h is scaled by cte_t(l, k) and changes sign on a reversed element, g by cte_u(l, k).
 template <int NN, class Pred>
@@ -61,16 +33,12 @@ __device__ __forceinline__ void por_scatter_row(const RAcc<NN>& a, int l, const 
                                                 const double* __restrict__ ecv, bool rev, const DevSystem& s, int row, double& bre, double& bim, Pred mine) {
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const cplx ct0 = (l == 0) ? c_por.cte_t[0][k] : c_por.cte_t[1][k];     // cte_t(l, k) depends on l only through l == 0
-    const cplx cu = (l == 0) ? c_por.cte_u[0][k] : c_por.cte_u[1][k];
-    const cplx ct = rev ? mk(-ct0.re, -ct0.im) : ct0;
 #pragma unroll
     for (int j = 0; j < NN; j++) {
       const int jk = j * 4 + k;
       if (!mine(jk)) continue;
-      const int q = k * NN + j;
-      const double hr = ct.re * a.hr[q] - ct.im * a.hi[q], hi = ct.re * a.hi[q] + ct.im * a.hr[q];
-      const double gr = cu.re * a.gr[q] - cu.im * a.gi[q], gi = cu.re * a.gi[q] + cu.im * a.gr[q];
+      double hr, hi, gr, gi;
+      por_finished_entry<NN>(a, c_por, l, k, j, rev, hr, hi, gr, gi);
       const int col = ecol[jk];
       const double cvr = ecv[2 * jk], cvi = ecv[2 * jk + 1];
       double ar, ai;
@@ -128,9 +96,7 @@ __global__ void __launch_bounds__(R1_WARPS * 32) k_por_regular(DevGroup g, DevCo
             double w[NN];
 #pragma unroll
             for (int j = 0; j < NN; j++) w[j] = __ldg(q + 6 + j);
-            cplx fu[4][4], ft[4][4];
-            por_exterior_blocks(c_por, x, n, xc, fu, ft);
-            por_accumulate_row<NN>(acc, fu, ft, l, w);
+            por_regular_point<NN>(acc, c_por, x, n, w, xc, l);
           }
           const int row = (l == 0) ? rows[0] : (l == 1 ? rows[1] : (l == 2 ? rows[2] : rows[3]));
           double br = 0.0, bi = 0.0;
@@ -204,11 +170,7 @@ __global__ void __launch_bounds__(128) k_por_adaptive(DevGroup g, DevColloc c, D
 #pragma unroll 1
       for (int idx = lane; idx < gln * gln; idx += 32) {
         const int k1 = idx / gln, k2 = idx - k1 * gln;
-        double x[3], n[3], w[NN];
-        leaf_point<ET>(xn, xi_s, tp1, tp2, __ldg(gx + off + k1), __ldg(gw + off + k1), __ldg(gx + off + k2), __ldg(gw + off + k2), x, n, w);
-        cplx fu[4][4], ft[4][4];
-        por_exterior_blocks(c_por, x, n, xc, fu, ft);
-        por_accumulate_row<NN>(acc, fu, ft, l, w);
+        por_leaf_point<ET>(acc, c_por, xn, xi_s, tp1, tp2, __ldg(gx + off + k1), __ldg(gw + off + k1), __ldg(gx + off + k2), __ldg(gw + off + k2), xc, l);
       }
     }
     por_warp_reduce<NN>(acc);
@@ -265,37 +227,10 @@ __global__ void __launch_bounds__(128) k_por_singular(DevGroup g, DevColloc c, D
       const double* R = a.rays + 4 * (size_t)(ray0 + kr_);
       const double ct = __ldg(R), sn = __ldg(R + 1), rhoij = __ldg(R + 2), wray = __ldg(R + 3);
       const double rho = rhoij * __ldg(gx + kk), wrad = __ldg(gw + kk);
-      double phi[NN], x[3], n[3], jg;
-      geometry_at<ET>(xn, xi_i0 + rho * ct, xi_i1 + rho * sn, phi, x, n, jg);
-      const double jw = jg * rho * wray * wrad;
-      double w[NN];
-#pragma unroll
-      for (int j = 0; j < NN; j++) w[j] = phi[j] * jw;
-      cplx fu[4][4], ft[4][4], fc[3][3];
-      por_interior_blocks(c_por, x, n, xc, fu, ft, fc);
-      por_accumulate_row<NN>(acc, fu, ft, l, w);
-      if (l > 0) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          const cplx f = (l == 1) ? fc[0][k] : (l == 2 ? fc[1][k] : fc[2][k]);
-#pragma unroll
-          for (int j = 0; j < NN; j++) {
-            const double wc = (phi[j] - phi_i[j]) * jw;
-            acc.hr[(k + 1) * NN + j] = fma(f.re, wc, acc.hr[(k + 1) * NN + j]); acc.hi[(k + 1) * NN + j] = fma(f.im, wc, acc.hi[(k + 1) * NN + j]);
-          }
-        }
-      }
+      por_singular_point<ET>(acc, c_por, xn, xi_i0, xi_i1, phi_i, ct, sn, rho, wray, wrad, xc, l);
     }
     por_warp_reduce<NN>(acc);
-    if (l > 0) {
-      const cplx t21 = c_por.T2[1];
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const double hl = D[5 + 3 * (l - 1) + k];
-#pragma unroll
-        for (int j = 0; j < NN; j++) { acc.hr[(k + 1) * NN + j] += phi_i[j] * t21.re * hl; acc.hi[(k + 1) * NN + j] += phi_i[j] * t21.im * hl; }
-      }
-    }
+    por_singular_line_terms<NN>(acc, c_por, phi_i, D + 5, l);
     const int row = c.crow[l * c.ldp + cpos];
     double br = 0.0, bi = 0.0;
     PorLane pl; pl.lane = lane;
