@@ -37,10 +37,11 @@ def test_assembly_and_solution_parity(gpu_ctx, oracle_lib, et, m, omega):
     assert s["PAIRS_ADAPTIVE"] == st["pairs_adaptive"] and s["LEAVES"] == st["leaves"] and s["PAIRS_SINGULAR"] == st["pairs_singular"]
     xo = np.linalg.solve(Ao, bo)
     x = pr.solve_frequency_poro(omega, PO)
-    for k in range(4):
-        for cols in (md.col_u[:, k][md.col_u[:, k] >= 0], md.col_t[:, k][md.col_t[:, k] >= 0]):
-            if len(cols):
-                assert np.abs(x[cols] - xo[cols]).max() <= TOL_X * max(np.abs(xo[cols]).max(), 1e-300)
+    # one scale per family (tau, Un, the displacement vector, the traction vector): a component that vanishes by symmetry has no scale of its own
+    for fam in (md.col_u[:, :1], md.col_t[:, :1], md.col_u[:, 1:], md.col_t[:, 1:]):
+        cols = fam[fam >= 0]
+        if len(cols):
+            assert np.abs(x[cols] - xo[cols]).max() <= TOL_X * np.abs(xo[cols]).max()
     pr.close()
 
 
