@@ -13,6 +13,7 @@ run static_internal    python -m pytest tests/test_gpu_driver.py -q -m gpu -k wi
 run coupled            python -m pytest tests/test_gpu_coupled.py -q -m gpu
 run poro_tri3          compute-sanitizer --error-exitcode 9 python -m pytest tests/test_gpu_poroelastic.py -q -m gpu -x -k "0.3-5-3"
 run poroelastic        python -m pytest tests/test_gpu_poroelastic.py -q -m gpu
+run golden_widening   python -m pytest tests/test_golden_widening.py -q -m gpu
 run acoustic_bench     python bench.py --workload acoustic --steps 3 --warmup 3
 run coupled_bench      python bench.py --workload coupled --steps 2 --warmup 3
 tail -n 3 gpurun_out/fc_*.log | tail -n 60
