@@ -96,3 +96,18 @@ def test_poroelastic_and_coupled_paths(stub):
     cp.close(); ctx.close()
     for name in ("mfb_harpor3d_setup", "mfb_harpor3d_assemble", "mfb_harpor3d_solve_frequency", "mfb_system_zero", "mfb_combine_columns", "mfb_add_entries", "mfb_freeterm_terms"):
         assert stub.called.get(name), name
+
+
+def test_driver_with_coupled_regions_through_the_stub(stub, tmp_path, monkeypatch):
+    """driver.run -> GpuSolver -> capi.CoupledProblem on a two-region case file (opt-in path): the glue runs end to end and writes the *.nso rows."""
+    import io
+    from multifebe_b200 import driver
+    from multifebe_b200.host.mesh import write_gmsh22
+    from test_casefile_driver import TWO_REGION_DAT
+    monkeypatch.setenv("MFB_RUN_UNVALIDATED", "1")
+    write_gmsh22(two_box_mesh(1, shape.QUAD9), str(tmp_path / "boxes.msh"))
+    path = str(tmp_path / "two.dat")
+    open(path, "w").write(TWO_REGION_DAT)
+    nso = driver.run(path, log=io.StringIO())
+    rows = [s for s in open(nso) if s.strip() and not s.startswith("#")]
+    assert len(rows) > 0 and stub.called.get("mfb_harela3d_setup") and stub.called.get("mfb_harpot3d_setup") and stub.called.get("mfb_zsolve")
