@@ -111,3 +111,36 @@ def test_driver_with_coupled_regions_through_the_stub(stub, tmp_path, monkeypatc
     nso = driver.run(path, log=io.StringIO())
     rows = [s for s in open(nso) if s.strip() and not s.startswith("#")]
     assert len(rows) > 0 and stub.called.get("mfb_harela3d_setup") and stub.called.get("mfb_harpot3d_setup") and stub.called.get("mfb_zsolve")
+
+
+def test_bench_device_arms_of_the_secondary_workloads_through_the_stub(stub, monkeypatch, capsys):
+    """bench.py --workload acoustic / coupled, device arms (not yet run on hardware): the glue from the workload to the JSON line runs with the
+    stub library (statistics and peaks read as 1.0) and prints the keys of the contract."""
+    import argparse
+    import ctypes as C
+    import json
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+
+    def get_stats(h, ptr):
+        C.memmove(ptr, (C.c_double * capi.STAT_COUNT)(*([1.0] * capi.STAT_COUNT)), 8 * capi.STAT_COUNT); return 0
+
+    def measure_peaks(h, a, b, c):
+        for r in (a, b, c):
+            r._obj.value = 1.0
+        return 0
+    stub.mfb_get_stats = get_stats; stub.mfb_measure_peaks = measure_peaks
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setenv("MFB_RUN_UNVALIDATED", "1")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    args = argparse.Namespace(impl="ours", gpus=1, steps=1, warmup=1, no_cpu_baseline=True, acoustic_etype="tri3", acoustic_m=2, coupled_etype="tri3", coupled_m=1)
+    for fn in (bench.run_acoustic, bench.run_coupled):
+        fn(args)
+        line = [s for s in capsys.readouterr().out.splitlines() if s.startswith("{")][-1]
+        d = json.loads(line)
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+                    "clocks", "e2e", "gpu_launches", "roofline"):
+            assert key in d, (fn.__name__, key)
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and "workload" in d["config"]
