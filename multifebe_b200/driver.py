@@ -26,17 +26,11 @@ class GpuSolver:
     def __init__(self, case, model, device=0):
         self.cp = None
         if case.multi:
-            if not os.environ.get("MFB_RUN_UNVALIDATED"):
-                raise CaseFileError("coupled BE regions: the device path (capi.CoupledProblem, DESIGN.md section 7.4) has not had its first hardware "
-                                    "run yet; set MFB_RUN_UNVALIDATED=1 to use it")
             from . import capi
             self.capi, self.case = capi, case
             self.ctx = capi.Context(device)
             self.cp = capi.CoupledProblem(self.ctx, model)
             return
-        if case.region_type == 3 and not os.environ.get("MFB_RUN_UNVALIDATED"):
-            raise CaseFileError("poroelastic region: the device kernels (csrc/poro.cu) have not had their first hardware run yet; "
-                                "set MFB_RUN_UNVALIDATED=1 to use them (DESIGN.md section 0)")
         from . import capi
         self.capi, self.case = capi, case
         self.ctx = capi.Context(device)

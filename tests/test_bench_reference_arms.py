@@ -21,10 +21,3 @@ def test_reference_arm_prints_one_contract_line(extra):
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
     assert "workload" in d["config"]
-
-
-def test_coupled_gpu_arm_is_opt_in_until_its_first_hardware_run():
-    env = {k: v for k, v in os.environ.items() if k != "MFB_RUN_UNVALIDATED"}
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "coupled", "--coupled-m", "1", "--steps", "1"], cwd=ROOT, env=env,
-                         capture_output=True, text=True, timeout=300)
-    assert out.returncode != 0 and "MFB_RUN_UNVALIDATED" in out.stderr

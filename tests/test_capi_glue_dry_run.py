@@ -99,12 +99,11 @@ def test_poroelastic_and_coupled_paths(stub):
 
 
 def test_driver_with_coupled_regions_through_the_stub(stub, tmp_path, monkeypatch):
-    """driver.run -> GpuSolver -> capi.CoupledProblem on a two-region case file (opt-in path): the glue runs end to end and writes the *.nso rows."""
+    """driver.run -> GpuSolver -> capi.CoupledProblem on a two-region case file : the glue runs end to end and writes the *.nso rows."""
     import io
     from multifebe_b200 import driver
     from multifebe_b200.host.mesh import write_gmsh22
     from test_casefile_driver import TWO_REGION_DAT
-    monkeypatch.setenv("MFB_RUN_UNVALIDATED", "1")
     write_gmsh22(two_box_mesh(1, shape.QUAD9), str(tmp_path / "boxes.msh"))
     path = str(tmp_path / "two.dat")
     open(path, "w").write(TWO_REGION_DAT)
@@ -114,7 +113,7 @@ def test_driver_with_coupled_regions_through_the_stub(stub, tmp_path, monkeypatc
 
 
 def test_bench_device_arms_of_the_secondary_workloads_through_the_stub(stub, monkeypatch, capsys):
-    """bench.py --workload acoustic / coupled, device arms (not yet run on hardware): the glue from the workload to the JSON line runs with the
+    """bench.py --workload acoustic / coupled, device arms: the glue from the workload to the JSON line runs with the
     stub library (statistics and peaks read as 1.0) and prints the keys of the contract."""
     import argparse
     import ctypes as C
@@ -132,7 +131,6 @@ def test_bench_device_arms_of_the_secondary_workloads_through_the_stub(stub, mon
         return 0
     stub.mfb_get_stats = get_stats; stub.mfb_measure_peaks = measure_peaks
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
-    monkeypatch.setenv("MFB_RUN_UNVALIDATED", "1")
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
     args = argparse.Namespace(impl="ours", gpus=1, steps=1, warmup=1, no_cpu_baseline=True, acoustic_etype="tri3", acoustic_m=2, coupled_etype="tri3", coupled_m=1)

@@ -36,7 +36,6 @@ def test_oracle_reproduces_the_committed_vectors(key):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("MFB_RUN_UNVALIDATED"), reason="first hardware run pending; set MFB_RUN_UNVALIDATED=1")
 @pytest.mark.parametrize("key", sorted(CASES))
 def test_gpu_against_the_committed_vectors(gpu_ctx, key):
     from multifebe_b200 import capi

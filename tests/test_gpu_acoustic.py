@@ -89,10 +89,6 @@ def test_wrong_family_is_refused(gpu_ctx):
     pe.close()
 
 
-# Written after the round's GPU budget was spent: never run on hardware.  It only uses entry points the tests above validate, but an unvalidated
-# test that faulted on the device would take the CUDA context of the whole pytest process with it, so it runs on request only
-# (MFB_RUN_UNVALIDATED=1 python -m pytest tests -m gpu -k "interior_pressures or with_internal_points"): first thing to do in round 2.
-@pytest.mark.skipif(not os.environ.get("MFB_RUN_UNVALIDATED"), reason="first hardware run pending; set MFB_RUN_UNVALIDATED=1")
 def test_interior_pressures_match_the_oracle_composition(gpu_ctx, oracle_lib):
     from multifebe_b200 import capi
     md = FluidModel(cube_mesh(3, shape.QUAD9), room_bcs(1.0))

@@ -1,6 +1,5 @@
 """Coupled BE regions on the GPU (capi.CoupledProblem: single-region kernels + the column combination of host/coupled.py) against the
-multi-region oracle.  Written after the round's GPU budget was spent: never run on hardware, runs on request only (MFB_RUN_UNVALIDATED=1).
-The solid / fluid pairings use GPU-validated kernels only; the poroelastic ones also need the unvalidated poro.cu."""
+multi-region oracle (first hardware run green in round 2: profiles/r02_first_contact.log)."""
 import os
 import numpy as np
 import pytest
@@ -9,7 +8,7 @@ from multifebe_b200.host.multiregion import PORO
 from test_oracle_multiregion import BPART, LAT1, LAT2, PO
 from test_coupled_from_single_region import MS, FL, bcs_for
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.environ.get("MFB_RUN_UNVALIDATED"), reason="first hardware run pending; set MFB_RUN_UNVALIDATED=1")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("kinds,ict", [((SOLID, SOLID), 0), ((FLUID, FLUID), 0), ((SOLID, FLUID), 0), ((FLUID, SOLID), 0), ((FLUID, PORO), 0), ((PORO, FLUID), 1),

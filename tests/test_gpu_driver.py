@@ -65,10 +65,6 @@ def test_command_line(tmp_path):
     assert r.returncode == 2 and "Input file does not exist" in r.stdout
 
 
-# Written after the round's GPU budget was spent: never run on hardware.  It only uses entry points the tests above validate, but an unvalidated
-# test that faulted on the device would take the CUDA context of the whole pytest process with it, so it runs on request only
-# (MFB_RUN_UNVALIDATED=1 python -m pytest tests -m gpu -k "interior_pressures or with_internal_points"): first thing to do in round 2.
-@pytest.mark.skipif(not os.environ.get("MFB_RUN_UNVALIDATED"), reason="first hardware run pending; set MFB_RUN_UNVALIDATED=1")
 def test_static_case_with_internal_points(tmp_path):
     text = (SOLID_DAT % dict(analysis="static", freq="", z="0.", one="1.")).replace("eng_double", "sci_double")
     text += "\n[internal points]\n2\n1 1 0.5 0.5 0.5\n2 1 0.2 0.7 0.4\n"

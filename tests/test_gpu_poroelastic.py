@@ -1,13 +1,11 @@
 """GPU parity tests of the Biot poroelastic BE region through the C ABI (mfb_harpor3d_*) against the CPU oracle.
-The kernels (multifebe_b200/csrc/poro.cu) were written after the round's GPU budget was spent and have NEVER run on hardware: the whole
-module runs on request only (MFB_RUN_UNVALIDATED=1), because a device fault in an unvalidated kernel would take the CUDA context of the
-pytest process with it.  First thing to run in round 2; remove the gate once green."""
+First hardware run (compute-sanitizer clean, all element types green): profiles/r02_first_contact.log."""
 import os
 import numpy as np
 import pytest
 from multifebe_b200.host import Poro, PoroModel, Model, Material, cube_mesh, cube_bcs, shape
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.environ.get("MFB_RUN_UNVALIDATED"), reason="first hardware run pending; set MFB_RUN_UNVALIDATED=1")]
+pytestmark = [pytest.mark.gpu]
 TOL_A, TOL_X = 1e-11, 1e-8
 PO = Poro(rhof=1.0, rhos=2.2, lam=1.2, mu=1.0, xi=0.02, phi=0.35, rhoa=0.15, R=0.8, Q=0.5, b=0.4)
 

@@ -7,7 +7,6 @@ mkdir -p gpurun_out
 run() { local name=$1; shift; timeout 300 "$@" > gpurun_out/fc_$name.log 2>&1; echo "$name exit $?" | tee -a gpurun_out/fc_summary.log; }
 : > gpurun_out/fc_summary.log
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/fc_validated.log 2>&1; echo "validated exit $?" | tee -a gpurun_out/fc_summary.log
-export MFB_RUN_UNVALIDATED=1
 run interior_pressures python -m pytest tests/test_gpu_acoustic.py -q -m gpu -k interior_pressures
 run static_internal    python -m pytest tests/test_gpu_driver.py -q -m gpu -k with_internal_points
 run coupled            python -m pytest tests/test_gpu_coupled.py -q -m gpu
