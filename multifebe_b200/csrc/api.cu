@@ -90,6 +90,11 @@ struct mfb_problem {
 extern "C" const char* mfb_last_error(void) { return g_err.c_str(); }
 extern "C" int mfb_version(void) { return 100; }
 
+struct DevBuf {   // scoped device allocation: released on every exit path of the function that owns it
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+
 template <class T>
 static int upload(std::vector<void*>& owned, const std::vector<T>& h, T** d, cudaStream_t st) {
   size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
@@ -716,7 +721,12 @@ static void host_kparams_static(double mu, double nu, KParams& K) {
   K.cte_d = c_1_4pi; K.cte_s = mk(c_1_4pi * mu, 0.0);
 }
 static int assemble_device_k(mfb_problem* p, const KParams& K, const KParams& Q, cd nu, const mfb_z* cvalue, bool statics);
+static bool finite_c(cd z) { return std::isfinite(z.real()) && std::isfinite(z.imag()); }
 static int assemble_device(mfb_problem* p, double omega, cd lambda, cd mu, double rho, cd nu, const mfb_z* cvalue) {
+  // omega = 0 gives 1/(i k)^2 = inf in the kernel parameters and NaN in every entry: refuse what the reference's own input checks refuse
+  if (!(omega > 0.0) || !std::isfinite(omega)) return fail(MFB_ERR_ARG, "harmonic assembly: omega must be positive and finite (the static problem is mfb_staela3d_*)");
+  if (!(rho > 0.0) || !std::isfinite(rho) || !finite_c(lambda) || !finite_c(mu) || !finite_c(nu) || mu == cd(0.0, 0.0) || lambda + 2.0 * mu == cd(0.0, 0.0) || nu == cd(1.0, 0.0))
+    return fail(MFB_ERR_ARG, "harmonic assembly: rho must be positive, lambda, mu, nu finite, mu and lambda + 2 mu nonzero, nu != 1");
   KParams K, Q; host_kparams(lambda, mu, rho, omega, K); scale_kparams(K, Q);
   return assemble_device_k(p, K, Q, nu, cvalue, false);
 }
@@ -812,7 +822,6 @@ static int assemble_pot_device(mfb_problem* p, double omega, double rho, cd c, c
 // ---------------------------------------------------------------------------------------------------------------------
 // Biot poroelastic BE region: fbem_bem_harpor3d_calculate_parameters (por_params_host) + build_lse_mechanics_bem_harpor
 // with the open-pore scatter of assemble_bem_harpor_equation.f90:78-110, :140-170, on a problem set up with ndof = 4.
-// STATUS: never executed on hardware (see poro.cu).
 // ---------------------------------------------------------------------------------------------------------------------
 static int assemble_por_device(mfb_problem* p, double omega, cd lambda, cd mu, double rho1, double rho2, double rhoa, cd R, cd Q, double b, const mfb_z* cvalue) {
   if (p->ndof != 4) return fail(MFB_ERR_ARG, "this problem was not set up for a poroelastic region (mfb_harpor3d_setup)");
@@ -853,27 +862,25 @@ static int download_matrix(mfb_problem* p, const double* re, const double* im, l
                            const int* colperm = nullptr) {
   cudaStream_t st = p->ctx->stream;
   int chunk = (int)std::max<long long>(1, std::min<long long>(cols, (256ll << 20) / (16ll * rows)));
-  double* stage; CK(cudaMalloc((void**)&stage, (size_t)chunk * rows * 16));
+  DevBuf sb; CK(cudaMalloc(&sb.p, (size_t)chunk * rows * 16)); double* stage = (double*)sb.p;
   for (int c0 = 0; c0 < cols; c0 += chunk) {
     int nc = std::min(chunk, cols - c0);
     launch_interleave(re, im, ld, rows, nc, stage, rows, rowperm, colperm, c0, st);
     CK(cudaMemcpy2DAsync(host + (long long)c0 * ldh, (size_t)ldh * 16, stage, (size_t)rows * 16, (size_t)rows * 16, nc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
-  cudaFree(stage);
   return MFB_OK;
 }
 static int upload_matrix(mfb_problem* p, const mfb_z* host, long long ldh, int rows, int cols, double* re, double* im, long long ld, const int* rowperm = nullptr) {
   cudaStream_t st = p->ctx->stream;
   int chunk = (int)std::max<long long>(1, std::min<long long>(cols, (256ll << 20) / (16ll * rows)));
-  double* stage; CK(cudaMalloc((void**)&stage, (size_t)chunk * rows * 16));
+  DevBuf sb; CK(cudaMalloc(&sb.p, (size_t)chunk * rows * 16)); double* stage = (double*)sb.p;
   for (int c0 = 0; c0 < cols; c0 += chunk) {
     int nc = std::min(chunk, cols - c0);
     CK(cudaMemcpy2DAsync(stage, (size_t)rows * 16, host + (long long)c0 * ldh, (size_t)ldh * 16, (size_t)rows * 16, nc, cudaMemcpyHostToDevice, st));
     launch_deinterleave(stage, rows, rows, nc, re + (long long)c0 * ld, im + (long long)c0 * ld, ld, rowperm, st);
     CK(cudaStreamSynchronize(st));
   }
-  cudaFree(stage);
   return MFB_OK;
 }
 
@@ -962,6 +969,8 @@ static int factor_device(mfb_problem* p, int n, bool timing) {
   p->stats[MFB_STAT_LU_LAUNCHES] = (double)p->lu.launches;
   p->stats[MFB_STAT_GEMM_LAUNCHES] = (double)p->lu.gemm_launches; p->stats[MFB_STAT_GEMM_FLOPS] = p->lu.gemm_flops; p->stats[MFB_STAT_GEMM_EXEC_FLOPS] = p->lu.gemm_exec_flops;
   p->stats[MFB_STAT_MS_PANEL] = p->lu.ms_panel; p->stats[MFB_STAT_MS_SWAP] = p->lu.ms_swap; p->stats[MFB_STAT_MS_TRSM] = p->lu.ms_trsm; p->stats[MFB_STAT_MS_GEMM] = p->lu.ms_gemm;
+  for (int i = 0; i < n; i++)   // never index with a pivot the device did not produce (a fault upstream must not become a host out-of-bounds swap)
+    if (p->h_ipiv[i] < i + 1 || p->h_ipiv[i] > n) { p->factored = false; return fail(MFB_ERR_CUDA, "zgetrf_planar: pivot index out of range (device fault during the factorisation?)"); }
   std::vector<int> perm(n);
   for (int i = 0; i < n; i++) perm[i] = i;
   for (int i = 0; i < n; i++) { int q = p->h_ipiv[i] - 1; if (q != i) std::swap(perm[i], perm[q]); }
@@ -981,6 +990,8 @@ extern "C" int mfb_zsolve(mfb_problem* p, int n, mfb_z* A, int lda, int* ipiv, m
   int r;
   if (factorize) {
     if (A) { r = upload_matrix(p, A, lda, n, n, p->sys.Are, p->sys.Aim, p->lda); if (r) return r; p->rows_permuted = false; p->real_resident = false; }
+    else if (!p->assembled) return fail(MFB_ERR_ARG, "mfb_zsolve: factorize=1 with A == NULL but no assembled system is resident (nothing assembled yet, or the resident "
+                                                     "matrix already holds the factors of an earlier solve: assemble again or pass factorize=0)");
     else if (p->real_resident) return fail(MFB_ERR_ARG, "mfb_zsolve: the resident system is real (static assembly); use mfb_dsolve");
     p->assembled = false;
     r = factor_device(p, n, lu_timing());
@@ -988,11 +999,12 @@ extern "C" int mfb_zsolve(mfb_problem* p, int n, mfb_z* A, int lda, int* ipiv, m
     if (A) { int r2 = download_matrix(p, p->sys.Are, p->sys.Aim, p->lda, n, n, A, lda); if (r2) return r2; }
     if (r) return r;
   } else if (!p->factored) return fail(MFB_ERR_ARG, "mfb_zsolve: factorize=0 but no factors are resident");
+  else if (p->real_resident) return fail(MFB_ERR_ARG, "mfb_zsolve: factorize=0 but the resident factors are real (mfb_dsolve / static path); use mfb_dsolve");
   if (nrhs == 0) return MFB_OK;
   double *bre = p->sys.bre, *bim = p->sys.bim; long long ldb = p->lda;
-  double* tmp = nullptr;
+  DevBuf tmp;   // freed on every exit path
   if (b) {
-    if (nrhs > 1) { CK(cudaMalloc((void**)&tmp, (size_t)2 * p->lda * nrhs * sizeof(double))); bre = tmp; bim = tmp + (size_t)p->lda * nrhs; }
+    if (nrhs > 1) { CK(cudaMalloc((void**)&tmp.p, (size_t)2 * p->lda * nrhs * sizeof(double))); bre = (double*)tmp.p; bim = bre + (size_t)p->lda * nrhs; }
     r = upload_matrix(p, b, n, n, nrhs, bre, bim, ldb, p->rows_permuted ? p->d_rowperm : nullptr); if (r) return r;
   } else if (nrhs != 1) return fail(MFB_ERR_ARG, "mfb_zsolve: device-resident rhs has a single column");
   CK(cudaEventRecord(p->ev[6], st));
@@ -1001,7 +1013,6 @@ extern "C" int mfb_zsolve(mfb_problem* p, int n, mfb_z* A, int lda, int* ipiv, m
   CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
   float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
   if (b) { r = download_matrix(p, bre, bim, ldb, n, nrhs, b, n, p->rows_permuted ? p->d_colperm : nullptr); if (r) return r; }
-  if (tmp) cudaFree(tmp);
   return MFB_OK;
 }
 
@@ -1191,8 +1202,7 @@ extern "C" int mfb_zgemm_minus(mfb_ctx* ctx, int m, int n, int k, const mfb_z* A
 // LU, NCCL to move row slabs to their column owners once and to broadcast each factorised panel.
 // ---------------------------------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------------------------------
-// Resident combination of assembled systems (coupled regions from single-region assemblies, multifebe_b200/host/coupled.py).  STATUS: never
-// executed on hardware.
+// Resident combination of assembled systems (coupled regions from single-region assemblies, multifebe_b200/host/coupled.py).
 //   mfb_system_zero      dst: zero the resident matrix and right-hand side and mark it "assembled, host order" (no row permutation), so that
 //                        mfb_zsolve(dst, n, NULL, ..., NULL, 1, 1) factorises and solves what the calls below accumulate
 //   mfb_combine_columns  dst(row_map[r], dst_col[i]) += coef[i] * src(r, src_col[i]) for the first n_rows host rows of the ASSEMBLED system of src
@@ -1485,27 +1495,25 @@ extern "C" int mfb_dist_zsolve(mfb_problem* p, int n, const mfb_z* A, int lda_h,
 static int download_real(mfb_problem* p, const double* re, long long ld, int rows, int cols, double* host, long long ldh, const int* rowperm, const int* colperm) {
   cudaStream_t st = p->ctx->stream;
   int chunk = (int)std::max<long long>(1, std::min<long long>(cols, (256ll << 20) / (8ll * rows)));
-  double* stage; CK(cudaMalloc((void**)&stage, (size_t)chunk * rows * 8));
+  DevBuf sb; CK(cudaMalloc(&sb.p, (size_t)chunk * rows * 8)); double* stage = (double*)sb.p;
   for (int c0 = 0; c0 < cols; c0 += chunk) {
     int nc = std::min(chunk, cols - c0);
     launch_gather_real(re, ld, rows, nc, stage, rows, rowperm, colperm, c0, st);
     CK(cudaMemcpy2DAsync(host + (long long)c0 * ldh, (size_t)ldh * 8, stage, (size_t)rows * 8, (size_t)rows * 8, nc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
-  cudaFree(stage);
   return MFB_OK;
 }
 static int upload_real(mfb_problem* p, const double* host, long long ldh, int rows, int cols, double* re, long long ld, const int* rowperm) {
   cudaStream_t st = p->ctx->stream;
   int chunk = (int)std::max<long long>(1, std::min<long long>(cols, (256ll << 20) / (8ll * rows)));
-  double* stage; CK(cudaMalloc((void**)&stage, (size_t)chunk * rows * 8));
+  DevBuf sb; CK(cudaMalloc(&sb.p, (size_t)chunk * rows * 8)); double* stage = (double*)sb.p;
   for (int c0 = 0; c0 < cols; c0 += chunk) {
     int nc = std::min(chunk, cols - c0);
     CK(cudaMemcpy2DAsync(stage, (size_t)rows * 8, host + (long long)c0 * ldh, (size_t)ldh * 8, (size_t)rows * 8, nc, cudaMemcpyHostToDevice, st));
     launch_scatter_real(stage, rows, rows, nc, re + (long long)c0 * ld, ld, rowperm, st);
     CK(cudaStreamSynchronize(st));
   }
-  cudaFree(stage);
   return MFB_OK;
 }
 static int assemble_static_device(mfb_problem* p, double mu, double nu, const double* cvalue) {
@@ -1539,6 +1547,7 @@ extern "C" int mfb_dsolve(mfb_problem* p, int n, double* A, int lda, int* ipiv, 
   int r;
   if (factorize) {
     if (A) { r = upload_real(p, A, lda, n, n, p->sys.Are, p->lda, nullptr); if (r) return r; p->rows_permuted = false; p->real_resident = true; }
+    else if (!p->assembled) return fail(MFB_ERR_ARG, "mfb_dsolve: factorize=1 with A == NULL but no assembled system is resident");
     else if (!p->real_resident) return fail(MFB_ERR_ARG, "mfb_dsolve: the resident system is complex (harmonic assembly); use mfb_zsolve");
     p->assembled = false;
     r = factor_device(p, n, lu_timing());
@@ -1548,9 +1557,9 @@ extern "C" int mfb_dsolve(mfb_problem* p, int n, double* A, int lda, int* ipiv, 
   } else if (!p->factored || !p->real_resident) return fail(MFB_ERR_ARG, "mfb_dsolve: factorize=0 but no real factors are resident");
   if (nrhs == 0) return MFB_OK;
   double* bre = p->sys.bre; long long ldb = p->lda;
-  double* tmp = nullptr;
+  DevBuf tmp;   // freed on every exit path
   if (b) {
-    if (nrhs > 1) { CK(cudaMalloc((void**)&tmp, (size_t)p->lda * nrhs * sizeof(double))); bre = tmp; }
+    if (nrhs > 1) { CK(cudaMalloc((void**)&tmp.p, (size_t)p->lda * nrhs * sizeof(double))); bre = (double*)tmp.p; }
     r = upload_real(p, b, n, n, nrhs, bre, ldb, p->rows_permuted ? p->d_rowperm : nullptr); if (r) return r;
   } else if (nrhs != 1) return fail(MFB_ERR_ARG, "mfb_dsolve: device-resident rhs has a single column");
   CK(cudaEventRecord(p->ev[6], st));
@@ -1559,7 +1568,6 @@ extern "C" int mfb_dsolve(mfb_problem* p, int n, double* A, int lda, int* ipiv, 
   CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
   float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
   if (b) { r = download_real(p, bre, ldb, n, nrhs, b, n, p->rows_permuted ? p->d_colperm : nullptr, nullptr); if (r) return r; }
-  if (tmp) cudaFree(tmp);
   return MFB_OK;
 }
 // assemble + dgetrf + dgetrs without leaving the device (the body of the static driver, src/multifebe.f90: build_lse_mechanics_static,

@@ -4,7 +4,7 @@
 //   k_add_entries  dst(rows[i], cols[i]) += v[i]                                  (free terms; cols == -1: right-hand side)
 // All indices arrive already translated to the internal (permuted) order of each system.  Several terms may hit the same destination entry
 // (three displacement columns feeding one pressure column ...), hence RED.ADD.
-// STATUS: written at the end of round 1 without GPU access -- compiled for sm_100a, never executed (tests/test_gpu_coupled.py, resident=True).
+// Parity: tests/test_gpu_coupled.py (resident=True) against the multi-region oracle, green on a B200 (profiles/r02_first_contact.log).
 #include "combine.cuh"
 
 namespace mfbd {

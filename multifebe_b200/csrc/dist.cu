@@ -36,7 +36,7 @@ bool load_nccl(std::string& err) {
   const char* names[4] = {getenv("MFB_NCCL_LIB"), "libnccl.so.2", "libnccl.so", nullptr};
   void* h = nullptr;
   for (int i = 0; i < 3 && !h; i++) if (names[i] && names[i][0]) h = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
-  if (!h) { err = std::string("cannot load NCCL (libnccl.so.2): ") + (dlerror() ? dlerror() : "not found") + "; set MFB_NCCL_LIB"; return false; }
+  if (!h) { const char* de = dlerror(); err = std::string("cannot load NCCL (libnccl.so.2): ") + (de ? de : "not found") + "; set MFB_NCCL_LIB"; return false; }
   bool ok = true;
   auto sym = [&](const char* n) { void* p = dlsym(h, n); if (!p) { ok = false; err = std::string("NCCL symbol missing: ") + n; } return p; };
   g_nccl.GetUniqueId = (int (*)(nccl_uid*))sym("ncclGetUniqueId");

@@ -481,6 +481,10 @@ __device__ __forceinline__ void block_argmax(double v, int row, double* s_val, i
   __syncthreads();
 }
 
+// Pivot-search key of an entry: |re| + |im| (izamax / idamax), with NaN ranked as +infinity so that the arg-max below is a total order: a NaN
+// entry is taken as the pivot (the lowest such row) and propagates through the factors as it does in LAPACK, instead of no row being selected.
+__device__ __forceinline__ double pivot_key(double t) { return (t != t) ? __longlong_as_double(0x7ff0000000000000LL) : t; }
+
 const int SP_MAXIB = 32;
 const int TS = 64;         // diagonal block of the triangular solves (zgetrs)
 void lu_invert_diagonal_blocks(const double* Are, const double* Aim, long long lda, int n, double* inv, cudaStream_t st);
@@ -509,7 +513,7 @@ __global__ void __launch_bounds__(256) k_subpanel(SubPanelArgs a) {
   // candidate for column 0
   {
     double v = -1.0; int r = BIG;
-    for (int i = tid; i < nloc; i += blockDim.x) { double t = fabs(sre[i]) + fabs(sim[i]); if (t > v) { v = t; r = rs + i; } }
+    for (int i = tid; i < nloc; i += blockDim.x) { double t = pivot_key(fabs(sre[i]) + fabs(sim[i])); if (t > v) { v = t; r = rs + i; } }
     double best; int brow; block_argmax(v, r, s_val, s_row, best, brow);
     if (tid == 0) { a.cand_val[c] = best; a.cand_row[c] = brow; }
     if (brow != BIG && tid < ib) {
@@ -565,7 +569,7 @@ __global__ void __launch_bounds__(256) k_subpanel(SubPanelArgs a) {
         xr -= lr * s_ure[jj] - li * s_uim[jj];
         xi -= lr * s_uim[jj] + li * s_ure[jj];
         sre[jj * rpcp + i] = xr; sim[jj * rpcp + i] = xi;
-        if (jj == j + 1) { double t = fabs(xr) + fabs(xi); if (t > nv) { nv = t; nr = rs + i; } }
+        if (jj == j + 1) { double t = pivot_key(fabs(xr) + fabs(xi)); if (t > nv) { nv = t; nr = rs + i; } }
       }
     }
     if (j + 1 < ib) {
@@ -622,7 +626,7 @@ __global__ void __launch_bounds__(256) k_subpanel_cluster(SubPanelArgs a) {
   __syncthreads();
   {
     double v = -1.0; int r = BIG;
-    for (int i = tid; i < nloc; i += blockDim.x) { double t = fabs(sre[i]) + (CX ? fabs(sim[i]) : 0.0); if (t > v) { v = t; r = rs + i; } }
+    for (int i = tid; i < nloc; i += blockDim.x) { double t = pivot_key(fabs(sre[i]) + (CX ? fabs(sim[i]) : 0.0)); if (t > v) { v = t; r = rs + i; } }
     double best; int brow; block_argmax(v, r, s_val, s_row, best, brow);
     if (tid == 0) { c_val[0] = best; c_row[0] = brow; }
     if (brow != BIG && tid < ib) { c_data[0][tid] = sre[tid * rpcp + brow - rs]; c_data[0][ib + tid] = CX ? sim[tid * rpcp + brow - rs] : 0.0; }
@@ -680,11 +684,11 @@ __global__ void __launch_bounds__(256) k_subpanel_cluster(SubPanelArgs a) {
           xr -= lr * s_ure[jj] - li * s_uim[jj];
           xi -= lr * s_uim[jj] + li * s_ure[jj];
           sre[jj * rpcp + i] = xr; sim[jj * rpcp + i] = xi;
-          if (jj == j + 1) { double t = fabs(xr) + fabs(xi); if (t > nv) { nv = t; nr = rs + i; } }
+          if (jj == j + 1) { double t = pivot_key(fabs(xr) + fabs(xi)); if (t > nv) { nv = t; nr = rs + i; } }
         } else {
           xr -= lr * s_ure[jj];
           sre[jj * rpcp + i] = xr;
-          if (jj == j + 1) { double t = fabs(xr); if (t > nv) { nv = t; nr = rs + i; } }
+          if (jj == j + 1) { double t = pivot_key(fabs(xr)); if (t > nv) { nv = t; nr = rs + i; } }
         }
       }
     }

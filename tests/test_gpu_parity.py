@@ -404,3 +404,38 @@ def test_static_against_committed_golden_vectors(gpu_ctx, et, m):
     assert relerr(A, gold[f"A:{et}:{m}"]) < TOL_A and relerr(b, gold[f"b:{et}:{m}"]) < TOL_A
     assert relerr(pr.solve_static(SMAT), gold[f"x:{et}:{m}"]) < TOL_X
     pr.close()
+
+
+def test_nan_input_and_state_misuse_do_not_fault_the_device(gpu_ctx):
+    """Round-1 advisor findings: a NaN column used to leave the pivot search without a row (illegal address, sticky context error); mfb_zsolve used to
+    factorise whatever was resident (unassembled memory, or the factors of an earlier solve); omega = 0 produced NaN kernel parameters."""
+    from multifebe_b200 import capi
+    from scipy.linalg import lapack
+    pr, n = _problem_of_size(gpu_ctx, 18 * 36)
+    rng = np.random.default_rng(5)
+    b = rng.standard_normal(n) + 0j
+    with pytest.raises(capi.MfbError) as e:                      # nothing assembled yet
+        pr.solve_lse_c(None, b, factorize=True)
+    assert e.value.code == -1 and "no assembled system" in str(e.value)
+    A = np.asfortranarray(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    An = A.copy(order="F"); An[:, 40] = np.nan; An[17, 300] = np.nan
+    x, ipiv = pr.solve_lse_c(An, b, want_ipiv=True)              # NaN propagates (as in LAPACK), pivots stay in range, no device fault
+    assert np.isnan(x).any() and ipiv.min() >= 1 and ipiv.max() <= n
+    Af = A.copy(order="F")
+    x = pr.solve_lse_c(Af, b)                                     # the context is still healthy
+    lu_ref, piv_ref, _ = lapack.zgetrf(A); x_ref, _ = lapack.zgetrs(lu_ref, piv_ref, b)
+    assert relerr(x, x_ref) < 1e-9
+    with pytest.raises(capi.MfbError) as e:                      # the resident matrix now holds L\U: refactorising it is refused
+        pr.solve_lse_c(None, b, factorize=True)
+    assert e.value.code == -1
+    assert relerr(pr.solve_lse_c(None, b, factorize=False), x_ref) < 1e-9
+    mat = Material(1.0, 1.0, 0.25, 0.03)
+    for bad in (0.0, -1.0, float("nan"), float("inf")):
+        with pytest.raises(capi.MfbError) as e:
+            pr.solve_frequency(bad, mat)
+        assert e.value.code == -1 and "omega" in str(e.value)
+    x = pr.solve_frequency(2.0, mat)
+    assert np.isfinite(x).all()
+    with pytest.raises(capi.MfbError):                           # real factors (static path) are not accepted by the complex solve
+        pr.solve_static(Material(1.0, 1.0, 0.25, 0.0)); pr.solve_lse_c(None, b, factorize=False)
+    pr.close()
