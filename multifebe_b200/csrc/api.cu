@@ -422,10 +422,18 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
     {
       // K1 element ranges: K1_ERANGE elements for the first 4/5 of the group, a quarter of that for the rest (the dynamic
       // schedule hands out the short tasks last, which trims the tail of the kernel)
+      // Small meshes: shorter ranges, so that the (tile x range) task list still covers the device several times over (BASELINE config C1, 744
+      // elements x 20-odd tiles, had 90 tasks for 1184 warp slots with 512-element ranges: K1 took 7 ms of latency-bound single warps).
+      int erange = K1_ERANGE;
+      {
+        const long long want = (long long)g.n_elem * n_tiles / 8192;      // ~8k tasks per group
+        while (erange > 16 && erange > want) erange >>= 1;
+        if (const char* e_r = getenv("MFB_K1_ERANGE")) { const int v = atoi(e_r); if (v >= 8 && v <= K1_ERANGE) erange = v; }
+      }
       std::vector<int> rs(1, 0), rof(g.n_elem);
       const int tail_from = g.n_elem - g.n_elem / 5;
       for (int e = 0; e < g.n_elem;) {
-        int len = (e < tail_from) ? K1_ERANGE : K1_ERANGE / 4;
+        int len = (e < tail_from) ? erange : std::max(erange / 4, 8);
         if (e < tail_from && e + len > tail_from) len = tail_from - e;
         const int e1 = std::min(g.n_elem, e + len);
         for (int q = e; q < e1; q++) rof[q] = (int)rs.size() - 1;
@@ -1186,7 +1194,11 @@ extern "C" int mfb_zgemm_minus(mfb_ctx* ctx, int m, int n, int k, const mfb_z* A
   launch_deinterleave(stage, m, m, n, dC, dC + lc * n, lc, nullptr, st);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   CK(cudaEventRecord(e0, st));
-  zgemm_minus_planar(m, n, k, dA, dA + la * k, la, dB, dB + lb * n, lb, dC, dC + lc * n, lc, st);
+  GemmTmaMaps tm; tm.ok = 0;
+  gemm_tma_make_maps(tm, dA, dA + la * k, la, m, k, dB, dB + lb * n, lb, k, n);
+  CK(cudaEventRecord(e0, st));   // the encoding of the maps (host work) is outside the timed launch
+  if (gemm_tma_usable(tm, m, n, k)) zgemm_minus_planar_tma(tm, m, n, k, 0, 0, 0, 0, dC, dC + lc * n, lc, st);
+  else zgemm_minus_planar(m, n, k, dA, dA + la * k, la, dB, dB + lb * n, lb, dC, dC + lc * n, lc, st);
   CK(cudaEventRecord(e1, st)); CK(cudaEventSynchronize(e1));
   float t; cudaEventElapsedTime(&t, e0, e1); if (ms) *ms = t;
   launch_interleave(dC, dC + lc * n, lc, m, n, stage, m, nullptr, nullptr, 0, st);

@@ -924,6 +924,7 @@ int lu_work_alloc(LuWork& w, int n, int nb) {
     }
   }
   { const char* e_fp = getenv("MFB_LU_FUSED_PANEL_UPDATE"); w.fused_panel_update = e_fp ? atoi(e_fp) : 2; }
+  w.tma.ok = 0; w.tma_key = nullptr;
   size_t G = (size_t)w.n_sm;
   cudaError_t e = cudaSuccess;
   auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
@@ -1047,9 +1048,13 @@ int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuW
   cudaMemsetAsync(w.info, 0, sizeof(int), st);
   w.launches = 0; w.gemm_launches = 0; w.gemm_flops = 0.0; w.gemm_exec_flops = 0.0; w.n_steps_timed = 0;
   cudaStream_t ps = w.lookahead ? w.panel_stream : st;
+  // tensor maps of the two planes for the TMA trailing-update kernel (gemm_tma.cu); rebuilt only when the matrix moves
+  if (Aim && (w.tma_key != Are || !w.tma.ok)) { gemm_tma_make_maps(w.tma, Are, Aim, lda, n, n, Are, Aim, lda, n, n); w.tma_key = Are; }
   auto gemm = [&](int r0, int k0, int kw, int c0, int c1) {   // A[r0:n, c0:c1] -= A[r0:n, k0:k0+kw] * A[k0:k0+kw, c0:c1]
     if (c1 <= c0 || r0 >= n) return;
-    if (Aim && w.asum[0] && gemm_cfg() == 15)
+    if (Aim && gemm_tma_usable(w.tma, n - r0, c1 - c0, kw) && gemm_cfg() == 15)
+      zgemm_minus_planar_tma(w.tma, n - r0, c1 - c0, kw, r0, k0, k0, c0, Are + (long long)c0 * lda + r0, Aim + (long long)c0 * lda + r0, lda, st);
+    else if (Aim && w.asum[0] && gemm_cfg() == 15)
       zgemm_minus_planar_psa(n - r0, c1 - c0, kw, Are + (long long)k0 * lda + r0, Aim + (long long)k0 * lda + r0, w.asum[(k0 / nb) & 1] + r0, lda,
                              Are + (long long)c0 * lda + k0, Aim + (long long)c0 * lda + k0, lda, Are + (long long)c0 * lda + r0, Aim + (long long)c0 * lda + r0, lda, st);
     else

@@ -6,6 +6,15 @@
 
 namespace mfbd {
 
+// Tensor maps of the operand planes of the TMA trailing-update kernel (gemm_tma.cu): m[0..1] = planes of the matrix the A operand is cut from,
+// m[2..3] = planes of the matrix the B operand is cut from (whole planes; the operands are addressed by row / column offsets at launch).
+struct GemmTmaMaps { alignas(64) unsigned char m[4][128]; int ok; int pad_; };
+int gemm_tma_make_maps(GemmTmaMaps& t, const double* Are, const double* Aim, long long lda, int a_rows, int a_cols, const double* Bre, const double* Bim, long long ldb,
+                       int b_rows, int b_cols);
+bool gemm_tma_usable(const GemmTmaMaps& t, int m, int n, int k);      // maps valid and k a positive multiple of 16
+// C[0:m, 0:n] -= A[a_row0 : a_row0 + m, a_col0 : a_col0 + k] * B[b_row0 : b_row0 + k, b_col0 : b_col0 + n]  (3M product on the FP64 tensor pipe)
+void zgemm_minus_planar_tma(const GemmTmaMaps& t, int m, int n, int k, int a_row0, int a_col0, int b_row0, int b_col0, double* Cre, double* Cim, long long ldc, cudaStream_t st);
+
 struct LuWork {
   int nb;                 // outer block size
   int ib;                 // sub-panel width (columns kept in shared memory by the cooperative panel kernel)
@@ -27,6 +36,7 @@ struct LuWork {
   int fused_panel_update;                      // 1: TRSM + update of the panel columns right of a sub-panel in one kernel (k_panel_update)
   int cluster_ib;                              // preferred sub-panel width of the cluster kernel (if the slab fits)
   int cluster, cluster_max_rows;               // CTAs of the cluster-resident panel kernel (0 = grid-wide kernel only); tallest panel it takes
+  GemmTmaMaps tma; const double* tma_key;      // tensor maps of the matrix being factorised (rebuilt when the matrix pointer changes)
 };
 // sums the per-phase event times of the last timed factorisation (call after the stream has been synchronised)
 void lu_collect_times(LuWork& w);
