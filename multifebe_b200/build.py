@@ -16,7 +16,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 GXX = "/usr/bin/g++"   # the image's $CXX wrapper lacks libgomp.spec
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 SOURCES_CU = ["api.cu", "assembly.cu", "potential.cu", "poro.cu", "combine.cu", "lu.cu", "gemm_tma.cu", "dist.cu"]
-DEPS = SOURCES_CU + ["plan_host.cpp", "plan_host.h", "assembly.cuh", "potential.cuh", "pot_math.cuh", "poro.cuh", "por_math.cuh", "por_pair.cuh", "combine.cuh", "lu.cuh", "dist.cuh", "bem_math.cuh",
+SOURCES_CPP = ["plan_host.cpp", "plan_values.cpp"]   # host planner: decision core (follows the reference op by op) and value geometry (independent derivations)
+DEPS = SOURCES_CU + SOURCES_CPP + ["plan_host.h", "plan_values.h", "assembly.cuh", "potential.cuh", "pot_math.cuh", "poro.cuh", "por_math.cuh", "por_pair.cuh", "combine.cuh", "lu.cuh", "dist.cuh", "bem_math.cuh",
                      os.path.join("..", "..", "include", "mfb.h"), os.path.join("..", "..", "data", "quad_tables.h")]
 
 
@@ -44,12 +45,12 @@ def build(force=False, verbose=False):
     bdir = os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
     objs = []
-    o = os.path.join(bdir, "plan_host.o")
-    cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-c",
-           os.path.join(CSRC, "plan_host.cpp"), "-o", o]
-    if force or _obj_stale(o, "plan_host.cpp"):
-        subprocess.check_call(cmd)
-    objs.append(o)
+    for src in SOURCES_CPP:
+        o = os.path.join(bdir, src.replace(".cpp", ".o"))
+        cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-c", os.path.join(CSRC, src), "-o", o]
+        if force or _obj_stale(o, src):
+            subprocess.check_call(cmd)
+        objs.append(o)
     for src in SOURCES_CU:
         o = os.path.join(bdir, src.replace(".cu", ".o"))
         cmd = [NVCC, "-ccbin", GXX, "-O3", "-std=c++17", "-lineinfo"] + os.environ.get("MFB_NVCC_FLAGS", "").split() + ARCH + [

@@ -155,10 +155,17 @@ k_zgemm3m_tma(const __grid_constant__ CUtensorMap tAre, const __grid_constant__ 
 
   for (int kt = 0; kt < KT; kt++) {
     const int s = kt % GT_STAGES;
-    if (tid == 0 && kt >= 1 && kt - 1 + GT_STAGES < KT) {   // refill the stage consumed in the previous iteration
+    if (kt >= 1) {
+      // Release of the stage consumed in the PREVIOUS iteration.  It must not be signalled right after that iteration's last LDS: the arrival
+      // does not wait for loads in flight, ptxas hoists it above the DMMAs that consume them, and the refill then overwrote fragments that had
+      // been requested but not yet read (first version of this kernel: one tile in ~600 wrong, always the last-read block of the straggling
+      // warp; profiles/r02_gemm_tma_race.md).  Here every load of that iteration has completed: its value fed a DMMA issued before the loop branch.
       const int sp = (kt - 1) % GT_STAGES;
-      gt_mbar_wait(bars + 8u * (GT_STAGES + sp), (unsigned)(((kt - 1) / GT_STAGES) & 1));
-      issue(sp, kt - 1 + GT_STAGES);
+      if (lane == 0) gt_mbar_arrive(bars + 8u * (GT_STAGES + sp));
+      if (tid == 0 && kt - 1 + GT_STAGES < KT) {            // refill it with the k-tile GT_STAGES ahead
+        gt_mbar_wait(bars + 8u * (GT_STAGES + sp), (unsigned)(((kt - 1) / GT_STAGES) & 1));
+        issue(sp, kt - 1 + GT_STAGES);
+      }
     }
     __syncwarp();
     gt_mbar_wait(bars + 8u * s, (unsigned)((kt / GT_STAGES) & 1));
@@ -184,8 +191,6 @@ k_zgemm3m_tma(const __grid_constant__ CUtensorMap tAre, const __grid_constant__ 
         }
       }
     }
-    __syncwarp();
-    if (lane == 0) gt_mbar_arrive(bars + 8u * (GT_STAGES + s));
   }
 #pragma unroll
   for (int mi = 0; mi < 4; mi++)

@@ -4,6 +4,7 @@
 // (rule order from ceiling()/nint() of a fit in d, nearest point in real128, subdivision depth), so they follow the
 // reference formulas operation by operation; file:line citations are relative to /root/reference.
 #include "plan_host.h"
+#include "plan_values.h"
 #include <cmath>
 #include <cstring>
 #include <cstdint>
@@ -251,29 +252,6 @@ static double telles_barr_any(double d) {  // fbem_telles_barr(d, fbem_f_any) :7
   double b = (d < 3.0) ? d / (0.89039 * d + 0.32883) : 1.0;
   if (b > 1.0) b = 1.0;
   return b;
-}
-static inline double cbrt_signed(double v, double d13) { return v >= 0.0 ? pow(v, d13) : -pow(fabs(v), d13); }
-static void telles11_parameters(double bar_xi, double bar_r, double* c) {  // :130-161
-  double w = bar_xi / (1.0 + 2.0 * bar_r);
-  double p = 1.0 / (3.0 * (1.0 + 2.0 * bar_r)) * (3.0 - 2.0 * bar_r - 3.0 * w * bar_xi);
-  double q = w / 2.0 * ((3.0 - 2.0 * bar_r) / (1.0 + 2.0 * bar_r) - 2.0 * (w * w) - 1.0);
-  double R2 = sqrt(q * q + p * p * p), d13 = 1.0 / 3.0;
-  double R31 = cbrt_signed(-q + R2, d13), R32 = cbrt_signed(-q - R2, d13);
-  double bg = R31 + R32 + w, Q = 1.0 + 3.0 * (bg * bg);
-  c[0] = (1.0 - bar_r) / Q; c[1] = -3.0 * bg * c[0]; c[2] = (bar_r + 3.0 * (bg * bg)) / Q; c[3] = -c[1];
-}
-static void telles01_parameters(double bar_xi, double bar_r, double* c) {  // :164-196
-  double waux = 1.0 + 2.0 * bar_r, w = (bar_xi + bar_r) / waux;
-  double p = (3.0 * bar_xi + bar_r) / (3.0 * waux) - w * w;
-  double q = w * ((3.0 * bar_xi + bar_r) / (2.0 * waux) - w * w) - bar_xi / (2.0 * waux);
-  double R2 = sqrt(q * q + p * p * p), d13 = 1.0 / 3.0;
-  double R31 = cbrt_signed(-q + R2, d13), R32 = cbrt_signed(-q - R2, d13);
-  double bg = R31 + R32 + w, Q = 3.0 * bg * (bg - 1.0) + 1.0;
-  c[0] = (1.0 - bar_r) / Q; c[1] = -3.0 * bg * c[0]; c[2] = (3.0 * bg * (bg - bar_r) + bar_r) / Q; c[3] = 0.0;
-}
-static inline void telles_xi_jac(const double* c, double g, double& xi, double& jac) {  // :221-232
-  xi = c[0] * (g * g * g) + c[1] * (g * g) + c[2] * g + c[3];
-  jac = 3.0 * c[0] * (g * g) + 2.0 * c[1] * g + c[2];
 }
 
 
@@ -569,8 +547,12 @@ static void nearest_element_point_bem(int et, const double* x, double cl, const 
 }
 
 
-// fbem_polar_transformation_setup: polar_transformation.f90:251-498
-static void polar_setup(int et, const double* xi_i, int& nsub, int* sub, double th[8][2], double thp[8][2]) {
+// DECISION part of fbem_polar_transformation_setup (polar_transformation.f90:251-498) + fbem_bem_harela3d_sbie_int :1298-1299: which of the 8 (6)
+// sub-triangles around xi_i exist and how many angular Gauss points each one gets, ngp = 5 + nint(25 (theta2 - theta1) / (pi/2)).  nint of a
+// continuous quantity (25 dtheta / (pi/2) = 12.5 for the very common dtheta = pi/4) is a discrete decision, so the angles are formed exactly as
+// the reference forms them.  The rays themselves (values) are computed independently in plan_values.cpp.  counts[sub - 1], 0 = absent.
+static void polar_theta_counts(int et, const double* xi_i, int* counts) {
+  int nsub; int sub[8]; double th[8][2];
   bool tri = (et == TRI3 || et == TRI6); const double tol = check_xi_tol;
   bool in_edge = check_xi1xi2_edge(et, xi_i);
   nsub = 0;
@@ -603,160 +585,51 @@ static void polar_setup(int et, const double* xi_i, int& nsub, int* sub, double 
     if (!tri) {
       switch (sub[k]) {
         case 1: t = c_pi - asin((-1.0 - b) / sqrt((-1.0 - a) * (-1.0 - a) + (-1.0 - b) * (-1.0 - b)));
-          th[k][0] = t; th[k][1] = 1.5 * c_pi;
-          thp[k][0] = (1.0 + b) * log(tan(0.5 * (th[k][0] - c_pi))); thp[k][1] = (1.0 + b) * log(tan(0.5 * (th[k][1] - c_pi))); break;
+          th[k][0] = t; th[k][1] = 1.5 * c_pi; break;
         case 2: t = c_2pi + asin((-1.0 - b) / sqrt((1.0 - a) * (1.0 - a) + (-1.0 - b) * (-1.0 - b)));
-          th[k][0] = 1.5 * c_pi; th[k][1] = t;
-          thp[k][0] = (1.0 + b) * log(tan(0.5 * (th[k][0] - c_pi))); thp[k][1] = (1.0 + b) * log(tan(0.5 * (th[k][1] - c_pi))); break;
+          th[k][0] = 1.5 * c_pi; th[k][1] = t; break;
         case 3: t = c_2pi + asin((-1.0 - b) / sqrt((1.0 - a) * (1.0 - a) + (-1.0 - b) * (-1.0 - b)));
-          th[k][0] = t; th[k][1] = c_2pi;
-          thp[k][0] = (1.0 - a) * log(tan(0.5 * (th[k][0] + c_pi_2))); thp[k][1] = (1.0 - a) * log(tan(0.5 * (th[k][1] + c_pi_2))); break;
+          th[k][0] = t; th[k][1] = c_2pi; break;
         case 4: t = asin((1.0 - b) / sqrt((1.0 - a) * (1.0 - a) + (1.0 - b) * (1.0 - b)));
-          th[k][0] = 0.0; th[k][1] = t;
-          thp[k][0] = (1.0 - a) * log(tan(0.5 * (th[k][0] + c_pi_2))); thp[k][1] = (1.0 - a) * log(tan(0.5 * (th[k][1] + c_pi_2))); break;
+          th[k][0] = 0.0; th[k][1] = t; break;
         case 5: t = asin((1.0 - b) / sqrt((1.0 - a) * (1.0 - a) + (1.0 - b) * (1.0 - b)));
-          th[k][0] = t; th[k][1] = c_pi_2;
-          thp[k][0] = (1.0 - b) * log(tan(0.5 * th[k][0])); thp[k][1] = (1.0 - b) * log(tan(0.5 * th[k][1])); break;
+          th[k][0] = t; th[k][1] = c_pi_2; break;
         case 6: t = c_pi - asin((1.0 - b) / sqrt((-1.0 - a) * (-1.0 - a) + (1.0 - b) * (1.0 - b)));
-          th[k][0] = c_pi_2; th[k][1] = t;
-          thp[k][0] = (1.0 - b) * log(tan(0.5 * th[k][0])); thp[k][1] = (1.0 - b) * log(tan(0.5 * th[k][1])); break;
+          th[k][0] = c_pi_2; th[k][1] = t; break;
         case 7: t = c_pi - asin((1.0 - b) / sqrt((-1.0 - a) * (-1.0 - a) + (1.0 - b) * (1.0 - b)));
-          th[k][0] = t; th[k][1] = c_pi;
-          thp[k][0] = (1.0 + a) * log(tan(0.5 * (th[k][0] - c_pi_2))); thp[k][1] = (1.0 + a) * log(tan(0.5 * (th[k][1] - c_pi_2))); break;
+          th[k][0] = t; th[k][1] = c_pi; break;
         case 8: t = c_pi - asin((-1.0 - b) / sqrt((-1.0 - a) * (-1.0 - a) + (-1.0 - b) * (-1.0 - b)));
-          th[k][0] = c_pi; th[k][1] = t;
-          thp[k][0] = (1.0 + a) * log(tan(0.5 * (th[k][0] - c_pi_2))); thp[k][1] = (1.0 + a) * log(tan(0.5 * (th[k][1] - c_pi_2))); break;
+          th[k][0] = c_pi; th[k][1] = t; break;
       }
     } else {
       switch (sub[k]) {
         case 1: t = c_2pi - asin(b / sqrt((1.0 - a) * (1.0 - a) + b * b));
-          th[k][0] = t; th[k][1] = c_pi_4 + c_2pi;
-          thp[k][0] = (1.0 - a - b) / c_sqrt2 * log(tan(0.5 * (th[k][0] + c_pi_4))); thp[k][1] = (1.0 - a - b) / c_sqrt2 * log(tan(0.5 * (th[k][1] + c_pi_4))); break;
+          th[k][0] = t; th[k][1] = c_pi_4 + c_2pi; break;
         case 2: t = c_pi - asin((1.0 - b) / sqrt(a * a + (1.0 - b) * (1.0 - b)));
-          th[k][0] = c_pi_4; th[k][1] = t;
-          thp[k][0] = (1.0 - a - b) / c_sqrt2 * log(tan(0.5 * (th[k][0] + c_pi_4))); thp[k][1] = (1.0 - a - b) / c_sqrt2 * log(tan(0.5 * (th[k][1] + c_pi_4))); break;
+          th[k][0] = c_pi_4; th[k][1] = t; break;
         case 3: t = c_pi - asin((1.0 - b) / sqrt(a * a + (1.0 - b) * (1.0 - b)));
-          th[k][0] = t; th[k][1] = c_pi;
-          thp[k][0] = a * log(tan(0.5 * (th[k][0] - c_pi_2))); thp[k][1] = a * log(tan(0.5 * (th[k][1] - c_pi_2))); break;
+          th[k][0] = t; th[k][1] = c_pi; break;
         case 4: t = c_pi + asin(b / sqrt(a * a + b * b));
-          th[k][0] = c_pi; th[k][1] = t;
-          thp[k][0] = a * log(tan(0.5 * (th[k][0] - c_pi_2))); thp[k][1] = a * log(tan(0.5 * (th[k][1] - c_pi_2))); break;
+          th[k][0] = c_pi; th[k][1] = t; break;
         case 5: t = c_pi + asin(b / sqrt(a * a + b * b));
-          th[k][0] = t; th[k][1] = 1.5 * c_pi;
-          thp[k][0] = b * log(tan(0.5 * (th[k][0] - c_pi))); thp[k][1] = b * log(tan(0.5 * (th[k][1] - c_pi))); break;
+          th[k][0] = t; th[k][1] = 1.5 * c_pi; break;
         case 6: t = c_2pi - asin(b / sqrt((1.0 - a) * (1.0 - a) + b * b));
-          th[k][0] = 1.5 * c_pi; th[k][1] = t;
-          thp[k][0] = b * log(tan(0.5 * (th[k][0] - c_pi))); thp[k][1] = b * log(tan(0.5 * (th[k][1] - c_pi))); break;
+          th[k][0] = 1.5 * c_pi; th[k][1] = t; break;
       }
     }
   }
-}
-// fbem_polar_transformation_angular: polar_transformation.f90:501-544
-static void polar_angular(int et, const double* xi_i, int sub, double thetap, double& theta, double& rhoij) {
-  bool tri = (et == TRI3 || et == TRI6); double a = xi_i[0], b = xi_i[1];
-  if (!tri) {
-    switch (sub) {
-      case 1: case 2: theta = 2.0 * atan(exp(thetap / (1.0 + b))) + c_pi; rhoij = (-1.0 - b) / sin(theta); break;
-      case 3: case 4: theta = 2.0 * atan(exp(thetap / (1.0 - a))) - c_pi_2; rhoij = (1.0 - a) / cos(theta); break;
-      case 5: case 6: theta = 2.0 * atan(exp(thetap / (1.0 - b))); rhoij = (1.0 - b) / sin(theta); break;
-      default: theta = 2.0 * atan(exp(thetap / (1.0 + a))) + c_pi_2; rhoij = (-1.0 - a) / cos(theta); break;
-    }
-  } else {
-    switch (sub) {
-      case 1: case 2: theta = 2.0 * atan(exp(c_sqrt2 * thetap / (1.0 - a - b))) - c_pi_4; rhoij = (1.0 - a - b) / (cos(theta) + sin(theta)); break;
-      case 3: case 4: theta = 2.0 * atan(exp(thetap / a)) + c_pi_2; rhoij = -a / cos(theta); break;
-      default: theta = 2.0 * atan(exp(thetap / b)) + c_pi; rhoij = -b / sin(theta); break;
-    }
+  for (int k = 0; k < 8; k++) counts[k] = 0;
+  for (int k = 0; k < nsub; k++) {
+    int ngp_theta = 5 + (int)lround(25.0 * (th[k][1] - th[k][0]) / c_pi_2);
+    if (ngp_theta > 32) ngp_theta = 32;
+    counts[sub[k] - 1] = ngp_theta;
   }
 }
-
-// Geometric part of the Mantic formula: c = cp*I - sum_b/(8 pi (1-nu))  (bem_harela3d.f90:365-542)
-static int mantic_geometry(int ne, const double* n_in, const double* t_in, double tol, double& cp_out, double sum_b_out[3][3]) {
-  double ltol = (tol < 1.0e-12 || tol > 1.0e-3) ? 1.0e-6 : tol;
-  std::vector<double> ln(3 * (ne + 2)), lt(3 * (ne + 2)), lti(3 * (ne + 1)), theta(ne + 1);
-  std::vector<int> tc(ne + 1);
-  for (int i = 1; i <= ne; i++) for (int k = 0; k < 3; k++) { ln[3 * i + k] = n_in[3 * (i - 1) + k]; lt[3 * i + k] = t_in[3 * (i - 1) + k]; }
-  for (int ki = 1; ki <= ne - 1; ki++) {
-    double e1[3], e2[3], e3[3];
-    for (int k = 0; k < 3; k++) { e1[k] = lt[3 * ki + k]; e3[k] = ln[3 * ki + k]; }
-    e2[0] = e3[1] * e1[2] - e3[2] * e1[1]; e2[1] = e3[2] * e1[0] - e3[0] * e1[2]; e2[2] = e3[0] * e1[1] - e3[1] * e1[0];
-    for (int kj = 1; kj <= ne; kj++) {
-      lti[3 * kj + 0] = e1[0] * lt[3 * kj] + e1[1] * lt[3 * kj + 1] + e1[2] * lt[3 * kj + 2];
-      lti[3 * kj + 1] = e2[0] * lt[3 * kj] + e2[1] * lt[3 * kj + 1] + e2[2] * lt[3 * kj + 2];
-      lti[3 * kj + 2] = e3[0] * lt[3 * kj] + e3[1] * lt[3 * kj + 1] + e3[2] * lt[3 * kj + 2];
-    }
-    int ntc = 0;
-    for (int kj = ki + 1; kj <= ne; kj++) if (fabs(lti[3 * kj + 2]) <= ltol) tc[ntc++] = kj;
-    if (ntc == 0) return 1;  // 'the normals/tangents configuration is not valid'
-    for (int kj = 0; kj < ntc; kj++) { theta[tc[kj]] = atan2(lti[3 * tc[kj] + 1], lti[3 * tc[kj]]); if (theta[tc[kj]] < 0.0) theta[tc[kj]] = theta[tc[kj]] + 2.0 * c_pi; }
-    double mint = theta[tc[0]]; int minkj = tc[0];
-    for (int kj = 1; kj < ntc; kj++) if (theta[tc[kj]] < mint) { mint = theta[tc[kj]]; minkj = tc[kj]; }
-    for (int k = 0; k < 3; k++) { std::swap(lt[3 * (ki + 1) + k], lt[3 * minkj + k]); std::swap(ln[3 * (ki + 1) + k], ln[3 * minkj + k]); }
-  }
-  for (int k = 0; k < 3; k++) { ln[k] = ln[3 * ne + k]; lt[k] = lt[3 * ne + k]; ln[3 * (ne + 1) + k] = ln[3 + k]; lt[3 * (ne + 1) + k] = lt[3 + k]; }
-  double sum_a = 0.0;
-  for (int ki = 1; ki <= ne; ki++) {
-    const double *a = &ln[3 * (ki - 1)], *b = &ln[3 * ki];
-    double nxn[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
-    double nxndr = nxn[0] * lt[3 * ki] + nxn[1] * lt[3 * ki + 1] + nxn[2] * lt[3 * ki + 2];
-    if (nxndr < 0.0) nxndr = -1.0;
-    if (nxndr > 0.0) nxndr = 1.0;
-    double ndn = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
-    if (ndn > 1.0) ndn = 1.0;
-    sum_a = sum_a + nxndr * acos(ndn);
-  }
-  double cp = 1.0 / (4.0 * c_pi) * (2.0 * c_pi + sum_a);
-  double sum_b[3][3] = {{0}};
-  for (int ki = 1; ki <= ne; ki++) {
-    double rmr[3]; for (int k = 0; k < 3; k++) rmr[k] = lt[3 * (ki + 1) + k] - lt[3 * ki + k];
-    const double* nn = &ln[3 * ki];
-    double v[3] = {rmr[1] * nn[2] - rmr[2] * nn[1], rmr[2] * nn[0] - rmr[0] * nn[2], rmr[0] * nn[1] - rmr[1] * nn[0]};
-    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) sum_b[a][b] = sum_b[a][b] + v[a] * nn[b];
-  }
-  cp_out = cp;
-  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) sum_b_out[a][b] = sum_b[a][b];
-  return 0;
-}
-
-static void node_normal_tangents(int et, const double* xn, int node, double* n, double* tbp, double* tbm) {
-  int nn = n_nodes_of(et); double xi[2]; xi_at_node(et, node, xi);
-  double d1[9], d2[9]; dphi2d<double>(et, xi, d1, d2);
-  double T1[3] = {0, 0, 0}, T2[3] = {0, 0, 0};
-  for (int k = 0; k < nn; k++) for (int c = 0; c < 3; c++) { T1[c] = T1[c] + d1[k] * xn[3 * k + c]; T2[c] = T2[c] + d2[k] * xn[3 * k + c]; }
-  double N[3] = {T1[1] * T2[2] - T1[2] * T2[1], T1[2] * T2[0] - T1[0] * T2[2], T1[0] * T2[1] - T1[1] * T2[0]};
-  double jn = sqrt(dot3(N, N)); for (int c = 0; c < 3; c++) n[c] = N[c] / jn;
-  double n1 = sqrt(T1[0] * T1[0] + T1[1] * T1[1] + T1[2] * T1[2]), n2 = sqrt(T2[0] * T2[0] + T2[1] * T2[1] + T2[2] * T2[2]);
-  double t1[3] = {T1[0] / n1, T1[1] / n1, T1[2] / n1}, t2[3] = {T2[0] / n2, T2[1] / n2, T2[2] / n2};
-  auto set = [&](double* o, const double* v, double s) { for (int c = 0; c < 3; c++) o[c] = s * v[c]; };
-  if (et == TRI3 || et == TRI6) {
-    double d3[6] = {0, 0, 0, 0, 0, 0};
-    if (et == TRI3) { d3[0] = 1.0; d3[1] = -1.0; }
-    else { d3[0] = 4.0 * xi[0] - 1.0; d3[1] = 4.0 * xi[0] - 3.0; d3[3] = 4.0 * (1.0 - 2.0 * xi[0]); }
-    double T3[3] = {0, 0, 0}; for (int k = 0; k < nn; k++) for (int c = 0; c < 3; c++) T3[c] = T3[c] + d3[k] * xn[3 * k + c];
-    double n3 = sqrt(T3[0] * T3[0] + T3[1] * T3[1] + T3[2] * T3[2]); double t3[3] = {T3[0] / n3, T3[1] / n3, T3[2] / n3};
-    switch (node) {
-      case 0: set(tbp, t3, -1); set(tbm, t1, -1); break; case 1: set(tbp, t2, -1); set(tbm, t3, 1); break;
-      case 2: set(tbp, t1, 1); set(tbm, t2, 1); break;   case 3: set(tbp, t3, -1); set(tbm, t3, 1); break;
-      case 4: set(tbp, t2, -1); set(tbm, t2, 1); break;  default: set(tbp, t1, 1); set(tbm, t1, -1); break;
-    }
-  } else {
-    switch (node) {
-      case 0: set(tbp, t1, 1); set(tbm, t2, 1); break;   case 1: set(tbp, t2, 1); set(tbm, t1, -1); break;
-      case 2: set(tbp, t1, -1); set(tbm, t2, -1); break; case 3: set(tbp, t2, -1); set(tbm, t1, 1); break;
-      case 4: set(tbp, t1, 1); set(tbm, t1, -1); break;  case 5: set(tbp, t2, 1); set(tbm, t2, -1); break;
-      case 6: set(tbp, t1, -1); set(tbm, t1, 1); break;  case 7: set(tbp, t2, -1); set(tbm, t2, 1); break;
-      default: set(tbp, t1, 0); set(tbm, t1, 0); break;
-    }
-  }
-}
-
 
 // =====================================================================================
 // Product-specific planning on top of the primitives above
 // =====================================================================================
 int nodes_of(int et) { return n_nodes_of(et); }
-void shape_values(int et, const double* xi, double* phi) { phi2d<double>(et, xi, phi); }
-void node_xi(int et, int node, double* xi) { xi_at_node(et, node, xi); }
 bool xi_on_element_boundary(int et, const double* xi) { return check_xi1xi2_edge(et, xi); }
 
 static inline int qs_n(bool telles, int et, int f, const QsTable& q, double d, const double* barxi) { return qs_n_estimation(telles, et, f, q, d, barxi); }
@@ -794,140 +667,82 @@ void element_data(Elem& e, const Settings& s) {
   element_ball(e.et, e.x, e.gln_far, e.bc, e.br);
 }
 
-int pointset_size(int et, int gln) { return ((et == TRI3 || et == TRI6) && gln <= 15) ? wan_n(2 * gln - 1) : gln * gln; }
-
-// fbem_bem_element%init_precalculated_datasets for one rule: lib/fbem/src/bem_general.f90:450-755
-void build_pointset(const Elem& e, int gln, double* out) {
-  bool tri = (e.et == TRI3 || e.et == TRI6), wan = tri && gln <= 15;
-  int ngp = pointset_size(e.et, gln), rec = 6 + e.nn;
-  for (int kt = 0; kt < ngp; kt++) {
-    double xi[2], w1, w2 = 1.0;
-    if (wan) { xi[0] = wan_x1(2 * gln - 1, kt); xi[1] = wan_x2(2 * gln - 1, kt); w1 = wan_w(2 * gln - 1, kt); }
+// Leaf list of the adaptive quasi-singular integration (the decisions of fbem_bem_harela3d_sbie_ext_adp, bem_harela3d.f90:1050-1172): a
+// sub-element is integrated when the Telles estimator returns a rule for its normalised distance (or the depth limit is reached), otherwise it is
+// split into four at its edge midpoints.  The recursion of the reference is run as an explicit work list (depth-first, children pushed in reverse
+// so that leaves come out in the reference's order); the DECISIONS (nearest point and distance of each sub-element, rule order, split or not) use
+// the decision core above, the leaf's transformation coefficients (values) come from plan_values.cpp.
+struct SubElem { double xi[8]; int depth; };
+static void collect_leaves(const Elem& e, const double* x_i, const Settings& s, NearPlan& out) {
+  const int nv = n_vertices_of(e.et);
+  std::vector<SubElem> work(1);
+  {
+    static const double T0[6] = {1, 0, 0, 1, 0, 0}, Q0[8] = {-1, -1, 1, -1, 1, 1, -1, 1};
+    memcpy(work[0].xi, nv == 3 ? T0 : Q0, sizeof(double) * 2 * nv); work[0].depth = 1;
+  }
+  while (!work.empty()) {
+    const SubElem cur = work.back(); work.pop_back();
+    double barxip[2], rmin, d; int method;
+    if (cur.depth == 1) nearest_element_point_bem(e.et, e.x, e.cl, x_i, barxip, rmin, d, method);
     else {
-      int k1 = kt / gln, k2 = kt % gln;
-      if (tri) { xi[0] = (1.0 - gj01_x(gln, k2)) * gl01_x(gln, k1); xi[1] = gj01_x(gln, k2); w1 = gl01_w(gln, k1); w2 = gj01_w(gln, k2); }
-      else { xi[0] = gl11_x(gln, k1); xi[1] = gl11_x(gln, k2); w1 = gl11_w(gln, k1); w2 = gl11_w(gln, k2); }
+      double x_s[27]; subdivision_coordinates(e.et, e.x, cur.xi, x_s);
+      const double cl = characteristic_length(e.et, x_s, 1.e-12);
+      nearest_element_point_bem(e.et, x_s, cl, x_i, barxip, rmin, d, method);
     }
-    double phi[9], xp[3], N[3], j; geom_at(e.et, e.nn, e.x, xi, phi, xp, N, j);
-    double* o = out + (size_t)kt * rec;
-    for (int c = 0; c < 3; c++) { o[c] = xp[c]; o[3 + c] = N[c] / j; }
-    for (int k = 0; k < e.nn; k++) o[6 + k] = wan ? phi[k] * j * w1 : phi[k] * j * w1 * w2;
-  }
-}
-
-// Flattened fbem_bem_harela3d_sbie_ext_adp (bem_harela3d.f90:1050-1172): instead of integrating, every terminal
-// sub-element becomes a Leaf (sub-element corners in the parent's xi space, the two Telles cubics, gln).
-static void collect_leaves(const Elem& e, double* xi_s, const double* x_i, const Settings& s, int ks, NearPlan& out) {
-  int nv = n_vertices_of(e.et);
-  double barxip[2], rmin, d; int method;
-  if (ks == 1) {
-    if (nv == 3) { xi_s[0] = 1; xi_s[1] = 0; xi_s[2] = 0; xi_s[3] = 1; xi_s[4] = 0; xi_s[5] = 0; }
-    else { xi_s[0] = -1; xi_s[1] = -1; xi_s[2] = 1; xi_s[3] = -1; xi_s[4] = 1; xi_s[5] = 1; xi_s[6] = -1; xi_s[7] = 1; }
-    nearest_element_point_bem(e.et, e.x, e.cl, x_i, barxip, rmin, d, method);
-  } else {
-    double x_s[27]; subdivision_coordinates(e.et, e.x, xi_s, x_s);
-    double cl = characteristic_length(e.et, x_s, 1.e-12);
-    nearest_element_point_bem(e.et, x_s, cl, x_i, barxip, rmin, d, method);
-  }
-  int gln_near = qs_n(true, e.et, s.f, s.qs, d, barxip);
-  bool subdivide = false;
-  if (ks == s.qsi_ns_max) { if (gln_near == 0) gln_near = 30; } else if (gln_near == 0) subdivide = true;
-  if (!subdivide) {
-    Leaf lf; memset(&lf, 0, sizeof(lf));
-    for (int i = 0; i < 2 * nv; i++) lf.xi_s[i] = xi_s[i];
-    double barr = telles_barr_any(d);
-    if (nv == 4) { telles11_parameters(barxip[0], barr, lf.tp1); telles11_parameters(barxip[1], barr, lf.tp2); }
-    else {
-      double bpp[2];
-      if (barxip[1] > 0.995) { bpp[0] = 0.5; bpp[1] = 1.0; } else { bpp[0] = barxip[0] / (1.0 - barxip[1]); bpp[1] = barxip[1]; }
-      telles01_parameters(bpp[0], barr, lf.tp1); telles01_parameters(bpp[1], barr, lf.tp2);
+    int gln_near = qs_n(true, e.et, s.f, s.qs, d, barxip);
+    if (gln_near == 0 && cur.depth == s.qsi_ns_max) gln_near = 30;
+    if (gln_near > 0) {
+      Leaf lf; memset(&lf, 0, sizeof(lf));
+      memcpy(lf.xi_s, cur.xi, sizeof(double) * 2 * nv);
+      const double barr = telles_barr_any(d);
+      if (nv == 4) { telles_cubic(false, barxip[0], barr, lf.tp1); telles_cubic(false, barxip[1], barr, lf.tp2); }
+      else {   // collapsed square of the triangle (bem_harela3d.f90:897-924): (xi1 / (1 - xi2), xi2), the apex mapped to the middle of its side
+        const bool apex = barxip[1] > 0.995;
+        telles_cubic(true, apex ? 0.5 : barxip[0] / (1.0 - barxip[1]), barr, lf.tp1); telles_cubic(true, apex ? 1.0 : barxip[1], barr, lf.tp2);
+      }
+      lf.gln = std::max(gln_near, e.gln_far);
+      out.leaves.push_back(lf); out.points += (long long)lf.gln * lf.gln;
+      continue;
     }
-    lf.gln = std::max(gln_near, e.gln_far);
-    out.leaves.push_back(lf); out.points += (long long)lf.gln * lf.gln;
-    return;
-  }
-  double t[8];
-  auto mid = [&](int a, int b, double* o) { o[0] = 0.50 * (xi_s[2 * a] + xi_s[2 * b]); o[1] = 0.50 * (xi_s[2 * a + 1] + xi_s[2 * b + 1]); };
-  auto cpy = [&](int a, double* o) { o[0] = xi_s[2 * a]; o[1] = xi_s[2 * a + 1]; };
-  if (nv == 3) {
-    cpy(0, t); mid(0, 1, t + 2); mid(0, 2, t + 4); collect_leaves(e, t, x_i, s, ks + 1, out);
-    cpy(1, t); mid(1, 2, t + 2); mid(0, 1, t + 4); collect_leaves(e, t, x_i, s, ks + 1, out);
-    cpy(2, t); mid(0, 2, t + 2); mid(1, 2, t + 4); collect_leaves(e, t, x_i, s, ks + 1, out);
-    mid(0, 1, t); mid(1, 2, t + 2); mid(0, 2, t + 4); collect_leaves(e, t, x_i, s, ks + 1, out);
-  } else {
-    auto ctr = [&](double* o) { o[0] = 0.25 * (xi_s[0] + xi_s[2] + xi_s[4] + xi_s[6]); o[1] = 0.25 * (xi_s[1] + xi_s[3] + xi_s[5] + xi_s[7]); };
-    cpy(0, t); mid(0, 1, t + 2); ctr(t + 4); mid(0, 3, t + 6); collect_leaves(e, t, x_i, s, ks + 1, out);
-    mid(0, 1, t); cpy(1, t + 2); mid(1, 2, t + 4); ctr(t + 6); collect_leaves(e, t, x_i, s, ks + 1, out);
-    ctr(t); mid(1, 2, t + 2); cpy(2, t + 4); mid(2, 3, t + 6); collect_leaves(e, t, x_i, s, ks + 1, out);
-    mid(0, 3, t); ctr(t + 2); mid(2, 3, t + 4); cpy(3, t + 6); collect_leaves(e, t, x_i, s, ks + 1, out);
+    // split: corner c keeps its vertex, the others become the midpoints of its two edges (and the centroid for a quadrilateral); a triangle has a
+    // fourth, central child made of the three midpoints
+    const double* v = cur.xi;
+    auto put = [&](double* o, double a, double b) { o[0] = a; o[1] = b; };
+    auto midp = [&](int i, int j, double* o) { put(o, 0.50 * (v[2 * i] + v[2 * j]), 0.50 * (v[2 * i + 1] + v[2 * j + 1])); };
+    SubElem ch[4];
+    for (int c = 0; c < 4; c++) ch[c].depth = cur.depth + 1;
+    if (nv == 3) {
+      for (int c = 0; c < 3; c++) { put(ch[c].xi, v[2 * c], v[2 * c + 1]); }
+      midp(0, 1, ch[0].xi + 2); midp(0, 2, ch[0].xi + 4);
+      midp(1, 2, ch[1].xi + 2); midp(0, 1, ch[1].xi + 4);
+      midp(0, 2, ch[2].xi + 2); midp(1, 2, ch[2].xi + 4);
+      midp(0, 1, ch[3].xi); midp(1, 2, ch[3].xi + 2); midp(0, 2, ch[3].xi + 4);
+    } else {
+      double ctr[2]; put(ctr, 0.25 * (v[0] + v[2] + v[4] + v[6]), 0.25 * (v[1] + v[3] + v[5] + v[7]));
+      for (int c = 0; c < 4; c++) {     // child c: vertex c stays in slot c, slot c + 2 is the centroid, the other two slots are edge midpoints
+        const int nx = (c + 1) & 3, pv = (c + 3) & 3;
+        put(ch[c].xi + 2 * c, v[2 * c], v[2 * c + 1]);
+        midp(c, nx, ch[c].xi + 2 * nx); midp(c, pv, ch[c].xi + 2 * pv);
+        put(ch[c].xi + 2 * ((c + 2) & 3), ctr[0], ctr[1]);
+      }
+    }
+    for (int c = 3; c >= 0; c--) work.push_back(ch[c]);
   }
 }
 
-// Adaptive line integral eps_ijk e_k.t / r over one element edge (real, geometry only, so it is evaluated here once
-// per mesh instead of once per frequency): fbem_bem_staela3d_sbie_int_li, lib/fbem/src/bem_staela3d.f90:2245-2376
-static void edge_line_integral(int et, const double* xn, double* xi_s, const double* x_i, int ngp_min, const QsTable& q, int ks, int ns, double* hli) {
-  int nn = n_nodes_of(et); double x_s[9];
-  if (ks == 1) { xi_s[0] = -1.0; xi_s[1] = 1.0; for (int i = 0; i < 3 * nn; i++) x_s[i] = xn[i]; }
-  else subdivision_coordinates(et, xn, xi_s, x_s);
-  double cl = characteristic_length(et, x_s, 1.e-12), barxip[1], rmin, d; int method;
-  nearest_element_point_bem(et, x_s, cl, x_i, barxip, rmin, d, method);
-  int gln_near = qs_n(true, et, 1, q, d, barxip);
-  bool subdivide = false;
-  if (ks == ns) { if (gln_near == 0) gln_near = 30; } else if (gln_near == 0) subdivide = true;
-  if (subdivide) {
-    double t[2];
-    t[0] = xi_s[0]; t[1] = 0.5 * (xi_s[0] + xi_s[1]); edge_line_integral(et, xn, t, x_i, ngp_min, q, ks + 1, ns, hli);
-    t[0] = 0.5 * (xi_s[0] + xi_s[1]); t[1] = xi_s[1]; edge_line_integral(et, xn, t, x_i, ngp_min, q, ks + 1, ns, hli);
-    return;
-  }
-  double h01 = 0.0, h02 = 0.0, h12 = 0.0;
-  int gln = std::max(gln_near, ngp_min);
-  double barr = telles_barr_any(d), tp[4]; telles11_parameters(barxip[0], barr, tp);
-  for (int kip = 0; kip < gln; kip++) {
-    double gam = gl11_x(gln, kip), w = gl11_w(gln, kip), xip, jt; telles_xi_jac(tp, gam, xip, jt);
-    double xi = 0.5 * (1.0 - xip) * xi_s[0] + 0.5 * (1.0 + xip) * xi_s[1], js = 0.5 * (xi_s[1] - xi_s[0]);
-    double gphi[3], dg[3], x[3] = {0, 0, 0}, T[3] = {0, 0, 0}; phi1d<double>(et, xi, gphi); dphi1d<double>(et, xi, dg);
-    for (int k = 0; k < nn; k++) for (int c = 0; c < 3; c++) { x[c] = x[c] + gphi[k] * xn[3 * k + c]; T[c] = T[c] + dg[k] * xn[3 * k + c]; }
-    double jg = sqrt(dot3(T, T)); double t[3] = {T[0] / jg, T[1] / jg, T[2] / jg};
-    double rv[3] = {x[0] - x_i[0], x[1] - x_i[1], x[2] - x_i[2]}; double r = sqrt(dot3(rv, rv)), dr1 = 1.0 / r;
-    double jw = jg * js * jt * w;
-    h01 = h01 - dr1 * t[2] * jw; h02 = h02 + dr1 * t[1] * jw; h12 = h12 - dr1 * t[0] * jw;
-  }
-  hli[1] = hli[1] + h01; hli[2] = hli[2] + h02; hli[5] = hli[5] + h12;
-  hli[3] = hli[3] + (-h01); hli[6] = hli[6] + (-h02); hli[7] = hli[7] + (-h12);
-}
-
-// omega-independent data of fbem_bem_harela3d_sbie_int (bem_harela3d.f90:1174-1472): angular rays of the polar
-// transformation (polar_transformation.f90:251-544) and the edge line integrals.
+// omega-independent data of the singular element integral (fbem_bem_harela3d_sbie_int, bem_harela3d.f90:1174-1472): the decision core says which
+// sub-triangles exist and how many angular points each gets; rays and edge line integrals are values (plan_values.cpp).
 static void plan_singular(const Elem& e, const double* xi_i, const Settings& s, NearPlan& out) {
-  int et = e.et, nn = e.nn;
+  (void)s;
   out.xi_i[0] = xi_i[0]; out.xi_i[1] = xi_i[1];
-  double phi_g[9]; phi2d<double>(et, xi_i, phi_g);
-  out.x_i[0] = out.x_i[1] = out.x_i[2] = 0.0;
-  for (int k = 0; k < nn; k++) for (int c = 0; c < 3; c++) out.x_i[c] = out.x_i[c] + phi_g[k] * e.x[3 * k + c];
-  int nsub, sub[8]; double th[8][2], thp[8][2];
-  polar_setup(et, xi_i, nsub, sub, th, thp);
-  for (int ks = 0; ks < nsub; ks++) {
-    int ngp_theta = 5 + (int)lround(25.0 * (th[ks][1] - th[ks][0]) / c_pi_2);
-    if (ngp_theta > 32) ngp_theta = 32;
-    for (int kt = 0; kt < ngp_theta; kt++) {
-      double jthetap = thp[ks][1] - thp[ks][0];
-      double thetap = jthetap * gl01_x(ngp_theta, kt) + thp[ks][0], theta, rhoij;
-      polar_angular(et, xi_i, sub[ks], thetap, theta, rhoij);
-      Ray r; r.ct = cos(theta); r.st = sin(theta); r.rhoij = rhoij; r.w = jthetap * gl01_w(ngp_theta, kt);
-      out.rays.push_back(r);
-    }
-  }
+  element_point(e.et, e.x, xi_i, out.x_i);
+  int counts[8]; polar_theta_counts(e.et, xi_i, counts);
+  polar_rays(e.et, xi_i, counts, out.rays);
   out.points = (long long)out.rays.size() * 15;
   for (int i = 0; i < 9; i++) out.hli[i] = 0.0;
-  int nedges = n_edges_of(et), ety = edge_type_of(et), nne = n_nodes_of(ety);
-  for (int ke = 1; ke <= nedges; ke++) {
-    bool integrate = false;
-    for (int ks = 0; ks < nsub; ks++) if (sub[ks] == 2 * ke - 1 || sub[ks] == 2 * ke) { integrate = true; break; }
-    if (!integrate) continue;
-    double xe[9]; for (int k = 0; k < nne; k++) for (int c = 0; c < 3; c++) xe[3 * k + c] = e.x[3 * edge_node(k, ke - 1, et) + c];
-    double xi_s[2]; edge_line_integral(ety, xe, xi_s, out.x_i, 5, s.qs_li, 1, 16, out.hli);
-  }
+  bool edge_on[4];
+  for (int k = 0; k < n_edges_of(e.et); k++) edge_on[k] = counts[2 * k] > 0 || counts[2 * k + 1] > 0;   // edges that do not contain the collocation point
+  edge_integrals(e.et, e.x, out.x_i, edge_on, out.hli);
 }
 
 // fbem_bem_harela3d_sbie_auto decisions for one pair the GPU classifier could not settle with the ball test
@@ -947,20 +762,7 @@ void plan_near_pair(const Elem& e, const double* x_i, const Settings& s, NearPla
   if (gln <= ps_gln_max && gln_near > 0) {
     for (size_t i = 0; i < s.ps_gln.size(); i++) if (s.ps_gln[i] >= gln) { out.mode = 0; out.set = (int)i; out.gln = s.ps_gln[i]; out.points = pointset_size(e.et, s.ps_gln[i]); return; }
   }
-  out.mode = 1; double xi_s[8]; collect_leaves(e, xi_s, x_i, s, 1, out);
-}
-
-int mantic_terms(int n_elements, const double* normals, const double* tangents, double tol, double* cp, double* sum_b /*9, [l][k]*/) {
-  double sb[3][3];
-  int err = mantic_geometry(n_elements, normals, tangents, tol, *cp, sb);
-  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) sum_b[3 * a + b] = sb[a][b];
-  return err;
-}
-// unit normal / forward element-boundary tangent of element `et` at its node, with the boundary-reversion rule of
-// src/build_lse_mechanics_bem_harela.f90:428-447 (n -> -n, tbp <-> tbm)
-void node_normal_tangent(int et, const double* xn, int node, bool reversed, double* n, double* t) {
-  double nn_[3], tbp[3], tbm[3]; node_normal_tangents(et, xn, node, nn_, tbp, tbm);
-  for (int c = 0; c < 3; c++) { n[c] = reversed ? -nn_[c] : nn_[c]; t[c] = reversed ? tbm[c] : tbp[c]; }
+  out.mode = 1; collect_leaves(e, x_i, s, out);
 }
 
 }  // namespace mfbh

@@ -17,10 +17,12 @@ ROOT = os.path.dirname(HERE)
 @pytest.fixture(scope="module")
 def pph(tmp_path_factory):
     d = tmp_path_factory.mktemp("pph")
-    o = str(d / "plan_host.o"); so = str(d / "libpph.so")
-    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fopenmp", "-c", os.path.join(ROOT, "multifebe_b200", "csrc", "plan_host.cpp"), "-o", o])
-    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", os.path.join(HERE, "native", "por_pair_host.cpp"), "-x", "none", o,
-                           "-o", so, "-lquadmath", "-fopenmp"])
+    so = str(d / "libpph.so"); objs = []
+    for src in ("plan_host.cpp", "plan_values.cpp"):      # the product's host planner: decision core + value geometry
+        o = str(d / src.replace(".cpp", ".o")); objs.append(o)
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fopenmp", "-c", os.path.join(ROOT, "multifebe_b200", "csrc", src), "-o", o])
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", os.path.join(HERE, "native", "por_pair_host.cpp"), "-x", "none"] + objs +
+                          ["-o", so, "-lquadmath", "-fopenmp"])
     L = C.CDLL(so)
     L.pph_pair.restype = C.c_int
     return L
@@ -60,6 +62,9 @@ def test_pair_integrals_of_the_kernel_bodies_against_the_oracle(pph, et, m, reve
             seen.add(mode)
             for a, b in ((h, h0), (g, g0)):
                 for blk in (np.s_[:, 0, 0], np.s_[:, 0, 1:], np.s_[:, 1:, 0], np.s_[:, 1:, 1:]):
-                    sc = np.abs(b[blk]).max()            # a block may vanish (point in the element's plane): floor from the whole array
-                    assert np.abs(a[blk] - b[blk]).max() <= 1e-10 * sc + 1e-14 * np.abs(b).max(), (mode, blk, np.abs(a[blk] - b[blk]).max() / sc)
+                    sc = np.abs(b[blk]).max()            # a block may vanish (point in the element's plane): floor from the whole array.  The product's
+                    # rays / line integrals / point sets are derived independently of the oracle's (csrc/plan_values.cpp), so a vanishing block is two
+                    # different sets of rounding errors, not a copy of the same ones: (x - x_i).n of a flat element is rounding noise ~1e-17 that the
+                    # polar quadrature divides by r^2 down to r ~ 1e-3, so both sides hold noise of ~1e-12 of the array's scale there
+                    assert np.abs(a[blk] - b[blk]).max() <= 1e-10 * sc + 1e-11 * np.abs(b).max(), (mode, blk, np.abs(a[blk] - b[blk]).max() / sc)
     assert seen == {0, 1, 2}
