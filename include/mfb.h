@@ -99,6 +99,28 @@ int mfb_harela3d_assemble(mfb_problem* problem, double omega, const mfb_z* lambd
  * Returns >0 (= LAPACK info) on an exactly singular pivot. */
 int mfb_zsolve(mfb_problem* problem, int n, mfb_z* A, int lda, int* ipiv, mfb_z* b, int nrhs, int factorize);
 
+/* == solve_lse_c with ALL its options (src/solve_lse_c.f90:25-46): scaling = zgeequ + zlaqge (:81-117), condition = zgecon (:140-165),
+ * refine = zgerfs (:191-206), computed on the device around the LU of mfb_zsolve (the reference's unfactorised copy `Ao` lives in device memory).
+ * A / lda / ipiv / factorize as in mfb_zsolve; b (host, ldb = n, nrhs columns) is overwritten by the solution.  equed (one character, 'N' 'R' 'C'
+ * 'B'), r[n], c[n]: the reference's arguments of the same names -- written when factorize && scaling, read when !factorize && scaling.
+ * rcond (written when condition && factorize), ferr[nrhs], berr[nrhs] (written when refine) may be NULL.  With all three flags 0 this is mfb_zsolve. */
+int mfb_zsolve_ex(mfb_problem* problem, int n, mfb_z* A, int lda, int* ipiv, mfb_z* b, int nrhs, int factorize, int scaling, int condition,
+                  int refine, char* equed, double* r, double* c, double* rcond, double* ferr, double* berr);
+
+/* mfb_harela3d_assemble with the seam's `+=` semantics on the HOST side (src/build_lse_mechanics_harmonic.f90:73-95: A_c and b_c are zeroed once and every
+ * region ADDS its rows): accumulate != 0 adds this region's assembled system to the caller's A (lda >= n_dof) and b instead of overwriting them, so that a
+ * host with several regions (one mfb_problem each, all numbered in the same global n_dof) or with finite-element rows written before the call keeps them.
+ * accumulate = 0 and lda = n_dof is mfb_harela3d_assemble. */
+int mfb_harela3d_assemble_acc(mfb_problem* problem, double omega, const mfb_z* lambda, const mfb_z* mu, double rho, const mfb_z* nu,
+                              const mfb_z* cvalue, mfb_z* A, int lda, mfb_z* b, int accumulate);
+
+/* The whole frequency loop (src/multifebe.f90:107-124) as one call, sharded over the ranks of a job: rank q assembles, factorises and
+ * solves the frequencies q, q + nranks, ... on its own GPU; one NCCL all-reduce (inside the library) gathers the solutions, and EVERY rank returns
+ * X[n_dof x n_freq] (column kf = solution of omega[kf]).  nranks = 1 uses no NCCL; otherwise nccl_id128 is the id rank 0 made with mfb_dist_unique_id.
+ * info[n_freq] (may be NULL): LAPACK info of a singular pivot per frequency (that column of X is zero). */
+int mfb_harela3d_sweep(mfb_problem* problem, int n_freq, const double* omega, const mfb_z* lambda, const mfb_z* mu, double rho, const mfb_z* nu,
+                       const mfb_z* cvalue, int rank, int nranks, const char* nccl_id128, mfb_z* X, int* info);
+
 /* One iteration of the frequency loop (src/multifebe.f90:107-124) kept on the device: assemble, factorise, solve;
  * x[n_dof] receives the solution (what assign_solution_mechanics_harmonic.f90:192-205 reads from b_c); x == NULL keeps it on
  * the device (mfb_get_solution).  cvalue == NULL (here and in mfb_harela3d_assemble) re-uses the prescribed values of the

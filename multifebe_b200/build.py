@@ -15,9 +15,9 @@ OUT = os.path.join(HERE, "libmfb.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 GXX = "/usr/bin/g++"   # the image's $CXX wrapper lacks libgomp.spec
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-SOURCES_CU = ["api.cu", "assembly.cu", "potential.cu", "poro.cu", "combine.cu", "lu.cu", "gemm_tma.cu", "dist.cu"]
+SOURCES_CU = ["api.cu", "assembly.cu", "potential.cu", "poro.cu", "combine.cu", "lu.cu", "gemm_tma.cu", "solve_ex.cu", "dist.cu"]
 SOURCES_CPP = ["plan_host.cpp", "plan_values.cpp"]   # host planner: decision core (follows the reference op by op) and value geometry (independent derivations)
-DEPS = SOURCES_CU + SOURCES_CPP + ["plan_host.h", "plan_values.h", "assembly.cuh", "potential.cuh", "pot_math.cuh", "poro.cuh", "por_math.cuh", "por_pair.cuh", "combine.cuh", "lu.cuh", "dist.cuh", "bem_math.cuh",
+DEPS = SOURCES_CU + SOURCES_CPP + ["plan_host.h", "plan_values.h", "assembly.cuh", "potential.cuh", "pot_math.cuh", "poro.cuh", "por_math.cuh", "por_pair.cuh", "combine.cuh", "lu.cuh", "solve_ex.cuh", "dist.cuh", "bem_math.cuh",
                      os.path.join("..", "..", "include", "mfb.h"), os.path.join("..", "..", "data", "quad_tables.h")]
 
 

@@ -326,6 +326,23 @@ class Problem:
         x = bb[:, 0] if np.ndim(b) == 1 else bb
         return (x, ipiv) if want_ipiv else x
 
+    def solve_lse_c_ex(self, A=None, b=None, factorize=True, scaling=False, condition=False, refine=False, equed="N", r=None, c=None):
+        """solve_lse_c with its optional stages (mfb_zsolve_ex): returns (x, info) with info = {equed, r, c, rcond, ferr, berr, ipiv}."""
+        n = self.m.n_dof
+        ipiv = np.zeros(n, dtype=np.int32)
+        if A is not None and not (A.flags.f_contiguous and A.dtype == np.complex128):
+            raise ValueError("A must be a Fortran-ordered complex128 array (it is overwritten by the LU factors)")
+        bb = np.asfortranarray(b, dtype=np.complex128).reshape(n, -1, order="F").copy(order="F")
+        nrhs = bb.shape[1]
+        eq = C.create_string_buffer(equed.encode()[:1], 2)
+        rr = np.ones(n) if r is None else np.ascontiguousarray(r, dtype=np.float64).copy()
+        cc = np.ones(n) if c is None else np.ascontiguousarray(c, dtype=np.float64).copy()
+        rcond = C.c_double(0.0); ferr = np.zeros(nrhs); berr = np.zeros(nrhs)
+        _check(lib().mfb_zsolve_ex(self.h, C.c_int(n), _p(A) if A is not None else None, C.c_int(n), _p(ipiv), _p(bb), C.c_int(nrhs), C.c_int(int(factorize)),
+                                   C.c_int(int(scaling)), C.c_int(int(condition)), C.c_int(int(refine)), eq, _p(rr), _p(cc), C.byref(rcond), _p(ferr), _p(berr)))
+        x = bb[:, 0] if np.ndim(b) == 1 else bb
+        return x, {"equed": eq.value.decode() or "N", "r": rr, "c": cc, "rcond": rcond.value, "ferr": ferr, "berr": berr, "ipiv": ipiv}
+
     # ---- one iteration of the frequency loop, device resident ----
     def solve_frequency(self, omega, mat, host=True):
         """host=True: prescribed values go up from host memory and the solution comes back to host memory (the call the
@@ -334,6 +351,24 @@ class Problem:
         _check(lib().mfb_harela3d_solve_frequency(self.h, C.c_double(omega), _p(_z(mat.lam)), _p(_z(mat.mu)), C.c_double(mat.rho),
                                                   _p(_z(mat.nu)), _p(self._cv) if host else None, _p(x) if host else None))
         return x
+
+    def sweep(self, omegas, mat, rank=0, nranks=1, unique_id=None):
+        """The whole frequency loop in one C-ABI call (mfb_harela3d_sweep): frequencies kf = rank, rank + nranks, ... on this GPU, NCCL all-reduce
+        of the solutions inside the library; returns (X [n_freq, n_dof], info [n_freq]) on every rank."""
+        om = np.ascontiguousarray(omegas, dtype=np.float64)
+        X = np.zeros((len(om), self.m.n_dof), dtype=np.complex128)
+        info = np.zeros(len(om), dtype=np.int32)
+        uid = (C.c_char * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        _check(lib().mfb_harela3d_sweep(self.h, C.c_int(len(om)), _p(om), _p(_z(mat.lam)), _p(_z(mat.mu)), C.c_double(mat.rho), _p(_z(mat.nu)), _p(self._cv),
+                                        C.c_int(rank), C.c_int(nranks), uid, _p(X), _p(info)))
+        return X, info
+
+    def build_lse_accumulate(self, omega, mat, A, b):
+        """seam 1 with the reference's `+=` on the caller's arrays (mfb_harela3d_assemble_acc, accumulate = 1): A (Fortran order, ld = A.shape[0]) and b
+        are ADDED to."""
+        assert A.flags.f_contiguous and A.dtype == np.complex128 and b.dtype == np.complex128
+        _check(lib().mfb_harela3d_assemble_acc(self.h, C.c_double(omega), _p(_z(mat.lam)), _p(_z(mat.mu)), C.c_double(mat.rho), _p(_z(mat.nu)), _p(self._cv),
+                                               _p(A), C.c_int(A.shape[0]), _p(b), C.c_int(1)))
 
     def get_solution(self):
         x = np.zeros(self.m.n_dof, dtype=np.complex128)

@@ -7,10 +7,12 @@
 #include "poro.cuh"
 #include "combine.cuh"
 #include "lu.cuh"
+#include "solve_ex.cuh"
 #include "dist.cuh"
 #include "plan_host.h"
 #include "../../data/quad_tables.h"
 #include <algorithm>
+#include <cfloat>
 #include <chrono>
 #include <complex>
 #include <cstdio>
@@ -84,6 +86,8 @@ struct mfb_problem {
   int ndof;                                                // equations / unknowns per node: 3 (elastic solid), 1 (inviscid fluid, mfb_harpot3d_*)
   bool hbie;                                               // hypersingular equation at points off the boundary (interior-point stresses)
   bool real_resident;                                      // the resident system / factors are real (static path): Are only
+  // optional stages of solve_lse_c (mfb_zsolve_ex): unfactorised (scaled) copy of A, scale factors in the order of the resident system
+  double* Ao = nullptr; double *d_rs = nullptr, *d_cs = nullptr, *d_xtmp = nullptr; char equed = 'N'; std::vector<double> rs_int, cs_int;
   alignas(64) unsigned char tmapA[128]; bool have_tmap;   // CUtensorMap of the planar system matrix (K1 flush)   // rows_permuted: the resident matrix/factors are in the internal order
 };
 
@@ -158,6 +162,7 @@ extern "C" void mfb_problem_free(mfb_problem* p) {
   for (void* q : p->owned) cudaFree(q);
   for (auto& g : p->groups) for (void* q : g.owned) cudaFree(q);
   if (p->lu_ready) lu_work_free(p->lu);
+  cudaFree(p->Ao); cudaFree(p->d_rs); cudaFree(p->d_cs); cudaFree(p->d_xtmp);
   for (int i = 0; i < 8; i++) cudaEventDestroy(p->ev[i]);
   dist_release(p);
   delete p;
@@ -867,15 +872,25 @@ static int assemble_por_device(mfb_problem* p, double omega, cd lambda, cd mu, d
 
 // copy a planar device matrix to an interleaved host matrix in column chunks (bounded staging buffer)
 static int download_matrix(mfb_problem* p, const double* re, const double* im, long long ld, int rows, int cols, mfb_z* host, long long ldh, const int* rowperm = nullptr,
-                           const int* colperm = nullptr) {
+                           const int* colperm = nullptr, bool accumulate = false) {
   cudaStream_t st = p->ctx->stream;
   int chunk = (int)std::max<long long>(1, std::min<long long>(cols, (256ll << 20) / (16ll * rows)));
   DevBuf sb; CK(cudaMalloc(&sb.p, (size_t)chunk * rows * 16)); double* stage = (double*)sb.p;
+  std::vector<mfb_z> hstage;                       // accumulate: the chunk lands here and is ADDED to the caller's matrix (the seam's `+=`)
+  if (accumulate) hstage.resize((size_t)chunk * rows);
   for (int c0 = 0; c0 < cols; c0 += chunk) {
     int nc = std::min(chunk, cols - c0);
     launch_interleave(re, im, ld, rows, nc, stage, rows, rowperm, colperm, c0, st);
-    CK(cudaMemcpy2DAsync(host + (long long)c0 * ldh, (size_t)ldh * 16, stage, (size_t)rows * 16, (size_t)rows * 16, nc, cudaMemcpyDeviceToHost, st));
+    if (!accumulate) CK(cudaMemcpy2DAsync(host + (long long)c0 * ldh, (size_t)ldh * 16, stage, (size_t)rows * 16, (size_t)rows * 16, nc, cudaMemcpyDeviceToHost, st));
+    else CK(cudaMemcpyAsync(hstage.data(), stage, (size_t)nc * rows * 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (accumulate) {
+#pragma omp parallel for schedule(static)
+      for (int c = 0; c < nc; c++) {
+        mfb_z* dst = host + (long long)(c0 + c) * ldh; const mfb_z* src = hstage.data() + (size_t)c * rows;
+        for (int i = 0; i < rows; i++) { dst[i].re += src[i].re; dst[i].im += src[i].im; }
+      }
+    }
   }
   return MFB_OK;
 }
@@ -892,18 +907,23 @@ static int upload_matrix(mfb_problem* p, const mfb_z* host, long long ldh, int r
   return MFB_OK;
 }
 
-extern "C" int mfb_harela3d_assemble(mfb_problem* p, double omega, const mfb_z* lambda, const mfb_z* mu, double rho, const mfb_z* nu,
-                                     const mfb_z* cvalue, mfb_z* A, mfb_z* b) {
+extern "C" int mfb_harela3d_assemble_acc(mfb_problem* p, double omega, const mfb_z* lambda, const mfb_z* mu, double rho, const mfb_z* nu,
+                                         const mfb_z* cvalue, mfb_z* A, int lda, mfb_z* b, int accumulate) {
   if (!p || !lambda || !mu || !nu) return fail(MFB_ERR_ARG, "mfb_harela3d_assemble: null argument");
+  if (A && lda < p->n_dof) return fail(MFB_ERR_ARG, "mfb_harela3d_assemble: lda < n_dof");
   CK(cudaSetDevice(p->ctx->device));
   int r = assemble_device(p, omega, cd(lambda->re, lambda->im), cd(mu->re, mu->im), rho, cd(nu->re, nu->im), cvalue);
   if (r) return r;
   r = collect_assembly_times(p);
   if (r) return r;
   // the device-resident system is in internal row order; the host sees the reference's row order
-  if (A) { r = download_matrix(p, p->sys.Are, p->sys.Aim, p->lda, p->n_dof, p->n_dof, A, p->n_dof, p->d_rowperm, p->d_colperm); if (r) return r; }
-  if (b) { r = download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, b, p->n_dof, p->d_rowperm); if (r) return r; }
+  if (A) { r = download_matrix(p, p->sys.Are, p->sys.Aim, p->lda, p->n_dof, p->n_dof, A, lda, p->d_rowperm, p->d_colperm, accumulate != 0); if (r) return r; }
+  if (b) { r = download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, b, p->n_dof, p->d_rowperm, nullptr, accumulate != 0); if (r) return r; }
   return MFB_OK;
+}
+extern "C" int mfb_harela3d_assemble(mfb_problem* p, double omega, const mfb_z* lambda, const mfb_z* mu, double rho, const mfb_z* nu,
+                                     const mfb_z* cvalue, mfb_z* A, mfb_z* b) {
+  return mfb_harela3d_assemble_acc(p, omega, lambda, mu, rho, nu, cvalue, A, p ? p->n_dof : 0, b, 0);
 }
 
 extern "C" int mfb_harpot3d_setup(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
@@ -1024,6 +1044,131 @@ extern "C" int mfb_zsolve(mfb_problem* p, int n, mfb_z* A, int lda, int* ipiv, m
   return MFB_OK;
 }
 
+// solve_lse_c with ALL its options (src/solve_lse_c.f90:25-219): scaling (zgeequ + zlaqge :81-117), condition (zgecon :140-165), refine (zgerfs :191-206)
+// around the LU of mfb_zsolve, everything on the device (solve_ex.cu).  Conventions of mfb_zsolve for A / ipiv / b / factorize.  equed (1 char, in/out),
+// r, c (n doubles each, in/out) are the reference's arguments of the same names: written when factorize && scaling, read when !factorize && scaling.
+// rcond (out, when condition && factorize), ferr / berr (out, nrhs each, when refine) may be NULL.  The unfactorised copy `Ao` of the reference lives
+// on the device.
+extern "C" int mfb_zsolve_ex(mfb_problem* p, int n, mfb_z* A, int lda, int* ipiv, mfb_z* b, int nrhs, int factorize, int scaling, int condition, int refine,
+                             char* equed, double* r, double* c, double* rcond, double* ferr, double* berr) {
+  if (!p) return fail(MFB_ERR_ARG, "mfb_zsolve_ex: null problem");
+  if (!scaling && !condition && !refine) return mfb_zsolve(p, n, A, lda, ipiv, b, nrhs, factorize);
+  if (n != p->n_dof) return fail(MFB_ERR_ARG, "mfb_zsolve_ex: n must equal the problem's n_dof");
+  if (nrhs < 0 || (A && lda < n)) return fail(MFB_ERR_ARG, "mfb_zsolve_ex: invalid nrhs/lda");
+  if (scaling && (!equed || !r || !c)) return fail(MFB_ERR_ARG, "mfb_zsolve_ex: scaling needs equed, r and c");
+  if (nrhs > 0 && !b) return fail(MFB_ERR_ARG, "mfb_zsolve_ex: pass the right-hand side b (host)");
+  CK(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  const size_t plane = (size_t)p->lda * n;
+  int rr;
+  if (!p->d_rs) { CK(cudaMalloc((void**)&p->d_rs, (size_t)n * 8)); CK(cudaMalloc((void**)&p->d_cs, (size_t)n * 8)); CK(cudaMalloc((void**)&p->d_xtmp, ((size_t)12 * p->lda + 256) * 8)); }
+  if ((condition || refine) && !p->Ao) CK(cudaMalloc((void**)&p->Ao, 2 * plane * 8));
+  if (factorize) {
+    if (A) { rr = upload_matrix(p, A, lda, n, n, p->sys.Are, p->sys.Aim, p->lda); if (rr) return rr; p->rows_permuted = false; p->real_resident = false; }
+    else if (!p->assembled) return fail(MFB_ERR_ARG, "mfb_zsolve_ex: factorize=1 with A == NULL but no assembled system is resident");
+    else if (p->real_resident) return fail(MFB_ERR_ARG, "mfb_zsolve_ex: the resident system is real; use mfb_dsolve");
+    p->assembled = false; p->equed = 'N';
+    if (scaling) {
+      double rowcnd, colcnd, amax; int info = 0;
+      int e = zequilibrate(p->sys.Are, p->sys.Aim, p->lda, n, p->d_rs, p->d_cs, p->rs_int, p->cs_int, &rowcnd, &colcnd, &amax, &p->equed, &info, st);
+      if (e) return fail(MFB_ERR_CUDA, "equilibration kernels failed");
+      if (info) { char buf[96]; snprintf(buf, sizeof(buf), "zgeequ: %s %d of A is exactly zero", info <= n ? "row" : "column", info <= n ? info : info - n); return fail(info, buf); }
+      *equed = p->equed;
+      for (int i = 0; i < n; i++) { r[i] = p->rs_int[p->rows_permuted ? p->rowperm[i] : i]; c[i] = p->cs_int[p->rows_permuted ? p->colperm[i] : i]; }
+    }
+    if (condition || refine) CK(cudaMemcpyAsync(p->Ao, p->sys.Are, 2 * plane * 8, cudaMemcpyDeviceToDevice, st));   // Are and Aim are one allocation (planes back to back)
+  } else {
+    if (!p->factored || p->real_resident) return fail(MFB_ERR_ARG, "mfb_zsolve_ex: factorize=0 but no complex factors are resident");
+    if (scaling) {
+      if (*equed != 'N' && *equed != 'R' && *equed != 'C' && *equed != 'B') return fail(MFB_ERR_ARG, "mfb_zsolve_ex: invalid value of equed");
+      p->equed = *equed; p->rs_int.assign(n, 1.0); p->cs_int.assign(n, 1.0);
+      for (int i = 0; i < n; i++) { p->rs_int[p->rows_permuted ? p->rowperm[i] : i] = r[i]; p->cs_int[p->rows_permuted ? p->colperm[i] : i] = c[i]; }
+      CK(cudaMemcpyAsync(p->d_rs, p->rs_int.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(p->d_cs, p->cs_int.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    }
+  }
+  if (factorize) {
+    rr = factor_device(p, n, lu_timing());
+    if (ipiv) memcpy(ipiv, p->h_ipiv.data(), (size_t)n * sizeof(int));
+    if (A) { int r2 = download_matrix(p, p->sys.Are, p->sys.Aim, p->lda, n, n, A, lda); if (r2) return r2; }
+    if (rr) return rr;
+  }
+  if (!p->lu.inv) return fail(MFB_ERR_UNSUPPORTED, "mfb_zsolve_ex needs the diagonal-block inverses of the factorisation (MFB_LU_SOLVE_INV=0 is set)");
+  typedef std::complex<double> zc;
+  // device scratch: v (2 ld) | transposed-solve workspace (4 ld + 128) | residual r (2 ld) + s (ld) | spare
+  double *vre = p->d_xtmp, *vim = vre + p->lda, *tws = vim + p->lda, *res = tws + 4 * p->lda + 128;
+  auto dev_solve = [&](std::vector<zc>& v, bool conjt) -> int {          // v := inv(A) v or inv(A)^H v (internal order of the resident factors)
+    std::vector<double> h(2 * (size_t)n);
+    for (int i = 0; i < n; i++) { h[i] = v[i].real(); h[n + i] = v[i].imag(); }
+    cudaMemcpyAsync(vre, h.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st); cudaMemcpyAsync(vim, h.data() + n, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+    int e = conjt ? zgetrs_conjtrans_planar(p->sys.Are, p->sys.Aim, p->lda, n, p->d_perm, p->lu.inv, vre, vim, tws, st)
+                  : zgetrs_planar(p->sys.Are, p->sys.Aim, p->lda, n, p->d_perm, vre, vim, p->lda, 1, st, p->lu.inv);
+    if (e) return e;
+    cudaMemcpyAsync(h.data(), vre, (size_t)n * 8, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(h.data() + n, vim, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    for (int i = 0; i < n; i++) v[i] = zc(h[i], h[n + i]);
+    return (int)cudaGetLastError();
+  };
+  int dev_err = 0;
+  if (condition && factorize) {
+    const double anorm = matrix_norm1(p->Ao, p->Ao + plane, p->lda, n, res, st);
+    const double ainvnm = norm1_estimate(n, [&](std::vector<zc>& v, bool conjt) { if (!dev_err) dev_err = dev_solve(v, conjt); });
+    if (dev_err) return fail(MFB_ERR_CUDA, "condition estimate: a device solve failed");
+    if (rcond) *rcond = (anorm > 0.0 && ainvnm > 0.0) ? (1.0 / ainvnm) / anorm : 0.0;
+  }
+  const double eps = DBL_EPSILON * 0.5, safmin = DBL_MIN;
+  for (int col = 0; col < nrhs; col++) {
+    // internal-order right-hand side (row scaling applied), solution, and the refinement of zgerfs
+    std::vector<zc> bb(n), x(n);
+    for (int i = 0; i < n; i++) { const int q = p->rows_permuted ? p->rowperm[i] : i; bb[q] = zc(b[(size_t)col * n + i].re, b[(size_t)col * n + i].im); }
+    if (scaling && (p->equed == 'R' || p->equed == 'B')) for (int i = 0; i < n; i++) bb[i] *= p->rs_int[i];
+    x = bb;
+    dev_err = dev_solve(x, false); if (dev_err) return fail(MFB_ERR_CUDA, "zgetrs_planar failed");
+    if (refine) {
+      DevSystem so = p->sys; so.Are = p->Ao; so.Aim = p->Ao + plane; so.bre = res + 3 * p->lda; so.bim = res + 4 * p->lda;   // b of the residual kernel
+      std::vector<double> hb(2 * (size_t)n), hx(2 * (size_t)n), hr(3 * (size_t)n);
+      for (int i = 0; i < n; i++) { hb[i] = bb[i].real(); hb[n + i] = bb[i].imag(); }
+      cudaMemcpyAsync(so.bre, hb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st); cudaMemcpyAsync(so.bim, hb.data() + n, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+      const int nz = n + 1; const double safe1 = nz * safmin, safe2 = safe1 / eps;
+      double lstres = 3.0, be = 0.0; int count = 1;
+      std::vector<zc> rv(n); std::vector<double> rw(n);
+      for (;;) {
+        for (int i = 0; i < n; i++) { hx[i] = x[i].real(); hx[n + i] = x[i].imag(); }
+        cudaMemcpyAsync(vre, hx.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st); cudaMemcpyAsync(vim, hx.data() + n, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+        cudaMemsetAsync(res, 0, (size_t)3 * p->lda * 8, st);
+        launch_residual(so, vre, vim, res, res + p->lda, res + 2 * p->lda, st);       // A x - b and |A||x| + |b| (1-norm moduli, as zgerfs)
+        cudaMemcpyAsync(hr.data(), res, (size_t)n * 8, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(hr.data() + n, res + p->lda, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(hr.data() + 2 * (size_t)n, res + 2 * p->lda, (size_t)n * 8, cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st);
+        be = 0.0;
+        for (int i = 0; i < n; i++) {
+          rv[i] = zc(-hr[i], -hr[n + i]); rw[i] = hr[2 * (size_t)n + i];
+          const double num = std::fabs(rv[i].real()) + std::fabs(rv[i].imag());
+          be = std::max(be, rw[i] > safe2 ? num / rw[i] : (num + safe1) / (rw[i] + safe1));
+        }
+        if (be > eps && 2.0 * be <= lstres && count <= 5) {
+          std::vector<zc> dx = rv; dev_err = dev_solve(dx, false); if (dev_err) return fail(MFB_ERR_CUDA, "refinement: a device solve failed");
+          for (int i = 0; i < n; i++) x[i] += dx[i];
+          lstres = be; count++;
+        } else break;
+      }
+      if (berr) berr[col] = be;
+      if (ferr) {
+        for (int i = 0; i < n; i++) { const double num = std::fabs(rv[i].real()) + std::fabs(rv[i].imag()); rw[i] = rw[i] > safe2 ? num + nz * eps * rw[i] : num + nz * eps * rw[i] + safe1; }
+        const double est = norm1_estimate(n, [&](std::vector<zc>& v, bool conjt) {      // operator diag(W) inv(A)^H and its adjoint inv(A) diag(W)
+          if (dev_err) return;
+          if (!conjt) { dev_err = dev_solve(v, true); for (int i = 0; i < n; i++) v[i] *= rw[i]; }
+          else { for (int i = 0; i < n; i++) v[i] *= rw[i]; dev_err = dev_solve(v, false); }
+        });
+        if (dev_err) return fail(MFB_ERR_CUDA, "forward error estimate: a device solve failed");
+        double xmax = 0.0; for (int i = 0; i < n; i++) xmax = std::max(xmax, std::fabs(x[i].real()) + std::fabs(x[i].imag()));
+        ferr[col] = xmax != 0.0 ? est / xmax : est;
+      }
+    }
+    if (scaling && (p->equed == 'C' || p->equed == 'B')) for (int i = 0; i < n; i++) x[i] *= p->cs_int[i];
+    for (int i = 0; i < n; i++) { const zc v = x[p->rows_permuted ? p->colperm[i] : i]; b[(size_t)col * n + i].re = v.real(); b[(size_t)col * n + i].im = v.imag(); }
+  }
+  return MFB_OK;
+}
+
 extern "C" int mfb_harela3d_solve_frequency(mfb_problem* p, double omega, const mfb_z* lambda, const mfb_z* mu, double rho, const mfb_z* nu,
                                             const mfb_z* cvalue, mfb_z* x) {
   if (!p || !lambda || !mu || !nu) return fail(MFB_ERR_ARG, "mfb_harela3d_solve_frequency: null argument");
@@ -1042,6 +1187,58 @@ extern "C" int mfb_harela3d_solve_frequency(mfb_problem* p, double omega, const 
   p->assembled = false;
   if (!x) return MFB_OK;   // solution stays on the device (mfb_get_solution)
   return download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, x, p->n_dof, p->d_colperm);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The frequency loop of src/multifebe.f90:107-124 as ONE C-ABI call, sharded over the ranks of a job: rank q owns the
+// frequencies kf = q, q + nranks, ...; each one is assembled, factorised and solved without leaving the device; the solutions are gathered
+// with one NCCL all-reduce (every rank contributes its own columns, zeros elsewhere) so that every rank returns the whole n_dof x n_freq
+// block X (column kf = solution of omega[kf], host column order).  No collective on the data path.  nranks = 1: no NCCL at all.
+// nccl_id128: the 128-byte unique id made by rank 0 with mfb_dist_unique_id and handed to the other ranks by the host's own means.
+// info[kf] (may be NULL): 0, or the LAPACK info of a singular pivot at that frequency (the sweep goes on).
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int mfb_harela3d_sweep(mfb_problem* p, int n_freq, const double* omega, const mfb_z* lambda, const mfb_z* mu, double rho, const mfb_z* nu,
+                                  const mfb_z* cvalue, int rank, int nranks, const char* nccl_id128, mfb_z* X, int* info) {
+  if (!p || !omega || !lambda || !mu || !nu || !X || n_freq < 1) return fail(MFB_ERR_ARG, "mfb_harela3d_sweep: invalid argument");
+  if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !nccl_id128)) return fail(MFB_ERR_ARG, "mfb_harela3d_sweep: invalid rank / nranks / unique id");
+  CK(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  const int n = p->n_dof;
+  const size_t plane = (size_t)p->lda * n_freq;
+  DevBuf xd; CK(cudaMalloc(&xd.p, 2 * plane * sizeof(double)));
+  double* Xre = (double*)xd.p; double* Xim = Xre + plane;
+  CK(cudaMemsetAsync(Xre, 0, 2 * plane * sizeof(double), st));
+  std::vector<int> linfo(n_freq, 0);
+  for (int kf = rank; kf < n_freq; kf += nranks) {
+    int r = mfb_harela3d_solve_frequency(p, omega[kf], lambda, mu, rho, nu, kf == rank ? cvalue : nullptr, nullptr);
+    if (r > 0) { linfo[kf] = r; continue; }          // singular at this frequency: reported, column left at zero
+    if (r) return r;
+    CK(cudaMemcpyAsync(Xre + (size_t)kf * p->lda, p->sys.bre, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(Xim + (size_t)kf * p->lda, p->sys.bim, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+  }
+  if (nranks > 1) {
+    std::string err;
+    DistComm* comm = make_nccl_comm(rank, nranks, nccl_id128, err);
+    if (!comm) return fail(MFB_ERR_CUDA, "mfb_harela3d_sweep: " + err);
+    double* bufs[1] = {Xre}; int ranks[1] = {rank}; cudaStream_t sts[1] = {st};
+    int e = comm->allreduce_sum(ranks, bufs, 2 * plane, sts, 1);
+    std::string ce = e ? std::string(comm->last_error()) : std::string();
+    DevBuf di; int e2 = 0;
+    if (!e && info) {       // the per-frequency info flags travel the same way
+      std::vector<double> fi(n_freq); for (int k = 0; k < n_freq; k++) fi[k] = linfo[k];
+      if (cudaMalloc(&di.p, (size_t)n_freq * 8) == cudaSuccess) {
+        cudaMemcpyAsync(di.p, fi.data(), (size_t)n_freq * 8, cudaMemcpyHostToDevice, st);
+        double* b2[1] = {(double*)di.p}; e2 = comm->allreduce_sum(ranks, b2, (size_t)n_freq, sts, 1);
+        cudaMemcpyAsync(fi.data(), di.p, (size_t)n_freq * 8, cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st);
+        for (int k = 0; k < n_freq; k++) linfo[k] = (int)fi[k];
+      }
+    }
+    CK(cudaStreamSynchronize(st));
+    delete comm;
+    if (e || e2) return fail(MFB_ERR_CUDA, "mfb_harela3d_sweep: NCCL all-reduce failed: " + ce);
+  }
+  if (info) for (int k = 0; k < n_freq; k++) info[k] = linfo[k];
+  return download_matrix(p, Xre, Xim, p->lda, n, n_freq, X, n, p->d_colperm);
 }
 
 extern "C" int mfb_harpot3d_solve_frequency(mfb_problem* p, double omega, double rho, const mfb_z* c, const mfb_z* cvalue, mfb_z* x) {

@@ -192,38 +192,51 @@ void polar_rays(int et, const double* xi_i, const int* counts /* [2 * n_edges], 
 // summed over the edges that do not contain the collocation point): I = sum_edges int t / r ds = int x'(u) / |x(u) - x_i| du (t ds = x' du),
 // delivered as hli[l][k] = -eps_lkm I_m.  Straight edges (2 nodes): with a = x_A - x_i, t the unit direction, s_a = a.t, p^2 = |a|^2 - s_a^2,
 //   int ds / sqrt(s^2 + p^2) = asinh(s_b / p) - asinh(s_a / p)   in closed form.
-// Curved edges (3 nodes): x(u) = M + u (B - A)/2 + u^2 (A + B - 2M)/2 on [-1, 1], integrated by a recursive 15-point Gauss-Kronrod rule to
-// 1e-15 (the reference uses its Telles + subdivision machinery with the same target).
+// Curved edges (3 nodes): x(u) = M + u (B - A)/2 + u^2 (A + B - 2M)/2 on [-1, 1], integrated with 20-point Gauss-Legendre panels graded
+// geometrically away from the nearest point (the reference uses its Telles + subdivision machinery with a 1e-15 target).
 // ----------------------------------------------------------------------------------------------------------------------------------
 static const int EDGE_T[3][3] = {{0, 1, 3}, {1, 2, 4}, {2, 0, 5}}, EDGE_Q[4][3] = {{0, 1, 4}, {1, 2, 5}, {2, 3, 6}, {3, 0, 7}};
-static const double GK_X[8] = {0.991455371120812639206854697526329, 0.949107912342758524526189684047851, 0.864864423359769072789712788640926, 0.741531185599394439863864773280788,
-                               0.586087235467691130294144838258730, 0.405845151377397166906606412076961, 0.207784955007898467600689403773245, 0.0};
-static const double GK_WK[8] = {0.022935322010529224963732008058970, 0.063092092629978553290700663189204, 0.104790010322250183839876322541518, 0.140653259715525918745189590510238,
-                                0.169004726639267902826583426598550, 0.190350578064785409913256402421014, 0.204432940075298892414161999234649, 0.209482141084727828012999174891714};
-static const double GK_WG[4] = {0.129484966168869693270611432679082, 0.279705391489276667901467771423780, 0.381830050505118944950369775488975, 0.417959183673469387755102040816327};
 struct CurvedEdge { double M[3], D[3], Q[3], xi[3]; };
-static void ce_eval(const CurvedEdge& E, double u, double* f) {
-  double r2 = 0.0, dx[3];
-  for (int c = 0; c < 3; c++) { const double x = E.M[c] + u * (E.D[c] + u * E.Q[c]) - E.xi[c]; dx[c] = E.D[c] + 2.0 * u * E.Q[c]; r2 += x * x; }
-  const double ir = 1.0 / std::sqrt(r2);
-  for (int c = 0; c < 3; c++) f[c] = dx[c] * ir;
+static inline double ce_dist2(const CurvedEdge& E, double u) {
+  double r2 = 0.0;
+  for (int c = 0; c < 3; c++) { const double x = E.M[c] + u * (E.D[c] + u * E.Q[c]) - E.xi[c]; r2 += x * x; }
+  return r2;
 }
-static void ce_gk(const CurvedEdge& E, double a, double b, double* K, double* err) {
+// 20-point Gauss-Legendre on [a, b] of f(u) = x'(u) / |x(u) - x_i|
+static void ce_panel(const CurvedEdge& E, double a, double b, double* I) {
   const double m = 0.5 * (a + b), hw = 0.5 * (b - a);
-  double G[3] = {0, 0, 0}; K[0] = K[1] = K[2] = 0.0;
-  for (int i = 0; i < 8; i++) {
-    double f1[3], f2[3]; ce_eval(E, m - hw * GK_X[i], f1);
-    if (i < 7) ce_eval(E, m + hw * GK_X[i], f2); else f2[0] = f2[1] = f2[2] = 0.0;
-    for (int c = 0; c < 3; c++) { K[c] += GK_WK[i] * (f1[c] + f2[c]); if (i & 1) G[c] += GK_WG[i / 2] * (f1[c] + f2[c]); }
+  for (int q = 0; q < 20; q++) {
+    const double u = m + hw * QT_GL11_X[QT_GL11_OFF[19] + q], w = hw * QT_GL11_W[QT_GL11_OFF[19] + q];
+    const double ir = 1.0 / std::sqrt(ce_dist2(E, u));
+    for (int c = 0; c < 3; c++) I[c] += w * (E.D[c] + 2.0 * u * E.Q[c]) * ir;
   }
-  *err = 0.0;
-  for (int c = 0; c < 3; c++) { K[c] *= hw; G[c] *= hw; *err = std::max(*err, std::fabs(K[c] - G[c])); }
 }
-static void ce_adapt(const CurvedEdge& E, double a, double b, double tol, int depth, double* I) {
-  double K[3], err; ce_gk(E, a, b, K, &err);
-  if (err <= tol || depth >= 48) { for (int c = 0; c < 3; c++) I[c] += K[c]; return; }
-  const double m = 0.5 * (a + b);
-  ce_adapt(E, a, m, 0.5 * tol, depth + 1, I); ce_adapt(E, m, b, 0.5 * tol, depth + 1, I);
+// The integrand is analytic on [-1, 1]; its complex singularities sit at a distance ~ rmin / |x'| from the parameter u0 of the nearest point.
+// Panels graded geometrically away from u0 (first panel as wide as that distance, every next one twice as wide) keep the ratio
+// panel width / distance to the singularity bounded, where 20 Gauss points reach machine precision.  Bounded work, no error-driven recursion.
+static void ce_integrate(const CurvedEdge& E, double* I) {
+  double u0 = 0.0, best = ce_dist2(E, 0.0);
+  for (int k = 0; k <= 256; k++) { const double u = -1.0 + k / 128.0, d2 = ce_dist2(E, u); if (d2 < best) { best = d2; u0 = u; } }
+  double lo = std::max(-1.0, u0 - 1.0 / 128.0), hi = std::min(1.0, u0 + 1.0 / 128.0);
+  for (int it = 0; it < 60; it++) {   // golden-section refinement of the minimiser (approximate is enough: it only places the panels)
+    const double g = 0.381966011250105, a = lo + g * (hi - lo), b = hi - g * (hi - lo);
+    if (ce_dist2(E, a) < ce_dist2(E, b)) hi = b; else lo = a;
+  }
+  u0 = 0.5 * (lo + hi);
+  double sp = 0.0;
+  for (int c = 0; c < 3; c++) { const double d = E.D[c] + 2.0 * u0 * E.Q[c]; sp += d * d; }
+  const double w0 = std::min(std::max(std::sqrt(ce_dist2(E, u0) / std::max(sp, 1e-300)), 1e-9), 2.0);
+  for (int side = -1; side <= 1; side += 2) {
+    double a = u0, w = w0;
+    for (int k = 0; k < 64; k++) {
+      double b = a + side * w;
+      const bool last = side > 0 ? b >= 1.0 : b <= -1.0;
+      if (last) b = side;
+      if (b != a) { if (side > 0) ce_panel(E, a, b, I); else ce_panel(E, b, a, I); }
+      if (last) break;
+      a = b; w *= 2.0;
+    }
+  }
 }
 void edge_integrals(int et, const double* xn, const double* x_i, const bool* edge_on /* [n_edges] */, double* hli /* 9, accumulated */) {
   const bool tri = (et == TRI3 || et == TRI6), curved = (et == TRI6 || et == QUAD8 || et == QUAD9);
@@ -237,7 +250,7 @@ void edge_integrals(int et, const double* xn, const double* x_i, const bool* edg
     if (curved) {   // a quadratic edge whose middle node sits exactly at the midpoint of the chord is the straight segment
       const double* M = xn + 3 * en[2]; double dev = 0.0, len = 0.0;
       for (int c = 0; c < 3; c++) { dev = std::max(dev, std::fabs(A[c] + B[c] - 2.0 * M[c])); len = std::max(len, std::fabs(B[c] - A[c])); }
-      straight = dev <= 4e-16 * len;
+      straight = dev <= 1e-13 * len;
     }
     if (straight) {
       double t[3], a[3], L = 0.0, sa = 0.0, a2 = 0.0;
@@ -250,10 +263,7 @@ void edge_integrals(int et, const double* xn, const double* x_i, const bool* edg
     } else {
       CurvedEdge E; const double* M = xn + 3 * en[2];
       for (int c = 0; c < 3; c++) { E.M[c] = M[c]; E.D[c] = 0.5 * (B[c] - A[c]); E.Q[c] = 0.5 * (A[c] + B[c] - 2.0 * M[c]); E.xi[c] = x_i[c]; }
-      double Ie[3] = {0, 0, 0}, K[3], err; ce_gk(E, -1.0, 1.0, K, &err);
-      const double scale = std::max(std::fabs(K[0]), std::max(std::fabs(K[1]), std::fabs(K[2])));
-      ce_adapt(E, -1.0, 1.0, 1e-15 * std::max(scale, 1e-300), 0, Ie);
-      for (int c = 0; c < 3; c++) I[c] += Ie[c];
+      ce_integrate(E, I);
     }
   }
   // hli[l][k] = -eps_lkm I_m

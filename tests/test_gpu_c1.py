@@ -59,3 +59,24 @@ def test_c1_through_the_standalone_driver(gpu_ctx, c1, tmp_path):
     nso = driver.run(str(tmp_path / "t3.dat"), log=io.StringIO())
     rows = [s for s in open(nso) if s.strip() and not s.startswith("#")]
     assert len(rows) == 300 * 462
+
+
+def test_c_abi_sweep_and_accumulating_assembly(gpu_ctx, c1):
+    """mfb_harela3d_sweep (the frequency loop as one C-ABI call; single rank: no NCCL) returns what per-frequency calls return, and
+    mfb_harela3d_assemble_acc(accumulate = 1) ADDS the region's system to the caller's arrays (the `+=` of src/build_lse_mechanics_harmonic.f90:73-95)."""
+    from multifebe_b200 import capi
+    case, md = c1
+    mat = case.material
+    pr = capi.Problem(gpu_ctx, md)
+    oms = [float(case.omega[k]) for k in (3, 50, 120, 299)]
+    X, info = pr.sweep(oms, mat)
+    assert (info == 0).all()
+    for k, om in enumerate(oms):
+        assert relerr(X[k], pr.solve_frequency(om, mat)) < 1e-13
+    A, b = pr.build_lse_mechanics_bem_harela(oms[1], mat)
+    rng = np.random.default_rng(0)
+    A0 = np.asfortranarray(rng.standard_normal(A.shape) + 1j * rng.standard_normal(A.shape)); b0 = rng.standard_normal(b.shape) + 0j
+    A1 = A0.copy(order="F"); b1 = b0.copy()
+    pr.build_lse_accumulate(oms[1], mat, A1, b1)
+    assert relerr(A1 - A0, A) < 1e-14 and relerr(b1 - b0, b) < 1e-14
+    pr.close()

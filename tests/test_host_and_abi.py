@@ -141,3 +141,16 @@ def test_tile_partition_keeps_row_blocks_whole_and_balanced():
         assert counts.max() - counts.min() <= 4
     tr, rb = capi.dist_partition_tiles([0, 0], [24 * 4, 0], 20, 4)      # fewer row blocks than ranks
     assert list(tr) == [0, 3] and list(rb) == [0, 12, 12, 12, 20]
+
+
+def test_plain_c_program_builds_against_the_header_and_runs(tmp_path):
+    """include/mfb.h is a C header (not C++ in disguise): a C99 program compiled with gcc -std=c99 -pedantic links against libmfb.so, computes through the
+    host-only entry points and sees MFB_ERR_NO_DEVICE from mfb_init on a box without a GPU (tests/native/abi_c_program.c)."""
+    import subprocess
+    from multifebe_b200 import build as b
+    so = b.build()
+    exe = str(tmp_path / "abi_c_program")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "native", "abi_c_program.c"),
+                           "-o", exe, so, "-lm", "-Wl,-rpath," + os.path.dirname(so)])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
