@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
     unsigned char m = PLAN_NONE, m_next = (valid && e0 < e1) ? pl[(size_t)e0 * c.ldp] : PLAN_NONE;
     unsigned info_next = g.einfo[e0], cvnz_next = g.ecvnz[e0];   // element class of the next element, requested one element ahead like its plan byte
     unsigned fullsets = 0u;      // sets whose queue holds >= 32 entries
-    bool inplace_todo = false;
+    unsigned inplace_sets = 0u;   // rules of the current element that enough lanes of the tile share to be integrated in place (bit = set index)
     for (;;) {
       // ---- select the next batch (all control flow here is warp-uniform) ----
       int sset, el, src; bool act, inplace;
@@ -417,9 +417,9 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
         __syncwarp();
         if (cnt < 32) fullsets &= ~(1u << sset);
         src = ent & 31; el = e0 + (ent >> 5); act = true; inplace = false;
-      } else if (inplace_todo) {
-        inplace_todo = false;
-        sset = 0; el = ecur; src = lane; act = (m == 0); inplace = true;
+      } else if (inplace_sets) {
+        sset = __ffs(inplace_sets) - 1; inplace_sets &= inplace_sets - 1u;
+        el = ecur; src = lane; act = ((int)m == sset); inplace = true;
       } else if (e < e1) {
         m = m_next; ecur = e; e++;
         m_next = (valid && e < e1) ? pl[(size_t)e * c.ldp] : PLAN_NONE;
@@ -429,18 +429,22 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
         if (mode_e != MODE) continue;
         const unsigned reg = __ballot_sync(0xffffffffu, m < MAX_SETS);
         if (reg == 0u) continue;
-        const unsigned in0 = __ballot_sync(0xffffffffu, m == 0);
-        inplace_todo = __popc(in0) >= KB_INPLACE_MIN;
-        if (inplace_todo && lane < 3) {   // pull the next element's first point set towards L1 while this one is integrated
+        // Every rule that at least KB_INPLACE_MIN lanes of the tile ask for is integrated IN PLACE (lane = collocation point, bulk-reduce flush): a
+        // tile is spatially compact, so near an element most of its 32 points want the same rule.  Round 1 did this for the lowest rule only and
+        // sent every other rule through the per-lane RED flush of the deferred queues: on a quad9 m = 20 mesh, where more than half of all pairs sit
+        // inside the gln >= 3 distance, that flush was the kernel (5.4 TFLOP/s algorithmic, 37.1 ms in round 1, profiles/r02_one_step_quad9_after_inplace.log after).
+        unsigned todo = reg;
+        inplace_sets = 0u;
+        if (lane < 3) {   // pull the next element's first point set towards L1 while this one is integrated
           const double* Pn = g.pts[0] + (size_t)(ecur + 1) * g.ngp[0] * RECN;
           if (ecur + 1 < e1) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(Pn) + 128 * lane));
         }
-        unsigned todo = inplace_todo ? (reg & ~in0) : reg;
         while (todo) {
           const int leader = __ffs(todo) - 1;
           const int qs = __shfl_sync(0xffffffffu, (int)m, leader);
           const unsigned grp = __ballot_sync(0xffffffffu, (int)m == qs) & todo;
           todo &= ~grp;
+          if (__popc(grp) >= KB_INPLACE_MIN && nbytes > 0) { inplace_sets |= 1u << qs; continue; }
           const int base = qcnt[qs];
           if ((grp >> lane) & 1u) queue[qs * KB_QCAP + base + __popc(grp & lt_mask)] = (unsigned short)(((ecur - e0) << 5) | lane);
           __syncwarp();
