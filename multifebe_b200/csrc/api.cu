@@ -36,6 +36,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 struct mfb_ctx {
   int device; cudaStream_t stream; DevTables tables; double* tables_buf; cudaEvent_t marks[8];
+  K1Launch k1;     // launch state of the regular kernel on this context's stream
 };
 
 struct GroupHost {
@@ -87,6 +88,10 @@ struct mfb_problem {
   bool hbie;                                               // hypersingular equation at points off the boundary (interior-point stresses)
   bool real_resident;                                      // the resident system / factors are real (static path): Are only
   // optional stages of solve_lse_c (mfb_zsolve_ex): unfactorised (scaled) copy of A, scale factors in the order of the resident system
+  // factorise + solve of a SMALL resident system as one CUDA graph (launch-bound regime: ~300 launches per frequency at 1386 DOF)
+  int lu_plain_calls = 0;
+  cudaGraphExec_t lu_graph = nullptr; int lu_graph_nodes = 0; int* d_graph_flags = nullptr; bool lu_graph_failed = false;
+  double* d_vstage = nullptr;                              // 2 n_dof doubles: staging of solution / right-hand-side downloads
   double* Ao = nullptr; double *d_rs = nullptr, *d_cs = nullptr, *d_xtmp = nullptr; char equed = 'N'; std::vector<double> rs_int, cs_int;
   alignas(64) unsigned char tmapA[128]; bool have_tmap;   // CUtensorMap of the planar system matrix (K1 flush)   // rows_permuted: the resident matrix/factors are in the internal order
 };
@@ -123,7 +128,7 @@ extern "C" int mfb_init(int device, mfb_ctx** out) {
   if (prop.major < 10) return fail(MFB_ERR_NO_DEVICE, "mfb_init: kernels are built for sm_100a only");
   mfb_ctx* c = new mfb_ctx();
   c->device = device;
-  CK(cudaStreamCreate(&c->stream));
+  CK(cudaStreamCreate(&c->stream));   // a blocking stream on purpose: set-up code reads results back with plain cudaMemcpy (legacy stream) and relies on its implicit ordering
   for (int i = 0; i < 8; i++) CK(cudaEventCreate(&c->marks[i]));
   // Gauss-Legendre tables on the device (packed: rule n starts at n(n-1)/2)
   CK(cudaMalloc((void**)&c->tables_buf, 4 * 528 * sizeof(double)));
@@ -131,6 +136,7 @@ extern "C" int mfb_init(int device, mfb_ctx** out) {
   CK(cudaMemcpy(c->tables_buf + 528, QT_GL11_W, 528 * 8, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->tables_buf + 2 * 528, QT_GL01_X, 528 * 8, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->tables_buf + 3 * 528, QT_GL01_W, 528 * 8, cudaMemcpyHostToDevice));
+  if (k1_launch_create(c->k1)) return fail(MFB_ERR_CUDA, "mfb_init: K1 launch state");
   c->tables.gl11_x = c->tables_buf; c->tables.gl11_w = c->tables_buf + 528; c->tables.gl01_x = c->tables_buf + 2 * 528; c->tables.gl01_w = c->tables_buf + 3 * 528;
   *out = c;
   return MFB_OK;
@@ -139,6 +145,7 @@ extern "C" void mfb_finalize(mfb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaFree(c->tables_buf);
+  k1_launch_destroy(c->k1);
   for (int i = 0; i < 8; i++) cudaEventDestroy(c->marks[i]);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -162,7 +169,8 @@ extern "C" void mfb_problem_free(mfb_problem* p) {
   for (void* q : p->owned) cudaFree(q);
   for (auto& g : p->groups) for (void* q : g.owned) cudaFree(q);
   if (p->lu_ready) lu_work_free(p->lu);
-  cudaFree(p->Ao); cudaFree(p->d_rs); cudaFree(p->d_cs); cudaFree(p->d_xtmp);
+  if (p->lu_graph) cudaGraphExecDestroy(p->lu_graph);
+  cudaFree(p->d_graph_flags); cudaFree(p->d_vstage); cudaFree(p->Ao); cudaFree(p->d_rs); cudaFree(p->d_cs); cudaFree(p->d_xtmp);
   for (int i = 0; i < 8; i++) cudaEventDestroy(p->ev[i]);
   dist_release(p);
   delete p;
@@ -623,6 +631,7 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
   p->lda = ((long long)n_dof + 31) / 32 * 32;
   double* dA; CK(cudaMalloc((void**)&dA, (size_t)2 * p->lda * n_dof * sizeof(double))); p->owned.push_back(dA);
   double* db; CK(cudaMalloc((void**)&db, (size_t)2 * p->lda * sizeof(double))); p->owned.push_back(db);
+  CK(cudaMalloc((void**)&p->d_vstage, (size_t)2 * std::max(n_dof, 1) * sizeof(double)));
   p->sys.Are = dA; p->sys.Aim = dA + (size_t)p->lda * n_dof; p->sys.lda = p->lda; p->sys.n_dof = n_dof; p->sys.bre = db; p->sys.bim = db + p->lda;
   p->have_tmap = make_matrix_tensor_map(p->tmapA, p->sys.Are, p->lda, n_dof, 2) == 0;
   p->have_tmapS = make_matrix_tensor_map(p->tmapS, p->sys.Are, p->lda, n_dof, 1) == 0;
@@ -746,7 +755,6 @@ static int assemble_device(mfb_problem* p, double omega, cd lambda, cd mu, doubl
 static int assemble_device_k(mfb_problem* p, const KParams& K, const KParams& Q, cd nu, const mfb_z* cvalue, bool statics) {
   if (p->ndof != 3) return fail(MFB_ERR_ARG, "this problem was set up for an inviscid fluid region (mfb_harpot3d_setup): use mfb_harpot3d_assemble / _solve_frequency");
   cudaStream_t st = p->ctx->stream;
-  set_kparams(K, Q, st);
   if (cvalue) {
     CK(cudaMemcpyAsync(p->d_cvalue, cvalue, (size_t)6 * p->n_node * sizeof(double), cudaMemcpyHostToDevice, st));
     for (auto& g : p->groups) launch_gather_cv(g.dev, p->d_cvalue, st);
@@ -758,12 +766,12 @@ static int assemble_device_k(mfb_problem* p, const KParams& K, const KParams& Q,
   CK(cudaEventRecord(p->ev[1], st));
   {
     const void* tm = statics ? (p->have_tmapS ? p->tmapS : nullptr) : (p->have_tmap ? p->tmapA : nullptr);
-    for (auto& g : p->groups) launch_regular(g.dev, p->colloc, p->sys, p->plan, tm, statics, st);
+    for (auto& g : p->groups) launch_regular(g.dev, p->colloc, p->sys, p->plan, tm, statics, K, Q, p->ctx->k1, st);
   }
   CK(cudaEventRecord(p->ev[2], st));
-  for (auto& g : p->groups) launch_adaptive(g.dev, p->colloc, p->sys, g.adp, p->ctx->tables, st);
+  for (auto& g : p->groups) launch_adaptive(g.dev, p->colloc, p->sys, g.adp, p->ctx->tables, K, st);
   CK(cudaEventRecord(p->ev[3], st));
-  for (auto& g : p->groups) launch_singular(g.dev, p->colloc, p->sys, g.sing, p->ctx->tables, st);
+  for (auto& g : p->groups) launch_singular(g.dev, p->colloc, p->sys, g.sing, p->ctx->tables, K, st);
   CK(cudaEventRecord(p->ev[4], st));
   const double c_pi = 3.14159265358979323846264338328;
   cd F = -1.0 / (8.0 * c_pi * (1.0 - nu));
@@ -875,7 +883,9 @@ static int download_matrix(mfb_problem* p, const double* re, const double* im, l
                            const int* colperm = nullptr, bool accumulate = false) {
   cudaStream_t st = p->ctx->stream;
   int chunk = (int)std::max<long long>(1, std::min<long long>(cols, (256ll << 20) / (16ll * rows)));
-  DevBuf sb; CK(cudaMalloc(&sb.p, (size_t)chunk * rows * 16)); double* stage = (double*)sb.p;
+  DevBuf sb; double* stage;
+  if (cols == 1 && rows <= p->n_dof && p->d_vstage) stage = p->d_vstage;   // a vector: persistent staging (cudaMalloc / cudaFree synchronise the whole device and would
+  else { CK(cudaMalloc(&sb.p, (size_t)chunk * rows * 16)); stage = (double*)sb.p; }   // serialise problems that work side by side on different streams)
   std::vector<mfb_z> hstage;                       // accumulate: the chunk lands here and is ADDED to the caller's matrix (the seam's `+=`)
   if (accumulate) hstage.resize((size_t)chunk * rows);
   for (int c0 = 0; c0 < cols; c0 += chunk) {
@@ -1009,6 +1019,71 @@ static int factor_device(mfb_problem* p, int n, bool timing) {
   return MFB_OK;
 }
 
+// Factorise the resident complex system and solve its resident right-hand side: the tail shared by the *_solve_frequency entry points.
+// Small systems (n <= MFB_LU_GRAPH_MAX_N, default 4096) run the whole sequence -- ~230 panel / update launches on two streams, the diagonal-block
+// inverses, the permutation (formed on the device), ~50 substitution launches -- as ONE CUDA graph captured at the first call: at 1386 DOF the
+// host spent ~12 us per launch when several problems were driven side by side (capi.ProblemLanes), i.e. 3.6 ms of launches per frequency.
+static int lu_graph_max_n() { static int v = -1; if (v < 0) { const char* e = getenv("MFB_LU_GRAPH_MAX_N"); v = e ? atoi(e) : 4096; } return v; }
+static int factor_and_solve_resident(mfb_problem* p) {
+  cudaStream_t st = p->ctx->stream;
+  const int n = p->n_dof;
+  int r = ensure_lu(p); if (r) return r;
+  // the first factorisation of a problem always takes the plain path: it performs the one-time set-up that must not happen inside a stream
+  // capture (function attributes, tensor maps, cluster-launch probing) and leaves per-phase timings of this size in the statistics
+  const bool want_graph = !p->real_resident && n <= lu_graph_max_n() && p->lu.inv && !p->lu_graph_failed && p->lu_plain_calls >= 1;
+  if (!want_graph) p->lu_plain_calls++;
+  if (!want_graph) {
+    r = factor_device(p, n, lu_timing());
+    if (r) return r;
+    CK(cudaEventRecord(p->ev[6], st));
+    int e = zgetrs_planar(p->sys.Are, p->real_resident ? nullptr : p->sys.Aim, p->lda, n, p->d_perm, p->sys.bre, p->real_resident ? nullptr : p->sys.bim, p->lda, 1, st, p->lu.inv,
+                          p->lu.solve_ws);
+    if (e) return fail(MFB_ERR_CUDA, std::string("zgetrs_planar: ") + cudaGetErrorString((cudaError_t)e));
+    CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
+    float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
+    return MFB_OK;
+  }
+  if (!p->d_graph_flags) { CK(cudaMalloc((void**)&p->d_graph_flags, 2 * sizeof(int))); }
+  if (!p->lu_graph) {
+    // capture (thread-local mode: other host threads keep issuing CUDA calls for their own problems meanwhile)
+    cudaGraph_t g = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    int e = 0;
+    if (ce == cudaSuccess) {
+      cudaMemsetAsync(p->d_graph_flags, 0, 2 * sizeof(int), st);
+      e = zgetrf_planar(p->sys.Are, p->sys.Aim, p->lda, n, p->d_ipiv, p->lu, st, false);
+      if (!e) e = launch_perm_from_ipiv(p->d_ipiv, p->d_perm, n, p->d_graph_flags, st);
+      if (!e) e = zgetrs_planar(p->sys.Are, p->sys.Aim, p->lda, n, p->d_perm, p->sys.bre, p->sys.bim, p->lda, 1, st, p->lu.inv, p->lu.solve_ws);
+      ce = cudaStreamEndCapture(st, &g);
+    }
+    if (ce != cudaSuccess || e || !g) {      // not capturable on this configuration: plain launches from now on
+      cudaGetLastError(); if (g) cudaGraphDestroy(g);
+      p->lu_graph_failed = true;
+      return factor_and_solve_resident(p);
+    }
+    size_t nn = 0; cudaGraphGetNodes(g, nullptr, &nn); p->lu_graph_nodes = (int)nn;
+    ce = cudaGraphInstantiate(&p->lu_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) { cudaGetLastError(); p->lu_graph = nullptr; p->lu_graph_failed = true; return factor_and_solve_resident(p); }
+  }
+  CK(cudaEventRecord(p->ev[6], st));
+  CK(cudaGraphLaunch(p->lu_graph, st));
+  CK(cudaEventRecord(p->ev[7], st));
+  int flags[2] = {0, 0}, info = 0;
+  CK(cudaMemcpyAsync(flags, p->d_graph_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&info, p->lu.info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]);
+  p->stats[MFB_STAT_MS_LU] = t; p->stats[MFB_STAT_MS_SOLVE] = 0.0;           // one graph: the split is not observable
+  p->stats[MFB_STAT_LU_LAUNCHES] = (double)p->lu_graph_nodes;
+  p->stats[MFB_STAT_GEMM_LAUNCHES] = (double)p->lu.gemm_launches; p->stats[MFB_STAT_GEMM_FLOPS] = p->lu.gemm_flops; p->stats[MFB_STAT_GEMM_EXEC_FLOPS] = p->lu.gemm_exec_flops;
+  p->stats[MFB_STAT_MS_PANEL] = p->stats[MFB_STAT_MS_SWAP] = p->stats[MFB_STAT_MS_TRSM] = p->stats[MFB_STAT_MS_GEMM] = 0.0;
+  p->factored = true;
+  if (flags[0]) return fail(MFB_ERR_CUDA, "zgetrf (graph): pivot index out of range");
+  if (info > 0) { char buf[128]; snprintf(buf, sizeof(buf), "zgetrf: U(%d,%d) is exactly zero, the matrix is singular", info, info); return fail(info, buf); }
+  return MFB_OK;
+}
+
 extern "C" int mfb_zsolve(mfb_problem* p, int n, mfb_z* A, int lda, int* ipiv, mfb_z* b, int nrhs, int factorize) {
   if (!p) return fail(MFB_ERR_ARG, "mfb_zsolve: null problem");
   if (n != p->n_dof) return fail(MFB_ERR_ARG, "mfb_zsolve: n must equal the problem's n_dof");
@@ -1101,7 +1176,7 @@ extern "C" int mfb_zsolve_ex(mfb_problem* p, int n, mfb_z* A, int lda, int* ipiv
     for (int i = 0; i < n; i++) { h[i] = v[i].real(); h[n + i] = v[i].imag(); }
     cudaMemcpyAsync(vre, h.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st); cudaMemcpyAsync(vim, h.data() + n, (size_t)n * 8, cudaMemcpyHostToDevice, st);
     int e = conjt ? zgetrs_conjtrans_planar(p->sys.Are, p->sys.Aim, p->lda, n, p->d_perm, p->lu.inv, vre, vim, tws, st)
-                  : zgetrs_planar(p->sys.Are, p->sys.Aim, p->lda, n, p->d_perm, vre, vim, p->lda, 1, st, p->lu.inv);
+                  : zgetrs_planar(p->sys.Are, p->sys.Aim, p->lda, n, p->d_perm, vre, vim, p->lda, 1, st, p->lu.inv, p->lu.solve_ws);
     if (e) return e;
     cudaMemcpyAsync(h.data(), vre, (size_t)n * 8, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(h.data() + n, vim, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
@@ -1175,15 +1250,9 @@ extern "C" int mfb_harela3d_solve_frequency(mfb_problem* p, double omega, const 
   CK(cudaSetDevice(p->ctx->device));
   int r = assemble_device(p, omega, cd(lambda->re, lambda->im), cd(mu->re, mu->im), rho, cd(nu->re, nu->im), cvalue);
   if (r) return r;
-  r = factor_device(p, p->n_dof, lu_timing());
+  r = factor_and_solve_resident(p);
   int r2 = collect_assembly_times(p); if (r2) return r2;
   if (r) return r;
-  cudaStream_t st = p->ctx->stream;
-  CK(cudaEventRecord(p->ev[6], st));
-  int e = zgetrs_planar(p->sys.Are, p->sys.Aim, p->lda, p->n_dof, p->d_perm, p->sys.bre, p->sys.bim, p->lda, 1, st, p->lu.inv);
-  if (e) return fail(MFB_ERR_CUDA, std::string("zgetrs_planar: ") + cudaGetErrorString((cudaError_t)e));
-  CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
-  float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
   p->assembled = false;
   if (!x) return MFB_OK;   // solution stays on the device (mfb_get_solution)
   return download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, x, p->n_dof, p->d_colperm);
@@ -1246,15 +1315,9 @@ extern "C" int mfb_harpot3d_solve_frequency(mfb_problem* p, double omega, double
   CK(cudaSetDevice(p->ctx->device));
   int r = assemble_pot_device(p, omega, rho, cd(c->re, c->im), cvalue);
   if (r) return r;
-  r = factor_device(p, p->n_dof, lu_timing());
+  r = factor_and_solve_resident(p);
   int r2 = collect_assembly_times(p); if (r2) return r2;
   if (r) return r;
-  cudaStream_t st = p->ctx->stream;
-  CK(cudaEventRecord(p->ev[6], st));
-  int e = zgetrs_planar(p->sys.Are, p->sys.Aim, p->lda, p->n_dof, p->d_perm, p->sys.bre, p->sys.bim, p->lda, 1, st, p->lu.inv);
-  if (e) return fail(MFB_ERR_CUDA, std::string("zgetrs_planar: ") + cudaGetErrorString((cudaError_t)e));
-  CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
-  float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
   p->assembled = false;
   if (!x) return MFB_OK;
   return download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, x, p->n_dof, p->d_colperm);
@@ -1266,15 +1329,9 @@ extern "C" int mfb_harpor3d_solve_frequency(mfb_problem* p, double omega, const 
   CK(cudaSetDevice(p->ctx->device));
   int r = assemble_por_device(p, omega, cd(lambda->re, lambda->im), cd(mu->re, mu->im), rho1, rho2, rhoa, cd(R->re, R->im), cd(Q->re, Q->im), b, cvalue);
   if (r) return r;
-  r = factor_device(p, p->n_dof, lu_timing());
+  r = factor_and_solve_resident(p);
   int r2 = collect_assembly_times(p); if (r2) return r2;
   if (r) return r;
-  cudaStream_t st = p->ctx->stream;
-  CK(cudaEventRecord(p->ev[6], st));
-  int e = zgetrs_planar(p->sys.Are, p->sys.Aim, p->lda, p->n_dof, p->d_perm, p->sys.bre, p->sys.bim, p->lda, 1, st, p->lu.inv);
-  if (e) return fail(MFB_ERR_CUDA, std::string("zgetrs_planar: ") + cudaGetErrorString((cudaError_t)e));
-  CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
-  float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;
   p->assembled = false;
   if (!x) return MFB_OK;
   return download_matrix(p, p->sys.bre, p->sys.bim, p->lda, p->n_dof, 1, x, p->n_dof, p->d_colperm);
@@ -1790,7 +1847,7 @@ extern "C" int mfb_staela3d_solve(mfb_problem* p, double mu, double nu, const do
   if (r) return r;
   cudaStream_t st = p->ctx->stream;
   CK(cudaEventRecord(p->ev[6], st));
-  int e = zgetrs_planar(p->sys.Are, nullptr, p->lda, p->n_dof, p->d_perm, p->sys.bre, nullptr, p->lda, 1, st, p->lu.inv);
+  int e = zgetrs_planar(p->sys.Are, nullptr, p->lda, p->n_dof, p->d_perm, p->sys.bre, nullptr, p->lda, 1, st, p->lu.inv, p->lu.solve_ws);
   if (e) return fail(MFB_ERR_CUDA, std::string("dgetrs (planar): ") + cudaGetErrorString((cudaError_t)e));
   CK(cudaEventRecord(p->ev[7], st)); CK(cudaEventSynchronize(p->ev[7]));
   float t; cudaEventElapsedTime(&t, p->ev[6], p->ev[7]); p->stats[MFB_STAT_MS_SOLVE] = t;

@@ -20,13 +20,9 @@
 
 namespace mfbd {
 
-__constant__ KParams c_kp;   // parameters as the reference defines them (K2, K3)
-__constant__ KParams c_kq;   // pre-scaled copy for K1 (see kernel_scalars_scaled)
-
-void set_kparams(const KParams& kp, const KParams& kp_scaled, cudaStream_t st) {
-  cudaMemcpyToSymbolAsync(c_kp, &kp, sizeof(KParams), 0, cudaMemcpyHostToDevice, st);
-  cudaMemcpyToSymbolAsync(c_kq, &kp_scaled, sizeof(KParams), 0, cudaMemcpyHostToDevice, st);
-}
+// The region / frequency parameters travel as __grid_constant__ kernel arguments (constant bank, like __constant__ memory, but private to the launch):
+// two problems assembling different frequencies on different streams of one process do not share them (round 1 kept them in __constant__ symbols,
+// which serialised a process to one frequency in flight).
 
 // ------------------------------------------------------------------------------------------------------------------
 // K0: classification.  d must be bit-identical to the host/reference value (it feeds a discrete decision), hence the
@@ -122,7 +118,7 @@ void launch_gather_cv(const DevGroup& g, const double* cvalue, cudaStream_t st) 
 template <int NN, int NL, class Pred>
 __device__ __forceinline__ void scatter_pair(const Acc<NN, NL>& a, const int* __restrict__ ecol, const unsigned char* __restrict__ ekind,
                                              const double* __restrict__ ecv, bool rev, const DevSystem& s, int il,
-                                             int r0, int r1, int r2, double* bre, double* bim, Pred mine, bool hbie = false) {
+                                             int r0, int r1, int r2, double* bre, double* bim, Pred mine, const KParams& c_kp, bool hbie = false) {
   // h (or m of the hypersingular equation) is scaled by cte_t (cte_s) and changes sign on a reversed element; g (l) by cte_u (cte_d)
   const cplx ch0 = hbie ? c_kp.cte_s : mk(c_kp.cte_t, 0.0);
   const cplx ch = rev ? mk(-ch0.re, -ch0.im) : ch0;
@@ -167,7 +163,7 @@ const int K1_ECHUNK = 32;
 
 // HB: hypersingular equation (interior-point stresses): the collocation point carries a unit normal (DevColloc::cn)
 template <int ET, int NL, bool HB>
-__global__ void __launch_bounds__(K1_WARPS * 32) k_regular(DevGroup g, DevColloc c, DevSystem s, const unsigned char* __restrict__ plan) {
+__global__ void __launch_bounds__(K1_WARPS * 32) k_regular(DevGroup g, DevColloc c, DevSystem s, const unsigned char* __restrict__ plan, const __grid_constant__ KParams c_kp) {
   const int NN = ElemTraits<ET>::NN;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cpos = (blockIdx.x * K1_WARPS + warp) * 32 + lane;
@@ -206,7 +202,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_regular(DevGroup g, DevColloc
             if (HB) accumulate_exterior_hbie<NN, NL>(acc, c_kp, x, n, xc, ni, w, il);
             else accumulate_exterior<NN, NL>(acc, c_kp, x, n, xc, w, il);
           }
-          scatter_pair<NN, NL>(acc, ecol, ekind, ecv, rev, s, il, r0, r1, r2, bre, bim, AllEntries(), HB);
+          scatter_pair<NN, NL>(acc, ecol, ekind, ecv, rev, s, il, r0, r1, r2, bre, bim, AllEntries(), c_kp, HB);
         }
       }
     }
@@ -264,7 +260,7 @@ struct AccA { double re[9 * NN], im[9 * NN]; };   // [(l*3+k)*NN + j]: entry of 
 template <int NW, int MODE, bool ST>
 __device__ __forceinline__ void k1_point(AccA<NW>& a, double* bacc, const double* rec, const double* w, const double* sk, bool do_b, const double* xc,
                                          double sgn, unsigned info, const unsigned char* __restrict__ ekind, const double* __restrict__ ecv, bool have_ks,
-                                         KScal& k) {
+                                         KScal& k, const KParams& c_kq) {
   const double n[3] = {sgn * rec[3], sgn * rec[4], sgn * rec[5]};
   const double rv0 = rec[0] - xc[0], rv1 = rec[1] - xc[1], rv2 = rec[2] - xc[2];
   const double r2 = fma(rv0, rv0, fma(rv1, rv1, rv2 * rv2));
@@ -368,7 +364,7 @@ const int KB_SMEM_QUEUE = MAX_SETS * KB_QCAP * 2;   // bytes per warp
 template <int ET, int MODE, int WARPS, bool ST>
 __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_constant__ CUtensorMap tmap, DevGroup g, DevColloc c, DevSystem s,
                                                                   const unsigned char* __restrict__ plan,
-                                                                  int* __restrict__ task_counter) {
+                                                                  int* __restrict__ task_counter, const __grid_constant__ KParams c_kq) {
   typedef K1Shape<ElemTraits<ET>::NN> SH;
   constexpr int NN = SH::NN, NC = 3 * NN, NW = SH::NW, NCH = SH::NCH, RECN = 6 + NN;
   extern __shared__ __align__(128) double k1_smem[];
@@ -444,7 +440,9 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
           const int qs = __shfl_sync(0xffffffffu, (int)m, leader);
           const unsigned grp = __ballot_sync(0xffffffffu, (int)m == qs) & todo;
           todo &= ~grp;
-          if (__popc(grp) >= KB_INPLACE_MIN && nbytes > 0) { inplace_sets |= 1u << qs; continue; }
+          // 3/4-node elements: only the lowest rule (their 27 / 36 entries per pair flush cheaply from a packed deferred batch, and a packed batch keeps
+          // all 32 lanes busy: with every rule in place K1 of the tri3 m = 40 mesh went from 47 to 53 ms)
+          if (__popc(grp) >= KB_INPLACE_MIN && nbytes > 0 && (NCH > 1 || qs == 0)) { inplace_sets |= 1u << qs; continue; }
           const int base = qcnt[qs];
           if ((grp >> lane) & 1u) queue[qs * KB_QCAP + base + __popc(grp & lt_mask)] = (unsigned short)(((ecur - e0) << 5) | lane);
           __syncwarp();
@@ -522,7 +520,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
               const double* kc = kcache + (size_t)kp * 320 + lane;
               ks.psi = mk(kc[0], kc[32]); ks.chi = mk(kc[64], kc[96]); ks.T1 = mk(kc[128], kc[160]); ks.T2 = mk(kc[192], kc[224]); ks.T3 = mk(kc[256], kc[288]);
             }
-            k1_point<NW, MODE, ST>(acc, bacc, cur, cur + 6, sk, ch == 0, xs, sgn, info, ekind, ecv, have_ks, ks);
+            k1_point<NW, MODE, ST>(acc, bacc, cur, cur + 6, sk, ch == 0, xs, sgn, info, ekind, ecv, have_ks, ks, c_kq);
             if (use_cache && ch == 0) {
               double* kc = kcache + (size_t)kp * 320 + lane;
               kc[0] = ks.psi.re; kc[32] = ks.psi.im; kc[64] = ks.chi.re; kc[96] = ks.chi.im; kc[128] = ks.T1.re; kc[160] = ks.T1.im;
@@ -592,40 +590,55 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
   if (pending && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-static int* g_task_counters = nullptr;   // one counter per kernel of a launch, zeroed before each launch
+// Per-context launch state of K1 (task counters of the persistent kernels, the two side streams on which the element classes run beside each
+// other, fork / join events): owned by the mfb_ctx, so that contexts on different streams (several frequencies in flight in one process) never
+// share it.  Round 1 kept it in function-local statics.
+int k1_launch_create(K1Launch& k) {
+  if (cudaMalloc((void**)&k.counters, 4 * sizeof(int)) != cudaSuccess) return 1;
+  for (int i = 0; i < 2; i++) { cudaStreamCreateWithFlags(&k.aux[i], cudaStreamNonBlocking); cudaEventCreateWithFlags(&k.ev_join[i], cudaEventDisableTiming); }
+  cudaEventCreateWithFlags(&k.ev_fork, cudaEventDisableTiming);
+  int dev = 0; k.n_sm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&k.n_sm, cudaDevAttrMultiProcessorCount, dev);
+  return (int)cudaGetLastError();
+}
+void k1_launch_destroy(K1Launch& k) {
+  if (!k.counters) return;
+  cudaFree(k.counters); k.counters = nullptr;
+  for (int i = 0; i < 2; i++) { cudaStreamDestroy(k.aux[i]); cudaEventDestroy(k.ev_join[i]); }
+  cudaEventDestroy(k.ev_fork);
+}
 template <int ET, int MODE, int WARPS, bool ST>
-static void launch_bulk_mode(const CUtensorMap& tmap, const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, int n_sm,
+static void launch_bulk_mode(const CUtensorMap& tmap, const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, const KParams& kq, K1Launch& k1,
                              cudaStream_t st) {
   const int smem = WARPS * K1Shape<ElemTraits<ET>::NN>::SMEM_PER_WARP;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(k_regular_bulk<ET, MODE, WARPS, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
   const int n_tasks = c.n_tiles * g.n_ranges;
-  int ctas = 2 * n_sm; if (ctas * WARPS > n_tasks) ctas = (n_tasks + WARPS - 1) / WARPS;
-  k_regular_bulk<ET, MODE, WARPS, ST><<<ctas, WARPS * 32, smem, st>>>(tmap, g, c, s, plan, g_task_counters + MODE);
+  int ctas = 2 * k1.n_sm; if (ctas * WARPS > n_tasks) ctas = (n_tasks + WARPS - 1) / WARPS;
+  k_regular_bulk<ET, MODE, WARPS, ST><<<ctas, WARPS * 32, smem, st>>>(tmap, g, c, s, plan, k1.counters + MODE, kq);
 }
 template <int ET, bool ST>
-static void launch_regular_bulk(const CUtensorMap& tmap, const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, cudaStream_t st) {
-  if (!g_task_counters) cudaMalloc((void**)&g_task_counters, 4 * sizeof(int));
-  cudaMemsetAsync(g_task_counters, 0, 4 * sizeof(int), st);
-  int dev = 0, n_sm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+static void launch_regular_bulk(const CUtensorMap& tmap, const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, const KParams& kq, K1Launch& k1,
+                                cudaStream_t st) {
+  cudaMemsetAsync(k1.counters, 0, 4 * sizeof(int), st);
+  if (c.n_tiles * g.n_ranges < 2048) {   // a small mesh: the classes one after the other on the caller's stream (no side streams: they only pay on long kernels,
+    launch_bulk_mode<ET, 1, KB_WARPS, ST>(tmap, g, c, s, plan, kq, k1, st);        // and a process that keeps many small problems in flight runs out of hardware queues)
+    if (g.has_mixed) launch_bulk_mode<ET, 2, KB_WARPS, ST>(tmap, g, c, s, plan, kq, k1, st);
+    launch_bulk_mode<ET, 0, KB_WARPS_FAST, ST>(tmap, g, c, s, plan, kq, k1, st);
+    return;
+  }
   // the three element classes run concurrently (their tails overlap); everything joins the caller's stream again
-  static cudaStream_t aux[2] = {nullptr, nullptr}; static cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
-  if (!aux[0]) {
-    for (int i = 0; i < 2; i++) { cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking); cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming); }
-    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
-  }
-  cudaEventRecord(ev_fork, st);
-  cudaStreamWaitEvent(aux[0], ev_fork, 0);
-  launch_bulk_mode<ET, 1, KB_WARPS, ST>(tmap, g, c, s, plan, n_sm, aux[0]);
-  cudaEventRecord(ev_join[0], aux[0]);
+  cudaEventRecord(k1.ev_fork, st);
+  cudaStreamWaitEvent(k1.aux[0], k1.ev_fork, 0);
+  launch_bulk_mode<ET, 1, KB_WARPS, ST>(tmap, g, c, s, plan, kq, k1, k1.aux[0]);
+  cudaEventRecord(k1.ev_join[0], k1.aux[0]);
   if (g.has_mixed) {
-    cudaStreamWaitEvent(aux[1], ev_fork, 0);
-    launch_bulk_mode<ET, 2, KB_WARPS, ST>(tmap, g, c, s, plan, n_sm, aux[1]);
-    cudaEventRecord(ev_join[1], aux[1]);
+    cudaStreamWaitEvent(k1.aux[1], k1.ev_fork, 0);
+    launch_bulk_mode<ET, 2, KB_WARPS, ST>(tmap, g, c, s, plan, kq, k1, k1.aux[1]);
+    cudaEventRecord(k1.ev_join[1], k1.aux[1]);
   }
-  launch_bulk_mode<ET, 0, KB_WARPS_FAST, ST>(tmap, g, c, s, plan, n_sm, st);
-  cudaStreamWaitEvent(st, ev_join[0], 0);
-  if (g.has_mixed) cudaStreamWaitEvent(st, ev_join[1], 0);
+  launch_bulk_mode<ET, 0, KB_WARPS_FAST, ST>(tmap, g, c, s, plan, kq, k1, st);
+  cudaStreamWaitEvent(st, k1.ev_join[0], 0);
+  if (g.has_mixed) cudaStreamWaitEvent(st, k1.ev_join[1], 0);
 }
 
 // 3-D tensor map of the planar system matrix for the K1 flush: (row, column, plane), box = 96 rows x 3 columns x 2 planes
@@ -649,38 +662,40 @@ int make_matrix_tensor_map(void* out_128B, double* Are, long long lda, int n_dof
 }
 
 template <int ET>
-static void launch_regular_et(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, const void* tmap, bool statics, cudaStream_t st) {
-  if (statics) launch_regular_bulk<ET, true>(*reinterpret_cast<const CUtensorMap*>(tmap), g, c, s, plan, st);
-  else launch_regular_bulk<ET, false>(*reinterpret_cast<const CUtensorMap*>(tmap), g, c, s, plan, st);
+static void launch_regular_et(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, const void* tmap, bool statics, const KParams& kq, K1Launch& k1,
+                              cudaStream_t st) {
+  if (statics) launch_regular_bulk<ET, true>(*reinterpret_cast<const CUtensorMap*>(tmap), g, c, s, plan, kq, k1, st);
+  else launch_regular_bulk<ET, false>(*reinterpret_cast<const CUtensorMap*>(tmap), g, c, s, plan, kq, k1, st);
 }
 // tmap: tensor map of the planar matrix whose box has two planes (harmonic) or one (statics = true); without it, or for
 // elements whose dof columns are not consecutive, the general kernel runs (in a static run it works with the harmonic
 // parameter set whose frequency-dependent coefficients are zero, see set_kparams).
-void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, const void* tmap, bool statics, cudaStream_t st) {
+void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, const void* tmap, bool statics, const KParams& kp, const KParams& kq,
+                    K1Launch& k1, cudaStream_t st) {
   if (g.n_elem == 0) return;
   dim3 grid((c.ldp + 32 * K1_WARPS - 1) / (32 * K1_WARPS), (g.n_elem + K1_ECHUNK - 1) / K1_ECHUNK);
   dim3 block(K1_WARPS * 32);
   if (c.cn) {   // hypersingular equation: the general kernel (a handful of interior points, not a hot path)
     switch (g.et) {
-      case 5: k_regular<5, 3, true><<<grid, block, 0, st>>>(g, c, s, plan); break;
-      case 7: k_regular<7, 3, true><<<grid, block, 0, st>>>(g, c, s, plan); break;
-      case 6: k_regular<6, 1, true><<<grid, block, 0, st>>>(g, c, s, plan); break;
-      case 8: k_regular<8, 1, true><<<grid, block, 0, st>>>(g, c, s, plan); break;
-      case 9: k_regular<9, 1, true><<<grid, block, 0, st>>>(g, c, s, plan); break;
+      case 5: k_regular<5, 3, true><<<grid, block, 0, st>>>(g, c, s, plan, kp); break;
+      case 7: k_regular<7, 3, true><<<grid, block, 0, st>>>(g, c, s, plan, kp); break;
+      case 6: k_regular<6, 1, true><<<grid, block, 0, st>>>(g, c, s, plan, kp); break;
+      case 8: k_regular<8, 1, true><<<grid, block, 0, st>>>(g, c, s, plan, kp); break;
+      case 9: k_regular<9, 1, true><<<grid, block, 0, st>>>(g, c, s, plan, kp); break;
     }
     return;
   }
   switch (g.et) {
-    case 5: if (g.cols3 && tmap) { launch_regular_et<5>(g, c, s, plan, tmap, statics, st); break; }
-            k_regular<5, 3, false><<<grid, block, 0, st>>>(g, c, s, plan); break;
-    case 7: if (g.cols3 && tmap) { launch_regular_et<7>(g, c, s, plan, tmap, statics, st); break; }
-            k_regular<7, 3, false><<<grid, block, 0, st>>>(g, c, s, plan); break;
-    case 6: if (g.cols3 && tmap) { launch_regular_et<6>(g, c, s, plan, tmap, statics, st); break; }
-            k_regular<6, 1, false><<<grid, block, 0, st>>>(g, c, s, plan); break;
-    case 8: if (g.cols3 && tmap) { launch_regular_et<8>(g, c, s, plan, tmap, statics, st); break; }
-            k_regular<8, 1, false><<<grid, block, 0, st>>>(g, c, s, plan); break;
-    case 9: if (g.cols3 && tmap) { launch_regular_et<9>(g, c, s, plan, tmap, statics, st); break; }
-            k_regular<9, 1, false><<<grid, block, 0, st>>>(g, c, s, plan); break;
+    case 5: if (g.cols3 && tmap) { launch_regular_et<5>(g, c, s, plan, tmap, statics, kq, k1, st); break; }
+            k_regular<5, 3, false><<<grid, block, 0, st>>>(g, c, s, plan, kp); break;
+    case 7: if (g.cols3 && tmap) { launch_regular_et<7>(g, c, s, plan, tmap, statics, kq, k1, st); break; }
+            k_regular<7, 3, false><<<grid, block, 0, st>>>(g, c, s, plan, kp); break;
+    case 6: if (g.cols3 && tmap) { launch_regular_et<6>(g, c, s, plan, tmap, statics, kq, k1, st); break; }
+            k_regular<6, 1, false><<<grid, block, 0, st>>>(g, c, s, plan, kp); break;
+    case 8: if (g.cols3 && tmap) { launch_regular_et<8>(g, c, s, plan, tmap, statics, kq, k1, st); break; }
+            k_regular<8, 1, false><<<grid, block, 0, st>>>(g, c, s, plan, kp); break;
+    case 9: if (g.cols3 && tmap) { launch_regular_et<9>(g, c, s, plan, tmap, statics, kq, k1, st); break; }
+            k_regular<9, 1, false><<<grid, block, 0, st>>>(g, c, s, plan, kp); break;
   }
 }
 
@@ -706,7 +721,7 @@ __device__ __forceinline__ void flush_b(const DevSystem& s, int r0, int r1, int 
 // K2: adaptive pairs -- one warp per pair, lanes stride over the gln x gln points of every leaf.
 // ------------------------------------------------------------------------------------------------------------------
 template <int ET, int NL, bool HB>
-__global__ void __launch_bounds__(128) k_adaptive(DevGroup g, DevColloc c, DevSystem s, DevAdaptive a, DevTables t) {
+__global__ void __launch_bounds__(128) k_adaptive(DevGroup g, DevColloc c, DevSystem s, DevAdaptive a, DevTables t, const __grid_constant__ KParams c_kp) {
   const int NN = ElemTraits<ET>::NN;
   const bool tri = (ElemTraits<ET>::NV == 3);
   const int lane = threadIdx.x & 31;
@@ -748,29 +763,29 @@ __global__ void __launch_bounds__(128) k_adaptive(DevGroup g, DevColloc c, DevSy
     warp_reduce<NN, NL>(acc);
     LaneEntries le; le.lane = lane;
     scatter_pair<NN, NL>(acc, g.ecol + (size_t)e * 3 * NN, g.ekind + (size_t)e * 3 * NN, g.ecv + (size_t)e * 6 * NN, g.erev[e] != 0, s, il,
-                         r0, r1, r2, bre, bim, le, HB);
+                         r0, r1, r2, bre, bim, le, c_kp, HB);
   }
   flush_b(s, r0, r1, r2, bre, bim);
 }
-void launch_adaptive(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevAdaptive& a, const DevTables& t, cudaStream_t st) {
+void launch_adaptive(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevAdaptive& a, const DevTables& t, const KParams& kp, cudaStream_t st) {
   if (a.n_pairs == 0) return;
   dim3 grid((a.n_pairs + 3) / 4), block(128);
   if (c.cn) {
     switch (g.et) {
-      case 5: k_adaptive<5, 3, true><<<grid, block, 0, st>>>(g, c, s, a, t); break;
-      case 7: k_adaptive<7, 3, true><<<grid, block, 0, st>>>(g, c, s, a, t); break;
-      case 6: k_adaptive<6, 1, true><<<grid, block, 0, st>>>(g, c, s, a, t); break;
-      case 8: k_adaptive<8, 1, true><<<grid, block, 0, st>>>(g, c, s, a, t); break;
-      case 9: k_adaptive<9, 1, true><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+      case 5: k_adaptive<5, 3, true><<<grid, block, 0, st>>>(g, c, s, a, t, kp); break;
+      case 7: k_adaptive<7, 3, true><<<grid, block, 0, st>>>(g, c, s, a, t, kp); break;
+      case 6: k_adaptive<6, 1, true><<<grid, block, 0, st>>>(g, c, s, a, t, kp); break;
+      case 8: k_adaptive<8, 1, true><<<grid, block, 0, st>>>(g, c, s, a, t, kp); break;
+      case 9: k_adaptive<9, 1, true><<<grid, block, 0, st>>>(g, c, s, a, t, kp); break;
     }
     return;
   }
   switch (g.et) {
-    case 5: k_adaptive<5, 3, false><<<grid, block, 0, st>>>(g, c, s, a, t); break;
-    case 7: k_adaptive<7, 3, false><<<grid, block, 0, st>>>(g, c, s, a, t); break;
-    case 6: k_adaptive<6, 1, false><<<grid, block, 0, st>>>(g, c, s, a, t); break;
-    case 8: k_adaptive<8, 1, false><<<grid, block, 0, st>>>(g, c, s, a, t); break;
-    case 9: k_adaptive<9, 1, false><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 5: k_adaptive<5, 3, false><<<grid, block, 0, st>>>(g, c, s, a, t, kp); break;
+    case 7: k_adaptive<7, 3, false><<<grid, block, 0, st>>>(g, c, s, a, t, kp); break;
+    case 6: k_adaptive<6, 1, false><<<grid, block, 0, st>>>(g, c, s, a, t, kp); break;
+    case 8: k_adaptive<8, 1, false><<<grid, block, 0, st>>>(g, c, s, a, t, kp); break;
+    case 9: k_adaptive<9, 1, false><<<grid, block, 0, st>>>(g, c, s, a, t, kp); break;
   }
 }
 
@@ -780,7 +795,7 @@ void launch_adaptive(const DevGroup& g, const DevColloc& c, const DevSystem& s, 
 // after the reduction.
 // ------------------------------------------------------------------------------------------------------------------
 template <int ET, int NL>
-__global__ void __launch_bounds__(128) k_singular(DevGroup g, DevColloc c, DevSystem s, DevSingular a, DevTables t) {
+__global__ void __launch_bounds__(128) k_singular(DevGroup g, DevColloc c, DevSystem s, DevSingular a, DevTables t, const __grid_constant__ KParams c_kp) {
   const int NN = ElemTraits<ET>::NN;
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -829,19 +844,19 @@ __global__ void __launch_bounds__(128) k_singular(DevGroup g, DevColloc c, DevSy
     }
     LaneEntries le; le.lane = lane;
     scatter_pair<NN, NL>(acc, g.ecol + (size_t)e * 3 * NN, g.ekind + (size_t)e * 3 * NN, g.ecv + (size_t)e * 6 * NN, g.erev[e] != 0, s, il,
-                         r0, r1, r2, bre, bim, le);
+                         r0, r1, r2, bre, bim, le, c_kp);
   }
   flush_b(s, r0, r1, r2, bre, bim);
 }
-void launch_singular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevSingular& a, const DevTables& t, cudaStream_t st) {
+void launch_singular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevSingular& a, const DevTables& t, const KParams& kp, cudaStream_t st) {
   if (a.n_pairs == 0) return;
   dim3 grid((a.n_pairs + 3) / 4), block(128);
   switch (g.et) {
-    case 5: k_singular<5, 3><<<grid, block, 0, st>>>(g, c, s, a, t); break;
-    case 7: k_singular<7, 3><<<grid, block, 0, st>>>(g, c, s, a, t); break;
-    case 6: k_singular<6, 1><<<grid, block, 0, st>>>(g, c, s, a, t); break;
-    case 8: k_singular<8, 1><<<grid, block, 0, st>>>(g, c, s, a, t); break;
-    case 9: k_singular<9, 1><<<grid, block, 0, st>>>(g, c, s, a, t); break;
+    case 5: k_singular<5, 3><<<grid, block, 0, st>>>(g, c, s, a, t, kp); break;
+    case 7: k_singular<7, 3><<<grid, block, 0, st>>>(g, c, s, a, t, kp); break;
+    case 6: k_singular<6, 1><<<grid, block, 0, st>>>(g, c, s, a, t, kp); break;
+    case 8: k_singular<8, 1><<<grid, block, 0, st>>>(g, c, s, a, t, kp); break;
+    case 9: k_singular<9, 1><<<grid, block, 0, st>>>(g, c, s, a, t, kp); break;
   }
 }
 

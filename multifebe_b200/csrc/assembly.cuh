@@ -81,19 +81,24 @@ struct DevFreeTerm {
 };
 struct DevTables { const double *gl11_x, *gl11_w, *gl01_x, *gl01_w; };  // packed, rule n at offset n(n-1)/2
 
-void set_kparams(const KParams& kp, const KParams& kp_scaled, cudaStream_t st);
+// per-context launch state of K1 (see assembly.cu)
+struct K1Launch { int* counters = nullptr; cudaStream_t aux[2]; cudaEvent_t ev_fork, ev_join[2]; int n_sm = 148; };
+int k1_launch_create(K1Launch& k);
+void k1_launch_destroy(K1Launch& k);
 void launch_classify(const DevGroup& g, const DevColloc& c, const DevClassify& k, unsigned char* plan, cudaStream_t st);
 void launch_count_near(const unsigned char* plan, long long n_slots, const DevColloc& c, unsigned long long* counter, int2* list,
                        unsigned long long capacity, cudaStream_t st);
 void launch_patch_plan(unsigned char* plan, const DevColloc& c, int n, const int* cpos, const int* slot, const unsigned char* val, cudaStream_t st);
 void launch_gather_cv(const DevGroup& g, const double* cvalue, cudaStream_t st);
-void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, const void* tmap, bool statics, cudaStream_t st);
+// kp: the region / frequency parameters as the reference defines them (K2, K3, the general K1); kq: the pre-scaled copy of the bulk K1 (kernel_scalars_scaled)
+void launch_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, const void* tmap, bool statics, const KParams& kp, const KParams& kq,
+                    K1Launch& k1, cudaStream_t st);
 int make_matrix_tensor_map(void* out_128B, double* Are, long long lda, int n_dof, int box_planes);
 // real plane only, host row/column order: out[:, 0:cols) = host columns [col0, col0 + cols)
 void launch_gather_real(const double* re, long long ld, int rows, int cols, double* out, long long ldo, const int* rowperm, const int* colperm, int col0, cudaStream_t st);
 void launch_scatter_real(const double* in, long long ldi, int rows, int cols, double* re, long long ld, const int* rowperm, cudaStream_t st);
-void launch_adaptive(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevAdaptive& a, const DevTables& t, cudaStream_t st);
-void launch_singular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevSingular& a, const DevTables& t, cudaStream_t st);
+void launch_adaptive(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevAdaptive& a, const DevTables& t, const KParams& kp, cudaStream_t st);
+void launch_singular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const DevSingular& a, const DevTables& t, const KParams& kp, cudaStream_t st);
 void launch_freeterm(const DevColloc& c, const DevSystem& s, const DevFreeTerm& f, cplx F, cudaStream_t st);
 void launch_residual(const DevSystem& s, const double* xre, const double* xim, double* rr, double* ri, double* ss, cudaStream_t st);
 void launch_get_entries(const DevSystem& s, int n, const int* rows, const int* cols, double* out, cudaStream_t st);

@@ -911,6 +911,7 @@ int lu_work_alloc(LuWork& w, int n, int nb) {
     w.cluster = 0;
     const char* e_mr = getenv("MFB_LU_CLUSTER_MAX_ROWS");
     w.cluster_max_rows = e_mr ? atoi(e_mr) : (1 << 30);
+    { const char* e_r = getenv("MFB_LU_CLUSTER_MIN_ROWS"); w.cluster_min_rows = e_r ? atoi(e_r) : 64; if (w.cluster_min_rows < 32) w.cluster_min_rows = 32; }
     const char* e_ci = getenv("MFB_LU_CLUSTER_IB");
     w.cluster_ib = e_ci ? atoi(e_ci) : 32;
     if (want > 0) {
@@ -934,8 +935,10 @@ int lu_work_alloc(LuWork& w, int n, int nb) {
   A((void**)&w.pu_arrive, 64 * sizeof(int));
   { const char* e_ps = getenv("MFB_GEMM_PRESUM"); w.asum[0] = w.asum[1] = nullptr;
     if (e_ps && atoi(e_ps) != 0) { const size_t ldn = ((size_t)n + 31) / 32 * 32; A((void**)&w.asum[0], ldn * nb * sizeof(double)); A((void**)&w.asum[1], ldn * nb * sizeof(double)); } }
+  w.solve_ws = nullptr; A((void**)&w.solve_ws, (size_t)2 * n * sizeof(double));
   { const char* e_si = getenv("MFB_LU_SOLVE_INV"); w.inv = nullptr; if (!e_si || atoi(e_si) != 0) A((void**)&w.inv, (size_t)((n + TS - 1) / TS) * 4 * TS * TS * sizeof(double)); }
-  if (e == cudaSuccess) e = cudaMemset(w.pu_arrive, 0, 64 * sizeof(int));
+  // (no cudaMemset here: it runs on the legacy default stream, which synchronises implicitly with every blocking stream of the process and is an error
+  // while another host thread captures a graph; pu_arrive is cleared on the panel stream below)
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_subpanel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_subpanel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   w.n_evs = 5 * ((n + nb - 1) / nb);
@@ -946,12 +949,14 @@ int lu_work_alloc(LuWork& w, int n, int nb) {
   for (int i = 0; i < 2 * n_steps; i++) cudaEventCreate(&w.pevs[i]);
   int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&w.panel_stream, cudaStreamNonBlocking, hi);
+  if (e == cudaSuccess) e = cudaMemsetAsync(w.pu_arrive, 0, 64 * sizeof(int), w.panel_stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(w.panel_stream);
   cudaEventCreateWithFlags(&w.ev_next_cols, cudaEventDisableTiming); cudaEventCreateWithFlags(&w.ev_panel_done, cudaEventDisableTiming);
   w.ms_panel = w.ms_swap = w.ms_trsm = w.ms_gemm = 0.f; w.n_steps_timed = 0; w.gemm_launches = 0; w.gemm_flops = 0.0;
   return (int)e;
 }
 void lu_work_free(LuWork& w) {
-  cudaFree(w.cand_val); cudaFree(w.cand_row); cudaFree(w.cand_data); cudaFree(w.diag_data); cudaFree(w.info); cudaFree(w.pu_arrive); cudaFree(w.inv); cudaFree(w.asum[0]); cudaFree(w.asum[1]);
+  cudaFree(w.cand_val); cudaFree(w.cand_row); cudaFree(w.cand_data); cudaFree(w.diag_data); cudaFree(w.info); cudaFree(w.pu_arrive); cudaFree(w.inv); cudaFree(w.solve_ws); cudaFree(w.asum[0]); cudaFree(w.asum[1]);
   for (int i = 0; i < w.n_evs; i++) cudaEventDestroy(w.evs[i]);
   for (int i = 0; i < 2 * (w.n_evs / 5); i++) cudaEventDestroy(w.pevs[i]);
   cudaEventDestroy(w.ev_next_cols); cudaEventDestroy(w.ev_panel_done); cudaStreamDestroy(w.panel_stream);
@@ -994,8 +999,11 @@ static int factor_panel(double* Are, double* Aim, long long lda, int n, int k0, 
     cudaError_t e = cudaSuccess;
     bool done = false;
     if (use_cluster) {
-      int G = w.cluster;                                    // a smaller (power of two) cluster for a short sub-panel: >= 64 rows per CTA
-      while (G > 1 && (m + G - 1) / G < 64) G >>= 1;
+      // a smaller (power of two) cluster for a short sub-panel: at least cluster_min_rows rows per CTA as long as its slab fits shared memory.  Small
+      // clusters also matter when several systems are factorised side by side (capi.ProblemLanes): a 16-CTA cluster needs 16 free SMs inside ONE GPC
+      // at the same moment, an 8- or 4-CTA cluster (portable sizes) is placed far more easily between the kernels of the other lanes.
+      int G = w.cluster;
+      while (G > 1 && (m + G - 1) / G < w.cluster_min_rows && (size_t)planes * ib * (((m + G / 2 - 1) / (G / 2)) | 1) * sizeof(double) <= (size_t)SP_CLUSTER_SMEM) G >>= 1;
       const int rpc = (m + G - 1) / G;
       pa.rpc = rpc; pa.rpcp = rpc | 1;
       const size_t smem = (size_t)planes * ib * pa.rpcp * sizeof(double);
@@ -1272,11 +1280,37 @@ void lu_invert_diagonal_blocks(const double* Are, const double* Aim, long long l
   k_trtri_blocks<<<dim3((n + TS - 1) / TS, 2), TS, sm, st>>>(Are, Aim, lda, n, inv);
 }
 
+// perm[i] = source row of row i after the interchanges ipiv[0 .. n) (what the host builds in factor_device), formed on the device by one thread in
+// shared memory: lets a whole factorise + solve sequence run without a host round trip (CUDA graph of small systems).  n <= 12000.
+__global__ void k_perm_from_ipiv(const int* __restrict__ ipiv, int* __restrict__ perm, int n, int* __restrict__ bad) {
+  extern __shared__ int sp[];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sp[i] = i;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n; i++) {
+      const int q = ipiv[i] - 1;
+      if (q < i || q >= n) { atomicExch(bad, 1); continue; }      // never index with a pivot the factorisation did not produce
+      if (q != i) { const int t = sp[i]; sp[i] = sp[q]; sp[q] = t; }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = sp[i];
+}
+int launch_perm_from_ipiv(const int* ipiv, int* perm, int n, int* bad, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_perm_from_ipiv, cudaFuncAttributeMaxDynamicSharedMemorySize, 48000); attr = true; }
+  if ((size_t)n * sizeof(int) > 48000) return -1;
+  k_perm_from_ipiv<<<1, 256, (size_t)n * sizeof(int), st>>>(ipiv, perm, n, bad);
+  return (int)cudaGetLastError();
+}
+
 int zgetrs_planar(const double* Are, const double* Aim, long long lda, int n, const int* ipiv_host_perm_dev, double* bre, double* bim, long long ldb,
-                  int nrhs, cudaStream_t st, const double* inv) {
+                  int nrhs, cudaStream_t st, const double* inv, double* ws) {
   // ipiv_host_perm_dev: device array perm[i] = source row of row i after all interchanges (built on the host from ipiv)
-  double* tmp = nullptr;
-  if (cudaMalloc((void**)&tmp, (size_t)2 * n * sizeof(double)) != cudaSuccess) return (int)cudaGetLastError();
+  // ws: 2 n doubles of caller-owned scratch (LuWork::solve_ws): no allocation, no cudaFree (a device-wide synchronisation) and no stream
+  // synchronisation inside the call, so that solves of different systems on different streams overlap
+  double* tmp = ws;
+  if (!tmp && cudaMalloc((void**)&tmp, (size_t)2 * n * sizeof(double)) != cudaSuccess) return (int)cudaGetLastError();
   if (inv) {   // diagonal-block inverses available: one fused launch per block step
     const int nblk = (n + TS - 1) / TS;
     for (int c = 0; c < nrhs; c++) {
@@ -1294,8 +1328,7 @@ int zgetrs_planar(const double* Are, const double* Aim, long long lda, int n, co
       cudaMemcpyAsync(br, wr, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
       if (bi) cudaMemcpyAsync(bi, wi, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
     }
-    cudaStreamSynchronize(st);
-    cudaFree(tmp);
+    if (!ws) { cudaStreamSynchronize(st); cudaFree(tmp); }
     return (int)cudaGetLastError();
   }
   const size_t dsm = (size_t)2 * TS * (TS + 1) * sizeof(double);
@@ -1319,8 +1352,7 @@ int zgetrs_planar(const double* Are, const double* Aim, long long lda, int n, co
       if (kb > 0) k_gemv_update<<<(kb + 63) / 64, 256, 0, st>>>(Are, Aim, lda, 0, kb, kb, nbw, br, bi);
     }
   }
-  cudaStreamSynchronize(st);
-  cudaFree(tmp);
+  if (!ws) { cudaStreamSynchronize(st); cudaFree(tmp); }
   return (int)cudaGetLastError();
 }
 

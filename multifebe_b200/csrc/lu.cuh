@@ -25,6 +25,7 @@ struct LuWork {
   double *diag_data;      // [2][2*32]         current diagonal row
   int *info;              // device flag: first zero pivot (1-based), 0 = ok
   double *asum[2];        // Ar + Ai of the L21 panel of the current / next step (pre-summed operand of the 3M trailing update)
+  double *solve_ws;       // 2 n doubles: scratch of zgetrs_planar
   double *inv;            // inverses of the 64 x 64 diagonal blocks of L and U of the last factorisation (NULL: substitution kernels)
   int *pu_arrive;         // [64] arrival counters of k_panel_update (one per column block; self re-arming)
   float ms_panel, ms_swap, ms_trsm, ms_gemm; long long launches; long long gemm_launches; double gemm_flops, gemm_exec_flops;   // algorithmic (8mnk) and executed (6mnk with the 3M kernel) flops of the trailing updates
@@ -35,6 +36,7 @@ struct LuWork {
   int lookahead, panel_ctas;
   int fused_panel_update;                      // 1: TRSM + update of the panel columns right of a sub-panel in one kernel (k_panel_update)
   int cluster_ib;                              // preferred sub-panel width of the cluster kernel (if the slab fits)
+  int cluster_min_rows;                        // rows per CTA below which a sub-panel takes a smaller cluster
   int cluster, cluster_max_rows;               // CTAs of the cluster-resident panel kernel (0 = grid-wide kernel only); tallest panel it takes
   GemmTmaMaps tma; const double* tma_key;      // tensor maps of the matrix being factorised (rebuilt when the matrix pointer changes)
 };
@@ -49,7 +51,9 @@ int zgetrf_planar(double* Are, double* Aim, long long lda, int n, int* ipiv, LuW
 // Solve with the factors: b (planar, n x nrhs, ldb) overwritten by the solution.
 // inv = LuWork::inv of the factorisation (or NULL: serial substitution on the diagonal blocks).
 int zgetrs_planar(const double* Are, const double* Aim, long long lda, int n, const int* ipiv, double* bre, double* bim, long long ldb,
-                  int nrhs, cudaStream_t st, const double* inv = nullptr);
+                  int nrhs, cudaStream_t st, const double* inv = nullptr, double* ws = nullptr);
+// perm (device) from ipiv (device, 1-based) without the host; bad (device int) is set when a pivot is out of range.  Returns -1 for n > 12000.
+int launch_perm_from_ipiv(const int* ipiv, int* perm, int n, int* bad, cudaStream_t st);
 // C -= A*B on planar storage (the trailing-matrix update; FP64 tensor pipe, mma.sync m8n8k4).  k must be a multiple of 4.
 void zgemm_minus_planar(int m, int n, int k, const double* Are, const double* Aim, long long lda, const double* Bre, const double* Bim,
                         long long ldb, double* Cre, double* Cim, long long ldc, cudaStream_t st);

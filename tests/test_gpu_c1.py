@@ -80,3 +80,21 @@ def test_c_abi_sweep_and_accumulating_assembly(gpu_ctx, c1):
     pr.build_lse_accumulate(oms[1], mat, A1, b1)
     assert relerr(A1 - A0, A) < 1e-14 and relerr(b1 - b0, b) < 1e-14
     pr.close()
+
+
+def test_frequencies_in_flight_on_lanes_match_one_at_a_time(gpu_ctx, c1):
+    """capi.ProblemLanes: 6 (context, problem) pairs on one GPU, one host thread each, 24 different frequencies assembled and solved side by side.
+    The kernel parameters are launch arguments and every context owns its K1 launch state (round 1 kept both in process-wide symbols), so the results are
+    those of the one-at-a-time path, bit for bit in the solution's leading digits."""
+    from multifebe_b200 import capi
+    case, md = c1
+    mat = case.material
+    oms = [float(case.omega[k]) for k in range(5, 300, 13)][:24]
+    pr = capi.Problem(gpu_ctx, md)
+    ref = np.array([pr.solve_frequency(om, mat) for om in oms])
+    pr.close()
+    lanes = capi.ProblemLanes(md, 0, n_lanes=6)
+    for rep in range(2):
+        X = lanes.run(oms, mat)
+        assert relerr(X, ref) < 1e-12
+    lanes.close()
