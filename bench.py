@@ -429,7 +429,7 @@ def run_acoustic(args):
                "e2e": {"value": world * 1e3 / ms_e2e, "unit": "solves/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(md.cvalue.size * 16 + 1024), "d2h_bytes_per_step": int(16 * n + 4 * n),
                        "api": "mfb_harpot3d_solve_frequency (host cvalue in, host x out)"},
                "gpu_launches": int(acc["LAUNCHES"] + acc["LU_LAUNCHES"]),
-               "roofline": {"kernel": "k_zgemm3m_minus (LU trailing update, 3M complex product on DMMA.8x8x4)", "bound": "tensor", "achieved": gemm_tf, "peak": peaks["dmma_tflops"], "unit": "TFLOP/s",
+               "roofline": {"kernel": "k_zgemm3m_tma (LU trailing update, 3M complex product on DMMA.8x8x4)", "bound": "tensor", "achieved": gemm_tf, "peak": peaks["dmma_tflops"], "unit": "TFLOP/s",
                             "frac": gemm_tf / peaks["dmma_tflops"], "traffic": None, "avg_launch_ms": acc["MS_GEMM"] / max(acc["GEMM_LAUNCHES"], 1),
                             "launches_per_step": acc["GEMM_LAUNCHES"] / K, "share_of_step": (acc["MS_GEMM"] / K) / ms_dev,
                             "note": "executed tensor-pipe flops (6mnk per complex product) / CUDA-event time of the trailing updates; at this size the factorisation is bound "
@@ -570,7 +570,7 @@ def run_c1(args):
                        "api": "mfb_harela3d_solve_frequency (host cvalue in, host x out), once per frequency"},
                "gpu_launches": int(acc["LAUNCHES"] + acc["LU_LAUNCHES"]),
                "per_frequency_ms": {k[3:].lower(): acc[k] / nfr for k in keys if k.startswith("MS_")},
-               "roofline": {"kernel": "k_zgemm3m_minus (LU trailing update)", "bound": "tensor", "achieved": gemm_tf, "peak": peaks["dmma_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["dmma_tflops"],
+               "roofline": {"kernel": "k_zgemm3m_tma (LU trailing update)", "bound": "tensor", "achieved": gemm_tf, "peak": peaks["dmma_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["dmma_tflops"],
                             "traffic": None, "share_of_step": acc["MS_GEMM"] / ms_dev,
                             "note": "at 1386 DOF the step is latency-bound (panel column chain, small grids), not pipe-bound: LU %.2f TFLOP/s of 8/3 n^3" % (8.0 / 3.0 * n ** 3 / (acc["MS_LU"] / nfr) / 1e9),
                             "peak_source": "FP64 tensor (DMMA) micro-benchmark measured live (mfb_measure_peaks)"},
@@ -716,7 +716,7 @@ def run_coupled(args):
                "e2e": {"value": world * 1e3 / ms_e2e, "unit": "solves/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(sum(m.cvalue.size for m3 in cp.locals for m in m3[:2]) * 16),
                        "d2h_bytes_per_step": int(16 * n + 4 * n), "api": "mfb_harpot3d_assemble / mfb_harpor3d_assemble x2, mfb_combine_columns, mfb_add_entries, mfb_zsolve, mfb_get_solution"},
                "gpu_launches": int(acc["LAUNCHES"] + acc["LU_LAUNCHES"]),
-               "roofline": {"kernel": "k_zgemm3m_minus (LU trailing update)", "bound": "tensor", "achieved": gemm_tf, "peak": peaks["dmma_tflops"], "unit": "TFLOP/s",
+               "roofline": {"kernel": "k_zgemm3m_tma (LU trailing update)", "bound": "tensor", "achieved": gemm_tf, "peak": peaks["dmma_tflops"], "unit": "TFLOP/s",
                             "frac": gemm_tf / peaks["dmma_tflops"], "traffic": None, "share_of_step": (acc["MS_GEMM"] / K) / ms_dev,
                             "peak_source": "FP64 tensor (DMMA) micro-benchmark measured live (mfb_measure_peaks)"},
                "assembly": {"ms": acc["MS_ASSEMBLE"] / K, "ms_regular": acc["MS_REGULAR"] / K, "ms_adaptive": acc["MS_ADAPTIVE"] / K, "ms_singular": acc["MS_SINGULAR"] / K},
@@ -899,13 +899,14 @@ def run_ours(args):
         gemm_tf = acc["GEMM_EXEC_FLOPS"] / max(acc["MS_GEMM"], 1e-9) / 1e9     # flops the tensor pipe executes (3M form: 6mnk)
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_zgemm3m_minus")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_zgemm3m_tma")
         except Exception:
             pass
-        roof = {"kernel": "k_zgemm3m_minus (LU trailing update, 3M complex product on DMMA.8x8x4)", "bound": "tensor", "achieved": gemm_tf, "peak": peaks["dmma_tflops"],
+        roof = {"kernel": "k_zgemm3m_tma (LU trailing update: 3M complex product on DMMA.8x8x4, operands staged by TMA)", "bound": "tensor", "achieved": gemm_tf, "peak": peaks["dmma_tflops"],
                 "unit": "TFLOP/s", "frac": gemm_tf / peaks["dmma_tflops"], "traffic": traffic,
                 "note": "achieved = EXECUTED tensor-pipe flops (6mnk: three real products per complex product) / CUDA-event time of the trailing updates "
-                        "(includes waiting for the look-ahead panel); algorithmic_tflops credits the standard 8mnk",
+                        "(includes waiting for the look-ahead panel); algorithmic_tflops credits the standard 8mnk; traffic = DRAM bytes of one ncu capture at "
+                        "M = N = 20480, K = 256 (an average trailing update), 1.115 x its algorithmic bytes (profiles/traffic.json)",
                 "algorithmic_tflops": gemm_alg_tf, "algorithmic_frac": gemm_alg_tf / peaks["dmma_tflops"],
                 "peak_source": "FP64 tensor (DMMA) micro-benchmark measured live on this GPU (mfb_measure_peaks); MEASURED_PEAKS.json carries no FP64 figure",
                 "avg_launch_ms": gemm_ms, "launches_per_step": acc["GEMM_LAUNCHES"] / K, "share_of_step": acc["MS_GEMM"] / (ms_dev if world == 1 else acc["MS_ASSEMBLE"] + acc["MS_LU"] + acc["MS_SOLVE"]),
