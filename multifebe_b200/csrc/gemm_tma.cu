@@ -32,12 +32,12 @@
 
 namespace mfbd {
 
-constexpr int GT_BM = 64, GT_BN = 32, GT_BK = 16, GT_STAGES = 3, GT_STRIP = 32;
+constexpr int GT_BM = 64, GT_BN = 32, GT_BK = 16, GT_STRIP = 32;
 constexpr int GT_BLOCK = 16 * 16 * 8;                               // one TMA box: 16 x 16 doubles
 constexpr int GT_A_PLANE = (GT_BM / 16) * GT_BLOCK;                 // 8 KB
 constexpr int GT_B_PLANE = (GT_BN / 16) * GT_BLOCK;                 // 4 KB
 constexpr int GT_STAGE_BYTES = 2 * GT_A_PLANE + 2 * GT_B_PLANE;     // 24 KB
-constexpr int GT_SMEM = GT_STAGES * GT_STAGE_BYTES + 1024 + 2 * GT_STAGES * 8;
+constexpr int gt_smem(int stages) { return stages * GT_STAGE_BYTES + 1024 + 2 * stages * 8; }
 
 __device__ __forceinline__ unsigned gt_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void gt_dmma(double& d0, double& d1, double a, double b) {
@@ -68,10 +68,13 @@ __device__ __forceinline__ void gt_tma_box(unsigned dst, const CUtensorMap* map,
 // A operand = rows [a_row0 + ..), columns [a_col0, a_col0 + K) of the planes behind tAre / tAim; B operand = rows [b_row0, b_row0 + K),
 // columns [b_col0 + ..) of the planes behind tBre / tBim (tensor maps of whole planes: rows x columns, box 16 x 16, SWIZZLE_128B).
 // K is a multiple of 16; a_row0 any row whose tiles the map covers (out-of-range rows are zero-filled by the TMA and never stored).
-__global__ void __launch_bounds__(128, 3)
+// GT_STAGES / MINB: depth of the operand ring and CTAs per SM.  (3, 3) = 12 warps per SM, (4, 2) = 8 warps per SM: the DMMA micro-benchmark with this
+// kernel's instruction mix (tools/microbench/dmma_sweep.cu, profiles/r02_dmma_sweep.log) runs 3.6 % faster with 2 or 4 warps per sub-partition than with 3.
+template <int GT_STAGES, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_zgemm3m_tma(const __grid_constant__ CUtensorMap tAre, const __grid_constant__ CUtensorMap tAim, const __grid_constant__ CUtensorMap tBre,
               const __grid_constant__ CUtensorMap tBim, int M, int N, int K, int a_row0, int a_col0, int b_row0, int b_col0, double* __restrict__ Cre,
-              double* __restrict__ Cim, long long ldc, int mt, int nt) {
+              double* __restrict__ Cim, long long ldc, int mt, int nt, int pf_dist) {
   extern __shared__ unsigned char gt_raw[];
   const unsigned raw = gt_smem_u32(gt_raw), base = (raw + 1023u) & ~1023u;      // SWIZZLE_128B atoms are 1024-byte aligned
   const unsigned bars = base + GT_STAGES * GT_STAGE_BYTES;                       // full[s] at bars + 8 s, empty[s] at bars + 8 (STAGES + s)
@@ -80,13 +83,25 @@ k_zgemm3m_tma(const __grid_constant__ CUtensorMap tAre, const __grid_constant__ 
   const int gid = lane >> 2, tig = lane & 3;
   // strip rasterisation: tiles of GT_STRIP consecutive n-tiles, m-tiles outer inside the strip
   int mtile, ntile;
-  {
-    const int t = blockIdx.x, per = GT_STRIP * mt, strip = t / per, w = t - strip * per;
+  auto tile_of = [&](int t, int& mtl, int& ntl) {
+    const int per = GT_STRIP * mt, strip = t / per, w = t - strip * per;
     const int sw = min(GT_STRIP, nt - strip * GT_STRIP);
-    mtile = w / sw; ntile = strip * GT_STRIP + (w - mtile * sw);
-  }
+    mtl = w / sw; ntl = strip * GT_STRIP + (w - mtl * sw);
+  };
+  tile_of(blockIdx.x, mtile, ntile);
   const int m0 = mtile * GT_BM, n0 = ntile * GT_BN;
   const int KT = K / GT_BK;
+  // The C tile is read once, at the start of a CTA, straight from DRAM (~1.5 us during which this CTA issues no DMMA: ~4 % of warp time in the ncu source
+  // page).  Each CTA therefore pulls into L2 the C tile of the CTA that will take its place: pf_dist tiles ahead (about the number of co-resident CTAs).
+  if (pf_dist > 0 && (int)blockIdx.x + pf_dist < mt * nt) {
+    int pm, pn; tile_of((int)blockIdx.x + pf_dist, pm, pn);
+    // 64 rows x 32 columns x 2 planes: a column of the tile is 512 bytes = 4 lines; thread -> (plane, column, line)
+    for (int q = tid; q < 2 * GT_BN * 4; q += 128) {
+      const int plane = q / (GT_BN * 4), rem = q - plane * (GT_BN * 4), col = rem >> 2, line = rem & 3;
+      const int rr = pm * GT_BM + line * 16, cc = pn * GT_BN + col;
+      if (rr < M && cc < N) asm volatile("prefetch.global.L2 [%0];" ::"l"((plane ? Cim : Cre) + (long long)cc * ldc + rr));
+    }
+  }
 
   auto issue = [&](int s, int kt) {
     const unsigned full = bars + 8u * s, st = base + (unsigned)s * GT_STAGE_BYTES;
@@ -241,7 +256,8 @@ int gemm_tma_make_maps(GemmTmaMaps& t, const double* Are, const double* Aim, lon
     return 2;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(k_zgemm3m_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM) != cudaSuccess) { cudaGetLastError(); return 3; }
+    if (cudaFuncSetAttribute(k_zgemm3m_tma<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, gt_smem(3)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_zgemm3m_tma<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gt_smem(4)) != cudaSuccess) { cudaGetLastError(); return 3; }
     attr = true;
   }
   t.ok = 1;
@@ -251,7 +267,11 @@ bool gemm_tma_usable(const GemmTmaMaps& t, int m, int n, int k) { return t.ok &&
 void zgemm_minus_planar_tma(const GemmTmaMaps& t, int m, int n, int k, int a_row0, int a_col0, int b_row0, int b_col0, double* Cre, double* Cim, long long ldc, cudaStream_t st) {
   const int mt = (m + GT_BM - 1) / GT_BM, nt = (n + GT_BN - 1) / GT_BN;
   const CUtensorMap* mp = reinterpret_cast<const CUtensorMap*>(t.m);
-  k_zgemm3m_tma<<<mt * nt, 128, GT_SMEM, st>>>(mp[0], mp[1], mp[2], mp[3], m, n, k, a_row0, a_col0, b_row0, b_col0, Cre, Cim, ldc, mt, nt);
+  static int pf = -1, cfg = -1;
+  if (pf < 0) { const char* e = getenv("MFB_GEMM_C_PREFETCH"); pf = e ? atoi(e) : 3 * 148; }
+  if (cfg < 0) { const char* e = getenv("MFB_GEMM_TMA_CFG"); cfg = e ? atoi(e) : 0; }
+  if (cfg == 1) k_zgemm3m_tma<4, 2><<<mt * nt, 128, gt_smem(4), st>>>(mp[0], mp[1], mp[2], mp[3], m, n, k, a_row0, a_col0, b_row0, b_col0, Cre, Cim, ldc, mt, nt, pf > 0 ? 2 * 148 : 0);
+  else k_zgemm3m_tma<3, 3><<<mt * nt, 128, gt_smem(3), st>>>(mp[0], mp[1], mp[2], mp[3], m, n, k, a_row0, a_col0, b_row0, b_col0, Cre, Cim, ldc, mt, nt, pf);
 }
 
 }  // namespace mfbd
