@@ -269,10 +269,14 @@ class Problem:
             self.h = C.c_void_p()
 
     # ---- seam 1: build_lse_mechanics_bem_harela(kf,kr) after A_c=0; b_c=0 ----
-    def build_lse_mechanics_bem_harela(self, omega, mat, want_host=True):
+    def build_lse_mechanics_bem_harela(self, omega, mat, want_host=True, out=None):
+        """out = (A, b): the caller's own A_c, b_c (Fortran-ordered complex128), overwritten -- what the Fortran host passes."""
         n = self.m.n_dof
         A = b = None
-        if want_host:
+        if want_host and out is not None:
+            A, b = out
+            assert A.flags.f_contiguous and A.dtype == np.complex128 and A.shape == (n, n) and b.dtype == np.complex128
+        elif want_host:
             A = np.zeros((n, n), dtype=np.complex128, order="F")
             b = np.zeros(n, dtype=np.complex128)
         _check(lib().mfb_harela3d_assemble(self.h, C.c_double(omega), _p(_z(mat.lam)), _p(_z(mat.mu)), C.c_double(mat.rho),

@@ -1440,7 +1440,16 @@ int zgetrf_dist(DistLU& D) {
     R.w.launches += launch_trsm_ext(Pre, Pim, mp, Bre, Bim, lda, nbw, c1 - c0, R.main);
     const int mrest = (int)m - nbw;
     if (mrest > 0) {
-      zgemm_minus_planar(mrest, c1 - c0, nbw, Pre + nbw, Pim + nbw, mp, Bre, Bim, lda, Bre + nbw, Bim + nbw, lda, R.main);
+      // TMA kernel (gemm_tma.cu): A from the packed panel (its leading dimension changes with the step, so its two maps are encoded per call: host work of a
+      // microsecond), B and C from the local columns.  Besides the faster kernel this removes the re-reads of the A panel: with the old tile order every rank
+      // streamed the whole 123 MB panel once per 32-column tile of its local columns.
+      GemmTmaMaps tm; tm.ok = 0;
+      if (gemm_cfg() == 15 && (nbw % 16) == 0)
+        gemm_tma_make_maps(tm, Pre, Pim, mp, (int)m, nbw, R.Lre, R.Lim, lda, n, R.ncl + 1);
+      if (gemm_tma_usable(tm, mrest, c1 - c0, nbw))
+        zgemm_minus_planar_tma(tm, mrest, c1 - c0, nbw, nbw, 0, k0, c0, Bre + nbw, Bim + nbw, lda, R.main);
+      else
+        zgemm_minus_planar(mrest, c1 - c0, nbw, Pre + nbw, Pim + nbw, mp, Bre, Bim, lda, Bre + nbw, Bim + nbw, lda, R.main);
       R.w.launches++; R.gemm_flops += 8.0 * (double)mrest * (double)(c1 - c0) * (double)nbw;
     }
   };

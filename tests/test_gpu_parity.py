@@ -439,3 +439,54 @@ def test_nan_input_and_state_misuse_do_not_fault_the_device(gpu_ctx):
     with pytest.raises(capi.MfbError):                           # real factors (static path) are not accepted by the complex solve
         pr.solve_static(Material(1.0, 1.0, 0.25, 0.0)); pr.solve_lse_c(None, b, factorize=False)
     pr.close()
+
+
+def test_full_size_singular_and_near_entries_30k_dof(gpu_ctx, oracle_lib):
+    """at the full 30258-DOF size the spot checks skipped every incident element.  Here the 3 x 3 blocks A[rows(sn), cols(j)] are compared
+    for j ON the elements of the collocation node and on their neighbours -- singular pairs, the quasi-singular pairs of the MCA points (0.05 h from the
+    neighbouring elements) and the free terms (1/2 delta at a smooth nodal point, phi_j(xi_i)/2 delta at an MCA point) -- for nodal and rim nodes."""
+    from multifebe_b200 import capi
+    md = Model(cube_mesh(40, shape.TRI3), cube_bcs())
+    mat = Material(1.0, 1.0, 0.25, 0.03)
+    omega = 9.0
+    pr = capi.Problem(gpu_ctx, md)
+    pr.build_lse_mechanics_bem_harela(omega, mat, want_host=False)
+    o = oracle_lib.Oracle(md)
+    node_elems = {}
+    for e, c in enumerate(md.mesh.conn):
+        for kn, v in enumerate(c):
+            node_elems.setdefault(int(v), []).append((e, kn))
+    colloc_of_node = {}
+    for c in range(md.n_colloc):
+        colloc_of_node.setdefault(int(md.colloc_node[c]), []).append(c)
+    rng = np.random.default_rng(23)
+    rim = np.flatnonzero(md.in_boundary); inner = np.flatnonzero(~md.in_boundary)
+    picks = [int(v) for v in rng.choice(inner, 8, replace=False)] + [int(v) for v in rng.choice(rim, 8, replace=False)]
+    rows, cols, expect, kinds = [], [], [], set()
+    for sn in picks:
+        own = sorted(set(e for e, _ in node_elems[sn]))
+        ring1 = sorted(set(int(v) for e in own for v in md.mesh.conn[e]))                                   # nodes of the incident elements (sn included)
+        ring2 = sorted(set(int(v) for j in ring1 for e, _ in node_elems[j] for v in md.mesh.conn[e]) - set(ring1))[:6]
+        for j in ring1 + ring2:
+            blk = np.zeros((3, 3), dtype=complex)
+            for c in colloc_of_node[sn]:
+                for e, kn in node_elems[j]:
+                    h, g, mode, _ = o.pair(e, md.colloc_x[c], omega, mat)
+                    kinds.add(int(mode) if mode in (100, 200) else 0)
+                    if md.in_boundary[sn] and e == int(md.colloc_elem[c]):                                   # MCA point inside element e: free term phi_j(xi_i) / 2
+                        h = h.copy(); h[kn] += 0.5 * shape.phi(int(md.etype[e]), md.colloc_xi[c])[kn] * np.eye(3)
+                    for k in range(3):
+                        blk[:, k] += (-g[kn, :, k]) if md.ctype[j, k] == 0 else h[kn, :, k]
+            if j == sn and not md.in_boundary[sn]:                                                           # smooth nodal point: c = I / 2
+                for k in range(3):
+                    if md.ctype[j, k] == 1:
+                        blk[k, k] += 0.5
+            for l in range(3):
+                for k in range(3):
+                    rows.append(md.row[sn, l]); cols.append(md.col_t[j, k] if md.ctype[j, k] == 0 else md.col_u[j, k]); expect.append(blk[l, k])
+    got = pr.get_entries(rows, cols)
+    expect = np.array(expect)
+    assert kinds == {0, 100, 200} and len(expect) > 1500                                                     # regular, quasi-singular and singular pairs all met
+    scale = np.abs(expect).reshape(-1, 9).max(axis=1).repeat(9)
+    assert (np.abs(got - expect) / scale).max() < TOL_A
+    pr.close()
