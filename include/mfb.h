@@ -81,6 +81,25 @@ int mfb_harela3d_setup_hbie(mfb_ctx* ctx, int n_node, const double* node_x, int 
                             const double* colloc_n, const int* row, const int* col_u, const int* col_t, const int* ctype, int n_dof,
                             double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
                             double geometric_tolerance, mfb_problem** problem);
+/* The set-up of a region with SYMMETRY PLANES (the reference's [symmetry planes] section, src/read_symmetry_planes.f90:76-283; image loop
+ * build_lse_mechanics_bem_harela.f90:1098-1107 with the multipliers of fbem_symmetry_multipliers, lib/fbem/src/symmetry.f90:60-171).
+ * Only a half, quarter or octant of the boundary is meshed; every element is integrated 2, 4 or 8 times -- itself and its mirror images,
+ * whose contributions take the sign symconf_t(k) on the columns of dof k and land on the columns of the root element.
+ *   n_symplanes = 0..3; symplane_eid[i] = axis the plane is normal to (1 = x: plane_n1 / plane_yz, 2 = y: plane_n2 / plane_zx,
+ *   3 = z: plane_n3 / plane_xy), ascending, all planes through the origin; symplane_t[3*i+k] = symplane_t(k,i): "symmetry" = -1 on the
+ *   normal axis and +1 on the others, "antisymmetry" = the opposite signs.
+ *   colloc_n = NULL for the displacement equation, or the unit normals of the hypersingular equation (interior points, as _setup_hbie).
+ * As in the reference the far test of an image uses the bounding ball of the ROOT element (the calculation element's bball_centre is not
+ * reflected), and a nodal collocation point lying in one or two planes gets its free term from the fan of elements completed with
+ * their mirror images (:496-555).  mfb_plan_modes addresses image ks of element r as element ks*n_elem + r (ks in the step order of
+ * fbem_symmetry_multipliers: 1 = plane 1, 2 = planes 1+2, 3 = plane 2, 4 = plane 3, 5 = 1+3, 6 = 1+2+3, 7 = 2+3). */
+int mfb_harela3d_setup_sym(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
+                           const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
+                           const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
+                           const double* colloc_n, const int* row, const int* col_u, const int* col_t, const int* ctype, int n_dof,
+                           double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
+                           double geometric_tolerance, int n_symplanes, const int* symplane_eid, const double* symplane_t,
+                           mfb_problem** problem);
 void mfb_problem_free(mfb_problem* problem);
 
 /* Once per frequency.  == `A_c=0; b_c=0` + build_lse_mechanics_bem_harela(kf,kr) for one elastic BE region with

@@ -248,6 +248,16 @@ class Problem:
                 C.c_int(m.n_colloc), _p(k[5]), _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9]), _p(k[10]), _p(k[11]), _p(k[12]), _p(k[13]),
                 C.c_int(m.n_dof), C.c_double(m.qsi_relative_error), C.c_int(m.qsi_ns_max), C.c_int(len(m.precalset_gln)), _p(k[14]),
                 C.c_double(m.geometric_tolerance), C.byref(self.h)))
+        elif len(getattr(m, "symplane_eid", ())) > 0:   # [symmetry planes]: every element is integrated with its mirror images
+            if cn is not None:
+                cn = np.ascontiguousarray(cn, dtype=np.float64); k.append(cn)
+            eid = np.ascontiguousarray(m.symplane_eid, dtype=np.int32); st = np.ascontiguousarray(m.symplane_t, dtype=np.float64); k += [eid, st]
+            _check(lib().mfb_harela3d_setup_sym(
+                ctx.h, C.c_int(m.n_node), _p(k[0]), C.c_int(m.n_elem), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]),
+                C.c_int(m.n_colloc), _p(k[5]), _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9]), _p(cn) if cn is not None else None,
+                _p(k[10]), _p(k[11]), _p(k[12]), _p(k[13]),
+                C.c_int(m.n_dof), C.c_double(m.qsi_relative_error), C.c_int(m.qsi_ns_max), C.c_int(len(m.precalset_gln)), _p(k[14]),
+                C.c_double(m.geometric_tolerance), C.c_int(len(eid)), _p(eid), _p(st), C.byref(self.h)))
         elif cn is None:
             _check(lib().mfb_harela3d_setup(
                 ctx.h, C.c_int(m.n_node), _p(k[0]), C.c_int(m.n_elem), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]),

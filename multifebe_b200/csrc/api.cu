@@ -187,13 +187,16 @@ static unsigned morton3(const double* x, const double* lo, double inv_ext) {
 
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+// Symmetry planes through the origin (src/read_symmetry_planes.f90:76-283): plane i is normal to axis eid[i] (1..3, ascending) and multiplies
+// the translation dof k of a reflected element by t[3*i+k] (symmetry: -1 on the normal axis, +1 elsewhere; antisymmetry: the opposite)
+struct SymSpec { int n_planes; int eid[3]; double t[9]; };
 static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
                       const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
                       const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
                       const int* row, const int* col_u, const int* col_t, const int* ctype, int n_dof,
                       double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
                       double geometric_tolerance, const double* colloc_n /* NULL, or 3 per collocation point: hypersingular equation */,
-                      int ndof /* 3: elastic solid, 1: inviscid fluid */, mfb_problem** out);
+                      int ndof /* 3: elastic solid, 1: inviscid fluid */, mfb_problem** out, const SymSpec* sym = nullptr);
 extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
                                   const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
                                   const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
@@ -202,6 +205,21 @@ extern "C" int mfb_harela3d_setup(mfb_ctx* ctx, int n_node, const double* node_x
                                   double geometric_tolerance, mfb_problem** out) {
   return setup_impl(ctx, n_node, node_x, n_elem, etype, elem_ptr, elem_node, elem_reversed, n_colloc, colloc_x, colloc_node, colloc_elem, colloc_kn, colloc_xi,
                     row, col_u, col_t, ctype, n_dof, qsi_relative_error, qsi_ns_max, n_precalsets, precalset_gln, geometric_tolerance, nullptr, 3, out);
+}
+// The same with symmetry planes: the reference's [symmetry planes] section (src/read_symmetry_planes.f90) -- up to three planes through the origin,
+// normal to the axes symplane_eid[i] (1 = x, 2 = y, 3 = z, ascending), symplane_t[3*i+k] = multiplier of translation dof k across plane i.
+// colloc_n may be NULL (displacement equation) or the unit normals of the hypersingular equation at interior points.
+extern "C" int mfb_harela3d_setup_sym(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
+                                      const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
+                                      const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi, const double* colloc_n,
+                                      const int* row, const int* col_u, const int* col_t, const int* ctype, int n_dof,
+                                      double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
+                                      double geometric_tolerance, int n_symplanes, const int* symplane_eid, const double* symplane_t, mfb_problem** out) {
+  if (n_symplanes < 0 || n_symplanes > 3 || (n_symplanes > 0 && (!symplane_eid || !symplane_t))) return fail(MFB_ERR_ARG, "mfb_harela3d_setup_sym: invalid symmetry planes");
+  SymSpec sp; sp.n_planes = n_symplanes;
+  for (int i = 0; i < n_symplanes; i++) { sp.eid[i] = symplane_eid[i]; for (int k = 0; k < 3; k++) sp.t[3 * i + k] = symplane_t[3 * i + k]; }
+  return setup_impl(ctx, n_node, node_x, n_elem, etype, elem_ptr, elem_node, elem_reversed, n_colloc, colloc_x, colloc_node, colloc_elem, colloc_kn, colloc_xi,
+                    row, col_u, col_t, ctype, n_dof, qsi_relative_error, qsi_ns_max, n_precalsets, precalset_gln, geometric_tolerance, colloc_n, 3, out, &sp);
 }
 // Hypersingular equation for points OFF the boundary (interior-point stresses): fbem_bem_harela3d_hbie_auto with its exterior
 // branches (_ext_pre :2573-2662, _ext_adp :3044-3167); colloc_n[3*n_colloc] = unit normal n_i of each collocation point.
@@ -220,7 +238,7 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
                       const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
                       const int* row, const int* col_u, const int* col_t, const int* ctype, int n_dof,
                       double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
-                      double geometric_tolerance, const double* colloc_n, int ndof, mfb_problem** out) {
+                      double geometric_tolerance, const double* colloc_n, int ndof, mfb_problem** out, const SymSpec* sym) {
   if (!ctx || !out || !node_x || !etype || !elem_ptr || !elem_node || !colloc_x || !colloc_node || !colloc_elem || !colloc_kn || !colloc_xi ||
       !row || !col_u || !col_t || !ctype || !precalset_gln)
     return fail(MFB_ERR_ARG, "mfb_harela3d_setup: null argument");
@@ -234,6 +252,47 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
   for (int i = 0; i < ndof * n_node; i++)
     if (ctype[i] != 0 && ctype[i] != 1) return fail(MFB_ERR_UNSUPPORTED, "mfb_harela3d_setup: only ctype 0 (u / p known) and 1 (t / Un known) are supported");
   double t_host0 = now_ms();
+  // ---- symmetry images (lib/fbem/src/symmetry.f90:60-171; image loop build_lse_mechanics_bem_harela.f90:1098-1107) ----
+  // Every root element gets n_sym - 1 image elements: element ks * n_root + r is image ks of root r, with the root's nodes (hence its columns and
+  // prescribed values), reflected coordinates, the orientation flipped by an odd number of reflections, and the sign symconf_t(k) on its dof-k
+  // columns (bits 5-7 of einfo).  From here on an image is an element like any other: the classifier, the planner and K1/K2/K3 never know.
+  const int n_root = n_elem;
+  int n_sym = 1;
+  double conf_m[8][3], conf_t[8][3]; bool conf_rev[8];
+  for (int ks = 0; ks < 8; ks++) { conf_rev[ks] = false; for (int c = 0; c < 3; c++) { conf_m[ks][c] = 1.0; conf_t[ks][c] = 1.0; } }
+  double plane_m[3][3] = {{1, 1, 1}, {1, 1, 1}, {1, 1, 1}};
+  std::vector<int> x_etype, x_ptr, x_node; std::vector<unsigned char> x_rev;
+  if (sym && sym->n_planes > 0) {
+    if (sym->n_planes > 3) return fail(MFB_ERR_ARG, "setup: at most three symmetry planes");
+    if (ndof != 3) return fail(MFB_ERR_UNSUPPORTED, "setup: symmetry planes are built for elastic regions only");
+    for (int i = 0; i < sym->n_planes; i++) {
+      if (sym->eid[i] < 1 || sym->eid[i] > 3 || (i > 0 && sym->eid[i] <= sym->eid[i - 1])) return fail(MFB_ERR_ARG, "setup: symmetry plane axes must be 1..3 in ascending order");
+      for (int c = 0; c < 3; c++) {
+        if (fabs(sym->t[3 * i + c]) != 1.0) return fail(MFB_ERR_ARG, "setup: symmetry multipliers must be +1 or -1");
+        plane_m[i][c] = (c == sym->eid[i] - 1) ? -1.0 : 1.0;
+      }
+    }
+    n_sym = 1 << sym->n_planes;
+    if ((long long)n_root * n_sym > 0x7fffffffLL / 64) return fail(MFB_ERR_ARG, "setup: too many elements");
+    static const int steps[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};   // fbem_symmetry_multipliers :81-170
+    for (int ks = 0; ks < n_sym; ks++) {
+      int cnt = 0;
+      for (int i = 0; i < sym->n_planes; i++) if (steps[ks][i]) { cnt++; for (int c = 0; c < 3; c++) { conf_m[ks][c] *= plane_m[i][c]; conf_t[ks][c] *= sym->t[3 * i + c]; } }
+      conf_rev[ks] = (cnt & 1) != 0;
+    }
+    const int nen = elem_ptr[n_root];
+    x_etype.resize((size_t)n_root * n_sym); x_rev.resize((size_t)n_root * n_sym); x_ptr.resize((size_t)n_root * n_sym + 1); x_node.resize((size_t)nen * n_sym);
+    for (int ks = 0; ks < n_sym; ks++) {
+      for (int r = 0; r < n_root; r++) {
+        const size_t e = (size_t)ks * n_root + r;
+        x_etype[e] = etype[r]; x_ptr[e] = ks * nen + elem_ptr[r];
+        x_rev[e] = (unsigned char)(((elem_reversed && elem_reversed[r]) != conf_rev[ks]) ? 1 : 0);
+      }
+      for (int q = 0; q < nen; q++) x_node[(size_t)ks * nen + q] = elem_node[q];
+    }
+    x_ptr[(size_t)n_root * n_sym] = n_sym * nen;
+    etype = x_etype.data(); elem_ptr = x_ptr.data(); elem_node = x_node.data(); elem_reversed = x_rev.data(); n_elem = n_root * n_sym;
+  }
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   mfb_problem* p = new mfb_problem();
@@ -257,8 +316,15 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
   for (int e = 0; e < n_elem; e++) {
     mfbh::Elem& el = p->elems[e];
     el.et = etype[e]; el.nn = mfbh::nodes_of(el.et); el.reversed = elem_reversed && elem_reversed[e];
-    for (int k = 0; k < el.nn; k++) for (int c = 0; c < 3; c++) el.x[3 * k + c] = node_x[3 * (size_t)elem_node[elem_ptr[e] + k] + c];
+    const double* cm = conf_m[e / n_root];
+    for (int k = 0; k < el.nn; k++) for (int c = 0; c < 3; c++) el.x[3 * k + c] = cm[c] * node_x[3 * (size_t)elem_node[elem_ptr[e] + k] + c];
     mfbh::element_data(el, S);
+  }
+  // the reference reflects the nodal coordinates of the calculation element only: csize, n_phi and the bounding ball -- its CENTRE included -- stay
+  // those of the root element (build_lse_mechanics_bem_harela.f90:1052-1069 set them once, :1103-1105 touch x alone), and they feed the far test
+  for (int e = n_root; e < n_elem; e++) {
+    mfbh::Elem& el = p->elems[e]; const mfbh::Elem& ro = p->elems[e % n_root];
+    el.cl = ro.cl; el.gln_far = ro.gln_far; el.br = ro.br; for (int c = 0; c < 3; c++) el.bc[c] = ro.bc[c];
   }
   // ---- bounding box of the mesh (Morton keys) ----
   double bb_lo[3] = {1e300, 1e300, 1e300}, bb_hi[3] = {-1e300, -1e300, -1e300};
@@ -416,6 +482,7 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
       int e = g.elem_ids[i]; const mfbh::Elem& el = p->elems[e];
       {
         unsigned info = 8u | (el.reversed ? 16u : 0u);
+        for (int k = 0; k < 3; k++) if (conf_t[e / n_root][k] < 0.0) info |= 32u << k;
         for (int k = 0; k < ndof; k++) {
           const int ct0 = ctype[ndof * elem_node[elem_ptr[e]] + k];
           for (int j = 1; j < g.nn; j++) if (ctype[ndof * elem_node[elem_ptr[e] + j] + k] != ct0) info &= ~8u;
@@ -565,16 +632,16 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
   {
     // node -> (element, local node) incidences
     std::vector<int> cnt(n_node + 1, 0);
-    for (int e = 0; e < n_elem; e++) for (int k = elem_ptr[e]; k < elem_ptr[e + 1]; k++) cnt[elem_node[k] + 1]++;
+    for (int e = 0; e < n_root; e++) for (int k = elem_ptr[e]; k < elem_ptr[e + 1]; k++) cnt[elem_node[k] + 1]++;
     for (int i = 0; i < n_node; i++) cnt[i + 1] += cnt[i];
     std::vector<int> n2e(cnt[n_node]), n2k(cnt[n_node]), pos(cnt.begin(), cnt.end() - 1);
-    for (int e = 0; e < n_elem; e++) for (int k = elem_ptr[e]; k < elem_ptr[e + 1]; k++) { int nd = elem_node[k]; n2e[pos[nd]] = e; n2k[pos[nd]] = k - elem_ptr[e]; pos[nd]++; }
+    for (int e = 0; e < n_root; e++) for (int k = elem_ptr[e]; k < elem_ptr[e + 1]; k++) { int nd = elem_node[k]; n2e[pos[nd]] = e; n2k[pos[nd]] = k - elem_ptr[e]; pos[nd]++; }
     std::vector<int> f_cpos, f_slot, f_jk, f_l; std::vector<double> f_val;
     std::vector<int> f0_cpos, f0_slot, f0_jk, f0_l; std::vector<double> f0_val;      // poroelastic fluid phase: value = beta * J
     for (int c = 0; c < n_colloc; c++) {
       int e = colloc_elem[c], kn = colloc_kn[c], sn = colloc_node[c];
       if (e == -1) continue;   // a point off the boundary (interior point of the region): Somigliana's identity has no free term there
-      if (e < 0 || e >= n_elem || kn < 0 || kn >= p->elems[e].nn) { mfb_problem_free(p); return fail(MFB_ERR_ARG, "mfb_harela3d_setup: invalid colloc_elem/colloc_kn"); }
+      if (e < 0 || e >= n_root || kn < 0 || kn >= p->elems[e].nn) { mfb_problem_free(p); return fail(MFB_ERR_ARG, "mfb_harela3d_setup: invalid colloc_elem/colloc_kn"); }
       const mfbh::Elem& el = p->elems[e];
       int cpos = p->cpos_of_colloc[c], slot = p->slot_of_elem[e];
       bool mca = !(colloc_xi[2 * c] == -9.0 && colloc_xi[2 * c + 1] == -9.0);
@@ -583,9 +650,29 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
         double cp = 0.5, sum_b[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         if (mfbh::xi_on_element_boundary(el.et, xi_i)) {
           int b0 = cnt[sn], ne = cnt[sn + 1] - b0;
-          std::vector<double> ns(3 * ne), ts(3 * ne);
-          for (int k = 0; k < ne; k++) { const mfbh::Elem& ee = p->elems[n2e[b0 + k]]; mfbh::node_normal_tangent(ee.et, ee.x, n2k[b0 + k], el.reversed, &ns[3 * k], &ts[3 * k]); }
-          if (mfbh::mantic_terms(ne, ns.data(), ts.data(), geometric_tolerance, &cp, sum_b)) { mfb_problem_free(p); return fail(2, "mfb_harela3d_setup: the normals/tangents configuration is not valid (free term)"); }
+          // planes that contain the node (fbem_node_symplanes_connectivity, lib/fbem/src/data_structures.f90:1116-1153): the fan of elements around it is
+          // completed with the mirrored normals and tangents (build_lse_mechanics_bem_harela.f90:496-555; a single reflection takes the tangent of the
+          // opposite orientation, a double one keeps it)
+          int planes[3], npl = 0;
+          if (sym) for (int i = 0; i < sym->n_planes; i++) if (fabs(node_x[3 * (size_t)sn + sym->eid[i] - 1]) <= geometric_tolerance) planes[npl++] = i;
+          if (npl > 2) { mfb_problem_free(p); return fail(MFB_ERR_UNSUPPORTED, "mfb_harela3d_setup: a nodal collocation point lies in three symmetry planes"); }
+          const int fan = ne << npl;
+          std::vector<double> ns(3 * fan), ts(3 * fan), tr(3 * ne), nr(3);
+          for (int k = 0; k < ne; k++) {
+            const mfbh::Elem& ee = p->elems[n2e[b0 + k]];
+            mfbh::node_normal_tangent(ee.et, ee.x, n2k[b0 + k], el.reversed, &ns[3 * k], &ts[3 * k]);
+            if (npl) mfbh::node_normal_tangent(ee.et, ee.x, n2k[b0 + k], !el.reversed, nr.data(), &tr[3 * k]);
+          }
+          for (int k = 0; k < ne && npl; k++) for (int cc = 0; cc < 3; cc++) {
+            const double m1 = plane_m[planes[0]][cc];
+            ns[3 * (k + ne) + cc] = m1 * ns[3 * k + cc]; ts[3 * (k + ne) + cc] = m1 * tr[3 * k + cc];
+            if (npl == 2) {
+              const double m2 = plane_m[planes[1]][cc];
+              ns[3 * (k + 2 * ne) + cc] = m1 * m2 * ns[3 * k + cc]; ts[3 * (k + 2 * ne) + cc] = m1 * m2 * ts[3 * k + cc];
+              ns[3 * (k + 3 * ne) + cc] = m2 * ns[3 * k + cc]; ts[3 * (k + 3 * ne) + cc] = m2 * tr[3 * k + cc];
+            }
+          }
+          if (mfbh::mantic_terms(fan, ns.data(), ts.data(), geometric_tolerance, &cp, sum_b)) { mfb_problem_free(p); return fail(2, "mfb_harela3d_setup: the normals/tangents configuration is not valid (free term)"); }
         }
         if (ndof == 4) {   // c(0,0) = J c_pot, c(1:3,1:3) = Mantic's matrix of the drained skeleton (build_lse_mechanics_bem_harpor.f90:583-615)
           f0_cpos.push_back(cpos); f0_slot.push_back(slot); f0_jk.push_back(kn * 4); f0_l.push_back(0); f0_val.push_back(0.0); f0_val.push_back(cp);

@@ -94,7 +94,8 @@ __global__ void k_gather_cv(DevGroup g, const double* __restrict__ cvalue) {
   for (int j = 0; j < g.nn; j++) {
     const int node = g.enode[e * g.nn + j];
     for (int k = 0; k < nd; k++) {
-      const double vr = cvalue[2 * (nd * (size_t)node + k)], vi = cvalue[2 * (nd * (size_t)node + k) + 1];
+      double vr = cvalue[2 * (nd * (size_t)node + k)], vi = cvalue[2 * (nd * (size_t)node + k) + 1];
+      if (k < 3 && ((g.einfo[e] >> (5 + k)) & 1u)) { vr = -vr; vi = -vi; }   // symmetry image: symconf_t(k) = -1 (the b term carries it through the value)
       const size_t i = (size_t)e * nd * g.nn + j * nd + k;
       g.ecv[2 * i] = vr; g.ecv[2 * i + 1] = vi;
       nz = nz || vr != 0.0 || vi != 0.0;
@@ -118,7 +119,8 @@ void launch_gather_cv(const DevGroup& g, const double* cvalue, cudaStream_t st) 
 template <int NN, int NL, class Pred>
 __device__ __forceinline__ void scatter_pair(const Acc<NN, NL>& a, const int* __restrict__ ecol, const unsigned char* __restrict__ ekind,
                                              const double* __restrict__ ecv, bool rev, const DevSystem& s, int il,
-                                             int r0, int r1, int r2, double* bre, double* bim, Pred mine, const KParams& c_kp, bool hbie = false) {
+                                             int r0, int r1, int r2, double* bre, double* bim, Pred mine, const KParams& c_kp, bool hbie = false,
+                                             unsigned symbits = 0u /* bit k: symconf_t(k) = -1 of a symmetry image (ecv already carries it) */) {
   // h (or m of the hypersingular equation) is scaled by cte_t (cte_s) and changes sign on a reversed element; g (l) by cte_u (cte_d)
   const cplx ch0 = hbie ? c_kp.cte_s : mk(c_kp.cte_t, 0.0);
   const cplx ch = rev ? mk(-ch0.re, -ch0.im) : ch0;
@@ -144,6 +146,7 @@ __device__ __forceinline__ void scatter_pair(const Acc<NN, NL>& a, const int* __
         double ar, ai, br, bi;
         if (kind == 0) { ar = -gr; ai = -gi; br = -(hr * cvr - hi * cvi); bi = -(hr * cvi + hi * cvr); }
         else { ar = hr; ai = hi; br = gr * cvr - gi * cvi; bi = gr * cvi + gi * cvr; }
+        if ((symbits >> k) & 1u) { ar = -ar; ai = -ai; }
         atomicAdd(Ar + row, ar);
         atomicAdd(Ai + row, ai);
         bre[l] += br; bim[l] += bi;
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_regular(DevGroup g, DevColloc
             if (HB) accumulate_exterior_hbie<NN, NL>(acc, c_kp, x, n, xc, ni, w, il);
             else accumulate_exterior<NN, NL>(acc, c_kp, x, n, xc, w, il);
           }
-          scatter_pair<NN, NL>(acc, ecol, ekind, ecv, rev, s, il, r0, r1, r2, bre, bim, AllEntries(), c_kp, HB);
+          scatter_pair<NN, NL>(acc, ecol, ekind, ecv, rev, s, il, r0, r1, r2, bre, bim, AllEntries(), c_kp, HB, (unsigned)g.einfo[e] >> 5);
         }
       }
     }
@@ -527,6 +530,16 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
               kc[192] = ks.T2.re; kc[224] = ks.T2.im; kc[256] = ks.T3.re; kc[288] = ks.T3.im;
             }
           }
+          if (info & 0xE0u) {   // symmetry image (build_lse_mechanics_bem_harela.f90:1203-1206): h(:,:,k), g(:,:,k) times symconf_t(k); b took it through ecv
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+              if ((info >> (5 + k)) & 1u) {
+#pragma unroll
+                for (int l = 0; l < 3; l++)
+#pragma unroll
+                  for (int j = 0; j < NW; j++) { acc.re[(l * 3 + k) * NW + j] = -acc.re[(l * 3 + k) * NW + j]; if (!ST) acc.im[(l * 3 + k) * NW + j] = -acc.im[(l * 3 + k) * NW + j]; }
+              }
+          }
         }
         // ---- flush of the chunk ----
         if (inplace && nbytes > 0) {
@@ -763,7 +776,7 @@ __global__ void __launch_bounds__(128) k_adaptive(DevGroup g, DevColloc c, DevSy
     warp_reduce<NN, NL>(acc);
     LaneEntries le; le.lane = lane;
     scatter_pair<NN, NL>(acc, g.ecol + (size_t)e * 3 * NN, g.ekind + (size_t)e * 3 * NN, g.ecv + (size_t)e * 6 * NN, g.erev[e] != 0, s, il,
-                         r0, r1, r2, bre, bim, le, c_kp, HB);
+                         r0, r1, r2, bre, bim, le, c_kp, HB, (unsigned)g.einfo[e] >> 5);
   }
   flush_b(s, r0, r1, r2, bre, bim);
 }
@@ -844,7 +857,7 @@ __global__ void __launch_bounds__(128) k_singular(DevGroup g, DevColloc c, DevSy
     }
     LaneEntries le; le.lane = lane;
     scatter_pair<NN, NL>(acc, g.ecol + (size_t)e * 3 * NN, g.ekind + (size_t)e * 3 * NN, g.ecv + (size_t)e * 6 * NN, g.erev[e] != 0, s, il,
-                         r0, r1, r2, bre, bim, le, c_kp);
+                         r0, r1, r2, bre, bim, le, c_kp, false, (unsigned)g.einfo[e] >> 5);
   }
   flush_b(s, r0, r1, r2, bre, bim);
 }

@@ -172,3 +172,36 @@ def halfspace_patch(m, etype=TRI3, L=1.0, footing=0.25):
     remap = {v: i for i, v in enumerate(ref)}
     conn = [[remap[int(v)] for v in c] for c in conn]
     return Mesh(np.array(nodes)[ref], et, pt, conn)
+
+
+_REVERSED_ORDER = {TRI3: [0, 2, 1], TRI6: [0, 2, 1, 5, 4, 3], QUAD4: [0, 3, 2, 1], QUAD8: [0, 3, 2, 1, 7, 6, 5, 4], QUAD9: [0, 3, 2, 1, 7, 6, 5, 4, 8]}
+
+
+def without_parts(mesh, parts):
+    """The mesh without the elements of the given parts (and without the nodes only they use)."""
+    keep = [e for e in range(mesh.n_elem) if int(mesh.part[e]) not in parts]
+    used = sorted(set(int(v) for e in keep for v in mesh.conn[e]))
+    new = {v: i for i, v in enumerate(used)}
+    return Mesh(mesh.nodes[used], [mesh.etype[e] for e in keep], [mesh.part[e] for e in keep], [[new[int(v)] for v in mesh.conn[e]] for e in keep])
+
+
+def mirror_mesh(mesh, axis, part_offset=100, tol=1e-9):
+    """The union of `mesh` and its mirror image across the plane through the origin normal to `axis` (0, 1, 2): the FULL model that a
+    half model with a [symmetry planes] entry stands for.  Nodes lying in the plane are shared by both halves (the open edge there
+    closes); a mirrored element lists its nodes in the reversed order, so that its normal stays outward.  A part that touches the
+    plane keeps its id on both sides (one boundary crossing the plane), any other mirrored part gets id + part_offset.
+    Returns (full mesh, image_of_node: index of every original node's mirror node in the full mesh)."""
+    n = len(mesh.nodes)
+    on_plane = np.abs(mesh.nodes[:, axis]) <= tol
+    image = np.arange(n)
+    extra = np.flatnonzero(~on_plane)
+    image[extra] = n + np.arange(len(extra))
+    mirrored = mesh.nodes[extra].copy(); mirrored[:, axis] *= -1.0
+    nodes = np.vstack([mesh.nodes, mirrored])
+    touching = set(int(mesh.part[e]) for e in range(mesh.n_elem) if on_plane[mesh.conn[e]].any())
+    et, pt, conn = list(mesh.etype), list(mesh.part), [list(c) for c in mesh.conn]
+    for e in range(mesh.n_elem):
+        t, p = int(mesh.etype[e]), int(mesh.part[e])
+        et.append(t); pt.append(p if p in touching else p + part_offset)
+        conn.append([int(image[mesh.conn[e][k]]) for k in _REVERSED_ORDER[t]])
+    return Mesh(nodes, et, pt, conn), image

@@ -25,13 +25,36 @@ class Material:
         self.c2 = np.sqrt(self.mu / self.rho)
 
 
+def symmetry_planes(symmetry):
+    """[(axis, kind), ...] -> (symplane_eid int32[n], symplane_t float64[n,3]) in the reference's internal order (x, y, z):
+    symmetry: t = -1 on the normal axis, +1 on the others; antisymmetry: the opposite signs (read_symmetry_planes.f90:160-228)."""
+    planes = {}
+    for axis, kind in (symmetry or ()):
+        ax = {"x": 1, "y": 2, "z": 3, 1: 1, 2: 2, 3: 3}[axis]
+        if ax in planes:
+            raise ValueError("symmetry plane %r given twice" % (axis,))
+        sgn = {"symmetry": 1.0, "antisymmetry": -1.0}[kind]
+        t = np.full(3, sgn); t[ax - 1] = -sgn
+        planes[ax] = t
+    eid = np.array(sorted(planes), dtype=np.int32)
+    t = np.ascontiguousarray([planes[a] for a in sorted(planes)], dtype=np.float64).reshape(len(eid), 3)
+    return eid, t
+
+
 class Model:
     """bcs: {part_id: ([ctype_x, ctype_y, ctype_z], [value_x, value_y, value_z])}, ctype 0 = u known, 1 = t known.
     ndof = equations / unknowns per node: 3 for an elastic solid region, 1 for an inviscid fluid region (FluidModel)."""
 
     def __init__(self, mesh, bcs, reversed_parts=(), qsi_relative_error=1e-6, qsi_ns_max=16,
-                 precalset_gln=(2, 3, 4, 5, 6, 7, 8, 9), geometric_tolerance=1e-6, ndof=3, part_order=None):
+                 precalset_gln=(2, 3, 4, 5, 6, 7, 8, 9), geometric_tolerance=1e-6, ndof=3, part_order=None,
+                 symmetry=None, nodal_on_symplanes=False):
+        """symmetry: the [symmetry planes] section (src/read_symmetry_planes.f90:76-283) as a list of (axis, kind), axis 'x' | 'y' | 'z'
+        (plane_n1 / plane_n2 / plane_n3: the plane through the origin normal to that axis), kind 'symmetry' | 'antisymmetry'.
+        nodal_on_symplanes: open edges that lie in a symmetry plane do not make their nodes boundary-of-the-boundary nodes, so those nodes
+        keep the nodal SBIE (what a user of the reference selects in [bem formulation over nodes]; by default the reference gives them the
+        SBIE with MCA like any other rim node, assign_default_bem_formulation.f90:85-92)."""
         self.mesh = mesh
+        self.symplane_eid, self.symplane_t = symmetry_planes(symmetry)
         self.ndof = nd = int(ndof)
         nn = len(mesh.nodes)
         ne = mesh.n_elem
@@ -61,6 +84,8 @@ class Model:
         in_boundary = np.zeros(nn, dtype=bool)
         for key, lst in edge_count.items():
             if len(lst) == 1:
+                if nodal_on_symplanes and any(np.all(np.abs(mesh.nodes[lst[0], ax - 1]) <= self.geometric_tolerance) for ax in self.symplane_eid):
+                    continue
                 in_boundary[lst[0]] = True
         self.in_boundary = in_boundary
         self.node_part = node_part
@@ -255,6 +280,7 @@ class InternalPointsModel:
         self.etype, self.elem_ptr, self.elem_node, self.elem_reversed = m.etype, m.elem_ptr, m.elem_node, m.elem_reversed
         self.qsi_relative_error, self.qsi_ns_max = m.qsi_relative_error, m.qsi_ns_max
         self.precalset_gln, self.geometric_tolerance = m.precalset_gln, m.geometric_tolerance
+        self.symplane_eid, self.symplane_t = getattr(m, "symplane_eid", np.zeros(0, np.int32)), getattr(m, "symplane_t", np.zeros((0, 3)))
         self.n_dof = m.n_dof + nd * nip
         dummy_rows = (m.n_dof + np.arange(nd * nip, dtype=np.int32)).reshape(nip, nd)
         none = -np.ones((nip, nd), dtype=np.int32)

@@ -1475,6 +1475,11 @@ struct Model {
   QsParams qsp; int ns_max; double geometric_tolerance;
   std::vector<int> n2e_ptr, n2e_elem, n2e_kn;  // node -> (element, local node) incidences
   Stats last;
+  // symmetry planes (lib/fbem/src/symmetry.f90:60-171, src/read_symmetry_planes.f90:228-283): image ks of every element, ks = 1..n_sym-1
+  std::vector<int> ps_gln; std::vector<double> node_x;
+  int n_planes = 0, n_sym = 1, plane_eid[3] = {0, 0, 0};
+  double plane_m[3][3], conf_m[8][3], conf_t[8][3]; bool conf_rev[8];
+  std::vector<std::vector<Element>> img;
 };
 
 extern "C" {
@@ -1493,6 +1498,7 @@ void* orc_setup(int n_node, const double* node_x, int n_elem, const int* etype, 
   m->row.assign(row, row + 3 * n_node); m->col_u.assign(col_u, col_u + 3 * n_node); m->col_t.assign(col_t, col_t + 3 * n_node);
   m->ctype.assign(ctype, ctype + 3 * n_node);
   qs_calculate_parameters(qsi_relative_error, m->qsp); m->ns_max = qsi_ns_max; m->geometric_tolerance = geometric_tolerance;
+  m->ps_gln.assign(precalset_gln, precalset_gln + n_precalsets); m->node_x.assign(node_x, node_x + 3 * n_node);
   m->elem.resize(n_elem);
   for (int e = 0; e < n_elem; e++) {
     Element& el = m->elem[e]; el.et = etype[e]; el.nn = n_nodes_of(el.et); el.reverse = elem_reversed[e] != 0;
@@ -1512,6 +1518,53 @@ void* orc_setup(int n_node, const double* node_x, int n_elem, const int* etype, 
   return m;
 }
 void orc_free(void* h) { delete (Model*)h; }
+
+// Symmetry planes through the origin, normal to axis eid[i] (1..3, ascending), with the translation multipliers t[3*i..] of
+// src/read_symmetry_planes.f90:76-228 (symmetry: -1 on the normal axis, +1 elsewhere; antisymmetry: the opposite signs).
+// The images follow the step table of fbem_symmetry_multipliers (lib/fbem/src/symmetry.f90:81-170): 1 root, 2 SP1, 3 SP1+SP2,
+// 4 SP2, 5 SP3, 6 SP1+SP3, 7 SP1+SP2+SP3, 8 SP2+SP3; an odd number of reflections reverses the orientation.  As in
+// build_lse_mechanics_bem_harela.f90:1052-1107 only the nodal coordinates of the calculation element are reflected: csize, n_phi
+// and the bounding ball (centre included) stay those of the root element.
+int orc_set_symmetry(void* h, int n_planes, const int* eid, const double* t) {
+  Model* m = (Model*)h;
+  if (n_planes < 0 || n_planes > 3) return 1;
+  m->n_planes = n_planes; m->n_sym = 1 << n_planes; m->img.clear();
+  double pt[3][3];
+  for (int i = 0; i < n_planes; i++) {
+    if (eid[i] < 1 || eid[i] > 3 || (i > 0 && eid[i] <= eid[i - 1])) return 1;
+    m->plane_eid[i] = eid[i];
+    for (int c = 0; c < 3; c++) { m->plane_m[i][c] = (c == eid[i] - 1) ? -1.0 : 1.0; pt[i][c] = t[3 * i + c]; }
+  }
+  static const int steps[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+  for (int ks = 0; ks < m->n_sym; ks++) {
+    int cnt = 0;
+    for (int c = 0; c < 3; c++) { m->conf_m[ks][c] = 1.0; m->conf_t[ks][c] = 1.0; }
+    for (int i = 0; i < n_planes; i++) if (steps[ks][i]) { cnt++; for (int c = 0; c < 3; c++) { m->conf_m[ks][c] *= m->plane_m[i][c]; m->conf_t[ks][c] *= pt[i][c]; } }
+    m->conf_rev[ks] = (cnt & 1) != 0;
+  }
+  m->img.resize(m->n_sym - 1);
+  for (int ks = 1; ks < m->n_sym; ks++) {
+    m->img[ks - 1] = m->elem;
+    for (int e = 0; e < m->n_elem; e++) {
+      Element& el = m->img[ks - 1][e];
+      for (int k = 0; k < el.nn; k++) for (int c = 0; c < 3; c++) el.x[3 * k + c] = m->conf_m[ks][c] * m->elem[e].x[3 * k + c];
+      el.reverse = m->elem[e].reverse != m->conf_rev[ks];
+      init_precalculated_datasets(el, (int)m->ps_gln.size(), m->ps_gln.data());
+    }
+  }
+  return 0;
+}
+// planes (indices into plane_eid) that contain the node: fbem_node_symplanes_connectivity (lib/fbem/src/data_structures.f90:1116-1153)
+static int node_planes(const Model* m, int sn, int* planes) {
+  int n = 0;
+  for (int i = 0; i < m->n_planes; i++) if (fabs(m->node_x[3 * sn + m->plane_eid[i] - 1]) <= m->geometric_tolerance) planes[n++] = i;
+  return n;
+}
+static inline const Element& image_of(const Model* m, int e, int ks) { return ks == 0 ? m->elem[e] : m->img[ks - 1][e]; }
+static inline void apply_symconf(const Model* m, int ks, int nn, cd* h, cd* g) {   // build_lse_mechanics_bem_harela.f90:1203-1206
+  if (ks == 0) return;
+  for (int kn = 0; kn < nn; kn++) for (int il = 0; il < 3; il++) for (int ik = 0; ik < 3; ik++) { h[(kn * 3 + il) * 3 + ik] *= m->conf_t[ks][ik]; g[(kn * 3 + il) * 3 + ik] *= m->conf_t[ks][ik]; }
+}
 
 void orc_element_data(void* h, int e, double* cl, int* gln_far, double* bc, double* br) {
   Model* m = (Model*)h; *cl = m->elem[e].cl; *gln_far = m->elem[e].gln_far; for (int c = 0; c < 3; c++) bc[c] = m->elem[e].bc[c]; *br = m->elem[e].br;
@@ -1578,12 +1631,15 @@ static int assemble_impl(Model* m, const Params& p, cd nu, const cd* cvalue, cd*
     Stats st; memset(&st, 0, sizeof(st));
 #pragma omp for schedule(dynamic)
     for (int e = 0; e < m->n_elem; e++) {
-      const Element& el = m->elem[e];
       cd hh[81], gg[81];
-      for (int c = 0; c < m->n_colloc; c++) {
-        sbie_auto(el, &m->cx[3 * c], p, m->qsp, m->ns_max, hh, gg, st);
+      for (int ks = 0; ks < m->n_sym; ks++) {
+        const Element& el = image_of(m, e, ks);
+        for (int c = 0; c < m->n_colloc; c++) {
+          sbie_auto(el, &m->cx[3 * c], p, m->qsp, m->ns_max, hh, gg, st);
+          apply_symconf(m, ks, el.nn, hh, gg);
 #pragma omp critical
-        scatter(m, e, m->cnode[c], hh, gg, cvalue, A, b);
+          scatter(m, e, m->cnode[c], hh, gg, cvalue, A, b);
+        }
       }
     }
 #pragma omp critical
@@ -1603,13 +1659,26 @@ static int assemble_impl(Model* m, const Params& p, cd nu, const cd* cvalue, cd*
       cd cplus[3][3];
       if (check_xi1xi2_edge(el.et, xi_i)) {
         int b0 = m->n2e_ptr[sn], ne = m->n2e_ptr[sn + 1] - b0;
-        std::vector<double> ns(3 * ne), ts(3 * ne);
+        int planes[3]; const int npl = node_planes(m, sn, planes);
+        if (npl > 2) { err = 1; continue; }   // the reference builds fans for nodes in one or two planes only (:500-555)
+        const int fan = ne << npl;
+        std::vector<double> ns(3 * fan), ts(3 * fan), tr(3 * fan);   // tr: tangent of the reversed orientation (t_set_at_gn_reversed)
         for (int k = 0; k < ne; k++) {
           const Element& ee = m->elem[m->n2e_elem[b0 + k]]; double n[3], tbp[3], tbm[3];
           node_normal_tangents(ee.et, ee.x, m->n2e_kn[b0 + k], n, tbp, tbm);
-          for (int cc = 0; cc < 3; cc++) { ns[3 * k + cc] = el.reverse ? -n[cc] : n[cc]; ts[3 * k + cc] = el.reverse ? tbm[cc] : tbp[cc]; }
+          for (int cc = 0; cc < 3; cc++) { ns[3 * k + cc] = el.reverse ? -n[cc] : n[cc]; ts[3 * k + cc] = el.reverse ? tbm[cc] : tbp[cc]; tr[3 * k + cc] = el.reverse ? tbp[cc] : tbm[cc]; }
         }
-        if (sbie_freeterm(ne, ns.data(), ts.data(), m->geometric_tolerance, nu, cplus)) err = 1;
+        if (npl >= 1) {   // build_lse_mechanics_bem_harela.f90:500-555
+          const double* m1 = m->plane_m[planes[0]]; const double* m2 = (npl == 2) ? m->plane_m[planes[1]] : nullptr;
+          for (int k = 0; k < ne; k++) for (int cc = 0; cc < 3; cc++) {
+            ns[3 * (k + ne) + cc] = m1[cc] * ns[3 * k + cc]; ts[3 * (k + ne) + cc] = m1[cc] * tr[3 * k + cc];
+            if (npl == 2) {
+              ns[3 * (k + 2 * ne) + cc] = m1[cc] * m2[cc] * ns[3 * k + cc]; ts[3 * (k + 2 * ne) + cc] = m1[cc] * m2[cc] * ts[3 * k + cc];
+              ns[3 * (k + 3 * ne) + cc] = m2[cc] * ns[3 * k + cc]; ts[3 * (k + 3 * ne) + cc] = m2[cc] * tr[3 * k + cc];
+            }
+          }
+        }
+        if (sbie_freeterm(fan, ns.data(), ts.data(), m->geometric_tolerance, nu, cplus)) err = 1;
       } else {
         for (int a = 0; a < 3; a++) for (int bb = 0; bb < 3; bb++) cplus[a][bb] = (a == bb) ? 0.5 : 0.0;
       }
@@ -1888,11 +1957,13 @@ static int sample_impl(Model* m, const Params& p, const cd* cvalue, int c_offset
   {
     Stats st; memset(&st, 0, sizeof(st));
 #pragma omp for schedule(dynamic)
-    for (int e = 0; e < m->n_elem; e++) {
-      const Element& el = m->elem[e];
+    for (int e = 0; e < m->n_elem; e++)
+    for (int ks = 0; ks < m->n_sym; ks++) {
+      const Element& el = image_of(m, e, ks);
       cd hh[81], gg[81];
       for (long long q = 0; q < ns; q++) {
         sbie_auto(el, &m->cx[3 * cs[q]], p, m->qsp, m->ns_max, hh, gg, st);
+        apply_symconf(m, ks, el.nn, hh, gg);
 #pragma omp critical
         for (int il = 0; il < 3; il++) {
           long long row = 3 * q + il;
@@ -1917,7 +1988,9 @@ static int sample_impl(Model* m, const Params& p, const cd* cvalue, int c_offset
 int orc_pair(void* h, int e, const double* x_i, double omega, const double* lambda_ri, const double* mu_ri, double rho, double* h_ri, double* g_ri, long long* stats_out) {
   Model* m = (Model*)h; Params p; calculate_parameters(cd(lambda_ri[0], lambda_ri[1]), cd(mu_ri[0], mu_ri[1]), rho, omega, p);
   Stats st; memset(&st, 0, sizeof(st));
-  int mode = sbie_auto(m->elem[e], x_i, p, m->qsp, m->ns_max, (cd*)h_ri, (cd*)g_ri, st);
+  const int ks = e / m->n_elem; const Element& el = image_of(m, e % m->n_elem, ks);   // e >= n_elem: image ks of a model with symmetry planes, signs applied
+  int mode = sbie_auto(el, x_i, p, m->qsp, m->ns_max, (cd*)h_ri, (cd*)g_ri, st);
+  apply_symconf(m, ks, el.nn, (cd*)h_ri, (cd*)g_ri);
   if (stats_out) { stats_out[0] = st.pts_regular; stats_out[1] = st.leaves; stats_out[2] = st.pts_adaptive; stats_out[3] = st.pts_singular; stats_out[4] = st.li_points; }
   return mode;
 }
@@ -1925,7 +1998,10 @@ int orc_pair(void* h, int e, const double* x_i, double omega, const double* lamb
 int orc_pair_hbie(void* h, int e, const double* x_i, const double* n_i, double omega, const double* lambda_ri, const double* mu_ri, double rho, double* m_ri, double* l_ri) {
   Model* md = (Model*)h; Params p; calculate_parameters(cd(lambda_ri[0], lambda_ri[1]), cd(mu_ri[0], mu_ri[1]), rho, omega, p);
   Stats st; memset(&st, 0, sizeof(st));
-  return sbie_auto(md->elem[e], x_i, p, md->qsp, md->ns_max, (cd*)m_ri, (cd*)l_ri, st, n_i);
+  const int ks = e / md->n_elem; const Element& el = image_of(md, e % md->n_elem, ks);
+  int mode = sbie_auto(el, x_i, p, md->qsp, md->ns_max, (cd*)m_ri, (cd*)l_ri, st, n_i);
+  apply_symconf(md, ks, el.nn, (cd*)m_ri, (cd*)l_ri);   // m(:,:,ik), l(:,:,ik) times symconf_t(ik): build_lse_mechanics_bem_harela.f90:1159-1164
+  return mode;
 }
 // d*, s* (fbem_bem_harela3d_hbie_d / _s, bem_harela3d.f90:2472-2568), [l][k] interleaved complex
 void orc_fundamental_solutions_hbie(const double* x, const double* n, const double* x_i, const double* n_i, double omega, const double* lambda_ri, const double* mu_ri, double rho,
@@ -1944,8 +2020,9 @@ int orc_pair_hbie_static(void* h, int e, const double* x_i, const double* n_i, d
   return mode;
 }
 // plan only (mode per pair) -- for comparing discrete decisions with the product's planner
+// (element index ks * n_elem + r addresses image ks of root element r of a model with symmetry planes)
 int orc_pair_mode(void* h, int e, const double* x_i, double* d_out, double* barxi_out) {
-  Model* m = (Model*)h; const Element& el = m->elem[e];
+  Model* m = (Model*)h; const Element& el = image_of(m, e % m->n_elem, e / m->n_elem);
   double r[3] = {el.bc[0] - x_i[0], el.bc[1] - x_i[1], el.bc[2] - x_i[2]};
   double rmin = sqrt(dot3(r, r)) - el.br, barxi[2], d; int method;
   if (rmin > (4.0 * el.br)) { barxi[0] = 0.0; barxi[1] = 0.0; d = rmin / el.cl; }

@@ -55,6 +55,11 @@ class Oracle:
             _p(k[10]), _p(k[11]), _p(k[12]), _p(k[13]), C.c_int(m.n_dof),
             C.c_double(m.qsi_relative_error), C.c_int(m.qsi_ns_max), C.c_int(len(m.precalset_gln)), _p(k[14]),
             C.c_double(m.geometric_tolerance)))
+        eid = np.ascontiguousarray(getattr(m, "symplane_eid", np.zeros(0)), dtype=np.int32)
+        if len(eid):
+            t = np.ascontiguousarray(m.symplane_t, dtype=np.float64)
+            if L.orc_set_symmetry(self.h, C.c_int(len(eid)), _p(eid), _p(t)):
+                raise ValueError("oracle: invalid symmetry planes")
 
     def __del__(self):
         try:
@@ -128,8 +133,9 @@ class Oracle:
         return A, b, ns, pts.value
 
     def pair(self, e, x_i, omega, mat):
-        """h, g (n,3,3) complex of one (collocation point, element) pair and the integration mode."""
-        nn = int(self.m.elem_ptr[e + 1] - self.m.elem_ptr[e])
+        """h, g (n,3,3) complex of one (collocation point, element) pair and the integration mode.
+        e >= n_elem addresses image e // n_elem of root element e % n_elem (symmetry planes), signs symconf_t applied."""
+        nn = int(self.m.elem_ptr[e % self.m.n_elem + 1] - self.m.elem_ptr[e % self.m.n_elem])
         h = np.zeros((nn, 3, 3), dtype=np.complex128)
         g = np.zeros((nn, 3, 3), dtype=np.complex128)
         st = np.zeros(8, dtype=np.int64)
@@ -139,8 +145,9 @@ class Oracle:
         return h, g, mode, st
 
     def pair_hbie(self, e, x_i, n_i, omega, mat):
-        """m, l (n,3,3) complex of the hypersingular equation for a point off the element with unit normal n_i, and the mode."""
-        nn = int(self.m.elem_ptr[e + 1] - self.m.elem_ptr[e])
+        """m, l (n,3,3) complex of the hypersingular equation for a point off the element with unit normal n_i, and the mode
+        (e >= n_elem: an image element, as in pair)."""
+        nn = int(self.m.elem_ptr[e % self.m.n_elem + 1] - self.m.elem_ptr[e % self.m.n_elem])
         m = np.zeros((nn, 3, 3), dtype=np.complex128); l = np.zeros((nn, 3, 3), dtype=np.complex128)
         x_i = np.ascontiguousarray(x_i, dtype=np.float64); n_i = np.ascontiguousarray(n_i, dtype=np.float64)
         mode = lib().orc_pair_hbie(self.h, C.c_int(e), _p(x_i), _p(n_i), C.c_double(omega), _p(_ri(mat.lam)), _p(_ri(mat.mu)), C.c_double(mat.rho), _p(m), _p(l))
