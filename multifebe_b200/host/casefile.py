@@ -13,9 +13,11 @@ Mirrors src/read_input_file.f90 for the sections the hot path consumes:
   [conditions over be boundaries]            src/read_conditions_bem_boundaries_mechanics_{harmonic,static}.f90: global-axes
                                              conditions 0 / 1 per component; defaults (not listed) = 1 with value 0
   [internal points]  src/read_internal_points.f90    `<id> <region> x1 x2 x3` (one elastic region)
+  [symmetry planes]  src/read_symmetry_planes.f90    `plane_n1|plane_yz : symmetry|antisymmetry` (also plane_n2|plane_zx, plane_n3|plane_xy) or the
+                                             explicit form `x = <s> <t1> <t2> <t3>` (y, z alike); one elastic region
   [export]       src/read_export.f90:61-240  export_nso, real_format, integer_format, complex_notation
 Anything else the reference accepts (be-fe coupling, crack-like boundaries, close-pore conditions, local-axes or spring conditions,
-half-spaces, body loads, incident fields, symmetry planes, internal points of fluid regions, FE regions ...) raises CaseFileError naming the feature:
+half-spaces, body loads, incident fields, internal points of fluid regions, FE regions ...) raises CaseFileError naming the feature:
 the Fortran host keeps those.
 """
 import os
@@ -149,7 +151,7 @@ class CaseFile:
         self.filename = os.path.basename(path)
         sec = _sections(open(path, encoding="utf-8", errors="replace").read())
         self._sec = sec
-        for unsupported in ("fe subregions", "be body loads", "be bodyloads", "symmetry planes", "internal elements",
+        for unsupported in ("fe subregions", "be body loads", "be bodyloads", "internal elements",
                             "incident waves", "groups", "cross sections", "sensitivity"):
             if sec.get(unsupported):
                 raise CaseFileError("section [%s] is outside the path this library covers" % unsupported)
@@ -302,6 +304,38 @@ class CaseFile:
         if cn not in ("polar", "cartesian"):
             raise CaseFileError("[export] complex_notation: polar or cartesian")
         self.complex_notation = cn
+        # ---- [symmetry planes] (src/read_symmetry_planes.f90:76-228): the explicit multipliers first, then the named kinds, x before y before z
+        self.symmetry = []
+        sp = sec.get("symmetry planes") or []
+        if sp:
+            if self.multi or self.region_type != 2:
+                raise CaseFileError("[symmetry planes]: covered for one elastic region")
+            for ax, names in (("x", ("plane_n1", "plane_yz")), ("y", ("plane_n2", "plane_zx")), ("z", ("plane_n3", "plane_xy"))):
+                given = []
+                v = _keyword(sp, ax)
+                if v is not None:
+                    w = v.split()
+                    try:
+                        t = [int(q) for q in w[1:4]]
+                    except ValueError:
+                        t = []
+                    if len(t) != 3 or any(abs(q) != 1 for q in t):
+                        raise CaseFileError("[symmetry planes] %s = <s> <t1> <t2> <t3>: multipliers must be +1 or -1" % ax)
+                    given.append(tuple(float(q) for q in t))
+                for nm in names:
+                    for line in sp:
+                        mm = re.match(r"\s*%s\s*:\s*(\S+)" % nm, line)
+                        if mm:
+                            kind = mm.group(1).strip("'\"").lower()
+                            if kind not in ("symmetry", "antisymmetry"):
+                                raise CaseFileError("[symmetry planes] %s: symmetry or antisymmetry" % nm)
+                            given.append(kind)
+                    if given and isinstance(given[-1], str):
+                        break      # plane_yz is looked for only when plane_n1 is absent
+                if len(given) > 1:
+                    raise CaseFileError("[symmetry planes]: plane %s is given twice" % ax)
+                if given:
+                    self.symmetry.append((ax, given[0]))
         # ---- mesh: parts are the physical groups of the Gmsh file; a boundary is one part
         self.mesh = read_gmsh22(self.mesh_file)
         part_of_boundary = dict(self.boundaries)
@@ -365,4 +399,4 @@ class CaseFile:
         if self.region_type == 3:
             return PoroModel(self.mesh, {part_of_boundary[b]: (ct, cv) for b, (ct, cv) in self.bcs.items()}, **kw)
         bcs = {part_of_boundary[b]: (ct, cv) for b, (ct, cv) in self.bcs.items()}
-        return Model(self.mesh, bcs, **kw)
+        return Model(self.mesh, bcs, symmetry=self.symmetry, **kw)

@@ -33,8 +33,13 @@ def symmetry_planes(symmetry):
         ax = {"x": 1, "y": 2, "z": 3, 1: 1, 2: 2, 3: 3}[axis]
         if ax in planes:
             raise ValueError("symmetry plane %r given twice" % (axis,))
-        sgn = {"symmetry": 1.0, "antisymmetry": -1.0}[kind]
-        t = np.full(3, sgn); t[ax - 1] = -sgn
+        if isinstance(kind, str):
+            sgn = {"symmetry": 1.0, "antisymmetry": -1.0}[kind]
+            t = np.full(3, sgn); t[ax - 1] = -sgn
+        else:      # the explicit form of the case file: the three translation multipliers themselves
+            t = np.array(kind, dtype=np.float64)
+            if t.shape != (3,) or not np.all(np.abs(t) == 1.0):
+                raise ValueError("symmetry multipliers must be three values +1 or -1")
         planes[ax] = t
     eid = np.array(sorted(planes), dtype=np.int32)
     t = np.ascontiguousarray([planes[a] for a in sorted(planes)], dtype=np.float64).reshape(len(eid), 3)
@@ -55,6 +60,11 @@ class Model:
         SBIE with MCA like any other rim node, assign_default_bem_formulation.f90:85-92)."""
         self.mesh = mesh
         self.symplane_eid, self.symplane_t = symmetry_planes(symmetry)
+        for ax in self.symplane_eid:   # fbem_check_nodes_symplanes_configuration (lib/fbem/src/data_structures.f90:1197-1230): the mesh stays on one side
+            xa = mesh.nodes[:, ax - 1]
+            off = xa[np.abs(xa) > float(geometric_tolerance)]
+            if len(off) and off.min() < 0.0 < off.max():
+                raise ValueError("the mesh crosses the symmetry plane normal to axis %d" % ax)
         self.ndof = nd = int(ndof)
         nn = len(mesh.nodes)
         ne = mesh.n_elem

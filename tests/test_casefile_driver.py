@@ -582,3 +582,94 @@ def test_poroelastic_case_to_nso(tmp_path):
     side = rows[:, 5] >= 3
     tau = rows[:, 12] + 1j * rows[:, 13]
     assert np.abs(tau[side] - ta[side]).max() < 4e-3 * np.abs(ta).max()
+
+
+# ---- [symmetry planes] (src/read_symmetry_planes.f90): the P-wave column modelled as a quarter, its lateral conditions on y = 0 and z = 0 replaced by planes ----
+SYM_DAT = """[problem]
+n = 3D
+type = mechanics
+analysis = %(analysis)s
+%(freq)s
+[settings]
+mesh_file_mode = 2 "quarter.msh"
+
+[materials]
+1
+1 elastic_solid rho 1. mu 1. nu 0.2 xi 0.02
+
+[boundaries]
+4
+1 1 ordinary
+2 2 ordinary
+4 4 ordinary
+6 6 ordinary
+
+[regions]
+1
+1 be
+4 1 2 4 6
+material 1
+0
+0
+
+[symmetry planes]
+%(planes)s
+
+[export]
+real_format = eng_double
+
+[conditions over be boundaries]
+boundary 1: 0 %(z)s
+            0 %(z)s
+            0 %(z)s
+boundary 2: 1 %(one)s
+            1 %(z)s
+            1 %(z)s
+boundary 4: 1 %(z)s
+            0 %(z)s
+            1 %(z)s
+boundary 6: 1 %(z)s
+            1 %(z)s
+            0 %(z)s
+"""
+
+
+def _write_quarter(tmp_path, text, et=shape.QUAD9, m=2):
+    from multifebe_b200.host import without_parts
+    write_gmsh22(without_parts(cube_mesh(m, et), {3, 5}), str(tmp_path / "quarter.msh"))
+    p = tmp_path / "case.dat"
+    p.write_text(text)
+    return str(p)
+
+
+def test_symmetry_planes_section_static_column(tmp_path):
+    path = _write_quarter(tmp_path, SYM_DAT % dict(analysis="static", freq="", z="0.", one="1.", planes="plane_n2: symmetry\nplane_xy : symmetry"))
+    nso, case = _run_with_oracle(path)
+    assert case.symmetry == [("y", "symmetry"), ("z", "symmetry")]
+    md = case.build_model()
+    assert list(md.symplane_eid) == [2, 3] and np.array_equal(md.symplane_t, [[1, -1, 1], [1, 1, -1]])
+    rows = read_nso(nso)
+    assert rows.shape == (md.n_node, 12 + 6)
+    mat = case.material
+    lam2mu = 2.0 * mat.mu_r * mat.nu_r / (1.0 - 2.0 * mat.nu_r) + 2.0 * mat.mu_r
+    assert np.abs(rows[:, 12] - rows[:, 9] / lam2mu).max() < 5e-6          # u1 = P x1 / (lambda + 2 mu), as the full column of test_static_case_to_nso
+    assert np.abs(rows[:, 13:15]).max() < 5e-6                             # no lateral displacement anywhere: the planes hold the column
+
+
+def test_symmetry_planes_section_forms_and_errors(tmp_path):
+    kw = dict(analysis="harmonic", freq="\n[frequencies]\nrad/s\nlist\n1\n2.0\n", z="(0.,0.)", one="(1.,0.)")
+    a = CaseFile(_write_quarter(tmp_path, SYM_DAT % dict(planes="plane_zx: symmetry\nplane_n3: antisymmetry", **kw)))
+    assert a.symmetry == [("y", "symmetry"), ("z", "antisymmetry")]
+    # the explicit form: scalar multiplier, then the three translation multipliers
+    b = CaseFile(_write_quarter(tmp_path, SYM_DAT % dict(planes="y = 1 1 -1 1\nz = -1 -1 -1 1", **kw)))
+    ma, mb = a.build_model(), b.build_model()
+    assert np.array_equal(ma.symplane_eid, mb.symplane_eid) and np.array_equal(ma.symplane_t, mb.symplane_t)
+    for planes, word in [("plane_n2: mirror", "symmetry or antisymmetry"), ("y = 1 1 2 1", "+1 or -1"), ("plane_n2: symmetry\ny = 1 1 -1 1", "twice")]:
+        with pytest.raises(CaseFileError) as ei:
+            CaseFile(_write_quarter(tmp_path, SYM_DAT % dict(planes=planes, **kw)))
+        assert word in str(ei.value)
+    # a mesh on both sides of a plane is refused (fbem_check_nodes_symplanes_configuration)
+    c = CaseFile(_write_quarter(tmp_path, SYM_DAT % dict(planes="plane_n1: symmetry", **kw)))
+    c.mesh.nodes[:, 0] -= 0.5
+    with pytest.raises(ValueError):
+        c.build_model()

@@ -77,3 +77,17 @@ def test_static_case_with_internal_points(tmp_path):
     a = np.array([[float(t) for t in s.split()] for s in la[-2:]]); b = np.array([[float(t) for t in s.split()] for s in lb[-2:]])
     assert np.array_equal(a[:, :12], b[:, :12])
     assert np.abs(a[:, 12:15] - b[:, 12:15]).max() <= 1e-8 * np.abs(b[:, 12:15]).max() and np.abs(a[:, 15:] - b[:, 15:]).max() <= 1e-8 * np.abs(b[:, 15:]).max()
+
+
+def test_case_with_symmetry_planes(tmp_path):
+    """[symmetry planes] through the stand-alone driver: the quarter column, harmonic (antisymmetric variant too) and static, against the oracle run."""
+    from test_casefile_driver import SYM_DAT, _write_quarter
+    freq = "\n[frequencies]\nrad/s\nlin\n2\n0.5\n6.0\n"
+    for k, (analysis, planes) in enumerate([("harmonic", "plane_n2: symmetry\nplane_n3: symmetry"), ("harmonic", "plane_n2: antisymmetry\nplane_n3: symmetry"),
+                                            ("static", "plane_n2: symmetry\nplane_n3: symmetry")]):
+        d = tmp_path / ("c%d" % k); d.mkdir()
+        harm = analysis == "harmonic"
+        text = (SYM_DAT % dict(analysis=analysis, freq=freq if harm else "", z="(0.,0.)" if harm else "0.", one="(1.,0.)" if harm else "1.", planes=planes)).replace("eng_double", "sci_double")
+        path = _write_quarter(d, text, et=shape.TRI6 if k else shape.QUAD9, m=2)
+        nso_cpu, _ = _run_with_oracle(path, output=path + ".cpu")
+        _compare(driver.run(path, log=io.StringIO()), nso_cpu, harm)
