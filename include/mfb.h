@@ -110,6 +110,12 @@ void mfb_problem_free(mfb_problem* problem);
 int mfb_harela3d_assemble(mfb_problem* problem, double omega, const mfb_z* lambda, const mfb_z* mu, double rho,
                           const mfb_z* nu, const mfb_z* cvalue, mfb_z* A, mfb_z* b);
 
+/* Incident wave field of the region (the reference's region%n_incidentfields > 0 path): u_inc, t_inc at the nodes of every element as held in
+ * element(se)%incident_c(1:3,kn,1) / (4:6,kn,1) (src/build_lse_mechanics_bem_harela.f90:291-304), index [(elem_ptr[e] + j) * 3 + k].  While set, every
+ * pair and every free term adds hp u_inc - gp t_inc to b (src/assemble_bem_harela_equation.f90:651-666).  Both NULL clears it.  The field depends on
+ * omega: call it before the assembly / solve_frequency of each frequency.  Displacement equation of elastic regions, harmonic analysis. */
+int mfb_harela3d_set_incident(mfb_problem* problem, const mfb_z* u_inc, const mfb_z* t_inc);
+
 /* == solve_lse_c(n_dof,A,ipiv,..,n_rhs,b,factorize,scaling=F,condition=F,refine=F): in-place LU with partial pivoting
  * (zgetrf) + triangular solves (zgetrs).  A == NULL: use the device-resident system of the last mfb_harela3d_assemble (and
  * keep the factors on the device); otherwise A (lda x n, host) is uploaded, overwritten by the LU factors on return.

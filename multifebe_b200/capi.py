@@ -278,6 +278,17 @@ class Problem:
             lib().mfb_problem_free(self.h)
             self.h = C.c_void_p()
 
+    def set_incident(self, u_inc=None, t_inc=None):
+        """Incident wave field at the nodes of every element ((sum nn, 3) complex each, element order; element()%incident_c of the reference);
+        None clears.  Every later assembly adds hp u_inc - gp t_inc to b (assemble_bem_harela_equation.f90:651-666)."""
+        if u_inc is None:
+            _check(lib().mfb_harela3d_set_incident(self.h, None, None))
+            return
+        u = np.ascontiguousarray(u_inc, dtype=np.complex128).reshape(-1, 3); t = np.ascontiguousarray(t_inc, dtype=np.complex128).reshape(-1, 3)
+        if not (len(u) == len(t) == int(self.m.elem_ptr[-1])):
+            raise ValueError("incident field: one row per element node")
+        _check(lib().mfb_harela3d_set_incident(self.h, _p(u), _p(t)))
+
     # ---- seam 1: build_lse_mechanics_bem_harela(kf,kr) after A_c=0; b_c=0 ----
     def build_lse_mechanics_bem_harela(self, omega, mat, want_host=True, out=None):
         """out = (A, b): the caller's own A_c, b_c (Fortran-ordered complex128), overwritten -- what the Fortran host passes."""

@@ -85,6 +85,8 @@ struct mfb_problem {
   DistState dist;
   alignas(64) unsigned char tmapS[128]; bool have_tmapS;   // one-plane box: K1 flush of the static (real) assembly
   int ndof;                                                // equations / unknowns per node: 3 (elastic solid), 1 (inviscid fluid, mfb_harpot3d_*)
+  // incident field (mfb_harela3d_set_incident): flat [slot_off[n_elem]][4] device array in slot order, images carry the root's values times symconf_t(k)
+  double* d_einc = nullptr; bool have_inc = false; std::vector<int> slot_off_h, root_elem_ptr; std::vector<unsigned char> elem_symbits; int n_elem_root = 0;
   bool hbie;                                               // hypersingular equation at points off the boundary (interior-point stresses)
   bool real_resident;                                      // the resident system / factors are real (static path): Are only
   // optional stages of solve_lse_c (mfb_zsolve_ex): unfactorised (scaled) copy of A, scale factors in the order of the resident system
@@ -456,6 +458,9 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
   // ---- flat scatter descriptors over all slots ----
   std::vector<int> slot_off(n_elem + 1, 0);
   for (int s = 0; s < n_elem; s++) slot_off[s + 1] = slot_off[s] + ndof * p->elems[p->elem_of_slot[s]].nn;
+  p->slot_off_h = slot_off; p->n_elem_root = n_root; p->root_elem_ptr.assign(elem_ptr, elem_ptr + n_root + 1);
+  p->elem_symbits.assign(n_elem, 0);
+  for (int e = 0; e < n_elem; e++) for (int k = 0; k < 3; k++) if (conf_t[e / n_root][k] < 0.0) p->elem_symbits[e] |= (unsigned char)(1u << k);
   std::vector<int> h_ecol(slot_off[n_elem]); std::vector<unsigned char> h_ekind(slot_off[n_elem]);
   for (int s = 0; s < n_elem; s++) {
     int e = p->elem_of_slot[s], nn = p->elems[e].nn;
@@ -524,6 +529,7 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
       D.n_ranges = (int)rs.size() - 1; D.range_start = d_rs; D.range_of = d_rof;
       CK(cudaMalloc((void**)&d_rm, sizeof(int) * D.n_ranges)); g.owned.push_back(d_rm); D.range_modes = d_rm;
     }
+    D.einc = nullptr;
     D.xn = d_xn; D.ball = d_ball; D.enode = d_enode; D.gln_far = d_glnfar; D.erev = d_rev; D.einfo = d_info; D.ecvnz = d_cvnz;
     D.ecol = d_ecol + slot_off[g.slot0]; D.ekind = d_ekind + slot_off[g.slot0]; D.ecv = d_ecv + 2 * (size_t)slot_off[g.slot0];
     D.has_mixed = 0;
@@ -705,7 +711,7 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
     int *d1, *d2, *d3, *d4; double* d5;
     UP(p->owned, f_cpos, &d1); UP(p->owned, f_slot, &d2); UP(p->owned, f_jk, &d3); UP(p->owned, f_l, &d4); UP(p->owned, f_val, &d5);
     p->ft.n = (int)f_cpos.size(); p->ft.cpos = d1; p->ft.slot = d2; p->ft.jk = d3; p->ft.l = d4; p->ft.val = d5;
-    p->ft.slot_off = d_slot_off; p->ft.ecol = d_ecol; p->ft.ekind = d_ekind; p->ft.ecv = d_ecv;
+    p->ft.slot_off = d_slot_off; p->ft.ecol = d_ecol; p->ft.ekind = d_ekind; p->ft.ecv = d_ecv; p->ft.einc = nullptr;
     {
       int *e1, *e2, *e3, *e4; double* e5;
       UP(p->owned, f0_cpos, &e1); UP(p->owned, f0_slot, &e2); UP(p->owned, f0_jk, &e3); UP(p->owned, f0_l, &e4); UP(p->owned, f0_val, &e5);
@@ -841,6 +847,7 @@ static int assemble_device(mfb_problem* p, double omega, cd lambda, cd mu, doubl
 }
 static int assemble_device_k(mfb_problem* p, const KParams& K, const KParams& Q, cd nu, const mfb_z* cvalue, bool statics) {
   if (p->ndof != 3) return fail(MFB_ERR_ARG, "this problem was set up for an inviscid fluid region (mfb_harpot3d_setup): use mfb_harpot3d_assemble / _solve_frequency");
+  if (statics && p->have_inc) return fail(MFB_ERR_ARG, "static assembly: an incident field is set (harmonic analysis only); clear it with mfb_harela3d_set_incident(problem, NULL, NULL)");
   cudaStream_t st = p->ctx->stream;
   if (cvalue) {
     CK(cudaMemcpyAsync(p->d_cvalue, cvalue, (size_t)6 * p->n_node * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -869,7 +876,46 @@ static int assemble_device_k(mfb_problem* p, const KParams& K, const KParams& Q,
   // our kernels only (memsets/copies are not counted): free term + per group regular, adaptive, singular (+ gather_cv)
   p->asm_launches = 1;
   for (auto& g : p->groups)   // K1: one kernel per element class on 3/4-node elements (classes 0, 1 and, if present, 2)
-    p->asm_launches += (((g.et == 5 || g.et == 7) && g.dev.cols3) ? 2 + g.dev.has_mixed : 1) + (cvalue ? 1 : 0) + (g.adp.n_pairs > 0) + (g.sing.n_pairs > 0);
+    p->asm_launches += (((g.et == 5 || g.et == 7) && g.dev.cols3) ? 2 + ((g.dev.has_mixed || g.dev.einc) ? 1 : 0) : 1) + (cvalue ? 1 : 0) + (g.adp.n_pairs > 0) + (g.sing.n_pairs > 0);
+  return MFB_OK;
+}
+// Incident wave field of the region (region%n_incidentfields > 0): u_inc, t_inc at the nodes of every element, as the reference holds them in
+// element(se)%incident_c(1:3,kn,1) and (4:6,kn,1) (t_inc belongs to the element: it is formed with the element's normal).  Every pair then adds
+// hp u_inc - gp t_inc to b (assemble_bem_harela_equation.f90:651-666), the free term included (it is part of hp, build_lse_mechanics_bem_harela.f90:715).
+// Arrays: [(elem_ptr[e] + j) * 3 + k] complex, e over the elements given to the set-up; both NULL: no incident field.  Valid until the next call
+// (set it before the assembly of every frequency: the field depends on omega).  An image of a symmetric model takes the root's values times symconf_t(k).
+extern "C" int mfb_harela3d_set_incident(mfb_problem* p, const mfb_z* u_inc, const mfb_z* t_inc) {
+  if (!p) return fail(MFB_ERR_ARG, "mfb_harela3d_set_incident: null problem");
+  if (p->ndof != 3 || p->hbie) return fail(MFB_ERR_UNSUPPORTED, "mfb_harela3d_set_incident: built for the displacement equation of elastic regions");
+  if ((u_inc == nullptr) != (t_inc == nullptr)) return fail(MFB_ERR_ARG, "mfb_harela3d_set_incident: give both u_inc and t_inc, or neither");
+  CK(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  const int n_elem = p->n_elem, n_root = p->n_elem_root;
+  const size_t total = (size_t)p->slot_off_h[n_elem];
+  if (u_inc) {
+    std::vector<double> h(4 * total);
+    for (int s = 0; s < n_elem; s++) {
+      const int e = p->elem_of_slot[s], r = e % n_root, nn = p->elems[e].nn, o = p->slot_off_h[s];
+      const unsigned bits = p->elem_symbits[e];
+      for (int j = 0; j < nn; j++) for (int k = 0; k < 3; k++) {
+        const size_t q = ((size_t)p->root_elem_ptr[r] + j) * 3 + k;
+        const double sg = ((bits >> k) & 1u) ? -1.0 : 1.0;
+        if (!std::isfinite(u_inc[q].re) || !std::isfinite(u_inc[q].im) || !std::isfinite(t_inc[q].re) || !std::isfinite(t_inc[q].im))
+          return fail(MFB_ERR_ARG, "mfb_harela3d_set_incident: non-finite value");
+        double* d = &h[4 * ((size_t)o + j * 3 + k)];
+        d[0] = sg * u_inc[q].re; d[1] = sg * u_inc[q].im; d[2] = sg * t_inc[q].re; d[3] = sg * t_inc[q].im;
+      }
+    }
+    if (!p->d_einc) { CK(cudaMalloc((void**)&p->d_einc, std::max<size_t>(total, 1) * 4 * sizeof(double))); p->owned.push_back(p->d_einc); }
+    CK(cudaMemcpyAsync(p->d_einc, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // h goes out of scope
+  }
+  p->have_inc = u_inc != nullptr;
+  for (auto& g : p->groups) g.dev.einc = p->have_inc ? p->d_einc + 4 * (size_t)p->slot_off_h[g.slot0] : nullptr;
+  p->ft.einc = p->have_inc ? p->d_einc : nullptr;
+  // the element classes of K1 depend on it (every element runs as the general class while a field is set)
+  if (p->have_cvalue) for (auto& g : p->groups) launch_gather_cv(g.dev, p->d_cvalue, st);
+  p->assembled = false;
   return MFB_OK;
 }
 static int collect_assembly_times(mfb_problem* p) {

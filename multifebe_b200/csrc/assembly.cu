@@ -102,7 +102,7 @@ __global__ void k_gather_cv(DevGroup g, const double* __restrict__ cvalue) {
     }
   }
   g.ecvnz[e] = nz ? 1 : 0;
-  const int mode = !(g.einfo[e] & 8u) ? 2 : (nz ? 1 : 0);
+  const int mode = (g.einc || !(g.einfo[e] & 8u)) ? 2 : (nz ? 1 : 0);   // an incident field needs both kernel combinations of every (node, dof): the general class
   atomicOr(g.range_modes + g.range_of[e], 1 << mode);
 }
 void launch_gather_cv(const DevGroup& g, const double* cvalue, cudaStream_t st) {
@@ -120,7 +120,8 @@ template <int NN, int NL, class Pred>
 __device__ __forceinline__ void scatter_pair(const Acc<NN, NL>& a, const int* __restrict__ ecol, const unsigned char* __restrict__ ekind,
                                              const double* __restrict__ ecv, bool rev, const DevSystem& s, int il,
                                              int r0, int r1, int r2, double* bre, double* bim, Pred mine, const KParams& c_kp, bool hbie = false,
-                                             unsigned symbits = 0u /* bit k: symconf_t(k) = -1 of a symmetry image (ecv already carries it) */) {
+                                             unsigned symbits = 0u /* bit k: symconf_t(k) = -1 of a symmetry image (ecv already carries it) */,
+                                             const double* __restrict__ einc = nullptr /* incident field of the element's (j,k), or NULL */) {
   // h (or m of the hypersingular equation) is scaled by cte_t (cte_s) and changes sign on a reversed element; g (l) by cte_u (cte_d)
   const cplx ch0 = hbie ? c_kp.cte_s : mk(c_kp.cte_t, 0.0);
   const cplx ch = rev ? mk(-ch0.re, -ch0.im) : ch0;
@@ -147,6 +148,10 @@ __device__ __forceinline__ void scatter_pair(const Acc<NN, NL>& a, const int* __
         if (kind == 0) { ar = -gr; ai = -gi; br = -(hr * cvr - hi * cvi); bi = -(hr * cvi + hi * cvr); }
         else { ar = hr; ai = hi; br = gr * cvr - gi * cvi; bi = gr * cvi + gi * cvr; }
         if ((symbits >> k) & 1u) { ar = -ar; ai = -ai; }
+        if (einc) {   // b += h u_inc - g t_inc (assemble_bem_harela_equation.f90:651-666); a symmetry image's sign is in the values
+          const double ur = einc[4 * jk], ui = einc[4 * jk + 1], tr = einc[4 * jk + 2], ti = einc[4 * jk + 3];
+          br += (hr * ur - hi * ui) - (gr * tr - gi * ti); bi += (hr * ui + hi * ur) - (gr * ti + gi * tr);
+        }
         atomicAdd(Ar + row, ar);
         atomicAdd(Ai + row, ai);
         bre[l] += br; bim[l] += bi;
@@ -205,7 +210,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_regular(DevGroup g, DevColloc
             if (HB) accumulate_exterior_hbie<NN, NL>(acc, c_kp, x, n, xc, ni, w, il);
             else accumulate_exterior<NN, NL>(acc, c_kp, x, n, xc, w, il);
           }
-          scatter_pair<NN, NL>(acc, ecol, ekind, ecv, rev, s, il, r0, r1, r2, bre, bim, AllEntries(), c_kp, HB, (unsigned)g.einfo[e] >> 5);
+          scatter_pair<NN, NL>(acc, ecol, ekind, ecv, rev, s, il, r0, r1, r2, bre, bim, AllEntries(), c_kp, HB, (unsigned)g.einfo[e] >> 5,
+                               (!HB && g.einc) ? g.einc + (size_t)e * 12 * NN : nullptr);
         }
       }
     }
@@ -263,7 +269,7 @@ struct AccA { double re[9 * NN], im[9 * NN]; };   // [(l*3+k)*NN + j]: entry of 
 template <int NW, int MODE, bool ST>
 __device__ __forceinline__ void k1_point(AccA<NW>& a, double* bacc, const double* rec, const double* w, const double* sk, bool do_b, const double* xc,
                                          double sgn, unsigned info, const unsigned char* __restrict__ ekind, const double* __restrict__ ecv, bool have_ks,
-                                         KScal& k, const KParams& c_kq) {
+                                         KScal& k, const KParams& c_kq, const double* __restrict__ einc = nullptr /* MODE 2: incident field of the chunk's (j,k) */) {
   const double n[3] = {sgn * rec[3], sgn * rec[4], sgn * rec[5]};
   const double rv0 = rec[0] - xc[0], rv1 = rec[1] - xc[1], rv2 = rec[2] - xc[2];
   const double r2 = fma(rv0, rv0, fma(rv1, rv1, rv2 * rv2));
@@ -340,6 +346,15 @@ __device__ __forceinline__ void k1_point(AccA<NW>& a, double* bacc, const double
             const double ai = tk ? fti[l] : fui[l], oi = tk ? fui[l] : fti[l];
             a.im[(l * 3 + kk) * NW + j] = fma(ai, w[j], a.im[(l * 3 + kk) * NW + j]);
             bacc[l] -= orr * cvr - oi * cvi; bacc[3 + l] -= orr * cvi + oi * cvr;
+          }
+        }
+        if (!ST && einc) {   // b += h u_inc - g t_inc: ft is h, fu is -g in this kernel's scaling (assemble_bem_harela_equation.f90:651-666)
+          const double ur = w[j] * __ldg(einc + 4 * (j * 3 + kk)), ui = w[j] * __ldg(einc + 4 * (j * 3 + kk) + 1);
+          const double tr = w[j] * __ldg(einc + 4 * (j * 3 + kk) + 2), ti = w[j] * __ldg(einc + 4 * (j * 3 + kk) + 3);
+#pragma unroll
+          for (int l = 0; l < 3; l++) {
+            bacc[l] += (ftr[l] * ur - fti[l] * ui) + (fur[l] * tr - fui[l] * ti);
+            bacc[3 + l] += (ftr[l] * ui + fti[l] * ur) + (fur[l] * ti + fui[l] * tr);
           }
         }
       }
@@ -424,7 +439,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
         m_next = (valid && e < e1) ? pl[(size_t)e * c.ldp] : PLAN_NONE;
         const unsigned info_e = info_next, cvnz_e = cvnz_next;
         if (e < e1) { info_next = g.einfo[e]; cvnz_next = g.ecvnz[e]; }
-        const int mode_e = !(info_e & 8u) ? 2 : (cvnz_e != 0 ? 1 : 0);
+        const int mode_e = (g.einc || !(info_e & 8u)) ? 2 : (cvnz_e != 0 ? 1 : 0);
         if (mode_e != MODE) continue;
         const unsigned reg = __ballot_sync(0xffffffffu, m < MAX_SETS);
         if (reg == 0u) continue;
@@ -523,7 +538,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
               const double* kc = kcache + (size_t)kp * 320 + lane;
               ks.psi = mk(kc[0], kc[32]); ks.chi = mk(kc[64], kc[96]); ks.T1 = mk(kc[128], kc[160]); ks.T2 = mk(kc[192], kc[224]); ks.T3 = mk(kc[256], kc[288]);
             }
-            k1_point<NW, MODE, ST>(acc, bacc, cur, cur + 6, sk, ch == 0, xs, sgn, info, ekind, ecv, have_ks, ks, c_kq);
+            k1_point<NW, MODE, ST>(acc, bacc, cur, cur + 6, sk, ch == 0, xs, sgn, info, ekind, ecv, have_ks, ks, c_kq,
+                                   (MODE == 2 && g.einc) ? g.einc + (size_t)el * 4 * NC + 12 * j0 : nullptr);
             if (use_cache && ch == 0) {
               double* kc = kcache + (size_t)kp * 320 + lane;
               kc[0] = ks.psi.re; kc[32] = ks.psi.im; kc[64] = ks.chi.re; kc[96] = ks.chi.im; kc[128] = ks.T1.re; kc[160] = ks.T1.im;
@@ -635,7 +651,7 @@ static void launch_regular_bulk(const CUtensorMap& tmap, const DevGroup& g, cons
   cudaMemsetAsync(k1.counters, 0, 4 * sizeof(int), st);
   if (c.n_tiles * g.n_ranges < 2048) {   // a small mesh: the classes one after the other on the caller's stream (no side streams: they only pay on long kernels,
     launch_bulk_mode<ET, 1, KB_WARPS, ST>(tmap, g, c, s, plan, kq, k1, st);        // and a process that keeps many small problems in flight runs out of hardware queues)
-    if (g.has_mixed) launch_bulk_mode<ET, 2, KB_WARPS, ST>(tmap, g, c, s, plan, kq, k1, st);
+    if (g.has_mixed || g.einc) launch_bulk_mode<ET, 2, KB_WARPS, ST>(tmap, g, c, s, plan, kq, k1, st);
     launch_bulk_mode<ET, 0, KB_WARPS_FAST, ST>(tmap, g, c, s, plan, kq, k1, st);
     return;
   }
@@ -644,14 +660,14 @@ static void launch_regular_bulk(const CUtensorMap& tmap, const DevGroup& g, cons
   cudaStreamWaitEvent(k1.aux[0], k1.ev_fork, 0);
   launch_bulk_mode<ET, 1, KB_WARPS, ST>(tmap, g, c, s, plan, kq, k1, k1.aux[0]);
   cudaEventRecord(k1.ev_join[0], k1.aux[0]);
-  if (g.has_mixed) {
+  if (g.has_mixed || g.einc) {
     cudaStreamWaitEvent(k1.aux[1], k1.ev_fork, 0);
     launch_bulk_mode<ET, 2, KB_WARPS, ST>(tmap, g, c, s, plan, kq, k1, k1.aux[1]);
     cudaEventRecord(k1.ev_join[1], k1.aux[1]);
   }
   launch_bulk_mode<ET, 0, KB_WARPS_FAST, ST>(tmap, g, c, s, plan, kq, k1, st);
   cudaStreamWaitEvent(st, k1.ev_join[0], 0);
-  if (g.has_mixed) cudaStreamWaitEvent(st, k1.ev_join[1], 0);
+  if (g.has_mixed || g.einc) cudaStreamWaitEvent(st, k1.ev_join[1], 0);
 }
 
 // 3-D tensor map of the planar system matrix for the K1 flush: (row, column, plane), box = 96 rows x 3 columns x 2 planes
@@ -776,7 +792,7 @@ __global__ void __launch_bounds__(128) k_adaptive(DevGroup g, DevColloc c, DevSy
     warp_reduce<NN, NL>(acc);
     LaneEntries le; le.lane = lane;
     scatter_pair<NN, NL>(acc, g.ecol + (size_t)e * 3 * NN, g.ekind + (size_t)e * 3 * NN, g.ecv + (size_t)e * 6 * NN, g.erev[e] != 0, s, il,
-                         r0, r1, r2, bre, bim, le, c_kp, HB, (unsigned)g.einfo[e] >> 5);
+                         r0, r1, r2, bre, bim, le, c_kp, HB, (unsigned)g.einfo[e] >> 5, (!HB && g.einc) ? g.einc + (size_t)e * 12 * NN : nullptr);
   }
   flush_b(s, r0, r1, r2, bre, bim);
 }
@@ -857,7 +873,7 @@ __global__ void __launch_bounds__(128) k_singular(DevGroup g, DevColloc c, DevSy
     }
     LaneEntries le; le.lane = lane;
     scatter_pair<NN, NL>(acc, g.ecol + (size_t)e * 3 * NN, g.ekind + (size_t)e * 3 * NN, g.ecv + (size_t)e * 6 * NN, g.erev[e] != 0, s, il,
-                         r0, r1, r2, bre, bim, le, c_kp, false, (unsigned)g.einfo[e] >> 5);
+                         r0, r1, r2, bre, bim, le, c_kp, false, (unsigned)g.einfo[e] >> 5, g.einc ? g.einc + (size_t)e * 12 * NN : nullptr);
   }
   flush_b(s, r0, r1, r2, bre, bim);
 }
@@ -885,6 +901,11 @@ __global__ void k_freeterm(DevColloc c, DevSystem s, DevFreeTerm f, cplx F) {
   const int o = f.slot_off[f.slot[i]] + f.jk[i];
   // value = alpha + beta*F, F = -1/(8 pi (1-nu)) (Mantic; bem_harela3d.f90:538) -- alpha,beta are geometry-only
   const double vr = f.val[2 * i] + f.val[2 * i + 1] * F.re, vi = f.val[2 * i + 1] * F.im;
+  if (f.einc) {   // the free term is part of h: b += c u_inc at the collocation node
+    const double ur = f.einc[4 * (size_t)o], ui = f.einc[4 * (size_t)o + 1];
+    atomicAdd(s.bre + row, vr * ur - vi * ui);
+    atomicAdd(s.bim + row, vr * ui + vi * ur);
+  }
   if (f.ekind[o] == 1) {
     atomicAdd(s.Are + (size_t)f.ecol[o] * s.lda + row, vr);
     atomicAdd(s.Aim + (size_t)f.ecol[o] * s.lda + row, vi);

@@ -24,6 +24,8 @@ struct DevGroup {
   double* ecv;                   // [n_elem][3*nn][2] prescribed value of (j,k), refreshed per frequency
   const unsigned char* einfo;    // [n_elem] bits 0-2: kind of dof k (when the same for every node j), bit 3: kinds uniform over j, bit 4: reversed
   unsigned char* ecvnz;          // [n_elem] 1 when some prescribed value of the element is nonzero (refreshed per frequency)
+  const double* einc;            // NULL, or [n_elem][3*nn][4]: incident field (u_k re, im, t_k re, im) at node j of the element (element()%incident_c): every
+                                 // pair then adds h u_inc - g t_inc to b (assemble_bem_harela_equation.f90:651-666); all elements run as K1 mode 2
   const double* ball;            // [n_elem][5]: centre(3), radius, characteristic length
   const int* gln_far;            // [n_elem]
   int n_ranges;                  // K1 tasks = (collocation tile) x (element range); long ranges first, short ones last (load balance)
@@ -78,6 +80,7 @@ struct DevFreeTerm {
   int n; const int* cpos; const int* slot; const int* jk; const int* l; const double* val;  // val[n][2] = (alpha, beta): value = alpha + beta*F
   const int* slot_off;           // [n_slots+1] offset of each element slot in the flat (j,k) arrays below
   const int* ecol; const unsigned char* ekind; const double* ecv;   // flat over all groups
+  const double* einc;            // flat [.][4] incident field per (element, j, k), or NULL
 };
 struct DevTables { const double *gl11_x, *gl11_w, *gl01_x, *gl01_w; };  // packed, rule n at offset n(n-1)/2
 

@@ -1480,6 +1480,8 @@ struct Model {
   int n_planes = 0, n_sym = 1, plane_eid[3] = {0, 0, 0};
   double plane_m[3][3], conf_m[8][3], conf_t[8][3]; bool conf_rev[8];
   std::vector<std::vector<Element>> img;
+  // incident field at the nodes of every element (element()%incident_c): [(eptr[e] + kn) * 3 + ik], empty = none
+  std::vector<cd> u_inc, t_inc;
 };
 
 extern "C" {
@@ -1554,6 +1556,13 @@ int orc_set_symmetry(void* h, int n_planes, const int* eid, const double* t) {
   }
   return 0;
 }
+// incident field of the region: u_inc, t_inc [(elem_ptr[e] + kn) * 3 + ik] interleaved complex, or NULL to clear
+void orc_set_incident(void* h, const double* u_ri, const double* t_ri) {
+  Model* m = (Model*)h; m->u_inc.clear(); m->t_inc.clear();
+  if (!u_ri || !t_ri) return;
+  size_t n = (size_t)m->eptr[m->n_elem] * 3;
+  m->u_inc.assign((const cd*)u_ri, (const cd*)u_ri + n); m->t_inc.assign((const cd*)t_ri, (const cd*)t_ri + n);
+}
 // planes (indices into plane_eid) that contain the node: fbem_node_symplanes_connectivity (lib/fbem/src/data_structures.f90:1116-1153)
 static int node_planes(const Model* m, int sn, int* planes) {
   int n = 0;
@@ -1583,6 +1592,8 @@ static void scatter(const Model* m, int e, int sn_col, const cd* hp, const cd* g
           case 0: { long long col = m->col_t[3 * sn + ik]; A[row + nd * col] = A[row + nd * col] - gg; b[row] = b[row] - hh * cvalue[3 * sn + ik]; break; }
           case 1: { long long col = m->col_u[3 * sn + ik]; A[row + nd * col] = A[row + nd * col] + hh; b[row] = b[row] + gg * cvalue[3 * sn + ik]; break; }
         }
+        // incident wave field: assemble_bem_harela_equation.f90:651-666 (ordinary boundary)
+        if (!m->u_inc.empty()) b[row] = b[row] + hh * m->u_inc[(size_t)(m->eptr[e] + kn) * 3 + ik] - gg * m->t_inc[(size_t)(m->eptr[e] + kn) * 3 + ik];
       }
   }
 }

@@ -67,6 +67,15 @@ class Oracle:
         except Exception:
             pass
 
+    def set_incident(self, u_inc=None, t_inc=None):
+        """Incident field at the nodes of every element, (sum nn, 3) complex each in element order (element()%incident_c); None clears."""
+        if u_inc is None:
+            lib().orc_set_incident(self.h, None, None)
+            return
+        u = np.ascontiguousarray(u_inc, dtype=np.complex128).reshape(-1, 3); t = np.ascontiguousarray(t_inc, dtype=np.complex128).reshape(-1, 3)
+        assert len(u) == len(t) == int(self.m.elem_ptr[-1])
+        lib().orc_set_incident(self.h, _p(u), _p(t))
+
     def assemble(self, omega, mat, nthreads=0):
         """-> A (n_dof x n_dof, Fortran order), b (n_dof), stats dict.  One frequency, A and b start at zero."""
         n = self.m.n_dof

@@ -1,0 +1,98 @@
+"""Incident wave field on the GPU path (mfb_harela3d_set_incident) against the oracle, whose term tests/test_oracle_incident.py pins by
+the integral identities of a plane wave: b within 1e-11, A untouched, the solution within 1e-8."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from multifebe_b200.host import Material, Model, cube_mesh, cube_bcs, without_parts, halfspace_patch, plane_wave, element_incident, shape  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+MAT = Material(rho=1.0, mu=1.0, nu=0.25, xi=0.02)
+TOL_A, TOL_X = 1e-11, 1e-8
+T_KNOWN = {p: ([1, 1, 1], [0, 0, 0]) for p in range(1, 7)}
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("etype,m", [(shape.TRI3, 4), (shape.QUAD4, 3), (shape.TRI6, 2), (shape.QUAD8, 2), (shape.QUAD9, 2)], ids=["tri3", "quad4", "tri6", "quad8", "quad9"])
+def test_incident_field_term_matches_the_oracle(gpu_ctx, oracle_lib, etype, m):
+    """Mixed kinds of condition, nonzero prescribed values (their b terms live beside the incident ones), rim nodes with non-nodal points."""
+    from multifebe_b200 import capi
+    bcs = {1: ([0, 0, 0], [0.1, 0, 0.2j]), 2: ([1, 1, 1], [1, 0, 0]), 3: ([1, 0, 1], [0, 0.3, 0]), 4: ([1, 0, 1], [0, 0, 0]), 5: ([1, 1, 0], [0, 0, 0]), 6: ([1, 1, 1], [0, 0, 0])}
+    md = Model(cube_mesh(m, etype), bcs, reversed_parts=(1, 2, 3, 4, 5, 6))
+    pr = capi.Problem(gpu_ctx, md); o = oracle_lib.Oracle(md)
+    A0, b0 = pr.build_lse_mechanics_bem_harela(2.5, MAT)
+    for omega, wave in [(2.5, ("P", [1.0, 0.5, 0.2], None)), (0.8, ("S", [0.0, 0.0, 1.0], [1.0, 0.0, 0.0]))]:
+        u, t = element_incident(md, plane_wave(wave[0], wave[1], MAT, omega, polarisation=wave[2], amplitude=0.5 + 0.2j))
+        pr.set_incident(u, t); o.set_incident(u, t)
+        A, b = pr.build_lse_mechanics_bem_harela(omega, MAT)
+        Ao, bo, _ = o.assemble(omega, MAT)
+        assert relerr(A, Ao) < TOL_A and relerr(b, bo) < TOL_A, (omega, relerr(A, Ao), relerr(b, bo))
+        xo, _, _ = oracle_lib.lu_solve(Ao, bo)
+        assert relerr(pr.solve_frequency(omega, MAT), xo) < TOL_X
+    # cleared: the system of the first call again
+    pr.set_incident(None)
+    A1, b1 = pr.build_lse_mechanics_bem_harela(2.5, MAT)
+    assert relerr(A1, A0) < 1e-13 and relerr(b1, b0) < 1e-12
+    pr.close()
+
+
+def test_total_field_equal_to_the_incident_field(gpu_ctx):
+    """Prescribed tractions = incident tractions on a cavity: u = u_inc, an algebraic identity of the assembled system (no oracle involved)."""
+    from multifebe_b200 import capi
+    omega = 3.0
+    field = plane_wave("S", [0.3, -0.4, 1.0], MAT, omega, polarisation=[1.0, 1.0, 0.0], amplitude=0.7)
+    for etype, m in [(shape.TRI3, 5), (shape.QUAD9, 3)]:
+        md = Model(cube_mesh(m, etype), T_KNOWN, reversed_parts=(1, 2, 3, 4, 5, 6))
+        u, t = element_incident(md, field)
+        for e in range(md.n_elem):
+            for kn, v in enumerate(md.mesh.conn[e]):
+                md.cvalue[v] = t[md.elem_ptr[e] + kn]
+        pr = capi.Problem(gpu_ctx, md)
+        pr.set_incident(u, t)
+        un, _ = md.nodal_solution(pr.solve_frequency(omega, MAT))
+        want = np.array([field(xv, [1.0, 0, 0])[0] for xv in md.node_x])
+        assert relerr(un, want) < 1e-9
+        pr.close()
+
+
+def test_incident_field_with_symmetry_planes_and_open_surfaces(gpu_ctx, oracle_lib):
+    """The images of a symmetric model take the root's incident values with the sign of the plane (the reference passes the root's u_inc, t_inc
+    together with the sign-multiplied hp, gp); a free-surface patch (soil-structure layout) with mixed conditions per node."""
+    from multifebe_b200 import capi
+    mesh = without_parts(cube_mesh(3, shape.QUAD4), {1, 3})
+    bcs = {2: ([0, 0, 0], [0, 0, 0]), 4: ([1, 1, 1], [0, 0.3, 0]), 5: ([1, 1, 1], [0, 0, 0]), 6: ([1, 1, 1], [0, 0, 0.5])}
+    cases = [Model(mesh, bcs, symmetry=[("x", "symmetry"), ("y", "antisymmetry")]),
+             Model(halfspace_patch(5, shape.TRI6), {1: ([1, 1, 1], [0.1, 0, 0.3j]), 2: ([0, 1, 0], [1.0, 0.5, 0.2])})]
+    for md in cases:
+        omega = 2.0
+        u, t = element_incident(md, plane_wave("P", [0.2, 0.1, 1.0], MAT, omega))
+        pr = capi.Problem(gpu_ctx, md); o = oracle_lib.Oracle(md)
+        pr.set_incident(u, t); o.set_incident(u, t)
+        A, b = pr.build_lse_mechanics_bem_harela(omega, MAT)
+        Ao, bo, _ = o.assemble(omega, MAT)
+        assert relerr(A, Ao) < TOL_A and relerr(b, bo) < TOL_A, (relerr(A, Ao), relerr(b, bo))
+        pr.close()
+
+
+def test_incident_field_misuse(gpu_ctx):
+    from multifebe_b200 import capi
+    md = Model(cube_mesh(2, shape.TRI3), cube_bcs())
+    pr = capi.Problem(gpu_ctx, md)
+    u, t = element_incident(md, plane_wave("P", [1.0, 0, 0], MAT, 1.0))
+    with pytest.raises(ValueError):
+        pr.set_incident(u[:-1], t[:-1])
+    bad = u.copy(); bad[3, 1] = np.nan
+    with pytest.raises(capi.MfbError):
+        pr.set_incident(bad, t)
+    pr.set_incident(u, t)
+    with pytest.raises(capi.MfbError):
+        pr.build_lse_mechanics_bem_staela(Material(rho=1.0, mu=1.0, nu=0.25, xi=0.0))      # a static assembly with an incident field set
+    pr.set_incident(None)
+    pr.build_lse_mechanics_bem_staela(Material(rho=1.0, mu=1.0, nu=0.25, xi=0.0))
+    pr.close()
