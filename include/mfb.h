@@ -110,6 +110,12 @@ void mfb_problem_free(mfb_problem* problem);
 int mfb_harela3d_assemble(mfb_problem* problem, double omega, const mfb_z* lambda, const mfb_z* mu, double rho,
                           const mfb_z* nu, const mfb_z* cvalue, mfb_z* A, mfb_z* b);
 
+/* Boundary condition ctype = 10 of an elastic region ("normal pressure known", assemble_bem_harela_equation.f90:97-106): accepted by the set-up calls in
+ * ctype[]; cvalue then holds the pressure p and the library forms t_k = p n_fn(k) (negated on a reversed boundary) with the nodal unit normals
+ * node(sn)%n_fn given here, n_fn[3 * n_node] (src/build_data_at_functional_nodes.f90:355-400).  Once, before the first assembly; a no-op for models without
+ * such conditions.  The unknown of such a dof is u_k in column col_u, as for ctype 1. */
+int mfb_set_node_normals(mfb_problem* problem, const double* n_fn);
+
 /* Incident wave field of the region (the reference's region%n_incidentfields > 0 path): u_inc, t_inc at the nodes of every element as held in
  * element(se)%incident_c(1:3,kn,1) / (4:6,kn,1) (src/build_lse_mechanics_bem_harela.f90:291-304), index [(elem_ptr[e] + j) * 3 + k].  While set, every
  * pair and every free term adds hp u_inc - gp t_inc to b (src/assemble_bem_harela_equation.f90:651-666).  Both NULL clears it.  The field depends on

@@ -86,6 +86,8 @@ struct mfb_problem {
   alignas(64) unsigned char tmapS[128]; bool have_tmapS;   // one-plane box: K1 flush of the static (real) assembly
   int ndof;                                                // equations / unknowns per node: 3 (elastic solid), 1 (inviscid fluid, mfb_harpot3d_*)
   // incident field (mfb_harela3d_set_incident): flat [slot_off[n_elem]][4] device array in slot order, images carry the root's values times symconf_t(k)
+  std::vector<unsigned char> node_rev;   // node belongs to a reversed boundary (from the root elements around it)
+  double* d_nfn = nullptr; bool need_normals = false, have_normals = false;   // ctype 10: nodal normals n_fn (mfb_set_node_normals)
   double* d_einc = nullptr; bool have_inc = false; std::vector<int> slot_off_h, root_elem_ptr; std::vector<unsigned char> elem_symbits; int n_elem_root = 0;
   bool hbie;                                               // hypersingular equation at points off the boundary (interior-point stresses)
   bool real_resident;                                      // the resident system / factors are real (static path): Are only
@@ -252,7 +254,13 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
   }
   if (ndof != 1 && ndof != 3 && ndof != 4) return fail(MFB_ERR_ARG, "setup: ndof must be 3 (elastic solid), 1 (inviscid fluid) or 4 (poroelastic medium)");
   for (int i = 0; i < ndof * n_node; i++)
-    if (ctype[i] != 0 && ctype[i] != 1) return fail(MFB_ERR_UNSUPPORTED, "mfb_harela3d_setup: only ctype 0 (u / p known) and 1 (t / Un known) are supported");
+    if (ctype[i] != 0 && ctype[i] != 1 && !(ctype[i] == 10 && ndof == 3))
+      return fail(MFB_ERR_UNSUPPORTED, "mfb_harela3d_setup: ctype 0 (u / p known), 1 (t / Un known) and, for elastic regions, 10 (normal pressure known) are supported");
+  // ctype 10 (assemble_bem_harela_equation.f90:97-106): the pressure p on the node is known, t_k = p n_fn(k): a traction-known dof (kind 1, unknown u_k, column
+  // col(k,1)) whose prescribed value is cvalue * n_fn(k), negated on a reversed boundary.  The nodal normals come with mfb_set_node_normals.
+  std::vector<int> kind_of; std::vector<unsigned char> c10;
+  for (int i = 0; i < ndof * n_node; i++) if (ctype[i] == 10) { if (c10.empty()) { c10.assign((size_t)ndof * n_node, 0); kind_of.assign(ctype, ctype + (size_t)ndof * n_node); } c10[i] = 1; kind_of[i] = 1; }
+  if (!c10.empty()) ctype = kind_of.data();
   double t_host0 = now_ms();
   // ---- symmetry images (lib/fbem/src/symmetry.f90:60-171; image loop build_lse_mechanics_bem_harela.f90:1098-1107) ----
   // Every root element gets n_sym - 1 image elements: element ks * n_root + r is image ks of root r, with the root's nodes (hence its columns and
@@ -529,7 +537,7 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
       D.n_ranges = (int)rs.size() - 1; D.range_start = d_rs; D.range_of = d_rof;
       CK(cudaMalloc((void**)&d_rm, sizeof(int) * D.n_ranges)); g.owned.push_back(d_rm); D.range_modes = d_rm;
     }
-    D.einc = nullptr;
+    D.einc = nullptr; D.c10 = nullptr; D.nfn = nullptr;
     D.xn = d_xn; D.ball = d_ball; D.enode = d_enode; D.gln_far = d_glnfar; D.erev = d_rev; D.einfo = d_info; D.ecvnz = d_cvnz;
     D.ecol = d_ecol + slot_off[g.slot0]; D.ekind = d_ekind + slot_off[g.slot0]; D.ecv = d_ecv + 2 * (size_t)slot_off[g.slot0];
     D.has_mixed = 0;
@@ -554,6 +562,14 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
     CK(cudaStreamSynchronize(st));
   }
 
+  if (!c10.empty()) {
+    unsigned char* d_c10; UP(p->owned, c10, &d_c10);
+    CK(cudaMalloc((void**)&p->d_nfn, (size_t)3 * n_node * sizeof(double))); p->owned.push_back(p->d_nfn);
+    for (auto& g : p->groups) { g.dev.c10 = d_c10; g.dev.nfn = p->d_nfn; }
+    p->need_normals = true;
+    p->node_rev.assign(n_node, 0);
+    for (int e = 0; e < n_root; e++) if (p->elems[e].reversed) for (int k = elem_ptr[e]; k < elem_ptr[e + 1]; k++) p->node_rev[elem_node[k]] = 1;
+  }
   // ---- K0: classify all pairs on the device, fetch the near list ----
   for (int n = 0; n < 32; n++) p->cls.far_thr[n] = S.far_thr[n];
   p->cls.far_dmax = S.far_dmax;
@@ -849,6 +865,7 @@ static int assemble_device_k(mfb_problem* p, const KParams& K, const KParams& Q,
   if (p->ndof != 3) return fail(MFB_ERR_ARG, "this problem was set up for an inviscid fluid region (mfb_harpot3d_setup): use mfb_harpot3d_assemble / _solve_frequency");
   if (statics && p->have_inc) return fail(MFB_ERR_ARG, "static assembly: an incident field is set (harmonic analysis only); clear it with mfb_harela3d_set_incident(problem, NULL, NULL)");
   cudaStream_t st = p->ctx->stream;
+  if (p->need_normals && !p->have_normals) return fail(MFB_ERR_ARG, "assembly: the model has ctype 10 conditions (normal pressure): give the nodal normals with mfb_set_node_normals first");
   if (cvalue) {
     CK(cudaMemcpyAsync(p->d_cvalue, cvalue, (size_t)6 * p->n_node * sizeof(double), cudaMemcpyHostToDevice, st));
     for (auto& g : p->groups) launch_gather_cv(g.dev, p->d_cvalue, st);
@@ -877,6 +894,21 @@ static int assemble_device_k(mfb_problem* p, const KParams& K, const KParams& Q,
   p->asm_launches = 1;
   for (auto& g : p->groups)   // K1: one kernel per element class on 3/4-node elements (classes 0, 1 and, if present, 2)
     p->asm_launches += (((g.et == 5 || g.et == 7) && g.dev.cols3) ? 2 + ((g.dev.has_mixed || g.dev.einc) ? 1 : 0) : 1) + (cvalue ? 1 : 0) + (g.adp.n_pairs > 0) + (g.sing.n_pairs > 0);
+  return MFB_OK;
+}
+// Nodal unit normals node(sn)%n_fn(1:3) (src/build_data_at_functional_nodes.f90:355-400: the normalised sum of the normals of the elements around the node, mirror
+// images included) for the nodes whose ctype is 10; n_fn[3 * n_node].  Needed once, before the first assembly of a model with such conditions.
+extern "C" int mfb_set_node_normals(mfb_problem* p, const double* n_fn) {
+  if (!p || !n_fn) return fail(MFB_ERR_ARG, "mfb_set_node_normals: null argument");
+  if (!p->need_normals) return MFB_OK;   // no ctype 10 in this model: nothing uses them
+  for (size_t i = 0; i < (size_t)3 * p->n_node; i++) if (!std::isfinite(n_fn[i])) return fail(MFB_ERR_ARG, "mfb_set_node_normals: non-finite value");
+  CK(cudaSetDevice(p->ctx->device));
+  std::vector<double> h(n_fn, n_fn + (size_t)3 * p->n_node);
+  for (int v = 0; v < p->n_node; v++) if (p->node_rev[v]) for (int k = 0; k < 3; k++) h[3 * (size_t)v + k] = -h[3 * (size_t)v + k];   // `if (sb_int_reversion) b -= ...` (:101-105)
+  CK(cudaMemcpyAsync(p->d_nfn, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, p->ctx->stream));
+  CK(cudaStreamSynchronize(p->ctx->stream));
+  p->have_normals = true;
+  if (p->have_cvalue) for (auto& g : p->groups) launch_gather_cv(g.dev, p->d_cvalue, p->ctx->stream);
   return MFB_OK;
 }
 // Incident wave field of the region (region%n_incidentfields > 0): u_inc, t_inc at the nodes of every element, as the reference holds them in

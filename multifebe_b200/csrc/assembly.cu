@@ -95,6 +95,10 @@ __global__ void k_gather_cv(DevGroup g, const double* __restrict__ cvalue) {
     const int node = g.enode[e * g.nn + j];
     for (int k = 0; k < nd; k++) {
       double vr = cvalue[2 * (nd * (size_t)node + k)], vi = cvalue[2 * (nd * (size_t)node + k) + 1];
+      if (g.c10 && g.c10[nd * (size_t)node + k]) {   // p known: t_k = p n_fn(k), with the sign of the orientation (assemble_bem_harela_equation.f90:97-106)
+        const double f = g.nfn[nd * (size_t)node + k];   // already negated for the nodes of a reversed boundary (the ROOT element's orientation counts, not an image's)
+        vr *= f; vi *= f;
+      }
       if (k < 3 && ((g.einfo[e] >> (5 + k)) & 1u)) { vr = -vr; vi = -vi; }   // symmetry image: symconf_t(k) = -1 (the b term carries it through the value)
       const size_t i = (size_t)e * nd * g.nn + j * nd + k;
       g.ecv[2 * i] = vr; g.ecv[2 * i + 1] = vi;

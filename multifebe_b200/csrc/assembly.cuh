@@ -24,6 +24,8 @@ struct DevGroup {
   double* ecv;                   // [n_elem][3*nn][2] prescribed value of (j,k), refreshed per frequency
   const unsigned char* einfo;    // [n_elem] bits 0-2: kind of dof k (when the same for every node j), bit 3: kinds uniform over j, bit 4: reversed
   unsigned char* ecvnz;          // [n_elem] 1 when some prescribed value of the element is nonzero (refreshed per frequency)
+  const unsigned char* c10;      // NULL, or [3*n_node]: 1 where ctype = 10 (normal pressure known): the prescribed value is cvalue * nfn
+  const double* nfn;             // [3*n_node] nodal unit normals, negated for the nodes of a reversed boundary (with c10)
   const double* einc;            // NULL, or [n_elem][3*nn][4]: incident field (u_k re, im, t_k re, im) at node j of the element (element()%incident_c): every
                                  // pair then adds h u_inc - g t_inc to b (assemble_bem_harela_equation.f90:651-666); all elements run as K1 mode 2
   const double* ball;            // [n_elem][5]: centre(3), radius, characteristic length

@@ -273,6 +273,14 @@ class CaseFile:
             ndof = ndof_of[bid]
             recs = [m.group(2)] + cl[i + 1:i + ndof]
             ct, cv = [], []
+            w0 = recs[0].split(None, 1)
+            if int(w0[0]) == 10:      # one record: normal pressure t_k = P n_k on the three components (read_conditions_bem_boundaries_mechanics_harmonic.f90:144-149)
+                if ndof != 3 or self.multi:
+                    raise CaseFileError("boundary %d: condition type 10 (normal pressure) is covered for one elastic region" % bid)
+                pval = _fortran_complex(w0[1])
+                self.bcs[bid] = ([10, 10, 10], [pval, pval, pval])
+                i += 1
+                continue
             for k in range(ndof):
                 w = recs[k].split(None, 1)
                 t = int(w[0])

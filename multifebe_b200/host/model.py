@@ -129,13 +129,26 @@ class Model:
                     self.row[v, k] = row; row += 1
                     if self.ctype[v, k] == 0:
                         self.col_t[v, k] = col
-                    elif self.ctype[v, k] == 1:
-                        self.col_u[v, k] = col
+                    elif self.ctype[v, k] == 1 or (self.ctype[v, k] == 10 and nd == 3):
+                        self.col_u[v, k] = col          # 10: normal pressure known, t_k = p n_fn(k); the unknown is u_k
                     else:
-                        raise ValueError("only ctype 0/1 are supported on this path")
+                        raise ValueError("only ctype 0 / 1 (and 10 on elastic regions) are supported on this path")
                     col += 1
         assert row == col
         self.n_dof = row
+
+        # --- nodal unit normals node()%n_fn (src/build_data_at_functional_nodes.f90:355-390): normalised sum of the normals of the elements around the
+        # node (as meshed: the orientation of the boundary in the region enters later, through the sign of the ctype-10 term), mirror images included
+        self.n_fn = np.zeros((nn, 3))
+        for e in range(ne):
+            et = int(mesh.etype[e]); c = mesh.conn[e]
+            for kn, v in enumerate(c):
+                self.n_fn[v] += sh.unit_normal(et, self.node_x[c], sh.XI_NODES[et][kn])
+        for ax in self.symplane_eid:
+            on = np.abs(self.node_x[:, ax - 1]) <= self.geometric_tolerance
+            self.n_fn[on, ax - 1] = 0.0       # n + M n, applied once per plane the node lies in: the component along the plane's axis cancels, the others double
+        norm = np.linalg.norm(self.n_fn, axis=1)
+        self.n_fn[norm > 0] /= norm[norm > 0, None]
 
         # --- collocation points (loop order of build_lse_mechanics_bem_harela.f90:1118-1136)
         cx, cnode, celem, ckn, cxi = [], [], [], [], []
@@ -170,6 +183,9 @@ class Model:
             t[known_u, k] = x[self.col_t[known_u, k]]
             t[~known_u, k] = self.cvalue[~known_u, k]
             u[~known_u, k] = x[self.col_u[~known_u, k]]
+            if self.ndof == 3:
+                p10 = self.ctype[:, k] == 10          # normal pressure known: t_k = p n_fn(k)
+                t[p10, k] = self.cvalue[p10, k] * self.n_fn[p10, k]
         return u, t
 
 
@@ -291,6 +307,8 @@ class InternalPointsModel:
         self.qsi_relative_error, self.qsi_ns_max = m.qsi_relative_error, m.qsi_ns_max
         self.precalset_gln, self.geometric_tolerance = m.precalset_gln, m.geometric_tolerance
         self.symplane_eid, self.symplane_t = getattr(m, "symplane_eid", np.zeros(0, np.int32)), getattr(m, "symplane_t", np.zeros((0, 3)))
+        if hasattr(m, "n_fn"):
+            self.n_fn = np.ascontiguousarray(np.vstack([m.n_fn, np.zeros((nip, 3))]))
         self.n_dof = m.n_dof + nd * nip
         dummy_rows = (m.n_dof + np.arange(nd * nip, dtype=np.int32)).reshape(nip, nd)
         none = -np.ones((nip, nd), dtype=np.int32)

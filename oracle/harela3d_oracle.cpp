@@ -1482,6 +1482,7 @@ struct Model {
   std::vector<std::vector<Element>> img;
   // incident field at the nodes of every element (element()%incident_c): [(eptr[e] + kn) * 3 + ik], empty = none
   std::vector<cd> u_inc, t_inc;
+  std::vector<double> n_fn;   // nodal unit normals node()%n_fn (ctype 10), empty = none
 };
 
 extern "C" {
@@ -1556,6 +1557,7 @@ int orc_set_symmetry(void* h, int n_planes, const int* eid, const double* t) {
   }
   return 0;
 }
+void orc_set_node_normals(void* h, const double* n_fn) { Model* m = (Model*)h; m->n_fn.assign(n_fn, n_fn + 3 * (size_t)m->n_node); }
 // incident field of the region: u_inc, t_inc [(elem_ptr[e] + kn) * 3 + ik] interleaved complex, or NULL to clear
 void orc_set_incident(void* h, const double* u_ri, const double* t_ri) {
   Model* m = (Model*)h; m->u_inc.clear(); m->t_inc.clear();
@@ -1591,6 +1593,11 @@ static void scatter(const Model* m, int e, int sn_col, const cd* hp, const cd* g
         switch (m->ctype[3 * sn + ik]) {
           case 0: { long long col = m->col_t[3 * sn + ik]; A[row + nd * col] = A[row + nd * col] - gg; b[row] = b[row] - hh * cvalue[3 * sn + ik]; break; }
           case 1: { long long col = m->col_u[3 * sn + ik]; A[row + nd * col] = A[row + nd * col] + hh; b[row] = b[row] + gg * cvalue[3 * sn + ik]; break; }
+          case 10: {   // p known (normal pressure), u_k unknown: assemble_bem_harela_equation.f90:97-106
+            long long col = m->col_u[3 * sn + ik]; A[row + nd * col] = A[row + nd * col] + hh;
+            if (!m->elem[e].reverse) b[row] = b[row] + gg * cvalue[3 * sn + ik] * m->n_fn[3 * sn + ik];
+            else b[row] = b[row] - gg * cvalue[3 * sn + ik] * m->n_fn[3 * sn + ik];
+            break; }
         }
         // incident wave field: assemble_bem_harela_equation.f90:651-666 (ordinary boundary)
         if (!m->u_inc.empty()) b[row] = b[row] + hh * m->u_inc[(size_t)(m->eptr[e] + kn) * 3 + ik] - gg * m->t_inc[(size_t)(m->eptr[e] + kn) * 3 + ik];

@@ -55,6 +55,9 @@ class Oracle:
             _p(k[10]), _p(k[11]), _p(k[12]), _p(k[13]), C.c_int(m.n_dof),
             C.c_double(m.qsi_relative_error), C.c_int(m.qsi_ns_max), C.c_int(len(m.precalset_gln)), _p(k[14]),
             C.c_double(m.geometric_tolerance)))
+        if (np.asarray(m.ctype) == 10).any():
+            nf = np.ascontiguousarray(m.n_fn, dtype=np.float64); self._keep.append(nf)
+            L.orc_set_node_normals(self.h, _p(nf))
         eid = np.ascontiguousarray(getattr(m, "symplane_eid", np.zeros(0)), dtype=np.int32)
         if len(eid):
             t = np.ascontiguousarray(m.symplane_t, dtype=np.float64)
