@@ -687,14 +687,15 @@ def run_coupled(args):
     clocks = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         x = cp.solve_frequency_resident(omega)
-    acc = {}
+    acc = {}; by_problem = {}
     barrier(); t0 = time.time(); w0 = t0
     for s in range(args.steps):
         x = cp.solve_frequency_resident(omega)
-        for pr in list(cp.problems.values()):
+        for key, pr in list(cp.problems.items()):
             st = pr.stats()
             for k in ("MS_ASSEMBLE", "MS_REGULAR", "MS_ADAPTIVE", "MS_SINGULAR", "LAUNCHES"):
                 acc[k] = acc.get(k, 0.0) + st[k]
+            by_problem["%s ndof=%d" % (str(key), pr.ndof)] = by_problem.get("%s ndof=%d" % (str(key), pr.ndof), 0.0) + st["MS_REGULAR"]
         st = cp._solver.stats()
         for k in ("MS_LU", "MS_SOLVE", "MS_GEMM", "MS_PANEL", "LU_LAUNCHES", "GEMM_LAUNCHES", "GEMM_FLOPS"):
             acc[k] = acc.get(k, 0.0) + st[k]
@@ -719,7 +720,8 @@ def run_coupled(args):
                "roofline": {"kernel": "k_zgemm3m_tma (LU trailing update)", "bound": "tensor", "achieved": gemm_tf, "peak": peaks["dmma_tflops"], "unit": "TFLOP/s",
                             "frac": gemm_tf / peaks["dmma_tflops"], "traffic": None, "share_of_step": (acc["MS_GEMM"] / K) / ms_dev,
                             "peak_source": "FP64 tensor (DMMA) micro-benchmark measured live (mfb_measure_peaks)"},
-               "assembly": {"ms": acc["MS_ASSEMBLE"] / K, "ms_regular": acc["MS_REGULAR"] / K, "ms_adaptive": acc["MS_ADAPTIVE"] / K, "ms_singular": acc["MS_SINGULAR"] / K},
+               "assembly": {"ms": acc["MS_ASSEMBLE"] / K, "ms_regular": acc["MS_REGULAR"] / K, "ms_adaptive": acc["MS_ADAPTIVE"] / K, "ms_singular": acc["MS_SINGULAR"] / K,
+                            "ms_regular_by_problem": {k: v / K for k, v in by_problem.items()}},
                "lu": {"ms": acc["MS_LU"] / K, "tflops": 8.0 / 3.0 * n ** 3 / (acc["MS_LU"] / K) / 1e9, "ms_gemm": acc["MS_GEMM"] / K, "ms_zgetrs": acc["MS_SOLVE"] / K},
                "peaks_measured_live": peaks}
         if world == 1 and not args.no_cpu_baseline:

@@ -56,10 +56,42 @@ struct PorLane { int lane; __device__ __forceinline__ bool operator()(int jk) co
 // ------------------------------------------------------------------------------------------------------------------
 const int R1_WARPS = 4;
 const int R1_ECHUNK = 32;
+const int R1_CACHE_GP = 4;   // points of a pair whose twelve radial scalars stay in shared memory between the four equation passes (24 doubles x 32 lanes each)
+
+// Row l of the two 4 x 4 blocks from the radial scalars (the formulas of por_exterior_blocks, one row of them)
+__device__ __forceinline__ void por_row_from_scalars(const PorScal& s, const double* dx, const double* n, double drdn, int l, cplx ur[4], cplx tr[4]) {
+  if (l == 0) {
+    ur[0] = s.eta; tr[0] = s.W0 * drdn;
+#pragma unroll
+    for (int c = 0; c < 3; c++) { ur[c + 1] = s.vartheta * dx[c]; tr[c + 1] = cfmar(s.T01, dx[c] * drdn, s.T02 * n[c]); }
+  } else {
+    const double dxl = (l == 1) ? dx[0] : (l == 2 ? dx[1] : dx[2]), nl = (l == 1) ? n[0] : (l == 2 ? n[1] : n[2]);
+    ur[0] = s.vartheta * dxl; tr[0] = cfmar(s.W1, dxl * drdn, s.W2 * nl);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const double dl = (l - 1 == k) ? 1.0 : 0.0, dd = dxl * dx[k];
+      ur[k + 1] = mk(s.psi.re * dl - s.chi.re * dd, s.psi.im * dl - s.chi.im * dd);
+      const double c1 = dd * drdn, c2 = drdn * dl + dx[k] * nl, c3 = dxl * n[k];
+      tr[k + 1] = mk(s.T1.re * c1 + s.T2.re * c2 + s.T3.re * c3, s.T1.im * c1 + s.T2.im * c2 + s.T3.im * c3);
+    }
+  }
+}
+#define POR_SCAL_FIELDS(X) X(eta, 0) X(vartheta, 1) X(psi, 2) X(chi, 3) X(W0, 4) X(T01, 5) X(T02, 6) X(W1, 7) X(W2, 8) X(T1, 9) X(T2, 10) X(T3, 11)
+__device__ __forceinline__ void por_scal_store(const PorScal& s, double* c) {
+#define X(f, i) c[(2 * i) * 32] = s.f.re; c[(2 * i + 1) * 32] = s.f.im;
+  POR_SCAL_FIELDS(X)
+#undef X
+}
+__device__ __forceinline__ void por_scal_load(PorScal& s, const double* c) {
+#define X(f, i) s.f = mk(c[(2 * i) * 32], c[(2 * i + 1) * 32]);
+  POR_SCAL_FIELDS(X)
+#undef X
+}
 
 template <int ET>
 __global__ void __launch_bounds__(R1_WARPS * 32) k_por_regular(DevGroup g, DevColloc c, DevSystem s, const unsigned char* __restrict__ plan) {
   constexpr int NN = ElemTraits<ET>::NN, RECN = 6 + NN;
+  extern __shared__ __align__(16) double por_smem[];   // [warp][R1_CACHE_GP][24 scalars][32 lanes]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tile = blockIdx.x * R1_WARPS + warp;
   if (tile >= c.n_tiles) return;
@@ -85,6 +117,60 @@ __global__ void __launch_bounds__(R1_WARPS * 32) k_por_regular(DevGroup g, DevCo
         const unsigned char* ekind = g.ekind + (size_t)e * 4 * NN;
         const double* ecv = g.ecv + (size_t)e * 8 * NN;
         const bool rev = g.erev[e] != 0;
+        // The common element: the same kind of condition on all its nodes, all prescribed values zero.  Only the combination that goes to the matrix is
+        // accumulated (4 NN complex numbers per equation: they stay in registers; the general path below keeps h AND g, 16 NN doubles, and for 8/9-node
+        // elements lives in local memory -- 4.6 KB of spills per thread, the kernel's cost in round 1), and the radial scalars of the first R1_CACHE_GP
+        // points are computed in the pass of equation 0 and read back from shared memory by the other three.
+        if ((g.einfo[e] & 8u) && !g.ecvnz[e]) {
+          unsigned kinds = 0u;
+#pragma unroll
+          for (int k = 0; k < 4; k++) kinds |= (ekind[k] != 0 ? 1u : 0u) << k;
+          double* sc = por_smem + ((size_t)warp * R1_CACHE_GP * 24) * 32 + lane;
+#pragma unroll 1
+          for (int l = 0; l < 4; l++) {
+            double ar[4 * NN], ai[4 * NN];
+#pragma unroll
+            for (int i = 0; i < 4 * NN; i++) { ar[i] = 0.0; ai[i] = 0.0; }
+#pragma unroll 1
+            for (int kp = 0; kp < ngp; kp++) {
+              const double* q = P + (size_t)kp * RECN;
+              const double n[3] = {__ldg(q + 3), __ldg(q + 4), __ldg(q + 5)};
+              const double rv0 = __ldg(q) - xc[0], rv1 = __ldg(q + 1) - xc[1], rv2 = __ldg(q + 2) - xc[2];
+              const double r = sqrt(rv0 * rv0 + rv1 * rv1 + rv2 * rv2), d1r1 = 1.0 / r;
+              const double dx[3] = {rv0 * d1r1, rv1 * d1r1, rv2 * d1r1};
+              const double drdn = dx[0] * n[0] + dx[1] * n[1] + dx[2] * n[2];
+              PorScal ps;
+              if (l > 0 && kp < R1_CACHE_GP) por_scal_load(ps, sc + (size_t)kp * 24 * 32);
+              else {
+                por_scalars<false>(c_por, r, d1r1, ps);
+                if (l == 0 && kp < R1_CACHE_GP) por_scal_store(ps, sc + (size_t)kp * 24 * 32);
+              }
+              cplx ur[4], tr[4];
+              por_row_from_scalars(ps, dx, n, drdn, l, ur, tr);
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const cplx f = ((kinds >> k) & 1u) ? tr[k] : ur[k];
+#pragma unroll
+                for (int j = 0; j < NN; j++) { const double wj = __ldg(q + 6 + j); ar[k * NN + j] = fma(f.re, wj, ar[k * NN + j]); ai[k * NN + j] = fma(f.im, wj, ai[k * NN + j]); }
+              }
+            }
+            const int row = (l == 0) ? rows[0] : (l == 1 ? rows[1] : (l == 2 ? rows[2] : rows[3]));
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              // A += cte_t h (sign of the orientation) for a dof whose secondary variable is known, A -= cte_u g otherwise (assemble_bem_harpor_equation.f90:78-110)
+              const bool tk = (kinds >> k) & 1u;
+              const cplx c0 = tk ? ((l == 0) ? c_por.cte_t[0][k] : c_por.cte_t[1][k]) : ((l == 0) ? c_por.cte_u[0][k] : c_por.cte_u[1][k]);
+              const double sg = tk ? (rev ? -1.0 : 1.0) : -1.0;
+#pragma unroll
+              for (int j = 0; j < NN; j++) {
+                const int col = ecol[j * 4 + k];
+                atomicAdd(s.Are + (size_t)col * s.lda + row, sg * (c0.re * ar[k * NN + j] - c0.im * ai[k * NN + j]));
+                atomicAdd(s.Aim + (size_t)col * s.lda + row, sg * (c0.re * ai[k * NN + j] + c0.im * ar[k * NN + j]));
+              }
+            }
+          }
+          continue;
+        }
 #pragma unroll 1
         for (int l = 0; l < 4; l++) {
           RAcc<NN> acc; acc.zero();
@@ -114,12 +200,20 @@ __global__ void __launch_bounds__(R1_WARPS * 32) k_por_regular(DevGroup g, DevCo
 void launch_por_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, cudaStream_t st) {
   if (g.n_elem == 0) return;
   dim3 grid((c.n_tiles + R1_WARPS - 1) / R1_WARPS, (g.n_elem + R1_ECHUNK - 1) / R1_ECHUNK), block(R1_WARPS * 32);
+  const int smem = R1_WARPS * R1_CACHE_GP * 24 * 32 * (int)sizeof(double);   // 96 KB: two CTAs per SM
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_por_regular<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); cudaFuncSetAttribute(k_por_regular<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_por_regular<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); cudaFuncSetAttribute(k_por_regular<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_por_regular<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
   switch (g.et) {
-    case 5: k_por_regular<5><<<grid, block, 0, st>>>(g, c, s, plan); break;
-    case 6: k_por_regular<6><<<grid, block, 0, st>>>(g, c, s, plan); break;
-    case 7: k_por_regular<7><<<grid, block, 0, st>>>(g, c, s, plan); break;
-    case 8: k_por_regular<8><<<grid, block, 0, st>>>(g, c, s, plan); break;
-    case 9: k_por_regular<9><<<grid, block, 0, st>>>(g, c, s, plan); break;
+    case 5: k_por_regular<5><<<grid, block, smem, st>>>(g, c, s, plan); break;
+    case 6: k_por_regular<6><<<grid, block, smem, st>>>(g, c, s, plan); break;
+    case 7: k_por_regular<7><<<grid, block, smem, st>>>(g, c, s, plan); break;
+    case 8: k_por_regular<8><<<grid, block, smem, st>>>(g, c, s, plan); break;
+    case 9: k_por_regular<9><<<grid, block, smem, st>>>(g, c, s, plan); break;
   }
 }
 
