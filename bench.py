@@ -562,7 +562,10 @@ def run_c1(args):
             u, t = md.nodal_solution(X[kf]); ua = column_analytic_u(md.node_x[:, 0], float(case.omega[kf]), mat)
             errs.append(float(np.abs(u[:, 0] - ua).max() / np.abs(ua).max()))
         nfr = len(mine) * K
-        gemm_tf = acc["GEMM_EXEC_FLOPS"] / max(acc["MS_GEMM"], 1e-9) / 1e9
+        lu_tf = 8.0 / 3.0 * n ** 3 / (acc["MS_LU"] / nfr) / 1e9
+        # the factorisation of a system this small runs as one CUDA graph: its trailing updates are not timed one by one (MS_GEMM = 0); the LU as a whole is
+        gemm_timed = acc["MS_GEMM"] > 1e-3
+        gemm_tf = acc["GEMM_EXEC_FLOPS"] / acc["MS_GEMM"] / 1e9 if gemm_timed else lu_tf
         out = {"metric": C1_METRIC, "value": world * nfr / (ms_dev * 1e-3), "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / K,
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "reference input (tests/golden/ME-TH-EL-001)",
                "config": config, "setup_s_once_per_mesh": t_setup, "clocks": clocks.summary(windows),
@@ -570,9 +573,10 @@ def run_c1(args):
                        "api": "mfb_harela3d_solve_frequency (host cvalue in, host x out), once per frequency"},
                "gpu_launches": int(acc["LAUNCHES"] + acc["LU_LAUNCHES"]),
                "per_frequency_ms": {k[3:].lower(): acc[k] / nfr for k in keys if k.startswith("MS_")},
-               "roofline": {"kernel": "k_zgemm3m_tma (LU trailing update)", "bound": "tensor", "achieved": gemm_tf, "peak": peaks["dmma_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["dmma_tflops"],
-                            "traffic": None, "share_of_step": acc["MS_GEMM"] / ms_dev,
-                            "note": "at 1386 DOF the step is latency-bound (panel column chain, small grids), not pipe-bound: LU %.2f TFLOP/s of 8/3 n^3" % (8.0 / 3.0 * n ** 3 / (acc["MS_LU"] / nfr) / 1e9),
+               "roofline": {"kernel": "k_zgemm3m_tma (LU trailing update)" if gemm_timed else "zgetrf + zgetrs of one frequency as ONE CUDA graph (panel columns, interchanges, triangular solves, trailing updates)",
+                            "bound": "tensor", "achieved": gemm_tf, "peak": peaks["dmma_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["dmma_tflops"],
+                            "traffic": None, "share_of_step": (acc["MS_GEMM"] if gemm_timed else acc["MS_LU"]) / ms_dev,
+                            "note": "at 1386 DOF the step is latency-bound (panel column chain, small grids), not pipe-bound: LU %.2f TFLOP/s of 8/3 n^3" % lu_tf,
                             "peak_source": "FP64 tensor (DMMA) micro-benchmark measured live (mfb_measure_peaks)"},
                "analytic_column_rel_error_first_frequencies": errs, "peaks_measured_live": peaks}
         if lanes_out is not None:      # the sweep with several frequencies in flight IS the end-to-end number; the one-at-a-time figures stay beside it
