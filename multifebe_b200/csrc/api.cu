@@ -1435,6 +1435,7 @@ extern "C" int mfb_harela3d_sweep(mfb_problem* p, int n_freq, const double* omeg
                                   const mfb_z* cvalue, int rank, int nranks, const char* nccl_id128, mfb_z* X, int* info) {
   if (!p || !omega || !lambda || !mu || !nu || !X || n_freq < 1) return fail(MFB_ERR_ARG, "mfb_harela3d_sweep: invalid argument");
   if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !nccl_id128)) return fail(MFB_ERR_ARG, "mfb_harela3d_sweep: invalid rank / nranks / unique id");
+  if (p->have_inc && n_freq > 1) return fail(MFB_ERR_ARG, "mfb_harela3d_sweep: an incident field is set; it depends on the frequency, so such a model is swept with one mfb_harela3d_set_incident + mfb_harela3d_solve_frequency per frequency");
   CK(cudaSetDevice(p->ctx->device));
   cudaStream_t st = p->ctx->stream;
   const int n = p->n_dof;
