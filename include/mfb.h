@@ -100,6 +100,23 @@ int mfb_harela3d_setup_sym(mfb_ctx* ctx, int n_node, const double* node_x, int n
                            double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
                            double geometric_tolerance, int n_symplanes, const int* symplane_eid, const double* symplane_t,
                            mfb_problem** problem);
+/* Symmetry planes for an inviscid fluid and for a poroelastic region (arguments of mfb_harpot3d_setup / mfb_harpor3d_setup, then the planes as in
+ * mfb_harela3d_setup_sym plus symplane_s[i] = symplane_s(i), the multiplier of scalar variables: +1 symmetry, -1 antisymmetry): image loops of
+ * src/build_lse_mechanics_bem_harpot.f90:790-800 (h, g times symconf_s) and _harpor.f90:855-865 (dof 0 times symconf_s, dofs 1..3 times symconf_t). */
+int mfb_harpot3d_setup_sym(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
+                           const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
+                           const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
+                           const int* row, const int* col_p, const int* col_un, const int* ctype, int n_dof,
+                           double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
+                           double geometric_tolerance, int n_symplanes, const int* symplane_eid, const double* symplane_s,
+                           const double* symplane_t, mfb_problem** problem);
+int mfb_harpor3d_setup_sym(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
+                           const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
+                           const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
+                           const int* row, const int* col_p, const int* col_s, const int* ctype, int n_dof,
+                           double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
+                           double geometric_tolerance, int n_symplanes, const int* symplane_eid, const double* symplane_s,
+                           const double* symplane_t, mfb_problem** problem);
 void mfb_problem_free(mfb_problem* problem);
 
 /* Once per frequency.  == `A_c=0; b_c=0` + build_lse_mechanics_bem_harela(kf,kr) for one elastic BE region with

@@ -236,7 +236,17 @@ class Problem:
         self.h = C.c_void_p()
         cn = getattr(m, "colloc_n", None)
         self.ndof = int(getattr(m, "ndof", 3))
-        if self.ndof == 4:   # poroelastic region: four equations / unknowns per node (col_u = columns of tau, u_k; col_t = columns of Un, t_k)
+        has_sym = len(getattr(m, "symplane_eid", ())) > 0
+        if has_sym and self.ndof in (1, 4):   # [symmetry planes] on a fluid / poroelastic region
+            eid = np.ascontiguousarray(m.symplane_eid, dtype=np.int32); st = np.ascontiguousarray(m.symplane_t, dtype=np.float64)
+            sc = np.ascontiguousarray(m.symplane_s, dtype=np.float64); k += [eid, st, sc]
+            fn = lib().mfb_harpor3d_setup_sym if self.ndof == 4 else lib().mfb_harpot3d_setup_sym
+            _check(fn(
+                ctx.h, C.c_int(m.n_node), _p(k[0]), C.c_int(m.n_elem), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]),
+                C.c_int(m.n_colloc), _p(k[5]), _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9]), _p(k[10]), _p(k[11]), _p(k[12]), _p(k[13]),
+                C.c_int(m.n_dof), C.c_double(m.qsi_relative_error), C.c_int(m.qsi_ns_max), C.c_int(len(m.precalset_gln)), _p(k[14]),
+                C.c_double(m.geometric_tolerance), C.c_int(len(eid)), _p(eid), _p(sc), _p(st), C.byref(self.h)))
+        elif self.ndof == 4:   # poroelastic region: four equations / unknowns per node (col_u = columns of tau, u_k; col_t = columns of Un, t_k)
             _check(lib().mfb_harpor3d_setup(
                 ctx.h, C.c_int(m.n_node), _p(k[0]), C.c_int(m.n_elem), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]),
                 C.c_int(m.n_colloc), _p(k[5]), _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9]), _p(k[10]), _p(k[11]), _p(k[12]), _p(k[13]),

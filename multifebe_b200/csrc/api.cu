@@ -193,7 +193,7 @@ static double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 
 // Symmetry planes through the origin (src/read_symmetry_planes.f90:76-283): plane i is normal to axis eid[i] (1..3, ascending) and multiplies
 // the translation dof k of a reflected element by t[3*i+k] (symmetry: -1 on the normal axis, +1 elsewhere; antisymmetry: the opposite)
-struct SymSpec { int n_planes; int eid[3]; double t[9]; };
+struct SymSpec { int n_planes; int eid[3]; double t[9]; double s[3]; };   // s: multiplier of the scalar variables (fluid pressure / fluid phase), symplane_s
 static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
                       const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
                       const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
@@ -221,9 +221,37 @@ extern "C" int mfb_harela3d_setup_sym(mfb_ctx* ctx, int n_node, const double* no
                                       double geometric_tolerance, int n_symplanes, const int* symplane_eid, const double* symplane_t, mfb_problem** out) {
   if (n_symplanes < 0 || n_symplanes > 3 || (n_symplanes > 0 && (!symplane_eid || !symplane_t))) return fail(MFB_ERR_ARG, "mfb_harela3d_setup_sym: invalid symmetry planes");
   SymSpec sp; sp.n_planes = n_symplanes;
-  for (int i = 0; i < n_symplanes; i++) { sp.eid[i] = symplane_eid[i]; for (int k = 0; k < 3; k++) sp.t[3 * i + k] = symplane_t[3 * i + k]; }
+  for (int i = 0; i < n_symplanes; i++) { sp.eid[i] = symplane_eid[i]; sp.s[i] = 1.0; for (int k = 0; k < 3; k++) sp.t[3 * i + k] = symplane_t[3 * i + k]; }
   return setup_impl(ctx, n_node, node_x, n_elem, etype, elem_ptr, elem_node, elem_reversed, n_colloc, colloc_x, colloc_node, colloc_elem, colloc_kn, colloc_xi,
                     row, col_u, col_t, ctype, n_dof, qsi_relative_error, qsi_ns_max, n_precalsets, precalset_gln, geometric_tolerance, colloc_n, 3, out, &sp);
+}
+// Symmetry planes for the other two region types: the image loops of build_lse_mechanics_bem_harpot.f90:790-800 (h, g times symconf_s, :947-948) and
+// build_lse_mechanics_bem_harpor.f90:855-865 (dof 0 times symconf_s, dofs 1..3 times symconf_t(k), :971-975).  symplane_s[i] = symplane_s(i): +1 symmetry, -1 antisymmetry.
+static int fill_sym(SymSpec& sp, int n_symplanes, const int* symplane_eid, const double* symplane_s, const double* symplane_t) {
+  if (n_symplanes < 0 || n_symplanes > 3 || (n_symplanes > 0 && (!symplane_eid || !symplane_s || !symplane_t))) return fail(MFB_ERR_ARG, "setup_sym: invalid symmetry planes");
+  sp.n_planes = n_symplanes;
+  for (int i = 0; i < n_symplanes; i++) { sp.eid[i] = symplane_eid[i]; sp.s[i] = symplane_s[i]; for (int k = 0; k < 3; k++) sp.t[3 * i + k] = symplane_t[3 * i + k]; }
+  return MFB_OK;
+}
+extern "C" int mfb_harpot3d_setup_sym(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
+                                      const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
+                                      const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
+                                      const int* row, const int* col_p, const int* col_un, const int* ctype, int n_dof,
+                                      double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
+                                      double geometric_tolerance, int n_symplanes, const int* symplane_eid, const double* symplane_s, const double* symplane_t, mfb_problem** out) {
+  SymSpec sp; int r = fill_sym(sp, n_symplanes, symplane_eid, symplane_s, symplane_t); if (r) return r;
+  return setup_impl(ctx, n_node, node_x, n_elem, etype, elem_ptr, elem_node, elem_reversed, n_colloc, colloc_x, colloc_node, colloc_elem, colloc_kn, colloc_xi,
+                    row, col_p, col_un, ctype, n_dof, qsi_relative_error, qsi_ns_max, n_precalsets, precalset_gln, geometric_tolerance, nullptr, 1, out, &sp);
+}
+extern "C" int mfb_harpor3d_setup_sym(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem, const int* etype, const int* elem_ptr,
+                                      const int* elem_node, const unsigned char* elem_reversed, int n_colloc, const double* colloc_x,
+                                      const int* colloc_node, const int* colloc_elem, const int* colloc_kn, const double* colloc_xi,
+                                      const int* row, const int* col_p, const int* col_s, const int* ctype, int n_dof,
+                                      double qsi_relative_error, int qsi_ns_max, int n_precalsets, const int* precalset_gln,
+                                      double geometric_tolerance, int n_symplanes, const int* symplane_eid, const double* symplane_s, const double* symplane_t, mfb_problem** out) {
+  SymSpec sp; int r = fill_sym(sp, n_symplanes, symplane_eid, symplane_s, symplane_t); if (r) return r;
+  return setup_impl(ctx, n_node, node_x, n_elem, etype, elem_ptr, elem_node, elem_reversed, n_colloc, colloc_x, colloc_node, colloc_elem, colloc_kn, colloc_xi,
+                    row, col_p, col_s, ctype, n_dof, qsi_relative_error, qsi_ns_max, n_precalsets, precalset_gln, geometric_tolerance, nullptr, 4, out, &sp);
 }
 // Hypersingular equation for points OFF the boundary (interior-point stresses): fbem_bem_harela3d_hbie_auto with its exterior
 // branches (_ext_pre :2573-2662, _ext_adp :3044-3167); colloc_n[3*n_colloc] = unit normal n_i of each collocation point.
@@ -268,17 +296,17 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
   // columns (bits 5-7 of einfo).  From here on an image is an element like any other: the classifier, the planner and K1/K2/K3 never know.
   const int n_root = n_elem;
   int n_sym = 1;
-  double conf_m[8][3], conf_t[8][3]; bool conf_rev[8];
-  for (int ks = 0; ks < 8; ks++) { conf_rev[ks] = false; for (int c = 0; c < 3; c++) { conf_m[ks][c] = 1.0; conf_t[ks][c] = 1.0; } }
+  double conf_m[8][3], conf_t[8][3], conf_s[8]; bool conf_rev[8];
+  for (int ks = 0; ks < 8; ks++) { conf_rev[ks] = false; conf_s[ks] = 1.0; for (int c = 0; c < 3; c++) { conf_m[ks][c] = 1.0; conf_t[ks][c] = 1.0; } }
   double plane_m[3][3] = {{1, 1, 1}, {1, 1, 1}, {1, 1, 1}};
   std::vector<int> x_etype, x_ptr, x_node; std::vector<unsigned char> x_rev;
   if (sym && sym->n_planes > 0) {
     if (sym->n_planes > 3) return fail(MFB_ERR_ARG, "setup: at most three symmetry planes");
-    if (ndof != 3) return fail(MFB_ERR_UNSUPPORTED, "setup: symmetry planes are built for elastic regions only");
+
     for (int i = 0; i < sym->n_planes; i++) {
       if (sym->eid[i] < 1 || sym->eid[i] > 3 || (i > 0 && sym->eid[i] <= sym->eid[i - 1])) return fail(MFB_ERR_ARG, "setup: symmetry plane axes must be 1..3 in ascending order");
       for (int c = 0; c < 3; c++) {
-        if (fabs(sym->t[3 * i + c]) != 1.0) return fail(MFB_ERR_ARG, "setup: symmetry multipliers must be +1 or -1");
+        if (fabs(sym->t[3 * i + c]) != 1.0 || fabs(sym->s[i]) != 1.0) return fail(MFB_ERR_ARG, "setup: symmetry multipliers must be +1 or -1");
         plane_m[i][c] = (c == sym->eid[i] - 1) ? -1.0 : 1.0;
       }
     }
@@ -287,7 +315,7 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
     static const int steps[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};   // fbem_symmetry_multipliers :81-170
     for (int ks = 0; ks < n_sym; ks++) {
       int cnt = 0;
-      for (int i = 0; i < sym->n_planes; i++) if (steps[ks][i]) { cnt++; for (int c = 0; c < 3; c++) { conf_m[ks][c] *= plane_m[i][c]; conf_t[ks][c] *= sym->t[3 * i + c]; } }
+      for (int i = 0; i < sym->n_planes; i++) if (steps[ks][i]) { cnt++; conf_s[ks] *= sym->s[i]; for (int c = 0; c < 3; c++) { conf_m[ks][c] *= plane_m[i][c]; conf_t[ks][c] *= sym->t[3 * i + c]; } }
       conf_rev[ks] = (cnt & 1) != 0;
     }
     const int nen = elem_ptr[n_root];
@@ -494,8 +522,11 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
     for (int i = 0; i < g.n_elem; i++) {
       int e = g.elem_ids[i]; const mfbh::Elem& el = p->elems[e];
       {
-        unsigned info = 8u | (el.reversed ? 16u : 0u);
-        for (int k = 0; k < 3; k++) if (conf_t[e / n_root][k] < 0.0) info |= 32u << k;
+        unsigned info = 8u | ((el.reversed && ndof != 4) ? 16u : 0u);
+        // multipliers of a symmetry image: elastic bits 5-7 = symconf_t(k); fluid bit 5 = symconf_s; poroelastic bits 4-7 = symconf_s, symconf_t(1:3)
+        if (ndof == 3) { for (int k = 0; k < 3; k++) if (conf_t[e / n_root][k] < 0.0) info |= 32u << k; }
+        else if (ndof == 1) { if (conf_s[e / n_root] < 0.0) info |= 32u; }
+        else { if (conf_s[e / n_root] < 0.0) info |= 16u; for (int k = 0; k < 3; k++) if (conf_t[e / n_root][k] < 0.0) info |= 32u << k; }
         for (int k = 0; k < ndof; k++) {
           const int ct0 = ctype[ndof * elem_node[elem_ptr[e]] + k];
           for (int j = 1; j < g.nn; j++) if (ctype[ndof * elem_node[elem_ptr[e] + j] + k] != ct0) info &= ~8u;

@@ -99,7 +99,7 @@ __global__ void k_gather_cv(DevGroup g, const double* __restrict__ cvalue) {
         const double f = g.nfn[nd * (size_t)node + k];   // already negated for the nodes of a reversed boundary (the ROOT element's orientation counts, not an image's)
         vr *= f; vi *= f;
       }
-      if (k < 3 && ((g.einfo[e] >> (5 + k)) & 1u)) { vr = -vr; vi = -vi; }   // symmetry image: symconf_t(k) = -1 (the b term carries it through the value)
+      if ((g.einfo[e] >> ((nd == 4 ? 4 : 5) + k)) & 1u) { vr = -vr; vi = -vi; }   // symmetry image: multiplier -1 on dof k (the b term carries it through the value); bits 5-7 (4-7 for a poroelastic node)
       const size_t i = (size_t)e * nd * g.nn + j * nd + k;
       g.ecv[2 * i] = vr; g.ecv[2 * i + 1] = vi;
       nz = nz || vr != 0.0 || vi != 0.0;

@@ -22,7 +22,8 @@ struct DevGroup {
   const int* enode;              // [n_elem][nn]   global node ids
   const unsigned char* erev;     // [n_elem] reversed orientation (h -> -h)
   double* ecv;                   // [n_elem][3*nn][2] prescribed value of (j,k), refreshed per frequency
-  const unsigned char* einfo;    // [n_elem] bits 0-2: kind of dof k (when the same for every node j), bit 3: kinds uniform over j, bit 4: reversed
+  const unsigned char* einfo;    // [n_elem] bits 0-2: kind of dof k (when the same for every node j), bit 3: kinds uniform over j, bit 4: reversed,
+                                 // bits 5-7: multiplier -1 of a symmetry image on dof k (elastic: symconf_t(k); fluid: bit 5 = symconf_s); poroelastic: bits 4-7 = dofs 0-3, no reversed bit
   unsigned char* ecvnz;          // [n_elem] 1 when some prescribed value of the element is nonzero (refreshed per frequency)
   const unsigned char* c10;      // NULL, or [3*n_node]: 1 where ctype = 10 (normal pressure known): the prescribed value is cvalue * nfn
   const double* nfn;             // [3*n_node] nodal unit normals, negated for the nodes of a reversed boundary (with c10)

@@ -29,7 +29,8 @@ void set_por_params(const PorParams& pp, cudaStream_t st) { cudaMemcpyToSymbolAs
 // `mine(j * 4 + k)`; h is scaled by cte_t(l, k) and changes sign on a reversed element, g by cte_u(l, k).
 template <int NN, class Pred>
 __device__ __forceinline__ void por_scatter_row(const RAcc<NN>& a, int l, const int* __restrict__ ecol, const unsigned char* __restrict__ ekind,
-                                                const double* __restrict__ ecv, bool rev, const DevSystem& s, int row, double& bre, double& bim, Pred mine) {
+                                                const double* __restrict__ ecv, bool rev, const DevSystem& s, int row, double& bre, double& bim, Pred mine,
+                                                unsigned symbits = 0u /* bit k: multiplier -1 of a symmetry image on dof k (symconf_s for k = 0, symconf_t(k) else) */) {
 #pragma unroll
   for (int k = 0; k < 4; k++) {
 #pragma unroll
@@ -43,6 +44,7 @@ __device__ __forceinline__ void por_scatter_row(const RAcc<NN>& a, int l, const 
       double ar, ai;
       if (ekind[jk] == 0) { ar = -gr; ai = -gi; bre -= hr * cvr - hi * cvi; bim -= hr * cvi + hi * cvr; }
       else { ar = hr; ai = hi; bre += gr * cvr - gi * cvi; bim += gr * cvi + gi * cvr; }
+      if ((symbits >> k) & 1u) { ar = -ar; ai = -ai; }   // build_lse_mechanics_bem_harpor.f90:971-975; the b terms carry the sign in ecv
       atomicAdd(s.Are + (size_t)col * s.lda + row, ar);
       atomicAdd(s.Aim + (size_t)col * s.lda + row, ai);
     }
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(R1_WARPS * 32) k_por_regular(DevGroup g, DevCo
               // A += cte_t h (sign of the orientation) for a dof whose secondary variable is known, A -= cte_u g otherwise (assemble_bem_harpor_equation.f90:78-110)
               const bool tk = (kinds >> k) & 1u;
               const cplx c0 = tk ? ((l == 0) ? c_por.cte_t[0][k] : c_por.cte_t[1][k]) : ((l == 0) ? c_por.cte_u[0][k] : c_por.cte_u[1][k]);
-              const double sg = tk ? (rev ? -1.0 : 1.0) : -1.0;
+              const double sg = (tk ? (rev ? -1.0 : 1.0) : -1.0) * (((g.einfo[e] >> (4 + k)) & 1u) ? -1.0 : 1.0);   // sign of a symmetry image on dof k
 #pragma unroll
               for (int j = 0; j < NN; j++) {
                 const int col = ecol[j * 4 + k];
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(R1_WARPS * 32) k_por_regular(DevGroup g, DevCo
           }
           const int row = (l == 0) ? rows[0] : (l == 1 ? rows[1] : (l == 2 ? rows[2] : rows[3]));
           double br = 0.0, bi = 0.0;
-          por_scatter_row<NN>(acc, l, ecol, ekind, ecv, rev, s, row, br, bi, PorAll());
+          por_scatter_row<NN>(acc, l, ecol, ekind, ecv, rev, s, row, br, bi, PorAll(), (unsigned)g.einfo[e] >> 4);
           if (l == 0) { bre[0] += br; bim[0] += bi; } else if (l == 1) { bre[1] += br; bim[1] += bi; } else if (l == 2) { bre[2] += br; bim[2] += bi; } else { bre[3] += br; bim[3] += bi; }
         }
       }
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(128) k_por_adaptive(DevGroup g, DevColloc c, D
     const int row = c.crow[l * c.ldp + cpos];
     double br = 0.0, bi = 0.0;
     PorLane pl; pl.lane = lane;
-    por_scatter_row<NN>(acc, l, g.ecol + (size_t)e * 4 * NN, g.ekind + (size_t)e * 4 * NN, g.ecv + (size_t)e * 8 * NN, rev, s, row, br, bi, pl);
+    por_scatter_row<NN>(acc, l, g.ecol + (size_t)e * 4 * NN, g.ekind + (size_t)e * 4 * NN, g.ecv + (size_t)e * 8 * NN, rev, s, row, br, bi, pl, (unsigned)g.einfo[e] >> 4);
     if (br != 0.0 || bi != 0.0) { atomicAdd(s.bre + row, br); atomicAdd(s.bim + row, bi); }
   }
 }
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(128) k_por_singular(DevGroup g, DevColloc c, D
     const int row = c.crow[l * c.ldp + cpos];
     double br = 0.0, bi = 0.0;
     PorLane pl; pl.lane = lane;
-    por_scatter_row<NN>(acc, l, g.ecol + (size_t)e * 4 * NN, g.ekind + (size_t)e * 4 * NN, g.ecv + (size_t)e * 8 * NN, rev, s, row, br, bi, pl);
+    por_scatter_row<NN>(acc, l, g.ecol + (size_t)e * 4 * NN, g.ekind + (size_t)e * 4 * NN, g.ecv + (size_t)e * 8 * NN, rev, s, row, br, bi, pl, (unsigned)g.einfo[e] >> 4);
     if (br != 0.0 || bi != 0.0) { atomicAdd(s.bre + row, br); atomicAdd(s.bim + row, bi); }
   }
 }

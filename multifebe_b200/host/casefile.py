@@ -316,18 +316,18 @@ class CaseFile:
         self.symmetry = []
         sp = sec.get("symmetry planes") or []
         if sp:
-            if self.multi or self.region_type != 2:
-                raise CaseFileError("[symmetry planes]: covered for one elastic region")
+            if self.multi:
+                raise CaseFileError("[symmetry planes]: covered for models of one region")
             for ax, names in (("x", ("plane_n1", "plane_yz")), ("y", ("plane_n2", "plane_zx")), ("z", ("plane_n3", "plane_xy"))):
                 given = []
                 v = _keyword(sp, ax)
                 if v is not None:
                     w = v.split()
                     try:
-                        t = [int(q) for q in w[1:4]]
+                        t = [int(q) for q in w[0:4]]
                     except ValueError:
                         t = []
-                    if len(t) != 3 or any(abs(q) != 1 for q in t):
+                    if len(t) != 4 or any(abs(q) != 1 for q in t):
                         raise CaseFileError("[symmetry planes] %s = <s> <t1> <t2> <t3>: multipliers must be +1 or -1" % ax)
                     given.append(tuple(float(q) for q in t))
                 for nm in names:
@@ -401,10 +401,11 @@ class CaseFile:
             bcs = {b: ((ct[0], cv[0]) if len(ct) == 1 else (ct, cv)) for b, (ct, cv) in self.bcs.items()}
             return MultiRegionModel(self.mesh, regs, part_of_boundary, bcs, **kw)
         kw["part_order"] = [part_of_boundary[b] for b in self.region_boundaries]
+        kw["symmetry"] = self.symmetry
         if self.region_type == 1:
             bcs = {part_of_boundary[b]: (ct[0], cv[0]) for b, (ct, cv) in self.bcs.items()}
             return FluidModel(self.mesh, bcs, **kw)
         if self.region_type == 3:
             return PoroModel(self.mesh, {part_of_boundary[b]: (ct, cv) for b, (ct, cv) in self.bcs.items()}, **kw)
         bcs = {part_of_boundary[b]: (ct, cv) for b, (ct, cv) in self.bcs.items()}
-        return Model(self.mesh, bcs, symmetry=self.symmetry, **kw)
+        return Model(self.mesh, bcs, **kw)

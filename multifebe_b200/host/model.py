@@ -36,14 +36,25 @@ def symmetry_planes(symmetry):
         if isinstance(kind, str):
             sgn = {"symmetry": 1.0, "antisymmetry": -1.0}[kind]
             t = np.full(3, sgn); t[ax - 1] = -sgn
-        else:      # the explicit form of the case file: the three translation multipliers themselves
-            t = np.array(kind, dtype=np.float64)
+        else:      # the explicit form of the case file: the three translation multipliers themselves (optionally preceded by the scalar one)
+            t = np.array(kind[-3:], dtype=np.float64)
             if t.shape != (3,) or not np.all(np.abs(t) == 1.0):
                 raise ValueError("symmetry multipliers must be three values +1 or -1")
         planes[ax] = t
     eid = np.array(sorted(planes), dtype=np.int32)
     t = np.ascontiguousarray([planes[a] for a in sorted(planes)], dtype=np.float64).reshape(len(eid), 3)
     return eid, t
+
+
+def symmetry_scalars(symmetry, eid, t):
+    """symplane_s of every plane: the multiplier of scalar variables (fluid pressure, fluid-phase stress): +1 symmetry, -1 antisymmetry
+    (read_symmetry_planes.f90:160-228); with the explicit multipliers of the case file, the first of the four values."""
+    given = {}
+    for axis, kind in (symmetry or ()):
+        ax = {"x": 1, "y": 2, "z": 3, 1: 1, 2: 2, 3: 3}[axis]
+        if not isinstance(kind, str) and len(kind) == 4:
+            given[ax] = float(kind[0])
+    return np.array([given.get(int(a), t[i, int(a) % 3]) for i, a in enumerate(eid)], dtype=np.float64)
 
 
 class Model:
@@ -60,6 +71,7 @@ class Model:
         SBIE with MCA like any other rim node, assign_default_bem_formulation.f90:85-92)."""
         self.mesh = mesh
         self.symplane_eid, self.symplane_t = symmetry_planes(symmetry)
+        self.symplane_s = symmetry_scalars(symmetry, self.symplane_eid, self.symplane_t)
         for ax in self.symplane_eid:   # fbem_check_nodes_symplanes_configuration (lib/fbem/src/data_structures.f90:1197-1230): the mesh stays on one side
             xa = mesh.nodes[:, ax - 1]
             off = xa[np.abs(xa) > float(geometric_tolerance)]
@@ -307,6 +319,7 @@ class InternalPointsModel:
         self.qsi_relative_error, self.qsi_ns_max = m.qsi_relative_error, m.qsi_ns_max
         self.precalset_gln, self.geometric_tolerance = m.precalset_gln, m.geometric_tolerance
         self.symplane_eid, self.symplane_t = getattr(m, "symplane_eid", np.zeros(0, np.int32)), getattr(m, "symplane_t", np.zeros((0, 3)))
+        self.symplane_s = getattr(m, "symplane_s", np.zeros(0))
         if hasattr(m, "n_fn"):
             self.n_fn = np.ascontiguousarray(np.vstack([m.n_fn, np.zeros((nip, 3))]))
         self.n_dof = m.n_dof + nd * nip

@@ -1478,7 +1478,7 @@ struct Model {
   // symmetry planes (lib/fbem/src/symmetry.f90:60-171, src/read_symmetry_planes.f90:228-283): image ks of every element, ks = 1..n_sym-1
   std::vector<int> ps_gln; std::vector<double> node_x;
   int n_planes = 0, n_sym = 1, plane_eid[3] = {0, 0, 0};
-  double plane_m[3][3], conf_m[8][3], conf_t[8][3]; bool conf_rev[8];
+  double plane_m[3][3], conf_m[8][3], conf_t[8][3], conf_s[8]; bool conf_rev[8];
   std::vector<std::vector<Element>> img;
   // incident field at the nodes of every element (element()%incident_c): [(eptr[e] + kn) * 3 + ik], empty = none
   std::vector<cd> u_inc, t_inc;
@@ -1502,6 +1502,7 @@ void* orc_setup(int n_node, const double* node_x, int n_elem, const int* etype, 
   m->ctype.assign(ctype, ctype + 3 * n_node);
   qs_calculate_parameters(qsi_relative_error, m->qsp); m->ns_max = qsi_ns_max; m->geometric_tolerance = geometric_tolerance;
   m->ps_gln.assign(precalset_gln, precalset_gln + n_precalsets); m->node_x.assign(node_x, node_x + 3 * n_node);
+  for (int ks = 0; ks < 8; ks++) { m->conf_s[ks] = 1.0; m->conf_rev[ks] = false; for (int c = 0; c < 3; c++) { m->conf_m[ks][c] = 1.0; m->conf_t[ks][c] = 1.0; } }
   m->elem.resize(n_elem);
   for (int e = 0; e < n_elem; e++) {
     Element& el = m->elem[e]; el.et = etype[e]; el.nn = n_nodes_of(el.et); el.reverse = elem_reversed[e] != 0;
@@ -1528,7 +1529,11 @@ void orc_free(void* h) { delete (Model*)h; }
 // 4 SP2, 5 SP3, 6 SP1+SP3, 7 SP1+SP2+SP3, 8 SP2+SP3; an odd number of reflections reverses the orientation.  As in
 // build_lse_mechanics_bem_harela.f90:1052-1107 only the nodal coordinates of the calculation element are reflected: csize, n_phi
 // and the bounding ball (centre included) stay those of the root element.
-int orc_set_symmetry(void* h, int n_planes, const int* eid, const double* t) {
+static int set_symmetry_impl(void* h, int n_planes, const int* eid, const double* t, const double* sc);
+int orc_set_symmetry(void* h, int n_planes, const int* eid, const double* t) { return set_symmetry_impl(h, n_planes, eid, t, nullptr); }
+// the same with the scalar multipliers symplane_s (fluid pressure / fluid-phase variables: +1 symmetry, -1 antisymmetry)
+int orc_set_symmetry_s(void* h, int n_planes, const int* eid, const double* t, const double* sc) { return set_symmetry_impl(h, n_planes, eid, t, sc); }
+static int set_symmetry_impl(void* h, int n_planes, const int* eid, const double* t, const double* sc) {
   Model* m = (Model*)h;
   if (n_planes < 0 || n_planes > 3) return 1;
   m->n_planes = n_planes; m->n_sym = 1 << n_planes; m->img.clear();
@@ -1542,7 +1547,12 @@ int orc_set_symmetry(void* h, int n_planes, const int* eid, const double* t) {
   for (int ks = 0; ks < m->n_sym; ks++) {
     int cnt = 0;
     for (int c = 0; c < 3; c++) { m->conf_m[ks][c] = 1.0; m->conf_t[ks][c] = 1.0; }
-    for (int i = 0; i < n_planes; i++) if (steps[ks][i]) { cnt++; for (int c = 0; c < 3; c++) { m->conf_m[ks][c] *= m->plane_m[i][c]; m->conf_t[ks][c] *= pt[i][c]; } }
+    m->conf_s[ks] = 1.0;
+    for (int i = 0; i < n_planes; i++) if (steps[ks][i]) {
+      cnt++; for (int c = 0; c < 3; c++) { m->conf_m[ks][c] *= m->plane_m[i][c]; m->conf_t[ks][c] *= pt[i][c]; }
+      // default: the multiplier of a tangential translation (symmetry +1, antisymmetry -1), as read_symmetry_planes.f90:160-228 pairs them
+      m->conf_s[ks] *= sc ? sc[i] : pt[i][eid[i] % 3];
+    }
     m->conf_rev[ks] = (cnt & 1) != 0;
   }
   m->img.resize(m->n_sym - 1);
@@ -1572,6 +1582,31 @@ static int node_planes(const Model* m, int sn, int* planes) {
   return n;
 }
 static inline const Element& image_of(const Model* m, int e, int ks) { return ks == 0 ? m->elem[e] : m->img[ks - 1][e]; }
+// normals / tangents of the fan of elements around node sn as seen from the region (reverse: the boundary is reversed in it), completed with the
+// mirror images when the node lies in one or two symmetry planes (build_lse_mechanics_bem_harela.f90:430-555); returns the fan size, -1 if unsupported
+static int node_fan(const Model* m, int sn, bool reverse, std::vector<double>& ns, std::vector<double>& ts) {
+  int b0 = m->n2e_ptr[sn], ne = m->n2e_ptr[sn + 1] - b0;
+  int planes[3]; const int npl = node_planes(m, sn, planes);
+  if (npl > 2) return -1;
+  const int fan = ne << npl;
+  ns.assign(3 * fan, 0.0); ts.assign(3 * fan, 0.0); std::vector<double> tr(3 * ne);
+  for (int k = 0; k < ne; k++) {
+    const Element& ee = m->elem[m->n2e_elem[b0 + k]]; double n[3], tbp[3], tbm[3];
+    node_normal_tangents(ee.et, ee.x, m->n2e_kn[b0 + k], n, tbp, tbm);
+    for (int cc = 0; cc < 3; cc++) { ns[3 * k + cc] = reverse ? -n[cc] : n[cc]; ts[3 * k + cc] = reverse ? tbm[cc] : tbp[cc]; tr[3 * k + cc] = reverse ? tbp[cc] : tbm[cc]; }
+  }
+  if (npl >= 1) {
+    const double* m1 = m->plane_m[planes[0]]; const double* m2 = (npl == 2) ? m->plane_m[planes[1]] : nullptr;
+    for (int k = 0; k < ne; k++) for (int cc = 0; cc < 3; cc++) {
+      ns[3 * (k + ne) + cc] = m1[cc] * ns[3 * k + cc]; ts[3 * (k + ne) + cc] = m1[cc] * tr[3 * k + cc];
+      if (npl == 2) {
+        ns[3 * (k + 2 * ne) + cc] = m1[cc] * m2[cc] * ns[3 * k + cc]; ts[3 * (k + 2 * ne) + cc] = m1[cc] * m2[cc] * ts[3 * k + cc];
+        ns[3 * (k + 3 * ne) + cc] = m2[cc] * ns[3 * k + cc]; ts[3 * (k + 3 * ne) + cc] = m2[cc] * tr[3 * k + cc];
+      }
+    }
+  }
+  return fan;
+}
 static inline void apply_symconf(const Model* m, int ks, int nn, cd* h, cd* g) {   // build_lse_mechanics_bem_harela.f90:1203-1206
   if (ks == 0) return;
   for (int kn = 0; kn < nn; kn++) for (int il = 0; il < 3; il++) for (int ik = 0; ik < 3; ik++) { h[(kn * 3 + il) * 3 + ik] *= m->conf_t[ks][ik]; g[(kn * 3 + il) * 3 + ik] *= m->conf_t[ks][ik]; }
@@ -1676,26 +1711,9 @@ static int assemble_impl(Model* m, const Params& p, cd nu, const cd* cvalue, cd*
       double xi_i[2]; xi_at_node(el.et, kn, xi_i);
       cd cplus[3][3];
       if (check_xi1xi2_edge(el.et, xi_i)) {
-        int b0 = m->n2e_ptr[sn], ne = m->n2e_ptr[sn + 1] - b0;
-        int planes[3]; const int npl = node_planes(m, sn, planes);
-        if (npl > 2) { err = 1; continue; }   // the reference builds fans for nodes in one or two planes only (:500-555)
-        const int fan = ne << npl;
-        std::vector<double> ns(3 * fan), ts(3 * fan), tr(3 * fan);   // tr: tangent of the reversed orientation (t_set_at_gn_reversed)
-        for (int k = 0; k < ne; k++) {
-          const Element& ee = m->elem[m->n2e_elem[b0 + k]]; double n[3], tbp[3], tbm[3];
-          node_normal_tangents(ee.et, ee.x, m->n2e_kn[b0 + k], n, tbp, tbm);
-          for (int cc = 0; cc < 3; cc++) { ns[3 * k + cc] = el.reverse ? -n[cc] : n[cc]; ts[3 * k + cc] = el.reverse ? tbm[cc] : tbp[cc]; tr[3 * k + cc] = el.reverse ? tbp[cc] : tbm[cc]; }
-        }
-        if (npl >= 1) {   // build_lse_mechanics_bem_harela.f90:500-555
-          const double* m1 = m->plane_m[planes[0]]; const double* m2 = (npl == 2) ? m->plane_m[planes[1]] : nullptr;
-          for (int k = 0; k < ne; k++) for (int cc = 0; cc < 3; cc++) {
-            ns[3 * (k + ne) + cc] = m1[cc] * ns[3 * k + cc]; ts[3 * (k + ne) + cc] = m1[cc] * tr[3 * k + cc];
-            if (npl == 2) {
-              ns[3 * (k + 2 * ne) + cc] = m1[cc] * m2[cc] * ns[3 * k + cc]; ts[3 * (k + 2 * ne) + cc] = m1[cc] * m2[cc] * ts[3 * k + cc];
-              ns[3 * (k + 3 * ne) + cc] = m2[cc] * ns[3 * k + cc]; ts[3 * (k + 3 * ne) + cc] = m2[cc] * tr[3 * k + cc];
-            }
-          }
-        }
+        std::vector<double> ns, ts;
+        const int fan = node_fan(m, sn, el.reverse, ns, ts);
+        if (fan < 0) { err = 1; continue; }   // the reference builds fans for nodes in one or two planes only (:500-555)
         if (sbie_freeterm(fan, ns.data(), ts.data(), m->geometric_tolerance, nu, cplus)) err = 1;
       } else {
         for (int a = 0; a < 3; a++) for (int bb = 0; bb < 3; bb++) cplus[a][bb] = (a == bb) ? 0.5 : 0.0;
@@ -1759,13 +1777,14 @@ int orc_assemble_pot(void* hd, double omega, double rho, const double* c_ri, con
   {
     Stats st; memset(&st, 0, sizeof(st));
 #pragma omp for schedule(dynamic)
-    for (int e = 0; e < m->n_elem; e++) {
-      const Element& el = m->elem[e];
+    for (int e = 0; e < m->n_elem; e++)
+    for (int ks = 0; ks < m->n_sym; ks++) {   // symmetry images: build_lse_mechanics_bem_harpot.f90:790-800, h, g times symconf_s (:947-948)
+      const Element& el = image_of(m, e, ks);
       cd hh[81], gg[81];
       for (int c = 0; c < m->n_colloc; c++) {
         sbie_auto(el, &m->cx[3 * c], p, m->qsp, m->ns_max, hh, gg, st);
         // the flux variable is the normal displacement Un = 1/(rho omega^2) dp/dn: gp=gp*d1J (build_lse_mechanics_bem_harpot.f90:751,1104)
-        for (int j = 0; j < el.nn; j++) gg[j] = gg[j] * d1J;
+        for (int j = 0; j < el.nn; j++) { gg[j] = gg[j] * d1J * m->conf_s[ks]; hh[j] = hh[j] * m->conf_s[ks]; }
 #pragma omp critical
         scatter_pot(m, e, m->cnode[c], hh, gg, cvalue, A, b);
       }
@@ -1783,13 +1802,9 @@ int orc_assemble_pot(void* hd, double omega, double rho, const double* c_ri, con
       double xi_i[2]; xi_at_node(el.et, kn, xi_i);
       double c_plus = 0.5;
       if (check_xi1xi2_edge(el.et, xi_i)) {
-        int b0 = m->n2e_ptr[sn], ne = m->n2e_ptr[sn + 1] - b0;
-        std::vector<double> ns(3 * ne), ts(3 * ne);
-        for (int k = 0; k < ne; k++) {
-          const Element& ee = m->elem[m->n2e_elem[b0 + k]]; double n[3], tbp[3], tbm[3];
-          node_normal_tangents(ee.et, ee.x, m->n2e_kn[b0 + k], n, tbp, tbm);
-          for (int cc = 0; cc < 3; cc++) { ns[3 * k + cc] = el.reverse ? -n[cc] : n[cc]; ts[3 * k + cc] = el.reverse ? tbm[cc] : tbp[cc]; }
-        }
+        std::vector<double> ns, ts;
+        const int ne = node_fan(m, sn, el.reverse, ns, ts);
+        if (ne < 0) { err = 1; continue; }
         cd dummy[3][3];
         if (sbie_freeterm(ne, ns.data(), ts.data(), m->geometric_tolerance, cd(0.0, 0.0), dummy, &c_plus)) err = 1;
       }
@@ -1874,11 +1889,17 @@ int orc_assemble_por(void* hd, double omega, const double* props, const double* 
   {
     Stats st; memset(&st, 0, sizeof(st));
 #pragma omp for schedule(dynamic)
-    for (int e = 0; e < m->n_elem; e++) {
-      const Element& el = m->elem[e];
+    for (int e = 0; e < m->n_elem; e++)
+    for (int ks = 0; ks < m->n_sym; ks++) {   // symmetry images: build_lse_mechanics_bem_harpor.f90:855-865
+      const Element& el = image_of(m, e, ks);
       cd hh[144], gg[144];
       for (int c = 0; c < m->n_colloc; c++) {
         sbie_auto(el, &m->cx[3 * c], p, m->qsp, m->ns_max, hh, gg, st);
+        if (ks > 0)   // h(:,:,0), g(:,:,0) times symconf_s, h(:,:,ik), g(:,:,ik) times symconf_t(ik) (:971-975)
+          for (int kn = 0; kn < el.nn; kn++) for (int il = 0; il < 4; il++) for (int ik = 0; ik < 4; ik++) {
+            const double f = (ik == 0) ? m->conf_s[ks] : m->conf_t[ks][ik - 1];
+            hh[(kn * 4 + il) * 4 + ik] *= f; gg[(kn * 4 + il) * 4 + ik] *= f;
+          }
 #pragma omp critical
         scatter_por(m, e, m->cnode[c], hh, gg, cvalue, A, b);
       }
@@ -1897,13 +1918,9 @@ int orc_assemble_por(void* hd, double omega, const double* props, const double* 
       double cpot = 0.5; cd cela[3][3];
       for (int a = 0; a < 3; a++) for (int bb = 0; bb < 3; bb++) cela[a][bb] = (a == bb) ? 0.5 : 0.0;
       if (check_xi1xi2_edge(el.et, xi_i)) {
-        int b0 = m->n2e_ptr[sn], ne = m->n2e_ptr[sn + 1] - b0;
-        std::vector<double> ns(3 * ne), ts(3 * ne);
-        for (int k = 0; k < ne; k++) {
-          const Element& ee = m->elem[m->n2e_elem[b0 + k]]; double n[3], tbp[3], tbm[3];
-          node_normal_tangents(ee.et, ee.x, m->n2e_kn[b0 + k], n, tbp, tbm);
-          for (int cc = 0; cc < 3; cc++) { ns[3 * k + cc] = el.reverse ? -n[cc] : n[cc]; ts[3 * k + cc] = el.reverse ? tbm[cc] : tbp[cc]; }
-        }
+        std::vector<double> ns, ts;
+        const int ne = node_fan(m, sn, el.reverse, ns, ts);
+        if (ne < 0) { err = 1; continue; }
         if (sbie_freeterm(ne, ns.data(), ts.data(), m->geometric_tolerance, P.nu, cela, &cpot)) err = 1;
       }
       hp[(kn * 4 + 0) * 4 + 0] += P.J * cpot;

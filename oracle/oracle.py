@@ -39,6 +39,16 @@ def _ri(z):
     return np.array([z.real, z.imag], dtype=np.float64)
 
 
+def _apply_symmetry(L, h, m):
+    """[symmetry planes] of the model: image elements and multipliers inside the oracle (orc_set_symmetry_s)."""
+    eid = np.ascontiguousarray(getattr(m, "symplane_eid", np.zeros(0)), dtype=np.int32)
+    if len(eid):
+        t = np.ascontiguousarray(m.symplane_t, dtype=np.float64)
+        sc = np.ascontiguousarray(m.symplane_s, dtype=np.float64)
+        if L.orc_set_symmetry_s(h, C.c_int(len(eid)), _p(eid), _p(t), _p(sc)):
+            raise ValueError("oracle: invalid symmetry planes")
+
+
 class Oracle:
     """Oracle handle for one Model (multifebe_b200.host.Model)."""
 
@@ -58,11 +68,7 @@ class Oracle:
         if (np.asarray(m.ctype) == 10).any():
             nf = np.ascontiguousarray(m.n_fn, dtype=np.float64); self._keep.append(nf)
             L.orc_set_node_normals(self.h, _p(nf))
-        eid = np.ascontiguousarray(getattr(m, "symplane_eid", np.zeros(0)), dtype=np.int32)
-        if len(eid):
-            t = np.ascontiguousarray(m.symplane_t, dtype=np.float64)
-            if L.orc_set_symmetry(self.h, C.c_int(len(eid)), _p(eid), _p(t)):
-                raise ValueError("oracle: invalid symmetry planes")
+        _apply_symmetry(L, self.h, m)
 
     def __del__(self):
         try:
@@ -299,6 +305,7 @@ class PotOracle:
             _p(k[10]), _p(k[11]), _p(k[12]), _p(k[13]), C.c_int(m.n_dof),
             C.c_double(m.qsi_relative_error), C.c_int(m.qsi_ns_max), C.c_int(len(m.precalset_gln)), _p(k[14]),
             C.c_double(m.geometric_tolerance)))
+        _apply_symmetry(L, self.h, m)
 
     def __del__(self):
         try:
@@ -357,6 +364,7 @@ class PorOracle:
             _p(k[10]), _p(k[11]), _p(k[12]), _p(k[13]), C.c_int(m.n_dof),
             C.c_double(m.qsi_relative_error), C.c_int(m.qsi_ns_max), C.c_int(len(m.precalset_gln)), _p(k[14]),
             C.c_double(m.geometric_tolerance)))
+        _apply_symmetry(L, self.h, m)
 
     def __del__(self):
         try:

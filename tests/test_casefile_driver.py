@@ -673,3 +673,60 @@ def test_symmetry_planes_section_forms_and_errors(tmp_path):
     c.mesh.nodes[:, 0] -= 0.5
     with pytest.raises(ValueError):
         c.build_model()
+
+
+def test_symmetry_planes_on_a_fluid_region(tmp_path):
+    """The acoustic room of ME-TH-AC-001 as a quarter model: its rigid walls y = 0, z = 0 replaced by [symmetry planes] (scalar multiplier symplane_s = +1)."""
+    from multifebe_b200.host import without_parts
+    write_gmsh22(without_parts(cube_mesh(2, shape.QUAD9), {3, 5}), str(tmp_path / "quarter.msh"))
+    text = """[problem]
+type = mechanics
+analysis = harmonic
+n = 3D
+
+[frequencies]
+Hz
+list
+1
+45.
+
+[settings]
+mesh_file_mode = 2 "quarter.msh"
+
+[boundaries]
+4
+1 1 ordinary
+2 2 ordinary
+4 4 ordinary
+6 6 ordinary
+
+[materials]
+1
+1 fluid c 343. rho 1.25
+
+[regions]
+1
+1 be
+4 1 2 4 6
+material 1
+0
+0
+
+[symmetry planes]
+plane_n2: symmetry
+z = 1 1 1 -1
+
+[conditions over be boundaries]
+boundary 1: 0 (0.,0.)
+boundary 2: 0 (1.,0.)
+boundary 4: 1 (0.,0.)
+boundary 6: 1 (0.,0.)
+"""
+    p = tmp_path / "case.dat"; p.write_text(text)
+    nso, case = _run_with_oracle(str(p))
+    md = case.build_model()
+    assert case.region_type == 1 and list(md.symplane_eid) == [2, 3] and list(md.symplane_s) == [1.0, 1.0]
+    rows = read_nso(nso)
+    pr = rows[:, 12] + 1j * rows[:, 13]
+    p_ex, _ = room_analytic(rows[:, 9], 2 * np.pi * 45.0, Fluid(1.25, 343.0))
+    assert np.abs(pr - p_ex).max() < 5e-4

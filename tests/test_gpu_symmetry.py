@@ -133,3 +133,50 @@ def test_setup_sym_rejects_bad_planes(gpu_ctx):
     md.symplane_eid = np.array([1, 2], dtype=np.int32); md.symplane_t = np.array([[-1, 1, 1], [1, 0.5, 1]], dtype=np.float64)
     with pytest.raises(capi.MfbError):
         capi.Problem(gpu_ctx, md)
+
+
+def test_fluid_and_poroelastic_regions_with_symmetry(gpu_ctx, oracle_lib):
+    """symconf_s on the scalar variables: image loops of build_lse_mechanics_bem_harpot / _harpor, against the oracles that
+    tests/test_oracle_symmetry.py pins on mirrored full models, the quarter room and the quarter Biot column."""
+    from multifebe_b200 import capi
+    from multifebe_b200.host import Fluid, FluidModel, Poro, PoroModel
+    from test_oracle_symmetry import FLUID_CASES, _generic_reduced_and_full
+    fl = Fluid(rho=1.0, c=1.0, xi=0.03)
+    for name, planes, flux in FLUID_CASES:
+        for etype, m in ((shape.TRI3, 3), (shape.QUAD9, 2)):
+            red, _ = _generic_reduced_and_full(m, etype, planes, lambda mesh, **kw: FluidModel(mesh, {1: (1, 0.0)}, **kw), flux)
+            pr = capi.Problem(gpu_ctx, red); o = oracle_lib.PotOracle(red)
+            A, b = pr.build_lse_mechanics_bem_harpot(2.5, fl)
+            Ao, bo, _ = o.assemble(2.5, fl)
+            assert relerr(A, Ao) < TOL_A and relerr(b, bo) < TOL_A, (name, relerr(A, Ao), relerr(b, bo))
+            assert relerr(pr.solve_frequency_fluid(2.5, fl), np.linalg.solve(Ao, bo)) < TOL_X
+            pr.close()
+    # default formulation (rim nodes with non-nodal points), mixed conditions, nonzero prescribed pressure
+    mesh = without_parts(cube_mesh(3, shape.QUAD8), {3, 5})
+    md = FluidModel(mesh, {1: (0, 0.0), 2: (0, 1.0 + 0.5j), 4: (1, 0.2), 6: (1, 0.0)}, symmetry=[("y", "symmetry"), ("z", "antisymmetry")])
+    pr = capi.Problem(gpu_ctx, md)
+    A, b = pr.build_lse_mechanics_bem_harpot(3.0, fl)
+    Ao, bo, _ = oracle_lib.PotOracle(md).assemble(3.0, fl)
+    assert relerr(A, Ao) < TOL_A and relerr(b, bo) < TOL_A
+    pr.close()
+    po = Poro(rhof=1.0, rhos=2.2, lam=1.2, mu=1.0, xi=0.03, phi=0.35, rhoa=0.15, R=0.8, Q=0.5, b=0.4)
+    cases = [([("x", "symmetry")], lambda x: (0.3 + x[1], x[0], 0.3 + x[1], 0.5 * x[2]), shape.QUAD9, 2),
+             ([("x", "antisymmetry"), ("z", "symmetry")], lambda x: (x[0], 1.0 + x[1], x[0], x[0] * x[2]), shape.TRI3, 3),
+             ([("x", "antisymmetry"), ("y", "antisymmetry"), ("z", "symmetry")], lambda x: (x[0] * x[1], x[1], x[0], x[0] * x[1] * x[2]), shape.QUAD4, 2)]
+    for planes, vals, etype, m in cases:
+        red, _ = _generic_reduced_and_full(m, etype, planes, lambda mesh, **kw: PoroModel(mesh, {1: ([1, 1, 1, 1], [0, 0, 0, 0])}, **kw), vals)
+        pr = capi.Problem(gpu_ctx, red); o = oracle_lib.PorOracle(red)
+        A, b = pr.build_lse_mechanics_bem_harpor(2.0, po)
+        Ao, bo, _ = o.assemble(2.0, po)
+        assert relerr(A, Ao) < TOL_A and relerr(b, bo) < TOL_A, (planes, relerr(A, Ao), relerr(b, bo))
+        assert relerr(pr.solve_frequency_poro(2.0, po), np.linalg.solve(Ao, bo)) < TOL_X
+        pr.close()
+    # quarter Biot column: mixed kinds per part (general path of the kernels), MCA points on the planes' rims
+    from test_oracle_poroelastic import column_bcs
+    mesh = without_parts(cube_mesh(2, shape.QUAD9), {3, 5})
+    md = PoroModel(mesh, {k: v for k, v in column_bcs().items() if k in (1, 2, 4, 6)}, symmetry=[("y", "symmetry"), ("z", "symmetry")])
+    pr = capi.Problem(gpu_ctx, md)
+    A, b = pr.build_lse_mechanics_bem_harpor(2.0, po)
+    Ao, bo, _ = oracle_lib.PorOracle(md).assemble(2.0, po)
+    assert relerr(A, Ao) < TOL_A and relerr(b, bo) < TOL_A
+    pr.close()

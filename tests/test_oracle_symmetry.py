@@ -156,3 +156,97 @@ def test_default_formulation_puts_mca_points_on_plane_nodes():
     (ua, _), _ = solve(a, 2.5, mat)
     (ub, _), _ = solve(b, 2.5, mat)
     assert np.abs(ua - ub).max() / np.abs(ub).max() < 0.05
+
+
+# ---- fluid (scalar) and poroelastic regions: symconf_s on the scalar variables (build_lse_mechanics_bem_harpot.f90:947-948, _harpor.f90:971-975) ----
+def _generic_reduced_and_full(m, etype, planes, make_model, values):
+    """As reduced_and_full, for any region type: make_model(mesh, symmetry=..., nodal_on_symplanes=...) builds the Model with every dof of the
+    secondary kind prescribed; values(x) are the prescribed values at a point (with the parity of every plane)."""
+    from multifebe_b200.host import Mesh  # noqa: F401
+    cube = closed_cube(m, etype)
+    drop = {"x": 1, "y": 3, "z": 5}
+    red_mesh = without_parts(cube, {drop[a] for a, _ in planes})
+    red_mesh.part[:] = 1
+    red = make_model(red_mesh, symmetry=planes, nodal_on_symplanes=True)
+    full_mesh = red_mesh
+    for a, _ in planes:
+        full_mesh, _ = mirror_mesh(full_mesh, AX[a])
+    full = make_model(full_mesh)
+    for mdl in (red, full):
+        assert not mdl.in_boundary.any()
+        mdl.cvalue = np.ascontiguousarray([np.atleast_1d(values(x)) for x in mdl.node_x], dtype=np.complex128)
+    return red, full
+
+
+FLUID_CASES = [
+    # parity of a scalar under a plane: symmetry q(Mx) = q(x), antisymmetry q(Mx) = -q(x)
+    ("x-sym", [("x", "symmetry")], lambda x: 1.0 + x[1] + x[0] ** 2),
+    ("x-anti", [("x", "antisymmetry")], lambda x: x[0] * (1.0 + x[2])),
+    ("xy-sym-anti", [("x", "symmetry"), ("y", "antisymmetry")], lambda x: x[1] * (1.0 + x[0] ** 2 + x[2])),
+    ("xyz-anti-sym-sym", [("x", "antisymmetry"), ("y", "symmetry"), ("z", "symmetry")], lambda x: x[0] * (1.0 + x[1] ** 2)),
+]
+
+
+@pytest.mark.parametrize("name,planes,flux", FLUID_CASES, ids=[c[0] for c in FLUID_CASES])
+def test_fluid_region_reduced_model_reproduces_the_full_model(name, planes, flux):
+    from multifebe_b200.host import Fluid, FluidModel
+    fl = Fluid(rho=1.0, c=1.0, xi=0.03)
+    for etype, m in ((TRI3, 3), (QUAD9, 2)):
+        red, full = _generic_reduced_and_full(m, etype, planes, lambda mesh, **kw: FluidModel(mesh, {1: (1, 0.0)}, **kw), flux)
+        out = []
+        for mdl in (red, full):
+            A, b, st = orc.PotOracle(mdl).assemble(2.5, fl)
+            out.append(mdl.nodal_solution(np.linalg.solve(A, b))[0])
+        pr, pf = out
+        assert np.abs(pf).max() > 1e-3
+        assert np.abs(pr - pf[:red.n_node]).max() / np.abs(pf).max() < 2e-5, name
+
+
+def test_room_tutorial_as_a_quarter_model():
+    """The rigid side walls of ME-TH-AC-001 are symmetry planes of the pressure: the quarter room (walls y = 0 and z = 0 removed, planes declared) has the
+    same standing wave p = P sin(k x) / sin(k L)."""
+    from multifebe_b200.host import Fluid, FluidModel, room_analytic
+    fl = Fluid(rho=1.25, c=343.0)
+    mesh = without_parts(cube_mesh(3, QUAD9), {3, 5})
+    md = FluidModel(mesh, {1: (0, 0.0), 2: (0, 1.0), 4: (1, 0.0), 6: (1, 0.0)}, symmetry=[("y", "symmetry"), ("z", "symmetry")])
+    omega = 2 * np.pi * 100.0
+    A, b, _ = orc.PotOracle(md).assemble(omega, fl)
+    p, _ = md.nodal_solution(np.linalg.solve(A, b))
+    p_ex, _ = room_analytic(md.node_x[:, 0], omega, fl)
+    assert np.abs(p - p_ex).max() < 2e-3 * np.abs(p_ex).max()
+
+
+def test_biot_column_as_a_quarter_model():
+    """Sliding impermeable side walls are symmetry planes of a poroelastic column: the quarter column against the exact two-wave solution."""
+    from multifebe_b200.host import Poro, PoroModel
+    from test_oracle_poroelastic import biot_column, column_bcs
+    po = Poro(rhof=1.0, rhos=2.2, lam=1.2, mu=1.0, xi=0.02, phi=0.35, rhoa=0.15, R=0.8, Q=0.5, b=0.6)
+    omega = 2.0
+    mesh = without_parts(cube_mesh(2, QUAD9), {3, 5})
+    bcs = {k: v for k, v in column_bcs().items() if k in (1, 2, 4, 6)}
+    md = PoroModel(mesh, bcs, symmetry=[("y", "symmetry"), ("z", "symmetry")])
+    A, bb, _ = orc.PorOracle(md).assemble(omega, po)
+    prim, sec = md.nodal_solution(np.linalg.solve(A, bb))
+    field, _ = biot_column(omega, po)
+    ua, Ua, sa, ta = field(md.node_x[:, 0])
+    assert np.abs(prim[:, 1] - ua).max() < 4e-3 * np.abs(ua).max() and np.abs(prim[:, 2:]).max() < 4e-3 * np.abs(ua).max()
+    side = md.node_part >= 3
+    assert np.abs(prim[side, 0] - ta[side]).max() < 4e-3 * np.abs(ta).max()
+
+
+def test_poroelastic_region_reduced_model_reproduces_the_full_model():
+    """Mixed parities on a poroelastic region: Un (scalar) and t_k (vector) prescribed everywhere with the parity of each plane."""
+    from multifebe_b200.host import Poro, PoroModel
+    po = Poro(rhof=1.0, rhos=2.2, lam=1.2, mu=1.0, xi=0.03, phi=0.35, rhoa=0.15, R=0.8, Q=0.5, b=0.4)
+    cases = [([("x", "symmetry")], lambda x: (0.3 + x[1], x[0], 0.3 + x[1], 0.5 * x[2])),
+             ([("x", "antisymmetry"), ("z", "symmetry")], lambda x: (x[0], 1.0 + x[1], x[0], x[0] * x[2]))]
+    for planes, vals in cases:
+        red, full = _generic_reduced_and_full(2, QUAD9, planes, lambda mesh, **kw: PoroModel(mesh, {1: ([1, 1, 1, 1], [0, 0, 0, 0])}, **kw), vals)
+        out = []
+        for mdl in (red, full):
+            A, b, _ = orc.PorOracle(mdl).assemble(2.0, po)
+            out.append(mdl.nodal_solution(np.linalg.solve(A, b))[0])
+        pr, pf = out
+        for k in range(4):
+            sc = np.abs(pf[:, k]).max()
+            assert sc > 1e-4 and np.abs(pr[:, k] - pf[:red.n_node, k]).max() / sc < 5e-5, (planes, k)
