@@ -316,8 +316,6 @@ class CaseFile:
         self.symmetry = []
         sp = sec.get("symmetry planes") or []
         if sp:
-            if self.multi:
-                raise CaseFileError("[symmetry planes]: covered for models of one region")
             for ax, names in (("x", ("plane_n1", "plane_yz")), ("y", ("plane_n2", "plane_zx")), ("z", ("plane_n3", "plane_xy"))):
                 given = []
                 v = _keyword(sp, ax)
@@ -399,7 +397,7 @@ class CaseFile:
             from .multiregion import PORO
             regs = [Region({1: FLUID, 2: SOLID, 3: PORO}[rtype], mat, rb) for _, rtype, mat, rb in self.regions]
             bcs = {b: ((ct[0], cv[0]) if len(ct) == 1 else (ct, cv)) for b, (ct, cv) in self.bcs.items()}
-            return MultiRegionModel(self.mesh, regs, part_of_boundary, bcs, **kw)
+            return MultiRegionModel(self.mesh, regs, part_of_boundary, bcs, symmetry=self.symmetry, **kw)
         kw["part_order"] = [part_of_boundary[b] for b in self.region_boundaries]
         kw["symmetry"] = self.symmetry
         if self.region_type == 1:

@@ -75,6 +75,7 @@ def local_models(mrm, kr):
         m.elem_node = np.ascontiguousarray(elem_node, dtype=np.int32)
         m.qsi_relative_error, m.qsi_ns_max = mrm.qsi_relative_error, mrm.qsi_ns_max
         m.precalset_gln, m.geometric_tolerance = mrm.precalset_gln, mrm.geometric_tolerance
+        m.symplane_eid, m.symplane_t, m.symplane_s = mrm.symplane_eid, mrm.symplane_t, mrm.symplane_s     # the local assemblies integrate the mirror images
         m.colloc_x = v.colloc_x
         m.colloc_node = v.colloc_node
         m.colloc_elem = -np.ones(v.n_colloc, dtype=np.int32)              # no free term: added by assemble_coupled

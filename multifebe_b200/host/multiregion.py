@@ -53,13 +53,18 @@ class RegionView:
 
 class MultiRegionModel:
     def __init__(self, mesh, regions, boundary_part, bcs, qsi_relative_error=1e-6, qsi_ns_max=16, precalset_gln=(2, 3, 4, 5, 6, 7, 8, 9),
-                 geometric_tolerance=1e-6, interface_ctype=None):
+                 geometric_tolerance=1e-6, interface_ctype=None, symmetry=None):
         """boundary_part {boundary id: part id of the mesh}; bcs {boundary id: (ctypes, values)} for the ORDINARY boundaries (solid: three
         components, fluid: scalars, poroelastic: tau / Un then the three skeleton components), 0 = primary variable known, 1 = secondary
         variable known.  interface_ctype {boundary id: 0 | 1}: condition of a fluid-poroelastic interface, 0 perfectly permeable (default),
         1 perfectly impermeable (node%ctype(1,1) of such a boundary)."""
         self.interface_ctype = dict(interface_ctype or {})
         self.mesh, self.regions = mesh, list(regions)
+        # [symmetry planes] of the model (every BE region integrates the mirror images of its elements; the nodes of the open edges in the planes are rim
+        # nodes with non-nodal collocation points, the reference's default)
+        from .model import symmetry_planes, symmetry_scalars
+        self.symplane_eid, self.symplane_t = symmetry_planes(symmetry)
+        self.symplane_s = symmetry_scalars(symmetry, self.symplane_eid, self.symplane_t)
         nn, ne = len(mesh.nodes), mesh.n_elem
         self.n_node, self.n_elem = nn, ne
         self.node_x = mesh.nodes
@@ -219,6 +224,7 @@ class MultiRegionModel:
         v.elem_reversed = np.array(rev, dtype=np.uint8)
         v.qsi_relative_error, v.qsi_ns_max = self.qsi_relative_error, self.qsi_ns_max
         v.precalset_gln, v.geometric_tolerance = self.precalset_gln, self.geometric_tolerance
+        v.symplane_eid, v.symplane_t, v.symplane_s = self.symplane_eid, self.symplane_t, self.symplane_s
         # collocation points of the region (loop order of the reference: boundaries, elements, nodes)
         cx, cnode, celem, ckn, cxi, ceq = [], [], [], [], [], []
         collocated = np.zeros(self.n_node, dtype=bool)

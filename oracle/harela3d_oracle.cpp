@@ -1827,8 +1827,10 @@ int orc_assemble_pot(void* hd, double omega, double rho, const double* c_ri, con
 int orc_pair_pot(void* hd, int e, const double* x_i, double omega, double rho, const double* c_ri, double* h_ri, double* g_ri) {
   Model* m = (Model*)hd; Params p; calculate_parameters_pot(rho, cd(c_ri[0], c_ri[1]), omega, p);
   Stats st; memset(&st, 0, sizeof(st)); cd hh[81], gg[81];
-  int mode = sbie_auto(m->elem[e], x_i, p, m->qsp, m->ns_max, hh, gg, st);
-  memcpy(h_ri, hh, sizeof(cd) * m->elem[e].nn); memcpy(g_ri, gg, sizeof(cd) * m->elem[e].nn);
+  const int ks = e / m->n_elem; const Element& el = image_of(m, e % m->n_elem, ks);   // e >= n_elem: a symmetry image, h and g times symconf_s
+  int mode = sbie_auto(el, x_i, p, m->qsp, m->ns_max, hh, gg, st);
+  for (int j = 0; j < el.nn; j++) { hh[j] *= m->conf_s[ks]; gg[j] *= m->conf_s[ks]; }
+  memcpy(h_ri, hh, sizeof(cd) * el.nn); memcpy(g_ri, gg, sizeof(cd) * el.nn);
   return mode;
 }
 // p*, q* (fbem_bem_harpot3d_sbie_p / _q, bem_harpot3d.f90:229-273)
@@ -1946,8 +1948,14 @@ int orc_assemble_por(void* hd, double omega, const double* props, const double* 
 int orc_pair_por(void* hd, int e, const double* x_i, double omega, const double* props, double* h_ri, double* g_ri) {
   Model* m = (Model*)hd; PorParams P; por_params_from(props, omega, P); Params p; p.por = &P;
   Stats st; memset(&st, 0, sizeof(st)); cd hh[144], gg[144];
-  int mode = sbie_auto(m->elem[e], x_i, p, m->qsp, m->ns_max, hh, gg, st);
-  memcpy(h_ri, hh, sizeof(cd) * 16 * m->elem[e].nn); memcpy(g_ri, gg, sizeof(cd) * 16 * m->elem[e].nn);
+  const int ks = e / m->n_elem; const Element& el = image_of(m, e % m->n_elem, ks);   // e >= n_elem: a symmetry image (dof 0 times symconf_s, dofs 1..3 times symconf_t)
+  int mode = sbie_auto(el, x_i, p, m->qsp, m->ns_max, hh, gg, st);
+  if (ks > 0)
+    for (int kn = 0; kn < el.nn; kn++) for (int il = 0; il < 4; il++) for (int ik = 0; ik < 4; ik++) {
+      const double f = (ik == 0) ? m->conf_s[ks] : m->conf_t[ks][ik - 1];
+      hh[(kn * 4 + il) * 4 + ik] *= f; gg[(kn * 4 + il) * 4 + ik] *= f;
+    }
+  memcpy(h_ri, hh, sizeof(cd) * 16 * el.nn); memcpy(g_ri, gg, sizeof(cd) * 16 * el.nn);
   return mode;
 }
 // u*, t* (4 x 4, [l][k]) and the wavenumbers k1, k2, k3, Z, J of the poroelastic fundamental solution

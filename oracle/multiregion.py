@@ -326,15 +326,17 @@ class MultiRegionOracle:
             for c in range(v.n_colloc):
                 x_i, sn_col, eq = v.colloc_x[c], int(v.colloc_node[c]), int(v.colloc_eq[c])
                 le_own, hfree = self._free_term(kr, c, omega)
-                for le in range(v.n_elem):
+                n_img = v.n_elem << len(getattr(m, "symplane_eid", ()))   # symmetry planes: element ks * n_elem + le is image ks of element le, multipliers applied
+                for li in range(n_img):
+                    le = li % v.n_elem
                     if v.kind == SOLID:
-                        h, g, _, _ = hd.pair(le, x_i, omega, mat)
+                        h, g, _, _ = hd.pair(li, x_i, omega, mat)
                     elif v.kind == PORO:
-                        h, g, _ = hd.pair(le, x_i, omega, mat)
+                        h, g, _ = hd.pair(li, x_i, omega, mat)
                     else:
-                        h, g, _ = hd.pair(le, x_i, omega, mat)
+                        h, g, _ = hd.pair(li, x_i, omega, mat)
                         g = g * d1J                                       # the flux unknown is Un = (dp/dn)/(rho omega^2)
-                    if le == le_own:
+                    if li == le_own:
                         h = h + hfree
                     if flat:
                         self._scatter_flat(kr, le, sn_col, eq, h, g, A, b, desc[kr])

@@ -119,7 +119,7 @@ class Oracle:
         return A, b, stats
 
     def pair_static(self, e, x_i, mat):
-        nn = int(self.m.elem_ptr[e + 1] - self.m.elem_ptr[e])
+        nn = int(self.m.elem_ptr[e % self.m.n_elem + 1] - self.m.elem_ptr[e % self.m.n_elem])   # e >= n_elem: a symmetry image
         h = np.zeros((nn, 3, 3)); g = np.zeros((nn, 3, 3))
         x_i = np.ascontiguousarray(x_i, dtype=np.float64)
         mode = lib().orc_pair_static(self.h, C.c_int(e), _p(x_i), C.c_double(mat.mu_r), C.c_double(mat.nu_r), _p(h), _p(g))
@@ -175,7 +175,7 @@ class Oracle:
 
     def pair_hbie_static(self, e, x_i, n_i, mat):
         """Static (Kelvin) m, l (n,3,3) of the hypersingular equation (fbem_bem_staela3d_hbie_ext_pre / _ext_adp)."""
-        nn = int(self.m.elem_ptr[e + 1] - self.m.elem_ptr[e])
+        nn = int(self.m.elem_ptr[e % self.m.n_elem + 1] - self.m.elem_ptr[e % self.m.n_elem])   # e >= n_elem: a symmetry image
         m = np.zeros((nn, 3, 3)); l = np.zeros((nn, 3, 3))
         x_i = np.ascontiguousarray(x_i, dtype=np.float64); n_i = np.ascontiguousarray(n_i, dtype=np.float64)
         mode = lib().orc_pair_hbie_static(self.h, C.c_int(e), _p(x_i), _p(n_i), C.c_double(mat.mu_r), C.c_double(mat.nu_r), _p(m), _p(l))
@@ -330,7 +330,7 @@ class PotOracle:
 
     def pair(self, e, x_i, omega, fluid):
         """h, g (n) complex of one (collocation point, element) pair (g NOT yet scaled by rho omega^2) and the integration mode."""
-        nn = int(self.m.elem_ptr[e + 1] - self.m.elem_ptr[e])
+        nn = int(self.m.elem_ptr[e % self.m.n_elem + 1] - self.m.elem_ptr[e % self.m.n_elem])
         h = np.zeros(nn, dtype=np.complex128); g = np.zeros(nn, dtype=np.complex128)
         x_i = np.ascontiguousarray(x_i, dtype=np.float64)
         mode = lib().orc_pair_pot(self.h, C.c_int(e), _p(x_i), C.c_double(omega), C.c_double(fluid.rho), _p(_ri(fluid.c)), _p(h), _p(g))
@@ -387,7 +387,7 @@ class PorOracle:
         return A, b, stats
 
     def pair(self, e, x_i, omega, poro):
-        nn = int(self.m.elem_ptr[e + 1] - self.m.elem_ptr[e])
+        nn = int(self.m.elem_ptr[e % self.m.n_elem + 1] - self.m.elem_ptr[e % self.m.n_elem])
         h = np.zeros((nn, 4, 4), dtype=np.complex128); g = np.zeros((nn, 4, 4), dtype=np.complex128)
         x_i = np.ascontiguousarray(x_i, dtype=np.float64)
         pr = poro.props()

@@ -34,3 +34,34 @@ def test_coupled_system_and_solution(gpu_ctx, kinds, ict):
     # variables of different families live on different scales: compare every unknown against the largest of its kind (by column scale)
     assert np.abs((x - x0) * sc).max() <= 1e-8 * np.abs(x0 * sc).max()
     cp.close()
+
+
+@pytest.mark.parametrize("kinds,ict,planes", [((SOLID, SOLID), 0, [("y", "symmetry"), ("z", "symmetry")]), ((SOLID, FLUID), 0, [("y", "symmetry"), ("z", "antisymmetry")]),
+                                              ((FLUID, PORO), 0, [("y", "symmetry"), ("z", "symmetry")]), ((PORO, PORO), 0, [("y", "antisymmetry")])])
+def test_coupled_regions_with_symmetry_planes(gpu_ctx, kinds, ict, planes):
+    """[symmetry planes] on a coupled model: every local assembly integrates the mirror images of its elements (quarter / half of the two-box model);
+    the oracle side is pinned by the layered columns as quarter models (tests/test_oracle_multiregion_symmetry.py)."""
+    from multifebe_b200 import capi
+    from multifebe_b200.host import without_parts
+    from oracle.multiregion import MultiRegionOracle
+    mats = {SOLID: MS, FLUID: FL, PORO: PO}
+    drop = {"y": (3, 13), "z": (5, 15)}
+    gone = set(p for a, _ in planes for p in drop[a])
+    lat1, lat2 = tuple(p for p in LAT1 if p not in gone), tuple(p for p in LAT2 if p not in gone)
+    bcs = bcs_for(kinds[0], LAT1, 1, True); bcs.update(bcs_for(kinds[1], LAT2, 2, False))
+    bcs = {k: v for k, v in bcs.items() if k not in gone}
+    bpart = {b: b for b in BPART if b not in gone}
+    mesh = without_parts(two_box_mesh(2, shape.QUAD9), gone)
+    mrm = MultiRegionModel(mesh, [Region(kinds[0], mats[kinds[0]], [1] + list(lat1) + [7]), Region(kinds[1], mats[kinds[1]], [-7, 2] + list(lat2))],
+                           bpart, bcs, interface_ctype={7: ict}, symmetry=planes)
+    omega = 1.7
+    cp = capi.CoupledProblem(gpu_ctx, mrm)
+    A, b = cp.assemble(omega)
+    A0, b0 = MultiRegionOracle(mrm).assemble(omega)
+    sc = np.abs(A0).max(axis=0)
+    assert (np.abs(A - A0).max(axis=0) <= 1e-11 * sc).all(), (np.abs(A - A0).max(axis=0) / sc).max()
+    assert np.abs(b - b0).max() <= 1e-11 * max(np.abs(b0).max(), 1e-300)
+    xr = cp.solve_frequency_resident(omega)
+    x0 = np.linalg.solve(A0, b0)
+    assert np.abs((xr - x0) * sc).max() <= 1e-8 * np.abs(x0 * sc).max()
+    cp.close()
