@@ -90,10 +90,98 @@ __device__ __forceinline__ void por_scal_load(PorScal& s, const double* c) {
 #undef X
 }
 
+const int R1_QCAP = 64;      // entries per deferred queue (at most 31 waiting + 32 new)
+
+// One regular pair (collocation point xs with matrix rows rws, element el of the group, rule sset), all four equations; sc = this lane's column of the
+// shared-memory scalar cache.  The pair's collocation point need not be the lane's own (packed batches), so the b terms go out with atomics.
+template <int ET>
+__device__ __forceinline__ void por_regular_pair(const DevGroup& g, const DevSystem& s, int sset, int el, const double* xs, const int* rws, double* sc) {
+  constexpr int NN = ElemTraits<ET>::NN, RECN = 6 + NN;
+  const int ngp = g.ngp[sset];
+  const double* P = g.pts[sset] + (size_t)el * ngp * RECN;
+  const int* ecol = g.ecol + (size_t)el * 4 * NN;
+  const unsigned char* ekind = g.ekind + (size_t)el * 4 * NN;
+  const double* ecv = g.ecv + (size_t)el * 8 * NN;
+  const bool rev = g.erev[el] != 0;
+  const unsigned info = g.einfo[el];
+  // The common element: the same kind of condition on all its nodes, all prescribed values zero.  Only the combination that goes to the matrix is
+  // accumulated (4 NN complex numbers per equation: they stay in registers; the general path below keeps h AND g, 16 NN doubles, and for 8/9-node
+  // elements lives in local memory -- 4.6 KB of spills per thread, the kernel's cost in round 1), and the radial scalars of the first R1_CACHE_GP
+  // points are computed in the pass of equation 0 and read back from shared memory by the other three.
+  if ((info & 8u) && !g.ecvnz[el]) {
+    unsigned kinds = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) kinds |= (ekind[k] != 0 ? 1u : 0u) << k;
+#pragma unroll 1
+    for (int l = 0; l < 4; l++) {
+      double ar[4 * NN], ai[4 * NN];
+#pragma unroll
+      for (int i = 0; i < 4 * NN; i++) { ar[i] = 0.0; ai[i] = 0.0; }
+#pragma unroll 1
+      for (int kp = 0; kp < ngp; kp++) {
+        const double* q = P + (size_t)kp * RECN;
+        const double n[3] = {__ldg(q + 3), __ldg(q + 4), __ldg(q + 5)};
+        const double rv0 = __ldg(q) - xs[0], rv1 = __ldg(q + 1) - xs[1], rv2 = __ldg(q + 2) - xs[2];
+        const double r = sqrt(rv0 * rv0 + rv1 * rv1 + rv2 * rv2), d1r1 = 1.0 / r;
+        const double dx[3] = {rv0 * d1r1, rv1 * d1r1, rv2 * d1r1};
+        const double drdn = dx[0] * n[0] + dx[1] * n[1] + dx[2] * n[2];
+        PorScal ps;
+        if (l > 0 && kp < R1_CACHE_GP) por_scal_load(ps, sc + (size_t)kp * 24 * 32);
+        else {
+          por_scalars<false>(c_por, r, d1r1, ps);
+          if (l == 0 && kp < R1_CACHE_GP) por_scal_store(ps, sc + (size_t)kp * 24 * 32);
+        }
+        cplx ur[4], tr[4];
+        por_row_from_scalars(ps, dx, n, drdn, l, ur, tr);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const cplx f = ((kinds >> k) & 1u) ? tr[k] : ur[k];
+#pragma unroll
+          for (int j = 0; j < NN; j++) { const double wj = __ldg(q + 6 + j); ar[k * NN + j] = fma(f.re, wj, ar[k * NN + j]); ai[k * NN + j] = fma(f.im, wj, ai[k * NN + j]); }
+        }
+      }
+      const int row = (l == 0) ? rws[0] : (l == 1 ? rws[1] : (l == 2 ? rws[2] : rws[3]));
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        // A += cte_t h (sign of the orientation) for a dof whose secondary variable is known, A -= cte_u g otherwise (assemble_bem_harpor_equation.f90:78-110)
+        const bool tk = (kinds >> k) & 1u;
+        const cplx c0 = tk ? ((l == 0) ? c_por.cte_t[0][k] : c_por.cte_t[1][k]) : ((l == 0) ? c_por.cte_u[0][k] : c_por.cte_u[1][k]);
+        const double sg = (tk ? (rev ? -1.0 : 1.0) : -1.0) * (((info >> (4 + k)) & 1u) ? -1.0 : 1.0);   // sign of a symmetry image on dof k
+#pragma unroll
+        for (int j = 0; j < NN; j++) {
+          const int col = ecol[j * 4 + k];
+          atomicAdd(s.Are + (size_t)col * s.lda + row, sg * (c0.re * ar[k * NN + j] - c0.im * ai[k * NN + j]));
+          atomicAdd(s.Aim + (size_t)col * s.lda + row, sg * (c0.re * ai[k * NN + j] + c0.im * ar[k * NN + j]));
+        }
+      }
+    }
+    return;
+  }
+#pragma unroll 1
+  for (int l = 0; l < 4; l++) {
+    RAcc<NN> acc; acc.zero();
+#pragma unroll 1
+    for (int kp = 0; kp < ngp; kp++) {
+      const double* q = P + (size_t)kp * RECN;
+      const double x[3] = {__ldg(q), __ldg(q + 1), __ldg(q + 2)}, n[3] = {__ldg(q + 3), __ldg(q + 4), __ldg(q + 5)};
+      double w[NN];
+#pragma unroll
+      for (int j = 0; j < NN; j++) w[j] = __ldg(q + 6 + j);
+      por_regular_point<NN>(acc, c_por, x, n, w, xs, l);
+    }
+    const int row = (l == 0) ? rws[0] : (l == 1 ? rws[1] : (l == 2 ? rws[2] : rws[3]));
+    double br = 0.0, bi = 0.0;
+    por_scatter_row<NN>(acc, l, ecol, ekind, ecv, rev, s, row, br, bi, PorAll(), info >> 4);
+    if (br != 0.0 || bi != 0.0) { atomicAdd(s.bre + row, br); atomicAdd(s.bim + row, bi); }
+  }
+}
+
+// A warp owns a collocation tile and walks a chunk of elements.  The 32 points of a tile ask for different rules near an element, so integrating "all lanes
+// on element e" left 36 % of the lanes busy (ncu, profiles/r02_ncu_por_regular.txt).  Pairs are therefore pushed to one queue per rule in shared memory and
+// integrated 32 at a time, one (point, element) pair per lane, as soon as a queue holds a full warp (the scheme of k_regular_bulk in assembly.cu).
 template <int ET>
 __global__ void __launch_bounds__(R1_WARPS * 32) k_por_regular(DevGroup g, DevColloc c, DevSystem s, const unsigned char* __restrict__ plan) {
-  constexpr int NN = ElemTraits<ET>::NN, RECN = 6 + NN;
-  extern __shared__ __align__(16) double por_smem[];   // [warp][R1_CACHE_GP][24 scalars][32 lanes]
+  extern __shared__ __align__(16) double por_smem[];   // [warp][R1_CACHE_GP][24 scalars][32 lanes], then the queues
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tile = blockIdx.x * R1_WARPS + warp;
   if (tile >= c.n_tiles) return;
@@ -102,107 +190,53 @@ __global__ void __launch_bounds__(R1_WARPS * 32) k_por_regular(DevGroup g, DevCo
   const int rows[4] = {c.crow[cpos], c.crow[c.ldp + cpos], c.crow[2 * c.ldp + cpos], c.crow[3 * c.ldp + cpos]};
   const bool valid = rows[0] >= 0;
   const double xc[3] = {c.cx[cpos], c.cx[c.ldp + cpos], c.cx[2 * c.ldp + cpos]};
-  double bre[4] = {0.0, 0.0, 0.0, 0.0}, bim[4] = {0.0, 0.0, 0.0, 0.0};
+  double* sc = por_smem + ((size_t)warp * R1_CACHE_GP * 24) * 32 + lane;
+  unsigned short* queue = reinterpret_cast<unsigned short*>(por_smem + (size_t)R1_WARPS * R1_CACHE_GP * 24 * 32) + (size_t)warp * (MAX_SETS * R1_QCAP);
+  int* qcnt = reinterpret_cast<int*>(reinterpret_cast<unsigned short*>(por_smem + (size_t)R1_WARPS * R1_CACHE_GP * 24 * 32) + (size_t)R1_WARPS * (MAX_SETS * R1_QCAP)) + warp * MAX_SETS;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  if (lane < MAX_SETS) qcnt[lane] = 0;
+  __syncwarp();
   const int e0 = blockIdx.y * R1_ECHUNK, e1 = min(e0 + R1_ECHUNK, g.n_elem);
+  auto batch = [&](int sset, unsigned short ent, bool act) {
+    const int src = ent & 31, el = e0 + (ent >> 5);
+    const double xs[3] = {__shfl_sync(0xffffffffu, xc[0], src), __shfl_sync(0xffffffffu, xc[1], src), __shfl_sync(0xffffffffu, xc[2], src)};
+    const int rws[4] = {__shfl_sync(0xffffffffu, rows[0], src), __shfl_sync(0xffffffffu, rows[1], src), __shfl_sync(0xffffffffu, rows[2], src), __shfl_sync(0xffffffffu, rows[3], src)};
+    if (act) por_regular_pair<ET>(g, s, sset, el, xs, rws, sc);
+    __syncwarp();
+  };
   for (int e = e0; e < e1; e++) {
     const unsigned char m = valid ? plan[(size_t)(g.slot0 + e) * c.ldp + cpos] : PLAN_NONE;
     unsigned todo = __ballot_sync(0xffffffffu, m < MAX_SETS);
     while (todo) {
       const int leader = __ffs(todo) - 1;
       const int sset = __shfl_sync(0xffffffffu, (int)m, leader);
-      const unsigned grp = __ballot_sync(0xffffffffu, (int)m == sset);
+      const unsigned grp = __ballot_sync(0xffffffffu, (int)m == sset) & todo;
       todo &= ~grp;
-      if ((int)m == sset) {
-        const int ngp = g.ngp[sset];
-        const double* P = g.pts[sset] + (size_t)e * ngp * RECN;
-        const int* ecol = g.ecol + (size_t)e * 4 * NN;
-        const unsigned char* ekind = g.ekind + (size_t)e * 4 * NN;
-        const double* ecv = g.ecv + (size_t)e * 8 * NN;
-        const bool rev = g.erev[e] != 0;
-        // The common element: the same kind of condition on all its nodes, all prescribed values zero.  Only the combination that goes to the matrix is
-        // accumulated (4 NN complex numbers per equation: they stay in registers; the general path below keeps h AND g, 16 NN doubles, and for 8/9-node
-        // elements lives in local memory -- 4.6 KB of spills per thread, the kernel's cost in round 1), and the radial scalars of the first R1_CACHE_GP
-        // points are computed in the pass of equation 0 and read back from shared memory by the other three.
-        if ((g.einfo[e] & 8u) && !g.ecvnz[e]) {
-          unsigned kinds = 0u;
-#pragma unroll
-          for (int k = 0; k < 4; k++) kinds |= (ekind[k] != 0 ? 1u : 0u) << k;
-          double* sc = por_smem + ((size_t)warp * R1_CACHE_GP * 24) * 32 + lane;
-#pragma unroll 1
-          for (int l = 0; l < 4; l++) {
-            double ar[4 * NN], ai[4 * NN];
-#pragma unroll
-            for (int i = 0; i < 4 * NN; i++) { ar[i] = 0.0; ai[i] = 0.0; }
-#pragma unroll 1
-            for (int kp = 0; kp < ngp; kp++) {
-              const double* q = P + (size_t)kp * RECN;
-              const double n[3] = {__ldg(q + 3), __ldg(q + 4), __ldg(q + 5)};
-              const double rv0 = __ldg(q) - xc[0], rv1 = __ldg(q + 1) - xc[1], rv2 = __ldg(q + 2) - xc[2];
-              const double r = sqrt(rv0 * rv0 + rv1 * rv1 + rv2 * rv2), d1r1 = 1.0 / r;
-              const double dx[3] = {rv0 * d1r1, rv1 * d1r1, rv2 * d1r1};
-              const double drdn = dx[0] * n[0] + dx[1] * n[1] + dx[2] * n[2];
-              PorScal ps;
-              if (l > 0 && kp < R1_CACHE_GP) por_scal_load(ps, sc + (size_t)kp * 24 * 32);
-              else {
-                por_scalars<false>(c_por, r, d1r1, ps);
-                if (l == 0 && kp < R1_CACHE_GP) por_scal_store(ps, sc + (size_t)kp * 24 * 32);
-              }
-              cplx ur[4], tr[4];
-              por_row_from_scalars(ps, dx, n, drdn, l, ur, tr);
-#pragma unroll
-              for (int k = 0; k < 4; k++) {
-                const cplx f = ((kinds >> k) & 1u) ? tr[k] : ur[k];
-#pragma unroll
-                for (int j = 0; j < NN; j++) { const double wj = __ldg(q + 6 + j); ar[k * NN + j] = fma(f.re, wj, ar[k * NN + j]); ai[k * NN + j] = fma(f.im, wj, ai[k * NN + j]); }
-              }
-            }
-            const int row = (l == 0) ? rows[0] : (l == 1 ? rows[1] : (l == 2 ? rows[2] : rows[3]));
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-              // A += cte_t h (sign of the orientation) for a dof whose secondary variable is known, A -= cte_u g otherwise (assemble_bem_harpor_equation.f90:78-110)
-              const bool tk = (kinds >> k) & 1u;
-              const cplx c0 = tk ? ((l == 0) ? c_por.cte_t[0][k] : c_por.cte_t[1][k]) : ((l == 0) ? c_por.cte_u[0][k] : c_por.cte_u[1][k]);
-              const double sg = (tk ? (rev ? -1.0 : 1.0) : -1.0) * (((g.einfo[e] >> (4 + k)) & 1u) ? -1.0 : 1.0);   // sign of a symmetry image on dof k
-#pragma unroll
-              for (int j = 0; j < NN; j++) {
-                const int col = ecol[j * 4 + k];
-                atomicAdd(s.Are + (size_t)col * s.lda + row, sg * (c0.re * ar[k * NN + j] - c0.im * ai[k * NN + j]));
-                atomicAdd(s.Aim + (size_t)col * s.lda + row, sg * (c0.re * ai[k * NN + j] + c0.im * ar[k * NN + j]));
-              }
-            }
-          }
-          continue;
-        }
-#pragma unroll 1
-        for (int l = 0; l < 4; l++) {
-          RAcc<NN> acc; acc.zero();
-#pragma unroll 1
-          for (int kp = 0; kp < ngp; kp++) {
-            const double* q = P + (size_t)kp * RECN;
-            const double x[3] = {__ldg(q), __ldg(q + 1), __ldg(q + 2)}, n[3] = {__ldg(q + 3), __ldg(q + 4), __ldg(q + 5)};
-            double w[NN];
-#pragma unroll
-            for (int j = 0; j < NN; j++) w[j] = __ldg(q + 6 + j);
-            por_regular_point<NN>(acc, c_por, x, n, w, xc, l);
-          }
-          const int row = (l == 0) ? rows[0] : (l == 1 ? rows[1] : (l == 2 ? rows[2] : rows[3]));
-          double br = 0.0, bi = 0.0;
-          por_scatter_row<NN>(acc, l, ecol, ekind, ecv, rev, s, row, br, bi, PorAll(), (unsigned)g.einfo[e] >> 4);
-          if (l == 0) { bre[0] += br; bim[0] += bi; } else if (l == 1) { bre[1] += br; bim[1] += bi; } else if (l == 2) { bre[2] += br; bim[2] += bi; } else { bre[3] += br; bim[3] += bi; }
-        }
+      const int base = qcnt[sset];
+      if ((grp >> lane) & 1u) queue[sset * R1_QCAP + base + __popc(grp & lt_mask)] = (unsigned short)(((e - e0) << 5) | lane);
+      __syncwarp();
+      int cnt = base + __popc(grp);
+      if (cnt >= 32) {
+        const unsigned short ent = queue[sset * R1_QCAP + cnt - 32 + lane];
+        __syncwarp();
+        cnt -= 32;
+        batch(sset, ent, true);
       }
+      if (lane == 0) qcnt[sset] = cnt;
+      __syncwarp();
     }
   }
-  if (valid) {
-#pragma unroll
-    for (int l = 0; l < 4; l++)
-      if (bre[l] != 0.0 || bim[l] != 0.0) { atomicAdd(s.bre + rows[l], bre[l]); atomicAdd(s.bim + rows[l], bim[l]); }
+  for (int sset = 0; sset < g.n_sets; sset++) {   // what is left in the queues
+    const int cnt = qcnt[sset];
+    if (cnt == 0) continue;
+    const unsigned short ent = (lane < cnt) ? queue[sset * R1_QCAP + lane] : (unsigned short)0;
+    batch(sset, ent, lane < cnt);
   }
 }
 void launch_por_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, cudaStream_t st) {
   if (g.n_elem == 0) return;
   dim3 grid((c.n_tiles + R1_WARPS - 1) / R1_WARPS, (g.n_elem + R1_ECHUNK - 1) / R1_ECHUNK), block(R1_WARPS * 32);
-  const int smem = R1_WARPS * R1_CACHE_GP * 24 * 32 * (int)sizeof(double);   // 96 KB: two CTAs per SM
+  const int smem = R1_WARPS * R1_CACHE_GP * 24 * 32 * (int)sizeof(double) + R1_WARPS * MAX_SETS * (R1_QCAP * 2 + 4);   // 96 KB of scalar cache + 8.5 KB of queues: two CTAs per SM
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(k_por_regular<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); cudaFuncSetAttribute(k_por_regular<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
