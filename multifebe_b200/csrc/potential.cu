@@ -45,21 +45,61 @@ __device__ __forceinline__ void pot_scatter_node(double hr, double hi, double gr
 const int P1_WARPS = 4;
 const int P1_ECHUNK = 64;
 
+const int P1_QCAP = 64;   // entries per deferred queue (at most 31 waiting + 32 new)
+
+// A warp owns a collocation tile and walks a chunk of elements.  Near an element the 32 points of a tile ask for different rules, and integrating "all lanes on
+// element e" kept 22 of 32 lanes busy (ncu, round 1).  Pairs are pushed to one queue per rule in shared memory and integrated 32 at a time, one (point, element)
+// pair per lane, as soon as a queue holds a full warp (the scheme of k_regular_bulk in assembly.cu and k_por_regular).
 template <int ET>
 __global__ void __launch_bounds__(P1_WARPS * 32) k_pot_regular(DevGroup g, DevColloc c, DevSystem s, const unsigned char* __restrict__ plan) {
   constexpr int NN = ElemTraits<ET>::NN, RECN = 6 + NN;
+  __shared__ unsigned short queue_all[P1_WARPS][MAX_SETS * P1_QCAP];
+  __shared__ int qcnt_all[P1_WARPS][MAX_SETS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tile = blockIdx.x * P1_WARPS + warp;
   if (tile >= c.n_tiles) return;
   if (c.tile_active && !c.tile_active[tile]) return;
+  unsigned short* queue = queue_all[warp]; int* qcnt = qcnt_all[warp];
+  const unsigned lt_mask = (1u << lane) - 1u;
+  if (lane < MAX_SETS) qcnt[lane] = 0;
+  __syncwarp();
   const int cpos = tile * 32 + lane;
   const int row = c.crow[cpos];
   const bool valid = row >= 0;
   const double xc[3] = {c.cx[cpos], c.cx[c.ldp + cpos], c.cx[2 * c.ldp + cpos]};
-  double bre = 0.0, bim = 0.0;
   const int e0 = blockIdx.y * P1_ECHUNK, e1 = min(e0 + P1_ECHUNK, g.n_elem);
   const unsigned char* pl = plan + (size_t)g.slot0 * c.ldp + cpos;
   unsigned char m_next = (valid && e0 < e1) ? pl[(size_t)e0 * c.ldp] : PLAN_NONE;
+  // one batch: lane integrates the pair (collocation point of lane src, element e0 + offset); the point need not be the lane's own: b goes out with atomics
+  auto batch = [&](int sset, unsigned short ent, bool act) {
+    const int src = ent & 31, el = e0 + (ent >> 5);
+    const double xs[3] = {__shfl_sync(0xffffffffu, xc[0], src), __shfl_sync(0xffffffffu, xc[1], src), __shfl_sync(0xffffffffu, xc[2], src)};
+    const int rs = __shfl_sync(0xffffffffu, row, src);
+    if (act) {
+      const int ngp = g.ngp[sset];
+      const double* P = g.pts[sset] + (size_t)el * ngp * RECN;
+      PAcc<NN> acc; acc.zero();
+#pragma unroll 1
+      for (int kp = 0; kp < ngp; kp++) {
+        const double* q = P + (size_t)kp * RECN;
+        const double x[3] = {__ldg(q), __ldg(q + 1), __ldg(q + 2)}, n[3] = {__ldg(q + 3), __ldg(q + 4), __ldg(q + 5)};
+        double w[NN];
+#pragma unroll
+        for (int j = 0; j < NN; j++) w[j] = __ldg(q + 6 + j);
+        pot_accumulate<NN>(acc, c_pp, x, n, xs, w);
+      }
+      const bool rev = g.erev[el] != 0, neg = (g.einfo[el] & 32u) != 0;
+      const int* ecol = g.ecol + (size_t)el * NN;
+      const unsigned char* ekind = g.ekind + (size_t)el * NN;
+      const double* ecv = g.ecv + (size_t)el * 2 * NN;
+      double bre = 0.0, bim = 0.0;
+#pragma unroll
+      for (int j = 0; j < NN; j++)
+        pot_scatter_node(acc.hr[j], acc.hi[j], acc.gr[j], acc.gi[j], rev, __ldg(ecol + j), ekind[j], ecv[2 * j], ecv[2 * j + 1], s, rs, bre, bim, neg);
+      if (bre != 0.0 || bim != 0.0) { atomicAdd(s.bre + rs, bre); atomicAdd(s.bim + rs, bim); }
+    }
+    __syncwarp();
+  };
   for (int e = e0; e < e1; e++) {
     const unsigned char m = m_next;
     m_next = (valid && e + 1 < e1) ? pl[(size_t)(e + 1) * c.ldp] : PLAN_NONE;   // requested one element ahead
@@ -67,32 +107,28 @@ __global__ void __launch_bounds__(P1_WARPS * 32) k_pot_regular(DevGroup g, DevCo
     while (todo) {
       const int leader = __ffs(todo) - 1;
       const int sset = __shfl_sync(0xffffffffu, (int)m, leader);
-      const unsigned grp = __ballot_sync(0xffffffffu, (int)m == sset);
+      const unsigned grp = __ballot_sync(0xffffffffu, (int)m == sset) & todo;
       todo &= ~grp;
-      if ((int)m == sset) {
-        const int ngp = g.ngp[sset];
-        const double* P = g.pts[sset] + (size_t)e * ngp * RECN;
-        PAcc<NN> acc; acc.zero();
-#pragma unroll 1
-        for (int kp = 0; kp < ngp; kp++) {
-          const double* q = P + (size_t)kp * RECN;
-          const double x[3] = {__ldg(q), __ldg(q + 1), __ldg(q + 2)}, n[3] = {__ldg(q + 3), __ldg(q + 4), __ldg(q + 5)};
-          double w[NN];
-#pragma unroll
-          for (int j = 0; j < NN; j++) w[j] = __ldg(q + 6 + j);
-          pot_accumulate<NN>(acc, c_pp, x, n, xc, w);
-        }
-        const bool rev = g.erev[e] != 0;
-        const int* ecol = g.ecol + (size_t)e * NN;
-        const unsigned char* ekind = g.ekind + (size_t)e * NN;
-        const double* ecv = g.ecv + (size_t)e * 2 * NN;
-#pragma unroll
-        for (int j = 0; j < NN; j++)
-          pot_scatter_node(acc.hr[j], acc.hi[j], acc.gr[j], acc.gi[j], rev, __ldg(ecol + j), ekind[j], ecv[2 * j], ecv[2 * j + 1], s, row, bre, bim, (g.einfo[e] & 32u) != 0);
+      const int base = qcnt[sset];
+      if ((grp >> lane) & 1u) queue[sset * P1_QCAP + base + __popc(grp & lt_mask)] = (unsigned short)(((e - e0) << 5) | lane);
+      __syncwarp();
+      int cnt = base + __popc(grp);
+      if (cnt >= 32) {
+        const unsigned short ent = queue[sset * P1_QCAP + cnt - 32 + lane];
+        __syncwarp();
+        cnt -= 32;
+        batch(sset, ent, true);
       }
+      if (lane == 0) qcnt[sset] = cnt;
+      __syncwarp();
     }
   }
-  if (valid && (bre != 0.0 || bim != 0.0)) { atomicAdd(s.bre + row, bre); atomicAdd(s.bim + row, bim); }
+  for (int sset = 0; sset < g.n_sets; sset++) {   // what is left in the queues
+    const int cnt = qcnt[sset];
+    if (cnt == 0) continue;
+    const unsigned short ent = (lane < cnt) ? queue[sset * P1_QCAP + lane] : (unsigned short)0;
+    batch(sset, ent, lane < cnt);
+  }
 }
 
 void launch_pot_regular(const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, cudaStream_t st) {
