@@ -618,10 +618,23 @@ __global__ void __launch_bounds__(256) k_subpanel_cluster(SubPanelArgs a) {
   double* sre = slab; double* sim = slab + (size_t)ib * rpcp;   // sim is used only when CX
   const long long lda = a.lda;
   const int BIG = 0x7fffffff;
-  for (int idx = tid; idx < ib * nloc; idx += blockDim.x) {
-    int jj = idx / nloc, i = idx - jj * nloc;
-    sre[jj * rpcp + i] = a.Are[(long long)(c0 + jj) * lda + rs + i];
-    if (CX) sim[jj * rpcp + i] = a.Aim[(long long)(c0 + jj) * lda + rs + i];
+  // slab load: eight independent loads in flight per thread (the one-element-per-iteration loop of round 1 waited a full memory latency per element:
+  // its store to shared memory held 18 % of the kernel's stall samples, profiles/r02_ncu_subpanel.txt)
+  {
+    const int total = ib * nloc;
+    for (int base = tid; base < total; base += 8 * blockDim.x) {
+      double vr[8], vi[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int idx = base + u * blockDim.x;
+        if (idx < total) { const int jj = idx / nloc, i = idx - jj * nloc; vr[u] = a.Are[(long long)(c0 + jj) * lda + rs + i]; vi[u] = CX ? a.Aim[(long long)(c0 + jj) * lda + rs + i] : 0.0; }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int idx = base + u * blockDim.x;
+        if (idx < total) { const int jj = idx / nloc, i = idx - jj * nloc; sre[jj * rpcp + i] = vr[u]; if (CX) sim[jj * rpcp + i] = vi[u]; }
+      }
+    }
   }
   __syncthreads();
   {
