@@ -127,6 +127,14 @@ void mfb_problem_free(mfb_problem* problem);
 int mfb_harela3d_assemble(mfb_problem* problem, double omega, const mfb_z* lambda, const mfb_z* mu, double rho,
                           const mfb_z* nu, const mfb_z* cvalue, mfb_z* A, mfb_z* b);
 
+/* Boundary conditions ctype = 2 / 3 of an elastic region (local axes: u.l = U / t.l = T; src/read_conditions_bem_boundaries_mechanics_harmonic.f90:124-128):
+ * accepted by the set-up calls in ctype[]; for such a dof BOTH u_k and t_k are unknowns (col_u AND col_t must be given) and the scatter is
+ * A(row, col_u) += h, A(row, col_t) -= g (assemble_bem_harela_equation.f90:107-112).  The three condition rows node%row(k,0) of such a node belong to the host
+ * (src/build_lse_mechanics_harmonic.f90:204-258): with the two-seam path it writes them into its A_c, b_c after mfb_harela3d_assemble as it does today; for the
+ * resident path (mfb_harela3d_solve_frequency, mfb_staela3d_solve) it hands them over once with mfb_set_condition_rows -- entries (rows[i], cols[i], values[i]),
+ * cols = -1 meaning the right-hand side -- and the library adds them after every assembly.  n = 0 clears them. */
+int mfb_set_condition_rows(mfb_problem* problem, int n, const int* rows, const int* cols, const mfb_z* values);
+
 /* Boundary condition ctype = 10 of an elastic region ("normal pressure known", assemble_bem_harela_equation.f90:97-106): accepted by the set-up calls in
  * ctype[]; cvalue then holds the pressure p and the library forms t_k = p n_fn(k) (negated on a reversed boundary) with the nodal unit normals
  * node(sn)%n_fn given here, n_fn[3 * n_node] (src/build_data_at_functional_nodes.f90:355-400).  Once, before the first assembly; a no-op for models without

@@ -282,6 +282,9 @@ class Problem:
                 C.c_int(m.n_dof), C.c_double(m.qsi_relative_error), C.c_int(m.qsi_ns_max), C.c_int(len(m.precalset_gln)), _p(k[14]),
                 C.c_double(m.geometric_tolerance), C.byref(self.h)))
         self._cv = np.ascontiguousarray(m.cvalue, dtype=np.complex128)
+        if self.ndof == 3 and np.isin(np.asarray(m.ctype), (2, 3)).any() and hasattr(m, "condition_rows"):   # local-axes conditions: the host's rows, added after every assembly
+            rr, cc, vv = m.condition_rows(); k += [rr, cc, vv]
+            _check(lib().mfb_set_condition_rows(self.h, C.c_int(len(rr)), _p(rr), _p(cc), _p(vv)))
         if self.ndof == 3 and (np.asarray(m.ctype) == 10).any():      # normal-pressure conditions need node()%n_fn
             nf = np.ascontiguousarray(m.n_fn, dtype=np.float64); k.append(nf)
             _check(lib().mfb_set_node_normals(self.h, _p(nf)))

@@ -87,6 +87,8 @@ struct mfb_problem {
   int ndof;                                                // equations / unknowns per node: 3 (elastic solid), 1 (inviscid fluid, mfb_harpot3d_*)
   // incident field (mfb_harela3d_set_incident): flat [slot_off[n_elem]][4] device array in slot order, images carry the root's values times symconf_t(k)
   std::vector<unsigned char> node_rev;   // node belongs to a reversed boundary (from the root elements around it)
+  // rows written by the host after every assembly (local-axes conditions of ctype 2 / 3 nodes): internal row / column (-1: rhs) and value
+  int n_cond = 0; int *d_cond_row = nullptr, *d_cond_col = nullptr; double* d_cond_val = nullptr;
   double* d_nfn = nullptr; bool need_normals = false, have_normals = false;   // ctype 10: nodal normals n_fn (mfb_set_node_normals)
   double* d_einc = nullptr; bool have_inc = false; std::vector<int> slot_off_h, root_elem_ptr; std::vector<unsigned char> elem_symbits; int n_elem_root = 0;
   bool hbie;                                               // hypersingular equation at points off the boundary (interior-point stresses)
@@ -174,6 +176,7 @@ extern "C" void mfb_problem_free(mfb_problem* p) {
   for (auto& g : p->groups) for (void* q : g.owned) cudaFree(q);
   if (p->lu_ready) lu_work_free(p->lu);
   if (p->lu_graph) cudaGraphExecDestroy(p->lu_graph);
+  cudaFree(p->d_cond_row); cudaFree(p->d_cond_col); cudaFree(p->d_cond_val);
   cudaFree(p->d_graph_flags); cudaFree(p->d_vstage); cudaFree(p->Ao); cudaFree(p->d_rs); cudaFree(p->d_cs); cudaFree(p->d_xtmp);
   for (int i = 0; i < 8; i++) cudaEventDestroy(p->ev[i]);
   dist_release(p);
@@ -282,13 +285,21 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
   }
   if (ndof != 1 && ndof != 3 && ndof != 4) return fail(MFB_ERR_ARG, "setup: ndof must be 3 (elastic solid), 1 (inviscid fluid) or 4 (poroelastic medium)");
   for (int i = 0; i < ndof * n_node; i++)
-    if (ctype[i] != 0 && ctype[i] != 1 && !(ctype[i] == 10 && ndof == 3))
-      return fail(MFB_ERR_UNSUPPORTED, "mfb_harela3d_setup: ctype 0 (u / p known), 1 (t / Un known) and, for elastic regions, 10 (normal pressure known) are supported");
+    if (ctype[i] != 0 && ctype[i] != 1 && !((ctype[i] == 10 || ctype[i] == 2 || ctype[i] == 3) && ndof == 3 && !colloc_n))
+      return fail(MFB_ERR_UNSUPPORTED, "mfb_harela3d_setup: ctype 0 (u / p known), 1 (t / Un known) and, for elastic regions, 2 / 3 (local axes) and 10 (normal pressure known) are supported");
   // ctype 10 (assemble_bem_harela_equation.f90:97-106): the pressure p on the node is known, t_k = p n_fn(k): a traction-known dof (kind 1, unknown u_k, column
   // col(k,1)) whose prescribed value is cvalue * n_fn(k), negated on a reversed boundary.  The nodal normals come with mfb_set_node_normals.
+  // ctype 2 / 3 (local-axes conditions u.l = U / t.l = T, assemble_bem_harela_equation.f90:107-112): u_k AND t_k are unknowns, h goes to the column of u_k and -g
+  // to the column of t_k (kind 2 of the scatter); the three condition rows of such a node are the host's (src/build_lse_mechanics_harmonic.f90:204-258,
+  // mfb_set_condition_rows).  Groups with such dofs run the general K1 kernel (their columns are not three consecutive ones).
   std::vector<int> kind_of; std::vector<unsigned char> c10;
-  for (int i = 0; i < ndof * n_node; i++) if (ctype[i] == 10) { if (c10.empty()) { c10.assign((size_t)ndof * n_node, 0); kind_of.assign(ctype, ctype + (size_t)ndof * n_node); } c10[i] = 1; kind_of[i] = 1; }
-  if (!c10.empty()) ctype = kind_of.data();
+  bool any_kind2 = false;
+  for (int i = 0; i < ndof * n_node; i++) if (ctype[i] == 10 || ctype[i] == 2 || ctype[i] == 3) {
+    if (kind_of.empty()) kind_of.assign(ctype, ctype + (size_t)ndof * n_node);
+    if (ctype[i] == 10) { if (c10.empty()) c10.assign((size_t)ndof * n_node, 0); c10[i] = 1; kind_of[i] = 1; }
+    else { kind_of[i] = 2; any_kind2 = true; if (col_u[i] < 0 || col_u[i] >= n_dof || col_t[i] < 0 || col_t[i] >= n_dof) return fail(MFB_ERR_ARG, "mfb_harela3d_setup: a ctype 2 / 3 dof needs the columns of both u_k and t_k"); }
+  }
+  if (!kind_of.empty()) ctype = kind_of.data();
   double t_host0 = now_ms();
   // ---- symmetry images (lib/fbem/src/symmetry.f90:60-171; image loop build_lse_mechanics_bem_harela.f90:1098-1107) ----
   // Every root element gets n_sym - 1 image elements: element ks * n_root + r is image ks of root r, with the root's nodes (hence its columns and
@@ -498,6 +509,7 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
   p->elem_symbits.assign(n_elem, 0);
   for (int e = 0; e < n_elem; e++) for (int k = 0; k < 3; k++) if (conf_t[e / n_root][k] < 0.0) p->elem_symbits[e] |= (unsigned char)(1u << k);
   std::vector<int> h_ecol(slot_off[n_elem]); std::vector<unsigned char> h_ekind(slot_off[n_elem]);
+  std::vector<int> h_ecol2; if (any_kind2) h_ecol2.assign(slot_off[n_elem], -1);
   for (int s = 0; s < n_elem; s++) {
     int e = p->elem_of_slot[s], nn = p->elems[e].nn;
     for (int j = 0; j < nn; j++) for (int k = 0; k < ndof; k++) {
@@ -506,10 +518,12 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
       int col = (ct == 0) ? col_t[ndof * node + k] : col_u[ndof * node + k];
       if (col < 0 || col >= n_dof) { mfb_problem_free(p); return fail(MFB_ERR_ARG, "mfb_harela3d_setup: missing column for an unknown"); }
       h_ecol[slot_off[s] + j * ndof + k] = p->colperm[col]; h_ekind[slot_off[s] + j * ndof + k] = (unsigned char)ct;
+      if (ct == 2) h_ecol2[slot_off[s] + j * ndof + k] = p->colperm[col_t[ndof * node + k]];
     }
   }
-  int *d_ecol, *d_slot_off; unsigned char* d_ekind; double* d_ecv;
+  int *d_ecol, *d_slot_off, *d_ecol2 = nullptr; unsigned char* d_ekind; double* d_ecv;
   UP(p->owned, h_ecol, &d_ecol); UP(p->owned, h_ekind, &d_ekind); UP(p->owned, slot_off, &d_slot_off);
+  if (any_kind2) UP(p->owned, h_ecol2, &d_ecol2);
   CK(cudaMalloc((void**)&d_ecv, (size_t)slot_off[n_elem] * 2 * sizeof(double))); p->owned.push_back(d_ecv);
 
   // ---- groups: geometry, point sets ----
@@ -568,12 +582,12 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
       D.n_ranges = (int)rs.size() - 1; D.range_start = d_rs; D.range_of = d_rof;
       CK(cudaMalloc((void**)&d_rm, sizeof(int) * D.n_ranges)); g.owned.push_back(d_rm); D.range_modes = d_rm;
     }
-    D.einc = nullptr; D.c10 = nullptr; D.nfn = nullptr;
+    D.einc = nullptr; D.c10 = nullptr; D.nfn = nullptr; D.ecol2 = d_ecol2 ? d_ecol2 + slot_off[g.slot0] : nullptr;
     D.xn = d_xn; D.ball = d_ball; D.enode = d_enode; D.gln_far = d_glnfar; D.erev = d_rev; D.einfo = d_info; D.ecvnz = d_cvnz;
     D.ecol = d_ecol + slot_off[g.slot0]; D.ekind = d_ekind + slot_off[g.slot0]; D.ecv = d_ecv + 2 * (size_t)slot_off[g.slot0];
     D.has_mixed = 0;
     for (int i = 0; i < g.n_elem; i++) if (!(h_info[i] & 8u)) D.has_mixed = 1;
-    D.cols3 = (ndof == 3) ? 1 : 0;
+    D.cols3 = (ndof == 3 && !any_kind2) ? 1 : 0;
     for (int i = 0; i < g.n_elem && D.cols3; i++) {
       const int so = slot_off[g.slot0 + i];
       for (int j = 0; j < g.nn; j++) for (int k = 1; k < 3; k++) if (h_ecol[so + j * 3 + k] != h_ecol[so + j * 3] + k) D.cols3 = 0;
@@ -918,6 +932,7 @@ static int assemble_device_k(mfb_problem* p, const KParams& K, const KParams& Q,
   const double c_pi = 3.14159265358979323846264338328;
   cd F = -1.0 / (8.0 * c_pi * (1.0 - nu));
   launch_freeterm(p->colloc, p->sys, p->ft, mk(F.real(), F.imag()), st);
+  if (p->n_cond > 0) launch_add_entries(p->sys, p->n_cond, p->d_cond_row, p->d_cond_col, p->d_cond_val, st);   // the host's condition rows (mfb_set_condition_rows)
   CK(cudaEventRecord(p->ev[5], st));
   CK(cudaGetLastError());
   p->factored = false; p->assembled = true; p->rows_permuted = true; p->real_resident = statics;
@@ -925,6 +940,26 @@ static int assemble_device_k(mfb_problem* p, const KParams& K, const KParams& Q,
   p->asm_launches = 1;
   for (auto& g : p->groups)   // K1: one kernel per element class on 3/4-node elements (classes 0, 1 and, if present, 2)
     p->asm_launches += (((g.et == 5 || g.et == 7) && g.dev.cols3) ? 2 + ((g.dev.has_mixed || g.dev.einc) ? 1 : 0) : 1) + (cvalue ? 1 : 0) + (g.adp.n_pairs > 0) + (g.sing.n_pairs > 0);
+  return MFB_OK;
+}
+// Rows that the HOST writes into the system after the BEM assembly: the local-axes conditions of ctype 2 / 3 nodes (src/build_lse_mechanics_harmonic.f90:204-258:
+// A_c(row(k,0), col) = n_fn / t1_fn / t2_fn components, b_c(row(k,0)) = cvalue).  entries: rows[i], cols[i] (host indices; cols = -1: the right-hand side),
+// values[i]; they are ADDED after every later assembly of this problem (elastic harmonic or static), so that the fused solve_frequency sees them.  n = 0 clears.
+extern "C" int mfb_set_condition_rows(mfb_problem* p, int n, const int* rows, const int* cols, const mfb_z* values) {
+  if (!p || n < 0 || (n > 0 && (!rows || !cols || !values))) return fail(MFB_ERR_ARG, "mfb_set_condition_rows: invalid argument");
+  for (int i = 0; i < n; i++) if (rows[i] < 0 || rows[i] >= p->n_dof || cols[i] < -1 || cols[i] >= p->n_dof) return fail(MFB_ERR_ARG, "mfb_set_condition_rows: index out of range");
+  CK(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  CK(cudaStreamSynchronize(st));
+  if (p->d_cond_row) { cudaFree(p->d_cond_row); cudaFree(p->d_cond_col); cudaFree(p->d_cond_val); p->d_cond_row = p->d_cond_col = nullptr; p->d_cond_val = nullptr; }
+  p->n_cond = 0;
+  if (n == 0) return MFB_OK;
+  std::vector<int> r(n), c(n); std::vector<double> v(2 * (size_t)n);
+  for (int i = 0; i < n; i++) { r[i] = p->rowperm[rows[i]]; c[i] = cols[i] < 0 ? -1 : p->colperm[cols[i]]; v[2 * i] = values[i].re; v[2 * i + 1] = values[i].im; }
+  CK(cudaMalloc((void**)&p->d_cond_row, n * sizeof(int))); CK(cudaMalloc((void**)&p->d_cond_col, n * sizeof(int))); CK(cudaMalloc((void**)&p->d_cond_val, 2 * (size_t)n * sizeof(double)));
+  CK(cudaMemcpy(p->d_cond_row, r.data(), n * sizeof(int), cudaMemcpyHostToDevice)); CK(cudaMemcpy(p->d_cond_col, c.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(p->d_cond_val, v.data(), 2 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+  p->n_cond = n; p->assembled = false;
   return MFB_OK;
 }
 // Nodal unit normals node(sn)%n_fn(1:3) (src/build_data_at_functional_nodes.f90:355-400: the normalised sum of the normals of the elements around the node, mirror

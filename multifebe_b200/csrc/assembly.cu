@@ -125,7 +125,8 @@ __device__ __forceinline__ void scatter_pair(const Acc<NN, NL>& a, const int* __
                                              const double* __restrict__ ecv, bool rev, const DevSystem& s, int il,
                                              int r0, int r1, int r2, double* bre, double* bim, Pred mine, const KParams& c_kp, bool hbie = false,
                                              unsigned symbits = 0u /* bit k: symconf_t(k) = -1 of a symmetry image (ecv already carries it) */,
-                                             const double* __restrict__ einc = nullptr /* incident field of the element's (j,k), or NULL */) {
+                                             const double* __restrict__ einc = nullptr /* incident field of the element's (j,k), or NULL */,
+                                             const int* __restrict__ ecol2 = nullptr /* columns of t_k for the dofs of kind 2, or NULL */) {
   // h (or m of the hypersingular equation) is scaled by cte_t (cte_s) and changes sign on a reversed element; g (l) by cte_u (cte_d)
   const cplx ch0 = hbie ? c_kp.cte_s : mk(c_kp.cte_t, 0.0);
   const cplx ch = rev ? mk(-ch0.re, -ch0.im) : ch0;
@@ -150,6 +151,12 @@ __device__ __forceinline__ void scatter_pair(const Acc<NN, NL>& a, const int* __
         double gr = cu.re * a.gr[q] - cu.im * a.gi[q], gi = cu.re * a.gi[q] + cu.im * a.gr[q];
         double ar, ai, br, bi;
         if (kind == 0) { ar = -gr; ai = -gi; br = -(hr * cvr - hi * cvi); bi = -(hr * cvi + hi * cvr); }
+        else if (kind == 2) {   // u_k and t_k both unknown (local-axes conditions, assemble_bem_harela_equation.f90:107-112): h to the column of u_k, -g to that of t_k
+          ar = hr; ai = hi; br = 0.0; bi = 0.0;
+          const double sg = ((symbits >> k) & 1u) ? 1.0 : -1.0;
+          double* A2r = s.Are + (size_t)ecol2[jk] * s.lda; double* A2i = s.Aim + (size_t)ecol2[jk] * s.lda;
+          atomicAdd(A2r + row, sg * gr); atomicAdd(A2i + row, sg * gi);
+        }
         else { ar = hr; ai = hi; br = gr * cvr - gi * cvi; bi = gr * cvi + gi * cvr; }
         if ((symbits >> k) & 1u) { ar = -ar; ai = -ai; }
         if (einc) {   // b += h u_inc - g t_inc (assemble_bem_harela_equation.f90:651-666); a symmetry image's sign is in the values
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_regular(DevGroup g, DevColloc
             else accumulate_exterior<NN, NL>(acc, c_kp, x, n, xc, w, il);
           }
           scatter_pair<NN, NL>(acc, ecol, ekind, ecv, rev, s, il, r0, r1, r2, bre, bim, AllEntries(), c_kp, HB, (unsigned)g.einfo[e] >> 5,
-                               (!HB && g.einc) ? g.einc + (size_t)e * 12 * NN : nullptr);
+                               (!HB && g.einc) ? g.einc + (size_t)e * 12 * NN : nullptr, g.ecol2 ? g.ecol2 + (size_t)e * 3 * NN : nullptr);
         }
       }
     }
@@ -796,7 +803,7 @@ __global__ void __launch_bounds__(128) k_adaptive(DevGroup g, DevColloc c, DevSy
     warp_reduce<NN, NL>(acc);
     LaneEntries le; le.lane = lane;
     scatter_pair<NN, NL>(acc, g.ecol + (size_t)e * 3 * NN, g.ekind + (size_t)e * 3 * NN, g.ecv + (size_t)e * 6 * NN, g.erev[e] != 0, s, il,
-                         r0, r1, r2, bre, bim, le, c_kp, HB, (unsigned)g.einfo[e] >> 5, (!HB && g.einc) ? g.einc + (size_t)e * 12 * NN : nullptr);
+                         r0, r1, r2, bre, bim, le, c_kp, HB, (unsigned)g.einfo[e] >> 5, (!HB && g.einc) ? g.einc + (size_t)e * 12 * NN : nullptr, g.ecol2 ? g.ecol2 + (size_t)e * 3 * NN : nullptr);
   }
   flush_b(s, r0, r1, r2, bre, bim);
 }
@@ -877,7 +884,7 @@ __global__ void __launch_bounds__(128) k_singular(DevGroup g, DevColloc c, DevSy
     }
     LaneEntries le; le.lane = lane;
     scatter_pair<NN, NL>(acc, g.ecol + (size_t)e * 3 * NN, g.ekind + (size_t)e * 3 * NN, g.ecv + (size_t)e * 6 * NN, g.erev[e] != 0, s, il,
-                         r0, r1, r2, bre, bim, le, c_kp, false, (unsigned)g.einfo[e] >> 5, g.einc ? g.einc + (size_t)e * 12 * NN : nullptr);
+                         r0, r1, r2, bre, bim, le, c_kp, false, (unsigned)g.einfo[e] >> 5, g.einc ? g.einc + (size_t)e * 12 * NN : nullptr, g.ecol2 ? g.ecol2 + (size_t)e * 3 * NN : nullptr);
   }
   flush_b(s, r0, r1, r2, bre, bim);
 }
@@ -910,7 +917,7 @@ __global__ void k_freeterm(DevColloc c, DevSystem s, DevFreeTerm f, cplx F) {
     atomicAdd(s.bre + row, vr * ur - vi * ui);
     atomicAdd(s.bim + row, vr * ui + vi * ur);
   }
-  if (f.ekind[o] == 1) {
+  if (f.ekind[o] != 0) {   // t_k known, or u_k and t_k both unknown: the free term multiplies the unknown u_k
     atomicAdd(s.Are + (size_t)f.ecol[o] * s.lda + row, vr);
     atomicAdd(s.Aim + (size_t)f.ecol[o] * s.lda + row, vi);
   } else {

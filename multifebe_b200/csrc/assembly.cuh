@@ -18,7 +18,8 @@ struct DevGroup {
   int ndof;                      // dofs per node: 3 (elastic; the strides below are written for it), 1 (inviscid fluid, potential.cuh: stride nn)
   const double* xn;              // [n_elem][3*nn] node coordinates
   const int* ecol;               // [n_elem][3*nn] column of A for (node j, dof k); index j*3+k
-  const unsigned char* ekind;    // [n_elem][3*nn] 0: u known (A -= g, b -= h*u), 1: t known (A += h, b += g*t)
+  const int* ecol2;              // NULL, or [n_elem][3*nn]: column of t_k for a dof whose u_k AND t_k are unknown (kind 2: local-axes conditions), -1 elsewhere
+  const unsigned char* ekind;    // [n_elem][3*nn] 0: u known (A -= g, b -= h*u), 1: t known (A += h, b += g*t), 2: both unknown (A(:,ecol) += h, A(:,ecol2) -= g)
   const int* enode;              // [n_elem][nn]   global node ids
   const unsigned char* erev;     // [n_elem] reversed orientation (h -> -h)
   double* ecv;                   // [n_elem][3*nn][2] prescribed value of (j,k), refreshed per frequency

@@ -63,7 +63,7 @@ class Model:
 
     def __init__(self, mesh, bcs, reversed_parts=(), qsi_relative_error=1e-6, qsi_ns_max=16,
                  precalset_gln=(2, 3, 4, 5, 6, 7, 8, 9), geometric_tolerance=1e-6, ndof=3, part_order=None,
-                 symmetry=None, nodal_on_symplanes=False):
+                 symmetry=None, nodal_on_symplanes=False, local_axes_reference=None):
         """symmetry: the [symmetry planes] section (src/read_symmetry_planes.f90:76-283) as a list of (axis, kind), axis 'x' | 'y' | 'z'
         (plane_n1 / plane_n2 / plane_n3: the plane through the origin normal to that axis), kind 'symmetry' | 'antisymmetry'.
         nodal_on_symplanes: open edges that lie in a symmetry plane do not make their nodes boundary-of-the-boundary nodes, so those nodes
@@ -128,6 +128,7 @@ class Model:
         order = [e for p in parts for e in range(ne) if int(mesh.part[e]) == p]
         self.elem_order = np.array(order, dtype=np.int32)
         self.row = -np.ones((nn, nd), dtype=np.int32)
+        self.row_bc = -np.ones((nn, nd), dtype=np.int32)      # node%row(k,0): the condition row of a local-axes dof (ctype 2 / 3)
         self.col_u = -np.ones((nn, nd), dtype=np.int32)
         self.col_t = -np.ones((nn, nd), dtype=np.int32)
         row = col = 0
@@ -143,8 +144,12 @@ class Model:
                         self.col_t[v, k] = col
                     elif self.ctype[v, k] == 1 or (self.ctype[v, k] == 10 and nd == 3):
                         self.col_u[v, k] = col          # 10: normal pressure known, t_k = p n_fn(k); the unknown is u_k
+                    elif self.ctype[v, k] in (2, 3) and nd == 3:
+                        # local axes (build_auxiliary_variables_mechanics_harmonic.f90:188-197): u_k and t_k are both unknowns, and the node gets a condition row
+                        self.col_u[v, k] = col; self.col_t[v, k] = col + 1; col += 1
+                        self.row_bc[v, k] = row; row += 1
                     else:
-                        raise ValueError("only ctype 0 / 1 (and 10 on elastic regions) are supported on this path")
+                        raise ValueError("only ctype 0 / 1 (and 2 / 3 / 10 on elastic regions) are supported on this path")
                     col += 1
         assert row == col
         self.n_dof = row
@@ -161,6 +166,20 @@ class Model:
             self.n_fn[on, ax - 1] = 0.0       # n + M n, applied once per plane the node lies in: the component along the plane's axis cancels, the others double
         norm = np.linalg.norm(self.n_fn, axis=1)
         self.n_fn[norm > 0] /= norm[norm > 0, None]
+        # unit tangents of the local axes (build_data_at_functional_nodes.f90:406-446): t2 = n x reference vector (the user's, else e1, e2, e3 in turn), t1 = t2 x n
+        self.t1_fn = np.zeros((nn, 3)); self.t2_fn = np.zeros((nn, 3))
+        refs = ([np.asarray(local_axes_reference, dtype=np.float64)] if local_axes_reference is not None else []) + [np.eye(3)[i] for i in range(3)]
+        for v in range(nn):
+            n = self.n_fn[v]
+            if not n.any():
+                continue
+            for ref in refs:
+                t2 = np.cross(n, ref)
+                if np.linalg.norm(t2) > self.geometric_tolerance:
+                    break
+            t2 = t2 / np.linalg.norm(t2)
+            t1 = np.cross(t2, n)
+            self.t1_fn[v], self.t2_fn[v] = t1 / np.linalg.norm(t1), t2
 
         # --- collocation points (loop order of build_lse_mechanics_bem_harela.f90:1118-1136)
         cx, cnode, celem, ckn, cxi = [], [], [], [], []
@@ -185,6 +204,34 @@ class Model:
         self.colloc_xi = np.ascontiguousarray(cxi, dtype=np.float64)
         self.n_colloc = len(cnode)
 
+    def condition_rows(self):
+        """The rows the host writes for local-axes conditions (src/build_lse_mechanics_harmonic.f90:204-258): dof k of such a node refers to the axis
+        l_1 = n, l_2 = t_1, l_3 = t_2; ctype 2: u . l_k = U, ctype 3: t . l_k = T.  -> rows, cols (-1: right-hand side), values."""
+        rows, cols, vals = [], [], []
+        if self.ndof != 3:
+            return np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.complex128)
+        axes = (self.n_fn, self.t1_fn, self.t2_fn)
+        for v in range(self.n_node):
+            for k in range(3):
+                ct = int(self.ctype[v, k])
+                if ct not in (2, 3):
+                    continue
+                r = int(self.row_bc[v, k]); target = self.col_u if ct == 2 else self.col_t
+                for kci in range(3):
+                    rows.append(r); cols.append(int(target[v, kci])); vals.append(complex(axes[k][v, kci]))
+                rows.append(r); cols.append(-1); vals.append(complex(self.cvalue[v, k]))
+        return np.array(rows, dtype=np.int32), np.array(cols, dtype=np.int32), np.array(vals, dtype=np.complex128)
+
+    def add_condition_rows(self, A, b):
+        """A, b of the BEM assembly plus the condition rows (what the reference's host does after build_lse_mechanics_bem_harela)."""
+        rows, cols, vals = self.condition_rows()
+        for r, c, v in zip(rows, cols, vals):
+            if c < 0:
+                b[r] += v
+            else:
+                A[r, c] += v
+        return A, b
+
     # --- reference's assign_solution_mechanics_harmonic.f90:192-205: nodal u,t from the solution vector
     def nodal_solution(self, x):
         u = np.zeros((self.n_node, self.ndof), dtype=np.complex128)
@@ -198,6 +245,8 @@ class Model:
             if self.ndof == 3:
                 p10 = self.ctype[:, k] == 10          # normal pressure known: t_k = p n_fn(k)
                 t[p10, k] = self.cvalue[p10, k] * self.n_fn[p10, k]
+                loc = (self.ctype[:, k] == 2) | (self.ctype[:, k] == 3)      # local axes: both are unknowns of the system
+                u[loc, k] = x[self.col_u[loc, k]]; t[loc, k] = x[self.col_t[loc, k]]
         return u, t
 
 

@@ -1628,6 +1628,10 @@ static void scatter(const Model* m, int e, int sn_col, const cd* hp, const cd* g
         switch (m->ctype[3 * sn + ik]) {
           case 0: { long long col = m->col_t[3 * sn + ik]; A[row + nd * col] = A[row + nd * col] - gg; b[row] = b[row] - hh * cvalue[3 * sn + ik]; break; }
           case 1: { long long col = m->col_u[3 * sn + ik]; A[row + nd * col] = A[row + nd * col] + hh; b[row] = b[row] + gg * cvalue[3 * sn + ik]; break; }
+          case 2: case 3: {   // u_k unknown, t_k unknown (local-axes conditions; their rows are the host's): assemble_bem_harela_equation.f90:107-112
+            long long col = m->col_u[3 * sn + ik]; A[row + nd * col] = A[row + nd * col] + hh;
+            col = m->col_t[3 * sn + ik]; A[row + nd * col] = A[row + nd * col] - gg;
+            break; }
           case 10: {   // p known (normal pressure), u_k unknown: assemble_bem_harela_equation.f90:97-106
             long long col = m->col_u[3 * sn + ik]; A[row + nd * col] = A[row + nd * col] + hh;
             if (!m->elem[e].reverse) b[row] = b[row] + gg * cvalue[3 * sn + ik] * m->n_fn[3 * sn + ik];

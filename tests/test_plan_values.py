@@ -95,3 +95,33 @@ def test_edge_line_integrals_closed_form_graded_panels_and_brute_force_agree():
         I += ((0.5 * (b - a) * gw)[:, None] * dx / np.linalg.norm(x - x_i[None], axis=1)[:, None]).sum(0)
     ref = np.zeros(9); ref[1] = -I[2]; ref[2] = I[1]; ref[5] = -I[0]; ref[3] = I[2]; ref[6] = -I[1]; ref[7] = I[0]
     assert np.abs(got - ref).max() < 1e-13 * np.abs(ref).max()
+
+
+def test_free_term_of_a_flat_fan_in_general_position(oracle_lib):
+    """A node inside a flat face has the free term c = 1/2 I whatever the orientation of the face.  The reference's formula
+    (fbem_bem_harela3d_sbie_freeterm, bem_harela3d.f90:478-492: sum of acos(n_i . n_i+1) with a sign from (n_i x n_i+1) . t) is ill-conditioned exactly there:
+    in general position the normals of coplanar neighbours agree only up to rounding, n . n' = 1 - O(1e-16), and acos makes O(1e-8) of it.  The oracle
+    restates that formula and shows the noise; the product's geometry (csrc/plan_values.cpp: angles from atan2 of triple products) does not.  This is
+    why parity of the free-term blocks on rotated meshes is asserted at 5e-8 (tests/test_gpu_local_axes.py) and at 1e-11 everywhere else."""
+    from multifebe_b200 import capi
+    rng = np.random.default_rng(7)
+    worst_o = worst_p = 0.0
+    for _ in range(40):
+        Q, _r = np.linalg.qr(rng.normal(size=(3, 3)))
+        if np.linalg.det(Q) < 0:
+            Q[:, 0] = -Q[:, 0]
+        ne = int(rng.integers(3, 9))
+        ang = np.sort(rng.uniform(0, 2 * np.pi, ne))
+        ang = ang + np.linspace(0, 1e-3, ne)                        # distinct
+        # element i spans the sector [ang_i, ang_i+1) of the plane z = 0; its boundary tangent at the node points along its first edge
+        n_loc = np.tile([0.0, 0.0, 1.0], (ne, 1)); t_loc = np.stack([np.cos(ang), np.sin(ang), np.zeros(ne)], axis=1)
+        n = n_loc @ Q.T; t = t_loc @ Q.T
+        # rounding as in a real mesh: normals come from cross products of slightly different edge vectors
+        n = n + rng.normal(scale=1e-16, size=n.shape); n /= np.linalg.norm(n, axis=1)[:, None]
+        perm = rng.permutation(ne)
+        cp_, _ = capi.freeterm(n[perm], t[perm], 0.3)
+        co, err = oracle_lib.freeterm(n[perm], t[perm], 0.3)
+        assert err == 0
+        worst_p = max(worst_p, np.abs(cp_ - 0.5 * np.eye(3)).max()); worst_o = max(worst_o, np.abs(co - 0.5 * np.eye(3)).max())
+    assert worst_p < 1e-13, worst_p
+    assert worst_o < 1e-6, worst_o          # the reference formula: right, but only to the square root of the rounding of n . n'
