@@ -284,9 +284,22 @@ class CaseFile:
             for k in range(ndof):
                 w = recs[k].split(None, 1)
                 t = int(w[0])
-                if t not in (0, 1):
-                    raise CaseFileError("boundary %d: condition type %d is not covered (0: primary variable known, 1: secondary variable known)" % (bid, t))
+                solid_single = ndof == 3 and not self.multi
+                if t == 4 and solid_single:
+                    # 4: infinitesimal rotation field u_k = theta (axis x (x - center)) . e_k: `4 cx cy cz ax ay az theta` (read_conditions_bem_boundaries_mechanics_harmonic.f90:129-143)
+                    q = w[1].replace(",", " ").replace("(", " ").replace(")", " ").split()
+                    if len(q) < 7:
+                        raise CaseFileError("boundary %d: condition type 4 needs center(3), axis(3), theta" % bid)
+                    num = [_fortran_float(z) for z in q]
+                    theta = complex(num[6], num[7]) if len(num) >= 8 else complex(num[6])
+                    ct.append(4); cv.append((num[0:3], num[3:6], theta))
+                    continue
+                if t not in (0, 1) and not (t in (2, 3) and solid_single):
+                    raise CaseFileError("boundary %d: condition type %d is not covered (0: primary variable known, 1: secondary variable known; on one elastic region also "
+                                        "2 / 3: local axes, 4: rotation field, 10: normal pressure)" % (bid, t))
                 ct.append(t); cv.append(_fortran_complex(w[1]))
+            if any(t in (2, 3) for t in ct) and not all(t in (2, 3) for t in ct):
+                raise CaseFileError("boundary %d: local axes B.C. and global axes B.C. can not be mixed" % bid)
             self.bcs[bid] = (ct, cv)
             i += ndof
         # ---- [internal points] (src/read_internal_points.f90: `<id> <region> x1 x2 x3`): displacements and stresses inside an elastic region

@@ -117,8 +117,16 @@ class Model:
         self.cvalue = np.zeros((nn, nd), dtype=np.complex128)
         for v in range(nn):
             ct, cv = bcs[int(node_part[v])]
-            self.ctype[v] = ct
-            self.cvalue[v] = cv
+            for k in range(nd):
+                if int(ct[k]) == 4 and nd == 3:
+                    # prescribed infinitesimal rotation field (transfer_conditions_bem_boundaries_mechanics_harmonic.f90:89-99): a ctype-0 condition with
+                    # u_k = theta (axis x (x - center))_k; the value is (center, axis, theta), axis normalised by the reader
+                    center, axis, theta = cv[k]
+                    axis = np.asarray(axis, dtype=np.float64); axis = axis / np.linalg.norm(axis)
+                    self.ctype[v, k] = 0
+                    self.cvalue[v, k] = complex(theta) * np.cross(axis, mesh.nodes[v] - np.asarray(center, dtype=np.float64))[k]
+                else:
+                    self.ctype[v, k] = int(ct[k]); self.cvalue[v, k] = cv[k]
 
         # --- DOF numbering: region -> boundary (part id order) -> element -> node, first visit
         # part_order: the boundaries in the order of the region's list in the case file (default: ascending part id)

@@ -276,7 +276,7 @@ def test_harmonic_solid_case_polar_notation(tmp_path):
 def test_unsupported_features_are_named(tmp_path):
     base = SOLID_DAT % dict(analysis="static", freq="", z="0.", one="1.")
     for old, new, word in [("1 1 ordinary", "1 1 crack-like", "ordinary"), ("[regions]\n1\n", "[regions]\n2\n", "regions announced"),
-                           ("boundary 2: 1 1.", "boundary 2: 2 1.", "condition type 2"), ("n = 3D", "n = 2D", "3D"),
+                           ("boundary 2: 1 1.", "boundary 2: 5 1.", "condition type 5"), ("n = 3D", "n = 2D", "3D"),
                            ("1 be\n", "1 fe\n", "`be`"), ('mesh_file_mode = 2 "cube.msh"', "mesh_file_mode = 0", "mesh_file_mode"),
                            ("6 1 2 3 4 5 6", "6 1 2 3 4 5 -6", "reversed")]:
         assert old in base
@@ -730,3 +730,47 @@ boundary 6: 1 (0.,0.)
     pr = rows[:, 12] + 1j * rows[:, 13]
     p_ex, _ = room_analytic(rows[:, 9], 2 * np.pi * 45.0, Fluid(1.25, 343.0))
     assert np.abs(pr - p_ex).max() < 5e-4
+
+
+def test_local_axes_rotation_field_and_pressure_conditions_in_a_case_file(tmp_path):
+    """Condition types 2 / 3 (local axes), 4 (infinitesimal rotation field -> a ctype-0 condition with values per node) and the refusal of mixed local /
+    global types (read_conditions_bem_boundaries_mechanics_harmonic.f90:124-162)."""
+    base = SOLID_DAT % dict(analysis="static", freq="", z="0.", one="1.")
+    walls = ("boundary 3: 1 0.\n            0 0.\n            1 0.\n", "boundary 3: 2 0.\n            3 0.\n            3 0.\n")
+    assert walls[0] in base
+    path = _write_case(tmp_path, base.replace(walls[0], walls[1]))
+    case = CaseFile(path); md = case.build_model()
+    assert case.bcs[3] == ([2, 3, 3], [0j, 0j, 0j])
+    w3 = md.node_part == 3
+    assert (md.ctype[w3] == [2, 3, 3]).all() and (md.row_bc[w3] >= 0).all() and md.n_dof == 3 * md.n_node + 3 * w3.sum()
+    # the sliding wall in local axes is the sliding wall of the global pattern: same exact column solution
+    nso, _ = _run_with_oracle_local(path)
+    rows = read_nso(nso)
+    mat = case.material
+    lam2mu = 2.0 * mat.mu_r * mat.nu_r / (1.0 - 2.0 * mat.nu_r) + 2.0 * mat.mu_r
+    assert np.abs(rows[:, 12] - rows[:, 9] / lam2mu).max() < 5e-6
+    with pytest.raises(CaseFileError) as ei:
+        CaseFile(_write_case(tmp_path, base.replace(walls[0], "boundary 3: 2 0.\n            0 0.\n            3 0.\n")))
+    assert "can not be mixed" in str(ei.value)
+    # rotation field about the z axis through the centre of the face x = 0
+    rot = "boundary 1: 4 0. 0.5 0.5  0. 0. 2.  0.01\n            4 0. 0.5 0.5  0. 0. 2.  0.01\n            4 0. 0.5 0.5  0. 0. 2.  0.01\n"
+    old1 = "boundary 1: 0 0.\n            0 0.\n            0 0.\n"
+    assert old1 in base
+    md = CaseFile(_write_case(tmp_path, base.replace(old1, rot))).build_model()
+    f1 = md.node_part == 1
+    assert (md.ctype[f1] == 0).all()
+    want = 0.01 * np.cross([0.0, 0.0, 1.0], md.node_x[f1] - np.array([0.0, 0.5, 0.5]))
+    assert np.abs(md.cvalue[f1] - want).max() < 1e-15
+
+
+def _run_with_oracle_local(path):
+    """The oracle as the solver of a single-region case with local-axes rows (the host adds them, as the reference's build_lse_mechanics_* does)."""
+    case = CaseFile(path)
+
+    class S(OracleSolver):
+        def static(self):
+            A, b, _ = self.o.assemble_static(self.case.material)
+            A = A.astype(np.complex128); b = b.astype(np.complex128)
+            self.model.add_condition_rows(A, b)
+            return np.linalg.solve(A, b)
+    return driver.run(path, solver=S(case, case.build_model()), log=io.StringIO()), case
