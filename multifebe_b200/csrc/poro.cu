@@ -9,12 +9,12 @@
 // Free terms (c_00 = J c_pot, c_lk = Mantic's matrix of the drained skeleton, or phi_j/2 at MCA points) go through k_freeterm with two
 // lists (multipliers F and J).  The point arithmetic is por_math.cuh (checked on the host against the oracle).
 //
-// STATUS: first hardware run in round 2 (compute-sanitizer clean; tests/test_gpu_poroelastic.py green on a B200, profiles/r02_first_contact.log).
+// STATUS: first hardware run in round 2 (compute-sanitizer clean; tests/test_gpu_poroelastic.py green on a B200, profiles/r02_first_contact.log); R1 rewritten
+// later in that round (BC-aware accumulators, scalar cache, packed batches: DESIGN.md section 9.10).
 //
-// Mapping: as k_regular<ET, 1> of assembly.cu -- a warp owns a collocation tile, lane = collocation point, ONE equation (row l of the node
-// block) per pass, so that the pair's accumulators are 2 * 4 * NN complex numbers; the 4 x 4 point blocks are recomputed in every pass
-// (4x the arithmetic of a one-pass kernel: the register file does not hold 32 * NN complex accumulators; a later version can stage them
-// in shared memory).
+// Mapping: a warp owns a collocation tile and walks a chunk of elements; R1 packs its pairs per rule (one pair per lane, see k_por_regular), R2 / R3 give
+// a warp to a pair.  ONE equation (row l of the node block) per pass, so that a pair's accumulators fit the register file; R1 keeps the radial scalars
+// of the first points in shared memory between the passes, R2 / R3 recompute the 4 x 4 point blocks in every pass.
 #include "poro.cuh"
 #include "por_pair.cuh"
 #include <cstdio>
