@@ -297,13 +297,15 @@ class Problem:
     def set_incident(self, u_inc=None, t_inc=None):
         """Incident wave field at the nodes of every element ((sum nn, 3) complex each, element order; element()%incident_c of the reference);
         None clears.  Every later assembly adds hp u_inc - gp t_inc to b (assemble_bem_harela_equation.f90:651-666)."""
+        fn = lib().mfb_harpot3d_set_incident if self.ndof == 1 else lib().mfb_harela3d_set_incident     # fluid region: p_inc, Un_inc, one value per element node
         if u_inc is None:
-            _check(lib().mfb_harela3d_set_incident(self.h, None, None))
+            _check(fn(self.h, None, None))
             return
-        u = np.ascontiguousarray(u_inc, dtype=np.complex128).reshape(-1, 3); t = np.ascontiguousarray(t_inc, dtype=np.complex128).reshape(-1, 3)
-        if not (len(u) == len(t) == int(self.m.elem_ptr[-1])):
+        nd = 1 if self.ndof == 1 else 3
+        u = np.ascontiguousarray(u_inc, dtype=np.complex128); t = np.ascontiguousarray(t_inc, dtype=np.complex128)
+        if u.size != nd * int(self.m.elem_ptr[-1]) or t.size != u.size:
             raise ValueError("incident field: one row per element node")
-        _check(lib().mfb_harela3d_set_incident(self.h, _p(u), _p(t)))
+        _check(fn(self.h, _p(u.reshape(-1, nd)), _p(t.reshape(-1, nd))))
 
     # ---- seam 1: build_lse_mechanics_bem_harela(kf,kr) after A_c=0; b_c=0 ----
     def build_lse_mechanics_bem_harela(self, omega, mat, want_host=True, out=None):

@@ -506,8 +506,12 @@ static int setup_impl(mfb_ctx* ctx, int n_node, const double* node_x, int n_elem
   std::vector<int> slot_off(n_elem + 1, 0);
   for (int s = 0; s < n_elem; s++) slot_off[s + 1] = slot_off[s] + ndof * p->elems[p->elem_of_slot[s]].nn;
   p->slot_off_h = slot_off; p->n_elem_root = n_root; p->root_elem_ptr.assign(elem_ptr, elem_ptr + n_root + 1);
-  p->elem_symbits.assign(n_elem, 0);
-  for (int e = 0; e < n_elem; e++) for (int k = 0; k < 3; k++) if (conf_t[e / n_root][k] < 0.0) p->elem_symbits[e] |= (unsigned char)(1u << k);
+  p->elem_symbits.assign(n_elem, 0);   // bit k: multiplier -1 of a symmetry image on dof k of the node (solid: symconf_t; fluid: symconf_s; poroelastic: s, then t)
+  for (int e = 0; e < n_elem; e++) {
+    const int ks = e / n_root;
+    if (ndof == 3) { for (int k = 0; k < 3; k++) if (conf_t[ks][k] < 0.0) p->elem_symbits[e] |= (unsigned char)(1u << k); }
+    else { if (conf_s[ks] < 0.0) p->elem_symbits[e] |= 1u; if (ndof == 4) for (int k = 0; k < 3; k++) if (conf_t[ks][k] < 0.0) p->elem_symbits[e] |= (unsigned char)(2u << k); }
+  }
   std::vector<int> h_ecol(slot_off[n_elem]); std::vector<unsigned char> h_ekind(slot_off[n_elem]);
   std::vector<int> h_ecol2; if (any_kind2) h_ecol2.assign(slot_off[n_elem], -1);
   for (int s = 0; s < n_elem; s++) {
@@ -982,9 +986,14 @@ extern "C" int mfb_set_node_normals(mfb_problem* p, const double* n_fn) {
 // hp u_inc - gp t_inc to b (assemble_bem_harela_equation.f90:651-666), the free term included (it is part of hp, build_lse_mechanics_bem_harela.f90:715).
 // Arrays: [(elem_ptr[e] + j) * 3 + k] complex, e over the elements given to the set-up; both NULL: no incident field.  Valid until the next call
 // (set it before the assembly of every frequency: the field depends on omega).  An image of a symmetric model takes the root's values times symconf_t(k).
-extern "C" int mfb_harela3d_set_incident(mfb_problem* p, const mfb_z* u_inc, const mfb_z* t_inc) {
+static int set_incident_impl(mfb_problem* p, const mfb_z* u_inc, const mfb_z* t_inc, int want_ndof);
+extern "C" int mfb_harela3d_set_incident(mfb_problem* p, const mfb_z* u_inc, const mfb_z* t_inc) { return set_incident_impl(p, u_inc, t_inc, 3); }
+// The same for an inviscid fluid region: p_inc, Un_inc at the nodes of every element, index [elem_ptr[e] + j] (element()%incident_c(1,kn,1) / (2,kn,1));
+// every pair and free term adds hp p_inc - gp Un_inc to b (src/assemble_bem_harpot_equation.f90:471-481; gp already carries rho omega^2).
+extern "C" int mfb_harpot3d_set_incident(mfb_problem* p, const mfb_z* p_inc, const mfb_z* un_inc) { return set_incident_impl(p, p_inc, un_inc, 1); }
+static int set_incident_impl(mfb_problem* p, const mfb_z* u_inc, const mfb_z* t_inc, int want_ndof) {
   if (!p) return fail(MFB_ERR_ARG, "mfb_harela3d_set_incident: null problem");
-  if (p->ndof != 3 || p->hbie) return fail(MFB_ERR_UNSUPPORTED, "mfb_harela3d_set_incident: built for the displacement equation of elastic regions");
+  if (p->ndof != want_ndof || p->hbie) return fail(MFB_ERR_UNSUPPORTED, "set_incident: built for the displacement equation of elastic regions (mfb_harela3d_set_incident) and for fluid regions (mfb_harpot3d_set_incident)");
   if ((u_inc == nullptr) != (t_inc == nullptr)) return fail(MFB_ERR_ARG, "mfb_harela3d_set_incident: give both u_inc and t_inc, or neither");
   CK(cudaSetDevice(p->ctx->device));
   cudaStream_t st = p->ctx->stream;
@@ -995,12 +1004,13 @@ extern "C" int mfb_harela3d_set_incident(mfb_problem* p, const mfb_z* u_inc, con
     for (int s = 0; s < n_elem; s++) {
       const int e = p->elem_of_slot[s], r = e % n_root, nn = p->elems[e].nn, o = p->slot_off_h[s];
       const unsigned bits = p->elem_symbits[e];
-      for (int j = 0; j < nn; j++) for (int k = 0; k < 3; k++) {
-        const size_t q = ((size_t)p->root_elem_ptr[r] + j) * 3 + k;
+      const int nd = p->ndof;
+      for (int j = 0; j < nn; j++) for (int k = 0; k < nd; k++) {
+        const size_t q = ((size_t)p->root_elem_ptr[r] + j) * nd + k;
         const double sg = ((bits >> k) & 1u) ? -1.0 : 1.0;
         if (!std::isfinite(u_inc[q].re) || !std::isfinite(u_inc[q].im) || !std::isfinite(t_inc[q].re) || !std::isfinite(t_inc[q].im))
           return fail(MFB_ERR_ARG, "mfb_harela3d_set_incident: non-finite value");
-        double* d = &h[4 * ((size_t)o + j * 3 + k)];
+        double* d = &h[4 * ((size_t)o + j * nd + k)];
         d[0] = sg * u_inc[q].re; d[1] = sg * u_inc[q].im; d[2] = sg * t_inc[q].re; d[3] = sg * t_inc[q].im;
       }
     }

@@ -28,13 +28,17 @@ void set_pot_params(const PotParams& pp, cudaStream_t st) { cudaMemcpyToSymbolAs
 // neg: the element is a symmetry image whose scalar multiplier symconf_s is -1 (build_lse_mechanics_bem_harpot.f90:947-948): the matrix entry changes sign
 // here, the b term through the prescribed value (k_gather_cv folds the sign into ecv)
 __device__ __forceinline__ void pot_scatter_node(double hr, double hi, double gr, double gi, bool rev, int col, int kind, double cvr, double cvi,
-                                                 const DevSystem& s, int row, double& bre, double& bim, bool neg = false) {
+                                                 const DevSystem& s, int row, double& bre, double& bim, bool neg = false,
+                                                 const double* __restrict__ inc = nullptr /* (p_inc re, im, Un_inc re, im) of this element node, or NULL */) {
   const double sh = rev ? c_pp.c4pi : -c_pp.c4pi, sg = c_pp.c4pi * c_pp.d1J;
   hr *= sh; hi *= sh; gr *= sg; gi *= sg;
   double ar, ai;
   if (kind == 0) { ar = -gr; ai = -gi; bre -= hr * cvr - hi * cvi; bim -= hr * cvi + hi * cvr; }
   else { ar = hr; ai = hi; bre += gr * cvr - gi * cvi; bim += gr * cvi + gi * cvr; }
   if (neg) { ar = -ar; ai = -ai; }
+  if (inc) {   // incident field: b += hp p_inc - gp Un_inc (assemble_bem_harpot_equation.f90:471-481); a symmetry image's sign is in the values
+    bre += (hr * inc[0] - hi * inc[1]) - (gr * inc[2] - gi * inc[3]); bim += (hr * inc[1] + hi * inc[0]) - (gr * inc[3] + gi * inc[2]);
+  }
   atomicAdd(s.Are + (size_t)col * s.lda + row, ar);
   atomicAdd(s.Aim + (size_t)col * s.lda + row, ai);
 }
@@ -95,7 +99,8 @@ __global__ void __launch_bounds__(P1_WARPS * 32) k_pot_regular(DevGroup g, DevCo
       double bre = 0.0, bim = 0.0;
 #pragma unroll
       for (int j = 0; j < NN; j++)
-        pot_scatter_node(acc.hr[j], acc.hi[j], acc.gr[j], acc.gi[j], rev, __ldg(ecol + j), ekind[j], ecv[2 * j], ecv[2 * j + 1], s, rs, bre, bim, neg);
+        pot_scatter_node(acc.hr[j], acc.hi[j], acc.gr[j], acc.gi[j], rev, __ldg(ecol + j), ekind[j], ecv[2 * j], ecv[2 * j + 1], s, rs, bre, bim, neg,
+                         g.einc ? g.einc + 4 * ((size_t)el * NN + j) : nullptr);
       if (bre != 0.0 || bim != 0.0) { atomicAdd(s.bre + rs, bre); atomicAdd(s.bim + rs, bim); }
     }
     __syncwarp();
@@ -164,7 +169,8 @@ __device__ __forceinline__ void pot_scatter_pair(const PAcc<NN>& a, const DevGro
   const bool rev = g.erev[e] != 0;
 #pragma unroll
   for (int j = 0; j < NN; j++)
-    if (lane == j) pot_scatter_node(a.hr[j], a.hi[j], a.gr[j], a.gi[j], rev, ecol[j], ekind[j], ecv[2 * j], ecv[2 * j + 1], s, row, bre, bim, (g.einfo[e] & 32u) != 0);
+    if (lane == j) pot_scatter_node(a.hr[j], a.hi[j], a.gr[j], a.gi[j], rev, ecol[j], ekind[j], ecv[2 * j], ecv[2 * j + 1], s, row, bre, bim, (g.einfo[e] & 32u) != 0,
+                                     g.einc ? g.einc + 4 * ((size_t)e * NN + j) : nullptr);
   if (bre != 0.0 || bim != 0.0) { atomicAdd(s.bre + row, bre); atomicAdd(s.bim + row, bim); }
 }
 

@@ -52,3 +52,29 @@ def element_incident(model, field):
             n = sgn * sh.unit_normal(et, xn, sh.XI_NODES[et][kn])
             u[model.elem_ptr[e] + kn], t[model.elem_ptr[e] + kn] = field(xn[kn], n)
     return u, t
+
+
+def plane_wave_fluid(direction, fluid, omega, amplitude=1.0):
+    """-> field(x, n) = (p, Un) of a plane pressure wave p = A exp(-i k d.x), k = omega / c, in an inviscid fluid; Un = (dp/dn) / (rho omega^2) is the normal
+    displacement, the flux variable of the reference's fluid regions (build_lse_mechanics_bem_harpot.f90:751)."""
+    d = np.asarray(direction, dtype=np.float64)
+    d = d / np.linalg.norm(d)
+    k = omega / fluid.c
+
+    def field(x, n):
+        p = amplitude * np.exp(-1j * k * np.dot(d, x))
+        return p, (-1j * k * np.dot(d, np.asarray(n, dtype=np.float64)) * p) / (fluid.rho * omega ** 2)
+    return field
+
+
+def element_incident_fluid(model, field):
+    """p_inc, Un_inc ((sum nn,) complex each, element order) at the nodes of every element of a fluid region, with the region's outward normal."""
+    n_rows = int(model.elem_ptr[-1])
+    p = np.zeros(n_rows, dtype=np.complex128); un = np.zeros(n_rows, dtype=np.complex128)
+    for e in range(model.n_elem):
+        et = int(model.etype[e]); c = model.mesh.conn[e]; xn = model.node_x[c]
+        sgn = -1.0 if model.elem_reversed[e] else 1.0
+        for kn in range(len(c)):
+            n = sgn * sh.unit_normal(et, xn, sh.XI_NODES[et][kn])
+            p[model.elem_ptr[e] + kn], un[model.elem_ptr[e] + kn] = field(xn[kn], n)
+    return p, un

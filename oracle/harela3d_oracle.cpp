@@ -1572,7 +1572,7 @@ void orc_set_node_normals(void* h, const double* n_fn) { Model* m = (Model*)h; m
 void orc_set_incident(void* h, const double* u_ri, const double* t_ri) {
   Model* m = (Model*)h; m->u_inc.clear(); m->t_inc.clear();
   if (!u_ri || !t_ri) return;
-  size_t n = (size_t)m->eptr[m->n_elem] * 3;
+  size_t n = (size_t)m->eptr[m->n_elem] * (size_t)m->nd;   // three values per element node for a solid, one (p_inc | Un_inc) for a fluid
   m->u_inc.assign((const cd*)u_ri, (const cd*)u_ri + n); m->t_inc.assign((const cd*)t_ri, (const cd*)t_ri + n);
 }
 // planes (indices into plane_eid) that contain the node: fbem_node_symplanes_connectivity (lib/fbem/src/data_structures.f90:1116-1153)
@@ -1767,6 +1767,8 @@ static void scatter_pot(const Model* m, int e, int sn_col, const cd* hp, const c
       case 0: { long long col = m->col_t[sn]; A[row + nd * col] = A[row + nd * col] - gp[kn]; b[row] = b[row] - hp[kn] * cvalue[sn]; break; }
       case 1: { long long col = m->col_u[sn]; A[row + nd * col] = A[row + nd * col] + hp[kn]; b[row] = b[row] + gp[kn] * cvalue[sn]; break; }
     }
+    // incident wave field: assemble_bem_harpot_equation.f90:471-481 (ordinary boundary)
+    if (!m->u_inc.empty()) b[row] = b[row] + hp[kn] * m->u_inc[(size_t)(m->eptr[e] + kn)] - gp[kn] * m->t_inc[(size_t)(m->eptr[e] + kn)];
   }
 }
 int orc_assemble_pot(void* hd, double omega, double rho, const double* c_ri, const double* cvalue_ri, double* A_ri, double* b_ri, int nthreads,

@@ -39,6 +39,15 @@ def _ri(z):
     return np.array([z.real, z.imag], dtype=np.float64)
 
 
+def _set_incident(o, u_inc, t_inc, nd):
+    if u_inc is None:
+        lib().orc_set_incident(o.h, None, None)
+        return
+    u = np.ascontiguousarray(u_inc, dtype=np.complex128).reshape(-1, nd); t = np.ascontiguousarray(t_inc, dtype=np.complex128).reshape(-1, nd)
+    assert len(u) == len(t) == int(o.m.elem_ptr[-1])
+    lib().orc_set_incident(o.h, _p(u), _p(t))
+
+
 def _apply_symmetry(L, h, m):
     """[symmetry planes] of the model: image elements and multipliers inside the oracle (orc_set_symmetry_s)."""
     eid = np.ascontiguousarray(getattr(m, "symplane_eid", np.zeros(0)), dtype=np.int32)
@@ -78,12 +87,7 @@ class Oracle:
 
     def set_incident(self, u_inc=None, t_inc=None):
         """Incident field at the nodes of every element, (sum nn, 3) complex each in element order (element()%incident_c); None clears."""
-        if u_inc is None:
-            lib().orc_set_incident(self.h, None, None)
-            return
-        u = np.ascontiguousarray(u_inc, dtype=np.complex128).reshape(-1, 3); t = np.ascontiguousarray(t_inc, dtype=np.complex128).reshape(-1, 3)
-        assert len(u) == len(t) == int(self.m.elem_ptr[-1])
-        lib().orc_set_incident(self.h, _p(u), _p(t))
+        _set_incident(self, u_inc, t_inc, 3)
 
     def assemble(self, omega, mat, nthreads=0):
         """-> A (n_dof x n_dof, Fortran order), b (n_dof), stats dict.  One frequency, A and b start at zero."""
@@ -312,6 +316,10 @@ class PotOracle:
             lib().orc_free(self.h)
         except Exception:
             pass
+
+    def set_incident(self, p_inc=None, un_inc=None):
+        """Incident field of a fluid region at the nodes of every element: pressure and normal displacement, (sum nn,) complex each; None clears."""
+        _set_incident(self, p_inc, un_inc, 1)
 
     def assemble(self, omega, fluid, nthreads=0):
         """-> A (n_dof x n_dof, Fortran order), b (n_dof), stats dict; one frequency, A and b start at zero."""

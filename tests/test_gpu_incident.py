@@ -96,3 +96,38 @@ def test_incident_field_misuse(gpu_ctx):
     pr.set_incident(None)
     pr.build_lse_mechanics_bem_staela(Material(rho=1.0, mu=1.0, nu=0.25, xi=0.0))
     pr.close()
+
+
+def test_fluid_region_incident_field(gpu_ctx, oracle_lib):
+    """mfb_harpot3d_set_incident: hp p_inc - gp Un_inc on b (assemble_bem_harpot_equation.f90:471-481), regular / adaptive / singular pairs and free terms,
+    mixed conditions with nonzero prescribed values, a symmetry plane; and the no-scattering identity p = p_inc when Un = Un_inc is prescribed on a cavity."""
+    from multifebe_b200 import capi
+    from multifebe_b200.host import Fluid, FluidModel, plane_wave_fluid, element_incident_fluid, room_bcs
+    fl = Fluid(rho=1.2, c=1.0, xi=0.01)
+    omega = 2.5
+    field = plane_wave_fluid([0.3, 1.0, -0.2], fl, omega, amplitude=0.8 + 0.1j)
+    cases = [FluidModel(cube_mesh(3, shape.TRI3), room_bcs(0.7), reversed_parts=(1, 2, 3, 4, 5, 6)),
+             FluidModel(cube_mesh(2, shape.QUAD9), {1: (0, 0.2), 2: (1, 0.1j), 3: (1, 0.0), 4: (0, 0.0), 5: (1, 0.3), 6: (1, 0.0)}),
+             FluidModel(without_parts(cube_mesh(2, shape.QUAD8), {3}), {1: (0, 0.0), 2: (0, 1.0), 4: (1, 0.0), 5: (1, 0.0), 6: (1, 0.0)}, symmetry=[("y", "antisymmetry")])]
+    for md in cases:
+        p_inc, un_inc = element_incident_fluid(md, field)
+        pr = capi.Problem(gpu_ctx, md); o = oracle_lib.PotOracle(md)
+        pr.set_incident(p_inc, un_inc); o.set_incident(p_inc, un_inc)
+        A, b = pr.build_lse_mechanics_bem_harpot(omega, fl)
+        Ao, bo, _ = o.assemble(omega, fl)
+        assert relerr(A, Ao) < TOL_A and relerr(b, bo) < TOL_A, (relerr(A, Ao), relerr(b, bo))
+        assert relerr(pr.solve_frequency_fluid(omega, fl), np.linalg.solve(Ao, bo)) < TOL_X
+        pr.set_incident(None); o.set_incident(None)
+        _, b0 = pr.build_lse_mechanics_bem_harpot(omega, fl)
+        assert relerr(b0, o.assemble(omega, fl)[1]) < TOL_A
+        pr.close()
+    md = FluidModel(cube_mesh(3, shape.QUAD9), {q: (1, 0.0) for q in range(1, 7)}, reversed_parts=(1, 2, 3, 4, 5, 6))
+    p_inc, un_inc = element_incident_fluid(md, field)
+    for e in range(md.n_elem):
+        for kn, v in enumerate(md.mesh.conn[e]):
+            md.cvalue[v] = un_inc[md.elem_ptr[e] + kn]
+    pr = capi.Problem(gpu_ctx, md)
+    pr.set_incident(p_inc, un_inc)
+    p, _ = md.nodal_solution(pr.solve_frequency_fluid(omega, fl))
+    assert relerr(p, np.array([field(x, [1.0, 0, 0])[0] for x in md.node_x])) < 1e-9
+    pr.close()

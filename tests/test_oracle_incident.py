@@ -72,3 +72,27 @@ def test_total_field_equal_to_the_incident_field_is_reproduced_exactly():
     un, _ = md.nodal_solution(x)
     want = np.array([field(xv, [1.0, 0, 0])[0] for xv in md.node_x])
     assert np.abs(un - want).max() < 1e-10 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("etype,m", [(shape.TRI3, 4), (shape.QUAD9, 2)], ids=["tri3", "quad9"])
+def test_fluid_plane_wave_identities_interior_and_exterior(etype, m):
+    """The same identities for a fluid region (assemble_bem_harpot_equation.f90:471-481): H p_inc - G Un_inc = 0 seen from inside, = p_inc seen from outside."""
+    from multifebe_b200.host import Fluid, FluidModel, plane_wave_fluid, element_incident_fluid
+    fl = Fluid(rho=1.2, c=1.0, xi=0.01)
+    omega = 2.0
+    field = plane_wave_fluid([1.0, 0.5, 0.2], fl, omega, amplitude=0.8 + 0.1j)
+    mesh = closed_cube(m, etype); mesh.part[:] = 1
+    tol = 4e-2 if etype == shape.TRI3 else 1e-2
+    for rev, expect_p in (((), False), ((1,), True)):
+        md = FluidModel(mesh, {1: (1, 0.0)}, reversed_parts=rev)
+        o = orc.PotOracle(md)
+        p_inc, un_inc = element_incident_fluid(md, field)
+        o.set_incident(p_inc, un_inc)
+        A, b, _ = o.assemble(omega, fl)
+        want = np.zeros(md.n_dof, dtype=np.complex128)
+        pn = np.array([field(x, [1.0, 0, 0])[0] for x in md.node_x])
+        if expect_p:
+            want[md.row[:, 0]] = pn
+        assert np.abs(b - want).max() < tol * np.abs(pn).max(), (rev, np.abs(b - want).max())
+        o.set_incident(None)
+        assert not o.assemble(omega, fl)[1].any()
