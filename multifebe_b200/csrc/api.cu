@@ -89,6 +89,7 @@ struct mfb_problem {
   std::vector<unsigned char> node_rev;   // node belongs to a reversed boundary (from the root elements around it)
   // rows written by the host after every assembly (local-axes conditions of ctype 2 / 3 nodes): internal row / column (-1: rhs) and value
   int n_cond = 0; int *d_cond_row = nullptr, *d_cond_col = nullptr; double* d_cond_val = nullptr;
+  bool skip_cond = false;   // multi-GPU row-block assembly: only the rank that owns the last rows (where the condition rows live) adds them
   double* d_nfn = nullptr; bool need_normals = false, have_normals = false;   // ctype 10: nodal normals n_fn (mfb_set_node_normals)
   double* d_einc = nullptr; bool have_inc = false; std::vector<int> slot_off_h, root_elem_ptr; std::vector<unsigned char> elem_symbits; int n_elem_root = 0;
   bool hbie;                                               // hypersingular equation at points off the boundary (interior-point stresses)
@@ -936,7 +937,7 @@ static int assemble_device_k(mfb_problem* p, const KParams& K, const KParams& Q,
   const double c_pi = 3.14159265358979323846264338328;
   cd F = -1.0 / (8.0 * c_pi * (1.0 - nu));
   launch_freeterm(p->colloc, p->sys, p->ft, mk(F.real(), F.imag()), st);
-  if (p->n_cond > 0) launch_add_entries(p->sys, p->n_cond, p->d_cond_row, p->d_cond_col, p->d_cond_val, st);   // the host's condition rows (mfb_set_condition_rows)
+  if (p->n_cond > 0 && !p->skip_cond) launch_add_entries(p->sys, p->n_cond, p->d_cond_row, p->d_cond_col, p->d_cond_val, st);   // the host's condition rows (mfb_set_condition_rows)
   CK(cudaEventRecord(p->ev[5], st));
   CK(cudaGetLastError());
   p->factored = false; p->assembled = true; p->rows_permuted = true; p->real_resident = statics;
@@ -1921,9 +1922,9 @@ extern "C" int mfb_dist_solve_frequency(mfb_problem* p, double omega, const mfb_
   CK(cudaEventRecord(d.ev[0], st));
   if (!d.loopback) {
     DistRank& R = d.lu.r[0];
-    p->colloc.tile_active = d.d_mask;
+    p->colloc.tile_active = d.d_mask; p->skip_cond = d.rank != P - 1;   // rows that no collocation point feeds belong to the last rank's row range
     int r = assemble_device(p, omega, la, m_, rho, nu_, cvalue);
-    p->colloc.tile_active = nullptr;
+    p->colloc.tile_active = nullptr; p->skip_cond = false;
     if (r) return r;
     CK(cudaEventRecord(d.ev[1], st));
     // the right-hand side: every rank holds the rows it assembled; sum -> replicated
@@ -1948,9 +1949,9 @@ extern "C" int mfb_dist_solve_frequency(mfb_problem* p, double omega, const mfb_
     for (int r = 0; r < P; r++) {
       for (int t = 0; t < p->colloc.n_tiles; t++) mask[t] = d.tile_rank[t] == r;
       CK(cudaMemcpyAsync(d.d_mask, mask.data(), mask.size(), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st));
-      p->colloc.tile_active = d.d_mask;
+      p->colloc.tile_active = d.d_mask; p->skip_cond = r != P - 1;
       int rr = assemble_device(p, omega, la, m_, rho, nu_, r == 0 ? cvalue : nullptr);
-      p->colloc.tile_active = nullptr;
+      p->colloc.tile_active = nullptr; p->skip_cond = false;
       if (rr) return rr;
       for (int q = 0; q < P; q++) launch_copy_own(p->sys.Are, p->sys.Aim, lda, n, nb, P, q, d.rb[r], d.rb[r + 1], d.lu.r[q].Lre, d.lu.r[q].Lim, st);
       launch_add_into(d.bsum, p->sys.bre, (size_t)2 * lda, st);

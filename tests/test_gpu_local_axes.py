@@ -93,3 +93,24 @@ def test_local_axes_static_symmetry_and_the_two_seam_path(gpu_ctx, oracle_lib):
     A2, _ = pr.build_lse_mechanics_bem_harela(2.0, MAT)
     assert relerr(A2, Abem) < 1e-11
     pr.close()
+
+
+def test_single_frequency_multi_gpu_mode_with_the_round_2_features(gpu_ctx):
+    """One frequency over several (virtual) ranks -- row-block assembly, block-cyclic distributed LU -- on a model that uses what round 2 added: a symmetry
+    plane, local-axes walls with nonzero prescribed values (their condition rows live in the last rank's row range and must be added once, not once per
+    rank), an incident field.  Same solution as the single-GPU path."""
+    from multifebe_b200 import capi
+    from multifebe_b200.host import plane_wave, element_incident
+    mesh = without_parts(cube_mesh(3, shape.QUAD4), {3})
+    bcs = {1: ([0, 0, 0], [0, 0, 0]), 2: ([1, 1, 1], [1.0, 0, 0]), 4: ([2, 3, 3], [0.003, 0.0, 0.02j]), 5: ([2, 3, 3], [0, 0.01, 0]), 6: ([10, 10, 10], [0.2, 0.2, 0.2])}
+    md = Model(mesh, bcs, symmetry=[("y", "symmetry")])
+    u_inc, t_inc = element_incident(md, plane_wave("P", [0.2, 0.0, 1.0], MAT, 2.0, amplitude=0.1))
+    pr = capi.Problem(gpu_ctx, md)
+    pr.set_incident(u_inc, t_inc)
+    x1 = pr.solve_frequency(2.0, MAT)
+    for nranks, nb in ((2, 64), (3, 32)):
+        pr.dist_init_loopback(nranks, nb)
+        x2 = pr.dist_solve_frequency(2.0, MAT)
+        sc = np.abs(x1).max()
+        assert np.abs(x2 - x1).max() < 1e-9 * sc, (nranks, np.abs(x2 - x1).max() / sc)
+    pr.close()
