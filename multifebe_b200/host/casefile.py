@@ -179,6 +179,7 @@ class CaseFile:
         pc = _keyword(st, "precalsets")
         self.precalset_gln = tuple(int(t) for t in pc.split()[1:1 + int(pc.split()[0])]) if pc else (2, 3, 4, 5, 6, 7, 8, 9)
         self.geometric_tolerance = _fortran_float(_keyword(st, "geometric_tolerance") or "1e-6")
+        self.collapse_nodal_pos = _logical(_keyword(st, "collapse_nodal_pos") or "T")      # default T (src/read_settings.f90:168-177)
         for k in ("lse_scaling", "lse_condition", "lse_refine"):
             if _keyword(st, k) and _logical(_keyword(st, k)):
                 raise CaseFileError("[settings] %s = T is not covered (plain zgesv / dgesv)" % k)
@@ -413,6 +414,7 @@ class CaseFile:
             return MultiRegionModel(self.mesh, regs, part_of_boundary, bcs, symmetry=self.symmetry, **kw)
         kw["part_order"] = [part_of_boundary[b] for b in self.region_boundaries]
         kw["symmetry"] = self.symmetry
+        kw["collapse_nodal_pos"] = self.collapse_nodal_pos
         if self.region_type == 1:
             bcs = {part_of_boundary[b]: (ct[0], cv[0]) for b, (ct, cv) in self.bcs.items()}
             return FluidModel(self.mesh, bcs, **kw)

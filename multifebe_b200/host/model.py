@@ -63,7 +63,7 @@ class Model:
 
     def __init__(self, mesh, bcs, reversed_parts=(), qsi_relative_error=1e-6, qsi_ns_max=16,
                  precalset_gln=(2, 3, 4, 5, 6, 7, 8, 9), geometric_tolerance=1e-6, ndof=3, part_order=None,
-                 symmetry=None, nodal_on_symplanes=False, local_axes_reference=None):
+                 symmetry=None, nodal_on_symplanes=False, local_axes_reference=None, collapse_nodal_pos=True):
         """symmetry: the [symmetry planes] section (src/read_symmetry_planes.f90:76-283) as a list of (axis, kind), axis 'x' | 'y' | 'z'
         (plane_n1 / plane_n2 / plane_n3: the plane through the origin normal to that axis), kind 'symmetry' | 'antisymmetry'.
         nodal_on_symplanes: open edges that lie in a symmetry plane do not make their nodes boundary-of-the-boundary nodes, so those nodes
@@ -72,6 +72,10 @@ class Model:
         self.mesh = mesh
         self.symplane_eid, self.symplane_t = symmetry_planes(symmetry)
         self.symplane_s = symmetry_scalars(symmetry, self.symplane_eid, self.symplane_t)
+        if collapse_nodal_pos:   # the nodes of a symmetry plane are put exactly in it (fbem_transformation_collapse_nodal_positions, lib/fbem/src/geometry.f90:5602-5610;
+            for ax in self.symplane_eid:   # the setting's default is T): an image then touches its root element in the SAME point, which the singular test needs
+                on = np.abs(mesh.nodes[:, ax - 1]) <= float(geometric_tolerance)
+                mesh.nodes[on, ax - 1] = 0.0
         for ax in self.symplane_eid:   # fbem_check_nodes_symplanes_configuration (lib/fbem/src/data_structures.f90:1197-1230): the mesh stays on one side
             xa = mesh.nodes[:, ax - 1]
             off = xa[np.abs(xa) > float(geometric_tolerance)]

@@ -250,3 +250,16 @@ def test_poroelastic_region_reduced_model_reproduces_the_full_model():
         for k in range(4):
             sc = np.abs(pf[:, k]).max()
             assert sc > 1e-4 and np.abs(pr[:, k] - pf[:red.n_node, k]).max() / sc < 5e-5, (planes, k)
+
+
+def test_plane_nodes_are_collapsed_into_the_plane():
+    """collapse_nodal_pos (default T, src/read_settings.f90:168-177; fbem_transformation_collapse_nodal_positions): a mesh whose plane nodes sit 3e-8 off the
+    plane (inside geometric_tolerance) is snapped, so that the images touch their root elements in the same points."""
+    mesh = without_parts(cube_mesh(2, QUAD4), {1})
+    on = np.abs(mesh.nodes[:, 0]) < 1e-9
+    mesh.nodes[on, 0] = 3e-8
+    bcs = {p: ([1, 1, 1], [0, 0, 0]) for p in set(int(q) for q in mesh.part)}
+    md = Model(mesh, bcs, symmetry=[("x", "symmetry")])
+    assert np.abs(md.node_x[on, 0]).max() == 0.0
+    mesh2 = without_parts(cube_mesh(2, QUAD4), {1}); mesh2.nodes[on, 0] = 3e-8
+    assert np.abs(Model(mesh2, bcs, symmetry=[("x", "symmetry")], collapse_nodal_pos=False).node_x[on, 0]).max() == 3e-8
