@@ -944,7 +944,7 @@ static int assemble_device_k(mfb_problem* p, const KParams& K, const KParams& Q,
   // our kernels only (memsets/copies are not counted): free term + per group regular, adaptive, singular (+ gather_cv)
   p->asm_launches = 1;
   for (auto& g : p->groups)   // K1: one kernel per element class on 3/4-node elements (classes 0, 1 and, if present, 2)
-    p->asm_launches += (((g.et == 5 || g.et == 7) && g.dev.cols3) ? 2 + ((g.dev.has_mixed || g.dev.einc) ? 1 : 0) : 1) + (cvalue ? 1 : 0) + (g.adp.n_pairs > 0) + (g.sing.n_pairs > 0);
+    p->asm_launches += (((g.et == 5 || g.et == 7) && g.dev.cols3) ? 2 + g.dev.has_mixed : 1) + (cvalue ? 1 : 0) + (g.adp.n_pairs > 0) + (g.sing.n_pairs > 0);
   return MFB_OK;
 }
 // Rows that the HOST writes into the system after the BEM assembly: the local-axes conditions of ctype 2 / 3 nodes (src/build_lse_mechanics_harmonic.f90:204-258:

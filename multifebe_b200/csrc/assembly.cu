@@ -106,7 +106,7 @@ __global__ void k_gather_cv(DevGroup g, const double* __restrict__ cvalue) {
     }
   }
   g.ecvnz[e] = nz ? 1 : 0;
-  const int mode = (g.einc || !(g.einfo[e] & 8u)) ? 2 : (nz ? 1 : 0);   // an incident field needs both kernel combinations of every (node, dof): the general class
+  const int mode = !(g.einfo[e] & 8u) ? 2 : (g.einc ? 3 : (nz ? 1 : 0));   // an incident field needs both kernel combinations: class 3 (uniform kinds) or 2
   atomicOr(g.range_modes + g.range_of[e], 1 << mode);
 }
 void launch_gather_cv(const DevGroup& g, const double* cvalue, cudaStream_t st) {
@@ -272,6 +272,7 @@ struct AccA { double re[9 * NN], im[9 * NN]; };   // [(l*3+k)*NN + j]: entry of 
 //         (the common case): only the combination that goes to the matrix is formed.
 // MODE 1: uniform kinds, some prescribed value nonzero: the other combination times S_k = sum_j w_j cv_jk (sk, over ALL nodes
 //         of the element, formed by the caller) goes to b when do_b.
+// MODE 3: MODE 1 with an incident field: besides S_k the sums of the incident values over the nodes (see the caller) multiply both combinations.
 // MODE 2: any element: both combinations, per (node, dof) one goes to A and the other, times the prescribed value, to b;
 //         ekind / ecv point at the chunk's first node.
 // have_ks: the kernel scalars of this point are already in ks (cached by the pass over the first chunk of nodes).
@@ -293,11 +294,11 @@ __device__ __forceinline__ void k1_point(AccA<NW>& a, double* bacc, const double
   const double dx[3] = {rv0 * d1r1, rv1 * d1r1, rv2 * d1r1};
   const double drdn = fma(dx[0], n[0], fma(dx[1], n[1], dx[2] * n[2]));
   const cplx t1d = k.T1 * drdn;
-  if (MODE < 2) {
+  if (MODE != 2) {
 #pragma unroll
     for (int kk = 0; kk < 3; kk++) {
       const bool tk = (info >> kk) & 1u;
-      const double skr = (MODE == 1) ? sk[kk] : 0.0, ski = (MODE == 1) ? sk[3 + kk] : 0.0;
+      const double skr = (MODE == 1 || MODE == 3) ? sk[kk] : 0.0, ski = (MODE == 1 || MODE == 3) ? sk[3 + kk] : 0.0;
       if (tk) {
 #pragma unroll
         for (int l = 0; l < 3; l++) {
@@ -305,12 +306,13 @@ __device__ __forceinline__ void k1_point(AccA<NW>& a, double* bacc, const double
           const double fr = fma(t1d.re, dd, fma(k.T2.re, c2, k.T3.re * c3)), fi = ST ? 0.0 : fma(t1d.im, dd, fma(k.T2.im, c2, k.T3.im * c3));
 #pragma unroll
           for (int j = 0; j < NW; j++) { a.re[(l * 3 + kk) * NW + j] = fma(fr, w[j], a.re[(l * 3 + kk) * NW + j]); if (!ST) a.im[(l * 3 + kk) * NW + j] = fma(fi, w[j], a.im[(l * 3 + kk) * NW + j]); }
-          if (MODE == 1 && do_b) {
+          if ((MODE == 1 || MODE == 3) && do_b) {
             const double orr = (l == kk) ? fma(-k.chi.re, dd, k.psi.re) : -k.chi.re * dd;
             if (ST) bacc[l] -= orr * skr;
             else {
               const double oi = (l == kk) ? fma(-k.chi.im, dd, k.psi.im) : -k.chi.im * dd;
               bacc[l] -= orr * skr - oi * ski; bacc[3 + l] -= orr * ski + oi * skr;
+              if (MODE == 3) { bacc[l] += fr * sk[6 + kk] - fi * sk[9 + kk]; bacc[3 + l] += fr * sk[9 + kk] + fi * sk[6 + kk]; }   // incident field: the matrix combination times M_k
             }
           }
         }
@@ -321,13 +323,14 @@ __device__ __forceinline__ void k1_point(AccA<NW>& a, double* bacc, const double
           const double fr = (l == kk) ? fma(-k.chi.re, dd, k.psi.re) : -k.chi.re * dd, fi = ST ? 0.0 : ((l == kk) ? fma(-k.chi.im, dd, k.psi.im) : -k.chi.im * dd);
 #pragma unroll
           for (int j = 0; j < NW; j++) { a.re[(l * 3 + kk) * NW + j] = fma(fr, w[j], a.re[(l * 3 + kk) * NW + j]); if (!ST) a.im[(l * 3 + kk) * NW + j] = fma(fi, w[j], a.im[(l * 3 + kk) * NW + j]); }
-          if (MODE == 1 && do_b) {
+          if ((MODE == 1 || MODE == 3) && do_b) {
             const double c2 = (l == kk) ? fma(dx[kk], n[l], drdn) : dx[kk] * n[l], c3 = dx[l] * n[kk];
             const double orr = fma(t1d.re, dd, fma(k.T2.re, c2, k.T3.re * c3));
             if (ST) bacc[l] -= orr * skr;
             else {
               const double oi = fma(t1d.im, dd, fma(k.T2.im, c2, k.T3.im * c3));
               bacc[l] -= orr * skr - oi * ski; bacc[3 + l] -= orr * ski + oi * skr;
+              if (MODE == 3) { bacc[l] += fr * sk[6 + kk] - fi * sk[9 + kk]; bacc[3 + l] += fr * sk[9 + kk] + fi * sk[6 + kk]; }
             }
           }
         }
@@ -450,7 +453,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
         m_next = (valid && e < e1) ? pl[(size_t)e * c.ldp] : PLAN_NONE;
         const unsigned info_e = info_next, cvnz_e = cvnz_next;
         if (e < e1) { info_next = g.einfo[e]; cvnz_next = g.ecvnz[e]; }
-        const int mode_e = (g.einc || !(info_e & 8u)) ? 2 : (cvnz_e != 0 ? 1 : 0);
+        const int mode_e = !(info_e & 8u) ? 2 : (g.einc ? 3 : (cvnz_e != 0 ? 1 : 0));
         if (mode_e != MODE) continue;
         const unsigned reg = __ballot_sync(0xffffffffu, m < MAX_SETS);
         if (reg == 0u) continue;
@@ -530,18 +533,33 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_regular_bulk(const __grid_con
 #pragma unroll
               for (int i = 0; i < NW; i++) rec[6 + i] = (j0 + i < NN) ? ldg_ahead(Pn + 6 + j0 + i) : 0.0;
             }
-            double sk[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            if (MODE == 1 && ch == 0) {   // S_k over all the nodes of the element
+            // sk[0..5]: O_k (re | im), the multiplier of the combination that does NOT go to the matrix (b -= other O_k); sk[6..11]: M_k, the multiplier of the
+            // one that does (b += main M_k).  Without an incident field O_k = S_k = sum_j w_j cv_jk, M_k = 0.  With one (assemble_bem_harela_equation.f90:651-666:
+            // b += h u_inc - g t_inc; in this kernel's scaling ft = h, fu = -g): a t-known dof has main = ft, other = fu: O_k = S_k - ST_k, M_k = SU_k; a u-known dof
+            // has main = fu, other = ft: O_k = S_k - SU_k, M_k = ST_k, with SU_k = sum_j w_j u_inc_jk, ST_k = sum_j w_j t_inc_jk.
+            double sk[12] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            if ((MODE == 1 || MODE == 3) && ch == 0) {   // sums over all the nodes of the element
               const double* wall = P + (size_t)kp * RECN + 6;
               const double* ecv0 = g.ecv + (size_t)el * 2 * NC;
+              const double* inc0 = (MODE == 3 && !ST && g.einc) ? g.einc + (size_t)el * 4 * NC : nullptr;   // class 3 = class 1 + incident field (its own instantiation: class 1 keeps its registers)
 #pragma unroll
-              for (int kk = 0; kk < 3; kk++)
+              for (int kk = 0; kk < 3; kk++) {
+                double sur = 0.0, sui = 0.0, str_ = 0.0, sti = 0.0;
 #pragma unroll
                 for (int j = 0; j < NN; j++) {
                   const double wj = (NCH == 1) ? cur[6 + j < 6 + NW ? 6 + j : 6] : __ldg(wall + j);
                   sk[kk] = fma(wj, __ldg(ecv0 + 2 * (j * 3 + kk)), sk[kk]);
                   if (!ST) sk[3 + kk] = fma(wj, __ldg(ecv0 + 2 * (j * 3 + kk) + 1), sk[3 + kk]);
+                  if (inc0) {
+                    const double* q4 = inc0 + 4 * (j * 3 + kk);
+                    sur = fma(wj, __ldg(q4), sur); sui = fma(wj, __ldg(q4 + 1), sui); str_ = fma(wj, __ldg(q4 + 2), str_); sti = fma(wj, __ldg(q4 + 3), sti);
+                  }
                 }
+                if (inc0) {
+                  if ((info >> kk) & 1u) { sk[kk] -= str_; sk[3 + kk] -= sti; sk[6 + kk] = sur; sk[9 + kk] = sui; }
+                  else { sk[kk] -= sur; sk[3 + kk] -= sui; sk[6 + kk] = str_; sk[9 + kk] = sti; }
+                }
+              }
             }
             KScal ks;
             const bool have_ks = use_cache && ch > 0;
@@ -660,9 +678,16 @@ template <int ET, bool ST>
 static void launch_regular_bulk(const CUtensorMap& tmap, const DevGroup& g, const DevColloc& c, const DevSystem& s, const unsigned char* plan, const KParams& kq, K1Launch& k1,
                                 cudaStream_t st) {
   cudaMemsetAsync(k1.counters, 0, 4 * sizeof(int), st);
+  if constexpr (!ST) {
+    if (g.einc) {   // incident field set: elements with uniform kinds are class 3, the others class 2
+      launch_bulk_mode<ET, 3, KB_WARPS, ST>(tmap, g, c, s, plan, kq, k1, st);
+      if (g.has_mixed) launch_bulk_mode<ET, 2, KB_WARPS, ST>(tmap, g, c, s, plan, kq, k1, st);
+      return;
+    }
+  }
   if (c.n_tiles * g.n_ranges < 2048) {   // a small mesh: the classes one after the other on the caller's stream (no side streams: they only pay on long kernels,
     launch_bulk_mode<ET, 1, KB_WARPS, ST>(tmap, g, c, s, plan, kq, k1, st);        // and a process that keeps many small problems in flight runs out of hardware queues)
-    if (g.has_mixed || g.einc) launch_bulk_mode<ET, 2, KB_WARPS, ST>(tmap, g, c, s, plan, kq, k1, st);
+    if (g.has_mixed) launch_bulk_mode<ET, 2, KB_WARPS, ST>(tmap, g, c, s, plan, kq, k1, st);
     launch_bulk_mode<ET, 0, KB_WARPS_FAST, ST>(tmap, g, c, s, plan, kq, k1, st);
     return;
   }
@@ -671,14 +696,14 @@ static void launch_regular_bulk(const CUtensorMap& tmap, const DevGroup& g, cons
   cudaStreamWaitEvent(k1.aux[0], k1.ev_fork, 0);
   launch_bulk_mode<ET, 1, KB_WARPS, ST>(tmap, g, c, s, plan, kq, k1, k1.aux[0]);
   cudaEventRecord(k1.ev_join[0], k1.aux[0]);
-  if (g.has_mixed || g.einc) {
+  if (g.has_mixed) {
     cudaStreamWaitEvent(k1.aux[1], k1.ev_fork, 0);
     launch_bulk_mode<ET, 2, KB_WARPS, ST>(tmap, g, c, s, plan, kq, k1, k1.aux[1]);
     cudaEventRecord(k1.ev_join[1], k1.aux[1]);
   }
   launch_bulk_mode<ET, 0, KB_WARPS_FAST, ST>(tmap, g, c, s, plan, kq, k1, st);
   cudaStreamWaitEvent(st, k1.ev_join[0], 0);
-  if (g.has_mixed || g.einc) cudaStreamWaitEvent(st, k1.ev_join[1], 0);
+  if (g.has_mixed) cudaStreamWaitEvent(st, k1.ev_join[1], 0);
 }
 
 // 3-D tensor map of the planar system matrix for the K1 flush: (row, column, plane), box = 96 rows x 3 columns x 2 planes

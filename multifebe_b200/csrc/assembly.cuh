@@ -29,7 +29,7 @@ struct DevGroup {
   const unsigned char* c10;      // NULL, or [3*n_node]: 1 where ctype = 10 (normal pressure known): the prescribed value is cvalue * nfn
   const double* nfn;             // [3*n_node] nodal unit normals, negated for the nodes of a reversed boundary (with c10)
   const double* einc;            // NULL, or [n_elem][3*nn][4]: incident field (u_k re, im, t_k re, im) at node j of the element (element()%incident_c): every
-                                 // pair then adds h u_inc - g t_inc to b (assemble_bem_harela_equation.f90:651-666); all elements run as K1 mode 2
+                                 // pair then adds h u_inc - g t_inc to b (assemble_bem_harela_equation.f90:651-666); elements with uniform kinds run as K1 mode 1, the others as mode 2
   const double* ball;            // [n_elem][5]: centre(3), radius, characteristic length
   const int* gln_far;            // [n_elem]
   int n_ranges;                  // K1 tasks = (collocation tile) x (element range); long ranges first, short ones last (load balance)
