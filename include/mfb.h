@@ -319,7 +319,7 @@ int mfb_dist_layout(int n, int nb, int nranks, int rank, int* n_local_cols, int*
 int mfb_dist_partition_tiles(int n_tiles, const int* tile_row0, const int* tile_nbytes, int n_dof, int nranks, int* tile_rank,
                              int* row_bounds);
 
-/* ---- Resident combination of assembled systems (coupled regions from single-region assemblies; see api.cu) -- not yet run on hardware ----
+/* ---- Resident combination of assembled systems (coupled regions from single-region assemblies; see api.cu; tests/test_gpu_coupled.py) ----
  * mfb_system_zero(dst) zeroes the resident system of dst and marks it assembled in host order; mfb_combine_columns adds
  * coef[i] * src(r, src_col[i]) to dst(row_map[r], dst_col[i]) for the first n_rows host rows of the assembled system of src (dst_col = -1: the
  * right-hand side); mfb_add_entries adds single entries (the free terms).  mfb_zsolve(dst, n, NULL, n, ipiv, NULL, 1, 1) then factorises and

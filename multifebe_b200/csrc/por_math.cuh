@@ -1,6 +1,6 @@
 // por_math.cuh -- per-Gauss-point arithmetic of the Biot poroelastic SBIE kernels (host+device inline, like bem_math.cuh / pot_math.cuh).
 //
-// Used by the kernels of poro.cu (compiled, not yet run on hardware).  The header is also compiled for the HOST by
+// Used by the kernels of poro.cu (validated on hardware in round 2: tests/test_gpu_poroelastic.py).  The header is also compiled for the HOST by
 // tests/test_por_math_host.py and held to the oracle there, so the point formulas and parameter tables are checked without a GPU.
 //
 // Node variables: 0 = fluid phase (tau | Un), 1..3 = skeleton (u_k | t_k).  The fundamental solution is evaluated in the reference's

@@ -293,7 +293,7 @@ class PoroModel(Model):
     """One Biot poroelastic BE region: four equations and four unknowns per node, component 0 = fluid phase (tau known: ctype 0, Un known:
     ctype 1), components 1..3 = solid skeleton (u_k known: 0, t_k known: 1) -- the open-pore conditions of an ordinary boundary
     (assemble_bem_harpor_equation.f90:78-110, :140-170).  bcs: {part_id: ([ct_tau, ct_1, ct_2, ct_3], [values])}.  col_u holds the columns
-    of (tau, u_k), col_t those of (Un, t_k).  CPU side only so far (oracle); the device path is not built."""
+    of (tau, u_k), col_t those of (Un, t_k).  Device path: mfb_harpor3d_* (csrc/poro.cu, tests/test_gpu_poroelastic.py)."""
 
     def __init__(self, mesh, bcs, **kw):
         Model.__init__(self, mesh, bcs, ndof=4, **kw)

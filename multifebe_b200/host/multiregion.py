@@ -14,7 +14,7 @@ per-region views, built the way the reference's host does.
                       writes the equation into rows (., eq) with eq = 1 when the region is region 1 of the collocation boundary, else 2
                       (src/build_lse_mechanics_bem_harela.f90:1118-1136, src/build_lse_mechanics_bem_harpot.f90).
 Only the numbering, the views and the nodal-solution map live here; the integrals are the single-region ones.  The device path for
-coupled regions is not built yet: this model feeds the multi-region oracle and the C ABI planned there.
+coupled regions is capi.CoupledProblem over host/coupled.py: this model feeds it and the multi-region oracle.
 Poroelastic regions (four components per node) couple to fluids (perfectly permeable or impermeable, `interface_ctype`), to solids (bonded,
 impervious) and to each other (perfectly permeable): numbering build_auxiliary_variables_mechanics_harmonic.f90:626-700, :895-1230.
 """
