@@ -105,34 +105,47 @@ __global__ void __launch_bounds__(P1_WARPS * 32) k_pot_regular(DevGroup g, DevCo
     }
     __syncwarp();
   };
-  for (int e = e0; e < e1; e++) {
-    const unsigned char m = m_next;
-    m_next = (valid && e + 1 < e1) ? pl[(size_t)(e + 1) * c.ldp] : PLAN_NONE;   // requested one element ahead
-    unsigned todo = __ballot_sync(0xffffffffu, m < MAX_SETS);
-    while (todo) {
-      const int leader = __ffs(todo) - 1;
-      const int sset = __shfl_sync(0xffffffffu, (int)m, leader);
-      const unsigned grp = __ballot_sync(0xffffffffu, (int)m == sset) & todo;
-      todo &= ~grp;
-      const int base = qcnt[sset];
-      if ((grp >> lane) & 1u) queue[sset * P1_QCAP + base + __popc(grp & lt_mask)] = (unsigned short)(((e - e0) << 5) | lane);
+  int e = e0, drain = 0;
+  unsigned fullsets = 0u;      // rules whose queue holds >= 32 entries
+  for (;;) {                   // one call site of the batch body (instruction cache)
+    int sset; unsigned short ent; bool act;
+    if (fullsets) {
+      sset = __ffs(fullsets) - 1;
+      int cnt = qcnt[sset];
+      ent = queue[sset * P1_QCAP + cnt - 32 + lane];
       __syncwarp();
-      int cnt = base + __popc(grp);
-      if (cnt >= 32) {
-        const unsigned short ent = queue[sset * P1_QCAP + cnt - 32 + lane];
-        __syncwarp();
-        cnt -= 32;
-        batch(sset, ent, true);
-      }
+      cnt -= 32;
       if (lane == 0) qcnt[sset] = cnt;
       __syncwarp();
-    }
-  }
-  for (int sset = 0; sset < g.n_sets; sset++) {   // what is left in the queues
-    const int cnt = qcnt[sset];
-    if (cnt == 0) continue;
-    const unsigned short ent = (lane < cnt) ? queue[sset * P1_QCAP + lane] : (unsigned short)0;
-    batch(sset, ent, lane < cnt);
+      if (cnt < 32) fullsets &= ~(1u << sset);
+      act = true;
+    } else if (e < e1) {
+      const unsigned char m = m_next;
+      m_next = (valid && e + 1 < e1) ? pl[(size_t)(e + 1) * c.ldp] : PLAN_NONE;   // requested one element ahead
+      unsigned todo = __ballot_sync(0xffffffffu, m < MAX_SETS);
+      while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int qs = __shfl_sync(0xffffffffu, (int)m, leader);
+        const unsigned grp = __ballot_sync(0xffffffffu, (int)m == qs) & todo;
+        todo &= ~grp;
+        const int base = qcnt[qs];
+        if ((grp >> lane) & 1u) queue[qs * P1_QCAP + base + __popc(grp & lt_mask)] = (unsigned short)(((e - e0) << 5) | lane);
+        __syncwarp();
+        const int cnt = base + __popc(grp);
+        if (lane == 0) qcnt[qs] = cnt;
+        if (cnt >= 32) fullsets |= 1u << qs;
+        __syncwarp();
+      }
+      e++;
+      continue;
+    } else if (drain < g.n_sets) {   // what is left in the queues
+      sset = drain++;
+      const int cnt = qcnt[sset];
+      if (cnt == 0) continue;
+      act = lane < cnt;
+      ent = act ? queue[sset * P1_QCAP + lane] : (unsigned short)0;
+    } else break;
+    batch(sset, ent, act);
   }
 }
 
