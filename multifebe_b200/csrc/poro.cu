@@ -280,6 +280,53 @@ __device__ __forceinline__ void por_warp_reduce(RAcc<NN>& a) {
   }
 }
 
+// Row l of the two blocks at a point of the element that holds the collocation point (por_interior_blocks, one row of it): ps = por_scalars<true>, the static
+// 1/r^2 parts of W0, T1 and of the dr/dn delta term of T2 are added back here; fc[k] = T2(1)/r^2 (n_l r,k - n_k r,l) is the CPV kernel of the skeleton block.
+__device__ __forceinline__ void por_interior_row_from_scalars(const PorParams& p, const PorScal& s, const double* dx, const double* n, double drdn, double d1r2, int l,
+                                                              cplx ur[4], cplx tr[4], cplx fc[3]) {
+  if (l == 0) {
+    ur[0] = s.eta; tr[0] = cfmar(p.W0[1], d1r2, s.W0) * drdn;
+#pragma unroll
+    for (int c = 0; c < 3; c++) { ur[c + 1] = s.vartheta * dx[c]; tr[c + 1] = cfmar(s.T01, dx[c] * drdn, s.T02 * n[c]); fc[c] = mk(0.0, 0.0); }
+  } else {
+    const double dxl = (l == 1) ? dx[0] : (l == 2 ? dx[1] : dx[2]), nl = (l == 1) ? n[0] : (l == 2 ? n[1] : n[2]);
+    ur[0] = s.vartheta * dxl; tr[0] = cfmar(s.W1, dxl * drdn, s.W2 * nl);
+    const cplx T1s = cfmar(p.T1[1], d1r2, s.T1), T2s = cfmar(p.T2[1], d1r2, s.T2), T21 = p.T2[1] * d1r2;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const double dl = (l - 1 == k) ? 1.0 : 0.0, dd = dxl * dx[k];
+      ur[k + 1] = mk(s.psi.re * dl - s.chi.re * dd, s.psi.im * dl - s.chi.im * dd);
+      const double c1 = dd * drdn, c2 = drdn * dl, c3 = dx[k] * nl, c4 = dxl * n[k];
+      tr[k + 1] = mk(T1s.re * c1 + T2s.re * c2 + s.T2.re * c3 + s.T3.re * c4, T1s.im * c1 + T2s.im * c2 + s.T2.im * c3 + s.T3.im * c4);
+      fc[k] = T21 * (nl * dx[k] - n[k] * dxl);
+    }
+  }
+}
+// warp sum of the BC-aware accumulators and their lane-strided scatter: entry (j, k) of equation l goes to the matrix with cte_t (and the sign of the
+// orientation) when the secondary variable of dof k is known, with -cte_u otherwise (assemble_bem_harpor_equation.f90:78-110); info bits 4-7: symmetry image
+template <int NN>
+__device__ __forceinline__ void por_reduce_scatter_fast(double* ar, double* ai, unsigned kinds, unsigned info, bool rev, int l, const int* __restrict__ ecol,
+                                                        const DevSystem& s, int row, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4 * NN; i++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { ar[i] += __shfl_xor_sync(0xffffffffu, ar[i], o); ai[i] += __shfl_xor_sync(0xffffffffu, ai[i], o); }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const bool tk = (kinds >> k) & 1u;
+    const cplx c0 = tk ? ((l == 0) ? c_por.cte_t[0][k] : c_por.cte_t[1][k]) : ((l == 0) ? c_por.cte_u[0][k] : c_por.cte_u[1][k]);
+    const double sg = (tk ? (rev ? -1.0 : 1.0) : -1.0) * (((info >> (4 + k)) & 1u) ? -1.0 : 1.0);
+#pragma unroll
+    for (int j = 0; j < NN; j++) {
+      if (((j * 4 + k) & 31) != lane) continue;
+      const int col = ecol[j * 4 + k];
+      atomicAdd(s.Are + (size_t)col * s.lda + row, sg * (c0.re * ar[k * NN + j] - c0.im * ai[k * NN + j]));
+      atomicAdd(s.Aim + (size_t)col * s.lda + row, sg * (c0.re * ai[k * NN + j] + c0.im * ar[k * NN + j]));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // R2: adaptive pairs -- one warp per pair, lanes stride over the gln x gln points of every leaf, one equation per pass
 // ------------------------------------------------------------------------------------------------------------------
@@ -299,6 +346,50 @@ __global__ void __launch_bounds__(128) k_por_adaptive(DevGroup g, DevColloc c, D
   const double* gx = tri ? t.gl01_x : t.gl11_x;
   const double* gw = tri ? t.gl01_w : t.gl11_w;
   const bool rev = g.erev[e] != 0;
+  if ((g.einfo[e] & 8u) && !g.ecvnz[e]) {   // the common element (uniform kinds, no prescribed value): only what goes to the matrix, in registers (see k_por_regular)
+    const unsigned info = g.einfo[e];
+    const unsigned char* ekind = g.ekind + (size_t)e * 4 * NN;
+    unsigned kinds = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) kinds |= (ekind[k] != 0 ? 1u : 0u) << k;
+#pragma unroll 1
+    for (int l = 0; l < 4; l++) {
+      double ar[4 * NN], ai[4 * NN];
+#pragma unroll
+      for (int i = 0; i < 4 * NN; i++) { ar[i] = 0.0; ai[i] = 0.0; }
+#pragma unroll 1
+      for (int lf = a.pair_leaf0[p]; lf < a.pair_leaf0[p + 1]; lf++) {
+        const double* L = a.leaf_d + 16 * (size_t)lf;
+        double xi_s[8], tp1[4], tp2[4];
+#pragma unroll
+        for (int i = 0; i < 8; i++) xi_s[i] = __ldg(L + i);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { tp1[i] = __ldg(L + 8 + i); tp2[i] = __ldg(L + 12 + i); }
+        const int gln = a.leaf_gln[lf], off = gln * (gln - 1) / 2;
+#pragma unroll 1
+        for (int idx = lane; idx < gln * gln; idx += 32) {
+          const int k1 = idx / gln, k2 = idx - k1 * gln;
+          double x[3], n[3], w[NN];
+          leaf_point<ET>(xn, xi_s, tp1, tp2, __ldg(gx + off + k1), __ldg(gw + off + k1), __ldg(gx + off + k2), __ldg(gw + off + k2), x, n, w);
+          const double rv0 = x[0] - xc[0], rv1 = x[1] - xc[1], rv2 = x[2] - xc[2];
+          const double r = sqrt(rv0 * rv0 + rv1 * rv1 + rv2 * rv2), d1r1 = 1.0 / r;
+          const double dx[3] = {rv0 * d1r1, rv1 * d1r1, rv2 * d1r1};
+          const double drdn = dx[0] * n[0] + dx[1] * n[1] + dx[2] * n[2];
+          PorScal ps; por_scalars<false>(c_por, r, d1r1, ps);
+          cplx ur[4], tr[4];
+          por_row_from_scalars(ps, dx, n, drdn, l, ur, tr);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const cplx f = ((kinds >> k) & 1u) ? tr[k] : ur[k];
+#pragma unroll
+            for (int j = 0; j < NN; j++) { ar[k * NN + j] = fma(f.re, w[j], ar[k * NN + j]); ai[k * NN + j] = fma(f.im, w[j], ai[k * NN + j]); }
+          }
+        }
+      }
+      por_reduce_scatter_fast<NN>(ar, ai, kinds, info, rev, l, g.ecol + (size_t)e * 4 * NN, s, c.crow[l * c.ldp + cpos], lane);
+    }
+    return;
+  }
 #pragma unroll 1
   for (int l = 0; l < 4; l++) {
     RAcc<NN> acc; acc.zero();
@@ -362,6 +453,66 @@ __global__ void __launch_bounds__(128) k_por_singular(DevGroup g, DevColloc c, D
   const double* gx = t.gl01_x + 15 * 14 / 2;
   const double* gw = t.gl01_w + 15 * 14 / 2;
   const bool rev = g.erev[e] != 0;
+  if ((g.einfo[e] & 8u) && !g.ecvnz[e]) {   // the common element: only what goes to the matrix, in registers
+    const unsigned info = g.einfo[e];
+    const unsigned char* ekind = g.ekind + (size_t)e * 4 * NN;
+    unsigned kinds = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) kinds |= (ekind[k] != 0 ? 1u : 0u) << k;
+#pragma unroll 1
+    for (int l = 0; l < 4; l++) {
+      double ar[4 * NN], ai[4 * NN];
+#pragma unroll
+      for (int i = 0; i < 4 * NN; i++) { ar[i] = 0.0; ai[i] = 0.0; }
+#pragma unroll 1
+      for (int idx = lane; idx < nray * 15; idx += 32) {
+        const int kr_ = idx / 15, kk = idx - kr_ * 15;
+        const double* R = a.rays + 4 * (size_t)(ray0 + kr_);
+        const double ct = __ldg(R), sn = __ldg(R + 1), rhoij = __ldg(R + 2), wray = __ldg(R + 3);
+        const double rho = rhoij * __ldg(gx + kk), wrad = __ldg(gw + kk);
+        double phi[NN], x[3], n[3], jg;
+        geometry_at<ET>(xn, xi_i0 + rho * ct, xi_i1 + rho * sn, phi, x, n, jg);
+        const double jw = jg * rho * wray * wrad;
+        const double rv0 = x[0] - xc[0], rv1 = x[1] - xc[1], rv2 = x[2] - xc[2];
+        const double r = sqrt(rv0 * rv0 + rv1 * rv1 + rv2 * rv2), d1r1 = 1.0 / r;
+        const double dx[3] = {rv0 * d1r1, rv1 * d1r1, rv2 * d1r1};
+        const double drdn = dx[0] * n[0] + dx[1] * n[1] + dx[2] * n[2];
+        PorScal ps; por_scalars<true>(c_por, r, d1r1, ps);
+        cplx ur[4], tr[4], fc[3];
+        por_interior_row_from_scalars(c_por, ps, dx, n, drdn, d1r1 * d1r1, l, ur, tr, fc);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const bool tk = (kinds >> k) & 1u;
+          const cplx f = tk ? tr[k] : ur[k];
+#pragma unroll
+          for (int j = 0; j < NN; j++) {
+            const double wj = phi[j] * jw;
+            ar[k * NN + j] = fma(f.re, wj, ar[k * NN + j]); ai[k * NN + j] = fma(f.im, wj, ai[k * NN + j]);
+          }
+          if (tk && l > 0 && k > 0) {   // CPV kernel of the skeleton block against phi_j - phi_j(xi_i)
+#pragma unroll
+            for (int j = 0; j < NN; j++) {
+              const double wc = (phi[j] - phi_i[j]) * jw;
+              ar[k * NN + j] = fma(fc[k - 1].re, wc, ar[k * NN + j]); ai[k * NN + j] = fma(fc[k - 1].im, wc, ai[k * NN + j]);
+            }
+          }
+        }
+      }
+      // + phi_j(xi_i) T2(1) hli(l, k) on the skeleton block of h (bem_harpor3d.f90:1876-1880), added once per warp: lane 0 before the warp sum
+      if (l > 0 && lane == 0) {
+        const cplx t21 = c_por.T2[1];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+          if ((kinds >> (k + 1)) & 1u) {
+            const double hl = D[5 + 3 * (l - 1) + k];
+#pragma unroll
+            for (int j = 0; j < NN; j++) { ar[(k + 1) * NN + j] += phi_i[j] * t21.re * hl; ai[(k + 1) * NN + j] += phi_i[j] * t21.im * hl; }
+          }
+      }
+      por_reduce_scatter_fast<NN>(ar, ai, kinds, info, rev, l, g.ecol + (size_t)e * 4 * NN, s, c.crow[l * c.ldp + cpos], lane);
+    }
+    return;
+  }
 #pragma unroll 1
   for (int l = 0; l < 4; l++) {
     RAcc<NN> acc; acc.zero();
