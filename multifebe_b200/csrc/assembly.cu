@@ -253,7 +253,10 @@ const int KB_WARPS = 4;
 #endif
 const int KB_WARPS_FAST = MFB_KB_WARPS_FAST;   // warps per CTA of the MODE 0 kernel (2 CTAs per SM)
 
-const int KB_CACHE_GP = 4;   // in-place batches of up to this many points keep their kernel scalars in shared memory between node chunks
+#ifndef MFB_KB_CACHE_GP
+#define MFB_KB_CACHE_GP 4
+#endif
+const int KB_CACHE_GP = MFB_KB_CACHE_GP;   // in-place batches of up to this many points keep their kernel scalars in shared memory between node chunks
 // 3/4-node elements are accumulated whole; 6/8/9-node elements in NCH chunks of NW = 3 nodes (27 complex accumulators)
 template <int NN_>
 struct K1Shape {
