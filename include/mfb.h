@@ -148,6 +148,8 @@ int mfb_set_node_normals(mfb_problem* problem, const double* n_fn);
 int mfb_harela3d_set_incident(mfb_problem* problem, const mfb_z* u_inc, const mfb_z* t_inc);
 /* The same for an inviscid fluid region (src/assemble_bem_harpot_equation.f90:471-481): p_inc, Un_inc at the nodes of every element, index [elem_ptr[e] + j]. */
 int mfb_harpot3d_set_incident(mfb_problem* problem, const mfb_z* p_inc, const mfb_z* un_inc);
+/* and for a poroelastic region (src/assemble_bem_harpor_equation.f90:1277-1289): (tau, u_k)_inc and (Un, t_k)_inc, index [(elem_ptr[e] + j) * 4 + k]. */
+int mfb_harpor3d_set_incident(mfb_problem* problem, const mfb_z* u_inc, const mfb_z* t_inc);
 
 /* == solve_lse_c(n_dof,A,ipiv,..,n_rhs,b,factorize,scaling=F,condition=F,refine=F): in-place LU with partial pivoting
  * (zgetrf) + triangular solves (zgetrs).  A == NULL: use the device-resident system of the last mfb_harela3d_assemble (and

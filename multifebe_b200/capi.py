@@ -297,11 +297,12 @@ class Problem:
     def set_incident(self, u_inc=None, t_inc=None):
         """Incident wave field at the nodes of every element ((sum nn, 3) complex each, element order; element()%incident_c of the reference);
         None clears.  Every later assembly adds hp u_inc - gp t_inc to b (assemble_bem_harela_equation.f90:651-666)."""
-        fn = lib().mfb_harpot3d_set_incident if self.ndof == 1 else lib().mfb_harela3d_set_incident     # fluid region: p_inc, Un_inc, one value per element node
+        # fluid region: p_inc, Un_inc, one value per element node; poroelastic region: (tau, u_k), (Un, t_k), four per element node
+        fn = {1: lib().mfb_harpot3d_set_incident, 4: lib().mfb_harpor3d_set_incident}.get(self.ndof, lib().mfb_harela3d_set_incident)
         if u_inc is None:
             _check(fn(self.h, None, None))
             return
-        nd = 1 if self.ndof == 1 else 3
+        nd = self.ndof
         u = np.ascontiguousarray(u_inc, dtype=np.complex128); t = np.ascontiguousarray(t_inc, dtype=np.complex128)
         if u.size != nd * int(self.m.elem_ptr[-1]) or t.size != u.size:
             raise ValueError("incident field: one row per element node")

@@ -992,6 +992,8 @@ extern "C" int mfb_harela3d_set_incident(mfb_problem* p, const mfb_z* u_inc, con
 // The same for an inviscid fluid region: p_inc, Un_inc at the nodes of every element, index [elem_ptr[e] + j] (element()%incident_c(1,kn,1) / (2,kn,1));
 // every pair and free term adds hp p_inc - gp Un_inc to b (src/assemble_bem_harpot_equation.f90:471-481; gp already carries rho omega^2).
 extern "C" int mfb_harpot3d_set_incident(mfb_problem* p, const mfb_z* p_inc, const mfb_z* un_inc) { return set_incident_impl(p, p_inc, un_inc, 1); }
+// and for a poroelastic region (src/assemble_bem_harpor_equation.f90:1277-1289): (tau, u_k)_inc and (Un, t_k)_inc, index [(elem_ptr[e] + j) * 4 + k]
+extern "C" int mfb_harpor3d_set_incident(mfb_problem* p, const mfb_z* u_inc, const mfb_z* t_inc) { return set_incident_impl(p, u_inc, t_inc, 4); }
 static int set_incident_impl(mfb_problem* p, const mfb_z* u_inc, const mfb_z* t_inc, int want_ndof) {
   if (!p) return fail(MFB_ERR_ARG, "mfb_harela3d_set_incident: null problem");
   if (p->ndof != want_ndof || p->hbie) return fail(MFB_ERR_UNSUPPORTED, "set_incident: built for the displacement equation of elastic regions (mfb_harela3d_set_incident) and for fluid regions (mfb_harpot3d_set_incident)");
@@ -1021,7 +1023,7 @@ static int set_incident_impl(mfb_problem* p, const mfb_z* u_inc, const mfb_z* t_
   }
   p->have_inc = u_inc != nullptr;
   for (auto& g : p->groups) g.dev.einc = p->have_inc ? p->d_einc + 4 * (size_t)p->slot_off_h[g.slot0] : nullptr;
-  p->ft.einc = p->have_inc ? p->d_einc : nullptr;
+  p->ft.einc = p->have_inc ? p->d_einc : nullptr; p->ft0.einc = p->ft.einc;
   // the element classes of K1 depend on it (every element runs as the general class while a field is set)
   if (p->have_cvalue) for (auto& g : p->groups) launch_gather_cv(g.dev, p->d_cvalue, st);
   p->assembled = false;

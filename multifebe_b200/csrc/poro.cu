@@ -30,7 +30,8 @@ void set_por_params(const PorParams& pp, cudaStream_t st) { cudaMemcpyToSymbolAs
 template <int NN, class Pred>
 __device__ __forceinline__ void por_scatter_row(const RAcc<NN>& a, int l, const int* __restrict__ ecol, const unsigned char* __restrict__ ekind,
                                                 const double* __restrict__ ecv, bool rev, const DevSystem& s, int row, double& bre, double& bim, Pred mine,
-                                                unsigned symbits = 0u /* bit k: multiplier -1 of a symmetry image on dof k (symconf_s for k = 0, symconf_t(k) else) */) {
+                                                unsigned symbits = 0u /* bit k: multiplier -1 of a symmetry image on dof k (symconf_s for k = 0, symconf_t(k) else) */,
+                                                const double* __restrict__ einc = nullptr /* incident field of the element's (j, k): (u re, im, t re, im), or NULL */) {
 #pragma unroll
   for (int k = 0; k < 4; k++) {
 #pragma unroll
@@ -45,6 +46,10 @@ __device__ __forceinline__ void por_scatter_row(const RAcc<NN>& a, int l, const 
       if (ekind[jk] == 0) { ar = -gr; ai = -gi; bre -= hr * cvr - hi * cvi; bim -= hr * cvi + hi * cvr; }
       else { ar = hr; ai = hi; bre += gr * cvr - gi * cvi; bim += gr * cvi + gi * cvr; }
       if ((symbits >> k) & 1u) { ar = -ar; ai = -ai; }   // build_lse_mechanics_bem_harpor.f90:971-975; the b terms carry the sign in ecv
+      if (einc) {   // b += hp u_inc - gp t_inc (assemble_bem_harpor_equation.f90:1277-1289); a symmetry image's sign is in the values
+        const double ur = einc[4 * jk], ui = einc[4 * jk + 1], tr = einc[4 * jk + 2], ti = einc[4 * jk + 3];
+        bre += (hr * ur - hi * ui) - (gr * tr - gi * ti); bim += (hr * ui + hi * ur) - (gr * ti + gi * tr);
+      }
       atomicAdd(s.Are + (size_t)col * s.lda + row, ar);
       atomicAdd(s.Aim + (size_t)col * s.lda + row, ai);
     }
@@ -108,7 +113,7 @@ __device__ __forceinline__ void por_regular_pair(const DevGroup& g, const DevSys
   // accumulated (4 NN complex numbers per equation: they stay in registers; the general path below keeps h AND g, 16 NN doubles, and for 8/9-node
   // elements lives in local memory -- 4.6 KB of spills per thread, the kernel's cost in round 1), and the radial scalars of the first R1_CACHE_GP
   // points are computed in the pass of equation 0 and read back from shared memory by the other three.
-  if ((info & 8u) && !g.ecvnz[el]) {
+  if ((info & 8u) && !g.ecvnz[el] && !g.einc) {
     unsigned kinds = 0u;
 #pragma unroll
     for (int k = 0; k < 4; k++) kinds |= (ekind[k] != 0 ? 1u : 0u) << k;
@@ -171,7 +176,7 @@ __device__ __forceinline__ void por_regular_pair(const DevGroup& g, const DevSys
     }
     const int row = (l == 0) ? rws[0] : (l == 1 ? rws[1] : (l == 2 ? rws[2] : rws[3]));
     double br = 0.0, bi = 0.0;
-    por_scatter_row<NN>(acc, l, ecol, ekind, ecv, rev, s, row, br, bi, PorAll(), info >> 4);
+    por_scatter_row<NN>(acc, l, ecol, ekind, ecv, rev, s, row, br, bi, PorAll(), info >> 4, g.einc ? g.einc + (size_t)el * 16 * NN : nullptr);
     if (br != 0.0 || bi != 0.0) { atomicAdd(s.bre + row, br); atomicAdd(s.bim + row, bi); }
   }
 }
@@ -346,7 +351,7 @@ __global__ void __launch_bounds__(128) k_por_adaptive(DevGroup g, DevColloc c, D
   const double* gx = tri ? t.gl01_x : t.gl11_x;
   const double* gw = tri ? t.gl01_w : t.gl11_w;
   const bool rev = g.erev[e] != 0;
-  if ((g.einfo[e] & 8u) && !g.ecvnz[e]) {   // the common element (uniform kinds, no prescribed value): only what goes to the matrix, in registers (see k_por_regular)
+  if ((g.einfo[e] & 8u) && !g.ecvnz[e] && !g.einc) {   // the common element (uniform kinds, no prescribed value): only what goes to the matrix, in registers (see k_por_regular)
     const unsigned info = g.einfo[e];
     const unsigned char* ekind = g.ekind + (size_t)e * 4 * NN;
     unsigned kinds = 0u;
@@ -412,7 +417,8 @@ __global__ void __launch_bounds__(128) k_por_adaptive(DevGroup g, DevColloc c, D
     const int row = c.crow[l * c.ldp + cpos];
     double br = 0.0, bi = 0.0;
     PorLane pl; pl.lane = lane;
-    por_scatter_row<NN>(acc, l, g.ecol + (size_t)e * 4 * NN, g.ekind + (size_t)e * 4 * NN, g.ecv + (size_t)e * 8 * NN, rev, s, row, br, bi, pl, (unsigned)g.einfo[e] >> 4);
+    por_scatter_row<NN>(acc, l, g.ecol + (size_t)e * 4 * NN, g.ekind + (size_t)e * 4 * NN, g.ecv + (size_t)e * 8 * NN, rev, s, row, br, bi, pl, (unsigned)g.einfo[e] >> 4,
+                         g.einc ? g.einc + (size_t)e * 16 * NN : nullptr);
     if (br != 0.0 || bi != 0.0) { atomicAdd(s.bre + row, br); atomicAdd(s.bim + row, bi); }
   }
 }
@@ -453,7 +459,7 @@ __global__ void __launch_bounds__(128) k_por_singular(DevGroup g, DevColloc c, D
   const double* gx = t.gl01_x + 15 * 14 / 2;
   const double* gw = t.gl01_w + 15 * 14 / 2;
   const bool rev = g.erev[e] != 0;
-  if ((g.einfo[e] & 8u) && !g.ecvnz[e]) {   // the common element: only what goes to the matrix, in registers
+  if ((g.einfo[e] & 8u) && !g.ecvnz[e] && !g.einc) {   // the common element: only what goes to the matrix, in registers
     const unsigned info = g.einfo[e];
     const unsigned char* ekind = g.ekind + (size_t)e * 4 * NN;
     unsigned kinds = 0u;
@@ -529,7 +535,8 @@ __global__ void __launch_bounds__(128) k_por_singular(DevGroup g, DevColloc c, D
     const int row = c.crow[l * c.ldp + cpos];
     double br = 0.0, bi = 0.0;
     PorLane pl; pl.lane = lane;
-    por_scatter_row<NN>(acc, l, g.ecol + (size_t)e * 4 * NN, g.ekind + (size_t)e * 4 * NN, g.ecv + (size_t)e * 8 * NN, rev, s, row, br, bi, pl, (unsigned)g.einfo[e] >> 4);
+    por_scatter_row<NN>(acc, l, g.ecol + (size_t)e * 4 * NN, g.ekind + (size_t)e * 4 * NN, g.ecv + (size_t)e * 8 * NN, rev, s, row, br, bi, pl, (unsigned)g.einfo[e] >> 4,
+                         g.einc ? g.einc + (size_t)e * 16 * NN : nullptr);
     if (br != 0.0 || bi != 0.0) { atomicAdd(s.bre + row, br); atomicAdd(s.bim + row, bi); }
   }
 }

@@ -1883,6 +1883,8 @@ static void scatter_por(const Model* m, int e, int sn_col, const cd* hp, const c
           case 0: { long long col = m->col_t[4 * sn + ik]; A[row + nd * col] = A[row + nd * col] - gg; b[row] = b[row] - hh * cvalue[4 * sn + ik]; break; }
           case 1: { long long col = m->col_u[4 * sn + ik]; A[row + nd * col] = A[row + nd * col] + hh; b[row] = b[row] + gg * cvalue[4 * sn + ik]; break; }
         }
+        // incident wave field: assemble_bem_harpor_equation.f90:1277-1289 (ordinary boundary), (tau | u_k)_inc and (Un | t_k)_inc per element node
+        if (!m->u_inc.empty()) b[row] = b[row] + hh * m->u_inc[(size_t)(m->eptr[e] + kn) * 4 + ik] - gg * m->t_inc[(size_t)(m->eptr[e] + kn) * 4 + ik];
       }
   }
 }

@@ -380,6 +380,10 @@ class PorOracle:
         except Exception:
             pass
 
+    def set_incident(self, u_inc=None, t_inc=None):
+        """Incident field of a poroelastic region at the nodes of every element: (tau, u_k) and (Un, t_k), (sum nn, 4) complex each; None clears."""
+        _set_incident(self, u_inc, t_inc, 4)
+
     def assemble(self, omega, poro, nthreads=0):
         n = self.m.n_dof
         A = np.zeros((n, n), dtype=np.complex128, order="F")

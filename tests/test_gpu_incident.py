@@ -131,3 +131,30 @@ def test_fluid_region_incident_field(gpu_ctx, oracle_lib):
     p, _ = md.nodal_solution(pr.solve_frequency_fluid(omega, fl))
     assert relerr(p, np.array([field(x, [1.0, 0, 0])[0] for x in md.node_x])) < 1e-9
     pr.close()
+
+
+def test_poroelastic_region_incident_field(gpu_ctx, oracle_lib):
+    """mfb_harpor3d_set_incident against the oracle (b <= 1e-11, A untouched), mixed conditions and a symmetry plane; clearing restores the plain system."""
+    from multifebe_b200 import capi
+    from multifebe_b200.host import Poro, PoroModel
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_oracle_poroelastic import column_bcs
+    po = Poro(rhof=1.0, rhos=2.2, lam=1.2, mu=1.0, xi=0.03, phi=0.35, rhoa=0.15, R=0.8, Q=0.5, b=0.4)
+    rng = np.random.default_rng(5)
+    cases = [PoroModel(cube_mesh(2, shape.QUAD9), column_bcs()),
+             PoroModel(cube_mesh(3, shape.TRI3), {q: ([1, 1, 1, 1], [0.1, 0, 0.2, 0]) for q in range(1, 7)}, reversed_parts=(1, 2, 3, 4, 5, 6)),
+             PoroModel(without_parts(cube_mesh(2, shape.QUAD4), {3}), {k: v for k, v in column_bcs().items() if k != 3}, symmetry=[("y", "symmetry")])]
+    for md in cases:
+        n_rows = int(md.elem_ptr[-1])
+        u_inc = rng.normal(size=(n_rows, 4)) + 1j * rng.normal(size=(n_rows, 4)); t_inc = rng.normal(size=(n_rows, 4)) + 1j * rng.normal(size=(n_rows, 4))
+        pr = capi.Problem(gpu_ctx, md); o = oracle_lib.PorOracle(md)
+        A0, b0 = pr.build_lse_mechanics_bem_harpor(2.0, po)
+        pr.set_incident(u_inc, t_inc); o.set_incident(u_inc, t_inc)
+        A, b = pr.build_lse_mechanics_bem_harpor(2.0, po)
+        Ao, bo, _ = o.assemble(2.0, po)
+        assert relerr(A, Ao) < TOL_A and relerr(b, bo) < TOL_A, (relerr(A, Ao), relerr(b, bo))
+        assert relerr(pr.solve_frequency_poro(2.0, po), np.linalg.solve(Ao, bo)) < TOL_X
+        pr.set_incident(None)
+        A1, b1 = pr.build_lse_mechanics_bem_harpor(2.0, po)
+        assert relerr(A1, A0) < 1e-13 and np.abs(b1 - b0).max() <= 1e-12 * max(np.abs(b0).max(), 1e-300)
+        pr.close()

@@ -96,3 +96,26 @@ def test_fluid_plane_wave_identities_interior_and_exterior(etype, m):
         assert np.abs(b - want).max() < tol * np.abs(pn).max(), (rev, np.abs(b - want).max())
         o.set_incident(None)
         assert not o.assemble(omega, fl)[1].any()
+
+
+def test_poroelastic_incident_term_no_scattering_identity():
+    """assemble_bem_harpor_equation.f90:1277-1289 in the oracle: with every secondary variable (Un, t_k) prescribed equal to the incident one, the assembled
+    system is A = H, b = G s + H p_inc - G s_inc = H p_inc, so the primary variables (tau, u_k) come out equal to the incident ones -- an algebraic identity
+    that holds for ANY incident arrays and fails if the signs of the two terms are not those of the H and G columns."""
+    from multifebe_b200.host import Poro, PoroModel
+    po = Poro(rhof=1.0, rhos=2.2, lam=1.2, mu=1.0, xi=0.03, phi=0.35, rhoa=0.15, R=0.8, Q=0.5, b=0.4)
+    md = PoroModel(cube_mesh(2, shape.QUAD9), {q: ([1, 1, 1, 1], [0, 0, 0, 0]) for q in range(1, 7)}, reversed_parts=(1, 2, 3, 4, 5, 6))
+    rng = np.random.default_rng(3)
+    prim_node = rng.normal(size=(md.n_node, 4)) + 1j * rng.normal(size=(md.n_node, 4))       # (tau, u_k)_inc per node
+    sec_node = rng.normal(size=(md.n_node, 4)) + 1j * rng.normal(size=(md.n_node, 4))        # (Un, t_k)_inc per node (unshared rims: one value per node)
+    n_rows = int(md.elem_ptr[-1])
+    u_inc = np.zeros((n_rows, 4), dtype=np.complex128); t_inc = np.zeros((n_rows, 4), dtype=np.complex128)
+    for e in range(md.n_elem):
+        for kn, v in enumerate(md.mesh.conn[e]):
+            u_inc[md.elem_ptr[e] + kn] = prim_node[v]; t_inc[md.elem_ptr[e] + kn] = sec_node[v]
+    md.cvalue[:] = sec_node
+    o = orc.PorOracle(md)
+    o.set_incident(u_inc, t_inc)
+    A, b, _ = o.assemble(2.0, po)
+    prim, _ = md.nodal_solution(np.linalg.solve(A, b))
+    assert np.abs(prim - prim_node).max() < 1e-9 * np.abs(prim_node).max()
