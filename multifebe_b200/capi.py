@@ -115,13 +115,27 @@ class CoupledProblem:
         self._solver = None
         self._terms = {}                                 # host/coupled.py::TermArrays per region, kept between frequencies
 
-    def _assemble_local(self, model, region, omega):
+    def _assemble_local(self, model, region, omega, incident=None):
         pr = self.problems[id(model)]
+        self._set_local_incident(pr, incident)
         if region.kind == "solid":
-            return pr.build_lse_mechanics_bem_harela(omega, region.material)[0]
-        if region.kind == "fluid":
-            return pr.build_lse_mechanics_bem_harpot(omega, region.material)[0]
-        return pr.build_lse_mechanics_bem_harpor(omega, region.material)[0]
+            A, b = pr.build_lse_mechanics_bem_harela(omega, region.material)
+        elif region.kind == "fluid":
+            A, b = pr.build_lse_mechanics_bem_harpot(omega, region.material)
+        else:
+            A, b = pr.build_lse_mechanics_bem_harpor(omega, region.material)
+        return A if incident is None else (A, b)
+
+    def _set_local_incident(self, pr, incident):
+        if incident is None and not getattr(pr, "_has_incident", False):
+            return                                       # nothing set, nothing to clear: models without incident fields make no extra call
+        pr.set_incident(*(incident if incident is not None else (None, None)))
+        pr._has_incident = incident is not None
+
+    def set_incident(self, kr, u_inc=None, t_inc=None):
+        """Incident wave field of region kr for the next assembly (MultiRegionModel.set_incident): it reaches the device through the region's H
+        problem (mfb_har{ela,pot,por}3d_set_incident), whose right-hand side then is sum_e (hp u_inc - gp t_inc); the free-term part is added on the host."""
+        self.m.set_incident(kr, u_inc, t_inc)
 
     def assemble(self, omega):
         """-> A, b of the coupled system (host arrays)."""
@@ -132,6 +146,7 @@ class CoupledProblem:
         """The same without moving matrices through the host: the local systems stay on the device, mfb_combine_columns / mfb_add_entries build
         the coupled system in the resident matrix of a solver problem, mfb_zsolve factorises and solves it there (not yet run on hardware)."""
         from .host.coupled import TermArrays
+        from .host import coupled as coupled_mod
         n = self.m.n_dof
         if self._solver is None or self._solver.m.n_dof != n:
             self._solver = _lu_only_problem(self.ctx, n)
@@ -142,8 +157,11 @@ class CoupledProblem:
             if kr not in self._terms:
                 self._terms[kr] = TermArrays(self.m, kr, mp, freeterm)
             ta = self._terms[kr].at(omega)
+            inc = self.m.incident.get(kr)
             for model, (sc, dc, cf) in ((mH, ta.H), (mG, ta.G)):
                 pr = self.problems[id(model)]
+                if model is mH:
+                    self._set_local_incident(pr, inc)
                 if region.kind == "solid":
                     pr.build_lse_mechanics_bem_harela(omega, region.material, want_host=False)
                 elif region.kind == "fluid":
@@ -151,6 +169,13 @@ class CoupledProblem:
                 else:
                     pr.build_lse_mechanics_bem_harpor(omega, region.material, want_host=False)
                 _check(lib().mfb_combine_columns(dst.h, pr.h, C.c_int(len(ta.row_map)), _p(ta.row_map), C.c_int(len(sc)), _p(sc), _p(dc), _p(cf)))
+                if model is mH and inc is not None:                      # b_loc of the H problem = sum_e (hp u_inc - gp t_inc): n_rows values through the host
+                    bl = -pr.residual_vector(np.zeros(pr.m.n_dof, dtype=np.complex128))[:len(ta.row_map)]      # A 0 - b, host row order
+                    fe = coupled_mod.incident_free_terms(self.m, kr, omega, freeterm)
+                    rows = np.concatenate([ta.row_map, np.array([e[0] for e in fe], dtype=np.int32)]).astype(np.int32)
+                    vals = np.concatenate([bl, np.array([e[1] for e in fe], dtype=np.complex128)]).astype(np.complex128)
+                    cols = -np.ones(len(rows), dtype=np.int32)
+                    _check(lib().mfb_add_entries(dst.h, C.c_int(len(rows)), _p(rows), _p(cols), _p(vals)))
             if len(ta.E[0]):
                 _check(lib().mfb_add_entries(dst.h, C.c_int(len(ta.E[0])), _p(ta.E[0]), _p(ta.E[1]), _p(ta.E[2])))
         ipiv = np.zeros(n, dtype=np.int32)

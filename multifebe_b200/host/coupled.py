@@ -232,8 +232,13 @@ def assemble_coupled(mrm, omega, local_assemble, freeterm, locals_=None):
         r = mrm.regions[kr]
         mH, mG, mp = locals_[kr] if locals_ is not None else local_models(mrm, kr)
         row_map, terms_H, terms_G, entries = combination_terms(mrm, kr, mp, omega, freeterm)
+        inc = mrm.incident.get(kr)
         for model, terms in ((mH, terms_H), (mG, terms_G)):
-            Aloc = local_assemble(model, r, omega)
+            if inc is not None and model is mH:                          # incident field: the H problem (all conditions "secondary known, 0") run with
+                Aloc, bloc = local_assemble(model, r, omega, incident=inc)     # the field set has b_loc = sum_e (hp u_inc - gp t_inc), free terms apart
+                b[row_map] += bloc[:mp["n_rows"]]
+            else:
+                Aloc = local_assemble(model, r, omega)
             for lcol, gcol, coef in terms:
                 if gcol >= 0:
                     A[row_map, gcol] += coef * Aloc[:mp["n_rows"], lcol]
@@ -244,4 +249,24 @@ def assemble_coupled(mrm, omega, local_assemble, freeterm, locals_=None):
                 A[row, gcol] += val
             else:
                 b[row] += val
+        for row, val in incident_free_terms(mrm, kr, omega, freeterm):
+            b[row] += val
     return A, b
+
+
+def incident_free_terms(mrm, kr, omega, freeterm):
+    """[(global row, value)]: the free term of every collocation point of region kr times the incident field at its own element, the part of
+    hp u_inc the auxiliary problems (set up without free terms) leave out.  Empty when the region has no incident field."""
+    inc = mrm.incident.get(kr)
+    if inc is None:
+        return []
+    v, nd, out = mrm.views[kr], mrm.regions[kr].ndof, []
+    for c in range(v.n_colloc):
+        le, blk = free_term_block(mrm, kr, c, omega, freeterm)
+        rows_g = mrm.row[(int(v.colloc_node[c]), int(v.colloc_eq[c]))]
+        ui = inc[0][int(v.elem_ptr[le]):int(v.elem_ptr[le + 1])]
+        for l in range(nd):
+            val = np.sum(blk[:, l, :] * ui)
+            if val != 0:
+                out.append((int(rows_g[l]), complex(val)))
+    return out

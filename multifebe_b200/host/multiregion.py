@@ -203,6 +203,7 @@ class MultiRegionModel:
         self.n_dof = row
         # --- per-region views
         self.views = [self._view(kr) for kr in range(len(self.regions))]
+        self.incident = {}                                  # region index -> (u_inc, t_inc) at the nodes of the region's elements, see set_incident
 
     def _view(self, kr):
         mesh, r = self.mesh, self.regions[kr]
@@ -258,6 +259,20 @@ class MultiRegionModel:
         return v
 
     # ---- flat scatter descriptors of one region: the form in which the coupling crosses the C ABI
+    def set_incident(self, kr, u_inc=None, t_inc=None):
+        """Incident wave field of region kr (region%n_incidentfields > 0): the primary and the secondary variables of the incident field at the
+        nodes of every element of the region's view, (sum nn, ndof) complex each in the view's element order, the secondary ones formed with the
+        REGION's outward normal (views[kr].elem_reversed applied by the caller).  Every (collocation point, element) pair of the region, ordinary
+        boundaries and interfaces alike, then adds hp u_inc - gp t_inc to the right-hand side, free term included
+        (src/assemble_bem_harela_equation.f90:651-666, assemble_bem_harpot_equation.f90:471-481, assemble_bem_harpor_equation.f90:1277-1289; the
+        unknowns of the coupled system are the TOTAL fields).  The field depends on the frequency: set it before every assembly.  None clears it."""
+        if u_inc is None:
+            self.incident.pop(kr, None); return
+        v = self.views[kr]
+        n = int(v.elem_ptr[-1])
+        u = np.ascontiguousarray(u_inc, dtype=np.complex128).reshape(n, v.ndof); t = np.ascontiguousarray(t_inc, dtype=np.complex128).reshape(n, v.ndof)
+        self.incident[kr] = (u, t)
+
     def impedance_coefficient(self, kr, b, omega):
         """Un = -coef * p on a fluid boundary with condition 2 (Un = -i/(rho c omega) p) or 3 (Un = -(i/(rho c omega) + 1/(2 R rho omega^2)) p,
         R = the prescribed value): assemble_bem_harpot_equation.f90:97-110."""

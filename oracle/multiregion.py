@@ -338,6 +338,15 @@ class MultiRegionOracle:
                         g = g * d1J                                       # the flux unknown is Un = (dp/dn)/(rho omega^2)
                     if li == le_own:
                         h = h + hfree
+                    if kr in m.incident:                                  # incident field of the region: b += hp u_inc - gp t_inc on every boundary class
+                        ui, ti = m.incident[kr]                           # (an image takes the root's values; its multipliers are already in h, g)
+                        sl = slice(int(v.elem_ptr[le]), int(v.elem_ptr[le + 1]))
+                        rows = m.row[(sn_col, eq)]
+                        if v.ndof == 1:
+                            b[rows[0]] += np.dot(h, ui[sl, 0]) - np.dot(g, ti[sl, 0])
+                        else:
+                            for il, row in enumerate(rows):
+                                b[row] += np.sum(h[:, il, :] * ui[sl]) - np.sum(g[:, il, :] * ti[sl])
                     if flat:
                         self._scatter_flat(kr, le, sn_col, eq, h, g, A, b, desc[kr])
                     else:

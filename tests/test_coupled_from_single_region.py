@@ -129,3 +129,65 @@ def test_term_arrays_kept_between_frequencies_equal_fresh_term_lists():
     for omega in (4.0, 2.5):
         _same_terms(ta.at(omega), combination_terms(duct, 0, mp, omega, oracle_freeterm))
     assert ta.omega_dependent is True
+
+
+def _random_incident(mrm, kr, seed):
+    v = mrm.views[kr]
+    rng = np.random.default_rng(seed)
+    n = int(v.elem_ptr[-1])
+    return (rng.normal(size=(n, v.ndof)) + 1j * rng.normal(size=(n, v.ndof)), rng.normal(size=(n, v.ndof)) + 1j * rng.normal(size=(n, v.ndof)))
+
+
+@pytest.mark.parametrize("kinds,where", [((SOLID, FLUID), (0,)), ((FLUID, PORO), (0, 1)), ((PORO, SOLID), (1,)), ((SOLID, SOLID), (0, 1))])
+def test_incident_field_of_a_coupled_region_through_the_single_region_route(kinds, where):
+    """region%n_incidentfields > 0 in a coupled model: every pair of the region, interface elements included, adds hp u_inc - gp t_inc to b
+    (assemble_bem_har{ela,pot,por}_equation.f90, the block after the coupling `select case`).  The H problem of the region run with the field set
+    must give the same right-hand side as the multi-region oracle, for any arrays."""
+    mats = {SOLID: MS, FLUID: FL, PORO: PO}
+    bcs = bcs_for(kinds[0], LAT1, 1, True); bcs.update(bcs_for(kinds[1], LAT2, 2, False))
+    mrm = MultiRegionModel(two_box_mesh(1, shape.QUAD8), [Region(kinds[0], mats[kinds[0]], [1, 3, 4, 5, 6, 7]), Region(kinds[1], mats[kinds[1]], [-7, 2, 13, 14, 15, 16])],
+                           BPART, bcs)
+    omega = 1.7
+    A_plain, b_plain = MultiRegionOracle(mrm).assemble(omega)
+    for kr in where:
+        mrm.set_incident(kr, *_random_incident(mrm, kr, 10 + kr))
+
+    def local(model, region, om, incident=None):
+        o = {SOLID: orc.Oracle, FLUID: orc.PotOracle}.get(region.kind, orc.PorOracle)(model)
+        if incident is not None:
+            o.set_incident(*incident)
+        res = o.assemble(om, region.material)
+        return res[0] if incident is None else (res[0], res[1])
+    A0, b0 = MultiRegionOracle(mrm).assemble(omega)
+    A1, b1 = assemble_coupled(mrm, omega, local, oracle_freeterm)
+    sc = np.abs(A0).max(axis=0)
+    assert np.array_equal(A0, A_plain) and np.abs(b0 - b_plain).max() > 0.1 * np.abs(b_plain).max()      # the field only changes b, and does change it
+    assert (np.abs(A1 - A0).max(axis=0) <= 1e-12 * sc).all()
+    assert np.abs(b1 - b0).max() <= 1e-12 * np.abs(b0).max()
+    mrm.set_incident(where[0])                                                                          # cleared again
+    assert where[0] not in mrm.incident
+
+
+def test_coupled_incident_no_scattering_identity():
+    """Two solid regions of the same material, the same incident field in both: with u_inc per node, t_inc = +-t per interface node (the outward normals
+    of the two regions are opposite) and zero on the traction-free outer faces, the total field IS the incident one -- an algebraic identity of
+    H (u - u_inc) = G (t - t_inc) per region with u1 = u2, t1 = -t2 on the interface, which pins the sign the reversed interface elements take."""
+    free = ([1, 1, 1], [0, 0, 0])
+    bcs = {q: free for q in (1, 2) + LAT1 + LAT2}
+    mrm = MultiRegionModel(two_box_mesh(2, shape.TRI6), [Region(SOLID, MS, [1, 3, 4, 5, 6, 7]), Region(SOLID, MS, [-7, 2, 13, 14, 15, 16])], BPART, bcs)
+    rng = np.random.default_rng(5)
+    u_node = rng.normal(size=(mrm.n_node, 3)) + 1j * rng.normal(size=(mrm.n_node, 3))
+    t_node = np.zeros((mrm.n_node, 3), dtype=np.complex128)
+    if_nodes = np.unique(np.concatenate([mrm.mesh.conn[e] for e in mrm.elems_of_boundary[7]]))
+    t_node[if_nodes] = rng.normal(size=(len(if_nodes), 3)) + 1j * rng.normal(size=(len(if_nodes), 3))   # traction of region 1 on the interface
+    for kr, sg in ((0, 1.0), (1, -1.0)):
+        v = mrm.views[kr]
+        mrm.set_incident(kr, u_node[v.elem_node], sg * t_node[v.elem_node])
+    A, b = MultiRegionOracle(mrm).assemble(1.3)
+    x = np.linalg.solve(A, b)
+    u1, t1 = mrm.nodal_solution(x, 0)
+    u2, t2 = mrm.nodal_solution(x, 1)
+    for u, t, sg in ((u1, t1, 1.0), (u2, t2, -1.0)):
+        ok = ~np.isnan(u[:, 0])
+        assert np.abs(u[ok] - u_node[ok]).max() < 1e-9 * np.abs(u_node).max()
+        assert np.abs(t[ok] - sg * t_node[ok]).max() < 1e-9 * np.abs(t_node).max()

@@ -65,3 +65,37 @@ def test_coupled_regions_with_symmetry_planes(gpu_ctx, kinds, ict, planes):
     x0 = np.linalg.solve(A0, b0)
     assert np.abs((xr - x0) * sc).max() <= 1e-8 * np.abs(x0 * sc).max()
     cp.close()
+
+
+@pytest.mark.parametrize("kinds,where", [((SOLID, FLUID), (0,)), ((FLUID, PORO), (0, 1)), ((PORO, SOLID), (1,))])
+def test_coupled_regions_with_incident_fields(gpu_ctx, kinds, where):
+    """An incident field in one or both regions of a coupled model (CoupledProblem.set_incident): the H problem of the region runs with the field set on the
+    device, its right-hand side and the free-term part join b -- host combination and resident combination against the multi-region oracle.
+    (quad9 like the other coupled cases: on the quad8 two-box mesh one free-term diagonal of the ORACLE sits 1.3e-11 off, with or without a field -- the acos
+    formula of DESIGN.md 9.9, profiles/r02_coupled_incident_check.log.)"""
+    from multifebe_b200 import capi
+    from oracle.multiregion import MultiRegionOracle
+    from test_coupled_from_single_region import _random_incident
+    mats = {SOLID: MS, FLUID: FL, PORO: PO}
+    bcs = bcs_for(kinds[0], LAT1, 1, True); bcs.update(bcs_for(kinds[1], LAT2, 2, False))
+    mrm = MultiRegionModel(two_box_mesh(2, shape.QUAD9), [Region(kinds[0], mats[kinds[0]], [1, 3, 4, 5, 6, 7]), Region(kinds[1], mats[kinds[1]], [-7, 2, 13, 14, 15, 16])],
+                           BPART, bcs)
+    omega = 1.7
+    cp = capi.CoupledProblem(gpu_ctx, mrm)
+    for kr in where:
+        cp.set_incident(kr, *_random_incident(mrm, kr, 20 + kr))
+    A0, b0 = MultiRegionOracle(mrm).assemble(omega)
+    A, b = cp.assemble(omega)
+    sc = np.abs(A0).max(axis=0)
+    assert (np.abs(A - A0).max(axis=0) <= 1e-11 * sc).all(), (np.abs(A - A0).max(axis=0) / sc).max()
+    assert np.abs(b - b0).max() <= 1e-11 * np.abs(b0).max()
+    x0 = np.linalg.solve(A0, b0)
+    xr = cp.solve_frequency_resident(omega)
+    assert np.abs((xr - x0) * sc).max() <= 1e-8 * np.abs(x0 * sc).max()
+    # cleared again: the plain system comes back (the H problems drop the field)
+    for kr in where:
+        cp.set_incident(kr)
+    _, b1 = cp.assemble(omega)
+    _, b10 = MultiRegionOracle(mrm).assemble(omega)
+    assert np.abs(b1 - b10).max() <= 1e-11 * np.abs(b10).max()
+    cp.close()
