@@ -45,6 +45,14 @@ class GpuSolver:
             return self.pr.solve_frequency_poro(omega, self.case.material)
         return self.pr.solve_frequency(omega, self.case.material)
 
+    def set_incident(self, arrays):
+        """arrays = CaseFile.incident_arrays(model, omega): the incident fields of the regions at the frequency about to be solved."""
+        if self.cp is not None:
+            for kr in range(len(self.case.regions)):
+                self.cp.set_incident(kr, *arrays.get(kr, (None, None)))
+        else:
+            self.pr.set_incident(*arrays.get(0, (None, None)))
+
     def static(self):
         return self.pr.solve_static(self.case.material)
 
@@ -104,7 +112,13 @@ def run(case_path, output=None, solver=None, verbose=1, rank=0, world=1, dist=No
                     if case.internal_points:
                         wr.static_internal(*solver.interior_static(x, ip_x))
         else:
-            sweep = FrequencySweep(case.omega, model.n_dof, lambda kf, om: solver.harmonic(om), rank=rank, world=world, dist=dist, device=device)
+            has_inc = any(case.region_incident)
+
+            def one_frequency(kf, om):
+                if has_inc:                     # [incident waves]: the arrays depend on the frequency (calculate_incident_mechanics_harmonic(kf))
+                    solver.set_incident(case.incident_arrays(model, om))
+                return solver.harmonic(om)
+            sweep = FrequencySweep(case.omega, model.n_dof, one_frequency, rank=rank, world=world, dist=dist, device=device)
             for r in range(sweep.n_rounds()):
                 sweep.round(r)
                 if rank == 0:

@@ -15,9 +15,12 @@ Mirrors src/read_input_file.f90 for the sections the hot path consumes:
   [internal points]  src/read_internal_points.f90    `<id> <region> x1 x2 x3` (one elastic region)
   [symmetry planes]  src/read_symmetry_planes.f90    `plane_n1|plane_yz : symmetry|antisymmetry` (also plane_n2|plane_zx, plane_n3|plane_xy) or the
                                              explicit form `x = <s> <t1> <t2> <t3>` (y, z alike); one elastic region
+  [incident waves]   src/read_incident_mechanics_harmonic.f90   plane / point waves in fluids, plane P / SV / SH waves in elastic solids, full space or
+                                             homogeneous half-space; listed per region by the last record of [regions] (`<n> <id> ...`)
   [export]       src/read_export.f90:61-240  export_nso, real_format, integer_format, complex_notation
 Anything else the reference accepts (be-fe coupling, crack-like boundaries, close-pore conditions, local-axes or spring conditions,
-half-spaces, body loads, incident fields, internal points of fluid regions, FE regions ...) raises CaseFileError naming the feature:
+half-space fundamental solutions, body loads, layered / Rayleigh / poroelastic incident fields, internal points of fluid regions, FE regions ...) raises
+CaseFileError naming the feature:
 the Fortran host keeps those.
 """
 import os
@@ -152,7 +155,7 @@ class CaseFile:
         sec = _sections(open(path, encoding="utf-8", errors="replace").read())
         self._sec = sec
         for unsupported in ("fe subregions", "be body loads", "be bodyloads", "internal elements",
-                            "incident waves", "groups", "cross sections", "sensitivity"):
+                            "groups", "cross sections", "sensitivity"):
             if sec.get(unsupported):
                 raise CaseFileError("section [%s] is outside the path this library covers" % unsupported)
         # ---- [problem]
@@ -217,6 +220,7 @@ class CaseFile:
             raise CaseFileError("[regions]: this section is required")
         n_regions = int(rl[0].split()[0])
         self.regions = []                     # (id, type code 1 fluid / 2 elastic, material, signed boundary ids)
+        self.region_incident = []             # per region: ids of its incident fields
         k = 1
         for kr_ in range(n_regions):
             if k + 2 >= len(rl):
@@ -231,13 +235,23 @@ class CaseFile:
             rb = w[1:1 + w[0]]
             material, rtype = self._material(rid, rl[k + 2].split())
             k += 3
-            # remaining records of the region: number of BE body loads and (harmonic analysis) of incident fields -- both must be 0
+            # remaining records of the region: number of BE body loads (must be 0) and, in the harmonic analysis, `<n> <id> ...` of its incident
+            # fields (src/read_regions.f90:1327-1330)
             n_tail = 2 if self.analysis == "harmonic" else 1
-            for s_ in rl[k:k + n_tail]:
-                if not re.fullmatch(r"[\s0]+", s_):
-                    raise CaseFileError("region %d: BE body loads / incident fields are not covered" % rid)
+            if k < len(rl) and not re.fullmatch(r"[\s0]+", rl[k]):
+                raise CaseFileError("region %d: BE body loads are not covered" % rid)
+            inc_ids = []
+            if n_tail == 2 and k + 1 < len(rl):
+                w = rl[k + 1].split()
+                try:
+                    inc_ids = [int(t) for t in w[1:1 + int(w[0])]]
+                    if len(inc_ids) != int(w[0]):
+                        raise ValueError
+                except ValueError:
+                    raise CaseFileError("region %d: the incident fields record is `<n> <id 1> ... <id n>`" % rid)
             k += n_tail
             self.regions.append((rid, rtype, material, rb))
+            self.region_incident.append(inc_ids)
         self.multi = n_regions > 1
         listed = [abs(b) for r in self.regions for b in r[3]]
         if not self.multi and any(b < 0 for b in self.regions[0][3]):
@@ -246,6 +260,7 @@ class CaseFile:
         if self.multi and self.analysis == "static":
             raise CaseFileError("[regions]: one BE region is covered in the static analysis")
         self.region_id, self.region_type, self.material, self.region_boundaries = self.regions[0]
+        self.incident_fields = self._incident_waves(sec.get("incident waves", []))
         self.interfaces = sorted(b for b in set(listed) if listed.count(b) == 2)
         if self.analysis == "static" and self.region_type != 2:
             raise CaseFileError("static analysis: only elastic solids are covered")
@@ -363,6 +378,117 @@ class CaseFile:
         keep = [e for e in range(self.mesh.n_elem) if int(self.mesh.part[e]) in used_parts]
         if len(keep) != self.mesh.n_elem:
             raise CaseFileError("the mesh holds surface elements of parts that no boundary of the regions uses")
+
+    def _incident_waves(self, lines):
+        """[incident waves] (src/read_incident_mechanics_harmonic.f90:22-42): per field `<id>`, `<class>`, `<space> [np xp bc]`,
+        `<variable> <amplitude> <x0(3)> <varphi> <theta>` (degrees), `<xs(3)> <symconf(3)>`, `<region type> <wave type>`.  Covered: plane and
+        point waves in fluids, plane P / SV / SH waves in elastic solids, full space or homogeneous half-space; the restrictions of the reference
+        (:290-347) are kept.  -> {id: dict}"""
+        fields = {}
+        if not lines or self.analysis != "harmonic":
+            if any(self.region_incident):
+                raise CaseFileError("[regions]: incident fields are listed, but there is no [incident waves] section (harmonic analysis)")
+            return fields
+        n = int(lines[0].split()[0])
+        k = 1
+        for _ in range(n):
+            if k + 6 > len(lines):
+                raise CaseFileError("[incident waves]: %d fields announced, records are missing" % n)
+            fid = int(lines[k].split()[0])
+            if fid <= 0:
+                raise CaseFileError("incident wave %d: the identifier must be greater than 0" % fid)
+            cls = lines[k + 1].split()[0].lower()
+            if cls not in ("point", "plane"):
+                raise CaseFileError("incident wave %d: class %r is not covered (point, plane)" % (fid, cls))
+            w = lines[k + 2].split()
+            f = dict(cls=cls, space=w[0].lower(), np=3, xp=0.0, bc=1)
+            if f["space"] == "half-space":
+                f["np"], f["xp"], f["bc"] = int(w[1]), _fortran_float(w[2]), int(w[3])
+                if not 1 <= f["np"] <= 3:
+                    raise CaseFileError("incident wave %d: 1 <= np <= 3" % fid)
+            elif f["space"] != "full-space":
+                raise CaseFileError("incident wave %d: space %r is not covered (full-space, half-space)" % (fid, w[0]))
+            m = re.match(r"\s*(\d+)\s+(\([^)]*\)|\S+)\s+(.*)$", lines[k + 3])
+            if not m:
+                raise CaseFileError("incident wave %d: cannot parse %r" % (fid, lines[k + 3]))
+            f["variable"], f["amplitude"] = int(m.group(1)), _fortran_complex(m.group(2))
+            num = [_fortran_float(t) for t in m.group(3).split()]
+            if len(num) < 5:
+                raise CaseFileError("incident wave %d: <variable> <amplitude> <x0(3)> <varphi> <theta> expected" % fid)
+            f["x0"], f["varphi"], f["theta"] = np.array(num[0:3]), np.deg2rad(num[3]), np.deg2rad(num[4])
+            num = [_fortran_float(t) for t in lines[k + 4].split()]
+            if len(num) < 6:
+                raise CaseFileError("incident wave %d: <xs(3)> <symconf(3)> expected" % fid)
+            f["xs"], f["symconf"] = np.array(num[0:3]), tuple(int(round(t)) for t in num[3:6])
+            if f["space"] == "half-space" and f["symconf"][f["np"] - 1] != 0:
+                raise CaseFileError("incident wave %d: symconf(np) must be 0" % fid)
+            w = lines[k + 5].split()
+            rt = {"fluid": 1, "elastic": 2, "viscoelastic": 2, "poroelastic": 3}.get(w[0].lower())
+            if rt is None:
+                raise CaseFileError('incident wave %d: the region type must be "fluid", "elastic", "viscoelastic" or "poroelastic"' % fid)
+            f["region_type"], f["wave"] = rt, w[1].lower()
+            if rt == 3:
+                raise CaseFileError("incident wave %d: incident fields of poroelastic media are not covered (the arrays can be given through set_incident)" % fid)
+            if rt == 1:
+                if f["wave"] != "p":
+                    raise CaseFileError('incident wave %d: the wave type for a fluid can be only "p"' % fid)
+                if f["variable"] != 0:
+                    raise CaseFileError("incident wave %d: a fluid field in terms of normal displacements is not implemented in the reference" % fid)
+                if cls == "point" and f["space"] != "full-space":
+                    raise CaseFileError("incident wave %d: a point wave in a half-space is not implemented in the reference" % fid)
+            else:
+                if cls != "plane":
+                    raise CaseFileError("incident wave %d: only plane waves are covered in elastic solids" % fid)
+                if f["wave"] not in ("p", "sv", "sh"):
+                    raise CaseFileError('incident wave %d: wave type %r is not covered (p, sv, sh)' % (fid, f["wave"]))
+                if np.any(f["x0"] != 0) or np.any(f["xs"] != 0):
+                    raise CaseFileError("incident wave %d: all components of x0 and xs can be only 0." % fid)
+                if f["space"] == "half-space" and (f["np"] != 3 or f["bc"] != 1):
+                    raise CaseFileError("incident wave %d: np can be only 3 and bc must be 1." % fid)
+                if f["symconf"][0] != 0 or f["symconf"][2] != 0:
+                    raise CaseFileError("incident wave %d: the symmetry/anti-symmetry decomposition can not be done for the x and z directions" % fid)
+                if f["variable"] not in (0, 1):
+                    raise CaseFileError("incident wave %d: variable 0 (displacements) or 1 (stresses)" % fid)
+            if fid in fields:
+                raise CaseFileError("incident wave %d is repeated" % fid)
+            fields[fid] = f
+            k += 6
+        for (rid, rtype, _, _), ids in zip(self.regions, self.region_incident):
+            for fid in ids:
+                if fid not in fields:
+                    raise CaseFileError("region %d: incident field %d does not exist" % (rid, fid))
+                if fields[fid]["region_type"] != rtype:
+                    raise CaseFileError("region %d: incident field %d is of a different type of region" % (rid, fid))
+        return fields
+
+    def incident_arrays(self, model, omega):
+        """{region index: (u_inc, t_inc)} at the frequency omega: the fields of every region summed at the nodes of its elements with the region's
+        outward normal (src/calculate_incident_mechanics_harmonic.f90:326-470), ready for Problem.set_incident / CoupledProblem.set_incident."""
+        from . import incident as inc
+        out = {}
+        for kr, ((rid, rtype, mat, _), ids) in enumerate(zip(self.regions, self.region_incident)):
+            if not ids:
+                continue
+            v = model.views[kr] if self.multi else model
+            tot = None
+            for fid in ids:
+                f = self.incident_fields[fid]
+                if rtype == 1:
+                    if f["cls"] == "point":
+                        fld = inc.fluid_point_wave_reference(mat, omega, f["amplitude"], f["x0"])
+                    else:
+                        fld = inc.fluid_plane_wave_reference(mat, omega, f["amplitude"], f["x0"], f["varphi"], f["theta"], f["space"], f["np"], f["xp"],
+                                                             f["bc"], f["symconf"], f["xs"])
+                    scale = 1.0
+                else:
+                    fld = inc.elastic_plane_wave_reference(f["wave"], mat, omega, f["varphi"], f["theta"], f["space"], f["xp"], f["symconf"][1])
+                    scale = 1.0
+                    if f["variable"] == 1:           # the field in terms of stresses (calculate_incident_mechanics_harmonic.f90:456-470)
+                        scale = 1.0 / (-1j * (omega / mat.c1) * (mat.lam + 2.0 * mat.mu)) if f["wave"] == "p" else 1.0 / (-1j * (omega / mat.c2) * mat.mu)
+                u, t = inc.element_incident_of(model.node_x, v.etype, v.elem_ptr, v.elem_node, v.elem_reversed, fld, 1 if rtype == 1 else 3)
+                tot = (scale * u, scale * t) if tot is None else (tot[0] + scale * u, tot[1] + scale * t)
+            out[kr] = tot
+        return out
 
     def _material(self, rid, w):
         """(material, region type code) of the material record of a region: `material <id>` or the legacy in-line forms."""

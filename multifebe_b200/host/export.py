@@ -4,7 +4,7 @@ Layout of src/export_solution_mechanics_harmonic_nso.f90 (header :62-150, rows :
 src/export_solution_mechanics_static_nso.f90 for one BE region with ordinary boundaries:
   harmonic row: kf, frequency (Hz or rad/s as in the case file), region id / class (1 = BE) / type (1 fluid, 2 elastic),
                 boundary id / class (1 = ordinary) / face (1), node id, x1 x2 x3, then the total field value_c(k_start:k_end) as
-                (Re, Im) or (|.|, arg) pairs -- fluid: p, Un; elastic: u1 u2 u3 t1 t2 t3 -- then the incident field (zero here).
+                (Re, Im) or (|.|, arg) pairs -- fluid: p, Un; elastic: u1 u2 u3 t1 t2 t3 -- then the incident field in the same order (zero without [incident waves]).
   static row:   0, 0.0, the same identification columns, then u1 u2 u3 t1 t2 t3 (real).
 Rows follow the region's boundary list; inside a boundary the nodes appear in first-visit order of the part's elements.
 """
@@ -103,13 +103,36 @@ class NsoWriter:
         omega = c.omega[kf - 1]
         value = omega * 0.159154943091895335768883763373 if c.frequency_units == "f" else omega   # c_1_2pi
         nodal = self._nodal(x)
+        incident = self._nodal_incident(omega)
         out = []
         for row in self.rows:
             prim, sec = nodal[row[0]]
             v = row[5]
             vals = "".join(self._cpair(complex(z)) for z in list(prim[v]) + list(sec[v]))
-            out.append(self._ident(kf, value, row) + vals + self._cpair(0j) * (2 * prim.shape[1]) + "\n")
+            if row[0] in incident:
+                pi, si = incident[row[0]]
+                tail = "".join(self._cpair(complex(z)) for z in list(pi[v]) + list(si[v]))
+            else:
+                tail = self._cpair(0j) * (2 * prim.shape[1])
+            out.append(self._ident(kf, value, row) + vals + tail + "\n")
         self.f.write("".join(out))
+
+    def _nodal_incident(self, omega):
+        """{region index: (primary, secondary)} incident field at the nodes, (n_node, nvar) each: node()%incident_c, the mean of element()%incident_c over
+        the elements of the node (src/calculate_incident_mechanics_harmonic.f90:628-638); regions without incident fields are absent (zeros in the file)."""
+        c = self.case
+        if not any(getattr(c, "region_incident", ())):
+            return {}
+        out = {}
+        for kr, (u, t) in c.incident_arrays(self.m, omega).items():
+            v = self.m.views[kr] if c.multi else self.m
+            nv = u.shape[1]
+            acc = np.zeros((2, self.m.n_node, nv), dtype=np.complex128); cnt = np.zeros(self.m.n_node)
+            nodes = np.asarray(v.elem_node[:int(v.elem_ptr[-1])])
+            np.add.at(acc[0], nodes, u); np.add.at(acc[1], nodes, t); np.add.at(cnt, nodes, 1.0)
+            cnt[cnt == 0] = 1.0
+            out[kr] = (acc[0] / cnt[:, None], acc[1] / cnt[:, None])
+        return out
 
     def _ip_ident(self, kf, value, pid, x):
         """Columns 1-12 of an internal-point row: no boundary (0 0 0), the point id and its position (export_solution_mechanics_harmonic_nso.f90:401-405)."""

@@ -78,3 +78,154 @@ def element_incident_fluid(model, field):
             n = sgn * sh.unit_normal(et, xn, sh.XI_NODES[et][kn])
             p[model.elem_ptr[e] + kn], un[model.elem_ptr[e] + kn] = field(xn[kn], n)
     return p, un
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# The incident fields of the [incident waves] section, in the REFERENCE's conventions (angles, normalisation, symmetry decomposition), so that
+# a case file that names them gives the arrays the Fortran host would hand to the assembly.  Restated from the formulas of
+# lib/fbem/src/harpot_incident_field.f90 (fluid: point wave :49-119, plane wave :122-290) and lib/fbem/src/harela_incident_field.f90:355-745
+# (elastic plane P / SV / SH wave in a full space or in a half-space z <= z_fs with a free surface), called as
+# src/calculate_incident_mechanics_harmonic.f90:366-378 and :434-441 call them.  There is no Fortran compiler in this image, so these are
+# pinned by the physics they must satisfy (tests/test_incident_waves.py: wave equation, stress-free / pressure-release / rigid plane, the
+# decomposition adding up to the whole field), not by outputs of the reference: "parity unpinned" for the constants read off the source.
+#
+# A field is held as a superposition of plane waves  f(x) = sum_w a_w pol_w exp(-i kv_w.(x - xs))  (pol_w scalar 1 for a fluid); the
+# symmetric / antisymmetric part about a coordinate plane is the half sum / half difference with the mirrored superposition, which is
+# what the W / Z products (fluid) and the eys / eya factors (elastic) of the reference spell out component by component.
+# ---------------------------------------------------------------------------------------------------------------------------------------
+def _direction(varphi, theta):
+    """Unit propagation vector of the reference's angles (radians): varphi from the y axis in the xy plane, theta from the xy plane."""
+    return np.array([np.cos(theta) * np.sin(varphi), np.cos(theta) * np.cos(varphi), np.sin(theta)])
+
+
+def _mirror_parts(waves, symconf, vector):
+    """waves [(a, pol, kv)] -> the superposition reduced to its symmetric (symconf[c] = 1) or antisymmetric (-1) part about the plane x_c = xs_c,
+    for every axis c; 0 leaves the axis alone.  A mirrored elastic wave has its polarisation reflected too (vector = True)."""
+    for c in range(3):
+        s = int(round(symconf[c]))
+        if s == 0:
+            continue
+        out = []
+        for a, pol, kv in waves:
+            m = np.ones(3); m[c] = -1.0
+            out.append((0.5 * a, pol, kv))
+            out.append((0.5 * a * s, pol * m if vector else pol, kv * m))
+        waves = out
+    return waves
+
+
+def fluid_plane_wave_reference(fluid, omega, amplitude=1.0, x0=(0, 0, 0), varphi=0.0, theta=0.0, space="full-space", np_axis=3, xp=0.0, bc=1,
+                               symconf=(0, 0, 0), xs=(0, 0, 0)):
+    """-> field(x, n) = (p_inc, Un_inc) of `plane` / fluid / `p` (fbem_harpot_planewave): p = A exp(-i k q.(x - x0)), time factor exp(i omega t);
+    half-space: plus the wave reflected at the plane x_np = xp, of amplitude -A (bc 0, p = 0 there) or +A (bc 1, Un = 0 there) times the phase
+    that makes the two meet at the plane.  symconf / xs: the symmetric (+1) / antisymmetric (-1) part about the planes through xs.
+    Kept as the reference has it: the phase of the reflected amplitude is written with the ALREADY reflected direction (harpot_incident_field.f90:227,
+    :238-243), so the condition on the plane holds when the origin x0 lies on the plane (x0(np) = xp; the case of every shipped example) and is off by
+    exp(4 i k q_np (xp - x0(np))) otherwise.  A drop-in gives what the reference gives; tests/test_incident_waves.py states the finding."""
+    k = omega / fluid.c
+    q = _direction(varphi, theta)
+    x0, xs = np.asarray(x0, dtype=np.float64), np.asarray(xs, dtype=np.float64)
+    A = complex(amplitude)
+    waves = [(A * np.exp(1j * k * np.dot(q, x0 - xs)), 1.0, k * q)]
+    if space == "half-space":
+        c = int(np_axis) - 1
+        if int(round(symconf[c])) != 0:
+            raise ValueError("incident wave: the half-space plane cannot be a symmetry plane (symconf(np) must be 0)")
+        qr = q.copy(); qr[c] = -qr[c]
+        Ar = (-A if int(bc) == 0 else A) * np.exp(-2j * k * qr[c] * (xp - x0[c]))
+        waves.append((Ar * np.exp(1j * k * np.dot(qr, x0 - xs)), 1.0, k * qr))
+    elif space != "full-space":
+        raise ValueError("incident wave: space %r of a fluid plane wave" % (space,))
+    waves = _mirror_parts(waves, symconf, vector=False)
+    rw2 = fluid.rho * omega ** 2
+
+    def field(x, n):
+        d = np.asarray(x, dtype=np.float64) - xs
+        p, grad = 0j, np.zeros(3, dtype=np.complex128)
+        for a, _, kv in waves:
+            e = a * np.exp(-1j * np.dot(kv, d))
+            p += e; grad += -1j * kv * e
+        return p, np.dot(grad, np.asarray(n, dtype=np.float64)) / rw2
+    return field
+
+
+def fluid_point_wave_reference(fluid, omega, amplitude=1.0, x0=(0, 0, 0)):
+    """-> field(x, n) = (p_inc, Un_inc) of `point` / fluid in a full space (fbem_harpot_pointwave, 3D): a monopole at x0 whose pressure is
+    `amplitude` at unit distance with the phase of that distance taken out, p = A exp(-i k (r - 1)) / r."""
+    k = omega / fluid.c
+    x0 = np.asarray(x0, dtype=np.float64)
+    A = complex(amplitude)
+    rw2 = fluid.rho * omega ** 2
+
+    def field(x, n):
+        rv = np.asarray(x, dtype=np.float64) - x0
+        r = np.linalg.norm(rv)
+        p = A * np.exp(-1j * k * (r - 1.0)) / r
+        dpdr = -p * (1.0 / r + 1j * k)
+        return p, dpdr * np.dot(rv / r, np.asarray(n, dtype=np.float64)) / rw2
+    return field
+
+
+def elastic_plane_wave_reference(wave, mat, omega, varphi=0.0, theta=np.pi / 2, space="full-space", z_fs=0.0, symconf_y=0):
+    """-> field(x, n) = (u_inc (3,), t_inc (3,)) of `plane` / elastic / `p` | `sv` | `sh` (fbem_harela_incident_plane_wave) with the halving of
+    its caller (calculate_incident_mechanics_harmonic.f90:439-440), which makes the free-field motion of the surface under vertical incidence 1.
+    The wave travels in the vertical plane that makes the angle varphi with the yz plane, rising at the angle theta over the horizontal; in the
+    half-space z <= z_fs (np = 3, bc = 1: stress-free surface) the reflected waves are added: SH -> SH; P -> P + SV; SV -> SV + P, the P wave
+    evanescent beyond the critical angle (cos theta > kappa = c2 / c1 = sqrt((1 - 2 nu) / (2 (1 - nu))), nu real as the reference takes it).
+    symconf_y = +1 / -1: only the part symmetric / antisymmetric about the plane y = 0 (the only decomposition the reference offers in 3D).
+    The amplitude record of the section is not used for elastic waves in the reference either."""
+    k1, k2 = omega / mat.c1, omega / mat.c2
+    kap = np.sqrt((1.0 - 2.0 * mat.nu_r) / (2.0 * (1.0 - mat.nu_r)))
+    c0, s0 = np.cos(theta), np.sin(theta)
+    inc, rfl = np.array([0.0, c0, s0], dtype=np.complex128), np.array([0.0, c0, -s0], dtype=np.complex128)
+    if wave == "sh":
+        ex = np.array([1.0, 0, 0], dtype=np.complex128)
+        local = [(1.0, ex, k2, inc), (1.0, ex, k2, rfl)]
+    elif wave == "p":
+        c2 = kap * c0; s2 = np.sqrt(complex(1.0 - c2 * c2))
+        s20, s22, c22 = 2.0 * s0 * c0, 2.0 * s2 * c2, c2 * c2 - s2 * s2
+        den = kap * kap * s20 * s22 + c22 * c22
+        local = [(1.0, inc.copy(), k1, inc), ((kap * kap * s20 * s22 - c22 * c22) / den, rfl.copy(), k1, rfl),
+                 (2.0 * kap * s20 * c22 / den, np.array([0.0, -s2, -c2]), k2, np.array([0.0, c2, -s2]))]
+    elif wave == "sv":
+        c2 = c0 / kap
+        s2 = np.sqrt(complex(1.0 - c2 * c2)) if abs(c0) <= kap else -1j * np.sqrt(c2 * c2 - 1.0)
+        s20, s22, c20 = 2.0 * s0 * c0, 2.0 * s2 * c2, c0 * c0 - s0 * s0
+        den = kap * kap * s20 * s22 + c20 * c20
+        local = [(1.0, np.array([0.0, s0, -c0], dtype=np.complex128), k2, inc), ((kap * kap * s20 * s22 - c20 * c20) / den, np.array([0.0, -s0, -c0], dtype=np.complex128), k2, rfl),
+                 (-kap * 2.0 * s20 * c20 / den, np.array([0.0, c2, -s2]), k1, np.array([0.0, c2, -s2]))]
+    else:
+        raise ValueError("incident wave: elastic wave type %r (p, sv, sh; Rayleigh waves are not covered)" % (wave,))
+    if space == "full-space":
+        local = local[:1]
+    elif space != "half-space":
+        raise ValueError("incident wave: space %r of an elastic plane wave (the layered half-space is not covered)" % (space,))
+    R = np.array([[np.cos(varphi), np.sin(varphi), 0.0], [-np.sin(varphi), np.cos(varphi), 0.0], [0.0, 0.0, 1.0]])     # local (in-plane y, z) -> global axes
+    waves = [(0.5 * a, R @ pol, kk * (R @ pdir)) for a, pol, kk, pdir in local]
+    waves = _mirror_parts(waves, (0, symconf_y, 0), vector=True)
+    org = np.array([0.0, 0.0, z_fs])
+    lam, mu = mat.lam, mat.mu
+
+    def field(x, n):
+        d = np.asarray(x, dtype=np.float64) - org
+        u, grad = np.zeros(3, dtype=np.complex128), np.zeros((3, 3), dtype=np.complex128)
+        for a, pol, kv in waves:
+            e = a * np.exp(-1j * np.dot(kv, d))
+            u += pol * e; grad += np.outer(pol, -1j * kv) * e
+        sigma = lam * np.trace(grad) * np.eye(3) + mu * (grad + grad.T)
+        return u, sigma @ np.asarray(n, dtype=np.float64)
+    return field
+
+
+def element_incident_of(node_x, etype, elem_ptr, elem_node, elem_reversed, field, ndof):
+    """element_incident / element_incident_fluid on flat arrays (a single-region model or the view of one region of a coupled model):
+    -> (u_inc, t_inc), (sum nn, ndof) complex each."""
+    n_rows = int(elem_ptr[-1])
+    u = np.zeros((n_rows, ndof), dtype=np.complex128); t = np.zeros((n_rows, ndof), dtype=np.complex128)
+    for e in range(len(etype)):
+        et = int(etype[e]); c = np.asarray(elem_node[elem_ptr[e]:elem_ptr[e + 1]]); xn = node_x[c]
+        sgn = -1.0 if elem_reversed[e] else 1.0
+        for kn in range(len(c)):
+            n = sgn * sh.unit_normal(et, xn, sh.XI_NODES[et][kn])
+            u[elem_ptr[e] + kn], t[elem_ptr[e] + kn] = field(xn[kn], n)
+    return u, t

@@ -183,6 +183,9 @@ class OracleSolver:
         self.orc, self.case, self.model = orc, case, model
         self.o = orc.PotOracle(model) if case.region_type == 1 else orc.Oracle(model)
 
+    def set_incident(self, arrays):
+        self.o.set_incident(*arrays.get(0, (None, None)))
+
     def harmonic(self, omega):
         A, b, _ = self.o.assemble(omega, self.case.material)
         return np.linalg.solve(A, b)

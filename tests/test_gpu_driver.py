@@ -91,3 +91,21 @@ def test_case_with_symmetry_planes(tmp_path):
         path = _write_quarter(d, text, et=shape.TRI6 if k else shape.QUAD9, m=2)
         nso_cpu, _ = _run_with_oracle(path, output=path + ".cpu")
         _compare(driver.run(path, log=io.StringIO()), nso_cpu, harm)
+
+
+@pytest.mark.parametrize("material,kind,space", [("fluid rho 1.2 c 1.5", "fluid p", "full-space"), ("elastic_solid rho 2. mu 1.5 nu 0.3 xi 0.01", "elastic sh", "half-space 3 5. 1")])
+def test_case_with_incident_waves(tmp_path, material, kind, space):
+    """[incident waves] through the stand-alone driver on the device (tests/test_incident_waves.py's transparent inclusion: two coupled regions, the field
+    in the outer one): the per-frequency arrays reach the H problem of the region, the result file carries the total and the incident field."""
+    from test_incident_waves import _transmission_case, _CoupledOracleSolver
+    path = _transmission_case(tmp_path, material=material, kind=kind, space=space, varphi="30.", theta="60.")
+    case = CaseFile(path)
+    nso_cpu = driver.run(path, output=path + ".cpu", solver=_CoupledOracleSolver(case.build_model()), log=io.StringIO())
+    nso_gpu = driver.run(path, log=io.StringIO())
+    a, b = read_nso(nso_gpu), read_nso(nso_cpu)
+    assert a.shape == b.shape and np.array_equal(a[:, :12], b[:, :12])
+    nv = (a.shape[1] - 12) // 2
+    assert np.array_equal(a[:, 12 + nv:], b[:, 12 + nv:]) and a[:, 12 + nv:].any()           # the incident columns: host arithmetic on both sides
+    h = nv // 2
+    for sl in (slice(12, 12 + h), slice(12 + h, 12 + nv)):
+        assert np.abs(a[:, sl] - b[:, sl]).max() <= 1e-8 * np.abs(b[:, sl]).max()

@@ -1,0 +1,309 @@
+"""The [incident waves] section: the fields in the reference's conventions (multifebe_b200/host/incident.py, restated from
+lib/fbem/src/harpot_incident_field.f90 and harela_incident_field.f90) and their way through the case file and the driver.
+
+No Fortran compiler here, so the fields are pinned by what they must satisfy -- the wave equation, the condition on the half-space plane, the
+symmetric and antisymmetric parts adding up to the whole field, the normalisation the caller applies -- and the way through the driver by a
+transmission problem whose answer is the incident field itself."""
+import io
+import os
+import numpy as np
+import pytest
+
+from multifebe_b200 import driver
+from multifebe_b200.host import Material, Fluid, shape, cube_mesh, write_gmsh22
+from multifebe_b200.host.casefile import CaseFile, CaseFileError
+from multifebe_b200.host import incident as inc
+
+MAT = Material(2.0, 1.5, 0.3, 0.01)
+FL = Fluid(1.2, 1.5, 0.0)
+E3 = np.eye(3)
+
+
+def _second_derivatives(f, x, h=2e-3):
+    H = np.zeros((3, 3) + np.shape(f(x)), dtype=np.complex128)
+    for j in range(3):
+        for k in range(3):
+            H[j, k] = (f(x + h * E3[j] + h * E3[k]) - f(x + h * E3[j] - h * E3[k]) - f(x - h * E3[j] + h * E3[k]) + f(x - h * E3[j] - h * E3[k])) / (4 * h * h)
+    return H
+
+
+@pytest.mark.parametrize("wave", ["p", "sv", "sh"])
+@pytest.mark.parametrize("theta", [90.0, 70.0, 50.0, 25.0])       # 25 degrees: beyond the critical angle of the SV wave (cos theta > c2 / c1 = 0.53)
+def test_elastic_plane_wave_in_a_half_space(wave, theta):
+    omega, z_fs, nz = 3.0, 0.2, np.array([0.0, 0.0, 1.0])
+    th, ph = np.deg2rad(theta), np.deg2rad(35.0)
+    full = inc.elastic_plane_wave_reference(wave, MAT, omega, ph, th, "half-space", z_fs, 0)
+    sym = inc.elastic_plane_wave_reference(wave, MAT, omega, ph, th, "half-space", z_fs, 1)
+    asym = inc.elastic_plane_wave_reference(wave, MAT, omega, ph, th, "half-space", z_fs, -1)
+    x = np.array([0.3, -0.4, -0.7])
+    for f in (full, sym, asym):
+        u = lambda y: f(y, nz)[0]
+        H = _second_derivatives(u, x)                                 # H[j, k, i] = d2 u_i / dx_j dx_k
+        navier = (MAT.lam + MAT.mu) * np.einsum("jij->i", H) + MAT.mu * np.einsum("jji->i", H) + MAT.rho * omega ** 2 * u(x)
+        assert np.abs(navier).max() < 2e-4 * MAT.rho * omega ** 2 * max(np.abs(full(x, nz)[0]).max(), 1e-3)
+        for xs_ in ([0.1, 0.5, z_fs], [-1.0, 0.3, z_fs]):            # stress-free surface
+            assert np.abs(f(np.array(xs_), nz)[1]).max() < 1e-13
+        # the traction is sigma(u) n: finite differences of u against the closed form
+        n = np.array([0.48, -0.6, 0.64]); h = 1e-5
+        grad = np.array([(u(x + h * E3[j]) - u(x - h * E3[j])) / (2 * h) for j in range(3)]).T       # grad[i, j]
+        sig = MAT.lam * np.trace(grad) * np.eye(3) + MAT.mu * (grad + grad.T)
+        assert np.abs(sig @ n - f(x, n)[1]).max() < 1e-7
+    # the two parts add up to the field; mirrored in y = 0, the symmetric part keeps u_x, u_z and flips u_y
+    n = np.array([0.0, 1.0, 0.0]); xm = x * [1, -1, 1]
+    assert np.abs(sym(x, n)[0] + asym(x, n)[0] - full(x, n)[0]).max() < 1e-15 and np.abs(sym(x, n)[1] + asym(x, n)[1] - full(x, n)[1]).max() < 1e-14
+    assert np.abs(sym(xm, n)[0] - sym(x, n)[0] * [1, -1, 1]).max() < 1e-15 and np.abs(asym(xm, n)[0] + asym(x, n)[0] * [1, -1, 1]).max() < 1e-15
+
+
+def test_elastic_plane_wave_normalisation_and_full_space():
+    """Vertical incidence: the free-field motion of the surface has modulus 1 (incident + reflected, halved by the caller); in the full space the
+    field is the single wave of amplitude 1/2 travelling along (cos th sin ph, cos th cos ph, sin th) with the speed of its kind."""
+    omega, nz = 2.0, np.array([0.0, 0.0, 1.0])
+    for wave, comp in (("p", 2), ("sv", 1), ("sh", 0)):
+        f = inc.elastic_plane_wave_reference(wave, MAT, omega, 0.0, np.pi / 2, "half-space", 0.0, 0)
+        u = f(np.zeros(3), nz)[0]
+        assert abs(abs(u[comp]) - 1.0) < 1e-14 and np.abs(np.delete(u, comp)).max() < 1e-15
+    ph, th = 0.4, 0.9
+    d = np.array([np.cos(th) * np.sin(ph), np.cos(th) * np.cos(ph), np.sin(th)])
+    for wave, c in (("p", MAT.c1), ("sv", MAT.c2), ("sh", MAT.c2)):
+        f = inc.elastic_plane_wave_reference(wave, MAT, omega, ph, th, "full-space")
+        u0, u1 = f(np.zeros(3), nz)[0], f(0.37 * d, nz)[0]
+        assert abs(np.linalg.norm(u0) - 0.5) < 1e-15
+        assert np.abs(u1 - u0 * np.exp(-1j * omega / c * 0.37)).max() < 1e-15
+        pol = u0 / np.linalg.norm(u0)
+        assert abs(abs(np.dot(pol, d)) - (1.0 if wave == "p" else 0.0)) < 1e-14           # longitudinal / transverse
+        if wave == "sh":
+            assert abs(pol[2]) < 1e-15                                                    # horizontal polarisation
+    # the same helper as the module's own full-space P wave, up to the factor 1/2
+    g = inc.plane_wave("P", d, MAT, omega)
+    x, n = np.array([0.2, -0.1, 0.5]), np.array([0.6, 0.0, 0.8])
+    f = inc.elastic_plane_wave_reference("p", MAT, omega, ph, th, "full-space")
+    assert np.abs(2 * f(x, n)[0] - g(x, n)[0]).max() < 1e-14 and np.abs(2 * f(x, n)[1] - g(x, n)[1]).max() < 1e-13
+
+
+@pytest.mark.parametrize("bc", [0, 1])
+@pytest.mark.parametrize("np_axis", [1, 3])
+def test_fluid_plane_wave(bc, np_axis):
+    omega, xp = 4.0, 0.3
+    x0, xs = np.array([0.2, -0.1, 0.4]), np.array([0.05, 0.1, -0.2])
+    ph, th = np.deg2rad(20.0), np.deg2rad(55.0)
+    sc = [0, 0, 0]
+    kw = dict(amplitude=0.7 - 0.2j, x0=x0, varphi=ph, theta=th, space="half-space", np_axis=np_axis, xp=xp, bc=bc, xs=xs)
+    full = inc.fluid_plane_wave_reference(FL, omega, symconf=sc, **kw)
+    k = omega / FL.c
+    x = np.array([0.3, 0.25, -0.6])
+    n = np.array([0.48, -0.6, 0.64])
+    p = lambda y: full(y, n)[0]
+    H = _second_derivatives(p, x)
+    assert abs(np.trace(H) + k * k * p(x)) < 2e-5 * abs(k * k)                           # Helmholtz
+    h = 1e-5
+    grad = np.array([(p(x + h * E3[j]) - p(x - h * E3[j])) / (2 * h) for j in range(3)])
+    assert abs(np.dot(grad, n) / (FL.rho * omega ** 2) - full(x, n)[1]) < 1e-9          # Un = (dp/dn) / (rho omega^2)
+    # p = 0 (bc 0) or Un = 0 (bc 1) on the plane -- with the origin of the wave on the plane.  Finding: with x0(np) != xp the reference's reflected
+    # amplitude carries the phase of the already reflected direction and the condition is missed by exp(4 i k q_np (xp - x0(np))); kept as is.
+    on_plane = np.array([0.7, -0.3, 0.9]); on_plane[np_axis - 1] = xp
+    x0p = x0.copy(); x0p[np_axis - 1] = xp
+    val = inc.fluid_plane_wave_reference(FL, omega, symconf=sc, **dict(kw, x0=x0p))(on_plane, E3[np_axis - 1])
+    assert abs(val[bc]) < 1e-14 and abs(val[1 - bc]) > 1e-3
+    q_np = [np.cos(th) * np.sin(ph), np.cos(th) * np.cos(ph), np.sin(th)][np_axis - 1]
+    off = full(on_plane, E3[np_axis - 1])[bc]
+    assert abs(off) > 1e-3 and abs(np.exp(4j * k * q_np * (xp - x0[np_axis - 1])) - 1.0) > 1e-3
+    # decomposition about the plane through xs normal to a free axis
+    ax = 1 if np_axis != 2 else 0
+    s1 = list(sc); s1[ax] = 1
+    s2 = list(sc); s2[ax] = -1
+    fs, fa = inc.fluid_plane_wave_reference(FL, omega, symconf=s1, **kw), inc.fluid_plane_wave_reference(FL, omega, symconf=s2, **kw)
+    assert abs(fs(x, n)[0] + fa(x, n)[0] - full(x, n)[0]) < 1e-15 and abs(fs(x, n)[1] + fa(x, n)[1] - full(x, n)[1]) < 1e-15
+    xm = x.copy(); xm[ax] = 2 * xs[ax] - x[ax]
+    assert abs(fs(xm, n)[0] - fs(x, n)[0]) < 1e-15 and abs(fa(xm, n)[0] + fa(x, n)[0]) < 1e-15
+    # full space: the plain wave through x0
+    f0 = inc.fluid_plane_wave_reference(FL, omega, amplitude=0.7 - 0.2j, x0=x0, varphi=ph, theta=th)
+    q = np.array([np.cos(th) * np.sin(ph), np.cos(th) * np.cos(ph), np.sin(th)])
+    assert abs(f0(x, n)[0] - (0.7 - 0.2j) * np.exp(-1j * k * np.dot(q, x - x0))) < 1e-15
+    with pytest.raises(ValueError):
+        bad = [0, 0, 0]; bad[np_axis - 1] = 1
+        inc.fluid_plane_wave_reference(FL, omega, symconf=bad, **kw)
+
+
+def test_fluid_point_wave():
+    omega, x0 = 3.0, np.array([0.1, 0.2, -0.3])
+    f = inc.fluid_point_wave_reference(FL, omega, 2.0 + 1.0j, x0)
+    k = omega / FL.c
+    n = np.array([0.0, 0.6, 0.8])
+    assert abs(f(x0 + np.array([0, 0, 1.0]), n)[0] - (2.0 + 1.0j)) < 1e-15              # the amplitude is the pressure at unit distance
+    x = np.array([0.9, -0.4, 0.5])
+    p = lambda y: f(y, n)[0]
+    assert abs(np.trace(_second_derivatives(p, x)) + k * k * p(x)) < 2e-5 * abs(k * k * p(x))
+    h = 1e-5
+    grad = np.array([(p(x + h * E3[j]) - p(x - h * E3[j])) / (2 * h) for j in range(3)])
+    assert abs(np.dot(grad, n) / (FL.rho * omega ** 2) - f(x, n)[1]) < 1e-9
+
+
+# ---- through the case file and the driver ------------------------------------------------------------------------------------------
+TRANSMISSION_DAT = """[problem]
+n = 3D
+type = mechanics
+analysis = harmonic
+
+[frequencies]
+rad/s
+list
+2
+1.0
+2.0
+
+[settings]
+mesh_file_mode = 2 "cube.msh"
+
+[materials]
+1
+1 %(material)s
+
+[boundaries]
+6
+1 1 ordinary
+2 2 ordinary
+3 3 ordinary
+4 4 ordinary
+5 5 ordinary
+6 6 ordinary
+
+[regions]
+2
+
+1 be
+6 1 2 3 4 5 6
+material 1
+0
+0
+
+2 be
+6 -1 -2 -3 -4 -5 -6
+material 1
+0
+1 4
+
+[incident waves]
+1
+4
+plane
+%(space)s
+0 (1.,0.) 0. 0. 0. %(varphi)s %(theta)s
+0. 0. 0. 0. 0. 0.
+%(kind)s
+"""
+
+
+def _transmission_case(tmp_path, **kw):
+    write_gmsh22(cube_mesh(2, shape.QUAD9), str(tmp_path / "cube.msh"))
+    path = str(tmp_path / "case.dat")
+    open(path, "w").write(TRANSMISSION_DAT % kw)
+    return path
+
+
+class _CoupledOracleSolver:
+    def __init__(self, md):
+        from oracle.multiregion import MultiRegionOracle
+        self.md, self.o = md, MultiRegionOracle(md)
+        self.x = []
+
+    def set_incident(self, arrays):
+        for kr in range(len(self.md.regions)):
+            self.md.set_incident(kr, *arrays.get(kr, (None, None)))
+
+    def harmonic(self, omega):
+        A, b = self.o.assemble(omega)
+        self.x.append(np.linalg.solve(A, b))
+        return self.x[-1]
+
+    def close(self):
+        pass
+
+
+@pytest.mark.parametrize("material,kind,space", [("fluid rho 1.2 c 1.5", "fluid p", "full-space"), ("elastic_solid rho 2. mu 1.5 nu 0.3 xi 0.01", "elastic sv", "full-space"),
+                                                 ("elastic_solid rho 2. mu 1.5 nu 0.3 xi 0.01", "elastic p", "half-space 3 5. 1")])
+def test_transparent_inclusion_sees_the_incident_field(tmp_path, material, kind, space):
+    """A cube of the SAME material as the unbounded medium around it, the incident wave defined in the outer region only: nothing scatters, so the
+    total field on the interface -- the unknowns of the coupled system -- is the incident field, up to the discretisation (a per cent at these
+    wavelengths).  Exercises the section reader, the per-frequency arrays, the reversed normals of the outer region and the coupled right-hand side."""
+    path = _transmission_case(tmp_path, material=material, kind=kind, space=space, varphi="30.", theta="60.")
+    case = CaseFile(path)
+    md = case.build_model()
+    assert case.region_incident == [[], [4]] and case.incident_fields[4]["wave"] == kind.split()[1] and abs(case.incident_fields[4]["theta"] - np.pi / 3) < 1e-15
+    solver = _CoupledOracleSolver(md)
+    nso = driver.run(path, solver=solver, log=io.StringIO())
+    assert os.path.exists(nso) and len(solver.x) == 2
+    mat = case.regions[0][2]
+    for omega, x in zip(case.omega, solver.x):
+        prim, sec = md.nodal_solution(x, 0)
+        if kind.startswith("fluid"):
+            fld = inc.fluid_plane_wave_reference(mat, omega, 1.0, (0, 0, 0), np.pi / 6, np.pi / 3)
+            ref = np.array([fld(xn, E3[0])[0] for xn in md.node_x])
+        else:
+            sp = space.split()
+            fld = inc.elastic_plane_wave_reference(kind.split()[1], mat, omega, np.pi / 6, np.pi / 3, sp[0], float(sp[2]) if len(sp) > 1 else 0.0)
+            ref = np.array([fld(xn, E3[0])[0] for xn in md.node_x])
+        assert np.abs(prim - ref).max() < 0.02 * np.abs(ref).max(), np.abs(prim - ref).max() / np.abs(ref).max()
+    # the result file: the total field, then node()%incident_c -- zero in the inclusion, the field itself (mean over the node's elements) in the outer region
+    from multifebe_b200.host.export import read_nso
+    rows = read_nso(nso)
+    nv = (rows.shape[1] - 12) // 2
+    inner, outer = rows[rows[:, 2] == case.regions[0][0]], rows[rows[:, 2] == case.regions[1][0]]
+    assert len(inner) == len(outer) == 2 * md.n_node and not inner[:, 12 + nv:].any()
+    tot, ic = outer[:, 12:12 + nv], outer[:, 12 + nv:]
+    npr = nv // 2                                                          # value columns of the primary variables (Re, Im pairs)
+    assert np.abs(tot[:, :npr] - ic[:, :npr]).max() < 0.02 * np.abs(ic[:, :npr]).max() and np.abs(ic[:, :npr]).max() > 0.3
+    assert (outer[:, 7] == 2).all() and (inner[:, 7] == 1).all()            # the outer region sees every boundary from its second face
+
+
+def test_incident_section_errors_are_named(tmp_path):
+    ok = dict(material="fluid rho 1.2 c 1.5", kind="fluid p", space="full-space", varphi="0.", theta="0.")
+    base = TRANSMISSION_DAT % ok
+    for old, new, word in [("\nplane\n", "\nline\n", "class"), ("fluid p\n", "fluid sv\n", 'only "p"'), ("fluid p\n", "poroelastic p1\n", "poroelastic"),
+                           ("0\n1 4\n", "0\n1 5\n", "does not exist"), ("fluid p\n", "elastic p\n", "different type"),
+                           ("full-space\n0 (1.", "multilayered_half-space 3 1 0. 1 1 0.\n0 (1.", "not covered"), ("0 (1.,0.) 0. 0.", "1 (1.,0.) 0. 0.", "not implemented")]:
+        assert old in base, old
+        write_gmsh22(cube_mesh(1, shape.QUAD4), str(tmp_path / "cube.msh"))
+        path = str(tmp_path / "bad.dat")
+        open(path, "w").write(base.replace(old, new, 1))
+        with pytest.raises(CaseFileError) as ei:
+            CaseFile(path)
+        assert word in str(ei.value), (word, str(ei.value))
+    solid = TRANSMISSION_DAT % dict(material="elastic_solid rho 2. mu 1.5 nu 0.3 xi 0.", kind="elastic sh", space="half-space 3 0. 1", varphi="0.", theta="90.")
+    for old, new, word in [("half-space 3 0. 1", "half-space 2 0. 1", "np can be only 3"), ("0. 0. 0. 0. 0. 0.\n", "0. 0. 0. 1. 0. 0.\n", "x and z"),
+                           ("(1.,0.) 0. 0. 0.", "(1.,0.) 0. 1. 0.", "x0 and xs"), ("elastic sh", "elastic rayleigh", "not covered")]:
+        assert old in solid, old
+        path = str(tmp_path / "bad.dat")
+        open(path, "w").write(solid.replace(old, new, 1))
+        with pytest.raises(CaseFileError) as ei:
+            CaseFile(path)
+        assert word in str(ei.value), (word, str(ei.value))
+
+
+def test_single_region_case_with_an_incident_wave(tmp_path):
+    """One fluid region, pressure-release walls, a plane wave from the section: the driver hands the arrays of every frequency to the solver; the result
+    equals the direct use of the API with the same field, and the file carries node()%incident_c."""
+    from test_casefile_driver import FLUID_DAT, _write_case, OracleSolver
+    from multifebe_b200.host.export import read_nso
+    from oracle import oracle as orc
+    text = FLUID_DAT.replace("0\n0\n\n[conditions", "0\n1 2\n\n[incident waves]\n1\n2\npoint\nfull-space\n0 (0.5,0.25) 3. 0.5 0.5 0. 0.\n0. 0. 0. 0. 0. 0.\nfluid p\n\n[conditions")
+    text = text.replace("boundary 2: 0 (1.,0.)", "boundary 2: 0 (0.,0.)")
+    assert "[incident waves]" in text
+    path = _write_case(tmp_path, text, et=shape.QUAD8, m=2)
+    case = CaseFile(path)
+    md = case.build_model()
+    assert case.region_incident == [[2]] and case.incident_fields[2]["cls"] == "point" and case.incident_fields[2]["amplitude"] == 0.5 + 0.25j
+    nso = driver.run(path, solver=OracleSolver(case, md), log=io.StringIO())
+    rows = read_nso(nso)
+    o = orc.PotOracle(md)
+    for kf, omega in enumerate(case.omega):
+        fld = inc.fluid_point_wave_reference(case.material, omega, 0.5 + 0.25j, (3.0, 0.5, 0.5))
+        p_inc, un_inc = inc.element_incident_fluid(md, fld)
+        o.set_incident(p_inc, un_inc)
+        A, b, _ = o.assemble(omega, case.material)
+        p, un = md.nodal_solution(np.linalg.solve(A, b))
+        r = rows[rows[:, 0] == kf + 1]
+        nodes = [md.mesh.node_ids.tolist().index(int(i)) for i in r[:, 8]]
+        assert np.abs(r[:, 12] + 1j * r[:, 13] - p[nodes]).max() < 1e-12 * max(np.abs(p).max(), 1e-30) + 1e-14
+        assert np.abs(r[:, 14] + 1j * r[:, 15] - un[nodes]).max() < 1e-9 * np.abs(un).max()
+        pi = np.array([fld(md.node_x[v], E3[0])[0] for v in nodes])
+        assert np.abs(r[:, 16] + 1j * r[:, 17] - pi).max() < 1e-9 * np.abs(pi).max()                 # the incident pressure at the nodes
