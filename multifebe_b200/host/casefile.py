@@ -3,7 +3,8 @@
 Mirrors src/read_input_file.f90 for the sections the hot path consumes:
   [problem]      src/read_problem.f90        n = 3D, type = mechanics, analysis = harmonic | static
   [frequencies]  src/read_frequencies.f90:20-120  Hz | rad/s; list | lin | log(10)
-  [settings]     src/read_settings.f90:74-216     mesh_file_mode = 2 "<gmsh 2.2 file>", qsi_relative_error, qsi_ns_max, precalsets,
+  [settings]     src/read_settings.f90:74-216     mesh_file_mode = 2 "<gmsh 2.2 file>" | 1 "<native file>" | 0 / absent ([nodes], [elements], [parts] of the
+                                             case file), qsi_relative_error, qsi_ns_max, precalsets,
                                                   geometric_tolerance
   [materials]    src/read_materials.f90      fluid (two of K, rho, c; xi) / elastic_solid (two of E, nu, lambda, mu, K; rho, xi) /
                                              biot_poroelastic_medium (phi, two elastic constants, Q, R, rho_f, rho_s, rho_a, xi, b)
@@ -15,9 +16,10 @@ Mirrors src/read_input_file.f90 for the sections the hot path consumes:
   [internal points]  src/read_internal_points.f90    `<id> <region> x1 x2 x3` (one elastic region)
   [symmetry planes]  src/read_symmetry_planes.f90    `plane_n1|plane_yz : symmetry|antisymmetry` (also plane_n2|plane_zx, plane_n3|plane_xy) or the
                                              explicit form `x = <s> <t1> <t2> <t3>` (y, z alike); one elastic region
+  [bem formulation over boundaries]  src/read_bem_formulation_boundaries.f90   `boundary <id>: sbie | sbie_boundary_mca <delta> | sbie_mca <delta>`
   [incident waves]   src/read_incident_mechanics_harmonic.f90   plane / point waves in fluids, plane P / SV / SH waves in elastic solids, full space or
                                              homogeneous half-space; listed per region by the last record of [regions] (`<n> <id> ...`)
-  [export]       src/read_export.f90:61-240  export_nso, real_format, integer_format, complex_notation
+  [export]       src/read_export.f90:61-293  export_nso, real_format, integer_format, complex_notation, nso_nodes
 Anything else the reference accepts (be-fe coupling, crack-like boundaries, close-pore conditions, local-axes or spring conditions,
 half-space fundamental solutions, body loads, layered / Rayleigh / poroelastic incident fields, internal points of fluid regions, FE regions ...) raises
 CaseFileError naming the feature:
@@ -27,7 +29,7 @@ import os
 import re
 import numpy as np
 
-from .mesh import read_gmsh22
+from .mesh import read_gmsh22, read_native_mesh, without_parts
 from .model import Model, FluidModel, PoroModel, Material, Fluid, Poro
 from .fortran_format import DEFAULT_REAL_FORMAT, REAL_FORMATS
 
@@ -154,8 +156,10 @@ class CaseFile:
         self.filename = os.path.basename(path)
         sec = _sections(open(path, encoding="utf-8", errors="replace").read())
         self._sec = sec
-        for unsupported in ("fe subregions", "be body loads", "be bodyloads", "internal elements",
-                            "groups", "cross sections", "sensitivity"):
+        for unsupported in ("fe subregions", "be body loads", "be bodyloads", "internal elements", "groups", "cross sections", "sensitivity",
+                            "conditions over nodes", "conditions over be bodyloads", "conditions over fe elements", "discontinuous be boundaries",
+                            "discontinuous be elements", "element options", "fem node options", "special be elements", "commands", "export sif",
+                            "internal points from mesh", "geometry"):
             if sec.get(unsupported):
                 raise CaseFileError("section [%s] is outside the path this library covers" % unsupported)
         # ---- [problem]
@@ -172,11 +176,20 @@ class CaseFile:
         self.description = _keyword(pb, "description") or ""
         # ---- [settings]
         st = sec.get("settings", [])
+        # mesh_file_mode (src/read_settings.f90:219-246): absent or 0 = the [nodes] / [elements] / [parts] sections of the case file itself, 1 = the same
+        # sections in an auxiliary file (native format), 2 = a Gmsh 2.2 file
         v = _keyword(st, "mesh_file_mode")
-        m = re.match(r'(\d+)\s+"?([^"]+)"?', v or "")
-        if not m or int(m.group(1)) != 2:
-            raise CaseFileError('[settings] mesh_file_mode = 2 "<gmsh 2.2 mesh>" is required (other mesh modes are not covered)')
-        self.mesh_file = os.path.join(self.dir, m.group(2).strip())
+        self.mesh_file_mode, self.mesh_file = 0, None
+        if v:
+            m = re.match(r'(\d+)\s*(?:"([^"]*)"|(\S+))?', v)
+            if not m or int(m.group(1)) not in (0, 1, 2):
+                raise CaseFileError('[settings] mesh_file_mode = <0, 1, 2> "<mesh file>": wrong type of mesh mode')
+            self.mesh_file_mode = int(m.group(1))
+            if self.mesh_file_mode:
+                name = (m.group(2) or m.group(3) or "").strip()
+                if not name:
+                    raise CaseFileError('[settings] mesh_file_mode = %d needs the name of the mesh file' % self.mesh_file_mode)
+                self.mesh_file = os.path.join(self.dir, name)
         self.qsi_relative_error = _fortran_float(_keyword(st, "qsi_relative_error") or "1e-6")
         self.qsi_ns_max = int(_keyword(st, "qsi_ns_max") or 16)
         pc = _keyword(st, "precalsets")
@@ -214,6 +227,23 @@ class CaseFile:
             if len(w) < 3 or w[2].lower() != "ordinary":
                 raise CaseFileError("boundary %s: only `ordinary` boundaries are covered (crack-like boundaries stay with the Fortran host)" % w[0])
             self.boundaries.append((int(w[0]), int(w[1])))
+        # ---- [bem formulation over boundaries]: `boundary <id>: sbie | sbie_boundary_mca <delta> | sbie_mca <delta>` (read_bem_formulation_selected_nodes.f90:74-160)
+        self.formulation = {}
+        for s_ in sec.get("bem formulation over boundaries", []):
+            m = re.match(r"(boundary|part)\s+(\d+)\s*:\s*(\S+)\s*(\S+)?", s_, re.I)
+            if not m:
+                raise CaseFileError("[bem formulation over boundaries]: cannot parse %r" % s_)
+            if m.group(1).lower() != "boundary":
+                raise CaseFileError("[bem formulation over boundaries]: only `boundary <id>: ...` records are covered")
+            bid, kind = int(m.group(2)), m.group(3).lower()
+            if bid not in dict(self.boundaries):
+                continue                                 # the reference looks the listed boundaries up and ignores anything else
+            if kind not in ("sbie", "sbie_boundary_mca", "sbie_mca"):
+                raise CaseFileError("boundary %d: BEM formulation %r is not covered (sbie, sbie_boundary_mca, sbie_mca; the hypersingular and dual formulations "
+                                    "stay with the Fortran host)" % (bid, kind))
+            if kind != "sbie" and not m.group(4):
+                raise CaseFileError("boundary %d: %s needs its delta (<= 0: the default)" % (bid, kind))
+            self.formulation[bid] = (kind, _fortran_float(m.group(4)) if kind != "sbie" else 0.0)
         # ---- [regions]
         rl = sec.get("regions")
         if not rl:
@@ -341,6 +371,17 @@ class CaseFile:
         if cn not in ("polar", "cartesian"):
             raise CaseFileError("[export] complex_notation: polar or cartesian")
         self.complex_notation = cn
+        # nso_nodes = <n> <id 1> ... <id n>: rows only for these nodes; n <= 0 or absent: every node (src/read_export.f90:254-293)
+        self.nso_nodes = None
+        v = _keyword(ex, "nso_nodes")
+        if v:
+            w = [int(t) for t in v.split()]
+            if w[0] > 0:
+                if len(w) < 1 + w[0]:
+                    raise CaseFileError("[export] nso_nodes: %d nodes announced, %d given" % (w[0], len(w) - 1))
+                if len(set(w[1:1 + w[0]])) != w[0]:
+                    raise CaseFileError("[export] nso_nodes: there are repeated nodes for export")
+                self.nso_nodes = set(w[1:1 + w[0]])
         # ---- [symmetry planes] (src/read_symmetry_planes.f90:76-228): the explicit multipliers first, then the named kinds, x before y before z
         self.symmetry = []
         sp = sec.get("symmetry planes") or []
@@ -372,12 +413,24 @@ class CaseFile:
                 if given:
                     self.symmetry.append((ax, given[0]))
         # ---- mesh: parts are the physical groups of the Gmsh file; a boundary is one part
-        self.mesh = read_gmsh22(self.mesh_file)
+        if self.mesh_file_mode == 2:
+            self.mesh = read_gmsh22(self.mesh_file)
+        else:
+            msec = sec if self.mesh_file_mode == 0 else _sections(open(self.mesh_file, encoding="utf-8", errors="replace").read())
+            if not msec.get("nodes") or not msec.get("elements"):
+                raise CaseFileError("the mesh: sections [nodes] and [elements] are required (%s)" % ("case file" if self.mesh_file_mode == 0 else self.mesh_file))
+            try:
+                self.mesh = read_native_mesh(msec["nodes"], msec["elements"])
+            except (ValueError, KeyError, IndexError) as e:
+                raise CaseFileError("the mesh: %s" % e)
+        # elements of parts that no boundary uses are left out, as the reference does (src/read_elements.f90:211-215: part()%entity = 0)
         part_of_boundary = dict(self.boundaries)
-        used_parts = [part_of_boundary[abs(b)] for r in self.regions for b in r[3]]
-        keep = [e for e in range(self.mesh.n_elem) if int(self.mesh.part[e]) in used_parts]
-        if len(keep) != self.mesh.n_elem:
-            raise CaseFileError("the mesh holds surface elements of parts that no boundary of the regions uses")
+        used_parts = set(part_of_boundary[abs(b)] for r in self.regions for b in r[3])
+        unused = set(int(p_) for p_ in self.mesh.part) - used_parts
+        if unused:
+            self.mesh = without_parts(self.mesh, unused)
+        if self.mesh.n_elem == 0:
+            raise CaseFileError("the mesh holds no surface element of the parts of the boundaries")
 
     def _incident_waves(self, lines):
         """[incident waves] (src/read_incident_mechanics_harmonic.f90:22-42): per field `<id>`, `<class>`, `<space> [np xp bc]`,
@@ -529,6 +582,14 @@ class CaseFile:
     def build_model(self):
         """The flat model (multifebe_b200.host.Model / FluidModel, or MultiRegionModel for coupled regions) with the reference's numbering:
         boundaries in the order of the regions' lists (build_auxiliary_variables_mechanics_harmonic.f90:151-198)."""
+        try:
+            return self._build_model()
+        except ValueError as e:
+            if isinstance(e, CaseFileError):
+                raise
+            raise CaseFileError(str(e))
+
+    def _build_model(self):
         part_of_boundary = dict(self.boundaries)
         kw = dict(qsi_relative_error=self.qsi_relative_error, qsi_ns_max=self.qsi_ns_max, precalset_gln=self.precalset_gln,
                   geometric_tolerance=self.geometric_tolerance)
@@ -537,8 +598,9 @@ class CaseFile:
             from .multiregion import PORO
             regs = [Region({1: FLUID, 2: SOLID, 3: PORO}[rtype], mat, rb) for _, rtype, mat, rb in self.regions]
             bcs = {b: ((ct[0], cv[0]) if len(ct) == 1 else (ct, cv)) for b, (ct, cv) in self.bcs.items()}
-            return MultiRegionModel(self.mesh, regs, part_of_boundary, bcs, symmetry=self.symmetry, **kw)
+            return MultiRegionModel(self.mesh, regs, part_of_boundary, bcs, symmetry=self.symmetry, formulation=self.formulation, **kw)
         kw["part_order"] = [part_of_boundary[b] for b in self.region_boundaries]
+        kw["formulation"] = {part_of_boundary[b]: f for b, f in self.formulation.items()}
         kw["symmetry"] = self.symmetry
         kw["collapse_nodal_pos"] = self.collapse_nodal_pos
         if self.region_type == 1:

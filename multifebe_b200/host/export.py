@@ -31,6 +31,7 @@ class NsoWriter:
         # rows: (region index, region id, region type, boundary id, face, node index) in the reference's order; face = 2 when the region is
         # region 2 of a be-be boundary (export_solution_mechanics_harmonic_nso.f90:326-333)
         part_of_boundary = dict(case.boundaries)
+        only = getattr(case, "nso_nodes", None)
         self.rows = []
         for kr, (rid, rtype, _, rb) in enumerate(case.regions):
             for sb in rb:
@@ -42,7 +43,9 @@ class NsoWriter:
                         continue
                     for v in model.mesh.conn[e]:
                         if int(v) not in seen:
-                            seen.add(int(v)); self.rows.append((kr, rid, rtype, b, face, int(v)))
+                            seen.add(int(v))
+                            if only is None or int(model.mesh.node_ids[v]) in only:       # [export] nso_nodes: node()%export
+                                self.rows.append((kr, rid, rtype, b, face, int(v)))
 
     def _i(self, n):
         return fmt_int(n, self.wi)

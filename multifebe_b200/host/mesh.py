@@ -61,6 +61,44 @@ def read_gmsh22(path):
     return Mesh(np.array(xyz)[used], et, part, conn, node_ids=np.array(nid)[used], elem_ids=eid)
 
 
+NATIVE_TYPE = {"tri3": TRI3, "tri6": TRI6, "quad4": QUAD4, "quad8": QUAD8, "quad9": QUAD9}
+
+
+def read_native_mesh(nodes, elements):
+    """The reference's own mesh sections (mesh_file_mode 0: inside the case file; 1: in an auxiliary file): `[nodes]` = count, then `<id> <x1> <x2> <x3>`
+    (src/read_nodes.f90:148-160); `[elements]` = count, then `<id> <type> <number of tags> <tag 1 = part> ... <node 1> ... <node N>` with the type by
+    name or by its Gmsh code and the node order of Gmsh (src/read_elements.f90:30-36, :236-248).  Arguments: the non-empty lines of the two sections.
+    Surface elements only; unused nodes are dropped, identifiers kept, as read_gmsh22 does."""
+    ids, xyz, nid = {}, [], []
+    n = int(nodes[0].split()[0])
+    if len(nodes) < n + 1:
+        raise ValueError("[nodes]: %d nodes announced, %d records found" % (n, len(nodes) - 1))
+    for k in range(n):
+        t = nodes[1 + k].replace(",", " ").split()
+        ids[int(t[0])] = k; nid.append(int(t[0]))
+        xyz.append([float(v.lower().replace("d", "e")) for v in t[1:4]])
+    et, part, conn, eid = [], [], [], []
+    n = int(elements[0].split()[0])
+    if len(elements) < n + 1:
+        raise ValueError("[elements]: %d elements announced, %d records found" % (n, len(elements) - 1))
+    for k in range(n):
+        t = elements[1 + k].split()
+        ty = NATIVE_TYPE.get(t[1].lower())
+        if ty is None and t[1].isdigit():
+            ty = GMSH_TYPE.get(int(t[1]))
+        if ty is None:
+            raise ValueError("element %s: type %r is not a surface boundary element (tri3, tri6, quad4, quad8, quad9)" % (t[0], t[1]))
+        ntags = int(t[2])
+        et.append(ty); part.append(int(t[3])); eid.append(int(t[0]))
+        conn.append([ids[int(v)] for v in t[3 + ntags:3 + ntags + N_NODES[ty]]])
+    used = np.zeros(len(xyz), dtype=bool)
+    for c in conn:
+        used[c] = True
+    remap = np.cumsum(used) - 1
+    conn = [[int(remap[v]) for v in c] for c in conn]
+    return Mesh(np.array(xyz)[used], et, part, conn, node_ids=np.array(nid)[used], elem_ids=eid)
+
+
 def write_gmsh22(mesh, path, names=None):
     with open(path, "w") as f:
         f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n")
@@ -182,7 +220,8 @@ def without_parts(mesh, parts):
     keep = [e for e in range(mesh.n_elem) if int(mesh.part[e]) not in parts]
     used = sorted(set(int(v) for e in keep for v in mesh.conn[e]))
     new = {v: i for i, v in enumerate(used)}
-    return Mesh(mesh.nodes[used], [mesh.etype[e] for e in keep], [mesh.part[e] for e in keep], [[new[int(v)] for v in mesh.conn[e]] for e in keep])
+    return Mesh(mesh.nodes[used], [mesh.etype[e] for e in keep], [mesh.part[e] for e in keep], [[new[int(v)] for v in mesh.conn[e]] for e in keep],
+                node_ids=np.asarray(mesh.node_ids)[used], elem_ids=[mesh.elem_ids[e] for e in keep])
 
 
 def mirror_mesh(mesh, axis, part_offset=100, tol=1e-9):

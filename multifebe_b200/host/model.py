@@ -25,6 +25,37 @@ class Material:
         self.c2 = np.sqrt(self.mu / self.rho)
 
 
+MCA_ORDER_DELTA = {1: 0.42264973, 2: 0.22540333}        # default_mca_linear_delta / _quadratic_delta (read_bem_formulation_selected_nodes.f90:42-43)
+
+
+def mca_deltas(in_boundary, node_group, formulation):
+    """Per node: the MCA displacement of its collocation points, 0 = nodal collocation, < 0 = the default of the element's order.
+    Default formulation (assign_default_bem_formulation.f90:74-93): the nodes of the rim of a boundary are SBIE-MCA with delta 0.05.
+    formulation {boundary (part) id: (kind, delta)} = the records of [bem formulation over boundaries] (read_bem_formulation_selected_nodes.f90:74-160):
+    `sbie` every node nodal; `sbie_boundary_mca <delta>` rim nodes MCA (delta <= 0: 0.05); `sbie_mca <delta>` every node MCA (delta <= 0: by element order).
+    node_group[v] = the boundary (part) id of node v."""
+    d = np.where(in_boundary, MCA_BOUNDARY_DELTA, 0.0)
+    for g, (kind, delta) in (formulation or {}).items():
+        sel = np.asarray(node_group) == g
+        if kind == "sbie":
+            if np.any(in_boundary & sel):
+                # nodal collocation on the rim of an open boundary: the free term and the singular integrals then run over the elements of the coincident
+                # ("common") nodes of the neighbouring boundaries (build_lse_mechanics_bem_harela.f90:452-492), which this library does not collect
+                raise ValueError("boundary %s: `sbie` (nodal collocation everywhere) on a boundary with an open rim is not covered; use sbie_boundary_mca" % (g,))
+            d[sel] = 0.0
+        elif kind == "sbie_boundary_mca":
+            d[sel] = np.where(in_boundary[sel], delta if delta > 0 else MCA_BOUNDARY_DELTA, 0.0)
+        elif kind == "sbie_mca":
+            d[sel] = delta if delta > 0 else -1.0
+        else:
+            raise ValueError("BEM formulation %r is not covered (sbie, sbie_boundary_mca, sbie_mca)" % (kind,))
+    return d
+
+
+def mca_delta_of(etype, d):
+    return d if d > 0 else MCA_ORDER_DELTA[1 if etype in (sh.TRI3, sh.QUAD4) else 2]
+
+
 def symmetry_planes(symmetry):
     """[(axis, kind), ...] -> (symplane_eid int32[n], symplane_t float64[n,3]) in the reference's internal order (x, y, z):
     symmetry: t = -1 on the normal axis, +1 on the others; antisymmetry: the opposite signs (read_symmetry_planes.f90:160-228)."""
@@ -63,7 +94,7 @@ class Model:
 
     def __init__(self, mesh, bcs, reversed_parts=(), qsi_relative_error=1e-6, qsi_ns_max=16,
                  precalset_gln=(2, 3, 4, 5, 6, 7, 8, 9), geometric_tolerance=1e-6, ndof=3, part_order=None,
-                 symmetry=None, nodal_on_symplanes=False, local_axes_reference=None, collapse_nodal_pos=True):
+                 symmetry=None, nodal_on_symplanes=False, local_axes_reference=None, collapse_nodal_pos=True, formulation=None):
         """symmetry: the [symmetry planes] section (src/read_symmetry_planes.f90:76-283) as a list of (axis, kind), axis 'x' | 'y' | 'z'
         (plane_n1 / plane_n2 / plane_n3: the plane through the origin normal to that axis), kind 'symmetry' | 'antisymmetry'.
         nodal_on_symplanes: open edges that lie in a symmetry plane do not make their nodes boundary-of-the-boundary nodes, so those nodes
@@ -115,6 +146,7 @@ class Model:
                 in_boundary[lst[0]] = True
         self.in_boundary = in_boundary
         self.node_part = node_part
+        self.mca_delta = mca_deltas(in_boundary, node_part, formulation)      # formulation {part id: (kind, delta)}: [bem formulation over boundaries]
 
         # --- boundary conditions per node
         self.ctype = np.zeros((nn, nd), dtype=np.int32)
@@ -200,8 +232,8 @@ class Model:
             et = int(mesh.etype[e]); c = mesh.conn[e]
             xn = self.node_x[c]
             for kn, v in enumerate(c):
-                if in_boundary[v]:
-                    xi = sh.move_xi_from_edge(et, sh.XI_NODES[et][kn], MCA_BOUNDARY_DELTA)
+                if self.mca_delta[v] != 0.0:
+                    xi = sh.move_xi_from_edge(et, sh.XI_NODES[et][kn], mca_delta_of(et, self.mca_delta[v]))
                     cx.append(sh.position(et, xn, xi)); cxi.append(xi)
                 elif not collocated[v]:
                     collocated[v] = True

@@ -20,7 +20,7 @@ impervious) and to each other (perfectly permeable): numbering build_auxiliary_v
 """
 import numpy as np
 from . import shape as sh
-from .model import MCA_BOUNDARY_DELTA, NODAL_XI_MARK
+from .model import MCA_BOUNDARY_DELTA, NODAL_XI_MARK, mca_deltas, mca_delta_of
 
 SOLID, FLUID, PORO = "solid", "fluid", "poro"
 
@@ -53,7 +53,7 @@ class RegionView:
 
 class MultiRegionModel:
     def __init__(self, mesh, regions, boundary_part, bcs, qsi_relative_error=1e-6, qsi_ns_max=16, precalset_gln=(2, 3, 4, 5, 6, 7, 8, 9),
-                 geometric_tolerance=1e-6, interface_ctype=None, symmetry=None):
+                 geometric_tolerance=1e-6, interface_ctype=None, symmetry=None, formulation=None):
         """boundary_part {boundary id: part id of the mesh}; bcs {boundary id: (ctypes, values)} for the ORDINARY boundaries (solid: three
         components, fluid: scalars, poroelastic: tau / Un then the three skeleton components), 0 = primary variable known, 1 = secondary
         variable known.  interface_ctype {boundary id: 0 | 1}: condition of a fluid-poroelastic interface, 0 perfectly permeable (default),
@@ -102,6 +102,7 @@ class MultiRegionModel:
             if len(lst) == 1:
                 in_boundary[lst[0]] = True
         self.node_boundary, self.in_boundary = node_b, in_boundary
+        self.mca_delta = mca_deltas(in_boundary, node_b, formulation)         # formulation {boundary id: (kind, delta)}: [bem formulation over boundaries]
         self.elems_of_boundary = {b: [e for e in range(ne) if int(mesh.part[e]) == p] for b, p in self.boundary_part.items()}
         # --- boundary conditions of the ordinary boundaries
         self.ctype = {}
@@ -235,8 +236,8 @@ class MultiRegionModel:
             eq = 1 if self.boundary_regions[ebnd[le]][0] == kr else 2
             for kn, nd in enumerate(c):
                 nd = int(nd)
-                if self.in_boundary[nd]:
-                    xi = sh.move_xi_from_edge(et, sh.XI_NODES[et][kn], MCA_BOUNDARY_DELTA)
+                if self.mca_delta[nd] != 0.0:
+                    xi = sh.move_xi_from_edge(et, sh.XI_NODES[et][kn], mca_delta_of(et, self.mca_delta[nd]))
                     cx.append(sh.position(et, xn, xi)); cxi.append(xi)
                 elif not collocated[nd]:
                     collocated[nd] = True
