@@ -280,7 +280,7 @@ def test_unsupported_features_are_named(tmp_path):
     base = SOLID_DAT % dict(analysis="static", freq="", z="0.", one="1.")
     for old, new, word in [("1 1 ordinary", "1 1 crack-like", "ordinary"), ("[regions]\n1\n", "[regions]\n2\n", "regions announced"),
                            ("boundary 2: 1 1.", "boundary 2: 5 1.", "condition type 5"), ("n = 3D", "n = 2D", "3D"),
-                           ("1 be\n", "1 fe\n", "`be`"), ('mesh_file_mode = 2 "cube.msh"', "mesh_file_mode = 0", "mesh_file_mode"),
+                           ("1 be\n", "1 fe\n", "`be`"), ('mesh_file_mode = 2 "cube.msh"', "mesh_file_mode = 0", "[nodes]"), ('mesh_file_mode = 2 "cube.msh"', "mesh_file_mode = 3", "wrong type of mesh mode"),
                            ("6 1 2 3 4 5 6", "6 1 2 3 4 5 -6", "reversed")]:
         assert old in base
         path = _write_case(tmp_path, base.replace(old, new, 1))
@@ -777,3 +777,75 @@ def _run_with_oracle_local(path):
             self.model.add_condition_rows(A, b)
             return np.linalg.solve(A, b)
     return driver.run(path, solver=S(case, case.build_model()), log=io.StringIO()), case
+
+
+def _native_sections(mesh):
+    names = {shape.TRI3: "tri3", shape.TRI6: "tri6", shape.QUAD4: "quad4", shape.QUAD8: "quad8", shape.QUAD9: "quad9"}
+    out = ["[nodes]", str(len(mesh.nodes))] + ["%d %.17g %.17g %.17g" % (k + 1, x[0], x[1], x[2]) for k, x in enumerate(mesh.nodes)]
+    out += ["", "[elements]", str(mesh.n_elem)]
+    out += ["%d %s 1 %d %s" % (k + 1, names[int(mesh.etype[k])], mesh.part[k], " ".join(str(int(v) + 1) for v in mesh.conn[k])) for k in range(mesh.n_elem)]
+    parts = sorted(set(int(p) for p in mesh.part))
+    out += ["", "[parts]", str(len(parts))] + ["%d face%d" % (p, p) for p in parts]
+    return "\n".join(out) + "\n"
+
+
+def test_mesh_inside_the_case_file_and_in_a_native_file(tmp_path):
+    """mesh_file_mode 0 / absent ([nodes], [elements], [parts] of the case file) and 1 (the same sections in an auxiliary file) give the model of the Gmsh file."""
+    base = SOLID_DAT % dict(analysis="static", freq="", z="0.", one="1.")
+    path = _write_case(tmp_path, base, et=shape.QUAD8, m=2)
+    ref = CaseFile(path).build_model()
+    mesh = cube_mesh(2, shape.QUAD8)
+    p0 = str(tmp_path / "inline.dat")
+    open(p0, "w").write(base.replace('mesh_file_mode = 2 "cube.msh"', "") + "\n" + _native_sections(mesh))
+    (tmp_path / "cube.native").write_text(_native_sections(mesh))
+    p1 = str(tmp_path / "native.dat")
+    open(p1, "w").write(base.replace('mesh_file_mode = 2 "cube.msh"', 'mesh_file_mode = 1 "cube.native"'))
+    for p, mode in ((p0, 0), (p1, 1)):
+        c = CaseFile(p)
+        md = c.build_model()
+        assert c.mesh_file_mode == mode and np.array_equal(md.node_x, ref.node_x) and np.array_equal(md.elem_node, ref.elem_node)
+        assert np.array_equal(md.row, ref.row) and np.array_equal(md.colloc_x, ref.colloc_x) and np.array_equal(md.mesh.node_ids, ref.mesh.node_ids)
+    # a part that no boundary uses is dropped with its nodes, as the reference drops it
+    extra = _native_sections(mesh).replace("[elements]\n%d\n" % mesh.n_elem, "[elements]\n%d\n%d quad4 1 99 1 2 3 4\n" % (mesh.n_elem + 1, mesh.n_elem + 1))
+    open(p0, "w").write(base.replace('mesh_file_mode = 2 "cube.msh"', "") + "\n" + extra)
+    assert CaseFile(p0).build_model().n_elem == ref.n_elem
+    open(p0, "w").write(base.replace('mesh_file_mode = 2 "cube.msh"', ""))
+    with pytest.raises(CaseFileError) as ei:
+        CaseFile(p0)
+    assert "[nodes]" in str(ei.value)
+
+
+def test_bem_formulation_section_and_selected_export_nodes(tmp_path):
+    """[bem formulation over boundaries]: the MCA displacement per boundary; the exact column solution survives every choice.  [export] nso_nodes: rows of those nodes only."""
+    from multifebe_b200.host.model import MCA_BOUNDARY_DELTA
+    base = (SOLID_DAT % dict(analysis="static", freq="", z="0.", one="1.")).replace("eng_double", "sci_double")
+    default = CaseFile(_write_case(tmp_path, base, et=shape.QUAD9, m=2)).build_model()
+    assert set(np.unique(default.mca_delta)) == {0.0, MCA_BOUNDARY_DELTA}
+    text = base + "\n[bem formulation over boundaries]\nboundary 1: sbie_boundary_mca 0.01\nboundary 2: sbie_mca 0.\nboundary 3: sbie_mca 0.3\nboundary 4: sbie_boundary_mca -1.\n"
+    text = text.replace("real_format = sci_double", "real_format = sci_double\nnso_nodes = 3 5 1 40")
+    path = _write_case(tmp_path, text, et=shape.QUAD9, m=2)
+    case = CaseFile(path)
+    md = case.build_model()
+    assert case.formulation == {1: ("sbie_boundary_mca", 0.01), 2: ("sbie_mca", 0.0), 3: ("sbie_mca", 0.3), 4: ("sbie_boundary_mca", -1.0)} and case.nso_nodes == {1, 5, 40}
+    for part, rim, inner in ((1, 0.01, 0.0), (2, -1.0, -1.0), (3, 0.3, 0.3), (4, MCA_BOUNDARY_DELTA, 0.0), (5, MCA_BOUNDARY_DELTA, 0.0)):
+        sel = md.node_part == part
+        assert set(md.mca_delta[sel & md.in_boundary]) == {rim} and set(md.mca_delta[sel & ~md.in_boundary]) == {inner}
+    # sbie_mca: one collocation point per element node of the boundary, moved by the default of the element order (quadratic: 0.2254) or by the given delta
+    e2 = [e for e in range(md.n_elem) if int(md.mesh.part[e]) == 2]
+    assert sum((md.colloc_elem == e).sum() for e in e2) == 9 * len(e2)
+    k = int(np.flatnonzero((md.colloc_elem == e2[0]) & (md.colloc_kn == 0))[0])
+    assert np.allclose(md.colloc_xi[k], np.array([-1.0, -1.0]) * (1.0 - 0.22540333))
+    assert md.n_colloc > default.n_colloc and md.n_dof == default.n_dof
+    nso, _ = _run_with_oracle(path)
+    rows = read_nso(nso)
+    assert sorted(rows[:, 8]) == [1, 5, 40]
+    lam2mu = 2.0 * case.material.mu_r * case.material.nu_r / (1.0 - 2.0 * case.material.nu_r) + 2.0 * case.material.mu_r
+    assert np.abs(rows[:, 12] - rows[:, 9] / lam2mu).max() < 2e-4                      # u1 = x1 / (lambda + 2 mu), ME-ST-EL-002's exact field
+    for old, new, word in [("boundary 3: sbie_mca 0.3", "boundary 3: sbie", "open rim"), ("boundary 3: sbie_mca 0.3", "boundary 3: hbie 0.2", "not covered"),
+                           ("boundary 3: sbie_mca 0.3", "boundary 3: sbie_mca", "needs its delta"), ("nso_nodes = 3 5 1 40", "nso_nodes = 3 5 5 40", "repeated"),
+                           ("[bem formulation", "[element options]\nx\n\n[bem formulation", "element options")]:
+        assert old in text
+        p = _write_case(tmp_path, text.replace(old, new, 1), et=shape.QUAD9, m=2)
+        with pytest.raises(CaseFileError) as ei:
+            CaseFile(p).build_model()
+        assert word in str(ei.value), (word, str(ei.value))

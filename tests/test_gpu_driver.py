@@ -109,3 +109,18 @@ def test_case_with_incident_waves(tmp_path, material, kind, space):
     h = nv // 2
     for sl in (slice(12, 12 + h), slice(12 + h, 12 + nv)):
         assert np.abs(a[:, sl] - b[:, sl]).max() <= 1e-8 * np.abs(b[:, sl]).max()
+
+
+def test_case_with_bem_formulation_section(tmp_path):
+    """[bem formulation over boundaries] on the device: MCA points at every node of two boundaries (sbie_mca, default and given delta), rim displacement 0.01
+    on a third -- harmonic and static against the oracle run of the same case."""
+    extra = "\n[bem formulation over boundaries]\nboundary 1: sbie_boundary_mca 0.01\nboundary 2: sbie_mca 0.\nboundary 3: sbie_mca 0.3\n"
+    freq = "\n[frequencies]\nrad/s\nlist\n2\n0.7\n3.1\n"
+    for k, analysis in enumerate(("harmonic", "static")):
+        d = tmp_path / ("f%d" % k); d.mkdir()
+        harm = analysis == "harmonic"
+        text = (SOLID_DAT % dict(analysis=analysis, freq=freq if harm else "", z="(0.,0.)" if harm else "0.", one="(1.,0.)" if harm else "1.")).replace("eng_double", "sci_double") + extra
+        path = _write_case(d, text, et=shape.QUAD9 if harm else shape.TRI6, m=2)
+        nso_cpu, case = _run_with_oracle(path, output=path + ".cpu")
+        assert case.formulation[2] == ("sbie_mca", 0.0)
+        _compare(driver.run(path, log=io.StringIO()), nso_cpu, harm)
