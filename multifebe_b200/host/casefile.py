@@ -17,11 +17,11 @@ Mirrors src/read_input_file.f90 for the sections the hot path consumes:
   [symmetry planes]  src/read_symmetry_planes.f90    `plane_n1|plane_yz : symmetry|antisymmetry` (also plane_n2|plane_zx, plane_n3|plane_xy) or the
                                              explicit form `x = <s> <t1> <t2> <t3>` (y, z alike); one elastic region
   [bem formulation over boundaries]  src/read_bem_formulation_boundaries.f90   `boundary <id>: sbie | sbie_boundary_mca <delta> | sbie_mca <delta>`
-  [incident waves]   src/read_incident_mechanics_harmonic.f90   plane / point waves in fluids, plane P / SV / SH waves in elastic solids, full space or
+  [incident waves]   src/read_incident_mechanics_harmonic.f90   plane / point waves in fluids, plane P / SV / SH / Rayleigh waves in elastic solids, full space or
                                              homogeneous half-space; listed per region by the last record of [regions] (`<n> <id> ...`)
   [export]       src/read_export.f90:61-293  export_nso, real_format, integer_format, complex_notation, nso_nodes
 Anything else the reference accepts (be-fe coupling, crack-like boundaries, close-pore conditions, local-axes or spring conditions,
-half-space fundamental solutions, body loads, layered / Rayleigh / poroelastic incident fields, internal points of fluid regions, FE regions ...) raises
+half-space fundamental solutions, body loads, layered / poroelastic incident fields, internal points of fluid regions, FE regions ...) raises
 CaseFileError naming the feature:
 the Fortran host keeps those.
 """
@@ -492,8 +492,10 @@ class CaseFile:
             else:
                 if cls != "plane":
                     raise CaseFileError("incident wave %d: only plane waves are covered in elastic solids" % fid)
-                if f["wave"] not in ("p", "sv", "sh"):
-                    raise CaseFileError('incident wave %d: wave type %r is not covered (p, sv, sh)' % (fid, f["wave"]))
+                if f["wave"] not in ("p", "sv", "sh", "rayleigh"):
+                    raise CaseFileError('incident wave %d: the wave type for a viscoelastic solid can be "p", "sv", "sh" or "rayleigh"' % fid)
+                if f["wave"] == "rayleigh" and (f["space"] != "half-space" or f["variable"] != 0):
+                    raise CaseFileError("incident wave %d: a Rayleigh wave needs the half-space and variable 0 (in terms of stresses it is not implemented in the reference)" % fid)
                 if np.any(f["x0"] != 0) or np.any(f["xs"] != 0):
                     raise CaseFileError("incident wave %d: all components of x0 and xs can be only 0." % fid)
                 if f["space"] == "half-space" and (f["np"] != 3 or f["bc"] != 1):

@@ -167,7 +167,7 @@ def fluid_point_wave_reference(fluid, omega, amplitude=1.0, x0=(0, 0, 0)):
 
 
 def elastic_plane_wave_reference(wave, mat, omega, varphi=0.0, theta=np.pi / 2, space="full-space", z_fs=0.0, symconf_y=0):
-    """-> field(x, n) = (u_inc (3,), t_inc (3,)) of `plane` / elastic / `p` | `sv` | `sh` (fbem_harela_incident_plane_wave) with the halving of
+    """-> field(x, n) = (u_inc (3,), t_inc (3,)) of `plane` / elastic / `p` | `sv` | `sh` | `rayleigh` (fbem_harela_incident_plane_wave) with the halving of
     its caller (calculate_incident_mechanics_harmonic.f90:439-440), which makes the free-field motion of the surface under vertical incidence 1.
     The wave travels in the vertical plane that makes the angle varphi with the yz plane, rising at the angle theta over the horizontal; in the
     half-space z <= z_fs (np = 3, bc = 1: stress-free surface) the reflected waves are added: SH -> SH; P -> P + SV; SV -> SV + P, the P wave
@@ -194,8 +194,24 @@ def elastic_plane_wave_reference(wave, mat, omega, varphi=0.0, theta=np.pi / 2, 
         den = kap * kap * s20 * s22 + c20 * c20
         local = [(1.0, np.array([0.0, s0, -c0], dtype=np.complex128), k2, inc), ((kap * kap * s20 * s22 - c20 * c20) / den, np.array([0.0, -s0, -c0], dtype=np.complex128), k2, rfl),
                  (-kap * 2.0 * s20 * c20 / den, np.array([0.0, c2, -s2]), k1, np.array([0.0, c2, -s2]))]
+    elif wave == "rayleigh":
+        # surface wave of the half-space (harela_incident_field.f90:576-611): gamma = (c_R / c_2)^2 from Rayleigh's cubic g^3 - 8 g^2 + 8 (3 - 2 kap^2) g - 16 (1 - kap^2) = 0
+        # (the reference evaluates Cardano's closed form, `obtenerc`, and between nu = 0.395 and 0.405 takes the six-digit constant 0.887732: kept); a shear-type and
+        # a dilatational-type partial wave with the horizontal wavenumber k_R = k_2 / sqrt(gamma), both decaying with depth, amplitudes 1 and -2 / (2 - gamma)
+        if space != "half-space":
+            raise ValueError("incident wave: a Rayleigh wave exists only in the half-space")
+        if 0.395 < mat.nu_r < 0.405:
+            gs = 0.887732
+        else:
+            roots = np.roots([1.0, -8.0, 8.0 * (3.0 - 2.0 * kap * kap), -16.0 * (1.0 - kap * kap)])
+            gs = float(min(r.real for r in roots if abs(r.imag) < 1e-9 and 0.0 < r.real < 1.0))
+        gp = kap * kap * gs
+        kr = k2 / np.sqrt(gs)
+        q1, q2 = 1j * np.sqrt(1.0 - gs), 1j * np.sqrt(1.0 - gp)
+        local = [(1.0, np.array([0.0, c0, 1j / np.sqrt(1.0 - gs)]), kr, np.array([0.0, c0, q1])),
+                 (-2.0 / (2.0 - gs), np.array([0.0, c0, q2]), kr, np.array([0.0, c0, q2]))]
     else:
-        raise ValueError("incident wave: elastic wave type %r (p, sv, sh; Rayleigh waves are not covered)" % (wave,))
+        raise ValueError("incident wave: elastic wave type %r (p, sv, sh, rayleigh)" % (wave,))
     if space == "full-space":
         local = local[:1]
     elif space != "half-space":

@@ -54,6 +54,31 @@ def test_elastic_plane_wave_in_a_half_space(wave, theta):
     assert np.abs(sym(xm, n)[0] - sym(x, n)[0] * [1, -1, 1]).max() < 1e-15 and np.abs(asym(xm, n)[0] + asym(x, n)[0] * [1, -1, 1]).max() < 1e-15
 
 
+@pytest.mark.parametrize("nu", [0.2, 0.33, 0.4, 0.45])
+def test_rayleigh_wave(nu):
+    """The surface wave of the half-space: Navier's equation, a stress-free surface, decay with depth, horizontal phase speed below c2.  At nu = 0.4 the
+    reference replaces the root of Rayleigh's cubic by the six-digit constant 0.887732 (`obtenerc`); kept, and it shows: the surface traction there is 5e-6, not 1e-15."""
+    mat = Material(2.0, 1.5, nu, 0.0)
+    omega, z_fs, nz = 3.0, 0.2, np.array([0.0, 0.0, 1.0])
+    ph = 0.6
+    f = inc.elastic_plane_wave_reference("rayleigh", mat, omega, ph, 0.0, "half-space", z_fs, 0)
+    x = np.array([0.3, -0.4, -0.7])
+    u = lambda y: f(y, nz)[0]
+    H = _second_derivatives(u, x)
+    navier = (mat.lam + mat.mu) * np.einsum("jij->i", H) + mat.mu * np.einsum("jji->i", H) + mat.rho * omega ** 2 * u(x)
+    assert np.abs(navier).max() < 2e-4 * mat.rho * omega ** 2 * np.abs(u(x)).max()
+    t_surf = np.abs(f(np.array([0.4, 0.1, z_fs]), nz)[1]).max()
+    assert t_surf < (1e-13 if nu != 0.4 else 2e-5) and (nu != 0.4 or t_surf > 1e-7)
+    assert np.abs(f(np.array([0.0, 0.0, -30.0]), nz)[0]).max() < 1e-12 and np.abs(f(np.array([0.0, 0.0, z_fs]), nz)[0]).max() > 0.3
+    d = np.array([np.sin(ph), np.cos(ph), 0.0])                         # horizontal propagation; phase speed c_R = c2 sqrt(gamma), 0.87 .. 0.96 c2
+    s = 0.05
+    ratio = u(np.array([0, 0, z_fs]) + s * d) / u(np.array([0, 0, z_fs]))
+    c_r = omega * s / (-np.angle(ratio[2]))
+    assert 0.85 * mat.c2.real < c_r < 0.97 * mat.c2.real and np.abs(np.abs(ratio[2]) - 1.0) < 1e-12
+    with pytest.raises(ValueError):
+        inc.elastic_plane_wave_reference("rayleigh", mat, omega, ph, 0.0, "full-space")
+
+
 def test_elastic_plane_wave_normalisation_and_full_space():
     """Vertical incidence: the free-field motion of the surface has modulus 1 (incident + reflected, halved by the caller); in the full space the
     field is the single wave of amplitude 1/2 travelling along (cos th sin ph, cos th cos ph, sin th) with the speed of its kind."""
@@ -270,7 +295,8 @@ def test_incident_section_errors_are_named(tmp_path):
         assert word in str(ei.value), (word, str(ei.value))
     solid = TRANSMISSION_DAT % dict(material="elastic_solid rho 2. mu 1.5 nu 0.3 xi 0.", kind="elastic sh", space="half-space 3 0. 1", varphi="0.", theta="90.")
     for old, new, word in [("half-space 3 0. 1", "half-space 2 0. 1", "np can be only 3"), ("0. 0. 0. 0. 0. 0.\n", "0. 0. 0. 1. 0. 0.\n", "x and z"),
-                           ("(1.,0.) 0. 0. 0.", "(1.,0.) 0. 1. 0.", "x0 and xs"), ("elastic sh", "elastic rayleigh", "not covered")]:
+                           ("(1.,0.) 0. 0. 0.", "(1.,0.) 0. 1. 0.", "x0 and xs"), ("elastic sh", "elastic love", '"p", "sv", "sh" or "rayleigh"'),
+                           ("half-space 3 0. 1\n0 (1.,0.) 0. 0. 0. 0. 90.\n0. 0. 0. 0. 0. 0.\nelastic sh", "full-space\n0 (1.,0.) 0. 0. 0. 0. 90.\n0. 0. 0. 0. 0. 0.\nelastic rayleigh", "Rayleigh")]:
         assert old in solid, old
         path = str(tmp_path / "bad.dat")
         open(path, "w").write(solid.replace(old, new, 1))
