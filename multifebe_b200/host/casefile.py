@@ -354,6 +354,10 @@ class CaseFile:
         if il:
             if self.multi or self.region_type != 2:
                 raise CaseFileError("[internal points]: covered for one elastic region (a fluid region would need the hypersingular fluid kernels)")
+            if any(self.region_incident):
+                # the interior identities would need the incident field at the points and its terms on the interior rows (calculate_internal_points_mechanics_bem_harela.f90
+                # adds them); not wired, and silently wrong otherwise
+                raise CaseFileError("[internal points] together with [incident waves] is not covered")
             for s_ in il[1:1 + int(il[0].split()[0])]:
                 w = s_.split()
                 if int(w[1]) != self.region_id:
@@ -481,7 +485,8 @@ class CaseFile:
                 raise CaseFileError('incident wave %d: the region type must be "fluid", "elastic", "viscoelastic" or "poroelastic"' % fid)
             f["region_type"], f["wave"] = rt, w[1].lower()
             if rt == 3:
-                raise CaseFileError("incident wave %d: incident fields of poroelastic media are not covered (the arrays can be given through set_incident)" % fid)
+                raise CaseFileError("incident wave %d: incident fields of poroelastic media are not covered -- the reference stops there too ('please, check poroelastic free-field', "
+                                    "calculate_incident_mechanics_harmonic.f90:511); arrays of the caller's own can be given through set_incident" % fid)
             if rt == 1:
                 if f["wave"] != "p":
                     raise CaseFileError('incident wave %d: the wave type for a fluid can be only "p"' % fid)
@@ -540,7 +545,10 @@ class CaseFile:
                     scale = 1.0
                     if f["variable"] == 1:           # the field in terms of stresses (calculate_incident_mechanics_harmonic.f90:456-470)
                         scale = 1.0 / (-1j * (omega / mat.c1) * (mat.lam + 2.0 * mat.mu)) if f["wave"] == "p" else 1.0 / (-1j * (omega / mat.c2) * mat.mu)
-                u, t = inc.element_incident_of(model.node_x, v.etype, v.elem_ptr, v.elem_node, v.elem_reversed, fld, 1 if rtype == 1 else 3)
+                geom = self.__dict__.setdefault("_incident_geometry", {})            # positions and normals: once per model, not per frequency
+                if (id(model), kr) not in geom:
+                    geom[(id(model), kr)] = inc.element_node_geometry(model.node_x, v.etype, v.elem_ptr, v.elem_node, v.elem_reversed)
+                u, t = inc.field_at(fld, *geom[(id(model), kr)], 1 if rtype == 1 else 3)
                 tot = (scale * u, scale * t) if tot is None else (tot[0] + scale * u, tot[1] + scale * t)
             out[kr] = tot
         return out

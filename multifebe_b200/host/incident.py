@@ -139,13 +139,15 @@ def fluid_plane_wave_reference(fluid, omega, amplitude=1.0, x0=(0, 0, 0), varphi
     waves = _mirror_parts(waves, symconf, vector=False)
     rw2 = fluid.rho * omega ** 2
 
-    def field(x, n):
+    def field(x, n):                                   # one point (3,), (3,) or a batch (m, 3), (m, 3)
         d = np.asarray(x, dtype=np.float64) - xs
-        p, grad = 0j, np.zeros(3, dtype=np.complex128)
+        nn = np.asarray(n, dtype=np.float64)
+        p, grad = np.zeros(d.shape[:-1], dtype=np.complex128), np.zeros(d.shape, dtype=np.complex128)
         for a, _, kv in waves:
-            e = a * np.exp(-1j * np.dot(kv, d))
-            p += e; grad += -1j * kv * e
-        return p, np.dot(grad, np.asarray(n, dtype=np.float64)) / rw2
+            e = a * np.exp(-1j * (d @ kv))
+            p = p + e; grad = grad + e[..., None] * (-1j * kv)
+        un = np.sum(grad * nn, axis=-1) / rw2
+        return (p, un) if d.ndim > 1 else (complex(p), complex(un))
     return field
 
 
@@ -157,12 +159,13 @@ def fluid_point_wave_reference(fluid, omega, amplitude=1.0, x0=(0, 0, 0)):
     A = complex(amplitude)
     rw2 = fluid.rho * omega ** 2
 
-    def field(x, n):
+    def field(x, n):                                   # one point or a batch, as above
         rv = np.asarray(x, dtype=np.float64) - x0
-        r = np.linalg.norm(rv)
+        r = np.linalg.norm(rv, axis=-1)
         p = A * np.exp(-1j * k * (r - 1.0)) / r
         dpdr = -p * (1.0 / r + 1j * k)
-        return p, dpdr * np.dot(rv / r, np.asarray(n, dtype=np.float64)) / rw2
+        un = dpdr * np.sum(rv * np.asarray(n, dtype=np.float64), axis=-1) / r / rw2
+        return (p, un) if rv.ndim > 1 else (complex(p), complex(un))
     return field
 
 
@@ -222,26 +225,46 @@ def elastic_plane_wave_reference(wave, mat, omega, varphi=0.0, theta=np.pi / 2, 
     org = np.array([0.0, 0.0, z_fs])
     lam, mu = mat.lam, mat.mu
 
-    def field(x, n):
+    def field(x, n):                                   # one point or a batch, as above
         d = np.asarray(x, dtype=np.float64) - org
-        u, grad = np.zeros(3, dtype=np.complex128), np.zeros((3, 3), dtype=np.complex128)
+        nn = np.asarray(n, dtype=np.float64)
+        u, grad = np.zeros(d.shape, dtype=np.complex128), np.zeros(d.shape + (3,), dtype=np.complex128)
         for a, pol, kv in waves:
-            e = a * np.exp(-1j * np.dot(kv, d))
-            u += pol * e; grad += np.outer(pol, -1j * kv) * e
-        sigma = lam * np.trace(grad) * np.eye(3) + mu * (grad + grad.T)
-        return u, sigma @ np.asarray(n, dtype=np.float64)
+            e = a * np.exp(-1j * (d @ kv))
+            u = u + e[..., None] * pol; grad = grad + e[..., None, None] * np.outer(pol, -1j * kv)     # grad[..., i, j] = du_i / dx_j
+        tr = np.trace(grad, axis1=-2, axis2=-1)
+        sigma = lam * tr[..., None, None] * np.eye(3) + mu * (grad + np.swapaxes(grad, -1, -2))
+        return u, np.einsum("...ij,...j->...i", sigma, nn)
     return field
 
 
 def element_incident_of(node_x, etype, elem_ptr, elem_node, elem_reversed, field, ndof):
     """element_incident / element_incident_fluid on flat arrays (a single-region model or the view of one region of a coupled model):
     -> (u_inc, t_inc), (sum nn, ndof) complex each."""
+    X, N = element_node_geometry(node_x, etype, elem_ptr, elem_node, elem_reversed)
+    return field_at(field, X, N, ndof)
+
+
+def element_node_geometry(node_x, etype, elem_ptr, elem_node, elem_reversed):
+    """(X, N), (sum nn, 3) each: position of every element node and the region's outward unit normal of its element there (element()%x_fn, n_fn with the
+    reversal applied) -- the part of the incident arrays that does not depend on the frequency."""
     n_rows = int(elem_ptr[-1])
-    u = np.zeros((n_rows, ndof), dtype=np.complex128); t = np.zeros((n_rows, ndof), dtype=np.complex128)
+    X = np.zeros((n_rows, 3)); N = np.zeros((n_rows, 3))
     for e in range(len(etype)):
         et = int(etype[e]); c = np.asarray(elem_node[elem_ptr[e]:elem_ptr[e + 1]]); xn = node_x[c]
         sgn = -1.0 if elem_reversed[e] else 1.0
         for kn in range(len(c)):
-            n = sgn * sh.unit_normal(et, xn, sh.XI_NODES[et][kn])
-            u[elem_ptr[e] + kn], t[elem_ptr[e] + kn] = field(xn[kn], n)
+            X[elem_ptr[e] + kn] = xn[kn]; N[elem_ptr[e] + kn] = sgn * sh.unit_normal(et, xn, sh.XI_NODES[et][kn])
+    return X, N
+
+
+def field_at(field, X, N, ndof):
+    """`field` over the batch (the *_reference fields take batches; any other callable is applied point by point) -> (primary, secondary), (m, ndof) each."""
+    try:
+        u, t = field(X, N)
+        u, t = np.asarray(u, dtype=np.complex128).reshape(len(X), ndof), np.asarray(t, dtype=np.complex128).reshape(len(X), ndof)
+    except (ValueError, TypeError):
+        u = np.zeros((len(X), ndof), dtype=np.complex128); t = np.zeros((len(X), ndof), dtype=np.complex128)
+        for i in range(len(X)):
+            u[i], t[i] = field(X[i], N[i])
     return u, t
