@@ -99,3 +99,59 @@ write("room", ROOM, "room.msh", cube_mesh(m, shape.QUAD9, L=3.0))
 freq = "\n[frequencies]\nrad/s\nlin\n8\n0.5\n7.5\n"
 write("column_harmonic", COLUMN % dict(analysis="harmonic", freq=freq, mesh="column.msh", z="(0.,0.)", one="(1.,0.)", incident="0\n"), "column.msh", cube_mesh(m, shape.TRI6))
 write("column_static", COLUMN % dict(analysis="static", freq="", mesh="column.msh", z="0.", one="1.", incident=""), "column.msh", cube_mesh(m, shape.QUAD8))
+
+# a soft cubic inclusion in an unbounded elastic medium under a plane P wave: two coupled regions sharing the six faces (the outer region lists them
+# reversed), the incident field of the [incident waves] section in the outer region only
+INCLUSION = """[problem]
+n = 3D
+type = mechanics
+analysis = harmonic
+description = soft cubic inclusion (side 1) in a full space, plane P wave travelling along (sin 30, cos 30, 0) cos 20 + z sin 20
+
+[frequencies]
+rad/s
+list
+3
+1.
+2.
+4.
+
+[settings]
+mesh_file_mode = 2 "inclusion.msh"
+
+[materials]
+2
+1 elastic_solid rho 1. mu 0.25 nu 0.3 xi 0.02
+2 elastic_solid rho 1. mu 1. nu 0.25 xi 0.01
+
+""" + BOUNDARIES + """
+[bem formulation over boundaries]
+""" + "".join("boundary %d: sbie_boundary_mca 0.05\n" % b for b in range(1, 7)) + """
+[regions]
+2
+
+1 be
+6 1 2 3 4 5 6
+material 1
+0
+0
+
+2 be
+6 -1 -2 -3 -4 -5 -6
+material 2
+0
+1 1
+
+[incident waves]
+1
+1
+plane
+full-space
+0 (1.,0.) 0. 0. 0. 30. 20.
+0. 0. 0. 0. 0. 0.
+elastic p
+
+[export]
+real_format = eng_simple
+"""
+write("inclusion_p_wave", INCLUSION, "inclusion.msh", cube_mesh(m, shape.QUAD9))
