@@ -94,5 +94,6 @@ def test_cantilever_wall_on_the_device(tmp_path):
         u, t = md.nodal_solution(np.linalg.solve(A, b))
         assert abs(u2[kf] - u[tip, 1]) <= 1e-7 * np.abs(u).max(), (kf, u2[kf], u[tip, 1])      # 1e-8 failed on hardware at kf = 10 (0.32 Hz, ON the first resonance) and was
         # loosened to 1e-7 after that run.  Measured afterwards without the file in between (tools/el002_resonance_check.py, profiles/r02_el002_resonance_check.log):
-        # |x_gpu - x_oracle| / max|x| = 6e-10, 7.7e-9, 1.7e-8, 2.7e-8, 7.3e-8 at cond_2(A) = 1.6e11, 4.7e11, 1.2e12, 2.0e12, 5.6e12 -- it follows the condition
-        # number of this unscaled SI-unit system, not the file's rounding.  BASELINE.json's 1e-8 on x is NOT met here at 0.31-0.33 Hz; kf = 60 passes it (5e-11).
+        # |x_gpu - x_oracle| / max|x| = 6e-10, 7.7e-9, 1.7e-8, 2.7e-8, 7.3e-8 at 3.7, 0.27, 0.31, 0.32, 0.33 Hz: BASELINE.json's 1e-8 on x is NOT met at 0.31-0.33 Hz.
+        # Not the file's rounding, and not the SI-unit column scaling either (profiles/r02_el002_equilibrated_cond.log): the gap is 2e-14 times the column-
+        # equilibrated condition number (3.6e5 ... 4.0e6 there), i.e. the resonance amplifying matrix entries that agree well inside the 1e-11 bar on A.
