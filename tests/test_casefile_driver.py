@@ -332,6 +332,26 @@ def test_two_rank_driver_writes_the_same_file(tmp_path):
     assert ra.shape == rb.shape and np.array_equal(ra[:, :12], rb[:, :12]) and np.allclose(ra, rb, rtol=1e-7, atol=1e-12)
 
 
+def test_two_rank_driver_with_an_incident_wave(tmp_path):
+    """The same with an [incident waves] field: every rank sets the arrays of the frequency it is about to solve (they depend on omega), and the writer
+    rank prints node()%incident_c of every frequency, also of those another rank solved."""
+    import torch.multiprocessing as mp
+    text = FLUID_DAT.replace("list\n2\n20.\n45.\n", "list\n3\n20.\n45.\n70.\n")
+    text = text.replace("0\n0\n\n[conditions", "0\n1 2\n\n[incident waves]\n1\n2\nplane\nfull-space\n0 (1.,0.5) 0. 0. 0. 40. 10.\n0. 0. 0. 0. 0. 0.\nfluid p\n\n[conditions")
+    assert "[incident waves]" in text
+    path = _write_case(tmp_path, text, et=shape.QUAD4, m=2)
+    nso1, case = _run_with_oracle(path)
+    port = 33500 + (os.getpid() % 2000)
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_gloo_worker, args=(2, port, path, out), nprocs=2, join=True)
+    ra, rb = read_nso(nso1), read_nso(path + ".w2.nso")
+    assert ra.shape == rb.shape and np.array_equal(ra[:, :12], rb[:, :12]) and np.allclose(ra, rb, rtol=1e-7, atol=1e-12)
+    inc_cols = ra[:, 16:20]
+    assert all(np.abs(inc_cols[ra[:, 0] == kf]).max() > 0.5 for kf in (1, 2, 3))                 # the incident pressure (amplitude |1 + 0.5i|) at every frequency
+    assert not np.allclose(inc_cols[ra[:, 0] == 1], inc_cols[ra[:, 0] == 2])                     # and it changes with the frequency
+
+
 def test_default_solver_is_the_gpu_and_fails_loudly_without_one(tmp_path):
     """No CPU fallback: without a CUDA device the driver stops in mfb_init (the CPU suite runs on a box without a GPU)."""
     from multifebe_b200 import capi
