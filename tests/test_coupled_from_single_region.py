@@ -191,3 +191,26 @@ def test_coupled_incident_no_scattering_identity():
         ok = ~np.isnan(u[:, 0])
         assert np.abs(u[ok] - u_node[ok]).max() < 1e-9 * np.abs(u_node).max()
         assert np.abs(t[ok] - sg * t_node[ok]).max() < 1e-9 * np.abs(t_node).max()
+
+
+def test_coupled_model_with_a_bem_formulation_per_boundary():
+    """[bem formulation over boundaries] on a coupled model: MCA points at every node of the interface (sbie_mca, default displacement of the element order) and a
+    rim displacement of 0.02 on another boundary; the views, the auxiliary single-region models and the multi-region oracle must all see the same points."""
+    bcs = bcs_for(SOLID, LAT1, 1, True); bcs.update(bcs_for(FLUID, LAT2, 2, False))
+    regs = [Region(SOLID, MS, [1, 3, 4, 5, 6, 7]), Region(FLUID, FL, [-7, 2, 13, 14, 15, 16])]
+    plain = MultiRegionModel(two_box_mesh(1, shape.QUAD8), regs, BPART, bcs)
+    mrm = MultiRegionModel(two_box_mesh(1, shape.QUAD8), regs, BPART, bcs, formulation={7: ("sbie_mca", 0.0), 1: ("sbie_boundary_mca", 0.02)})
+    on7 = mrm.node_boundary == 7
+    assert set(mrm.mca_delta[on7]) == {-1.0} and set(mrm.mca_delta[(mrm.node_boundary == 1) & mrm.in_boundary]) == {0.02}
+    assert mrm.n_dof == plain.n_dof and mrm.views[0].n_colloc == plain.views[0].n_colloc          # one quad8 per face: every node is a rim node already ...
+    k = int(np.flatnonzero(mrm.views[0].colloc_node == np.flatnonzero(on7)[0])[0])
+    assert not np.allclose(mrm.views[0].colloc_x[k], plain.views[0].colloc_x[k])                   # ... but the points sit at 0.2254 instead of 0.05 from the rim
+    A0, b0 = MultiRegionOracle(mrm).assemble(1.7)
+    A1, b1 = assemble_coupled(mrm, 1.7, oracle_local_assemble, oracle_freeterm)
+    sc = np.abs(A0).max(axis=0)
+    assert (np.abs(A1 - A0).max(axis=0) <= 1e-12 * sc).all() and np.abs(b1 - b0).max() <= 1e-12 * np.abs(b0).max()
+    # the physics does not depend on where the points are: the solutions of the two collocation schemes agree to the discretisation error
+    Ap, bp = MultiRegionOracle(plain).assemble(1.7)
+    u0, _ = mrm.nodal_solution(np.linalg.solve(A0, b0), 0); up, _ = plain.nodal_solution(np.linalg.solve(Ap, bp), 0)
+    ok = ~np.isnan(u0[:, 0])
+    assert np.abs(u0[ok] - up[ok]).max() < 0.1 * np.abs(up[ok]).max()
