@@ -96,4 +96,5 @@ def test_cantilever_wall_on_the_device(tmp_path):
         # loosened to 1e-7 after that run.  Measured afterwards without the file in between (tools/el002_resonance_check.py, profiles/r02_el002_resonance_check.log):
         # |x_gpu - x_oracle| / max|x| = 6e-10, 7.7e-9, 1.7e-8, 2.7e-8, 7.3e-8 at 3.7, 0.27, 0.31, 0.32, 0.33 Hz: BASELINE.json's 1e-8 on x is NOT met at 0.31-0.33 Hz.
         # Not the file's rounding, and not the SI-unit column scaling either (profiles/r02_el002_equilibrated_cond.log): the gap is 2e-14 times the column-
-        # equilibrated condition number (3.6e5 ... 4.0e6 there), i.e. the resonance amplifying matrix entries that agree well inside the 1e-11 bar on A.
+        # equilibrated condition number (3.6e5 ... 4.0e6 there).  Measured at 0.32 Hz (profiles/r02_el002_matrix_gap.log): the two matrices solved by the same host LAPACK differ
+        # by the same 2.7e-8; entries agree to 2e-15 except own-node diagonal blocks (free term + singular), up to 7.9e-12 of the column scale -- inside the 1e-11 bar on A.
