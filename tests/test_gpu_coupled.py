@@ -71,8 +71,10 @@ def test_coupled_regions_with_symmetry_planes(gpu_ctx, kinds, ict, planes):
 def test_coupled_regions_with_incident_fields(gpu_ctx, kinds, where):
     """An incident field in one or both regions of a coupled model (CoupledProblem.set_incident): the H problem of the region runs with the field set on the
     device, its right-hand side and the free-term part join b -- host combination and resident combination against the multi-region oracle.
-    (quad9 like the other coupled cases: on the quad8 two-box mesh one free-term diagonal of the ORACLE sits 1.3e-11 off, with or without a field -- the acos
-    formula of DESIGN.md 9.9, profiles/r02_coupled_incident_check.log.)"""
+    (quad9 like the other coupled cases.  On the quad8 two-box mesh this test failed its 1e-11 bar on A at one diagonal entry, 1.27e-11 of the column scale, with or
+    without a field (profiles/r02_coupled_incident_check.log).  That entry belongs to a corner node of the poroelastic box, a rim node with an MCA collocation point: its
+    free term is phi/2 on both sides, so the difference is in the singular integral of the point's own quad8 element in the poroelastic kernel -- a miss of the bar on
+    quad8 that is open, not a property of the incident field.  An earlier version of this note blamed the oracle's acos free term; that was wrong.)"""
     from multifebe_b200 import capi
     from oracle.multiregion import MultiRegionOracle
     from test_coupled_from_single_region import _random_incident
